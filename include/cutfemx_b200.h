@@ -1,0 +1,212 @@
+/* cutfemx_b200.h -- C ABI of libcutfemx_b200: the sm_100a cut-cell hot path of CutFEMx.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one
+ * seam of the reference's host code; the reference file:line it stands in for is cited
+ * on each declaration (paths relative to the CutFEMx source tree).  The reference's C++
+ * host library and nanobind layer stay as they are and call these functions with the flat
+ * arrays they already hold (DOLFINx host layouts); INTEGRATION.md shows the edits.
+ *
+ * Conventions
+ *  - plain C types only; all arrays are caller-owned; `memspace` says where a pointer
+ *    lives (CFX_HOST: the library copies to / from the GPU; CFX_DEVICE: borrowed as is).
+ *  - every function returns 0 on success or a negative cfx_status; the message is
+ *    available from cfx_last_error().  The host patch rethrows it as std::runtime_error,
+ *    which is what the reference throws at the same places (e.g. cut.cpp:97-106).
+ *  - one context per (process, GPU); calls on one context are not re-entrant (the
+ *    reference is single-threaded per MPI rank, SURVEY.md section 8b "Threading").
+ *  - there is NO CPU fallback: without a CUDA device cfx_ctx_create fails.
+ */
+#ifndef CUTFEMX_B200_H
+#define CUTFEMX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cfx_ctx cfx_ctx;
+typedef struct cfx_list cfx_list;       /* device-resident int32 array (entity ids / facet rows) */
+typedef struct cfx_rules cfx_rules;     /* device-resident cutcells::quadrature::QuadratureRules */
+typedef struct cfx_pattern cfx_pattern; /* device-resident CSR pattern + values (la::MatrixCSR) */
+typedef struct cfx_form cfx_form;       /* integral table of one Form (Form.h:46-89)            */
+typedef int cfx_status;
+
+enum { CFX_OK = 0, CFX_ERR_INVALID = -1, CFX_ERR_CUDA = -2, CFX_ERR_STATE = -3, CFX_ERR_RANGE = -4,
+       CFX_ERR_UNSUPPORTED = -5 };
+enum { CFX_HOST = 0, CFX_DEVICE = 1 };
+/* cell types: value == number of vertices (mesh/convert.h:14-38 maps the DOLFINx enum) */
+enum { CFX_TRIANGLE = 3, CFX_TETRAHEDRON = 4 };
+/* cutcells::cell::domain codes written by cfx_update (cut.cpp:292-321) */
+enum { CFX_DOMAIN_UNSET = 0, CFX_DOMAIN_INSIDE = 1, CFX_DOMAIN_INTERSECTED = 2, CFX_DOMAIN_OUTSIDE = 3 };
+/* cutcells::Relation (cut.cpp:323-342) */
+enum { CFX_REL_LT = 0, CFX_REL_LE = 1, CFX_REL_GT = 2, CFX_REL_GE = 3, CFX_REL_EQ = 4 };
+enum { CFX_MAX_LEVEL_SETS = 4, CFX_MAX_SPACES = 4, CFX_MAX_CLAUSES = 32, CFX_MAX_CONSTANTS = 8 };
+
+/* Hand-written element-kernel families (the role of the runintgen/FFCx generated
+ * tabulate_tensor functions called at assemble_matrix_impl.h:142,:323,:534 and
+ * assemble_vector_impl.h:103,:211,:333; forms: python/demo/demo_poisson.py:183-201). */
+enum {
+  CFX_K_LAPLACE = 1,        /* rank 2, cells:           c0 * inner(grad u, grad v)                                  */
+  CFX_K_MASS = 2,           /* rank 2, cells:           c0 * u * v                                                  */
+  CFX_K_NITSCHE = 3,        /* rank 2, interface rules: -(grad u.n) v - (grad v.n) u + c0/h u v   (needs normals)   */
+  CFX_K_GHOST_GRAD_JUMP = 4,/* rank 2, interior facets: c0 * avg(h) * jump(grad u,n) * jump(grad v,n)               */
+  CFX_K_SOURCE = 5,         /* rank 1, cells:           c0 * v                                                      */
+  CFX_K_NITSCHE_RHS = 6,    /* rank 1, interface rules: -(grad v.n) c1 + c0/h c1 v                (needs normals)   */
+  CFX_K_ONE = 7             /* rank 0, cells / rules:   c0  (volume, area, perimeter)                               */
+};
+
+/* ------------------------------------------------------------------ context */
+/* `stream` is a cudaStream_t (NULL = legacy default stream). */
+cfx_status cfx_ctx_create(int device, void* stream, cfx_ctx** out);
+void cfx_ctx_destroy(cfx_ctx* ctx);
+const char* cfx_last_error(const cfx_ctx* ctx); /* ctx may be NULL: last error of the calling thread */
+cfx_status cfx_sync(cfx_ctx* ctx);
+int cfx_version(void);
+/* number of kernel launches issued through this context since creation (bench.py "gpu_launches") */
+int64_t cfx_launch_count(const cfx_ctx* ctx);
+
+/* ------------------------------------------------------------------ mesh views
+ * replaces build_mesh_view, cut.cpp:500-538: x is geometry().x() (stride 3),
+ * x_dofmap the geometry dofmap (n_cells_total rows of nv int32).  Only the first
+ * n_cells_owned cells are cut (cell index_map size_local(), cut.cpp:507,532). */
+cfx_status cfx_mesh_bind(cfx_ctx* ctx, const double* x, int64_t n_nodes, const int32_t* x_dofmap,
+                         int64_t n_cells_owned, int64_t n_cells_total, int cell_type, int gdim, int memspace);
+/* topology()->connectivity(tdim,tdim-1) as (n_cells_total, tdim+1) int32 and, optionally,
+ * connectivity(tdim-1,tdim) as an AdjacencyList (offsets n_facets+1, data); when f2c is NULL
+ * it is derived on the device.  Used by cut.py:340-380, cut.cpp:926-994, wrappers/cut.cpp:54-115. */
+cfx_status cfx_topology_bind(cfx_ctx* ctx, const int32_t* c2f, const int32_t* f2c_offsets, const int32_t* f2c,
+                             int64_t n_facets, int64_t n_owned_facets, int memspace);
+
+/* ------------------------------------------------------------------ level sets
+ * replaces build_level_set_function, cut.cpp:593-636 (dofmap span + dof_values span).
+ * dofmap == NULL means "the geometry dofmap" (P1 on vertex numbering). With memspace
+ * CFX_HOST and pin_host != 0 the value array is page-locked for the life of the binding
+ * so that cfx_update re-reads it at full PCIe rate (it is the array cut.cpp:854-855 re-binds). */
+cfx_status cfx_levelset_bind(cfx_ctx* ctx, int ls, const int32_t* dofmap, int nd, int degree, const double* values,
+                             int64_t n_dofs, int memspace, int pin_host);
+/* cutfemx::update, cut.cpp:845-868 -> cutcells::cut: re-read every level set's values and
+ * classify all owned cells (cut.cpp:292-321: all dofs < 0 inside, all > 0 outside, else intersected). */
+cfx_status cfx_update(cfx_ctx* ctx);
+cfx_status cfx_counts(cfx_ctx* ctx, int ls, int64_t counts[3]); /* inside, intersected, outside */
+cfx_status cfx_domain_fetch(cfx_ctx* ctx, int ls, int8_t* out, int memspace);
+
+/* ------------------------------------------------------------------ selectors
+ * cutfemx::locate_entities, cut.cpp:877-924.  The selector is the compiled DNF of
+ * cutcells::SelectionExpr: term t is the AND of clauses term_offsets[t]..term_offsets[t+1],
+ * terms are OR-ed; clause k is "level set clause_ls[k]  clause_rel[k]  0".
+ * Result: ascending owned cell ids. */
+cfx_status cfx_locate_entities(cfx_ctx* ctx, int n_terms, const int32_t* term_offsets, const int32_t* clause_ls,
+                               const int32_t* clause_rel, cfx_list** out);
+int64_t cfx_list_size(const cfx_list* l);
+const int32_t* cfx_list_device_ptr(const cfx_list* l);
+cfx_status cfx_list_fetch(cfx_ctx* ctx, const cfx_list* l, int32_t* out, int memspace);
+void cfx_list_free(cfx_ctx* ctx, cfx_list* l);
+
+/* ------------------------------------------------------------------ run-time quadrature
+ * cutfemx::runtime_quadrature, cut.cpp:1311-1335 -> cutcells::select_part +
+ * cutcells::output::quadrature_rules, for a single-clause selector "ls rel 0".
+ * Points are parent-cell reference coordinates, weights are physical.
+ * If *inout is non-NULL its buffers are reused. */
+cfx_status cfx_runtime_quadrature(cfx_ctx* ctx, int ls, int relation, int order, cfx_rules** inout);
+cfx_status cfx_rules_sizes(const cfx_rules* r, int64_t* npts, int64_t* nrules, int* tdim);
+/* export in the reference's container layout (runtime_quadrature.h:107-137,
+ * wrappers/cut.cpp:185-226): points AoS (npts,tdim), weights, offsets (nrules+1), parent_map. */
+cfx_status cfx_rules_fetch(cfx_ctx* ctx, const cfx_rules* r, double* points_aos, double* weights, int32_t* offsets,
+                           int32_t* parent_map, int memspace);
+/* RuntimeQuadrature::physical_points, runtime_quadrature.h:102-221: SoA (gdim, npts). */
+cfx_status cfx_rules_physical_points(cfx_ctx* ctx, const cfx_rules* r, double* out_soa, int memspace);
+void cfx_rules_free(cfx_ctx* ctx, cfx_rules* r);
+/* sub-simplex rule tables: query the built-in one / override it (e.g. with basix::make_quadrature) */
+cfx_status cfx_simplex_rule(int dim, int order, int* npts, double* points, double* weights, int capacity);
+cfx_status cfx_set_simplex_rule(cfx_ctx* ctx, int dim, int order, int npts, const double* points,
+                                const double* weights);
+
+/* cutfemx::level_set::evaluate_normals, level_set/normal.h:39-188 (floor 1e-14 at :176-177):
+ * sign * grad(phi)/|grad(phi)| at the rules' points, AoS (npts, gdim) float64.  The result is
+ * also kept with the rules for the CFX_K_NITSCHE* kernels. out may be NULL. */
+cfx_status cfx_evaluate_normals(cfx_ctx* ctx, int ls, cfx_rules* r, double sign, double* out_aos, int memspace);
+/* cutfemx::level_set::evaluate_values, level_set/value.h:34-119 */
+cfx_status cfx_evaluate_values(cfx_ctx* ctx, int ls, const cfx_rules* r, double* out, int memspace);
+
+/* ------------------------------------------------------------------ ghost-penalty facets
+ * cutfemx.ghost_penalty_facets, python/cutfemx/cut.py:340-380: owned interior facets of the
+ * cells intersected by level set `cut_ls` whose two cells are both in (cut cells U selector). */
+cfx_status cfx_ghost_penalty_facets(cfx_ctx* ctx, int cut_ls, int n_terms, const int32_t* term_offsets,
+                                    const int32_t* clause_ls, const int32_t* clause_rel, int include_ghosts,
+                                    cfx_list** out);
+/* cutfemx::interior_facets_for_cells, cut.cpp:926-994 */
+cfx_status cfx_interior_facets_for_cells(cfx_ctx* ctx, const int32_t* cells, int64_t n, int memspace,
+                                         int include_ghosts, cfx_list** out);
+/* facet_integration_rows("interior_facet"), wrappers/cut.cpp:54-115: (cell0, lf0, cell1, lf1) per facet */
+cfx_status cfx_facet_integration_rows(cfx_ctx* ctx, const int32_t* facets, int64_t n, int memspace, cfx_list** out);
+
+/* ------------------------------------------------------------------ function spaces
+ * dolfinx::fem::DofMap of a Lagrange space of `degree` (1|2) on the bound mesh:
+ * dofmap (n_cells_total, nd) int32, block size bs, index_map size_local / +num_ghosts. */
+cfx_status cfx_space_bind(cfx_ctx* ctx, int space, const int32_t* dofmap, int nd, int bs, int degree,
+                          int64_t n_dofs_owned, int64_t n_dofs_total, int memspace);
+
+/* ------------------------------------------------------------------ forms (Form.h:46-89,119-677)
+ * One integral = (kernel family, entity list, constants, run-time rules as custom_data), the
+ * tuple python/cutfemx/fem.py:346-351 hands to create_form_*.  A cell integral over the mixed
+ * measure subdomain_data=[cells, rules] (demo_poisson.py:165-167) passes both `cells`
+ * (standard compile-time quadrature) and `rules` (loop index -> rule). */
+cfx_status cfx_form_create(cfx_ctx* ctx, int space, int rank, cfx_form** out);
+cfx_status cfx_form_add_cell_integral(cfx_ctx* ctx, cfx_form* f, int kernel, const int32_t* cells, int64_t n_cells,
+                                      int memspace, cfx_rules* rules, const double* constants, int n_constants);
+cfx_status cfx_form_add_interior_facet_integral(cfx_ctx* ctx, cfx_form* f, int kernel, const int32_t* rows4,
+                                                int64_t n_facets, int memspace, const double* constants,
+                                                int n_constants);
+void cfx_form_free(cfx_ctx* ctx, cfx_form* f);
+
+/* create_sparsity_pattern + finalize + MatrixCSR(sp): assembler.h:442-592, wrappers/fem.cpp:266-276.
+ * Pattern = union of cell cliques and facet macro cliques of the form's domains, plus the
+ * diagonal of every owned+ghost row (insert_deactivation_diagonal, assembler.h:538-560). */
+cfx_status cfx_create_sparsity(cfx_ctx* ctx, const cfx_form* a, cfx_pattern** inout);
+/* adopt a pattern built elsewhere (la::MatrixCSR row_ptr int64 / cols int32, sorted per row) */
+cfx_status cfx_pattern_import(cfx_ctx* ctx, int space, const int64_t* row_ptr, const int32_t* cols, int64_t n_rows,
+                              int memspace, cfx_pattern** out);
+cfx_status cfx_pattern_sizes(const cfx_pattern* p, int64_t* n_rows, int64_t* nnz);
+cfx_status cfx_pattern_fetch(cfx_ctx* ctx, const cfx_pattern* p, int64_t* row_ptr, int32_t* cols, int memspace);
+const double* cfx_pattern_values_device_ptr(const cfx_pattern* p);
+void cfx_pattern_free(cfx_ctx* ctx, cfx_pattern* p);
+
+/* assemble_matrix: assembler.h:596-703 -> assemble_matrix_impl.h:629-810 (cells :68-189, interior
+ * facets :409-607) with mat_set = MatrixCSR::mat_add_values (wrappers/fem.cpp:340-385).  Like the
+ * reference it ADDS into the matrix unless zero_first != 0.  Deterministic: every CSR entry is
+ * accumulated by one thread in a fixed order (no floating-point atomics).
+ * diag_inactive != 0 additionally writes that value on the diagonal of rows no active entity
+ * touches (deactivate_outside, fem/deactivate.h:402-418).  values_out may be NULL. */
+cfx_status cfx_assemble_matrix(cfx_ctx* ctx, const cfx_form* a, cfx_pattern* A, int zero_first, double diag_inactive,
+                               double* values_out, int memspace);
+/* assemble_vector: assemble_vector_impl.h:62-122,259-364,573-767; b has n_dofs_total*bs entries */
+cfx_status cfx_assemble_vector(cfx_ctx* ctx, const cfx_form* L, double* b, int zero_first, int memspace);
+/* assemble_scalar: assemble_scalar_impl.h:26-275 (fixed-order tree reduction) */
+cfx_status cfx_assemble_scalar(cfx_ctx* ctx, const cfx_form* M, double* out);
+
+/* ------------------------------------------------------------------ profiling hooks
+ * per-stage CUDA-event timings of the most recent calls, for bench.py's roofline block.
+ * names/ms are library-owned, valid until the next call on this context. */
+int cfx_stage_count(const cfx_ctx* ctx);
+const char* cfx_stage_name(const cfx_ctx* ctx, int i);
+cfx_status cfx_stage_timing_enable(cfx_ctx* ctx, int on);
+cfx_status cfx_stage_ms(cfx_ctx* ctx, int i, double* ms, double* bytes);
+cfx_status cfx_stage_reset(cfx_ctx* ctx);
+
+/* ------------------------------------------------------------------ synthetic meshes (harness)
+ * Device-side generator of the Kuhn box / right-diagonal rectangle meshes of
+ * cutfemx_b200/mesh.py (same numbering), so that 256^3 never has to exist on the host.
+ * All outputs are caller-allocated DEVICE arrays. f2c is dense (n_facets, 2), -1 padded. */
+cfx_status cfx_meshgen_box(cfx_ctx* ctx, int nx, int ny, int nz, const double p0[3], const double p1[3],
+                           double* x, int32_t* x_dofmap, int32_t* c2f);
+cfx_status cfx_meshgen_rectangle(cfx_ctx* ctx, int nx, int ny, const double p0[2], const double p1[2], double* x,
+                                 int32_t* x_dofmap, int32_t* c2f);
+/* level-set nodal interpolation on the device: kind 0 sphere/circle (c, R), 1 torus (c, R, r) */
+cfx_status cfx_meshgen_level_set(cfx_ctx* ctx, const double* x, int64_t n_nodes, int kind, const double params[5],
+                                 double* values);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUTFEMX_B200_H */

@@ -1,0 +1,262 @@
+"""ctypes front end of oracle/liboracle.so (the CPU restatement in cutfem_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import rules as _rules
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+REL = {"<": 0, "<=": 1, ">": 2, ">=": 3, "=": 4}
+INSIDE, INTERSECTED, OUTSIDE = 1, 2, 3
+
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_i8p = C.POINTER(C.c_int8)
+_f64p = C.POINTER(C.c_double)
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "cutfem_oracle.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_last_error.restype = C.c_char_p
+        for name in ("orc_locate", "orc_runtime_quadrature", "orc_ghost_penalty_facets",
+                     "orc_interior_facets_for_cells", "orc_sparsity"):
+            getattr(_LIB, name).restype = C.c_int64
+        _registered.clear()
+    return _LIB
+
+
+_registered: set = set()
+
+
+def _need_rule(dim: int, order: int):
+    if (dim, order) in _registered:
+        return
+    p, w = _rules.simplex_rule(dim, order)
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    lib().orc_set_rule(dim, order, int(w.size), _p(p, _f64p), _p(w, _f64p))
+    _registered.add((dim, order))
+
+
+def _p(a, t):
+    if a is None:
+        return None
+    return a.ctypes.data_as(t)
+
+
+def _chk(rc):
+    if rc < 0:
+        raise RuntimeError(lib().orc_last_error().decode())
+    return rc
+
+
+def _ci32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _cf64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def classify(ls_dofmap, values, ncells=None):
+    ls_dofmap = _ci32(ls_dofmap)
+    values = _cf64(values)
+    n = ls_dofmap.shape[0] if ncells is None else int(ncells)
+    dom = np.zeros(n, dtype=np.int8)
+    lib().orc_classify(_p(ls_dofmap, _i32p), int(ls_dofmap.shape[1]), _p(values, _f64p), C.c_int64(n), _p(dom, _i8p))
+    return dom
+
+
+def parse_selector(expr: str, names):
+    """cutcells::parse_selection_expr + compile_selection_expr as used at cut.cpp:881-882:
+    spaces ignored (cut.cpp:47-57), 'and' inside terms, 'or' between terms."""
+    s = expr.replace(" ", "")
+    term_offsets, cls, crel = [0], [], []
+    for term in s.split("or"):
+        for clause in term.split("and"):
+            for op in ("<=", ">=", "<", ">", "="):
+                if op in clause:
+                    name, rhs = clause.split(op)
+                    if rhs != "0":
+                        raise ValueError(f"selector clause '{clause}' must compare with 0")
+                    if name not in names:
+                        raise ValueError(f"unknown level set '{name}'")
+                    cls.append(list(names).index(name))
+                    crel.append(REL[op])
+                    break
+            else:
+                raise ValueError(f"cannot parse selector clause '{clause}'")
+        term_offsets.append(len(cls))
+    return _ci32(term_offsets), _ci32(cls), _ci32(crel)
+
+
+def locate(domain, expr: str, names=("phi",)):
+    domain = np.ascontiguousarray(np.atleast_2d(domain), dtype=np.int8)
+    to, cl, cr = parse_selector(expr, names)
+    ncells = domain.shape[1]
+    out = np.zeros(ncells, dtype=np.int32)
+    n = lib().orc_locate(_p(domain, _i8p), C.c_int64(domain.shape[1]), C.c_int64(ncells), int(to.size - 1),
+                         _p(to, _i32p), _p(cl, _i32p), _p(cr, _i32p), _p(out, _i32p))
+    return out[:n].copy()
+
+
+class Rules:
+    def __init__(self, tdim, points, weights, offsets, parent_map):
+        self.tdim, self.points, self.weights, self.offsets, self.parent_map = tdim, points, weights, offsets, parent_map
+        self.normals = None
+
+
+def runtime_quadrature(mesh, ls_dofmap, values, domain, relation: str, order: int) -> Rules:
+    """relation in '<', '<=', '>', '>=', '='; rules in ascending parent-cell order."""
+    tdim = mesh.tdim
+    _need_rule(tdim - 1 if relation == "=" else tdim, order)
+    x, xd, ld, v = _cf64(mesh.x), _ci32(mesh.x_dofmap), _ci32(ls_dofmap), _cf64(values)
+    dom = np.ascontiguousarray(domain, dtype=np.int8)
+    nc = C.c_int64(mesh.num_cells_local)
+    nr = C.c_int64(0)
+    args = (mesh.cell_type, _p(x, _f64p), _p(xd, _i32p), _p(ld, _i32p), _p(v, _f64p), _p(dom, _i8p), nc, REL[relation],
+            order)
+    npts = _chk(lib().orc_runtime_quadrature(*args, None, None, None, None, C.byref(nr)))
+    pts = np.zeros((npts, tdim))
+    wts = np.zeros(npts)
+    off = np.zeros(nr.value + 1, dtype=np.int32)
+    pm = np.zeros(nr.value, dtype=np.int32)
+    _chk(lib().orc_runtime_quadrature(*args, _p(pts, _f64p), _p(wts, _f64p), _p(off, _i32p), _p(pm, _i32p),
+                                      C.byref(nr)))
+    return Rules(tdim, pts, wts, off, pm)
+
+
+def physical_points(mesh, r: Rules):
+    out = np.zeros((mesh.gdim, r.weights.size))
+    x, xd = _cf64(mesh.x), _ci32(mesh.x_dofmap)
+    lib().orc_physical_points(mesh.cell_type, mesh.gdim, _p(x, _f64p), _p(xd, _i32p), _p(r.points, _f64p),
+                              _p(r.offsets, _i32p), _p(r.parent_map, _i32p), C.c_int64(r.parent_map.size),
+                              C.c_int64(r.weights.size), _p(out, _f64p))
+    return out
+
+
+def normals(mesh, ls_dofmap, ls_degree, values, r: Rules, sign: float = 1.0):
+    out = np.zeros((r.weights.size, mesh.gdim))
+    x, xd, ld, v = _cf64(mesh.x), _ci32(mesh.x_dofmap), _ci32(ls_dofmap), _cf64(values)
+    lib().orc_normals(mesh.cell_type, mesh.gdim, _p(x, _f64p), _p(xd, _i32p), _p(ld, _i32p), int(ld.shape[1]),
+                      ls_degree, _p(v, _f64p), _p(r.points, _f64p), _p(r.offsets, _i32p), _p(r.parent_map, _i32p),
+                      C.c_int64(r.parent_map.size), C.c_double(sign), _p(out, _f64p))
+    return out
+
+
+def values(mesh, ls_dofmap, ls_degree, vals, r: Rules):
+    out = np.zeros(r.weights.size)
+    ld, v = _ci32(ls_dofmap), _cf64(vals)
+    lib().orc_values(mesh.cell_type, _p(ld, _i32p), int(ld.shape[1]), ls_degree, _p(v, _f64p), _p(r.points, _f64p),
+                     _p(r.offsets, _i32p), _p(r.parent_map, _i32p), C.c_int64(r.parent_map.size), _p(out, _f64p))
+    return out
+
+
+def ghost_penalty_facets(mesh, cut_cells, selected_cells, include_ghosts=False):
+    cc, sc = _ci32(cut_cells), _ci32(selected_cells)
+    c2f, off, f2c = _ci32(mesh.c2f), _ci32(mesh.f2c_offsets), _ci32(mesh.f2c)
+    out = np.zeros(cc.size * c2f.shape[1] + 1, dtype=np.int32)
+    n = lib().orc_ghost_penalty_facets(_p(cc, _i32p), C.c_int64(cc.size), _p(sc, _i32p), C.c_int64(sc.size),
+                                       C.c_int64(mesh.num_cells), _p(c2f, _i32p), int(c2f.shape[1]), _p(off, _i32p),
+                                       _p(f2c, _i32p), C.c_int64(mesh.num_owned_facets), int(include_ghosts),
+                                       _p(out, _i32p))
+    return out[:n].copy()
+
+
+def interior_facets_for_cells(mesh, cells, include_ghosts=False):
+    cc = _ci32(cells)
+    c2f, off, f2c = _ci32(mesh.c2f), _ci32(mesh.f2c_offsets), _ci32(mesh.f2c)
+    out = np.zeros(cc.size * c2f.shape[1] + 1, dtype=np.int32)
+    n = lib().orc_interior_facets_for_cells(_p(cc, _i32p), C.c_int64(cc.size), C.c_int64(mesh.num_cells),
+                                            _p(c2f, _i32p), int(c2f.shape[1]), _p(off, _i32p), _p(f2c, _i32p),
+                                            C.c_int64(mesh.num_owned_facets), int(include_ghosts), _p(out, _i32p))
+    return out[:n].copy()
+
+
+def facet_rows(mesh, facets):
+    f = _ci32(facets)
+    c2f, off, f2c = _ci32(mesh.c2f), _ci32(mesh.f2c_offsets), _ci32(mesh.f2c)
+    rows = np.zeros((f.size, 4), dtype=np.int32)
+    _chk(lib().orc_facet_rows(_p(f, _i32p), C.c_int64(f.size), _p(c2f, _i32p), int(c2f.shape[1]), _p(off, _i32p),
+                              _p(f2c, _i32p), _p(rows, _i32p)))
+    return rows
+
+
+def sparsity(space, cells, rows4=None, insert_diagonal=True):
+    dm = _ci32(space.dofmap)
+    cells = _ci32(cells)
+    rows4 = _ci32(rows4 if rows4 is not None else np.zeros((0, 4)))
+    n_rows = space.num_dofs
+    rp = np.zeros(n_rows + 1, dtype=np.int64)
+    args = (_p(dm, _i32p), int(dm.shape[1]), C.c_int64(n_rows), _p(cells, _i32p), C.c_int64(cells.size),
+            _p(rows4, _i32p), C.c_int64(rows4.shape[0]), int(insert_diagonal), _p(rp, _i64p))
+    nnz = lib().orc_sparsity(*args, None)
+    cols = np.zeros(nnz, dtype=np.int32)
+    lib().orc_sparsity(*args, _p(cols, _i32p))
+    return rp, cols
+
+
+K = {"laplace": 1, "mass": 2, "nitsche": 3, "ghost_grad_jump": 4, "source": 5, "nitsche_rhs": 6, "one": 7}
+_RANK = {1: 2, 2: 2, 3: 2, 4: 2, 5: 1, 6: 1, 7: 0}
+
+
+def _register_std_rules(space, kernel_id):
+    td, p = space.mesh.tdim, space.degree
+    for o in {2 * (p - 1), 2 * p, p, 0}:
+        _need_rule(td, o)
+    _need_rule(td - 1, 2 * (p - 1))
+
+
+def assemble_cells(space, kernel: str, out, std_cells=None, rules: Rules | None = None, constants=(1.0,),
+                   row_ptr=None, cols=None):
+    """Adds the integral over entity list [std_cells ++ rules.parent_map] into `out`
+    (CSR values for rank 2, vector for rank 1, out[0] for rank 0)."""
+    mesh = space.mesh
+    kid = K[kernel]
+    _register_std_rules(space, kid)
+    x, xd, dm = _cf64(mesh.x), _ci32(mesh.x_dofmap), _ci32(space.dofmap)
+    sc = _ci32(std_cells if std_cells is not None else [])
+    cst = _cf64(list(constants) + [0.0] * 8)
+    if rules is not None:
+        pts, wts, off, pm, nr = rules.points, rules.weights, rules.offsets, rules.parent_map, rules.parent_map.size
+        nrm = rules.normals
+    else:
+        pts = wts = off = pm = nrm = None
+        nr = 0
+    _chk(lib().orc_assemble_cells(kid, _RANK[kid], mesh.cell_type, space.degree, _p(x, _f64p), _p(xd, _i32p),
+                                  _p(dm, _i32p), _p(sc, _i32p), C.c_int64(sc.size), _p(pts, _f64p), _p(wts, _f64p),
+                                  _p(off, _i32p), _p(pm, _i32p), C.c_int64(nr), _p(nrm, _f64p), _p(cst, _f64p),
+                                  _p(row_ptr, _i64p), _p(cols, _i32p), _p(out, _f64p)))
+    return out
+
+
+def assemble_interior_facets(space, kernel: str, vals, rows4, constants, row_ptr, cols):
+    mesh = space.mesh
+    kid = K[kernel]
+    _register_std_rules(space, kid)
+    x, xd, dm = _cf64(mesh.x), _ci32(mesh.x_dofmap), _ci32(space.dofmap)
+    rows4 = _ci32(rows4)
+    cst = _cf64(list(constants) + [0.0] * 8)
+    _chk(lib().orc_assemble_interior_facets(kid, mesh.cell_type, space.degree, _p(x, _f64p), _p(xd, _i32p),
+                                            _p(dm, _i32p), _p(rows4, _i32p), C.c_int64(rows4.shape[0]),
+                                            _p(cst, _f64p), _p(row_ptr, _i64p), _p(cols, _i32p), _p(vals, _f64p)))
+    return vals
