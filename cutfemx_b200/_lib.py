@@ -1,0 +1,135 @@
+"""ctypes binding of libcutfemx_b200.so (the C ABI in include/cutfemx_b200.h).
+
+There is no CPU fallback: if the shared library is missing or cannot be loaded this module
+raises, and every entry point raises `CfxError` when the C side reports a failure (e.g. no
+CUDA device).  The library is built in-tree by `cutfemx_b200._build.build_library()`
+(`__graft_entry__.build()` calls it).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcutfemx_b200.so")
+
+HOST, DEVICE = 0, 1
+TRIANGLE, TETRAHEDRON = 3, 4
+DOMAIN_INSIDE, DOMAIN_INTERSECTED, DOMAIN_OUTSIDE = 1, 2, 3
+REL = {"<": 0, "<=": 1, ">": 2, ">=": 3, "=": 4}
+KERNEL = {"laplace": 1, "mass": 2, "nitsche": 3, "ghost_grad_jump": 4, "source": 5, "nitsche_rhs": 6, "one": 7}
+KERNEL_RANK = {1: 2, 2: 2, 3: 2, 4: 2, 5: 1, 6: 1, 7: 0}
+
+# every symbol include/cutfemx_b200.h declares (tests/test_abi.py checks the .so exports them all)
+SYMBOLS = [
+    "cfx_ctx_create", "cfx_ctx_destroy", "cfx_last_error", "cfx_sync", "cfx_version", "cfx_launch_count",
+    "cfx_mesh_bind", "cfx_topology_bind", "cfx_levelset_bind", "cfx_update", "cfx_counts", "cfx_domain_fetch",
+    "cfx_locate_entities", "cfx_list_size", "cfx_list_device_ptr", "cfx_list_fetch", "cfx_list_free",
+    "cfx_runtime_quadrature", "cfx_rules_sizes", "cfx_rules_fetch", "cfx_rules_physical_points", "cfx_rules_free",
+    "cfx_simplex_rule", "cfx_set_simplex_rule", "cfx_evaluate_normals", "cfx_evaluate_values",
+    "cfx_ghost_penalty_facets", "cfx_interior_facets_for_cells", "cfx_facet_integration_rows", "cfx_space_bind",
+    "cfx_form_create", "cfx_form_add_cell_integral", "cfx_form_add_interior_facet_integral", "cfx_form_free",
+    "cfx_create_sparsity", "cfx_pattern_import", "cfx_pattern_sizes", "cfx_pattern_fetch",
+    "cfx_pattern_values_device_ptr", "cfx_pattern_values_fetch", "cfx_pattern_free", "cfx_assemble_matrix", "cfx_assemble_vector",
+    "cfx_assemble_scalar", "cfx_stage_count", "cfx_stage_name", "cfx_stage_timing_enable", "cfx_stage_ms",
+    "cfx_stage_reset", "cfx_meshgen_box", "cfx_meshgen_rectangle", "cfx_meshgen_level_set",
+]
+
+
+class CfxError(RuntimeError):
+    """Raised where the reference raises std::runtime_error / invalid_argument / out_of_range."""
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(libcutfemx_b200 has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.cfx_last_error.restype = C.c_char_p
+        L.cfx_last_error.argtypes = [C.c_void_p]
+        L.cfx_stage_name.restype = C.c_char_p
+        L.cfx_stage_name.argtypes = [C.c_void_p, C.c_int]
+        L.cfx_list_size.restype = C.c_int64
+        L.cfx_list_size.argtypes = [C.c_void_p]
+        L.cfx_launch_count.restype = C.c_int64
+        L.cfx_launch_count.argtypes = [C.c_void_p]
+        L.cfx_list_device_ptr.restype = C.c_void_p
+        L.cfx_list_device_ptr.argtypes = [C.c_void_p]
+        L.cfx_pattern_values_device_ptr.restype = C.c_void_p
+        L.cfx_pattern_values_device_ptr.argtypes = [C.c_void_p]
+        L.cfx_ctx_destroy.restype = None
+        for name in ("cfx_list_free", "cfx_rules_free", "cfx_pattern_free", "cfx_form_free"):
+            getattr(L, name).restype = None
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def check(ctx, status: int):
+    if status != 0:
+        msg = lib().cfx_last_error(ctx)
+        raise CfxError((msg.decode() if msg else "unknown error") + f" [status {status}]")
+
+
+def is_device_array(a) -> bool:
+    return hasattr(a, "data_ptr") and getattr(a, "is_cuda", False)
+
+
+def as_arg(a, dtype):
+    """(pointer, memspace, keepalive) for a numpy array (host) or a torch CUDA tensor (device)."""
+    if a is None:
+        return None, HOST, None
+    if is_device_array(a):
+        import torch
+
+        want = {np.float64: torch.float64, np.int32: torch.int32, np.int64: torch.int64, np.int8: torch.int8,
+                np.uint8: torch.uint8}[dtype]
+        if a.dtype != want or not a.is_contiguous():
+            a = a.to(want).contiguous()
+        return C.c_void_p(a.data_ptr()), DEVICE, a
+    arr = np.ascontiguousarray(a, dtype=dtype)
+    return C.c_void_p(arr.ctypes.data), HOST, arr
+
+
+def parse_selector(expr: str, names):
+    """The selector grammar of cutcells::parse_selection_expr as the reference uses it
+    (cut.cpp:881-882): whitespace ignored (cut.cpp:47-57), clauses `name rel 0` joined by
+    `and` inside a term, terms joined by `or`."""
+    import re
+
+    s = "".join(str(expr).split())
+    if not s:
+        raise ValueError("empty level-set selector")
+    clause_re = re.compile(r"([A-Za-z_]\w*?)(<=|>=|<|>|=)(0(?:\.0*)?)(?=and|or|$)")
+    term_offsets, cls, crel = [0], [], []
+    pos = 0
+    while True:
+        m = clause_re.match(s, pos)
+        if not m:
+            raise ValueError(f"cannot parse selector '{expr}' at '{s[pos:]}' (expected `name rel 0`)")
+        name, op = m.group(1), m.group(2)
+        if name not in names:
+            raise ValueError(f"selector references unknown level set '{name}' (known: {list(names)})")
+        cls.append(list(names).index(name))
+        crel.append(REL[op])
+        pos = m.end()
+        if pos == len(s):
+            break
+        if s.startswith("and", pos):
+            pos += 3
+        elif s.startswith("or", pos):
+            pos += 2
+            term_offsets.append(len(cls))
+        else:
+            raise ValueError(f"cannot parse selector '{expr}' at '{s[pos:]}' (expected `and` / `or`)")
+    term_offsets.append(len(cls))
+    return (np.asarray(term_offsets, dtype=np.int32), np.asarray(cls, dtype=np.int32),
+            np.asarray(crel, dtype=np.int32))

@@ -1,0 +1,172 @@
+// classify.cu -- K1: level-set cell classification, and cutfemx::locate_entities.
+//
+// Replaces the classification half of cutcells::cut (called at cpp/cutfemx/cut/cut.cpp:857) and
+// the selector scan cut.cpp:877-924.  Rule (cut.cpp:292-321): all dofs < 0 -> inside, all > 0 ->
+// outside, otherwise intersected (a zero dof makes the cell intersected).
+//
+// Roofline: HBM.  Algorithmic bytes = Nc*(4*nd + 1) + 8*Nd (dofmap row in, one code byte out,
+// every level-set value once) -- SURVEY.md section 8(d) "K1".
+#include "compact.cuh"
+
+namespace cfx
+{
+namespace
+{
+constexpr int CB = 256;
+
+template <int ND>
+__device__ __forceinline__ void load_row(const int32_t* __restrict__ dofmap, int64_t c, int32_t (&d)[ND])
+{
+  if constexpr (ND == 4)
+  {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(dofmap) + c);
+    d[0] = v.x;
+    d[1] = v.y;
+    d[2] = v.z;
+    d[3] = v.w;
+  }
+  else
+  {
+#pragma unroll
+    for (int k = 0; k < ND; ++k)
+      d[k] = __ldg(dofmap + c * ND + k);
+  }
+}
+
+// One thread per cell; a warp reads 32 consecutive dofmap rows (coalesced) and writes 32
+// consecutive code bytes. Ghost cells (c >= nc_owned) are classified too (their codes feed the
+// ghost-penalty band across partition boundaries) but are not counted.
+template <int ND>
+__global__ void __launch_bounds__(CB)
+    classify_kernel(const int32_t* __restrict__ dofmap, const double* __restrict__ vals, int64_t nc_total,
+                    int64_t nc_owned, int8_t* __restrict__ domain, unsigned long long* __restrict__ counts)
+{
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * CB + threadIdx.x;
+  int code = 0;
+  if (c < nc_total)
+  {
+    int32_t d[ND];
+    load_row<ND>(dofmap, c, d);
+    bool all_neg = true, all_pos = true;
+#pragma unroll
+    for (int k = 0; k < ND; ++k)
+    {
+      const double v = __ldg(vals + d[k]);
+      all_neg = all_neg && (v < 0.0);
+      all_pos = all_pos && (v > 0.0);
+    }
+    code = all_neg ? CFX_DOMAIN_INSIDE : (all_pos ? CFX_DOMAIN_OUTSIDE : CFX_DOMAIN_INTERSECTED);
+    domain[c] = static_cast<int8_t>(code);
+  }
+  const bool owned = c < nc_owned;
+  const unsigned b_in = __ballot_sync(0xffffffffu, owned && code == CFX_DOMAIN_INSIDE);
+  const unsigned b_cut = __ballot_sync(0xffffffffu, owned && code == CFX_DOMAIN_INTERSECTED);
+  const unsigned b_out = __ballot_sync(0xffffffffu, owned && code == CFX_DOMAIN_OUTSIDE);
+  __shared__ int s_cnt[3];
+  if (threadIdx.x < 3)
+    s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0)
+  {
+    atomicAdd(&s_cnt[0], __popc(b_in));
+    atomicAdd(&s_cnt[1], __popc(b_cut));
+    atomicAdd(&s_cnt[2], __popc(b_out));
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 && s_cnt[threadIdx.x] != 0)
+    atomicAdd(&counts[threadIdx.x], static_cast<unsigned long long>(s_cnt[threadIdx.x]));
+}
+
+template <int ND>
+void launch_classify(cfx_ctx* c, const LevelSet& L, int8_t* domain, unsigned long long* counts)
+{
+  CFX_LAUNCH(c, classify_kernel<ND>, grid_for(c->nc_total, CB), CB, 0, L.dofmap, L.values, c->nc_total, c->nc_owned,
+             domain, counts);
+}
+} // namespace
+
+void classify_all(cfx_ctx* c)
+{
+  c->scratch64.reserve(c->pool, 64);
+  unsigned long long* counts = reinterpret_cast<unsigned long long*>(c->scratch64.p) + 8;
+  CFX_CUDA(cudaMemsetAsync(counts, 0, 3 * CFX_MAX_LEVEL_SETS * sizeof(unsigned long long), c->stream));
+  for (int l = 0; l < CFX_MAX_LEVEL_SETS; ++l)
+  {
+    LevelSet& L = c->ls[l];
+    if (!L.bound)
+      continue;
+    StageScope st(c, "classify",
+                  static_cast<double>(c->nc_total) * (4.0 * L.nd + 1.0) + 8.0 * static_cast<double>(L.n_dofs));
+    int8_t* dom = c->domain.p + static_cast<size_t>(l) * c->domain_stride;
+    unsigned long long* cnt = counts + 3 * l;
+    switch (L.nd)
+    {
+    case 3: launch_classify<3>(c, L, dom, cnt); break;
+    case 4: launch_classify<4>(c, L, dom, cnt); break;
+    case 6: launch_classify<6>(c, L, dom, cnt); break;
+    case 10: launch_classify<10>(c, L, dom, cnt); break;
+    default: throw Error(CFX_ERR_UNSUPPORTED, "classify: unsupported level-set dofmap width");
+    }
+  }
+  const int64_t* h = read_back(c, c->scratch64.p + 8, 3 * CFX_MAX_LEVEL_SETS);
+  for (int l = 0; l < CFX_MAX_LEVEL_SETS; ++l)
+    for (int k = 0; k < 3; ++k)
+      c->ls[l].counts[k] = h[3 * l + k];
+}
+
+Dnf make_dnf(cfx_ctx* c, int n_terms, const int32_t* term_offsets, const int32_t* clause_ls, const int32_t* clause_rel)
+{
+  CFX_REQUIRE(n_terms >= 1 && term_offsets && clause_ls && clause_rel, CFX_ERR_INVALID, "selector: empty expression");
+  CFX_REQUIRE(n_terms <= CFX_MAX_CLAUSES && term_offsets[0] == 0 && term_offsets[n_terms] <= CFX_MAX_CLAUSES,
+              CFX_ERR_RANGE, "selector: too many clauses");
+  Dnf d;
+  std::memset(&d, 0, sizeof(d));
+  d.n_terms = n_terms;
+  for (int t = 0; t <= n_terms; ++t)
+    d.term_off[t] = term_offsets[t];
+  for (int k = 0; k < term_offsets[n_terms]; ++k)
+  {
+    // cut.cpp:895-902: "Compiled selector contains an invalid level-set index"
+    CFX_REQUIRE(clause_ls[k] >= 0 && clause_ls[k] < CFX_MAX_LEVEL_SETS && c->ls[clause_ls[k]].bound, CFX_ERR_INVALID,
+                "Compiled selector contains an invalid level-set index");
+    CFX_REQUIRE(clause_rel[k] >= CFX_REL_LT && clause_rel[k] <= CFX_REL_EQ, CFX_ERR_INVALID,
+                "selector: invalid relation");
+    d.ls[k] = static_cast<int8_t>(clause_ls[k]);
+    d.relmask[k] = relation_mask(clause_rel[k]);
+  }
+  return d;
+}
+
+void ensure_cut_list(cfx_ctx* c, int ls)
+{
+  LevelSet& L = c->ls[ls];
+  if (L.n_cut >= 0)
+    return;
+  Dnf d;
+  std::memset(&d, 0, sizeof(d));
+  d.n_terms = 1;
+  d.term_off[1] = 1;
+  d.ls[0] = static_cast<int8_t>(ls);
+  d.relmask[0] = relation_mask(CFX_REL_EQ);
+  DnfPred p{d, c->domain.p, c->domain_stride};
+  StageScope st(c, "locate_cut", static_cast<double>(c->nc_owned) * 2.0 + 4.0 * static_cast<double>(L.counts[1]));
+  L.n_cut = compact_indices(c, c->nc_owned, p, L.cut_list);
+}
+} // namespace cfx
+
+using namespace cfx;
+
+extern "C" cfx_status cfx_locate_entities(cfx_ctx* ctx, int n_terms, const int32_t* term_offsets,
+                                          const int32_t* clause_ls, const int32_t* clause_rel, cfx_list** out)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && ctx->classified, CFX_ERR_STATE, "cfx_locate_entities: call cfx_update first");
+  CFX_REQUIRE(out != nullptr, CFX_ERR_INVALID, "cfx_locate_entities: out is NULL");
+  DnfPred p{make_dnf(ctx, n_terms, term_offsets, clause_ls, clause_rel), ctx->domain.p, ctx->domain_stride};
+  if (*out == nullptr)
+    *out = new cfx_list();
+  StageScope st(ctx, "locate", static_cast<double>(ctx->nc_owned) * 2.0);
+  (*out)->n = compact_indices(ctx, ctx->nc_owned, p, (*out)->data);
+  st.set_bytes(static_cast<double>(ctx->nc_owned) * 2.0 + 4.0 * static_cast<double>((*out)->n));
+  CFX_API_END(ctx)
+}

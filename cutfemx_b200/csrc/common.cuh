@@ -1,0 +1,457 @@
+// common.cuh -- context, device-memory pool, launch/scan helpers shared by all translation units
+// of libcutfemx_b200 (sm_100a only; there is no CPU path in this library).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/cutfemx_b200.h"
+
+namespace cfx
+{
+struct Error : std::runtime_error
+{
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define CFX_CUDA(call)                                                                                                 \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    cudaError_t e_ = (call);                                                                                           \
+    if (e_ != cudaSuccess)                                                                                             \
+      throw cfx::Error(CFX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                              \
+  } while (0)
+
+#define CFX_REQUIRE(cond, code, msg)                                                                                   \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    if (!(cond))                                                                                                       \
+      throw cfx::Error(code, msg);                                                                                     \
+  } while (0)
+
+// ---- caching device allocator: handles are created/freed every step of a moving-level-set
+// loop; cudaMalloc/cudaFree would serialise the stream each time.
+class DevPool
+{
+public:
+  void* alloc(size_t bytes)
+  {
+    if (bytes == 0)
+      bytes = 256;
+    bytes = (bytes + 255) & ~size_t(255);
+    auto it = free_.lower_bound(bytes);
+    if (it != free_.end() && it->first <= 2 * bytes + (size_t(1) << 20))
+    {
+      void* p = it->second;
+      size_t sz = it->first;
+      free_.erase(it);
+      live_[p] = sz;
+      return p;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess)
+    {
+      release_cached();
+      e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess)
+      throw Error(CFX_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    live_[p] = bytes;
+    total_ += bytes;
+    return p;
+  }
+  void free(void* p)
+  {
+    if (!p)
+      return;
+    auto it = live_.find(p);
+    if (it == live_.end())
+      return;
+    free_.emplace(it->second, p);
+    live_.erase(it);
+  }
+  void release_cached()
+  {
+    for (auto& kv : free_)
+    {
+      cudaFree(kv.second);
+      total_ -= kv.first;
+    }
+    free_.clear();
+  }
+  void release_all()
+  {
+    release_cached();
+    for (auto& kv : live_)
+      cudaFree(kv.first);
+    live_.clear();
+    total_ = 0;
+  }
+  size_t total_bytes() const { return total_; }
+
+private:
+  std::multimap<size_t, void*> free_;
+  std::unordered_map<void*, size_t> live_;
+  size_t total_ = 0;
+};
+
+// grow-only typed device buffer bound to a pool
+template <class T>
+struct DevBuf
+{
+  T* p = nullptr;
+  size_t cap = 0; // elements
+  DevPool* pool = nullptr;
+  void reserve(DevPool& pl, size_t n)
+  {
+    if (n <= cap && p)
+      return;
+    if (p)
+      pool->free(p);
+    pool = &pl;
+    p = static_cast<T*>(pl.alloc(n * sizeof(T)));
+    cap = n;
+  }
+  void release()
+  {
+    if (p && pool)
+      pool->free(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct LevelSet
+{
+  bool bound = false;
+  const int32_t* dofmap = nullptr; // device
+  int nd = 0, degree = 0;
+  int64_t n_dofs = 0;
+  const double* values = nullptr;      // device (owned copy or borrowed)
+  const double* host_values = nullptr; // re-read by cfx_update when bound from the host
+  bool host_pinned = false;
+  DevBuf<double> values_own;
+  DevBuf<int32_t> dofmap_own;
+  int64_t counts[3] = {0, 0, 0};
+  DevBuf<int32_t> cut_list; // intersected owned cells, ascending (cached per update)
+  int64_t n_cut = -1;
+};
+
+struct Space
+{
+  bool bound = false;
+  const int32_t* dofmap = nullptr; // device (n_cells_total, nd)
+  DevBuf<int32_t> dofmap_own;
+  int nd = 0, bs = 1, degree = 0;
+  int64_t n_owned = 0, n_total = 0;
+  // static incidence dof -> cells (ascending), built once per bind
+  DevBuf<int64_t> inc_ptr;
+  DevBuf<int32_t> inc_cell;
+  int64_t n_inc = 0;
+};
+
+struct RuleTable
+{
+  int dim = 0, order = 0, npts = 0;
+  std::vector<double> pts, wts; // host
+  double* d_pts = nullptr;      // device, (npts, dim) AoS
+  double* d_wts = nullptr;
+};
+
+struct Stage
+{
+  std::string name;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  double bytes = 0.0;
+};
+} // namespace cfx
+
+struct cfx_list
+{
+  cfx::DevBuf<int32_t> data;
+  int64_t n = 0; // number of int32 entries
+};
+
+struct cfx_rules
+{
+  int tdim = 0, gdim = 0, relation = 0, order = 0, ls = 0;
+  int64_t npts = 0, nrules = 0;
+  cfx::DevBuf<double> points;  // SoA (tdim, npts)
+  cfx::DevBuf<double> weights; // (npts)
+  cfx::DevBuf<int32_t> offsets;    // (nrules + 1)
+  cfx::DevBuf<int32_t> parent_map; // (nrules)
+  cfx::DevBuf<double> normals;     // SoA (gdim, npts), valid if has_normals
+  bool has_normals = false;
+};
+
+struct cfx_pattern
+{
+  int space = 0;
+  int64_t n_rows = 0, nnz = 0;
+  cfx::DevBuf<int64_t> row_ptr;
+  cfx::DevBuf<int32_t> cols;
+  cfx::DevBuf<double> values;
+};
+
+struct cfx_integral
+{
+  int kernel = 0;
+  bool facet = false;
+  const int32_t* entities = nullptr; // device: std cells (cells) or rows4 (facets)
+  int64_t n = 0;
+  cfx::DevBuf<int32_t> own;
+  cfx_rules* rules = nullptr; // borrowed
+  double constants[CFX_MAX_CONSTANTS] = {};
+};
+
+struct cfx_form
+{
+  int space = 0, rank = 0;
+  std::vector<cfx_integral> integrals;
+  // prepared state (recomputed when dirty)
+  bool dirty = true;
+  cfx::DevBuf<uint8_t> cell_flags; // bit0: has a cell tensor, bit1: touches a facet-integral facet
+  cfx::DevBuf<int32_t> cell_slot;  // rank among flagged cells (valid where bit0)
+  cfx::DevBuf<int32_t> active;     // ascending cell ids with bit0 (slot i <-> cell active[i])
+  cfx::DevBuf<uint8_t> row_flag;   // per dof: touched by a flagged cell
+  int64_t n_active = 0;
+  cfx::DevBuf<double> Ae;      // (n_active, nd^rank)
+  cfx::DevBuf<uint8_t> written; // per slot
+  cfx::DevBuf<double> Fe;      // facet macro tensors
+};
+
+struct cfx_ctx
+{
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  cfx::DevPool pool;
+  int64_t launches = 0;
+
+  // mesh views
+  bool mesh_bound = false;
+  const double* x = nullptr;
+  const int32_t* x_dofmap = nullptr;
+  cfx::DevBuf<double> x_own;
+  cfx::DevBuf<int32_t> x_dofmap_own;
+  int64_t n_nodes = 0, nc_owned = 0, nc_total = 0;
+  int cell_type = 0, nv = 0, tdim = 0, gdim = 0;
+
+  // topology
+  bool topo_bound = false;
+  const int32_t* c2f = nullptr;
+  cfx::DevBuf<int32_t> c2f_own;
+  cfx::DevBuf<int32_t> f2c2; // dense (n_facets, 2), -1 padded, ascending
+  cfx::DevBuf<uint8_t> facet_flag;  // zero between calls
+  cfx::DevBuf<int32_t> facet_slot;  // -1 between calls
+  int64_t n_facets = 0, n_owned_facets = 0;
+
+  cfx::LevelSet ls[CFX_MAX_LEVEL_SETS];
+  cfx::DevBuf<int8_t> domain; // (CFX_MAX_LEVEL_SETS, domain_stride)
+  int64_t domain_stride = 0;
+  bool classified = false;
+
+  cfx::Space spaces[CFX_MAX_SPACES];
+
+  std::map<std::pair<int, int>, cfx::RuleTable> rules; // (dim, order) -> table (built-in or override)
+
+  // scratch
+  cfx::DevBuf<int32_t> blk_counts;
+  cfx::DevBuf<int64_t> blk_offsets;
+  cfx::DevBuf<int64_t> scratch64;
+  cfx::DevBuf<uint8_t> scratch8;
+  cfx::DevBuf<int32_t> err_flag; // device int[4]
+  int64_t* h_pinned = nullptr;   // 64 x int64 pinned host scratch
+
+  bool timing = false;
+  std::vector<cfx::Stage> stages;
+};
+
+namespace cfx
+{
+// ---------------------------------------------------------------- launch helper
+#define CFX_LAUNCH(ctx, kernel, grid, block, smem, ...)                                                                \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                                                   \
+    ++(ctx)->launches;                                                                                                 \
+    cudaError_t le_ = cudaGetLastError();                                                                              \
+    if (le_ != cudaSuccess)                                                                                            \
+      throw cfx::Error(CFX_ERR_CUDA, std::string(#kernel) + " launch: " + cudaGetErrorString(le_));                    \
+  } while (0)
+
+inline unsigned grid_for(int64_t n, int per_block)
+{
+  int64_t g = (n + per_block - 1) / per_block;
+  if (g < 1)
+    g = 1;
+  if (g > 2147483647LL)
+    throw Error(CFX_ERR_RANGE, "grid too large");
+  return static_cast<unsigned>(g);
+}
+
+struct StageScope
+{
+  cfx_ctx* c;
+  int idx = -1;
+  StageScope(cfx_ctx* ctx, const char* name, double bytes = 0.0) : c(ctx)
+  {
+    if (!c->timing)
+      return;
+    Stage s;
+    s.name = name;
+    s.bytes = bytes;
+    cudaEventCreate(&s.e0);
+    cudaEventCreate(&s.e1);
+    cudaEventRecord(s.e0, c->stream);
+    c->stages.push_back(s);
+    idx = static_cast<int>(c->stages.size()) - 1;
+  }
+  void set_bytes(double b)
+  {
+    if (idx >= 0)
+      c->stages[idx].bytes = b;
+  }
+  ~StageScope()
+  {
+    if (idx >= 0)
+      cudaEventRecord(c->stages[idx].e1, c->stream);
+  }
+};
+
+// copy helpers ------------------------------------------------------------------------
+template <class T>
+inline const T* adopt(cfx_ctx* c, DevBuf<T>& own, const T* src, size_t n, int memspace)
+{
+  if (memspace == CFX_DEVICE)
+    return src;
+  own.reserve(c->pool, n);
+  CFX_CUDA(cudaMemcpyAsync(own.p, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  return own.p;
+}
+
+template <class T>
+inline void export_to(cfx_ctx* c, T* dst, const T* src_dev, size_t n, int memspace)
+{
+  if (!dst || n == 0)
+    return;
+  CFX_CUDA(cudaMemcpyAsync(dst, src_dev, n * sizeof(T),
+                           memspace == CFX_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+  if (memspace == CFX_HOST)
+    CFX_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+// read `n` int64 from device into pinned host scratch (synchronises the stream)
+inline const int64_t* read_back(cfx_ctx* c, const int64_t* dev, int n)
+{
+  CFX_CUDA(cudaMemcpyAsync(c->h_pinned, dev, n * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  CFX_CUDA(cudaStreamSynchronize(c->stream));
+  return c->h_pinned;
+}
+
+void check_device_error(cfx_ctx* c, const char* where); // api.cu
+
+// ---------------------------------------------------------------- device primitives
+#ifdef __CUDACC__
+constexpr int SCAN_BLOCK = 256;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+
+__device__ __forceinline__ int warp_incl_scan(int v)
+{
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) >= o)
+      v += t;
+  }
+  return v;
+}
+
+// exclusive scan of one int per thread over a block of NT threads; *total = block sum
+template <int NT>
+__device__ __forceinline__ int block_excl_scan(int v, int* total)
+{
+  __shared__ int s_warp[NT / 32];
+  __shared__ int s_total;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int incl = warp_incl_scan(v);
+  if (lane == 31)
+    s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0)
+  {
+    int w = lane < NT / 32 ? s_warp[lane] : 0;
+    int wi = warp_incl_scan(w);
+    if (lane < NT / 32)
+      s_warp[lane] = wi - w;
+    if (lane == NT / 32 - 1)
+      s_total = wi;
+  }
+  __syncthreads();
+  const int r = s_warp[wid] + incl - v;
+  *total = s_total;
+  __syncthreads();
+  return r;
+}
+
+__device__ __forceinline__ long long warp_incl_scan_ll(long long v)
+{
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    long long t = __shfl_up_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) >= o)
+      v += t;
+  }
+  return v;
+}
+#endif
+
+// host-callable device-wide utilities (scan.cu)
+// out[i] = sum_{j<i} in[j] (int32 in, int64 out), out[n] = total; total also left in c->scratch64[0]
+void exclusive_scan_i32_to_i64(cfx_ctx* c, const int32_t* in, int64_t n, int64_t* out);
+void exclusive_scan_i64(cfx_ctx* c, const int64_t* in, int64_t n, int64_t* out);
+// block-count scan used by the compaction passes: offsets[b] = sum_{j<b} counts[j]; total -> scratch64[0]
+void scan_block_counts(cfx_ctx* c, const int32_t* counts, int64_t nblocks, int64_t* offsets);
+
+RuleTable& get_rule(cfx_ctx* c, int dim, int order); // quadrature.cu: built-in or override, uploaded on demand
+void builtin_simplex_rule(int dim, int order, std::vector<double>& pts, std::vector<double>& wts);
+void classify_all(cfx_ctx* c);                          // classify.cu
+void ensure_cut_list(cfx_ctx* c, int ls);               // classify.cu
+void build_incidence(cfx_ctx* c, Space& s);             // sparsity.cu
+void derive_f2c(cfx_ctx* c);                            // facets.cu
+void dense_f2c_from_adjacency(cfx_ctx* c, const int32_t* off_dev, const int32_t* data_dev); // facets.cu
+void prepare_form(cfx_ctx* c, cfx_form* f);             // sparsity.cu
+const cfx_integral* facet_integral_domain(const cfx_form* f);          // sparsity.cu
+void set_facet_slots(cfx_ctx* c, const cfx_integral* I, bool clear);   // sparsity.cu
+} // namespace cfx
+
+#define CFX_API_BEGIN                                                                                                  \
+  try                                                                                                                  \
+  {
+#define CFX_API_END(ctx)                                                                                               \
+  }                                                                                                                    \
+  catch (const cfx::Error& e)                                                                                          \
+  {                                                                                                                    \
+    cfx_set_error(ctx, e.what());                                                                                      \
+    return e.code;                                                                                                     \
+  }                                                                                                                    \
+  catch (const std::exception& e)                                                                                      \
+  {                                                                                                                    \
+    cfx_set_error(ctx, e.what());                                                                                      \
+    return CFX_ERR_INVALID;                                                                                            \
+  }                                                                                                                    \
+  return CFX_OK;
+
+void cfx_set_error(cfx_ctx* ctx, const char* msg);

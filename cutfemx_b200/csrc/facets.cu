@@ -1,0 +1,284 @@
+// facets.cu -- ghost-penalty facet band, interior facets of a cell set, facet integration rows.
+//
+// Replaces cutfemx.ghost_penalty_facets (python/cutfemx/cut.py:340-380, a pure-Python set loop),
+// cutfemx::interior_facets_for_cells (cpp/cutfemx/cut/cut.cpp:926-994) and
+// facet_integration_rows / local_facet_index (python/cutfemx/wrappers/cut.cpp:38-115).
+//
+// All integer work; results are sorted-unique facet ids exactly as the reference's
+// sorted(set(...)) / sort+unique produce.  Marking a facet is an idempotent byte store (no
+// atomics), the ascending list comes from the order-preserving compaction in compact.cuh.
+// Roofline: HBM; bytes ~ Nc (active flags) + 4*(tdim+1)*Ncut (c2f rows) + Nf (facet flags).
+#include "compact.cuh"
+
+namespace cfx
+{
+namespace
+{
+constexpr int FB = 256;
+
+// facet -> (min cell, max cell) by integer atomics: deterministic, any c2f numbering
+__global__ void f2c_minmax_kernel(const int32_t* __restrict__ c2f, int64_t n_entries, int nf, int64_t n_facets,
+                                  int32_t* __restrict__ f2c2, int32_t* __restrict__ err)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * FB + threadIdx.x;
+  if (i >= n_entries)
+    return;
+  const int32_t f = c2f[i];
+  if (f < 0 || f >= n_facets)
+  {
+    err[0] = 11;
+    err[1] = f;
+    return;
+  }
+  const int32_t cell = static_cast<int32_t>(i / nf);
+  atomicMin(&f2c2[2 * static_cast<int64_t>(f)], cell);
+  atomicMax(&f2c2[2 * static_cast<int64_t>(f) + 1], cell);
+}
+
+__global__ void f2c_fix_kernel(int64_t n_facets, int32_t* __restrict__ f2c2)
+{
+  const int64_t f = static_cast<int64_t>(blockIdx.x) * FB + threadIdx.x;
+  if (f >= n_facets)
+    return;
+  const int32_t lo = f2c2[2 * f], hi = f2c2[2 * f + 1];
+  if (lo == 0x7fffffff)
+  { // no cell
+    f2c2[2 * f] = -1;
+    f2c2[2 * f + 1] = -1;
+  }
+  else if (hi == lo)
+    f2c2[2 * f + 1] = -1; // boundary facet
+}
+
+__global__ void f2c_init_kernel(int64_t n_facets, int32_t* __restrict__ f2c2)
+{
+  const int64_t f = static_cast<int64_t>(blockIdx.x) * FB + threadIdx.x;
+  if (f >= n_facets)
+    return;
+  f2c2[2 * f] = 0x7fffffff;
+  f2c2[2 * f + 1] = -1;
+}
+
+__global__ void f2c_from_adj_kernel(const int32_t* __restrict__ off, const int32_t* __restrict__ data,
+                                    int64_t n_facets, int32_t* __restrict__ f2c2, int32_t* __restrict__ err)
+{
+  const int64_t f = static_cast<int64_t>(blockIdx.x) * FB + threadIdx.x;
+  if (f >= n_facets)
+    return;
+  const int32_t b = off[f], e = off[f + 1];
+  int32_t c0 = -1, c1 = -1;
+  if (e - b >= 1)
+    c0 = data[b];
+  if (e - b >= 2)
+    c1 = data[b + 1];
+  if (e - b > 2)
+  {
+    err[0] = 12;
+    err[1] = static_cast<int32_t>(f);
+  }
+  f2c2[2 * f] = c0;
+  f2c2[2 * f + 1] = c1;
+}
+
+// active[c] = intersected by cut_ls  OR  selector matches   (cut.py:364-366), over ALL local cells
+__global__ void active_flag_kernel(Dnf d, int cut_ls, const int8_t* __restrict__ domain, int64_t stride, int64_t nc,
+                                   uint8_t* __restrict__ active)
+{
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * FB + threadIdx.x;
+  if (c >= nc)
+    return;
+  const bool cut = domain[static_cast<int64_t>(cut_ls) * stride + c] == CFX_DOMAIN_INTERSECTED;
+  active[c] = (cut || dnf_match(d, domain, stride, c)) ? 1 : 0;
+}
+
+__global__ void set_flag_kernel(const int32_t* __restrict__ cells, int64_t n, int64_t nc, uint8_t* __restrict__ flag,
+                                int32_t* __restrict__ err)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * FB + threadIdx.x;
+  if (i >= n)
+    return;
+  const int32_t c = cells[i];
+  if (c < 0 || c >= nc)
+  { // cut.cpp:963-964 "Cell index is out of range."
+    err[0] = 13;
+    err[1] = c;
+    return;
+  }
+  flag[c] = 1;
+}
+
+// cut.py:369-379 / cut.cpp:967-987: for every source cell, every facet that is owned, has two
+// cells, both flagged -> mark
+__global__ void mark_facets_kernel(const int32_t* __restrict__ src_cells, int64_t n_src, int nf,
+                                   const int32_t* __restrict__ c2f, const int32_t* __restrict__ f2c2,
+                                   const uint8_t* __restrict__ active, int64_t n_owned_facets, int include_ghosts,
+                                   uint8_t* __restrict__ facet_flag)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * FB + threadIdx.x;
+  if (i >= n_src * nf)
+    return;
+  const int64_t cell = src_cells[i / nf];
+  const int32_t f = c2f[cell * nf + (i % nf)];
+  if (!include_ghosts && f >= n_owned_facets)
+    return;
+  const int32_t c0 = f2c2[2 * static_cast<int64_t>(f)], c1 = f2c2[2 * static_cast<int64_t>(f) + 1];
+  if (c1 < 0)
+    return; // not exactly two cells
+  if (active[c0] && active[c1])
+    facet_flag[f] = 1;
+}
+
+__global__ void clear_flags_kernel(const int32_t* __restrict__ idx, int64_t n, uint8_t* __restrict__ flag)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * FB + threadIdx.x;
+  if (i < n)
+    flag[idx[i]] = 0;
+}
+
+__global__ void facet_rows_kernel(const int32_t* __restrict__ facets, int64_t n, int nf, int64_t n_facets,
+                                  const int32_t* __restrict__ c2f, const int32_t* __restrict__ f2c2,
+                                  int32_t* __restrict__ rows4, int32_t* __restrict__ err)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * FB + threadIdx.x;
+  if (i >= n)
+    return;
+  const int32_t f = facets[i];
+  if (f < 0 || f >= n_facets)
+  {
+    err[0] = 14;
+    err[1] = f;
+    return;
+  }
+  const int32_t cs[2] = {f2c2[2 * static_cast<int64_t>(f)], f2c2[2 * static_cast<int64_t>(f) + 1]};
+  if (cs[0] < 0 || cs[1] < 0)
+  { // wrappers/cut.cpp:101-105 "Interior facet domain contains a facet without two adjacent cells."
+    err[0] = 15;
+    err[1] = f;
+    return;
+  }
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+  {
+    int lf = -1;
+    for (int k = 0; k < nf; ++k)
+      if (c2f[static_cast<int64_t>(cs[s]) * nf + k] == f)
+      {
+        lf = k;
+        break;
+      }
+    if (lf < 0)
+    { // wrappers/cut.cpp:49-50 "Could not resolve local facet index."
+      err[0] = 16;
+      err[1] = f;
+    }
+    rows4[4 * i + 2 * s] = cs[s];
+    rows4[4 * i + 2 * s + 1] = lf;
+  }
+}
+
+int64_t band_from_flags(cfx_ctx* c, const int32_t* src_cells, int64_t n_src, const uint8_t* active,
+                        int include_ghosts, cfx_list* out)
+{
+  const int nf = c->tdim + 1;
+  if (n_src > 0)
+    CFX_LAUNCH(c, mark_facets_kernel, grid_for(n_src * nf, FB), FB, 0, src_cells, n_src, nf, c->c2f, c->f2c2.p, active,
+               c->n_owned_facets, include_ghosts, c->facet_flag.p);
+  FlagPred p{c->facet_flag.p};
+  out->n = compact_indices(c, c->n_facets, p, out->data);
+  if (out->n > 0)
+    CFX_LAUNCH(c, clear_flags_kernel, grid_for(out->n, FB), FB, 0, out->data.p, out->n, c->facet_flag.p);
+  return out->n;
+}
+} // namespace
+
+void derive_f2c(cfx_ctx* c)
+{
+  const int nf = c->tdim + 1;
+  CFX_LAUNCH(c, f2c_init_kernel, grid_for(c->n_facets, FB), FB, 0, c->n_facets, c->f2c2.p);
+  const int64_t n_entries = c->nc_total * nf;
+  CFX_LAUNCH(c, f2c_minmax_kernel, grid_for(n_entries, FB), FB, 0, c->c2f, n_entries, nf, c->n_facets, c->f2c2.p,
+             c->err_flag.p);
+  CFX_LAUNCH(c, f2c_fix_kernel, grid_for(c->n_facets, FB), FB, 0, c->n_facets, c->f2c2.p);
+}
+
+void dense_f2c_from_adjacency(cfx_ctx* c, const int32_t* off_dev, const int32_t* data_dev)
+{
+  CFX_LAUNCH(c, f2c_from_adj_kernel, grid_for(c->n_facets, FB), FB, 0, off_dev, data_dev, c->n_facets, c->f2c2.p,
+             c->err_flag.p);
+}
+} // namespace cfx
+
+using namespace cfx;
+
+extern "C"
+{
+cfx_status cfx_ghost_penalty_facets(cfx_ctx* ctx, int cut_ls, int n_terms, const int32_t* term_offsets,
+                                    const int32_t* clause_ls, const int32_t* clause_rel, int include_ghosts,
+                                    cfx_list** out)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && ctx->classified, CFX_ERR_STATE, "cfx_ghost_penalty_facets: call cfx_update first");
+  CFX_REQUIRE(ctx->topo_bound, CFX_ERR_STATE, "Facet-cell connectivity is unavailable."); // cut.py:361-362
+  CFX_REQUIRE(out != nullptr, CFX_ERR_INVALID, "cfx_ghost_penalty_facets: out is NULL");
+  CFX_REQUIRE(cut_ls >= 0 && cut_ls < CFX_MAX_LEVEL_SETS && ctx->ls[cut_ls].bound, CFX_ERR_INVALID,
+              "cfx_ghost_penalty_facets: invalid cut level set");
+  const Dnf d = make_dnf(ctx, n_terms, term_offsets, clause_ls, clause_rel);
+  ensure_cut_list(ctx, cut_ls);
+  if (*out == nullptr)
+    *out = new cfx_list();
+  LevelSet& L = ctx->ls[cut_ls];
+  StageScope st(ctx, "ghost_penalty_facets",
+                2.0 * static_cast<double>(ctx->nc_total) + 4.0 * (ctx->tdim + 1) * static_cast<double>(L.n_cut)
+                    + static_cast<double>(ctx->n_facets));
+  ctx->scratch8.reserve(ctx->pool, static_cast<size_t>(ctx->nc_total) + 16);
+  CFX_LAUNCH(ctx, active_flag_kernel, grid_for(ctx->nc_total, FB), FB, 0, d, cut_ls, ctx->domain.p, ctx->domain_stride,
+             ctx->nc_total, ctx->scratch8.p);
+  band_from_flags(ctx, L.cut_list.p, L.n_cut, ctx->scratch8.p, include_ghosts, *out);
+  CFX_API_END(ctx)
+}
+
+cfx_status cfx_interior_facets_for_cells(cfx_ctx* ctx, const int32_t* cells, int64_t n, int memspace,
+                                         int include_ghosts, cfx_list** out)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && ctx->topo_bound, CFX_ERR_STATE, "Facet-cell connectivity is unavailable."); // cut.cpp:945-946
+  CFX_REQUIRE(out != nullptr && (cells != nullptr || n == 0), CFX_ERR_INVALID,
+              "cfx_interior_facets_for_cells: NULL argument");
+  if (*out == nullptr)
+    *out = new cfx_list();
+  DevBuf<int32_t> own;
+  const int32_t* d_cells = n > 0 ? adopt(ctx, own, cells, static_cast<size_t>(n), memspace) : nullptr;
+  ctx->scratch8.reserve(ctx->pool, static_cast<size_t>(ctx->nc_total) + 16);
+  CFX_CUDA(cudaMemsetAsync(ctx->scratch8.p, 0, static_cast<size_t>(ctx->nc_total), ctx->stream));
+  if (n > 0)
+    CFX_LAUNCH(ctx, set_flag_kernel, grid_for(n, FB), FB, 0, d_cells, n, ctx->nc_total, ctx->scratch8.p,
+               ctx->err_flag.p);
+  band_from_flags(ctx, d_cells, n, ctx->scratch8.p, include_ghosts, *out);
+  own.release();
+  check_device_error(ctx, "cfx_interior_facets_for_cells (Cell index is out of range.)");
+  CFX_API_END(ctx)
+}
+
+cfx_status cfx_facet_integration_rows(cfx_ctx* ctx, const int32_t* facets, int64_t n, int memspace, cfx_list** out)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && ctx->topo_bound, CFX_ERR_STATE, "Facet-cell connectivity is unavailable.");
+  CFX_REQUIRE(out != nullptr && (facets != nullptr || n == 0), CFX_ERR_INVALID,
+              "cfx_facet_integration_rows: NULL argument");
+  if (*out == nullptr)
+    *out = new cfx_list();
+  (*out)->data.reserve(ctx->pool, static_cast<size_t>(4 * n) + 1);
+  (*out)->n = 4 * n;
+  if (n > 0)
+  {
+    DevBuf<int32_t> own;
+    const int32_t* d_f = adopt(ctx, own, facets, static_cast<size_t>(n), memspace);
+    CFX_LAUNCH(ctx, facet_rows_kernel, grid_for(n, FB), FB, 0, d_f, n, ctx->tdim + 1, ctx->n_facets, ctx->c2f,
+               ctx->f2c2.p, (*out)->data.p, ctx->err_flag.p);
+    own.release();
+    check_device_error(ctx, "cfx_facet_integration_rows (Interior facet domain contains a facet without two "
+                            "adjacent cells / could not resolve local facet index)");
+  }
+  CFX_API_END(ctx)
+}
+} // extern "C"

@@ -1,0 +1,164 @@
+// scan.cu -- device-wide exclusive scans (hand-written; no CUB).  All counts are integers,
+// so every result is bit-reproducible.
+#include "common.cuh"
+
+namespace cfx
+{
+namespace
+{
+constexpr int SB = 1024;
+
+// single block: offsets[i] = sum_{j<i} in[j]; *total = sum.  n up to a few 10^5.
+template <class Tin>
+__global__ void __launch_bounds__(SB) scan_small_kernel(const Tin* __restrict__ in, int64_t n,
+                                                        int64_t* __restrict__ offsets, int64_t* __restrict__ total)
+{
+  __shared__ long long s_warp[SB / 32];
+  __shared__ long long s_carry;
+  if (threadIdx.x == 0)
+    s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int64_t base = 0; base < n; base += SB)
+  {
+    const int64_t i = base + threadIdx.x;
+    const long long v = i < n ? static_cast<long long>(in[i]) : 0;
+    const long long incl = warp_incl_scan_ll(v);
+    if (lane == 31)
+      s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0)
+    {
+      long long w = s_warp[lane];
+      long long wi = warp_incl_scan_ll(w);
+      s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    const long long excl = s_carry + s_warp[wid] + incl - v;
+    if (i < n)
+      offsets[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == SB - 1)
+      s_carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    *total = s_carry;
+}
+
+constexpr int TB = 256;
+constexpr int TILE = TB * 4;
+
+template <class Tin>
+__global__ void __launch_bounds__(TB) tile_sum_kernel(const Tin* __restrict__ in, int64_t n,
+                                                      int64_t* __restrict__ sums)
+{
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * TILE + threadIdx.x * 4;
+  long long v = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (base + k < n)
+      v += in[base + k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_down_sync(0xffffffffu, v, o);
+  __shared__ long long s[TB / 32];
+  if ((threadIdx.x & 31) == 0)
+    s[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    long long t = 0;
+#pragma unroll
+    for (int w = 0; w < TB / 32; ++w)
+      t += s[w];
+    sums[blockIdx.x] = t;
+  }
+}
+
+// exclusive scan of one long long per thread over a block of TB threads
+__device__ __forceinline__ long long block_excl_scan_ll(long long v)
+{
+  __shared__ long long s_w[TB / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long incl = warp_incl_scan_ll(v);
+  if (lane == 31)
+    s_w[wid] = incl;
+  __syncthreads();
+  if (wid == 0)
+  {
+    long long w = lane < TB / 32 ? s_w[lane] : 0;
+    long long wi = warp_incl_scan_ll(w);
+    if (lane < TB / 32)
+      s_w[lane] = wi - w;
+  }
+  __syncthreads();
+  const long long r = s_w[wid] + incl - v;
+  __syncthreads();
+  return r;
+}
+
+template <class Tin>
+__global__ void __launch_bounds__(TB) tile_scan_kernel(const Tin* __restrict__ in, int64_t n,
+                                                       const int64_t* __restrict__ tile_off,
+                                                       const int64_t* __restrict__ total, int64_t* __restrict__ out)
+{
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * TILE + threadIdx.x * 4;
+  long long v[4];
+  long long s = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+  {
+    v[k] = (base + k < n) ? static_cast<long long>(in[base + k]) : 0;
+    s += v[k];
+  }
+  const long long excl = block_excl_scan_ll(s);
+  long long run = tile_off[blockIdx.x] + excl;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+  {
+    if (base + k < n)
+      out[base + k] = run;
+    run += v[k];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    out[n] = *total;
+}
+} // namespace
+
+void scan_block_counts(cfx_ctx* c, const int32_t* counts, int64_t nblocks, int64_t* offsets)
+{
+  c->scratch64.reserve(c->pool, 64);
+  CFX_LAUNCH(c, scan_small_kernel<int32_t>, 1, SB, 0, counts, nblocks, offsets, c->scratch64.p);
+}
+
+template <class Tin>
+static void exclusive_scan_impl(cfx_ctx* c, const Tin* in, int64_t n, int64_t* out)
+{
+  c->scratch64.reserve(c->pool, 64);
+  if (n == 0)
+  {
+    CFX_CUDA(cudaMemsetAsync(out, 0, sizeof(int64_t), c->stream));
+    CFX_CUDA(cudaMemsetAsync(c->scratch64.p, 0, sizeof(int64_t), c->stream));
+    return;
+  }
+  const int64_t ntiles = (n + TILE - 1) / TILE;
+  DevBuf<int64_t> sums, offs;
+  sums.reserve(c->pool, ntiles);
+  offs.reserve(c->pool, ntiles);
+  CFX_LAUNCH(c, tile_sum_kernel<Tin>, grid_for(n, TILE), TB, 0, in, n, sums.p);
+  CFX_LAUNCH(c, scan_small_kernel<int64_t>, 1, SB, 0, sums.p, ntiles, offs.p, c->scratch64.p);
+  CFX_LAUNCH(c, tile_scan_kernel<Tin>, grid_for(n, TILE), TB, 0, in, n, offs.p, c->scratch64.p, out);
+  sums.release(); // stream-ordered reuse is safe: the pool hands memory back to this stream only
+  offs.release();
+}
+
+void exclusive_scan_i32_to_i64(cfx_ctx* c, const int32_t* in, int64_t n, int64_t* out)
+{
+  exclusive_scan_impl<int32_t>(c, in, n, out);
+}
+void exclusive_scan_i64(cfx_ctx* c, const int64_t* in, int64_t n, int64_t* out)
+{
+  exclusive_scan_impl<int64_t>(c, in, n, out);
+}
+} // namespace cfx

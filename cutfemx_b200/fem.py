@@ -1,0 +1,217 @@
+"""Mirror of `cutfemx.fem` for the hot path (python/cutfemx/fem.py of the reference):
+`form`, `create_matrix`, `assemble_matrix`, `assemble_vector`, `assemble_scalar`.
+
+The reference compiles arbitrary UFL with runintgen/FFCx; this build ships hand-written kernel
+families instead (include/cutfemx_b200.h, CFX_K_*), so a form is described by the same tuples
+the reference feeds to `create_form_*` (fem.py:346-351): per integral
+`(kernel, entities, constants, custom_data)` with `custom_data` = the run-time rules.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import DEVICE, HOST, KERNEL, KERNEL_RANK, CfxError, as_arg, check, is_device_array, lib
+from .cut import RuntimeQuadratureRules, _List, _bind_topology, _mesh_context, facet_integration_rows_device
+from .mesh import FunctionSpace
+
+
+class CutForm:
+    """Integral table of one form (dolfinx_custom_data::fem::Form, Form.h:119-677)."""
+
+    def __init__(self, space: FunctionSpace, rank: int):
+        self.function_space = space
+        self.rank = rank
+        self.ctx = _mesh_context(space.mesh)
+        self._h = C.c_void_p()
+        self._owners = []  # fem.py:57,327-328: keeps custom_data alive
+        sidx = self.ctx.space_index(space)
+        check(self.ctx.handle, lib().cfx_form_create(self.ctx.handle, sidx, rank, C.byref(self._h)))
+
+    def add_cell_integral(self, kernel: str, cells=None, rules: RuntimeQuadratureRules | None = None,
+                          constants=(1.0,)):
+        """Cell integral over the mixed measure subdomain_data=[cells, rules]
+        (demo_poisson.py:165-167): `cells` use the compile-time rule, `rules` the run-time one."""
+        kid = KERNEL[kernel]
+        if KERNEL_RANK[kid] != self.rank:
+            raise ValueError(f"kernel '{kernel}' has rank {KERNEL_RANK[kid]}, form has rank {self.rank}")
+        if isinstance(cells, _List):
+            p, ms, n, keep = C.c_void_p(cells.device_ptr), DEVICE, cells.size, cells
+        elif cells is None:
+            p, ms, n, keep = None, HOST, 0, None
+        else:
+            p, ms, keep = as_arg(cells, np.int32)
+            n = int(keep.numel() if is_device_array(keep) else keep.size)
+        cst = np.ascontiguousarray(list(constants), dtype=np.float64)
+        h = self.ctx.handle
+        check(h, lib().cfx_form_add_cell_integral(h, self._h, kid, p, C.c_int64(n), ms,
+                                                  rules._h if rules is not None else None,
+                                                  C.c_void_p(cst.ctypes.data), int(cst.size)))
+        self._owners += [keep, rules]
+        return self
+
+    def add_interior_facet_integral(self, kernel: str, facets=None, rows=None, constants=(1.0,)):
+        """Interior-facet integral over raw facet ids (converted with facet_integration_rows,
+        _runintgen_adapter.py:416-435) or over ready (cell0, lf0, cell1, lf1) rows."""
+        kid = KERNEL[kernel]
+        msh = self.function_space.mesh
+        _bind_topology(msh, self.ctx)
+        if rows is None:
+            rows = facet_integration_rows_device(msh, facets)
+        if isinstance(rows, _List):
+            p, ms, n, keep = C.c_void_p(rows.device_ptr), DEVICE, rows.size // 4, rows
+        else:
+            p, ms, keep = as_arg(rows, np.int32)
+            n = int(keep.numel() if is_device_array(keep) else keep.size) // 4
+        cst = np.ascontiguousarray(list(constants), dtype=np.float64)
+        h = self.ctx.handle
+        check(h, lib().cfx_form_add_interior_facet_integral(h, self._h, kid, p, C.c_int64(n), ms,
+                                                            C.c_void_p(cst.ctypes.data), int(cst.size)))
+        self._owners += [keep]
+        return self
+
+    def free(self):
+        if self._h:
+            lib().cfx_form_free(self.ctx.handle, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.free()
+        except Exception:
+            pass
+
+
+def form(space: FunctionSpace, rank: int, integrals=()) -> CutForm:
+    """Build a form from integral tuples `(itype, kernel, entities, constants, custom_data)`
+    with itype in {"cell", "interior_facet"}."""
+    f = CutForm(space, rank)
+    for itype, kernel, entities, constants, custom_data in integrals:
+        if itype == "cell":
+            f.add_cell_integral(kernel, entities, custom_data, constants)
+        elif itype == "interior_facet":
+            f.add_interior_facet_integral(kernel, facets=entities, constants=constants)
+        else:
+            raise ValueError(f"unsupported integral type '{itype}'")
+    return f
+
+
+class MatrixCSR:
+    """dolfinx.la.MatrixCSR stand-in: device-resident pattern + values, exported on demand."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        self._cache = {}
+
+    def _sizes(self):
+        nr, nnz = C.c_int64(), C.c_int64()
+        check(self.ctx.handle, lib().cfx_pattern_sizes(self._h, C.byref(nr), C.byref(nnz)))
+        return nr.value, nnz.value
+
+    @property
+    def shape(self):
+        n = self._sizes()[0]
+        return (n, n)
+
+    @property
+    def nnz(self) -> int:
+        return self._sizes()[1]
+
+    def _fetch_pattern(self):
+        if "indptr" not in self._cache:
+            nr, nnz = self._sizes()
+            rp = np.empty(nr + 1, dtype=np.int64)
+            cols = np.empty(nnz, dtype=np.int32)
+            h = self.ctx.handle
+            check(h, lib().cfx_pattern_fetch(h, self._h, C.c_void_p(rp.ctypes.data), C.c_void_p(cols.ctypes.data), HOST))
+            self._cache.update(indptr=rp, indices=cols)
+
+    @property
+    def indptr(self):
+        self._fetch_pattern()
+        return self._cache["indptr"]
+
+    @property
+    def indices(self):
+        self._fetch_pattern()
+        return self._cache["indices"]
+
+    @property
+    def data(self):
+        """Copy of the values on the host."""
+        out = np.empty(self.nnz)
+        if out.size:
+            h = self.ctx.handle
+            check(h, lib().cfx_pattern_values_fetch(h, self._h, C.c_void_p(out.ctypes.data), HOST))
+        return out
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+
+        return sp.csr_matrix((self.data, self.indices, self.indptr), shape=self.shape)
+
+    def scatter_reverse(self):  # single rank: no-op (multi-rank: parallel.py)
+        return None
+
+    def free(self):
+        if self._h:
+            lib().cfx_pattern_free(self.ctx.handle, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.free()
+        except Exception:
+            pass
+
+
+def create_matrix(a: CutForm, A: MatrixCSR | None = None) -> MatrixCSR:
+    """create_sparsity_pattern + finalize + MatrixCSR (assembler.h:567-592, wrappers/fem.cpp:266-276)."""
+    if a.rank != 2:
+        raise RuntimeError("Cannot create sparsity pattern. Form is not a bilinear.")
+    if A is None:
+        A = MatrixCSR(a.ctx)
+    A._cache.clear()
+    check(a.ctx.handle, lib().cfx_create_sparsity(a.ctx.handle, a._h, C.byref(A._h)))
+    return A
+
+
+def assemble_matrix(a: CutForm, A: MatrixCSR | None = None, *, diag_inactive: float = 0.0) -> MatrixCSR:
+    """fem.py:886-942: create the matrix if none is given, then add the form into it.
+    `diag_inactive` writes that value on the diagonal of rows outside the active domain
+    (deactivate_outside, fem/deactivate.h:402-418)."""
+    zero = 0
+    if A is None:
+        A = create_matrix(a)
+        zero = 1
+    check(a.ctx.handle, lib().cfx_assemble_matrix(a.ctx.handle, a._h, A._h, zero, C.c_double(diag_inactive), None, HOST))
+    return A
+
+
+def assemble_vector(L: CutForm, b: np.ndarray | None = None) -> np.ndarray:
+    """fem.py:851-883: adds into `b` (owned+ghost entries) or creates a zero vector first."""
+    if L.rank != 1:
+        raise RuntimeError("assemble_vector expects a linear form")
+    n = L.function_space.num_dofs * L.function_space.bs
+    zero = 0
+    if b is None:
+        b = np.zeros(n)
+        zero = 1
+    p, ms, keep = as_arg(b, np.float64)
+    check(L.ctx.handle, lib().cfx_assemble_vector(L.ctx.handle, L._h, p, zero, ms))
+    if ms == HOST and keep is not b:
+        b[:] = keep
+    return b
+
+
+def assemble_scalar(M: CutForm) -> float:
+    """fem.py assemble_scalar -> assemble_scalar_impl.h:26-275 (local value; allreduce is the caller's)."""
+    if M.rank != 0:
+        raise RuntimeError("assemble_scalar expects a functional")
+    out = C.c_double()
+    check(M.ctx.handle, lib().cfx_assemble_scalar(M.ctx.handle, M._h, C.byref(out)))
+    return float(out.value)

@@ -234,3 +234,26 @@ def sphere_level_set(center, radius):
 def torus_level_set(center, R, r):
     cx, cy, cz = center
     return lambda x, y, z: np.sqrt((np.sqrt((x - cx) ** 2 + (y - cy) ** 2) - R) ** 2 + (z - cz) ** 2) - r
+
+
+class _Vector:
+    """dolfinx.la.Vector stand-in: `.array` is the owned+ghost value array."""
+
+    def __init__(self, array):
+        self.array = array
+
+    def scatter_forward(self):  # single-rank meshes: nothing to do (multi-rank: parallel.py)
+        return None
+
+
+class Function:
+    """dolfinx.fem.Function stand-in: a function space, a name and `.x.array`."""
+
+    def __init__(self, space: FunctionSpace, name: str = "f", array=None):
+        self.function_space = space
+        self.name = name
+        self.x = _Vector(np.zeros(space.num_dofs) if array is None else array)
+
+    def interpolate(self, fn):
+        self.x.array[:] = interpolate(self.function_space, fn)
+        return self

@@ -95,7 +95,7 @@ cfx_status cfx_domain_fetch(cfx_ctx* ctx, int ls, int8_t* out, int memspace);
  * cutfemx::locate_entities, cut.cpp:877-924.  The selector is the compiled DNF of
  * cutcells::SelectionExpr: term t is the AND of clauses term_offsets[t]..term_offsets[t+1],
  * terms are OR-ed; clause k is "level set clause_ls[k]  clause_rel[k]  0".
- * Result: ascending owned cell ids. */
+ * Result: ascending owned cell ids.  If *out is non-NULL the list object is reused. */
 cfx_status cfx_locate_entities(cfx_ctx* ctx, int n_terms, const int32_t* term_offsets, const int32_t* clause_ls,
                                const int32_t* clause_rel, cfx_list** out);
 int64_t cfx_list_size(const cfx_list* l);
@@ -170,6 +170,7 @@ cfx_status cfx_pattern_import(cfx_ctx* ctx, int space, const int64_t* row_ptr, c
 cfx_status cfx_pattern_sizes(const cfx_pattern* p, int64_t* n_rows, int64_t* nnz);
 cfx_status cfx_pattern_fetch(cfx_ctx* ctx, const cfx_pattern* p, int64_t* row_ptr, int32_t* cols, int memspace);
 const double* cfx_pattern_values_device_ptr(const cfx_pattern* p);
+cfx_status cfx_pattern_values_fetch(cfx_ctx* ctx, const cfx_pattern* p, double* values, int memspace);
 void cfx_pattern_free(cfx_ctx* ctx, cfx_pattern* p);
 
 /* assemble_matrix: assembler.h:596-703 -> assemble_matrix_impl.h:629-810 (cells :68-189, interior

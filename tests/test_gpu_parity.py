@@ -1,0 +1,100 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): classification, cut/inside/outside lists, facet lists and CSR
+sparsity bit-exact; quadrature weights summing to the oracle's cut volume/area to 1e-12 relative;
+matrix and vector entries to 1e-11 relative in Frobenius norm.
+"""
+import numpy as np
+import pytest
+
+from util import GpuRun, OracleRun, make_problem
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("line", 3, 1),      # test_locate_entities.py:13-35 geometry (3x3, phi = x - 0.51)
+    ("circle", 21, 1),   # quickstart / test_cut_api.py:1268-1300
+    ("circle", 64, 1),   # BASELINE configs[0] (has phi == 0 vertices -> degenerate cuts)
+    ("circle", 32, 2),   # P2 on triangles (configs[1] element)
+    ("sphere", 12, 1),   # configs[2] element
+    ("sphere", 6, 2),
+    ("torus", 14, 1),
+]
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.fixture(scope="module", params=CASES, ids=lambda c: f"{c[0]}{c[1]}-P{c[2]}")
+def runs(request, built_lib):
+    kind, n, deg = request.param
+    mesh, Vphi, phi, V = make_problem(kind, n, deg)
+    return OracleRun(mesh, Vphi, phi, V), GpuRun(mesh, Vphi, phi, V)
+
+
+def test_classification_bit_exact(runs):
+    o, g = runs
+    assert np.array_equal(o.domain, g.domain[: o.domain.size])
+    counts = g.cut_data.counts()
+    assert counts == (o.inside.size, o.cut.size, o.outside.size)
+
+
+def test_lists_bit_exact(runs):
+    o, g = runs
+    for name in ("inside", "cut", "outside"):
+        a, b = getattr(o, name), getattr(g, name)
+        assert a.dtype == b.dtype == np.int32
+        assert np.array_equal(a, b), name
+
+
+def test_rules(runs):
+    o, g = runs
+    for ro, rg in ((o.rv, g.rv), (o.ro, g.ro), (o.ri, g.ri)):
+        assert np.array_equal(ro.offsets, rg.offsets)
+        assert np.array_equal(ro.parent_map, rg.parent_map)
+        assert rg.offsets.dtype == np.int32 and rg.parent_map.dtype == np.int32
+        assert rg.points.shape == ro.points.shape
+        np.testing.assert_allclose(rg.points, ro.points, rtol=0, atol=1e-14)
+        np.testing.assert_allclose(rg.weights, ro.weights, rtol=1e-12, atol=1e-18)
+        assert abs(rg.weights.sum() - ro.weights.sum()) <= 1e-12 * abs(ro.weights.sum())
+
+
+def test_physical_points_and_normals(runs):
+    import oracle as O
+
+    o, g = runs
+    mesh = o.mesh
+    np.testing.assert_allclose(g.ri.physical_points, O.physical_points(mesh, o.ri), rtol=0, atol=1e-14)
+    np.testing.assert_allclose(g.normals, o.ri.normals, rtol=0, atol=1e-12)
+
+
+def test_ghost_facets_bit_exact(runs):
+    o, g = runs
+    assert np.array_equal(o.ghost, g.ghost)
+    assert np.array_equal(o.rows4, g.rows4)
+
+
+def test_sparsity_bit_exact(runs):
+    o, g = runs
+    assert np.array_equal(o.row_ptr, g.row_ptr)
+    assert np.array_equal(o.cols, g.cols)
+
+
+def test_matrix_vector_scalar(runs):
+    o, g = runs
+    assert rel(g.vals, o.vals) < 1e-11
+    assert rel(g.b, o.b) < 1e-11
+    assert abs(g.volume - o.volume) <= 1e-12 * abs(o.volume)
+    assert abs(g.area - o.area) <= 1e-12 * abs(o.area)
+
+
+def test_deterministic(runs):
+    """Two assemblies give bit-identical values (no floating-point atomics anywhere)."""
+    import cutfemx_b200 as cfx
+
+    o, g = runs
+    A2 = cfx.fem.assemble_matrix(g.a)
+    assert np.array_equal(A2.data, g.vals)
+    b2 = cfx.fem.assemble_vector(g.L)
+    assert np.array_equal(b2, g.b)
