@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- cut-cell quadrature + assembly throughput of the CutFEMx hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3] [--n 256] [--impl ours|reference]
+
+One "step" = one pass of the whole hot path over the synthetic workload (demo_poisson.py:156-201):
+classify -> locate -> volume/interface run-time quadrature -> normals -> ghost-penalty facets ->
+sparsity -> matrix + vector assembly.  Prints ONE JSON line (see DESIGN.md "Measurement").
+
+Workloads (BASELINE.json configs / SURVEY.md section 8 sizing):
+  C1  2D circle R=0.5 on [-1,1]^2, 64x64 right-diagonal triangles, P1, order 4
+  C3  3D sphere R=0.35 on [0,1]^3, n^3 Kuhn tetrahedra (default n=256), P1, order 4   <- default
+  C2p 2D circle on 4096^2 triangles with P1 u (the P2 variant of configs[1] is a parity-test case)
+`value` = cut cells / s with all inputs resident in HBM; `e2e` = the same through host buffers
+(level-set values H2D from pinned memory, CSR pattern + values + rhs D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "C1": dict(tdim=2, n=64, p0=(-1.0, -1.0), p1=(1.0, 1.0), ls=("sphere", (0.0, 0.0, 0.0, 0.5, 0.0)), order=4,
+               name="2D circle R=0.5, {n}x{n} right-diagonal triangles, P1, order 4"),
+    "C2p": dict(tdim=2, n=4096, p0=(-1.0, -1.0), p1=(1.0, 1.0), ls=("sphere", (0.0, 0.0, 0.0, 0.5, 0.0)), order=4,
+                name="2D circle R=0.5, {n}x{n} right-diagonal triangles, P1, order 4"),
+    "C3": dict(tdim=3, n=256, p0=(0.0, 0.0, 0.0), p1=(1.0, 1.0, 1.0), ls=("sphere", (0.5, 0.5, 0.5, 0.35, 0.0)),
+               order=4, name="3D sphere R=0.35, {n}^3 Kuhn tetrahedra, P1 volume+interface quadrature order 4, "
+                             "Nitsche + ghost-penalty facets"),
+}
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def _oracle_slab(args):
+    """One serial 'MPI rank' of the reference: a z-slab (3D) / y-strip (2D) of the workload."""
+    wl, n, rank, nparts = args
+    sys.path.insert(0, ROOT)
+    from cutfemx_b200 import mesh as M
+    from oracle import pipeline
+
+    tdim = wl["tdim"]
+    lo = (n * rank) // nparts
+    hi = (n * (rank + 1)) // nparts
+    p0, p1 = list(wl["p0"]), list(wl["p1"])
+    ax = tdim - 1
+    h = (p1[ax] - p0[ax]) / n
+    q0, q1 = list(p0), list(p1)
+    q0[ax], q1[ax] = p0[ax] + lo * h, p0[ax] + hi * h
+    if tdim == 3:
+        mesh = M.create_box(n, n, hi - lo, q0, q1)
+    else:
+        mesh = M.create_rectangle(n, hi - lo, q0, q1)
+    V = M.functionspace(mesh, 1)
+    kind, prm = wl["ls"]
+    ls = M.sphere_level_set(prm[:3], prm[3]) if kind == "sphere" else M.torus_level_set(prm[:3], prm[3], prm[4])
+    phi = M.interpolate(V, ls)
+    out = pipeline.run_pipeline(mesh, V.dofmap, phi, V, order=wl["order"])
+    return dict(time=out["total_s"], times=out["times"], cut=int(out["cut"].size), cells=int(mesh.num_cells),
+                nnz=int(out["cols"].size))
+
+
+def cpu_reference(wl, n, nparts, repeats=1):
+    """The reference's CPU path restated (oracle), one serial process per partition like its MPI
+    model; wall time of a step = slowest partition.  Returns cut-cells/s and details."""
+    import multiprocessing as mp
+
+    import oracle
+
+    oracle.build()
+    ctx = mp.get_context("fork")
+    best = None
+    for _ in range(repeats):
+        with ctx.Pool(nparts) as pool:
+            res = pool.map(_oracle_slab, [(wl, n, r, nparts) for r in range(nparts)])
+        t = max(r["time"] for r in res)
+        cur = dict(time=t, cut=sum(r["cut"] for r in res), cells=sum(r["cells"] for r in res),
+                   nnz=sum(r["nnz"] for r in res))
+        if best is None or cur["time"] < best["time"]:
+            best = cur
+    return best
+
+
+def run_reference(args, wl):
+    n = args.ref_n or (128 if wl["tdim"] == 3 else 2048)
+    n = min(n, args.n or wl["n"])
+    cores = os.cpu_count() or 1
+    nparts = max(1, min(cores, 8 * args.gpus, n))
+    times = []
+    res = None
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference(wl, n, nparts)
+        if i >= args.warmup:
+            times.append(r["time"])
+        res = r
+    t = float(np.mean(times))
+    value = res["cut"] / t
+    sample = (f"same workload at n={n} ({res['cells']} cells, {res['cut']} cut cells) split into {nparts} "
+              f"serial slab processes; CPU restatement of reference loops -- reference binary unavailable")
+    line = {
+        "impl": "reference", "metric": "cut_cells_per_s", "value": value, "unit": "cut-cells/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["name"].format(n=n), "sample_of": wl["name"].format(n=args.n or wl["n"])},
+        "nnz_per_s": res["nnz"] / t, "total_cells_per_s": res["cells"] / t,
+        "cpu_baseline": {"value": value, "unit": "cut-cells/s", "cores": nparts, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "cut-cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    dev = f"cuda:{local_rank}"
+
+    import cutfemx_b200 as cfx
+    from cutfemx_b200 import demo_poisson as dp
+    from cutfemx_b200.mesh import Function, FunctionSpace
+
+    n = args.n or wl["n"]
+    tdim = wl["tdim"]
+    # strong scaling: the fixed n^tdim mesh is split into z-slabs (y-strips in 2D), one per rank
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    p0, p1 = list(wl["p0"]), list(wl["p1"])
+    ax = tdim - 1
+    h = (p1[ax] - p0[ax]) / n
+    q0, q1 = list(p0), list(p1)
+    q0[ax], q1[ax] = p0[ax] + lo * h, p0[ax] + hi * h
+    shape = [n] * tdim
+    shape[ax] = hi - lo
+    mesh = dp.device_mesh(local_rank, shape, q0, q1)
+    kind, prm = wl["ls"]
+    vals = dp.device_level_set(mesh, kind, prm)
+    V = FunctionSpace(mesh, 1, mesh.x_dofmap, int(mesh.x.shape[0]), int(mesh.x.shape[0]), 1, None)
+    phi = Function(V, "phi", vals)
+    prob = dp.CutPoisson(mesh, phi, V, order=wl["order"])
+    ctx = prob.ctx
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg ("value")
+    for _ in range(max(args.warmup, 3)):
+        stats = prob.step()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)  # 256 MiB > 126 MB L2
+    sampler = ClockSampler(local_rank)
+    ctx.stage_timing(True)
+    ctx.stage_reset()
+    launches0 = ctx.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    sampler.start()
+    for i in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (untimed)
+        torch.cuda.synchronize()
+        ev[i][0].record()
+        stats = prob.step()
+        ev[i][1].record()
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    ms = [a.elapsed_time(b) for a, b in ev]
+    t_dev = torch.tensor([sum(ms) / 1e3], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([stats["cut"], stats["nnz"], stats["inside"] + stats["cut"] + stats["outside"],
+                        stats["inside"] + stats["volume_rules"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    t_total = float(t_dev.item())
+    cut_total, nnz_total, cells_total, active_total = (float(v) for v in cnt.tolist())
+    stages = ctx.stages()
+    ctx.stage_timing(False)
+    ctx.stage_reset()
+
+    # ---- end-to-end leg: host buffers in, host buffers out, through the public API
+    h_phi = torch.empty(vals.shape, dtype=torch.float64, pin_memory=True)
+    h_phi.copy_(vals)
+    torch.cuda.synchronize()
+    Vh = FunctionSpace(mesh, 1, mesh.x_dofmap, V.num_dofs, V.num_dofs, 1, None)
+    mesh_h = mesh  # the mesh stays bound on the device (bound once, like cutfemx.cut's mesh views)
+    phi_h = Function(Vh, "phi", h_phi.numpy())
+    import ctypes as C
+
+    from cutfemx_b200._lib import HOST, check, lib
+
+    # re-bind level set 0 to the pinned host array: cfx_update now does the H2D copy every step
+    pd = C.c_void_p(mesh.x_dofmap.data_ptr())
+    hnd = ctx.handle
+    d_dofmap_host = None
+    check(hnd, lib().cfx_levelset_bind(hnd, 0, None, tdim + 1, 1, C.c_void_p(h_phi.data_ptr()),
+                                       C.c_int64(V.num_dofs), HOST, 1))
+    nnz_cap = int(stats["nnz"] * 1.1) + 1024
+    h_vals = torch.empty(nnz_cap, dtype=torch.float64, pin_memory=True)
+    h_cols = torch.empty(nnz_cap, dtype=torch.int32, pin_memory=True)
+    h_rp = torch.empty(V.num_dofs + 1, dtype=torch.int64, pin_memory=True)
+    h_b = torch.empty(V.num_dofs, dtype=torch.float64, pin_memory=True)
+
+    def e2e_step():
+        st = prob.step()
+        A = prob.A
+        check(hnd, lib().cfx_pattern_fetch(hnd, A._h, C.c_void_p(h_rp.data_ptr()), C.c_void_p(h_cols.data_ptr()), HOST))
+        check(hnd, lib().cfx_pattern_values_fetch(hnd, A._h, C.c_void_p(h_vals.data_ptr()), HOST))
+        h_b.copy_(prob.b, non_blocking=False)
+        return st
+
+    for _ in range(2):
+        st = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        st = e2e_step()
+    e1.record()
+    barrier()
+    t_e2e = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    t_e2e = float(t_e2e.item())
+    h2d = 8 * V.num_dofs
+    d2h = 12 * st["nnz"] + 8 * (V.num_dofs + 1) + 8 * V.num_dofs
+
+    # ---- per-stage summary, roofline of the dominant kernel stage
+    agg = {}
+    for name, msv, by in stages:
+        a = agg.setdefault(name, [0.0, 0.0, 0])
+        a[0] += msv
+        a[1] += by
+        a[2] += 1
+    per_stage = {k: {"ms_per_step": v[0] / args.steps, "alg_GB_per_step": v[1] / args.steps / 1e9,
+                     "GBps": (v[1] / 1e9) / (v[0] / 1e3) if v[0] > 0 else None} for k, v in agg.items()}
+    peak, peak_src = load_peaks()
+    dom = max(per_stage.items(), key=lambda kv: kv[1]["ms_per_step"])
+    roof = {"bound": "hbm", "kernel": dom[0], "achieved": dom[1]["GBps"], "peak": peak, "unit": "GB/s",
+            "frac": (dom[1]["GBps"] or 0.0) / peak, "traffic": None, "peak_source": peak_src}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": "cut_cells_per_s", "value": cut_total * args.steps / t_total, "unit": "cut-cells/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_total / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["name"].format(n=n), "cells": int(cells_total), "cut_cells": int(cut_total),
+                   "active_cells": int(active_total), "nnz": int(nnz_total), "l2": "flushed between timed steps "
+                   "(256 MiB write); inputs 2.2 GB >> L2", "partition": f"{world} z-slab(s), no ghost exchange yet"},
+        "nnz_per_s": nnz_total * args.steps / t_total, "total_cells_per_s": cells_total * args.steps / t_total,
+        "e2e": {"value": cut_total * args.steps / t_e2e, "unit": "cut-cells/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e / args.steps * 1e3},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "stages": per_stage,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        nb = args.ref_n or (96 if tdim == 3 else 1536)
+        nb = min(nb, n)
+        r = cpu_reference(wl, nb, 1)
+        line["cpu_baseline"] = {
+            "value": r["cut"] / r["time"], "unit": "cut-cells/s", "cores": 1, "kind": "port",
+            "sample": f"same workload at n={nb} ({r['cells']} cells, {r['cut']} cut cells), one serial process; "
+                      f"{r['time']:.2f} s; CPU restatement of reference loops -- reference binary unavailable",
+            "total_cells_per_s": r["cells"] / r["time"], "nnz_per_s": r["nnz"] / r["time"]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=0, help="override the mesh resolution of the workload")
+    ap.add_argument("--ref-n", type=int, default=0, help="resolution of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -75,7 +75,7 @@ void cfx_ctx_destroy(cfx_ctx* ctx)
   cudaStreamSynchronize(ctx->stream);
   for (auto& l : ctx->ls)
     if (l.host_pinned && l.host_values)
-      cudaHostUnregister(const_cast<double*>(l.host_values));
+      cudaHostUnregister(const_cast<double*>(l.host_values + l.pin_begin));
   for (auto& s : ctx->stages)
   {
     cudaEventDestroy(s.e0);
@@ -190,7 +190,7 @@ cfx_status cfx_levelset_bind(cfx_ctx* ctx, int ls, const int32_t* dofmap, int nd
   LevelSet& L = ctx->ls[ls];
   if (L.host_pinned && L.host_values)
   {
-    cudaHostUnregister(const_cast<double*>(L.host_values));
+    cudaHostUnregister(const_cast<double*>(L.host_values + L.pin_begin));
     L.host_pinned = false;
   }
   if (dofmap == nullptr)
@@ -214,13 +214,27 @@ cfx_status cfx_levelset_bind(cfx_ctx* ctx, int ls, const int32_t* dofmap, int nd
     L.values_own.reserve(ctx->pool, static_cast<size_t>(n_dofs));
     L.values = L.values_own.p;
     L.host_values = values;
+    L.pin_begin = L.pin_end = 0;
     if (pin_host)
     {
-      cudaError_t e = cudaHostRegister(const_cast<double*>(values), static_cast<size_t>(n_dofs) * sizeof(double),
-                                       cudaHostRegisterDefault);
-      L.host_pinned = (e == cudaSuccess);
-      if (e != cudaSuccess)
-        cudaGetLastError(); // already pinned by the caller (e.g. torch pinned memory) is fine
+      // Page-lock only the whole pages INSIDE the array: registering partial pages would also pin
+      // whatever neighbours share them, and a later copy from such a neighbour that straddles
+      // pinned and pageable memory fails with cudaErrorInvalidValue.
+      const uintptr_t page = 4096;
+      const uintptr_t a = (reinterpret_cast<uintptr_t>(values) + page - 1) & ~(page - 1);
+      const uintptr_t b = (reinterpret_cast<uintptr_t>(values + n_dofs)) & ~(page - 1);
+      if (b > a && b - a >= (uintptr_t(1) << 16))
+      {
+        cudaError_t e = cudaHostRegister(reinterpret_cast<void*>(a), b - a, cudaHostRegisterDefault);
+        if (e == cudaSuccess)
+        {
+          L.host_pinned = true;
+          L.pin_begin = (a - reinterpret_cast<uintptr_t>(values)) / sizeof(double);
+          L.pin_end = (b - reinterpret_cast<uintptr_t>(values)) / sizeof(double);
+        }
+        else
+          cudaGetLastError(); // already pinned by the caller (e.g. torch pinned memory) is fine
+      }
     }
   }
   L.bound = true;
@@ -242,8 +256,19 @@ cfx_status cfx_update(cfx_ctx* ctx)
       continue;
     any = true;
     if (L.host_values) // cut.cpp:854-855: re-bind dof_values to the (possibly changed) array
-      CFX_CUDA(cudaMemcpyAsync(L.values_own.p, L.host_values, static_cast<size_t>(L.n_dofs) * sizeof(double),
-                               cudaMemcpyHostToDevice, ctx->stream));
+    {
+      const size_t n = static_cast<size_t>(L.n_dofs);
+      const size_t pb = L.host_pinned ? L.pin_begin : n, pe = L.host_pinned ? L.pin_end : n;
+      auto copy = [&](size_t b, size_t e)
+      {
+        if (e > b)
+          CFX_CUDA(cudaMemcpyAsync(L.values_own.p + b, L.host_values + b, (e - b) * sizeof(double),
+                                   cudaMemcpyHostToDevice, ctx->stream));
+      };
+      copy(0, pb);  // pageable head
+      copy(pb, pe); // page-locked interior (full PCIe rate)
+      copy(pe, n);  // pageable tail
+    }
     L.n_cut = -1;
   }
   CFX_REQUIRE(any, CFX_ERR_STATE, "cfx_update: no level set bound");

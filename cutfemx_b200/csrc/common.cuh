@@ -139,6 +139,7 @@ struct LevelSet
   const double* values = nullptr;      // device (owned copy or borrowed)
   const double* host_values = nullptr; // re-read by cfx_update when bound from the host
   bool host_pinned = false;
+  size_t pin_begin = 0, pin_end = 0; // element range [begin, end) of host_values that is page-locked
   DevBuf<double> values_own;
   DevBuf<int32_t> dofmap_own;
   int64_t counts[3] = {0, 0, 0};

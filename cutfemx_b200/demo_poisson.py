@@ -1,0 +1,127 @@
+"""The cut Poisson pipeline of the reference's demo (python/demo/demo_poisson.py:156-201) written
+against this package's public API, device-resident where the reference holds numpy arrays.
+
+One `step()` is one pass of the whole hot path:
+  update (classify) -> locate inside cells -> volume / interface run-time quadrature -> normals
+  -> ghost-penalty facets + integration rows -> sparsity -> matrix + vector assembly.
+bench.py times it, __graft_entry__.smoke() runs it once, tests compare it with the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+import importlib
+
+_cut = importlib.import_module(__package__ + ".cut")  # the package exports a function named `cut` too
+from . import fem as _fem
+from . import level_set as _ls
+from ._lib import DEVICE, HOST, check, lib
+from .cut import Context
+from .mesh import TETRAHEDRON, TRIANGLE, Function, FunctionSpace, Mesh
+
+
+def device_mesh(ctx_device: int, shape, p0, p1):
+    """Generate a Kuhn box / right-diagonal rectangle mesh on the GPU (csrc/meshgen.cu)."""
+    import torch
+
+    dev = f"cuda:{ctx_device}"
+    tdim = len(shape)
+    nn = int(np.prod([s + 1 for s in shape]))
+    nc = int(np.prod(shape)) * (2 if tdim == 2 else 6)
+    nv = tdim + 1
+    x = torch.empty((nn, 3), dtype=torch.float64, device=dev)
+    x_dofmap = torch.empty((nc, nv), dtype=torch.int32, device=dev)
+    c2f = torch.empty((nc, nv), dtype=torch.int32, device=dev)
+    nfac = (3 if tdim == 2 else 12) * nn
+    mesh = Mesh(TRIANGLE if tdim == 2 else TETRAHEDRON, tdim, tdim, x, x_dofmap, c2f, None, None, nc, nfac, nfac,
+                shape=tuple(shape), p0=tuple(p0), p1=tuple(p1))
+    mesh.extra["device"] = ctx_device
+    # generate into the tensors with a scratch context, then bind them
+    gen = Context(ctx_device)
+    P0 = (C.c_double * 3)(*(list(p0) + [0.0] * 3)[:3])
+    P1 = (C.c_double * 3)(*(list(p1) + [0.0] * 3)[:3])
+    if tdim == 3:
+        check(gen.handle, lib().cfx_meshgen_box(gen.handle, shape[0], shape[1], shape[2], P0, P1,
+                                                C.c_void_p(x.data_ptr()), C.c_void_p(x_dofmap.data_ptr()),
+                                                C.c_void_p(c2f.data_ptr())))
+    else:
+        check(gen.handle, lib().cfx_meshgen_rectangle(gen.handle, shape[0], shape[1], P0, P1,
+                                                      C.c_void_p(x.data_ptr()), C.c_void_p(x_dofmap.data_ptr()),
+                                                      C.c_void_p(c2f.data_ptr())))
+    gen.sync()
+    gen.close()
+    return mesh
+
+
+def device_level_set(mesh: Mesh, kind: str, params):
+    """Nodal interpolation of a sphere/circle (c, R) or torus (c, R, r) level set on the GPU."""
+    import torch
+
+    ctx = _cut._mesh_context(mesh)
+    vals = torch.empty(mesh.x.shape[0], dtype=torch.float64, device=mesh.x.device)
+    p = (C.c_double * 5)(*(list(params) + [0.0] * 5)[:5])
+    check(ctx.handle, lib().cfx_meshgen_level_set(ctx.handle, C.c_void_p(mesh.x.data_ptr()),
+                                                  C.c_int64(mesh.x.shape[0]), 0 if kind == "sphere" else 1, p,
+                                                  C.c_void_p(vals.data_ptr())))
+    return vals
+
+
+class CutPoisson:
+    """demo_poisson.py:156-201 with constant source f and constant Dirichlet value g."""
+
+    def __init__(self, mesh: Mesh, phi: Function, V: FunctionSpace, order: int = 4, gamma: float = 40.0,
+                 gamma_g: float = 0.1, f_value: float = 1.0, g_value: float = 0.0):
+        self.mesh, self.phi, self.V = mesh, phi, V
+        self.order, self.gamma, self.gamma_g, self.f_value, self.g_value = order, gamma, gamma_g, f_value, g_value
+        self.cut_data = _cut.cut(phi)
+        self.ctx = self.cut_data._ctx
+        self.A = None
+        self.b = None
+        self.stats = {}
+
+    def step(self, assemble_rhs: bool = True, keep: bool = False):
+        cd = self.cut_data
+        _cut.update(cd)                                                     # cutfemx.update
+        inside = _cut.locate_entities_device(cd, "phi<0")                   # locate_entities
+        rv = _cut.runtime_quadrature(cd, "phi<0", self.order)               # volume rules
+        ri = _cut.runtime_quadrature(cd, "phi=0", self.order)               # interface rules
+        _ls.attach_normal(cd, self.phi, ri)                                 # n = normal(phi)
+        ghost = _cut.ghost_penalty_facets_device(cd, "phi<0")               # ghost_penalty_facets
+        rows = _cut.facet_integration_rows_device(self.mesh, ghost)         # facet_integration_rows
+        a = _fem.CutForm(self.V, 2)
+        a.add_cell_integral("laplace", inside, rv, (1.0,))
+        a.add_cell_integral("nitsche", None, ri, (self.gamma,))
+        if ghost.size > 0:
+            a.add_interior_facet_integral("ghost_grad_jump", rows=rows, constants=(self.gamma_g,))
+        self.A = _fem.create_matrix(a, self.A)                              # create_sparsity_pattern
+        _fem.assemble_matrix(a, self.A)                                     # assemble_matrix
+        L = None
+        if assemble_rhs:
+            L = _fem.CutForm(self.V, 1)
+            L.add_cell_integral("source", inside, rv, (self.f_value,))
+            L.add_cell_integral("nitsche_rhs", None, ri, (self.gamma, self.g_value))
+            self.b = self._assemble_vector_device(L)
+        counts = cd.counts()
+        self.stats = dict(inside=counts[0], cut=counts[1], outside=counts[2], nnz=self.A.nnz,
+                          n_rows=self.A.shape[0], ghost_facets=ghost.size, volume_points=rv.total_points,
+                          interface_points=ri.total_points, volume_rules=rv.num_rules)
+        if keep:
+            self.last = dict(inside=inside, rv=rv, ri=ri, ghost=ghost, rows=rows, a=a, L=L)
+        else:
+            a.free()
+            if L is not None:
+                L.free()
+            for o in (inside, rv, ri, ghost, rows):
+                o.free()
+        return self.stats
+
+    def _assemble_vector_device(self, L):
+        import torch
+
+        n = self.V.num_dofs
+        if self.b is None or not hasattr(self.b, "data_ptr"):
+            self.b = torch.empty(n, dtype=torch.float64, device=f"cuda:{self.ctx.device}")
+        check(self.ctx.handle, lib().cfx_assemble_vector(self.ctx.handle, L._h, C.c_void_p(self.b.data_ptr()), 1, DEVICE))
+        return self.b
