@@ -182,7 +182,8 @@ template <int TDIM, int DEG, int KID, bool RUNTIME>
 __global__ void __launch_bounds__(EB)
     cell_kernel(const int32_t* __restrict__ cells, int64_t n, RuleView rv, StdRule sr, Consts cs,
                 const double* __restrict__ x, const int32_t* __restrict__ x_dofmap,
-                const int32_t* __restrict__ cell_slot, double* __restrict__ out, uint8_t* __restrict__ written)
+                const int32_t* __restrict__ dofmap, const int32_t* __restrict__ cell_slot, double* __restrict__ out,
+                uint8_t* __restrict__ written)
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
   constexpr int ES = ESize<ND, KernelTraits<KID>::RANK>::value;
@@ -237,19 +238,42 @@ __global__ void __launch_bounds__(EB)
   }
   const int64_t slot = cell_slot[cell];
   double* o = out + slot * ES;
-  if (written[slot])
+  const bool add = written[slot] != 0;
+  if constexpr (KernelTraits<KID>::RANK == 2)
   {
+    // Element-tensor rows are stored with their columns in ascending global-dof order, i.e. in the
+    // order of the CSR row they are gathered into (assemble.cu gather kernels, sparsity.cu gtab).
+    int32_t d[ND];
+    int rank[ND];
 #pragma unroll
-    for (int i = 0; i < ES; ++i)
-      o[i] += acc[i];
+    for (int j = 0; j < ND; ++j)
+      d[j] = __ldg(dofmap + cell * ND + j);
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+    {
+      int rk = 0;
+#pragma unroll
+      for (int jj = 0; jj < ND; ++jj)
+        rk += (d[jj] < d[j]) ? 1 : 0;
+      rank[j] = rk;
+    }
+#pragma unroll
+    for (int i = 0; i < ND; ++i)
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+      {
+        double* p = o + i * ND + rank[j];
+        *p = add ? *p + acc[i * ND + j] : acc[i * ND + j];
+      }
   }
   else
   {
 #pragma unroll
     for (int i = 0; i < ES; ++i)
-      o[i] = acc[i];
-    written[slot] = 1;
+      o[i] = add ? o[i] + acc[i] : acc[i];
   }
+  if (!add)
+    written[slot] = 1;
 }
 
 // Interior-facet ghost penalty, one thread per (facet, macro row).
@@ -410,80 +434,250 @@ struct GatherCtx
   int nf;
 };
 
-__device__ __forceinline__ int64_t find_col(const int32_t* __restrict__ cols, int64_t b, int64_t e, int32_t v)
+constexpr int GW = 4; // rows (warps) per block
+
+// rows no active entity touches: optional identity diagonal (deactivate_outside, deactivate.h:402-418)
+__global__ void inactive_diag_kernel(const uint8_t* __restrict__ row_flag, int64_t n_rows,
+                                     const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ cols,
+                                     double* __restrict__ vals, double diag)
 {
-  int64_t lo = b, hi = e;
-  while (lo < hi)
-  {
-    const int64_t mid = (lo + hi) >> 1;
-    if (cols[mid] < v)
-      lo = mid + 1;
-    else
-      hi = mid;
-  }
-  return (lo < e && cols[lo] == v) ? lo : -1;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (r >= n_rows || row_flag[r])
+    return;
+  for (int64_t p = row_ptr[r]; p < row_ptr[r + 1]; ++p)
+    if (cols[p] == r)
+      vals[p] = diag;
 }
 
+// One WARP per active row ("owner gathers").
+//  phase 1: lanes take the row's incident cells: gather dofmap row, slot and the matching
+//           element-tensor row (one 32 B sector for P1 tets) into shared memory -- up to 32
+//           independent gather chains in flight per warp;
+//  phase 2: lanes own the row's CSR entries (coalesced cols/vals access); every lane walks the
+//           staged cells in ascending order (broadcast shared-memory reads) and adds the entry
+//           whose dof equals its column.  Fixed order, no atomics -> bit-reproducible.
+// Interior-facet macro tensors are added afterwards, cell by cell, facet by facet.
 template <int ND>
-__global__ void __launch_bounds__(128)
-    gather_matrix_kernel(GatherCtx gc, int64_t n_rows, const int64_t* __restrict__ row_ptr,
+__global__ void __launch_bounds__(GW * 32)
+    gather_matrix_kernel(GatherCtx gc, const int32_t* __restrict__ act_rows, int64_t n_act,
+                         const uint8_t* __restrict__ skip_fast, const int64_t* __restrict__ row_ptr,
                          const int32_t* __restrict__ cols, double* __restrict__ vals, int zero_first,
-                         double diag_inactive, int32_t* __restrict__ err)
+                         int32_t* __restrict__ err)
 {
-  const int64_t r = static_cast<int64_t>(blockIdx.x) * 128 + threadIdx.x;
-  if (r >= n_rows)
+  __shared__ int32_t s_dofs[GW][32][ND];
+  __shared__ double s_a[GW][32][ND];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * GW + w;
+  if (idx >= n_act)
     return;
-  const int64_t b = row_ptr[r], e = row_ptr[r + 1];
-  if (zero_first)
-    for (int64_t p = b; p < e; ++p)
-      vals[p] = 0.0;
-  if (!gc.row_flag[r])
+  if (skip_fast && (skip_fast[idx] & 1))
+    return; // handled by gather_matrix_fast_kernel
+  const unsigned full = 0xffffffffu;
+  const int64_t r = act_rows[idx];
+  const int64_t ib = gc.inc_ptr[r];
+  const int n_inc = static_cast<int>(gc.inc_ptr[r + 1] - ib);
+  const int64_t rb = row_ptr[r];
+  const int rn = static_cast<int>(row_ptr[r + 1] - rb);
+  int matched = 0, expected = 0; // entries found in the pattern vs entries contributed
+  for (int kc = 0; kc < rn; kc += 32)
   {
-    if (diag_inactive != 0.0)
+    const bool have_col = kc + lane < rn;
+    const int32_t mycol = have_col ? cols[rb + kc + lane] : -2;
+    double acc = (have_col && !zero_first) ? vals[rb + kc + lane] : 0.0;
+    for (int k0 = 0; k0 < n_inc; k0 += 32)
     {
-      const int64_t p = find_col(cols, b, e, static_cast<int32_t>(r));
-      if (p >= 0)
-        vals[p] = diag_inactive;
+      // ---- phase 1
+      const int k = k0 + lane;
+      int64_t c = -1;
+      uint8_t fl = 0;
+      int li = 0;
+      if (k < n_inc)
+      {
+        c = gc.inc_cell[ib + k];
+        fl = gc.cell_flags[c];
+      }
+      if (fl)
+      {
+        int32_t d[ND];
+#pragma unroll
+        for (int j = 0; j < ND; ++j)
+        {
+          d[j] = gc.dofmap[c * ND + j];
+          li = (d[j] == r) ? j : li;
+        }
+        if (fl & 1)
+        {
+          const double* a = gc.Ae + (static_cast<int64_t>(gc.cell_slot[c]) * ND + li) * ND;
+          // element-tensor rows are stored in ascending-dof column order (cell_kernel)
+#pragma unroll
+          for (int pass = 0; pass < ND; ++pass)
+#pragma unroll
+            for (int i = pass & 1; i + 1 < ND; i += 2)
+            {
+              const int32_t lo = min(d[i], d[i + 1]), hi = max(d[i], d[i + 1]);
+              d[i] = lo;
+              d[i + 1] = hi;
+            }
+#pragma unroll
+          for (int j = 0; j < ND; ++j)
+          {
+            s_dofs[w][lane][j] = d[j];
+            s_a[w][lane][j] = a[j];
+          }
+        }
+      }
+      if (!(fl & 1))
+      {
+#pragma unroll
+        for (int j = 0; j < ND; ++j)
+          s_dofs[w][lane][j] = -1;
+      }
+      __syncwarp();
+      // ---- phase 2
+      const int nl = (n_inc - k0 < 32) ? n_inc - k0 : 32;
+      for (int l = 0; l < nl; ++l)
+      {
+#pragma unroll
+        for (int j = 0; j < ND; ++j)
+          if (s_dofs[w][l][j] == mycol)
+          {
+            acc += s_a[w][l][j];
+            ++matched;
+          }
+      }
+      if (kc == 0)
+        expected += (fl & 1) ? ND : 0;
+      // ---- interior-facet macro rows of the band cells of this chunk
+      unsigned band = __ballot_sync(full, (fl & 2) != 0);
+      while (band)
+      {
+        const int l = __ffs(band) - 1;
+        band &= band - 1;
+        const int64_t cl = __shfl_sync(full, c, l);
+        const int lil = __shfl_sync(full, li, l);
+        for (int lf = 0; lf < gc.nf; ++lf)
+        {
+          const int64_t fs = gc.facet_slot[gc.c2f[cl * gc.nf + lf]];
+          if (fs < 0)
+            continue;
+          const int64_t c0 = gc.rows4[4 * fs], c1 = gc.rows4[4 * fs + 2];
+          const int mrow = (cl == c0 ? 0 : ND) + lil;
+          const double* F = gc.Fe + (fs * 2 * ND + mrow) * 2 * ND;
+#pragma unroll
+          for (int s = 0; s < 2; ++s)
+          {
+            const int64_t cc = s ? c1 : c0;
+#pragma unroll
+            for (int j = 0; j < ND; ++j)
+              if (gc.dofmap[cc * ND + j] == mycol)
+              {
+                acc += F[s * ND + j];
+                ++matched;
+              }
+          }
+          if (kc == 0 && lane == 0)
+            expected += 2 * ND;
+        }
+      }
+      __syncwarp();
     }
-    return;
+    if (have_col)
+      vals[rb + kc + lane] = acc;
   }
-  bool missing = false;
-  for (int64_t k = gc.inc_ptr[r]; k < gc.inc_ptr[r + 1]; ++k)
+  // MatrixCSR::mat_add_values throws when an entry is not in the pattern: every contributed
+  // (cell, j) pair must have matched exactly one column of this row.
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
   {
-    const int64_t c = gc.inc_cell[k];
-    const uint8_t fl = gc.cell_flags[c];
-    if (!fl)
-      continue;
-    int32_t dofs[ND];
-    int li = 0;
+    matched += __shfl_down_sync(full, matched, o);
+    expected += __shfl_down_sync(full, expected, o);
+  }
+  if (lane == 0 && matched != expected)
+  {
+    err[0] = 31;
+    err[1] = static_cast<int32_t>(r);
+  }
+}
+
+// Fast rows (<= 32 columns, <= 32 incident cells): the pattern pass left, per incident cell l,
+// gtab = (element-tensor row index, bit mask of the CSR positions of the cell's dofs).  Lane l
+// loads its cell's row (already in column order) into shared memory; lane k owns CSR entry k and
+// walks the staged cells in ascending order: cell l contributes iff bit k of its mask is set, and
+// the value is entry popc(mask & lanes_below_k) of its row.  No dofmap read, no column search.
+template <int ND>
+__global__ void __launch_bounds__(GW * 32)
+    gather_matrix_fast_kernel(GatherCtx gc, const int32_t* __restrict__ act_rows, int64_t n_act,
+                              const uint8_t* __restrict__ row_fast, const int2* __restrict__ gtab,
+                              const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ cols,
+                              double* __restrict__ vals, int zero_first)
+{
+  __shared__ double s_a[GW][32][ND];
+  __shared__ uint32_t s_mask[GW][32];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * GW + w;
+  if (idx >= n_act)
+    return;
+  const uint8_t rf = row_fast[idx];
+  if (!(rf & 1))
+    return; // handled by gather_matrix_kernel
+  const unsigned full = 0xffffffffu;
+  const int2 g = gtab[idx * 32 + lane];
+  const int64_t r = act_rows[idx];
+  const int64_t rb = row_ptr[r];
+  const int rn = static_cast<int>(row_ptr[r + 1] - rb);
+  const bool have_col = lane < rn;
+  double acc = (have_col && !zero_first) ? vals[rb + lane] : 0.0;
+  if (g.x >= 0)
+  {
+    const double* a = gc.Ae + static_cast<int64_t>(g.x) * ND;
 #pragma unroll
     for (int j = 0; j < ND; ++j)
+      s_a[w][lane][j] = a[j];
+  }
+  s_mask[w][lane] = g.x >= 0 ? static_cast<uint32_t>(g.y) : 0u;
+  const unsigned contrib = __ballot_sync(full, g.x >= 0);
+  __syncwarp();
+  const int nl = 32 - __clz(contrib);
+  const uint32_t below = (1u << lane) - 1u;
+  for (int l = 0; l < nl; ++l)
+  {
+    const uint32_t M = s_mask[w][l];
+    if ((M >> lane) & 1u)
+      acc += s_a[w][l][__popc(M & below)];
+  }
+  if (rf & 2)
+  { // interior-facet macro rows of the band cells (rare): column matched by value
+    const int64_t ib = gc.inc_ptr[r];
+    const int n_inc = static_cast<int>(gc.inc_ptr[r + 1] - ib);
+    const int32_t mycol = have_col ? cols[rb + lane] : -2;
+    int64_t c = -1;
+    uint8_t fl = 0;
+    int li = 0;
+    if (lane < n_inc)
     {
-      dofs[j] = gc.dofmap[c * ND + j];
-      li = (dofs[j] == r) ? j : li;
-    }
-    if (fl & 1)
-    {
-      const double* a = gc.Ae + (static_cast<int64_t>(gc.cell_slot[c]) * ND + li) * ND;
-#pragma unroll
-      for (int j = 0; j < ND; ++j)
-      {
-        const int64_t p = find_col(cols, b, e, dofs[j]);
-        if (p >= 0)
-          vals[p] += a[j];
-        else
-          missing = true;
-      }
+      c = gc.inc_cell[ib + lane];
+      fl = gc.cell_flags[c];
     }
     if (fl & 2)
     {
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+        li = (gc.dofmap[c * ND + j] == r) ? j : li;
+    }
+    unsigned band = __ballot_sync(full, (fl & 2) != 0);
+    while (band)
+    {
+      const int l = __ffs(band) - 1;
+      band &= band - 1;
+      const int64_t cl = __shfl_sync(full, c, l);
+      const int lil = __shfl_sync(full, li, l);
       for (int lf = 0; lf < gc.nf; ++lf)
       {
-        const int64_t fs = gc.facet_slot[gc.c2f[c * gc.nf + lf]];
+        const int64_t fs = gc.facet_slot[gc.c2f[cl * gc.nf + lf]];
         if (fs < 0)
           continue;
         const int64_t c0 = gc.rows4[4 * fs], c1 = gc.rows4[4 * fs + 2];
-        const int mrow = (c == c0 ? 0 : ND) + li;
+        const int mrow = (cl == c0 ? 0 : ND) + lil;
         const double* F = gc.Fe + (fs * 2 * ND + mrow) * 2 * ND;
 #pragma unroll
         for (int s = 0; s < 2; ++s)
@@ -491,47 +685,46 @@ __global__ void __launch_bounds__(128)
           const int64_t cc = s ? c1 : c0;
 #pragma unroll
           for (int j = 0; j < ND; ++j)
-          {
-            const int64_t p = find_col(cols, b, e, gc.dofmap[cc * ND + j]);
-            if (p >= 0)
-              vals[p] += F[s * ND + j];
-            else
-              missing = true;
-          }
+            if (gc.dofmap[cc * ND + j] == mycol)
+              acc += F[s * ND + j];
         }
       }
     }
   }
-  if (missing)
-  { // MatrixCSR::mat_add_values throws "Entry not in sparsity pattern"
-    err[0] = 31;
-    err[1] = static_cast<int32_t>(r);
-  }
+  if (have_col)
+    vals[rb + lane] = acc;
 }
 
+// One warp per active row: lanes take incident cells, fixed-order warp tree sum.
 template <int ND>
-__global__ void __launch_bounds__(128)
-    gather_vector_kernel(GatherCtx gc, int64_t n_rows, double* __restrict__ b, int zero_first)
+__global__ void __launch_bounds__(GW * 32)
+    gather_vector_kernel(GatherCtx gc, const int32_t* __restrict__ act_rows, int64_t n_act, double* __restrict__ b,
+                         int zero_first)
 {
-  const int64_t r = static_cast<int64_t>(blockIdx.x) * 128 + threadIdx.x;
-  if (r >= n_rows)
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * GW + w;
+  if (idx >= n_act)
     return;
-  double s = zero_first ? 0.0 : b[r];
-  if (gc.row_flag[r])
+  const int64_t r = act_rows[idx];
+  const int64_t ib = gc.inc_ptr[r];
+  const int n_inc = static_cast<int>(gc.inc_ptr[r + 1] - ib);
+  double s = 0.0;
+  for (int k = lane; k < n_inc; k += 32)
   {
-    for (int64_t k = gc.inc_ptr[r]; k < gc.inc_ptr[r + 1]; ++k)
-    {
-      const int64_t c = gc.inc_cell[k];
-      if (!(gc.cell_flags[c] & 1))
-        continue;
-      int li = 0;
+    const int64_t c = gc.inc_cell[ib + k];
+    if (!(gc.cell_flags[c] & 1))
+      continue;
+    int li = 0;
 #pragma unroll
-      for (int j = 0; j < ND; ++j)
-        li = (gc.dofmap[c * ND + j] == r) ? j : li;
-      s += gc.Ae[static_cast<int64_t>(gc.cell_slot[c]) * ND + li];
-    }
+    for (int j = 0; j < ND; ++j)
+      li = (gc.dofmap[c * ND + j] == r) ? j : li;
+    s += gc.Ae[static_cast<int64_t>(gc.cell_slot[c]) * ND + li];
   }
-  b[r] = s;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0)
+    b[r] = zero_first ? s : b[r] + s;
 }
 
 // fixed-shape two-level sum: bit-reproducible
@@ -579,8 +772,8 @@ void launch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f)
     RuleTable& rt = get_rule(c, TDIM, order);
     sr = StdRule{rt.d_pts, rt.d_wts, rt.npts};
     auto k = cell_kernel<TDIM, DEG, KID, false>;
-    CFX_LAUNCH(c, k, grid_for(I.n, EB), EB, 0, I.entities, I.n, rv, sr, cs, c->x, c->x_dofmap, f->cell_slot.p, f->Ae.p,
-               f->written.p);
+    CFX_LAUNCH(c, k, grid_for(I.n, EB), EB, 0, I.entities, I.n, rv, sr, cs, c->x, c->x_dofmap,
+               c->spaces[f->space].dofmap, f->cell_slot.p, f->Ae.p, f->written.p);
   }
   if (I.rules && I.rules->nrules > 0)
   {
@@ -590,7 +783,7 @@ void launch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f)
                   R->npts};
     auto k = cell_kernel<TDIM, DEG, KID, true>;
     CFX_LAUNCH(c, k, grid_for(R->nrules, EB), EB, 0, nullptr, R->nrules, rv, sr, cs, c->x, c->x_dofmap,
-               f->cell_slot.p, f->Ae.p, f->written.p);
+               c->spaces[f->space].dofmap, f->cell_slot.p, f->Ae.p, f->written.p);
   }
 }
 
@@ -699,13 +892,31 @@ cfx_status cfx_assemble_matrix(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
                   12.0 * static_cast<double>(A->nnz) + 8.0 * nd * nd * static_cast<double>(a->n_active));
     set_facet_slots(ctx, FI, false);
     GatherCtx gc = make_gather_ctx(ctx, a, FI);
-    const unsigned g = grid_for(A->n_rows, 128);
+    if (zero_first)
+      CFX_CUDA(cudaMemsetAsync(A->values.p, 0, static_cast<size_t>(A->nnz) * sizeof(double), ctx->stream));
+    if (diag_inactive != 0.0)
+      CFX_LAUNCH(ctx, inactive_diag_kernel, grid_for(A->n_rows, 256), 256, 0, a->row_flag.p, A->n_rows, A->row_ptr.p,
+                 A->cols.p, A->values.p, diag_inactive);
     auto k = nd == 3 ? gather_matrix_kernel<3>
              : nd == 4 ? gather_matrix_kernel<4>
              : nd == 6 ? gather_matrix_kernel<6>
                        : gather_matrix_kernel<10>;
-    CFX_LAUNCH(ctx, k, g, 128, 0, gc, A->n_rows, A->row_ptr.p, A->cols.p, A->values.p, zero_first, diag_inactive,
-               ctx->err_flag.p);
+    auto kf = nd == 3 ? gather_matrix_fast_kernel<3>
+              : nd == 4 ? gather_matrix_fast_kernel<4>
+              : nd == 6 ? gather_matrix_fast_kernel<6>
+                        : gather_matrix_fast_kernel<10>;
+    // the gather table is valid only for the pattern that was built from this very form
+    const bool fast = a->gtab_serial == A->serial && a->gtab_serial > 0;
+    if (a->n_act_rows > 0)
+    {
+      const unsigned g = grid_for(a->n_act_rows, GW);
+      if (fast)
+        CFX_LAUNCH(ctx, kf, g, GW * 32, 0, gc, a->act_rows.p, a->n_act_rows, a->row_fast.p, a->gtab.p, A->row_ptr.p,
+                   A->cols.p, A->values.p, zero_first);
+      if (!fast || a->n_slow_rows > 0)
+        CFX_LAUNCH(ctx, k, g, GW * 32, 0, gc, a->act_rows.p, a->n_act_rows, fast ? a->row_fast.p : nullptr,
+                   A->row_ptr.p, A->cols.p, A->values.p, zero_first, ctx->err_flag.p);
+    }
     set_facet_slots(ctx, FI, true);
   }
   if (values_out)
@@ -744,7 +955,10 @@ cfx_status cfx_assemble_vector(cfx_ctx* ctx, const cfx_form* L_const, double* b,
              : S.nd == 4 ? gather_vector_kernel<4>
              : S.nd == 6 ? gather_vector_kernel<6>
                          : gather_vector_kernel<10>;
-    CFX_LAUNCH(ctx, k, grid_for(S.n_total, 128), 128, 0, gc, S.n_total, d_b, zero_first);
+    if (zero_first)
+      CFX_CUDA(cudaMemsetAsync(d_b, 0, static_cast<size_t>(S.n_total) * sizeof(double), ctx->stream));
+    if (L->n_act_rows > 0)
+      CFX_LAUNCH(ctx, k, grid_for(L->n_act_rows, GW), GW * 32, 0, gc, L->act_rows.p, L->n_act_rows, d_b, zero_first);
   }
   if (memspace == CFX_HOST)
   {

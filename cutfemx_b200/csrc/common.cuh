@@ -198,6 +198,7 @@ struct cfx_pattern
 {
   int space = 0;
   int64_t n_rows = 0, nnz = 0;
+  int64_t serial = 0;
   cfx::DevBuf<int64_t> row_ptr;
   cfx::DevBuf<int32_t> cols;
   cfx::DevBuf<double> values;
@@ -224,6 +225,13 @@ struct cfx_form
   cfx::DevBuf<int32_t> cell_slot;  // rank among flagged cells (valid where bit0)
   cfx::DevBuf<int32_t> active;     // ascending cell ids with bit0 (slot i <-> cell active[i])
   cfx::DevBuf<uint8_t> row_flag;   // per dof: touched by a flagged cell
+  cfx::DevBuf<int32_t> act_rows;   // ascending dofs with row_flag set
+  int64_t n_act_rows = 0;
+  // gather table of the pattern built from this form (sparsity.cu pattern_rows_kernel)
+  cfx::DevBuf<int2> gtab;
+  cfx::DevBuf<uint8_t> row_fast;
+  int64_t n_slow_rows = 0;
+  int64_t gtab_serial = -1;
   int64_t n_active = 0;
   cfx::DevBuf<double> Ae;      // (n_active, nd^rank)
   cfx::DevBuf<uint8_t> written; // per slot
@@ -237,6 +245,7 @@ struct cfx_ctx
   std::string err;
   cfx::DevPool pool;
   int64_t launches = 0;
+  int64_t pattern_serial = 0;
 
   // mesh views
   bool mesh_bound = false;

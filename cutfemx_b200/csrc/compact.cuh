@@ -7,17 +7,21 @@
 
 namespace cfx
 {
-// Pred: __device__ unsigned operator()(int64_t base, int64_t n) -> 4-bit mask for base..base+3
-// (base is a multiple of 4; bits for indices >= n must be 0).
+// Pred: __device__ unsigned operator()(int64_t base, int64_t n) -> 16-bit mask for base..base+15
+// (base is a multiple of 16; bits for indices >= n must be 0).  One 16-byte load per thread for
+// byte-array predicates, so a 100 M-cell scan streams at HBM rate.
+constexpr int CP_BLOCK = 256;
+constexpr int CP_ITEMS = 16;
+constexpr int CP_TILE = CP_BLOCK * CP_ITEMS;
 template <class Pred>
-__global__ void __launch_bounds__(SCAN_BLOCK) compact_count_kernel(Pred pred, int64_t n, int32_t* __restrict__ counts)
+__global__ void __launch_bounds__(CP_BLOCK) compact_count_kernel(Pred pred, int64_t n, int32_t* __restrict__ counts)
 {
-  const int64_t base = static_cast<int64_t>(blockIdx.x) * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * CP_TILE + threadIdx.x * CP_ITEMS;
   int cnt = base < n ? __popc(pred(base, n)) : 0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
     cnt += __shfl_down_sync(0xffffffffu, cnt, o);
-  __shared__ int s[SCAN_BLOCK / 32];
+  __shared__ int s[CP_BLOCK / 32];
   if ((threadIdx.x & 31) == 0)
     s[threadIdx.x >> 5] = cnt;
   __syncthreads();
@@ -25,25 +29,27 @@ __global__ void __launch_bounds__(SCAN_BLOCK) compact_count_kernel(Pred pred, in
   {
     int t = 0;
 #pragma unroll
-    for (int w = 0; w < SCAN_BLOCK / 32; ++w)
+    for (int w = 0; w < CP_BLOCK / 32; ++w)
       t += s[w];
     counts[blockIdx.x] = t;
   }
 }
 
 template <class Pred>
-__global__ void __launch_bounds__(SCAN_BLOCK)
+__global__ void __launch_bounds__(CP_BLOCK)
     compact_write_kernel(Pred pred, int64_t n, const int64_t* __restrict__ tile_off, int32_t* __restrict__ out)
 {
-  const int64_t base = static_cast<int64_t>(blockIdx.x) * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-  const unsigned mask = base < n ? pred(base, n) : 0u;
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * CP_TILE + threadIdx.x * CP_ITEMS;
+  unsigned mask = base < n ? pred(base, n) : 0u;
   int tot;
-  const int excl = block_excl_scan<SCAN_BLOCK>(__popc(mask), &tot);
+  const int excl = block_excl_scan<CP_BLOCK>(__popc(mask), &tot);
   int64_t o = tile_off[blockIdx.x] + excl;
-#pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; ++k)
-    if (mask & (1u << k))
-      out[o++] = static_cast<int32_t>(base + k);
+  while (mask)
+  {
+    const int k = __ffs(mask) - 1;
+    mask &= mask - 1;
+    out[o++] = static_cast<int32_t>(base + k);
+  }
 }
 
 // Returns the number of selected indices; `out` is (re)allocated to exactly that size.
@@ -55,34 +61,41 @@ int64_t compact_indices(cfx_ctx* c, int64_t n, Pred pred, DevBuf<int32_t>& out)
     out.reserve(c->pool, 1);
     return 0;
   }
-  const unsigned nb = grid_for(n, SCAN_TILE);
+  const unsigned nb = grid_for(n, CP_TILE);
   c->blk_counts.reserve(c->pool, nb);
   c->blk_offsets.reserve(c->pool, nb);
-  CFX_LAUNCH(c, compact_count_kernel<Pred>, nb, SCAN_BLOCK, 0, pred, n, c->blk_counts.p);
+  CFX_LAUNCH(c, compact_count_kernel<Pred>, nb, CP_BLOCK, 0, pred, n, c->blk_counts.p);
   scan_block_counts(c, c->blk_counts.p, nb, c->blk_offsets.p);
   const int64_t total = read_back(c, c->scratch64.p, 1)[0];
   out.reserve(c->pool, static_cast<size_t>(total > 0 ? total : 1));
   if (total > 0)
-    CFX_LAUNCH(c, compact_write_kernel<Pred>, nb, SCAN_BLOCK, 0, pred, n, c->blk_offsets.p, out.p);
+    CFX_LAUNCH(c, compact_write_kernel<Pred>, nb, CP_BLOCK, 0, pred, n, c->blk_offsets.p, out.p);
   return total;
 }
 
 // byte-array predicate: flag[i] != 0
+__device__ __forceinline__ unsigned nonzero_bytes16(uint4 v)
+{
+  unsigned m = 0;
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      m |= ((w[q] >> (8 * k)) & 0xffu) ? (1u << (4 * q + k)) : 0u;
+  return m;
+}
+
 struct FlagPred
 {
-  const uint8_t* flag; // 4-byte aligned base
+  const uint8_t* flag; // 16-byte aligned base
   __device__ unsigned operator()(int64_t base, int64_t n) const
   {
+    if (base + 16 <= n)
+      return nonzero_bytes16(*reinterpret_cast<const uint4*>(flag + base));
     unsigned m = 0;
-    if (base + 4 <= n)
-    {
-      const uint32_t v = *reinterpret_cast<const uint32_t*>(flag + base);
-      m = ((v & 0xffu) ? 1u : 0u) | ((v & 0xff00u) ? 2u : 0u) | ((v & 0xff0000u) ? 4u : 0u)
-          | ((v & 0xff000000u) ? 8u : 0u);
-    }
-    else
-      for (int k = 0; base + k < n; ++k)
-        m |= flag[base + k] ? (1u << k) : 0u;
+    for (int k = 0; base + k < n; ++k)
+      m |= flag[base + k] ? (1u << k) : 0u;
     return m;
   }
 };
@@ -129,21 +142,23 @@ struct DnfPred
 {
   Dnf d;
   const int8_t* domain;
-  int64_t stride;
+  int64_t stride; // multiple of 16
   __device__ unsigned operator()(int64_t base, int64_t n) const
   {
     unsigned m = 0;
-    if (d.n_terms == 1 && d.term_off[1] == 1 && base + 4 <= n)
-    { // single clause fast path: one 32-bit load of four domain codes
-      const uint32_t v
-          = *reinterpret_cast<const uint32_t*>(domain + static_cast<int64_t>(d.ls[0]) * stride + base);
+    if (d.n_terms == 1 && d.term_off[1] == 1 && base + 16 <= n)
+    { // single clause fast path: one 16-byte load of sixteen domain codes
+      const uint4 v = *reinterpret_cast<const uint4*>(domain + static_cast<int64_t>(d.ls[0]) * stride + base);
       const unsigned rm = d.relmask[0];
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        m |= ((rm >> ((v >> (8 * k)) & 0xffu)) & 1u) << k;
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          m |= ((rm >> ((w[q] >> (8 * k)) & 0x7u)) & 1u) << (4 * q + k);
       return m;
     }
-    for (int k = 0; k < 4 && base + k < n; ++k)
+    for (int k = 0; k < 16 && base + k < n; ++k)
       m |= dnf_match(d, domain, stride, base + k) ? (1u << k) : 0u;
     return m;
   }

@@ -80,16 +80,24 @@ __global__ void f2c_from_adj_kernel(const int32_t* __restrict__ off, const int32
   f2c2[2 * f + 1] = c1;
 }
 
-// active[c] = intersected by cut_ls  OR  selector matches   (cut.py:364-366), over ALL local cells
-__global__ void active_flag_kernel(Dnf d, int cut_ls, const int8_t* __restrict__ domain, int64_t stride, int64_t nc,
-                                   uint8_t* __restrict__ active)
+// active(c) = intersected by cut_ls  OR  selector matches   (cut.py:364-366), for ANY local cell
+struct BandPredDnf
 {
-  const int64_t c = static_cast<int64_t>(blockIdx.x) * FB + threadIdx.x;
-  if (c >= nc)
-    return;
-  const bool cut = domain[static_cast<int64_t>(cut_ls) * stride + c] == CFX_DOMAIN_INTERSECTED;
-  active[c] = (cut || dnf_match(d, domain, stride, c)) ? 1 : 0;
-}
+  Dnf d;
+  int cut_ls;
+  const int8_t* domain;
+  int64_t stride;
+  __device__ bool operator()(int64_t c) const
+  {
+    return domain[static_cast<int64_t>(cut_ls) * stride + c] == CFX_DOMAIN_INTERSECTED
+           || dnf_match(d, domain, stride, c);
+  }
+};
+struct BandPredFlags
+{
+  const uint8_t* flag;
+  __device__ bool operator()(int64_t c) const { return flag[c] != 0; }
+};
 
 __global__ void set_flag_kernel(const int32_t* __restrict__ cells, int64_t n, int64_t nc, uint8_t* __restrict__ flag,
                                 int32_t* __restrict__ err)
@@ -109,10 +117,10 @@ __global__ void set_flag_kernel(const int32_t* __restrict__ cells, int64_t n, in
 
 // cut.py:369-379 / cut.cpp:967-987: for every source cell, every facet that is owned, has two
 // cells, both flagged -> mark
+template <class Active>
 __global__ void mark_facets_kernel(const int32_t* __restrict__ src_cells, int64_t n_src, int nf,
-                                   const int32_t* __restrict__ c2f, const int32_t* __restrict__ f2c2,
-                                   const uint8_t* __restrict__ active, int64_t n_owned_facets, int include_ghosts,
-                                   uint8_t* __restrict__ facet_flag)
+                                   const int32_t* __restrict__ c2f, const int32_t* __restrict__ f2c2, Active active,
+                                   int64_t n_owned_facets, int include_ghosts, uint8_t* __restrict__ facet_flag)
 {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * FB + threadIdx.x;
   if (i >= n_src * nf)
@@ -124,7 +132,7 @@ __global__ void mark_facets_kernel(const int32_t* __restrict__ src_cells, int64_
   const int32_t c0 = f2c2[2 * static_cast<int64_t>(f)], c1 = f2c2[2 * static_cast<int64_t>(f) + 1];
   if (c1 < 0)
     return; // not exactly two cells
-  if (active[c0] && active[c1])
+  if (active(c0) && active(c1))
     facet_flag[f] = 1;
 }
 
@@ -176,13 +184,14 @@ __global__ void facet_rows_kernel(const int32_t* __restrict__ facets, int64_t n,
   }
 }
 
-int64_t band_from_flags(cfx_ctx* c, const int32_t* src_cells, int64_t n_src, const uint8_t* active,
-                        int include_ghosts, cfx_list* out)
+template <class Active>
+int64_t band_from_flags(cfx_ctx* c, const int32_t* src_cells, int64_t n_src, Active active, int include_ghosts,
+                        cfx_list* out)
 {
   const int nf = c->tdim + 1;
   if (n_src > 0)
-    CFX_LAUNCH(c, mark_facets_kernel, grid_for(n_src * nf, FB), FB, 0, src_cells, n_src, nf, c->c2f, c->f2c2.p, active,
-               c->n_owned_facets, include_ghosts, c->facet_flag.p);
+    CFX_LAUNCH(c, mark_facets_kernel<Active>, grid_for(n_src * nf, FB), FB, 0, src_cells, n_src, nf, c->c2f,
+               c->f2c2.p, active, c->n_owned_facets, include_ghosts, c->facet_flag.p);
   FlagPred p{c->facet_flag.p};
   out->n = compact_indices(c, c->n_facets, p, out->data);
   if (out->n > 0)
@@ -228,12 +237,9 @@ cfx_status cfx_ghost_penalty_facets(cfx_ctx* ctx, int cut_ls, int n_terms, const
     *out = new cfx_list();
   LevelSet& L = ctx->ls[cut_ls];
   StageScope st(ctx, "ghost_penalty_facets",
-                2.0 * static_cast<double>(ctx->nc_total) + 4.0 * (ctx->tdim + 1) * static_cast<double>(L.n_cut)
-                    + static_cast<double>(ctx->n_facets));
-  ctx->scratch8.reserve(ctx->pool, static_cast<size_t>(ctx->nc_total) + 16);
-  CFX_LAUNCH(ctx, active_flag_kernel, grid_for(ctx->nc_total, FB), FB, 0, d, cut_ls, ctx->domain.p, ctx->domain_stride,
-             ctx->nc_total, ctx->scratch8.p);
-  band_from_flags(ctx, L.cut_list.p, L.n_cut, ctx->scratch8.p, include_ghosts, *out);
+                4.0 * (ctx->tdim + 1) * static_cast<double>(L.n_cut) + 2.0 * static_cast<double>(ctx->n_facets));
+  band_from_flags(ctx, L.cut_list.p, L.n_cut, BandPredDnf{d, cut_ls, ctx->domain.p, ctx->domain_stride},
+                  include_ghosts, *out);
   CFX_API_END(ctx)
 }
 
@@ -253,7 +259,7 @@ cfx_status cfx_interior_facets_for_cells(cfx_ctx* ctx, const int32_t* cells, int
   if (n > 0)
     CFX_LAUNCH(ctx, set_flag_kernel, grid_for(n, FB), FB, 0, d_cells, n, ctx->nc_total, ctx->scratch8.p,
                ctx->err_flag.p);
-  band_from_flags(ctx, d_cells, n, ctx->scratch8.p, include_ghosts, *out);
+  band_from_flags(ctx, d_cells, n, BandPredFlags{ctx->scratch8.p}, include_ghosts, *out);
   own.release();
   check_device_error(ctx, "cfx_interior_facets_for_cells (Cell index is out of range.)");
   CFX_API_END(ctx)

@@ -9,6 +9,8 @@ namespace
 constexpr int SB = 1024;
 
 // single block: offsets[i] = sum_{j<i} in[j]; *total = sum.  n up to a few 10^5.
+// Each thread scans SI consecutive items per round, so 24.5 K tile counts take 3 rounds.
+constexpr int SI = 8;
 template <class Tin>
 __global__ void __launch_bounds__(SB) scan_small_kernel(const Tin* __restrict__ in, int64_t n,
                                                         int64_t* __restrict__ offsets, int64_t* __restrict__ total)
@@ -19,11 +21,18 @@ __global__ void __launch_bounds__(SB) scan_small_kernel(const Tin* __restrict__ 
     s_carry = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int64_t base = 0; base < n; base += SB)
+  for (int64_t base = 0; base < n; base += SB * SI)
   {
-    const int64_t i = base + threadIdx.x;
-    const long long v = i < n ? static_cast<long long>(in[i]) : 0;
-    const long long incl = warp_incl_scan_ll(v);
+    const int64_t i0 = base + static_cast<int64_t>(threadIdx.x) * SI;
+    long long v[SI];
+    long long sum = 0;
+#pragma unroll
+    for (int k = 0; k < SI; ++k)
+    {
+      v[k] = (i0 + k < n) ? static_cast<long long>(in[i0 + k]) : 0;
+      sum += v[k];
+    }
+    const long long incl = warp_incl_scan_ll(sum);
     if (lane == 31)
       s_warp[wid] = incl;
     __syncthreads();
@@ -34,12 +43,17 @@ __global__ void __launch_bounds__(SB) scan_small_kernel(const Tin* __restrict__ 
       s_warp[lane] = wi - w;
     }
     __syncthreads();
-    const long long excl = s_carry + s_warp[wid] + incl - v;
-    if (i < n)
-      offsets[i] = excl;
+    long long run = s_carry + s_warp[wid] + incl - sum;
+#pragma unroll
+    for (int k = 0; k < SI; ++k)
+    {
+      if (i0 + k < n)
+        offsets[i0 + k] = run;
+      run += v[k];
+    }
     __syncthreads();
     if (threadIdx.x == SB - 1)
-      s_carry = excl + v;
+      s_carry = run;
     __syncthreads();
   }
   if (threadIdx.x == 0)

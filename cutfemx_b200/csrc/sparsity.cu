@@ -91,15 +91,15 @@ __global__ void scatter_slot_kernel(const int32_t* __restrict__ act, int64_t n, 
     slot[act[i]] = static_cast<int32_t>(i);
 }
 
-// row_flag[dof] = 1 for every dof of a flagged cell
-__global__ void row_flag_kernel(const uint8_t* __restrict__ cell_flags, int64_t nc, const int32_t* __restrict__ dofmap,
-                                int nd, uint8_t* __restrict__ row_flag)
+// row_flag[dof] = 1 for every dof of the listed cells (cells[i * stride])
+__global__ void row_flag_kernel(const int32_t* __restrict__ cells, int64_t n, int stride,
+                                const int32_t* __restrict__ dofmap, int nd, uint8_t* __restrict__ row_flag)
 {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x;
-  if (i >= nc * nd)
+  if (i >= n * nd)
     return;
-  if (cell_flags[i / nd])
-    row_flag[dofmap[i]] = 1;
+  const int64_t c = cells[(i / nd) * stride];
+  row_flag[dofmap[c * nd + (i % nd)]] = 1;
 }
 
 __global__ void facet_slot_set_kernel(const int32_t* __restrict__ rows4, int64_t n, int nf,
@@ -110,29 +110,6 @@ __global__ void facet_slot_set_kernel(const int32_t* __restrict__ rows4, int64_t
     return;
   const int32_t f = c2f[static_cast<int64_t>(rows4[4 * i]) * nf + rows4[4 * i + 1]];
   facet_slot[f] = clear ? -1 : static_cast<int32_t>(i);
-}
-
-template <int CAP>
-__device__ __forceinline__ bool insert_sorted(int32_t (&a)[CAP], int& n, int32_t v)
-{
-  int lo = 0, hi = n;
-  while (lo < hi)
-  {
-    const int mid = (lo + hi) >> 1;
-    if (a[mid] < v)
-      lo = mid + 1;
-    else
-      hi = mid;
-  }
-  if (lo < n && a[lo] == v)
-    return true;
-  if (n >= CAP)
-    return false;
-  for (int i = n; i > lo; --i)
-    a[i] = a[i - 1];
-  a[lo] = v;
-  ++n;
-  return true;
 }
 
 struct RowCtx
@@ -149,76 +126,232 @@ struct RowCtx
   int insert_diagonal;
 };
 
-template <int ND, int CAP>
-__device__ __forceinline__ int collect_row(const RowCtx& rc, int64_t r, int32_t (&cols)[CAP], bool& overflow)
+constexpr int RW = 4;      // rows (warps) per block
+// partner-dof candidates per row (facet macro cliques): 128 * ND
+constexpr int IMAX = 0x7fffffff;
+
+// inactive rows: only the deactivation diagonal (assembler.h:538-560)
+__global__ void pattern_inactive_count_kernel(const uint8_t* __restrict__ row_flag, int64_t n_rows, int diag,
+                                              int32_t* __restrict__ row_nnz)
 {
-  int n = 0;
-  if (rc.insert_diagonal)
-    cols[n++] = static_cast<int32_t>(r);
-  if (!rc.row_flag[r])
-    return n;
-  for (int64_t k = rc.inc_ptr[r]; k < rc.inc_ptr[r + 1]; ++k)
-  {
-    const int64_t c = rc.inc_cell[k];
-    const uint8_t fl = rc.cell_flags[c];
-    if (!fl)
-      continue;
-    bool own_needed = fl & 1;
-    if (fl & 2)
-    {
-      for (int lf = 0; lf < rc.nf; ++lf)
-      {
-        const int64_t f = rc.c2f[c * rc.nf + lf];
-        if (rc.facet_slot[f] < 0)
-          continue;
-        own_needed = true;
-        const int32_t c0 = rc.f2c2[2 * f], c1 = rc.f2c2[2 * f + 1];
-        const int64_t other = (c0 == c) ? c1 : c0;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x;
+  if (r < n_rows && !row_flag[r])
+    row_nnz[r] = diag;
+}
+
+__global__ void pattern_inactive_fill_kernel(const uint8_t* __restrict__ row_flag, int64_t n_rows, int diag,
+                                             const int64_t* __restrict__ row_ptr, int32_t* __restrict__ cols)
+{
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x;
+  if (r < n_rows && !row_flag[r] && diag)
+    cols[row_ptr[r]] = static_cast<int32_t>(r);
+}
+
+// ascending sort of a small register array (odd-even transposition network, fully unrolled)
+template <int N>
+__device__ __forceinline__ void sort_small(int32_t (&v)[N])
+{
 #pragma unroll
-        for (int j = 0; j < ND; ++j)
-          overflow |= !insert_sorted<CAP>(cols, n, rc.dofmap[other * ND + j]);
+  for (int pass = 0; pass < N; ++pass)
+#pragma unroll
+    for (int i = pass & 1; i + 1 < N; i += 2)
+    {
+      const int32_t lo = min(v[i], v[i + 1]), hi = max(v[i], v[i + 1]);
+      v[i] = lo;
+      v[i + 1] = hi;
+    }
+}
+
+// One WARP per active row.  Lanes take the row's incident cells (coalesced inc_cell read, ND-wide
+// dofmap gathers in parallel), sort their cell's dofs, and the warp extracts the sorted unique
+// column set by repeated warp-wide minimum over the list heads (one REDUX per column).
+//
+// FILL = false (first pass over every active row): counts the columns and, for rows with at most
+// 32 columns and 32 incident cells ("fast rows"), also stores
+//   tmp[idx*32 + k]  = k-th column                      (copied to the CSR after the scan)
+//   gtab[idx*32 + l] = (slot*ND + local row, bit mask of the CSR positions of cell l's dofs)
+// so that the assembly gather (assemble.cu) needs neither the dofmap nor a column search.
+// FILL = true (second pass, slow rows only): writes the columns straight into the CSR.
+template <int ND, bool FILL>
+__global__ void __launch_bounds__(RW * 32)
+    pattern_rows_kernel(RowCtx rc, const int32_t* __restrict__ act_rows, int64_t n_act,
+                        int32_t* __restrict__ row_nnz, const int64_t* __restrict__ row_ptr,
+                        int32_t* __restrict__ cols_out, const int32_t* __restrict__ cell_slot,
+                        int32_t* __restrict__ tmp, int2* __restrict__ gtab, uint8_t* __restrict__ row_fast,
+                        unsigned long long* __restrict__ n_slow, int32_t* __restrict__ err)
+{
+  constexpr int XCAP = 128 * ND; // partner-dof candidates per row (facet macro cliques)
+  __shared__ int32_t s_extra[RW][XCAP];
+  __shared__ int s_nextra[RW];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * RW + w;
+  if (idx >= n_act)
+    return;
+  if constexpr (FILL)
+  {
+    if (row_fast[idx] & 1)
+      return; // already copied from tmp
+  }
+  const unsigned full = 0xffffffffu;
+  const int64_t r = act_rows[idx];
+  const int64_t ib = rc.inc_ptr[r];
+  const int n_inc = static_cast<int>(rc.inc_ptr[r + 1] - ib);
+  if (lane == 0)
+    s_nextra[w] = 0;
+  __syncwarp();
+  int32_t h[ND]; // this lane's sorted candidate list (first 32 incidences live in registers)
+#pragma unroll
+  for (int j = 0; j < ND; ++j)
+    h[j] = IMAX;
+  int32_t src = -1;
+  bool band = false;
+  for (int k0 = 0; k0 < n_inc; k0 += 32)
+  {
+    const int k = k0 + lane;
+    if (k < n_inc)
+    {
+      const int64_t c = rc.inc_cell[ib + k];
+      const uint8_t fl = rc.cell_flags[c];
+      bool own_needed = fl & 1;
+      if (fl & 2)
+      {
+        band = true;
+        for (int lf = 0; lf < rc.nf; ++lf)
+        {
+          const int64_t f = rc.c2f[c * rc.nf + lf];
+          if (rc.facet_slot[f] < 0)
+            continue;
+          own_needed = true;
+          const int32_t c0 = rc.f2c2[2 * f], c1 = rc.f2c2[2 * f + 1];
+          const int64_t other = (c0 == c) ? c1 : c0;
+          const int pos = atomicAdd(&s_nextra[w], ND);
+          if (pos + ND <= XCAP)
+          {
+#pragma unroll
+            for (int j = 0; j < ND; ++j)
+              s_extra[w][pos + j] = rc.dofmap[other * ND + j];
+          }
+        }
+      }
+      if (own_needed)
+      {
+        if (k0 == 0)
+        {
+          int li = 0;
+#pragma unroll
+          for (int j = 0; j < ND; ++j)
+          {
+            h[j] = rc.dofmap[c * ND + j];
+            li = (h[j] == r) ? j : li;
+          }
+          if (fl & 1)
+            src = cell_slot[c] * ND + li;
+        }
+        else
+        { // rare: more than 32 incident cells -> spill this cell's dofs to the shared candidate list
+          const int pos = atomicAdd(&s_nextra[w], ND);
+          if (pos + ND <= XCAP)
+          {
+#pragma unroll
+            for (int j = 0; j < ND; ++j)
+              s_extra[w][pos + j] = rc.dofmap[c * ND + j];
+          }
+        }
       }
     }
-    if (own_needed)
+  }
+  __syncwarp();
+  const int n_extra = s_nextra[w];
+  if (n_extra > XCAP)
+  {
+    if (lane == 0)
     {
+      err[0] = 23;
+      err[1] = static_cast<int32_t>(r);
+    }
+    return;
+  }
+  sort_small<ND>(h);
+  int32_t dg = (rc.insert_diagonal && lane == 0) ? static_cast<int32_t>(r) : IMAX;
+  const int64_t ob = FILL ? row_ptr[r] : 0;
+  int32_t last = -1, keep = 0;
+  uint32_t M = 0;
+  int count = 0;
+  while (true)
+  {
+    int32_t m = min(h[0], dg);
+    for (int e = lane; e < n_extra; e += 32)
+    {
+      const int32_t v = s_extra[w][e];
+      m = (v > last && v < m) ? v : m;
+    }
+    m = __reduce_min_sync(full, m);
+    if (m == IMAX)
+      break;
+    if (h[0] == m)
+    { // pop: this cell's dof sits at CSR position `count` of the row
+      M |= (count < 32) ? (1u << count) : 0u;
 #pragma unroll
-      for (int j = 0; j < ND; ++j)
-        overflow |= !insert_sorted<CAP>(cols, n, rc.dofmap[c * ND + j]);
+      for (int j = 0; j + 1 < ND; ++j)
+        h[j] = h[j + 1];
+      h[ND - 1] = IMAX;
+    }
+    dg = (dg == m) ? IMAX : dg;
+    if constexpr (FILL)
+    {
+      if (lane == (count & 31))
+        keep = m;
+      if ((count & 31) == 31)
+        cols_out[ob + (count & ~31) + lane] = keep; // coalesced flush of 32 columns
+    }
+    else
+    {
+      if (lane == count)
+        keep = m;
+    }
+    last = m;
+    ++count;
+  }
+  if constexpr (FILL)
+  {
+    if ((count & 31) != 0 && lane < (count & 31))
+      cols_out[ob + (count & ~31) + lane] = keep;
+  }
+  else
+  {
+    const bool fast = count <= 32 && n_inc <= 32;
+    const bool any_band = __any_sync(full, band);
+    if (fast)
+    {
+      if (lane < count)
+        tmp[idx * 32 + lane] = keep;
+      gtab[idx * 32 + lane] = make_int2(src, static_cast<int>(M));
+    }
+    if (lane == 0)
+    {
+      row_nnz[r] = count;
+      row_fast[idx] = (fast ? 1 : 0) | (any_band ? 2 : 0);
+      if (!fast)
+        atomicAdd(n_slow, 1ULL);
     }
   }
-  return n;
 }
 
-template <int ND, int CAP>
-__global__ void __launch_bounds__(128)
-    pattern_count_kernel(RowCtx rc, int64_t n_rows, int32_t* __restrict__ row_nnz, int32_t* __restrict__ err)
+// fast rows: columns were staged in tmp during the count pass
+__global__ void __launch_bounds__(256)
+    pattern_copy_kernel(const int32_t* __restrict__ act_rows, int64_t n_act, const uint8_t* __restrict__ row_fast,
+                        const int32_t* __restrict__ tmp, const int64_t* __restrict__ row_ptr,
+                        int32_t* __restrict__ cols)
 {
-  const int64_t r = static_cast<int64_t>(blockIdx.x) * 128 + threadIdx.x;
-  if (r >= n_rows)
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t idx = t >> 5;
+  const int lane = threadIdx.x & 31;
+  if (idx >= n_act || !(row_fast[idx] & 1))
     return;
-  int32_t cols[CAP];
-  bool overflow = false;
-  row_nnz[r] = collect_row<ND, CAP>(rc, r, cols, overflow);
-  if (overflow)
-  {
-    err[0] = 23;
-    err[1] = static_cast<int32_t>(r);
-  }
-}
-
-template <int ND, int CAP>
-__global__ void __launch_bounds__(128)
-    pattern_fill_kernel(RowCtx rc, int64_t n_rows, const int64_t* __restrict__ row_ptr, int32_t* __restrict__ out)
-{
-  const int64_t r = static_cast<int64_t>(blockIdx.x) * 128 + threadIdx.x;
-  if (r >= n_rows)
-    return;
-  int32_t cols[CAP];
-  bool overflow = false;
-  const int n = collect_row<ND, CAP>(rc, r, cols, overflow);
+  const int64_t r = act_rows[idx];
   const int64_t b = row_ptr[r];
-  for (int i = 0; i < n; ++i)
-    out[b + i] = cols[i];
+  if (lane < static_cast<int>(row_ptr[r + 1] - b))
+    cols[b + lane] = tmp[idx * 32 + lane];
 }
 
 __global__ void check_sorted_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ cols,
@@ -294,10 +427,25 @@ void prepare_form(cfx_ctx* c, cfx_form* f)
                f->cell_flags.p, c->err_flag.p);
   }
   f->row_flag.reserve(c->pool, static_cast<size_t>(S.n_total) + 16);
-  CFX_CUDA(cudaMemsetAsync(f->row_flag.p, 0, static_cast<size_t>(S.n_total), c->stream));
-  CFX_LAUNCH(c, row_flag_kernel, grid_for(c->nc_total * S.nd, SBK), SBK, 0, f->cell_flags.p, c->nc_total, S.dofmap,
-             S.nd, f->row_flag.p);
+  CFX_CUDA(cudaMemsetAsync(f->row_flag.p, 0, static_cast<size_t>(S.n_total) + 16, c->stream));
+  if (f->n_active > 0)
+    CFX_LAUNCH(c, row_flag_kernel, grid_for(f->n_active * S.nd, SBK), SBK, 0, f->active.p, f->n_active, 1, S.dofmap,
+               S.nd, f->row_flag.p);
+  for (auto& I : f->integrals)
+  {
+    if (!I.facet || I.n == 0)
+      continue;
+    CFX_LAUNCH(c, row_flag_kernel, grid_for(I.n * S.nd, SBK), SBK, 0, I.entities, I.n, 4, S.dofmap, S.nd,
+               f->row_flag.p);
+    CFX_LAUNCH(c, row_flag_kernel, grid_for(I.n * S.nd, SBK), SBK, 0, I.entities + 2, I.n, 4, S.dofmap, S.nd,
+               f->row_flag.p);
+  }
+  {
+    FlagPred p{f->row_flag.p};
+    f->n_act_rows = compact_indices(c, S.n_total, p, f->act_rows);
+  }
   check_device_error(c, "form domains (entity index out of range)");
+  f->gtab_serial = -1;
   f->dirty = false;
 }
 
@@ -425,6 +573,9 @@ void cfx_form_free(cfx_ctx* ctx, cfx_form* f)
   f->cell_slot.release();
   f->active.release();
   f->row_flag.release();
+  f->act_rows.release();
+  f->gtab.release();
+  f->row_fast.release();
   f->Ae.release();
   f->written.release();
   f->Fe.release();
@@ -452,22 +603,50 @@ cfx_status cfx_create_sparsity(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
             ctx->f2c2.p, ctx->facet_slot.p, ctx->tdim + 1, 1};
   DevBuf<int32_t> row_nnz;
   row_nnz.reserve(ctx->pool, static_cast<size_t>(S.n_total) + 1);
-  const unsigned g = grid_for(S.n_total, 128);
-  auto kcount = S.nd == 3 ? pattern_count_kernel<3, 48>
-                : S.nd == 4 ? pattern_count_kernel<4, 96>
-                : S.nd == 6 ? pattern_count_kernel<6, 96>
-                            : pattern_count_kernel<10, 320>;
-  auto kfill = S.nd == 3 ? pattern_fill_kernel<3, 48>
-               : S.nd == 4 ? pattern_fill_kernel<4, 96>
-               : S.nd == 6 ? pattern_fill_kernel<6, 96>
-                           : pattern_fill_kernel<10, 320>;
-  CFX_LAUNCH(ctx, kcount, g, 128, 0, rc, S.n_total, row_nnz.p, ctx->err_flag.p);
+  auto kcount = S.nd == 3 ? pattern_rows_kernel<3, false>
+                : S.nd == 4 ? pattern_rows_kernel<4, false>
+                : S.nd == 6 ? pattern_rows_kernel<6, false>
+                            : pattern_rows_kernel<10, false>;
+  auto kfill = S.nd == 3 ? pattern_rows_kernel<3, true>
+               : S.nd == 4 ? pattern_rows_kernel<4, true>
+               : S.nd == 6 ? pattern_rows_kernel<6, true>
+                           : pattern_rows_kernel<10, true>;
+  CFX_LAUNCH(ctx, pattern_inactive_count_kernel, grid_for(S.n_total, SBK), SBK, 0, a->row_flag.p, S.n_total, 1,
+             row_nnz.p);
+  const unsigned ga = grid_for(a->n_act_rows, RW);
+  DevBuf<int32_t> tmp;
+  unsigned long long* n_slow = reinterpret_cast<unsigned long long*>(ctx->scratch64.p) + 1;
+  CFX_CUDA(cudaMemsetAsync(n_slow, 0, sizeof(unsigned long long), ctx->stream));
+  if (a->n_act_rows > 0)
+  {
+    tmp.reserve(ctx->pool, static_cast<size_t>(a->n_act_rows) * 32);
+    a->gtab.reserve(ctx->pool, static_cast<size_t>(a->n_act_rows) * 32);
+    a->row_fast.reserve(ctx->pool, static_cast<size_t>(a->n_act_rows) + 16);
+    CFX_LAUNCH(ctx, kcount, ga, RW * 32, 0, rc, a->act_rows.p, a->n_act_rows, row_nnz.p, nullptr, nullptr,
+               a->cell_slot.p, tmp.p, a->gtab.p, a->row_fast.p, n_slow, ctx->err_flag.p);
+  }
   P->row_ptr.reserve(ctx->pool, static_cast<size_t>(S.n_total) + 2);
   exclusive_scan_i32_to_i64(ctx, row_nnz.p, S.n_total, P->row_ptr.p);
-  P->nnz = read_back(ctx, ctx->scratch64.p, 1)[0];
+  {
+    const int64_t* h = read_back(ctx, ctx->scratch64.p, 2);
+    P->nnz = h[0];
+    a->n_slow_rows = h[1];
+  }
   P->cols.reserve(ctx->pool, static_cast<size_t>(P->nnz) + 1);
   P->values.reserve(ctx->pool, static_cast<size_t>(P->nnz) + 1);
-  CFX_LAUNCH(ctx, kfill, g, 128, 0, rc, S.n_total, P->row_ptr.p, P->cols.p);
+  CFX_LAUNCH(ctx, pattern_inactive_fill_kernel, grid_for(S.n_total, SBK), SBK, 0, a->row_flag.p, S.n_total, 1,
+             P->row_ptr.p, P->cols.p);
+  if (a->n_act_rows > 0)
+  {
+    CFX_LAUNCH(ctx, pattern_copy_kernel, grid_for(a->n_act_rows * 32, 256), 256, 0, a->act_rows.p, a->n_act_rows,
+               a->row_fast.p, tmp.p, P->row_ptr.p, P->cols.p);
+    if (a->n_slow_rows > 0)
+      CFX_LAUNCH(ctx, kfill, ga, RW * 32, 0, rc, a->act_rows.p, a->n_act_rows, nullptr, P->row_ptr.p, P->cols.p,
+                 a->cell_slot.p, nullptr, nullptr, a->row_fast.p, nullptr, ctx->err_flag.p);
+  }
+  tmp.release();
+  P->serial = ++ctx->pattern_serial;
+  a->gtab_serial = P->serial;
   set_facet_slots(ctx, FI, true);
   CFX_CUDA(cudaMemsetAsync(P->values.p, 0, (static_cast<size_t>(P->nnz) + 1) * sizeof(double), ctx->stream));
   row_nnz.release();
@@ -499,6 +678,7 @@ cfx_status cfx_pattern_import(cfx_ctx* ctx, int space, const int64_t* row_ptr, c
   P->space = space;
   P->n_rows = n_rows;
   P->nnz = nnz;
+  P->serial = ++ctx->pattern_serial;
   P->row_ptr.reserve(ctx->pool, static_cast<size_t>(n_rows) + 1);
   P->cols.reserve(ctx->pool, static_cast<size_t>(nnz) + 1);
   P->values.reserve(ctx->pool, static_cast<size_t>(nnz) + 1);
