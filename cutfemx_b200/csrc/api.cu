@@ -250,6 +250,7 @@ cfx_status cfx_update(cfx_ctx* ctx)
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && ctx->mesh_bound, CFX_ERR_STATE, "cfx_update: bind the mesh first");
   bool any = false;
+  ++ctx->update_serial;
   for (auto& L : ctx->ls)
   {
     if (!L.bound)

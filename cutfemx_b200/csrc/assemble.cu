@@ -187,93 +187,150 @@ __global__ void __launch_bounds__(EB)
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
   constexpr int ES = ESize<ND, KernelTraits<KID>::RANK>::value;
+  // rank-2 tensors of even size up to 64 doubles leave through shared memory (coalesced stores)
+  constexpr bool STAGED = KernelTraits<KID>::RANK == 2 && ES % 2 == 0 && ES <= 64;
+  constexpr int CH = STAGED ? ES / 2 : 1; // 16-byte chunks per tensor
+  __shared__ double2 s_t[STAGED ? EB : 1][CH];
+  __shared__ int64_t s_slot[STAGED ? EB : 1];
+  __shared__ uint8_t s_add[STAGED ? EB : 1];
+
   const int64_t e = static_cast<int64_t>(blockIdx.x) * EB + threadIdx.x;
-  if (e >= n)
+  const bool valid = e < n;
+  if (!STAGED && !valid)
     return;
-  const int64_t cell = RUNTIME ? rv.parent_map[e] : cells[e];
-  double X[TDIM + 1][TDIM];
-  load_cell_coords<TDIM>(x, x_dofmap, cell, X);
-  Geo<TDIM> g;
-  make_geo<TDIM>(X, g);
-  double h = 1.0;
-  if constexpr (KernelTraits<KID>::H)
-    h = cell_diameter<TDIM>(X);
-  double acc[ES];
-#pragma unroll
-  for (int i = 0; i < ES; ++i)
-    acc[i] = 0.0;
-  double nq[TDIM];
-#pragma unroll
-  for (int r = 0; r < TDIM; ++r)
-    nq[r] = 0.0;
-  if constexpr (RUNTIME)
+  if (valid)
   {
-    const int32_t q0 = rv.offsets[e], q1 = rv.offsets[e + 1];
-    for (int32_t q = q0; q < q1; ++q)
-    {
-      double xi[TDIM];
+    const int64_t cell = RUNTIME ? rv.parent_map[e] : cells[e];
+    double X[TDIM + 1][TDIM];
+    load_cell_coords<TDIM>(x, x_dofmap, cell, X);
+    Geo<TDIM> g;
+    make_geo<TDIM>(X, g);
+    double h = 1.0;
+    if constexpr (KernelTraits<KID>::H)
+      h = cell_diameter<TDIM>(X);
+    double acc[ES];
 #pragma unroll
-      for (int t = 0; t < TDIM; ++t)
-        xi[t] = rv.pts[static_cast<int64_t>(t) * rv.npts + q];
-      if constexpr (KernelTraits<KID>::N)
+    for (int i = 0; i < ES; ++i)
+      acc[i] = 0.0;
+    double nq[TDIM];
+#pragma unroll
+    for (int r = 0; r < TDIM; ++r)
+      nq[r] = 0.0;
+    if constexpr (RUNTIME)
+    {
+      const int32_t q0 = rv.offsets[e], q1 = rv.offsets[e + 1];
+      for (int32_t q = q0; q < q1; ++q)
       {
+        double xi[TDIM];
 #pragma unroll
-        for (int r = 0; r < TDIM; ++r)
-          nq[r] = rv.nrm[static_cast<int64_t>(r) * rv.npts + q];
+        for (int t = 0; t < TDIM; ++t)
+          xi[t] = rv.pts[static_cast<int64_t>(t) * rv.npts + q];
+        if constexpr (KernelTraits<KID>::N)
+        {
+#pragma unroll
+          for (int r = 0; r < TDIM; ++r)
+            nq[r] = rv.nrm[static_cast<int64_t>(r) * rv.npts + q];
+        }
+        point_contribution<TDIM, DEG, KID>(g, xi, rv.wts[q], nq, h, cs, acc);
       }
-      point_contribution<TDIM, DEG, KID>(g, xi, rv.wts[q], nq, h, cs, acc);
     }
-  }
-  else
-  {
-    const double s = fabs(g.detJ);
-    for (int q = 0; q < sr.npts; ++q)
+    else
     {
-      double xi[TDIM];
+      const double s = fabs(g.detJ);
+      for (int q = 0; q < sr.npts; ++q)
+      {
+        double xi[TDIM];
 #pragma unroll
-      for (int t = 0; t < TDIM; ++t)
-        xi[t] = __ldg(sr.pts + q * TDIM + t);
-      point_contribution<TDIM, DEG, KID>(g, xi, __ldg(sr.wts + q) * s, nq, h, cs, acc);
+        for (int t = 0; t < TDIM; ++t)
+          xi[t] = __ldg(sr.pts + q * TDIM + t);
+        point_contribution<TDIM, DEG, KID>(g, xi, __ldg(sr.wts + q) * s, nq, h, cs, acc);
+      }
     }
-  }
-  const int64_t slot = cell_slot[cell];
-  double* o = out + slot * ES;
-  const bool add = written[slot] != 0;
-  if constexpr (KernelTraits<KID>::RANK == 2)
-  {
-    // Element-tensor rows are stored with their columns in ascending global-dof order, i.e. in the
-    // order of the CSR row they are gathered into (assemble.cu gather kernels, sparsity.cu gtab).
-    int32_t d[ND];
-    int rank[ND];
-#pragma unroll
-    for (int j = 0; j < ND; ++j)
-      d[j] = __ldg(dofmap + cell * ND + j);
-#pragma unroll
-    for (int j = 0; j < ND; ++j)
+    const int64_t slot = cell_slot[cell];
+    const bool add = written[slot] != 0;
+    if (!add)
+      written[slot] = 1;
+    if constexpr (KernelTraits<KID>::RANK == 2)
     {
-      int rk = 0;
+      // Element-tensor rows are stored with their columns in ascending global-dof order, i.e. in
+      // the order of the CSR row they are gathered into (gather kernels below, sparsity.cu gtab).
+      int32_t d[ND];
+      int rank[ND];
 #pragma unroll
-      for (int jj = 0; jj < ND; ++jj)
-        rk += (d[jj] < d[j]) ? 1 : 0;
-      rank[j] = rk;
-    }
-#pragma unroll
-    for (int i = 0; i < ND; ++i)
+      for (int j = 0; j < ND; ++j)
+        d[j] = __ldg(dofmap + cell * ND + j);
 #pragma unroll
       for (int j = 0; j < ND; ++j)
       {
-        double* p = o + i * ND + rank[j];
-        *p = add ? *p + acc[i * ND + j] : acc[i * ND + j];
-      }
-  }
-  else
-  {
+        int rk = 0;
 #pragma unroll
-    for (int i = 0; i < ES; ++i)
-      o[i] = add ? o[i] + acc[i] : acc[i];
+        for (int jj = 0; jj < ND; ++jj)
+          rk += (d[jj] < d[j]) ? 1 : 0;
+        rank[j] = rk;
+      }
+      if constexpr (STAGED)
+      {
+        // 16-byte chunks rotated by thread so that the 8*ES-byte-strided tensors do not pile onto
+        // the same shared-memory banks
+        double* mine = reinterpret_cast<double*>(&s_t[threadIdx.x][0]);
+        const int sw = threadIdx.x % CH;
+#pragma unroll
+        for (int i = 0; i < ND; ++i)
+#pragma unroll
+          for (int j = 0; j < ND; ++j)
+          {
+            const int pos = i * ND + rank[j];
+            int ch = (pos >> 1) + sw;
+            ch = ch >= CH ? ch - CH : ch;
+            mine[(ch << 1) | (pos & 1)] = acc[i * ND + j];
+          }
+        s_slot[threadIdx.x] = slot;
+        s_add[threadIdx.x] = add ? 1 : 0;
+      }
+      else
+      {
+        double* o = out + slot * ES;
+#pragma unroll
+        for (int i = 0; i < ND; ++i)
+#pragma unroll
+          for (int j = 0; j < ND; ++j)
+          {
+            double* p = o + i * ND + rank[j];
+            *p = add ? *p + acc[i * ND + j] : acc[i * ND + j];
+          }
+      }
+    }
+    else
+    {
+      double* o = out + slot * ES;
+#pragma unroll
+      for (int i = 0; i < ES; ++i)
+        o[i] = add ? o[i] + acc[i] : acc[i];
+    }
   }
-  if (!add)
-    written[slot] = 1;
+  if constexpr (STAGED)
+  {
+    // cooperative store: CH consecutive lanes write one tensor, so every warp store covers whole
+    // 128-byte lines instead of 32 scattered 8-byte pieces (4x fewer L2 write sectors)
+    __syncthreads();
+    const int64_t left = n - static_cast<int64_t>(blockIdx.x) * EB;
+    const int n_here = left < EB ? static_cast<int>(left) : EB;
+    for (int t = threadIdx.x; t < n_here * CH; t += EB)
+    {
+      const int cellq = t / CH, ch = t % CH;
+      int pc = ch + cellq % CH;
+      pc = pc >= CH ? pc - CH : pc;
+      const double2 v = s_t[cellq][pc];
+      double2* dst = reinterpret_cast<double2*>(out + s_slot[cellq] * ES) + ch;
+      if (s_add[cellq])
+      {
+        const double2 old = *dst;
+        *dst = make_double2(old.x + v.x, old.y + v.y);
+      }
+      else
+        *dst = v;
+    }
+  }
 }
 
 // Interior-facet ghost penalty, one thread per (facet, macro row).
@@ -600,10 +657,12 @@ __global__ void __launch_bounds__(GW * 32)
 }
 
 // Fast rows (<= 32 columns, <= 32 incident cells): the pattern pass left, per incident cell l,
-// gtab = (element-tensor row index, bit mask of the CSR positions of the cell's dofs).  Lane l
-// loads its cell's row (already in column order) into shared memory; lane k owns CSR entry k and
-// walks the staged cells in ascending order: cell l contributes iff bit k of its mask is set, and
-// the value is entry popc(mask & lanes_below_k) of its row.  No dofmap read, no column search.
+// gtab = (element-tensor row index, bit mask of the CSR positions of the cell's dofs).  Lane k owns
+// CSR entry k of the row and walks the incident cells in ascending order (gtab entries broadcast by
+// shuffle): cell l contributes iff bit k of its mask is set, and the value is entry
+// popc(mask & lanes_below_k) of its element-tensor row, which cell_kernel stored in column order.
+// The (at most ND) lanes that hit one cell read one 8*ND-byte row -> a single sector request for
+// P1 tets; no shared memory, no dofmap read, no column search, fixed summation order.
 template <int ND>
 __global__ void __launch_bounds__(GW * 32)
     gather_matrix_fast_kernel(GatherCtx gc, const int32_t* __restrict__ act_rows, int64_t n_act,
@@ -611,8 +670,6 @@ __global__ void __launch_bounds__(GW * 32)
                               const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ cols,
                               double* __restrict__ vals, int zero_first)
 {
-  __shared__ double s_a[GW][32][ND];
-  __shared__ uint32_t s_mask[GW][32];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * GW + w;
   if (idx >= n_act)
@@ -627,23 +684,27 @@ __global__ void __launch_bounds__(GW * 32)
   const int rn = static_cast<int>(row_ptr[r + 1] - rb);
   const bool have_col = lane < rn;
   double acc = (have_col && !zero_first) ? vals[rb + lane] : 0.0;
-  if (g.x >= 0)
-  {
-    const double* a = gc.Ae + static_cast<int64_t>(g.x) * ND;
-#pragma unroll
-    for (int j = 0; j < ND; ++j)
-      s_a[w][lane][j] = a[j];
-  }
-  s_mask[w][lane] = g.x >= 0 ? static_cast<uint32_t>(g.y) : 0u;
   const unsigned contrib = __ballot_sync(full, g.x >= 0);
-  __syncwarp();
   const int nl = 32 - __clz(contrib);
   const uint32_t below = (1u << lane) - 1u;
-  for (int l = 0; l < nl; ++l)
+  const uint32_t gm = g.x >= 0 ? static_cast<uint32_t>(g.y) : 0u;
+  const double* __restrict__ Ae = gc.Ae;
+  // batches of 8 cells: all (predicated) loads of a batch are issued before the first add, so up
+  // to 8 gathers are in flight per lane; the adds keep the ascending-cell order (x + 0.0 == x)
+  for (int l0 = 0; l0 < nl; l0 += 8)
   {
-    const uint32_t M = s_mask[w][l];
-    if ((M >> lane) & 1u)
-      acc += s_a[w][l][__popc(M & below)];
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+    {
+      const int l = (l0 + u) & 31;
+      const int src = __shfl_sync(full, g.x, l);
+      const uint32_t M = __shfl_sync(full, gm, l);
+      v[u] = ((M >> lane) & 1u) ? __ldg(Ae + static_cast<int64_t>(src) * ND + __popc(M & below)) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      acc += v[u];
   }
   if (rf & 2)
   { // interior-facet macro rows of the band cells (rare): column matched by value
@@ -695,35 +756,42 @@ __global__ void __launch_bounds__(GW * 32)
     vals[rb + lane] = acc;
 }
 
-// One warp per active row: lanes take incident cells, fixed-order warp tree sum.
+// Four rows per warp (8 lanes each, 3 independent gather chains per lane for a 24-cell row);
+// fixed-order partial sums + fixed shuffle tree -> bit-reproducible.
 template <int ND>
 __global__ void __launch_bounds__(GW * 32)
     gather_vector_kernel(GatherCtx gc, const int32_t* __restrict__ act_rows, int64_t n_act, double* __restrict__ b,
                          int zero_first)
 {
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * GW + w;
-  if (idx >= n_act)
-    return;
-  const int64_t r = act_rows[idx];
-  const int64_t ib = gc.inc_ptr[r];
-  const int n_inc = static_cast<int>(gc.inc_ptr[r + 1] - ib);
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & 7;
+  const int64_t idx = (static_cast<int64_t>(blockIdx.x) * (GW * 32) + threadIdx.x) >> 3;
+  const bool valid = idx < n_act;
   double s = 0.0;
-  for (int k = lane; k < n_inc; k += 32)
+  int64_t r = 0;
+  if (valid)
   {
-    const int64_t c = gc.inc_cell[ib + k];
-    if (!(gc.cell_flags[c] & 1))
-      continue;
-    int li = 0;
+    r = act_rows[idx];
+    const int64_t ib = gc.inc_ptr[r];
+    const int n_inc = static_cast<int>(gc.inc_ptr[r + 1] - ib);
+#pragma unroll 4
+    for (int k = gl; k < n_inc; k += 8)
+    {
+      const int64_t c = gc.inc_cell[ib + k];
+      if (gc.cell_flags[c] & 1)
+      {
+        int li = 0;
 #pragma unroll
-    for (int j = 0; j < ND; ++j)
-      li = (gc.dofmap[c * ND + j] == r) ? j : li;
-    s += gc.Ae[static_cast<int64_t>(gc.cell_slot[c]) * ND + li];
+        for (int j = 0; j < ND; ++j)
+          li = (gc.dofmap[c * ND + j] == r) ? j : li;
+        s += gc.Ae[static_cast<int64_t>(gc.cell_slot[c]) * ND + li];
+      }
+    }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-    s += __shfl_down_sync(0xffffffffu, s, o);
-  if (lane == 0)
+  for (int o = 4; o > 0; o >>= 1)
+    s += __shfl_down_sync(0xffffffffu, s, o, 8);
+  if (valid && gl == 0)
     b[r] = zero_first ? s : b[r] + s;
 }
 
@@ -773,7 +841,7 @@ void launch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f)
     sr = StdRule{rt.d_pts, rt.d_wts, rt.npts};
     auto k = cell_kernel<TDIM, DEG, KID, false>;
     CFX_LAUNCH(c, k, grid_for(I.n, EB), EB, 0, I.entities, I.n, rv, sr, cs, c->x, c->x_dofmap,
-               c->spaces[f->space].dofmap, f->cell_slot.p, f->Ae.p, f->written.p);
+               c->spaces[f->space].dofmap, f->prep->cell_slot.p, f->Ae.p, f->written.p);
   }
   if (I.rules && I.rules->nrules > 0)
   {
@@ -783,7 +851,7 @@ void launch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f)
                   R->npts};
     auto k = cell_kernel<TDIM, DEG, KID, true>;
     CFX_LAUNCH(c, k, grid_for(R->nrules, EB), EB, 0, nullptr, R->nrules, rv, sr, cs, c->x, c->x_dofmap,
-               c->spaces[f->space].dofmap, f->cell_slot.p, f->Ae.p, f->written.p);
+               c->spaces[f->space].dofmap, f->prep->cell_slot.p, f->Ae.p, f->written.p);
   }
 }
 
@@ -805,9 +873,9 @@ void dispatch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f)
 void run_cell_integrals(cfx_ctx* c, cfx_form* f, int esize)
 {
   const Space& S = c->spaces[f->space];
-  f->Ae.reserve(c->pool, static_cast<size_t>(f->n_active) * esize + 1);
-  f->written.reserve(c->pool, static_cast<size_t>(f->n_active) + 1);
-  CFX_CUDA(cudaMemsetAsync(f->written.p, 0, static_cast<size_t>(f->n_active) + 1, c->stream));
+  f->Ae.reserve(c->pool, static_cast<size_t>(f->prep->n_active) * esize + 1);
+  f->written.reserve(c->pool, static_cast<size_t>(f->prep->n_active) + 1);
+  CFX_CUDA(cudaMemsetAsync(f->written.p, 0, static_cast<size_t>(f->prep->n_active) + 1, c->stream));
   for (auto& I : f->integrals)
   {
     if (I.facet)
@@ -839,8 +907,8 @@ void launch_facet(cfx_ctx* c, const cfx_integral& I, cfx_form* f, bool accumulat
 GatherCtx make_gather_ctx(cfx_ctx* c, cfx_form* f, const cfx_integral* FI)
 {
   const Space& S = c->spaces[f->space];
-  return GatherCtx{S.inc_ptr.p, S.inc_cell.p,    S.dofmap,           f->cell_flags.p,        f->row_flag.p,
-                   f->cell_slot.p, f->Ae.p,       c->c2f,             c->facet_slot.p,        FI ? FI->entities : nullptr,
+  return GatherCtx{S.inc_ptr.p, S.inc_cell.p,    S.dofmap,           f->prep->cell_flags.p,        f->prep->row_flag.p,
+                   f->prep->cell_slot.p, f->Ae.p,       c->c2f,             c->facet_slot.p,        FI ? FI->entities : nullptr,
                    f->Fe.p,        c->tdim + 1};
 }
 } // namespace
@@ -865,7 +933,7 @@ cfx_status cfx_assemble_matrix(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
   {
     StageScope st(ctx, "element_cells");
     run_cell_integrals(ctx, a, nd * nd);
-    st.set_bytes(static_cast<double>(a->n_active) * (4.0 * ctx->nv + 8.0 * nd * nd));
+    st.set_bytes(static_cast<double>(a->prep->n_active) * (4.0 * ctx->nv + 8.0 * nd * nd));
   }
   if (FI)
   {
@@ -889,13 +957,13 @@ cfx_status cfx_assemble_matrix(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
   }
   {
     StageScope st(ctx, "gather_matrix",
-                  12.0 * static_cast<double>(A->nnz) + 8.0 * nd * nd * static_cast<double>(a->n_active));
+                  12.0 * static_cast<double>(A->nnz) + 8.0 * nd * nd * static_cast<double>(a->prep->n_active));
     set_facet_slots(ctx, FI, false);
     GatherCtx gc = make_gather_ctx(ctx, a, FI);
     if (zero_first)
       CFX_CUDA(cudaMemsetAsync(A->values.p, 0, static_cast<size_t>(A->nnz) * sizeof(double), ctx->stream));
     if (diag_inactive != 0.0)
-      CFX_LAUNCH(ctx, inactive_diag_kernel, grid_for(A->n_rows, 256), 256, 0, a->row_flag.p, A->n_rows, A->row_ptr.p,
+      CFX_LAUNCH(ctx, inactive_diag_kernel, grid_for(A->n_rows, 256), 256, 0, a->prep->row_flag.p, A->n_rows, A->row_ptr.p,
                  A->cols.p, A->values.p, diag_inactive);
     auto k = nd == 3 ? gather_matrix_kernel<3>
              : nd == 4 ? gather_matrix_kernel<4>
@@ -907,14 +975,14 @@ cfx_status cfx_assemble_matrix(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
                         : gather_matrix_fast_kernel<10>;
     // the gather table is valid only for the pattern that was built from this very form
     const bool fast = a->gtab_serial == A->serial && a->gtab_serial > 0;
-    if (a->n_act_rows > 0)
+    if (a->prep->n_act_rows > 0)
     {
-      const unsigned g = grid_for(a->n_act_rows, GW);
+      const unsigned g = grid_for(a->prep->n_act_rows, GW);
       if (fast)
-        CFX_LAUNCH(ctx, kf, g, GW * 32, 0, gc, a->act_rows.p, a->n_act_rows, a->row_fast.p, a->gtab.p, A->row_ptr.p,
+        CFX_LAUNCH(ctx, kf, g, GW * 32, 0, gc, a->prep->act_rows.p, a->prep->n_act_rows, a->row_fast.p, a->gtab.p, A->row_ptr.p,
                    A->cols.p, A->values.p, zero_first);
       if (!fast || a->n_slow_rows > 0)
-        CFX_LAUNCH(ctx, k, g, GW * 32, 0, gc, a->act_rows.p, a->n_act_rows, fast ? a->row_fast.p : nullptr,
+        CFX_LAUNCH(ctx, k, g, GW * 32, 0, gc, a->prep->act_rows.p, a->prep->n_act_rows, fast ? a->row_fast.p : nullptr,
                    A->row_ptr.p, A->cols.p, A->values.p, zero_first, ctx->err_flag.p);
     }
     set_facet_slots(ctx, FI, true);
@@ -936,7 +1004,7 @@ cfx_status cfx_assemble_vector(cfx_ctx* ctx, const cfx_form* L_const, double* b,
   {
     StageScope st(ctx, "element_cells_vector");
     run_cell_integrals(ctx, L, S.nd);
-    st.set_bytes(static_cast<double>(L->n_active) * (4.0 * ctx->nv + 8.0 * S.nd));
+    st.set_bytes(static_cast<double>(L->prep->n_active) * (4.0 * ctx->nv + 8.0 * S.nd));
   }
   DevBuf<double> tmp;
   double* d_b = b;
@@ -949,7 +1017,7 @@ cfx_status cfx_assemble_vector(cfx_ctx* ctx, const cfx_form* L_const, double* b,
                                ctx->stream));
   }
   {
-    StageScope st(ctx, "gather_vector", 8.0 * static_cast<double>(S.n_total) + 8.0 * S.nd * L->n_active);
+    StageScope st(ctx, "gather_vector", 8.0 * static_cast<double>(S.n_total) + 8.0 * S.nd * L->prep->n_active);
     GatherCtx gc = make_gather_ctx(ctx, L, nullptr);
     auto k = S.nd == 3 ? gather_vector_kernel<3>
              : S.nd == 4 ? gather_vector_kernel<4>
@@ -957,8 +1025,9 @@ cfx_status cfx_assemble_vector(cfx_ctx* ctx, const cfx_form* L_const, double* b,
                          : gather_vector_kernel<10>;
     if (zero_first)
       CFX_CUDA(cudaMemsetAsync(d_b, 0, static_cast<size_t>(S.n_total) * sizeof(double), ctx->stream));
-    if (L->n_act_rows > 0)
-      CFX_LAUNCH(ctx, k, grid_for(L->n_act_rows, GW), GW * 32, 0, gc, L->act_rows.p, L->n_act_rows, d_b, zero_first);
+    if (L->prep->n_act_rows > 0)
+      CFX_LAUNCH(ctx, k, grid_for(L->prep->n_act_rows * 8, GW * 32), GW * 32, 0, gc, L->prep->act_rows.p, L->prep->n_act_rows, d_b,
+                 zero_first);
   }
   if (memspace == CFX_HOST)
   {
@@ -979,7 +1048,7 @@ cfx_status cfx_assemble_scalar(cfx_ctx* ctx, const cfx_form* M_const, double* ou
   constexpr int NB = 256;
   DevBuf<double> partial;
   partial.reserve(ctx->pool, NB + 1);
-  CFX_LAUNCH(ctx, sum_partial_kernel, NB, 256, 0, M->Ae.p, M->n_active, partial.p);
+  CFX_LAUNCH(ctx, sum_partial_kernel, NB, 256, 0, M->Ae.p, M->prep->n_active, partial.p);
   CFX_LAUNCH(ctx, sum_partial_kernel, 1, 256, 0, partial.p, static_cast<int64_t>(NB), partial.p + NB);
   CFX_CUDA(cudaMemcpyAsync(out, partial.p + NB, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CFX_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -215,24 +215,34 @@ struct cfx_integral
   double constants[CFX_MAX_CONSTANTS] = {};
 };
 
-struct cfx_form
+// active cells / rows of a set of integration domains (Form.h:46-89 domains)
+struct cfx_prepared
 {
-  int space = 0, rank = 0;
-  std::vector<cfx_integral> integrals;
-  // prepared state (recomputed when dirty)
-  bool dirty = true;
+  int refs = 0;
+  int space = 0;
+  int64_t update_serial = 0;
+  std::vector<std::pair<const void*, int64_t>> cell_key; // (entity list, n) and (rules parent_map, nrules)
+  std::pair<const void*, int64_t> facet_key{nullptr, 0};
   cfx::DevBuf<uint8_t> cell_flags; // bit0: has a cell tensor, bit1: touches a facet-integral facet
   cfx::DevBuf<int32_t> cell_slot;  // rank among flagged cells (valid where bit0)
   cfx::DevBuf<int32_t> active;     // ascending cell ids with bit0 (slot i <-> cell active[i])
   cfx::DevBuf<uint8_t> row_flag;   // per dof: touched by a flagged cell
   cfx::DevBuf<int32_t> act_rows;   // ascending dofs with row_flag set
-  int64_t n_act_rows = 0;
+  int64_t n_active = 0, n_act_rows = 0;
+};
+
+struct cfx_form
+{
+  int space = 0, rank = 0;
+  std::vector<cfx_integral> integrals;
+  // prepared state (recomputed when dirty); shared between forms with the same cell domains
+  bool dirty = true;
+  cfx_prepared* prep = nullptr;
   // gather table of the pattern built from this form (sparsity.cu pattern_rows_kernel)
   cfx::DevBuf<int2> gtab;
   cfx::DevBuf<uint8_t> row_fast;
   int64_t n_slow_rows = 0;
   int64_t gtab_serial = -1;
-  int64_t n_active = 0;
   cfx::DevBuf<double> Ae;      // (n_active, nd^rank)
   cfx::DevBuf<uint8_t> written; // per slot
   cfx::DevBuf<double> Fe;      // facet macro tensors
@@ -246,6 +256,8 @@ struct cfx_ctx
   cfx::DevPool pool;
   int64_t launches = 0;
   int64_t pattern_serial = 0;
+  int64_t update_serial = 0;
+  std::vector<cfx_prepared*> preps; // live prepared domains (owned by the forms that reference them)
 
   // mesh views
   bool mesh_bound = false;
@@ -443,6 +455,7 @@ void build_incidence(cfx_ctx* c, Space& s);             // sparsity.cu
 void derive_f2c(cfx_ctx* c);                            // facets.cu
 void dense_f2c_from_adjacency(cfx_ctx* c, const int32_t* off_dev, const int32_t* data_dev); // facets.cu
 void prepare_form(cfx_ctx* c, cfx_form* f);             // sparsity.cu
+void release_prepared(cfx_ctx* c, cfx_form* f);         // sparsity.cu
 const cfx_integral* facet_integral_domain(const cfx_form* f);          // sparsity.cu
 void set_facet_slots(cfx_ctx* c, const cfx_integral* I, bool clear);   // sparsity.cu
 } // namespace cfx

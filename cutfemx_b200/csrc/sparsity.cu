@@ -11,6 +11,8 @@
 // cfx_space_bind, lets one thread own one matrix row: it walks the row's cells, unions their
 // dofs into a sorted unique list (pattern) or accumulates their element-tensor rows
 // (assemble.cu) in a fixed order.  No sort of (row, col) pairs, no atomics, bit-reproducible.
+#include <algorithm>
+
 #include "compact.cuh"
 
 namespace cfx
@@ -272,45 +274,68 @@ __global__ void __launch_bounds__(RW * 32)
     return;
   }
   sort_small<ND>(h);
-  int32_t dg = (rc.insert_diagonal && lane == 0) ? static_cast<int32_t>(r) : IMAX;
+  // An active row always finds its own dof among its cells' dofs, so the diagonal needs no extra
+  // candidate here (inactive rows get theirs from pattern_inactive_*_kernel).
   const int64_t ob = FILL ? row_ptr[r] : 0;
-  int32_t last = -1, keep = 0;
+  int32_t keep = 0;
   uint32_t M = 0;
   int count = 0;
-  while (true)
-  {
-    int32_t m = min(h[0], dg);
-    for (int e = lane; e < n_extra; e += 32)
+  if (!FILL && n_extra == 0)
+  { // common case: no facet partners, columns kept in lane registers (first 32)
+    uint32_t bit = 1u;
+    while (true)
     {
-      const int32_t v = s_extra[w][e];
-      m = (v > last && v < m) ? v : m;
-    }
-    m = __reduce_min_sync(full, m);
-    if (m == IMAX)
-      break;
-    if (h[0] == m)
-    { // pop: this cell's dof sits at CSR position `count` of the row
-      M |= (count < 32) ? (1u << count) : 0u;
+      const int32_t m = __reduce_min_sync(full, h[0]);
+      if (m == IMAX)
+        break;
+      const bool p = h[0] == m;
+      M |= p ? bit : 0u;
 #pragma unroll
       for (int j = 0; j + 1 < ND; ++j)
-        h[j] = h[j + 1];
-      h[ND - 1] = IMAX;
+        h[j] = p ? h[j + 1] : h[j];
+      h[ND - 1] = p ? IMAX : h[ND - 1];
+      keep = (lane == count) ? m : keep;
+      bit <<= 1;
+      ++count;
     }
-    dg = (dg == m) ? IMAX : dg;
-    if constexpr (FILL)
+  }
+  else
+  {
+    int32_t last = -1;
+    while (true)
     {
-      if (lane == (count & 31))
-        keep = m;
-      if ((count & 31) == 31)
-        cols_out[ob + (count & ~31) + lane] = keep; // coalesced flush of 32 columns
+      int32_t m = h[0];
+      for (int e = lane; e < n_extra; e += 32)
+      {
+        const int32_t v = s_extra[w][e];
+        m = (v > last && v < m) ? v : m;
+      }
+      m = __reduce_min_sync(full, m);
+      if (m == IMAX)
+        break;
+      if (h[0] == m)
+      { // pop: this cell's dof sits at CSR position `count` of the row
+        M |= (count < 32) ? (1u << count) : 0u;
+#pragma unroll
+        for (int j = 0; j + 1 < ND; ++j)
+          h[j] = h[j + 1];
+        h[ND - 1] = IMAX;
+      }
+      if constexpr (FILL)
+      {
+        if (lane == (count & 31))
+          keep = m;
+        if ((count & 31) == 31)
+          cols_out[ob + (count & ~31) + lane] = keep; // coalesced flush of 32 columns
+      }
+      else
+      {
+        if (lane == count)
+          keep = m;
+      }
+      last = m;
+      ++count;
     }
-    else
-    {
-      if (lane == count)
-        keep = m;
-    }
-    last = m;
-    ++count;
   }
   if constexpr (FILL)
   {
@@ -337,21 +362,34 @@ __global__ void __launch_bounds__(RW * 32)
   }
 }
 
-// fast rows: columns were staged in tmp during the count pass
+// fast rows: columns were staged in tmp during the count pass.  One warp moves 32 rows: the
+// per-row scalars are loaded once, lane-parallel, then every row is one coalesced copy.
 __global__ void __launch_bounds__(256)
     pattern_copy_kernel(const int32_t* __restrict__ act_rows, int64_t n_act, const uint8_t* __restrict__ row_fast,
                         const int32_t* __restrict__ tmp, const int64_t* __restrict__ row_ptr,
                         int32_t* __restrict__ cols)
 {
-  const int64_t t = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-  const int64_t idx = t >> 5;
   const int lane = threadIdx.x & 31;
-  if (idx >= n_act || !(row_fast[idx] & 1))
+  const int64_t idx0 = ((static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x) >> 5) * 32;
+  if (idx0 >= n_act)
     return;
-  const int64_t r = act_rows[idx];
-  const int64_t b = row_ptr[r];
-  if (lane < static_cast<int>(row_ptr[r + 1] - b))
-    cols[b + lane] = tmp[idx * 32 + lane];
+  const int64_t idx = idx0 + lane;
+  int64_t b = 0;
+  int n = 0;
+  if (idx < n_act && (row_fast[idx] & 1))
+  {
+    const int64_t r = act_rows[idx];
+    b = row_ptr[r];
+    n = static_cast<int>(row_ptr[r + 1] - b);
+  }
+#pragma unroll 4
+  for (int i = 0; i < 32; ++i)
+  {
+    const int64_t bi = __shfl_sync(0xffffffffu, b, i);
+    const int ni = __shfl_sync(0xffffffffu, n, i);
+    if (lane < ni)
+      cols[bi + lane] = tmp[(idx0 + i) * 32 + lane];
+  }
 }
 
 __global__ void check_sorted_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ cols,
@@ -389,60 +427,118 @@ void build_incidence(cfx_ctx* c, Space& S)
   deg.release();
 }
 
-// cell_flags / cell_slot / active list / row flags of a form (Form.h:46-89 domains)
+void release_prepared(cfx_ctx* c, cfx_form* f)
+{
+  cfx_prepared* p = f->prep;
+  f->prep = nullptr;
+  if (!p || --p->refs > 0)
+    return;
+  for (auto it = c->preps.begin(); it != c->preps.end(); ++it)
+    if (*it == p)
+    {
+      c->preps.erase(it);
+      break;
+    }
+  p->cell_flags.release();
+  p->cell_slot.release();
+  p->active.release();
+  p->row_flag.release();
+  p->act_rows.release();
+  delete p;
+}
+
+// cell_flags / cell_slot / active list / row flags of a form (Form.h:46-89 domains).  Forms over
+// the same cell domains (the bilinear and the linear form of one problem) share the result; a form
+// without facet integrals may also reuse the prepared domain of one with them (a superset of rows).
 void prepare_form(cfx_ctx* c, cfx_form* f)
 {
-  if (!f->dirty)
+  if (!f->dirty && f->prep)
     return;
+  release_prepared(c, f);
   Space& S = c->spaces[f->space];
+  std::vector<std::pair<const void*, int64_t>> key;
+  std::pair<const void*, int64_t> fkey{nullptr, 0};
+  for (auto& I : f->integrals)
+  {
+    if (I.facet)
+    {
+      if (I.n > 0)
+        fkey = {I.entities, I.n};
+      continue;
+    }
+    if (I.n > 0)
+      key.emplace_back(I.entities, I.n);
+    if (I.rules && I.rules->nrules > 0)
+      key.emplace_back(I.rules->parent_map.p, I.rules->nrules);
+  }
+  std::sort(key.begin(), key.end());
+  key.erase(std::unique(key.begin(), key.end()), key.end());
+  for (cfx_prepared* p : c->preps)
+    if (p->space == f->space && p->update_serial == c->update_serial && p->cell_key == key
+        && (p->facet_key == fkey || fkey.first == nullptr))
+    {
+      f->prep = p;
+      ++p->refs;
+      f->gtab_serial = -1;
+      f->dirty = false;
+      return;
+    }
+  cfx_prepared* P = new cfx_prepared();
+  P->refs = 1;
+  P->space = f->space;
+  P->update_serial = c->update_serial;
+  P->cell_key = key;
+  P->facet_key = fkey;
+  c->preps.push_back(P);
+  f->prep = P;
   StageScope st(c, "prepare_form", 6.0 * static_cast<double>(c->nc_total));
-  f->cell_flags.reserve(c->pool, static_cast<size_t>(c->nc_total) + 16);
-  CFX_CUDA(cudaMemsetAsync(f->cell_flags.p, 0, static_cast<size_t>(c->nc_total), c->stream));
+  P->cell_flags.reserve(c->pool, static_cast<size_t>(c->nc_total) + 16);
+  CFX_CUDA(cudaMemsetAsync(P->cell_flags.p, 0, static_cast<size_t>(c->nc_total) + 16, c->stream));
   for (auto& I : f->integrals)
   {
     if (I.facet)
       continue;
     if (I.n > 0)
       CFX_LAUNCH(c, or_flag_kernel, grid_for(I.n, SBK), SBK, 0, I.entities, I.n, 1, c->nc_total, uint8_t(1),
-                 f->cell_flags.p, c->err_flag.p);
+                 P->cell_flags.p, c->err_flag.p);
     if (I.rules && I.rules->nrules > 0)
       CFX_LAUNCH(c, or_flag_kernel, grid_for(I.rules->nrules, SBK), SBK, 0, I.rules->parent_map.p, I.rules->nrules, 1,
-                 c->nc_total, uint8_t(1), f->cell_flags.p, c->err_flag.p);
+                 c->nc_total, uint8_t(1), P->cell_flags.p, c->err_flag.p);
   }
   // active list + slots (before the facet bit is added, so the predicate is just "byte != 0")
   {
-    FlagPred p{f->cell_flags.p};
-    f->n_active = compact_indices(c, c->nc_total, p, f->active);
+    FlagPred p{P->cell_flags.p};
+    P->n_active = compact_indices(c, c->nc_total, p, P->active);
   }
-  f->cell_slot.reserve(c->pool, static_cast<size_t>(c->nc_total) + 1);
-  if (f->n_active > 0)
-    CFX_LAUNCH(c, scatter_slot_kernel, grid_for(f->n_active, SBK), SBK, 0, f->active.p, f->n_active, f->cell_slot.p);
+  P->cell_slot.reserve(c->pool, static_cast<size_t>(c->nc_total) + 1);
+  if (P->n_active > 0)
+    CFX_LAUNCH(c, scatter_slot_kernel, grid_for(P->n_active, SBK), SBK, 0, P->active.p, P->n_active, P->cell_slot.p);
   for (auto& I : f->integrals)
   {
     if (!I.facet || I.n == 0)
       continue;
     CFX_LAUNCH(c, or_flag_kernel, grid_for(I.n, SBK), SBK, 0, I.entities, I.n, 4, c->nc_total, uint8_t(2),
-               f->cell_flags.p, c->err_flag.p);
+               P->cell_flags.p, c->err_flag.p);
     CFX_LAUNCH(c, or_flag_kernel, grid_for(I.n, SBK), SBK, 0, I.entities + 2, I.n, 4, c->nc_total, uint8_t(2),
-               f->cell_flags.p, c->err_flag.p);
+               P->cell_flags.p, c->err_flag.p);
   }
-  f->row_flag.reserve(c->pool, static_cast<size_t>(S.n_total) + 16);
-  CFX_CUDA(cudaMemsetAsync(f->row_flag.p, 0, static_cast<size_t>(S.n_total) + 16, c->stream));
-  if (f->n_active > 0)
-    CFX_LAUNCH(c, row_flag_kernel, grid_for(f->n_active * S.nd, SBK), SBK, 0, f->active.p, f->n_active, 1, S.dofmap,
-               S.nd, f->row_flag.p);
+  P->row_flag.reserve(c->pool, static_cast<size_t>(S.n_total) + 16);
+  CFX_CUDA(cudaMemsetAsync(P->row_flag.p, 0, static_cast<size_t>(S.n_total) + 16, c->stream));
+  if (P->n_active > 0)
+    CFX_LAUNCH(c, row_flag_kernel, grid_for(P->n_active * S.nd, SBK), SBK, 0, P->active.p, P->n_active, 1, S.dofmap,
+               S.nd, P->row_flag.p);
   for (auto& I : f->integrals)
   {
     if (!I.facet || I.n == 0)
       continue;
     CFX_LAUNCH(c, row_flag_kernel, grid_for(I.n * S.nd, SBK), SBK, 0, I.entities, I.n, 4, S.dofmap, S.nd,
-               f->row_flag.p);
+               P->row_flag.p);
     CFX_LAUNCH(c, row_flag_kernel, grid_for(I.n * S.nd, SBK), SBK, 0, I.entities + 2, I.n, 4, S.dofmap, S.nd,
-               f->row_flag.p);
+               P->row_flag.p);
   }
   {
-    FlagPred p{f->row_flag.p};
-    f->n_act_rows = compact_indices(c, S.n_total, p, f->act_rows);
+    FlagPred p{P->row_flag.p};
+    P->n_act_rows = compact_indices(c, S.n_total, p, P->act_rows);
   }
   check_device_error(c, "form domains (entity index out of range)");
   f->gtab_serial = -1;
@@ -569,11 +665,8 @@ void cfx_form_free(cfx_ctx* ctx, cfx_form* f)
     return;
   for (auto& I : f->integrals)
     I.own.release();
-  f->cell_flags.release();
-  f->cell_slot.release();
-  f->active.release();
-  f->row_flag.release();
-  f->act_rows.release();
+  if (ctx)
+    release_prepared(ctx, f);
   f->gtab.release();
   f->row_fast.release();
   f->Ae.release();
@@ -599,7 +692,7 @@ cfx_status cfx_create_sparsity(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
   P->n_rows = S.n_total;
   StageScope st(ctx, "create_sparsity");
   set_facet_slots(ctx, FI, false);
-  RowCtx rc{S.inc_ptr.p, S.inc_cell.p, S.dofmap, a->cell_flags.p, a->row_flag.p, ctx->c2f,
+  RowCtx rc{S.inc_ptr.p, S.inc_cell.p, S.dofmap, a->prep->cell_flags.p, a->prep->row_flag.p, ctx->c2f,
             ctx->f2c2.p, ctx->facet_slot.p, ctx->tdim + 1, 1};
   DevBuf<int32_t> row_nnz;
   row_nnz.reserve(ctx->pool, static_cast<size_t>(S.n_total) + 1);
@@ -611,19 +704,19 @@ cfx_status cfx_create_sparsity(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
                : S.nd == 4 ? pattern_rows_kernel<4, true>
                : S.nd == 6 ? pattern_rows_kernel<6, true>
                            : pattern_rows_kernel<10, true>;
-  CFX_LAUNCH(ctx, pattern_inactive_count_kernel, grid_for(S.n_total, SBK), SBK, 0, a->row_flag.p, S.n_total, 1,
+  CFX_LAUNCH(ctx, pattern_inactive_count_kernel, grid_for(S.n_total, SBK), SBK, 0, a->prep->row_flag.p, S.n_total, 1,
              row_nnz.p);
-  const unsigned ga = grid_for(a->n_act_rows, RW);
+  const unsigned ga = grid_for(a->prep->n_act_rows, RW);
   DevBuf<int32_t> tmp;
   unsigned long long* n_slow = reinterpret_cast<unsigned long long*>(ctx->scratch64.p) + 1;
   CFX_CUDA(cudaMemsetAsync(n_slow, 0, sizeof(unsigned long long), ctx->stream));
-  if (a->n_act_rows > 0)
+  if (a->prep->n_act_rows > 0)
   {
-    tmp.reserve(ctx->pool, static_cast<size_t>(a->n_act_rows) * 32);
-    a->gtab.reserve(ctx->pool, static_cast<size_t>(a->n_act_rows) * 32);
-    a->row_fast.reserve(ctx->pool, static_cast<size_t>(a->n_act_rows) + 16);
-    CFX_LAUNCH(ctx, kcount, ga, RW * 32, 0, rc, a->act_rows.p, a->n_act_rows, row_nnz.p, nullptr, nullptr,
-               a->cell_slot.p, tmp.p, a->gtab.p, a->row_fast.p, n_slow, ctx->err_flag.p);
+    tmp.reserve(ctx->pool, static_cast<size_t>(a->prep->n_act_rows) * 32);
+    a->gtab.reserve(ctx->pool, static_cast<size_t>(a->prep->n_act_rows) * 32);
+    a->row_fast.reserve(ctx->pool, static_cast<size_t>(a->prep->n_act_rows) + 16);
+    CFX_LAUNCH(ctx, kcount, ga, RW * 32, 0, rc, a->prep->act_rows.p, a->prep->n_act_rows, row_nnz.p, nullptr, nullptr,
+               a->prep->cell_slot.p, tmp.p, a->gtab.p, a->row_fast.p, n_slow, ctx->err_flag.p);
   }
   P->row_ptr.reserve(ctx->pool, static_cast<size_t>(S.n_total) + 2);
   exclusive_scan_i32_to_i64(ctx, row_nnz.p, S.n_total, P->row_ptr.p);
@@ -634,15 +727,15 @@ cfx_status cfx_create_sparsity(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
   }
   P->cols.reserve(ctx->pool, static_cast<size_t>(P->nnz) + 1);
   P->values.reserve(ctx->pool, static_cast<size_t>(P->nnz) + 1);
-  CFX_LAUNCH(ctx, pattern_inactive_fill_kernel, grid_for(S.n_total, SBK), SBK, 0, a->row_flag.p, S.n_total, 1,
+  CFX_LAUNCH(ctx, pattern_inactive_fill_kernel, grid_for(S.n_total, SBK), SBK, 0, a->prep->row_flag.p, S.n_total, 1,
              P->row_ptr.p, P->cols.p);
-  if (a->n_act_rows > 0)
+  if (a->prep->n_act_rows > 0)
   {
-    CFX_LAUNCH(ctx, pattern_copy_kernel, grid_for(a->n_act_rows * 32, 256), 256, 0, a->act_rows.p, a->n_act_rows,
+    CFX_LAUNCH(ctx, pattern_copy_kernel, grid_for(a->prep->n_act_rows, 256), 256, 0, a->prep->act_rows.p, a->prep->n_act_rows,
                a->row_fast.p, tmp.p, P->row_ptr.p, P->cols.p);
     if (a->n_slow_rows > 0)
-      CFX_LAUNCH(ctx, kfill, ga, RW * 32, 0, rc, a->act_rows.p, a->n_act_rows, nullptr, P->row_ptr.p, P->cols.p,
-                 a->cell_slot.p, nullptr, nullptr, a->row_fast.p, nullptr, ctx->err_flag.p);
+      CFX_LAUNCH(ctx, kfill, ga, RW * 32, 0, rc, a->prep->act_rows.p, a->prep->n_act_rows, nullptr, P->row_ptr.p, P->cols.p,
+                 a->prep->cell_slot.p, nullptr, nullptr, a->row_fast.p, nullptr, ctx->err_flag.p);
   }
   tmp.release();
   P->serial = ++ctx->pattern_serial;
