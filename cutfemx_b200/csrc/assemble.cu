@@ -176,161 +176,170 @@ __device__ __forceinline__ void point_contribution(const Geo<TDIM>& g, const dou
   }
 }
 
+// where a cell kernel puts its element tensor
+struct OutCtx
+{
+  const int32_t* dofmap;     // argument-space dofmap (n_cells, ND)
+  const int32_t* row_slot;   // dof -> index of its matrix row among the active rows
+  const uint8_t* cell_inc_l; // (n_cells, ND): position of the cell in the incidence list of its i-th dof
+  const int32_t* cell_slot;  // cell -> index among the active cells
+  double* out;
+  uint8_t* written;          // per active cell: an earlier integral already stored this cell's tensor
+  int stride;                // incidence slots per matrix row
+};
+
+__device__ __forceinline__ void st256(double* p, double a, double b, double c, double d)
+{
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void ld256(const double* p, double& a, double& b, double& c, double& d)
+{
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
 // One thread per entity of a cell integral.  RUNTIME = false: entity e is standard cell
 // cells[e] with the compile-time rule; true: entity e is rule e (parent cell parent_map[e]).
+//
+// Output layout ("owner-major"): row i of the element tensor goes straight to the storage of the
+// matrix row it will be gathered into: slot (row_slot[dof_i] * stride + l) * ND, l = position of
+// this cell among the cells around dof_i, columns in ascending global-dof order.  The gather then
+// streams contiguous memory (the scattered 32-byte accesses happen here, as stores that the L2
+// merges, instead of as dependent random loads in the gather).  For P1 tetrahedra one row is one
+// 32-byte sector, written with a single 256-bit store.
 template <int TDIM, int DEG, int KID, bool RUNTIME>
 __global__ void __launch_bounds__(EB)
     cell_kernel(const int32_t* __restrict__ cells, int64_t n, RuleView rv, StdRule sr, Consts cs,
-                const double* __restrict__ x, const int32_t* __restrict__ x_dofmap,
-                const int32_t* __restrict__ dofmap, const int32_t* __restrict__ cell_slot, double* __restrict__ out,
-                uint8_t* __restrict__ written)
+                const double* __restrict__ x, const int32_t* __restrict__ x_dofmap, OutCtx oc)
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
-  constexpr int ES = ESize<ND, KernelTraits<KID>::RANK>::value;
-  // rank-2 tensors of even size up to 64 doubles leave through shared memory (coalesced stores)
-  constexpr bool STAGED = KernelTraits<KID>::RANK == 2 && ES % 2 == 0 && ES <= 64;
-  constexpr int CH = STAGED ? ES / 2 : 1; // 16-byte chunks per tensor
-  __shared__ double2 s_t[STAGED ? EB : 1][CH];
-  __shared__ int64_t s_slot[STAGED ? EB : 1];
-  __shared__ uint8_t s_add[STAGED ? EB : 1];
-
+  constexpr int RANK = KernelTraits<KID>::RANK;
+  constexpr int ES = ESize<ND, RANK>::value;
   const int64_t e = static_cast<int64_t>(blockIdx.x) * EB + threadIdx.x;
-  const bool valid = e < n;
-  if (!STAGED && !valid)
+  if (e >= n)
     return;
-  if (valid)
+  const int64_t cell = RUNTIME ? rv.parent_map[e] : cells[e];
+  // issue the output-side gathers early: they are independent of the arithmetic
+  const int64_t slot = oc.cell_slot[cell];
+  int32_t d[ND];
+  int64_t dest[ND];
+  if constexpr (RANK >= 1)
   {
-    const int64_t cell = RUNTIME ? rv.parent_map[e] : cells[e];
-    double X[TDIM + 1][TDIM];
-    load_cell_coords<TDIM>(x, x_dofmap, cell, X);
-    Geo<TDIM> g;
-    make_geo<TDIM>(X, g);
-    double h = 1.0;
-    if constexpr (KernelTraits<KID>::H)
-      h = cell_diameter<TDIM>(X);
-    double acc[ES];
 #pragma unroll
-    for (int i = 0; i < ES; ++i)
-      acc[i] = 0.0;
-    double nq[TDIM];
+    for (int j = 0; j < ND; ++j)
+      d[j] = __ldg(oc.dofmap + cell * ND + j);
 #pragma unroll
-    for (int r = 0; r < TDIM; ++r)
-      nq[r] = 0.0;
-    if constexpr (RUNTIME)
+    for (int j = 0; j < ND; ++j)
+      dest[j] = static_cast<int64_t>(__ldg(oc.row_slot + d[j])) * oc.stride + __ldg(oc.cell_inc_l + cell * ND + j);
+  }
+  const bool add = oc.written[slot] != 0;
+  double X[TDIM + 1][TDIM];
+  load_cell_coords<TDIM>(x, x_dofmap, cell, X);
+  Geo<TDIM> g;
+  make_geo<TDIM>(X, g);
+  double h = 1.0;
+  if constexpr (KernelTraits<KID>::H)
+    h = cell_diameter<TDIM>(X);
+  double acc[ES];
+#pragma unroll
+  for (int i = 0; i < ES; ++i)
+    acc[i] = 0.0;
+  double nq[TDIM];
+#pragma unroll
+  for (int r = 0; r < TDIM; ++r)
+    nq[r] = 0.0;
+  if constexpr (RUNTIME)
+  {
+    const int32_t q0 = rv.offsets[e], q1 = rv.offsets[e + 1];
+    for (int32_t q = q0; q < q1; ++q)
     {
-      const int32_t q0 = rv.offsets[e], q1 = rv.offsets[e + 1];
-      for (int32_t q = q0; q < q1; ++q)
-      {
-        double xi[TDIM];
+      double xi[TDIM];
 #pragma unroll
-        for (int t = 0; t < TDIM; ++t)
-          xi[t] = rv.pts[static_cast<int64_t>(t) * rv.npts + q];
-        if constexpr (KernelTraits<KID>::N)
+      for (int t = 0; t < TDIM; ++t)
+        xi[t] = rv.pts[static_cast<int64_t>(t) * rv.npts + q];
+      if constexpr (KernelTraits<KID>::N)
+      {
+#pragma unroll
+        for (int r = 0; r < TDIM; ++r)
+          nq[r] = rv.nrm[static_cast<int64_t>(r) * rv.npts + q];
+      }
+      point_contribution<TDIM, DEG, KID>(g, xi, rv.wts[q], nq, h, cs, acc);
+    }
+  }
+  else
+  {
+    const double s = fabs(g.detJ);
+    for (int q = 0; q < sr.npts; ++q)
+    {
+      double xi[TDIM];
+#pragma unroll
+      for (int t = 0; t < TDIM; ++t)
+        xi[t] = __ldg(sr.pts + q * TDIM + t);
+      point_contribution<TDIM, DEG, KID>(g, xi, __ldg(sr.wts + q) * s, nq, h, cs, acc);
+    }
+  }
+  if (!add)
+    oc.written[slot] = 1;
+  if constexpr (RANK == 2)
+  {
+    int rank[ND];
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+    {
+      int rk = 0;
+#pragma unroll
+      for (int jj = 0; jj < ND; ++jj)
+        rk += (d[jj] < d[j]) ? 1 : 0;
+      rank[j] = rk;
+    }
+    if constexpr (ND == 4)
+    {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+      {
+        double rowv[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
         {
+          double v = acc[i * 4 + 0];
 #pragma unroll
-          for (int r = 0; r < TDIM; ++r)
-            nq[r] = rv.nrm[static_cast<int64_t>(r) * rv.npts + q];
+          for (int j = 1; j < 4; ++j)
+            v = (rank[j] == r) ? acc[i * 4 + j] : v;
+          rowv[r] = v;
         }
-        point_contribution<TDIM, DEG, KID>(g, xi, rv.wts[q], nq, h, cs, acc);
+        double* p = oc.out + dest[i] * 4;
+        if (add)
+        {
+          double o0, o1, o2, o3;
+          ld256(p, o0, o1, o2, o3);
+          st256(p, o0 + rowv[0], o1 + rowv[1], o2 + rowv[2], o3 + rowv[3]);
+        }
+        else
+          st256(p, rowv[0], rowv[1], rowv[2], rowv[3]);
       }
     }
     else
     {
-      const double s = fabs(g.detJ);
-      for (int q = 0; q < sr.npts; ++q)
-      {
-        double xi[TDIM];
 #pragma unroll
-        for (int t = 0; t < TDIM; ++t)
-          xi[t] = __ldg(sr.pts + q * TDIM + t);
-        point_contribution<TDIM, DEG, KID>(g, xi, __ldg(sr.wts + q) * s, nq, h, cs, acc);
-      }
-    }
-    const int64_t slot = cell_slot[cell];
-    const bool add = written[slot] != 0;
-    if (!add)
-      written[slot] = 1;
-    if constexpr (KernelTraits<KID>::RANK == 2)
-    {
-      // Element-tensor rows are stored with their columns in ascending global-dof order, i.e. in
-      // the order of the CSR row they are gathered into (gather kernels below, sparsity.cu gtab).
-      int32_t d[ND];
-      int rank[ND];
+      for (int i = 0; i < ND; ++i)
 #pragma unroll
-      for (int j = 0; j < ND; ++j)
-        d[j] = __ldg(dofmap + cell * ND + j);
-#pragma unroll
-      for (int j = 0; j < ND; ++j)
-      {
-        int rk = 0;
-#pragma unroll
-        for (int jj = 0; jj < ND; ++jj)
-          rk += (d[jj] < d[j]) ? 1 : 0;
-        rank[j] = rk;
-      }
-      if constexpr (STAGED)
-      {
-        // 16-byte chunks rotated by thread so that the 8*ES-byte-strided tensors do not pile onto
-        // the same shared-memory banks
-        double* mine = reinterpret_cast<double*>(&s_t[threadIdx.x][0]);
-        const int sw = threadIdx.x % CH;
-#pragma unroll
-        for (int i = 0; i < ND; ++i)
-#pragma unroll
-          for (int j = 0; j < ND; ++j)
-          {
-            const int pos = i * ND + rank[j];
-            int ch = (pos >> 1) + sw;
-            ch = ch >= CH ? ch - CH : ch;
-            mine[(ch << 1) | (pos & 1)] = acc[i * ND + j];
-          }
-        s_slot[threadIdx.x] = slot;
-        s_add[threadIdx.x] = add ? 1 : 0;
-      }
-      else
-      {
-        double* o = out + slot * ES;
-#pragma unroll
-        for (int i = 0; i < ND; ++i)
-#pragma unroll
-          for (int j = 0; j < ND; ++j)
-          {
-            double* p = o + i * ND + rank[j];
-            *p = add ? *p + acc[i * ND + j] : acc[i * ND + j];
-          }
-      }
-    }
-    else
-    {
-      double* o = out + slot * ES;
-#pragma unroll
-      for (int i = 0; i < ES; ++i)
-        o[i] = add ? o[i] + acc[i] : acc[i];
+        for (int j = 0; j < ND; ++j)
+        {
+          double* p = oc.out + dest[i] * ND + rank[j];
+          *p = add ? *p + acc[i * ND + j] : acc[i * ND + j];
+        }
     }
   }
-  if constexpr (STAGED)
+  else if constexpr (RANK == 1)
   {
-    // cooperative store: CH consecutive lanes write one tensor, so every warp store covers whole
-    // 128-byte lines instead of 32 scattered 8-byte pieces (4x fewer L2 write sectors)
-    __syncthreads();
-    const int64_t left = n - static_cast<int64_t>(blockIdx.x) * EB;
-    const int n_here = left < EB ? static_cast<int>(left) : EB;
-    for (int t = threadIdx.x; t < n_here * CH; t += EB)
+#pragma unroll
+    for (int i = 0; i < ND; ++i)
     {
-      const int cellq = t / CH, ch = t % CH;
-      int pc = ch + cellq % CH;
-      pc = pc >= CH ? pc - CH : pc;
-      const double2 v = s_t[cellq][pc];
-      double2* dst = reinterpret_cast<double2*>(out + s_slot[cellq] * ES) + ch;
-      if (s_add[cellq])
-      {
-        const double2 old = *dst;
-        *dst = make_double2(old.x + v.x, old.y + v.y);
-      }
-      else
-        *dst = v;
+      double* p = oc.out + dest[i];
+      *p = add ? *p + acc[i] : acc[i];
     }
   }
+  else
+    oc.out[slot] = add ? oc.out[slot] + acc[0] : acc[0];
 }
 
 // Interior-facet ghost penalty, one thread per (facet, macro row).
@@ -489,6 +498,7 @@ struct GatherCtx
   const int32_t* rows4;
   const double* Fe;
   int nf;
+  int stride; // incidence slots per matrix row in the owner-major element storage
 };
 
 constexpr int GW = 4; // rows (warps) per block
@@ -564,7 +574,7 @@ __global__ void __launch_bounds__(GW * 32)
         }
         if (fl & 1)
         {
-          const double* a = gc.Ae + (static_cast<int64_t>(gc.cell_slot[c]) * ND + li) * ND;
+          const double* a = gc.Ae + (idx * gc.stride + k) * ND; // owner-major: slot k of this row
           // element-tensor rows are stored in ascending-dof column order (cell_kernel)
 #pragma unroll
           for (int pass = 0; pass < ND; ++pass)
@@ -657,16 +667,16 @@ __global__ void __launch_bounds__(GW * 32)
 }
 
 // Fast rows (<= 32 columns, <= 32 incident cells): the pattern pass left, per incident cell l,
-// gtab = (element-tensor row index, bit mask of the CSR positions of the cell's dofs).  Lane k owns
-// CSR entry k of the row and walks the incident cells in ascending order (gtab entries broadcast by
-// shuffle): cell l contributes iff bit k of its mask is set, and the value is entry
-// popc(mask & lanes_below_k) of its element-tensor row, which cell_kernel stored in column order.
-// The (at most ND) lanes that hit one cell read one 8*ND-byte row -> a single sector request for
-// P1 tets; no shared memory, no dofmap read, no column search, fixed summation order.
+// gmask[idx*stride + l] = bit mask of the CSR positions of the cell's dofs, and the cell kernels
+// stored the cell's tensor row at Ae[(idx*stride + l)*ND ..] in column order.  Lane k owns CSR entry
+// k of the row and walks the incident cells in ascending order (masks broadcast by shuffle): cell l
+// contributes iff bit k of its mask is set, and the value is entry popc(mask & lanes_below_k) of its
+// row.  Everything a row reads is contiguous: stride masks, stride*ND doubles, its CSR segment.
+// No shared memory, no dofmap read, no column search, fixed summation order.
 template <int ND>
 __global__ void __launch_bounds__(GW * 32)
     gather_matrix_fast_kernel(GatherCtx gc, const int32_t* __restrict__ act_rows, int64_t n_act,
-                              const uint8_t* __restrict__ row_fast, const int2* __restrict__ gtab,
+                              const uint8_t* __restrict__ row_fast, const uint32_t* __restrict__ gmask,
                               const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ cols,
                               double* __restrict__ vals, int zero_first)
 {
@@ -678,29 +688,27 @@ __global__ void __launch_bounds__(GW * 32)
   if (!(rf & 1))
     return; // handled by gather_matrix_kernel
   const unsigned full = 0xffffffffu;
-  const int2 g = gtab[idx * 32 + lane];
   const int64_t r = act_rows[idx];
+  const int64_t ib = gc.inc_ptr[r];
+  const int n_inc = static_cast<int>(gc.inc_ptr[r + 1] - ib);
   const int64_t rb = row_ptr[r];
   const int rn = static_cast<int>(row_ptr[r + 1] - rb);
+  const uint32_t gm = lane < n_inc ? gmask[idx * gc.stride + lane] : 0u;
   const bool have_col = lane < rn;
   double acc = (have_col && !zero_first) ? vals[rb + lane] : 0.0;
-  const unsigned contrib = __ballot_sync(full, g.x >= 0);
-  const int nl = 32 - __clz(contrib);
   const uint32_t below = (1u << lane) - 1u;
-  const uint32_t gm = g.x >= 0 ? static_cast<uint32_t>(g.y) : 0u;
-  const double* __restrict__ Ae = gc.Ae;
-  // batches of 8 cells: all (predicated) loads of a batch are issued before the first add, so up
-  // to 8 gathers are in flight per lane; the adds keep the ascending-cell order (x + 0.0 == x)
-  for (int l0 = 0; l0 < nl; l0 += 8)
+  const double* __restrict__ rowbase = gc.Ae + idx * gc.stride * ND;
+  // batches of 8 cells: all (predicated) loads of a batch are issued before the first add; the adds
+  // keep the ascending-cell order (x + 0.0 == x)
+  for (int l0 = 0; l0 < n_inc; l0 += 8)
   {
     double v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u)
     {
       const int l = (l0 + u) & 31;
-      const int src = __shfl_sync(full, g.x, l);
       const uint32_t M = __shfl_sync(full, gm, l);
-      v[u] = ((M >> lane) & 1u) ? __ldg(Ae + static_cast<int64_t>(src) * ND + __popc(M & below)) : 0.0;
+      v[u] = ((M >> lane) & 1u) ? __ldg(rowbase + l * ND + __popc(M & below)) : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u)
@@ -708,8 +716,6 @@ __global__ void __launch_bounds__(GW * 32)
   }
   if (rf & 2)
   { // interior-facet macro rows of the band cells (rare): column matched by value
-    const int64_t ib = gc.inc_ptr[r];
-    const int n_inc = static_cast<int>(gc.inc_ptr[r + 1] - ib);
     const int32_t mycol = have_col ? cols[rb + lane] : -2;
     int64_t c = -1;
     uint8_t fl = 0;
@@ -756,8 +762,9 @@ __global__ void __launch_bounds__(GW * 32)
     vals[rb + lane] = acc;
 }
 
-// Four rows per warp (8 lanes each, 3 independent gather chains per lane for a 24-cell row);
-// fixed-order partial sums + fixed shuffle tree -> bit-reproducible.
+// Four rows per warp (8 lanes each).  The owner-major vector storage holds one slot per incident
+// cell (zero where the cell is inactive), so a row is one contiguous read; fixed-order partial sums
+// + fixed shuffle tree -> bit-reproducible.
 template <int ND>
 __global__ void __launch_bounds__(GW * 32)
     gather_vector_kernel(GatherCtx gc, const int32_t* __restrict__ act_rows, int64_t n_act, double* __restrict__ b,
@@ -772,21 +779,11 @@ __global__ void __launch_bounds__(GW * 32)
   if (valid)
   {
     r = act_rows[idx];
-    const int64_t ib = gc.inc_ptr[r];
-    const int n_inc = static_cast<int>(gc.inc_ptr[r + 1] - ib);
+    const int n_inc = static_cast<int>(gc.inc_ptr[r + 1] - gc.inc_ptr[r]);
+    const double* __restrict__ base = gc.Ae + idx * gc.stride;
 #pragma unroll 4
     for (int k = gl; k < n_inc; k += 8)
-    {
-      const int64_t c = gc.inc_cell[ib + k];
-      if (gc.cell_flags[c] & 1)
-      {
-        int li = 0;
-#pragma unroll
-        for (int j = 0; j < ND; ++j)
-          li = (gc.dofmap[c * ND + j] == r) ? j : li;
-        s += gc.Ae[static_cast<int64_t>(gc.cell_slot[c]) * ND + li];
-      }
-    }
+      s += base[k];
   }
 #pragma unroll
   for (int o = 4; o > 0; o >>= 1)
@@ -827,6 +824,8 @@ void launch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f)
   Consts cs;
   for (int k = 0; k < CFX_MAX_CONSTANTS; ++k)
     cs.c[k] = I.constants[k];
+  const Space& S = c->spaces[f->space];
+  OutCtx oc{S.dofmap, f->prep->row_slot.p, S.cell_inc_l.p, f->prep->cell_slot.p, f->Ae.p, f->written.p, S.stride};
   if (I.n > 0)
   {
     int order = 0;
@@ -840,8 +839,7 @@ void launch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f)
     RuleTable& rt = get_rule(c, TDIM, order);
     sr = StdRule{rt.d_pts, rt.d_wts, rt.npts};
     auto k = cell_kernel<TDIM, DEG, KID, false>;
-    CFX_LAUNCH(c, k, grid_for(I.n, EB), EB, 0, I.entities, I.n, rv, sr, cs, c->x, c->x_dofmap,
-               c->spaces[f->space].dofmap, f->prep->cell_slot.p, f->Ae.p, f->written.p);
+    CFX_LAUNCH(c, k, grid_for(I.n, EB), EB, 0, I.entities, I.n, rv, sr, cs, c->x, c->x_dofmap, oc);
   }
   if (I.rules && I.rules->nrules > 0)
   {
@@ -850,8 +848,7 @@ void launch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f)
     rv = RuleView{R->points.p, R->weights.p, R->has_normals ? R->normals.p : nullptr, R->offsets.p, R->parent_map.p,
                   R->npts};
     auto k = cell_kernel<TDIM, DEG, KID, true>;
-    CFX_LAUNCH(c, k, grid_for(R->nrules, EB), EB, 0, nullptr, R->nrules, rv, sr, cs, c->x, c->x_dofmap,
-               c->spaces[f->space].dofmap, f->prep->cell_slot.p, f->Ae.p, f->written.p);
+    CFX_LAUNCH(c, k, grid_for(R->nrules, EB), EB, 0, nullptr, R->nrules, rv, sr, cs, c->x, c->x_dofmap, oc);
   }
 }
 
@@ -873,7 +870,13 @@ void dispatch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f)
 void run_cell_integrals(cfx_ctx* c, cfx_form* f, int esize)
 {
   const Space& S = c->spaces[f->space];
-  f->Ae.reserve(c->pool, static_cast<size_t>(f->prep->n_active) * esize + 1);
+  // owner-major storage: (active rows, stride, ND) for matrices, (active rows, stride) for vectors
+  const size_t n_out = f->rank == 0 ? static_cast<size_t>(f->prep->n_active)
+                                    : static_cast<size_t>(f->prep->n_act_rows) * S.stride * (f->rank == 2 ? S.nd : 1);
+  (void)esize;
+  f->Ae.reserve(c->pool, n_out + 4);
+  if (f->rank == 1) // the vector gather sums every slot of a row: slots of inactive cells must read 0
+    CFX_CUDA(cudaMemsetAsync(f->Ae.p, 0, (n_out + 4) * sizeof(double), c->stream));
   f->written.reserve(c->pool, static_cast<size_t>(f->prep->n_active) + 1);
   CFX_CUDA(cudaMemsetAsync(f->written.p, 0, static_cast<size_t>(f->prep->n_active) + 1, c->stream));
   for (auto& I : f->integrals)
@@ -909,7 +912,7 @@ GatherCtx make_gather_ctx(cfx_ctx* c, cfx_form* f, const cfx_integral* FI)
   const Space& S = c->spaces[f->space];
   return GatherCtx{S.inc_ptr.p, S.inc_cell.p,    S.dofmap,           f->prep->cell_flags.p,        f->prep->row_flag.p,
                    f->prep->cell_slot.p, f->Ae.p,       c->c2f,             c->facet_slot.p,        FI ? FI->entities : nullptr,
-                   f->Fe.p,        c->tdim + 1};
+                   f->Fe.p,        c->tdim + 1, S.stride};
 }
 } // namespace
 } // namespace cfx
@@ -979,7 +982,7 @@ cfx_status cfx_assemble_matrix(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
     {
       const unsigned g = grid_for(a->prep->n_act_rows, GW);
       if (fast)
-        CFX_LAUNCH(ctx, kf, g, GW * 32, 0, gc, a->prep->act_rows.p, a->prep->n_act_rows, a->row_fast.p, a->gtab.p, A->row_ptr.p,
+        CFX_LAUNCH(ctx, kf, g, GW * 32, 0, gc, a->prep->act_rows.p, a->prep->n_act_rows, a->row_fast.p, a->gmask.p, A->row_ptr.p,
                    A->cols.p, A->values.p, zero_first);
       if (!fast || a->n_slow_rows > 0)
         CFX_LAUNCH(ctx, k, g, GW * 32, 0, gc, a->prep->act_rows.p, a->prep->n_act_rows, fast ? a->row_fast.p : nullptr,

@@ -158,6 +158,13 @@ struct Space
   DevBuf<int64_t> inc_ptr;
   DevBuf<int32_t> inc_cell;
   int64_t n_inc = 0;
+  int stride = 0;               // max number of cells around a dof
+  DevBuf<uint8_t> cell_inc_l;   // (n_cells, nd): position of the cell in the incidence list of its i-th dof
+  // static full-mesh structure (every cell active), only if all its rows have <= 32 columns:
+  bool has_static = false;
+  DevBuf<int64_t> frow_ptr;     // full pattern row pointers
+  DevBuf<int32_t> fcols;        // full pattern columns (sorted)
+  DevBuf<uint32_t> fmask;       // per incidence: bit mask of the full-row positions of the cell's dofs
 };
 
 struct RuleTable
@@ -228,6 +235,7 @@ struct cfx_prepared
   cfx::DevBuf<int32_t> active;     // ascending cell ids with bit0 (slot i <-> cell active[i])
   cfx::DevBuf<uint8_t> row_flag;   // per dof: touched by a flagged cell
   cfx::DevBuf<int32_t> act_rows;   // ascending dofs with row_flag set
+  cfx::DevBuf<int32_t> row_slot;   // per dof: index into act_rows (valid where row_flag set)
   int64_t n_active = 0, n_act_rows = 0;
 };
 
@@ -239,11 +247,12 @@ struct cfx_form
   bool dirty = true;
   cfx_prepared* prep = nullptr;
   // gather table of the pattern built from this form (sparsity.cu pattern_rows_kernel)
-  cfx::DevBuf<int2> gtab;
+  cfx::DevBuf<uint32_t> gmask;  // (n_act_rows, stride): CSR positions of the dofs of incident cell l
   cfx::DevBuf<uint8_t> row_fast;
   int64_t n_slow_rows = 0;
   int64_t gtab_serial = -1;
-  cfx::DevBuf<double> Ae;      // (n_active, nd^rank)
+  cfx::DevBuf<double> Ae;      // rank 2: (n_act_rows, stride, nd) element-tensor rows grouped by matrix row;
+                               // rank 1: (n_act_rows, stride); rank 0: (n_active)
   cfx::DevBuf<uint8_t> written; // per slot
   cfx::DevBuf<double> Fe;      // facet macro tensors
 };

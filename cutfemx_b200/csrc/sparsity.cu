@@ -70,6 +70,36 @@ __global__ void inc_sort_kernel(int64_t n_dofs, const int64_t* __restrict__ inc_
   }
 }
 
+// largest incidence-list length (device max, exact)
+__global__ void max_degree_kernel(const int64_t* __restrict__ inc_ptr, int64_t n_dofs, int* __restrict__ out)
+{
+  const int64_t d = static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x;
+  int v = d < n_dofs ? static_cast<int>(inc_ptr[d + 1] - inc_ptr[d]) : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v = max(v, __shfl_down_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0 && v > 0)
+    atomicMax(out, v);
+}
+
+// cell_inc_l[c*nd + i] = position of cell c in the (sorted) incidence list of its i-th dof
+__global__ void cell_inc_l_kernel(int64_t n_dofs, const int64_t* __restrict__ inc_ptr,
+                                  const int32_t* __restrict__ inc_cell, const int32_t* __restrict__ dofmap, int nd,
+                                  uint8_t* __restrict__ cell_inc_l)
+{
+  const int64_t d = static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x;
+  if (d >= n_dofs)
+    return;
+  const int64_t b = inc_ptr[d], e = inc_ptr[d + 1];
+  for (int64_t k = b; k < e; ++k)
+  {
+    const int64_t c = inc_cell[k];
+    for (int i = 0; i < nd; ++i)
+      if (dofmap[c * nd + i] == d)
+        cell_inc_l[c * nd + i] = static_cast<uint8_t>(k - b);
+  }
+}
+
 __global__ void or_flag_kernel(const int32_t* __restrict__ idx, int64_t n, int stride, int64_t limit, uint8_t bit,
                                uint8_t* __restrict__ flags, int32_t* __restrict__ err)
 {
@@ -95,13 +125,14 @@ __global__ void scatter_slot_kernel(const int32_t* __restrict__ act, int64_t n, 
 
 // row_flag[dof] = 1 for every dof of the listed cells (cells[i * stride])
 __global__ void row_flag_kernel(const int32_t* __restrict__ cells, int64_t n, int stride,
-                                const int32_t* __restrict__ dofmap, int nd, uint8_t* __restrict__ row_flag)
+                                const int32_t* __restrict__ dofmap, int nd, uint8_t value,
+                                uint8_t* __restrict__ row_flag)
 {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x;
   if (i >= n * nd)
     return;
   const int64_t c = cells[(i / nd) * stride];
-  row_flag[dofmap[c * nd + (i % nd)]] = 1;
+  row_flag[dofmap[c * nd + (i % nd)]] = value; // all writers of one launch store the same value
 }
 
 __global__ void facet_slot_set_kernel(const int32_t* __restrict__ rows4, int64_t n, int nf,
@@ -164,38 +195,45 @@ __device__ __forceinline__ void sort_small(int32_t (&v)[N])
     }
 }
 
-// One WARP per active row.  Lanes take the row's incident cells (coalesced inc_cell read, ND-wide
-// dofmap gathers in parallel), sort their cell's dofs, and the warp extracts the sorted unique
-// column set by repeated warp-wide minimum over the list heads (one REDUX per column).
+// One WARP per row.  Lanes take the row's incident cells (coalesced inc_cell read, ND-wide dofmap
+// gathers in parallel), sort their cell's dofs, and the warp extracts the sorted unique column set
+// by repeated warp-wide minimum over the list heads (one REDUX per column).
 //
-// FILL = false (first pass over every active row): counts the columns and, for rows with at most
-// 32 columns and 32 incident cells ("fast rows"), also stores
-//   tmp[idx*32 + k]  = k-th column                      (copied to the CSR after the scan)
-//   gtab[idx*32 + l] = (slot*ND + local row, bit mask of the CSR positions of cell l's dofs)
+// FILL = false (first pass): counts the columns and, for rows with at most 32 columns and 32
+// incident cells ("fast rows"), also stores
+//   tmp[idx*32 + k]        = k-th column                 (copied to the CSR after the scan)
+//   mask[idx*stride + l]   = bit mask of the CSR positions of the dofs of incident cell l
 // so that the assembly gather (assemble.cu) needs neither the dofmap nor a column search.
 // FILL = true (second pass, slow rows only): writes the columns straight into the CSR.
+//
+// Modes: act_rows == nullptr walks ALL rows with every cell active (static full-mesh structure,
+// masks stored per global incidence); otherwise the active rows of a prepared form, optionally
+// only those with a facet-band cell (only_band: the others take pattern_static_kernel).
 template <int ND, bool FILL>
 __global__ void __launch_bounds__(RW * 32)
-    pattern_rows_kernel(RowCtx rc, const int32_t* __restrict__ act_rows, int64_t n_act,
+    pattern_rows_kernel(RowCtx rc, const int32_t* __restrict__ act_rows, int64_t n_rows_in, int only_band, int stride,
                         int32_t* __restrict__ row_nnz, const int64_t* __restrict__ row_ptr,
-                        int32_t* __restrict__ cols_out, const int32_t* __restrict__ cell_slot,
-                        int32_t* __restrict__ tmp, int2* __restrict__ gtab, uint8_t* __restrict__ row_fast,
-                        unsigned long long* __restrict__ n_slow, int32_t* __restrict__ err)
+                        int32_t* __restrict__ cols_out, int32_t* __restrict__ tmp, uint32_t* __restrict__ mask_out,
+                        uint8_t* __restrict__ row_fast, unsigned long long* __restrict__ n_slow,
+                        int32_t* __restrict__ err)
 {
   constexpr int XCAP = 128 * ND; // partner-dof candidates per row (facet macro cliques)
   __shared__ int32_t s_extra[RW][XCAP];
   __shared__ int s_nextra[RW];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * RW + w;
-  if (idx >= n_act)
+  if (idx >= n_rows_in)
     return;
+  const bool all_mode = act_rows == nullptr;
+  const int64_t r = all_mode ? idx : act_rows[idx];
+  if (only_band && !(rc.row_flag[r] & 2))
+    return; // non-band rows of a mesh with a static structure: pattern_static_kernel
   if constexpr (FILL)
   {
     if (row_fast[idx] & 1)
       return; // already copied from tmp
   }
   const unsigned full = 0xffffffffu;
-  const int64_t r = act_rows[idx];
   const int64_t ib = rc.inc_ptr[r];
   const int n_inc = static_cast<int>(rc.inc_ptr[r + 1] - ib);
   if (lane == 0)
@@ -205,7 +243,6 @@ __global__ void __launch_bounds__(RW * 32)
 #pragma unroll
   for (int j = 0; j < ND; ++j)
     h[j] = IMAX;
-  int32_t src = -1;
   bool band = false;
   for (int k0 = 0; k0 < n_inc; k0 += 32)
   {
@@ -213,7 +250,7 @@ __global__ void __launch_bounds__(RW * 32)
     if (k < n_inc)
     {
       const int64_t c = rc.inc_cell[ib + k];
-      const uint8_t fl = rc.cell_flags[c];
+      const uint8_t fl = all_mode ? uint8_t(1) : rc.cell_flags[c];
       bool own_needed = fl & 1;
       if (fl & 2)
       {
@@ -239,15 +276,9 @@ __global__ void __launch_bounds__(RW * 32)
       {
         if (k0 == 0)
         {
-          int li = 0;
 #pragma unroll
           for (int j = 0; j < ND; ++j)
-          {
             h[j] = rc.dofmap[c * ND + j];
-            li = (h[j] == r) ? j : li;
-          }
-          if (fl & 1)
-            src = cell_slot[c] * ND + li;
         }
         else
         { // rare: more than 32 incident cells -> spill this cell's dofs to the shared candidate list
@@ -274,8 +305,8 @@ __global__ void __launch_bounds__(RW * 32)
     return;
   }
   sort_small<ND>(h);
-  // An active row always finds its own dof among its cells' dofs, so the diagonal needs no extra
-  // candidate here (inactive rows get theirs from pattern_inactive_*_kernel).
+  // A row with at least one contributing cell finds its own dof among the cells' dofs; rows
+  // without any (all_mode cannot have them, active rows neither) are the inactive-row kernels' job.
   const int64_t ob = FILL ? row_ptr[r] : 0;
   int32_t keep = 0;
   uint32_t M = 0;
@@ -350,15 +381,58 @@ __global__ void __launch_bounds__(RW * 32)
     {
       if (lane < count)
         tmp[idx * 32 + lane] = keep;
-      gtab[idx * 32 + lane] = make_int2(src, static_cast<int>(M));
+      if (lane < n_inc)
+        mask_out[(all_mode ? ib : idx * stride) + lane] = M;
     }
     if (lane == 0)
     {
       row_nnz[r] = count;
-      row_fast[idx] = (fast ? 1 : 0) | (any_band ? 2 : 0);
+      if (row_fast)
+        row_fast[idx] = (fast ? 1 : 0) | (any_band ? 2 : 0);
       if (!fast)
         atomicAdd(n_slow, 1ULL);
     }
+  }
+}
+
+// Per-step pattern of a row WITHOUT facet-band cells, from the static full-mesh structure: the
+// row's columns are the full-mesh columns whose bit is set in R = OR of the full-row masks of the
+// ACTIVE incident cells; new positions are prefix popcounts.  ~60 instructions per row instead of
+// a sort: one REDUX.OR, a few POPC.  Only meshes whose full rows have <= 32 columns get here.
+__global__ void __launch_bounds__(RW * 32)
+    pattern_static_kernel(RowCtx rc, const int32_t* __restrict__ act_rows, int64_t n_act, int stride,
+                          const int64_t* __restrict__ frow_ptr, const int32_t* __restrict__ fcols,
+                          const uint32_t* __restrict__ fmask, int32_t* __restrict__ row_nnz, int32_t* __restrict__ tmp,
+                          uint32_t* __restrict__ gmask, uint8_t* __restrict__ row_fast)
+{
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * RW + w;
+  if (idx >= n_act)
+    return;
+  const int64_t r = act_rows[idx];
+  if (rc.row_flag[r] & 2)
+    return; // band rows: pattern_rows_kernel
+  const unsigned full = 0xffffffffu;
+  const int64_t ib = rc.inc_ptr[r];
+  const int n_inc = static_cast<int>(rc.inc_ptr[r + 1] - ib);
+  uint32_t Ml = 0;
+  if (lane < n_inc && (rc.cell_flags[rc.inc_cell[ib + lane]] & 1))
+    Ml = fmask[ib + lane];
+  const uint32_t R = __reduce_or_sync(full, Ml);
+  uint32_t Mn = 0;
+  for (uint32_t t = Ml; t; t &= t - 1)
+  {
+    const int p = __ffs(t) - 1;
+    Mn |= 1u << __popc(R & ((1u << p) - 1u));
+  }
+  if (lane < n_inc)
+    gmask[idx * stride + lane] = Mn;
+  if ((R >> lane) & 1u)
+    tmp[idx * 32 + __popc(R & ((1u << lane) - 1u))] = fcols[frow_ptr[r] + lane];
+  if (lane == 0)
+  {
+    row_nnz[r] = __popc(R);
+    row_fast[idx] = 1;
   }
 }
 
@@ -376,9 +450,9 @@ __global__ void __launch_bounds__(256)
   const int64_t idx = idx0 + lane;
   int64_t b = 0;
   int n = 0;
-  if (idx < n_act && (row_fast[idx] & 1))
+  if (idx < n_act && (!row_fast || (row_fast[idx] & 1)))
   {
-    const int64_t r = act_rows[idx];
+    const int64_t r = act_rows ? act_rows[idx] : idx;
     b = row_ptr[r];
     n = static_cast<int>(row_ptr[r + 1] - b);
   }
@@ -407,6 +481,57 @@ __global__ void check_sorted_kernel(const int64_t* __restrict__ row_ptr, const i
 }
 } // namespace
 
+// Static full-mesh structure (every cell active): full pattern + per-incidence position masks.
+// Built once per cfx_space_bind with the generic row kernel; kept only if every full row has at
+// most 32 columns and 32 incident cells (P1 and P2 triangles, P1 tetrahedra on usual meshes).
+template <int ND>
+static void build_static_structure_nd(cfx_ctx* c, Space& S)
+{
+  S.has_static = false;
+  if (S.stride > 32)
+    return;
+  RowCtx rc{S.inc_ptr.p, S.inc_cell.p, S.dofmap, nullptr, nullptr, nullptr, nullptr, nullptr, c->tdim + 1, 0};
+  DevBuf<int32_t> row_nnz, tmp;
+  row_nnz.reserve(c->pool, static_cast<size_t>(S.n_total) + 1);
+  tmp.reserve(c->pool, static_cast<size_t>(S.n_total) * 32);
+  S.fmask.reserve(c->pool, static_cast<size_t>(S.n_inc) + 1);
+  unsigned long long* n_slow = reinterpret_cast<unsigned long long*>(c->scratch64.p) + 1;
+  CFX_CUDA(cudaMemsetAsync(n_slow, 0, sizeof(unsigned long long), c->stream));
+  CFX_CUDA(cudaMemsetAsync(row_nnz.p, 0, (static_cast<size_t>(S.n_total) + 1) * sizeof(int32_t), c->stream));
+  auto k = pattern_rows_kernel<ND, false>;
+  CFX_LAUNCH(c, k, grid_for(S.n_total, RW), RW * 32, 0, rc, nullptr, S.n_total, 0, S.stride, row_nnz.p, nullptr,
+             nullptr, tmp.p, S.fmask.p, nullptr, n_slow, c->err_flag.p);
+  S.frow_ptr.reserve(c->pool, static_cast<size_t>(S.n_total) + 2);
+  exclusive_scan_i32_to_i64(c, row_nnz.p, S.n_total, S.frow_ptr.p);
+  const int64_t* h = read_back(c, c->scratch64.p, 2);
+  const int64_t fnnz = h[0], slow = h[1];
+  if (slow == 0)
+  {
+    S.fcols.reserve(c->pool, static_cast<size_t>(fnnz) + 1);
+    CFX_LAUNCH(c, pattern_copy_kernel, grid_for(S.n_total, 256), 256, 0, nullptr, S.n_total, nullptr, tmp.p,
+               S.frow_ptr.p, S.fcols.p);
+    S.has_static = true;
+  }
+  else
+  {
+    S.fmask.release();
+    S.frow_ptr.release();
+  }
+  row_nnz.release();
+  tmp.release();
+}
+
+static void build_static_structure(cfx_ctx* c, Space& S)
+{
+  switch (S.nd)
+  {
+  case 3: build_static_structure_nd<3>(c, S); break;
+  case 4: build_static_structure_nd<4>(c, S); break;
+  case 6: build_static_structure_nd<6>(c, S); break;
+  default: S.has_static = false; // P2 tetrahedra: rows have more than 32 columns
+  }
+}
+
 void build_incidence(cfx_ctx* c, Space& S)
 {
   const int64_t n_entries = c->nc_total * S.nd;
@@ -424,7 +549,18 @@ void build_incidence(cfx_ctx* c, Space& S)
   CFX_LAUNCH(c, inc_fill_kernel, grid_for(n_entries, SBK), SBK, 0, S.dofmap, n_entries, S.nd, S.inc_ptr.p, deg.p,
              S.inc_cell.p);
   CFX_LAUNCH(c, inc_sort_kernel, grid_for(S.n_total, SBK), SBK, 0, S.n_total, S.inc_ptr.p, S.inc_cell.p);
+  // stride = longest incidence list; cell -> position-in-list table
+  int* d_max = reinterpret_cast<int*>(c->scratch64.p + 2);
+  CFX_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int64_t), c->stream));
+  CFX_LAUNCH(c, max_degree_kernel, grid_for(S.n_total, SBK), SBK, 0, S.inc_ptr.p, S.n_total, d_max);
+  S.stride = static_cast<int>(read_back(c, c->scratch64.p + 2, 1)[0] & 0xffffffffLL);
+  CFX_REQUIRE(S.stride >= 1 && S.stride <= 255, CFX_ERR_UNSUPPORTED,
+              "cfx_space_bind: a dof with more than 255 (or no) incident cells is not supported");
+  S.cell_inc_l.reserve(c->pool, static_cast<size_t>(n_entries) + 16);
+  CFX_LAUNCH(c, cell_inc_l_kernel, grid_for(S.n_total, SBK), SBK, 0, S.n_total, S.inc_ptr.p, S.inc_cell.p, S.dofmap,
+             S.nd, S.cell_inc_l.p);
   deg.release();
+  build_static_structure(c, S);
 }
 
 void release_prepared(cfx_ctx* c, cfx_form* f)
@@ -444,6 +580,7 @@ void release_prepared(cfx_ctx* c, cfx_form* f)
   p->active.release();
   p->row_flag.release();
   p->act_rows.release();
+  p->row_slot.release();
   delete p;
 }
 
@@ -526,20 +663,25 @@ void prepare_form(cfx_ctx* c, cfx_form* f)
   CFX_CUDA(cudaMemsetAsync(P->row_flag.p, 0, static_cast<size_t>(S.n_total) + 16, c->stream));
   if (P->n_active > 0)
     CFX_LAUNCH(c, row_flag_kernel, grid_for(P->n_active * S.nd, SBK), SBK, 0, P->active.p, P->n_active, 1, S.dofmap,
-               S.nd, P->row_flag.p);
+               S.nd, uint8_t(1), P->row_flag.p);
   for (auto& I : f->integrals)
   {
     if (!I.facet || I.n == 0)
       continue;
+    // rows touching a facet-integral cell: bit 1 too (launched after the bit-0 pass above)
     CFX_LAUNCH(c, row_flag_kernel, grid_for(I.n * S.nd, SBK), SBK, 0, I.entities, I.n, 4, S.dofmap, S.nd,
-               P->row_flag.p);
+               uint8_t(3), P->row_flag.p);
     CFX_LAUNCH(c, row_flag_kernel, grid_for(I.n * S.nd, SBK), SBK, 0, I.entities + 2, I.n, 4, S.dofmap, S.nd,
-               P->row_flag.p);
+               uint8_t(3), P->row_flag.p);
   }
   {
     FlagPred p{P->row_flag.p};
     P->n_act_rows = compact_indices(c, S.n_total, p, P->act_rows);
   }
+  P->row_slot.reserve(c->pool, static_cast<size_t>(S.n_total) + 1);
+  if (P->n_act_rows > 0)
+    CFX_LAUNCH(c, scatter_slot_kernel, grid_for(P->n_act_rows, SBK), SBK, 0, P->act_rows.p, P->n_act_rows,
+               P->row_slot.p);
   check_device_error(c, "form domains (entity index out of range)");
   f->gtab_serial = -1;
   f->dirty = false;
@@ -667,7 +809,7 @@ void cfx_form_free(cfx_ctx* ctx, cfx_form* f)
     I.own.release();
   if (ctx)
     release_prepared(ctx, f);
-  f->gtab.release();
+  f->gmask.release();
   f->row_fast.release();
   f->Ae.release();
   f->written.release();
@@ -704,19 +846,25 @@ cfx_status cfx_create_sparsity(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
                : S.nd == 4 ? pattern_rows_kernel<4, true>
                : S.nd == 6 ? pattern_rows_kernel<6, true>
                            : pattern_rows_kernel<10, true>;
-  CFX_LAUNCH(ctx, pattern_inactive_count_kernel, grid_for(S.n_total, SBK), SBK, 0, a->prep->row_flag.p, S.n_total, 1,
+  cfx_prepared* PR = a->prep;
+  CFX_LAUNCH(ctx, pattern_inactive_count_kernel, grid_for(S.n_total, SBK), SBK, 0, PR->row_flag.p, S.n_total, 1,
              row_nnz.p);
-  const unsigned ga = grid_for(a->prep->n_act_rows, RW);
+  const unsigned ga = grid_for(PR->n_act_rows, RW);
   DevBuf<int32_t> tmp;
   unsigned long long* n_slow = reinterpret_cast<unsigned long long*>(ctx->scratch64.p) + 1;
   CFX_CUDA(cudaMemsetAsync(n_slow, 0, sizeof(unsigned long long), ctx->stream));
-  if (a->prep->n_act_rows > 0)
+  const int only_band = S.has_static ? 1 : 0;
+  if (PR->n_act_rows > 0)
   {
-    tmp.reserve(ctx->pool, static_cast<size_t>(a->prep->n_act_rows) * 32);
-    a->gtab.reserve(ctx->pool, static_cast<size_t>(a->prep->n_act_rows) * 32);
-    a->row_fast.reserve(ctx->pool, static_cast<size_t>(a->prep->n_act_rows) + 16);
-    CFX_LAUNCH(ctx, kcount, ga, RW * 32, 0, rc, a->prep->act_rows.p, a->prep->n_act_rows, row_nnz.p, nullptr, nullptr,
-               a->prep->cell_slot.p, tmp.p, a->gtab.p, a->row_fast.p, n_slow, ctx->err_flag.p);
+    tmp.reserve(ctx->pool, static_cast<size_t>(PR->n_act_rows) * 32);
+    a->gmask.reserve(ctx->pool, static_cast<size_t>(PR->n_act_rows) * S.stride);
+    a->row_fast.reserve(ctx->pool, static_cast<size_t>(PR->n_act_rows) + 16);
+    if (S.has_static)
+      CFX_LAUNCH(ctx, pattern_static_kernel, ga, RW * 32, 0, rc, PR->act_rows.p, PR->n_act_rows, S.stride,
+                 S.frow_ptr.p, S.fcols.p, S.fmask.p, row_nnz.p, tmp.p, a->gmask.p, a->row_fast.p);
+    if (!S.has_static || FI)
+      CFX_LAUNCH(ctx, kcount, ga, RW * 32, 0, rc, PR->act_rows.p, PR->n_act_rows, only_band, S.stride, row_nnz.p,
+                 nullptr, nullptr, tmp.p, a->gmask.p, a->row_fast.p, n_slow, ctx->err_flag.p);
   }
   P->row_ptr.reserve(ctx->pool, static_cast<size_t>(S.n_total) + 2);
   exclusive_scan_i32_to_i64(ctx, row_nnz.p, S.n_total, P->row_ptr.p);
@@ -727,15 +875,15 @@ cfx_status cfx_create_sparsity(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
   }
   P->cols.reserve(ctx->pool, static_cast<size_t>(P->nnz) + 1);
   P->values.reserve(ctx->pool, static_cast<size_t>(P->nnz) + 1);
-  CFX_LAUNCH(ctx, pattern_inactive_fill_kernel, grid_for(S.n_total, SBK), SBK, 0, a->prep->row_flag.p, S.n_total, 1,
+  CFX_LAUNCH(ctx, pattern_inactive_fill_kernel, grid_for(S.n_total, SBK), SBK, 0, PR->row_flag.p, S.n_total, 1,
              P->row_ptr.p, P->cols.p);
-  if (a->prep->n_act_rows > 0)
+  if (PR->n_act_rows > 0)
   {
-    CFX_LAUNCH(ctx, pattern_copy_kernel, grid_for(a->prep->n_act_rows, 256), 256, 0, a->prep->act_rows.p, a->prep->n_act_rows,
+    CFX_LAUNCH(ctx, pattern_copy_kernel, grid_for(PR->n_act_rows, 256), 256, 0, PR->act_rows.p, PR->n_act_rows,
                a->row_fast.p, tmp.p, P->row_ptr.p, P->cols.p);
     if (a->n_slow_rows > 0)
-      CFX_LAUNCH(ctx, kfill, ga, RW * 32, 0, rc, a->prep->act_rows.p, a->prep->n_act_rows, nullptr, P->row_ptr.p, P->cols.p,
-                 a->prep->cell_slot.p, nullptr, nullptr, a->row_fast.p, nullptr, ctx->err_flag.p);
+      CFX_LAUNCH(ctx, kfill, ga, RW * 32, 0, rc, PR->act_rows.p, PR->n_act_rows, only_band, S.stride, nullptr,
+                 P->row_ptr.p, P->cols.p, nullptr, nullptr, a->row_fast.p, nullptr, ctx->err_flag.p);
   }
   tmp.release();
   P->serial = ++ctx->pattern_serial;
