@@ -124,6 +124,10 @@ cfx_status cfx_mesh_bind(cfx_ctx* ctx, const double* x, int64_t n_nodes, const i
   ctx->domain.reserve(ctx->pool, static_cast<size_t>(ctx->domain_stride) * CFX_MAX_LEVEL_SETS);
   CFX_CUDA(cudaMemsetAsync(ctx->domain.p, 0, static_cast<size_t>(ctx->domain_stride) * CFX_MAX_LEVEL_SETS,
                            ctx->stream));
+  ctx->mat_slot.reserve(ctx->pool, static_cast<size_t>(n_cells_total) + 1);
+  CFX_CUDA(cudaMemsetAsync(ctx->mat_slot.p, 0xff, (static_cast<size_t>(n_cells_total) + 1) * sizeof(int32_t),
+                           ctx->stream));
+  build_geometry_cache(ctx);
   if (memspace == CFX_HOST)
     CFX_CUDA(cudaStreamSynchronize(ctx->stream));
   CFX_API_END(ctx)

@@ -179,13 +179,9 @@ __device__ __forceinline__ void point_contribution(const Geo<TDIM>& g, const dou
 // where a cell kernel puts its element tensor
 struct OutCtx
 {
-  const int32_t* dofmap;     // argument-space dofmap (n_cells, ND)
-  const int32_t* row_slot;   // dof -> index of its matrix row among the active rows
-  const uint8_t* cell_inc_l; // (n_cells, ND): position of the cell in the incidence list of its i-th dof
-  const int32_t* cell_slot;  // cell -> index among the active cells
+  int32_t* mat_slot; // cell -> slot of its materialised tensor (-1: none yet); ranks 1 and 2
   double* out;
-  uint8_t* written;          // per active cell: an earlier integral already stored this cell's tensor
-  int stride;                // incidence slots per matrix row
+  int64_t base;      // first slot (rank 1, 2) / first entity index (rank 0) of this integral
 };
 
 __device__ __forceinline__ void st256(double* p, double a, double b, double c, double d)
@@ -197,15 +193,16 @@ __device__ __forceinline__ void ld256(const double* p, double& a, double& b, dou
   asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 
-// One thread per entity of a cell integral.  RUNTIME = false: entity e is standard cell
-// cells[e] with the compile-time rule; true: entity e is rule e (parent cell parent_map[e]).
+// One thread per entity of a cell integral whose tensor is MATERIALISED: every run-time-rule entity
+// (RUNTIME = true: entity e is rule e, parent cell parent_map[e], rule looked up by loop index --
+// SURVEY.md fact 5), and the entities of rank-0 functionals.  Standard-quadrature cells of rank-1/2
+// forms are NOT materialised: the owner of each matrix row computes their tensor rows on the fly
+// (gather kernels below).
 //
-// Output layout ("owner-major"): row i of the element tensor goes straight to the storage of the
-// matrix row it will be gathered into: slot (row_slot[dof_i] * stride + l) * ND, l = position of
-// this cell among the cells around dof_i, columns in ascending global-dof order.  The gather then
-// streams contiguous memory (the scattered 32-byte accesses happen here, as stores that the L2
-// merges, instead of as dependent random loads in the gather).  For P1 tetrahedra one row is one
-// 32-byte sector, written with a single 256-bit store.
+// Output: cell-major, natural dof order, ES doubles per slot.  The first integral that reaches a
+// cell claims slot base + e and records it in mat_slot[cell]; later integrals of the same form
+// (launched afterwards on the same stream) add into that slot.  Rules hold at most one entity per
+// cell, so there is no race inside a launch.
 template <int TDIM, int DEG, int KID, bool RUNTIME>
 __global__ void __launch_bounds__(EB)
     cell_kernel(const int32_t* __restrict__ cells, int64_t n, RuleView rv, StdRule sr, Consts cs,
@@ -218,20 +215,14 @@ __global__ void __launch_bounds__(EB)
   if (e >= n)
     return;
   const int64_t cell = RUNTIME ? rv.parent_map[e] : cells[e];
-  // issue the output-side gathers early: they are independent of the arithmetic
-  const int64_t slot = oc.cell_slot[cell];
-  int32_t d[ND];
-  int64_t dest[ND];
+  int64_t slot = oc.base + e;
+  bool add = false;
   if constexpr (RANK >= 1)
   {
-#pragma unroll
-    for (int j = 0; j < ND; ++j)
-      d[j] = __ldg(oc.dofmap + cell * ND + j);
-#pragma unroll
-    for (int j = 0; j < ND; ++j)
-      dest[j] = static_cast<int64_t>(__ldg(oc.row_slot + d[j])) * oc.stride + __ldg(oc.cell_inc_l + cell * ND + j);
+    const int32_t s0 = oc.mat_slot[cell];
+    add = s0 >= 0;
+    slot = add ? s0 : slot;
   }
-  const bool add = oc.written[slot] != 0;
   double X[TDIM + 1][TDIM];
   load_cell_coords<TDIM>(x, x_dofmap, cell, X);
   Geo<TDIM> g;
@@ -277,69 +268,40 @@ __global__ void __launch_bounds__(EB)
       point_contribution<TDIM, DEG, KID>(g, xi, __ldg(sr.wts + q) * s, nq, h, cs, acc);
     }
   }
-  if (!add)
-    oc.written[slot] = 1;
-  if constexpr (RANK == 2)
+  if constexpr (RANK >= 1)
   {
-    int rank[ND];
-#pragma unroll
-    for (int j = 0; j < ND; ++j)
-    {
-      int rk = 0;
-#pragma unroll
-      for (int jj = 0; jj < ND; ++jj)
-        rk += (d[jj] < d[j]) ? 1 : 0;
-      rank[j] = rk;
-    }
-    if constexpr (ND == 4)
-    {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-      {
-        double rowv[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-        {
-          double v = acc[i * 4 + 0];
-#pragma unroll
-          for (int j = 1; j < 4; ++j)
-            v = (rank[j] == r) ? acc[i * 4 + j] : v;
-          rowv[r] = v;
-        }
-        double* p = oc.out + dest[i] * 4;
-        if (add)
-        {
-          double o0, o1, o2, o3;
-          ld256(p, o0, o1, o2, o3);
-          st256(p, o0 + rowv[0], o1 + rowv[1], o2 + rowv[2], o3 + rowv[3]);
-        }
-        else
-          st256(p, rowv[0], rowv[1], rowv[2], rowv[3]);
-      }
-    }
-    else
-    {
-#pragma unroll
-      for (int i = 0; i < ND; ++i)
-#pragma unroll
-        for (int j = 0; j < ND; ++j)
-        {
-          double* p = oc.out + dest[i] * ND + rank[j];
-          *p = add ? *p + acc[i * ND + j] : acc[i * ND + j];
-        }
-    }
+    if (!add)
+      oc.mat_slot[cell] = static_cast<int32_t>(slot);
   }
-  else if constexpr (RANK == 1)
+  double* p = oc.out + slot * ES;
+  if constexpr (ES % 4 == 0)
   {
 #pragma unroll
-    for (int i = 0; i < ND; ++i)
+    for (int i = 0; i < ES; i += 4)
     {
-      double* p = oc.out + dest[i];
-      *p = add ? *p + acc[i] : acc[i];
+      if (add)
+      {
+        double o0, o1, o2, o3;
+        ld256(p + i, o0, o1, o2, o3);
+        st256(p + i, o0 + acc[i], o1 + acc[i + 1], o2 + acc[i + 2], o3 + acc[i + 3]);
+      }
+      else
+        st256(p + i, acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
     }
   }
   else
-    oc.out[slot] = add ? oc.out[slot] + acc[0] : acc[0];
+  {
+#pragma unroll
+    for (int i = 0; i < ES; ++i)
+      p[i] = add ? p[i] + acc[i] : acc[i];
+  }
+}
+
+__global__ void reset_slots_kernel(const int32_t* __restrict__ cells, int64_t n, int32_t* __restrict__ mat_slot)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i < n)
+    mat_slot[cells[i]] = -1;
 }
 
 // Interior-facet ghost penalty, one thread per (facet, macro row).
@@ -351,8 +313,8 @@ __global__ void __launch_bounds__(EB)
 template <int TDIM, int DEG>
 __global__ void __launch_bounds__(EB)
     facet_kernel(const int32_t* __restrict__ rows4, int64_t n_facets, StdRule fr, Consts cs,
-                 const double* __restrict__ x, const int32_t* __restrict__ x_dofmap, double* __restrict__ Fe,
-                 bool accumulate)
+                 const double* __restrict__ x, const int32_t* __restrict__ x_dofmap, const double* __restrict__ geo,
+                 double* __restrict__ Fe, bool accumulate)
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
   constexpr int NV = TDIM + 1;
@@ -363,6 +325,68 @@ __global__ void __launch_bounds__(EB)
   const int64_t f = t / (2 * ND);
   const int mrow = static_cast<int>(t - f * 2 * ND);
   const int32_t c0 = rows4[4 * f], lf0 = rows4[4 * f + 1], c1 = rows4[4 * f + 2];
+  if constexpr (DEG == 1)
+  { // P1: the normal-gradient jump is constant on the facet and everything follows from the two
+    // cached geometry records: grad lam_j = rows of K, n = -grad lam_lf0 / |.|, |F| (tdim-1)! = |detJ| |grad lam_lf0|
+    Geo<TDIM> g[2];
+    load_geo_cached<TDIM>(geo, c0, g[0]);
+    load_geo_cached<TDIM>(geo, c1, g[1]);
+    const double havg = 0.5 * (__ldg(geo + static_cast<int64_t>(c0) * GeoRec<TDIM>::STRIDE + TDIM * TDIM + 1)
+                               + __ldg(geo + static_cast<int64_t>(c1) * GeoRec<TDIM>::STRIDE + TDIM * TDIM + 1));
+    double G[2][ND][TDIM];
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int r = 0; r < TDIM; ++r)
+      {
+        double s0 = 0.0;
+#pragma unroll
+        for (int tt = 0; tt < TDIM; ++tt)
+        {
+          G[s][tt + 1][r] = g[s].K[tt * TDIM + r];
+          s0 -= g[s].K[tt * TDIM + r];
+        }
+        G[s][0][r] = s0;
+      }
+    double nrm[TDIM], nn = 0.0;
+#pragma unroll
+    for (int r = 0; r < TDIM; ++r)
+    {
+      double v = G[0][0][r];
+#pragma unroll
+      for (int j = 1; j < ND; ++j)
+        v = (j == lf0) ? G[0][j][r] : v;
+      nrm[r] = -v;
+      nn += v * v;
+    }
+    nn = sqrt(nn);
+    const double measure = fabs(g[0].detJ) * nn;
+    double jn[2 * ND];
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+      {
+        double v = 0.0;
+#pragma unroll
+        for (int r = 0; r < TDIM; ++r)
+          v += G[s][i][r] * (nrm[r] / nn);
+        jn[s * ND + i] = s ? -v : v;
+      }
+    double ji = jn[0];
+#pragma unroll
+    for (int j = 1; j < 2 * ND; ++j)
+      ji = (j == mrow) ? jn[j] : ji;
+    const double w = (TDIM == 3 ? 0.5 : 1.0) * measure * cs.c[0] * havg;
+    double* o = Fe + t * 2 * ND;
+#pragma unroll
+    for (int j = 0; j < 2 * ND; ++j)
+    {
+      const double v = w * ji * jn[j];
+      o[j] = accumulate ? o[j] + v : v;
+    }
+    return;
+  }
   double X0[NV][TDIM], X1[NV][TDIM];
   load_cell_coords<TDIM>(x, x_dofmap, c0, X0);
   load_cell_coords<TDIM>(x, x_dofmap, c1, X1);
@@ -483,23 +507,194 @@ __global__ void __launch_bounds__(EB)
     o[j] = accumulate ? o[j] + acc[j] : acc[j];
 }
 
-// ------------------------------------------------------------------ K5 gather
+// ------------------------------------------------------------------ K5 gather ("owner gathers")
+// standard-quadrature cell integrals of a form, evaluated on the fly by the row owners
+struct StdTab
+{
+  int n;
+  int kernel[CFX_MAX_STD_LISTS];
+  unsigned bit[CFX_MAX_STD_LISTS]; // cell_flags bit of the integral's cell list
+  double c[CFX_MAX_STD_LISTS][2];
+  const double* pts[CFX_MAX_STD_LISTS]; // AoS (npts, tdim) reference rule, weights sum to 1/tdim!
+  const double* wts[CFX_MAX_STD_LISTS];
+  int npts[CFX_MAX_STD_LISTS];
+};
+
 struct GatherCtx
 {
   const int64_t* inc_ptr;
   const int32_t* inc_cell;
+  const uint32_t* fperm;
+  const uint32_t* fmask;
   const int32_t* dofmap;
   const uint8_t* cell_flags;
-  const uint8_t* row_flag;
-  const int32_t* cell_slot;
+  const int32_t* mat_slot;
   const double* Ae;
+  const double* geo; // static per-cell geometry records (element.cuh GeoRec)
   const int32_t* c2f;
   const int32_t* facet_slot;
   const int32_t* rows4;
   const double* Fe;
   int nf;
-  int stride; // incidence slots per matrix row in the owner-major element storage
+  int stride;
 };
+
+template <int N>
+__device__ __forceinline__ double pick(const double (&a)[N], int i)
+{
+  double v = a[0];
+#pragma unroll
+  for (int j = 1; j < N; ++j)
+    v = (j == i) ? a[j] : v;
+  return v;
+}
+
+// Row `li` of the element tensor of standard cell `c` (sum over the form's standard integrals the
+// cell belongs to) plus row `li` of its materialised run-time tensor, natural dof order.
+template <int TDIM, int DEG>
+__device__ __forceinline__ void cell_row_values(const GatherCtx& gc, const StdTab& st, int64_t c, unsigned fl, int li,
+                                                double (&v)[Elem<TDIM, DEG>::ND])
+{
+  constexpr int ND = Elem<TDIM, DEG>::ND;
+#pragma unroll
+  for (int j = 0; j < ND; ++j)
+    v[j] = 0.0;
+  if (fl >> 2)
+  {
+    Geo<TDIM> g;
+    load_geo_cached<TDIM>(gc.geo, c, g);
+    const double s = fabs(g.detJ);
+    for (int k = 0; k < st.n; ++k)
+    {
+      if (!(fl & st.bit[k]))
+        continue;
+      const double c0 = st.c[k][0];
+      const bool mass = st.kernel[k] == CFX_K_MASS;
+      if (DEG == 1 && !mass)
+      { // P1 Laplace: constant gradients grad lam_0 = -(sum of the rows of K), grad lam_j = row j-1 of K;
+        // the degree-0 rule's weights sum to 1/tdim!
+        double G[ND][TDIM];
+#pragma unroll
+        for (int r = 0; r < TDIM; ++r)
+        {
+          double s0 = 0.0;
+#pragma unroll
+          for (int t = 0; t < TDIM; ++t)
+          {
+            G[t + 1][r] = g.K[t * TDIM + r];
+            s0 -= g.K[t * TDIM + r];
+          }
+          G[0][r] = s0;
+        }
+        const double w = c0 * s * (TDIM == 3 ? 1.0 / 6.0 : 0.5);
+        double gi[TDIM];
+#pragma unroll
+        for (int r = 0; r < TDIM; ++r)
+        {
+          double t = G[0][r];
+#pragma unroll
+          for (int j = 1; j < ND; ++j)
+            t = (j == li) ? G[j][r] : t;
+          gi[r] = t * w;
+        }
+#pragma unroll
+        for (int j = 0; j < ND; ++j)
+        {
+          double d = 0.0;
+#pragma unroll
+          for (int r = 0; r < TDIM; ++r)
+            d += gi[r] * G[j][r];
+          v[j] += d;
+        }
+        continue;
+      }
+      for (int q = 0; q < st.npts[k]; ++q)
+      {
+        double xi[TDIM];
+#pragma unroll
+        for (int t = 0; t < TDIM; ++t)
+          xi[t] = __ldg(st.pts[k] + q * TDIM + t);
+        const double w = __ldg(st.wts[k] + q) * s * c0;
+        double phi[ND], dphi[ND][TDIM];
+        tabulate<TDIM, DEG>(xi, phi, dphi);
+        if (mass)
+        {
+          const double pi = pick<ND>(phi, li) * w;
+#pragma unroll
+          for (int j = 0; j < ND; ++j)
+            v[j] += pi * phi[j];
+        }
+        else
+        { // CFX_K_LAPLACE
+          double grad[ND][TDIM];
+          push_gradients<TDIM, ND>(g, dphi, grad);
+          double gi[TDIM];
+#pragma unroll
+          for (int r = 0; r < TDIM; ++r)
+          {
+            double t = grad[0][r];
+#pragma unroll
+            for (int j = 1; j < ND; ++j)
+              t = (j == li) ? grad[j][r] : t;
+            gi[r] = t * w;
+          }
+#pragma unroll
+          for (int j = 0; j < ND; ++j)
+          {
+            double d = 0.0;
+#pragma unroll
+            for (int r = 0; r < TDIM; ++r)
+              d += gi[r] * grad[j][r];
+            v[j] += d;
+          }
+        }
+      }
+    }
+  }
+  if (fl & 1)
+  {
+    const double* a = gc.Ae + (static_cast<int64_t>(__ldg(gc.mat_slot + c)) * ND + li) * ND;
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+      v[j] += a[j];
+  }
+}
+
+// rank 1: entry `li` of the element vector of cell c
+template <int TDIM, int DEG>
+__device__ __forceinline__ double cell_entry_value(const GatherCtx& gc, const StdTab& st, int64_t c, unsigned fl,
+                                                   int li)
+{
+  constexpr int ND = Elem<TDIM, DEG>::ND;
+  double e = 0.0;
+  if (fl >> 2)
+  {
+    const double s = fabs(__ldg(gc.geo + c * GeoRec<TDIM>::STRIDE + TDIM * TDIM));
+    for (int k = 0; k < st.n; ++k)
+    {
+      if (!(fl & st.bit[k]))
+        continue;
+      if constexpr (DEG == 1)
+      { // P1 source: int phi_i = |detJ| / (tdim+1)!
+        e += st.c[k][0] * s * (TDIM == 3 ? 1.0 / 24.0 : 1.0 / 6.0);
+      }
+      else
+      for (int q = 0; q < st.npts[k]; ++q)
+      { // CFX_K_SOURCE
+        double xi[TDIM];
+#pragma unroll
+        for (int t = 0; t < TDIM; ++t)
+          xi[t] = __ldg(st.pts[k] + q * TDIM + t);
+        double phi[ND], dphi[ND][TDIM];
+        tabulate<TDIM, DEG>(xi, phi, dphi);
+        e += st.c[k][0] * (__ldg(st.wts[k] + q) * s) * pick<ND>(phi, li);
+      }
+    }
+  }
+  if (fl & 1)
+    e += gc.Ae[static_cast<int64_t>(__ldg(gc.mat_slot + c)) * ND + li];
+  return e;
+}
 
 constexpr int GW = 4; // rows (warps) per block
 
@@ -516,23 +711,83 @@ __global__ void inactive_diag_kernel(const uint8_t* __restrict__ row_flag, int64
       vals[p] = diag;
 }
 
-// One WARP per active row ("owner gathers").
-//  phase 1: lanes take the row's incident cells: gather dofmap row, slot and the matching
-//           element-tensor row (one 32 B sector for P1 tets) into shared memory -- up to 32
-//           independent gather chains in flight per warp;
+// Interior-facet macro rows of the band cells among this warp's (<= 32) incident cells.  Lane l owns
+// incident cell l and probes its own local facets (up to 32 independent gather chains in flight);
+// hits are staged in shared memory (the two cells' dofs + the macro-tensor row) and the column lanes
+// add them facet round by facet round, cell by cell -- a fixed order.  Returns the number of matches.
+template <int ND>
+__device__ __forceinline__ int add_facet_rows(const GatherCtx& gc, int32_t (*s_fd)[2 * ND], double (*s_fv)[2 * ND],
+                                              bool band_cell, int64_t c, int li, int32_t mycol, double& acc,
+                                              int& expected, bool count)
+{
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  int matched = 0;
+  if (__ballot_sync(full, band_cell) == 0)
+    return 0;
+  for (int lf = 0; lf < gc.nf; ++lf)
+  {
+    int64_t fs = -1;
+    if (band_cell)
+      fs = gc.facet_slot[gc.c2f[c * gc.nf + lf]];
+    const bool valid = fs >= 0;
+    if (valid)
+    {
+      const int64_t c0 = gc.rows4[4 * fs], c1 = gc.rows4[4 * fs + 2];
+      const int mrow = (c == c0 ? 0 : ND) + li;
+      const double* F = gc.Fe + (fs * 2 * ND + mrow) * 2 * ND;
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+      {
+        s_fd[lane][j] = gc.dofmap[c0 * ND + j];
+        s_fd[lane][ND + j] = gc.dofmap[c1 * ND + j];
+      }
+#pragma unroll
+      for (int j = 0; j < 2 * ND; ++j)
+        s_fv[lane][j] = F[j];
+      if (count)
+        expected += 2 * ND;
+    }
+    __syncwarp();
+    unsigned m = __ballot_sync(full, valid);
+    while (m)
+    {
+      const int l = __ffs(m) - 1;
+      m &= m - 1;
+#pragma unroll
+      for (int j = 0; j < 2 * ND; ++j)
+        if (s_fd[l][j] == mycol)
+        {
+          acc += s_fv[l][j];
+          ++matched;
+        }
+    }
+    __syncwarp();
+  }
+  return matched;
+}
+
+// Generic rows (any number of columns / incident cells, or a pattern this form did not build):
+// one WARP per active row.
+//  phase 1: lanes take the row's incident cells and compute (standard cells) or load
+//           (materialised cells) the element-tensor row of this matrix row, staged with the
+//           cell's dofs in shared memory;
 //  phase 2: lanes own the row's CSR entries (coalesced cols/vals access); every lane walks the
 //           staged cells in ascending order (broadcast shared-memory reads) and adds the entry
-//           whose dof equals its column.  Fixed order, no atomics -> bit-reproducible.
-// Interior-facet macro tensors are added afterwards, cell by cell, facet by facet.
-template <int ND>
+//           whose dof equals its column -- the search MatrixCSR::mat_add_values does, but with a
+//           fixed summation order and no atomics -> bit-reproducible.
+template <int TDIM, int DEG>
 __global__ void __launch_bounds__(GW * 32)
-    gather_matrix_kernel(GatherCtx gc, const int32_t* __restrict__ act_rows, int64_t n_act,
+    gather_matrix_kernel(GatherCtx gc, StdTab st, const int32_t* __restrict__ act_rows, int64_t n_act,
                          const uint8_t* __restrict__ skip_fast, const int64_t* __restrict__ row_ptr,
                          const int32_t* __restrict__ cols, double* __restrict__ vals, int zero_first,
                          int32_t* __restrict__ err)
 {
+  constexpr int ND = Elem<TDIM, DEG>::ND;
   __shared__ int32_t s_dofs[GW][32][ND];
   __shared__ double s_a[GW][32][ND];
+  __shared__ int32_t s_fd[GW][32][2 * ND];
+  __shared__ double s_fv[GW][32][2 * ND];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * GW + w;
   if (idx >= n_act)
@@ -556,13 +811,14 @@ __global__ void __launch_bounds__(GW * 32)
       // ---- phase 1
       const int k = k0 + lane;
       int64_t c = -1;
-      uint8_t fl = 0;
+      unsigned fl = 0;
       int li = 0;
       if (k < n_inc)
       {
         c = gc.inc_cell[ib + k];
         fl = gc.cell_flags[c];
       }
+      const bool contributes = (fl & 0xFDu) != 0;
       if (fl)
       {
         int32_t d[ND];
@@ -572,28 +828,19 @@ __global__ void __launch_bounds__(GW * 32)
           d[j] = gc.dofmap[c * ND + j];
           li = (d[j] == r) ? j : li;
         }
-        if (fl & 1)
+        if (contributes)
         {
-          const double* a = gc.Ae + (idx * gc.stride + k) * ND; // owner-major: slot k of this row
-          // element-tensor rows are stored in ascending-dof column order (cell_kernel)
-#pragma unroll
-          for (int pass = 0; pass < ND; ++pass)
-#pragma unroll
-            for (int i = pass & 1; i + 1 < ND; i += 2)
-            {
-              const int32_t lo = min(d[i], d[i + 1]), hi = max(d[i], d[i + 1]);
-              d[i] = lo;
-              d[i + 1] = hi;
-            }
+          double v[ND];
+          cell_row_values<TDIM, DEG>(gc, st, c, fl, li, v);
 #pragma unroll
           for (int j = 0; j < ND; ++j)
           {
             s_dofs[w][lane][j] = d[j];
-            s_a[w][lane][j] = a[j];
+            s_a[w][lane][j] = v[j];
           }
         }
       }
-      if (!(fl & 1))
+      if (!contributes)
       {
 #pragma unroll
         for (int j = 0; j < ND; ++j)
@@ -613,39 +860,8 @@ __global__ void __launch_bounds__(GW * 32)
           }
       }
       if (kc == 0)
-        expected += (fl & 1) ? ND : 0;
-      // ---- interior-facet macro rows of the band cells of this chunk
-      unsigned band = __ballot_sync(full, (fl & 2) != 0);
-      while (band)
-      {
-        const int l = __ffs(band) - 1;
-        band &= band - 1;
-        const int64_t cl = __shfl_sync(full, c, l);
-        const int lil = __shfl_sync(full, li, l);
-        for (int lf = 0; lf < gc.nf; ++lf)
-        {
-          const int64_t fs = gc.facet_slot[gc.c2f[cl * gc.nf + lf]];
-          if (fs < 0)
-            continue;
-          const int64_t c0 = gc.rows4[4 * fs], c1 = gc.rows4[4 * fs + 2];
-          const int mrow = (cl == c0 ? 0 : ND) + lil;
-          const double* F = gc.Fe + (fs * 2 * ND + mrow) * 2 * ND;
-#pragma unroll
-          for (int s = 0; s < 2; ++s)
-          {
-            const int64_t cc = s ? c1 : c0;
-#pragma unroll
-            for (int j = 0; j < ND; ++j)
-              if (gc.dofmap[cc * ND + j] == mycol)
-              {
-                acc += F[s * ND + j];
-                ++matched;
-              }
-          }
-          if (kc == 0 && lane == 0)
-            expected += 2 * ND;
-        }
-      }
+        expected += contributes ? ND : 0;
+      matched += add_facet_rows<ND>(gc, s_fd[w], s_fv[w], (fl & 2u) != 0, c, li, mycol, acc, expected, kc == 0);
       __syncwarp();
     }
     if (have_col)
@@ -666,25 +882,35 @@ __global__ void __launch_bounds__(GW * 32)
   }
 }
 
-// Fast rows (<= 32 columns, <= 32 incident cells): the pattern pass left, per incident cell l,
-// gmask[idx*stride + l] = bit mask of the CSR positions of the cell's dofs, and the cell kernels
-// stored the cell's tensor row at Ae[(idx*stride + l)*ND ..] in column order.  Lane k owns CSR entry
-// k of the row and walks the incident cells in ascending order (masks broadcast by shuffle): cell l
-// contributes iff bit k of its mask is set, and the value is entry popc(mask & lanes_below_k) of its
-// row.  Everything a row reads is contiguous: stride masks, stride*ND doubles, its CSR segment.
-// No shared memory, no dofmap read, no column search, fixed summation order.
-template <int ND>
-__global__ void __launch_bounds__(GW * 32)
-    gather_matrix_fast_kernel(GatherCtx gc, const int32_t* __restrict__ act_rows, int64_t n_act,
+// Fast rows (<= 32 columns, <= 32 incident cells, pattern built from this form): one WARP per row.
+//  phase 1: lane l takes incident cell l: one coalesced read each of inc_cell / fperm / fmask,
+//           the cell's flag byte, then the tensor row of this matrix row -- computed on the fly
+//           from the cell geometry for standard cells, loaded (one 32 B sector for P1 tets) for
+//           materialised cut cells -- staged in shared memory in ascending-dof order.  The CSR
+//           positions of the cell's dofs are a bit mask: static rows derive it from the static
+//           full-mesh mask and the row's kept-column mask R (prefix popcounts), band rows read the
+//           mask the pattern pass stored.
+//  phase 2: lane k owns CSR entry k and walks the cells in ascending order (masks broadcast by
+//           shuffle): cell l contributes iff bit k of its mask is set; the value is entry
+//           popc(mask & lanes_below_k) of its staged row.
+// No dofmap read, no column search, no element-tensor round trip through HBM for standard cells,
+// fixed summation order -> bit-reproducible.
+template <int TDIM, int DEG>
+__global__ void __launch_bounds__(GW * 32, 8)
+    gather_matrix_fast_kernel(GatherCtx gc, StdTab st, const int32_t* __restrict__ act_rows, int64_t n_act,
                               const uint8_t* __restrict__ row_fast, const uint32_t* __restrict__ gmask,
-                              const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ cols,
-                              double* __restrict__ vals, int zero_first)
+                              const uint32_t* __restrict__ Rrow, const int64_t* __restrict__ row_ptr,
+                              const int32_t* __restrict__ cols, double* __restrict__ vals, int zero_first)
 {
+  constexpr int ND = Elem<TDIM, DEG>::ND;
+  __shared__ double s_v[GW][32][ND];
+  __shared__ int32_t s_fd[GW][32][2 * ND];
+  __shared__ double s_fv[GW][32][2 * ND];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * GW + w;
   if (idx >= n_act)
     return;
-  const uint8_t rf = row_fast[idx];
+  const unsigned rf = row_fast[idx];
   if (!(rf & 1))
     return; // handled by gather_matrix_kernel
   const unsigned full = 0xffffffffu;
@@ -693,102 +919,107 @@ __global__ void __launch_bounds__(GW * 32)
   const int n_inc = static_cast<int>(gc.inc_ptr[r + 1] - ib);
   const int64_t rb = row_ptr[r];
   const int rn = static_cast<int>(row_ptr[r + 1] - rb);
-  const uint32_t gm = lane < n_inc ? gmask[idx * gc.stride + lane] : 0u;
+  // ---- phase 1
+  int64_t c = -1;
+  unsigned fl = 0, fp = 0, Mn = 0;
+  if (lane < n_inc)
+  {
+    c = gc.inc_cell[ib + lane];
+    fp = gc.fperm[ib + lane];
+    fl = gc.cell_flags[c];
+  }
+  const bool contributes = (fl & 0xFDu) != 0;
+  const int li = static_cast<int>(fp & 15u);
+  if (rf & 4)
+  {
+    const uint32_t R = Rrow[idx];
+    if (contributes)
+      for (uint32_t t = gc.fmask[ib + lane]; t; t &= t - 1)
+        Mn |= 1u << __popc(R & ((1u << (__ffs(t) - 1)) - 1u));
+  }
+  else if (contributes)
+    Mn = gmask[idx * gc.stride + lane];
+  if (contributes)
+  {
+    double v[ND];
+    cell_row_values<TDIM, DEG>(gc, st, c, fl, li, v);
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+      s_v[w][lane][(fp >> (4 + 4 * j)) & 15u] = v[j];
+  }
+  __syncwarp();
+  // ---- phase 2
   const bool have_col = lane < rn;
   double acc = (have_col && !zero_first) ? vals[rb + lane] : 0.0;
   const uint32_t below = (1u << lane) - 1u;
-  const double* __restrict__ rowbase = gc.Ae + idx * gc.stride * ND;
-  // batches of 8 cells: all (predicated) loads of a batch are issued before the first add; the adds
-  // keep the ascending-cell order (x + 0.0 == x)
   for (int l0 = 0; l0 < n_inc; l0 += 8)
   {
-    double v[8];
+    double t[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u)
     {
       const int l = (l0 + u) & 31;
-      const uint32_t M = __shfl_sync(full, gm, l);
-      v[u] = ((M >> lane) & 1u) ? __ldg(rowbase + l * ND + __popc(M & below)) : 0.0;
+      const uint32_t M = __shfl_sync(full, Mn, l);
+      t[u] = ((M >> lane) & 1u) ? s_v[w][l][__popc(M & below)] : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u)
-      acc += v[u];
+      acc += t[u]; // ascending-cell order (x + 0.0 == x)
   }
   if (rf & 2)
-  { // interior-facet macro rows of the band cells (rare): column matched by value
+  {
     const int32_t mycol = have_col ? cols[rb + lane] : -2;
-    int64_t c = -1;
-    uint8_t fl = 0;
-    int li = 0;
-    if (lane < n_inc)
-    {
-      c = gc.inc_cell[ib + lane];
-      fl = gc.cell_flags[c];
-    }
-    if (fl & 2)
-    {
-#pragma unroll
-      for (int j = 0; j < ND; ++j)
-        li = (gc.dofmap[c * ND + j] == r) ? j : li;
-    }
-    unsigned band = __ballot_sync(full, (fl & 2) != 0);
-    while (band)
-    {
-      const int l = __ffs(band) - 1;
-      band &= band - 1;
-      const int64_t cl = __shfl_sync(full, c, l);
-      const int lil = __shfl_sync(full, li, l);
-      for (int lf = 0; lf < gc.nf; ++lf)
-      {
-        const int64_t fs = gc.facet_slot[gc.c2f[cl * gc.nf + lf]];
-        if (fs < 0)
-          continue;
-        const int64_t c0 = gc.rows4[4 * fs], c1 = gc.rows4[4 * fs + 2];
-        const int mrow = (cl == c0 ? 0 : ND) + lil;
-        const double* F = gc.Fe + (fs * 2 * ND + mrow) * 2 * ND;
-#pragma unroll
-        for (int s = 0; s < 2; ++s)
-        {
-          const int64_t cc = s ? c1 : c0;
-#pragma unroll
-          for (int j = 0; j < ND; ++j)
-            if (gc.dofmap[cc * ND + j] == mycol)
-              acc += F[s * ND + j];
-        }
-      }
-    }
+    int expected = 0;
+    add_facet_rows<ND>(gc, s_fd[w], s_fv[w], (fl & 2u) != 0, c, li, mycol, acc, expected, false);
   }
   if (have_col)
     vals[rb + lane] = acc;
 }
 
-// Four rows per warp (8 lanes each).  The owner-major vector storage holds one slot per incident
-// cell (zero where the cell is inactive), so a row is one contiguous read; fixed-order partial sums
-// + fixed shuffle tree -> bit-reproducible.
-template <int ND>
+// One warp per active row: lanes take the incident cells, compute / load the cell's entry for this
+// row, fixed shuffle tree -> bit-reproducible.
+template <int TDIM, int DEG, bool PERM>
 __global__ void __launch_bounds__(GW * 32)
-    gather_vector_kernel(GatherCtx gc, const int32_t* __restrict__ act_rows, int64_t n_act, double* __restrict__ b,
-                         int zero_first)
+    gather_vector_kernel(GatherCtx gc, StdTab st, const int32_t* __restrict__ act_rows, int64_t n_act,
+                         double* __restrict__ b, int zero_first)
 {
-  const int lane = threadIdx.x & 31;
-  const int gl = lane & 7;
-  const int64_t idx = (static_cast<int64_t>(blockIdx.x) * (GW * 32) + threadIdx.x) >> 3;
-  const bool valid = idx < n_act;
+  constexpr int ND = Elem<TDIM, DEG>::ND;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * GW + w;
+  if (idx >= n_act)
+    return;
+  const int64_t r = act_rows[idx];
+  const int64_t ib = gc.inc_ptr[r];
+  const int n_inc = static_cast<int>(gc.inc_ptr[r + 1] - ib);
   double s = 0.0;
-  int64_t r = 0;
-  if (valid)
+  for (int k0 = 0; k0 < n_inc; k0 += 32)
   {
-    r = act_rows[idx];
-    const int n_inc = static_cast<int>(gc.inc_ptr[r + 1] - gc.inc_ptr[r]);
-    const double* __restrict__ base = gc.Ae + idx * gc.stride;
-#pragma unroll 4
-    for (int k = gl; k < n_inc; k += 8)
-      s += base[k];
-  }
+    const int k = k0 + lane;
+    double e = 0.0;
+    if (k < n_inc)
+    {
+      const int64_t c = gc.inc_cell[ib + k];
+      const unsigned fl = gc.cell_flags[c];
+      if (fl & 0xFDu)
+      {
+        int li = 0;
+        if constexpr (PERM)
+          li = static_cast<int>(gc.fperm[ib + k] & 15u);
+        else
+        {
 #pragma unroll
-  for (int o = 4; o > 0; o >>= 1)
-    s += __shfl_down_sync(0xffffffffu, s, o, 8);
-  if (valid && gl == 0)
+          for (int j = 0; j < ND; ++j)
+            li = (gc.dofmap[c * ND + j] == r) ? j : li;
+        }
+        e = cell_entry_value<TDIM, DEG>(gc, st, c, fl, li);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      e += __shfl_down_sync(0xffffffffu, e, o);
+    s += e;
+  }
+  if (lane == 0)
     b[r] = zero_first ? s : b[r] + s;
 }
 
@@ -816,30 +1047,35 @@ __global__ void __launch_bounds__(256) sum_partial_kernel(const double* __restri
 }
 
 // ------------------------------------------------------------------ host dispatch
-template <int TDIM, int DEG, int KID>
-void launch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f)
+int std_rule_order(int kernel, int deg)
 {
+  switch (kernel)
+  {
+  case CFX_K_LAPLACE: return 2 * (deg - 1);
+  case CFX_K_MASS: return 2 * deg;
+  case CFX_K_SOURCE: return deg;
+  default: return 0;
+  }
+}
+
+template <int TDIM, int DEG, int KID>
+void launch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t& base)
+{
+  constexpr int RANK = KernelTraits<KID>::RANK;
   RuleView rv{};
   StdRule sr{};
   Consts cs;
   for (int k = 0; k < CFX_MAX_CONSTANTS; ++k)
     cs.c[k] = I.constants[k];
-  const Space& S = c->spaces[f->space];
-  OutCtx oc{S.dofmap, f->prep->row_slot.p, S.cell_inc_l.p, f->prep->cell_slot.p, f->Ae.p, f->written.p, S.stride};
-  if (I.n > 0)
-  {
-    int order = 0;
-    switch (KID)
-    {
-    case CFX_K_LAPLACE: order = 2 * (DEG - 1); break;
-    case CFX_K_MASS: order = 2 * DEG; break;
-    case CFX_K_SOURCE: order = DEG; break;
-    default: order = 0;
-    }
-    RuleTable& rt = get_rule(c, TDIM, order);
+  OutCtx oc{c->mat_slot.p, f->Ae.p, base};
+  if (RANK == 0 && I.n > 0)
+  { // only functionals materialise their standard entities (one value each)
+    RuleTable& rt = get_rule(c, TDIM, std_rule_order(KID, DEG));
     sr = StdRule{rt.d_pts, rt.d_wts, rt.npts};
     auto k = cell_kernel<TDIM, DEG, KID, false>;
     CFX_LAUNCH(c, k, grid_for(I.n, EB), EB, 0, I.entities, I.n, rv, sr, cs, c->x, c->x_dofmap, oc);
+    base += I.n;
+    oc.base = base;
   }
   if (I.rules && I.rules->nrules > 0)
   {
@@ -849,49 +1085,89 @@ void launch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f)
                   R->npts};
     auto k = cell_kernel<TDIM, DEG, KID, true>;
     CFX_LAUNCH(c, k, grid_for(R->nrules, EB), EB, 0, nullptr, R->nrules, rv, sr, cs, c->x, c->x_dofmap, oc);
+    base += R->nrules;
   }
 }
 
 template <int TDIM, int DEG>
-void dispatch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f)
+void dispatch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t& base)
 {
   switch (I.kernel)
   {
-  case CFX_K_LAPLACE: launch_cell<TDIM, DEG, CFX_K_LAPLACE>(c, I, f); break;
-  case CFX_K_MASS: launch_cell<TDIM, DEG, CFX_K_MASS>(c, I, f); break;
-  case CFX_K_NITSCHE: launch_cell<TDIM, DEG, CFX_K_NITSCHE>(c, I, f); break;
-  case CFX_K_SOURCE: launch_cell<TDIM, DEG, CFX_K_SOURCE>(c, I, f); break;
-  case CFX_K_NITSCHE_RHS: launch_cell<TDIM, DEG, CFX_K_NITSCHE_RHS>(c, I, f); break;
-  case CFX_K_ONE: launch_cell<TDIM, DEG, CFX_K_ONE>(c, I, f); break;
+  case CFX_K_LAPLACE: launch_cell<TDIM, DEG, CFX_K_LAPLACE>(c, I, f, base); break;
+  case CFX_K_MASS: launch_cell<TDIM, DEG, CFX_K_MASS>(c, I, f, base); break;
+  case CFX_K_NITSCHE: launch_cell<TDIM, DEG, CFX_K_NITSCHE>(c, I, f, base); break;
+  case CFX_K_SOURCE: launch_cell<TDIM, DEG, CFX_K_SOURCE>(c, I, f, base); break;
+  case CFX_K_NITSCHE_RHS: launch_cell<TDIM, DEG, CFX_K_NITSCHE_RHS>(c, I, f, base); break;
+  case CFX_K_ONE: launch_cell<TDIM, DEG, CFX_K_ONE>(c, I, f, base); break;
   default: throw Error(CFX_ERR_UNSUPPORTED, "unknown cell kernel family");
   }
 }
 
-void run_cell_integrals(cfx_ctx* c, cfx_form* f, int esize)
+// materialise the run-time-rule tensors (ranks 1, 2) / all entity values (rank 0); returns the
+// number of slots used
+int64_t run_cell_integrals(cfx_ctx* c, cfx_form* f)
 {
   const Space& S = c->spaces[f->space];
-  // owner-major storage: (active rows, stride, ND) for matrices, (active rows, stride) for vectors
-  const size_t n_out = f->rank == 0 ? static_cast<size_t>(f->prep->n_active)
-                                    : static_cast<size_t>(f->prep->n_act_rows) * S.stride * (f->rank == 2 ? S.nd : 1);
-  (void)esize;
-  f->Ae.reserve(c->pool, n_out + 4);
-  if (f->rank == 1) // the vector gather sums every slot of a row: slots of inactive cells must read 0
-    CFX_CUDA(cudaMemsetAsync(f->Ae.p, 0, (n_out + 4) * sizeof(double), c->stream));
-  f->written.reserve(c->pool, static_cast<size_t>(f->prep->n_active) + 1);
-  CFX_CUDA(cudaMemsetAsync(f->written.p, 0, static_cast<size_t>(f->prep->n_active) + 1, c->stream));
+  const int es = f->rank == 2 ? S.nd * S.nd : (f->rank == 1 ? S.nd : 1);
+  int64_t cap = 0;
+  for (auto& I : f->integrals)
+  {
+    if (I.facet)
+      continue;
+    if (f->rank == 0)
+      cap += I.n;
+    if (I.rules)
+      cap += I.rules->nrules;
+  }
+  f->Ae.reserve(c->pool, static_cast<size_t>(cap) * es + 4);
+  int64_t base = 0;
   for (auto& I : f->integrals)
   {
     if (I.facet)
       continue;
     if (c->tdim == 2 && S.degree == 1)
-      dispatch_cell<2, 1>(c, I, f);
+      dispatch_cell<2, 1>(c, I, f, base);
     else if (c->tdim == 2)
-      dispatch_cell<2, 2>(c, I, f);
+      dispatch_cell<2, 2>(c, I, f, base);
     else if (S.degree == 1)
-      dispatch_cell<3, 1>(c, I, f);
+      dispatch_cell<3, 1>(c, I, f, base);
     else
-      dispatch_cell<3, 2>(c, I, f);
+      dispatch_cell<3, 2>(c, I, f, base);
   }
+  return base;
+}
+
+void reset_slots(cfx_ctx* c, cfx_form* f)
+{
+  for (auto& I : f->integrals)
+    if (!I.facet && I.rules && I.rules->nrules > 0)
+      CFX_LAUNCH(c, reset_slots_kernel, grid_for(I.rules->nrules, 256), 256, 0, I.rules->parent_map.p, I.rules->nrules,
+                 c->mat_slot.p);
+}
+
+StdTab make_std_tab(cfx_ctx* c, cfx_form* f)
+{
+  const Space& S = c->spaces[f->space];
+  StdTab st{};
+  for (auto& I : f->integrals)
+  {
+    if (I.facet || I.n == 0)
+      continue;
+    CFX_REQUIRE(st.n < CFX_MAX_STD_LISTS, CFX_ERR_UNSUPPORTED, "too many standard cell integrals in one form");
+    const bool ok = f->rank == 2 ? (I.kernel == CFX_K_LAPLACE || I.kernel == CFX_K_MASS) : I.kernel == CFX_K_SOURCE;
+    CFX_REQUIRE(ok, CFX_ERR_UNSUPPORTED, "kernel family has no standard-quadrature cell variant");
+    RuleTable& rt = get_rule(c, c->tdim, std_rule_order(I.kernel, S.degree));
+    const int k = st.n++;
+    st.kernel[k] = I.kernel;
+    st.bit[k] = std_list_bit(f->prep, I.entities, I.n);
+    st.c[k][0] = I.constants[0];
+    st.c[k][1] = I.constants[1];
+    st.pts[k] = rt.d_pts;
+    st.wts[k] = rt.d_wts;
+    st.npts[k] = rt.npts;
+  }
+  return st;
 }
 
 template <int TDIM, int DEG>
@@ -904,17 +1180,123 @@ void launch_facet(cfx_ctx* c, const cfx_integral& I, cfx_form* f, bool accumulat
   for (int k = 0; k < CFX_MAX_CONSTANTS; ++k)
     cs.c[k] = I.constants[k];
   auto k = facet_kernel<TDIM, DEG>;
-  CFX_LAUNCH(c, k, grid_for(I.n * 2 * ND, EB), EB, 0, I.entities, I.n, fr, cs, c->x, c->x_dofmap, f->Fe.p, accumulate);
+  CFX_LAUNCH(c, k, grid_for(I.n * 2 * ND, EB), EB, 0, I.entities, I.n, fr, cs, c->x, c->x_dofmap, c->geo.p, f->Fe.p,
+             accumulate);
 }
 
 GatherCtx make_gather_ctx(cfx_ctx* c, cfx_form* f, const cfx_integral* FI)
 {
   const Space& S = c->spaces[f->space];
-  return GatherCtx{S.inc_ptr.p, S.inc_cell.p,    S.dofmap,           f->prep->cell_flags.p,        f->prep->row_flag.p,
-                   f->prep->cell_slot.p, f->Ae.p,       c->c2f,             c->facet_slot.p,        FI ? FI->entities : nullptr,
-                   f->Fe.p,        c->tdim + 1, S.stride};
+  GatherCtx g{};
+  g.inc_ptr = S.inc_ptr.p;
+  g.inc_cell = S.inc_cell.p;
+  g.fperm = S.fperm.p;
+  g.fmask = S.fmask.p;
+  g.dofmap = S.dofmap;
+  g.cell_flags = f->prep->cell_flags.p;
+  g.mat_slot = c->mat_slot.p;
+  g.Ae = f->Ae.p;
+  g.geo = c->geo.p;
+  g.c2f = c->c2f;
+  g.facet_slot = c->facet_slot.p;
+  g.rows4 = FI ? FI->entities : nullptr;
+  g.Fe = f->Fe.p;
+  g.nf = c->tdim + 1;
+  g.stride = S.stride;
+  return g;
+}
+
+template <int TDIM, int DEG>
+void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const GatherCtx& gc, const StdTab& st,
+                          int zero_first)
+{
+  const Space& S = ctx->spaces[a->space];
+  cfx_prepared* PR = a->prep;
+  if (PR->n_act_rows == 0)
+    return;
+  // the gather tables are valid only for the pattern that was built from this very form
+  const bool fast = a->gtab_serial == A->serial && a->gtab_serial > 0 && S.has_perm;
+  const unsigned g = grid_for(PR->n_act_rows, GW);
+  if (fast)
+  {
+    auto kf = gather_matrix_fast_kernel<TDIM, DEG>;
+    CFX_LAUNCH(ctx, kf, g, GW * 32, 0, gc, st, PR->act_rows.p, PR->n_act_rows, a->row_fast.p, a->gmask.p, a->Rrow.p,
+               A->row_ptr.p, A->cols.p, A->values.p, zero_first);
+  }
+  if (!fast || a->n_slow_rows > 0)
+  {
+    auto k = gather_matrix_kernel<TDIM, DEG>;
+    CFX_LAUNCH(ctx, k, g, GW * 32, 0, gc, st, PR->act_rows.p, PR->n_act_rows, fast ? a->row_fast.p : nullptr,
+               A->row_ptr.p, A->cols.p, A->values.p, zero_first, ctx->err_flag.p);
+  }
+}
+
+template <int TDIM, int DEG>
+void launch_gather_vector(cfx_ctx* ctx, cfx_form* L, const GatherCtx& gc, const StdTab& st, double* d_b,
+                          int zero_first)
+{
+  const Space& S = ctx->spaces[L->space];
+  cfx_prepared* PR = L->prep;
+  if (PR->n_act_rows == 0)
+    return;
+  const unsigned g = grid_for(PR->n_act_rows, GW);
+  if (S.has_perm)
+  {
+    auto k = gather_vector_kernel<TDIM, DEG, true>;
+    CFX_LAUNCH(ctx, k, g, GW * 32, 0, gc, st, PR->act_rows.p, PR->n_act_rows, d_b, zero_first);
+  }
+  else
+  {
+    auto k = gather_vector_kernel<TDIM, DEG, false>;
+    CFX_LAUNCH(ctx, k, g, GW * 32, 0, gc, st, PR->act_rows.p, PR->n_act_rows, d_b, zero_first);
+  }
+}
+
+#define CFX_DISPATCH_ELEM(ctx, S, FN, ...)                                                                             \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    if ((ctx)->tdim == 2 && (S).degree == 1)                                                                           \
+      FN<2, 1>(__VA_ARGS__);                                                                                           \
+    else if ((ctx)->tdim == 2)                                                                                         \
+      FN<2, 2>(__VA_ARGS__);                                                                                           \
+    else if ((S).degree == 1)                                                                                          \
+      FN<3, 1>(__VA_ARGS__);                                                                                           \
+    else                                                                                                               \
+      FN<3, 2>(__VA_ARGS__);                                                                                           \
+  } while (0)
+template <int TDIM>
+__global__ void __launch_bounds__(256) geo_cache_kernel(const double* __restrict__ x, const int32_t* __restrict__ x_dofmap,
+                                                        int64_t n, double* __restrict__ geo)
+{
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (c >= n)
+    return;
+  double X[TDIM + 1][TDIM];
+  load_cell_coords<TDIM>(x, x_dofmap, c, X);
+  Geo<TDIM> g;
+  make_geo<TDIM>(X, g);
+  double* o = geo + c * GeoRec<TDIM>::STRIDE;
+#pragma unroll
+  for (int i = 0; i < TDIM * TDIM; ++i)
+    o[i] = g.K[i];
+  o[TDIM * TDIM] = g.detJ;
+  o[TDIM * TDIM + 1] = cell_diameter<TDIM>(X);
+#pragma unroll
+  for (int i = TDIM * TDIM + 2; i < GeoRec<TDIM>::STRIDE; ++i)
+    o[i] = 0.0;
 }
 } // namespace
+
+// K = J^-1, detJ and the cell diameter of every local cell: static while the mesh is bound
+void build_geometry_cache(cfx_ctx* c)
+{
+  const int stride = c->tdim == 3 ? GeoRec<3>::STRIDE : GeoRec<2>::STRIDE;
+  c->geo.reserve(c->pool, static_cast<size_t>(c->nc_total) * stride + 4);
+  if (c->tdim == 3)
+    CFX_LAUNCH(c, geo_cache_kernel<3>, grid_for(c->nc_total, 256), 256, 0, c->x, c->x_dofmap, c->nc_total, c->geo.p);
+  else
+    CFX_LAUNCH(c, geo_cache_kernel<2>, grid_for(c->nc_total, 256), 256, 0, c->x, c->x_dofmap, c->nc_total, c->geo.p);
+}
 } // namespace cfx
 
 using namespace cfx;
@@ -933,10 +1315,19 @@ cfx_status cfx_assemble_matrix(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
   prepare_form(ctx, a);
   const cfx_integral* FI = facet_integral_domain(a);
   const int nd = S.nd;
+  int64_t n_mat = 0, n_std = 0;
+  for (auto& I : a->integrals)
+    if (!I.facet)
+      n_std += I.n;
   {
     StageScope st(ctx, "element_cells");
-    run_cell_integrals(ctx, a, nd * nd);
-    st.set_bytes(static_cast<double>(a->prep->n_active) * (4.0 * ctx->nv + 8.0 * nd * nd));
+    n_mat = run_cell_integrals(ctx, a);
+    double by = 0.0;
+    for (auto& I : a->integrals)
+      if (!I.facet && I.rules)
+        by += 8.0 * (ctx->tdim + 1 + (I.rules->has_normals ? ctx->tdim : 0)) * static_cast<double>(I.rules->npts)
+              + (8.0 + 28.0 * ctx->nv + 8.0 * nd * nd) * static_cast<double>(I.rules->nrules);
+    st.set_bytes(by);
   }
   if (FI)
   {
@@ -947,48 +1338,26 @@ cfx_status cfx_assemble_matrix(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
     {
       if (!I.facet || I.n == 0)
         continue;
-      if (ctx->tdim == 2 && S.degree == 1)
-        launch_facet<2, 1>(ctx, I, a, acc);
-      else if (ctx->tdim == 2)
-        launch_facet<2, 2>(ctx, I, a, acc);
-      else if (S.degree == 1)
-        launch_facet<3, 1>(ctx, I, a, acc);
-      else
-        launch_facet<3, 2>(ctx, I, a, acc);
+      CFX_DISPATCH_ELEM(ctx, S, launch_facet, ctx, I, a, acc);
       acc = true;
     }
   }
   {
+    // fused K4 (standard cells: dofmap row + coordinates + dofs in) + K5 (each CSR value and column once)
     StageScope st(ctx, "gather_matrix",
-                  12.0 * static_cast<double>(A->nnz) + 8.0 * nd * nd * static_cast<double>(a->prep->n_active));
+                  12.0 * static_cast<double>(A->nnz) + (28.0 * ctx->nv + 4.0 * nd) * static_cast<double>(n_std)
+                      + 8.0 * nd * nd * static_cast<double>(n_mat));
     set_facet_slots(ctx, FI, false);
     GatherCtx gc = make_gather_ctx(ctx, a, FI);
+    const StdTab stt = make_std_tab(ctx, a);
     if (zero_first)
       CFX_CUDA(cudaMemsetAsync(A->values.p, 0, static_cast<size_t>(A->nnz) * sizeof(double), ctx->stream));
     if (diag_inactive != 0.0)
       CFX_LAUNCH(ctx, inactive_diag_kernel, grid_for(A->n_rows, 256), 256, 0, a->prep->row_flag.p, A->n_rows, A->row_ptr.p,
                  A->cols.p, A->values.p, diag_inactive);
-    auto k = nd == 3 ? gather_matrix_kernel<3>
-             : nd == 4 ? gather_matrix_kernel<4>
-             : nd == 6 ? gather_matrix_kernel<6>
-                       : gather_matrix_kernel<10>;
-    auto kf = nd == 3 ? gather_matrix_fast_kernel<3>
-              : nd == 4 ? gather_matrix_fast_kernel<4>
-              : nd == 6 ? gather_matrix_fast_kernel<6>
-                        : gather_matrix_fast_kernel<10>;
-    // the gather table is valid only for the pattern that was built from this very form
-    const bool fast = a->gtab_serial == A->serial && a->gtab_serial > 0;
-    if (a->prep->n_act_rows > 0)
-    {
-      const unsigned g = grid_for(a->prep->n_act_rows, GW);
-      if (fast)
-        CFX_LAUNCH(ctx, kf, g, GW * 32, 0, gc, a->prep->act_rows.p, a->prep->n_act_rows, a->row_fast.p, a->gmask.p, A->row_ptr.p,
-                   A->cols.p, A->values.p, zero_first);
-      if (!fast || a->n_slow_rows > 0)
-        CFX_LAUNCH(ctx, k, g, GW * 32, 0, gc, a->prep->act_rows.p, a->prep->n_act_rows, fast ? a->row_fast.p : nullptr,
-                   A->row_ptr.p, A->cols.p, A->values.p, zero_first, ctx->err_flag.p);
-    }
+    CFX_DISPATCH_ELEM(ctx, S, launch_gather_matrix, ctx, a, A, gc, stt, zero_first);
     set_facet_slots(ctx, FI, true);
+    reset_slots(ctx, a);
   }
   if (values_out)
     export_to(ctx, values_out, A->values.p, static_cast<size_t>(A->nnz), memspace);
@@ -1004,10 +1373,19 @@ cfx_status cfx_assemble_vector(cfx_ctx* ctx, const cfx_form* L_const, double* b,
   CFX_REQUIRE(L->rank == 1, CFX_ERR_INVALID, "cfx_assemble_vector: form is not linear");
   const Space& S = ctx->spaces[L->space];
   prepare_form(ctx, L);
+  int64_t n_mat = 0, n_std = 0;
+  for (auto& I : L->integrals)
+    if (!I.facet)
+      n_std += I.n;
   {
     StageScope st(ctx, "element_cells_vector");
-    run_cell_integrals(ctx, L, S.nd);
-    st.set_bytes(static_cast<double>(L->prep->n_active) * (4.0 * ctx->nv + 8.0 * S.nd));
+    n_mat = run_cell_integrals(ctx, L);
+    double by = 0.0;
+    for (auto& I : L->integrals)
+      if (!I.facet && I.rules)
+        by += 8.0 * (ctx->tdim + 1 + (I.rules->has_normals ? ctx->tdim : 0)) * static_cast<double>(I.rules->npts)
+              + (8.0 + 28.0 * ctx->nv + 8.0 * S.nd) * static_cast<double>(I.rules->nrules);
+    st.set_bytes(by);
   }
   DevBuf<double> tmp;
   double* d_b = b;
@@ -1020,17 +1398,15 @@ cfx_status cfx_assemble_vector(cfx_ctx* ctx, const cfx_form* L_const, double* b,
                                ctx->stream));
   }
   {
-    StageScope st(ctx, "gather_vector", 8.0 * static_cast<double>(S.n_total) + 8.0 * S.nd * L->prep->n_active);
+    StageScope st(ctx, "gather_vector",
+                  8.0 * static_cast<double>(S.n_total) + (28.0 * ctx->nv + 4.0 * S.nd) * static_cast<double>(n_std)
+                      + 8.0 * S.nd * static_cast<double>(n_mat));
     GatherCtx gc = make_gather_ctx(ctx, L, nullptr);
-    auto k = S.nd == 3 ? gather_vector_kernel<3>
-             : S.nd == 4 ? gather_vector_kernel<4>
-             : S.nd == 6 ? gather_vector_kernel<6>
-                         : gather_vector_kernel<10>;
+    const StdTab stt = make_std_tab(ctx, L);
     if (zero_first)
       CFX_CUDA(cudaMemsetAsync(d_b, 0, static_cast<size_t>(S.n_total) * sizeof(double), ctx->stream));
-    if (L->prep->n_act_rows > 0)
-      CFX_LAUNCH(ctx, k, grid_for(L->prep->n_act_rows * 8, GW * 32), GW * 32, 0, gc, L->prep->act_rows.p, L->prep->n_act_rows, d_b,
-                 zero_first);
+    CFX_DISPATCH_ELEM(ctx, S, launch_gather_vector, ctx, L, gc, stt, d_b, zero_first);
+    reset_slots(ctx, L);
   }
   if (memspace == CFX_HOST)
   {
@@ -1046,12 +1422,11 @@ cfx_status cfx_assemble_scalar(cfx_ctx* ctx, const cfx_form* M_const, double* ou
   cfx_form* M = const_cast<cfx_form*>(M_const);
   CFX_REQUIRE(ctx && M && out, CFX_ERR_INVALID, "cfx_assemble_scalar: NULL argument");
   CFX_REQUIRE(M->rank == 0, CFX_ERR_INVALID, "cfx_assemble_scalar: form is not a functional");
-  prepare_form(ctx, M);
-  run_cell_integrals(ctx, M, 1);
+  const int64_t n = run_cell_integrals(ctx, M); // one value per entity, entity order
   constexpr int NB = 256;
   DevBuf<double> partial;
   partial.reserve(ctx->pool, NB + 1);
-  CFX_LAUNCH(ctx, sum_partial_kernel, NB, 256, 0, M->Ae.p, M->prep->n_active, partial.p);
+  CFX_LAUNCH(ctx, sum_partial_kernel, NB, 256, 0, M->Ae.p, n, partial.p);
   CFX_LAUNCH(ctx, sum_partial_kernel, 1, 256, 0, partial.p, static_cast<int64_t>(NB), partial.p + NB);
   CFX_CUDA(cudaMemcpyAsync(out, partial.p + NB, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CFX_CUDA(cudaStreamSynchronize(ctx->stream));

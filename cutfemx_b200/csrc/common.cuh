@@ -159,7 +159,10 @@ struct Space
   DevBuf<int32_t> inc_cell;
   int64_t n_inc = 0;
   int stride = 0;               // max number of cells around a dof
-  DevBuf<uint8_t> cell_inc_l;   // (n_cells, nd): position of the cell in the incidence list of its i-th dof
+  // per incidence (nd <= 6): bits 0..3 = local index of the dof in the cell, bits 4+4j.. = rank of
+  // the cell's j-th dof among the cell's dofs (ascending global number)
+  bool has_perm = false;
+  DevBuf<uint32_t> fperm;
   // static full-mesh structure (every cell active), only if all its rows have <= 32 columns:
   bool has_static = false;
   DevBuf<int64_t> frow_ptr;     // full pattern row pointers
@@ -223,20 +226,22 @@ struct cfx_integral
 };
 
 // active cells / rows of a set of integration domains (Form.h:46-89 domains)
+enum { CFX_MAX_STD_LISTS = 6 };
 struct cfx_prepared
 {
   int refs = 0;
   int space = 0;
   int64_t update_serial = 0;
-  std::vector<std::pair<const void*, int64_t>> cell_key; // (entity list, n) and (rules parent_map, nrules)
+  std::vector<std::pair<const void*, int64_t>> std_key;  // distinct standard-quadrature cell lists (bit 2+i)
+  std::vector<std::pair<const void*, int64_t>> rule_key; // distinct (rules parent_map, nrules)
   std::pair<const void*, int64_t> facet_key{nullptr, 0};
-  cfx::DevBuf<uint8_t> cell_flags; // bit0: has a cell tensor, bit1: touches a facet-integral facet
-  cfx::DevBuf<int32_t> cell_slot;  // rank among flagged cells (valid where bit0)
-  cfx::DevBuf<int32_t> active;     // ascending cell ids with bit0 (slot i <-> cell active[i])
-  cfx::DevBuf<uint8_t> row_flag;   // per dof: touched by a flagged cell
+  // bit0: has a materialised (run-time rule) tensor, bit1: touches a facet-integral facet,
+  // bit 2+i: member of standard cell list i (its tensor rows are computed on the fly by the row owner)
+  cfx::DevBuf<uint8_t> cell_flags;
+  cfx::DevBuf<uint8_t> row_flag;   // per dof: bit0 touched by an active cell, bit1 by a facet-band cell
   cfx::DevBuf<int32_t> act_rows;   // ascending dofs with row_flag set
-  cfx::DevBuf<int32_t> row_slot;   // per dof: index into act_rows (valid where row_flag set)
-  int64_t n_active = 0, n_act_rows = 0;
+  int64_t n_act_rows = 0;
+  int64_t n_active_entities = 0;   // sum of the list sizes (for the byte accounting only)
 };
 
 struct cfx_form
@@ -246,14 +251,14 @@ struct cfx_form
   // prepared state (recomputed when dirty); shared between forms with the same cell domains
   bool dirty = true;
   cfx_prepared* prep = nullptr;
-  // gather table of the pattern built from this form (sparsity.cu pattern_rows_kernel)
-  cfx::DevBuf<uint32_t> gmask;  // (n_act_rows, stride): CSR positions of the dofs of incident cell l
-  cfx::DevBuf<uint8_t> row_fast;
+  // gather table of the pattern built from this form (sparsity.cu)
+  cfx::DevBuf<uint32_t> gmask;  // (n_act_rows, stride): CSR positions of the dofs of incident cell l (band rows)
+  cfx::DevBuf<uint32_t> Rrow;   // (n_act_rows): static rows: which full-mesh columns the row keeps
+  cfx::DevBuf<uint8_t> row_fast; // bit0: mask path, bit1: has band cells, bit2: static row
   int64_t n_slow_rows = 0;
   int64_t gtab_serial = -1;
-  cfx::DevBuf<double> Ae;      // rank 2: (n_act_rows, stride, nd) element-tensor rows grouped by matrix row;
-                               // rank 1: (n_act_rows, stride); rank 0: (n_active)
-  cfx::DevBuf<uint8_t> written; // per slot
+  cfx::DevBuf<double> Ae;      // materialised run-time-rule tensors, cell-major (slot, nd^rank) natural order;
+                               // rank 0: one value per entity
   cfx::DevBuf<double> Fe;      // facet macro tensors
 };
 
@@ -292,6 +297,10 @@ struct cfx_ctx
   bool classified = false;
 
   cfx::Space spaces[CFX_MAX_SPACES];
+  cfx::DevBuf<int32_t> mat_slot; // (nc_total): slot of a cell's materialised tensor; -1 between assemblies
+  // static per-cell affine geometry (the mesh does not move between cfx_update calls): K = J^-1
+  // row-major (tdim^2), detJ, cell diameter; record stride 12 doubles (3D, 96 B) / 8 doubles (2D, 64 B)
+  cfx::DevBuf<double> geo;
 
   std::map<std::pair<int, int>, cfx::RuleTable> rules; // (dim, order) -> table (built-in or override)
 
@@ -462,9 +471,11 @@ void classify_all(cfx_ctx* c);                          // classify.cu
 void ensure_cut_list(cfx_ctx* c, int ls);               // classify.cu
 void build_incidence(cfx_ctx* c, Space& s);             // sparsity.cu
 void derive_f2c(cfx_ctx* c);                            // facets.cu
+void build_geometry_cache(cfx_ctx* c);                  // assemble.cu
 void dense_f2c_from_adjacency(cfx_ctx* c, const int32_t* off_dev, const int32_t* data_dev); // facets.cu
 void prepare_form(cfx_ctx* c, cfx_form* f);             // sparsity.cu
 void release_prepared(cfx_ctx* c, cfx_form* f);         // sparsity.cu
+uint8_t std_list_bit(const cfx_prepared* P, const void* entities, int64_t n); // sparsity.cu
 const cfx_integral* facet_integral_domain(const cfx_form* f);          // sparsity.cu
 void set_facet_slots(cfx_ctx* c, const cfx_integral* I, bool clear);   // sparsity.cu
 } // namespace cfx

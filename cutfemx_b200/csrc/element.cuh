@@ -88,6 +88,35 @@ __device__ __forceinline__ void load_cell_coords(const double* __restrict__ x, c
       X[v][r] = __ldg(x + 3 * static_cast<int64_t>(node[v]) + r);
 }
 
+// static geometry cache record (common.cuh cfx_ctx::geo): K row-major, detJ, h
+template <int TDIM>
+struct GeoRec
+{
+  static constexpr int STRIDE = TDIM == 3 ? 12 : 8;
+};
+
+// K and detJ of a cell from the cache (J and x0 are not filled).  Records are 32-byte aligned:
+// 256-bit loads (one L1 wavefront per 32 B sector instead of two)
+template <int TDIM>
+__device__ __forceinline__ void load_geo_cached(const double* __restrict__ geo, int64_t cell, Geo<TDIM>& g)
+{
+  const double* p = geo + cell * GeoRec<TDIM>::STRIDE;
+  double a0, a1, a2, a3, b0, b1, b2, b3;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3) : "l"(p));
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(b0), "=d"(b1), "=d"(b2), "=d"(b3) : "l"(p + 4));
+  if constexpr (TDIM == 3)
+  {
+    double c0, c1, c2, c3;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(c0), "=d"(c1), "=d"(c2), "=d"(c3) : "l"(p + 8));
+    g.K[0] = a0; g.K[1] = a1; g.K[2] = a2; g.K[3] = a3; g.K[4] = b0;
+    g.K[5] = b1; g.K[6] = b2; g.K[7] = b3; g.K[8] = c0; g.detJ = c1;
+  }
+  else
+  {
+    g.K[0] = a0; g.K[1] = a1; g.K[2] = a2; g.K[3] = a3; g.detJ = b0;
+  }
+}
+
 // UFL CellDiameter: largest vertex-to-vertex distance
 template <int TDIM>
 __device__ __forceinline__ double cell_diameter(const double (&X)[TDIM + 1][TDIM])

@@ -82,10 +82,10 @@ __global__ void max_degree_kernel(const int64_t* __restrict__ inc_ptr, int64_t n
     atomicMax(out, v);
 }
 
-// cell_inc_l[c*nd + i] = position of cell c in the (sorted) incidence list of its i-th dof
-__global__ void cell_inc_l_kernel(int64_t n_dofs, const int64_t* __restrict__ inc_ptr,
-                                  const int32_t* __restrict__ inc_cell, const int32_t* __restrict__ dofmap, int nd,
-                                  uint8_t* __restrict__ cell_inc_l)
+// fperm[k] for incidence k = (dof d, cell c): bits 0..3 local index of d in c, bits 4+4j.. rank of
+// the cell's j-th dof among the cell's dofs (ascending).  Static per space, nd <= 6.
+__global__ void fperm_kernel(int64_t n_dofs, const int64_t* __restrict__ inc_ptr, const int32_t* __restrict__ inc_cell,
+                             const int32_t* __restrict__ dofmap, int nd, uint32_t* __restrict__ fperm)
 {
   const int64_t d = static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x;
   if (d >= n_dofs)
@@ -94,45 +94,44 @@ __global__ void cell_inc_l_kernel(int64_t n_dofs, const int64_t* __restrict__ in
   for (int64_t k = b; k < e; ++k)
   {
     const int64_t c = inc_cell[k];
+    int32_t dd[6];
     for (int i = 0; i < nd; ++i)
-      if (dofmap[c * nd + i] == d)
-        cell_inc_l[c * nd + i] = static_cast<uint8_t>(k - b);
+      dd[i] = dofmap[c * nd + i];
+    uint32_t v = 0;
+    for (int i = 0; i < nd; ++i)
+    {
+      if (dd[i] == d)
+        v |= static_cast<uint32_t>(i);
+      uint32_t rk = 0;
+      for (int j = 0; j < nd; ++j)
+        rk += dd[j] < dd[i] ? 1u : 0u;
+      v |= rk << (4 + 4 * i);
+    }
+    fperm[k] = v;
   }
 }
 
-__global__ void or_flag_kernel(const int32_t* __restrict__ idx, int64_t n, int stride, int64_t limit, uint8_t bit,
-                               uint8_t* __restrict__ flags, int32_t* __restrict__ err)
+// One thread per listed cell (cells[i * stride]): set `bit` in the cell's flag byte and store
+// `rowval` in the row flag of each of its dofs.  All writers of one launch store the same values,
+// so the plain byte stores are race-free in effect (idempotent).
+__global__ void mark_cells_kernel(const int32_t* __restrict__ cells, int64_t n, int stride, int64_t limit, uint8_t bit,
+                                  const int32_t* __restrict__ dofmap, int nd, uint8_t rowval,
+                                  uint8_t* __restrict__ cell_flags, uint8_t* __restrict__ row_flag,
+                                  int32_t* __restrict__ err)
 {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x;
   if (i >= n)
     return;
-  const int32_t c = idx[i * stride];
+  const int32_t c = cells[i * stride];
   if (c < 0 || c >= limit)
   {
     err[0] = 22;
     err[1] = c;
     return;
   }
-  flags[c] |= bit; // every writer of one launch stores the same bit: idempotent
-}
-
-__global__ void scatter_slot_kernel(const int32_t* __restrict__ act, int64_t n, int32_t* __restrict__ slot)
-{
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x;
-  if (i < n)
-    slot[act[i]] = static_cast<int32_t>(i);
-}
-
-// row_flag[dof] = 1 for every dof of the listed cells (cells[i * stride])
-__global__ void row_flag_kernel(const int32_t* __restrict__ cells, int64_t n, int stride,
-                                const int32_t* __restrict__ dofmap, int nd, uint8_t value,
-                                uint8_t* __restrict__ row_flag)
-{
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x;
-  if (i >= n * nd)
-    return;
-  const int64_t c = cells[(i / nd) * stride];
-  row_flag[dofmap[c * nd + (i % nd)]] = value; // all writers of one launch store the same value
+  cell_flags[c] |= bit;
+  for (int j = 0; j < nd; ++j)
+    row_flag[dofmap[static_cast<int64_t>(c) * nd + j]] = rowval;
 }
 
 __global__ void facet_slot_set_kernel(const int32_t* __restrict__ rows4, int64_t n, int nf,
@@ -251,7 +250,7 @@ __global__ void __launch_bounds__(RW * 32)
     {
       const int64_t c = rc.inc_cell[ib + k];
       const uint8_t fl = all_mode ? uint8_t(1) : rc.cell_flags[c];
-      bool own_needed = fl & 1;
+      bool own_needed = (fl & 0xFD) != 0; // has a cell tensor (materialised or on the fly)
       if (fl & 2)
       {
         band = true;
@@ -396,14 +395,15 @@ __global__ void __launch_bounds__(RW * 32)
 }
 
 // Per-step pattern of a row WITHOUT facet-band cells, from the static full-mesh structure: the
-// row's columns are the full-mesh columns whose bit is set in R = OR of the full-row masks of the
-// ACTIVE incident cells; new positions are prefix popcounts.  ~60 instructions per row instead of
-// a sort: one REDUX.OR, a few POPC.  Only meshes whose full rows have <= 32 columns get here.
+// row keeps the full-mesh columns whose bit is set in R = OR of the full-row masks of its ACTIVE
+// incident cells.  Count pass: one warp per row, coalesced inc_cell / fmask reads, one REDUX.OR,
+// one POPC; only R (4 B) and the count are stored -- the columns are expanded after the scan by
+// pattern_static_fill_kernel, and the assembly gather recomputes each cell's CSR positions from
+// (fmask, R) instead of reading a gather table.  Only meshes whose full rows have <= 32 columns.
 __global__ void __launch_bounds__(RW * 32)
-    pattern_static_kernel(RowCtx rc, const int32_t* __restrict__ act_rows, int64_t n_act, int stride,
-                          const int64_t* __restrict__ frow_ptr, const int32_t* __restrict__ fcols,
-                          const uint32_t* __restrict__ fmask, int32_t* __restrict__ row_nnz, int32_t* __restrict__ tmp,
-                          uint32_t* __restrict__ gmask, uint8_t* __restrict__ row_fast)
+    pattern_static_kernel(RowCtx rc, const int32_t* __restrict__ act_rows, int64_t n_act,
+                          const uint32_t* __restrict__ fmask, int32_t* __restrict__ row_nnz,
+                          uint32_t* __restrict__ Rrow, uint8_t* __restrict__ row_fast)
 {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * RW + w;
@@ -412,32 +412,46 @@ __global__ void __launch_bounds__(RW * 32)
   const int64_t r = act_rows[idx];
   if (rc.row_flag[r] & 2)
     return; // band rows: pattern_rows_kernel
-  const unsigned full = 0xffffffffu;
   const int64_t ib = rc.inc_ptr[r];
   const int n_inc = static_cast<int>(rc.inc_ptr[r + 1] - ib);
   uint32_t Ml = 0;
-  if (lane < n_inc && (rc.cell_flags[rc.inc_cell[ib + lane]] & 1))
+  if (lane < n_inc && (rc.cell_flags[rc.inc_cell[ib + lane]] & 0xFD))
     Ml = fmask[ib + lane];
-  const uint32_t R = __reduce_or_sync(full, Ml);
-  uint32_t Mn = 0;
-  for (uint32_t t = Ml; t; t &= t - 1)
-  {
-    const int p = __ffs(t) - 1;
-    Mn |= 1u << __popc(R & ((1u << p) - 1u));
-  }
-  if (lane < n_inc)
-    gmask[idx * stride + lane] = Mn;
-  if ((R >> lane) & 1u)
-    tmp[idx * 32 + __popc(R & ((1u << lane) - 1u))] = fcols[frow_ptr[r] + lane];
+  const uint32_t R = __reduce_or_sync(0xffffffffu, Ml);
   if (lane == 0)
   {
     row_nnz[r] = __popc(R);
-    row_fast[idx] = 1;
+    Rrow[idx] = R;
+    row_fast[idx] = 1 | 4;
   }
 }
 
-// fast rows: columns were staged in tmp during the count pass.  One warp moves 32 rows: the
-// per-row scalars are loaded once, lane-parallel, then every row is one coalesced copy.
+// static rows after the scan: cols[row_ptr[r] + k] = k-th kept full-mesh column.  16 lanes per row.
+__global__ void __launch_bounds__(256)
+    pattern_static_fill_kernel(const int32_t* __restrict__ act_rows, int64_t n_act,
+                               const uint8_t* __restrict__ row_fast, const uint32_t* __restrict__ Rrow,
+                               const int64_t* __restrict__ frow_ptr, const int32_t* __restrict__ fcols,
+                               const int64_t* __restrict__ row_ptr, int32_t* __restrict__ cols)
+{
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t idx = t >> 4;
+  const int sl = static_cast<int>(t & 15);
+  if (idx >= n_act || !(row_fast[idx] & 4))
+    return;
+  const int64_t r = act_rows[idx];
+  const uint32_t R = Rrow[idx];
+  const int64_t fb = frow_ptr[r], ob = row_ptr[r];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+  {
+    const int bit = sl + 16 * h;
+    if ((R >> bit) & 1u)
+      cols[ob + __popc(R & ((1u << bit) - 1u))] = fcols[fb + bit];
+  }
+}
+
+// fast NON-static rows: columns were staged in tmp during the count pass.  One warp moves 32 rows:
+// the per-row scalars are loaded once, lane-parallel, then every row is one coalesced copy.
 __global__ void __launch_bounds__(256)
     pattern_copy_kernel(const int32_t* __restrict__ act_rows, int64_t n_act, const uint8_t* __restrict__ row_fast,
                         const int32_t* __restrict__ tmp, const int64_t* __restrict__ row_ptr,
@@ -450,12 +464,14 @@ __global__ void __launch_bounds__(256)
   const int64_t idx = idx0 + lane;
   int64_t b = 0;
   int n = 0;
-  if (idx < n_act && (!row_fast || (row_fast[idx] & 1)))
+  if (idx < n_act && (!row_fast || (row_fast[idx] & 5) == 1))
   {
     const int64_t r = act_rows ? act_rows[idx] : idx;
     b = row_ptr[r];
     n = static_cast<int>(row_ptr[r + 1] - b);
   }
+  if (__ballot_sync(0xffffffffu, n > 0) == 0)
+    return;
 #pragma unroll 4
   for (int i = 0; i < 32; ++i)
   {
@@ -556,9 +572,13 @@ void build_incidence(cfx_ctx* c, Space& S)
   S.stride = static_cast<int>(read_back(c, c->scratch64.p + 2, 1)[0] & 0xffffffffLL);
   CFX_REQUIRE(S.stride >= 1 && S.stride <= 255, CFX_ERR_UNSUPPORTED,
               "cfx_space_bind: a dof with more than 255 (or no) incident cells is not supported");
-  S.cell_inc_l.reserve(c->pool, static_cast<size_t>(n_entries) + 16);
-  CFX_LAUNCH(c, cell_inc_l_kernel, grid_for(S.n_total, SBK), SBK, 0, S.n_total, S.inc_ptr.p, S.inc_cell.p, S.dofmap,
-             S.nd, S.cell_inc_l.p);
+  S.has_perm = S.nd <= 6;
+  if (S.has_perm)
+  {
+    S.fperm.reserve(c->pool, static_cast<size_t>(n_entries) + 16);
+    CFX_LAUNCH(c, fperm_kernel, grid_for(S.n_total, SBK), SBK, 0, S.n_total, S.inc_ptr.p, S.inc_cell.p, S.dofmap, S.nd,
+               S.fperm.p);
+  }
   deg.release();
   build_static_structure(c, S);
 }
@@ -576,24 +596,21 @@ void release_prepared(cfx_ctx* c, cfx_form* f)
       break;
     }
   p->cell_flags.release();
-  p->cell_slot.release();
-  p->active.release();
   p->row_flag.release();
   p->act_rows.release();
-  p->row_slot.release();
   delete p;
 }
 
-// cell_flags / cell_slot / active list / row flags of a form (Form.h:46-89 domains).  Forms over
-// the same cell domains (the bilinear and the linear form of one problem) share the result; a form
-// without facet integrals may also reuse the prepared domain of one with them (a superset of rows).
+// cell flags / row flags / active rows of a form (Form.h:46-89 domains).  Forms over the same
+// cell domains (the bilinear and the linear form of one problem) share the result; a form without
+// facet integrals may also reuse the prepared domain of one with them (a superset of rows).
 void prepare_form(cfx_ctx* c, cfx_form* f)
 {
   if (!f->dirty && f->prep)
     return;
   release_prepared(c, f);
   Space& S = c->spaces[f->space];
-  std::vector<std::pair<const void*, int64_t>> key;
+  std::vector<std::pair<const void*, int64_t>> skey, rkey;
   std::pair<const void*, int64_t> fkey{nullptr, 0};
   for (auto& I : f->integrals)
   {
@@ -604,14 +621,19 @@ void prepare_form(cfx_ctx* c, cfx_form* f)
       continue;
     }
     if (I.n > 0)
-      key.emplace_back(I.entities, I.n);
+      skey.emplace_back(I.entities, I.n);
     if (I.rules && I.rules->nrules > 0)
-      key.emplace_back(I.rules->parent_map.p, I.rules->nrules);
+      rkey.emplace_back(I.rules->parent_map.p, I.rules->nrules);
   }
-  std::sort(key.begin(), key.end());
-  key.erase(std::unique(key.begin(), key.end()), key.end());
+  for (auto* k : {&skey, &rkey})
+  {
+    std::sort(k->begin(), k->end());
+    k->erase(std::unique(k->begin(), k->end()), k->end());
+  }
+  CFX_REQUIRE(static_cast<int>(skey.size()) <= CFX_MAX_STD_LISTS, CFX_ERR_UNSUPPORTED,
+              "a form may use at most 6 distinct standard-quadrature cell lists");
   for (cfx_prepared* p : c->preps)
-    if (p->space == f->space && p->update_serial == c->update_serial && p->cell_key == key
+    if (p->space == f->space && p->update_serial == c->update_serial && p->std_key == skey && p->rule_key == rkey
         && (p->facet_key == fkey || fkey.first == nullptr))
     {
       f->prep = p;
@@ -624,67 +646,56 @@ void prepare_form(cfx_ctx* c, cfx_form* f)
   P->refs = 1;
   P->space = f->space;
   P->update_serial = c->update_serial;
-  P->cell_key = key;
+  P->std_key = skey;
+  P->rule_key = rkey;
   P->facet_key = fkey;
   c->preps.push_back(P);
   f->prep = P;
-  StageScope st(c, "prepare_form", 6.0 * static_cast<double>(c->nc_total));
+  StageScope st(c, "prepare_form");
   P->cell_flags.reserve(c->pool, static_cast<size_t>(c->nc_total) + 16);
   CFX_CUDA(cudaMemsetAsync(P->cell_flags.p, 0, static_cast<size_t>(c->nc_total) + 16, c->stream));
-  for (auto& I : f->integrals)
-  {
-    if (I.facet)
-      continue;
-    if (I.n > 0)
-      CFX_LAUNCH(c, or_flag_kernel, grid_for(I.n, SBK), SBK, 0, I.entities, I.n, 1, c->nc_total, uint8_t(1),
-                 P->cell_flags.p, c->err_flag.p);
-    if (I.rules && I.rules->nrules > 0)
-      CFX_LAUNCH(c, or_flag_kernel, grid_for(I.rules->nrules, SBK), SBK, 0, I.rules->parent_map.p, I.rules->nrules, 1,
-                 c->nc_total, uint8_t(1), P->cell_flags.p, c->err_flag.p);
-  }
-  // active list + slots (before the facet bit is added, so the predicate is just "byte != 0")
-  {
-    FlagPred p{P->cell_flags.p};
-    P->n_active = compact_indices(c, c->nc_total, p, P->active);
-  }
-  P->cell_slot.reserve(c->pool, static_cast<size_t>(c->nc_total) + 1);
-  if (P->n_active > 0)
-    CFX_LAUNCH(c, scatter_slot_kernel, grid_for(P->n_active, SBK), SBK, 0, P->active.p, P->n_active, P->cell_slot.p);
-  for (auto& I : f->integrals)
-  {
-    if (!I.facet || I.n == 0)
-      continue;
-    CFX_LAUNCH(c, or_flag_kernel, grid_for(I.n, SBK), SBK, 0, I.entities, I.n, 4, c->nc_total, uint8_t(2),
-               P->cell_flags.p, c->err_flag.p);
-    CFX_LAUNCH(c, or_flag_kernel, grid_for(I.n, SBK), SBK, 0, I.entities + 2, I.n, 4, c->nc_total, uint8_t(2),
-               P->cell_flags.p, c->err_flag.p);
-  }
   P->row_flag.reserve(c->pool, static_cast<size_t>(S.n_total) + 16);
   CFX_CUDA(cudaMemsetAsync(P->row_flag.p, 0, static_cast<size_t>(S.n_total) + 16, c->stream));
-  if (P->n_active > 0)
-    CFX_LAUNCH(c, row_flag_kernel, grid_for(P->n_active * S.nd, SBK), SBK, 0, P->active.p, P->n_active, 1, S.dofmap,
-               S.nd, uint8_t(1), P->row_flag.p);
-  for (auto& I : f->integrals)
+  P->n_active_entities = 0;
+  for (size_t i = 0; i < skey.size(); ++i)
   {
-    if (!I.facet || I.n == 0)
-      continue;
-    // rows touching a facet-integral cell: bit 1 too (launched after the bit-0 pass above)
-    CFX_LAUNCH(c, row_flag_kernel, grid_for(I.n * S.nd, SBK), SBK, 0, I.entities, I.n, 4, S.dofmap, S.nd,
-               uint8_t(3), P->row_flag.p);
-    CFX_LAUNCH(c, row_flag_kernel, grid_for(I.n * S.nd, SBK), SBK, 0, I.entities + 2, I.n, 4, S.dofmap, S.nd,
-               uint8_t(3), P->row_flag.p);
+    CFX_LAUNCH(c, mark_cells_kernel, grid_for(skey[i].second, SBK), SBK, 0, static_cast<const int32_t*>(skey[i].first),
+               skey[i].second, 1, c->nc_total, static_cast<uint8_t>(4u << i), S.dofmap, S.nd, uint8_t(1),
+               P->cell_flags.p, P->row_flag.p, c->err_flag.p);
+    P->n_active_entities += skey[i].second;
+  }
+  for (auto& k : rkey)
+  {
+    CFX_LAUNCH(c, mark_cells_kernel, grid_for(k.second, SBK), SBK, 0, static_cast<const int32_t*>(k.first), k.second, 1,
+               c->nc_total, uint8_t(1), S.dofmap, S.nd, uint8_t(1), P->cell_flags.p, P->row_flag.p, c->err_flag.p);
+    P->n_active_entities += k.second;
+  }
+  if (fkey.first)
+  { // both cells of every facet row (cell0, lf0, cell1, lf1); launched after the cell lists: 3 supersedes 1
+    const int32_t* rows4 = static_cast<const int32_t*>(fkey.first);
+    CFX_LAUNCH(c, mark_cells_kernel, grid_for(fkey.second, SBK), SBK, 0, rows4, fkey.second, 4, c->nc_total, uint8_t(2),
+               S.dofmap, S.nd, uint8_t(3), P->cell_flags.p, P->row_flag.p, c->err_flag.p);
+    CFX_LAUNCH(c, mark_cells_kernel, grid_for(fkey.second, SBK), SBK, 0, rows4 + 2, fkey.second, 4, c->nc_total,
+               uint8_t(2), S.dofmap, S.nd, uint8_t(3), P->cell_flags.p, P->row_flag.p, c->err_flag.p);
   }
   {
     FlagPred p{P->row_flag.p};
     P->n_act_rows = compact_indices(c, S.n_total, p, P->act_rows);
   }
-  P->row_slot.reserve(c->pool, static_cast<size_t>(S.n_total) + 1);
-  if (P->n_act_rows > 0)
-    CFX_LAUNCH(c, scatter_slot_kernel, grid_for(P->n_act_rows, SBK), SBK, 0, P->act_rows.p, P->n_act_rows,
-               P->row_slot.p);
+  st.set_bytes(static_cast<double>(c->nc_total) + 3.0 * static_cast<double>(S.n_total)
+               + (4.0 + 4.0 * S.nd) * static_cast<double>(P->n_active_entities) + 4.0 * static_cast<double>(P->n_act_rows));
   check_device_error(c, "form domains (entity index out of range)");
   f->gtab_serial = -1;
   f->dirty = false;
+}
+
+// bit mask (cell_flags) of the standard cell list `entities` inside a prepared domain
+uint8_t std_list_bit(const cfx_prepared* P, const void* entities, int64_t n)
+{
+  for (size_t i = 0; i < P->std_key.size(); ++i)
+    if (P->std_key[i].first == entities && P->std_key[i].second == n)
+      return static_cast<uint8_t>(4u << i);
+  throw Error(CFX_ERR_STATE, "internal: standard cell list missing from the prepared domain");
 }
 
 const cfx_integral* facet_integral_domain(const cfx_form* f)
@@ -810,9 +821,9 @@ void cfx_form_free(cfx_ctx* ctx, cfx_form* f)
   if (ctx)
     release_prepared(ctx, f);
   f->gmask.release();
+  f->Rrow.release();
   f->row_fast.release();
   f->Ae.release();
-  f->written.release();
   f->Fe.release();
   delete f;
 }
@@ -854,17 +865,23 @@ cfx_status cfx_create_sparsity(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
   unsigned long long* n_slow = reinterpret_cast<unsigned long long*>(ctx->scratch64.p) + 1;
   CFX_CUDA(cudaMemsetAsync(n_slow, 0, sizeof(unsigned long long), ctx->stream));
   const int only_band = S.has_static ? 1 : 0;
+  const bool need_generic = !S.has_static || PR->facet_key.first != nullptr; // band rows exist
   if (PR->n_act_rows > 0)
   {
-    tmp.reserve(ctx->pool, static_cast<size_t>(PR->n_act_rows) * 32);
-    a->gmask.reserve(ctx->pool, static_cast<size_t>(PR->n_act_rows) * S.stride);
     a->row_fast.reserve(ctx->pool, static_cast<size_t>(PR->n_act_rows) + 16);
     if (S.has_static)
-      CFX_LAUNCH(ctx, pattern_static_kernel, ga, RW * 32, 0, rc, PR->act_rows.p, PR->n_act_rows, S.stride,
-                 S.frow_ptr.p, S.fcols.p, S.fmask.p, row_nnz.p, tmp.p, a->gmask.p, a->row_fast.p);
-    if (!S.has_static || FI)
+    {
+      a->Rrow.reserve(ctx->pool, static_cast<size_t>(PR->n_act_rows) + 1);
+      CFX_LAUNCH(ctx, pattern_static_kernel, ga, RW * 32, 0, rc, PR->act_rows.p, PR->n_act_rows, S.fmask.p, row_nnz.p,
+                 a->Rrow.p, a->row_fast.p);
+    }
+    if (need_generic)
+    {
+      tmp.reserve(ctx->pool, static_cast<size_t>(PR->n_act_rows) * 32);
+      a->gmask.reserve(ctx->pool, static_cast<size_t>(PR->n_act_rows) * S.stride);
       CFX_LAUNCH(ctx, kcount, ga, RW * 32, 0, rc, PR->act_rows.p, PR->n_act_rows, only_band, S.stride, row_nnz.p,
                  nullptr, nullptr, tmp.p, a->gmask.p, a->row_fast.p, n_slow, ctx->err_flag.p);
+    }
   }
   P->row_ptr.reserve(ctx->pool, static_cast<size_t>(S.n_total) + 2);
   exclusive_scan_i32_to_i64(ctx, row_nnz.p, S.n_total, P->row_ptr.p);
@@ -879,8 +896,12 @@ cfx_status cfx_create_sparsity(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
              P->row_ptr.p, P->cols.p);
   if (PR->n_act_rows > 0)
   {
-    CFX_LAUNCH(ctx, pattern_copy_kernel, grid_for(PR->n_act_rows, 256), 256, 0, PR->act_rows.p, PR->n_act_rows,
-               a->row_fast.p, tmp.p, P->row_ptr.p, P->cols.p);
+    if (S.has_static)
+      CFX_LAUNCH(ctx, pattern_static_fill_kernel, grid_for(PR->n_act_rows * 16, 256), 256, 0, PR->act_rows.p,
+                 PR->n_act_rows, a->row_fast.p, a->Rrow.p, S.frow_ptr.p, S.fcols.p, P->row_ptr.p, P->cols.p);
+    if (need_generic)
+      CFX_LAUNCH(ctx, pattern_copy_kernel, grid_for(PR->n_act_rows, 256), 256, 0, PR->act_rows.p, PR->n_act_rows,
+                 a->row_fast.p, tmp.p, P->row_ptr.p, P->cols.p);
     if (a->n_slow_rows > 0)
       CFX_LAUNCH(ctx, kfill, ga, RW * 32, 0, rc, PR->act_rows.p, PR->n_act_rows, only_band, S.stride, nullptr,
                  P->row_ptr.p, P->cols.p, nullptr, nullptr, a->row_fast.p, nullptr, ctx->err_flag.p);
