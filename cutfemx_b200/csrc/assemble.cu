@@ -531,6 +531,8 @@ struct GatherCtx
   const int32_t* mat_slot;
   const double* Ae;
   const double* geo; // static per-cell geometry records (element.cuh GeoRec)
+  const int64_t* frow_ptr;
+  const uint64_t* fclist;
   const int32_t* c2f;
   const int32_t* facet_slot;
   const int32_t* rows4;
@@ -552,17 +554,11 @@ __device__ __forceinline__ double pick(const double (&a)[N], int i)
 // Row `li` of the element tensor of standard cell `c` (sum over the form's standard integrals the
 // cell belongs to) plus row `li` of its materialised run-time tensor, natural dof order.
 template <int TDIM, int DEG>
-__device__ __forceinline__ void cell_row_values(const GatherCtx& gc, const StdTab& st, int64_t c, unsigned fl, int li,
-                                                double (&v)[Elem<TDIM, DEG>::ND])
+__device__ __forceinline__ void std_row_values(const StdTab& st, const Geo<TDIM>& g, unsigned fl, int li,
+                                               double (&v)[Elem<TDIM, DEG>::ND])
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
-#pragma unroll
-  for (int j = 0; j < ND; ++j)
-    v[j] = 0.0;
-  if (fl >> 2)
   {
-    Geo<TDIM> g;
-    load_geo_cached<TDIM>(gc.geo, c, g);
     const double s = fabs(g.detJ);
     for (int k = 0; k < st.n; ++k)
     {
@@ -651,6 +647,22 @@ __device__ __forceinline__ void cell_row_values(const GatherCtx& gc, const StdTa
       }
     }
   }
+}
+
+template <int TDIM, int DEG>
+__device__ __forceinline__ void cell_row_values(const GatherCtx& gc, const StdTab& st, int64_t c, unsigned fl, int li,
+                                                double (&v)[Elem<TDIM, DEG>::ND])
+{
+  constexpr int ND = Elem<TDIM, DEG>::ND;
+#pragma unroll
+  for (int j = 0; j < ND; ++j)
+    v[j] = 0.0;
+  if (fl >> 2)
+  {
+    Geo<TDIM> g;
+    load_geo_cached<TDIM>(gc.geo, c, g);
+    std_row_values<TDIM, DEG>(st, g, fl, li, v);
+  }
   if (fl & 1)
   {
     const double* a = gc.Ae + (static_cast<int64_t>(__ldg(gc.mat_slot + c)) * ND + li) * ND;
@@ -696,7 +708,9 @@ __device__ __forceinline__ double cell_entry_value(const GatherCtx& gc, const St
   return e;
 }
 
-constexpr int GW = 4; // rows (warps) per block
+constexpr int GW = 4;  // rows (warps) per block
+constexpr int GWC = 4; // rows per block of the contribution-list kernel
+constexpr int GWM = 4; // rows per block of the mask kernel
 
 // rows no active entity touches: optional identity diagonal (deactivate_outside, deactivate.h:402-418)
 __global__ void inactive_diag_kernel(const uint8_t* __restrict__ row_flag, int64_t n_rows,
@@ -896,23 +910,23 @@ __global__ void __launch_bounds__(GW * 32)
 // No dofmap read, no column search, no element-tensor round trip through HBM for standard cells,
 // fixed summation order -> bit-reproducible.
 template <int TDIM, int DEG>
-__global__ void __launch_bounds__(GW * 32, 8)
+__global__ void __launch_bounds__(GWM * 32, 8)
     gather_matrix_fast_kernel(GatherCtx gc, StdTab st, const int32_t* __restrict__ act_rows, int64_t n_act,
                               const uint8_t* __restrict__ row_fast, const uint32_t* __restrict__ gmask,
                               const uint32_t* __restrict__ Rrow, const int64_t* __restrict__ row_ptr,
                               const int32_t* __restrict__ cols, double* __restrict__ vals, int zero_first)
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
-  __shared__ double s_v[GW][32][ND];
-  __shared__ int32_t s_fd[GW][32][2 * ND];
-  __shared__ double s_fv[GW][32][2 * ND];
+  __shared__ double s_v[GWM][32][ND];
+  __shared__ int32_t s_fd[GWM][32][2 * ND];
+  __shared__ double s_fv[GWM][32][2 * ND];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * GW + w;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * GWM + w;
   if (idx >= n_act)
     return;
   const unsigned rf = row_fast[idx];
-  if (!(rf & 1))
-    return; // handled by gather_matrix_kernel
+  if (!(rf & 1) || (rf & 12u) == 12u)
+    return; // handled by gather_matrix_kernel / gather_matrix_clist_kernel
   const unsigned full = 0xffffffffu;
   const int64_t r = act_rows[idx];
   const int64_t ib = gc.inc_ptr[r];
@@ -930,9 +944,10 @@ __global__ void __launch_bounds__(GW * 32, 8)
   }
   const bool contributes = (fl & 0xFDu) != 0;
   const int li = static_cast<int>(fp & 15u);
+  uint32_t R = 0;
   if (rf & 4)
   {
-    const uint32_t R = Rrow[idx];
+    R = Rrow[idx];
     if (contributes)
       for (uint32_t t = gc.fmask[ib + lane]; t; t &= t - 1)
         Mn |= 1u << __popc(R & ((1u << (__ffs(t) - 1)) - 1u));
@@ -945,13 +960,13 @@ __global__ void __launch_bounds__(GW * 32, 8)
     cell_row_values<TDIM, DEG>(gc, st, c, fl, li, v);
 #pragma unroll
     for (int j = 0; j < ND; ++j)
-      s_v[w][lane][(fp >> (4 + 4 * j)) & 15u] = v[j];
+      s_v[w][lane][(fp >> (4 + 4 * j)) & 15u] = v[j]; // ascending-dof order
   }
   __syncwarp();
   // ---- phase 2
+  const uint32_t below = (1u << lane) - 1u;
   const bool have_col = lane < rn;
   double acc = (have_col && !zero_first) ? vals[rb + lane] : 0.0;
-  const uint32_t below = (1u << lane) - 1u;
   for (int l0 = 0; l0 < n_inc; l0 += 8)
   {
     double t[8];
@@ -974,6 +989,103 @@ __global__ void __launch_bounds__(GW * 32, 8)
   }
   if (have_col)
     vals[rb + lane] = acc;
+}
+
+// Static rows whose contribution lists fit (Space::fclist) -- the bulk of the matrix.  One WARP per
+// row, three dependent load levels:
+//   (0) by row slot:  row flags, row id, kept-column mask R
+//   (1) by row id:    incidence range, CSR row start, full-pattern row start
+//   (2) by position:  lane l: incident cell l and the local index of the row's dof in it;
+//                     lane k: the contribution list of full-pattern column k and the CSR value it updates
+//   (3) by cell:      flag byte + geometry record (+ materialised tensor row for cut cells)
+// then the tensor row of every incident cell is computed on the fly and staged (transposed, conflict-
+// free) in shared memory; lane k sums the <= 8 listed (cell, local dof) entries in ascending cell
+// order, the diagonal takes one entry per cell through a fixed shuffle tree.  No atomics, no dofmap
+// read, no column search, no element tensors through HBM for standard cells.
+template <int TDIM, int DEG>
+__global__ void __launch_bounds__(GWC * 32, 8)
+    gather_matrix_clist_kernel(GatherCtx gc, StdTab st, const int32_t* __restrict__ act_rows, int64_t n_act,
+                               const uint8_t* __restrict__ row_fast, const uint32_t* __restrict__ Rrow,
+                               const int64_t* __restrict__ row_ptr, double* __restrict__ vals, int zero_first)
+{
+  constexpr int ND = Elem<TDIM, DEG>::ND;
+  __shared__ double s_v[GWC][ND][32];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * GWC + w;
+  if (idx >= n_act)
+    return;
+  const unsigned full = 0xffffffffu;
+  // level 0
+  const unsigned rf = row_fast[idx];
+  const int64_t r = act_rows[idx];
+  const uint32_t R = Rrow[idx];
+  if ((rf & 13u) != 13u)
+    return;
+  // level 1
+  const int64_t ib = gc.inc_ptr[r];
+  const int64_t ie = gc.inc_ptr[r + 1];
+  const int64_t rb = row_ptr[r];
+  const int64_t fb = gc.frow_ptr[r];
+  // level 2
+  const int n_inc = static_cast<int>(ie - ib);
+  const bool in = lane < n_inc;
+  const int64_t kk = ib + (in ? lane : 0);
+  const int64_t c = gc.inc_cell[kk];
+  const int li = static_cast<int>(gc.fperm[kk] & 15u);
+  const uint32_t below = (1u << lane) - 1u;
+  const bool kept = (R >> lane) & 1u;
+  const uint64_t word = __ldg(gc.fclist + fb + lane); // padded allocation: safe for every lane
+  double* const pv = vals + rb + __popc(R & below);
+  double acc = (kept && !zero_first) ? *pv : 0.0;
+  // level 3
+  const unsigned fl = in ? gc.cell_flags[c] : 0u;
+  Geo<TDIM> g;
+  load_geo_cached<TDIM>(gc.geo, c, g);
+  const int32_t ms = __ldg(gc.mat_slot + c);
+  const bool contributes = (fl & 0xFDu) != 0;
+  double dval = 0.0;
+  if (contributes)
+  {
+    double v[ND];
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+      v[j] = 0.0;
+    if (fl >> 2)
+      std_row_values<TDIM, DEG>(st, g, fl, li, v);
+    if (fl & 1)
+    {
+      const double* a = gc.Ae + (static_cast<int64_t>(ms) * ND + li) * ND;
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+        v[j] += a[j];
+    }
+    dval = pick<ND>(v, li);
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+      s_v[w][j][lane] = v[j];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    dval += __shfl_down_sync(full, dval, o);
+  dval = __shfl_sync(full, dval, 0);
+  const unsigned cmask = __ballot_sync(full, contributes);
+  if (!kept)
+    return;
+  if ((word & 0xFFull) == 0xFEull)
+    acc += dval;
+  else
+  {
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+    {
+      const unsigned b = static_cast<unsigned>(word >> (8 * e)) & 0xFFu;
+      const unsigned l = b & 31u;
+      if (b != 0xFFu && ((cmask >> l) & 1u))
+        acc += s_v[w][b >> 5][l];
+    }
+  }
+  *pv = acc;
 }
 
 // One warp per active row: lanes take the incident cells, compute / load the cell's entry for this
@@ -1197,6 +1309,8 @@ GatherCtx make_gather_ctx(cfx_ctx* c, cfx_form* f, const cfx_integral* FI)
   g.mat_slot = c->mat_slot.p;
   g.Ae = f->Ae.p;
   g.geo = c->geo.p;
+  g.frow_ptr = S.frow_ptr.p;
+  g.fclist = S.fclist.p;
   g.c2f = c->c2f;
   g.facet_slot = c->facet_slot.p;
   g.rows4 = FI ? FI->entities : nullptr;
@@ -1217,11 +1331,20 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
   // the gather tables are valid only for the pattern that was built from this very form
   const bool fast = a->gtab_serial == A->serial && a->gtab_serial > 0 && S.has_perm;
   const unsigned g = grid_for(PR->n_act_rows, GW);
-  if (fast)
-  {
-    auto kf = gather_matrix_fast_kernel<TDIM, DEG>;
-    CFX_LAUNCH(ctx, kf, g, GW * 32, 0, gc, st, PR->act_rows.p, PR->n_act_rows, a->row_fast.p, a->gmask.p, a->Rrow.p,
-               A->row_ptr.p, A->cols.p, A->values.p, zero_first);
+  if constexpr (Elem<TDIM, DEG>::ND <= 6)
+  { // the mask / contribution-list kernels need the packed incidence tables (nd <= 6)
+    if (fast && S.has_static)
+    {
+      auto kc = gather_matrix_clist_kernel<TDIM, DEG>;
+      CFX_LAUNCH(ctx, kc, grid_for(PR->n_act_rows, GWC), GWC * 32, 0, gc, st, PR->act_rows.p, PR->n_act_rows,
+                 a->row_fast.p, a->Rrow.p, A->row_ptr.p, A->values.p, zero_first);
+    }
+    if (fast && (a->n_mask_rows != 0))
+    {
+      auto kf = gather_matrix_fast_kernel<TDIM, DEG>;
+      CFX_LAUNCH(ctx, kf, grid_for(PR->n_act_rows, GWM), GWM * 32, 0, gc, st, PR->act_rows.p, PR->n_act_rows,
+                 a->row_fast.p, a->gmask.p, a->Rrow.p, A->row_ptr.p, A->cols.p, A->values.p, zero_first);
+    }
   }
   if (!fast || a->n_slow_rows > 0)
   {

@@ -168,6 +168,11 @@ struct Space
   DevBuf<int64_t> frow_ptr;     // full pattern row pointers
   DevBuf<int32_t> fcols;        // full pattern columns (sorted)
   DevBuf<uint32_t> fmask;       // per incidence: bit mask of the full-row positions of the cell's dofs
+  // per full-pattern entry (row r, column k): the (incident cell l, local dof j) pairs that contribute
+  // to it, 8 bits each (l | j << 5), ascending l, 0xFF = none; the diagonal entry is 0x..FE (every
+  // incident cell contributes).  frow_ok[r] = 0 if some entry of the row has more than 8 cells.
+  DevBuf<uint64_t> fclist;
+  DevBuf<uint8_t> frow_ok;
 };
 
 struct RuleTable
@@ -256,6 +261,7 @@ struct cfx_form
   cfx::DevBuf<uint32_t> Rrow;   // (n_act_rows): static rows: which full-mesh columns the row keeps
   cfx::DevBuf<uint8_t> row_fast; // bit0: mask path, bit1: has band cells, bit2: static row
   int64_t n_slow_rows = 0;
+  int64_t n_mask_rows = -1; // rows of the mask gather kernel (band rows, long contribution lists); -1 unknown
   int64_t gtab_serial = -1;
   cfx::DevBuf<double> Ae;      // materialised run-time-rule tensors, cell-major (slot, nd^rank) natural order;
                                // rank 0: one value per entity

@@ -253,21 +253,52 @@ __global__ void __launch_bounds__(RW * 32)
       bool own_needed = (fl & 0xFD) != 0; // has a cell tensor (materialised or on the fly)
       if (fl & 2)
       {
+        // facet macro cliques: the partner cell's dofs that this cell does not have.  All NF
+        // facets are probed with independent loads (c2f row -> slots -> partner cells -> their
+        // dofmap rows in flight together) instead of one dependent chain per facet.
         band = true;
-        for (int lf = 0; lf < rc.nf; ++lf)
+        constexpr int NF = (ND == 3 || ND == 6) ? 3 : 4;
+        int64_t fct[NF];
+        int32_t slot[NF], oc[NF], d[ND];
+#pragma unroll
+        for (int lf = 0; lf < NF; ++lf)
+          fct[lf] = rc.c2f[c * NF + lf];
+#pragma unroll
+        for (int j = 0; j < ND; ++j)
+          d[j] = rc.dofmap[c * ND + j];
+#pragma unroll
+        for (int lf = 0; lf < NF; ++lf)
+          slot[lf] = rc.facet_slot[fct[lf]];
+#pragma unroll
+        for (int lf = 0; lf < NF; ++lf)
         {
-          const int64_t f = rc.c2f[c * rc.nf + lf];
-          if (rc.facet_slot[f] < 0)
+          oc[lf] = -1;
+          if (slot[lf] >= 0)
+          {
+            const int32_t c0 = rc.f2c2[2 * fct[lf]], c1 = rc.f2c2[2 * fct[lf] + 1];
+            oc[lf] = (c0 == c) ? c1 : c0;
+          }
+        }
+#pragma unroll
+        for (int lf = 0; lf < NF; ++lf)
+        {
+          if (oc[lf] < 0)
             continue;
           own_needed = true;
-          const int32_t c0 = rc.f2c2[2 * f], c1 = rc.f2c2[2 * f + 1];
-          const int64_t other = (c0 == c) ? c1 : c0;
-          const int pos = atomicAdd(&s_nextra[w], ND);
-          if (pos + ND <= XCAP)
-          {
 #pragma unroll
-            for (int j = 0; j < ND; ++j)
-              s_extra[w][pos + j] = rc.dofmap[other * ND + j];
+          for (int j = 0; j < ND; ++j)
+          {
+            const int32_t od = rc.dofmap[static_cast<int64_t>(oc[lf]) * ND + j];
+            bool dup = false;
+#pragma unroll
+            for (int jj = 0; jj < ND; ++jj)
+              dup = dup || (od == d[jj]);
+            if (!dup)
+            {
+              const int pos = atomicAdd(&s_nextra[w], 1);
+              if (pos < XCAP)
+                s_extra[w][pos] = od;
+            }
           }
         }
       }
@@ -400,29 +431,38 @@ __global__ void __launch_bounds__(RW * 32)
 // one POPC; only R (4 B) and the count are stored -- the columns are expanded after the scan by
 // pattern_static_fill_kernel, and the assembly gather recomputes each cell's CSR positions from
 // (fmask, R) instead of reading a gather table.  Only meshes whose full rows have <= 32 columns.
-__global__ void __launch_bounds__(RW * 32)
+__global__ void __launch_bounds__(256)
     pattern_static_kernel(RowCtx rc, const int32_t* __restrict__ act_rows, int64_t n_act,
-                          const uint32_t* __restrict__ fmask, int32_t* __restrict__ row_nnz,
-                          uint32_t* __restrict__ Rrow, uint8_t* __restrict__ row_fast)
+                          const uint32_t* __restrict__ fmask, const uint8_t* __restrict__ frow_ok,
+                          int32_t* __restrict__ row_nnz, uint32_t* __restrict__ Rrow, uint8_t* __restrict__ row_fast)
 {
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * RW + w;
-  if (idx >= n_act)
-    return;
-  const int64_t r = act_rows[idx];
-  if (rc.row_flag[r] & 2)
-    return; // band rows: pattern_rows_kernel
-  const int64_t ib = rc.inc_ptr[r];
-  const int n_inc = static_cast<int>(rc.inc_ptr[r + 1] - ib);
-  uint32_t Ml = 0;
-  if (lane < n_inc && (rc.cell_flags[rc.inc_cell[ib + lane]] & 0xFD))
-    Ml = fmask[ib + lane];
-  const uint32_t R = __reduce_or_sync(0xffffffffu, Ml);
-  if (lane == 0)
+  // 8 lanes per row (4 rows per warp): three independent gather chains per lane for 24 incident cells
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t idx = t >> 3;
+  const int sl = static_cast<int>(t & 7);
+  const bool valid = idx < n_act;
+  const int64_t r = valid ? act_rows[idx] : 0;
+  const bool band = valid && (rc.row_flag[r] & 2); // band rows: pattern_rows_kernel
+  uint32_t M = 0;
+  if (valid && !band)
   {
-    row_nnz[r] = __popc(R);
-    Rrow[idx] = R;
-    row_fast[idx] = 1 | 4;
+    const int64_t ib = rc.inc_ptr[r];
+    const int n_inc = static_cast<int>(rc.inc_ptr[r + 1] - ib);
+#pragma unroll 4
+    for (int k = sl; k < n_inc; k += 8)
+    {
+      const uint32_t fm = fmask[ib + k];
+      M |= (rc.cell_flags[rc.inc_cell[ib + k]] & 0xFD) ? fm : 0u;
+    }
+  }
+  M |= __shfl_xor_sync(0xffffffffu, M, 1);
+  M |= __shfl_xor_sync(0xffffffffu, M, 2);
+  M |= __shfl_xor_sync(0xffffffffu, M, 4);
+  if (valid && !band && sl == 0)
+  {
+    row_nnz[r] = __popc(M);
+    Rrow[idx] = M;
+    row_fast[idx] = 1 | 4 | (frow_ok[r] ? 8 : 0);
   }
 }
 
@@ -482,6 +522,56 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// static contribution lists (Space::fclist): one warp per row; lanes own the row's full-pattern
+// columns, the incident cells' dofs are staged in shared memory and walked in ascending cell order.
+template <int ND>
+__global__ void __launch_bounds__(RW * 32)
+    clist_kernel(int64_t n_rows, const int64_t* __restrict__ inc_ptr, const int32_t* __restrict__ inc_cell,
+                 const int32_t* __restrict__ dofmap, const int64_t* __restrict__ frow_ptr,
+                 const int32_t* __restrict__ fcols, uint64_t* __restrict__ fclist, uint8_t* __restrict__ frow_ok)
+{
+  __shared__ int32_t s_d[RW][32][ND];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * RW + w;
+  if (r >= n_rows)
+    return;
+  const int64_t ib = inc_ptr[r];
+  const int n_inc = static_cast<int>(inc_ptr[r + 1] - ib);
+  const int64_t fb = frow_ptr[r];
+  const int nfull = static_cast<int>(frow_ptr[r + 1] - fb);
+  if (lane < n_inc)
+  {
+    const int64_t c = inc_cell[ib + lane];
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+      s_d[w][lane][j] = dofmap[c * ND + j];
+  }
+  __syncwarp();
+  const int32_t mycol = lane < nfull ? fcols[fb + lane] : -1;
+  uint64_t word = ~0ull;
+  int cnt = 0;
+  bool ok = true;
+  if (mycol == r)
+    word = ~0ull ^ 1ull; // lowest byte 0xFE: diagonal
+  else if (mycol >= 0)
+    for (int l = 0; l < n_inc; ++l)
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+        if (s_d[w][l][j] == mycol)
+        {
+          if (cnt < 8)
+            word = (word & ~(0xFFull << (8 * cnt))) | (static_cast<uint64_t>(l | (j << 5)) << (8 * cnt));
+          else
+            ok = false;
+          ++cnt;
+        }
+  if (lane < nfull)
+    fclist[fb + lane] = word;
+  const bool all_ok = __all_sync(0xffffffffu, ok);
+  if (lane == 0)
+    frow_ok[r] = all_ok ? 1 : 0;
+}
+
 __global__ void check_sorted_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ cols,
                                     int64_t n_rows, int32_t* __restrict__ err)
 {
@@ -526,6 +616,10 @@ static void build_static_structure_nd(cfx_ctx* c, Space& S)
     S.fcols.reserve(c->pool, static_cast<size_t>(fnnz) + 1);
     CFX_LAUNCH(c, pattern_copy_kernel, grid_for(S.n_total, 256), 256, 0, nullptr, S.n_total, nullptr, tmp.p,
                S.frow_ptr.p, S.fcols.p);
+    S.fclist.reserve(c->pool, static_cast<size_t>(fnnz) + 64);
+    S.frow_ok.reserve(c->pool, static_cast<size_t>(S.n_total) + 16);
+    CFX_LAUNCH(c, clist_kernel<ND>, grid_for(S.n_total, RW), RW * 32, 0, S.n_total, S.inc_ptr.p, S.inc_cell.p, S.dofmap,
+               S.frow_ptr.p, S.fcols.p, S.fclist.p, S.frow_ok.p);
     S.has_static = true;
   }
   else
@@ -872,8 +966,8 @@ cfx_status cfx_create_sparsity(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
     if (S.has_static)
     {
       a->Rrow.reserve(ctx->pool, static_cast<size_t>(PR->n_act_rows) + 1);
-      CFX_LAUNCH(ctx, pattern_static_kernel, ga, RW * 32, 0, rc, PR->act_rows.p, PR->n_act_rows, S.fmask.p, row_nnz.p,
-                 a->Rrow.p, a->row_fast.p);
+      CFX_LAUNCH(ctx, pattern_static_kernel, grid_for(PR->n_act_rows * 8, 256), 256, 0, rc, PR->act_rows.p,
+                 PR->n_act_rows, S.fmask.p, S.frow_ok.p, row_nnz.p, a->Rrow.p, a->row_fast.p);
     }
     if (need_generic)
     {
