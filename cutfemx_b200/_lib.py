@@ -32,9 +32,11 @@ SYMBOLS = [
     "cfx_ghost_penalty_facets", "cfx_interior_facets_for_cells", "cfx_facet_integration_rows", "cfx_space_bind",
     "cfx_form_create", "cfx_form_add_cell_integral", "cfx_form_add_interior_facet_integral", "cfx_form_free",
     "cfx_create_sparsity", "cfx_pattern_import", "cfx_pattern_sizes", "cfx_pattern_fetch",
-    "cfx_pattern_values_device_ptr", "cfx_pattern_values_fetch", "cfx_pattern_free", "cfx_assemble_matrix", "cfx_assemble_vector",
+    "cfx_pattern_values_device_ptr", "cfx_pattern_row_ptr_device_ptr", "cfx_pattern_cols_device_ptr",
+    "cfx_pattern_values_fetch", "cfx_pattern_free", "cfx_assemble_matrix", "cfx_assemble_vector",
     "cfx_assemble_scalar", "cfx_stage_count", "cfx_stage_name", "cfx_stage_timing_enable", "cfx_stage_ms",
-    "cfx_stage_reset", "cfx_meshgen_box", "cfx_meshgen_rectangle", "cfx_meshgen_level_set",
+    "cfx_stage_reset", "cfx_form_insert_pattern_entries", "cfx_create_sparsity_rows", "cfx_pattern_positions",
+    "cfx_gather_f64", "cfx_scatter_add_f64", "cfx_meshgen_box", "cfx_meshgen_rectangle", "cfx_meshgen_level_set",
 ]
 
 
@@ -63,8 +65,9 @@ def lib():
         L.cfx_launch_count.argtypes = [C.c_void_p]
         L.cfx_list_device_ptr.restype = C.c_void_p
         L.cfx_list_device_ptr.argtypes = [C.c_void_p]
-        L.cfx_pattern_values_device_ptr.restype = C.c_void_p
-        L.cfx_pattern_values_device_ptr.argtypes = [C.c_void_p]
+        for name in ("cfx_pattern_values_device_ptr", "cfx_pattern_row_ptr_device_ptr", "cfx_pattern_cols_device_ptr"):
+            getattr(L, name).restype = C.c_void_p
+            getattr(L, name).argtypes = [C.c_void_p]
         L.cfx_ctx_destroy.restype = None
         for name in ("cfx_list_free", "cfx_rules_free", "cfx_pattern_free", "cfx_form_free"):
             getattr(L, name).restype = None
@@ -77,6 +80,27 @@ def check(ctx, status: int):
     if status != 0:
         msg = lib().cfx_last_error(ctx)
         raise CfxError((msg.decode() if msg else "unknown error") + f" [status {status}]")
+
+
+class _CudaView:
+    """Zero-copy torch view of library-owned device memory (__cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str, owner):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+        self._owner = owner
+
+
+def device_view(ptr: int, n: int, dtype, device: int, owner=None):
+    """torch tensor aliasing `n` elements of `dtype` at device pointer `ptr` (valid while `owner` lives
+    and the library does not reallocate the buffer)."""
+    import torch
+
+    typestr = {np.float64: "<f8", np.int64: "<i8", np.int32: "<i4"}[dtype]
+    if n == 0 or not ptr:
+        tdt = {np.float64: torch.float64, np.int64: torch.int64, np.int32: torch.int32}[dtype]
+        return torch.empty(0, dtype=tdt, device=f"cuda:{device}")
+    return torch.as_tensor(_CudaView(ptr, n, typestr, owner), device=f"cuda:{device}")
 
 
 def is_device_array(a) -> bool:

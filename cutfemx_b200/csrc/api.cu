@@ -243,6 +243,7 @@ cfx_status cfx_levelset_bind(cfx_ctx* ctx, int ls, const int32_t* dofmap, int nd
   }
   L.bound = true;
   L.n_cut = -1;
+  L.n_cut_all = -1;
   ctx->classified = false;
   if (memspace == CFX_HOST)
     CFX_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -275,6 +276,7 @@ cfx_status cfx_update(cfx_ctx* ctx)
       copy(pe, n);  // pageable tail
     }
     L.n_cut = -1;
+    L.n_cut_all = -1;
   }
   CFX_REQUIRE(any, CFX_ERR_STATE, "cfx_update: no level set bound");
   classify_all(ctx);

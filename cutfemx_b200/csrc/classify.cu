@@ -152,6 +152,29 @@ void ensure_cut_list(cfx_ctx* c, int ls)
   StageScope st(c, "locate_cut", static_cast<double>(c->nc_owned) * 2.0 + 4.0 * static_cast<double>(L.counts[1]));
   L.n_cut = compact_indices(c, c->nc_owned, p, L.cut_list);
 }
+// intersected cells among ALL local cells (owned + ghost).  The reference's Python loop
+// (cut.py:364-379) starts from locate_entities(...), i.e. owned cells only, and therefore drops band
+// facets whose cut cell is a ghost of the facet's owner; classifying ghosts too makes the assembled
+// matrix independent of the partition (equal to the serial one).
+void ensure_cut_list_all(cfx_ctx* c, int ls)
+{
+  LevelSet& L = c->ls[ls];
+  if (c->nc_total == c->nc_owned)
+  {
+    ensure_cut_list(c, ls);
+    return;
+  }
+  if (L.n_cut_all >= 0)
+    return;
+  Dnf d;
+  std::memset(&d, 0, sizeof(d));
+  d.n_terms = 1;
+  d.term_off[1] = 1;
+  d.ls[0] = static_cast<int8_t>(ls);
+  d.relmask[0] = relation_mask(CFX_REL_EQ);
+  DnfPred p{d, c->domain.p, c->domain_stride};
+  L.n_cut_all = compact_indices(c, c->nc_total, p, L.cut_list_all);
+}
 } // namespace cfx
 
 using namespace cfx;

@@ -145,6 +145,8 @@ struct LevelSet
   int64_t counts[3] = {0, 0, 0};
   DevBuf<int32_t> cut_list; // intersected owned cells, ascending (cached per update)
   int64_t n_cut = -1;
+  DevBuf<int32_t> cut_list_all; // intersected owned + ghost cells (sources of the ghost-penalty band)
+  int64_t n_cut_all = -1;
 };
 
 struct Space
@@ -240,6 +242,7 @@ struct cfx_prepared
   std::vector<std::pair<const void*, int64_t>> std_key;  // distinct standard-quadrature cell lists (bit 2+i)
   std::vector<std::pair<const void*, int64_t>> rule_key; // distinct (rules parent_map, nrules)
   std::pair<const void*, int64_t> facet_key{nullptr, 0};
+  std::pair<const void*, int64_t> extra_key{nullptr, 0}; // inserted pattern entries (rows made active + generic)
   // bit0: has a materialised (run-time rule) tensor, bit1: touches a facet-integral facet,
   // bit 2+i: member of standard cell list i (its tensor rows are computed on the fly by the row owner)
   cfx::DevBuf<uint8_t> cell_flags;
@@ -253,6 +256,9 @@ struct cfx_form
 {
   int space = 0, rank = 0;
   std::vector<cfx_integral> integrals;
+  // SparsityPattern::insert entries from other ranks (cfx_form_insert_pattern_entries), sorted by row
+  cfx::DevBuf<int32_t> xrows, xcols;
+  int64_t n_x = 0;
   // prepared state (recomputed when dirty); shared between forms with the same cell domains
   bool dirty = true;
   cfx_prepared* prep = nullptr;
@@ -295,6 +301,8 @@ struct cfx_ctx
   cfx::DevBuf<int32_t> f2c2; // dense (n_facets, 2), -1 padded, ascending
   cfx::DevBuf<uint8_t> facet_flag;  // zero between calls
   cfx::DevBuf<int32_t> facet_slot;  // -1 between calls
+  cfx::DevBuf<int32_t> xslot;       // per dof: first inserted pattern entry of the row; -1 between calls
+  size_t xslot_init = 0;            // capacity that has been initialised to -1
   int64_t n_facets = 0, n_owned_facets = 0;
 
   cfx::LevelSet ls[CFX_MAX_LEVEL_SETS];
@@ -475,6 +483,7 @@ RuleTable& get_rule(cfx_ctx* c, int dim, int order); // quadrature.cu: built-in 
 void builtin_simplex_rule(int dim, int order, std::vector<double>& pts, std::vector<double>& wts);
 void classify_all(cfx_ctx* c);                          // classify.cu
 void ensure_cut_list(cfx_ctx* c, int ls);               // classify.cu
+void ensure_cut_list_all(cfx_ctx* c, int ls);           // classify.cu
 void build_incidence(cfx_ctx* c, Space& s);             // sparsity.cu
 void derive_f2c(cfx_ctx* c);                            // facets.cu
 void build_geometry_cache(cfx_ctx* c);                  // assemble.cu

@@ -232,14 +232,16 @@ cfx_status cfx_ghost_penalty_facets(cfx_ctx* ctx, int cut_ls, int n_terms, const
   CFX_REQUIRE(cut_ls >= 0 && cut_ls < CFX_MAX_LEVEL_SETS && ctx->ls[cut_ls].bound, CFX_ERR_INVALID,
               "cfx_ghost_penalty_facets: invalid cut level set");
   const Dnf d = make_dnf(ctx, n_terms, term_offsets, clause_ls, clause_rel);
-  ensure_cut_list(ctx, cut_ls);
+  ensure_cut_list_all(ctx, cut_ls);
   if (*out == nullptr)
     *out = new cfx_list();
   LevelSet& L = ctx->ls[cut_ls];
+  const bool all = ctx->nc_total != ctx->nc_owned;
+  const int32_t* src = all ? L.cut_list_all.p : L.cut_list.p;
+  const int64_t n_src = all ? L.n_cut_all : L.n_cut;
   StageScope st(ctx, "ghost_penalty_facets",
-                4.0 * (ctx->tdim + 1) * static_cast<double>(L.n_cut) + 2.0 * static_cast<double>(ctx->n_facets));
-  band_from_flags(ctx, L.cut_list.p, L.n_cut, BandPredDnf{d, cut_ls, ctx->domain.p, ctx->domain_stride},
-                  include_ghosts, *out);
+                4.0 * (ctx->tdim + 1) * static_cast<double>(n_src) + 2.0 * static_cast<double>(ctx->n_facets));
+  band_from_flags(ctx, src, n_src, BandPredDnf{d, cut_ls, ctx->domain.p, ctx->domain_stride}, include_ghosts, *out);
   CFX_API_END(ctx)
 }
 

@@ -27,10 +27,11 @@ __global__ void box_nodes_kernel(int nx, int ny, int nz, double x0, double y0, d
   const int i = static_cast<int>(v % (nx + 1));
   const int j = static_cast<int>((v / (nx + 1)) % (ny + 1));
   const int k = static_cast<int>(v / (static_cast<int64_t>(nx + 1) * (ny + 1)));
-  // numpy.linspace: start + i * step, last point exact
-  x[3 * v + 0] = i == nx ? x1 : x0 + i * ((x1 - x0) / nx);
-  x[3 * v + 1] = j == ny ? y1 : y0 + j * ((y1 - y0) / ny);
-  x[3 * v + 2] = (nz > 0) ? (k == nz ? z1 : z0 + k * ((z1 - z0) / nz)) : 0.0;
+  // numpy.linspace: start + i * step with separately rounded product and sum (no FMA contraction,
+  // so that host- and device-generated meshes agree bit for bit), last point exact
+  x[3 * v + 0] = i == nx ? x1 : __dadd_rn(x0, __dmul_rn(static_cast<double>(i), (x1 - x0) / nx));
+  x[3 * v + 1] = j == ny ? y1 : __dadd_rn(y0, __dmul_rn(static_cast<double>(j), (y1 - y0) / ny));
+  x[3 * v + 2] = (nz > 0) ? (k == nz ? z1 : __dadd_rn(z0, __dmul_rn(static_cast<double>(k), (z1 - z0) / nz))) : 0.0;
 }
 
 __global__ void box_cells_kernel(int nx, int ny, int nz, int32_t* __restrict__ x_dofmap, int32_t* __restrict__ c2f)

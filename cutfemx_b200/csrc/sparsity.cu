@@ -134,6 +134,47 @@ __global__ void mark_cells_kernel(const int32_t* __restrict__ cells, int64_t n, 
     row_flag[dofmap[static_cast<int64_t>(c) * nd + j]] = rowval;
 }
 
+// rows of inserted pattern entries: active (bit0) and generic (bit1)
+__global__ void mark_rows_kernel(const int32_t* __restrict__ rows, int64_t n, int64_t limit,
+                                 uint8_t* __restrict__ row_flag, int32_t* __restrict__ err)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x;
+  if (i >= n)
+    return;
+  const int32_t r = rows[i];
+  if (r < 0 || r >= limit || (i > 0 && rows[i - 1] > r))
+  {
+    err[0] = 25;
+    err[1] = r;
+    return;
+  }
+  row_flag[r] = 3;
+}
+
+__global__ void xslot_set_kernel(const int32_t* __restrict__ rows, int64_t n, int32_t* __restrict__ xslot, bool clear)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x;
+  if (i >= n)
+    return;
+  if (i == 0 || rows[i - 1] != rows[i])
+    xslot[rows[i]] = clear ? -1 : static_cast<int32_t>(i);
+}
+
+// number of entries of the ascending list `a` that are < bound (single thread, binary search)
+__global__ void lower_bound_kernel(const int32_t* __restrict__ a, int64_t n, int64_t bound, int64_t* __restrict__ out)
+{
+  int64_t lo = 0, hi = n;
+  while (lo < hi)
+  {
+    const int64_t mid = (lo + hi) >> 1;
+    if (a[mid] < bound)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  *out = lo;
+}
+
 __global__ void facet_slot_set_kernel(const int32_t* __restrict__ rows4, int64_t n, int nf,
                                       const int32_t* __restrict__ c2f, int32_t* __restrict__ facet_slot, bool clear)
 {
@@ -156,6 +197,10 @@ struct RowCtx
   const int32_t* facet_slot;
   int nf;
   int insert_diagonal;
+  const int32_t* xslot; // per row: first inserted entry (or -1); null if the form has none
+  const int32_t* xrows;
+  const int32_t* xcols;
+  int64_t n_x;
 };
 
 constexpr int RW = 4;      // rows (warps) per block
@@ -322,6 +367,17 @@ __global__ void __launch_bounds__(RW * 32)
         }
       }
     }
+  }
+  if (rc.xslot != nullptr && !all_mode)
+  { // SparsityPattern::insert entries received from other ranks
+    const int32_t xs = rc.xslot[r];
+    if (xs >= 0)
+      for (int64_t i = xs + lane; i < rc.n_x && rc.xrows[i] == r; i += 32)
+      {
+        const int pos = atomicAdd(&s_nextra[w], 1);
+        if (pos < XCAP)
+          s_extra[w][pos] = rc.xcols[i];
+      }
   }
   __syncwarp();
   const int n_extra = s_nextra[w];
@@ -726,9 +782,10 @@ void prepare_form(cfx_ctx* c, cfx_form* f)
   }
   CFX_REQUIRE(static_cast<int>(skey.size()) <= CFX_MAX_STD_LISTS, CFX_ERR_UNSUPPORTED,
               "a form may use at most 6 distinct standard-quadrature cell lists");
+  const std::pair<const void*, int64_t> xkey{f->n_x > 0 ? f->xrows.p : nullptr, f->n_x};
   for (cfx_prepared* p : c->preps)
     if (p->space == f->space && p->update_serial == c->update_serial && p->std_key == skey && p->rule_key == rkey
-        && (p->facet_key == fkey || fkey.first == nullptr))
+        && (p->facet_key == fkey || fkey.first == nullptr) && (p->extra_key == xkey || xkey.first == nullptr))
     {
       f->prep = p;
       ++p->refs;
@@ -743,6 +800,7 @@ void prepare_form(cfx_ctx* c, cfx_form* f)
   P->std_key = skey;
   P->rule_key = rkey;
   P->facet_key = fkey;
+  P->extra_key = xkey;
   c->preps.push_back(P);
   f->prep = P;
   StageScope st(c, "prepare_form");
@@ -772,6 +830,9 @@ void prepare_form(cfx_ctx* c, cfx_form* f)
     CFX_LAUNCH(c, mark_cells_kernel, grid_for(fkey.second, SBK), SBK, 0, rows4 + 2, fkey.second, 4, c->nc_total,
                uint8_t(2), S.dofmap, S.nd, uint8_t(3), P->cell_flags.p, P->row_flag.p, c->err_flag.p);
   }
+  if (xkey.first)
+    CFX_LAUNCH(c, mark_rows_kernel, grid_for(xkey.second, SBK), SBK, 0, static_cast<const int32_t*>(xkey.first),
+               xkey.second, S.n_total, P->row_flag.p, c->err_flag.p);
   {
     FlagPred p{P->row_flag.p};
     P->n_act_rows = compact_indices(c, S.n_total, p, P->act_rows);
@@ -914,6 +975,8 @@ void cfx_form_free(cfx_ctx* ctx, cfx_form* f)
     I.own.release();
   if (ctx)
     release_prepared(ctx, f);
+  f->xrows.release();
+  f->xcols.release();
   f->gmask.release();
   f->Rrow.release();
   f->row_fast.release();
@@ -922,25 +985,41 @@ void cfx_form_free(cfx_ctx* ctx, cfx_form* f)
   delete f;
 }
 
-cfx_status cfx_create_sparsity(cfx_ctx* ctx, const cfx_form* a_const, cfx_pattern** inout)
+// row_begin == 0: the whole pattern (create_sparsity_pattern + finalize).  row_begin > 0: only the
+// active rows >= row_begin, generic kernels, no diagonal -- what finalize() ships to other ranks.
+static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row_begin)
 {
-  CFX_API_BEGIN
-  cfx_form* a = const_cast<cfx_form*>(a_const);
-  CFX_REQUIRE(ctx && a && inout, CFX_ERR_INVALID, "cfx_create_sparsity: NULL argument");
-  // assembler.h:444-448 "Cannot create sparsity pattern. Form is not a bilinear."
-  CFX_REQUIRE(a->rank == 2, CFX_ERR_INVALID, "Cannot create sparsity pattern. Form is not a bilinear.");
   Space& S = ctx->spaces[a->space];
   prepare_form(ctx, a);
   const cfx_integral* FI = facet_integral_domain(a);
-  if (*inout == nullptr)
-    *inout = new cfx_pattern();
-  cfx_pattern* P = *inout;
+  cfx_prepared* PR = a->prep;
+  const bool part = row_begin > 0;
   P->space = a->space;
   P->n_rows = S.n_total;
-  StageScope st(ctx, "create_sparsity");
+  StageScope st(ctx, part ? "ghost_row_pattern" : "create_sparsity");
   set_facet_slots(ctx, FI, false);
-  RowCtx rc{S.inc_ptr.p, S.inc_cell.p, S.dofmap, a->prep->cell_flags.p, a->prep->row_flag.p, ctx->c2f,
-            ctx->f2c2.p, ctx->facet_slot.p, ctx->tdim + 1, 1};
+  const bool has_x = a->n_x > 0 && !part;
+  if (has_x)
+  {
+    ctx->xslot.reserve(ctx->pool, static_cast<size_t>(S.n_total) + 1);
+    if (ctx->xslot.cap != ctx->xslot_init)
+    {
+      CFX_CUDA(cudaMemsetAsync(ctx->xslot.p, 0xff, ctx->xslot.cap * sizeof(int32_t), ctx->stream));
+      ctx->xslot_init = ctx->xslot.cap;
+    }
+    CFX_LAUNCH(ctx, xslot_set_kernel, grid_for(a->n_x, SBK), SBK, 0, a->xrows.p, a->n_x, ctx->xslot.p, false);
+  }
+  RowCtx rc{S.inc_ptr.p, S.inc_cell.p, S.dofmap, PR->cell_flags.p, PR->row_flag.p, ctx->c2f, ctx->f2c2.p,
+            ctx->facet_slot.p, ctx->tdim + 1, 1, has_x ? ctx->xslot.p : nullptr, a->xrows.p, a->xcols.p, a->n_x};
+  // active rows handled by this call: the tail of the ascending list when row_begin > 0
+  int64_t i0 = 0;
+  if (part && PR->n_act_rows > 0)
+  {
+    CFX_LAUNCH(ctx, lower_bound_kernel, 1, 1, 0, PR->act_rows.p, PR->n_act_rows, row_begin, ctx->scratch64.p + 4);
+    i0 = read_back(ctx, ctx->scratch64.p + 4, 1)[0];
+  }
+  const int32_t* act = PR->act_rows.p + i0;
+  const int64_t n_act = PR->n_act_rows - i0;
   DevBuf<int32_t> row_nnz;
   row_nnz.reserve(ctx->pool, static_cast<size_t>(S.n_total) + 1);
   auto kcount = S.nd == 3 ? pattern_rows_kernel<3, false>
@@ -951,30 +1030,33 @@ cfx_status cfx_create_sparsity(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
                : S.nd == 4 ? pattern_rows_kernel<4, true>
                : S.nd == 6 ? pattern_rows_kernel<6, true>
                            : pattern_rows_kernel<10, true>;
-  cfx_prepared* PR = a->prep;
-  CFX_LAUNCH(ctx, pattern_inactive_count_kernel, grid_for(S.n_total, SBK), SBK, 0, PR->row_flag.p, S.n_total, 1,
-             row_nnz.p);
-  const unsigned ga = grid_for(PR->n_act_rows, RW);
+  if (part)
+    CFX_CUDA(cudaMemsetAsync(row_nnz.p, 0, (static_cast<size_t>(S.n_total) + 1) * sizeof(int32_t), ctx->stream));
+  else
+    CFX_LAUNCH(ctx, pattern_inactive_count_kernel, grid_for(S.n_total, SBK), SBK, 0, PR->row_flag.p, S.n_total, 1,
+               row_nnz.p);
+  const unsigned ga = grid_for(n_act, RW);
   DevBuf<int32_t> tmp;
   unsigned long long* n_slow = reinterpret_cast<unsigned long long*>(ctx->scratch64.p) + 1;
   CFX_CUDA(cudaMemsetAsync(n_slow, 0, sizeof(unsigned long long), ctx->stream));
-  const int only_band = S.has_static ? 1 : 0;
-  const bool need_generic = !S.has_static || PR->facet_key.first != nullptr; // band rows exist
-  if (PR->n_act_rows > 0)
+  const bool use_static = S.has_static && !part;
+  const int only_band = use_static ? 1 : 0;
+  const bool need_generic = !use_static || PR->facet_key.first != nullptr || PR->extra_key.first != nullptr;
+  if (n_act > 0)
   {
-    a->row_fast.reserve(ctx->pool, static_cast<size_t>(PR->n_act_rows) + 16);
-    if (S.has_static)
+    a->row_fast.reserve(ctx->pool, static_cast<size_t>(n_act) + 16);
+    if (use_static)
     {
-      a->Rrow.reserve(ctx->pool, static_cast<size_t>(PR->n_act_rows) + 1);
-      CFX_LAUNCH(ctx, pattern_static_kernel, grid_for(PR->n_act_rows * 8, 256), 256, 0, rc, PR->act_rows.p,
-                 PR->n_act_rows, S.fmask.p, S.frow_ok.p, row_nnz.p, a->Rrow.p, a->row_fast.p);
+      a->Rrow.reserve(ctx->pool, static_cast<size_t>(n_act) + 1);
+      CFX_LAUNCH(ctx, pattern_static_kernel, grid_for(n_act * 8, 256), 256, 0, rc, act, n_act, S.fmask.p, S.frow_ok.p,
+                 row_nnz.p, a->Rrow.p, a->row_fast.p);
     }
     if (need_generic)
     {
-      tmp.reserve(ctx->pool, static_cast<size_t>(PR->n_act_rows) * 32);
-      a->gmask.reserve(ctx->pool, static_cast<size_t>(PR->n_act_rows) * S.stride);
-      CFX_LAUNCH(ctx, kcount, ga, RW * 32, 0, rc, PR->act_rows.p, PR->n_act_rows, only_band, S.stride, row_nnz.p,
-                 nullptr, nullptr, tmp.p, a->gmask.p, a->row_fast.p, n_slow, ctx->err_flag.p);
+      tmp.reserve(ctx->pool, static_cast<size_t>(n_act) * 32);
+      a->gmask.reserve(ctx->pool, static_cast<size_t>(n_act) * S.stride);
+      CFX_LAUNCH(ctx, kcount, ga, RW * 32, 0, rc, act, n_act, only_band, S.stride, row_nnz.p, nullptr, nullptr, tmp.p,
+                 a->gmask.p, a->row_fast.p, n_slow, ctx->err_flag.p);
     }
   }
   P->row_ptr.reserve(ctx->pool, static_cast<size_t>(S.n_total) + 2);
@@ -986,28 +1068,126 @@ cfx_status cfx_create_sparsity(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
   }
   P->cols.reserve(ctx->pool, static_cast<size_t>(P->nnz) + 1);
   P->values.reserve(ctx->pool, static_cast<size_t>(P->nnz) + 1);
-  CFX_LAUNCH(ctx, pattern_inactive_fill_kernel, grid_for(S.n_total, SBK), SBK, 0, PR->row_flag.p, S.n_total, 1,
-             P->row_ptr.p, P->cols.p);
-  if (PR->n_act_rows > 0)
+  if (!part)
+    CFX_LAUNCH(ctx, pattern_inactive_fill_kernel, grid_for(S.n_total, SBK), SBK, 0, PR->row_flag.p, S.n_total, 1,
+               P->row_ptr.p, P->cols.p);
+  if (n_act > 0)
   {
-    if (S.has_static)
-      CFX_LAUNCH(ctx, pattern_static_fill_kernel, grid_for(PR->n_act_rows * 16, 256), 256, 0, PR->act_rows.p,
-                 PR->n_act_rows, a->row_fast.p, a->Rrow.p, S.frow_ptr.p, S.fcols.p, P->row_ptr.p, P->cols.p);
+    if (use_static)
+      CFX_LAUNCH(ctx, pattern_static_fill_kernel, grid_for(n_act * 16, 256), 256, 0, act, n_act, a->row_fast.p,
+                 a->Rrow.p, S.frow_ptr.p, S.fcols.p, P->row_ptr.p, P->cols.p);
     if (need_generic)
-      CFX_LAUNCH(ctx, pattern_copy_kernel, grid_for(PR->n_act_rows, 256), 256, 0, PR->act_rows.p, PR->n_act_rows,
-                 a->row_fast.p, tmp.p, P->row_ptr.p, P->cols.p);
+      CFX_LAUNCH(ctx, pattern_copy_kernel, grid_for(n_act, 256), 256, 0, act, n_act, a->row_fast.p, tmp.p,
+                 P->row_ptr.p, P->cols.p);
     if (a->n_slow_rows > 0)
-      CFX_LAUNCH(ctx, kfill, ga, RW * 32, 0, rc, PR->act_rows.p, PR->n_act_rows, only_band, S.stride, nullptr,
-                 P->row_ptr.p, P->cols.p, nullptr, nullptr, a->row_fast.p, nullptr, ctx->err_flag.p);
+      CFX_LAUNCH(ctx, kfill, ga, RW * 32, 0, rc, act, n_act, only_band, S.stride, nullptr, P->row_ptr.p, P->cols.p,
+                 nullptr, nullptr, a->row_fast.p, nullptr, ctx->err_flag.p);
   }
   tmp.release();
   P->serial = ++ctx->pattern_serial;
-  a->gtab_serial = P->serial;
+  a->gtab_serial = part ? -1 : P->serial; // the gather tables of a partial build index a sub-list of rows
   set_facet_slots(ctx, FI, true);
+  if (has_x)
+    CFX_LAUNCH(ctx, xslot_set_kernel, grid_for(a->n_x, SBK), SBK, 0, a->xrows.p, a->n_x, ctx->xslot.p, true);
   CFX_CUDA(cudaMemsetAsync(P->values.p, 0, (static_cast<size_t>(P->nnz) + 1) * sizeof(double), ctx->stream));
   row_nnz.release();
   st.set_bytes(12.0 * static_cast<double>(P->nnz) + 8.0 * static_cast<double>(S.n_total));
-  check_device_error(ctx, "cfx_create_sparsity (row capacity exceeded)");
+  check_device_error(ctx, "cfx_create_sparsity (row capacity exceeded / inserted entries not sorted by row)");
+}
+
+cfx_status cfx_create_sparsity(cfx_ctx* ctx, const cfx_form* a_const, cfx_pattern** inout)
+{
+  CFX_API_BEGIN
+  cfx_form* a = const_cast<cfx_form*>(a_const);
+  CFX_REQUIRE(ctx && a && inout, CFX_ERR_INVALID, "cfx_create_sparsity: NULL argument");
+  // assembler.h:444-448 "Cannot create sparsity pattern. Form is not a bilinear."
+  CFX_REQUIRE(a->rank == 2, CFX_ERR_INVALID, "Cannot create sparsity pattern. Form is not a bilinear.");
+  if (*inout == nullptr)
+    *inout = new cfx_pattern();
+  build_pattern(ctx, a, *inout, 0);
+  CFX_API_END(ctx)
+}
+
+cfx_status cfx_create_sparsity_rows(cfx_ctx* ctx, const cfx_form* a_const, int64_t row_begin, cfx_pattern** inout)
+{
+  CFX_API_BEGIN
+  cfx_form* a = const_cast<cfx_form*>(a_const);
+  CFX_REQUIRE(ctx && a && inout, CFX_ERR_INVALID, "cfx_create_sparsity_rows: NULL argument");
+  CFX_REQUIRE(a->rank == 2, CFX_ERR_INVALID, "Cannot create sparsity pattern. Form is not a bilinear.");
+  CFX_REQUIRE(row_begin > 0 && row_begin <= ctx->spaces[a->space].n_total, CFX_ERR_INVALID,
+              "cfx_create_sparsity_rows: row_begin must be in (0, owned+ghost dofs]");
+  if (*inout == nullptr)
+    *inout = new cfx_pattern();
+  build_pattern(ctx, a, *inout, row_begin);
+  CFX_API_END(ctx)
+}
+
+cfx_status cfx_form_insert_pattern_entries(cfx_ctx* ctx, cfx_form* f, const int32_t* rows, const int32_t* cols,
+                                           int64_t n, int memspace)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && f, CFX_ERR_INVALID, "cfx_form_insert_pattern_entries: NULL argument");
+  CFX_REQUIRE(f->rank == 2, CFX_ERR_INVALID, "cfx_form_insert_pattern_entries: form is not bilinear");
+  CFX_REQUIRE(n == 0 || (rows && cols), CFX_ERR_INVALID, "cfx_form_insert_pattern_entries: NULL entries");
+  f->n_x = n;
+  if (n > 0)
+  {
+    const cudaMemcpyKind kind = memspace == CFX_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    f->xrows.reserve(ctx->pool, static_cast<size_t>(n));
+    f->xcols.reserve(ctx->pool, static_cast<size_t>(n));
+    CFX_CUDA(cudaMemcpyAsync(f->xrows.p, rows, static_cast<size_t>(n) * sizeof(int32_t), kind, ctx->stream));
+    CFX_CUDA(cudaMemcpyAsync(f->xcols.p, cols, static_cast<size_t>(n) * sizeof(int32_t), kind, ctx->stream));
+    if (memspace == CFX_HOST)
+      CFX_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  f->dirty = true;
+  CFX_API_END(ctx)
+}
+
+__global__ void positions_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ cols_csr,
+                                 int64_t n_rows, const int32_t* __restrict__ rows, const int32_t* __restrict__ cols,
+                                 int64_t n, int64_t* __restrict__ pos, int32_t* __restrict__ err)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n)
+    return;
+  const int32_t r = rows[i], c = cols[i];
+  if (r < 0 || r >= n_rows)
+  {
+    err[0] = 26;
+    err[1] = r;
+    return;
+  }
+  int64_t lo = row_ptr[r], hi = row_ptr[r + 1];
+  while (lo < hi)
+  {
+    const int64_t mid = (lo + hi) >> 1;
+    if (cols_csr[mid] < c)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  if (lo >= row_ptr[r + 1] || cols_csr[lo] != c)
+  {
+    err[0] = 27;
+    err[1] = r;
+    return;
+  }
+  pos[i] = lo;
+}
+
+cfx_status cfx_pattern_positions(cfx_ctx* ctx, const cfx_pattern* p, const int32_t* rows, const int32_t* cols,
+                                 int64_t n, int64_t* positions)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && p && (n == 0 || (rows && cols && positions)), CFX_ERR_INVALID,
+              "cfx_pattern_positions: NULL argument");
+  if (n > 0)
+  {
+    CFX_LAUNCH(ctx, positions_kernel, grid_for(n, 256), 256, 0, p->row_ptr.p, p->cols.p, p->n_rows, rows, cols, n,
+               positions, ctx->err_flag.p);
+    check_device_error(ctx, "cfx_pattern_positions (entry not in the sparsity pattern)");
+  }
   CFX_API_END(ctx)
 }
 
@@ -1071,6 +1251,8 @@ cfx_status cfx_pattern_fetch(cfx_ctx* ctx, const cfx_pattern* p, int64_t* row_pt
 }
 
 const double* cfx_pattern_values_device_ptr(const cfx_pattern* p) { return p ? p->values.p : nullptr; }
+const int64_t* cfx_pattern_row_ptr_device_ptr(const cfx_pattern* p) { return p ? p->row_ptr.p : nullptr; }
+const int32_t* cfx_pattern_cols_device_ptr(const cfx_pattern* p) { return p ? p->cols.p : nullptr; }
 
 cfx_status cfx_pattern_values_fetch(cfx_ctx* ctx, const cfx_pattern* p, double* values, int memspace)
 {

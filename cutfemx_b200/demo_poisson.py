@@ -80,8 +80,10 @@ class CutPoisson:
         self.A = None
         self.b = None
         self.stats = {}
+        self.last = None
 
-    def step(self, assemble_rhs: bool = True, keep: bool = False):
+    def build_forms(self, assemble_rhs: bool = True):
+        """update -> locate -> rules -> normals -> ghost facets -> the forms a and L."""
         cd = self.cut_data
         _cut.update(cd)                                                     # cutfemx.update
         inside = _cut.locate_entities_device(cd, "phi<0")                   # locate_entities
@@ -95,27 +97,44 @@ class CutPoisson:
         a.add_cell_integral("nitsche", None, ri, (self.gamma,))
         if ghost.size > 0:
             a.add_interior_facet_integral("ghost_grad_jump", rows=rows, constants=(self.gamma_g,))
-        self.A = _fem.create_matrix(a, self.A)                              # create_sparsity_pattern
-        _fem.assemble_matrix(a, self.A)                                     # assemble_matrix
         L = None
         if assemble_rhs:
             L = _fem.CutForm(self.V, 1)
             L.add_cell_integral("source", inside, rv, (self.f_value,))
             L.add_cell_integral("nitsche_rhs", None, ri, (self.gamma, self.g_value))
+        self.last = dict(inside=inside, rv=rv, ri=ri, ghost=ghost, rows=rows, a=a, L=L)
+        return a, L
+
+    def assemble(self):
+        """create_sparsity_pattern + assemble_matrix (+ assemble_vector) of the current forms."""
+        a, L = self.last["a"], self.last["L"]
+        self.A = _fem.create_matrix(a, self.A)                              # create_sparsity_pattern
+        _fem.assemble_matrix(a, self.A)                                     # assemble_matrix
+        if L is not None:
             self.b = self._assemble_vector_device(L)
+        cd, t = self.cut_data, self.last
         counts = cd.counts()
         self.stats = dict(inside=counts[0], cut=counts[1], outside=counts[2], nnz=self.A.nnz,
-                          n_rows=self.A.shape[0], ghost_facets=ghost.size, volume_points=rv.total_points,
-                          interface_points=ri.total_points, volume_rules=rv.num_rules)
-        if keep:
-            self.last = dict(inside=inside, rv=rv, ri=ri, ghost=ghost, rows=rows, a=a, L=L)
-        else:
-            a.free()
-            if L is not None:
-                L.free()
-            for o in (inside, rv, ri, ghost, rows):
-                o.free()
+                          n_rows=self.A.shape[0], ghost_facets=t["ghost"].size, volume_points=t["rv"].total_points,
+                          interface_points=t["ri"].total_points, volume_rules=t["rv"].num_rules)
         return self.stats
+
+    def release_step(self):
+        t, self.last = self.last, None
+        if not t:
+            return
+        t["a"].free()
+        if t["L"] is not None:
+            t["L"].free()
+        for k in ("inside", "rv", "ri", "ghost", "rows"):
+            t[k].free()
+
+    def step(self, assemble_rhs: bool = True, keep: bool = False):
+        self.build_forms(assemble_rhs)
+        stats = self.assemble()
+        if not keep:
+            self.release_step()
+        return stats
 
     def _assemble_vector_device(self, L):
         import torch

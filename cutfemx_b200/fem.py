@@ -148,6 +148,23 @@ class MatrixCSR:
             check(h, lib().cfx_pattern_values_fetch(h, self._h, C.c_void_p(out.ctypes.data), HOST))
         return out
 
+    # zero-copy device views (valid until the next create_matrix on this object)
+    def indptr_device(self):
+        from ._lib import device_view
+
+        nr, _ = self._sizes()
+        return device_view(lib().cfx_pattern_row_ptr_device_ptr(self._h), nr + 1, np.int64, self.ctx.device, self)
+
+    def indices_device(self):
+        from ._lib import device_view
+
+        return device_view(lib().cfx_pattern_cols_device_ptr(self._h), self.nnz, np.int32, self.ctx.device, self)
+
+    def values_device(self):
+        from ._lib import device_view
+
+        return device_view(lib().cfx_pattern_values_device_ptr(self._h), self.nnz, np.float64, self.ctx.device, self)
+
     def to_scipy(self):
         import scipy.sparse as sp
 
@@ -178,6 +195,29 @@ def create_matrix(a: CutForm, A: MatrixCSR | None = None) -> MatrixCSR:
     A._cache.clear()
     check(a.ctx.handle, lib().cfx_create_sparsity(a.ctx.handle, a._h, C.byref(A._h)))
     return A
+
+
+def create_ghost_row_pattern(a: CutForm, row_begin: int, A: MatrixCSR | None = None) -> MatrixCSR:
+    """The entries SparsityPattern::finalize() ships to other ranks: pattern of the rows >= row_begin
+    (the ghost rows) only, without the deactivation diagonal (cfx_create_sparsity_rows)."""
+    if A is None:
+        A = MatrixCSR(a.ctx)
+    A._cache.clear()
+    check(a.ctx.handle, lib().cfx_create_sparsity_rows(a.ctx.handle, a._h, C.c_int64(row_begin), C.byref(A._h)))
+    return A
+
+
+def insert_pattern_entries(a: CutForm, rows, cols) -> None:
+    """la::SparsityPattern::insert for entries received from other ranks (sorted by row)."""
+    if rows is None or int(rows.numel() if is_device_array(rows) else np.size(rows)) == 0:
+        check(a.ctx.handle, lib().cfx_form_insert_pattern_entries(a.ctx.handle, a._h, None, None, C.c_int64(0), HOST))
+        return
+    pr, msr, kr = as_arg(rows, np.int32)
+    pc, msc, kc = as_arg(cols, np.int32)
+    if msr != msc:
+        raise CfxError("inserted pattern rows and columns must live in the same memory space")
+    n = int(kr.numel() if is_device_array(kr) else kr.size)
+    check(a.ctx.handle, lib().cfx_form_insert_pattern_entries(a.ctx.handle, a._h, pr, pc, C.c_int64(n), msr))
 
 
 def assemble_matrix(a: CutForm, A: MatrixCSR | None = None, *, diag_inactive: float = 0.0) -> MatrixCSR:

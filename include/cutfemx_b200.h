@@ -164,12 +164,29 @@ void cfx_form_free(cfx_ctx* ctx, cfx_form* f);
  * Pattern = union of cell cliques and facet macro cliques of the form's domains, plus the
  * diagonal of every owned+ghost row (insert_deactivation_diagonal, assembler.h:538-560). */
 cfx_status cfx_create_sparsity(cfx_ctx* ctx, const cfx_form* a, cfx_pattern** inout);
+/* la::SparsityPattern::insert(rows, cols) for entries that do not come from this rank's integration
+ * domains: on a partitioned mesh SparsityPattern::finalize() sends the entries of ghost rows to the
+ * owning rank, which merges them into its own rows (DOLFINx 0.11, reached from assembler.h:567-592
+ * create_sparsity_pattern -> wrappers/fem.cpp:266-276).  `rows` ascending, (row, col) local indices;
+ * a column >= the space's owned+ghost dof count is a NEW ghost column of the matrix (finalize()
+ * extends the column index map the same way).  Used by the next cfx_create_sparsity of this form. */
+cfx_status cfx_form_insert_pattern_entries(cfx_ctx* ctx, cfx_form* f, const int32_t* rows, const int32_t* cols,
+                                           int64_t n, int memspace);
+/* The part of the pattern finalize() ships to other ranks: rows >= row_begin only (the ghost rows,
+ * numbered after the owned ones), no deactivation diagonal; other rows are left empty. */
+cfx_status cfx_create_sparsity_rows(cfx_ctx* ctx, const cfx_form* a, int64_t row_begin, cfx_pattern** inout);
+/* position of entry (rows[i], cols[i]) in the values array (MatrixCSR keeps the same map for
+ * scatter_rev); DEVICE arrays; fails if an entry is not in the pattern */
+cfx_status cfx_pattern_positions(cfx_ctx* ctx, const cfx_pattern* p, const int32_t* rows, const int32_t* cols,
+                                 int64_t n, int64_t* positions);
 /* adopt a pattern built elsewhere (la::MatrixCSR row_ptr int64 / cols int32, sorted per row) */
 cfx_status cfx_pattern_import(cfx_ctx* ctx, int space, const int64_t* row_ptr, const int32_t* cols, int64_t n_rows,
                               int memspace, cfx_pattern** out);
 cfx_status cfx_pattern_sizes(const cfx_pattern* p, int64_t* n_rows, int64_t* nnz);
 cfx_status cfx_pattern_fetch(cfx_ctx* ctx, const cfx_pattern* p, int64_t* row_ptr, int32_t* cols, int memspace);
 const double* cfx_pattern_values_device_ptr(const cfx_pattern* p);
+const int64_t* cfx_pattern_row_ptr_device_ptr(const cfx_pattern* p);
+const int32_t* cfx_pattern_cols_device_ptr(const cfx_pattern* p);
 cfx_status cfx_pattern_values_fetch(cfx_ctx* ctx, const cfx_pattern* p, double* values, int memspace);
 void cfx_pattern_free(cfx_ctx* ctx, cfx_pattern* p);
 
@@ -185,6 +202,17 @@ cfx_status cfx_assemble_matrix(cfx_ctx* ctx, const cfx_form* a, cfx_pattern* A, 
 cfx_status cfx_assemble_vector(cfx_ctx* ctx, const cfx_form* L, double* b, int zero_first, int memspace);
 /* assemble_scalar: assemble_scalar_impl.h:26-275 (fixed-order tree reduction) */
 cfx_status cfx_assemble_scalar(cfx_ctx* ctx, const cfx_form* M, double* out);
+
+/* ------------------------------------------------------------------ ghost exchange (one rank per GPU)
+ * la::MatrixCSR::scatter_rev / la::Vector::scatter_rev(add) as called by the user after assembly
+ * (python/demo/demo_poisson.py:52,54): values of ghost rows / ghost entries travel to the owning
+ * rank and are added there.  The library provides the pack and unpack-add kernels around the
+ * neighbour exchange (NCCL send/recv on the device buffers, cutfemx_b200/parallel.py); all pointers
+ * are DEVICE pointers.  scatter_add requires distinct indices within one call (one neighbour's
+ * entries are distinct matrix positions), so it needs no atomics and the result is bit-reproducible
+ * when neighbours are applied in a fixed order. */
+cfx_status cfx_gather_f64(cfx_ctx* ctx, const double* src, const int64_t* index, int64_t n, double* dst);
+cfx_status cfx_scatter_add_f64(cfx_ctx* ctx, const double* src, const int64_t* index, int64_t n, double* dst);
 
 /* ------------------------------------------------------------------ profiling hooks
  * per-stage CUDA-event timings of the most recent calls, for bench.py's roofline block.

@@ -1,0 +1,279 @@
+"""-m "not gpu": the N>1 path on the CPU -- slab partitions, index maps, SparsityPattern::finalize-
+style entry exchange and scatter_reverse plans of cutfemx_b200/parallel.py, driven
+
+* in one process through LocalTransport (2 and 3 ranks: first / middle / last rank), and
+* as two real processes over torch.distributed with the gloo backend (world_size 2).
+
+The local compute of every rank is the CPU oracle (test infrastructure); the product's device
+kernels are exercised by tests/test_parallel_gpu.py.  Check: the union of the ranks' owned rows
+after the exchange equals the serial assembly of the same problem (sparsity bit-exact, values and
+right-hand side to 1e-11), whatever the number of ranks.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+import oracle as O
+from cutfemx_b200 import mesh as M
+from cutfemx_b200 import parallel as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORDER, GAMMA, GAMMA_G, F_VALUE, G_VALUE = 4, 40.0, 0.1, 1.0, 2.5
+
+
+def level_set(tdim):
+    return M.sphere_level_set((0.5, 0.5, 0.5), 0.35) if tdim == 3 else M.sphere_level_set((0.0, 0.0, 0.0), 0.5)
+
+
+def box(tdim):
+    return ((0.0, 0.0, 0.0), (1.0, 1.0, 1.0)) if tdim == 3 else ((-1.0, -1.0), (1.0, 1.0))
+
+
+def serial_reference(shape):
+    from oracle import pipeline
+
+    tdim = len(shape)
+    p0, p1 = box(tdim)
+    mesh = M.create_box(*shape, p0, p1) if tdim == 3 else M.create_rectangle(*shape, p0, p1)
+    V = M.functionspace(mesh, 1)
+    phi = M.interpolate(V, level_set(tdim))
+    out = pipeline.run_pipeline(mesh, V.dofmap, phi, V, order=ORDER, gamma=GAMMA, gamma_g=GAMMA_G, f_value=F_VALUE,
+                                g_value=G_VALUE)
+    n = V.num_dofs
+    A = sp.csr_matrix((out["vals"], out["cols"], out["row_ptr"]), shape=(n, n))
+    return A, out["b"]
+
+
+class OracleRank:
+    """One rank's local work through the oracle, same phases as parallel.RankPipeline."""
+
+    def __init__(self, shape, world, rank):
+        tdim = len(shape)
+        p0, p1 = box(tdim)
+        self.mesh, self.V, self.imap = P.partition_slab(shape, p0, p1, world, rank)
+        self.world, self.rank = world, rank
+        self.phi = M.interpolate(self.V, level_set(tdim))
+        self.vx = P.VectorExchange(self.imap)
+        self.mx = P.MatrixExchange(self.imap)
+
+    def phase_a(self):
+        mesh, V, phi = self.mesh, self.V, self.phi
+        nco = mesh.num_cells_local
+        dom = O.classify(V.dofmap, phi)  # every local cell, ghosts included
+        self.inside = O.locate(dom[:nco], "phi<0")
+        self.rv = O.runtime_quadrature(mesh, V.dofmap, phi, dom, "<", ORDER)
+        self.ri = O.runtime_quadrature(mesh, V.dofmap, phi, dom, "=", ORDER)
+        self.ri.normals = O.normals(mesh, V.dofmap, 1, phi, self.ri)
+        assert np.all(self.rv.parent_map < nco) and np.all(self.ri.parent_map < nco)
+        ghost = O.ghost_penalty_facets(mesh, O.locate(dom, "phi=0"), O.locate(dom, "phi<0"))
+        assert np.all(ghost < mesh.num_owned_facets)
+        self.rows4 = O.facet_rows(mesh, ghost)
+        self.active = np.concatenate([self.inside, self.rv.parent_map])
+        if self.world == 1:
+            return {}
+        rp, cols = O.sparsity(V, self.active, self.rows4, insert_diagonal=False)
+        rows, cols = P.coo_of_rows(torch.from_numpy(rp), torch.from_numpy(cols), self.imap.n_owned, self.imap.n_total)
+        return self.mx.begin(rows, cols)
+
+    def phase_b(self, recv):
+        V = self.V
+        rp, cols = O.sparsity(V, self.active, self.rows4)
+        n, ncols = V.num_dofs, V.num_dofs
+        pat = sp.csr_matrix((np.ones(cols.size), cols, rp), shape=(n, n))
+        if self.world > 1:
+            xr, xc = self.mx.inserted_entries(recv)
+            ncols += int(self.mx.new_ghost_globals.numel())
+            pat = sp.csr_matrix((pat.data, pat.indices, pat.indptr), shape=(n, ncols))
+            if xr is not None:
+                pat = pat + sp.csr_matrix((np.ones(xr.numel()), (xr.numpy(), xc.numpy())), shape=(n, ncols))
+        pat.sort_indices()
+        self.row_ptr, self.cols = pat.indptr.astype(np.int64), pat.indices.astype(np.int32)
+        self.vals = np.zeros(self.cols.size)
+        O.assemble_cells(V, "laplace", self.vals, self.inside, self.rv, (1.0,), self.row_ptr, self.cols)
+        O.assemble_cells(V, "nitsche", self.vals, None, self.ri, (GAMMA,), self.row_ptr, self.cols)
+        O.assemble_interior_facets(V, "ghost_grad_jump", self.vals, self.rows4, (GAMMA_G,), self.row_ptr, self.cols)
+        self.b = np.zeros(n)
+        O.assemble_cells(V, "source", self.b, self.inside, self.rv, (F_VALUE,))
+        O.assemble_cells(V, "nitsche_rhs", self.b, None, self.ri, (GAMMA, G_VALUE))
+        if self.world == 1:
+            return {}
+        self.mx.finish(self.positions)
+        vals_t, b_t = torch.from_numpy(self.vals), torch.from_numpy(self.b)
+        sends = {}
+        for q in sorted(set(self.mx.send_pos) | set(self.vx.send_sel)):
+            parts = []
+            if q in self.mx.send_pos:
+                parts.append(vals_t[self.mx.send_pos[q]])
+            if q in self.vx.send_sel:
+                parts.append(b_t[self.vx.send_sel[q]])
+            sends[q] = torch.cat(parts)
+        return sends
+
+    def positions(self, rows, cols):
+        """what cfx_pattern_positions does: row_ptr[r] + lower_bound(cols of r, c)."""
+        out = np.empty(rows.numel(), dtype=np.int64)
+        for i, (r, c) in enumerate(zip(rows.tolist(), cols.tolist())):
+            seg = self.cols[self.row_ptr[r]:self.row_ptr[r + 1]]
+            k = int(np.searchsorted(seg, c))
+            assert k < seg.size and seg[k] == c, "entry not in the pattern"
+            out[i] = self.row_ptr[r] + k
+        return torch.from_numpy(out)
+
+    def recv_counts(self):
+        m, v = self.mx.recv_counts(), self.vx.recv_counts()
+        return {q: m.get(q, 0) + v.get(q, 0) for q in set(m) | set(v)}
+
+    def phase_c(self, recv):
+        for q in sorted(recv):
+            t = recv[q].numpy()
+            nm = int(self.mx.recv_pos[q].numel()) if q in self.mx.recv_pos else 0
+            pos = self.mx.recv_pos[q].numpy() if nm else np.zeros(0, np.int64)
+            assert np.unique(pos).size == pos.size  # distinct positions per neighbour: no atomics needed
+            self.vals[pos] += t[:nm]
+            if q in self.vx.recv_pos:
+                self.b[self.vx.recv_pos[q].numpy()] += t[nm:]
+
+    def owned_global(self):
+        no, off = self.imap.n_owned, self.imap.offset
+        colmap = np.concatenate([self.imap.l2g.numpy(), self.mx.new_ghost_globals.numpy()
+                                 if self.mx.new_ghost_globals is not None else np.zeros(0, np.int64)])
+        e = int(self.row_ptr[no])
+        rows = np.repeat(np.arange(no), np.diff(self.row_ptr[: no + 1])) + off
+        return rows, colmap[self.cols[:e]], self.vals[:e], self.b[:no], off
+
+
+def run_ranks(ranks, transport):
+    recv = transport.exchange([r.vx.begin() for r in ranks])
+    for r, rc in zip(ranks, recv):
+        r.vx.finish(rc)
+    recv = transport.exchange([r.phase_a() for r in ranks])
+    sends = [r.phase_b(rc) for r, rc in zip(ranks, recv)]
+    recv = transport.exchange(sends, counts=[r.recv_counts() for r in ranks])
+    for r, rc in zip(ranks, recv):
+        r.phase_c(rc)
+
+
+def compare_with_serial(parts, shape):
+    A_ref, b_ref = serial_reference(shape)
+    n = A_ref.shape[0]
+    rows = np.concatenate([p[0] for p in parts])
+    cols = np.concatenate([p[1] for p in parts])
+    vals = np.concatenate([p[2] for p in parts])
+    A = sp.csr_matrix((vals, (rows, cols)), shape=(n, n))
+    A.sort_indices()
+    # every rank's owned rows are disjoint: no duplicate (row, col) was summed by the constructor
+    assert A.nnz == rows.size
+    assert np.array_equal(A.indptr, A_ref.indptr) and np.array_equal(A.indices, A_ref.indices)
+    assert np.linalg.norm(A.data - A_ref.data) <= 1e-11 * np.linalg.norm(A_ref.data)
+    b = np.zeros(n)
+    for p in parts:
+        b[p[4]:p[4] + p[3].size] = p[3]
+    assert np.linalg.norm(b - b_ref) <= 1e-11 * np.linalg.norm(b_ref)
+
+
+# ----------------------------------------------------------------------------- partition invariants
+@pytest.mark.parametrize("shape,world", [((6, 5, 7), 3), ((9, 8), 2), ((4, 4, 8), 4)])
+def test_partition_invariants(shape, world):
+    tdim = len(shape)
+    p0, p1 = box(tdim)
+    full = M.create_box(*shape, p0, p1) if tdim == 3 else M.create_rectangle(*shape, p0, p1)
+    seen_cells, owned = 0, []
+    for rank in range(world):
+        mesh, V, im = P.partition_slab(shape, p0, p1, world, rank)
+        seen_cells += mesh.num_cells_local
+        l2g = im.l2g.numpy()
+        owned.append(l2g[: im.n_owned])
+        assert np.array_equal(l2g[: im.n_owned], np.arange(im.offset, im.offset + im.n_owned))
+        assert np.all(np.diff(im.ghost_global.numpy()) > 0)
+        assert np.array_equal(mesh.x, full.x[l2g])                            # same vertices BIT FOR BIT, global lexicographic ids
+        # every local cell is a cell of the global mesh (as a vertex set)
+        gl = np.sort(l2g[mesh.x_dofmap], axis=1)
+        key = {tuple(r) for r in np.sort(full.x_dofmap, axis=1).tolist()}
+        assert all(tuple(r) in key for r in gl.tolist())
+        # facet numbering: c2f consistent with f2c, owned facets first and each has an owned cell
+        ncell = np.diff(mesh.f2c_offsets)
+        for f in np.unique(mesh.c2f):
+            cs = mesh.f2c[mesh.f2c_offsets[f]:mesh.f2c_offsets[f + 1]]
+            assert 1 <= cs.size <= 2
+            if f < mesh.num_owned_facets:
+                assert cs.min() < mesh.num_cells_local
+        # ghost owners are the neighbouring ranks
+        if im.ghost_owner.numel():
+            assert set(im.ghost_owner.tolist()) <= {rank - 1, rank + 1}
+    assert seen_cells == full.num_cells
+    allowned = np.concatenate(owned)
+    assert np.array_equal(np.sort(allowned), np.arange(full.num_nodes))        # a partition of the dofs
+
+    # each interior facet of the global mesh is owned by exactly one rank
+    count = {}
+    for rank in range(world):
+        mesh, V, im = P.partition_slab(shape, p0, p1, world, rank)
+        l2g = im.l2g.numpy()
+        for f in np.unique(mesh.c2f):
+            if f >= mesh.num_owned_facets:
+                continue
+            c = mesh.f2c[mesh.f2c_offsets[f]]
+            lf = int(np.nonzero(mesh.c2f[c] == f)[0][0])
+            verts = tuple(sorted(l2g[np.delete(mesh.x_dofmap[c], lf)].tolist()))
+            count[verts] = count.get(verts, 0) + 1
+    assert set(count.values()) == {1}
+    nf_global = np.unique(full.c2f).size
+    assert len(count) == nf_global
+
+
+# ----------------------------------------------------------------------------- in-process ranks
+@pytest.mark.parametrize("shape,world", [((8, 8, 8), 2), ((6, 6, 9), 3), ((16, 16), 2), ((12, 12), 3), ((6, 6, 6), 1)])
+def test_local_transport_matches_serial(shape, world):
+    ranks = [OracleRank(shape, world, r) for r in range(world)]
+    run_ranks(ranks, P.LocalTransport(world))
+    compare_with_serial([r.owned_global() for r in ranks], shape)
+
+
+def test_new_ghost_columns_appear_with_facet_terms():
+    """Ghost-penalty macro cliques reach two planes beyond the owner's own: finalize() must add
+    ghost COLUMNS the owner's dofmap does not know."""
+    shape, world = (6, 6, 9), 3
+    ranks = [OracleRank(shape, world, r) for r in range(world)]
+    run_ranks(ranks, P.LocalTransport(world))
+    assert sum(int(r.mx.new_ghost_globals.numel()) for r in ranks) > 0
+
+
+# ----------------------------------------------------------------------------- two processes, gloo
+def _worker(rank, world, shape, port, outdir):
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        r = OracleRank(shape, world, rank)
+        run_ranks([r], P.TorchDistTransport())
+        rows, cols, vals, b, off = r.owned_global()
+        np.savez(os.path.join(outdir, f"part{rank}.npz"), rows=rows, cols=cols, vals=vals, b=b, off=off)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape", [(8, 8, 8), (20, 20)])
+def test_gloo_world_size_2_matches_serial(shape, tmp_path):
+    import socket
+
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    O.build()
+    mp.spawn(_worker, args=(2, shape, port, str(tmp_path)), nprocs=2, join=True)
+    parts = []
+    for rank in range(2):
+        d = np.load(tmp_path / f"part{rank}.npz")
+        parts.append((d["rows"], d["cols"], d["vals"], d["b"], int(d["off"])))
+    compare_with_serial(parts, shape)
