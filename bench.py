@@ -48,6 +48,17 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic(kernel, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this workload (profiles/ncu_traffic.json, written by tools/ncu_summary.py)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        return t.get(f"{kernel}@n{n}")
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -190,28 +201,26 @@ def run_ours(args, wl):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     dev = f"cuda:{local_rank}"
 
-    import cutfemx_b200 as cfx
-    from cutfemx_b200 import demo_poisson as dp
-    from cutfemx_b200.mesh import Function, FunctionSpace
+    import ctypes as C
+
+    from cutfemx_b200 import parallel as P
+    from cutfemx_b200._lib import HOST, check, lib
 
     n = args.n or wl["n"]
     tdim = wl["tdim"]
-    # strong scaling: the fixed n^tdim mesh is split into z-slabs (y-strips in 2D), one per rank
-    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
-    p0, p1 = list(wl["p0"]), list(wl["p1"])
-    ax = tdim - 1
-    h = (p1[ax] - p0[ax]) / n
-    q0, q1 = list(p0), list(p1)
-    q0[ax], q1[ax] = p0[ax] + lo * h, p0[ax] + hi * h
-    shape = [n] * tdim
-    shape[ax] = hi - lo
-    mesh = dp.device_mesh(local_rank, shape, q0, q1)
     kind, prm = wl["ls"]
-    vals = dp.device_level_set(mesh, kind, prm)
-    V = FunctionSpace(mesh, 1, mesh.x_dofmap, int(mesh.x.shape[0]), int(mesh.x.shape[0]), 1, None)
-    phi = Function(V, "phi", vals)
-    prob = dp.CutPoisson(mesh, phi, V, order=wl["order"])
-    ctx = prob.ctx
+    # strong scaling: the fixed n^tdim mesh is split into z-slabs (y-strips in 2D), one rank per GPU, with a
+    # shared-facet ghost layer; ghost rows travel to their owners over NCCL every step
+    pipe = P.RankPipeline([n] * tdim, list(wl["p0"]), list(wl["p1"]), world, rank, local_rank, kind, prm,
+                          order=wl["order"])
+    transport = P.TorchDistTransport() if world > 1 else P.LocalTransport(1)
+    P.plan([pipe], transport)
+    prob, ctx, V = pipe.prob, pipe.ctx, pipe.V
+
+    def step():
+        st = P.run_step([pipe], transport)[0]
+        pipe.finish_step()
+        return st
 
     def barrier():
         if world > 1:
@@ -220,7 +229,7 @@ def run_ours(args, wl):
 
     # ---- device-resident leg ("value")
     for _ in range(max(args.warmup, 3)):
-        stats = prob.step()
+        stats = step()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)  # 256 MiB > 126 MB L2
     sampler = ClockSampler(local_rank)
     ctx.stage_timing(True)
@@ -231,41 +240,35 @@ def run_ours(args, wl):
     sampler.start()
     for i in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations (untimed)
-        torch.cuda.synchronize()
+        barrier()
         ev[i][0].record()
-        stats = prob.step()
+        stats = step()
         ev[i][1].record()
     barrier()
     clocks = sampler.stop()
     launches = ctx.launch_count - launches0
     ms = [a.elapsed_time(b) for a, b in ev]
-    t_dev = torch.tensor([sum(ms) / 1e3], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([stats["cut"], stats["nnz"], stats["inside"] + stats["cut"] + stats["outside"],
-                        stats["inside"] + stats["volume_rules"]], dtype=torch.float64, device=dev)
+    # per step: the slowest rank; then summed over the steps
+    t_steps = torch.tensor(ms, dtype=torch.float64, device=dev) / 1e3
+    nnz_owned = int(prob.A.indptr_device()[pipe.imap.n_owned].item())
+    cnt = torch.tensor([stats["cut"], nnz_owned, stats["inside"] + stats["cut"] + stats["outside"],
+                        stats["inside"] + stats["volume_rules"], launches], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_steps, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    t_total = float(t_dev.item())
-    cut_total, nnz_total, cells_total, active_total = (float(v) for v in cnt.tolist())
+    t_total = float(t_steps.sum().item())
+    cut_total, nnz_total, cells_total, active_total, launches_total = (float(v) for v in cnt.tolist())
     stages = ctx.stages()
     ctx.stage_timing(False)
     ctx.stage_reset()
 
     # ---- end-to-end leg: host buffers in, host buffers out, through the public API
+    vals = pipe.phi.x.array
     h_phi = torch.empty(vals.shape, dtype=torch.float64, pin_memory=True)
     h_phi.copy_(vals)
     torch.cuda.synchronize()
-    Vh = FunctionSpace(mesh, 1, mesh.x_dofmap, V.num_dofs, V.num_dofs, 1, None)
-    mesh_h = mesh  # the mesh stays bound on the device (bound once, like cutfemx.cut's mesh views)
-    phi_h = Function(Vh, "phi", h_phi.numpy())
-    import ctypes as C
-
-    from cutfemx_b200._lib import HOST, check, lib
-
-    # re-bind level set 0 to the pinned host array: cfx_update now does the H2D copy every step
-    pd = C.c_void_p(mesh.x_dofmap.data_ptr())
     hnd = ctx.handle
-    d_dofmap_host = None
+    # re-bind level set 0 to the pinned host array: cfx_update now does the H2D copy every step
     check(hnd, lib().cfx_levelset_bind(hnd, 0, None, tdim + 1, 1, C.c_void_p(h_phi.data_ptr()),
                                        C.c_int64(V.num_dofs), HOST, 1))
     nnz_cap = int(stats["nnz"] * 1.1) + 1024
@@ -275,31 +278,33 @@ def run_ours(args, wl):
     h_b = torch.empty(V.num_dofs, dtype=torch.float64, pin_memory=True)
 
     def e2e_step():
-        st = prob.step()
+        st = P.run_step([pipe], transport)[0]
         A = prob.A
         check(hnd, lib().cfx_pattern_fetch(hnd, A._h, C.c_void_p(h_rp.data_ptr()), C.c_void_p(h_cols.data_ptr()), HOST))
         check(hnd, lib().cfx_pattern_values_fetch(hnd, A._h, C.c_void_p(h_vals.data_ptr()), HOST))
         h_b.copy_(prob.b, non_blocking=False)
+        pipe.finish_step()
         return st
 
     for _ in range(2):
         st = e2e_step()
     barrier()
-    t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         st = e2e_step()
     e1.record()
     barrier()
-    t_e2e = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device=dev)
+    e2e = torch.tensor([e0.elapsed_time(e1) / 1e3, 8.0 * V.num_dofs,
+                        12.0 * st["nnz"] + 8.0 * (V.num_dofs + 1) + 8.0 * V.num_dofs], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    t_e2e = float(t_e2e.item())
-    h2d = 8 * V.num_dofs
-    d2h = 12 * st["nnz"] + 8 * (V.num_dofs + 1) + 8 * V.num_dofs
+        tmax = e2e[:1].clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e, op=dist.ReduceOp.SUM)
+        e2e[0] = tmax[0]
+    t_e2e, h2d, d2h = (float(v) for v in e2e.tolist())
 
-    # ---- per-stage summary, roofline of the dominant kernel stage
+    # ---- per-stage summary (rank 0), roofline of the dominant kernel
     agg = {}
     for name, msv, by in stages:
         a = agg.setdefault(name, [0.0, 0.0, 0])
@@ -309,9 +314,12 @@ def run_ours(args, wl):
     per_stage = {k: {"ms_per_step": v[0] / args.steps, "alg_GB_per_step": v[1] / args.steps / 1e9,
                      "GBps": (v[1] / 1e9) / (v[0] / 1e3) if v[0] > 0 else None} for k, v in agg.items()}
     peak, peak_src = load_peaks()
-    dom = max(per_stage.items(), key=lambda kv: kv[1]["ms_per_step"])
+    # "gather_matrix" is the parent stage of the kernel stage "gather_matrix_clist_kernel": single kernels only
+    cand = {k: v for k, v in per_stage.items() if k != "gather_matrix" or "gather_matrix_clist_kernel" not in per_stage}
+    dom = max(cand.items(), key=lambda kv: kv[1]["ms_per_step"])
     roof = {"bound": "hbm", "kernel": dom[0], "achieved": dom[1]["GBps"], "peak": peak, "unit": "GB/s",
-            "frac": (dom[1]["GBps"] or 0.0) / peak, "traffic": None, "peak_source": peak_src}
+            "frac": (dom[1]["GBps"] or 0.0) / peak, "traffic": load_traffic(dom[0], n), "peak_source": peak_src,
+            "ms_per_launch": dom[1]["ms_per_step"], "alg_GB_per_launch": dom[1]["alg_GB_per_step"]}
 
     if rank != 0:
         if world > 1:
@@ -323,11 +331,13 @@ def run_ours(args, wl):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["name"].format(n=n), "cells": int(cells_total), "cut_cells": int(cut_total),
                    "active_cells": int(active_total), "nnz": int(nnz_total), "l2": "flushed between timed steps "
-                   "(256 MiB write); inputs 2.2 GB >> L2", "partition": f"{world} z-slab(s), no ghost exchange yet"},
+                   "(256 MiB write); inputs 2.2 GB >> L2",
+                   "partition": f"{world} slab(s) along the last axis, shared-facet ghost layer, ghost rows "
+                                f"exchanged over NCCL" if world > 1 else "1 rank (no exchange)"},
         "nnz_per_s": nnz_total * args.steps / t_total, "total_cells_per_s": cells_total * args.steps / t_total,
         "e2e": {"value": cut_total * args.steps / t_e2e, "unit": "cut-cells/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e / args.steps * 1e3},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "stages": per_stage,
+        "gpu_launches": int(launches_total), "clocks": clocks, "roofline": roof, "stages": per_stage,
     }
     if world == 1 and not args.no_cpu_baseline:
         nb = args.ref_n or (96 if tdim == 3 else 1536)

@@ -1333,8 +1333,17 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
   const unsigned g = grid_for(PR->n_act_rows, GW);
   if constexpr (Elem<TDIM, DEG>::ND <= 6)
   { // the mask / contribution-list kernels need the packed incidence tables (nd <= 6)
-    if (fast && S.has_static)
+    if (fast && S.has_static && a->n_clist_rows > 0)
     {
+      // the dominant kernel, timed on its own: fused K4 (every standard cell's dofmap row, coordinates and
+      // dofs: 4 nv + 24 nv + 4 nd B) + K5 (12 B per CSR entry of its rows) -- SURVEY.md section 8(d)
+      int64_t n_std = 0;
+      for (auto& I : a->integrals)
+        if (!I.facet)
+          n_std += I.n;
+      StageScope sk(ctx, "gather_matrix_clist_kernel",
+                    12.0 * static_cast<double>(a->n_clist_nnz)
+                        + (28.0 * ctx->nv + 4.0 * S.nd) * static_cast<double>(n_std));
       auto kc = gather_matrix_clist_kernel<TDIM, DEG>;
       CFX_LAUNCH(ctx, kc, grid_for(PR->n_act_rows, GWC), GWC * 32, 0, gc, st, PR->act_rows.p, PR->n_act_rows,
                  a->row_fast.p, a->Rrow.p, A->row_ptr.p, A->values.p, zero_first);

@@ -268,6 +268,7 @@ struct cfx_form
   cfx::DevBuf<uint8_t> row_fast; // bit0: mask path, bit1: has band cells, bit2: static row
   int64_t n_slow_rows = 0;
   int64_t n_mask_rows = -1; // rows of the mask gather kernel (band rows, long contribution lists); -1 unknown
+  int64_t n_clist_rows = 0, n_clist_nnz = 0; // rows / CSR entries of the contribution-list gather kernel
   int64_t gtab_serial = -1;
   cfx::DevBuf<double> Ae;      // materialised run-time-rule tensors, cell-major (slot, nd^rank) natural order;
                                // rank 0: one value per entity

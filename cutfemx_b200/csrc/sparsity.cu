@@ -490,7 +490,8 @@ __global__ void __launch_bounds__(RW * 32)
 __global__ void __launch_bounds__(256)
     pattern_static_kernel(RowCtx rc, const int32_t* __restrict__ act_rows, int64_t n_act,
                           const uint32_t* __restrict__ fmask, const uint8_t* __restrict__ frow_ok,
-                          int32_t* __restrict__ row_nnz, uint32_t* __restrict__ Rrow, uint8_t* __restrict__ row_fast)
+                          int32_t* __restrict__ row_nnz, uint32_t* __restrict__ Rrow, uint8_t* __restrict__ row_fast,
+                          unsigned long long* __restrict__ n_clist /* [0] rows, [1] nnz of contribution-list rows */)
 {
   // 8 lanes per row (4 rows per warp): three independent gather chains per lane for 24 incident cells
   const int64_t t = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
@@ -514,12 +515,33 @@ __global__ void __launch_bounds__(256)
   M |= __shfl_xor_sync(0xffffffffu, M, 1);
   M |= __shfl_xor_sync(0xffffffffu, M, 2);
   M |= __shfl_xor_sync(0xffffffffu, M, 4);
-  if (valid && !band && sl == 0)
+  const bool lead = valid && !band && sl == 0;
+  bool clist = false;
+  if (lead)
   {
+    clist = frow_ok[r] != 0;
     row_nnz[r] = __popc(M);
     Rrow[idx] = M;
-    row_fast[idx] = 1 | 4 | (frow_ok[r] ? 8 : 0);
+    row_fast[idx] = 1 | 4 | (clist ? 8 : 0);
   }
+  // integer counters (exact, order-independent): one atomic pair per block
+  __shared__ int s_cnt[2];
+  if (threadIdx.x < 2)
+    s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const unsigned b = __ballot_sync(0xffffffffu, clist);
+  int nz = clist ? __popc(M) : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    nz += __shfl_down_sync(0xffffffffu, nz, o);
+  if ((threadIdx.x & 31) == 0 && b)
+  {
+    atomicAdd(&s_cnt[0], __popc(b));
+    atomicAdd(&s_cnt[1], nz);
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 && s_cnt[threadIdx.x])
+    atomicAdd(&n_clist[threadIdx.x], static_cast<unsigned long long>(s_cnt[threadIdx.x]));
 }
 
 // static rows after the scan: cols[row_ptr[r] + k] = k-th kept full-mesh column.  16 lanes per row.
@@ -1038,7 +1060,7 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
   const unsigned ga = grid_for(n_act, RW);
   DevBuf<int32_t> tmp;
   unsigned long long* n_slow = reinterpret_cast<unsigned long long*>(ctx->scratch64.p) + 1;
-  CFX_CUDA(cudaMemsetAsync(n_slow, 0, sizeof(unsigned long long), ctx->stream));
+  CFX_CUDA(cudaMemsetAsync(n_slow, 0, 3 * sizeof(unsigned long long), ctx->stream)); // [1] slow, [2..3] clist rows/nnz
   const bool use_static = S.has_static && !part;
   const int only_band = use_static ? 1 : 0;
   const bool need_generic = !use_static || PR->facet_key.first != nullptr || PR->extra_key.first != nullptr;
@@ -1049,7 +1071,7 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
     {
       a->Rrow.reserve(ctx->pool, static_cast<size_t>(n_act) + 1);
       CFX_LAUNCH(ctx, pattern_static_kernel, grid_for(n_act * 8, 256), 256, 0, rc, act, n_act, S.fmask.p, S.frow_ok.p,
-                 row_nnz.p, a->Rrow.p, a->row_fast.p);
+                 row_nnz.p, a->Rrow.p, a->row_fast.p, n_slow + 1);
     }
     if (need_generic)
     {
@@ -1062,9 +1084,12 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
   P->row_ptr.reserve(ctx->pool, static_cast<size_t>(S.n_total) + 2);
   exclusive_scan_i32_to_i64(ctx, row_nnz.p, S.n_total, P->row_ptr.p);
   {
-    const int64_t* h = read_back(ctx, ctx->scratch64.p, 2);
+    const int64_t* h = read_back(ctx, ctx->scratch64.p, 4);
     P->nnz = h[0];
     a->n_slow_rows = h[1];
+    a->n_clist_rows = h[2];
+    a->n_clist_nnz = h[3];
+    a->n_mask_rows = n_act - h[1] - h[2];
   }
   P->cols.reserve(ctx->pool, static_cast<size_t>(P->nnz) + 1);
   P->values.reserve(ctx->pool, static_cast<size_t>(P->nnz) + 1);
