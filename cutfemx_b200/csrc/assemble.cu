@@ -22,6 +22,8 @@
 // FFCx would pick (sum of argument degrees) scaled by |detJ|.
 //
 // Roofline: HBM for P1/P2 scalar forms (SURVEY.md section 8d "K4", "K5").
+#include <algorithm>
+
 #include "common.cuh"
 #include "element.cuh"
 
@@ -992,18 +994,53 @@ __global__ void __launch_bounds__(GWM * 32, 8)
 }
 
 // Static rows whose contribution lists fit (Space::fclist) -- the bulk of the matrix.  One WARP per
-// row, three dependent load levels:
-//   (0) by row slot:  row flags, row id, kept-column mask R
-//   (1) by row id:    incidence range, CSR row start, full-pattern row start
-//   (2) by position:  lane l: incident cell l and the local index of the row's dof in it;
+// row.  A row needs four DEPENDENT load levels before any arithmetic:
+//   (A) by row slot:  row flags, row id, kept-column mask R
+//   (B) by row id:    incidence range, CSR row start, full-pattern row start
+//   (C) by position:  lane l: incident cell l and the local index of the row's dof in it;
 //                     lane k: the contribution list of full-pattern column k and the CSR value it updates
-//   (3) by cell:      flag byte + geometry record (+ materialised tensor row for cut cells)
-// then the tensor row of every incident cell is computed on the fly and staged (transposed, conflict-
-// free) in shared memory; lane k sums the <= 8 listed (cell, local dof) entries in ascending cell
-// order, the diagonal takes one entry per cell through a fixed shuffle tree.  No atomics, no dofmap
-// read, no column search, no element tensors through HBM for standard cells.
+//   (D) by cell:      flag byte + geometry record (+ materialised tensor row for cut cells)
+// so the kernel is latency-bound unless the levels of different rows overlap.  Each warp therefore walks
+// its rows (grid-stride) in a software pipeline: while row i is computed (D), the loads of level C for
+// row i+s, level B for row i+2s and level A for row i+3s are in flight, and the cell records of row
+// i+s are prefetched into L2 as soon as its cell ids have arrived.
+// Per row: the tensor row of every incident cell is computed on the fly and staged (transposed,
+// conflict-free) in shared memory; lane k sums the <= 8 listed (cell, local dof) entries in
+// ascending cell order, the diagonal takes one entry per cell through a fixed shuffle tree.  No
+// atomics, no dofmap read, no column search, no element tensors through HBM for standard cells.
+struct ClistA
+{
+  unsigned rf;
+  int32_t r;
+  uint32_t R;
+};
+struct ClistB
+{
+  bool ok;
+  uint32_t R;
+  int64_t ib, rb, fb;
+  int n_inc;
+};
+struct ClistC
+{
+  bool ok;
+  uint32_t R;
+  int n_inc;
+  int32_t c;
+  int li;
+  uint64_t word;
+  double* pv;
+  double old;
+};
+
+struct ClistD
+{
+  unsigned fl;
+  int32_t ms;
+};
+
 template <int TDIM, int DEG>
-__global__ void __launch_bounds__(GWC * 32, 8)
+__global__ void __launch_bounds__(GWC * 32, 4)
     gather_matrix_clist_kernel(GatherCtx gc, StdTab st, const int32_t* __restrict__ act_rows, int64_t n_act,
                                const uint8_t* __restrict__ row_fast, const uint32_t* __restrict__ Rrow,
                                const int64_t* __restrict__ row_ptr, double* __restrict__ vals, int zero_first)
@@ -1011,81 +1048,144 @@ __global__ void __launch_bounds__(GWC * 32, 8)
   constexpr int ND = Elem<TDIM, DEG>::ND;
   __shared__ double s_v[GWC][ND][32];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * GWC + w;
-  if (idx >= n_act)
-    return;
   const unsigned full = 0xffffffffu;
-  // level 0
-  const unsigned rf = row_fast[idx];
-  const int64_t r = act_rows[idx];
-  const uint32_t R = Rrow[idx];
-  if ((rf & 13u) != 13u)
-    return;
-  // level 1
-  const int64_t ib = gc.inc_ptr[r];
-  const int64_t ie = gc.inc_ptr[r + 1];
-  const int64_t rb = row_ptr[r];
-  const int64_t fb = gc.frow_ptr[r];
-  // level 2
-  const int n_inc = static_cast<int>(ie - ib);
-  const bool in = lane < n_inc;
-  const int64_t kk = ib + (in ? lane : 0);
-  const int64_t c = gc.inc_cell[kk];
-  const int li = static_cast<int>(gc.fperm[kk] & 15u);
   const uint32_t below = (1u << lane) - 1u;
-  const bool kept = (R >> lane) & 1u;
-  const uint64_t word = __ldg(gc.fclist + fb + lane); // padded allocation: safe for every lane
-  double* const pv = vals + rb + __popc(R & below);
-  double acc = (kept && !zero_first) ? *pv : 0.0;
-  // level 3
-  const unsigned fl = in ? gc.cell_flags[c] : 0u;
-  Geo<TDIM> g;
-  load_geo_cached<TDIM>(gc.geo, c, g);
-  const int32_t ms = __ldg(gc.mat_slot + c);
-  const bool contributes = (fl & 0xFDu) != 0;
-  double dval = 0.0;
-  if (contributes)
-  {
-    double v[ND];
-#pragma unroll
-    for (int j = 0; j < ND; ++j)
-      v[j] = 0.0;
-    if (fl >> 2)
-      std_row_values<TDIM, DEG>(st, g, fl, li, v);
-    if (fl & 1)
-    {
-      const double* a = gc.Ae + (static_cast<int64_t>(ms) * ND + li) * ND;
-#pragma unroll
-      for (int j = 0; j < ND; ++j)
-        v[j] += a[j];
-    }
-    dval = pick<ND>(v, li);
-#pragma unroll
-    for (int j = 0; j < ND; ++j)
-      s_v[w][j][lane] = v[j];
-  }
-  __syncwarp();
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-    dval += __shfl_down_sync(full, dval, o);
-  dval = __shfl_sync(full, dval, 0);
-  const unsigned cmask = __ballot_sync(full, contributes);
-  if (!kept)
+  // each block walks a contiguous chunk of rows (its warps interleaved): rows that share cells are
+  // processed close in time by the same SM (L1) or by blocks at the same relative position (L2)
+  const int64_t stride = GWC;
+  const int64_t chunk = ((n_act + gridDim.x - 1) / gridDim.x + GWC - 1) / GWC * GWC;
+  int64_t i = static_cast<int64_t>(blockIdx.x) * chunk + w;
+  const int64_t i_end = (i - w + chunk < n_act) ? i - w + chunk : n_act;
+  if (i >= i_end)
     return;
-  if ((word & 0xFFull) == 0xFEull)
-    acc += dval;
-  else
+
+  auto stageA = [&](int64_t idx) -> ClistA
   {
-#pragma unroll
-    for (int e = 0; e < 8; ++e)
-    {
-      const unsigned b = static_cast<unsigned>(word >> (8 * e)) & 0xFFu;
-      const unsigned l = b & 31u;
-      if (b != 0xFFu && ((cmask >> l) & 1u))
-        acc += s_v[w][b >> 5][l];
-    }
+    ClistA a;
+    const int64_t k = idx < i_end ? idx : i_end - 1; // clamped: the loads are always legal
+    a.rf = idx < i_end ? row_fast[k] : 0u;
+    a.r = act_rows[k];
+    a.R = Rrow[k];
+    return a;
+  };
+  auto stageB = [&](const ClistA& a) -> ClistB
+  {
+    ClistB b;
+    b.ok = (a.rf & 13u) == 13u;
+    b.R = a.R;
+    b.ib = gc.inc_ptr[a.r];
+    b.n_inc = static_cast<int>(gc.inc_ptr[a.r + 1] - b.ib);
+    b.rb = row_ptr[a.r];
+    b.fb = gc.frow_ptr[a.r];
+    return b;
+  };
+  auto stageC = [&](const ClistB& b) -> ClistC
+  {
+    ClistC c;
+    c.ok = b.ok;
+    c.R = b.R;
+    c.n_inc = b.n_inc;
+    const int64_t kk = b.ib + (lane < b.n_inc ? lane : 0);
+    c.c = gc.inc_cell[kk];
+    c.li = static_cast<int>(gc.fperm[kk] & 15u);
+    c.word = __ldg(gc.fclist + b.fb + lane); // padded allocation: legal for every lane
+    c.pv = vals + b.rb + __popc(b.R & below);
+    const bool kept = (b.R >> lane) & 1u;
+    c.old = (b.ok && kept && !zero_first) ? *c.pv : 0.0;
+    return c;
+  };
+  // level D: the cell's flag byte, geometry record and tensor slot, loaded into registers one row ahead
+  auto stageD = [&](const ClistC& c, Geo<TDIM>& g) -> ClistD
+  {
+    ClistD d;
+    d.fl = (c.ok && lane < c.n_inc) ? gc.cell_flags[c.c] : 0u;
+    load_geo_cached<TDIM>(gc.geo, c.c, g);
+    d.ms = __ldg(gc.mat_slot + c.c);
+    return d;
+  };
+
+  // prologue: rows i (D), i+s (C), i+2s (B), i+3s (A)
+  ClistA a3;
+  ClistB b2;
+  ClistC c0, c1;
+  ClistD d0;
+  Geo<TDIM> g0;
+  {
+    const ClistA a0 = stageA(i), a1 = stageA(i + stride), a2 = stageA(i + 2 * stride);
+    a3 = stageA(i + 3 * stride);
+    const ClistB b0 = stageB(a0), b1 = stageB(a1);
+    b2 = stageB(a2);
+    c0 = stageC(b0);
+    c1 = stageC(b1);
+    d0 = stageD(c0, g0);
   }
-  *pv = acc;
+  for (; i < i_end; i += stride)
+  {
+    // loads of the rows ahead, issued before this row's arithmetic
+    const ClistA a4 = stageA(i + 4 * stride);
+    const ClistB b3 = stageB(a3);
+    const ClistC c2 = stageC(b2);
+    Geo<TDIM> g1;
+    const ClistD d1 = stageD(c1, g1);
+    // ---- arithmetic of row i: everything it needs is already in registers
+    if (c0.ok)
+    {
+      const unsigned fl = d0.fl;
+      const bool contributes = (fl & 0xFDu) != 0;
+      double dval = 0.0;
+      if (contributes)
+      {
+        double v[ND];
+#pragma unroll
+        for (int j = 0; j < ND; ++j)
+          v[j] = 0.0;
+        if (fl >> 2)
+          std_row_values<TDIM, DEG>(st, g0, fl, c0.li, v);
+        if (fl & 1)
+        {
+          const double* a = gc.Ae + (static_cast<int64_t>(d0.ms) * ND + c0.li) * ND;
+#pragma unroll
+          for (int j = 0; j < ND; ++j)
+            v[j] += a[j];
+        }
+        dval = pick<ND>(v, c0.li);
+#pragma unroll
+        for (int j = 0; j < ND; ++j)
+          s_v[w][j][lane] = v[j];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        dval += __shfl_down_sync(full, dval, o);
+      dval = __shfl_sync(full, dval, 0);
+      const unsigned cmask = __ballot_sync(full, contributes);
+      if ((c0.R >> lane) & 1u)
+      {
+        double acc = c0.old;
+        if ((c0.word & 0xFFull) == 0xFEull)
+          acc += dval;
+        else
+        {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+          {
+            const unsigned b = static_cast<unsigned>(c0.word >> (8 * e)) & 0xFFu;
+            const unsigned l = b & 31u;
+            if (b != 0xFFu && ((cmask >> l) & 1u))
+              acc += s_v[w][b >> 5][l];
+          }
+        }
+        *c0.pv = acc;
+      }
+      __syncwarp(); // s_v is reused by the next row
+    }
+    a3 = a4;
+    b2 = b3;
+    c0 = c1;
+    c1 = c2;
+    d0 = d1;
+    g0 = g1;
+  }
 }
 
 // One warp per active row: lanes take the incident cells, compute / load the cell's entry for this
@@ -1345,8 +1445,13 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
                     12.0 * static_cast<double>(a->n_clist_nnz)
                         + (28.0 * ctx->nv + 4.0 * S.nd) * static_cast<double>(n_std));
       auto kc = gather_matrix_clist_kernel<TDIM, DEG>;
-      CFX_LAUNCH(ctx, kc, grid_for(PR->n_act_rows, GWC), GWC * 32, 0, gc, st, PR->act_rows.p, PR->n_act_rows,
-                 a->row_fast.p, a->Rrow.p, A->row_ptr.p, A->values.p, zero_first);
+      // persistent: 4 blocks per SM walk the rows grid-stride through the software pipeline
+      int n_sm = 148;
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+      const unsigned gp = static_cast<unsigned>(std::min<int64_t>(static_cast<int64_t>(n_sm) * 4,
+                                                                  (PR->n_act_rows + GWC - 1) / GWC));
+      CFX_LAUNCH(ctx, kc, gp, GWC * 32, 0, gc, st, PR->act_rows.p, PR->n_act_rows, a->row_fast.p, a->Rrow.p,
+                 A->row_ptr.p, A->values.p, zero_first);
     }
     if (fast && (a->n_mask_rows != 0))
     {

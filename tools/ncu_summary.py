@@ -51,8 +51,31 @@ def raw(path):
                 print(f"   {w} [{units[idx[w]]}] = {r[idx[w]]}")
 
 
+def traffic(path, key, out='profiles/ncu_traffic.json'):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the first profiled launch -> profiles/ncu_traffic.json[key]
+    (bench.py reports it as roofline.traffic)."""
+    import json
+    import os
+
+    res = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(res.splitlines()))
+    hdr, units, r = rows[0], rows[1], rows[2]
+    mult = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    tot = 0.0
+    for name in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+        i = hdr.index(name)
+        tot += float(r[i].replace(',', '')) * mult[units[i]]
+    d = json.load(open(out)) if os.path.exists(out) else {}
+    d[key] = int(tot)
+    d[key + ':source'] = os.path.basename(path)
+    json.dump(d, open(out, 'w'), indent=1, sort_keys=True)
+    print(key, int(tot))
+
+
 if __name__ == '__main__':
-    if sys.argv[1] == 'launches':
+    if sys.argv[1] == 'traffic':
+        traffic(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == 'launches':
         launches(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 1)
     else:
         raw(sys.argv[2])
