@@ -913,7 +913,8 @@ __global__ void __launch_bounds__(GW * 32)
 // fixed summation order -> bit-reproducible.
 template <int TDIM, int DEG>
 __global__ void __launch_bounds__(GWM * 32, 8)
-    gather_matrix_fast_kernel(GatherCtx gc, StdTab st, const int32_t* __restrict__ act_rows, int64_t n_act,
+    gather_matrix_fast_kernel(GatherCtx gc, StdTab st, const int32_t* __restrict__ act_rows,
+                              const int32_t* __restrict__ slots, int64_t n_act,
                               const uint8_t* __restrict__ row_fast, const uint32_t* __restrict__ gmask,
                               const uint32_t* __restrict__ Rrow, const int64_t* __restrict__ row_ptr,
                               const int32_t* __restrict__ cols, double* __restrict__ vals, int zero_first)
@@ -923,12 +924,15 @@ __global__ void __launch_bounds__(GWM * 32, 8)
   __shared__ int32_t s_fd[GWM][32][2 * ND];
   __shared__ double s_fv[GWM][32][2 * ND];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * GWM + w;
-  if (idx >= n_act)
+  const int64_t it = static_cast<int64_t>(blockIdx.x) * GWM + w;
+  if (it >= n_act)
     return;
+  // two launches: over the band slot list (slots != null), and -- only if some static row has no
+  // contribution list -- over all rows, skipping the listed ones (row_fast bit 16)
+  const int64_t idx = slots ? slots[it] : it;
   const unsigned rf = row_fast[idx];
-  if (!(rf & 1) || (rf & 12u) == 12u)
-    return; // handled by gather_matrix_kernel / gather_matrix_clist_kernel
+  if (!(rf & 1) || (rf & 12u) == 12u || (!slots && (rf & 16u)))
+    return; // handled by gather_matrix_kernel / gather_matrix_clist_kernel / the listed launch
   const unsigned full = 0xffffffffu;
   const int64_t r = act_rows[idx];
   const int64_t ib = gc.inc_ptr[r];
@@ -1455,9 +1459,19 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
     }
     if (fast && (a->n_mask_rows != 0))
     {
+      // band rows (facet macro rows) and rows with long contribution lists: cell rows through the position
+      // masks of the pattern pass, macro-tensor rows matched by column value
+      StageScope sk(ctx, "gather_matrix_mask_kernel", static_cast<double>(a->n_mask_rows));
       auto kf = gather_matrix_fast_kernel<TDIM, DEG>;
-      CFX_LAUNCH(ctx, kf, grid_for(PR->n_act_rows, GWM), GWM * 32, 0, gc, st, PR->act_rows.p, PR->n_act_rows,
-                 a->row_fast.p, a->gmask.p, a->Rrow.p, A->row_ptr.p, A->cols.p, A->values.p, zero_first);
+      if (a->n_band_listed > 0)
+        CFX_LAUNCH(ctx, kf, grid_for(a->n_band_listed, GWM), GWM * 32, 0, gc, st, PR->act_rows.p, PR->band_idx.p,
+                   a->n_band_listed, a->row_fast.p, a->gmask.p, a->Rrow.p, A->row_ptr.p, A->cols.p, A->values.p,
+                   zero_first);
+      // static rows without a contribution list (an edge with more than 8 cells), or no slot list at all
+      if (a->n_band_listed == 0 || PR->n_act_rows - a->n_band_listed - a->n_clist_rows > 0)
+        CFX_LAUNCH(ctx, kf, grid_for(PR->n_act_rows, GWM), GWM * 32, 0, gc, st, PR->act_rows.p, nullptr,
+                   PR->n_act_rows, a->row_fast.p, a->gmask.p, a->Rrow.p, A->row_ptr.p, A->cols.p, A->values.p,
+                   zero_first);
     }
   }
   if (!fast || a->n_slow_rows > 0)

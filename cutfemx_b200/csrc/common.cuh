@@ -249,6 +249,8 @@ struct cfx_prepared
   cfx::DevBuf<uint8_t> row_flag;   // per dof: bit0 touched by an active cell, bit1 by a facet-band cell
   cfx::DevBuf<int32_t> act_rows;   // ascending dofs with row_flag set
   int64_t n_act_rows = 0;
+  cfx::DevBuf<int32_t> band_idx;   // ascending slots (indices into act_rows) of the rows with row_flag bit1:
+  int64_t n_band = 0;              // facet-band rows and rows with inserted entries (generic pattern path)
   int64_t n_active_entities = 0;   // sum of the list sizes (for the byte accounting only)
 };
 
@@ -269,6 +271,7 @@ struct cfx_form
   int64_t n_slow_rows = 0;
   int64_t n_mask_rows = -1; // rows of the mask gather kernel (band rows, long contribution lists); -1 unknown
   int64_t n_clist_rows = 0, n_clist_nnz = 0; // rows / CSR entries of the contribution-list gather kernel
+  int64_t n_band_listed = 0; // generic-pattern rows reached through the prepared band slot list (row_fast bit 16)
   int64_t gtab_serial = -1;
   cfx::DevBuf<double> Ae;      // materialised run-time-rule tensors, cell-major (slot, nd^rank) natural order;
                                // rank 0: one value per entity

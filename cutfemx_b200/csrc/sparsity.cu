@@ -185,6 +185,22 @@ __global__ void facet_slot_set_kernel(const int32_t* __restrict__ rows4, int64_t
   facet_slot[f] = clear ? -1 : static_cast<int32_t>(i);
 }
 
+// slots of act_rows whose row has flag bit1 (compact.cuh predicate: 16 consecutive slots per call)
+struct BandSlotPred
+{
+  const int32_t* act_rows;
+  const uint8_t* row_flag;
+  __device__ unsigned operator()(int64_t base, int64_t n) const
+  {
+    unsigned m = 0;
+#pragma unroll 4
+    for (int k = 0; k < 16; ++k)
+      if (base + k < n && (row_flag[act_rows[base + k]] & 2))
+        m |= 1u << k;
+    return m;
+  }
+};
+
 struct RowCtx
 {
   const int64_t* inc_ptr;
@@ -255,8 +271,9 @@ __device__ __forceinline__ void sort_small(int32_t (&v)[N])
 // only those with a facet-band cell (only_band: the others take pattern_static_kernel).
 template <int ND, bool FILL>
 __global__ void __launch_bounds__(RW * 32)
-    pattern_rows_kernel(RowCtx rc, const int32_t* __restrict__ act_rows, int64_t n_rows_in, int only_band, int stride,
-                        int32_t* __restrict__ row_nnz, const int64_t* __restrict__ row_ptr,
+    pattern_rows_kernel(RowCtx rc, const int32_t* __restrict__ act_rows, const int32_t* __restrict__ slots,
+                        int64_t n_rows_in, int only_band, int stride, int32_t* __restrict__ row_nnz,
+                        const int64_t* __restrict__ row_ptr,
                         int32_t* __restrict__ cols_out, int32_t* __restrict__ tmp, uint32_t* __restrict__ mask_out,
                         uint8_t* __restrict__ row_fast, unsigned long long* __restrict__ n_slow,
                         int32_t* __restrict__ err)
@@ -265,9 +282,11 @@ __global__ void __launch_bounds__(RW * 32)
   __shared__ int32_t s_extra[RW][XCAP];
   __shared__ int s_nextra[RW];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * RW + w;
-  if (idx >= n_rows_in)
+  const int64_t it = static_cast<int64_t>(blockIdx.x) * RW + w;
+  if (it >= n_rows_in)
     return;
+  // `slots` (optional): the band rows only, so that no warp is launched just to find out it has no work
+  const int64_t idx = slots ? slots[it] : it;
   const bool all_mode = act_rows == nullptr;
   const int64_t r = all_mode ? idx : act_rows[idx];
   if (only_band && !(rc.row_flag[r] & 2))
@@ -474,7 +493,7 @@ __global__ void __launch_bounds__(RW * 32)
     {
       row_nnz[r] = count;
       if (row_fast)
-        row_fast[idx] = (fast ? 1 : 0) | (any_band ? 2 : 0);
+        row_fast[idx] = (fast ? 1 : 0) | (any_band ? 2 : 0) | (slots ? 16 : 0);
       if (!fast)
         atomicAdd(n_slow, 1ULL);
     }
@@ -683,8 +702,8 @@ static void build_static_structure_nd(cfx_ctx* c, Space& S)
   CFX_CUDA(cudaMemsetAsync(n_slow, 0, sizeof(unsigned long long), c->stream));
   CFX_CUDA(cudaMemsetAsync(row_nnz.p, 0, (static_cast<size_t>(S.n_total) + 1) * sizeof(int32_t), c->stream));
   auto k = pattern_rows_kernel<ND, false>;
-  CFX_LAUNCH(c, k, grid_for(S.n_total, RW), RW * 32, 0, rc, nullptr, S.n_total, 0, S.stride, row_nnz.p, nullptr,
-             nullptr, tmp.p, S.fmask.p, nullptr, n_slow, c->err_flag.p);
+  CFX_LAUNCH(c, k, grid_for(S.n_total, RW), RW * 32, 0, rc, nullptr, nullptr, S.n_total, 0, S.stride, row_nnz.p,
+             nullptr, nullptr, tmp.p, S.fmask.p, nullptr, n_slow, c->err_flag.p);
   S.frow_ptr.reserve(c->pool, static_cast<size_t>(S.n_total) + 2);
   exclusive_scan_i32_to_i64(c, row_nnz.p, S.n_total, S.frow_ptr.p);
   const int64_t* h = read_back(c, c->scratch64.p, 2);
@@ -770,6 +789,7 @@ void release_prepared(cfx_ctx* c, cfx_form* f)
   p->cell_flags.release();
   p->row_flag.release();
   p->act_rows.release();
+  p->band_idx.release();
   delete p;
 }
 
@@ -858,6 +878,12 @@ void prepare_form(cfx_ctx* c, cfx_form* f)
   {
     FlagPred p{P->row_flag.p};
     P->n_act_rows = compact_indices(c, S.n_total, p, P->act_rows);
+  }
+  P->n_band = 0;
+  if (fkey.first || xkey.first)
+  {
+    BandSlotPred bp{P->act_rows.p, P->row_flag.p};
+    P->n_band = compact_indices(c, P->n_act_rows, bp, P->band_idx);
   }
   st.set_bytes(static_cast<double>(c->nc_total) + 3.0 * static_cast<double>(S.n_total)
                + (4.0 + 4.0 * S.nd) * static_cast<double>(P->n_active_entities) + 4.0 * static_cast<double>(P->n_act_rows));
@@ -1064,6 +1090,11 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
   const bool use_static = S.has_static && !part;
   const int only_band = use_static ? 1 : 0;
   const bool need_generic = !use_static || PR->facet_key.first != nullptr || PR->extra_key.first != nullptr;
+  // with a static structure the generic kernels visit the band rows only, through their slot list
+  const int32_t* gslots = use_static ? PR->band_idx.p : nullptr;
+  const int64_t n_generic = use_static ? PR->n_band : n_act;
+  const unsigned gg = grid_for(n_generic, RW);
+  a->n_band_listed = use_static ? PR->n_band : 0;
   if (n_act > 0)
   {
     a->row_fast.reserve(ctx->pool, static_cast<size_t>(n_act) + 16);
@@ -1077,8 +1108,8 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
     {
       tmp.reserve(ctx->pool, static_cast<size_t>(n_act) * 32);
       a->gmask.reserve(ctx->pool, static_cast<size_t>(n_act) * S.stride);
-      CFX_LAUNCH(ctx, kcount, ga, RW * 32, 0, rc, act, n_act, only_band, S.stride, row_nnz.p, nullptr, nullptr, tmp.p,
-                 a->gmask.p, a->row_fast.p, n_slow, ctx->err_flag.p);
+      CFX_LAUNCH(ctx, kcount, gg, RW * 32, 0, rc, act, gslots, n_generic, only_band, S.stride, row_nnz.p, nullptr,
+                 nullptr, tmp.p, a->gmask.p, a->row_fast.p, n_slow, ctx->err_flag.p);
     }
   }
   P->row_ptr.reserve(ctx->pool, static_cast<size_t>(S.n_total) + 2);
@@ -1105,8 +1136,8 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
       CFX_LAUNCH(ctx, pattern_copy_kernel, grid_for(n_act, 256), 256, 0, act, n_act, a->row_fast.p, tmp.p,
                  P->row_ptr.p, P->cols.p);
     if (a->n_slow_rows > 0)
-      CFX_LAUNCH(ctx, kfill, ga, RW * 32, 0, rc, act, n_act, only_band, S.stride, nullptr, P->row_ptr.p, P->cols.p,
-                 nullptr, nullptr, a->row_fast.p, nullptr, ctx->err_flag.p);
+      CFX_LAUNCH(ctx, kfill, gg, RW * 32, 0, rc, act, gslots, n_generic, only_band, S.stride, nullptr, P->row_ptr.p,
+                 P->cols.p, nullptr, nullptr, a->row_fast.p, nullptr, ctx->err_flag.p);
   }
   tmp.release();
   P->serial = ++ctx->pattern_serial;
