@@ -327,68 +327,6 @@ __global__ void __launch_bounds__(EB)
   const int64_t f = t / (2 * ND);
   const int mrow = static_cast<int>(t - f * 2 * ND);
   const int32_t c0 = rows4[4 * f], lf0 = rows4[4 * f + 1], c1 = rows4[4 * f + 2];
-  if constexpr (DEG == 1)
-  { // P1: the normal-gradient jump is constant on the facet and everything follows from the two
-    // cached geometry records: grad lam_j = rows of K, n = -grad lam_lf0 / |.|, |F| (tdim-1)! = |detJ| |grad lam_lf0|
-    Geo<TDIM> g[2];
-    load_geo_cached<TDIM>(geo, c0, g[0]);
-    load_geo_cached<TDIM>(geo, c1, g[1]);
-    const double havg = 0.5 * (__ldg(geo + static_cast<int64_t>(c0) * GeoRec<TDIM>::STRIDE + TDIM * TDIM + 1)
-                               + __ldg(geo + static_cast<int64_t>(c1) * GeoRec<TDIM>::STRIDE + TDIM * TDIM + 1));
-    double G[2][ND][TDIM];
-#pragma unroll
-    for (int s = 0; s < 2; ++s)
-#pragma unroll
-      for (int r = 0; r < TDIM; ++r)
-      {
-        double s0 = 0.0;
-#pragma unroll
-        for (int tt = 0; tt < TDIM; ++tt)
-        {
-          G[s][tt + 1][r] = g[s].K[tt * TDIM + r];
-          s0 -= g[s].K[tt * TDIM + r];
-        }
-        G[s][0][r] = s0;
-      }
-    double nrm[TDIM], nn = 0.0;
-#pragma unroll
-    for (int r = 0; r < TDIM; ++r)
-    {
-      double v = G[0][0][r];
-#pragma unroll
-      for (int j = 1; j < ND; ++j)
-        v = (j == lf0) ? G[0][j][r] : v;
-      nrm[r] = -v;
-      nn += v * v;
-    }
-    nn = sqrt(nn);
-    const double measure = fabs(g[0].detJ) * nn;
-    double jn[2 * ND];
-#pragma unroll
-    for (int s = 0; s < 2; ++s)
-#pragma unroll
-      for (int i = 0; i < ND; ++i)
-      {
-        double v = 0.0;
-#pragma unroll
-        for (int r = 0; r < TDIM; ++r)
-          v += G[s][i][r] * (nrm[r] / nn);
-        jn[s * ND + i] = s ? -v : v;
-      }
-    double ji = jn[0];
-#pragma unroll
-    for (int j = 1; j < 2 * ND; ++j)
-      ji = (j == mrow) ? jn[j] : ji;
-    const double w = (TDIM == 3 ? 0.5 : 1.0) * measure * cs.c[0] * havg;
-    double* o = Fe + t * 2 * ND;
-#pragma unroll
-    for (int j = 0; j < 2 * ND; ++j)
-    {
-      const double v = w * ji * jn[j];
-      o[j] = accumulate ? o[j] + v : v;
-    }
-    return;
-  }
   double X0[NV][TDIM], X1[NV][TDIM];
   load_cell_coords<TDIM>(x, x_dofmap, c0, X0);
   load_cell_coords<TDIM>(x, x_dofmap, c1, X1);
@@ -509,6 +447,70 @@ __global__ void __launch_bounds__(EB)
     o[j] = accumulate ? o[j] + acc[j] : acc[j];
 }
 
+// P1 ghost penalty, one thread per facet, FACTORED output: the normal-gradient jump is constant on the
+// facet, so the macro tensor is the rank-one matrix w * jn (x) jn with jn the 2 nd jump coefficients and
+// w = c0 * avg(h) * |F|.  Only jn (2 nd doubles) and w are stored; the row owners rebuild the entries
+// they need (512 B -> 72 B per P1 tetrahedron facet).  Everything follows from the two cached geometry
+// records: grad lam_j = rows of K, n = -grad lam_lf0 / |.|, |F| (tdim-1)! = |detJ| |grad lam_lf0|.
+template <int TDIM>
+__global__ void __launch_bounds__(EB)
+    facet_p1_kernel(const int32_t* __restrict__ rows4, int64_t n_facets, Consts cs, const double* __restrict__ geo,
+                    double* __restrict__ Fj, double* __restrict__ Fw, bool accumulate)
+{
+  constexpr int ND = TDIM + 1;
+  const int64_t f = static_cast<int64_t>(blockIdx.x) * EB + threadIdx.x;
+  if (f >= n_facets)
+    return;
+  const int32_t c0 = rows4[4 * f], lf0 = rows4[4 * f + 1], c1 = rows4[4 * f + 2];
+  Geo<TDIM> g[2];
+  load_geo_cached<TDIM>(geo, c0, g[0]);
+  load_geo_cached<TDIM>(geo, c1, g[1]);
+  const double havg = 0.5 * (__ldg(geo + static_cast<int64_t>(c0) * GeoRec<TDIM>::STRIDE + TDIM * TDIM + 1)
+                             + __ldg(geo + static_cast<int64_t>(c1) * GeoRec<TDIM>::STRIDE + TDIM * TDIM + 1));
+  double G[2][ND][TDIM];
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int r = 0; r < TDIM; ++r)
+    {
+      double s0 = 0.0;
+#pragma unroll
+      for (int tt = 0; tt < TDIM; ++tt)
+      {
+        G[s][tt + 1][r] = g[s].K[tt * TDIM + r];
+        s0 -= g[s].K[tt * TDIM + r];
+      }
+      G[s][0][r] = s0;
+    }
+  double nrm[TDIM], nn = 0.0;
+#pragma unroll
+  for (int r = 0; r < TDIM; ++r)
+  {
+    double v = G[0][0][r];
+#pragma unroll
+    for (int j = 1; j < ND; ++j)
+      v = (j == lf0) ? G[0][j][r] : v;
+    nrm[r] = -v;
+    nn += v * v;
+  }
+  nn = sqrt(nn);
+  const double measure = fabs(g[0].detJ) * nn;
+  double* o = Fj + f * 2 * ND;
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int i = 0; i < ND; ++i)
+    {
+      double v = 0.0;
+#pragma unroll
+      for (int r = 0; r < TDIM; ++r)
+        v += G[s][i][r] * (nrm[r] / nn);
+      o[s * ND + i] = s ? -v : v;
+    }
+  const double w = (TDIM == 3 ? 0.5 : 1.0) * measure * cs.c[0] * havg;
+  Fw[f] = accumulate ? Fw[f] + w : w;
+}
+
 // ------------------------------------------------------------------ K5 gather ("owner gathers")
 // standard-quadrature cell integrals of a form, evaluated on the fly by the row owners
 struct StdTab
@@ -538,7 +540,8 @@ struct GatherCtx
   const int32_t* c2f;
   const int32_t* facet_slot;
   const int32_t* rows4;
-  const double* Fe;
+  const double* Fe; // full macro tensors (n_facets, 2nd, 2nd), or the P1 jump coefficients (n_facets, 2nd)
+  const double* Fw; // P1 only: the facet weights; null = Fe holds full tensors
   int nf;
   int stride;
 };
@@ -751,16 +754,27 @@ __device__ __forceinline__ int add_facet_rows(const GatherCtx& gc, int32_t (*s_f
     {
       const int64_t c0 = gc.rows4[4 * fs], c1 = gc.rows4[4 * fs + 2];
       const int mrow = (c == c0 ? 0 : ND) + li;
-      const double* F = gc.Fe + (fs * 2 * ND + mrow) * 2 * ND;
 #pragma unroll
       for (int j = 0; j < ND; ++j)
       {
         s_fd[lane][j] = gc.dofmap[c0 * ND + j];
         s_fd[lane][ND + j] = gc.dofmap[c1 * ND + j];
       }
+      if (gc.Fw)
+      { // factored P1 tensor: row mrow of w * jn (x) jn
+        const double* jn = gc.Fe + fs * 2 * ND;
+        const double jm = jn[mrow] * gc.Fw[fs];
 #pragma unroll
-      for (int j = 0; j < 2 * ND; ++j)
-        s_fv[lane][j] = F[j];
+        for (int j = 0; j < 2 * ND; ++j)
+          s_fv[lane][j] = jm * jn[j];
+      }
+      else
+      {
+        const double* F = gc.Fe + (fs * 2 * ND + mrow) * 2 * ND;
+#pragma unroll
+        for (int j = 0; j < 2 * ND; ++j)
+          s_fv[lane][j] = F[j];
+      }
       if (count)
         expected += 2 * ND;
     }
@@ -1390,14 +1404,23 @@ template <int TDIM, int DEG>
 void launch_facet(cfx_ctx* c, const cfx_integral& I, cfx_form* f, bool accumulate)
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
-  RuleTable& rt = get_rule(c, TDIM - 1, 2 * (DEG - 1));
-  StdRule fr{rt.d_pts, rt.d_wts, rt.npts};
   Consts cs;
   for (int k = 0; k < CFX_MAX_CONSTANTS; ++k)
     cs.c[k] = I.constants[k];
-  auto k = facet_kernel<TDIM, DEG>;
-  CFX_LAUNCH(c, k, grid_for(I.n * 2 * ND, EB), EB, 0, I.entities, I.n, fr, cs, c->x, c->x_dofmap, c->geo.p, f->Fe.p,
-             accumulate);
+  if constexpr (DEG == 1)
+  { // factored storage: jump coefficients (n, 2nd) followed by the weights (n)
+    double* Fj = f->Fe.p;
+    double* Fw = f->Fe.p + I.n * 2 * ND;
+    CFX_LAUNCH(c, facet_p1_kernel<TDIM>, grid_for(I.n, EB), EB, 0, I.entities, I.n, cs, c->geo.p, Fj, Fw, accumulate);
+  }
+  else
+  {
+    RuleTable& rt = get_rule(c, TDIM - 1, 2 * (DEG - 1));
+    StdRule fr{rt.d_pts, rt.d_wts, rt.npts};
+    auto k = facet_kernel<TDIM, DEG>;
+    CFX_LAUNCH(c, k, grid_for(I.n * 2 * ND, EB), EB, 0, I.entities, I.n, fr, cs, c->x, c->x_dofmap, c->geo.p, f->Fe.p,
+               accumulate);
+  }
 }
 
 GatherCtx make_gather_ctx(cfx_ctx* c, cfx_form* f, const cfx_integral* FI)
@@ -1419,6 +1442,7 @@ GatherCtx make_gather_ctx(cfx_ctx* c, cfx_form* f, const cfx_integral* FI)
   g.facet_slot = c->facet_slot.p;
   g.rows4 = FI ? FI->entities : nullptr;
   g.Fe = f->Fe.p;
+  g.Fw = (FI && S.degree == 1) ? f->Fe.p + FI->n * 2 * S.nd : nullptr;
   g.nf = c->tdim + 1;
   g.stride = S.stride;
   return g;
@@ -1582,7 +1606,8 @@ cfx_status cfx_assemble_matrix(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
   }
   if (FI)
   {
-    StageScope st(ctx, "element_facets", static_cast<double>(FI->n) * (16.0 + 8.0 * 4.0 * nd * nd));
+    StageScope st(ctx, "element_facets",
+                  static_cast<double>(FI->n) * (16.0 + (S.degree == 1 ? 8.0 * (2.0 * nd + 1.0) : 8.0 * 4.0 * nd * nd)));
     a->Fe.reserve(ctx->pool, static_cast<size_t>(FI->n) * 4 * nd * nd + 1);
     bool acc = false;
     for (auto& I : a->integrals)
