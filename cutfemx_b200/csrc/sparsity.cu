@@ -1079,7 +1079,8 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
                : S.nd == 6 ? pattern_rows_kernel<6, true>
                            : pattern_rows_kernel<10, true>;
   if (part)
-    CFX_CUDA(cudaMemsetAsync(row_nnz.p, 0, (static_cast<size_t>(S.n_total) + 1) * sizeof(int32_t), ctx->stream));
+    CFX_CUDA(cudaMemsetAsync(row_nnz.p + row_begin, 0, (static_cast<size_t>(S.n_total - row_begin) + 1) * sizeof(int32_t),
+                             ctx->stream));
   else
     CFX_LAUNCH(ctx, pattern_inactive_count_kernel, grid_for(S.n_total, SBK), SBK, 0, PR->row_flag.p, S.n_total, 1,
                row_nnz.p);
@@ -1113,7 +1114,13 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
     }
   }
   P->row_ptr.reserve(ctx->pool, static_cast<size_t>(S.n_total) + 2);
-  exclusive_scan_i32_to_i64(ctx, row_nnz.p, S.n_total, P->row_ptr.p);
+  if (part)
+  { // only the tail rows can be non-empty: scan them alone
+    CFX_CUDA(cudaMemsetAsync(P->row_ptr.p, 0, static_cast<size_t>(row_begin) * sizeof(int64_t), ctx->stream));
+    exclusive_scan_i32_to_i64(ctx, row_nnz.p + row_begin, S.n_total - row_begin, P->row_ptr.p + row_begin);
+  }
+  else
+    exclusive_scan_i32_to_i64(ctx, row_nnz.p, S.n_total, P->row_ptr.p);
   {
     const int64_t* h = read_back(ctx, ctx->scratch64.p, 4);
     P->nnz = h[0];
