@@ -76,11 +76,44 @@ class IndexMap:
         return torch.where(own, g - self.offset, torch.where(hit, pos + self.n_owned, torch.full_like(g, -1)))
 
 
-def slab_ranges(n_layers: int, world: int):
-    return [((n_layers * p) // world, (n_layers * (p + 1)) // world) for p in range(world)]
+def slab_ranges(n_layers: int, world: int, weights=None):
+    """[lo, hi) cell layers of every rank.  Uniform by default; with per-layer `weights` (estimated work,
+    e.g. cells + k * active cells) the cuts balance the cumulative weight -- the role vertex weights
+    play in the graph partitioner behind DOLFINx's cell partition.  Every rank gets >= 1 layer."""
+    if weights is None:
+        return [((n_layers * p) // world, (n_layers * (p + 1)) // world) for p in range(world)]
+    w = np.asarray(weights, dtype=np.float64)
+    assert w.size == n_layers and world <= n_layers
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    cuts = [0]
+    for p in range(1, world):
+        k = int(np.searchsorted(cum, cum[-1] * p / world))
+        k = min(max(k, cuts[-1] + 1), n_layers - (world - p))
+        cuts.append(k)
+    cuts.append(n_layers)
+    return [(cuts[p], cuts[p + 1]) for p in range(world)]
 
 
-def partition_slab(shape, p0, p1, world: int, rank: int, device=None):
+def layer_weights(shape, p0, p1, level_set, active_cost: float = 40.0, samples: int = 48):
+    """Work estimate per cell layer along the last axis: 1 per cell + `active_cost` per cell with
+    phi < 0 at its centre, from a coarse sample of the level-set function (host, numpy)."""
+    tdim = len(shape)
+    ax = tdim - 1
+    n_ax = shape[ax]
+    z = p0[ax] + (np.arange(n_ax) + 0.5) * (p1[ax] - p0[ax]) / n_ax
+    g = [p0[d] + (np.arange(samples) + 0.5) * (p1[d] - p0[d]) / samples for d in range(ax)]
+    out = np.empty(n_ax)
+    for k in range(n_ax):
+        if tdim == 3:
+            X, Y = np.meshgrid(g[0], g[1], indexing="ij")
+            frac = np.mean(level_set(X, Y, np.full_like(X, z[k])) < 0)
+        else:
+            frac = np.mean(level_set(g[0], np.full_like(g[0], z[k]), np.zeros_like(g[0])) < 0)
+        out[k] = 1.0 + active_cost * frac
+    return out
+
+
+def partition_slab(shape, p0, p1, world: int, rank: int, device=None, ranges=None):
     """Local mesh + P1 space + index map of rank `rank` for a slab partition of the Kuhn box /
     right-diagonal rectangle with `shape` cells, split along the last axis.
 
@@ -96,7 +129,8 @@ def partition_slab(shape, p0, p1, world: int, rank: int, device=None):
     tdim = len(shape)
     ax = tdim - 1
     n_ax = shape[ax]
-    lo, hi = slab_ranges(n_ax, world)[rank]
+    ranges = slab_ranges(n_ax, world) if ranges is None else list(ranges)
+    lo, hi = ranges[rank]
     if hi <= lo:
         raise ValueError(f"rank {rank} would own no cell layer: {n_ax} layers on {world} ranks")
     g0, g1 = int(rank > 0), int(rank < world - 1)
@@ -184,7 +218,6 @@ def partition_slab(shape, p0, p1, world: int, rank: int, device=None):
         x_new.view(n_planes, vpp, 3)[:, :, ax] = zc.view(-1, 1)
     l2g = (z_of_new.view(-1, 1) * vpp + torch.arange(vpp, device=dev).view(1, -1)).reshape(-1)
     n_owned = len(owned_planes) * vpp
-    ranges = slab_ranges(n_ax, world)
     owner_of_plane = lambda z: 0 if z == 0 else next(q for q, (a, b) in enumerate(ranges) if a < z <= b)  # noqa: E731
     gown = torch.tensor([owner_of_plane(L0 + k) for k in below + above], dtype=torch.int64, device=dev)
     ghost_owner = gown.view(-1, 1).expand(len(below) + len(above), vpp).reshape(-1)
@@ -207,24 +240,29 @@ def partition_slab(shape, p0, p1, world: int, rank: int, device=None):
 class TorchDistTransport:
     """One rank per process (`torch.distributed`, backend nccl on GPUs / gloo on the CPU)."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, device=None):
+        import torch
         import torch.distributed as dist
 
         self.dist, self.group = dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.local_ranks = [self.rank]
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" \
+                else torch.device("cpu")
+        self.device = torch.device(device)
 
-    def exchange(self, sends, counts=None):
+    def exchange(self, sends, counts=None, dtype=None):
         """sends: [ {dest rank: 1-D tensor} ] for the one local rank.  `counts`: optional
-        [ {src rank: n} ] when the receive sizes are already known (no size exchange)."""
+        [ {src rank: n} ] when the receive sizes are already known (no size exchange).  `dtype`: element
+        type of this exchange -- every rank must name the same one, also a rank that sends nothing."""
         import torch
 
         dist = self.dist
         send = sends[0]
         ref = next(iter(send.values())) if send else None
-        device = ref.device if ref is not None else torch.device("cpu")
-        dtype = ref.dtype if ref is not None else torch.float64
-        # every rank must agree on dtype/device even when it sends nothing: callers pass zero-size tensors
+        device = self.device
+        dtype = dtype if dtype is not None else (ref.dtype if ref is not None else torch.float64)
         in_split = [int(send[q].numel()) if q in send else 0 for q in range(self.world)]
         if counts is None:
             s = torch.tensor(in_split, dtype=torch.int64, device=device)
@@ -252,7 +290,7 @@ class LocalTransport:
         self.world = world
         self.local_ranks = list(range(world))
 
-    def exchange(self, sends, counts=None):
+    def exchange(self, sends, counts=None, dtype=None):
         res = [dict() for _ in range(self.world)]
         for p, send in enumerate(sends):
             for q, t in send.items():
@@ -491,12 +529,13 @@ class RankPipeline:
     phase_c: unpack-add (A.scatter_reverse(), b.scatter_reverse(add))
     """
 
-    def __init__(self, shape, p0, p1, world, rank, device, ls_kind, ls_params, order=4, **kw):
+    def __init__(self, shape, p0, p1, world, rank, device, ls_kind, ls_params, order=4, ranges=None, **kw):
         from . import demo_poisson as dp
         from .mesh import Function
 
         self.world, self.rank = world, rank
-        self.mesh, self.V, self.imap = partition_slab(shape, p0, p1, world, rank, device=device)
+        self.ranges = slab_ranges(int(shape[-1]), world) if ranges is None else list(ranges)
+        self.mesh, self.V, self.imap = partition_slab(shape, p0, p1, world, rank, device=device, ranges=self.ranges)
         if callable(ls_kind):
             # nodal interpolation on the host (numpy), as the tests do for the serial problem
             import torch
@@ -513,7 +552,7 @@ class RankPipeline:
         self.mx = MatrixExchange(self.imap)
         self.Ag = None
         # slab neighbours send rows of different mesh planes: below-neighbour rows < above-neighbour rows
-        lo, hi = slab_ranges(int(shape[-1]), world)[rank]
+        lo, hi = self.ranges[rank]
         self.disjoint_sources = hi - lo >= 3
 
     # static vector plan (once)
@@ -605,15 +644,19 @@ class RankPipeline:
 
 def run_step(pipes, transport):
     """One step of the pipeline for the ranks this process hosts (1 with torch.distributed)."""
-    recv = transport.exchange([p.phase_a() for p in pipes])
+    import torch
+
+    recv = transport.exchange([p.phase_a() for p in pipes], dtype=torch.int64)
     out = [p.phase_b(r) for p, r in zip(pipes, recv)]
-    recv = transport.exchange([o[0] for o in out], counts=[p.recv_counts() for p in pipes])
+    recv = transport.exchange([o[0] for o in out], counts=[p.recv_counts() for p in pipes], dtype=torch.float64)
     for p, r in zip(pipes, recv):
         p.phase_c(r)
     return [o[1] for o in out]
 
 
 def plan(pipes, transport):
-    recv = transport.exchange([p.plan_begin() for p in pipes])
+    import torch
+
+    recv = transport.exchange([p.plan_begin() for p in pipes], dtype=torch.int64)
     for p, r in zip(pipes, recv):
         p.plan_finish(r)

@@ -51,10 +51,10 @@ def serial_reference(shape):
 class OracleRank:
     """One rank's local work through the oracle, same phases as parallel.RankPipeline."""
 
-    def __init__(self, shape, world, rank):
+    def __init__(self, shape, world, rank, ranges=None):
         tdim = len(shape)
         p0, p1 = box(tdim)
-        self.mesh, self.V, self.imap = P.partition_slab(shape, p0, p1, world, rank)
+        self.mesh, self.V, self.imap = P.partition_slab(shape, p0, p1, world, rank, ranges=ranges)
         self.world, self.rank = world, rank
         self.phi = M.interpolate(self.V, level_set(tdim))
         self.vx = P.VectorExchange(self.imap)
@@ -147,12 +147,12 @@ class OracleRank:
 
 
 def run_ranks(ranks, transport):
-    recv = transport.exchange([r.vx.begin() for r in ranks])
+    recv = transport.exchange([r.vx.begin() for r in ranks], dtype=torch.int64)
     for r, rc in zip(ranks, recv):
         r.vx.finish(rc)
-    recv = transport.exchange([r.phase_a() for r in ranks])
+    recv = transport.exchange([r.phase_a() for r in ranks], dtype=torch.int64)
     sends = [r.phase_b(rc) for r, rc in zip(ranks, recv)]
-    recv = transport.exchange(sends, counts=[r.recv_counts() for r in ranks])
+    recv = transport.exchange(sends, counts=[r.recv_counts() for r in ranks], dtype=torch.float64)
     for r, rc in zip(ranks, recv):
         r.phase_c(rc)
 
@@ -226,9 +226,27 @@ def test_partition_invariants(shape, world):
 
 
 # ----------------------------------------------------------------------------- in-process ranks
-@pytest.mark.parametrize("shape,world", [((8, 8, 8), 2), ((6, 6, 9), 3), ((16, 16), 2), ((12, 12), 3), ((6, 6, 6), 1)])
+@pytest.mark.parametrize("shape,world", [((8, 8, 8), 2), ((6, 6, 9), 3), ((16, 16), 2), ((12, 12), 3), ((6, 6, 6), 1),
+                                         ((6, 6, 16), 8)])  # 8 thin slabs: the end ranks own no active cell
 def test_local_transport_matches_serial(shape, world):
     ranks = [OracleRank(shape, world, r) for r in range(world)]
+    run_ranks(ranks, P.LocalTransport(world))
+    compare_with_serial([r.owned_global() for r in ranks], shape)
+
+
+def test_work_balanced_slabs_match_serial():
+    """Non-uniform slab cuts from per-layer work estimates (bench.py uses them at N > 1)."""
+    shape, world = (6, 6, 14), 4
+    p0, p1 = box(3)
+    w = P.layer_weights(shape, p0, p1, level_set(3))
+    ranges = P.slab_ranges(shape[-1], world, w)
+    assert ranges[0][0] == 0 and ranges[-1][1] == shape[-1] and all(b > a for a, b in ranges)
+    assert all(ranges[k][1] == ranges[k + 1][0] for k in range(world - 1))
+    sizes = [b - a for a, b in ranges]
+    assert sizes[0] > sizes[1] and sizes[-1] > sizes[-2]  # thick slabs where the sphere is absent
+    loads = [w[a:b].sum() for a, b in ranges]
+    assert max(loads) < 1.6 * w.sum() / world
+    ranks = [OracleRank(shape, world, r, ranges) for r in range(world)]
     run_ranks(ranks, P.LocalTransport(world))
     compare_with_serial([r.owned_global() for r in ranks], shape)
 

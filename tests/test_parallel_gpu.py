@@ -26,7 +26,7 @@ def make_pipes(shape, world, devices):
 
 
 @pytest.mark.parametrize("shape,world", [((8, 8, 8), 2), ((6, 6, 9), 3), ((16, 16), 2), ((20, 20), 2), ((6, 6, 6), 1),
-                                         ((12, 10, 16), 4)])
+                                         ((12, 10, 16), 4), ((6, 6, 16), 8)])
 def test_emulated_ranks_match_serial(shape, world, built_lib):
     from cutfemx_b200 import parallel as P
 
