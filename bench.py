@@ -277,30 +277,53 @@ def run_ours(args, wl):
     # re-bind level set 0 to the pinned host array: cfx_update now does the H2D copy every step
     check(hnd, lib().cfx_levelset_bind(hnd, 0, None, tdim + 1, 1, C.c_void_p(h_phi.data_ptr()),
                                        C.c_int64(V.num_dofs), HOST, 1))
+    # Results leave through a copy stream into pinned host buffers, double-buffered: the device->host copy of
+    # step k (CSR pattern + values + rhs, ~1 GB) overlaps the compute of step k+1; every step's inputs still
+    # arrive from the host and every step's results still reach it inside the timed region.
+    from cutfemx_b200 import fem as _fem
+
     nnz_cap = int(stats["nnz"] * 1.1) + 1024
-    h_vals = torch.empty(nnz_cap, dtype=torch.float64, pin_memory=True)
-    h_cols = torch.empty(nnz_cap, dtype=torch.int32, pin_memory=True)
-    h_rp = torch.empty(V.num_dofs + 1, dtype=torch.int64, pin_memory=True)
-    h_b = torch.empty(V.num_dofs, dtype=torch.float64, pin_memory=True)
+    hb = [dict(vals=torch.empty(nnz_cap, dtype=torch.float64, pin_memory=True),
+               cols=torch.empty(nnz_cap, dtype=torch.int32, pin_memory=True),
+               rp=torch.empty(V.num_dofs + 1, dtype=torch.int64, pin_memory=True),
+               b=torch.empty(V.num_dofs, dtype=torch.float64, pin_memory=True)) for _ in range(2)]
+    As = [prob.A, _fem.MatrixCSR(ctx)]
+    bs = [prob.b, torch.empty_like(prob.b)]
+    side = torch.cuda.Stream()
+    done = [None, None]
+    kstep = [0]
 
     def e2e_step():
+        k = kstep[0] % 2
+        kstep[0] += 1
+        if done[k] is not None:
+            torch.cuda.current_stream().wait_event(done[k])  # buffers of step k-2 have left the device
+        prob.A, prob.b = As[k], bs[k]
         st = P.run_step([pipe], transport)[0]
-        A = prob.A
-        check(hnd, lib().cfx_pattern_fetch(hnd, A._h, C.c_void_p(h_rp.data_ptr()), C.c_void_p(h_cols.data_ptr()), HOST))
-        check(hnd, lib().cfx_pattern_values_fetch(hnd, A._h, C.c_void_p(h_vals.data_ptr()), HOST))
-        h_b.copy_(prob.b, non_blocking=False)
+        ready = torch.cuda.Event()
+        ready.record()
+        side.wait_event(ready)
+        prob.A.copy_to_host_async(hb[k]["rp"], hb[k]["cols"], hb[k]["vals"], side)
+        with torch.cuda.stream(side):
+            hb[k]["b"].copy_(prob.b, non_blocking=True)
+            done[k] = torch.cuda.Event()
+            done[k].record()
         pipe.finish_step()
         return st
 
     for _ in range(2):
         st = e2e_step()
+    side.synchronize()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         st = e2e_step()
+    for ev_done in done:
+        torch.cuda.current_stream().wait_event(ev_done)
     e1.record()
     barrier()
+    side.synchronize()
     e2e = torch.tensor([e0.elapsed_time(e1) / 1e3, 8.0 * V.num_dofs,
                         12.0 * st["nnz"] + 8.0 * (V.num_dofs + 1) + 8.0 * V.num_dofs], dtype=torch.float64, device=dev)
     if world > 1:

@@ -14,13 +14,29 @@ void cfx_set_error(cfx_ctx* ctx, const char* msg)
 
 namespace cfx
 {
+namespace
+{
+__global__ void to_mapped_kernel(const int64_t* __restrict__ src, int n, volatile int64_t* dst)
+{
+  if (threadIdx.x < n)
+    dst[threadIdx.x] = src[threadIdx.x];
+}
+} // namespace
+
+const int64_t* read_back(cfx_ctx* c, const int64_t* dev, int n)
+{
+  CFX_REQUIRE(n >= 0 && n <= 64, CFX_ERR_RANGE, "read_back: at most 64 values");
+  to_mapped_kernel<<<1, 64, 0, c->stream>>>(dev, n, c->h_pinned_dev);
+  ++c->launches;
+  CFX_CUDA(cudaGetLastError());
+  CFX_CUDA(cudaStreamSynchronize(c->stream));
+  return c->h_pinned;
+}
+
 void check_device_error(cfx_ctx* c, const char* where)
 {
-  const int64_t* h = nullptr;
   // err_flag is int32[4]; read as two int64
-  CFX_CUDA(cudaMemcpyAsync(c->h_pinned, c->err_flag.p, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-  CFX_CUDA(cudaStreamSynchronize(c->stream));
-  h = c->h_pinned;
+  const int64_t* h = read_back(c, reinterpret_cast<const int64_t*>(c->err_flag.p), 2);
   const int32_t* f = reinterpret_cast<const int32_t*>(h);
   if (f[0] != 0)
   {
@@ -58,7 +74,8 @@ cfx_status cfx_ctx_create(int device, void* stream, cfx_ctx** out)
   ctx = new cfx_ctx();
   ctx->device = device;
   ctx->stream = static_cast<cudaStream_t>(stream);
-  CFX_CUDA(cudaMallocHost(&ctx->h_pinned, 64 * sizeof(int64_t)));
+  CFX_CUDA(cudaHostAlloc(&ctx->h_pinned, 64 * sizeof(int64_t), cudaHostAllocMapped));
+  CFX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->h_pinned_dev), ctx->h_pinned, 0));
   ctx->err_flag.reserve(ctx->pool, 4);
   CFX_CUDA(cudaMemsetAsync(ctx->err_flag.p, 0, 4 * sizeof(int32_t), ctx->stream));
   ctx->scratch64.reserve(ctx->pool, 64);

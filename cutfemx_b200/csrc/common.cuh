@@ -328,7 +328,8 @@ struct cfx_ctx
   cfx::DevBuf<int64_t> scratch64;
   cfx::DevBuf<uint8_t> scratch8;
   cfx::DevBuf<int32_t> err_flag; // device int[4]
-  int64_t* h_pinned = nullptr;   // 64 x int64 pinned host scratch
+  int64_t* h_pinned = nullptr;   // 64 x int64 mapped pinned host scratch
+  int64_t* h_pinned_dev = nullptr; // its device address
 
   bool timing = false;
   std::vector<cfx::Stage> stages;
@@ -408,13 +409,11 @@ inline void export_to(cfx_ctx* c, T* dst, const T* src_dev, size_t n, int memspa
     CFX_CUDA(cudaStreamSynchronize(c->stream));
 }
 
-// read `n` int64 from device into pinned host scratch (synchronises the stream)
-inline const int64_t* read_back(cfx_ctx* c, const int64_t* dev, int n)
-{
-  CFX_CUDA(cudaMemcpyAsync(c->h_pinned, dev, n * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
-  CFX_CUDA(cudaStreamSynchronize(c->stream));
-  return c->h_pinned;
-}
+// read `n` (<= 64) int64 from device memory into host scratch (synchronises the stream).  A tiny
+// kernel writes them straight into MAPPED pinned host memory: no DMA copy is enqueued, so the
+// read-back never waits behind a large device->host transfer the caller has in flight on another
+// stream (api.cu).
+const int64_t* read_back(cfx_ctx* c, const int64_t* dev, int n);
 
 void check_device_error(cfx_ctx* c, const char* where); // api.cu
 

@@ -165,6 +165,19 @@ class MatrixCSR:
 
         return device_view(lib().cfx_pattern_values_device_ptr(self._h), self.nnz, np.float64, self.ctx.device, self)
 
+    def copy_to_host_async(self, h_indptr, h_indices, h_values, stream=None):
+        """Enqueue the device->host copy of the CSR arrays into (pinned) torch host tensors on `stream`
+        (a torch.cuda.Stream; default: the current one).  Returns (n_rows + 1, nnz).  The caller owns the
+        ordering: record an event after assembly and make `stream` wait for it."""
+        import torch
+
+        nr, nnz = self._sizes()
+        with torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream()):
+            h_indptr[: nr + 1].copy_(self.indptr_device(), non_blocking=True)
+            h_indices[:nnz].copy_(self.indices_device(), non_blocking=True)
+            h_values[:nnz].copy_(self.values_device(), non_blocking=True)
+        return nr + 1, nnz
+
     def to_scipy(self):
         import scipy.sparse as sp
 
