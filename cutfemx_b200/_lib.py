@@ -36,7 +36,8 @@ SYMBOLS = [
     "cfx_pattern_values_fetch", "cfx_pattern_free", "cfx_assemble_matrix", "cfx_assemble_vector",
     "cfx_assemble_scalar", "cfx_stage_count", "cfx_stage_name", "cfx_stage_timing_enable", "cfx_stage_ms",
     "cfx_stage_reset", "cfx_form_insert_pattern_entries", "cfx_create_sparsity_rows", "cfx_pattern_positions",
-    "cfx_gather_f64", "cfx_scatter_add_f64", "cfx_meshgen_box", "cfx_meshgen_rectangle", "cfx_meshgen_level_set",
+    "cfx_gather_f64", "cfx_scatter_add_f64", "cfx_active_domain", "cfx_active_indicator_device_ptr",
+    "cfx_inactive_dofs", "cfx_deactivate_outside", "cfx_meshgen_box", "cfx_meshgen_rectangle", "cfx_meshgen_level_set",
 ]
 
 
@@ -68,6 +69,8 @@ def lib():
         for name in ("cfx_pattern_values_device_ptr", "cfx_pattern_row_ptr_device_ptr", "cfx_pattern_cols_device_ptr"):
             getattr(L, name).restype = C.c_void_p
             getattr(L, name).argtypes = [C.c_void_p]
+        L.cfx_active_indicator_device_ptr.restype = C.c_void_p
+        L.cfx_active_indicator_device_ptr.argtypes = [C.c_void_p, C.c_void_p]
         L.cfx_ctx_destroy.restype = None
         for name in ("cfx_list_free", "cfx_rules_free", "cfx_pattern_free", "cfx_form_free"):
             getattr(L, name).restype = None

@@ -1336,3 +1336,130 @@ void cfx_pattern_free(cfx_ctx* ctx, cfx_pattern* p)
   delete p;
 }
 } // extern "C"
+
+namespace cfx
+{
+namespace
+{
+struct ZeroBytePred
+{ // indices whose byte is 0 (compact.cuh predicate)
+  const uint8_t* flag;
+  __device__ unsigned operator()(int64_t base, int64_t n) const
+  {
+    unsigned m = 0;
+    for (int k = 0; k < 16 && base + k < n; ++k)
+      m |= flag[base + k] == 0 ? (1u << k) : 0u;
+    return m;
+  }
+};
+
+__global__ void set_diagonal_kernel(const int32_t* __restrict__ rows, int64_t n, int64_t n_rows,
+                                    const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ cols,
+                                    double* __restrict__ vals, double diagonal, double* __restrict__ b,
+                                    double rhs_value, int32_t* __restrict__ err)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x;
+  if (i >= n)
+    return;
+  const int32_t r = rows[i];
+  if (r < 0 || r >= n_rows)
+  {
+    err[0] = 29;
+    err[1] = r;
+    return;
+  }
+  int64_t lo = row_ptr[r], hi = row_ptr[r + 1];
+  const int64_t end = hi;
+  while (lo < hi)
+  {
+    const int64_t mid = (lo + hi) >> 1;
+    if (cols[mid] < r)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  if (lo >= end || cols[lo] != r)
+  {
+    err[0] = 30;
+    err[1] = r;
+    return;
+  }
+  vals[lo] = diagonal;
+  if (b)
+    b[r] = rhs_value;
+}
+} // namespace
+} // namespace cfx
+
+extern "C"
+{
+const uint8_t* cfx_active_indicator_device_ptr(cfx_ctx* ctx, const cfx_form* a_const)
+{
+  cfx_form* a = const_cast<cfx_form*>(a_const);
+  if (!ctx || !a)
+    return nullptr;
+  try
+  {
+    prepare_form(ctx, a);
+  }
+  catch (const std::exception& e)
+  {
+    cfx_set_error(ctx, e.what());
+    return nullptr;
+  }
+  return a->prep->row_flag.p;
+}
+
+cfx_status cfx_inactive_dofs(cfx_ctx* ctx, const uint8_t* indicator, int64_t n_dofs_owned, cfx_list** inactive_dofs)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && indicator && inactive_dofs && n_dofs_owned >= 0, CFX_ERR_INVALID,
+              "cfx_inactive_dofs: NULL argument");
+  if (*inactive_dofs == nullptr)
+    *inactive_dofs = new cfx_list();
+  ZeroBytePred p{indicator};
+  (*inactive_dofs)->n = compact_indices(ctx, n_dofs_owned, p, (*inactive_dofs)->data);
+  CFX_API_END(ctx)
+}
+
+cfx_status cfx_active_domain(cfx_ctx* ctx, const cfx_form* a_const, cfx_list** active_cells, cfx_list** inactive_dofs)
+{
+  CFX_API_BEGIN
+  cfx_form* a = const_cast<cfx_form*>(a_const);
+  CFX_REQUIRE(ctx && a && active_cells && inactive_dofs, CFX_ERR_INVALID, "cfx_active_domain: NULL argument");
+  // deactivate.h:76-101: a bilinear form on one space
+  CFX_REQUIRE(a->rank == 2, CFX_ERR_INVALID, "cutfemx.fem.active_domain requires a bilinear form");
+  Space& S = ctx->spaces[a->space];
+  prepare_form(ctx, a);
+  if (*active_cells == nullptr)
+    *active_cells = new cfx_list();
+  {
+    FlagPred p{a->prep->cell_flags.p};
+    (*active_cells)->n = compact_indices(ctx, ctx->nc_owned, p, (*active_cells)->data);
+  }
+  // deactivate.h:160-164
+  CFX_REQUIRE((*active_cells)->n > 0, CFX_ERR_INVALID, "cutfemx.fem.active_domain found no active background cells");
+  if (*inactive_dofs == nullptr)
+    *inactive_dofs = new cfx_list();
+  ZeroBytePred p{a->prep->row_flag.p};
+  (*inactive_dofs)->n = compact_indices(ctx, S.n_owned, p, (*inactive_dofs)->data);
+  CFX_API_END(ctx)
+}
+
+cfx_status cfx_deactivate_outside(cfx_ctx* ctx, cfx_pattern* A, const int32_t* inactive_dofs, int64_t n, int memspace,
+                                  double diagonal, double* b, double rhs_value)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && A && (n == 0 || inactive_dofs), CFX_ERR_INVALID, "cfx_deactivate_outside: NULL argument");
+  if (n > 0)
+  {
+    DevBuf<int32_t> own;
+    const int32_t* d = adopt(ctx, own, inactive_dofs, static_cast<size_t>(n), memspace);
+    CFX_LAUNCH(ctx, set_diagonal_kernel, grid_for(n, SBK), SBK, 0, d, n, A->n_rows, A->row_ptr.p, A->cols.p,
+               A->values.p, diagonal, b, rhs_value, ctx->err_flag.p);
+    check_device_error(ctx, "cfx_deactivate_outside (row out of range or without a diagonal entry)");
+    own.release();
+  }
+  CFX_API_END(ctx)
+}
+} // extern "C"

@@ -261,6 +261,62 @@ def assemble_vector(L: CutForm, b: np.ndarray | None = None) -> np.ndarray:
     return b
 
 
+class ActiveDomain:
+    """Mirror of cutfemx.fem.ActiveDomain (python/cutfemx/fem.py:88-123): `active_cells`, `inactive_dofs`."""
+
+    def __init__(self, form: CutForm, cells: _List, dofs: _List):
+        self.form, self._cells, self._dofs = form, cells, dofs
+        self.function_space = form.function_space
+
+    @property
+    def active_cells(self) -> np.ndarray:
+        return self._cells.numpy()
+
+    @property
+    def inactive_dofs(self) -> np.ndarray:
+        return self._dofs.numpy()
+
+
+def active_domain(a: CutForm) -> ActiveDomain:
+    """cutfemx.fem.active_domain (fem.py:683-695 -> fem/deactivate.h:387-400): the cells the form
+    integrates over and the owned dofs none of them touches."""
+    if a.rank != 2:
+        raise ValueError("cutfemx.fem.active_domain requires a bilinear form")
+    cells, dofs = _List(a.ctx), _List(a.ctx)
+    check(a.ctx.handle, lib().cfx_active_domain(a.ctx.handle, a._h, C.byref(cells._h), C.byref(dofs._h)))
+    return ActiveDomain(a, cells, dofs)
+
+
+def deactivate_outside(A: MatrixCSR, b_or_active_domain, active_domain_or_none=None, *, diagonal: float = 1.0,
+                       rhs_value: float = 0.0) -> ActiveDomain:
+    """cutfemx.fem.deactivate_outside (fem.py:698-736 -> deactivate.h:402-418): set the diagonal of the
+    inactive rows (and, with a right-hand side, its inactive entries).  `b`: torch CUDA tensor (in place) or
+    numpy array (updated in place through a device copy)."""
+    if isinstance(b_or_active_domain, ActiveDomain):
+        if active_domain_or_none is not None:
+            raise TypeError("deactivate_outside(A, active_domain) takes no RHS vector")
+        domain, b = b_or_active_domain, None
+    else:
+        if active_domain_or_none is None:
+            raise TypeError("deactivate_outside(A, b, active_domain) requires active_domain")
+        domain, b = active_domain_or_none, b_or_active_domain
+    dofs = domain._dofs
+    h = A.ctx.handle
+    if b is None or is_device_array(b):
+        pb = C.c_void_p(b.data_ptr()) if b is not None else None
+        check(h, lib().cfx_deactivate_outside(h, A._h, C.c_void_p(dofs.device_ptr), C.c_int64(dofs.size), DEVICE,
+                                              C.c_double(diagonal), pb, C.c_double(rhs_value)))
+    else:
+        import torch
+
+        tb = torch.from_numpy(np.ascontiguousarray(b, dtype=np.float64)).to(f"cuda:{A.ctx.device}")
+        check(h, lib().cfx_deactivate_outside(h, A._h, C.c_void_p(dofs.device_ptr), C.c_int64(dofs.size), DEVICE,
+                                              C.c_double(diagonal), C.c_void_p(tb.data_ptr()), C.c_double(rhs_value)))
+        b[:] = tb.cpu().numpy()
+    A._cache.pop("data", None)
+    return domain
+
+
 def assemble_scalar(M: CutForm) -> float:
     """fem.py assemble_scalar -> assemble_scalar_impl.h:26-275 (local value; allreduce is the caller's)."""
     if M.rank != 0:

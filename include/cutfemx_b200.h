@@ -203,6 +203,24 @@ cfx_status cfx_assemble_vector(cfx_ctx* ctx, const cfx_form* L, double* b, int z
 /* assemble_scalar: assemble_scalar_impl.h:26-275 (fixed-order tree reduction) */
 cfx_status cfx_assemble_scalar(cfx_ctx* ctx, const cfx_form* M, double* out);
 
+/* ------------------------------------------------------------------ active domain / deactivation
+ * cutfemx::fem::active_domain, cpp/cutfemx/fem/deactivate.h:387-400: active cells = sorted unique OWNED
+ * cells of every integral domain of the bilinear form (collect_active_cells :103-165, both cells of an
+ * interior-facet row included); the indicator marks the dofs of those cells (:167-185); inactive dofs =
+ * OWNED dofs the indicator leaves at zero (deactivated_dofs(.., owned_only = true) :49-64).  On more than
+ * one rank the caller reverse/forward-scatters the indicator (cfx_active_indicator_device_ptr) exactly as
+ * :180-181 does and takes the inactive dofs from the scattered copy with cfx_inactive_dofs. */
+cfx_status cfx_active_domain(cfx_ctx* ctx, const cfx_form* a, cfx_list** active_cells, cfx_list** inactive_dofs);
+/* the indicator itself: 1 byte per owned+ghost dof (DEVICE pointer, library-owned, valid until the form changes) */
+const uint8_t* cfx_active_indicator_device_ptr(cfx_ctx* ctx, const cfx_form* a);
+/* inactive dofs from a (scattered) indicator: owned dofs with indicator == 0 (DEVICE array of n_dofs_owned bytes) */
+cfx_status cfx_inactive_dofs(cfx_ctx* ctx, const uint8_t* indicator, int64_t n_dofs_owned, cfx_list** inactive_dofs);
+/* deactivate_outside, deactivate.h:402-418: dolfinx::fem::set_diagonal(A.mat_set_values, inactive_dofs,
+ * diagonal) -- SETS A[r][r] -- and, if b != NULL (DEVICE), b[r] = rhs_value.  Fails if a row lacks its
+ * diagonal entry (the pattern always reserves it: assembler.h:538-560, :589-590). */
+cfx_status cfx_deactivate_outside(cfx_ctx* ctx, cfx_pattern* A, const int32_t* inactive_dofs, int64_t n, int memspace,
+                                  double diagonal, double* b, double rhs_value);
+
 /* ------------------------------------------------------------------ ghost exchange (one rank per GPU)
  * la::MatrixCSR::scatter_rev / la::Vector::scatter_rev(add) as called by the user after assembly
  * (python/demo/demo_poisson.py:52,54): values of ghost rows / ghost entries travel to the owning

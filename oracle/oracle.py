@@ -260,3 +260,35 @@ def assemble_interior_facets(space, kernel: str, vals, rows4, constants, row_ptr
                                             _p(dm, _i32p), _p(rows4, _i32p), C.c_int64(rows4.shape[0]),
                                             _p(cst, _f64p), _p(row_ptr, _i64p), _p(cols, _i32p), _p(vals, _f64p)))
     return vals
+
+
+# ---------------------------------------------------------------- active domain / deactivation
+def active_domain(space, cell_lists, rows4=None):
+    """cpp/cutfemx/fem/deactivate.h:103-185,387-400: active cells = sorted unique owned cells of all
+    integral domains (both cells of interior-facet rows); indicator = dofs of those cells; inactive
+    dofs = owned dofs with indicator 0."""
+    nco = space.mesh.num_cells_local
+    parts = [np.asarray(c, dtype=np.int64).ravel() for c in cell_lists if c is not None]
+    if rows4 is not None and len(rows4):
+        r = np.asarray(rows4, dtype=np.int64).reshape(-1, 4)
+        parts += [r[:, 0], r[:, 2]]
+    cells = np.unique(np.concatenate(parts)) if parts else np.zeros(0, np.int64)
+    cells = cells[(cells >= 0) & (cells < nco)].astype(np.int32)
+    indicator = np.zeros(space.num_dofs)
+    for c in cells:  # mark_cell_dofs
+        indicator[space.dofmap[c]] = 1.0
+    inactive = np.nonzero(np.abs(indicator[: space.num_dofs_owned]) < 1.0e-8)[0].astype(np.int32)
+    return cells, inactive
+
+
+def deactivate_outside(row_ptr, cols, vals, inactive_dofs, diagonal=1.0, b=None, rhs_value=0.0):
+    """deactivate.h:402-418: dolfinx::fem::set_diagonal (sets A[r][r]) and b[r] = rhs_value."""
+    for r in inactive_dofs:
+        seg = cols[row_ptr[r]:row_ptr[r + 1]]
+        k = int(np.searchsorted(seg, r))
+        if k >= seg.size or seg[k] != r:
+            raise RuntimeError("inactive row has no diagonal entry")
+        vals[row_ptr[r] + k] = diagonal
+        if b is not None:
+            b[r] = rhs_value
+    return vals

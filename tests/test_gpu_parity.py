@@ -98,3 +98,29 @@ def test_deterministic(runs):
     assert np.array_equal(A2.data, g.vals)
     b2 = cfx.fem.assemble_vector(g.L)
     assert np.array_equal(b2, g.b)
+
+
+def test_active_domain_and_deactivation(runs):
+    """cutfemx.fem.active_domain / deactivate_outside (fem/deactivate.h:387-418); reference test:
+    test_cut_api.py:841-845 (active cells = unique(inside U parent_map), here plus the facet cells)."""
+    import oracle as O
+
+    import cutfemx_b200 as cfx
+
+    o, g = runs
+    cells_o, inactive_o = O.active_domain(o.V, [o.inside, o.rv.parent_map, o.ri.parent_map], o.rows4)
+    dom = cfx.fem.active_domain(g.a)
+    assert np.array_equal(dom.active_cells, cells_o) and dom.active_cells.dtype == np.int32
+    assert np.array_equal(dom.inactive_dofs, inactive_o)
+    assert np.array_equal(np.unique(np.concatenate([o.inside, o.rv.parent_map])),
+                          np.setdiff1d(cells_o, np.setdiff1d(np.concatenate([o.rows4[:, 0], o.rows4[:, 2]]),
+                                                             np.concatenate([o.inside, o.rv.parent_map]))))
+    vals_o, b_o = o.vals.copy(), o.b.copy()
+    O.deactivate_outside(o.row_ptr, o.cols, vals_o, inactive_o, 2.0, b_o, -3.0)
+    A = cfx.fem.assemble_matrix(g.a)
+    b = g.b.copy()
+    cfx.fem.deactivate_outside(A, b, dom, diagonal=2.0, rhs_value=-3.0)
+    assert rel(A.data, vals_o) < 1e-11 and rel(b, b_o) < 1e-11
+    assert np.all(A.data[np.isin(np.repeat(np.arange(o.V.num_dofs), np.diff(o.row_ptr)), inactive_o)] == 2.0)
+    with pytest.raises(ValueError):
+        cfx.fem.active_domain(g.L)
