@@ -33,7 +33,7 @@ SYMBOLS = [
     "cfx_form_create", "cfx_form_add_cell_integral", "cfx_form_add_interior_facet_integral", "cfx_form_free",
     "cfx_create_sparsity", "cfx_pattern_import", "cfx_pattern_sizes", "cfx_pattern_fetch",
     "cfx_pattern_values_device_ptr", "cfx_pattern_row_ptr_device_ptr", "cfx_pattern_cols_device_ptr",
-    "cfx_pattern_values_fetch", "cfx_pattern_free", "cfx_assemble_matrix", "cfx_assemble_vector",
+    "cfx_pattern_values_fetch", "cfx_pattern_free", "cfx_assemble_matrix", "cfx_assemble_system", "cfx_assemble_vector",
     "cfx_assemble_scalar", "cfx_stage_count", "cfx_stage_name", "cfx_stage_timing_enable", "cfx_stage_ms",
     "cfx_stage_reset", "cfx_form_insert_pattern_entries", "cfx_create_sparsity_rows", "cfx_pattern_positions",
     "cfx_gather_f64", "cfx_scatter_add_f64", "cfx_active_domain", "cfx_active_indicator_device_ptr",

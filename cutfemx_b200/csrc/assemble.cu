@@ -183,7 +183,9 @@ struct OutCtx
 {
   int32_t* mat_slot; // cell -> slot of its materialised tensor (-1: none yet); ranks 1 and 2
   double* out;
-  int64_t base;      // first slot (rank 1, 2) / first entity index (rank 0) of this integral
+  int64_t base;      // first slot (rank 1, 2) / first entity index (rank 0) of this integral;
+                     // < 0: FOLLOW mode -- use the slots another form of the same domains has claimed and add
+                     // into a zero-initialised buffer (cfx_assemble_system: the linear form follows the bilinear one)
 };
 
 __device__ __forceinline__ void st256(double* p, double a, double b, double c, double d)
@@ -219,11 +221,14 @@ __global__ void __launch_bounds__(EB)
   const int64_t cell = RUNTIME ? rv.parent_map[e] : cells[e];
   int64_t slot = oc.base + e;
   bool add = false;
+  const bool follow = oc.base < 0;
   if constexpr (RANK >= 1)
   {
     const int32_t s0 = oc.mat_slot[cell];
     add = s0 >= 0;
     slot = add ? s0 : slot;
+    if (follow && !add)
+      return; // cannot happen for forms over the same prepared domains
   }
   double X[TDIM + 1][TDIM];
   load_cell_coords<TDIM>(x, x_dofmap, cell, X);
@@ -272,7 +277,7 @@ __global__ void __launch_bounds__(EB)
   }
   if constexpr (RANK >= 1)
   {
-    if (!add)
+    if (!add && !follow)
       oc.mat_slot[cell] = static_cast<int32_t>(slot);
   }
   double* p = oc.out + slot * ES;
@@ -542,6 +547,11 @@ struct GatherCtx
   const int32_t* rows4;
   const double* Fe; // full macro tensors (n_facets, 2nd, 2nd), or the P1 jump coefficients (n_facets, 2nd)
   const double* Fw; // P1 only: the facet weights; null = Fe holds full tensors
+  // fused system assembly (cfx_assemble_system): the linear form's materialised entries (same slots) and
+  // the vector the contribution-list kernel also fills; null otherwise
+  const double* AeL;
+  double* bvec;
+  int zero_first_b;
   int nf;
   int stride;
 };
@@ -1035,6 +1045,7 @@ struct ClistA
 struct ClistB
 {
   bool ok;
+  int32_t r;
   uint32_t R;
   int64_t ib, rb, fb;
   int n_inc;
@@ -1042,6 +1053,7 @@ struct ClistB
 struct ClistC
 {
   bool ok;
+  int32_t r;
   uint32_t R;
   int n_inc;
   int32_t c;
@@ -1057,9 +1069,9 @@ struct ClistD
   int32_t ms;
 };
 
-template <int TDIM, int DEG>
+template <int TDIM, int DEG, bool FUSED>
 __global__ void __launch_bounds__(GWC * 32, 4)
-    gather_matrix_clist_kernel(GatherCtx gc, StdTab st, const int32_t* __restrict__ act_rows, int64_t n_act,
+    gather_matrix_clist_kernel(GatherCtx gc, StdTab st, StdTab stL, const int32_t* __restrict__ act_rows, int64_t n_act,
                                const uint8_t* __restrict__ row_fast, const uint32_t* __restrict__ Rrow,
                                const int64_t* __restrict__ row_ptr, double* __restrict__ vals, int zero_first)
 {
@@ -1090,6 +1102,7 @@ __global__ void __launch_bounds__(GWC * 32, 4)
   {
     ClistB b;
     b.ok = (a.rf & 13u) == 13u;
+    b.r = a.r;
     b.R = a.R;
     b.ib = gc.inc_ptr[a.r];
     b.n_inc = static_cast<int>(gc.inc_ptr[a.r + 1] - b.ib);
@@ -1101,6 +1114,7 @@ __global__ void __launch_bounds__(GWC * 32, 4)
   {
     ClistC c;
     c.ok = b.ok;
+    c.r = b.r;
     c.R = b.R;
     c.n_inc = b.n_inc;
     const int64_t kk = b.ib + (lane < b.n_inc ? lane : 0);
@@ -1172,9 +1186,50 @@ __global__ void __launch_bounds__(GWC * 32, 4)
           s_v[w][j][lane] = v[j];
       }
       __syncwarp();
+      double e = 0.0;
+      if constexpr (FUSED)
+      { // fused right-hand side: this cell's entry for the row (same order and tree as gather_vector_kernel)
+        if (contributes)
+        {
+          if (fl >> 2)
+          {
+            const double s = fabs(g0.detJ);
+            for (int k = 0; k < stL.n; ++k)
+            {
+              if (!(fl & stL.bit[k]))
+                continue;
+              if constexpr (DEG == 1)
+                e += stL.c[k][0] * s * (TDIM == 3 ? 1.0 / 24.0 : 1.0 / 6.0);
+              else
+                for (int q = 0; q < stL.npts[k]; ++q)
+                {
+                  double xi[TDIM];
+#pragma unroll
+                  for (int t = 0; t < TDIM; ++t)
+                    xi[t] = __ldg(stL.pts[k] + q * TDIM + t);
+                  double phi[ND], dphi[ND][TDIM];
+                  tabulate<TDIM, DEG>(xi, phi, dphi);
+                  e += stL.c[k][0] * (__ldg(stL.wts[k] + q) * s) * pick<ND>(phi, c0.li);
+                }
+            }
+          }
+          if (fl & 1)
+            e += gc.AeL[static_cast<int64_t>(d0.ms) * ND + c0.li];
+        }
+      }
+      // two fixed shuffle trees, interleaved: the diagonal entry and (fused) the right-hand-side entry
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1)
+      {
         dval += __shfl_down_sync(full, dval, o);
+        if constexpr (FUSED)
+          e += __shfl_down_sync(full, e, o);
+      }
+      if constexpr (FUSED)
+      {
+        if (lane == 0)
+          gc.bvec[c0.r] = gc.zero_first_b ? e : gc.bvec[c0.r] + e;
+      }
       dval = __shfl_sync(full, dval, 0);
       const unsigned cmask = __ballot_sync(full, contributes);
       if ((c0.R >> lane) & 1u)
@@ -1211,13 +1266,23 @@ __global__ void __launch_bounds__(GWC * 32, 4)
 template <int TDIM, int DEG, bool PERM>
 __global__ void __launch_bounds__(GW * 32)
     gather_vector_kernel(GatherCtx gc, StdTab st, const int32_t* __restrict__ act_rows, int64_t n_act,
-                         double* __restrict__ b, int zero_first)
+                         double* __restrict__ b, int zero_first, const int32_t* __restrict__ slots,
+                         const uint8_t* __restrict__ row_fast, int skip_mode)
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * GW + w;
-  if (idx >= n_act)
+  const int64_t it = static_cast<int64_t>(blockIdx.x) * GW + w;
+  if (it >= n_act)
     return;
+  // skip_mode (fused system assembly): 1 = rows of the slot list that gather_matrix_clist_kernel did not
+  // fill; 2 = all rows except those it filled and the listed ones (row_fast bit 16)
+  const int64_t idx = slots ? slots[it] : it;
+  if (skip_mode)
+  {
+    const unsigned rf = row_fast[idx];
+    if ((rf & 13u) == 13u || (skip_mode == 2 && (rf & 16u)))
+      return;
+  }
   const int64_t r = act_rows[idx];
   const int64_t ib = gc.inc_ptr[r];
   const int n_inc = static_cast<int>(gc.inc_ptr[r + 1] - ib);
@@ -1315,7 +1380,8 @@ void launch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t& base)
                   R->npts};
     auto k = cell_kernel<TDIM, DEG, KID, true>;
     CFX_LAUNCH(c, k, grid_for(R->nrules, EB), EB, 0, nullptr, R->nrules, rv, sr, cs, c->x, c->x_dofmap, oc);
-    base += R->nrules;
+    if (base >= 0)
+      base += R->nrules;
   }
 }
 
@@ -1336,10 +1402,30 @@ void dispatch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t& base
 
 // materialise the run-time-rule tensors (ranks 1, 2) / all entity values (rank 0); returns the
 // number of slots used
-int64_t run_cell_integrals(cfx_ctx* c, cfx_form* f)
+int64_t run_cell_integrals(cfx_ctx* c, cfx_form* f, int64_t follow_slots = -1)
 {
   const Space& S = c->spaces[f->space];
   const int es = f->rank == 2 ? S.nd * S.nd : (f->rank == 1 ? S.nd : 1);
+  if (follow_slots >= 0)
+  { // FOLLOW mode: same slots as the form that ran before, zero-initialised accumulation
+    f->Ae.reserve(c->pool, static_cast<size_t>(follow_slots) * es + 4);
+    CFX_CUDA(cudaMemsetAsync(f->Ae.p, 0, (static_cast<size_t>(follow_slots) * es + 4) * sizeof(double), c->stream));
+    for (auto& I : f->integrals)
+    {
+      if (I.facet)
+        continue;
+      int64_t base = -1;
+      if (c->tdim == 2 && S.degree == 1)
+        dispatch_cell<2, 1>(c, I, f, base);
+      else if (c->tdim == 2)
+        dispatch_cell<2, 2>(c, I, f, base);
+      else if (S.degree == 1)
+        dispatch_cell<3, 1>(c, I, f, base);
+      else
+        dispatch_cell<3, 2>(c, I, f, base);
+    }
+    return follow_slots;
+  }
   int64_t cap = 0;
   for (auto& I : f->integrals)
   {
@@ -1450,7 +1536,7 @@ GatherCtx make_gather_ctx(cfx_ctx* c, cfx_form* f, const cfx_integral* FI)
 
 template <int TDIM, int DEG>
 void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const GatherCtx& gc, const StdTab& st,
-                          int zero_first)
+                          const StdTab& stL, int zero_first)
 {
   const Space& S = ctx->spaces[a->space];
   cfx_prepared* PR = a->prep;
@@ -1472,13 +1558,13 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
       StageScope sk(ctx, "gather_matrix_clist_kernel",
                     12.0 * static_cast<double>(a->n_clist_nnz)
                         + (28.0 * ctx->nv + 4.0 * S.nd) * static_cast<double>(n_std));
-      auto kc = gather_matrix_clist_kernel<TDIM, DEG>;
+      auto kc = gc.bvec ? gather_matrix_clist_kernel<TDIM, DEG, true> : gather_matrix_clist_kernel<TDIM, DEG, false>;
       // persistent: 4 blocks per SM walk the rows grid-stride through the software pipeline
       int n_sm = 148;
       cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
       const unsigned gp = static_cast<unsigned>(std::min<int64_t>(static_cast<int64_t>(n_sm) * 4,
                                                                   (PR->n_act_rows + GWC - 1) / GWC));
-      CFX_LAUNCH(ctx, kc, gp, GWC * 32, 0, gc, st, PR->act_rows.p, PR->n_act_rows, a->row_fast.p, a->Rrow.p,
+      CFX_LAUNCH(ctx, kc, gp, GWC * 32, 0, gc, st, stL, PR->act_rows.p, PR->n_act_rows, a->row_fast.p, a->Rrow.p,
                  A->row_ptr.p, A->values.p, zero_first);
     }
     if (fast && (a->n_mask_rows != 0))
@@ -1508,23 +1594,37 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
 
 template <int TDIM, int DEG>
 void launch_gather_vector(cfx_ctx* ctx, cfx_form* L, const GatherCtx& gc, const StdTab& st, double* d_b,
-                          int zero_first)
+                          int zero_first, const cfx_form* fused_with = nullptr)
 {
   const Space& S = ctx->spaces[L->space];
   cfx_prepared* PR = L->prep;
   if (PR->n_act_rows == 0)
     return;
-  const unsigned g = grid_for(PR->n_act_rows, GW);
-  if (S.has_perm)
+  auto run = [&](const int32_t* slots, int64_t n, const uint8_t* row_fast, int skip_mode)
   {
-    auto k = gather_vector_kernel<TDIM, DEG, true>;
-    CFX_LAUNCH(ctx, k, g, GW * 32, 0, gc, st, PR->act_rows.p, PR->n_act_rows, d_b, zero_first);
-  }
-  else
+    const unsigned g = grid_for(n, GW);
+    if (S.has_perm)
+    {
+      auto k = gather_vector_kernel<TDIM, DEG, true>;
+      CFX_LAUNCH(ctx, k, g, GW * 32, 0, gc, st, PR->act_rows.p, n, d_b, zero_first, slots, row_fast, skip_mode);
+    }
+    else
+    {
+      auto k = gather_vector_kernel<TDIM, DEG, false>;
+      CFX_LAUNCH(ctx, k, g, GW * 32, 0, gc, st, PR->act_rows.p, n, d_b, zero_first, slots, row_fast, skip_mode);
+    }
+  };
+  if (!fused_with)
   {
-    auto k = gather_vector_kernel<TDIM, DEG, false>;
-    CFX_LAUNCH(ctx, k, g, GW * 32, 0, gc, st, PR->act_rows.p, PR->n_act_rows, d_b, zero_first);
+    run(nullptr, PR->n_act_rows, nullptr, 0);
+    return;
   }
+  // the rows gather_matrix_clist_kernel did not fill
+  const cfx_form* a = fused_with;
+  if (a->n_band_listed > 0)
+    run(PR->band_idx.p, a->n_band_listed, a->row_fast.p, 1);
+  if (PR->n_act_rows - a->n_band_listed - a->n_clist_rows > 0)
+    run(nullptr, PR->n_act_rows, a->row_fast.p, 2);
 }
 
 #define CFX_DISPATCH_ELEM(ctx, S, FN, ...)                                                                             \
@@ -1576,16 +1676,13 @@ void build_geometry_cache(cfx_ctx* c)
 
 using namespace cfx;
 
-extern "C"
+
+// assemble_matrix, optionally fused with the right-hand side of a linear form over the same prepared
+// domains (L != null): its run-time-rule entries are materialised into the bilinear form's slots and the
+// contribution-list kernel fills b for its rows in the same pass over the incidence.
+static void assemble_matrix_impl(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, int zero_first, double diag_inactive,
+                                 cfx_form* L, double* d_b, int zero_first_b)
 {
-cfx_status cfx_assemble_matrix(cfx_ctx* ctx, const cfx_form* a_const, cfx_pattern* A, int zero_first,
-                               double diag_inactive, double* values_out, int memspace)
-{
-  CFX_API_BEGIN
-  cfx_form* a = const_cast<cfx_form*>(a_const);
-  CFX_REQUIRE(ctx && a && A, CFX_ERR_INVALID, "cfx_assemble_matrix: NULL argument");
-  CFX_REQUIRE(a->rank == 2, CFX_ERR_INVALID, "cfx_assemble_matrix: form is not bilinear");
-  CFX_REQUIRE(A->space == a->space, CFX_ERR_INVALID, "cfx_assemble_matrix: matrix and form use different spaces");
   const Space& S = ctx->spaces[a->space];
   prepare_form(ctx, a);
   const cfx_integral* FI = facet_integral_domain(a);
@@ -1602,6 +1699,17 @@ cfx_status cfx_assemble_matrix(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
       if (!I.facet && I.rules)
         by += 8.0 * (ctx->tdim + 1 + (I.rules->has_normals ? ctx->tdim : 0)) * static_cast<double>(I.rules->npts)
               + (8.0 + 28.0 * ctx->nv + 8.0 * nd * nd) * static_cast<double>(I.rules->nrules);
+    st.set_bytes(by);
+  }
+  if (L)
+  {
+    StageScope st(ctx, "element_cells_vector");
+    run_cell_integrals(ctx, L, n_mat);
+    double by = 0.0;
+    for (auto& I : L->integrals)
+      if (!I.facet && I.rules)
+        by += 8.0 * (ctx->tdim + 1 + (I.rules->has_normals ? ctx->tdim : 0)) * static_cast<double>(I.rules->npts)
+              + (8.0 + 28.0 * ctx->nv + 8.0 * nd) * static_cast<double>(I.rules->nrules);
     st.set_bytes(by);
   }
   if (FI)
@@ -1626,18 +1734,79 @@ cfx_status cfx_assemble_matrix(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
     set_facet_slots(ctx, FI, false);
     GatherCtx gc = make_gather_ctx(ctx, a, FI);
     const StdTab stt = make_std_tab(ctx, a);
+    StdTab stL{};
+    const bool fuse_b = L && a->gtab_serial == A->serial && a->gtab_serial > 0 && S.has_perm && S.has_static
+                        && a->n_clist_rows > 0 && S.nd <= 6;
+    if (fuse_b)
+    {
+      stL = make_std_tab(ctx, L);
+      gc.AeL = L->Ae.p;
+      gc.bvec = d_b;
+      gc.zero_first_b = zero_first_b;
+    }
     if (zero_first)
       CFX_CUDA(cudaMemsetAsync(A->values.p, 0, static_cast<size_t>(A->nnz) * sizeof(double), ctx->stream));
     if (diag_inactive != 0.0)
       CFX_LAUNCH(ctx, inactive_diag_kernel, grid_for(A->n_rows, 256), 256, 0, a->prep->row_flag.p, A->n_rows, A->row_ptr.p,
                  A->cols.p, A->values.p, diag_inactive);
-    CFX_DISPATCH_ELEM(ctx, S, launch_gather_matrix, ctx, a, A, gc, stt, zero_first);
+    CFX_DISPATCH_ELEM(ctx, S, launch_gather_matrix, ctx, a, A, gc, stt, stL, zero_first);
     set_facet_slots(ctx, FI, true);
-    reset_slots(ctx, a);
   }
+  if (L)
+  {
+    // rows the contribution-list kernel did not own (band rows, generic rows); inactive rows keep 0 / b
+    StageScope st(ctx, "gather_vector", 8.0 * static_cast<double>(S.n_total));
+    GatherCtx gl = make_gather_ctx(ctx, L, nullptr);
+    const StdTab stl = make_std_tab(ctx, L);
+    const bool fused = a->gtab_serial == A->serial && a->gtab_serial > 0 && S.has_perm && S.has_static
+                       && a->n_clist_rows > 0 && S.nd <= 6; // same condition as fuse_b above
+    CFX_DISPATCH_ELEM(ctx, S, launch_gather_vector, ctx, L, gl, stl, d_b, zero_first_b, fused ? a : nullptr);
+  }
+  reset_slots(ctx, a);
+}
+
+extern "C"
+{
+cfx_status cfx_assemble_matrix(cfx_ctx* ctx, const cfx_form* a_const, cfx_pattern* A, int zero_first,
+                               double diag_inactive, double* values_out, int memspace)
+{
+  CFX_API_BEGIN
+  cfx_form* a = const_cast<cfx_form*>(a_const);
+  CFX_REQUIRE(ctx && a && A, CFX_ERR_INVALID, "cfx_assemble_matrix: NULL argument");
+  CFX_REQUIRE(a->rank == 2, CFX_ERR_INVALID, "cfx_assemble_matrix: form is not bilinear");
+  CFX_REQUIRE(A->space == a->space, CFX_ERR_INVALID, "cfx_assemble_matrix: matrix and form use different spaces");
+  assemble_matrix_impl(ctx, a, A, zero_first, diag_inactive, nullptr, nullptr, 0);
   if (values_out)
     export_to(ctx, values_out, A->values.p, static_cast<size_t>(A->nnz), memspace);
   check_device_error(ctx, "cfx_assemble_matrix (entry not in sparsity pattern)");
+  CFX_API_END(ctx)
+}
+
+cfx_status cfx_assemble_system(cfx_ctx* ctx, const cfx_form* a_const, cfx_pattern* A, int zero_first_A,
+                               double diag_inactive, const cfx_form* L_const, double* b, int zero_first_b)
+{
+  CFX_API_BEGIN
+  cfx_form* a = const_cast<cfx_form*>(a_const);
+  cfx_form* L = const_cast<cfx_form*>(L_const);
+  CFX_REQUIRE(ctx && a && A && L && b, CFX_ERR_INVALID, "cfx_assemble_system: NULL argument");
+  CFX_REQUIRE(a->rank == 2 && L->rank == 1, CFX_ERR_INVALID, "cfx_assemble_system: needs a bilinear and a linear form");
+  CFX_REQUIRE(A->space == a->space && L->space == a->space, CFX_ERR_INVALID,
+              "cfx_assemble_system: forms and matrix must use the same space");
+  const Space& S = ctx->spaces[a->space];
+  prepare_form(ctx, a);
+  prepare_form(ctx, L);
+  if (zero_first_b)
+    CFX_CUDA(cudaMemsetAsync(b, 0, static_cast<size_t>(S.n_total) * sizeof(double), ctx->stream));
+  if (a->prep == L->prep)
+    assemble_matrix_impl(ctx, a, A, zero_first_A, diag_inactive, L, b, zero_first_b);
+  else
+  { // different integration domains: nothing to share, two passes
+    assemble_matrix_impl(ctx, a, A, zero_first_A, diag_inactive, nullptr, nullptr, 0);
+    cfx_status rc = cfx_assemble_vector(ctx, L, b, zero_first_b, CFX_DEVICE);
+    if (rc != CFX_OK)
+      return rc;
+  }
+  check_device_error(ctx, "cfx_assemble_system (entry not in sparsity pattern)");
   CFX_API_END(ctx)
 }
 

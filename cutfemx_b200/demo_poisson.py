@@ -81,6 +81,7 @@ class CutPoisson:
         self.b = None
         self.stats = {}
         self.last = None
+        self.fused = True  # matrix and right-hand side in one pass (cfx_assemble_system)
 
     def build_forms(self, assemble_rhs: bool = True):
         """update -> locate -> rules -> normals -> ghost facets -> the forms a and L."""
@@ -109,9 +110,16 @@ class CutPoisson:
         """create_sparsity_pattern + assemble_matrix (+ assemble_vector) of the current forms."""
         a, L = self.last["a"], self.last["L"]
         self.A = _fem.create_matrix(a, self.A)                              # create_sparsity_pattern
-        _fem.assemble_matrix(a, self.A)                                     # assemble_matrix
-        if L is not None:
-            self.b = self._assemble_vector_device(L)
+        if L is not None and self.fused:
+            import torch
+
+            if self.b is None or not hasattr(self.b, "data_ptr"):
+                self.b = torch.empty(self.V.num_dofs, dtype=torch.float64, device=f"cuda:{self.ctx.device}")
+            _fem.assemble_system(a, self.A, L, self.b)                      # assemble_matrix + assemble_vector
+        else:
+            _fem.assemble_matrix(a, self.A)                                 # assemble_matrix
+            if L is not None:
+                self.b = self._assemble_vector_device(L)
         cd, t = self.cut_data, self.last
         counts = cd.counts()
         self.stats = dict(inside=counts[0], cut=counts[1], outside=counts[2], nnz=self.A.nnz,

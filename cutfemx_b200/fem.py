@@ -245,6 +245,19 @@ def assemble_matrix(a: CutForm, A: MatrixCSR | None = None, *, diag_inactive: fl
     return A
 
 
+def assemble_system(a: CutForm, A: MatrixCSR, L: CutForm, b, *, zero_b: bool = True, diag_inactive: float = 0.0):
+    """assemble_matrix(a, A) and assemble_vector(L, b) in one pass over the mesh where the two forms share
+    their integration domains (cfx_assemble_system).  `b`: torch CUDA tensor of owned+ghost entries.
+    Adds into A (like assemble_matrix); bit-identical to the two separate calls."""
+    if a.rank != 2 or L.rank != 1:
+        raise RuntimeError("assemble_system expects a bilinear and a linear form")
+    if not is_device_array(b):
+        raise TypeError("assemble_system needs a device vector (torch CUDA tensor)")
+    check(a.ctx.handle, lib().cfx_assemble_system(a.ctx.handle, a._h, A._h, 0, C.c_double(diag_inactive), L._h,
+                                                  C.c_void_p(b.data_ptr()), int(zero_b)))
+    return A, b
+
+
 def assemble_vector(L: CutForm, b: np.ndarray | None = None) -> np.ndarray:
     """fem.py:851-883: adds into `b` (owned+ghost entries) or creates a zero vector first."""
     if L.rank != 1:

@@ -198,6 +198,13 @@ void cfx_pattern_free(cfx_ctx* ctx, cfx_pattern* p);
  * touches (deactivate_outside, fem/deactivate.h:402-418).  values_out may be NULL. */
 cfx_status cfx_assemble_matrix(cfx_ctx* ctx, const cfx_form* a, cfx_pattern* A, int zero_first, double diag_inactive,
                                double* values_out, int memspace);
+/* assemble_matrix + assemble_vector of one problem in one pass (demo_poisson.py:51-54 calls them back to
+ * back on forms over the same measures): where the two forms share their integration domains the row
+ * owners fill b while they walk the incidence for A, so the second sweep disappears; otherwise the call
+ * is the two calls above.  b: DEVICE vector of n_dofs_total entries.  Results are bit-identical to the
+ * separate calls. */
+cfx_status cfx_assemble_system(cfx_ctx* ctx, const cfx_form* a, cfx_pattern* A, int zero_first_A, double diag_inactive,
+                               const cfx_form* L, double* b, int zero_first_b);
 /* assemble_vector: assemble_vector_impl.h:62-122,259-364,573-767; b has n_dofs_total*bs entries */
 cfx_status cfx_assemble_vector(cfx_ctx* ctx, const cfx_form* L, double* b, int zero_first, int memspace);
 /* assemble_scalar: assemble_scalar_impl.h:26-275 (fixed-order tree reduction) */

@@ -124,3 +124,24 @@ def test_active_domain_and_deactivation(runs):
     assert np.all(A.data[np.isin(np.repeat(np.arange(o.V.num_dofs), np.diff(o.row_ptr)), inactive_o)] == 2.0)
     with pytest.raises(ValueError):
         cfx.fem.active_domain(g.L)
+
+
+def test_assemble_system_is_bit_identical_to_separate_calls(runs):
+    """cfx_assemble_system fuses the right-hand side into the matrix gather; same bits as the two calls."""
+    import torch
+
+    import cutfemx_b200 as cfx
+
+    o, g = runs
+    A = cfx.fem.create_matrix(g.a)
+    b = torch.full((o.V.num_dofs,), 7.0, dtype=torch.float64, device="cuda:0")
+    cfx.fem.assemble_system(g.a, A, g.L, b)
+    assert np.array_equal(A.data, g.vals)
+    assert np.array_equal(b.cpu().numpy(), g.b)
+    # adding into an existing vector
+    b2 = torch.ones(o.V.num_dofs, dtype=torch.float64, device="cuda:0")
+    A2 = cfx.fem.create_matrix(g.a)
+    cfx.fem.assemble_system(g.a, A2, g.L, b2, zero_b=False)
+    ref = np.ones(o.V.num_dofs)
+    cfx.fem.assemble_vector(g.L, ref)
+    assert np.array_equal(b2.cpu().numpy(), ref)
