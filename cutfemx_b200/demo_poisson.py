@@ -55,12 +55,13 @@ def device_mesh(ctx_device: int, shape, p0, p1):
     return mesh
 
 
-def device_level_set(mesh: Mesh, kind: str, params):
-    """Nodal interpolation of a sphere/circle (c, R) or torus (c, R, r) level set on the GPU."""
+def device_level_set(mesh: Mesh, kind: str, params, out=None):
+    """Nodal interpolation of a sphere/circle (c, R) or torus (c, R, r) level set on the GPU
+    (into `out` if given)."""
     import torch
 
     ctx = _cut._mesh_context(mesh)
-    vals = torch.empty(mesh.x.shape[0], dtype=torch.float64, device=mesh.x.device)
+    vals = torch.empty(mesh.x.shape[0], dtype=torch.float64, device=mesh.x.device) if out is None else out
     p = (C.c_double * 5)(*(list(params) + [0.0] * 5)[:5])
     check(ctx.handle, lib().cfx_meshgen_level_set(ctx.handle, C.c_void_p(mesh.x.data_ptr()),
                                                   C.c_int64(mesh.x.shape[0]), 0 if kind == "sphere" else 1, p,

@@ -529,7 +529,7 @@ class RankPipeline:
     phase_c: unpack-add (A.scatter_reverse(), b.scatter_reverse(add))
     """
 
-    def __init__(self, shape, p0, p1, world, rank, device, ls_kind, ls_params, order=4, ranges=None, **kw):
+    def __init__(self, shape, p0, p1, world, rank, device, ls_kind, ls_params, order=4, ranges=None, degree=1, **kw):
         from . import demo_poisson as dp
         from .mesh import Function
 
@@ -544,7 +544,23 @@ class RankPipeline:
             vals = torch.from_numpy(np.ascontiguousarray(ls_kind(xh[:, 0], xh[:, 1], xh[:, 2]))).to(self.mesh.x.device)
         else:
             vals = dp.device_level_set(self.mesh, ls_kind, ls_params)  # phi on owned + ghost dofs ("scattered")
-        self.phi = Function(self.V, "phi", vals)
+        self.phi = Function(self.V, "phi", vals)  # the level set is P1 on the mesh vertices
+        self.ls_kind, self.ls_params = ls_kind, ls_params
+        if degree == 2:
+            # P2 on triangles: vertex dofs + one dof per edge; on these meshes edge == facet and local edge e is
+            # opposite local vertex e (Basix), exactly the c2f convention -> edge dof = n_vertices + facet id
+            if world != 1 or self.mesh.tdim != 2:
+                raise NotImplementedError("P2 spaces: single-rank triangle meshes only")
+            import torch
+
+            nn = int(self.mesh.x.shape[0])
+            dm = torch.cat([self.mesh.x_dofmap, self.mesh.c2f + nn], dim=1).contiguous()
+            nd = nn + int(self.mesh.num_facets)
+            self.V = FunctionSpace(self.mesh, 2, dm, nd, nd, 1, None)
+            self.imap = IndexMap(rank, world, nd, 0, self.imap.ghost_global, self.imap.ghost_owner,
+                                 torch.arange(nd, device=dm.device))
+        elif degree != 1:
+            raise ValueError("degree must be 1 or 2")
         self.prob = dp.CutPoisson(self.mesh, self.phi, self.V, order=order, **kw)
         self.ctx = self.prob.ctx
         self.ops = _DeviceOps(self.ctx)
@@ -625,6 +641,14 @@ class RankPipeline:
 
     def finish_step(self):
         self.prob.release_step()
+
+    def move_level_set(self, params):
+        """Re-interpolate the (device-resident) level set with new parameters, in place: the next
+        cutfemx.update() re-cuts it (demo_moving_poisson.py:69-73)."""
+        from . import demo_poisson as dp
+
+        dp.device_level_set(self.mesh, self.ls_kind, params, out=self.phi.x.array)
+        self.ls_params = params
 
     # results in global numbering (owned rows only) -- for the parity tests
     def owned_matrix_global(self):

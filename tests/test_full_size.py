@@ -94,3 +94,44 @@ def test_symmetry_128(built_lib):
     D = (M - M.T).tocsr()
     assert abs(D).max() <= 1e-12 * abs(M).max()
     assert (M.indptr != M.T.tocsr().indptr).sum() == 0  # structurally symmetric pattern
+
+
+def test_c2_p2_4096_properties(built_lib):
+    """configs[1]: 2D circle R=0.5 on 4096x4096 triangles, P2 u / P1 level set (SURVEY.md sizing: 6 581 196
+    inside, 13 994 cut cells).  Properties: partition of unity for P2 (sum b = f * area), area and perimeter
+    within the O(h^2) geometric error, Laplace row sums vanish."""
+    import torch
+
+    import cutfemx_b200 as cfx
+    from cutfemx_b200 import parallel as P
+    import importlib
+
+    cutm = importlib.import_module("cutfemx_b200.cut")
+    n = 4096
+    pipe = P.RankPipeline([n, n], [-1.0, -1.0], [1.0, 1.0], 1, 0, 0, "sphere", (0.0, 0.0, 0.0, 0.5, 0.0), order=4,
+                          degree=2)
+    V, phi, mesh = pipe.V, pipe.phi, pipe.mesh
+    assert V.nd == 6
+    cd = pipe.prob.cut_data
+    n_in, n_cut, n_out = cd.counts()
+    assert (n_in, n_cut) == (6581196, 13994) and n_in + n_cut + n_out == 2 * n * n
+    inside = cutm.locate_entities_device(cd, "phi<0")
+    rv = cfx.runtime_quadrature(cd, "phi<0", 4)
+    ri = cfx.runtime_quadrature(cd, "phi=0", 4)
+    area = cfx.fem.assemble_scalar(cfx.fem.CutForm(V, 0).add_cell_integral("one", inside, rv, (1.0,)))
+    per = cfx.fem.assemble_scalar(cfx.fem.CutForm(V, 0).add_cell_integral("one", None, ri, (1.0,)))
+    h = 2.0 / n
+    assert 0 < math.pi * 0.25 - area < 2 * h * h and 0 < math.pi - per < 4 * h * h
+    f = 0.6
+    L = cfx.fem.CutForm(V, 1).add_cell_integral("source", inside, rv, (f,))
+    b = torch.zeros(V.num_dofs, dtype=torch.float64, device=mesh.x.device)
+    cfx.fem.assemble_vector(L, b)
+    assert abs(float(b.sum(dtype=torch.float64)) - f * area) <= 1e-11 * f * area
+    a = cfx.fem.CutForm(V, 2).add_cell_integral("laplace", inside, rv, (1.0,))
+    A = cfx.fem.assemble_matrix(a)
+    vals, rp = A.values_device(), A.indptr_device()
+    rows = torch.repeat_interleave(torch.arange(V.num_dofs, device=vals.device), rp[1:] - rp[:-1],
+                                   output_size=int(A.nnz))
+    rs = torch.zeros(V.num_dofs, dtype=torch.float64, device=vals.device).index_add_(0, rows, vals)
+    ra = torch.zeros(V.num_dofs, dtype=torch.float64, device=vals.device).index_add_(0, rows, vals.abs())
+    assert float((rs.abs() / ra.clamp(min=1e-300)).max()) < 1e-10
