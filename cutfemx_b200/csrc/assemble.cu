@@ -1080,12 +1080,12 @@ __global__ void __launch_bounds__(GWC * 32, 4)
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
   const uint32_t below = (1u << lane) - 1u;
-  // each block walks a contiguous chunk of rows (its warps interleaved): rows that share cells are
-  // processed close in time by the same SM (L1) or by blocks at the same relative position (L2)
-  const int64_t stride = GWC;
-  const int64_t chunk = ((n_act + gridDim.x - 1) / gridDim.x + GWC - 1) / GWC * GWC;
-  int64_t i = static_cast<int64_t>(blockIdx.x) * chunk + w;
-  const int64_t i_end = (i - w + chunk < n_act) ? i - w + chunk : n_act;
+  // grid-stride over the rows: at any time the warps of the whole grid work on one contiguous window of
+  // rows, so the sweep over the mesh stays ordered and cell records shared by neighbouring rows / planes are
+  // re-used from L2 (a contiguous chunk per block measured 8.4 GB of DRAM traffic per launch, this 5.2 GB)
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * GWC;
+  int64_t i = static_cast<int64_t>(blockIdx.x) * GWC + w;
+  const int64_t i_end = n_act;
   if (i >= i_end)
     return;
 
