@@ -744,39 +744,92 @@ __global__ void inactive_diag_kernel(const uint8_t* __restrict__ row_flag, int64
 // incident cell l and probes its own local facets (up to 32 independent gather chains in flight);
 // hits are staged in shared memory (the two cells' dofs + the macro-tensor row) and the column lanes
 // add them facet round by facet round, cell by cell -- a fixed order.  Returns the number of matches.
+// staged macro rows are padded to a multiple of 4 entries so that the column lanes can read them with
+// 128-bit broadcast loads (6 shared-memory instructions per P1-tetrahedron hit instead of 16)
 template <int ND>
-__device__ __forceinline__ int add_facet_rows(const GatherCtx& gc, int32_t (*s_fd)[2 * ND], double (*s_fv)[2 * ND],
-                                              bool band_cell, int64_t c, int li, int32_t mycol, double& acc,
-                                              int& expected, bool count)
+struct FacetStage
 {
+  static constexpr int W = (2 * ND + 3) / 4 * 4;
+};
+
+template <int ND>
+__device__ __forceinline__ int add_facet_rows(const GatherCtx& gc, int32_t (*s_fd)[FacetStage<ND>::W],
+                                              double (*s_fv)[FacetStage<ND>::W], bool band_cell, int64_t c, int li,
+                                              int32_t mycol, double& acc, int& expected, bool count)
+{
+  constexpr int W = FacetStage<ND>::W;
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   int matched = 0;
   if (__ballot_sync(full, band_cell) == 0)
     return 0;
+  // the cell's facet ids: one 16-byte load for tetrahedra (lane-distinct gathers cost one L1 wavefront per
+  // lane and instruction, so rows are fetched with the widest load that fits them)
+  int32_t fct[4] = {0, 0, 0, 0};
+  if (band_cell)
+  {
+    if (gc.nf == 4)
+    {
+      const int4 q = __ldg(reinterpret_cast<const int4*>(gc.c2f) + c);
+      fct[0] = q.x;
+      fct[1] = q.y;
+      fct[2] = q.z;
+      fct[3] = q.w;
+    }
+    else
+      for (int lf = 0; lf < gc.nf; ++lf)
+        fct[lf] = gc.c2f[c * gc.nf + lf];
+  }
   for (int lf = 0; lf < gc.nf; ++lf)
   {
     int64_t fs = -1;
     if (band_cell)
-      fs = gc.facet_slot[gc.c2f[c * gc.nf + lf]];
+      fs = gc.facet_slot[fct[lf]];
     const bool valid = fs >= 0;
     if (valid)
     {
-      const int64_t c0 = gc.rows4[4 * fs], c1 = gc.rows4[4 * fs + 2];
+      const int4 row = __ldg(reinterpret_cast<const int4*>(gc.rows4) + fs); // (cell0, lf0, cell1, lf1)
+      const int64_t c0 = row.x, c1 = row.z;
       const int mrow = (c == c0 ? 0 : ND) + li;
-#pragma unroll
-      for (int j = 0; j < ND; ++j)
+      if constexpr (ND == 4)
       {
-        s_fd[lane][j] = gc.dofmap[c0 * ND + j];
-        s_fd[lane][ND + j] = gc.dofmap[c1 * ND + j];
+        *reinterpret_cast<int4*>(&s_fd[lane][0]) = __ldg(reinterpret_cast<const int4*>(gc.dofmap) + c0);
+        *reinterpret_cast<int4*>(&s_fd[lane][4]) = __ldg(reinterpret_cast<const int4*>(gc.dofmap) + c1);
+      }
+      else
+      {
+#pragma unroll
+        for (int j = 0; j < ND; ++j)
+        {
+          s_fd[lane][j] = gc.dofmap[c0 * ND + j];
+          s_fd[lane][ND + j] = gc.dofmap[c1 * ND + j];
+        }
+      }
+#pragma unroll
+      for (int j = 2 * ND; j < W; ++j)
+      {
+        s_fd[lane][j] = -3; // padding: matches no column
+        s_fv[lane][j] = 0.0;
       }
       if (gc.Fw)
       { // factored P1 tensor: row mrow of w * jn (x) jn
         const double* jn = gc.Fe + fs * 2 * ND;
-        const double jm = jn[mrow] * gc.Fw[fs];
+        double jv[2 * ND];
+        if constexpr (ND == 4)
+        { // 64-byte record: two 256-bit loads
+          ld256(jn, jv[0], jv[1], jv[2], jv[3]);
+          ld256(jn + 4, jv[4], jv[5], jv[6], jv[7]);
+        }
+        else
+        {
+#pragma unroll
+          for (int j = 0; j < 2 * ND; ++j)
+            jv[j] = jn[j];
+        }
+        const double jm = pick<2 * ND>(jv, mrow) * gc.Fw[fs];
 #pragma unroll
         for (int j = 0; j < 2 * ND; ++j)
-          s_fv[lane][j] = jm * jn[j];
+          s_fv[lane][j] = jm * jv[j];
       }
       else
       {
@@ -794,13 +847,34 @@ __device__ __forceinline__ int add_facet_rows(const GatherCtx& gc, int32_t (*s_f
     {
       const int l = __ffs(m) - 1;
       m &= m - 1;
+      const int4* pd = reinterpret_cast<const int4*>(s_fd[l]);
+      const double2* pv = reinterpret_cast<const double2*>(s_fv[l]);
 #pragma unroll
-      for (int j = 0; j < 2 * ND; ++j)
-        if (s_fd[l][j] == mycol)
+      for (int q = 0; q < W / 4; ++q)
+      {
+        const int4 d = pd[q];
+        const double2 v0 = pv[2 * q], v1 = pv[2 * q + 1];
+        if (d.x == mycol)
         {
-          acc += s_fv[l][j];
+          acc += v0.x;
           ++matched;
         }
+        if (d.y == mycol)
+        {
+          acc += v0.y;
+          ++matched;
+        }
+        if (d.z == mycol)
+        {
+          acc += v1.x;
+          ++matched;
+        }
+        if (d.w == mycol)
+        {
+          acc += v1.y;
+          ++matched;
+        }
+      }
     }
     __syncwarp();
   }
@@ -826,8 +900,8 @@ __global__ void __launch_bounds__(GW * 32)
   constexpr int ND = Elem<TDIM, DEG>::ND;
   __shared__ int32_t s_dofs[GW][32][ND];
   __shared__ double s_a[GW][32][ND];
-  __shared__ int32_t s_fd[GW][32][2 * ND];
-  __shared__ double s_fv[GW][32][2 * ND];
+  __shared__ __align__(16) int32_t s_fd[GW][32][FacetStage<ND>::W];
+  __shared__ __align__(16) double s_fv[GW][32][FacetStage<ND>::W];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * GW + w;
   if (idx >= n_act)
@@ -945,8 +1019,8 @@ __global__ void __launch_bounds__(GWM * 32, 8)
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
   __shared__ double s_v[GWM][32][ND];
-  __shared__ int32_t s_fd[GWM][32][2 * ND];
-  __shared__ double s_fv[GWM][32][2 * ND];
+  __shared__ __align__(16) int32_t s_fd[GWM][32][FacetStage<ND>::W];
+  __shared__ __align__(16) double s_fv[GWM][32][FacetStage<ND>::W];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t it = static_cast<int64_t>(blockIdx.x) * GWM + w;
   if (it >= n_act)
