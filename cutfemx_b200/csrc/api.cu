@@ -353,7 +353,8 @@ cfx_status cfx_space_bind(cfx_ctx* ctx, int space, const int32_t* dofmap, int nd
   CFX_REQUIRE(degree == 1 || degree == 2, CFX_ERR_UNSUPPORTED, "cfx_space_bind: Lagrange degree must be 1 or 2");
   const int expect = degree == 1 ? ctx->nv : (ctx->tdim == 2 ? 6 : 10);
   CFX_REQUIRE(nd == expect, CFX_ERR_INVALID, "cfx_space_bind: dofmap width does not match the element");
-  CFX_REQUIRE(bs == 1, CFX_ERR_UNSUPPORTED, "cfx_space_bind: blocked (vector) spaces are not implemented yet");
+  CFX_REQUIRE(bs == 1 || bs == ctx->gdim, CFX_ERR_UNSUPPORTED,
+              "cfx_space_bind: block size must be 1 (scalar) or the geometric dimension (vector space)");
   CFX_REQUIRE(n_dofs_total < (int64_t(1) << 31), CFX_ERR_RANGE, "cfx_space_bind: dof count exceeds int32");
   Space& S = ctx->spaces[space];
   S.dofmap = adopt(ctx, S.dofmap_own, dofmap, static_cast<size_t>(ctx->nc_total) * nd, memspace);

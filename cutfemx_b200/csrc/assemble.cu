@@ -1459,6 +1459,403 @@ void launch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t& base)
   }
 }
 
+// ================================================================== blocked (vector) Lagrange spaces
+// demo_elasticity.py:213-238, test_assembly_elasticity.py: V = ("Lagrange", p, (gdim,)).  The dofmap and
+// the sparsity pattern stay scalar (one row / column per dof), every CSR entry is a row-major bs x bs
+// block (la::MatrixCSR::mat_add_values<BS, BS>, wrappers/fem.cpp:340-385), vectors hold bs values per dof
+// (assemble_vector_impl.h:109-120), local index of (dof i, component a) = i*bs + a.  Parity-first path:
+// every element tensor (standard cells too) is materialised, the generic row gather adds the blocks.
+// 30 x 30 P2-vector tensors are where FP64 tensor-core MMA would be tried.
+
+// elasticity tensor, one thread per (entity, tensor row ra = i*bs + a): the row's N = nd*bs entries
+//   A[(i,a),(j,b)] = w ( lambda d_a phi_i d_b phi_j + mu d_b phi_i d_a phi_j + mu delta_ab grad phi_i . grad phi_j )
+// c0 = mu, c1 = lambda.  Slots as in cell_kernel; the threads of one entity race benignly on mat_slot
+// (they all store the same value) and recognise their own claim by its value.
+template <int TDIM, int DEG, bool RUNTIME>
+__global__ void __launch_bounds__(EB)
+    elasticity_kernel(const int32_t* __restrict__ cells, int64_t n, RuleView rv, StdRule sr, Consts cs,
+                      const double* __restrict__ x, const int32_t* __restrict__ x_dofmap, OutCtx oc)
+{
+  constexpr int ND = Elem<TDIM, DEG>::ND;
+  constexpr int BS = TDIM, N = ND * BS;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * EB + threadIdx.x;
+  if (t >= n * N)
+    return;
+  const int64_t e = t / N;
+  const int ra = static_cast<int>(t - e * N);
+  const int i = ra / BS, a = ra - i * BS;
+  const int64_t cell = RUNTIME ? rv.parent_map[e] : cells[e];
+  const bool follow = oc.base < 0;
+  const int64_t mine = oc.base + e;
+  const int32_t s0 = oc.mat_slot[cell];
+  const bool add = follow || (s0 >= 0 && s0 != mine);
+  if (follow && s0 < 0)
+    return;
+  const int64_t slot = add ? s0 : mine;
+  double X[TDIM + 1][TDIM];
+  load_cell_coords<TDIM>(x, x_dofmap, cell, X);
+  Geo<TDIM> g;
+  make_geo<TDIM>(X, g);
+  double acc[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+    acc[k] = 0.0;
+  auto point = [&](const double (&xi)[TDIM], double w)
+  {
+    double phi[ND], dphi[ND][TDIM], grad[ND][TDIM];
+    tabulate<TDIM, DEG>(xi, phi, dphi);
+    push_gradients<TDIM, ND>(g, dphi, grad);
+    double gi[TDIM];
+#pragma unroll
+    for (int r = 0; r < TDIM; ++r)
+    {
+      double v = grad[0][r];
+#pragma unroll
+      for (int j = 1; j < ND; ++j)
+        v = (j == i) ? grad[j][r] : v;
+      gi[r] = v;
+    }
+    double gia = gi[0];
+#pragma unroll
+    for (int r = 1; r < TDIM; ++r)
+      gia = (r == a) ? gi[r] : gia;
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+    {
+      double gg = 0.0, gja = grad[j][0];
+#pragma unroll
+      for (int r = 0; r < TDIM; ++r)
+      {
+        gg += gi[r] * grad[j][r];
+        gja = (r == a) ? grad[j][r] : gja;
+      }
+#pragma unroll
+      for (int b = 0; b < BS; ++b)
+        acc[j * BS + b] += w * (cs.c[1] * gia * grad[j][b] + cs.c[0] * gi[b] * gja + ((a == b) ? cs.c[0] * gg : 0.0));
+    }
+  };
+  if constexpr (RUNTIME)
+  {
+    const int32_t q0 = rv.offsets[e], q1 = rv.offsets[e + 1];
+    for (int32_t q = q0; q < q1; ++q)
+    {
+      double xi[TDIM];
+#pragma unroll
+      for (int tt = 0; tt < TDIM; ++tt)
+        xi[tt] = rv.pts[static_cast<int64_t>(tt) * rv.npts + q];
+      point(xi, rv.wts[q]);
+    }
+  }
+  else
+  {
+    const double sdet = fabs(g.detJ);
+    for (int q = 0; q < sr.npts; ++q)
+    {
+      double xi[TDIM];
+#pragma unroll
+      for (int tt = 0; tt < TDIM; ++tt)
+        xi[tt] = __ldg(sr.pts + q * TDIM + tt);
+      point(xi, __ldg(sr.wts + q) * sdet);
+    }
+  }
+  if (!add)
+    oc.mat_slot[cell] = static_cast<int32_t>(slot);
+  double* p = oc.out + (slot * N + ra) * N;
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+    p[k] = add ? p[k] + acc[k] : acc[k];
+}
+
+// inner(f, v) dx with a constant vector f = (c0, c1, c2): one thread per entity, N values
+template <int TDIM, int DEG, bool RUNTIME>
+__global__ void __launch_bounds__(EB)
+    source_vec_kernel(const int32_t* __restrict__ cells, int64_t n, RuleView rv, StdRule sr, Consts cs,
+                      const double* __restrict__ x, const int32_t* __restrict__ x_dofmap, OutCtx oc)
+{
+  constexpr int ND = Elem<TDIM, DEG>::ND;
+  constexpr int BS = TDIM, N = ND * BS;
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * EB + threadIdx.x;
+  if (e >= n)
+    return;
+  const int64_t cell = RUNTIME ? rv.parent_map[e] : cells[e];
+  const bool follow = oc.base < 0;
+  const int32_t s0 = oc.mat_slot[cell];
+  const bool add = follow || s0 >= 0;
+  if (follow && s0 < 0)
+    return;
+  const int64_t slot = add ? s0 : oc.base + e;
+  double acc[ND];
+#pragma unroll
+  for (int k = 0; k < ND; ++k)
+    acc[k] = 0.0;
+  if constexpr (RUNTIME)
+  {
+    const int32_t q0 = rv.offsets[e], q1 = rv.offsets[e + 1];
+    for (int32_t q = q0; q < q1; ++q)
+    {
+      double xi[TDIM], phi[ND], dphi[ND][TDIM];
+#pragma unroll
+      for (int tt = 0; tt < TDIM; ++tt)
+        xi[tt] = rv.pts[static_cast<int64_t>(tt) * rv.npts + q];
+      tabulate<TDIM, DEG>(xi, phi, dphi);
+#pragma unroll
+      for (int k = 0; k < ND; ++k)
+        acc[k] += rv.wts[q] * phi[k];
+    }
+  }
+  else
+  {
+    double X[TDIM + 1][TDIM];
+    load_cell_coords<TDIM>(x, x_dofmap, cell, X);
+    Geo<TDIM> g;
+    make_geo<TDIM>(X, g);
+    const double sdet = fabs(g.detJ);
+    for (int q = 0; q < sr.npts; ++q)
+    {
+      double xi[TDIM], phi[ND], dphi[ND][TDIM];
+#pragma unroll
+      for (int tt = 0; tt < TDIM; ++tt)
+        xi[tt] = __ldg(sr.pts + q * TDIM + tt);
+      tabulate<TDIM, DEG>(xi, phi, dphi);
+#pragma unroll
+      for (int k = 0; k < ND; ++k)
+        acc[k] += __ldg(sr.wts + q) * sdet * phi[k];
+    }
+  }
+  if (!add)
+    oc.mat_slot[cell] = static_cast<int32_t>(slot);
+  double* p = oc.out + slot * N;
+#pragma unroll
+  for (int k = 0; k < ND; ++k)
+#pragma unroll
+    for (int b = 0; b < BS; ++b)
+    {
+      const double v = cs.c[b] * acc[k];
+      p[k * BS + b] = add ? p[k * BS + b] + v : v;
+    }
+}
+
+// Generic row gather for blocked spaces: one warp per active row, one row per block.  Lanes stage the
+// block row (bs x nd*bs values) of each incident cell's materialised tensor with the cell's dofs; the
+// column lanes add the matching bs x bs blocks in ascending cell order (fixed order, no atomics).  A
+// scalar interior-facet tensor (ghost penalty on jump(grad u, n)) acts on every component alike: its
+// entry goes on the diagonal of the block.
+template <int TDIM, int DEG>
+__global__ void __launch_bounds__(32)
+    gather_matrix_blocked_kernel(GatherCtx gc, const int32_t* __restrict__ act_rows, int64_t n_act,
+                                 const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ cols,
+                                 double* __restrict__ vals, int zero_first, int32_t* __restrict__ err)
+{
+  constexpr int ND = Elem<TDIM, DEG>::ND;
+  constexpr int BS = TDIM, N = ND * BS;
+  __shared__ int32_t s_dofs[32][ND];
+  __shared__ double s_a[32][BS * N];
+  __shared__ __align__(16) int32_t s_fd[32][FacetStage<ND>::W];
+  __shared__ __align__(16) double s_fv[32][FacetStage<ND>::W];
+  const int lane = threadIdx.x;
+  const int64_t idx = blockIdx.x;
+  if (idx >= n_act)
+    return;
+  const unsigned full = 0xffffffffu;
+  const int64_t r = act_rows[idx];
+  const int64_t ib = gc.inc_ptr[r];
+  const int n_inc = static_cast<int>(gc.inc_ptr[r + 1] - ib);
+  const int64_t rb = row_ptr[r];
+  const int rn = static_cast<int>(row_ptr[r + 1] - rb);
+  int matched = 0, expected = 0;
+  for (int kc = 0; kc < rn; kc += 32)
+  {
+    const bool have_col = kc + lane < rn;
+    const int32_t mycol = have_col ? cols[rb + kc + lane] : -2;
+    double acc[BS * BS];
+#pragma unroll
+    for (int q = 0; q < BS * BS; ++q)
+      acc[q] = (have_col && !zero_first) ? vals[(rb + kc + lane) * BS * BS + q] : 0.0;
+    for (int k0 = 0; k0 < n_inc; k0 += 32)
+    {
+      const int k = k0 + lane;
+      int64_t c = -1;
+      unsigned fl = 0;
+      int li = 0;
+      if (k < n_inc)
+      {
+        c = gc.inc_cell[ib + k];
+        fl = gc.cell_flags[c];
+      }
+      const bool contributes = (fl & 1u) != 0;
+      if (fl)
+      {
+        int32_t d[ND];
+#pragma unroll
+        for (int j = 0; j < ND; ++j)
+        {
+          d[j] = gc.dofmap[c * ND + j];
+          li = (d[j] == r) ? j : li;
+        }
+        if (contributes)
+        {
+          const double* a = gc.Ae + (static_cast<int64_t>(gc.mat_slot[c]) * N + li * BS) * N;
+#pragma unroll
+          for (int j = 0; j < ND; ++j)
+            s_dofs[lane][j] = d[j];
+          for (int q = 0; q < BS * N; ++q)
+            s_a[lane][q] = a[q];
+        }
+      }
+      if (!contributes)
+      {
+#pragma unroll
+        for (int j = 0; j < ND; ++j)
+          s_dofs[lane][j] = -1;
+      }
+      __syncwarp();
+      const int nl = (n_inc - k0 < 32) ? n_inc - k0 : 32;
+      for (int l = 0; l < nl; ++l)
+      {
+#pragma unroll
+        for (int j = 0; j < ND; ++j)
+          if (s_dofs[l][j] == mycol)
+          {
+#pragma unroll
+            for (int a = 0; a < BS; ++a)
+#pragma unroll
+              for (int b = 0; b < BS; ++b)
+                acc[a * BS + b] += s_a[l][a * N + j * BS + b];
+            ++matched;
+          }
+      }
+      if (kc == 0)
+        expected += contributes ? ND : 0;
+      double facc = 0.0;
+      matched += add_facet_rows<ND>(gc, s_fd, s_fv, (fl & 2u) != 0, c, li, mycol, facc, expected, kc == 0);
+#pragma unroll
+      for (int a = 0; a < BS; ++a)
+        acc[a * BS + a] += facc;
+      __syncwarp();
+    }
+    if (have_col)
+    {
+#pragma unroll
+      for (int q = 0; q < BS * BS; ++q)
+        vals[(rb + kc + lane) * BS * BS + q] = acc[q];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    matched += __shfl_down_sync(full, matched, o);
+    expected += __shfl_down_sync(full, expected, o);
+  }
+  if (lane == 0 && matched != expected)
+  {
+    err[0] = 31;
+    err[1] = static_cast<int32_t>(r);
+  }
+}
+
+// b[bs*dof + a] += element-vector entries of the incident cells, ascending cell order + fixed shuffle tree
+template <int TDIM, int DEG>
+__global__ void __launch_bounds__(GW * 32)
+    gather_vector_blocked_kernel(GatherCtx gc, const int32_t* __restrict__ act_rows, int64_t n_act,
+                                 double* __restrict__ b, int zero_first)
+{
+  constexpr int ND = Elem<TDIM, DEG>::ND;
+  constexpr int BS = TDIM, N = ND * BS;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * GW + w;
+  if (idx >= n_act)
+    return;
+  const int64_t r = act_rows[idx];
+  const int64_t ib = gc.inc_ptr[r];
+  const int n_inc = static_cast<int>(gc.inc_ptr[r + 1] - ib);
+  double s[BS];
+#pragma unroll
+  for (int a = 0; a < BS; ++a)
+    s[a] = 0.0;
+  for (int k0 = 0; k0 < n_inc; k0 += 32)
+  {
+    const int k = k0 + lane;
+    double e[BS];
+#pragma unroll
+    for (int a = 0; a < BS; ++a)
+      e[a] = 0.0;
+    if (k < n_inc)
+    {
+      const int64_t c = gc.inc_cell[ib + k];
+      if (gc.cell_flags[c] & 1u)
+      {
+        int li = 0;
+#pragma unroll
+        for (int j = 0; j < ND; ++j)
+          li = (gc.dofmap[c * ND + j] == r) ? j : li;
+        const double* p = gc.Ae + static_cast<int64_t>(gc.mat_slot[c]) * N + li * BS;
+#pragma unroll
+        for (int a = 0; a < BS; ++a)
+          e[a] = p[a];
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < BS; ++a)
+    {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        e[a] += __shfl_down_sync(0xffffffffu, e[a], o);
+      s[a] += e[a];
+    }
+  }
+  if (lane == 0)
+  {
+#pragma unroll
+    for (int a = 0; a < BS; ++a)
+      b[r * BS + a] = zero_first ? s[a] : b[r * BS + a] + s[a];
+  }
+}
+
+template <int TDIM, int DEG>
+void launch_blocked_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t& base)
+{
+  constexpr int N = Elem<TDIM, DEG>::ND * TDIM;
+  RuleView rv{};
+  StdRule sr{};
+  Consts cs;
+  for (int k = 0; k < CFX_MAX_CONSTANTS; ++k)
+    cs.c[k] = I.constants[k];
+  OutCtx oc{c->mat_slot.p, f->Ae.p, base};
+  const bool el = I.kernel == CFX_K_ELASTICITY;
+  CFX_REQUIRE(el || I.kernel == CFX_K_SOURCE_VEC, CFX_ERR_UNSUPPORTED,
+              "kernel family is not defined on blocked (vector) spaces");
+  if (I.n > 0)
+  {
+    RuleTable& rt = get_rule(c, TDIM, el ? 2 * (DEG - 1) : DEG);
+    sr = StdRule{rt.d_pts, rt.d_wts, rt.npts};
+    if (el)
+      CFX_LAUNCH(c, (elasticity_kernel<TDIM, DEG, false>), grid_for(I.n * N, EB), EB, 0, I.entities, I.n, rv, sr, cs,
+                 c->x, c->x_dofmap, oc);
+    else
+      CFX_LAUNCH(c, (source_vec_kernel<TDIM, DEG, false>), grid_for(I.n, EB), EB, 0, I.entities, I.n, rv, sr, cs, c->x,
+                 c->x_dofmap, oc);
+    if (base >= 0)
+    {
+      base += I.n;
+      oc.base = base;
+    }
+  }
+  if (I.rules && I.rules->nrules > 0)
+  {
+    const cfx_rules* R = I.rules;
+    CFX_REQUIRE(R->tdim == TDIM, CFX_ERR_INVALID, "run-time rules have the wrong reference dimension");
+    rv = RuleView{R->points.p, R->weights.p, nullptr, R->offsets.p, R->parent_map.p, R->npts};
+    if (el)
+      CFX_LAUNCH(c, (elasticity_kernel<TDIM, DEG, true>), grid_for(R->nrules * N, EB), EB, 0, nullptr, R->nrules, rv, sr,
+                 cs, c->x, c->x_dofmap, oc);
+    else
+      CFX_LAUNCH(c, (source_vec_kernel<TDIM, DEG, true>), grid_for(R->nrules, EB), EB, 0, nullptr, R->nrules, rv, sr, cs,
+                 c->x, c->x_dofmap, oc);
+    if (base >= 0)
+      base += R->nrules;
+  }
+}
+
 template <int TDIM, int DEG>
 void dispatch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t& base)
 {
@@ -1479,7 +1876,31 @@ void dispatch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t& base
 int64_t run_cell_integrals(cfx_ctx* c, cfx_form* f, int64_t follow_slots = -1)
 {
   const Space& S = c->spaces[f->space];
-  const int es = f->rank == 2 ? S.nd * S.nd : (f->rank == 1 ? S.nd : 1);
+  const bool blocked = S.bs > 1 && f->rank > 0;
+  const int n1 = S.nd * (blocked ? S.bs : 1);
+  const int es = f->rank == 2 ? n1 * n1 : (f->rank == 1 ? n1 : 1);
+  auto dispatch = [&](const cfx_integral& I, int64_t& base)
+  {
+    if (blocked)
+    {
+      if (c->tdim == 2 && S.degree == 1)
+        launch_blocked_cell<2, 1>(c, I, f, base);
+      else if (c->tdim == 2)
+        launch_blocked_cell<2, 2>(c, I, f, base);
+      else if (S.degree == 1)
+        launch_blocked_cell<3, 1>(c, I, f, base);
+      else
+        launch_blocked_cell<3, 2>(c, I, f, base);
+    }
+    else if (c->tdim == 2 && S.degree == 1)
+      dispatch_cell<2, 1>(c, I, f, base);
+    else if (c->tdim == 2)
+      dispatch_cell<2, 2>(c, I, f, base);
+    else if (S.degree == 1)
+      dispatch_cell<3, 1>(c, I, f, base);
+    else
+      dispatch_cell<3, 2>(c, I, f, base);
+  };
   if (follow_slots >= 0)
   { // FOLLOW mode: same slots as the form that ran before, zero-initialised accumulation
     f->Ae.reserve(c->pool, static_cast<size_t>(follow_slots) * es + 4);
@@ -1489,14 +1910,7 @@ int64_t run_cell_integrals(cfx_ctx* c, cfx_form* f, int64_t follow_slots = -1)
       if (I.facet)
         continue;
       int64_t base = -1;
-      if (c->tdim == 2 && S.degree == 1)
-        dispatch_cell<2, 1>(c, I, f, base);
-      else if (c->tdim == 2)
-        dispatch_cell<2, 2>(c, I, f, base);
-      else if (S.degree == 1)
-        dispatch_cell<3, 1>(c, I, f, base);
-      else
-        dispatch_cell<3, 2>(c, I, f, base);
+      dispatch(I, base);
     }
     return follow_slots;
   }
@@ -1505,7 +1919,7 @@ int64_t run_cell_integrals(cfx_ctx* c, cfx_form* f, int64_t follow_slots = -1)
   {
     if (I.facet)
       continue;
-    if (f->rank == 0)
+    if (f->rank == 0 || blocked)
       cap += I.n;
     if (I.rules)
       cap += I.rules->nrules;
@@ -1516,30 +1930,32 @@ int64_t run_cell_integrals(cfx_ctx* c, cfx_form* f, int64_t follow_slots = -1)
   {
     if (I.facet)
       continue;
-    if (c->tdim == 2 && S.degree == 1)
-      dispatch_cell<2, 1>(c, I, f, base);
-    else if (c->tdim == 2)
-      dispatch_cell<2, 2>(c, I, f, base);
-    else if (S.degree == 1)
-      dispatch_cell<3, 1>(c, I, f, base);
-    else
-      dispatch_cell<3, 2>(c, I, f, base);
+    dispatch(I, base);
   }
   return base;
 }
 
 void reset_slots(cfx_ctx* c, cfx_form* f)
 {
+  const bool blocked = c->spaces[f->space].bs > 1 && f->rank > 0;
   for (auto& I : f->integrals)
-    if (!I.facet && I.rules && I.rules->nrules > 0)
+  {
+    if (I.facet)
+      continue;
+    if (I.rules && I.rules->nrules > 0)
       CFX_LAUNCH(c, reset_slots_kernel, grid_for(I.rules->nrules, 256), 256, 0, I.rules->parent_map.p, I.rules->nrules,
                  c->mat_slot.p);
+    if (blocked && I.n > 0) // blocked spaces materialise the standard cells too
+      CFX_LAUNCH(c, reset_slots_kernel, grid_for(I.n, 256), 256, 0, I.entities, I.n, c->mat_slot.p);
+  }
 }
 
 StdTab make_std_tab(cfx_ctx* c, cfx_form* f)
 {
   const Space& S = c->spaces[f->space];
   StdTab st{};
+  if (S.bs > 1)
+    return st; // blocked spaces: standard cells are materialised like cut cells
   for (auto& I : f->integrals)
   {
     if (I.facet || I.n == 0)
@@ -1616,6 +2032,14 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
   cfx_prepared* PR = a->prep;
   if (PR->n_act_rows == 0)
     return;
+  if (S.bs > 1)
+  {
+    CFX_REQUIRE(S.bs == TDIM, CFX_ERR_UNSUPPORTED, "blocked spaces need block size == gdim");
+    auto kb = gather_matrix_blocked_kernel<TDIM, DEG>;
+    CFX_LAUNCH(ctx, kb, grid_for(PR->n_act_rows, 1), 32, 0, gc, PR->act_rows.p, PR->n_act_rows, A->row_ptr.p, A->cols.p,
+               A->values.p, zero_first, ctx->err_flag.p);
+    return;
+  }
   // the gather tables are valid only for the pattern that was built from this very form
   const bool fast = a->gtab_serial == A->serial && a->gtab_serial > 0 && S.has_perm;
   const unsigned g = grid_for(PR->n_act_rows, GW);
@@ -1674,6 +2098,12 @@ void launch_gather_vector(cfx_ctx* ctx, cfx_form* L, const GatherCtx& gc, const 
   cfx_prepared* PR = L->prep;
   if (PR->n_act_rows == 0)
     return;
+  if (S.bs > 1)
+  {
+    auto kb = gather_vector_blocked_kernel<TDIM, DEG>;
+    CFX_LAUNCH(ctx, kb, grid_for(PR->n_act_rows, GW), GW * 32, 0, gc, PR->act_rows.p, PR->n_act_rows, d_b, zero_first);
+    return;
+  }
   auto run = [&](const int32_t* slots, int64_t n, const uint8_t* row_fast, int skip_mode)
   {
     const unsigned g = grid_for(n, GW);
@@ -1809,8 +2239,8 @@ static void assemble_matrix_impl(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, int 
     GatherCtx gc = make_gather_ctx(ctx, a, FI);
     const StdTab stt = make_std_tab(ctx, a);
     StdTab stL{};
-    const bool fuse_b = L && a->gtab_serial == A->serial && a->gtab_serial > 0 && S.has_perm && S.has_static
-                        && a->n_clist_rows > 0 && S.nd <= 6;
+    const bool fuse_b = L && S.bs == 1 && a->gtab_serial == A->serial && a->gtab_serial > 0 && S.has_perm
+                        && S.has_static && a->n_clist_rows > 0 && S.nd <= 6;
     if (fuse_b)
     {
       stL = make_std_tab(ctx, L);
@@ -1819,7 +2249,9 @@ static void assemble_matrix_impl(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, int 
       gc.zero_first_b = zero_first_b;
     }
     if (zero_first)
-      CFX_CUDA(cudaMemsetAsync(A->values.p, 0, static_cast<size_t>(A->nnz) * sizeof(double), ctx->stream));
+      CFX_CUDA(cudaMemsetAsync(A->values.p, 0, static_cast<size_t>(A->nnz) * S.bs * S.bs * sizeof(double), ctx->stream));
+    CFX_REQUIRE(diag_inactive == 0.0 || S.bs == 1, CFX_ERR_UNSUPPORTED,
+                "diag_inactive is not supported for blocked matrices yet");
     if (diag_inactive != 0.0)
       CFX_LAUNCH(ctx, inactive_diag_kernel, grid_for(A->n_rows, 256), 256, 0, a->prep->row_flag.p, A->n_rows, A->row_ptr.p,
                  A->cols.p, A->values.p, diag_inactive);
@@ -1832,7 +2264,7 @@ static void assemble_matrix_impl(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, int 
     StageScope st(ctx, "gather_vector", 8.0 * static_cast<double>(S.n_total));
     GatherCtx gl = make_gather_ctx(ctx, L, nullptr);
     const StdTab stl = make_std_tab(ctx, L);
-    const bool fused = a->gtab_serial == A->serial && a->gtab_serial > 0 && S.has_perm && S.has_static
+    const bool fused = S.bs == 1 && a->gtab_serial == A->serial && a->gtab_serial > 0 && S.has_perm && S.has_static
                        && a->n_clist_rows > 0 && S.nd <= 6; // same condition as fuse_b above
     CFX_DISPATCH_ELEM(ctx, S, launch_gather_vector, ctx, L, gl, stl, d_b, zero_first_b, fused ? a : nullptr);
   }
@@ -1851,7 +2283,7 @@ cfx_status cfx_assemble_matrix(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
   CFX_REQUIRE(A->space == a->space, CFX_ERR_INVALID, "cfx_assemble_matrix: matrix and form use different spaces");
   assemble_matrix_impl(ctx, a, A, zero_first, diag_inactive, nullptr, nullptr, 0);
   if (values_out)
-    export_to(ctx, values_out, A->values.p, static_cast<size_t>(A->nnz), memspace);
+    export_to(ctx, values_out, A->values.p, static_cast<size_t>(A->nnz) * A->bs * A->bs, memspace);
   check_device_error(ctx, "cfx_assemble_matrix (entry not in sparsity pattern)");
   CFX_API_END(ctx)
 }
@@ -1870,7 +2302,7 @@ cfx_status cfx_assemble_system(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
   prepare_form(ctx, a);
   prepare_form(ctx, L);
   if (zero_first_b)
-    CFX_CUDA(cudaMemsetAsync(b, 0, static_cast<size_t>(S.n_total) * sizeof(double), ctx->stream));
+    CFX_CUDA(cudaMemsetAsync(b, 0, static_cast<size_t>(S.n_total) * S.bs * sizeof(double), ctx->stream));
   if (a->prep == L->prep)
     assemble_matrix_impl(ctx, a, A, zero_first_A, diag_inactive, L, b, zero_first_b);
   else
@@ -1910,10 +2342,10 @@ cfx_status cfx_assemble_vector(cfx_ctx* ctx, const cfx_form* L_const, double* b,
   double* d_b = b;
   if (memspace == CFX_HOST)
   {
-    tmp.reserve(ctx->pool, static_cast<size_t>(S.n_total));
+    tmp.reserve(ctx->pool, static_cast<size_t>(S.n_total) * S.bs);
     d_b = tmp.p;
     if (!zero_first)
-      CFX_CUDA(cudaMemcpyAsync(d_b, b, static_cast<size_t>(S.n_total) * sizeof(double), cudaMemcpyHostToDevice,
+      CFX_CUDA(cudaMemcpyAsync(d_b, b, static_cast<size_t>(S.n_total) * S.bs * sizeof(double), cudaMemcpyHostToDevice,
                                ctx->stream));
   }
   {
@@ -1923,13 +2355,13 @@ cfx_status cfx_assemble_vector(cfx_ctx* ctx, const cfx_form* L_const, double* b,
     GatherCtx gc = make_gather_ctx(ctx, L, nullptr);
     const StdTab stt = make_std_tab(ctx, L);
     if (zero_first)
-      CFX_CUDA(cudaMemsetAsync(d_b, 0, static_cast<size_t>(S.n_total) * sizeof(double), ctx->stream));
+      CFX_CUDA(cudaMemsetAsync(d_b, 0, static_cast<size_t>(S.n_total) * S.bs * sizeof(double), ctx->stream));
     CFX_DISPATCH_ELEM(ctx, S, launch_gather_vector, ctx, L, gc, stt, d_b, zero_first);
     reset_slots(ctx, L);
   }
   if (memspace == CFX_HOST)
   {
-    export_to(ctx, b, tmp.p, static_cast<size_t>(S.n_total), CFX_HOST);
+    export_to(ctx, b, tmp.p, static_cast<size_t>(S.n_total) * S.bs, CFX_HOST);
     tmp.release();
   }
   CFX_API_END(ctx)

@@ -214,6 +214,7 @@ struct cfx_rules
 struct cfx_pattern
 {
   int space = 0;
+  int bs = 1; // values: nnz * bs * bs
   int64_t n_rows = 0, nnz = 0;
   int64_t serial = 0;
   cfx::DevBuf<int64_t> row_ptr;

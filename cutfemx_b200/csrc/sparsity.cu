@@ -817,6 +817,11 @@ void prepare_form(cfx_ctx* c, cfx_form* f)
     if (I.rules && I.rules->nrules > 0)
       rkey.emplace_back(I.rules->parent_map.p, I.rules->nrules);
   }
+  if (S.bs > 1 && f->rank > 0)
+  { // blocked spaces: every element tensor is materialised (bit0), standard cells included
+    rkey.insert(rkey.end(), skey.begin(), skey.end());
+    skey.clear();
+  }
   for (auto* k : {&skey, &rkey})
   {
     std::sort(k->begin(), k->end());
@@ -952,8 +957,10 @@ static int kernel_rank(int k)
   case CFX_K_LAPLACE:
   case CFX_K_MASS:
   case CFX_K_NITSCHE:
-  case CFX_K_GHOST_GRAD_JUMP: return 2;
+  case CFX_K_GHOST_GRAD_JUMP:
+  case CFX_K_ELASTICITY: return 2;
   case CFX_K_SOURCE:
+  case CFX_K_SOURCE_VEC:
   case CFX_K_NITSCHE_RHS: return 1;
   case CFX_K_ONE: return 0;
   }
@@ -969,6 +976,12 @@ cfx_status cfx_form_add_cell_integral(cfx_ctx* ctx, cfx_form* f, int kernel, con
               "cfx_form_add_cell_integral: kernel family does not match the form rank / integral type");
   CFX_REQUIRE(n_constants >= 0 && n_constants <= CFX_MAX_CONSTANTS, CFX_ERR_INVALID, "too many constants");
   CFX_REQUIRE(n_cells == 0 || cells != nullptr, CFX_ERR_INVALID, "cfx_form_add_cell_integral: NULL cells");
+  {
+    const bool vec_kernel = kernel == CFX_K_ELASTICITY || kernel == CFX_K_SOURCE_VEC;
+    const int bs = ctx->spaces[f->space].bs;
+    CFX_REQUIRE(f->rank == 0 || (vec_kernel ? bs == ctx->gdim : bs == 1), CFX_ERR_INVALID,
+                "cfx_form_add_cell_integral: kernel family does not match the block size of the space");
+  }
   if (kernel == CFX_K_NITSCHE || kernel == CFX_K_NITSCHE_RHS)
   {
     CFX_REQUIRE(n_cells == 0, CFX_ERR_INVALID, "interface kernels take run-time rules only");
@@ -1043,6 +1056,7 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
   cfx_prepared* PR = a->prep;
   const bool part = row_begin > 0;
   P->space = a->space;
+  P->bs = S.bs;
   P->n_rows = S.n_total;
   StageScope st(ctx, part ? "ghost_row_pattern" : "create_sparsity");
   set_facet_slots(ctx, FI, false);
@@ -1130,7 +1144,7 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
     a->n_mask_rows = n_act - h[1] - h[2];
   }
   P->cols.reserve(ctx->pool, static_cast<size_t>(P->nnz) + 1);
-  P->values.reserve(ctx->pool, static_cast<size_t>(P->nnz) + 1);
+  P->values.reserve(ctx->pool, static_cast<size_t>(P->nnz) * S.bs * S.bs + 1);
   if (!part)
     CFX_LAUNCH(ctx, pattern_inactive_fill_kernel, grid_for(S.n_total, SBK), SBK, 0, PR->row_flag.p, S.n_total, 1,
                P->row_ptr.p, P->cols.p);
@@ -1152,7 +1166,8 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
   set_facet_slots(ctx, FI, true);
   if (has_x)
     CFX_LAUNCH(ctx, xslot_set_kernel, grid_for(a->n_x, SBK), SBK, 0, a->xrows.p, a->n_x, ctx->xslot.p, true);
-  CFX_CUDA(cudaMemsetAsync(P->values.p, 0, (static_cast<size_t>(P->nnz) + 1) * sizeof(double), ctx->stream));
+  CFX_CUDA(cudaMemsetAsync(P->values.p, 0, (static_cast<size_t>(P->nnz) * S.bs * S.bs + 1) * sizeof(double),
+                           ctx->stream));
   row_nnz.release();
   st.set_bytes(12.0 * static_cast<double>(P->nnz) + 8.0 * static_cast<double>(S.n_total));
   check_device_error(ctx, "cfx_create_sparsity (row capacity exceeded / inserted entries not sorted by row)");
@@ -1245,6 +1260,7 @@ cfx_status cfx_pattern_positions(cfx_ctx* ctx, const cfx_pattern* p, const int32
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && p && (n == 0 || (rows && cols && positions)), CFX_ERR_INVALID,
               "cfx_pattern_positions: NULL argument");
+  CFX_REQUIRE(p->bs == 1, CFX_ERR_UNSUPPORTED, "cfx_pattern_positions: blocked matrices are not supported yet");
   if (n > 0)
   {
     CFX_LAUNCH(ctx, positions_kernel, grid_for(n, 256), 256, 0, p->row_ptr.p, p->cols.p, p->n_rows, rows, cols, n,
@@ -1275,17 +1291,19 @@ cfx_status cfx_pattern_import(cfx_ctx* ctx, int space, const int64_t* row_ptr, c
     *out = new cfx_pattern();
   cfx_pattern* P = *out;
   P->space = space;
+  P->bs = ctx->spaces[space].bs;
+  const size_t bb = static_cast<size_t>(P->bs) * P->bs;
   P->n_rows = n_rows;
   P->nnz = nnz;
   P->serial = ++ctx->pattern_serial;
   P->row_ptr.reserve(ctx->pool, static_cast<size_t>(n_rows) + 1);
   P->cols.reserve(ctx->pool, static_cast<size_t>(nnz) + 1);
-  P->values.reserve(ctx->pool, static_cast<size_t>(nnz) + 1);
+  P->values.reserve(ctx->pool, static_cast<size_t>(nnz) * bb + 1);
   const cudaMemcpyKind kind = memspace == CFX_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   CFX_CUDA(cudaMemcpyAsync(P->row_ptr.p, row_ptr, (static_cast<size_t>(n_rows) + 1) * sizeof(int64_t), kind,
                            ctx->stream));
   CFX_CUDA(cudaMemcpyAsync(P->cols.p, cols, static_cast<size_t>(nnz) * sizeof(int32_t), kind, ctx->stream));
-  CFX_CUDA(cudaMemsetAsync(P->values.p, 0, (static_cast<size_t>(nnz) + 1) * sizeof(double), ctx->stream));
+  CFX_CUDA(cudaMemsetAsync(P->values.p, 0, (static_cast<size_t>(nnz) * bb + 1) * sizeof(double), ctx->stream));
   CFX_LAUNCH(ctx, check_sorted_kernel, grid_for(n_rows, SBK), SBK, 0, P->row_ptr.p, P->cols.p, n_rows,
              ctx->err_flag.p);
   CFX_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1321,9 +1339,11 @@ cfx_status cfx_pattern_values_fetch(cfx_ctx* ctx, const cfx_pattern* p, double* 
 {
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && p && values, CFX_ERR_INVALID, "cfx_pattern_values_fetch: NULL argument");
-  export_to(ctx, values, p->values.p, static_cast<size_t>(p->nnz), memspace);
+  export_to(ctx, values, p->values.p, static_cast<size_t>(p->nnz) * p->bs * p->bs, memspace);
   CFX_API_END(ctx)
 }
+
+int cfx_pattern_block_size(const cfx_pattern* p) { return p ? p->bs : 0; }
 
 void cfx_pattern_free(cfx_ctx* ctx, cfx_pattern* p)
 {
@@ -1451,6 +1471,7 @@ cfx_status cfx_deactivate_outside(cfx_ctx* ctx, cfx_pattern* A, const int32_t* i
 {
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && A && (n == 0 || inactive_dofs), CFX_ERR_INVALID, "cfx_deactivate_outside: NULL argument");
+  CFX_REQUIRE(A->bs == 1, CFX_ERR_UNSUPPORTED, "cfx_deactivate_outside: blocked matrices are not supported yet");
   if (n > 0)
   {
     DevBuf<int32_t> own;

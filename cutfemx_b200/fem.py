@@ -140,9 +140,13 @@ class MatrixCSR:
         return self._cache["indices"]
 
     @property
+    def block_size(self) -> int:
+        return int(lib().cfx_pattern_block_size(self._h))
+
+    @property
     def data(self):
-        """Copy of the values on the host."""
-        out = np.empty(self.nnz)
+        """Copy of the values on the host: nnz entries, or nnz row-major bs x bs blocks for vector spaces."""
+        out = np.empty(self.nnz * self.block_size ** 2)
         if out.size:
             h = self.ctx.handle
             check(h, lib().cfx_pattern_values_fetch(h, self._h, C.c_void_p(out.ctypes.data), HOST))
@@ -163,7 +167,8 @@ class MatrixCSR:
     def values_device(self):
         from ._lib import device_view
 
-        return device_view(lib().cfx_pattern_values_device_ptr(self._h), self.nnz, np.float64, self.ctx.device, self)
+        return device_view(lib().cfx_pattern_values_device_ptr(self._h), self.nnz * self.block_size ** 2, np.float64,
+                           self.ctx.device, self)
 
     def copy_to_host_async(self, h_indptr, h_indices, h_values, stream=None):
         """Enqueue the device->host copy of the CSR arrays into (pinned) torch host tensors on `stream`
@@ -181,6 +186,10 @@ class MatrixCSR:
     def to_scipy(self):
         import scipy.sparse as sp
 
+        bs = self.block_size
+        if bs > 1:
+            n = self.shape[0] * bs
+            return sp.bsr_matrix((self.data.reshape(-1, bs, bs), self.indices, self.indptr), shape=(n, n)).tocsr()
         return sp.csr_matrix((self.data, self.indices, self.indptr), shape=self.shape)
 
     def scatter_reverse(self):  # single rank: no-op (multi-rank: parallel.py)

@@ -53,7 +53,11 @@ enum {
   CFX_K_GHOST_GRAD_JUMP = 4,/* rank 2, interior facets: c0 * avg(h) * jump(grad u,n) * jump(grad v,n)               */
   CFX_K_SOURCE = 5,         /* rank 1, cells:           c0 * v                                                      */
   CFX_K_NITSCHE_RHS = 6,    /* rank 1, interface rules: -(grad v.n) c1 + c0/h c1 v                (needs normals)   */
-  CFX_K_ONE = 7             /* rank 0, cells / rules:   c0  (volume, area, perimeter)                               */
+  CFX_K_ONE = 7,            /* rank 0, cells / rules:   c0  (volume, area, perimeter)                               */
+  /* blocked (vector) Lagrange spaces, block size == gdim (demo_elasticity.py:213-238): */
+  CFX_K_ELASTICITY = 8,     /* rank 2, cells:           inner(sigma(u), eps(v)), sigma = 2 c0 eps + c1 tr(eps) I        */
+  CFX_K_SOURCE_VEC = 9      /* rank 1, cells:           inner((c0, c1, c2), v)                                         */
+  /* CFX_K_GHOST_GRAD_JUMP on a blocked space acts on every component: c0 avg(h) inner(jump(grad u, n), jump(grad v, n)) */
 };
 
 /* ------------------------------------------------------------------ context */
@@ -143,7 +147,9 @@ cfx_status cfx_facet_integration_rows(cfx_ctx* ctx, const int32_t* facets, int64
 
 /* ------------------------------------------------------------------ function spaces
  * dolfinx::fem::DofMap of a Lagrange space of `degree` (1|2) on the bound mesh:
- * dofmap (n_cells_total, nd) int32, block size bs, index_map size_local / +num_ghosts. */
+ * dofmap (n_cells_total, nd) int32 (scalar dofs), block size bs (1, or gdim for vector spaces: matrices
+ * then hold row-major bs x bs blocks per pattern entry, vectors bs values per dof -- wrappers/fem.cpp:330-385,
+ * assemble_vector_impl.h:109-120), index_map size_local / +num_ghosts. */
 cfx_status cfx_space_bind(cfx_ctx* ctx, int space, const int32_t* dofmap, int nd, int bs, int degree,
                           int64_t n_dofs_owned, int64_t n_dofs_total, int memspace);
 
@@ -183,6 +189,7 @@ cfx_status cfx_pattern_positions(cfx_ctx* ctx, const cfx_pattern* p, const int32
 cfx_status cfx_pattern_import(cfx_ctx* ctx, int space, const int64_t* row_ptr, const int32_t* cols, int64_t n_rows,
                               int memspace, cfx_pattern** out);
 cfx_status cfx_pattern_sizes(const cfx_pattern* p, int64_t* n_rows, int64_t* nnz);
+int cfx_pattern_block_size(const cfx_pattern* p); /* values hold nnz * bs * bs doubles */
 cfx_status cfx_pattern_fetch(cfx_ctx* ctx, const cfx_pattern* p, int64_t* row_ptr, int32_t* cols, int memspace);
 const double* cfx_pattern_values_device_ptr(const cfx_pattern* p);
 const int64_t* cfx_pattern_row_ptr_device_ptr(const cfx_pattern* p);

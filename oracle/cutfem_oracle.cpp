@@ -627,6 +627,56 @@ void k_ghost_grad_jump(double* A, const double*, const double* c, const double* 
   }
 }
 
+// demo_elasticity.py:222-224 / test_assembly_elasticity.py:38-45: inner(sigma(u), epsilon(v)) dx with
+// sigma = 2 mu eps + lambda tr(eps) I on a blocked (vector) Lagrange space, block size = gdim, local
+// index of (dof i, component a) = i*bs + a.  c[0] = mu, c[1] = lambda.
+//   A[(i,a),(j,b)] = w ( lambda d_a phi_i d_b phi_j + mu d_b phi_i d_a phi_j + mu delta_ab grad phi_i . grad phi_j )
+void k_elasticity(double* A, const double*, const double* c, const double* cdofs, const int* eli, const uint8_t*,
+                  void* p)
+{
+  const CustomData& cd = *static_cast<CustomData*>(p);
+  const int td = cd.tdim, nd = space_dim(td, cd.degree), bs = td, n = nd * bs;
+  const Geo g = make_geo(td, cdofs);
+  double phi[10], dphi[30], grad[30];
+  for_each_point(cd, g, eli[0],
+                 [&](const double* X, double w, const double*)
+                 {
+                   tabulate(td, cd.degree, X, phi, dphi);
+                   push_gradients(g, nd, dphi, grad);
+                   for (int i = 0; i < nd; ++i)
+                     for (int j = 0; j < nd; ++j)
+                     {
+                       double gg = 0.0;
+                       for (int r = 0; r < td; ++r)
+                         gg += grad[i * td + r] * grad[j * td + r];
+                       for (int a = 0; a < bs; ++a)
+                         for (int b = 0; b < bs; ++b)
+                           A[(i * bs + a) * n + j * bs + b]
+                               += w
+                                  * (c[1] * grad[i * td + a] * grad[j * td + b]
+                                     + c[0] * grad[i * td + b] * grad[j * td + a] + (a == b ? c[0] * gg : 0.0));
+                     }
+                 });
+}
+
+// inner(f, v) dx with a constant vector f = (c0, c1, c2) (demo_elasticity.py:238)
+void k_source_vec(double* b, const double*, const double* c, const double* cdofs, const int* eli, const uint8_t*,
+                  void* p)
+{
+  const CustomData& cd = *static_cast<CustomData*>(p);
+  const int td = cd.tdim, nd = space_dim(td, cd.degree), bs = td;
+  const Geo g = make_geo(td, cdofs);
+  double phi[10], dphi[30];
+  for_each_point(cd, g, eli[0],
+                 [&](const double* X, double w, const double*)
+                 {
+                   tabulate(td, cd.degree, X, phi, dphi);
+                   for (int i = 0; i < nd; ++i)
+                     for (int a = 0; a < bs; ++a)
+                       b[i * bs + a] += c[a] * w * phi[i];
+                 });
+}
+
 kernel_fn kernel_by_id(int id)
 {
   switch (id)
@@ -638,6 +688,8 @@ kernel_fn kernel_by_id(int id)
   case 5: return k_source;
   case 6: return k_nitsche_rhs;
   case 7: return k_one;
+  case 8: return k_elasticity;
+  case 9: return k_source_vec;
   }
   throw std::runtime_error("oracle: unknown kernel id");
 }
@@ -650,6 +702,8 @@ int std_order_for(int id, int degree)
   case 2: return 2 * degree;
   case 5: return degree;
   case 7: return 0;
+  case 8: return 2 * (degree - 1);
+  case 9: return degree;
   }
   return 0;
 }
@@ -669,6 +723,29 @@ void mat_add(const int64_t* row_ptr, const int32_t* cols, double* vals, int nr, 
       if (it == e || *it != cs[j])
         throw std::runtime_error("oracle: entry not in sparsity pattern");
       vals[it - cols] += Ae[i * nc + j];
+    }
+  }
+}
+
+// la::MatrixCSR::mat_add_values<BS, BS> (wrappers/fem.cpp:340-385): scalar-dof pattern, row-major bs x bs
+// blocks; Ae has (nr*bs) x (nc*bs) entries indexed (i*bs + a, j*bs + b)
+void mat_add_blocked(const int64_t* row_ptr, const int32_t* cols, double* vals, int bs, int nr, const int32_t* rows,
+                     int nc, const int32_t* cs, const double* Ae)
+{
+  for (int i = 0; i < nr; ++i)
+  {
+    const int32_t r = rows[i];
+    const int32_t* b = cols + row_ptr[r];
+    const int32_t* e = cols + row_ptr[r + 1];
+    for (int j = 0; j < nc; ++j)
+    {
+      const int32_t* it = std::lower_bound(b, e, cs[j]);
+      if (it == e || *it != cs[j])
+        throw std::runtime_error("oracle: entry not in sparsity pattern");
+      double* blk = vals + (it - cols) * bs * bs;
+      for (int a = 0; a < bs; ++a)
+        for (int k = 0; k < bs; ++k)
+          blk[a * bs + k] += Ae[(i * bs + a) * (nc * bs) + j * bs + k];
     }
   }
 }
@@ -1070,6 +1147,80 @@ int orc_assemble_interior_facets(int kernel_id, int cell_type, int degree, const
     uint8_t perm[2] = {0, 0};
     kernel(Ae.data(), nullptr, constants, cdofs.data(), entity_local_index, perm, &cd);
     mat_add(row_ptr, cols, vals, 2 * nd, dmapjoint.data(), 2 * nd, dmapjoint.data(), Ae.data());
+  }
+  return 0;
+  ORC_CATCH(-1)
+}
+
+// the same loops for blocked (vector) spaces: dofmap holds scalar dofs, bs components each
+int orc_assemble_cells_blocked(int kernel_id, int rank, int cell_type, int degree, int bs, const double* x,
+                               const int32_t* x_dofmap, const int32_t* dofmap, const int32_t* std_cells, int64_t n_std,
+                               const double* points, const double* weights, const int32_t* offsets,
+                               const int32_t* parent_map, int64_t n_rules, const double* normals,
+                               const double* constants, const int64_t* row_ptr, const int32_t* cols, double* out)
+{
+  ORC_TRY
+  const int nv = cell_type, tdim = nv - 1, nd = space_dim(tdim, degree), n = nd * bs;
+  if (bs != tdim)
+    throw std::runtime_error("oracle: vector kernels need block size == gdim");
+  CustomData cd{tdim, degree, n_std, points, weights, offsets, normals, std_order_for(kernel_id, degree)};
+  kernel_fn kernel = kernel_by_id(kernel_id);
+  std::vector<double> Ae(rank == 2 ? (size_t)n * n : (size_t)n);
+  std::vector<double> cdofs(3 * nv);
+  const int64_t ne = n_std + n_rules;
+  for (int64_t c = 0; c < ne; ++c)
+  {
+    const int32_t cell = c < n_std ? std_cells[c] : parent_map[c - n_std];
+    for (int i = 0; i < nv; ++i)
+      std::copy_n(x + 3 * (int64_t)x_dofmap[(int64_t)cell * nv + i], 3, cdofs.begin() + 3 * i);
+    std::fill(Ae.begin(), Ae.end(), 0.0);
+    int entity_local_index = (int)c;
+    kernel(Ae.data(), nullptr, constants, cdofs.data(), &entity_local_index, nullptr, &cd);
+    const int32_t* dofs = dofmap + (int64_t)cell * nd;
+    if (rank == 2)
+      mat_add_blocked(row_ptr, cols, out, bs, nd, dofs, nd, dofs, Ae.data());
+    else
+      for (int i = 0; i < nd; ++i)
+        for (int a = 0; a < bs; ++a)
+          out[(int64_t)dofs[i] * bs + a] += Ae[i * bs + a]; // assemble_vector_impl.h:109-120: b[bs*dof + k]
+  }
+  return 0;
+  ORC_CATCH(-1)
+}
+
+// gamma * h_avg * inner(jump(grad(u), n), jump(grad(v), n)) dS on a vector space (demo_elasticity.py:226-236):
+// the scalar ghost-penalty tensor on every component, no coupling between components
+int orc_assemble_interior_facets_blocked(int kernel_id, int cell_type, int degree, int bs, const double* x,
+                                         const int32_t* x_dofmap, const int32_t* dofmap, const int32_t* rows4,
+                                         int64_t n_facets, const double* constants, const int64_t* row_ptr,
+                                         const int32_t* cols, double* vals)
+{
+  ORC_TRY
+  const int nv = cell_type, tdim = nv - 1, nd = space_dim(tdim, degree);
+  CustomData cd{tdim, degree, n_facets, nullptr, nullptr, nullptr, nullptr, 0};
+  kernel_fn kernel = kernel_by_id(kernel_id);
+  const int m = 2 * nd;
+  std::vector<double> As((size_t)m * m), Ae((size_t)m * bs * m * bs), cdofs((size_t)6 * nv);
+  std::vector<int32_t> dmapjoint(m);
+  for (int64_t f = 0; f < n_facets; ++f)
+  {
+    const int32_t cells[2] = {rows4[4 * f], rows4[4 * f + 2]};
+    const int local_facet[2] = {rows4[4 * f + 1], rows4[4 * f + 3]};
+    for (int s = 0; s < 2; ++s)
+      for (int i = 0; i < nv; ++i)
+        std::copy_n(x + 3 * (int64_t)x_dofmap[(int64_t)cells[s] * nv + i], 3, cdofs.begin() + 3 * (s * nv + i));
+    for (int s = 0; s < 2; ++s)
+      std::copy_n(dofmap + (int64_t)cells[s] * nd, nd, dmapjoint.begin() + s * nd);
+    std::fill(As.begin(), As.end(), 0.0);
+    int entity_local_index[3] = {local_facet[0], local_facet[1], (int)f};
+    uint8_t perm[2] = {0, 0};
+    kernel(As.data(), nullptr, constants, cdofs.data(), entity_local_index, perm, &cd);
+    std::fill(Ae.begin(), Ae.end(), 0.0);
+    for (int i = 0; i < m; ++i)
+      for (int j = 0; j < m; ++j)
+        for (int a = 0; a < bs; ++a)
+          Ae[(size_t)(i * bs + a) * (m * bs) + j * bs + a] = As[(size_t)i * m + j];
+    mat_add_blocked(row_ptr, cols, vals, bs, m, dmapjoint.data(), m, dmapjoint.data(), Ae.data());
   }
   return 0;
   ORC_CATCH(-1)

@@ -215,13 +215,14 @@ def sparsity(space, cells, rows4=None, insert_diagonal=True):
     return rp, cols
 
 
-K = {"laplace": 1, "mass": 2, "nitsche": 3, "ghost_grad_jump": 4, "source": 5, "nitsche_rhs": 6, "one": 7}
-_RANK = {1: 2, 2: 2, 3: 2, 4: 2, 5: 1, 6: 1, 7: 0}
+K = {"laplace": 1, "mass": 2, "nitsche": 3, "ghost_grad_jump": 4, "source": 5, "nitsche_rhs": 6, "one": 7,
+     "elasticity": 8, "source_vec": 9}
+_RANK = {1: 2, 2: 2, 3: 2, 4: 2, 5: 1, 6: 1, 7: 0, 8: 2, 9: 1}
 
 
 def _register_std_rules(space, kernel_id):
     td, p = space.mesh.tdim, space.degree
-    for o in {2 * (p - 1), 2 * p, p, 0}:
+    for o in {2 * (p - 1), 2 * p, p, 0}:  # covers every family incl. elasticity (2(p-1)) and source_vec (p)
         _need_rule(td, o)
     _need_rule(td - 1, 2 * (p - 1))
 
@@ -242,6 +243,13 @@ def assemble_cells(space, kernel: str, out, std_cells=None, rules: Rules | None 
     else:
         pts = wts = off = pm = nrm = None
         nr = 0
+    if space.bs > 1:
+        _chk(lib().orc_assemble_cells_blocked(kid, _RANK[kid], mesh.cell_type, space.degree, int(space.bs),
+                                              _p(x, _f64p), _p(xd, _i32p), _p(dm, _i32p), _p(sc, _i32p),
+                                              C.c_int64(sc.size), _p(pts, _f64p), _p(wts, _f64p), _p(off, _i32p),
+                                              _p(pm, _i32p), C.c_int64(nr), _p(nrm, _f64p), _p(cst, _f64p),
+                                              _p(row_ptr, _i64p), _p(cols, _i32p), _p(out, _f64p)))
+        return out
     _chk(lib().orc_assemble_cells(kid, _RANK[kid], mesh.cell_type, space.degree, _p(x, _f64p), _p(xd, _i32p),
                                   _p(dm, _i32p), _p(sc, _i32p), C.c_int64(sc.size), _p(pts, _f64p), _p(wts, _f64p),
                                   _p(off, _i32p), _p(pm, _i32p), C.c_int64(nr), _p(nrm, _f64p), _p(cst, _f64p),
@@ -256,6 +264,12 @@ def assemble_interior_facets(space, kernel: str, vals, rows4, constants, row_ptr
     x, xd, dm = _cf64(mesh.x), _ci32(mesh.x_dofmap), _ci32(space.dofmap)
     rows4 = _ci32(rows4)
     cst = _cf64(list(constants) + [0.0] * 8)
+    if space.bs > 1:
+        _chk(lib().orc_assemble_interior_facets_blocked(kid, mesh.cell_type, space.degree, int(space.bs),
+                                                        _p(x, _f64p), _p(xd, _i32p), _p(dm, _i32p), _p(rows4, _i32p),
+                                                        C.c_int64(rows4.shape[0]), _p(cst, _f64p), _p(row_ptr, _i64p),
+                                                        _p(cols, _i32p), _p(vals, _f64p)))
+        return vals
     _chk(lib().orc_assemble_interior_facets(kid, mesh.cell_type, space.degree, _p(x, _f64p), _p(xd, _i32p),
                                             _p(dm, _i32p), _p(rows4, _i32p), C.c_int64(rows4.shape[0]),
                                             _p(cst, _f64p), _p(row_ptr, _i64p), _p(cols, _i32p), _p(vals, _f64p)))

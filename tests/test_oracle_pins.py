@@ -349,3 +349,47 @@ def test_cutcell_sizing_matches_survey():
     mesh, V, phi = _circle_problem(64)
     dom = O.classify(V.dofmap, phi)
     assert O.locate(dom, "phi<0").size == 1480 and O.locate(dom, "phi=0").size == 226
+
+
+# ------------------------------------------------------------------------------------------ vector spaces
+@pytest.mark.parametrize("tdim,deg", [(2, 1), (3, 1), (2, 2), (3, 2)])
+def test_elasticity_oracle_pins(tdim, deg):
+    """Blocked (vector) spaces + inner(sigma(u), eps(v)) (demo_elasticity.py:213-224).  Reference pin:
+    test_assembly_elasticity.py:18-70 -- a run-time rule covering whole cells assembles the standard matrix
+    (1e-9 there, 1e-12 relative here).  Analytic pins: symmetric; translations and infinitesimal rotations
+    are in the kernel; the load vector of a constant force sums to force * volume per component."""
+    import scipy.sparse as sp
+
+    mesh = M.create_rectangle(4, 4, (0.0, 0.0), (1.0, 1.0)) if tdim == 2 else M.create_box(3, 2, 2)
+    bs = tdim
+    V = M.functionspace(mesh, deg, bs=bs, permute_seed=3)
+    cells = np.arange(mesh.num_cells, dtype=np.int32)
+    rp, cols = O.sparsity(V, cells)
+    mu, lam = 3.0, 5.0
+    a = O.assemble_cells(V, "elasticity", np.zeros(cols.size * bs * bs), cells, None, (mu, lam), rp, cols)
+    A = sp.bsr_matrix((a.reshape(-1, bs, bs), cols, rp), shape=(V.num_dofs * bs,) * 2).tocsr()
+    assert abs(A - A.T).max() < 1e-12 * abs(A).max()
+    X = V.dof_coords
+    modes = []
+    for c in range(bs):
+        t = np.zeros((V.num_dofs, bs))
+        t[:, c] = 1.0
+        modes.append(t.ravel())
+    for i, j in ([(0, 1)] if bs == 2 else [(0, 1), (0, 2), (1, 2)]):
+        r = np.zeros((V.num_dofs, bs))
+        r[:, i], r[:, j] = -X[:, j], X[:, i]
+        modes.append(r.ravel())
+    for m in modes:
+        assert np.abs(A @ m).max() < 1e-10 * abs(A).max()
+    Xc = mesh.x[mesh.x_dofmap][:, :, :tdim]
+    detJ = np.abs(np.linalg.det((Xc[:, 1:] - Xc[:, :1]).transpose(0, 2, 1)))
+    p, w = R.simplex_rule(tdim, 2 * (deg - 1))
+    p = np.asarray(p).reshape(w.size, tdim)
+    rules = O.Rules(tdim, np.tile(p, (cells.size, 1)), (detJ[:, None] * w[None, :]).reshape(-1),
+                    (np.arange(cells.size + 1) * w.size).astype(np.int32), cells.copy())
+    a2 = O.assemble_cells(V, "elasticity", np.zeros(cols.size * bs * bs), None, rules, (mu, lam), rp, cols)
+    assert np.linalg.norm(a - a2) < 1e-12 * np.linalg.norm(a)
+    force = (1.0, 2.0, 3.0)
+    b = O.assemble_cells(V, "source_vec", np.zeros(V.num_dofs * bs), cells, None, force)
+    vol = np.prod(np.asarray(mesh.p1) - np.asarray(mesh.p0))
+    np.testing.assert_allclose(b.reshape(-1, bs).sum(axis=0), np.asarray(force[:bs]) * vol, rtol=1e-12)
