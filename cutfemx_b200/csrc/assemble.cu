@@ -527,6 +527,11 @@ struct StdTab
   const double* pts[CFX_MAX_STD_LISTS]; // AoS (npts, tdim) reference rule, weights sum to 1/tdim!
   const double* wts[CFX_MAX_STD_LISTS];
   int npts[CFX_MAX_STD_LISTS];
+  // P1 closed forms: the summed coefficient of the form's standard integrals a cell belongs to, indexed by
+  // the cell's list bits (cell_flags >> 2).  t0 = Laplace (rank 2) / source (rank 1), t1 = mass.
+  double t0[1 << CFX_MAX_STD_LISTS];
+  double t1[1 << CFX_MAX_STD_LISTS];
+  int has_mass;
 };
 
 struct GatherCtx
@@ -573,6 +578,53 @@ __device__ __forceinline__ void std_row_values(const StdTab& st, const Geo<TDIM>
                                                double (&v)[Elem<TDIM, DEG>::ND])
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
+  if constexpr (DEG == 1)
+  { // P1: no quadrature loop and no loop over the integrals -- one table lookup gives the summed coefficient.
+    // Laplace: constant gradients grad lam_0 = -(sum of the rows of K), grad lam_j = row j-1 of K, |T| = |detJ|/tdim!
+    const double s = fabs(g.detJ);
+    const unsigned m = fl >> 2;
+    double G[ND][TDIM];
+#pragma unroll
+    for (int r = 0; r < TDIM; ++r)
+    {
+      double s0 = 0.0;
+#pragma unroll
+      for (int t = 0; t < TDIM; ++t)
+      {
+        G[t + 1][r] = g.K[t * TDIM + r];
+        s0 -= g.K[t * TDIM + r];
+      }
+      G[0][r] = s0;
+    }
+    const double w = st.t0[m] * s * (TDIM == 3 ? 1.0 / 6.0 : 0.5);
+    double gi[TDIM];
+#pragma unroll
+    for (int r = 0; r < TDIM; ++r)
+    {
+      double t = G[0][r];
+#pragma unroll
+      for (int j = 1; j < ND; ++j)
+        t = (j == li) ? G[j][r] : t;
+      gi[r] = t * w;
+    }
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+    {
+      double d = 0.0;
+#pragma unroll
+      for (int r = 0; r < TDIM; ++r)
+        d += gi[r] * G[j][r];
+      v[j] += d;
+    }
+    if (st.has_mass)
+    { // int lam_i lam_j = |T| (1 + delta_ij) / ((tdim+1)(tdim+2))
+      const double wm = st.t1[m] * s * (TDIM == 3 ? 1.0 / 120.0 : 1.0 / 24.0);
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+        v[j] += (j == li) ? 2.0 * wm : wm;
+    }
+    return;
+  }
   {
     const double s = fabs(g.detJ);
     for (int k = 0; k < st.n; ++k)
@@ -697,15 +749,13 @@ __device__ __forceinline__ double cell_entry_value(const GatherCtx& gc, const St
   if (fl >> 2)
   {
     const double s = fabs(__ldg(gc.geo + c * GeoRec<TDIM>::STRIDE + TDIM * TDIM));
+    if constexpr (DEG == 1) // P1 source: int phi_i = |detJ| / (tdim+1)!, summed coefficient from the table
+      e += st.t0[fl >> 2] * s * (TDIM == 3 ? 1.0 / 24.0 : 1.0 / 6.0);
+    else
     for (int k = 0; k < st.n; ++k)
     {
       if (!(fl & st.bit[k]))
         continue;
-      if constexpr (DEG == 1)
-      { // P1 source: int phi_i = |detJ| / (tdim+1)!
-        e += st.c[k][0] * s * (TDIM == 3 ? 1.0 / 24.0 : 1.0 / 6.0);
-      }
-      else
       for (int q = 0; q < st.npts[k]; ++q)
       { // CFX_K_SOURCE
         double xi[TDIM];
@@ -1150,23 +1200,30 @@ __global__ void __launch_bounds__(GWC * 32, 4)
                                const int64_t* __restrict__ row_ptr, double* __restrict__ vals, int zero_first)
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
-  __shared__ double s_v[GWC][ND][32];
+  static_assert(ND * 32 <= 255, "contribution-list bytes index the staging array directly");
+  // staged tensor rows: entry (local dof j, lane l) at index j * 32 + l == the byte the contribution list
+  // stores; index 255 (the list's "empty" byte) holds 0.0, so the column lanes add their eight slots
+  // without a test
+  __shared__ double s_v[GWC][256];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
   const uint32_t below = (1u << lane) - 1u;
+  double* const sv = s_v[w];
+  if (lane == 0)
+    sv[255] = 0.0;
   // grid-stride over the rows: at any time the warps of the whole grid work on one contiguous window of
   // rows, so the sweep over the mesh stays ordered and cell records shared by neighbouring rows / planes are
   // re-used from L2 (a contiguous chunk per block measured 8.4 GB of DRAM traffic per launch, this 5.2 GB)
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * GWC;
-  int64_t i = static_cast<int64_t>(blockIdx.x) * GWC + w;
-  const int64_t i_end = n_act;
+  const int stride = static_cast<int>(gridDim.x) * GWC;
+  int i = static_cast<int>(blockIdx.x) * GWC + w;
+  const int i_end = static_cast<int>(n_act);
   if (i >= i_end)
     return;
 
-  auto stageA = [&](int64_t idx) -> ClistA
+  auto stageA = [&](int idx) -> ClistA
   {
     ClistA a;
-    const int64_t k = idx < i_end ? idx : i_end - 1; // clamped: the loads are always legal
+    const int k = idx < i_end ? idx : i_end - 1; // clamped: the loads are always legal
     a.rf = idx < i_end ? row_fast[k] : 0u;
     a.r = act_rows[k];
     a.R = Rrow[k];
@@ -1225,6 +1282,7 @@ __global__ void __launch_bounds__(GWC * 32, 4)
     c1 = stageC(b1);
     d0 = stageD(c0, g0);
   }
+#pragma unroll 2
   for (; i < i_end; i += stride)
   {
     // loads of the rows ahead, issued before this row's arithmetic
@@ -1238,43 +1296,27 @@ __global__ void __launch_bounds__(GWC * 32, 4)
     {
       const unsigned fl = d0.fl;
       const bool contributes = (fl & 0xFDu) != 0;
-      double dval = 0.0;
+      // every lane stages a row (zeros for a lane without a contributing cell): no activity test later
+      double v[ND];
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+        v[j] = 0.0;
+      double e = 0.0;
       if (contributes)
       {
-        double v[ND];
-#pragma unroll
-        for (int j = 0; j < ND; ++j)
-          v[j] = 0.0;
         if (fl >> 2)
+        {
           std_row_values<TDIM, DEG>(st, g0, fl, c0.li, v);
-        if (fl & 1)
-        {
-          const double* a = gc.Ae + (static_cast<int64_t>(d0.ms) * ND + c0.li) * ND;
-#pragma unroll
-          for (int j = 0; j < ND; ++j)
-            v[j] += a[j];
-        }
-        dval = pick<ND>(v, c0.li);
-#pragma unroll
-        for (int j = 0; j < ND; ++j)
-          s_v[w][j][lane] = v[j];
-      }
-      __syncwarp();
-      double e = 0.0;
-      if constexpr (FUSED)
-      { // fused right-hand side: this cell's entry for the row (same order and tree as gather_vector_kernel)
-        if (contributes)
-        {
-          if (fl >> 2)
-          {
+          if constexpr (FUSED)
+          { // fused right-hand side: this cell's entry for the row (same order and tree as gather_vector_kernel)
             const double s = fabs(g0.detJ);
-            for (int k = 0; k < stL.n; ++k)
-            {
-              if (!(fl & stL.bit[k]))
-                continue;
-              if constexpr (DEG == 1)
-                e += stL.c[k][0] * s * (TDIM == 3 ? 1.0 / 24.0 : 1.0 / 6.0);
-              else
+            if constexpr (DEG == 1)
+              e += stL.t0[fl >> 2] * s * (TDIM == 3 ? 1.0 / 24.0 : 1.0 / 6.0);
+            else
+              for (int k = 0; k < stL.n; ++k)
+              {
+                if (!(fl & stL.bit[k]))
+                  continue;
                 for (int q = 0; q < stL.npts[k]; ++q)
                 {
                   double xi[TDIM];
@@ -1285,12 +1327,24 @@ __global__ void __launch_bounds__(GWC * 32, 4)
                   tabulate<TDIM, DEG>(xi, phi, dphi);
                   e += stL.c[k][0] * (__ldg(stL.wts[k] + q) * s) * pick<ND>(phi, c0.li);
                 }
-            }
+              }
           }
-          if (fl & 1)
+        }
+        if (fl & 1)
+        {
+          const double* a = gc.Ae + (static_cast<int64_t>(d0.ms) * ND + c0.li) * ND;
+#pragma unroll
+          for (int j = 0; j < ND; ++j)
+            v[j] += a[j];
+          if constexpr (FUSED)
             e += gc.AeL[static_cast<int64_t>(d0.ms) * ND + c0.li];
         }
       }
+      double dval = pick<ND>(v, c0.li);
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+        sv[j * 32 + lane] = v[j];
+      __syncwarp();
       // two fixed shuffle trees, interleaved: the diagonal entry and (fused) the right-hand-side entry
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1)
@@ -1305,22 +1359,24 @@ __global__ void __launch_bounds__(GWC * 32, 4)
           gc.bvec[c0.r] = gc.zero_first_b ? e : gc.bvec[c0.r] + e;
       }
       dval = __shfl_sync(full, dval, 0);
-      const unsigned cmask = __ballot_sync(full, contributes);
       if ((c0.R >> lane) & 1u)
       {
         double acc = c0.old;
-        if ((c0.word & 0xFFull) == 0xFEull)
+        const uint32_t lo = static_cast<uint32_t>(c0.word), hi = static_cast<uint32_t>(c0.word >> 32);
+        if ((lo & 0xFFu) == 0xFEu)
           acc += dval;
         else
-        {
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-          {
-            const unsigned b = static_cast<unsigned>(c0.word >> (8 * e)) & 0xFFu;
-            const unsigned l = b & 31u;
-            if (b != 0xFFu && ((cmask >> l) & 1u))
-              acc += s_v[w][b >> 5][l];
-          }
+        { // ascending-cell order; empty slots read the 0.0 at index 255 (x + 0.0 == x)
+          const double t0 = sv[lo & 0xFFu], t1 = sv[(lo >> 8) & 0xFFu], t2 = sv[(lo >> 16) & 0xFFu], t3 = sv[lo >> 24];
+          const double t4 = sv[hi & 0xFFu], t5 = sv[(hi >> 8) & 0xFFu], t6 = sv[(hi >> 16) & 0xFFu], t7 = sv[hi >> 24];
+          acc += t0;
+          acc += t1;
+          acc += t2;
+          acc += t3;
+          acc += t4;
+          acc += t5;
+          acc += t6;
+          acc += t7;
         }
         *c0.pv = acc;
       }
@@ -1972,7 +2028,14 @@ StdTab make_std_tab(cfx_ctx* c, cfx_form* f)
     st.pts[k] = rt.d_pts;
     st.wts[k] = rt.d_wts;
     st.npts[k] = rt.npts;
+    if (I.kernel == CFX_K_MASS)
+      st.has_mass = 1;
   }
+  // P1 closed forms: coefficient sums per combination of list bits (ascending integral order)
+  for (unsigned m = 0; m < (1u << CFX_MAX_STD_LISTS); ++m)
+    for (int k = 0; k < st.n; ++k)
+      if ((st.bit[k] >> 2) & m)
+        (st.kernel[k] == CFX_K_MASS ? st.t1[m] : st.t0[m]) += st.c[k][0];
   return st;
 }
 

@@ -120,12 +120,15 @@ __global__ void set_flag_kernel(const int32_t* __restrict__ cells, int64_t n, in
 template <class Active>
 __global__ void mark_facets_kernel(const int32_t* __restrict__ src_cells, int64_t n_src, int nf,
                                    const int32_t* __restrict__ c2f, const int32_t* __restrict__ f2c2, Active active,
-                                   int64_t n_owned_facets, int include_ghosts, uint8_t* __restrict__ facet_flag)
+                                   int64_t n_owned_facets, int include_ghosts, uint8_t* __restrict__ facet_flag,
+                                   int64_t n_cells)
 {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * FB + threadIdx.x;
   if (i >= n_src * nf)
     return;
   const int64_t cell = src_cells[i / nf];
+  if (cell < 0 || cell >= n_cells)
+    return; // caller-supplied list with a bad index: set_flag_kernel has raised the error flag
   const int32_t f = c2f[cell * nf + (i % nf)];
   if (!include_ghosts && f >= n_owned_facets)
     return;
@@ -191,7 +194,7 @@ int64_t band_from_flags(cfx_ctx* c, const int32_t* src_cells, int64_t n_src, Act
   const int nf = c->tdim + 1;
   if (n_src > 0)
     CFX_LAUNCH(c, mark_facets_kernel<Active>, grid_for(n_src * nf, FB), FB, 0, src_cells, n_src, nf, c->c2f,
-               c->f2c2.p, active, c->n_owned_facets, include_ghosts, c->facet_flag.p);
+               c->f2c2.p, active, c->n_owned_facets, include_ghosts, c->facet_flag.p, c->nc_total);
   FlagPred p{c->facet_flag.p};
   out->n = compact_indices(c, c->n_facets, p, out->data);
   if (out->n > 0)
