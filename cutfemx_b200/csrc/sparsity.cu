@@ -349,19 +349,31 @@ __global__ void __launch_bounds__(RW * 32)
           if (oc[lf] < 0)
             continue;
           own_needed = true;
+          int32_t od[ND];
+          bool has_r = false;
 #pragma unroll
           for (int j = 0; j < ND; ++j)
           {
-            const int32_t od = rc.dofmap[static_cast<int64_t>(oc[lf]) * ND + j];
+            od[j] = rc.dofmap[static_cast<int64_t>(oc[lf]) * ND + j];
+            has_r = has_r || (od[j] == r);
+          }
+          // a partner cell that holds this row's dof is itself an incident cell of the row (and needed, it
+          // has the same band facet): its dofs enter through its own lane.  Only facets that do not touch
+          // the row's dof bring new columns.
+          if (has_r)
+            continue;
+#pragma unroll
+          for (int j = 0; j < ND; ++j)
+          {
             bool dup = false;
 #pragma unroll
             for (int jj = 0; jj < ND; ++jj)
-              dup = dup || (od == d[jj]);
+              dup = dup || (od[j] == d[jj]);
             if (!dup)
             {
               const int pos = atomicAdd(&s_nextra[w], 1);
               if (pos < XCAP)
-                s_extra[w][pos] = od;
+                s_extra[w][pos] = od[j];
             }
           }
         }

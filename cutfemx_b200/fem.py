@@ -242,16 +242,106 @@ def insert_pattern_entries(a: CutForm, rows, cols) -> None:
     check(a.ctx.handle, lib().cfx_form_insert_pattern_entries(a.ctx.handle, a._h, pr, pc, C.c_int64(n), msr))
 
 
-def assemble_matrix(a: CutForm, A: MatrixCSR | None = None, *, diag_inactive: float = 0.0) -> MatrixCSR:
-    """fem.py:886-942: create the matrix if none is given, then add the form into it.
+class DirichletBC:
+    """Stand-in for dolfinx.fem.DirichletBC on the flat-array spaces of this mirror: `dofs` are blocked dof
+    indices bs*dof + k (what DirichletBC::dof_indices returns unrolled), `value` a scalar or an array over all
+    blocked dofs (the `g` function's x.array)."""
+
+    def __init__(self, value, dofs, V: FunctionSpace):
+        self.function_space = V
+        self.dofs = np.unique(np.asarray(dofs, dtype=np.int32))
+        n = V.num_dofs * V.bs
+        if self.dofs.size and (self.dofs[0] < 0 or self.dofs[-1] >= n):
+            raise ValueError("Dirichlet dof index out of range")
+        self.g = np.full(n, float(value)) if np.isscalar(value) else np.ascontiguousarray(value, dtype=np.float64)
+        if self.g.size != n:
+            raise ValueError("Dirichlet values must cover all (blocked) dofs of the space")
+
+    def owned_dofs(self) -> np.ndarray:
+        V = self.function_space
+        return self.dofs[self.dofs < V.num_dofs_owned * V.bs]
+
+
+def dirichletbc(value, dofs, V: FunctionSpace) -> DirichletBC:
+    return DirichletBC(value, dofs, V)
+
+
+def _bc_arrays(V: FunctionSpace, bcs):
+    """marker / value arrays over the blocked dofs (assembler.h:657-672: DirichletBC::mark_dofs / set)."""
+    n = V.num_dofs * V.bs
+    markers, values = np.zeros(n, dtype=np.int8), np.zeros(n)
+    for bc in bcs:
+        if bc.function_space is not V:
+            raise ValueError("Dirichlet condition defined on a different function space")
+        markers[bc.dofs] = 1
+        values[bc.dofs] = bc.g[bc.dofs]
+    return markers, values
+
+
+def assemble_matrix(a: CutForm, A: MatrixCSR | None = None, *, bcs=None, diag: float = 1.0,
+                    diag_inactive: float = 0.0) -> MatrixCSR:
+    """fem.py:886-942: create the matrix if none is given, then add the form into it; with `bcs` the
+    Dirichlet rows and columns of every element tensor are dropped (assembler.h:643-683) and `diag` is set on
+    the owned Dirichlet rows afterwards (insert_diagonal, fem.py:935-941 -> assembler.h:745-787).
     `diag_inactive` writes that value on the diagonal of rows outside the active domain
     (deactivate_outside, fem/deactivate.h:402-418)."""
     zero = 0
     if A is None:
         A = create_matrix(a)
         zero = 1
-    check(a.ctx.handle, lib().cfx_assemble_matrix(a.ctx.handle, a._h, A._h, zero, C.c_double(diag_inactive), None, HOST))
+    h = a.ctx.handle
+    if not bcs:
+        check(h, lib().cfx_assemble_matrix(h, a._h, A._h, zero, C.c_double(diag_inactive), None, HOST))
+        return A
+    markers, _ = _bc_arrays(a.function_space, bcs)
+    pm = C.c_void_p(markers.ctypes.data)
+    check(h, lib().cfx_assemble_matrix_bc(h, a._h, A._h, zero, C.c_double(diag_inactive), pm, pm, HOST, None, HOST))
+    for bc in bcs:
+        rows = np.ascontiguousarray(bc.owned_dofs(), dtype=np.int32)
+        check(h, lib().cfx_set_diagonal(h, A._h, C.c_void_p(rows.ctypes.data), C.c_int64(rows.size), C.c_double(diag),
+                                        HOST))
+    A._cache.pop("data", None)
     return A
+
+
+def apply_lifting(b: np.ndarray, a, bcs, x0=None, alpha: float = 1.0, *, A=None) -> None:
+    """cutfemx.fem.apply_lifting (fem.py:604-635 -> assemble_vector_impl.h:383-564):
+    b -= alpha * A_j (g_j - x0_j) for every bilinear form a[j] with conditions bcs[j].  `A`: matrices (or one
+    matrix) carrying the sparsity pattern of each form; created from the form when omitted."""
+    if isinstance(a, CutForm):
+        a, bcs = [a], [bcs]
+        x0 = None if x0 is None else [x0]
+        A = None if A is None else [A]
+    for j, form in enumerate(a):
+        if form is None or not bcs[j]:
+            continue
+        Aj = A[j] if A is not None and A[j] is not None else create_matrix(form)
+        markers, values = _bc_arrays(form.function_space, bcs[j])
+        x0j = None if x0 is None or x0[j] is None else np.ascontiguousarray(x0[j], dtype=np.float64)
+        bb = np.ascontiguousarray(b, dtype=np.float64)
+        h = form.ctx.handle
+        check(h, lib().cfx_apply_lifting(h, form._h, Aj._h, C.c_void_p(bb.ctypes.data), C.c_void_p(values.ctypes.data),
+                                         C.c_void_p(markers.ctypes.data),
+                                         None if x0j is None else C.c_void_p(x0j.ctypes.data), C.c_double(alpha), HOST))
+        if bb is not b:
+            b[:] = bb
+
+
+def set_bc(b: np.ndarray, bcs, x0=None, alpha: float = 1.0) -> None:
+    """dolfinx.fem.set_bc as demo_elasticity.py:84 calls it: b[dofs] = alpha * (g - x0)."""
+    if not bcs:
+        return
+    ctx = _mesh_context(bcs[0].function_space.mesh)
+    bb = np.ascontiguousarray(b, dtype=np.float64)
+    x0a = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
+    for bc in bcs:
+        d = np.ascontiguousarray(bc.dofs, dtype=np.int32)
+        check(ctx.handle, lib().cfx_set_bc(ctx.handle, C.c_void_p(bb.ctypes.data), C.c_int64(bb.size),
+                                           C.c_void_p(d.ctypes.data), C.c_int64(d.size), C.c_void_p(bc.g.ctypes.data),
+                                           None if x0a is None else C.c_void_p(x0a.ctypes.data), C.c_double(alpha),
+                                           HOST))
+    if bb is not b:
+        b[:] = bb
 
 
 def assemble_system(a: CutForm, A: MatrixCSR, L: CutForm, b, *, zero_b: bool = True, diag_inactive: float = 0.0):

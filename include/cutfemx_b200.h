@@ -217,6 +217,30 @@ cfx_status cfx_assemble_vector(cfx_ctx* ctx, const cfx_form* L, double* b, int z
 /* assemble_scalar: assemble_scalar_impl.h:26-275 (fixed-order tree reduction) */
 cfx_status cfx_assemble_scalar(cfx_ctx* ctx, const cfx_form* M, double* out);
 
+/* ------------------------------------------------------------------ Dirichlet conditions
+ * Markers are int8 per blocked dof index bs*dof + k over the owned+ghost dofs (what DOLFINx builds from the
+ * DirichletBC list, assembler.h:657-672); value arrays are doubles with the same indexing.
+ *
+ * cfx_assemble_matrix_bc: assemble_matrix(A, a, bcs), assembler.h:643-683 -- the Dirichlet rows (bc_markers0) and
+ * columns (bc_markers1) of every element tensor are zeroed before mat_set (assemble_matrix_impl.h:146-185,
+ * :537-603).  Either marker array may be NULL.  Like the reference it ADDS the masked contributions unless
+ * zero_first != 0, and it does not touch the diagonal (cfx_set_diagonal does). */
+cfx_status cfx_assemble_matrix_bc(cfx_ctx* ctx, const cfx_form* a, cfx_pattern* A, int zero_first, double diag_inactive,
+                                  const int8_t* bc_markers0, const int8_t* bc_markers1, int memspace_bc,
+                                  double* values_out, int memspace);
+/* set_diagonal, assembler.h:745-787 (called from fem.py:935-941 after assembly when test == trial space):
+ * A[r][r] = diagonal for the listed OWNED Dirichlet rows; rows are blocked indices bs*dof + k. */
+cfx_status cfx_set_diagonal(cfx_ctx* ctx, cfx_pattern* A, const int32_t* rows, int64_t n, double diagonal, int memspace);
+/* apply_lifting, assemble_vector_impl.h:383-564 (lift_bc): b -= alpha * A_unconstrained[:, bc] (bc_values1 - x0),
+ * A generated by the bilinear form a on the pattern A (its values are left as they were).  x0 may be NULL.
+ * b, bc_values1, bc_markers1 and x0 live in `memspace`, n_dofs_total*bs entries each. */
+cfx_status cfx_apply_lifting(cfx_ctx* ctx, const cfx_form* a, cfx_pattern* A, double* b, const double* bc_values1,
+                             const int8_t* bc_markers1, const double* x0, double alpha, int memspace);
+/* DirichletBC::set as fem.set_bc uses it: b[d] = alpha * (bc_values[d] - x0[d]) for the listed blocked dof
+ * indices d; b, bc_values and x0 (may be NULL) have n_total entries. */
+cfx_status cfx_set_bc(cfx_ctx* ctx, double* b, int64_t n_total, const int32_t* dofs, int64_t n, const double* bc_values,
+                      const double* x0, double alpha, int memspace);
+
 /* ------------------------------------------------------------------ active domain / deactivation
  * cutfemx::fem::active_domain, cpp/cutfemx/fem/deactivate.h:387-400: active cells = sorted unique OWNED
  * cells of every integral domain of the bilinear form (collect_active_cells :103-165, both cells of an

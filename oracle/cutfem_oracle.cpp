@@ -750,6 +750,65 @@ void mat_add_blocked(const int64_t* row_ptr, const int32_t* cols, double* vals, 
   }
 }
 
+// ---- Dirichlet conditions.  Matrix assembly zeroes the rows (bc0) and columns (bc1) of every element tensor
+// before mat_set (assemble_matrix_impl.h:146-185, :537-603); lifting re-runs the same loops in LiftingMode and
+// feeds the element tensors to lifting_fn instead of the matrix (assemble_vector_impl.h:383-439).
+struct BcState
+{
+  int mode = 0;              // 0 none, 1 zero rows/cols, 2 lifting
+  const int8_t* bc0 = nullptr;
+  const int8_t* bc1 = nullptr;
+  const double* values1 = nullptr;
+  const double* x0 = nullptr;
+  double alpha = 1.0;
+  double* b = nullptr;
+};
+thread_local BcState g_bc;
+
+// Ae is (nr*bs) x (nc*bs) row-major; returns false when the element is skipped (LiftingMode without BC columns)
+bool apply_bcs(double* Ae, int bs, int nr, const int32_t* rows, int nc, const int32_t* cs)
+{
+  const int ndim0 = nr * bs, ndim1 = nc * bs;
+  if (g_bc.mode == 1)
+  {
+    if (g_bc.bc0)
+      for (int i = 0; i < nr; ++i)
+        for (int k = 0; k < bs; ++k)
+          if (g_bc.bc0[(int64_t)bs * rows[i] + k])
+            std::fill_n(Ae + (size_t)ndim1 * (bs * i + k), ndim1, 0.0);
+    if (g_bc.bc1)
+      for (int j = 0; j < nc; ++j)
+        for (int k = 0; k < bs; ++k)
+          if (g_bc.bc1[(int64_t)bs * cs[j] + k])
+            for (int row = 0; row < ndim0; ++row)
+              Ae[(size_t)row * ndim1 + bs * j + k] = 0.0;
+    return true;
+  }
+  if (g_bc.mode == 2)
+  { // lifting_fn, assemble_vector_impl.h:405-432
+    bool has_bc = false;
+    for (int j = 0; j < nc && !has_bc; ++j)
+      for (int k = 0; k < bs; ++k)
+        has_bc = has_bc || g_bc.bc1[(int64_t)bs * cs[j] + k];
+    if (!has_bc)
+      return false;
+    for (int i = 0; i < nc; ++i)
+      for (int k = 0; k < bs; ++k)
+      {
+        const int64_t ii = (int64_t)cs[i] * bs + k;
+        if (!g_bc.bc1[ii])
+          continue;
+        const double x_bc = g_bc.values1[ii];
+        const double x0 = g_bc.x0 ? g_bc.x0[ii] : 0.0;
+        for (int j = 0; j < nr; ++j)
+          for (int m = 0; m < bs; ++m)
+            g_bc.b[(int64_t)rows[j] * bs + m] -= Ae[(size_t)(j * bs + m) * ndim1 + (i * bs + k)] * g_bc.alpha * (x_bc - x0);
+      }
+    return false; // nothing goes to the matrix
+  }
+  return true;
+}
+
 thread_local std::string g_err;
 } // namespace
 
@@ -765,6 +824,15 @@ thread_local std::string g_err;
 extern "C"
 {
 const char* orc_last_error() { return g_err.c_str(); }
+
+// Dirichlet state for the following orc_assemble_* calls (rank 2 only).  mode 0 clears it; 1 = assemble_matrix
+// with bcs (rows bc0 / columns bc1 of each element tensor zeroed); 2 = apply_lifting into b.
+int orc_set_bcs(int mode, const int8_t* bc0, const int8_t* bc1, const double* values1, const double* x0, double alpha,
+                double* b)
+{
+  g_bc = BcState{mode, bc0, bc1, values1, x0, alpha, b};
+  return 0;
+}
 
 int orc_set_rule(int dim, int order, int npts, const double* pts, const double* wts)
 {
@@ -1111,7 +1179,10 @@ int orc_assemble_cells(int kernel_id, int rank, int cell_type, int degree, const
     kernel(Ae.data(), nullptr, constants, cdofs.data(), &entity_local_index, nullptr, &cd);
     const int32_t* dofs = dofmap + (int64_t)cell * nd;
     if (rank == 2)
-      mat_add(row_ptr, cols, out, nd, dofs, nd, dofs, Ae.data());
+    {
+      if (apply_bcs(Ae.data(), 1, nd, dofs, nd, dofs))
+        mat_add(row_ptr, cols, out, nd, dofs, nd, dofs, Ae.data());
+    }
     else if (rank == 1)
       for (int i = 0; i < nd; ++i)
         out[dofs[i]] += Ae[i];
@@ -1146,7 +1217,8 @@ int orc_assemble_interior_facets(int kernel_id, int cell_type, int degree, const
     int entity_local_index[3] = {local_facet[0], local_facet[1], (int)f};
     uint8_t perm[2] = {0, 0};
     kernel(Ae.data(), nullptr, constants, cdofs.data(), entity_local_index, perm, &cd);
-    mat_add(row_ptr, cols, vals, 2 * nd, dmapjoint.data(), 2 * nd, dmapjoint.data(), Ae.data());
+    if (apply_bcs(Ae.data(), 1, 2 * nd, dmapjoint.data(), 2 * nd, dmapjoint.data()))
+      mat_add(row_ptr, cols, vals, 2 * nd, dmapjoint.data(), 2 * nd, dmapjoint.data(), Ae.data());
   }
   return 0;
   ORC_CATCH(-1)
@@ -1178,7 +1250,10 @@ int orc_assemble_cells_blocked(int kernel_id, int rank, int cell_type, int degre
     kernel(Ae.data(), nullptr, constants, cdofs.data(), &entity_local_index, nullptr, &cd);
     const int32_t* dofs = dofmap + (int64_t)cell * nd;
     if (rank == 2)
-      mat_add_blocked(row_ptr, cols, out, bs, nd, dofs, nd, dofs, Ae.data());
+    {
+      if (apply_bcs(Ae.data(), bs, nd, dofs, nd, dofs))
+        mat_add_blocked(row_ptr, cols, out, bs, nd, dofs, nd, dofs, Ae.data());
+    }
     else
       for (int i = 0; i < nd; ++i)
         for (int a = 0; a < bs; ++a)
@@ -1220,7 +1295,8 @@ int orc_assemble_interior_facets_blocked(int kernel_id, int cell_type, int degre
       for (int j = 0; j < m; ++j)
         for (int a = 0; a < bs; ++a)
           Ae[(size_t)(i * bs + a) * (m * bs) + j * bs + a] = As[(size_t)i * m + j];
-    mat_add_blocked(row_ptr, cols, vals, bs, m, dmapjoint.data(), m, dmapjoint.data(), Ae.data());
+    if (apply_bcs(Ae.data(), bs, m, dmapjoint.data(), m, dmapjoint.data()))
+      mat_add_blocked(row_ptr, cols, vals, bs, m, dmapjoint.data(), m, dmapjoint.data(), Ae.data());
   }
   return 0;
   ORC_CATCH(-1)

@@ -306,3 +306,56 @@ def deactivate_outside(row_ptr, cols, vals, inactive_dofs, diagonal=1.0, b=None,
         if b is not None:
             b[r] = rhs_value
     return vals
+
+
+# ---------------------------------------------------------------- Dirichlet conditions
+class dirichlet:
+    """Context for the orc_assemble_* calls inside it (rank 2 only).
+
+    mode "matrix": assemble_matrix(A, a, bcs) -- rows bc0 / columns bc1 of every element tensor are zeroed
+    before mat_set (assemble_matrix_impl.h:146-185).  mode "lifting": apply_lifting -- the same loops in
+    LiftingMode, b -= alpha * Ae[:, bc] (x_bc - x0) (assemble_vector_impl.h:383-439); nothing reaches the matrix.
+    Markers are int8 per (blocked) dof index bs*dof + k."""
+
+    def __init__(self, mode, bc0=None, bc1=None, values1=None, x0=None, alpha=1.0, b=None):
+        self.mode = {"matrix": 1, "lifting": 2}[mode]
+        self.bc0 = None if bc0 is None else np.ascontiguousarray(bc0, dtype=np.int8)
+        self.bc1 = None if bc1 is None else np.ascontiguousarray(bc1, dtype=np.int8)
+        self.values1 = None if values1 is None else _cf64(values1)
+        self.x0 = None if x0 is None else _cf64(x0)
+        self.alpha = float(alpha)
+        self.b = b
+        if self.mode == 2:
+            assert self.bc1 is not None and self.values1 is not None and b is not None
+            assert b.dtype == np.float64 and b.flags.c_contiguous
+
+    def __enter__(self):
+        q = lambda a, t: None if a is None else _p(a, t)
+        lib().orc_set_bcs(self.mode, q(self.bc0, _i8p), q(self.bc1, _i8p), q(self.values1, _f64p), q(self.x0, _f64p),
+                          C.c_double(self.alpha), q(self.b, _f64p))
+        return self
+
+    def __exit__(self, *exc):
+        lib().orc_set_bcs(0, None, None, None, None, C.c_double(1.0), None)
+        return False
+
+
+def set_diagonal(row_ptr, cols, vals, rows, diagonal=1.0, bs=1):
+    """assembler.h:745-753 with MatrixCSR::mat_set_values: A[r, r] = diagonal for every listed (blocked) row.
+    rows are blocked dof indices bs*dof + k (DirichletBC::dof_indices, unrolled)."""
+    for r in np.asarray(rows, dtype=np.int64):
+        blk, k = divmod(int(r), bs)
+        seg = cols[row_ptr[blk]:row_ptr[blk + 1]]
+        p = int(np.searchsorted(seg, blk))
+        if p >= seg.size or seg[p] != blk:
+            raise RuntimeError("Dirichlet row has no diagonal entry")
+        vals[(row_ptr[blk] + p) * bs * bs + k * bs + k] = diagonal
+    return vals
+
+
+def set_bc(b, dofs, values, x0=None, alpha=1.0):
+    """DirichletBC::set (dolfinx 0.11, fem.set_bc): b[d] = alpha * (g[d] - x0[d]) on the constrained dofs."""
+    d = np.asarray(dofs, dtype=np.int64)
+    g = np.asarray(values, dtype=np.float64)
+    b[d] = alpha * (g[d] - (0.0 if x0 is None else np.asarray(x0)[d]))
+    return b

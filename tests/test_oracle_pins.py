@@ -393,3 +393,54 @@ def test_elasticity_oracle_pins(tdim, deg):
     b = O.assemble_cells(V, "source_vec", np.zeros(V.num_dofs * bs), cells, None, force)
     vol = np.prod(np.asarray(mesh.p1) - np.asarray(mesh.p0))
     np.testing.assert_allclose(b.reshape(-1, bs).sum(axis=0), np.asarray(force[:bs]) * vol, rtol=1e-12)
+
+
+# ---------------------------------------------------------------- Dirichlet conditions
+def test_dirichlet_restatement_is_consistent_with_the_unconstrained_matrix():
+    """assemble_matrix(bcs) zeroes rows/columns of every element tensor (assemble_matrix_impl.h:146-185) and
+    lift_bc subtracts alpha * Ae[:, bc] (x_bc - x0) (assemble_vector_impl.h:405-432).  Both are linear in the
+    element tensors, so against the unconstrained oracle matrix A: masked == A with rows/cols zeroed, and the
+    lifting == alpha * A[:, bc] (g - x0)[bc].  Blocked and scalar spaces."""
+    import scipy.sparse as sp
+
+    from cutfemx_b200 import mesh as M
+    from util import make_problem
+
+    for kind, n, deg, bs in (("circle", 8, 1, 1), ("circle", 6, 2, 2), ("sphere", 4, 1, 3)):
+        mesh, Vphi, phi, _ = make_problem(kind, n, 1)
+        V = M.functionspace(mesh, deg, bs=bs)
+        dom = O.classify(Vphi.dofmap, phi.x.array)
+        inside, cut = O.locate(dom, "phi<0"), O.locate(dom, "phi=0")
+        rv = O.runtime_quadrature(mesh, Vphi.dofmap, phi.x.array, dom, "<", 2)
+        rows4 = O.facet_rows(mesh, O.ghost_penalty_facets(mesh, cut, inside))
+        rp, cols = O.sparsity(V, np.concatenate([inside, rv.parent_map]), rows4)
+        kern, cc = ("laplace", (1.0,)) if bs == 1 else ("elasticity", (1.0, 2.0))
+
+        def assemble(out):
+            O.assemble_cells(V, kern, out, inside, rv, cc, rp, cols)
+            O.assemble_interior_facets(V, "ghost_grad_jump", out, rows4, (0.1,), rp, cols)
+            return out
+
+        nb = V.num_dofs * bs
+        rng = np.random.default_rng(1)
+        markers = (rng.random(nb) < 0.2).astype(np.int8)
+        g, x0, alpha = rng.standard_normal(nb), rng.standard_normal(nb), 0.6
+        full = assemble(np.zeros(cols.size * bs * bs))
+        to_csr = lambda v: (sp.bsr_matrix((v.reshape(-1, bs, bs), cols, rp), shape=(nb, nb)).tocsr() if bs > 1
+                            else sp.csr_matrix((v, cols, rp), shape=(nb, nb)))
+        Af = to_csr(full)
+        with O.dirichlet("matrix", markers, markers):
+            masked = assemble(np.zeros_like(full))
+        keep = sp.diags((1 - markers).astype(float))
+        assert abs(to_csr(masked) - keep @ Af @ keep).max() <= 1e-13 * abs(Af).max()
+        b = np.zeros(nb)
+        with O.dirichlet("lifting", None, markers, g, x0, alpha, b):
+            assemble(np.zeros_like(full))
+        expect = -alpha * (Af @ (markers * (g - x0)))
+        assert np.linalg.norm(b - expect) <= 1e-12 * np.linalg.norm(expect)
+        # set_diagonal / set_bc
+        d = np.nonzero(markers)[0]
+        O.set_diagonal(rp, cols, masked, d, 2.5, bs)
+        assert np.all(to_csr(masked).diagonal()[d] == 2.5)
+        O.set_bc(b, d, g, x0, alpha)
+        np.testing.assert_allclose(b[d], alpha * (g - x0)[d])
