@@ -55,6 +55,28 @@ struct Consts
   double c[CFX_MAX_CONSTANTS];
 };
 
+// entry i of a small register array without dynamic indexing
+template <int N>
+__device__ __forceinline__ double pick(const double (&a)[N], int i)
+{
+  double v = a[0];
+#pragma unroll
+  for (int j = 1; j < N; ++j)
+    v = (j == i) ? a[j] : v;
+  return v;
+}
+
+template <int N>
+__device__ __forceinline__ int32_t pick_i(const int32_t (&a)[N], int i)
+{
+  int32_t v = a[0];
+#pragma unroll
+  for (int j = 1; j < N; ++j)
+    v = (j == i) ? a[j] : v;
+  return v;
+}
+
+
 template <int KID>
 struct KernelTraits;
 template <>
@@ -452,21 +474,30 @@ __global__ void __launch_bounds__(EB)
     o[j] = accumulate ? o[j] + acc[j] : acc[j];
 }
 
-// P1 ghost penalty, one thread per facet, FACTORED output: the normal-gradient jump is constant on the
-// facet, so the macro tensor is the rank-one matrix w * jn (x) jn with jn the 2 nd jump coefficients and
-// w = c0 * avg(h) * |F|.  Only jn (2 nd doubles) and w are stored; the row owners rebuild the entries
-// they need (512 B -> 72 B per P1 tetrahedron facet).  Everything follows from the two cached geometry
-// records: grad lam_j = rows of K, n = -grad lam_lf0 / |.|, |F| (tdim-1)! = |detJ| |grad lam_lf0|.
+// P1 ghost penalty, one thread per facet, FACTORED and COMBINED output.  The normal-gradient jump is constant
+// on the facet, so the macro tensor is the rank-one matrix w * jn (x) jn with jn the 2 nd jump coefficients and
+// w = c0 * avg(h) * |F|.  The two cells share nd - 1 dofs: adding the two coefficients of a shared dof gives one
+// coefficient J per DISTINCT dof (nd + 1 of them), and the assembled contribution of the facet to entry (r, s)
+// is w * J_r * J_s.  The record a row owner reads is therefore 80 B -- the distinct dofs, J and w -- instead of
+// two dofmap rows, 2 nd coefficients and the weight, and a row meets every facet once instead of once per cell:
+//   int32 d[5]  : shared dofs in the order of cell 0, then the dof opposite the facet in cell 0, then in cell 1
+//                 (P1: local facet lf is opposite local vertex lf); triangles use d[0..3], d[4] = -3
+//   int32 c0    : first cell of the facet row (the lane of c0 owns the facet for rows both cells touch)
+//   double J[5] : combined jump coefficients in the order of d;  double w
+// Everything follows from the two cached geometry records: grad lam_j = rows of K, n = -grad lam_lf0 / |.|,
+// |F| (tdim-1)! = |detJ| |grad lam_lf0|.
+constexpr int FREC = 10; // record stride in doubles (80 B)
+
 template <int TDIM>
 __global__ void __launch_bounds__(EB)
     facet_p1_kernel(const int32_t* __restrict__ rows4, int64_t n_facets, Consts cs, const double* __restrict__ geo,
-                    double* __restrict__ Fj, double* __restrict__ Fw, bool accumulate)
+                    const int32_t* __restrict__ dofmap, double* __restrict__ Frec, bool accumulate)
 {
   constexpr int ND = TDIM + 1;
   const int64_t f = static_cast<int64_t>(blockIdx.x) * EB + threadIdx.x;
   if (f >= n_facets)
     return;
-  const int32_t c0 = rows4[4 * f], lf0 = rows4[4 * f + 1], c1 = rows4[4 * f + 2];
+  const int32_t c0 = rows4[4 * f], lf0 = rows4[4 * f + 1], c1 = rows4[4 * f + 2], lf1 = rows4[4 * f + 3];
   Geo<TDIM> g[2];
   load_geo_cached<TDIM>(geo, c0, g[0]);
   load_geo_cached<TDIM>(geo, c1, g[1]);
@@ -500,7 +531,7 @@ __global__ void __launch_bounds__(EB)
   }
   nn = sqrt(nn);
   const double measure = fabs(g[0].detJ) * nn;
-  double* o = Fj + f * 2 * ND;
+  double jn[2][ND];
 #pragma unroll
   for (int s = 0; s < 2; ++s)
 #pragma unroll
@@ -510,10 +541,51 @@ __global__ void __launch_bounds__(EB)
 #pragma unroll
       for (int r = 0; r < TDIM; ++r)
         v += G[s][i][r] * (nrm[r] / nn);
-      o[s * ND + i] = s ? -v : v;
+      jn[s][i] = s ? -v : v;
     }
+  int32_t d0[ND], d1[ND];
+#pragma unroll
+  for (int j = 0; j < ND; ++j)
+  {
+    d0[j] = dofmap[static_cast<int64_t>(c0) * ND + j];
+    d1[j] = dofmap[static_cast<int64_t>(c1) * ND + j];
+  }
+  int32_t d[5] = {-3, -3, -3, -3, -3};
+  double J[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  int k = 0;
+#pragma unroll
+  for (int j = 0; j < ND; ++j)
+  {
+    if (j == lf0)
+      continue;
+    double other = 0.0;
+#pragma unroll
+    for (int i = 0; i < ND; ++i)
+      other = (d1[i] == d0[j]) ? jn[1][i] : other;
+    // k runs 0 .. nd-2 over the shared dofs (compile-time unrolled: the index stays in registers)
+#pragma unroll
+    for (int q = 0; q < ND - 1; ++q)
+      if (q == k)
+      {
+        d[q] = d0[j];
+        J[q] = jn[0][j] + other;
+      }
+    ++k;
+  }
+  d[ND - 1] = pick_i<ND>(d0, lf0);
+  J[ND - 1] = pick<ND>(jn[0], lf0);
+  d[ND] = pick_i<ND>(d1, lf1);
+  J[ND] = pick<ND>(jn[1], lf1);
   const double w = (TDIM == 3 ? 0.5 : 1.0) * measure * cs.c[0] * havg;
-  Fw[f] = accumulate ? Fw[f] + w : w;
+  double* o = Frec + f * FREC;
+  int32_t* oi = reinterpret_cast<int32_t*>(o);
+  const double w_old = accumulate ? o[9] : 0.0;
+  *reinterpret_cast<int4*>(oi) = make_int4(d[0], d[1], d[2], d[3]);
+  *reinterpret_cast<int4*>(oi + 4) = make_int4(d[4], c0, 0, 0);
+#pragma unroll
+  for (int q = 0; q < 5; ++q)
+    o[4 + q] = J[q];
+  o[9] = w_old + w;
 }
 
 // ------------------------------------------------------------------ K5 gather ("owner gathers")
@@ -550,8 +622,8 @@ struct GatherCtx
   const int32_t* c2f;
   const int32_t* facet_slot;
   const int32_t* rows4;
-  const double* Fe; // full macro tensors (n_facets, 2nd, 2nd), or the P1 jump coefficients (n_facets, 2nd)
-  const double* Fw; // P1 only: the facet weights; null = Fe holds full tensors
+  const double* Fe; // full macro tensors (n_facets, 2nd, 2nd), or the P1 records of facet_p1_kernel (n_facets, FREC)
+  const double* Fw; // non-null: Fe holds P1 records; null: full tensors
   // fused system assembly (cfx_assemble_system): the linear form's materialised entries (same slots) and
   // the vector the contribution-list kernel also fills; null otherwise
   const double* AeL;
@@ -560,16 +632,6 @@ struct GatherCtx
   int nf;
   int stride;
 };
-
-template <int N>
-__device__ __forceinline__ double pick(const double (&a)[N], int i)
-{
-  double v = a[0];
-#pragma unroll
-  for (int j = 1; j < N; ++j)
-    v = (j == i) ? a[j] : v;
-  return v;
-}
 
 // Row `li` of the element tensor of standard cell `c` (sum over the form's standard integrals the
 // cell belongs to) plus row `li` of its materialised run-time tensor, natural dof order.
@@ -802,12 +864,117 @@ struct FacetStage
   static constexpr int W = (2 * ND + 3) / 4 * 4;
 };
 
+// P1 (factored, combined records of facet_p1_kernel): the row's contribution from facet F is w J_r J_s over the
+// nd + 1 distinct dofs s.  Lane l probes the facets of its band cell; a facet whose two cells both hold the row's
+// dof is taken by the lane of its first cell only.  `r` is the row's dof.
+template <int ND>
+__device__ __forceinline__ int add_facet_rows_p1(const GatherCtx& gc, int32_t (*s_fd)[FacetStage<ND>::W],
+                                                 double (*s_fv)[FacetStage<ND>::W], bool band_cell, int64_t c,
+                                                 int32_t r, int32_t mycol, double& acc, int& expected, bool count)
+{
+  static_assert(FacetStage<ND>::W >= 6 || ND == 3, "staging rows hold the nd + 1 combined entries");
+  constexpr int NE = ND + 1;                    // distinct dofs of the macro element
+  constexpr int NQ = (NE + 1) / 2;              // 128-bit value reads per staged row (entries padded to even)
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  int matched = 0;
+  if (__ballot_sync(full, band_cell) == 0)
+    return 0;
+  int32_t fct[4] = {0, 0, 0, 0};
+  if (band_cell)
+  {
+    if (gc.nf == 4)
+    {
+      const int4 q = __ldg(reinterpret_cast<const int4*>(gc.c2f) + c);
+      fct[0] = q.x;
+      fct[1] = q.y;
+      fct[2] = q.z;
+      fct[3] = q.w;
+    }
+    else
+      for (int lf = 0; lf < gc.nf; ++lf)
+        fct[lf] = gc.c2f[c * gc.nf + lf];
+  }
+  // all slot probes first: independent gathers in flight together
+  int32_t fsl[4] = {-1, -1, -1, -1};
+  if (band_cell)
+    for (int lf = 0; lf < gc.nf; ++lf)
+      fsl[lf] = gc.facet_slot[fct[lf]];
+  for (int lf = 0; lf < gc.nf; ++lf)
+  {
+    const int64_t fs = fsl[lf];
+    bool valid = fs >= 0;
+    if (valid)
+    {
+      const double* rec = gc.Fe + fs * FREC;
+      const int4 q0 = __ldg(reinterpret_cast<const int4*>(rec));
+      const int4 q1 = __ldg(reinterpret_cast<const int4*>(rec) + 1);
+      const int32_t dd[5] = {q0.x, q0.y, q0.z, q0.w, q1.x};
+      // the facet belongs to this lane if its cell is the facet's first cell, or if the first cell does not
+      // hold the row's dof at all (then the row's dof is the one opposite the facet in the second cell)
+      valid = (c == q1.y) || (dd[ND] == r);
+      if (valid)
+      {
+        const double2 j01 = __ldg(reinterpret_cast<const double2*>(rec) + 2);
+        const double2 j23 = __ldg(reinterpret_cast<const double2*>(rec) + 3);
+        const double2 j4w = __ldg(reinterpret_cast<const double2*>(rec) + 4);
+        const double J[5] = {j01.x, j01.y, j23.x, j23.y, j4w.x};
+        double jr = 0.0;
+#pragma unroll
+        for (int k = 0; k < NE; ++k)
+          jr = (dd[k] == r) ? J[k] : jr;
+        const double jm = jr * j4w.y;
+#pragma unroll
+        for (int k = 0; k < 2 * NQ; ++k)
+        {
+          s_fd[lane][k] = (k < NE) ? dd[k < 5 ? k : 4] : -3; // padding matches no column
+          s_fv[lane][k] = (k < NE) ? jm * J[k < 5 ? k : 4] : 0.0;
+        }
+        if (count)
+          expected += NE;
+      }
+    }
+    __syncwarp();
+    unsigned m = __ballot_sync(full, valid);
+    while (m)
+    {
+      const int l = __ffs(m) - 1;
+      m &= m - 1;
+      const int2* pd = reinterpret_cast<const int2*>(s_fd[l]);
+      const double2* pv = reinterpret_cast<const double2*>(s_fv[l]);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+      {
+        const int2 d = pd[q];
+        const double2 v = pv[q];
+        if (d.x == mycol)
+        {
+          acc += v.x;
+          ++matched;
+        }
+        if (d.y == mycol)
+        {
+          acc += v.y;
+          ++matched;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  return matched;
+}
+
 template <int ND>
 __device__ __forceinline__ int add_facet_rows(const GatherCtx& gc, int32_t (*s_fd)[FacetStage<ND>::W],
                                               double (*s_fv)[FacetStage<ND>::W], bool band_cell, int64_t c, int li,
-                                              int32_t mycol, double& acc, int& expected, bool count)
+                                              int32_t r, int32_t mycol, double& acc, int& expected, bool count)
 {
   constexpr int W = FacetStage<ND>::W;
+  if constexpr (ND <= 4)
+  {
+    if (gc.Fw) // P1: combined records
+      return add_facet_rows_p1<ND>(gc, s_fd, s_fv, band_cell, c, r, mycol, acc, expected, count);
+  }
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   int matched = 0;
@@ -841,19 +1008,11 @@ __device__ __forceinline__ int add_facet_rows(const GatherCtx& gc, int32_t (*s_f
       const int4 row = __ldg(reinterpret_cast<const int4*>(gc.rows4) + fs); // (cell0, lf0, cell1, lf1)
       const int64_t c0 = row.x, c1 = row.z;
       const int mrow = (c == c0 ? 0 : ND) + li;
-      if constexpr (ND == 4)
-      {
-        *reinterpret_cast<int4*>(&s_fd[lane][0]) = __ldg(reinterpret_cast<const int4*>(gc.dofmap) + c0);
-        *reinterpret_cast<int4*>(&s_fd[lane][4]) = __ldg(reinterpret_cast<const int4*>(gc.dofmap) + c1);
-      }
-      else
-      {
 #pragma unroll
-        for (int j = 0; j < ND; ++j)
-        {
-          s_fd[lane][j] = gc.dofmap[c0 * ND + j];
-          s_fd[lane][ND + j] = gc.dofmap[c1 * ND + j];
-        }
+      for (int j = 0; j < ND; ++j)
+      {
+        s_fd[lane][j] = gc.dofmap[c0 * ND + j];
+        s_fd[lane][ND + j] = gc.dofmap[c1 * ND + j];
       }
 #pragma unroll
       for (int j = 2 * ND; j < W; ++j)
@@ -861,33 +1020,10 @@ __device__ __forceinline__ int add_facet_rows(const GatherCtx& gc, int32_t (*s_f
         s_fd[lane][j] = -3; // padding: matches no column
         s_fv[lane][j] = 0.0;
       }
-      if (gc.Fw)
-      { // factored P1 tensor: row mrow of w * jn (x) jn
-        const double* jn = gc.Fe + fs * 2 * ND;
-        double jv[2 * ND];
-        if constexpr (ND == 4)
-        { // 64-byte record: two 256-bit loads
-          ld256(jn, jv[0], jv[1], jv[2], jv[3]);
-          ld256(jn + 4, jv[4], jv[5], jv[6], jv[7]);
-        }
-        else
-        {
+      const double* F = gc.Fe + (fs * 2 * ND + mrow) * 2 * ND;
 #pragma unroll
-          for (int j = 0; j < 2 * ND; ++j)
-            jv[j] = jn[j];
-        }
-        const double jm = pick<2 * ND>(jv, mrow) * gc.Fw[fs];
-#pragma unroll
-        for (int j = 0; j < 2 * ND; ++j)
-          s_fv[lane][j] = jm * jv[j];
-      }
-      else
-      {
-        const double* F = gc.Fe + (fs * 2 * ND + mrow) * 2 * ND;
-#pragma unroll
-        for (int j = 0; j < 2 * ND; ++j)
-          s_fv[lane][j] = F[j];
-      }
+      for (int j = 0; j < 2 * ND; ++j)
+        s_fv[lane][j] = F[j];
       if (count)
         expected += 2 * ND;
     }
@@ -1025,7 +1161,7 @@ __global__ void __launch_bounds__(GW * 32)
       }
       if (kc == 0)
         expected += contributes ? ND : 0;
-      matched += add_facet_rows<ND>(gc, s_fd[w], s_fv[w], (fl & 2u) != 0, c, li, mycol, acc, expected, kc == 0);
+      matched += add_facet_rows<ND>(gc, s_fd[w], s_fv[w], (fl & 2u) != 0, c, li, static_cast<int32_t>(r), mycol, acc, expected, kc == 0);
       __syncwarp();
     }
     if (have_col)
@@ -1139,7 +1275,7 @@ __global__ void __launch_bounds__(GWM * 32, 8)
   {
     const int32_t mycol = have_col ? cols[rb + lane] : -2;
     int expected = 0;
-    add_facet_rows<ND>(gc, s_fd[w], s_fv[w], (fl & 2u) != 0, c, li, mycol, acc, expected, false);
+    add_facet_rows<ND>(gc, s_fd[w], s_fv[w], (fl & 2u) != 0, c, li, static_cast<int32_t>(r), mycol, acc, expected, false);
   }
   if (have_col)
     vals[rb + lane] = acc;
@@ -1783,7 +1919,7 @@ __global__ void __launch_bounds__(32)
       if (kc == 0)
         expected += contributes ? ND : 0;
       double facc = 0.0;
-      matched += add_facet_rows<ND>(gc, s_fd, s_fv, (fl & 2u) != 0, c, li, mycol, facc, expected, kc == 0);
+      matched += add_facet_rows<ND>(gc, s_fd, s_fv, (fl & 2u) != 0, c, li, static_cast<int32_t>(r), mycol, facc, expected, kc == 0);
 #pragma unroll
       for (int a = 0; a < BS; ++a)
         acc[a * BS + a] += facc;
@@ -2047,10 +2183,10 @@ void launch_facet(cfx_ctx* c, const cfx_integral& I, cfx_form* f, bool accumulat
   for (int k = 0; k < CFX_MAX_CONSTANTS; ++k)
     cs.c[k] = I.constants[k];
   if constexpr (DEG == 1)
-  { // factored storage: jump coefficients (n, 2nd) followed by the weights (n)
-    double* Fj = f->Fe.p;
-    double* Fw = f->Fe.p + I.n * 2 * ND;
-    CFX_LAUNCH(c, facet_p1_kernel<TDIM>, grid_for(I.n, EB), EB, 0, I.entities, I.n, cs, c->geo.p, Fj, Fw, accumulate);
+  { // factored, combined storage: one 80-byte record per facet (distinct dofs, combined jump coefficients, weight)
+    static_assert(FREC <= 4 * ND * ND, "the facet buffer is sized for full macro tensors");
+    CFX_LAUNCH(c, facet_p1_kernel<TDIM>, grid_for(I.n, EB), EB, 0, I.entities, I.n, cs, c->geo.p,
+               c->spaces[f->space].dofmap, f->Fe.p, accumulate);
   }
   else
   {
@@ -2081,7 +2217,7 @@ GatherCtx make_gather_ctx(cfx_ctx* c, cfx_form* f, const cfx_integral* FI)
   g.facet_slot = c->facet_slot.p;
   g.rows4 = FI ? FI->entities : nullptr;
   g.Fe = f->Fe.p;
-  g.Fw = (FI && S.degree == 1) ? f->Fe.p + FI->n * 2 * S.nd : nullptr;
+  g.Fw = (FI && S.degree == 1) ? f->Fe.p : nullptr; // non-null marks the P1 record format of facet_p1_kernel
   g.nf = c->tdim + 1;
   g.stride = S.stride;
   return g;
@@ -2132,7 +2268,10 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
     {
       // band rows (facet macro rows) and rows with long contribution lists: cell rows through the position
       // masks of the pattern pass, macro-tensor rows matched by column value
-      StageScope sk(ctx, "gather_matrix_mask_kernel", static_cast<double>(a->n_mask_rows));
+      // K5 for the rows the contribution-list kernel does not own: 12 B per CSR entry of the active rows left
+      const double nnz_mask = static_cast<double>(A->nnz) - static_cast<double>(a->n_clist_nnz)
+                              - static_cast<double>(A->n_rows - PR->n_act_rows);
+      StageScope sk(ctx, "gather_matrix_mask_kernel", 12.0 * (nnz_mask > 0.0 ? nnz_mask : 0.0));
       auto kf = gather_matrix_fast_kernel<TDIM, DEG>;
       if (a->n_band_listed > 0)
         CFX_LAUNCH(ctx, kf, grid_for(a->n_band_listed, GWM), GWM * 32, 0, gc, st, PR->act_rows.p, PR->band_idx.p,

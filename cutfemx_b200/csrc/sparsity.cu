@@ -330,9 +330,21 @@ __global__ void __launch_bounds__(RW * 32)
 #pragma unroll
         for (int j = 0; j < ND; ++j)
           d[j] = rc.dofmap[c * ND + j];
+        // a band cell has a band facet by construction, so its own dofs are needed whatever the probes find
+        own_needed = true;
+        // P1: local facet lf is opposite local vertex lf, so the only facet that does not touch the row's dof is
+        // the one with the dof's own local index -- one probe instead of NF (the others could only bring
+        // dofs of cells that are themselves incident to the row, see below)
+        int li = -1;
+        if constexpr (ND == NF)
+        {
+#pragma unroll
+          for (int j = 0; j < ND; ++j)
+            li = (d[j] == r) ? j : li;
+        }
 #pragma unroll
         for (int lf = 0; lf < NF; ++lf)
-          slot[lf] = rc.facet_slot[fct[lf]];
+          slot[lf] = (ND != NF || lf == li) ? rc.facet_slot[fct[lf]] : -1;
 #pragma unroll
         for (int lf = 0; lf < NF; ++lf)
         {
