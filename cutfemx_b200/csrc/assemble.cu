@@ -1481,20 +1481,30 @@ __global__ void __launch_bounds__(GWC * 32, 4)
       for (int j = 0; j < ND; ++j)
         sv[j * 32 + lane] = v[j];
       __syncwarp();
-      // two fixed shuffle trees, interleaved: the diagonal entry and (fused) the right-hand-side entry
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-      {
-        dval += __shfl_down_sync(full, dval, o);
-        if constexpr (FUSED)
-          e += __shfl_down_sync(full, e, o);
-      }
+      // two fixed shuffle trees: the diagonal entry and (fused) the right-hand-side entry.  Shuffles share the
+      // L1 data pipe with the gathers, so the fused case folds both trees into one: after ONE exchange at
+      // distance 16 the lower half-warp carries the diagonal tree and the upper half the right-hand-side tree;
+      // the four remaining levels serve both.  Each tree keeps the operands and the shape of the plain
+      // shfl_down tree (result in lane 0 / lane 16), so b stays bit-identical to gather_vector_kernel's.
       if constexpr (FUSED)
       {
-        if (lane == 0)
-          gc.bvec[c0.r] = gc.zero_first_b ? e : gc.bvec[c0.r] + e;
+        const bool lower = lane < 16;
+        const double recv = __shfl_xor_sync(full, lower ? e : dval, 16);
+        double x = lower ? dval + recv : e + recv;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1)
+          x += __shfl_down_sync(full, x, o);
+        if (lane == 16)
+          gc.bvec[c0.r] = gc.zero_first_b ? x : gc.bvec[c0.r] + x;
+        dval = __shfl_sync(full, x, 0);
       }
-      dval = __shfl_sync(full, dval, 0);
+      else
+      {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+          dval += __shfl_down_sync(full, dval, o);
+        dval = __shfl_sync(full, dval, 0);
+      }
       if ((c0.R >> lane) & 1u)
       {
         double acc = c0.old;

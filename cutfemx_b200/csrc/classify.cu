@@ -33,44 +33,70 @@ __device__ __forceinline__ void load_row(const int32_t* __restrict__ dofmap, int
   }
 }
 
-// One thread per cell; a warp reads 32 consecutive dofmap rows (coalesced) and writes 32
-// consecutive code bytes. Ghost cells (c >= nc_owned) are classified too (their codes feed the
-// ghost-penalty band across partition boundaries) but are not counted.
+// CPT cells per thread, strided by the warp: in round i a warp reads 32 consecutive dofmap rows (coalesced)
+// and writes 32 consecutive code bytes, and the gathers of all CPT rounds are in flight together (the kernel
+// is a dependent pair of loads per cell, so bytes in flight per thread set its bandwidth).  Ghost cells
+// (c >= nc_owned) are classified too (their codes feed the ghost-penalty band across partition boundaries)
+// but are not counted.
+constexpr int CPT = 4;
+
 template <int ND>
 __global__ void __launch_bounds__(CB)
     classify_kernel(const int32_t* __restrict__ dofmap, const double* __restrict__ vals, int64_t nc_total,
                     int64_t nc_owned, int8_t* __restrict__ domain, unsigned long long* __restrict__ counts)
 {
-  const int64_t c = static_cast<int64_t>(blockIdx.x) * CB + threadIdx.x;
-  int code = 0;
-  if (c < nc_total)
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * CB + threadIdx.x) >> 5;
+  const int64_t c0 = warp * (32 * CPT) + lane;
+  int32_t d[CPT][ND];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i)
   {
-    int32_t d[ND];
-    load_row<ND>(dofmap, c, d);
+    const int64_t c = c0 + 32 * i;
+    if (c < nc_total)
+      load_row<ND>(dofmap, c, d[i]);
+    else
+    {
+#pragma unroll
+      for (int k = 0; k < ND; ++k)
+        d[i][k] = 0;
+    }
+  }
+  double v[CPT][ND];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i)
+#pragma unroll
+    for (int k = 0; k < ND; ++k)
+      v[i][k] = __ldg(vals + d[i][k]);
+  int n_in = 0, n_cut = 0, n_out = 0;
+#pragma unroll
+  for (int i = 0; i < CPT; ++i)
+  {
+    const int64_t c = c0 + 32 * i;
     bool all_neg = true, all_pos = true;
 #pragma unroll
     for (int k = 0; k < ND; ++k)
     {
-      const double v = __ldg(vals + d[k]);
-      all_neg = all_neg && (v < 0.0);
-      all_pos = all_pos && (v > 0.0);
+      all_neg = all_neg && (v[i][k] < 0.0);
+      all_pos = all_pos && (v[i][k] > 0.0);
     }
-    code = all_neg ? CFX_DOMAIN_INSIDE : (all_pos ? CFX_DOMAIN_OUTSIDE : CFX_DOMAIN_INTERSECTED);
-    domain[c] = static_cast<int8_t>(code);
+    const int code = all_neg ? CFX_DOMAIN_INSIDE : (all_pos ? CFX_DOMAIN_OUTSIDE : CFX_DOMAIN_INTERSECTED);
+    if (c < nc_total)
+      domain[c] = static_cast<int8_t>(code);
+    const bool owned = c < nc_owned;
+    n_in += __popc(__ballot_sync(0xffffffffu, owned && code == CFX_DOMAIN_INSIDE));
+    n_cut += __popc(__ballot_sync(0xffffffffu, owned && code == CFX_DOMAIN_INTERSECTED));
+    n_out += __popc(__ballot_sync(0xffffffffu, owned && code == CFX_DOMAIN_OUTSIDE));
   }
-  const bool owned = c < nc_owned;
-  const unsigned b_in = __ballot_sync(0xffffffffu, owned && code == CFX_DOMAIN_INSIDE);
-  const unsigned b_cut = __ballot_sync(0xffffffffu, owned && code == CFX_DOMAIN_INTERSECTED);
-  const unsigned b_out = __ballot_sync(0xffffffffu, owned && code == CFX_DOMAIN_OUTSIDE);
   __shared__ int s_cnt[3];
   if (threadIdx.x < 3)
     s_cnt[threadIdx.x] = 0;
   __syncthreads();
-  if ((threadIdx.x & 31) == 0)
+  if (lane == 0)
   {
-    atomicAdd(&s_cnt[0], __popc(b_in));
-    atomicAdd(&s_cnt[1], __popc(b_cut));
-    atomicAdd(&s_cnt[2], __popc(b_out));
+    atomicAdd(&s_cnt[0], n_in);
+    atomicAdd(&s_cnt[1], n_cut);
+    atomicAdd(&s_cnt[2], n_out);
   }
   __syncthreads();
   if (threadIdx.x < 3 && s_cnt[threadIdx.x] != 0)
@@ -80,7 +106,7 @@ __global__ void __launch_bounds__(CB)
 template <int ND>
 void launch_classify(cfx_ctx* c, const LevelSet& L, int8_t* domain, unsigned long long* counts)
 {
-  CFX_LAUNCH(c, classify_kernel<ND>, grid_for(c->nc_total, CB), CB, 0, L.dofmap, L.values, c->nc_total, c->nc_owned,
+  CFX_LAUNCH(c, classify_kernel<ND>, grid_for(c->nc_total, CB * CPT), CB, 0, L.dofmap, L.values, c->nc_total, c->nc_owned,
              domain, counts);
 }
 } // namespace

@@ -536,58 +536,92 @@ __global__ void __launch_bounds__(256)
                           int32_t* __restrict__ row_nnz, uint32_t* __restrict__ Rrow, uint8_t* __restrict__ row_fast,
                           unsigned long long* __restrict__ n_clist /* [0] rows, [1] nnz of contribution-list rows */)
 {
-  // 8 lanes per row (4 rows per warp): three independent gather chains per lane for 24 incident cells
+  // 8 lanes per row and CROWS rows per lane group, the dependent load levels (slot -> row -> incidence ->
+  // cell flags) of all of them batched: up to 3 * CROWS independent gather chains in flight per lane
+  constexpr int CROWS = 4;
   const int64_t t = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-  const int64_t idx = t >> 3;
+  const int64_t idx0 = (t >> 3) * CROWS;
   const int sl = static_cast<int>(t & 7);
-  const bool valid = idx < n_act;
-  const int64_t r = valid ? act_rows[idx] : 0;
-  const bool band = valid && (rc.row_flag[r] & 2); // band rows: pattern_rows_kernel
-  uint32_t M = 0;
-  if (valid && !band)
+  bool go[CROWS];
+  int64_t r[CROWS];
+#pragma unroll
+  for (int i = 0; i < CROWS; ++i)
   {
-    const int64_t ib = rc.inc_ptr[r];
-    const int n_inc = static_cast<int>(rc.inc_ptr[r + 1] - ib);
-#pragma unroll 4
-    for (int k = sl; k < n_inc; k += 8)
-    {
-      const uint32_t fm = fmask[ib + k];
-      M |= (rc.cell_flags[rc.inc_cell[ib + k]] & 0xFD) ? fm : 0u;
-    }
+    go[i] = idx0 + i < n_act;
+    r[i] = go[i] ? act_rows[idx0 + i] : 0;
   }
-  M |= __shfl_xor_sync(0xffffffffu, M, 1);
-  M |= __shfl_xor_sync(0xffffffffu, M, 2);
-  M |= __shfl_xor_sync(0xffffffffu, M, 4);
-  const bool lead = valid && !band && sl == 0;
-  bool clist = false;
-  if (lead)
+  int64_t ib[CROWS];
+  int n_inc[CROWS];
+#pragma unroll
+  for (int i = 0; i < CROWS; ++i)
   {
-    clist = frow_ok[r] != 0;
-    row_nnz[r] = __popc(M);
-    Rrow[idx] = M;
-    row_fast[idx] = 1 | 4 | (clist ? 8 : 0);
+    go[i] = go[i] && !(rc.row_flag[r[i]] & 2); // band rows: pattern_rows_kernel
+    ib[i] = rc.inc_ptr[r[i]];
+    n_inc[i] = go[i] ? static_cast<int>(rc.inc_ptr[r[i] + 1] - ib[i]) : 0;
+  }
+  uint32_t M[CROWS];
+  bool clist = false;
+  int nz = 0;
+#pragma unroll
+  for (int i = 0; i < CROWS; ++i)
+  {
+    uint32_t m = 0;
+#pragma unroll 4
+    for (int k = sl; k < n_inc[i]; k += 8)
+    {
+      const uint32_t fm = fmask[ib[i] + k];
+      m |= (rc.cell_flags[rc.inc_cell[ib[i] + k]] & 0xFD) ? fm : 0u;
+    }
+    M[i] = m;
+  }
+#pragma unroll
+  for (int i = 0; i < CROWS; ++i)
+  {
+    uint32_t m = M[i];
+    m |= __shfl_xor_sync(0xffffffffu, m, 1);
+    m |= __shfl_xor_sync(0xffffffffu, m, 2);
+    m |= __shfl_xor_sync(0xffffffffu, m, 4);
+    if (go[i] && sl == 0)
+    {
+      const bool cl = frow_ok[r[i]] != 0;
+      row_nnz[r[i]] = __popc(m);
+      Rrow[idx0 + i] = m;
+      row_fast[idx0 + i] = 1 | 4 | (cl ? 8 : 0);
+      if (cl)
+      {
+        clist = true; // per thread: number of its contribution-list rows and their entries
+        nz += __popc(m) | (1 << 16);
+      }
+    }
   }
   // integer counters (exact, order-independent): one atomic pair per block
   __shared__ int s_cnt[2];
   if (threadIdx.x < 2)
     s_cnt[threadIdx.x] = 0;
   __syncthreads();
+  // nz packs (rows << 16 | entries) of this thread's <= CROWS rows; a warp holds 4 lane groups: no overflow
   const unsigned b = __ballot_sync(0xffffffffu, clist);
-  int nz = clist ? __popc(M) : 0;
+  int nrows = nz >> 16, nent = nz & 0xFFFF;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
-    nz += __shfl_down_sync(0xffffffffu, nz, o);
+  {
+    nrows += __shfl_down_sync(0xffffffffu, nrows, o);
+    nent += __shfl_down_sync(0xffffffffu, nent, o);
+  }
   if ((threadIdx.x & 31) == 0 && b)
   {
-    atomicAdd(&s_cnt[0], __popc(b));
-    atomicAdd(&s_cnt[1], nz);
+    atomicAdd(&s_cnt[0], nrows);
+    atomicAdd(&s_cnt[1], nent);
   }
   __syncthreads();
   if (threadIdx.x < 2 && s_cnt[threadIdx.x])
     atomicAdd(&n_clist[threadIdx.x], static_cast<unsigned long long>(s_cnt[threadIdx.x]));
 }
 
-// static rows after the scan: cols[row_ptr[r] + k] = k-th kept full-mesh column.  16 lanes per row.
+// static rows after the scan: cols[row_ptr[r] + k] = k-th kept full-mesh column.  16 lanes per row, SROWS rows
+// per half-warp with the three dependent load levels (slot -> row -> columns) of all of them batched: a warp
+// that lives for one row spends its whole life waiting on three round trips.
+constexpr int SROWS = 4;
 __global__ void __launch_bounds__(256)
     pattern_static_fill_kernel(const int32_t* __restrict__ act_rows, int64_t n_act,
                                const uint8_t* __restrict__ row_fast, const uint32_t* __restrict__ Rrow,
@@ -595,20 +629,44 @@ __global__ void __launch_bounds__(256)
                                const int64_t* __restrict__ row_ptr, int32_t* __restrict__ cols)
 {
   const int64_t t = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-  const int64_t idx = t >> 4;
+  const int64_t idx0 = (t >> 4) * SROWS;
   const int sl = static_cast<int>(t & 15);
-  if (idx >= n_act || !(row_fast[idx] & 4))
-    return;
-  const int64_t r = act_rows[idx];
-  const uint32_t R = Rrow[idx];
-  const int64_t fb = frow_ptr[r], ob = row_ptr[r];
+  bool ok[SROWS];
+  int64_t r[SROWS];
+  uint32_t R[SROWS];
 #pragma unroll
-  for (int h = 0; h < 2; ++h)
+  for (int i = 0; i < SROWS; ++i)
   {
-    const int bit = sl + 16 * h;
-    if ((R >> bit) & 1u)
-      cols[ob + __popc(R & ((1u << bit) - 1u))] = fcols[fb + bit];
+    const int64_t idx = idx0 + i;
+    ok[i] = idx < n_act && (row_fast[idx] & 4);
+    r[i] = ok[i] ? act_rows[idx] : 0;
+    R[i] = ok[i] ? Rrow[idx] : 0u;
   }
+  int64_t fb[SROWS], ob[SROWS];
+#pragma unroll
+  for (int i = 0; i < SROWS; ++i)
+  {
+    fb[i] = frow_ptr[r[i]];
+    ob[i] = row_ptr[r[i]];
+  }
+  int32_t cv[SROWS][2];
+#pragma unroll
+  for (int i = 0; i < SROWS; ++i)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+    {
+      const int bit = sl + 16 * h;
+      cv[i][h] = ((R[i] >> bit) & 1u) ? fcols[fb[i] + bit] : 0;
+    }
+#pragma unroll
+  for (int i = 0; i < SROWS; ++i)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+    {
+      const int bit = sl + 16 * h;
+      if ((R[i] >> bit) & 1u)
+        cols[ob[i] + __popc(R[i] & ((1u << bit) - 1u))] = cv[i][h];
+    }
 }
 
 // fast NON-static rows: columns were staged in tmp during the count pass.  One warp moves 32 rows:
@@ -1140,7 +1198,7 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
     if (use_static)
     {
       a->Rrow.reserve(ctx->pool, static_cast<size_t>(n_act) + 1);
-      CFX_LAUNCH(ctx, pattern_static_kernel, grid_for(n_act * 8, 256), 256, 0, rc, act, n_act, S.fmask.p, S.frow_ok.p,
+      CFX_LAUNCH(ctx, pattern_static_kernel, grid_for((n_act + 3) / 4 * 8, 256), 256, 0, rc, act, n_act, S.fmask.p, S.frow_ok.p,
                  row_nnz.p, a->Rrow.p, a->row_fast.p, n_slow + 1);
     }
     if (need_generic)
@@ -1175,7 +1233,7 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
   if (n_act > 0)
   {
     if (use_static)
-      CFX_LAUNCH(ctx, pattern_static_fill_kernel, grid_for(n_act * 16, 256), 256, 0, act, n_act, a->row_fast.p,
+      CFX_LAUNCH(ctx, pattern_static_fill_kernel, grid_for((n_act + SROWS - 1) / SROWS * 16, 256), 256, 0, act, n_act, a->row_fast.p,
                  a->Rrow.p, S.frow_ptr.p, S.fcols.p, P->row_ptr.p, P->cols.p);
     if (need_generic)
       CFX_LAUNCH(ctx, pattern_copy_kernel, grid_for(n_act, 256), 256, 0, act, n_act, a->row_fast.p, tmp.p,
