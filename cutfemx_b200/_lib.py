@@ -20,8 +20,8 @@ TRIANGLE, TETRAHEDRON = 3, 4
 DOMAIN_INSIDE, DOMAIN_INTERSECTED, DOMAIN_OUTSIDE = 1, 2, 3
 REL = {"<": 0, "<=": 1, ">": 2, ">=": 3, "=": 4}
 KERNEL = {"laplace": 1, "mass": 2, "nitsche": 3, "ghost_grad_jump": 4, "source": 5, "nitsche_rhs": 6, "one": 7,
-          "elasticity": 8, "source_vec": 9}
-KERNEL_RANK = {1: 2, 2: 2, 3: 2, 4: 2, 5: 1, 6: 1, 7: 0, 8: 2, 9: 1}
+          "elasticity": 8, "source_vec": 9, "square_fn": 10}
+KERNEL_RANK = {1: 2, 2: 2, 3: 2, 4: 2, 5: 1, 6: 1, 7: 0, 8: 2, 9: 1, 10: 0}
 
 # every symbol include/cutfemx_b200.h declares (tests/test_abi.py checks the .so exports them all)
 SYMBOLS = [
@@ -31,7 +31,7 @@ SYMBOLS = [
     "cfx_runtime_quadrature", "cfx_rules_sizes", "cfx_rules_fetch", "cfx_rules_physical_points", "cfx_rules_free",
     "cfx_simplex_rule", "cfx_set_simplex_rule", "cfx_evaluate_normals", "cfx_evaluate_values",
     "cfx_ghost_penalty_facets", "cfx_interior_facets_for_cells", "cfx_facet_integration_rows", "cfx_space_bind",
-    "cfx_form_create", "cfx_form_add_cell_integral", "cfx_form_add_interior_facet_integral", "cfx_form_free",
+    "cfx_form_create", "cfx_form_set_coefficient", "cfx_form_add_cell_integral", "cfx_form_add_interior_facet_integral", "cfx_form_free",
     "cfx_create_sparsity", "cfx_pattern_import", "cfx_pattern_sizes", "cfx_pattern_block_size", "cfx_pattern_fetch",
     "cfx_pattern_values_device_ptr", "cfx_pattern_row_ptr_device_ptr", "cfx_pattern_cols_device_ptr",
     "cfx_pattern_values_fetch", "cfx_pattern_free", "cfx_assemble_matrix", "cfx_assemble_system", "cfx_assemble_vector",

@@ -116,6 +116,19 @@ struct KernelTraits<CFX_K_ONE>
   static constexpr bool H = false, N = false;
 };
 
+template <>
+struct KernelTraits<CFX_K_SQUARE_FN>
+{
+  static constexpr int RANK = 0;
+  static constexpr bool H = false, N = false;
+};
+// kernels that read an ordinary Function coefficient (its nd cell-local dof values)
+template <int KID>
+struct KernelCoef
+{
+  static constexpr bool value = KID == CFX_K_SQUARE_FN;
+};
+
 template <int ND, int RANK>
 struct ESize
 {
@@ -129,9 +142,9 @@ __device__ __forceinline__ void point_contribution(const Geo<TDIM>& g, const dou
                                                    double (&acc)[ESize<Elem<TDIM, DEG>::ND, KernelTraits<KID>::RANK>::value])
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
-  if constexpr (KID == CFX_K_ONE)
+  if constexpr (KID == CFX_K_ONE || KID == CFX_K_SQUARE_FN)
   {
-    acc[0] += cs.c[0] * w;
+    acc[0] += cs.c[0] * w; // CFX_K_SQUARE_FN: the caller has folded w_h(xi)^2 into the weight
   }
   else
   {
@@ -232,7 +245,8 @@ __device__ __forceinline__ void ld256(const double* p, double& a, double& b, dou
 template <int TDIM, int DEG, int KID, bool RUNTIME>
 __global__ void __launch_bounds__(EB)
     cell_kernel(const int32_t* __restrict__ cells, int64_t n, RuleView rv, StdRule sr, Consts cs,
-                const double* __restrict__ x, const int32_t* __restrict__ x_dofmap, OutCtx oc)
+                const double* __restrict__ x, const int32_t* __restrict__ x_dofmap, OutCtx oc,
+                const double* __restrict__ coeff, const int32_t* __restrict__ dofmap)
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
   constexpr int RANK = KernelTraits<KID>::RANK;
@@ -267,6 +281,30 @@ __global__ void __launch_bounds__(EB)
 #pragma unroll
   for (int r = 0; r < TDIM; ++r)
     nq[r] = 0.0;
+  // pack_coefficients (pack_form.h:98-131) fused into the kernel: the cell's nd dof values of the Function
+  double wl[ND];
+  if constexpr (KernelCoef<KID>::value)
+  {
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+      wl[j] = coeff[dofmap[cell * ND + j]];
+  }
+  // value of the coefficient at a reference point, squared (CFX_K_SQUARE_FN), folded into the weight
+  auto coef_weight = [&](const double (&xi)[TDIM], double w) -> double
+  {
+    if constexpr (KernelCoef<KID>::value)
+    {
+      double phi[ND], dphi[ND][TDIM];
+      tabulate<TDIM, DEG>(xi, phi, dphi);
+      double v = 0.0;
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+        v += phi[j] * wl[j];
+      return w * (v * v);
+    }
+    else
+      return w;
+  };
   if constexpr (RUNTIME)
   {
     const int32_t q0 = rv.offsets[e], q1 = rv.offsets[e + 1];
@@ -282,7 +320,7 @@ __global__ void __launch_bounds__(EB)
         for (int r = 0; r < TDIM; ++r)
           nq[r] = rv.nrm[static_cast<int64_t>(r) * rv.npts + q];
       }
-      point_contribution<TDIM, DEG, KID>(g, xi, rv.wts[q], nq, h, cs, acc);
+      point_contribution<TDIM, DEG, KID>(g, xi, coef_weight(xi, rv.wts[q]), nq, h, cs, acc);
     }
   }
   else
@@ -294,7 +332,7 @@ __global__ void __launch_bounds__(EB)
 #pragma unroll
       for (int t = 0; t < TDIM; ++t)
         xi[t] = __ldg(sr.pts + q * TDIM + t);
-      point_contribution<TDIM, DEG, KID>(g, xi, __ldg(sr.wts + q) * s, nq, h, cs, acc);
+      point_contribution<TDIM, DEG, KID>(g, xi, coef_weight(xi, __ldg(sr.wts + q) * s), nq, h, cs, acc);
     }
   }
   if constexpr (RANK >= 1)
@@ -1625,6 +1663,7 @@ int std_rule_order(int kernel, int deg)
   case CFX_K_LAPLACE: return 2 * (deg - 1);
   case CFX_K_MASS: return 2 * deg;
   case CFX_K_SOURCE: return deg;
+  case CFX_K_SQUARE_FN: return 2 * deg; // (uh - u_exact)**2 with both in the space: estimated degree 2 deg
   default: return 0;
   }
 }
@@ -1639,12 +1678,16 @@ void launch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t& base)
   for (int k = 0; k < CFX_MAX_CONSTANTS; ++k)
     cs.c[k] = I.constants[k];
   OutCtx oc{c->mat_slot.p, f->Ae.p, base};
+  if (KernelCoef<KID>::value)
+    CFX_REQUIRE(f->coeff != nullptr, CFX_ERR_STATE,
+                "the kernel reads a Function coefficient: call cfx_form_set_coefficient first");
   if (RANK == 0 && I.n > 0)
   { // only functionals materialise their standard entities (one value each)
     RuleTable& rt = get_rule(c, TDIM, std_rule_order(KID, DEG));
     sr = StdRule{rt.d_pts, rt.d_wts, rt.npts};
     auto k = cell_kernel<TDIM, DEG, KID, false>;
-    CFX_LAUNCH(c, k, grid_for(I.n, EB), EB, 0, I.entities, I.n, rv, sr, cs, c->x, c->x_dofmap, oc);
+    CFX_LAUNCH(c, k, grid_for(I.n, EB), EB, 0, I.entities, I.n, rv, sr, cs, c->x, c->x_dofmap, oc, f->coeff,
+               c->spaces[f->space].dofmap);
     base += I.n;
     oc.base = base;
   }
@@ -1655,7 +1698,8 @@ void launch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t& base)
     rv = RuleView{R->points.p, R->weights.p, R->has_normals ? R->normals.p : nullptr, R->offsets.p, R->parent_map.p,
                   R->npts};
     auto k = cell_kernel<TDIM, DEG, KID, true>;
-    CFX_LAUNCH(c, k, grid_for(R->nrules, EB), EB, 0, nullptr, R->nrules, rv, sr, cs, c->x, c->x_dofmap, oc);
+    CFX_LAUNCH(c, k, grid_for(R->nrules, EB), EB, 0, nullptr, R->nrules, rv, sr, cs, c->x, c->x_dofmap, oc, f->coeff,
+               c->spaces[f->space].dofmap);
     if (base >= 0)
       base += R->nrules;
   }
@@ -2069,6 +2113,7 @@ void dispatch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t& base
   case CFX_K_SOURCE: launch_cell<TDIM, DEG, CFX_K_SOURCE>(c, I, f, base); break;
   case CFX_K_NITSCHE_RHS: launch_cell<TDIM, DEG, CFX_K_NITSCHE_RHS>(c, I, f, base); break;
   case CFX_K_ONE: launch_cell<TDIM, DEG, CFX_K_ONE>(c, I, f, base); break;
+  case CFX_K_SQUARE_FN: launch_cell<TDIM, DEG, CFX_K_SQUARE_FN>(c, I, f, base); break;
   default: throw Error(CFX_ERR_UNSUPPORTED, "unknown cell kernel family");
   }
 }
@@ -2576,6 +2621,27 @@ cfx_status cfx_assemble_vector(cfx_ctx* ctx, const cfx_form* L_const, double* b,
     export_to(ctx, b, tmp.p, static_cast<size_t>(S.n_total) * S.bs, CFX_HOST);
     tmp.release();
   }
+  CFX_API_END(ctx)
+}
+
+cfx_status cfx_form_set_coefficient(cfx_ctx* ctx, cfx_form* f, const double* values, int64_t n, int memspace)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && f && values, CFX_ERR_INVALID, "cfx_form_set_coefficient: NULL argument");
+  const Space& S = ctx->spaces[f->space];
+  CFX_REQUIRE(S.bs == 1, CFX_ERR_UNSUPPORTED, "Function coefficients are implemented for scalar spaces");
+  CFX_REQUIRE(n == S.n_total, CFX_ERR_INVALID,
+              "cfx_form_set_coefficient: the array must hold one value per owned+ghost dof of the form's space");
+  if (memspace == CFX_HOST)
+  {
+    f->coeff_own.reserve(ctx->pool, static_cast<size_t>(n));
+    CFX_CUDA(cudaMemcpyAsync(f->coeff_own.p, values, static_cast<size_t>(n) * sizeof(double), cudaMemcpyHostToDevice,
+                             ctx->stream));
+    CFX_CUDA(cudaStreamSynchronize(ctx->stream));
+    f->coeff = f->coeff_own.p;
+  }
+  else
+    f->coeff = values;
   CFX_API_END(ctx)
 }
 

@@ -277,6 +277,9 @@ struct cfx_form
   cfx::DevBuf<double> Ae;      // materialised run-time-rule tensors, cell-major (slot, nd^rank) natural order;
                                // rank 0: one value per entity
   cfx::DevBuf<double> Fe;      // facet macro tensors
+  // ordinary Function coefficient (cfx_form_set_coefficient): dof values over the form's space
+  const double* coeff = nullptr;
+  cfx::DevBuf<double> coeff_own;
 };
 
 struct cfx_ctx

@@ -43,13 +43,20 @@ __global__ void __launch_bounds__(CP_BLOCK)
   unsigned mask = base < n ? pred(base, n) : 0u;
   int tot;
   const int excl = block_excl_scan<CP_BLOCK>(__popc(mask), &tot);
-  int64_t o = tile_off[blockIdx.x] + excl;
+  // the tile's selected indices are staged in shared memory and leave as one contiguous, coalesced run
+  // (a thread storing its up to 16 hits one by one issues 16 strided store instructions per warp)
+  __shared__ int32_t s_out[CP_TILE];
+  int o = excl;
   while (mask)
   {
     const int k = __ffs(mask) - 1;
     mask &= mask - 1;
-    out[o++] = static_cast<int32_t>(base + k);
+    s_out[o++] = static_cast<int32_t>(base + k);
   }
+  __syncthreads();
+  int32_t* dst = out + tile_off[blockIdx.x];
+  for (int i = threadIdx.x; i < tot; i += CP_BLOCK)
+    dst[i] = s_out[i];
 }
 
 // Returns the number of selected indices; `out` is (re)allocated to exactly that size.

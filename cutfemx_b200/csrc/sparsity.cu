@@ -1044,7 +1044,8 @@ static int kernel_rank(int k)
   case CFX_K_SOURCE:
   case CFX_K_SOURCE_VEC:
   case CFX_K_NITSCHE_RHS: return 1;
-  case CFX_K_ONE: return 0;
+  case CFX_K_ONE:
+  case CFX_K_SQUARE_FN: return 0;
   }
   return -1;
 }
@@ -1124,6 +1125,7 @@ void cfx_form_free(cfx_ctx* ctx, cfx_form* f)
   f->Rrow.release();
   f->row_fast.release();
   f->Ae.release();
+  f->coeff_own.release();
   f->Fe.release();
   delete f;
 }

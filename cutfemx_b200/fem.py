@@ -51,6 +51,16 @@ class CutForm:
         self._owners += [keep, rules]
         return self
 
+    def set_coefficient(self, values):
+        """The form's ordinary Function coefficient (its x.array over owned+ghost dofs).  The reference packs it per
+        entity before every assembly (pack_coefficients, pack_form.h:68-158, called from assembler.h:213-219); here
+        the kernels gather the cell's values through the dofmap while they run."""
+        p, ms, keep = as_arg(values, np.float64)
+        n = int(keep.numel() if is_device_array(keep) else keep.size)
+        check(self.ctx.handle, lib().cfx_form_set_coefficient(self.ctx.handle, self._h, p, C.c_int64(n), ms))
+        self._owners.append(keep)
+        return self
+
     def add_interior_facet_integral(self, kernel: str, facets=None, rows=None, constants=(1.0,)):
         """Interior-facet integral over raw facet ids (converted with facet_integration_rows,
         _runintgen_adapter.py:416-435) or over ready (cell0, lf0, cell1, lf1) rows."""

@@ -56,7 +56,11 @@ enum {
   CFX_K_ONE = 7,            /* rank 0, cells / rules:   c0  (volume, area, perimeter)                               */
   /* blocked (vector) Lagrange spaces, block size == gdim (demo_elasticity.py:213-238): */
   CFX_K_ELASTICITY = 8,     /* rank 2, cells:           inner(sigma(u), eps(v)), sigma = 2 c0 eps + c1 tr(eps) I        */
-  CFX_K_SOURCE_VEC = 9      /* rank 1, cells:           inner((c0, c1, c2), v)                                         */
+  CFX_K_SOURCE_VEC = 9,     /* rank 1, cells:           inner((c0, c1, c2), v)                                         */
+  CFX_K_SQUARE_FN = 10      /* rank 0, cells / rules:   c0 * w^2, w a Function of the form's (scalar) space -- the error
+                               functional (uh - u_exact)**2 of demo_poisson.py:213 with w = uh - I(u_exact); the dof
+                               values are restricted to each entity's cell like pack_coefficients does
+                               (pack_form.h:68-158), set with cfx_form_set_coefficient                                 */
   /* CFX_K_GHOST_GRAD_JUMP on a blocked space acts on every component: c0 avg(h) inner(jump(grad u, n), jump(grad v, n)) */
 };
 
@@ -164,6 +168,11 @@ cfx_status cfx_form_add_cell_integral(cfx_ctx* ctx, cfx_form* f, int kernel, con
 cfx_status cfx_form_add_interior_facet_integral(cfx_ctx* ctx, cfx_form* f, int kernel, const int32_t* rows4,
                                                 int64_t n_facets, int memspace, const double* constants,
                                                 int n_constants);
+/* The ordinary Function coefficient of a form (pack_form.h:30-158 allocate_coefficient_storage / pack_coefficients):
+ * values over the owned+ghost dofs of the form's space.  The kernels gather each entity's cstride = nd values
+ * through the dofmap while they run, so no packed (n_entities, cstride) array is materialised.  The array is
+ * copied (HOST) or borrowed until the next call (DEVICE). */
+cfx_status cfx_form_set_coefficient(cfx_ctx* ctx, cfx_form* f, const double* values, int64_t n, int memspace);
 void cfx_form_free(cfx_ctx* ctx, cfx_form* f);
 
 /* create_sparsity_pattern + finalize + MatrixCSR(sp): assembler.h:442-592, wrappers/fem.cpp:266-276.

@@ -524,6 +524,25 @@ void k_one(double* m, const double*, const double* c, const double* cdofs, const
   for_each_point(cd, g, eli[0], [&](const double*, double w, const double*) { m[0] += c[0] * w; });
 }
 
+// demo_poisson.py:213: c0 * (uh - u_exact)**2 with the difference given as one Function w of the space; the kernel
+// receives its cell-local dof values in the packed coefficient array (kernel argument 2, pack_form.h:98-131)
+void k_square_fn(double* m, const double* w, const double* c, const double* cdofs, const int* eli, const uint8_t*, void* p)
+{
+  const CustomData& cd = *static_cast<CustomData*>(p);
+  const Geo g = make_geo(cd.tdim, cdofs);
+  const int nd = space_dim(cd.tdim, cd.degree);
+  std::vector<double> phi(nd), dphi((size_t)nd * cd.tdim);
+  for_each_point(cd, g, eli[0],
+                 [&](const double* X, double wq, const double*)
+                 {
+                   tabulate(cd.tdim, cd.degree, X, phi.data(), dphi.data());
+                   double v = 0.0;
+                   for (int j = 0; j < nd; ++j)
+                     v += phi[j] * w[j];
+                   m[0] += c[0] * wq * (v * v);
+                 });
+}
+
 // demo_poisson.py:191-199: gamma_g * avg(h) * inner(jump(grad(u), n), jump(grad(v), n)) * dS
 // coordinate_dofs = [cell0 | cell1]; entity_local_index = {lf0, lf1, loop idx}
 // (assemble_matrix_impl.h:532-535); macro layout [[++,+-],[-+,--]] (:537-542).
@@ -690,6 +709,7 @@ kernel_fn kernel_by_id(int id)
   case 7: return k_one;
   case 8: return k_elasticity;
   case 9: return k_source_vec;
+  case 10: return k_square_fn;
   }
   throw std::runtime_error("oracle: unknown kernel id");
 }
@@ -704,6 +724,7 @@ int std_order_for(int id, int degree)
   case 7: return 0;
   case 8: return 2 * (degree - 1);
   case 9: return degree;
+  case 10: return 2 * degree;
   }
   return 0;
 }
@@ -764,6 +785,8 @@ struct BcState
   double* b = nullptr;
 };
 thread_local BcState g_bc;
+// dof values of the form's ordinary Function coefficient (orc_set_coefficient); packed per entity in the loop
+thread_local const double* g_coeff = nullptr;
 
 // Ae is (nr*bs) x (nc*bs) row-major; returns false when the element is skipped (LiftingMode without BC columns)
 bool apply_bcs(double* Ae, int bs, int nr, const int32_t* rows, int nc, const int32_t* cs)
@@ -827,6 +850,12 @@ const char* orc_last_error() { return g_err.c_str(); }
 
 // Dirichlet state for the following orc_assemble_* calls (rank 2 only).  mode 0 clears it; 1 = assemble_matrix
 // with bcs (rows bc0 / columns bc1 of each element tensor zeroed); 2 = apply_lifting into b.
+int orc_set_coefficient(const double* values)
+{
+  g_coeff = values;
+  return 0;
+}
+
 int orc_set_bcs(int mode, const int8_t* bc0, const int8_t* bc1, const double* values1, const double* x0, double alpha,
                 double* b)
 {
@@ -1166,7 +1195,7 @@ int orc_assemble_cells(int kernel_id, int rank, int cell_type, int degree, const
   CustomData cd{tdim, degree, n_std, points, weights, offsets, normals, std_order_for(kernel_id, degree)};
   kernel_fn kernel = kernel_by_id(kernel_id);
   const int esize = rank == 2 ? nd * nd : (rank == 1 ? nd : 1);
-  std::vector<double> Ae(esize);
+  std::vector<double> Ae(esize), wpack(nd);
   std::vector<double> cdofs(3 * nv);
   const int64_t n = n_std + n_rules;
   for (int64_t c = 0; c < n; ++c)
@@ -1176,8 +1205,11 @@ int orc_assemble_cells(int kernel_id, int rank, int cell_type, int degree, const
       std::copy_n(x + 3 * (int64_t)x_dofmap[(int64_t)cell * nv + i], 3, cdofs.begin() + 3 * i);
     std::fill(Ae.begin(), Ae.end(), 0.0);
     int entity_local_index = (int)c; // loop index, not cell id
-    kernel(Ae.data(), nullptr, constants, cdofs.data(), &entity_local_index, nullptr, &cd);
     const int32_t* dofs = dofmap + (int64_t)cell * nd;
+    if (g_coeff) // pack_coefficient_entity (pack_form.h:98-131): the cell's dof values, cstride = nd
+      for (int i = 0; i < nd; ++i)
+        wpack[i] = g_coeff[dofs[i]];
+    kernel(Ae.data(), g_coeff ? wpack.data() : nullptr, constants, cdofs.data(), &entity_local_index, nullptr, &cd);
     if (rank == 2)
     {
       if (apply_bcs(Ae.data(), 1, nd, dofs, nd, dofs))

@@ -216,8 +216,8 @@ def sparsity(space, cells, rows4=None, insert_diagonal=True):
 
 
 K = {"laplace": 1, "mass": 2, "nitsche": 3, "ghost_grad_jump": 4, "source": 5, "nitsche_rhs": 6, "one": 7,
-     "elasticity": 8, "source_vec": 9}
-_RANK = {1: 2, 2: 2, 3: 2, 4: 2, 5: 1, 6: 1, 7: 0, 8: 2, 9: 1}
+     "elasticity": 8, "source_vec": 9, "square_fn": 10}
+_RANK = {1: 2, 2: 2, 3: 2, 4: 2, 5: 1, 6: 1, 7: 0, 8: 2, 9: 1, 10: 0}
 
 
 def _register_std_rules(space, kernel_id):
@@ -359,3 +359,19 @@ def set_bc(b, dofs, values, x0=None, alpha=1.0):
     g = np.asarray(values, dtype=np.float64)
     b[d] = alpha * (g[d] - (0.0 if x0 is None else np.asarray(x0)[d]))
     return b
+
+
+class coefficient:
+    """Context: the ordinary Function coefficient of the orc_assemble_cells calls inside it (dof values over the
+    space; packed per entity by the loop like pack_coefficients, pack_form.h:68-158)."""
+
+    def __init__(self, values):
+        self.values = _cf64(values)
+
+    def __enter__(self):
+        lib().orc_set_coefficient(_p(self.values, _f64p))
+        return self
+
+    def __exit__(self, *exc):
+        lib().orc_set_coefficient(None)
+        return False

@@ -155,3 +155,30 @@ def test_form_errors(built_lib):
     with pytest.raises(cfx.CfxError):  # entity index out of range
         a = cfx.fem.CutForm(V, 2).add_cell_integral("laplace", np.array([mesh.num_cells + 3], dtype=np.int32))
         cfx.fem.assemble_matrix(a)
+
+
+@pytest.mark.parametrize("kind,n,deg", [("circle", 12, 1), ("circle", 7, 2), ("sphere", 6, 1), ("sphere", 4, 2)])
+def test_square_functional_of_a_function_coefficient(built_lib, kind, n, deg):
+    """pack_coefficients (pack_form.h:68-158) + the error functional of demo_poisson.py:213 as c0 * w_h**2."""
+    import cutfemx_b200 as cfx
+    from util import make_problem
+
+    mesh, Vphi, phi, _ = make_problem(kind, n, 1)
+    V = M.functionspace(mesh, deg, permute_seed=3)
+    dom = O.classify(Vphi.dofmap, phi.x.array)
+    inside = O.locate(dom, "phi<0")
+    rv = O.runtime_quadrature(mesh, Vphi.dofmap, phi.x.array, dom, "<", 4)
+    w = np.sin(3.0 * V.dof_coords[:, 0]) + V.dof_coords[:, 1] ** 2
+    ref = np.zeros(1)
+    with O.coefficient(w):
+        O.assemble_cells(V, "square_fn", ref, inside, rv, (1.5,))
+    cd = cfx.cut(phi)
+    form = cfx.fem.CutForm(V, 0).add_cell_integral("square_fn", cfx.locate_entities(cd, "phi<0"),
+                                                    cfx.runtime_quadrature(cd, "phi<0", 4), (1.5,))
+    with pytest.raises(cfx.CfxError):  # the kernel needs its coefficient
+        cfx.fem.assemble_scalar(form)
+    form.set_coefficient(w)
+    got = cfx.fem.assemble_scalar(form)
+    assert abs(got - ref[0]) <= 1e-12 * abs(ref[0])
+    with pytest.raises(cfx.CfxError):  # one value per dof of the space
+        form.set_coefficient(w[:-1])

@@ -444,3 +444,38 @@ def test_dirichlet_restatement_is_consistent_with_the_unconstrained_matrix():
         assert np.all(to_csr(masked).diagonal()[d] == 2.5)
         O.set_bc(b, d, g, x0, alpha)
         np.testing.assert_allclose(b[d], alpha * (g - x0)[d])
+
+
+# ---------------------------------------------------------------- Function coefficients
+def test_square_functional_of_a_packed_coefficient():
+    """demo_poisson.py:213 error functional: int (w_h)^2 over the cut domain with w_h the P1 / P2 interpolant of a
+    linear function is exact with the degree-2p rules (standard and run-time), so it equals int (a + b.x)^2 over
+    the polygon/polyhedron the cut produces -- computed here from the oracle's own order-2 moments."""
+    from cutfemx_b200 import mesh as M
+    from util import make_problem
+
+    for kind, n, deg in (("circle", 9, 1), ("circle", 6, 2), ("sphere", 4, 1)):
+        mesh, Vphi, phi, _ = make_problem(kind, n, 1)
+        V = M.functionspace(mesh, deg)
+        dom = O.classify(Vphi.dofmap, phi.x.array)
+        inside = O.locate(dom, "phi<0")
+        rv = O.runtime_quadrature(mesh, Vphi.dofmap, phi.x.array, dom, "<", 2 * deg)
+        a0, b = 0.3, np.array([1.1, -0.7, 0.4])[: mesh.tdim]
+        w = a0 + V.dof_coords[:, : mesh.tdim] @ b
+        val = np.zeros(1)
+        with O.coefficient(w):
+            O.assemble_cells(V, "square_fn", val, inside, rv, (2.0,))
+        # the same integral from physical quadrature points of a degree-2 rule on every entity
+        ref = 0.0
+        X = mesh.x[mesh.x_dofmap][:, :, : mesh.tdim]
+        from oracle import rules as R
+
+        p2, w2 = R.simplex_rule(mesh.tdim, 2)
+        p2 = np.asarray(p2).reshape(w2.size, mesh.tdim)
+        for c in inside:
+            J = (X[c, 1:] - X[c, :1]).T
+            xq = X[c, 0] + p2 @ J.T
+            ref += 2.0 * np.sum(w2 * abs(np.linalg.det(J)) * (a0 + xq @ b) ** 2)
+        xp = O.physical_points(mesh, rv).T
+        ref += 2.0 * np.sum(rv.weights * (a0 + xp @ b) ** 2)
+        assert abs(val[0] - ref) <= 1e-12 * abs(ref)
