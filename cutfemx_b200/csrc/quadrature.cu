@@ -606,6 +606,77 @@ __global__ void normals_kernel(const double* __restrict__ pts, int64_t npts, con
   }
 }
 
+// P1 level sets: grad phi is constant on the cell, so every point of a rule gets the same normal -- one thread
+// per RULE evaluates the reference's per-point expression once (same operations in the same order, hence the
+// same bits as normals_kernel<TDIM, 1>; dphi of P1 does not depend on the point) and stores it for the rule's
+// points.  No per-point rule search, one geometry evaluation per cut cell instead of one per point.
+template <int TDIM>
+__global__ void normals_p1_kernel(const double* __restrict__ pts, int64_t npts, const int32_t* __restrict__ offsets,
+                                  const int32_t* __restrict__ parent_map, int64_t nrules,
+                                  const int32_t* __restrict__ x_dofmap, const double* __restrict__ x,
+                                  const int32_t* __restrict__ ls_dofmap, const double* __restrict__ vals, double sign,
+                                  double* __restrict__ out_soa, double* __restrict__ out_aos)
+{
+  constexpr int ND = TDIM + 1;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= nrules)
+    return;
+  const int32_t q0 = offsets[r], q1 = offsets[r + 1];
+  if (q1 <= q0)
+    return;
+  const int64_t cell = parent_map[r];
+  double X[TDIM + 1][TDIM];
+  load_cell_coords<TDIM>(x, x_dofmap, cell, X);
+  Geo<TDIM> g;
+  make_geo<TDIM>(X, g);
+  double xi[TDIM];
+#pragma unroll
+  for (int t = 0; t < TDIM; ++t)
+    xi[t] = pts[static_cast<int64_t>(t) * npts + q0];
+  double phi[ND], dphi[ND][TDIM];
+  tabulate<TDIM, 1>(xi, phi, dphi);
+  double gref[TDIM];
+#pragma unroll
+  for (int t = 0; t < TDIM; ++t)
+    gref[t] = 0.0;
+#pragma unroll
+  for (int j = 0; j < ND; ++j)
+  {
+    const double v = __ldg(vals + __ldg(ls_dofmap + cell * ND + j));
+#pragma unroll
+    for (int t = 0; t < TDIM; ++t)
+      gref[t] += dphi[j][t] * v;
+  }
+  double gp[TDIM], nrm = 0.0;
+#pragma unroll
+  for (int i = 0; i < TDIM; ++i)
+  {
+    double s = 0.0;
+#pragma unroll
+    for (int t = 0; t < TDIM; ++t)
+      s += g.K[t * TDIM + i] * gref[t];
+    gp[i] = s;
+    nrm += s * s;
+  }
+  nrm = sqrt(nrm);
+  if (nrm < 1.0e-14)
+    nrm = 1.0e-14;
+  double nv[TDIM];
+#pragma unroll
+  for (int i = 0; i < TDIM; ++i)
+    nv[i] = sign * gp[i] / nrm;
+  for (int32_t q = q0; q < q1; ++q)
+  {
+#pragma unroll
+    for (int i = 0; i < TDIM; ++i)
+    {
+      out_soa[static_cast<int64_t>(i) * npts + q] = nv[i];
+      if (out_aos)
+        out_aos[static_cast<int64_t>(q) * TDIM + i] = nv[i];
+    }
+  }
+}
+
 template <int TDIM, int DEG>
 __global__ void values_kernel(const double* __restrict__ pts, int64_t npts, const int32_t* __restrict__ offsets,
                               const int32_t* __restrict__ parent_map, int64_t nrules,
@@ -862,9 +933,16 @@ cfx_status cfx_evaluate_normals(cfx_ctx* ctx, int ls, cfx_rules* r, double sign,
 #define NARGS                                                                                                          \
   r->points.p, r->npts, r->offsets.p, r->parent_map.p, r->nrules, ctx->x_dofmap, ctx->x, L.dofmap, L.values, sign,     \
       r->normals.p, aos
-    auto nk = ctx->tdim == 2 ? (L.degree == 1 ? normals_kernel<2, 1> : normals_kernel<2, 2>)
-                             : (L.degree == 1 ? normals_kernel<3, 1> : normals_kernel<3, 2>);
-    CFX_LAUNCH(ctx, nk, g, 256, 0, NARGS);
+    if (L.degree == 1)
+    { // constant gradient per cell: one thread per rule
+      auto nk = ctx->tdim == 2 ? normals_p1_kernel<2> : normals_p1_kernel<3>;
+      CFX_LAUNCH(ctx, nk, grid_for(r->nrules, 128), 128, 0, NARGS);
+    }
+    else
+    {
+      auto nk = ctx->tdim == 2 ? normals_kernel<2, 2> : normals_kernel<3, 2>;
+      CFX_LAUNCH(ctx, nk, g, 256, 0, NARGS);
+    }
 #undef NARGS
   }
   if (out_aos && memspace == CFX_HOST)

@@ -307,6 +307,9 @@ __global__ void __launch_bounds__(RW * 32)
   for (int j = 0; j < ND; ++j)
     h[j] = IMAX;
   bool band = false;
+  // P1, count pass: a band cell brings at most ONE new column (the dof opposite the facet opposite the row's
+  // dof), kept in a register and merged like a fifth list entry instead of going through shared memory
+  int32_t xreg = IMAX;
   for (int k0 = 0; k0 < n_inc; k0 += 32)
   {
     const int k = k0 + lane;
@@ -383,9 +386,14 @@ __global__ void __launch_bounds__(RW * 32)
               dup = dup || (od[j] == d[jj]);
             if (!dup)
             {
-              const int pos = atomicAdd(&s_nextra[w], 1);
-              if (pos < XCAP)
-                s_extra[w][pos] = od[j];
+              if (ND == NF && !FILL && k0 == 0)
+                xreg = od[j];
+              else
+              {
+                const int pos = atomicAdd(&s_nextra[w], 1);
+                if (pos < XCAP)
+                  s_extra[w][pos] = od[j];
+              }
             }
           }
         }
@@ -423,6 +431,18 @@ __global__ void __launch_bounds__(RW * 32)
       }
   }
   __syncwarp();
+  if (s_nextra[w] != 0)
+  { // the general merge below reads its extra candidates from shared memory only: move the register ones there
+    __syncwarp();
+    if (xreg != IMAX)
+    {
+      const int pos = atomicAdd(&s_nextra[w], 1);
+      if (pos < XCAP)
+        s_extra[w][pos] = xreg;
+      xreg = IMAX;
+    }
+    __syncwarp();
+  }
   const int n_extra = s_nextra[w];
   if (n_extra > XCAP)
   {
@@ -445,7 +465,7 @@ __global__ void __launch_bounds__(RW * 32)
     uint32_t bit = 1u;
     while (true)
     {
-      const int32_t m = __reduce_min_sync(full, h[0]);
+      const int32_t m = __reduce_min_sync(full, min(h[0], xreg));
       if (m == IMAX)
         break;
       const bool p = h[0] == m;
@@ -454,6 +474,7 @@ __global__ void __launch_bounds__(RW * 32)
       for (int j = 0; j + 1 < ND; ++j)
         h[j] = p ? h[j + 1] : h[j];
       h[ND - 1] = p ? IMAX : h[ND - 1];
+      xreg = (xreg == m) ? IMAX : xreg;
       keep = (lane == count) ? m : keep;
       bit <<= 1;
       ++count;
