@@ -642,7 +642,76 @@ struct StdTab
   double t0[1 << CFX_MAX_STD_LISTS];
   double t1[1 << CFX_MAX_STD_LISTS];
   int has_mass;
+  // P2 closed forms: reference-element tables (RefTab layout below), device memory
+  const double* ref;
 };
+
+// Reference-element integrals of a Lagrange space on the affine simplex, computed once per (tdim, degree) on the
+// device with the library's own tabulate and an exact rule:
+//   R[a][b][i][j] = int d_a phi_i d_b phi_j,  M[i][j] = int phi_i phi_j,  S[i] = int phi_i   (reference cell)
+// so that on a cell with K = J^-1 and C = K K^T (grad phi = K^T grad_ref phi):
+//   Laplace_ij = |detJ| sum_ab C_ab R[a][b][i][j],  mass_ij = |detJ| M[i][j],  source_i = |detJ| S[i].
+template <int TDIM, int ND>
+struct RefTab
+{
+  static constexpr int R = 0, M = TDIM * TDIM * ND * ND, S = M + ND * ND, SIZE = S + ND;
+};
+
+template <int TDIM, int DEG>
+__global__ void ref_tables_kernel(const double* __restrict__ pts, const double* __restrict__ wts, int npts,
+                                  double* __restrict__ out)
+{
+  constexpr int ND = Elem<TDIM, DEG>::ND;
+  using T = RefTab<TDIM, ND>;
+  const int t = threadIdx.x;
+  if (t >= ND * ND)
+    return;
+  const int i = t / ND, j = t % ND;
+  double r[TDIM][TDIM], m = 0.0, sv = 0.0;
+#pragma unroll
+  for (int a = 0; a < TDIM; ++a)
+#pragma unroll
+    for (int b = 0; b < TDIM; ++b)
+      r[a][b] = 0.0;
+  for (int q = 0; q < npts; ++q)
+  {
+    double xi[TDIM];
+#pragma unroll
+    for (int a = 0; a < TDIM; ++a)
+      xi[a] = pts[q * TDIM + a];
+    double phi[ND], dphi[ND][TDIM];
+    tabulate<TDIM, DEG>(xi, phi, dphi);
+    const double w = wts[q];
+    double pi = 0.0, pj = 0.0, di[TDIM], dj[TDIM];
+#pragma unroll
+    for (int k = 0; k < ND; ++k)
+    {
+      pi = (k == i) ? phi[k] : pi;
+      pj = (k == j) ? phi[k] : pj;
+#pragma unroll
+      for (int a = 0; a < TDIM; ++a)
+      {
+        di[a] = (k == i) ? dphi[k][a] : (k == 0 ? 0.0 : di[a]);
+        dj[a] = (k == j) ? dphi[k][a] : (k == 0 ? 0.0 : dj[a]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < TDIM; ++a)
+#pragma unroll
+      for (int b = 0; b < TDIM; ++b)
+        r[a][b] += w * di[a] * dj[b];
+    m += w * pi * pj;
+    sv += w * pi;
+  }
+#pragma unroll
+  for (int a = 0; a < TDIM; ++a)
+#pragma unroll
+    for (int b = 0; b < TDIM; ++b)
+      out[T::R + ((a * TDIM + b) * ND + i) * ND + j] = r[a][b];
+  out[T::M + i * ND + j] = m;
+  if (j == 0)
+    out[T::S + i] = sv;
+}
 
 struct GatherCtx
 {
@@ -722,6 +791,36 @@ __device__ __forceinline__ void std_row_values(const StdTab& st, const Geo<TDIM>
 #pragma unroll
       for (int j = 0; j < ND; ++j)
         v[j] += (j == li) ? 2.0 * wm : wm;
+    }
+    return;
+  }
+  if (st.ref != nullptr)
+  { // P2 (any tabulated degree): reference-element tables, no quadrature loop, no loop over the integrals
+    using T = RefTab<TDIM, ND>;
+    const double s = fabs(g.detJ);
+    const unsigned m = fl >> 2;
+    const double wl = st.t0[m] * s;
+    const double* Rr = st.ref + T::R + li * ND;
+#pragma unroll
+    for (int a = 0; a < TDIM; ++a)
+#pragma unroll
+      for (int b = 0; b < TDIM; ++b)
+      {
+        double cab = 0.0; // C = K K^T
+#pragma unroll
+        for (int t = 0; t < TDIM; ++t)
+          cab += g.K[a * TDIM + t] * g.K[b * TDIM + t];
+        cab *= wl;
+#pragma unroll
+        for (int j = 0; j < ND; ++j)
+          v[j] += cab * Rr[(a * TDIM + b) * ND * ND + j];
+      }
+    if (st.has_mass)
+    {
+      const double wm = st.t1[m] * s;
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+        v[j] += wm * st.ref[T::M + li * ND + j];
     }
     return;
   }
@@ -851,6 +950,8 @@ __device__ __forceinline__ double cell_entry_value(const GatherCtx& gc, const St
     const double s = fabs(__ldg(gc.geo + c * GeoRec<TDIM>::STRIDE + TDIM * TDIM));
     if constexpr (DEG == 1) // P1 source: int phi_i = |detJ| / (tdim+1)!, summed coefficient from the table
       e += st.t0[fl >> 2] * s * (TDIM == 3 ? 1.0 / 24.0 : 1.0 / 6.0);
+    else if (st.ref != nullptr) // int phi_i = |detJ| S[i]
+      e += st.t0[fl >> 2] * s * st.ref[RefTab<TDIM, ND>::S + li];
     else
     for (int k = 0; k < st.n; ++k)
     {
@@ -1486,6 +1587,8 @@ __global__ void __launch_bounds__(GWC * 32, 4)
             const double s = fabs(g0.detJ);
             if constexpr (DEG == 1)
               e += stL.t0[fl >> 2] * s * (TDIM == 3 ? 1.0 / 24.0 : 1.0 / 6.0);
+            else if (stL.ref != nullptr)
+              e += stL.t0[fl >> 2] * s * stL.ref[RefTab<TDIM, ND>::S + c0.li];
             else
               for (int k = 0; k < stL.n; ++k)
               {
@@ -2221,6 +2324,28 @@ StdTab make_std_tab(cfx_ctx* c, cfx_form* f)
     st.npts[k] = rt.npts;
     if (I.kernel == CFX_K_MASS)
       st.has_mass = 1;
+  }
+  if (S.degree == 2 && st.n > 0)
+  { // reference-element tables, built once per (tdim, degree) with an exact rule (mass: degree 2p)
+    auto key = std::make_pair(c->tdim, S.degree);
+    auto it = c->ref_tabs.find(key);
+    if (it == c->ref_tabs.end())
+    {
+      DevBuf<double> buf;
+      RuleTable& rt = get_rule(c, c->tdim, 2 * S.degree);
+      if (c->tdim == 2)
+      {
+        buf.reserve(c->pool, RefTab<2, 6>::SIZE);
+        CFX_LAUNCH(c, (ref_tables_kernel<2, 2>), 1, 64, 0, rt.d_pts, rt.d_wts, rt.npts, buf.p);
+      }
+      else
+      {
+        buf.reserve(c->pool, RefTab<3, 10>::SIZE);
+        CFX_LAUNCH(c, (ref_tables_kernel<3, 2>), 1, 128, 0, rt.d_pts, rt.d_wts, rt.npts, buf.p);
+      }
+      it = c->ref_tabs.emplace(key, buf).first;
+    }
+    st.ref = it->second.p;
   }
   // P1 closed forms: coefficient sums per combination of list bits (ascending integral order)
   for (unsigned m = 0; m < (1u << CFX_MAX_STD_LISTS); ++m)

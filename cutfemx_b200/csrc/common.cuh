@@ -325,6 +325,7 @@ struct cfx_ctx
   cfx::DevBuf<double> geo;
 
   std::map<std::pair<int, int>, cfx::RuleTable> rules; // (dim, order) -> table (built-in or override)
+  std::map<std::pair<int, int>, cfx::DevBuf<double>> ref_tabs; // (tdim, degree) -> reference-element integrals
 
   // scratch
   cfx::DevBuf<int32_t> blk_counts;
