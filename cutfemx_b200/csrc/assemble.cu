@@ -1336,7 +1336,7 @@ __global__ void __launch_bounds__(GW * 32)
 // fixed summation order -> bit-reproducible.
 template <int TDIM, int DEG>
 __global__ void __launch_bounds__(GWM * 32, 8)
-    gather_matrix_fast_kernel(GatherCtx gc, StdTab st, const int32_t* __restrict__ act_rows,
+    gather_matrix_fast_kernel(GatherCtx gc, StdTab st, StdTab stL, const int32_t* __restrict__ act_rows,
                               const int32_t* __restrict__ slots, int64_t n_act,
                               const uint8_t* __restrict__ row_fast, const uint32_t* __restrict__ gmask,
                               const uint32_t* __restrict__ Rrow, const int64_t* __restrict__ row_ptr,
@@ -1390,6 +1390,24 @@ __global__ void __launch_bounds__(GWM * 32, 8)
 #pragma unroll
     for (int j = 0; j < ND; ++j)
       s_v[w][lane][(fp >> (4 + 4 * j)) & 15u] = v[j]; // ascending-dof order
+  }
+  if (gc.bvec)
+  { // fused right-hand side (cfx_assemble_system): the same entry, tree and update as gather_vector_kernel
+    double e = 0.0;
+    if (contributes)
+    {
+      GatherCtx gl = gc;
+      gl.Ae = gc.AeL;
+      e = cell_entry_value<TDIM, DEG>(gl, stL, c, fl, li);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      e += __shfl_down_sync(full, e, o);
+    if (lane == 0)
+    {
+      const double s0 = 0.0 + e; // gather_vector_kernel adds the chunk sum to a zero accumulator
+      gc.bvec[r] = gc.zero_first_b ? s0 : gc.bvec[r] + s0;
+    }
   }
   __syncwarp();
   // ---- phase 2
@@ -1697,7 +1715,12 @@ __global__ void __launch_bounds__(GW * 32)
   if (skip_mode)
   {
     const unsigned rf = row_fast[idx];
-    if ((rf & 13u) == 13u || (skip_mode == 2 && (rf & 16u)))
+    if (skip_mode == 3)
+    { // fused system assembly: the contribution-list and mask kernels have filled b for every fast row
+      if (rf & 1u)
+        return;
+    }
+    else if ((rf & 13u) == 13u || (skip_mode == 2 && (rf & 16u)))
       return;
   }
   const int64_t r = act_rows[idx];
@@ -2454,12 +2477,12 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
       StageScope sk(ctx, "gather_matrix_mask_kernel", 12.0 * (nnz_mask > 0.0 ? nnz_mask : 0.0));
       auto kf = gather_matrix_fast_kernel<TDIM, DEG>;
       if (a->n_band_listed > 0)
-        CFX_LAUNCH(ctx, kf, grid_for(a->n_band_listed, GWM), GWM * 32, 0, gc, st, PR->act_rows.p, PR->band_idx.p,
+        CFX_LAUNCH(ctx, kf, grid_for(a->n_band_listed, GWM), GWM * 32, 0, gc, st, stL, PR->act_rows.p, PR->band_idx.p,
                    a->n_band_listed, a->row_fast.p, a->gmask.p, a->Rrow.p, A->row_ptr.p, A->cols.p, A->values.p,
                    zero_first);
       // static rows without a contribution list (an edge with more than 8 cells), or no slot list at all
       if (a->n_band_listed == 0 || PR->n_act_rows - a->n_band_listed - a->n_clist_rows > 0)
-        CFX_LAUNCH(ctx, kf, grid_for(PR->n_act_rows, GWM), GWM * 32, 0, gc, st, PR->act_rows.p, nullptr,
+        CFX_LAUNCH(ctx, kf, grid_for(PR->n_act_rows, GWM), GWM * 32, 0, gc, st, stL, PR->act_rows.p, nullptr,
                    PR->n_act_rows, a->row_fast.p, a->gmask.p, a->Rrow.p, A->row_ptr.p, A->cols.p, A->values.p,
                    zero_first);
     }
@@ -2505,12 +2528,11 @@ void launch_gather_vector(cfx_ctx* ctx, cfx_form* L, const GatherCtx& gc, const 
     run(nullptr, PR->n_act_rows, nullptr, 0);
     return;
   }
-  // the rows gather_matrix_clist_kernel did not fill
+  // the matrix gather kernels (contribution-list and mask kernels) fill b for every fast row; what is left are
+  // the rows of the generic kernel
   const cfx_form* a = fused_with;
-  if (a->n_band_listed > 0)
-    run(PR->band_idx.p, a->n_band_listed, a->row_fast.p, 1);
-  if (PR->n_act_rows - a->n_band_listed - a->n_clist_rows > 0)
-    run(nullptr, PR->n_act_rows, a->row_fast.p, 2);
+  if (a->n_slow_rows > 0)
+    run(nullptr, PR->n_act_rows, a->row_fast.p, 3);
 }
 
 #define CFX_DISPATCH_ELEM(ctx, S, FN, ...)                                                                             \
