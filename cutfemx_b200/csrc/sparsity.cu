@@ -1513,6 +1513,20 @@ __global__ void set_diagonal_kernel(const int32_t* __restrict__ rows, int64_t n,
   if (b)
     b[r] = rhs_value;
 }
+// blocked spaces: dof d -> blocked indices bs*d .. bs*d + bs-1 (deactivate.h:37-64 works on the unrolled array)
+__global__ void unroll_blocked_kernel(const int32_t* __restrict__ in, int64_t n, int bs, int32_t* __restrict__ out)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x;
+  if (i < n * bs)
+    out[i] = in[i / bs] * bs + static_cast<int32_t>(i % bs);
+}
+
+__global__ void set_entries_kernel(const int32_t* __restrict__ idx, int64_t n, double* __restrict__ b, double value)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x;
+  if (i < n)
+    b[idx[i]] = value;
+}
 } // namespace
 } // namespace cfx
 
@@ -1568,6 +1582,17 @@ cfx_status cfx_active_domain(cfx_ctx* ctx, const cfx_form* a_const, cfx_list** a
     *inactive_dofs = new cfx_list();
   ZeroBytePred p{a->prep->row_flag.p};
   (*inactive_dofs)->n = compact_indices(ctx, S.n_owned, p, (*inactive_dofs)->data);
+  if (S.bs > 1 && (*inactive_dofs)->n > 0)
+  { // the reference lists the rows of the unrolled (blocked) array: bs*dof + k
+    const int64_t n = (*inactive_dofs)->n;
+    DevBuf<int32_t> un;
+    un.reserve(ctx->pool, static_cast<size_t>(n) * S.bs);
+    CFX_LAUNCH(ctx, unroll_blocked_kernel, grid_for(n * S.bs, SBK), SBK, 0, (*inactive_dofs)->data.p, n, S.bs, un.p);
+    CFX_CUDA(cudaStreamSynchronize(ctx->stream));
+    (*inactive_dofs)->data.release();
+    (*inactive_dofs)->data = un;
+    (*inactive_dofs)->n = n * S.bs;
+  }
   CFX_API_END(ctx)
 }
 
@@ -1576,7 +1601,19 @@ cfx_status cfx_deactivate_outside(cfx_ctx* ctx, cfx_pattern* A, const int32_t* i
 {
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && A && (n == 0 || inactive_dofs), CFX_ERR_INVALID, "cfx_deactivate_outside: NULL argument");
-  CFX_REQUIRE(A->bs == 1, CFX_ERR_UNSUPPORTED, "cfx_deactivate_outside: blocked matrices are not supported yet");
+  if (n > 0 && A->bs > 1)
+  { // blocked matrix: the rows are blocked indices bs*dof + k (cfx_active_domain on a blocked space)
+    DevBuf<int32_t> own;
+    const int32_t* d = adopt(ctx, own, inactive_dofs, static_cast<size_t>(n), memspace);
+    cfx_status rc = cfx_set_diagonal(ctx, A, d, n, diagonal, CFX_DEVICE);
+    if (rc != CFX_OK)
+      return rc;
+    if (b)
+      CFX_LAUNCH(ctx, set_entries_kernel, grid_for(n, SBK), SBK, 0, d, n, b, rhs_value);
+    CFX_CUDA(cudaStreamSynchronize(ctx->stream));
+    own.release();
+    return CFX_OK;
+  }
   if (n > 0)
   {
     DevBuf<int32_t> own;

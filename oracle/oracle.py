@@ -288,15 +288,22 @@ def active_domain(space, cell_lists, rows4=None):
         parts += [r[:, 0], r[:, 2]]
     cells = np.unique(np.concatenate(parts)) if parts else np.zeros(0, np.int64)
     cells = cells[(cells >= 0) & (cells < nco)].astype(np.int32)
-    indicator = np.zeros(space.num_dofs)
-    for c in cells:  # mark_cell_dofs
-        indicator[space.dofmap[c]] = 1.0
-    inactive = np.nonzero(np.abs(indicator[: space.num_dofs_owned]) < 1.0e-8)[0].astype(np.int32)
+    bs = int(getattr(space, "bs", 1))
+    indicator = np.zeros(space.num_dofs * bs)
+    for c in cells:  # mark_cell_dofs (deactivate.h:37-46): values[bs * dof + k] = 1
+        for k in range(bs):
+            indicator[space.dofmap[c] * bs + k] = 1.0
+    inactive = np.nonzero(np.abs(indicator[: space.num_dofs_owned * bs]) < 1.0e-8)[0].astype(np.int32)
     return cells, inactive
 
 
-def deactivate_outside(row_ptr, cols, vals, inactive_dofs, diagonal=1.0, b=None, rhs_value=0.0):
+def deactivate_outside(row_ptr, cols, vals, inactive_dofs, diagonal=1.0, b=None, rhs_value=0.0, bs=1):
     """deactivate.h:402-418: dolfinx::fem::set_diagonal (sets A[r][r]) and b[r] = rhs_value."""
+    if bs > 1:
+        set_diagonal(row_ptr, cols, vals, inactive_dofs, diagonal, bs)
+        if b is not None:
+            b[np.asarray(inactive_dofs, dtype=np.int64)] = rhs_value
+        return vals
     for r in inactive_dofs:
         seg = cols[row_ptr[r]:row_ptr[r + 1]]
         k = int(np.searchsorted(seg, r))

@@ -54,7 +54,8 @@ def problem(request, built_lib):
     a.add_cell_integral("elasticity", g_inside, g_rv, (MU, LAM))
     a.add_interior_facet_integral("ghost_grad_jump", facets=g_ghost, constants=(GAMMA_G * (2 * MU + LAM),))
     L = cfx.fem.CutForm(V, 1).add_cell_integral("source_vec", g_inside, g_rv, FORCE)
-    return dict(cfx=cfx, mesh=mesh, V=V, bs=bs, rp=rp, cols=cols, ref=ref, bref=bref, a=a, L=L, inside=inside, rv=rv)
+    return dict(cfx=cfx, mesh=mesh, V=V, bs=bs, rp=rp, cols=cols, ref=ref, bref=bref, a=a, L=L, inside=inside, rv=rv,
+                rows4=rows4)
 
 
 def test_blocked_matrix_and_vector(problem):
@@ -139,3 +140,51 @@ def test_block_size_validation(built_lib):
         cfx.fem.CutForm(Vs, 2).add_cell_integral("elasticity", cells, None, (1.0, 1.0))
     with pytest.raises(cfx.CfxError):
         cfx.fem.CutForm(Vv, 2).add_cell_integral("laplace", cells, None, (1.0,))
+
+
+def test_blocked_active_domain_deactivation_and_clamped_solve(problem):
+    """demo_elasticity.py:78-95 on the vector space: assemble with Dirichlet conditions, lift, set_bc, deactivate the
+    dofs outside the active domain (unrolled blocked rows, deactivate.h:37-64,402-418) and solve: a rigid
+    translation prescribed on a clamped patch with zero load must come back as that translation everywhere."""
+    import scipy.sparse.linalg as spla
+
+    p = problem
+    cfx, V, bs = p["cfx"], p["V"], p["bs"]
+    a = p["a"]
+    ad = cfx.fem.active_domain(a)
+    cells_ref, inactive_ref = O.active_domain(V, [p["inside"], p["rv"].parent_map], p["rows4"])
+    assert np.array_equal(ad.active_cells, cells_ref) and np.array_equal(ad.inactive_dofs, inactive_ref)
+    n = V.num_dofs * bs
+    active = np.setdiff1d(np.arange(n), ad.inactive_dofs)
+    # clamp the blocked dofs of the active vertices in the lower half (x0 < median) to the translation t
+    t = np.array([0.2, -0.1, 0.05])[:bs]
+    x0 = V.dof_coords[:, 0]
+    med = np.median(x0[np.unique(active // bs)])
+    clamped = active[x0[active // bs] < med]
+    g = np.tile(t, V.num_dofs)
+    bc = cfx.fem.dirichletbc(g, clamped, V)
+    A = cfx.fem.assemble_matrix(a, bcs=[bc])
+    b = np.zeros(n)
+    cfx.fem.apply_lifting(b, [a], [[bc]], A=[A])
+    cfx.fem.set_bc(b, [bc])
+    # oracle for the same sequence
+    ref = np.zeros(p["cols"].size * bs * bs)
+    markers, values = cfx.fem._bc_arrays(V, [bc])
+    rows4 = p["rows4"]
+    with O.dirichlet("matrix", markers, markers):
+        O.assemble_cells(V, "elasticity", ref, p["inside"], p["rv"], (MU, LAM), p["rp"], p["cols"])
+        O.assemble_interior_facets(V, "ghost_grad_jump", ref, rows4, (GAMMA_G * (2 * MU + LAM),), p["rp"], p["cols"])
+    O.set_diagonal(p["rp"], p["cols"], ref, bc.owned_dofs(), 1.0, bs)
+    assert rel(A.data, ref) < 1e-11
+    cfx.fem.deactivate_outside(A, b, ad)
+    O.deactivate_outside(p["rp"], p["cols"], ref, inactive_ref, 1.0, None, 0.0, bs)
+    assert rel(A.data, ref) < 1e-11
+    # the translation (zero outside the active domain) solves the constrained, deactivated system
+    Ms = A.to_scipy()
+    gv = np.zeros(n)
+    gv[active] = g[active]
+    assert np.abs(Ms @ gv - b).max() <= 1e-9 * abs(Ms).max()
+    if V.degree == 1:  # P2 with the first-order jump penalty only is too ill-conditioned on sliver cuts to invert
+        u = spla.spsolve(Ms.tocsc(), b)
+        np.testing.assert_allclose(u[active].reshape(-1), g[active], rtol=0, atol=1e-9)
+        assert np.all(u[ad.inactive_dofs] == 0.0)
