@@ -22,6 +22,7 @@
 // FFCx would pick (sum of argument degrees) scaled by |detJ|.
 //
 // Roofline: HBM for P1/P2 scalar forms (SURVEY.md section 8d "K4", "K5").
+#include <cstdlib>
 #include <algorithm>
 
 #include "common.cuh"
@@ -1438,120 +1439,131 @@ __global__ void __launch_bounds__(GWM * 32, 8)
     vals[rb + lane] = acc;
 }
 
-// Static rows whose contribution lists fit (Space::fclist) -- the bulk of the matrix.  One WARP per
-// row.  A row needs four DEPENDENT load levels before any arithmetic:
+// Static rows whose contribution lists fit (Space::fclist) -- the bulk of the matrix.  One WARP per row.  A row
+// needs four DEPENDENT load levels before any arithmetic:
 //   (A) by row slot:  row flags, row id, kept-column mask R
 //   (B) by row id:    incidence range, CSR row start, full-pattern row start
 //   (C) by position:  lane l: incident cell l and the local index of the row's dof in it;
 //                     lane k: the contribution list of full-pattern column k and the CSR value it updates
 //   (D) by cell:      flag byte + geometry record (+ materialised tensor row for cut cells)
-// so the kernel is latency-bound unless the levels of different rows overlap.  Each warp therefore walks
-// its rows (grid-stride) in a software pipeline: while row i is computed (D), the loads of level C for
-// row i+s, level B for row i+2s and level A for row i+3s are in flight, and the cell records of row
-// i+s are prefetched into L2 as soon as its cell ids have arrived.
 // Per row: the tensor row of every incident cell is computed on the fly and staged (transposed,
 // conflict-free) in shared memory; lane k sums the <= 8 listed (cell, local dof) entries in
 // ascending cell order, the diagonal takes one entry per cell through a fixed shuffle tree.  No
 // atomics, no dofmap read, no column search, no element tensors through HBM for standard cells.
-struct ClistA
-{
-  unsigned rf;
-  int32_t r;
-  uint32_t R;
-};
-struct ClistB
-{
-  bool ok;
-  int32_t r;
-  uint32_t R;
-  int64_t ib, rb, fb;
-  int n_inc;
-};
-struct ClistC
-{
-  bool ok;
-  int32_t r;
-  uint32_t R;
-  int n_inc;
-  int32_t c;
-  int li;
-  uint64_t word;
-  double* pv;
-  double old;
-};
-
 struct ClistD
 {
   unsigned fl;
   int32_t ms;
 };
 
+// Rows in chunks of 32 per warp.  ncu on the first, per-row four-level software pipeline (row slot -> row id ->
+// incidence -> cell record, one row per stage) showed it bound by per-warp latency: time scales 1/warps up to
+// the register-limited 16 warps per SM, and the long-scoreboard stalls sat on values the PREVIOUS iteration had
+// loaded -- a pipelined load and its consumer are the same two static instructions every iteration, they share
+// a scoreboard, and the consumer also waits for the load just issued.  So the two row-level levels leave the
+// per-row chain: a warp takes 32 consecutive rows, lane l loads the scalars of row l (coalesced, two dependent
+// levels for 32 rows at once, issued one chunk ahead) and parks them in shared memory; the per-row pipeline
+// keeps only the per-cell levels (incidence -> cell record, one row ahead each) and reads its row record with
+// three broadcast 128-bit shared loads instead of seven global loads.
+struct alignas(16) ClistRow
+{
+  int32_t r;
+  uint32_t R;
+  int32_t n_inc; // < 0: not a contribution-list row (or past the end)
+  int32_t pad;
+  int64_t ib, rb, fb, pad2;
+};
+
 template <int TDIM, int DEG, bool FUSED>
 __global__ void __launch_bounds__(GWC * 32, 4)
     gather_matrix_clist_kernel(GatherCtx gc, StdTab st, StdTab stL, const int32_t* __restrict__ act_rows, int64_t n_act,
-                               const uint8_t* __restrict__ row_fast, const uint32_t* __restrict__ Rrow,
-                               const int64_t* __restrict__ row_ptr, double* __restrict__ vals, int zero_first)
+                                const uint8_t* __restrict__ row_fast, const uint32_t* __restrict__ Rrow,
+                                const int64_t* __restrict__ row_ptr, double* __restrict__ vals, int zero_first)
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
   static_assert(ND * 32 <= 255, "contribution-list bytes index the staging array directly");
-  // staged tensor rows: entry (local dof j, lane l) at index j * 32 + l == the byte the contribution list
-  // stores; index 255 (the list's "empty" byte) holds 0.0, so the column lanes add their eight slots
-  // without a test
   __shared__ double s_v[GWC][256];
+  __shared__ ClistRow s_rec[GWC][2][32];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
   const uint32_t below = (1u << lane) - 1u;
   double* const sv = s_v[w];
   if (lane == 0)
     sv[255] = 0.0;
-  // grid-stride over the rows: at any time the warps of the whole grid work on one contiguous window of
-  // rows, so the sweep over the mesh stays ordered and cell records shared by neighbouring rows / planes are
-  // re-used from L2 (a contiguous chunk per block measured 8.4 GB of DRAM traffic per launch, this 5.2 GB)
-  const int stride = static_cast<int>(gridDim.x) * GWC;
-  int i = static_cast<int>(blockIdx.x) * GWC + w;
-  const int i_end = static_cast<int>(n_act);
-  if (i >= i_end)
+  const int n_rows = static_cast<int>(n_act);
+  const int n_chunks = (n_rows + 31) >> 5;
+  const int cstride = static_cast<int>(gridDim.x) * GWC;
+  int chunk = static_cast<int>(blockIdx.x) * GWC + w;
+  if (chunk >= n_chunks)
     return;
 
-  auto stageA = [&](int idx) -> ClistA
+  // lane-parallel row records of one chunk: level 1 (by slot), level 2 (by row id)
+  struct L1
   {
-    ClistA a;
-    const int k = idx < i_end ? idx : i_end - 1; // clamped: the loads are always legal
-    a.rf = idx < i_end ? row_fast[k] : 0u;
+    unsigned rf;
+    int32_t r;
+    uint32_t R;
+  };
+  auto load1 = [&](int ch) -> L1
+  {
+    L1 a;
+    const int idx = ch * 32 + lane;
+    const bool in = ch < n_chunks && idx < n_rows;
+    const int k = in ? idx : n_rows - 1; // clamped: the loads are always legal
+    a.rf = in ? row_fast[k] : 0u;
     a.r = act_rows[k];
     a.R = Rrow[k];
     return a;
   };
-  auto stageB = [&](const ClistA& a) -> ClistB
+  auto load2 = [&](const L1& a) -> ClistRow
   {
-    ClistB b;
-    b.ok = (a.rf & 13u) == 13u;
-    b.r = a.r;
-    b.R = a.R;
-    b.ib = gc.inc_ptr[a.r];
-    b.n_inc = static_cast<int>(gc.inc_ptr[a.r + 1] - b.ib);
-    b.rb = row_ptr[a.r];
-    b.fb = gc.frow_ptr[a.r];
-    return b;
+    ClistRow q;
+    q.r = a.r;
+    q.R = a.R;
+    q.ib = gc.inc_ptr[a.r];
+    const int n_inc = static_cast<int>(gc.inc_ptr[a.r + 1] - q.ib);
+    q.n_inc = ((a.rf & 13u) == 13u) ? n_inc : -1;
+    q.pad = 0;
+    q.rb = row_ptr[a.r];
+    q.fb = gc.frow_ptr[a.r];
+    q.pad2 = 0;
+    return q;
   };
-  auto stageC = [&](const ClistB& b) -> ClistC
+  struct RowC
   {
-    ClistC c;
-    c.ok = b.ok;
-    c.r = b.r;
-    c.R = b.R;
-    c.n_inc = b.n_inc;
-    const int64_t kk = b.ib + (lane < b.n_inc ? lane : 0);
-    c.c = gc.inc_cell[kk];
-    c.li = static_cast<int>(gc.fperm[kk] & 15u);
-    c.word = __ldg(gc.fclist + b.fb + lane); // padded allocation: legal for every lane
-    c.pv = vals + b.rb + __popc(b.R & below);
-    const bool kept = (b.R >> lane) & 1u;
-    c.old = (b.ok && kept && !zero_first) ? *c.pv : 0.0;
+    bool ok;
+    int32_t r;
+    uint32_t R;
+    int n_inc;
+    int32_t c;
+    int li;
+    uint64_t word;
+    double* pv;
+    double old;
+  };
+  // level C of row k of the chunk in buffer `buf`: the row record (three broadcast shared loads), then by position
+  // lane l: incident cell l and the local index of the row's dof in it; lane k: contribution list + old value
+  auto stageC = [&](int buf, int k, int nk) -> RowC
+  {
+    RowC c;
+    const int kk = k < nk ? k : nk - 1;
+    const int4 q0 = *reinterpret_cast<const int4*>(&s_rec[w][buf][kk]);
+    const longlong2 q1 = *reinterpret_cast<const longlong2*>(&s_rec[w][buf][kk].ib);
+    const int64_t fb = s_rec[w][buf][kk].fb;
+    c.ok = k < nk && q0.z >= 0;
+    c.r = q0.x;
+    c.R = static_cast<uint32_t>(q0.y);
+    c.n_inc = q0.z < 0 ? 0 : q0.z;
+    const int64_t pos = q1.x + (lane < c.n_inc ? lane : 0);
+    c.c = gc.inc_cell[pos];
+    c.li = static_cast<int>(gc.fperm[pos] & 15u);
+    c.word = __ldg(gc.fclist + fb + lane); // padded allocation: legal for every lane
+    c.pv = vals + q1.y + __popc(c.R & below);
+    const bool kept = (c.R >> lane) & 1u;
+    c.old = (c.ok && kept && !zero_first) ? *c.pv : 0.0;
     return c;
   };
-  // level D: the cell's flag byte, geometry record and tensor slot, loaded into registers one row ahead
-  auto stageD = [&](const ClistC& c, Geo<TDIM>& g) -> ClistD
+  auto stageD = [&](const RowC& c, Geo<TDIM>& g) -> ClistD
   {
     ClistD d;
     d.fl = (c.ok && lane < c.n_inc) ? gc.cell_flags[c.c] : 0u;
@@ -1560,139 +1572,131 @@ __global__ void __launch_bounds__(GWC * 32, 4)
     return d;
   };
 
-  // prologue: rows i (D), i+s (C), i+2s (B), i+3s (A)
-  ClistA a3;
-  ClistB b2;
-  ClistC c0, c1;
-  ClistD d0;
-  Geo<TDIM> g0;
+  // first chunk: both levels exposed once per warp
   {
-    const ClistA a0 = stageA(i), a1 = stageA(i + stride), a2 = stageA(i + 2 * stride);
-    a3 = stageA(i + 3 * stride);
-    const ClistB b0 = stageB(a0), b1 = stageB(a1);
-    b2 = stageB(a2);
-    c0 = stageC(b0);
-    c1 = stageC(b1);
-    d0 = stageD(c0, g0);
+    const ClistRow q = load2(load1(chunk));
+    s_rec[w][0][lane] = q;
   }
-#pragma unroll 2
-  for (; i < i_end; i += stride)
+  __syncwarp();
+  int buf = 0;
+  for (; chunk < n_chunks; chunk += cstride, buf ^= 1)
   {
-    // loads of the rows ahead, issued before this row's arithmetic
-    const ClistA a4 = stageA(i + 4 * stride);
-    const ClistB b3 = stageB(a3);
-    const ClistC c2 = stageC(b2);
-    Geo<TDIM> g1;
-    const ClistD d1 = stageD(c1, g1);
-    // ---- arithmetic of row i: everything it needs is already in registers
-    if (c0.ok)
+    // the next chunk's level 1 goes out now, its level 2 after the first rows, both are parked at the chunk's end
+    const L1 n1 = load1(chunk + cstride);
+    const int nk = min(32, n_rows - chunk * 32);
+    RowC c0 = stageC(buf, 0, nk), c1 = stageC(buf, 1, nk);
+    Geo<TDIM> g0;
+    ClistD d0 = stageD(c0, g0);
+    ClistRow nq = load2(n1);
+#pragma unroll 2
+    for (int k = 0; k < nk; ++k)
     {
-      const unsigned fl = d0.fl;
-      const bool contributes = (fl & 0xFDu) != 0;
-      // every lane stages a row (zeros for a lane without a contributing cell): no activity test later
-      double v[ND];
-#pragma unroll
-      for (int j = 0; j < ND; ++j)
-        v[j] = 0.0;
-      double e = 0.0;
-      if (contributes)
+      Geo<TDIM> g1;
+      const ClistD d1 = stageD(c1, g1);
+      const RowC c2 = stageC(buf, k + 2, nk);
+      if (c0.ok)
       {
-        if (fl >> 2)
-        {
-          std_row_values<TDIM, DEG>(st, g0, fl, c0.li, v);
-          if constexpr (FUSED)
-          { // fused right-hand side: this cell's entry for the row (same order and tree as gather_vector_kernel)
-            const double s = fabs(g0.detJ);
-            if constexpr (DEG == 1)
-              e += stL.t0[fl >> 2] * s * (TDIM == 3 ? 1.0 / 24.0 : 1.0 / 6.0);
-            else if (stL.ref != nullptr)
-              e += stL.t0[fl >> 2] * s * stL.ref[RefTab<TDIM, ND>::S + c0.li];
-            else
-              for (int k = 0; k < stL.n; ++k)
-              {
-                if (!(fl & stL.bit[k]))
-                  continue;
-                for (int q = 0; q < stL.npts[k]; ++q)
-                {
-                  double xi[TDIM];
+        const unsigned fl = d0.fl;
+        const bool contributes = (fl & 0xFDu) != 0;
+        double v[ND];
 #pragma unroll
-                  for (int t = 0; t < TDIM; ++t)
-                    xi[t] = __ldg(stL.pts[k] + q * TDIM + t);
-                  double phi[ND], dphi[ND][TDIM];
-                  tabulate<TDIM, DEG>(xi, phi, dphi);
-                  e += stL.c[k][0] * (__ldg(stL.wts[k] + q) * s) * pick<ND>(phi, c0.li);
+        for (int j = 0; j < ND; ++j)
+          v[j] = 0.0;
+        double e = 0.0;
+        if (contributes)
+        {
+          if (fl >> 2)
+          {
+            std_row_values<TDIM, DEG>(st, g0, fl, c0.li, v);
+            if constexpr (FUSED)
+            {
+              const double s = fabs(g0.detJ);
+              if constexpr (DEG == 1)
+                e += stL.t0[fl >> 2] * s * (TDIM == 3 ? 1.0 / 24.0 : 1.0 / 6.0);
+              else if (stL.ref != nullptr)
+                e += stL.t0[fl >> 2] * s * stL.ref[RefTab<TDIM, ND>::S + c0.li];
+              else
+                for (int kk = 0; kk < stL.n; ++kk)
+                {
+                  if (!(fl & stL.bit[kk]))
+                    continue;
+                  for (int q = 0; q < stL.npts[kk]; ++q)
+                  {
+                    double xi[TDIM];
+#pragma unroll
+                    for (int t = 0; t < TDIM; ++t)
+                      xi[t] = __ldg(stL.pts[kk] + q * TDIM + t);
+                    double phi[ND], dphi[ND][TDIM];
+                    tabulate<TDIM, DEG>(xi, phi, dphi);
+                    e += stL.c[kk][0] * (__ldg(stL.wts[kk] + q) * s) * pick<ND>(phi, c0.li);
+                  }
                 }
-              }
+            }
+          }
+          if (fl & 1)
+          {
+            const double* a = gc.Ae + (static_cast<int64_t>(d0.ms) * ND + c0.li) * ND;
+#pragma unroll
+            for (int j = 0; j < ND; ++j)
+              v[j] += a[j];
+            if constexpr (FUSED)
+              e += gc.AeL[static_cast<int64_t>(d0.ms) * ND + c0.li];
           }
         }
-        if (fl & 1)
+        double dval = pick<ND>(v, c0.li);
+#pragma unroll
+        for (int j = 0; j < ND; ++j)
+          sv[j * 32 + lane] = v[j];
+        __syncwarp();
+        if constexpr (FUSED)
         {
-          const double* a = gc.Ae + (static_cast<int64_t>(d0.ms) * ND + c0.li) * ND;
+          const bool lower = lane < 16;
+          const double recv = __shfl_xor_sync(full, lower ? e : dval, 16);
+          double x = lower ? dval + recv : e + recv;
 #pragma unroll
-          for (int j = 0; j < ND; ++j)
-            v[j] += a[j];
-          if constexpr (FUSED)
-            e += gc.AeL[static_cast<int64_t>(d0.ms) * ND + c0.li];
+          for (int o = 8; o > 0; o >>= 1)
+            x += __shfl_down_sync(full, x, o);
+          if (lane == 16)
+            gc.bvec[c0.r] = gc.zero_first_b ? x : gc.bvec[c0.r] + x;
+          dval = __shfl_sync(full, x, 0);
         }
-      }
-      double dval = pick<ND>(v, c0.li);
-#pragma unroll
-      for (int j = 0; j < ND; ++j)
-        sv[j * 32 + lane] = v[j];
-      __syncwarp();
-      // two fixed shuffle trees: the diagonal entry and (fused) the right-hand-side entry.  Shuffles share the
-      // L1 data pipe with the gathers, so the fused case folds both trees into one: after ONE exchange at
-      // distance 16 the lower half-warp carries the diagonal tree and the upper half the right-hand-side tree;
-      // the four remaining levels serve both.  Each tree keeps the operands and the shape of the plain
-      // shfl_down tree (result in lane 0 / lane 16), so b stays bit-identical to gather_vector_kernel's.
-      if constexpr (FUSED)
-      {
-        const bool lower = lane < 16;
-        const double recv = __shfl_xor_sync(full, lower ? e : dval, 16);
-        double x = lower ? dval + recv : e + recv;
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1)
-          x += __shfl_down_sync(full, x, o);
-        if (lane == 16)
-          gc.bvec[c0.r] = gc.zero_first_b ? x : gc.bvec[c0.r] + x;
-        dval = __shfl_sync(full, x, 0);
-      }
-      else
-      {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-          dval += __shfl_down_sync(full, dval, o);
-        dval = __shfl_sync(full, dval, 0);
-      }
-      if ((c0.R >> lane) & 1u)
-      {
-        double acc = c0.old;
-        const uint32_t lo = static_cast<uint32_t>(c0.word), hi = static_cast<uint32_t>(c0.word >> 32);
-        if ((lo & 0xFFu) == 0xFEu)
-          acc += dval;
         else
-        { // ascending-cell order; empty slots read the 0.0 at index 255 (x + 0.0 == x)
-          const double t0 = sv[lo & 0xFFu], t1 = sv[(lo >> 8) & 0xFFu], t2 = sv[(lo >> 16) & 0xFFu], t3 = sv[lo >> 24];
-          const double t4 = sv[hi & 0xFFu], t5 = sv[(hi >> 8) & 0xFFu], t6 = sv[(hi >> 16) & 0xFFu], t7 = sv[hi >> 24];
-          acc += t0;
-          acc += t1;
-          acc += t2;
-          acc += t3;
-          acc += t4;
-          acc += t5;
-          acc += t6;
-          acc += t7;
+        {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+            dval += __shfl_down_sync(full, dval, o);
+          dval = __shfl_sync(full, dval, 0);
         }
-        *c0.pv = acc;
+        if ((c0.R >> lane) & 1u)
+        {
+          double acc = c0.old;
+          const uint32_t lo = static_cast<uint32_t>(c0.word), hi = static_cast<uint32_t>(c0.word >> 32);
+          if ((lo & 0xFFu) == 0xFEu)
+            acc += dval;
+          else
+          {
+            const double t0 = sv[lo & 0xFFu], t1 = sv[(lo >> 8) & 0xFFu], t2 = sv[(lo >> 16) & 0xFFu], t3 = sv[lo >> 24];
+            const double t4 = sv[hi & 0xFFu], t5 = sv[(hi >> 8) & 0xFFu], t6 = sv[(hi >> 16) & 0xFFu], t7 = sv[hi >> 24];
+            acc += t0;
+            acc += t1;
+            acc += t2;
+            acc += t3;
+            acc += t4;
+            acc += t5;
+            acc += t6;
+            acc += t7;
+          }
+          *c0.pv = acc;
+        }
+        __syncwarp(); // s_v is reused by the next row
       }
-      __syncwarp(); // s_v is reused by the next row
+      c0 = c1;
+      c1 = c2;
+      d0 = d1;
+      g0 = g1;
     }
-    a3 = a4;
-    b2 = b3;
-    c0 = c1;
-    c1 = c2;
-    d0 = d1;
-    g0 = g1;
+    s_rec[w][buf ^ 1][lane] = nq;
+    __syncwarp();
   }
 }
 
