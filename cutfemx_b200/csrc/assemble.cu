@@ -42,6 +42,7 @@ struct RuleView
   const int32_t* offsets;
   const int32_t* parent_map;
   int64_t npts;
+  const double* mom;  // (nrules, tdim + 1) measure and first moments, or null (cfx_rules::moments)
 };
 
 struct StdRule
@@ -306,9 +307,28 @@ __global__ void __launch_bounds__(EB)
     else
       return w;
   };
+  // P1 integrands that are constant (Laplace, measure) or linear (source) in xi: the rule's measure W and its
+  // first moments give the sum over the points exactly -- one evaluation at the rule's centroid with weight W
+  // instead of a pass over the points (the generator computed W and the moments, quadrature.cu)
+  constexpr bool LINEAR = DEG == 1 && (KID == CFX_K_LAPLACE || KID == CFX_K_SOURCE || KID == CFX_K_ONE);
+  bool done = false;
+  if constexpr (RUNTIME && LINEAR)
+  {
+    if (rv.mom != nullptr)
+    {
+      const double* mo = rv.mom + e * (TDIM + 1);
+      const double W = mo[0];
+      double xi[TDIM];
+#pragma unroll
+      for (int t = 0; t < TDIM; ++t)
+        xi[t] = W != 0.0 ? mo[1 + t] / W : 0.0;
+      point_contribution<TDIM, DEG, KID>(g, xi, W, nq, h, cs, acc);
+      done = true;
+    }
+  }
   if constexpr (RUNTIME)
   {
-    const int32_t q0 = rv.offsets[e], q1 = rv.offsets[e + 1];
+    const int32_t q0 = rv.offsets[e], q1 = done ? rv.offsets[e] : rv.offsets[e + 1];
     for (int32_t q = q0; q < q1; ++q)
     {
       double xi[TDIM];
@@ -1826,7 +1846,7 @@ void launch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t& base)
     const cfx_rules* R = I.rules;
     CFX_REQUIRE(R->tdim == TDIM, CFX_ERR_INVALID, "run-time rules have the wrong reference dimension");
     rv = RuleView{R->points.p, R->weights.p, R->has_normals ? R->normals.p : nullptr, R->offsets.p, R->parent_map.p,
-                  R->npts};
+                  R->npts, R->has_moments ? R->moments.p : nullptr};
     auto k = cell_kernel<TDIM, DEG, KID, true>;
     CFX_LAUNCH(c, k, grid_for(R->nrules, EB), EB, 0, nullptr, R->nrules, rv, sr, cs, c->x, c->x_dofmap, oc, f->coeff,
                c->spaces[f->space].dofmap);
@@ -2589,6 +2609,17 @@ void build_geometry_cache(cfx_ctx* c)
 using namespace cfx;
 
 
+// bytes a cell kernel reads from an integral's run-time rules: every point (coordinates, weight, normal), or --
+// P1 kernels served by the rule moments (cell_kernel, LINEAR) -- tdim + 1 doubles per rule
+static double rule_read_bytes(const cfx_ctx* ctx, const Space& S, const cfx_integral& I)
+{
+  const bool linear = S.degree == 1 && S.bs == 1 && I.rules->has_moments
+                      && (I.kernel == CFX_K_LAPLACE || I.kernel == CFX_K_SOURCE || I.kernel == CFX_K_ONE);
+  if (linear)
+    return 8.0 * (ctx->tdim + 1) * static_cast<double>(I.rules->nrules);
+  return 8.0 * (ctx->tdim + 1 + (I.rules->has_normals ? ctx->tdim : 0)) * static_cast<double>(I.rules->npts);
+}
+
 // assemble_matrix, optionally fused with the right-hand side of a linear form over the same prepared
 // domains (L != null): its run-time-rule entries are materialised into the bilinear form's slots and the
 // contribution-list kernel fills b for its rows in the same pass over the incidence.
@@ -2609,7 +2640,7 @@ static void assemble_matrix_impl(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, int 
     double by = 0.0;
     for (auto& I : a->integrals)
       if (!I.facet && I.rules)
-        by += 8.0 * (ctx->tdim + 1 + (I.rules->has_normals ? ctx->tdim : 0)) * static_cast<double>(I.rules->npts)
+        by += rule_read_bytes(ctx, S, I)
               + (8.0 + 28.0 * ctx->nv + 8.0 * nd * nd) * static_cast<double>(I.rules->nrules);
     st.set_bytes(by);
   }
@@ -2620,7 +2651,7 @@ static void assemble_matrix_impl(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, int 
     double by = 0.0;
     for (auto& I : L->integrals)
       if (!I.facet && I.rules)
-        by += 8.0 * (ctx->tdim + 1 + (I.rules->has_normals ? ctx->tdim : 0)) * static_cast<double>(I.rules->npts)
+        by += rule_read_bytes(ctx, S, I)
               + (8.0 + 28.0 * ctx->nv + 8.0 * nd) * static_cast<double>(I.rules->nrules);
     st.set_bytes(by);
   }
@@ -2742,7 +2773,7 @@ cfx_status cfx_assemble_vector(cfx_ctx* ctx, const cfx_form* L_const, double* b,
     double by = 0.0;
     for (auto& I : L->integrals)
       if (!I.facet && I.rules)
-        by += 8.0 * (ctx->tdim + 1 + (I.rules->has_normals ? ctx->tdim : 0)) * static_cast<double>(I.rules->npts)
+        by += rule_read_bytes(ctx, S, I)
               + (8.0 + 28.0 * ctx->nv + 8.0 * S.nd) * static_cast<double>(I.rules->nrules);
     st.set_bytes(by);
   }

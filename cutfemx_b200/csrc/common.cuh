@@ -180,6 +180,7 @@ struct Space
 struct RuleTable
 {
   int dim = 0, order = 0, npts = 0;
+  bool builtin = true; // false: supplied through cfx_set_simplex_rule (exactness unknown)
   std::vector<double> pts, wts; // host
   double* d_pts = nullptr;      // device, (npts, dim) AoS
   double* d_wts = nullptr;
@@ -209,6 +210,11 @@ struct cfx_rules
   cfx::DevBuf<int32_t> parent_map; // (nrules)
   cfx::DevBuf<double> normals;     // SoA (gdim, npts), valid if has_normals
   bool has_normals = false;
+  // volume rules from the built-in tables (exact for degree >= 1): per rule W = sum_q w_q and the first moments
+  // sum_q w_q xi_q, computed in the generator from the sub-simplex measures and centroids -- the P1 kernels whose
+  // integrand is linear in xi (Laplace, source, measure) need nothing else.  Layout (nrules, tdim + 1).
+  cfx::DevBuf<double> moments;
+  bool has_moments = false;
 };
 
 struct cfx_pattern

@@ -321,7 +321,8 @@ __global__ void __launch_bounds__(QB)
                      const int32_t* __restrict__ x_dofmap, const double* __restrict__ x, bool positive, bool interface,
                      int npts_s, const double* __restrict__ rule_pts, const double* __restrict__ rule_wts,
                      int64_t npts_total, double* __restrict__ points /* SoA (TDIM, npts_total) */,
-                     double* __restrict__ weights, int32_t* __restrict__ offsets, int32_t* __restrict__ parent_map)
+                     double* __restrict__ weights, int32_t* __restrict__ offsets, int32_t* __restrict__ parent_map,
+                     double* __restrict__ moments /* (nrules, TDIM + 1) or null */)
 {
   constexpr int NV = TDIM + 1;
   __shared__ CutSmem<TDIM> sm;
@@ -389,6 +390,10 @@ __global__ void __launch_bounds__(QB)
       Geo<TDIM> g;
       make_geo<TDIM>(X, g);
       const int nsub = num_sub(TDIM, interface, n_in);
+      double mW = 0.0, mX[TDIM];
+#pragma unroll
+      for (int t = 0; t < TDIM; ++t)
+        mX[t] = 0.0;
       for (int s = 0; s < nsub; ++s)
       {
         double scale;
@@ -408,6 +413,18 @@ __global__ void __launch_bounds__(QB)
             det = M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0])
                   + M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
           scale = fabs(det) * fabs(g.detJ);
+          // measure and first moments of the sub-simplex: W_s = scale / tdim!, centroid = vertex mean
+          const double Ws = scale * (TDIM == 2 ? 0.5 : 1.0 / 6.0);
+          mW += Ws;
+#pragma unroll
+          for (int t = 0; t < TDIM; ++t)
+          {
+            double cs = 0.0;
+#pragma unroll
+            for (int vtx = 0; vtx < NV; ++vtx)
+              cs += P[sv[vtx] * TDIM + t];
+            mX[t] += Ws * (cs * (1.0 / NV));
+          }
         }
         else
         {
@@ -438,6 +455,14 @@ __global__ void __launch_bounds__(QB)
           }
         }
         sm.scale[tid][s] = scale;
+      }
+      if (moments && !interface)
+      {
+        double* mo = moments + rule * (TDIM + 1);
+        mo[0] = mW;
+#pragma unroll
+        for (int t = 0; t < TDIM; ++t)
+          mo[1 + t] = mX[t];
       }
     }
   }
@@ -708,6 +733,7 @@ void run_quadrature(cfx_ctx* c, const LevelSet& L, cfx_rules* R, bool positive, 
   if (n_cut == 0)
   {
     R->nrules = R->npts = 0;
+    R->has_moments = false;
     R->points.reserve(c->pool, 1);
     R->weights.reserve(c->pool, 1);
     R->offsets.reserve(c->pool, 1);
@@ -729,9 +755,13 @@ void run_quadrature(cfx_ctx* c, const LevelSet& L, cfx_rules* R, bool positive, 
   R->weights.reserve(c->pool, static_cast<size_t>(R->npts) + 1);
   R->offsets.reserve(c->pool, static_cast<size_t>(R->nrules) + 1);
   R->parent_map.reserve(c->pool, static_cast<size_t>(R->nrules) + 1);
+  // moments only where the point sums they replace are exact: built-in rule of degree >= 1, volume part
+  R->has_moments = !interface && rt.builtin && rt.order >= 1;
+  if (R->has_moments)
+    R->moments.reserve(c->pool, static_cast<size_t>(R->nrules) * (TDIM + 1) + 1);
   CFX_LAUNCH(c, rule_fill_kernel<TDIM>, grid_for(n_cut, QB), QB, 0, L.cut_list.p, n_cut, packed_excl.p, L.dofmap,
              L.values, c->x_dofmap, c->x, positive, interface, rt.npts, rt.d_pts, rt.d_wts, R->npts, R->points.p,
-             R->weights.p, R->offsets.p, R->parent_map.p);
+             R->weights.p, R->offsets.p, R->parent_map.p, R->has_moments ? R->moments.p : nullptr);
   packed.release();
   packed_excl.release();
 }
@@ -769,6 +799,7 @@ cfx_status cfx_set_simplex_rule(cfx_ctx* ctx, int dim, int order, int npts, cons
   t.dim = dim;
   t.order = order;
   t.npts = npts;
+  t.builtin = false;
   t.pts.assign(points, points + static_cast<size_t>(npts) * dim);
   t.wts.assign(weights, weights + npts);
   auto key = std::make_pair(dim, order);
@@ -899,6 +930,7 @@ void cfx_rules_free(cfx_ctx* ctx, cfx_rules* r)
   r->offsets.release();
   r->parent_map.release();
   r->normals.release();
+  r->moments.release();
   delete r;
 }
 

@@ -111,27 +111,54 @@ __global__ void fperm_kernel(int64_t n_dofs, const int64_t* __restrict__ inc_ptr
   }
 }
 
-// One thread per listed cell (cells[i * stride]): set `bit` in the cell's flag byte and store
-// `rowval` in the row flag of each of its dofs.  All writers of one launch store the same values,
-// so the plain byte stores are race-free in effect (idempotent).
+// MC listed cells per thread (cells[i * stride]), warp-strided: set `bit` in each cell's flag byte and store
+// `rowval` in the row flag of each of its dofs.  All writers of one launch store the same values, so the plain
+// byte stores are race-free in effect (idempotent).  The kernel is a chain list -> (flag byte, dofmap row) ->
+// stores and nothing else: the loads of the MC cells are batched level by level.
+constexpr int MC = 4;
 __global__ void mark_cells_kernel(const int32_t* __restrict__ cells, int64_t n, int stride, int64_t limit, uint8_t bit,
                                   const int32_t* __restrict__ dofmap, int nd, uint8_t rowval,
                                   uint8_t* __restrict__ cell_flags, uint8_t* __restrict__ row_flag,
                                   int32_t* __restrict__ err)
 {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x;
-  if (i >= n)
-    return;
-  const int32_t c = cells[i * stride];
-  if (c < 0 || c >= limit)
+  constexpr int NDMAX = 10;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x) >> 5;
+  const int64_t i0 = warp * (32 * MC) + lane;
+  int32_t c[MC];
+#pragma unroll
+  for (int q = 0; q < MC; ++q)
   {
-    err[0] = 22;
-    err[1] = c;
-    return;
+    const int64_t i = i0 + 32 * q;
+    c[q] = i < n ? cells[i * stride] : -1;
+    if (i < n && (c[q] < 0 || c[q] >= limit))
+    {
+      err[0] = 22;
+      err[1] = c[q];
+      c[q] = -1;
+    }
   }
-  cell_flags[c] |= bit;
-  for (int j = 0; j < nd; ++j)
-    row_flag[dofmap[static_cast<int64_t>(c) * nd + j]] = rowval;
+  uint8_t f[MC];
+  int32_t d[MC][NDMAX];
+#pragma unroll
+  for (int q = 0; q < MC; ++q)
+  {
+    f[q] = c[q] >= 0 ? cell_flags[c[q]] : uint8_t(0);
+#pragma unroll
+    for (int j = 0; j < NDMAX; ++j)
+      d[q][j] = (c[q] >= 0 && j < nd) ? dofmap[static_cast<int64_t>(c[q]) * nd + j] : -1;
+  }
+#pragma unroll
+  for (int q = 0; q < MC; ++q)
+  {
+    if (c[q] < 0)
+      continue;
+    cell_flags[c[q]] = f[q] | bit;
+#pragma unroll
+    for (int j = 0; j < NDMAX; ++j)
+      if (d[q][j] >= 0)
+        row_flag[d[q][j]] = rowval;
+  }
 }
 
 // rows of inserted pattern entries: active (bit0) and generic (bit1)
@@ -961,23 +988,23 @@ void prepare_form(cfx_ctx* c, cfx_form* f)
   P->n_active_entities = 0;
   for (size_t i = 0; i < skey.size(); ++i)
   {
-    CFX_LAUNCH(c, mark_cells_kernel, grid_for(skey[i].second, SBK), SBK, 0, static_cast<const int32_t*>(skey[i].first),
+    CFX_LAUNCH(c, mark_cells_kernel, grid_for((skey[i].second + MC - 1) / MC, SBK), SBK, 0, static_cast<const int32_t*>(skey[i].first),
                skey[i].second, 1, c->nc_total, static_cast<uint8_t>(4u << i), S.dofmap, S.nd, uint8_t(1),
                P->cell_flags.p, P->row_flag.p, c->err_flag.p);
     P->n_active_entities += skey[i].second;
   }
   for (auto& k : rkey)
   {
-    CFX_LAUNCH(c, mark_cells_kernel, grid_for(k.second, SBK), SBK, 0, static_cast<const int32_t*>(k.first), k.second, 1,
+    CFX_LAUNCH(c, mark_cells_kernel, grid_for((k.second + MC - 1) / MC, SBK), SBK, 0, static_cast<const int32_t*>(k.first), k.second, 1,
                c->nc_total, uint8_t(1), S.dofmap, S.nd, uint8_t(1), P->cell_flags.p, P->row_flag.p, c->err_flag.p);
     P->n_active_entities += k.second;
   }
   if (fkey.first)
   { // both cells of every facet row (cell0, lf0, cell1, lf1); launched after the cell lists: 3 supersedes 1
     const int32_t* rows4 = static_cast<const int32_t*>(fkey.first);
-    CFX_LAUNCH(c, mark_cells_kernel, grid_for(fkey.second, SBK), SBK, 0, rows4, fkey.second, 4, c->nc_total, uint8_t(2),
+    CFX_LAUNCH(c, mark_cells_kernel, grid_for((fkey.second + MC - 1) / MC, SBK), SBK, 0, rows4, fkey.second, 4, c->nc_total, uint8_t(2),
                S.dofmap, S.nd, uint8_t(3), P->cell_flags.p, P->row_flag.p, c->err_flag.p);
-    CFX_LAUNCH(c, mark_cells_kernel, grid_for(fkey.second, SBK), SBK, 0, rows4 + 2, fkey.second, 4, c->nc_total,
+    CFX_LAUNCH(c, mark_cells_kernel, grid_for((fkey.second + MC - 1) / MC, SBK), SBK, 0, rows4 + 2, fkey.second, 4, c->nc_total,
                uint8_t(2), S.dofmap, S.nd, uint8_t(3), P->cell_flags.p, P->row_flag.p, c->err_flag.p);
   }
   if (xkey.first)
