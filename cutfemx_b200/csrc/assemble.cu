@@ -42,7 +42,8 @@ struct RuleView
   const int32_t* offsets;
   const int32_t* parent_map;
   int64_t npts;
-  const double* mom;  // (nrules, tdim + 1) measure and first moments, or null (cfx_rules::moments)
+  const double* mom;  // per rule: measure, first (and, interface rules, second) moments, or null (cfx_rules::moments)
+  int mom_stride;     // tdim + 1 (volume rules) or 1 + tdim + tdim (tdim + 1) / 2 (interface rules)
 };
 
 struct StdRule
@@ -316,13 +317,113 @@ __global__ void __launch_bounds__(EB)
   {
     if (rv.mom != nullptr)
     {
-      const double* mo = rv.mom + e * (TDIM + 1);
+      const double* mo = rv.mom + e * rv.mom_stride;
       const double W = mo[0];
       double xi[TDIM];
 #pragma unroll
       for (int t = 0; t < TDIM; ++t)
         xi[t] = W != 0.0 ? mo[1 + t] / W : 0.0;
       point_contribution<TDIM, DEG, KID>(g, xi, W, nq, h, cs, acc);
+      done = true;
+    }
+  }
+  // P1 Nitsche terms on an interface rule: the normal is constant on the cell (P1 level set), the integrand is
+  // quadratic in xi -> measure, first and second moments give the point sums exactly:
+  //   phi_i = a_i + b_i . xi (a_0 = 1, b_0 = -1, a_t = 0, b_t = e_t)
+  //   S_i = sum w phi_i = a_i W + b_i . M1,   Q_ij = sum w phi_i phi_j = a_i a_j W + a_i b_j.M1 + a_j b_i.M1 + b_i^T M2 b_j
+  constexpr bool QUAD = DEG == 1 && (KID == CFX_K_NITSCHE || KID == CFX_K_NITSCHE_RHS);
+  if constexpr (RUNTIME && QUAD)
+  {
+    constexpr int NM2 = TDIM * (TDIM + 1) / 2;
+    if (rv.mom != nullptr && rv.mom_stride == 1 + TDIM + NM2 && rv.offsets[e + 1] > rv.offsets[e])
+    {
+      const double* mo = rv.mom + e * rv.mom_stride;
+      const double W = mo[0];
+      double M1[TDIM], M2[TDIM][TDIM];
+#pragma unroll
+      for (int t = 0; t < TDIM; ++t)
+        M1[t] = mo[1 + t];
+      {
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < TDIM; ++a)
+#pragma unroll
+          for (int b = a; b < TDIM; ++b)
+          {
+            M2[a][b] = mo[1 + TDIM + k];
+            M2[b][a] = M2[a][b];
+            ++k;
+          }
+      }
+      const int32_t qf = rv.offsets[e];
+#pragma unroll
+      for (int r = 0; r < TDIM; ++r)
+        nq[r] = rv.nrm[static_cast<int64_t>(r) * rv.npts + qf];
+      // constant gradients and their normal components
+      double xi0[TDIM];
+#pragma unroll
+      for (int t = 0; t < TDIM; ++t)
+        xi0[t] = 0.0;
+      double phi0[ND], dphi[ND][TDIM], grad[ND][TDIM], gn[ND];
+      tabulate<TDIM, DEG>(xi0, phi0, dphi);
+      push_gradients<TDIM, ND>(g, dphi, grad);
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+      {
+        double sgn = 0.0;
+#pragma unroll
+        for (int r = 0; r < TDIM; ++r)
+          sgn += grad[i][r] * nq[r];
+        gn[i] = sgn;
+      }
+      double Sv[ND];
+      double m1sum = 0.0;
+#pragma unroll
+      for (int t = 0; t < TDIM; ++t)
+        m1sum += M1[t];
+      Sv[0] = W - m1sum;
+#pragma unroll
+      for (int t = 0; t < TDIM; ++t)
+        Sv[t + 1] = M1[t];
+      if constexpr (KID == CFX_K_NITSCHE)
+      {
+        // Q: rows/cols >= 1 are M2; row 0 follows from phi_0 = 1 - sum_t phi_t
+        double Q[ND][ND];
+#pragma unroll
+        for (int a = 0; a < TDIM; ++a)
+#pragma unroll
+          for (int b = 0; b < TDIM; ++b)
+            Q[a + 1][b + 1] = M2[a][b];
+#pragma unroll
+        for (int b = 0; b < TDIM; ++b)
+        {
+          double rs = 0.0;
+#pragma unroll
+          for (int a = 0; a < TDIM; ++a)
+            rs += M2[a][b];
+          Q[0][b + 1] = M1[b] - rs; // sum w (1 - sum_a xi_a) xi_b
+          Q[b + 1][0] = Q[0][b + 1];
+        }
+        {
+          double q00 = Sv[0];
+#pragma unroll
+          for (int b = 0; b < TDIM; ++b)
+            q00 -= Q[0][b + 1]; // sum w phi_0 (1 - sum_b xi_b)
+          Q[0][0] = q00;
+        }
+        const double pen = cs.c[0] / h;
+#pragma unroll
+        for (int i = 0; i < ND; ++i)
+#pragma unroll
+          for (int j = 0; j < ND; ++j)
+            acc[i * ND + j] += -gn[j] * Sv[i] - gn[i] * Sv[j] + pen * Q[i][j];
+      }
+      else
+      { // CFX_K_NITSCHE_RHS
+#pragma unroll
+        for (int i = 0; i < ND; ++i)
+          acc[i] += -gn[i] * cs.c[1] * W + cs.c[0] / h * cs.c[1] * Sv[i];
+      }
       done = true;
     }
   }
@@ -1846,7 +1947,8 @@ void launch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t& base)
     const cfx_rules* R = I.rules;
     CFX_REQUIRE(R->tdim == TDIM, CFX_ERR_INVALID, "run-time rules have the wrong reference dimension");
     rv = RuleView{R->points.p, R->weights.p, R->has_normals ? R->normals.p : nullptr, R->offsets.p, R->parent_map.p,
-                  R->npts, R->has_moments ? R->moments.p : nullptr};
+                  R->npts, R->has_moments ? R->moments.p : nullptr,
+                  1 + TDIM + (R->relation == CFX_REL_EQ ? TDIM * (TDIM + 1) / 2 : 0)};
     auto k = cell_kernel<TDIM, DEG, KID, true>;
     CFX_LAUNCH(c, k, grid_for(R->nrules, EB), EB, 0, nullptr, R->nrules, rv, sr, cs, c->x, c->x_dofmap, oc, f->coeff,
                c->spaces[f->space].dofmap);
@@ -2613,10 +2715,13 @@ using namespace cfx;
 // P1 kernels served by the rule moments (cell_kernel, LINEAR) -- tdim + 1 doubles per rule
 static double rule_read_bytes(const cfx_ctx* ctx, const Space& S, const cfx_integral& I)
 {
+  const bool ifc = I.rules->relation == CFX_REL_EQ;
   const bool linear = S.degree == 1 && S.bs == 1 && I.rules->has_moments
-                      && (I.kernel == CFX_K_LAPLACE || I.kernel == CFX_K_SOURCE || I.kernel == CFX_K_ONE);
+                      && (I.kernel == CFX_K_LAPLACE || I.kernel == CFX_K_SOURCE || I.kernel == CFX_K_ONE
+                          || (ifc && (I.kernel == CFX_K_NITSCHE || I.kernel == CFX_K_NITSCHE_RHS)));
   if (linear)
-    return 8.0 * (ctx->tdim + 1) * static_cast<double>(I.rules->nrules);
+    return 8.0 * (1 + ctx->tdim + (ifc ? ctx->tdim * (ctx->tdim + 1) / 2 + ctx->tdim : 0))
+           * static_cast<double>(I.rules->nrules);
   return 8.0 * (ctx->tdim + 1 + (I.rules->has_normals ? ctx->tdim : 0)) * static_cast<double>(I.rules->npts);
 }
 
@@ -2700,11 +2805,13 @@ static void assemble_matrix_impl(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, int 
   if (L)
   {
     // rows the contribution-list kernel did not own (band rows, generic rows); inactive rows keep 0 / b
-    StageScope st(ctx, "gather_vector", 8.0 * static_cast<double>(S.n_total));
-    GatherCtx gl = make_gather_ctx(ctx, L, nullptr);
-    const StdTab stl = make_std_tab(ctx, L);
     const bool fused = S.bs == 1 && a->gtab_serial == A->serial && a->gtab_serial > 0 && S.has_perm && S.has_static
                        && a->n_clist_rows > 0 && S.nd <= 6; // same condition as fuse_b above
+    // fused: the matrix gather kernels have written b for every fast row; only generic rows are left
+    StageScope st(ctx, "gather_vector", fused ? 8.0 * static_cast<double>(a->n_slow_rows)
+                                              : 8.0 * static_cast<double>(S.n_total));
+    GatherCtx gl = make_gather_ctx(ctx, L, nullptr);
+    const StdTab stl = make_std_tab(ctx, L);
     CFX_DISPATCH_ELEM(ctx, S, launch_gather_vector, ctx, L, gl, stl, d_b, zero_first_b, fused ? a : nullptr);
   }
   reset_slots(ctx, a);

@@ -213,6 +213,8 @@ struct cfx_rules
   // volume rules from the built-in tables (exact for degree >= 1): per rule W = sum_q w_q and the first moments
   // sum_q w_q xi_q, computed in the generator from the sub-simplex measures and centroids -- the P1 kernels whose
   // integrand is linear in xi (Laplace, source, measure) need nothing else.  Layout (nrules, tdim + 1).
+  // Interface rules (exact for degree >= 2) add the second moments sum_q w_q xi_a xi_b (upper triangle): layout
+  // (nrules, 1 + tdim + tdim (tdim+1)/2) -- enough for the P1 Nitsche kernels, whose normal is constant per rule.
   cfx::DevBuf<double> moments;
   bool has_moments = false;
 };

@@ -314,11 +314,11 @@ struct CutSmem
   int8_t n_in[QB];
 };
 
-template <int TDIM>
+template <int TDIM, bool interface>
 __global__ void __launch_bounds__(QB)
     rule_fill_kernel(const int32_t* __restrict__ cut_cells, int64_t n_cut, const int64_t* __restrict__ packed_excl,
                      const int32_t* __restrict__ ls_dofmap, const double* __restrict__ vals,
-                     const int32_t* __restrict__ x_dofmap, const double* __restrict__ x, bool positive, bool interface,
+                     const int32_t* __restrict__ x_dofmap, const double* __restrict__ x, bool positive,
                      int npts_s, const double* __restrict__ rule_pts, const double* __restrict__ rule_wts,
                      int64_t npts_total, double* __restrict__ points /* SoA (TDIM, npts_total) */,
                      double* __restrict__ weights, int32_t* __restrict__ offsets, int32_t* __restrict__ parent_map,
@@ -390,10 +390,13 @@ __global__ void __launch_bounds__(QB)
       Geo<TDIM> g;
       make_geo<TDIM>(X, g);
       const int nsub = num_sub(TDIM, interface, n_in);
-      double mW = 0.0, mX[TDIM];
+      double mW = 0.0, mX[TDIM], mXX[TDIM * (TDIM + 1) / 2];
 #pragma unroll
       for (int t = 0; t < TDIM; ++t)
         mX[t] = 0.0;
+#pragma unroll
+      for (int t = 0; t < TDIM * (TDIM + 1) / 2; ++t)
+        mXX[t] = 0.0;
       for (int s = 0; s < nsub; ++s)
       {
         double scale;
@@ -453,16 +456,50 @@ __global__ void __launch_bounds__(QB)
             const double cx = u1 * w2 - u2 * w1, cy = u2 * w0 - u0 * w2, cz = u0 * w1 - u1 * w0;
             scale = sqrt(cx * cx + cy * cy + cz * cz); // = 2 * area = area * (tdim-1)!
           }
+          // measure, first and second moments (reference coordinates) of the interface simplex with vertices v:
+          // int xi_a = |T| mean(v_a),  int xi_a xi_b = |T| (sum v_a sum v_b + sum v_a v_b) / (n (n + 1)), n = tdim
+          const double Ws = scale * (TDIM == 3 ? 0.5 : 1.0);
+          mW += Ws;
+          double sa[TDIM];
+#pragma unroll
+          for (int t = 0; t < TDIM; ++t)
+          {
+            double cs = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < TDIM; ++kk)
+              cs += P[sv[kk] * TDIM + t];
+            sa[t] = cs;
+            mX[t] += Ws * (cs * (1.0 / TDIM));
+          }
+          int m2 = 0;
+#pragma unroll
+          for (int a = 0; a < TDIM; ++a)
+#pragma unroll
+            for (int b = a; b < TDIM; ++b)
+            {
+              double pp = 0.0;
+#pragma unroll
+              for (int kk = 0; kk < TDIM; ++kk)
+                pp += P[sv[kk] * TDIM + a] * P[sv[kk] * TDIM + b];
+              mXX[m2++] += Ws * ((sa[a] * sa[b] + pp) * (1.0 / (TDIM * (TDIM + 1))));
+            }
         }
         sm.scale[tid][s] = scale;
       }
-      if (moments && !interface)
-      {
-        double* mo = moments + rule * (TDIM + 1);
+      if (moments)
+      { // volume rules: (W, first moments); interface rules: (W, first, second moments, upper triangle)
+        constexpr int NM2 = TDIM * (TDIM + 1) / 2;
+        double* mo = moments + rule * (interface ? 1 + TDIM + NM2 : 1 + TDIM);
         mo[0] = mW;
 #pragma unroll
         for (int t = 0; t < TDIM; ++t)
           mo[1 + t] = mX[t];
+        if (interface)
+        {
+#pragma unroll
+          for (int t = 0; t < NM2; ++t)
+            mo[1 + TDIM + t] = mXX[t];
+        }
       }
     }
   }
@@ -756,12 +793,18 @@ void run_quadrature(cfx_ctx* c, const LevelSet& L, cfx_rules* R, bool positive, 
   R->offsets.reserve(c->pool, static_cast<size_t>(R->nrules) + 1);
   R->parent_map.reserve(c->pool, static_cast<size_t>(R->nrules) + 1);
   // moments only where the point sums they replace are exact: built-in rule of degree >= 1, volume part
-  R->has_moments = !interface && rt.builtin && rt.order >= 1;
+  // (interface rules also carry second moments: exact from degree 2 on)
+  R->has_moments = rt.builtin && rt.order >= (interface ? 2 : 1);
   if (R->has_moments)
-    R->moments.reserve(c->pool, static_cast<size_t>(R->nrules) * (TDIM + 1) + 1);
-  CFX_LAUNCH(c, rule_fill_kernel<TDIM>, grid_for(n_cut, QB), QB, 0, L.cut_list.p, n_cut, packed_excl.p, L.dofmap,
-             L.values, c->x_dofmap, c->x, positive, interface, rt.npts, rt.d_pts, rt.d_wts, R->npts, R->points.p,
-             R->weights.p, R->offsets.p, R->parent_map.p, R->has_moments ? R->moments.p : nullptr);
+    R->moments.reserve(c->pool, static_cast<size_t>(R->nrules) * (1 + TDIM + (interface ? TDIM * (TDIM + 1) / 2 : 0)) + 1);
+  if (interface)
+    CFX_LAUNCH(c, (rule_fill_kernel<TDIM, true>), grid_for(n_cut, QB), QB, 0, L.cut_list.p, n_cut, packed_excl.p, L.dofmap,
+               L.values, c->x_dofmap, c->x, positive, rt.npts, rt.d_pts, rt.d_wts, R->npts, R->points.p, R->weights.p,
+               R->offsets.p, R->parent_map.p, R->has_moments ? R->moments.p : nullptr);
+  else
+    CFX_LAUNCH(c, (rule_fill_kernel<TDIM, false>), grid_for(n_cut, QB), QB, 0, L.cut_list.p, n_cut, packed_excl.p,
+               L.dofmap, L.values, c->x_dofmap, c->x, positive, rt.npts, rt.d_pts, rt.d_wts, R->npts, R->points.p,
+               R->weights.p, R->offsets.p, R->parent_map.p, R->has_moments ? R->moments.p : nullptr);
   packed.release();
   packed_excl.release();
 }
