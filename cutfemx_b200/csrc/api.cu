@@ -16,20 +16,43 @@ namespace cfx
 {
 namespace
 {
-__global__ void to_mapped_kernel(const int64_t* __restrict__ src, int n, volatile int64_t* dst)
+// values first, then (after a system-wide fence) the ticket of this read-back in slot 64
+__global__ void to_mapped_kernel(const int64_t* __restrict__ src, int n, volatile int64_t* dst, int64_t ticket)
 {
   if (threadIdx.x < n)
     dst[threadIdx.x] = src[threadIdx.x];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0)
+    dst[64] = ticket;
 }
 } // namespace
 
+// The path has about a dozen of these per step (list sizes the host needs to size the next buffers), so the
+// wake-up latency of a blocking stream synchronisation is paid a dozen times with the GPU idle.  The host spins
+// on the ticket in mapped memory instead and only falls back to the stream (to pick up an error, or after a
+// long wait) -- the kernel is the last work on the stream, so seeing its ticket means everything before it is done.
 const int64_t* read_back(cfx_ctx* c, const int64_t* dev, int n)
 {
   CFX_REQUIRE(n >= 0 && n <= 64, CFX_ERR_RANGE, "read_back: at most 64 values");
-  to_mapped_kernel<<<1, 64, 0, c->stream>>>(dev, n, c->h_pinned_dev);
+  const int64_t ticket = ++c->read_ticket;
+  to_mapped_kernel<<<1, 64, 0, c->stream>>>(dev, n, c->h_pinned_dev, ticket);
   ++c->launches;
   CFX_CUDA(cudaGetLastError());
-  CFX_CUDA(cudaStreamSynchronize(c->stream));
+  volatile int64_t* flag = c->h_pinned + 64;
+  for (int64_t spins = 0; *flag != ticket; ++spins)
+  {
+    if ((spins & 0x3fff) == 0x3fff)
+    { // every 16 K polls: has the stream failed or finished without the ticket becoming visible?
+      const cudaError_t q = cudaStreamQuery(c->stream);
+      if (q == cudaSuccess)
+        break;
+      if (q != cudaErrorNotReady)
+        CFX_CUDA(q);
+    }
+  }
+  if (*flag != ticket)
+    CFX_CUDA(cudaStreamSynchronize(c->stream));
   return c->h_pinned;
 }
 
@@ -74,7 +97,8 @@ cfx_status cfx_ctx_create(int device, void* stream, cfx_ctx** out)
   ctx = new cfx_ctx();
   ctx->device = device;
   ctx->stream = static_cast<cudaStream_t>(stream);
-  CFX_CUDA(cudaHostAlloc(&ctx->h_pinned, 64 * sizeof(int64_t), cudaHostAllocMapped));
+  CFX_CUDA(cudaHostAlloc(&ctx->h_pinned, 72 * sizeof(int64_t), cudaHostAllocMapped));
+  ctx->h_pinned[64] = 0;
   CFX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->h_pinned_dev), ctx->h_pinned, 0));
   ctx->err_flag.reserve(ctx->pool, 4);
   CFX_CUDA(cudaMemsetAsync(ctx->err_flag.p, 0, 4 * sizeof(int32_t), ctx->stream));

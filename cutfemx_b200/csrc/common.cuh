@@ -341,7 +341,8 @@ struct cfx_ctx
   cfx::DevBuf<int64_t> scratch64;
   cfx::DevBuf<uint8_t> scratch8;
   cfx::DevBuf<int32_t> err_flag; // device int[4]
-  int64_t* h_pinned = nullptr;   // 64 x int64 mapped pinned host scratch
+  int64_t* h_pinned = nullptr;   // 64 x int64 mapped pinned host scratch + the read-back ticket in slot 64
+  int64_t read_ticket = 0;
   int64_t* h_pinned_dev = nullptr; // its device address
 
   bool timing = false;
