@@ -43,7 +43,8 @@ constexpr int CPT = 4;
 template <int ND>
 __global__ void __launch_bounds__(CB)
     classify_kernel(const int32_t* __restrict__ dofmap, const double* __restrict__ vals, int64_t nc_total,
-                    int64_t nc_owned, int8_t* __restrict__ domain, unsigned long long* __restrict__ counts)
+                    int64_t nc_owned, int8_t* __restrict__ domain, unsigned long long* __restrict__ counts,
+                    const uint8_t* __restrict__ host /* null: every cell is a host of the cut */)
 {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * CB + threadIdx.x) >> 5;
@@ -80,7 +81,9 @@ __global__ void __launch_bounds__(CB)
       all_neg = all_neg && (v[i][k] < 0.0);
       all_pos = all_pos && (v[i][k] > 0.0);
     }
-    const int code = all_neg ? CFX_DOMAIN_INSIDE : (all_pos ? CFX_DOMAIN_OUTSIDE : CFX_DOMAIN_INTERSECTED);
+    int code = all_neg ? CFX_DOMAIN_INSIDE : (all_pos ? CFX_DOMAIN_OUTSIDE : CFX_DOMAIN_INTERSECTED);
+    if (host != nullptr && c < nc_total && !host[c])
+      code = 0; // not a host entity of this cut (cut.cpp:507-537: the view holds the selected cells only)
     if (c < nc_total)
       domain[c] = static_cast<int8_t>(code);
     const bool owned = c < nc_owned;
@@ -107,7 +110,7 @@ template <int ND>
 void launch_classify(cfx_ctx* c, const LevelSet& L, int8_t* domain, unsigned long long* counts)
 {
   CFX_LAUNCH(c, classify_kernel<ND>, grid_for(c->nc_total, CB * CPT), CB, 0, L.dofmap, L.values, c->nc_total, c->nc_owned,
-             domain, counts);
+             domain, counts, c->has_host_mask ? c->host_mask.p : nullptr);
 }
 } // namespace
 
@@ -204,6 +207,56 @@ void ensure_cut_list_all(cfx_ctx* c, int ls)
 } // namespace cfx
 
 using namespace cfx;
+
+namespace cfx
+{
+namespace
+{
+__global__ void host_mask_kernel(const int32_t* __restrict__ cells, int64_t n, int64_t nc, uint8_t* __restrict__ mask,
+                                 int32_t* __restrict__ err)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * CB + threadIdx.x;
+  if (i >= n)
+    return;
+  const int32_t c = cells[i];
+  if (c < 0 || c >= nc)
+  { // cut.cpp validate_local_entities: entity index outside the local range
+    err[0] = 14;
+    err[1] = c;
+    return;
+  }
+  mask[c] = 1;
+}
+} // namespace
+} // namespace cfx
+
+// cutfemx.cut(level_set, entities, entity_dim = tdim): only the listed (owned) cells host the cut
+// (cut.cpp:500-538 build_mesh_view over the selected cells; test_cut_api.py:160-168).  cells == NULL: all cells.
+// Takes effect at the next cfx_update.
+extern "C" cfx_status cfx_set_host_cells(cfx_ctx* ctx, const int32_t* cells, int64_t n, int memspace)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && ctx->mesh_bound, CFX_ERR_STATE, "cfx_set_host_cells: bind the mesh first");
+  CFX_REQUIRE(n >= 0 && (cells != nullptr || n == 0), CFX_ERR_INVALID, "cfx_set_host_cells: NULL argument");
+  ctx->classified = false;
+  if (cells == nullptr)
+  {
+    ctx->has_host_mask = false;
+    return CFX_OK;
+  }
+  ctx->host_mask.reserve(ctx->pool, static_cast<size_t>(ctx->nc_total) + 16);
+  CFX_CUDA(cudaMemsetAsync(ctx->host_mask.p, 0, static_cast<size_t>(ctx->nc_total), ctx->stream));
+  if (n > 0)
+  {
+    DevBuf<int32_t> own;
+    const int32_t* d = adopt(ctx, own, cells, static_cast<size_t>(n), memspace);
+    CFX_LAUNCH(ctx, host_mask_kernel, grid_for(n, CB), CB, 0, d, n, ctx->nc_owned, ctx->host_mask.p, ctx->err_flag.p);
+    check_device_error(ctx, "cfx_set_host_cells (entity index out of range)");
+    own.release();
+  }
+  ctx->has_host_mask = true;
+  CFX_API_END(ctx)
+}
 
 extern "C" cfx_status cfx_locate_entities(cfx_ctx* ctx, int n_terms, const int32_t* term_offsets,
                                           const int32_t* clause_ls, const int32_t* clause_rel, cfx_list** out)

@@ -322,6 +322,10 @@ struct cfx_ctx
   int64_t n_facets = 0, n_owned_facets = 0;
 
   cfx::LevelSet ls[CFX_MAX_LEVEL_SETS];
+  // host cells of the cut (cutfemx.cut(level_set, entities, entity_dim = tdim)): cells outside the subset get
+  // domain code 0, which no selector matches; null = every local cell is a host
+  cfx::DevBuf<uint8_t> host_mask;
+  bool has_host_mask = false;
   cfx::DevBuf<int8_t> domain; // (CFX_MAX_LEVEL_SETS, domain_stride)
   int64_t domain_stride = 0;
   bool classified = false;

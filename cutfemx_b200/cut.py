@@ -261,6 +261,7 @@ class CutData:
         self._level_sets = tuple(level_sets)
         self._names = tuple(names)
         self._keep = []
+        self._entities, self._entity_dim = None, None  # python/cutfemx/cut.py:102-108,141-146
 
     def update(self) -> None:
         update(self)
@@ -291,11 +292,11 @@ class CutData:
 
     @property
     def entity_dim(self):
-        return None
+        return self._entity_dim
 
     @property
     def entities(self):
-        return None
+        return self._entities
 
     def counts(self, ls: int = 0):
         """(inside, intersected, outside) owned-cell counts."""
@@ -342,8 +343,11 @@ def cut(level_set, entities=None, entity_dim=None, *, cut_approximation: str = "
         device: int | None = None) -> CutData:
     """Cut one or more scalar level-set functions on the cells of their mesh
     (python/cutfemx/cut.py:186-249 -> cut.cpp:639-659, 742-786, 845-868)."""
-    if entities is not None or entity_dim is not None:
-        raise NotImplementedError("entity-hosted cuts (facets as hosts) are outside the accelerated path")
+    # python/cutfemx/cut.py:149-160
+    if entities is None and entity_dim is not None:
+        raise ValueError("entity_dim is only valid when entities are supplied")
+    if entities is not None and entity_dim is None:
+        raise ValueError("entity_dim must be supplied when entities are supplied")
     if cut_approximation not in ("auto", "linear") or cut_approximation_order != 1:
         raise NotImplementedError("only the straight (order 1) cut approximation is implemented")
     level_sets = _normalise_level_sets(level_set)
@@ -355,10 +359,19 @@ def cut(level_set, entities=None, entity_dim=None, *, cut_approximation: str = "
             raise ValueError("level set must be a scalar Lagrange function")  # cut.cpp:444-460
     if len(level_sets) > 4:
         raise ValueError("at most 4 level sets per CutData")
+    if entities is not None and int(entity_dim) != mesh.tdim:
+        raise NotImplementedError("facet-hosted cuts (entity_dim < tdim) are not on the accelerated path yet")
     names = _freeze_names(level_sets)
     ctx = _mesh_context(mesh, device)
     cd = CutData(ctx, level_sets, names)
     h = ctx.handle
+    if entities is None:
+        check(h, lib().cfx_set_host_cells(h, None, C.c_int64(0), HOST))
+        cd._entities, cd._entity_dim = None, None
+    else:  # cell subset as host (cut.cpp:500-538, test_cut_api.py:160-168); lists come back ascending
+        ent = np.ascontiguousarray(np.asarray(entities, dtype=np.int32))
+        check(h, lib().cfx_set_host_cells(h, C.c_void_p(ent.ctypes.data), C.c_int64(ent.size), HOST))
+        cd._entities, cd._entity_dim = ent, int(entity_dim)
     for i, f in enumerate(level_sets):
         V = f.function_space
         pd, msd, kd = as_arg(V.dofmap, np.int32)

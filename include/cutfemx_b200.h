@@ -95,6 +95,11 @@ cfx_status cfx_levelset_bind(cfx_ctx* ctx, int ls, const int32_t* dofmap, int nd
                              int64_t n_dofs, int memspace, int pin_host);
 /* cutfemx::update, cut.cpp:845-868 -> cutcells::cut: re-read every level set's values and
  * classify all owned cells (cut.cpp:292-321: all dofs < 0 inside, all > 0 outside, else intersected). */
+/* cutfemx.cut(level_set, entities, entity_dim = tdim) (python/cutfemx/cut.py:186-249, cut.cpp:500-538): restrict
+ * the hosts of the cut to the listed OWNED cells; every other cell is in no domain (no selector matches it, it
+ * gets no rule).  cells == NULL restores "all cells".  Takes effect at the next cfx_update.  Facet hosts
+ * (entity_dim < tdim, cut.cpp:540-591) are not on the accelerated path yet. */
+cfx_status cfx_set_host_cells(cfx_ctx* ctx, const int32_t* cells, int64_t n, int memspace);
 cfx_status cfx_update(cfx_ctx* ctx);
 cfx_status cfx_counts(cfx_ctx* ctx, int ls, int64_t counts[3]); /* inside, intersected, outside */
 cfx_status cfx_domain_fetch(cfx_ctx* ctx, int ls, int8_t* out, int memspace);

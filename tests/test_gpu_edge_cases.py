@@ -182,3 +182,34 @@ def test_square_functional_of_a_function_coefficient(built_lib, kind, n, deg):
     assert abs(got - ref[0]) <= 1e-12 * abs(ref[0])
     with pytest.raises(cfx.CfxError):  # one value per dof of the space
         form.set_coefficient(w[:-1])
+
+
+def test_cell_subset_as_host(built_lib):
+    """cutfemx.cut(level_set, entities, entity_dim = tdim) (test_cut_api.py:160-168, :211-222, :728-745): only the
+    listed cells host the cut -- the three domains partition the subset, rules exist only for its cut cells."""
+    cfx, mesh, V, phi = _setup(2, 9, M.sphere_level_set((0.1, -0.05, 0.0), 0.55))
+    dom_all = O.classify(V.dofmap, phi.x.array)
+    rng = np.random.default_rng(5)
+    subset = np.sort(rng.choice(mesh.num_cells, size=mesh.num_cells // 3, replace=False)).astype(np.int32)
+    cd = cfx.cut(phi, subset, mesh.tdim)
+    neg, cut, pos = (cfx.locate_entities(cd, s) for s in ("phi<0", "phi=0", "phi>0"))
+    assert np.array_equal(cut, np.intersect1d(O.locate(dom_all, "phi=0"), subset)) and cut.size > 0
+    assert np.array_equal(neg, np.intersect1d(O.locate(dom_all, "phi<0"), subset))
+    assert np.array_equal(np.sort(np.concatenate([neg, cut, pos])), subset)
+    rules = cfx.runtime_quadrature(cd, "phi<0", 2)
+    ro = O.runtime_quadrature(mesh, V.dofmap, phi.x.array, dom_all, "<", 2)
+    keep = np.isin(ro.parent_map, subset)
+    assert np.array_equal(rules.parent_map, ro.parent_map[keep])
+    w_ref = sum(ro.weights[ro.offsets[i]:ro.offsets[i + 1]].sum() for i in np.nonzero(keep)[0])
+    np.testing.assert_allclose(rules.weights.sum(), w_ref, rtol=1e-12)
+    # the next plain cut sees every cell again
+    cd2 = cfx.cut(phi)
+    assert np.array_equal(cfx.locate_entities(cd2, "phi=0"), O.locate(dom_all, "phi=0"))
+    with pytest.raises(ValueError, match="entity_dim must be supplied"):
+        cfx.cut(phi, entities=np.arange(11, dtype=np.int32))
+    with pytest.raises(ValueError, match="entity_dim is only valid"):
+        cfx.cut(phi, entity_dim=0)
+    with pytest.raises(NotImplementedError):
+        cfx.cut(phi, np.arange(4, dtype=np.int32), mesh.tdim - 1)
+    with pytest.raises(cfx.CfxError):
+        cfx.cut(phi, np.array([mesh.num_cells], dtype=np.int32), mesh.tdim)
