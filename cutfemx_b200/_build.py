@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcutfemx_b200.so")
 SOURCES = ["api.cu", "scan.cu", "classify.cu", "quadrature.cu", "facets.cu", "sparsity.cu", "assemble.cu",
-           "meshgen.cu", "exchange.cu", "dirichlet.cu"]
+           "meshgen.cu", "exchange.cu", "dirichlet.cu", "entity.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
 
 

@@ -217,6 +217,10 @@ struct cfx_rules
   // (nrules, 1 + tdim + tdim (tdim+1)/2) -- enough for the P1 Nitsche kernels, whose normal is constant per rule.
   cfx::DevBuf<double> moments;
   bool has_moments = false;
+  // facet-hosted rules (entity.cu): tdim = mesh tdim - 1, parent_map = facet ids, and the facet's vertices per rule
+  // (nrules, tdim + 1) so that physical points need no topology lookup
+  bool entity_hosted = false;
+  cfx::DevBuf<int32_t> rule_verts;
 };
 
 struct cfx_pattern
@@ -507,6 +511,7 @@ void ensure_cut_list(cfx_ctx* c, int ls);               // classify.cu
 void ensure_cut_list_all(cfx_ctx* c, int ls);           // classify.cu
 void build_incidence(cfx_ctx* c, Space& s);             // sparsity.cu
 void derive_f2c(cfx_ctx* c);                            // facets.cu
+void entity_physical_points(cfx_ctx* c, const cfx_rules* r, double* dst_soa); // entity.cu
 void build_geometry_cache(cfx_ctx* c);                  // assemble.cu
 void dense_f2c_from_adjacency(cfx_ctx* c, const int32_t* off_dev, const int32_t* data_dev); // facets.cu
 void prepare_form(cfx_ctx* c, cfx_form* f);             // sparsity.cu

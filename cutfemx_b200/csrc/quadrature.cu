@@ -883,6 +883,7 @@ cfx_status cfx_runtime_quadrature(cfx_ctx* ctx, int ls, int relation, int order,
   R->tdim = ctx->tdim;
   R->gdim = ctx->gdim;
   R->relation = relation;
+  R->entity_hosted = false;
   R->order = order;
   R->ls = ls;
   R->has_normals = false;
@@ -949,7 +950,9 @@ cfx_status cfx_rules_physical_points(cfx_ctx* ctx, const cfx_rules* r, double* o
     tmp.reserve(ctx->pool, static_cast<size_t>(r->npts) * r->gdim);
     dst = tmp.p;
   }
-  if (r->tdim == 2)
+  if (r->entity_hosted)
+    entity_physical_points(ctx, r, dst);
+  else if (r->tdim == 2)
     CFX_LAUNCH(ctx, physical_points_kernel<2>, grid_for(r->npts, 256), 256, 0, r->points.p, r->npts, r->offsets.p,
                r->parent_map.p, r->nrules, ctx->x_dofmap, ctx->x, dst);
   else
@@ -974,6 +977,7 @@ void cfx_rules_free(cfx_ctx* ctx, cfx_rules* r)
   r->parent_map.release();
   r->normals.release();
   r->moments.release();
+  r->rule_verts.release();
   delete r;
 }
 

@@ -1107,6 +1107,9 @@ cfx_status cfx_form_add_cell_integral(cfx_ctx* ctx, cfx_form* f, int kernel, con
               "cfx_form_add_cell_integral: kernel family does not match the form rank / integral type");
   CFX_REQUIRE(n_constants >= 0 && n_constants <= CFX_MAX_CONSTANTS, CFX_ERR_INVALID, "too many constants");
   CFX_REQUIRE(n_cells == 0 || cells != nullptr, CFX_ERR_INVALID, "cfx_form_add_cell_integral: NULL cells");
+  CFX_REQUIRE(!rules || !rules->entity_hosted, CFX_ERR_UNSUPPORTED,
+              "facet-hosted rules belong to exterior / interior facet integrals, which the shipped kernel families do "
+              "not cover yet");
   {
     const bool vec_kernel = kernel == CFX_K_ELASTICITY || kernel == CFX_K_SOURCE_VEC;
     const int bs = ctx->spaces[f->space].bs;

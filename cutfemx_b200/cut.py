@@ -262,13 +262,26 @@ class CutData:
         self._names = tuple(names)
         self._keep = []
         self._entities, self._entity_dim = None, None  # python/cutfemx/cut.py:102-108,141-146
+        self._ecut = C.c_void_p()  # facet-hosted cut (cfx_cut_facets)
+
+    @property
+    def facet_hosted(self) -> bool:
+        return self._entity_dim is not None and self._entity_dim == self.mesh.tdim - 1
+
+    def __del__(self):
+        try:
+            if self._ecut and self._ctx._h:
+                lib().cfx_ecut_free(self._ctx.handle, self._ecut)
+                self._ecut = C.c_void_p()
+        except Exception:
+            pass
 
     def update(self) -> None:
         update(self)
 
     @property
-    def tdim(self) -> int:
-        return self.mesh.tdim
+    def tdim(self) -> int:  # dimension of the host entities (test_cut_api.py:361: cutter.tdim == 1 for facets)
+        return self._entity_dim if self.facet_hosted else self.mesh.tdim
 
     @property
     def gdim(self) -> int:
@@ -359,13 +372,20 @@ def cut(level_set, entities=None, entity_dim=None, *, cut_approximation: str = "
             raise ValueError("level set must be a scalar Lagrange function")  # cut.cpp:444-460
     if len(level_sets) > 4:
         raise ValueError("at most 4 level sets per CutData")
-    if entities is not None and int(entity_dim) != mesh.tdim:
-        raise NotImplementedError("facet-hosted cuts (entity_dim < tdim) are not on the accelerated path yet")
+    if entities is not None and int(entity_dim) not in (mesh.tdim, mesh.tdim - 1):
+        # cut.cpp:545-550 accepts every positive entity dimension; edges of tetrahedra are not implemented here
+        if int(entity_dim) <= 0 or int(entity_dim) > mesh.tdim:
+            raise ValueError("cutfemx::cut entity_dim must select positive-dimensional mesh entities")
+        raise NotImplementedError("entity-hosted cuts are implemented for cells and facets")
     names = _freeze_names(level_sets)
     ctx = _mesh_context(mesh, device)
     cd = CutData(ctx, level_sets, names)
     h = ctx.handle
-    if entities is None:
+    if entities is not None and int(entity_dim) == mesh.tdim - 1:
+        # facets as hosts (cut.cpp:540-591, 1022-1063): classified after the level sets are bound, below
+        check(h, lib().cfx_set_host_cells(h, None, C.c_int64(0), HOST))
+        cd._entities, cd._entity_dim = np.ascontiguousarray(np.asarray(entities, dtype=np.int32)), int(entity_dim)
+    elif entities is None:
         check(h, lib().cfx_set_host_cells(h, None, C.c_int64(0), HOST))
         cd._entities, cd._entity_dim = None, None
     else:  # cell subset as host (cut.cpp:500-538, test_cut_api.py:160-168); lists come back ascending
@@ -395,7 +415,13 @@ def cut(level_set, entities=None, entity_dim=None, *, cut_approximation: str = "
 
 def update(cut_data: CutData) -> None:
     """Refresh cut data from the current level-set values (cut.cpp:845-868)."""
-    check(cut_data._ctx.handle, lib().cfx_update(cut_data._ctx.handle))
+    h = cut_data._ctx.handle
+    check(h, lib().cfx_update(h))
+    if cut_data.facet_hosted:
+        _bind_topology(cut_data.mesh, cut_data._ctx)
+        ent = cut_data._entities
+        check(h, lib().cfx_cut_facets(h, C.c_void_p(ent.ctypes.data), C.c_int64(ent.size), HOST,
+                                      C.byref(cut_data._ecut)))
 
 
 def _selector_args(cut_data: CutData, ls_part: str):
@@ -408,7 +434,10 @@ def locate_entities_device(cut_data: CutData, ls_part: str) -> _List:
     n, pto, pcl, pcr, keep = _selector_args(cut_data, ls_part)
     out = _List(cut_data._ctx)
     h = cut_data._ctx.handle
-    check(h, lib().cfx_locate_entities(h, n, pto, pcl, pcr, C.byref(out._h)))
+    if cut_data.facet_hosted:  # facet ids in the order of the host list (cut.cpp:344-359)
+        check(h, lib().cfx_ecut_locate(h, cut_data._ecut, n, pto, pcl, pcr, C.byref(out._h)))
+    else:
+        check(h, lib().cfx_locate_entities(h, n, pto, pcl, pcr, C.byref(out._h)))
     return out
 
 
@@ -433,7 +462,11 @@ def runtime_quadrature(cut_data: CutData, ls_part: str, order: int, *, backend: 
     rules = RuntimeQuadratureRules(cut_data._ctx, ls_part, int(cl[0]), int(order))
     rules.ctx_gdim = cut_data.gdim
     h = cut_data._ctx.handle
-    check(h, lib().cfx_runtime_quadrature(h, int(cl[0]), int(cr[0]), int(order), C.byref(rules._h)))
+    if cut_data.facet_hosted:
+        check(h, lib().cfx_ecut_runtime_quadrature(h, cut_data._ecut, int(cl[0]), int(cr[0]), int(order),
+                                                   C.byref(rules._h)))
+    else:
+        check(h, lib().cfx_runtime_quadrature(h, int(cl[0]), int(cr[0]), int(order), C.byref(rules._h)))
     return rules
 
 
@@ -459,6 +492,8 @@ def ghost_penalty_facets(cut_data: CutData, selector: str, *, depth: int = 1,
     """Owned raw interior facet ids of the cut-cell stabilisation band (cut.py:340-380)."""
     if depth != 1:
         raise NotImplementedError("ghost_penalty_facets currently supports depth=1.")
+    if cut_data.entity_dim is not None and cut_data.entity_dim != cut_data.mesh.tdim:
+        raise ValueError("ghost_penalty_facets expects cell-hosted CutData.")  # cut.py:350-351
     lst = ghost_penalty_facets_device(cut_data, selector, include_ghosts=include_ghosts)
     out = lst.numpy()
     lst.free()

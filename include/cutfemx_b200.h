@@ -142,6 +142,23 @@ cfx_status cfx_evaluate_normals(cfx_ctx* ctx, int ls, cfx_rules* r, double sign,
 /* cutfemx::level_set::evaluate_values, level_set/value.h:34-119 */
 cfx_status cfx_evaluate_values(cfx_ctx* ctx, int ls, const cfx_rules* r, double* out, int memspace);
 
+/* ------------------------------------------------------------------ facets as hosts of the cut
+ * cutfemx.cut(level_set, facets, entity_dim = tdim - 1): build_entity_mesh_view (cut.cpp:540-591) +
+ * build_entity_level_sets (cut.cpp:1022-1063, fem/entity_dofmap.cpp:11-88).  The listed facets are classified by the
+ * level-set values at their vertices (every bound P1 level set, current values); locate returns FACET ids in the
+ * order of the list (host_parent_index, cut.cpp:344-359); the rules have tdim = mesh tdim - 1, points in the facet's
+ * reference coordinates (vertices in ascending vertex number), physical weights and parent_map = facet ids
+ * (test_cut_api.py:171-188, :349-367, :424-501).  cfx_rules_physical_points / _fetch / _sizes work on them; they
+ * cannot be attached to cell integrals.  Needs cfx_topology_bind.  Relation "=" (the interface inside a facet) is
+ * not implemented. */
+typedef struct cfx_ecut cfx_ecut;
+cfx_status cfx_cut_facets(cfx_ctx* ctx, const int32_t* facets, int64_t n, int memspace, cfx_ecut** inout);
+cfx_status cfx_ecut_locate(cfx_ctx* ctx, const cfx_ecut* e, int n_terms, const int32_t* term_offsets,
+                           const int32_t* clause_ls, const int32_t* clause_rel, cfx_list** out);
+cfx_status cfx_ecut_runtime_quadrature(cfx_ctx* ctx, const cfx_ecut* e, int ls, int relation, int order,
+                                       cfx_rules** inout);
+void cfx_ecut_free(cfx_ctx* ctx, cfx_ecut* e);
+
 /* ------------------------------------------------------------------ ghost-penalty facets
  * cutfemx.ghost_penalty_facets, python/cutfemx/cut.py:340-380: owned interior facets of the
  * cells intersected by level set `cut_ls` whose two cells are both in (cut cells U selector). */

@@ -382,3 +382,80 @@ class coefficient:
     def __exit__(self, *exc):
         lib().orc_set_coefficient(None)
         return False
+
+
+# ---------------------------------------------------------------- facets as hosts of the cut
+def facet_vertices(mesh, facets):
+    """Vertices of the listed facets, ascending vertex number per facet (DOLFINx keeps entity vertices sorted;
+    build_entity_mesh_view, cut.cpp:540-591), and for each the local vertex index in the facet's first cell."""
+    nv = mesh.x_dofmap.shape[1]
+    verts = np.zeros((len(facets), nv - 1), dtype=np.int32)
+    local = np.zeros((len(facets), nv - 1), dtype=np.int32)
+    cells = np.zeros(len(facets), dtype=np.int64)
+    for i, f in enumerate(np.asarray(facets, dtype=np.int64)):
+        c = int(mesh.f2c[mesh.f2c_offsets[f]])
+        lf = int(np.nonzero(mesh.c2f[c] == f)[0][0])
+        lj = np.array([j for j in range(nv) if j != lf])  # facet lf is opposite local vertex lf
+        v = mesh.x_dofmap[c][lj]
+        o = np.argsort(v, kind="stable")
+        verts[i], local[i], cells[i] = v[o], lj[o], c
+    return verts, local, cells
+
+
+def classify_facets(mesh, ls_dofmap, values, facets):
+    """Domain codes of facet hosts from the level-set values at their vertices (P1: the entity dofmap of
+    fem/entity_dofmap.cpp:11-88 lists the vertices' dofs) -- the rule of cut.cpp:292-321 one dimension down."""
+    verts, local, cells = facet_vertices(mesh, facets)
+    phi = np.asarray(values)[np.asarray(ls_dofmap)[cells[:, None], local]]
+    code = np.full(len(facets), INTERSECTED, dtype=np.int8)
+    code[np.all(phi < 0.0, axis=1)] = INSIDE
+    code[np.all(phi > 0.0, axis=1)] = OUTSIDE
+    return code, verts, phi
+
+
+def facet_runtime_quadrature(mesh, ls_dofmap, values, facets, relation: str, order: int) -> "Rules":
+    """Rules on the cut facets in the facets' own reference coordinates with physical weights (cutfemx.cut(...,
+    entity_dim = tdim - 1) + runtime_quadrature, test_cut_api.py:424-501).  Segments (2D meshes) in closed form;
+    triangles (3D meshes) through the cell generator applied to an ISOMETRIC planar copy of each facet -- reference
+    points do not depend on the embedding and the weights only on lengths and areas."""
+    code, verts, phi = classify_facets(mesh, ls_dofmap, values, facets)
+    edim = verts.shape[1] - 1
+    positive = relation in (">", ">=")
+    X = mesh.x[verts][:, :, : edim + 1]
+    cutf = np.nonzero(code == INTERSECTED)[0]
+    if edim == 1:
+        p, w = _rules.simplex_rule(1, order)
+        p, w = np.asarray(p).reshape(-1), np.asarray(w)
+        pts, wts, off, pm = [], [], [0], []
+        for i in cutf:
+            inside = (phi[i] > 0.0) if positive else (phi[i] < 0.0)
+            if inside.sum() != 1:
+                continue
+            a = int(np.nonzero(inside)[0][0])
+            b = 1 - a
+            t = phi[i, a] / (phi[i, a] - phi[i, b])
+            xa, xc = float(a), float(a) + t * (float(b) - float(a))  # reference coordinate of vertex q is q
+            length = np.linalg.norm(X[i, 1] - X[i, 0])
+            pts.append(xa + p * (xc - xa))
+            wts.append(w * abs(xc - xa) * length)
+            off.append(off[-1] + w.size)
+            pm.append(int(np.asarray(facets)[i]))
+        P = np.concatenate(pts).reshape(-1, 1) if pts else np.zeros((0, 1))
+        W = np.concatenate(wts) if wts else np.zeros(0)
+        return Rules(1, P, W, np.asarray(off, dtype=np.int32), np.asarray(pm, dtype=np.int32))
+    # triangles: planar isometric copies as a pseudo mesh of independent cells
+    from types import SimpleNamespace
+
+    e1, e2 = X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]
+    l1 = np.linalg.norm(e1, axis=1)
+    u = e1 / l1[:, None]
+    a2 = np.einsum("ij,ij->i", e2, u)
+    h2 = np.linalg.norm(e2 - a2[:, None] * u, axis=1)
+    n = len(facets)
+    xp = np.zeros((3 * n, 3))
+    xp[1::3, 0] = l1
+    xp[2::3, 0], xp[2::3, 1] = a2, h2
+    xd = np.arange(3 * n, dtype=np.int32).reshape(n, 3)
+    pseudo = SimpleNamespace(x=xp, x_dofmap=xd, cell_type=3, tdim=2, gdim=2, num_cells=n, num_cells_local=n)
+    r = runtime_quadrature(pseudo, xd, phi.reshape(-1), code, relation, order)
+    return Rules(2, r.points, r.weights, r.offsets, np.asarray(facets, dtype=np.int32)[r.parent_map])

@@ -209,7 +209,7 @@ def test_cell_subset_as_host(built_lib):
         cfx.cut(phi, entities=np.arange(11, dtype=np.int32))
     with pytest.raises(ValueError, match="entity_dim is only valid"):
         cfx.cut(phi, entity_dim=0)
-    with pytest.raises(NotImplementedError):
-        cfx.cut(phi, np.arange(4, dtype=np.int32), mesh.tdim - 1)
+    with pytest.raises(ValueError):  # cut.cpp:545-550: positive-dimensional entities only
+        cfx.cut(phi, np.arange(4, dtype=np.int32), 0)
     with pytest.raises(cfx.CfxError):
         cfx.cut(phi, np.array([mesh.num_cells], dtype=np.int32), mesh.tdim)

@@ -479,3 +479,34 @@ def test_square_functional_of_a_packed_coefficient():
         xp = O.physical_points(mesh, rv).T
         ref += 2.0 * np.sum(rv.weights * (a0 + xp @ b) ** 2)
         assert abs(val[0] - ref) <= 1e-12 * abs(ref)
+
+
+# ---------------------------------------------------------------- facets as hosts
+def test_facet_hosted_rules_measure_the_wet_boundary_exactly():
+    """Planar level sets cut the boundary of the unit square / cube in straight pieces, so the wet part of the boundary
+    (full inside facets + the run-time rules of the cut facets) has a closed form: 2.02 for phi = x - 0.51 on the
+    square, 1 + 0.52 + 0.22 + 2 * 0.37 = 2.48 for phi = x + 0.3 y - 0.52 on the cube.  Also the invariants the
+    reference's tests assert (test_cut_api.py:171-188, :424-462)."""
+    from cutfemx_b200 import mesh as M
+
+    for tdim, n, fn, exact in ((2, 9, lambda x, y, z: x - 0.51, 2.02), (3, 5, lambda x, y, z: x + 0.3 * y - 0.52, 2.48)):
+        mesh = M.create_rectangle(n, n, (0.0, 0.0), (1.0, 1.0)) if tdim == 2 else M.create_box(n, n, n)
+        V = M.functionspace(mesh, 1, permute_seed=9)
+        phi = M.Function(V, "phi").interpolate(fn)
+        facets = np.nonzero(np.diff(mesh.f2c_offsets) == 1)[0].astype(np.int32)
+        code, verts, _ = O.classify_facets(mesh, V.dofmap, phi.x.array, facets)
+        assert set(np.unique(code)) <= {O.INSIDE, O.INTERSECTED, O.OUTSIDE}
+        for order in (1, 2, 4):
+            r = O.facet_runtime_quadrature(mesh, V.dofmap, phi.x.array, facets, "<", order)
+            assert r.offsets[0] == 0 and r.offsets[-1] == r.weights.size and r.parent_map.size == r.offsets.size - 1
+            assert set(r.parent_map.tolist()) <= set(facets[code == O.INTERSECTED].tolist())
+            X = mesh.x[verts[code == O.INSIDE]]
+            full = (np.linalg.norm(X[:, 1] - X[:, 0], axis=1).sum() if tdim == 2 else
+                    0.5 * np.linalg.norm(np.cross(X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]), axis=1).sum())
+            np.testing.assert_allclose(full + r.weights.sum(), exact, rtol=1e-12)
+            rp = O.facet_runtime_quadrature(mesh, V.dofmap, phi.x.array, facets, ">", order)
+            Xo = mesh.x[verts[code == O.OUTSIDE]]
+            dry = (np.linalg.norm(Xo[:, 1] - Xo[:, 0], axis=1).sum() if tdim == 2 else
+                   0.5 * np.linalg.norm(np.cross(Xo[:, 1] - Xo[:, 0], Xo[:, 2] - Xo[:, 0]), axis=1).sum())
+            np.testing.assert_allclose(full + r.weights.sum() + dry + rp.weights.sum(), 4.0 if tdim == 2 else 6.0,
+                                       rtol=1e-12)
