@@ -55,8 +55,12 @@ def test_cut_argument_validation_before_any_device_work():
     V, W = M.functionspace(mesh, 1), M.functionspace(other, 1)
     with pytest.raises(ValueError):  # cut.cpp:462-498: same mesh for every level set
         cutmod.cut([M.Function(V, "a"), M.Function(W, "b")])
-    with pytest.raises(NotImplementedError):
-        cutmod.cut(M.Function(V, "a"), entities=np.arange(3), entity_dim=1)
+    with pytest.raises(ValueError, match="entity_dim must be supplied"):  # python/cutfemx/cut.py:157-158
+        cutmod.cut(M.Function(V, "a"), entities=np.arange(3))
+    with pytest.raises(ValueError, match="entity_dim is only valid"):  # python/cutfemx/cut.py:153-154
+        cutmod.cut(M.Function(V, "a"), entity_dim=1)
+    with pytest.raises(ValueError, match="positive-dimensional"):  # cut.cpp:545-550
+        cutmod.cut(M.Function(V, "a"), entities=np.arange(3), entity_dim=0)
     Vv = M.functionspace(mesh, 1, bs=2)
     with pytest.raises(ValueError):  # cut.cpp:444-460: scalar Lagrange
         cutmod.cut(M.Function(Vv, "a"))
