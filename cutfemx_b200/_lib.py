@@ -32,7 +32,7 @@ SYMBOLS = [
     "cfx_runtime_quadrature", "cfx_rules_sizes", "cfx_rules_fetch", "cfx_rules_physical_points", "cfx_rules_free",
     "cfx_simplex_rule", "cfx_set_simplex_rule", "cfx_evaluate_normals", "cfx_evaluate_values",
     "cfx_ghost_penalty_facets", "cfx_interior_facets_for_cells", "cfx_facet_integration_rows", "cfx_space_bind",
-    "cfx_form_create", "cfx_form_set_coefficient", "cfx_form_add_cell_integral", "cfx_form_add_interior_facet_integral", "cfx_form_free",
+    "cfx_form_create", "cfx_form_set_coefficient", "cfx_form_add_exterior_facet_integral", "cfx_form_add_cell_integral", "cfx_form_add_interior_facet_integral", "cfx_form_free",
     "cfx_create_sparsity", "cfx_pattern_import", "cfx_pattern_sizes", "cfx_pattern_block_size", "cfx_pattern_fetch",
     "cfx_pattern_values_device_ptr", "cfx_pattern_row_ptr_device_ptr", "cfx_pattern_cols_device_ptr",
     "cfx_pattern_values_fetch", "cfx_pattern_free", "cfx_assemble_matrix", "cfx_assemble_system", "cfx_assemble_vector",

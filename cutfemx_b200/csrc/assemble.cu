@@ -2356,6 +2356,19 @@ void launch_blocked_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t
   }
 }
 
+// one value per rule: c0 * (sum of the rule's weights) -- the measure functional on rules of any host dimension
+__global__ void rule_measure_kernel(const int32_t* __restrict__ offsets, const double* __restrict__ weights,
+                                    int64_t nrules, double c0, double* __restrict__ out)
+{
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (r >= nrules)
+    return;
+  double s = 0.0;
+  for (int32_t q = offsets[r]; q < offsets[r + 1]; ++q)
+    s += weights[q];
+  out[r] = c0 * s;
+}
+
 template <int TDIM, int DEG>
 void dispatch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t& base)
 {
@@ -2382,6 +2395,14 @@ int64_t run_cell_integrals(cfx_ctx* c, cfx_form* f, int64_t follow_slots = -1)
   const int es = f->rank == 2 ? n1 * n1 : (f->rank == 1 ? n1 : 1);
   auto dispatch = [&](const cfx_integral& I, int64_t& base)
   {
+    if (I.rules && I.rules->entity_hosted)
+    { // exterior-facet functional on facet-hosted rules (cfx_form_add_exterior_facet_integral): c0 * sum of weights
+      if (I.rules->nrules > 0)
+        CFX_LAUNCH(c, rule_measure_kernel, grid_for(I.rules->nrules, 256), 256, 0, I.rules->offsets.p, I.rules->weights.p,
+                   I.rules->nrules, I.constants[0], f->Ae.p + base);
+      base += I.rules->nrules;
+      return;
+    }
     if (blocked)
     {
       if (c->tdim == 2 && S.degree == 1)

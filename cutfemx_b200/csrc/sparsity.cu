@@ -1098,6 +1098,33 @@ static int kernel_rank(int k)
   return -1;
 }
 
+// exterior-facet integral over facet-hosted run-time rules (ds measure with subdomain_data = rules,
+// test_cut_api.py:504-527).  Shipped family: CFX_K_ONE (rank 0): c0 * measure of the selected part of the facets.
+cfx_status cfx_form_add_exterior_facet_integral(cfx_ctx* ctx, cfx_form* f, int kernel, cfx_rules* rules,
+                                                const double* constants, int n_constants)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && f && rules, CFX_ERR_INVALID, "cfx_form_add_exterior_facet_integral: NULL argument");
+  CFX_REQUIRE(rules->entity_hosted, CFX_ERR_INVALID,
+              "cfx_form_add_exterior_facet_integral: the rules must come from a facet-hosted cut");
+  CFX_REQUIRE(kernel == CFX_K_ONE && f->rank == 0, CFX_ERR_UNSUPPORTED,
+              "run-time exterior-facet integrals: only the measure functional (CFX_K_ONE, rank 0) is shipped");
+  CFX_REQUIRE(n_constants >= 0 && n_constants <= CFX_MAX_CONSTANTS, CFX_ERR_INVALID, "too many constants");
+  f->integrals.emplace_back();
+  cfx_integral& I = f->integrals.back();
+  I.kernel = kernel;
+  I.facet = false;
+  I.entities = nullptr;
+  I.n = 0;
+  I.rules = rules;
+  for (int k = 0; k < n_constants; ++k)
+    I.constants[k] = constants[k];
+  if (n_constants == 0)
+    I.constants[0] = 1.0;
+  f->dirty = true;
+  CFX_API_END(ctx)
+}
+
 cfx_status cfx_form_add_cell_integral(cfx_ctx* ctx, cfx_form* f, int kernel, const int32_t* cells, int64_t n_cells,
                                       int memspace, cfx_rules* rules, const double* constants, int n_constants)
 {

@@ -51,6 +51,15 @@ class CutForm:
         self._owners += [keep, rules]
         return self
 
+    def add_exterior_facet_integral(self, kernel: str, rules: RuntimeQuadratureRules, constants=(1.0,)):
+        """`one * ds(subdomain_data=rules)` on facet-hosted rules (test_cut_api.py:504-527): the measure functional."""
+        cst = np.ascontiguousarray(list(constants), dtype=np.float64)
+        h = self.ctx.handle
+        check(h, lib().cfx_form_add_exterior_facet_integral(h, self._h, KERNEL[kernel], rules._h,
+                                                            C.c_void_p(cst.ctypes.data), int(cst.size)))
+        self._owners.append(rules)
+        return self
+
     def set_coefficient(self, values):
         """The form's ordinary Function coefficient (its x.array over owned+ghost dofs).  The reference packs it per
         entity before every assembly (pack_coefficients, pack_form.h:68-158, called from assembler.h:213-219); here

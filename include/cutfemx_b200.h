@@ -190,6 +190,11 @@ cfx_status cfx_form_add_cell_integral(cfx_ctx* ctx, cfx_form* f, int kernel, con
 cfx_status cfx_form_add_interior_facet_integral(cfx_ctx* ctx, cfx_form* f, int kernel, const int32_t* rows4,
                                                 int64_t n_facets, int memspace, const double* constants,
                                                 int n_constants);
+/* Exterior-facet integral over facet-hosted run-time rules (ufl.Measure("ds", subdomain_data=rules) on rules from a
+ * facet-hosted cut, test_cut_api.py:504-527).  Shipped family: CFX_K_ONE on a rank-0 form -- c0 times the measure of
+ * the selected part of the host facets. */
+cfx_status cfx_form_add_exterior_facet_integral(cfx_ctx* ctx, cfx_form* f, int kernel, cfx_rules* rules,
+                                                const double* constants, int n_constants);
 /* The ordinary Function coefficient of a form (pack_form.h:30-158 allocate_coefficient_storage / pack_coefficients):
  * values over the owned+ghost dofs of the form's space.  The kernels gather each entity's cstride = nd values
  * through the dofmap while they run, so no packed (n_entities, cstride) array is materialised.  The array is

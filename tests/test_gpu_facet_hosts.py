@@ -81,6 +81,11 @@ def test_weight_sum_does_not_depend_on_the_host_list(built_lib):
     verts, _, _ = O.facet_vertices(mesh, inside)
     full = np.linalg.norm(mesh.x[verts[:, 1]] - mesh.x[verts[:, 0]], axis=1).sum()
     np.testing.assert_allclose(full + r_all.weights.sum(), 0.51 + 0.51 + 1.0, rtol=1e-12)
+    # test_cut_api.py:504-527: one * ds(subdomain_data=rules) assembled as a scalar
+    form = cfx.fem.CutForm(V, 0).add_exterior_facet_integral("one", r_all, (2.0,))
+    value = cfx.fem.assemble_scalar(form)
+    assert np.isfinite(value) and value > 0.0
+    np.testing.assert_allclose(value, 2.0 * r_all.weights.sum(), rtol=1e-13)
 
 
 def test_facet_host_errors(built_lib):
