@@ -143,6 +143,7 @@ struct ECut
   int n_in = 0, nsub = 0;
   double P[4][EDIM > 1 ? EDIM : 1];
   int sub[2][NE];
+  int ifc[EDIM > 1 ? EDIM : 1]; // the interface simplex (dimension EDIM - 1) inside the facet: local point indices
 };
 
 template <int EDIM>
@@ -178,13 +179,17 @@ __device__ __forceinline__ void ecut_build(const double* phi, bool positive, ECu
         E.P[np][t] = refv(I[a], t) + tp * (refv(O[b], t) - refv(I[a], t));
     }
   if constexpr (EDIM == 1)
-  { // one inside vertex: the segment from it to the cut point
+  { // one inside vertex: the segment from it to the cut point; the interface is the cut point
     E.nsub = 1;
     E.sub[0][0] = 0;
     E.sub[0][1] = 1;
+    E.ifc[0] = 1;
   }
   else
   { // triangle: 1 inside -> (I0, c00, c01); 2 inside -> (I0, I1, c10), (I0, c10, c00)   [tri case table]
+    // interface segment: the two edge cuts (tri interface table {1,2} / {2,3})
+    E.ifc[0] = ni == 1 ? 1 : 2;
+    E.ifc[1] = ni == 1 ? 2 : 3;
     if (ni == 1)
     {
       E.nsub = 1;
@@ -208,7 +213,7 @@ __device__ __forceinline__ void ecut_build(const double* phi, bool positive, ECu
 template <int EDIM>
 __global__ void __launch_bounds__(EB2)
     ecut_count_kernel(const int8_t* __restrict__ codes, const double* __restrict__ phi, int64_t n, bool positive,
-                      int npts_s, int64_t* __restrict__ packed)
+                      bool interface, int npts_s, int64_t* __restrict__ packed)
 {
   constexpr int NE = EDIM + 1;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * EB2 + threadIdx.x;
@@ -220,7 +225,7 @@ __global__ void __launch_bounds__(EB2)
     ECut<EDIM> E;
     ecut_build<EDIM>(phi + i * NE, positive, E);
     if (E.nsub > 0)
-      pk = (int64_t(1) << 32) | static_cast<int64_t>(E.nsub * npts_s);
+      pk = (int64_t(1) << 32) | static_cast<int64_t>((interface ? 1 : E.nsub) * npts_s);
   }
   packed[i] = pk;
 }
@@ -229,7 +234,7 @@ template <int EDIM>
 __global__ void __launch_bounds__(EB2)
     ecut_fill_kernel(const int32_t* __restrict__ entities, const int32_t* __restrict__ verts,
                      const double* __restrict__ phi, const int8_t* __restrict__ codes, int64_t n,
-                     const int64_t* __restrict__ packed_excl, bool positive, int npts_s,
+                     const int64_t* __restrict__ packed_excl, bool positive, bool interface, int npts_s,
                      const double* __restrict__ rule_pts, const double* __restrict__ rule_wts,
                      const double* __restrict__ x, int64_t npts_total, double* __restrict__ points,
                      double* __restrict__ weights, int32_t* __restrict__ offsets, int32_t* __restrict__ parent_map,
@@ -277,6 +282,39 @@ __global__ void __launch_bounds__(EB2)
   ecut_build<EDIM>(phi + i * NE, positive, E);
   (void)codes;
   int64_t gp = p0;
+  if (interface)
+  { // phi = 0 inside the facet: a point (segment facets, weight 1) or a segment (triangle facets, physical length)
+    if constexpr (EDIM == 1)
+    {
+      points[gp] = E.P[E.ifc[0]][0];
+      weights[gp] = 1.0;
+    }
+    else
+    {
+      double Xa[GD], Xb[GD];
+#pragma unroll
+      for (int d = 0; d < GD; ++d)
+      {
+        const double a0 = E.P[E.ifc[0]][0], a1 = E.P[E.ifc[0]][1], b0 = E.P[E.ifc[1]][0], b1 = E.P[E.ifc[1]][1];
+        Xa[d] = (1.0 - a0 - a1) * X[0][d] + a0 * X[1][d] + a1 * X[2][d];
+        Xb[d] = (1.0 - b0 - b1) * X[0][d] + b0 * X[1][d] + b1 * X[2][d];
+      }
+      double len = 0.0;
+#pragma unroll
+      for (int d = 0; d < GD; ++d)
+        len += (Xb[d] - Xa[d]) * (Xb[d] - Xa[d]);
+      len = sqrt(len);
+      for (int q = 0; q < npts_s; ++q, ++gp)
+      {
+        const double lam = rule_pts[q]; // 1-D rule on [0, 1]
+#pragma unroll
+        for (int d = 0; d < EDIM; ++d)
+          points[static_cast<int64_t>(d) * npts_total + gp] = (1.0 - lam) * E.P[E.ifc[0]][d] + lam * E.P[E.ifc[1]][d];
+        weights[gp] = rule_wts[q] * len;
+      }
+    }
+    return;
+  }
   for (int s = 0; s < E.nsub; ++s)
   {
     double det;
@@ -435,8 +473,8 @@ cfx_status cfx_ecut_runtime_quadrature(cfx_ctx* ctx, const cfx_ecut* E, int ls, 
   CFX_REQUIRE(ctx && E && inout, CFX_ERR_INVALID, "cfx_ecut_runtime_quadrature: NULL argument");
   CFX_REQUIRE(ls >= 0 && ls < CFX_MAX_LEVEL_SETS && ctx->ls[ls].bound, CFX_ERR_INVALID,
               "cfx_ecut_runtime_quadrature: invalid level-set index");
-  CFX_REQUIRE(relation >= CFX_REL_LT && relation <= CFX_REL_GE, CFX_ERR_UNSUPPORTED,
-              "facet-hosted rules: only the parts phi<0, phi<=0, phi>0, phi>=0 are implemented");
+  CFX_REQUIRE(relation >= CFX_REL_LT && relation <= CFX_REL_EQ, CFX_ERR_INVALID,
+              "cfx_ecut_runtime_quadrature: invalid relation");
   CFX_REQUIRE(order >= 0, CFX_ERR_INVALID, "runtime_quadrature: order must be >= 0"); // cut.cpp:164-168
   if (*inout == nullptr)
     *inout = new cfx_rules();
@@ -451,7 +489,12 @@ cfx_status cfx_ecut_runtime_quadrature(cfx_ctx* ctx, const cfx_ecut* E, int ls, 
   R->has_moments = false;
   R->entity_hosted = true;
   const bool positive = relation == CFX_REL_GT || relation == CFX_REL_GE;
-  RuleTable& rt = get_rule(ctx, edim, order);
+  const bool interface = relation == CFX_REL_EQ;
+  // the interface inside a segment facet is a point: one "rule point" of weight 1, no table needed
+  RuleTable* rtp = (interface && edim == 1) ? nullptr : &get_rule(ctx, interface ? edim - 1 : edim, order);
+  const int npts_s = rtp ? rtp->npts : 1;
+  const double* d_pts = rtp ? rtp->d_pts : nullptr;
+  const double* d_wts = rtp ? rtp->d_wts : nullptr;
   const int64_t n = E->n;
   R->nrules = R->npts = 0;
   R->offsets.reserve(ctx->pool, static_cast<size_t>(n) + 2);
@@ -464,9 +507,9 @@ cfx_status cfx_ecut_runtime_quadrature(cfx_ctx* ctx, const cfx_ecut* E, int ls, 
   const int8_t* codes = E->codes.p + static_cast<size_t>(ls) * E->stride;
   const double* phi = E->phi.p + static_cast<size_t>(ls) * n * ne;
   if (edim == 1)
-    CFX_LAUNCH(ctx, ecut_count_kernel<1>, grid_for(n, EB2), EB2, 0, codes, phi, n, positive, rt.npts, packed.p);
+    CFX_LAUNCH(ctx, ecut_count_kernel<1>, grid_for(n, EB2), EB2, 0, codes, phi, n, positive, interface, npts_s, packed.p);
   else
-    CFX_LAUNCH(ctx, ecut_count_kernel<2>, grid_for(n, EB2), EB2, 0, codes, phi, n, positive, rt.npts, packed.p);
+    CFX_LAUNCH(ctx, ecut_count_kernel<2>, grid_for(n, EB2), EB2, 0, codes, phi, n, positive, interface, npts_s, packed.p);
   exclusive_scan_i64(ctx, packed.p, n, packed_excl.p);
   const int64_t tot = read_back(ctx, ctx->scratch64.p, 1)[0];
   R->nrules = tot >> 32;
@@ -477,11 +520,11 @@ cfx_status cfx_ecut_runtime_quadrature(cfx_ctx* ctx, const cfx_ecut* E, int ls, 
   R->rule_verts.reserve(ctx->pool, static_cast<size_t>(R->nrules) * ne + 1);
   if (edim == 1)
     CFX_LAUNCH(ctx, ecut_fill_kernel<1>, grid_for(n, EB2), EB2, 0, E->entities.p, E->verts.p, phi, codes, n,
-               packed_excl.p, positive, rt.npts, rt.d_pts, rt.d_wts, ctx->x, R->npts, R->points.p, R->weights.p,
+               packed_excl.p, positive, interface, npts_s, d_pts, d_wts, ctx->x, R->npts, R->points.p, R->weights.p,
                R->offsets.p, R->parent_map.p, R->rule_verts.p);
   else
     CFX_LAUNCH(ctx, ecut_fill_kernel<2>, grid_for(n, EB2), EB2, 0, E->entities.p, E->verts.p, phi, codes, n,
-               packed_excl.p, positive, rt.npts, rt.d_pts, rt.d_wts, ctx->x, R->npts, R->points.p, R->weights.p,
+               packed_excl.p, positive, interface, npts_s, d_pts, d_wts, ctx->x, R->npts, R->points.p, R->weights.p,
                R->offsets.p, R->parent_map.p, R->rule_verts.p);
   CFX_CUDA(cudaStreamSynchronize(ctx->stream));
   packed.release();

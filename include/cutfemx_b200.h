@@ -149,8 +149,8 @@ cfx_status cfx_evaluate_values(cfx_ctx* ctx, int ls, const cfx_rules* r, double*
  * order of the list (host_parent_index, cut.cpp:344-359); the rules have tdim = mesh tdim - 1, points in the facet's
  * reference coordinates (vertices in ascending vertex number), physical weights and parent_map = facet ids
  * (test_cut_api.py:171-188, :349-367, :424-501).  cfx_rules_physical_points / _fetch / _sizes work on them; they
- * cannot be attached to cell integrals.  Needs cfx_topology_bind.  Relation "=" (the interface inside a facet) is
- * not implemented. */
+ * cannot be attached to cell integrals.  Needs cfx_topology_bind.  Relation "=" gives the interface inside each cut
+ * facet: a segment with its physical length (triangle facets) or the cut point with weight 1 (segment facets). */
 typedef struct cfx_ecut cfx_ecut;
 cfx_status cfx_cut_facets(cfx_ctx* ctx, const int32_t* facets, int64_t n, int memspace, cfx_ecut** inout);
 cfx_status cfx_ecut_locate(cfx_ctx* ctx, const cfx_ecut* e, int n_terms, const int32_t* term_offsets,

@@ -436,6 +436,12 @@ def facet_runtime_quadrature(mesh, ls_dofmap, values, facets, relation: str, ord
             t = phi[i, a] / (phi[i, a] - phi[i, b])
             xa, xc = float(a), float(a) + t * (float(b) - float(a))  # reference coordinate of vertex q is q
             length = np.linalg.norm(X[i, 1] - X[i, 0])
+            if relation == "=":  # the interface inside a segment is the cut point, counting measure
+                pts.append(np.array([xc]))
+                wts.append(np.array([1.0]))
+                off.append(off[-1] + 1)
+                pm.append(int(np.asarray(facets)[i]))
+                continue
             pts.append(xa + p * (xc - xa))
             wts.append(w * abs(xc - xa) * length)
             off.append(off[-1] + w.size)

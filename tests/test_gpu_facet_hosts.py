@@ -41,7 +41,7 @@ def test_facet_hosts_against_the_oracle(built_lib, tdim, n, fn):
         # test_cut_api.py:171-188: the three parts are disjoint and cover the host list
         assert np.array_equal(np.sort(np.concatenate([neg, cut, pos])), np.sort(facets))
         assert np.array_equal(cfx.locate_entities(cd, "phi<=0"), facets[code != O.OUTSIDE])
-        for rel, sel, order in (("<", "phi<0", 2), (">", "phi>0", 3), ("<=", "phi<=0", 1)):
+        for rel, sel, order in (("<", "phi<0", 2), (">", "phi>0", 3), ("<=", "phi<=0", 1), ("=", "phi=0", 2)):
             r = cfx.runtime_quadrature(cd, sel, order)
             ro = O.facet_runtime_quadrature(mesh, V.dofmap, phi.x.array, facets, rel, order)
             # test_cut_api.py:405-421 / :439-455
@@ -63,7 +63,10 @@ def test_facet_hosts_against_the_oracle(built_lib, tdim, n, fn):
                 np.testing.assert_allclose(xp.T, xref, rtol=0, atol=1e-14)
                 _, _, pv = O.classify_facets(mesh, V.dofmap, phi.x.array, r.parent_map)
                 phi_h = np.einsum("pk,pk->p", lam, pv[rule_of_pt])
-                assert np.all(phi_h < 1e-12) if rel in ("<", "<=") else np.all(phi_h > -1e-12)
+                if rel == "=":
+                    assert np.all(np.abs(phi_h) < 1e-12)
+                else:
+                    assert np.all(phi_h < 1e-12) if rel in ("<", "<=") else np.all(phi_h > -1e-12)
 
 
 def test_weight_sum_does_not_depend_on_the_host_list(built_lib):
@@ -95,8 +98,9 @@ def test_facet_host_errors(built_lib):
     cd = cfx.cut(phi, np.nonzero(np.diff(mesh.f2c_offsets) >= 1)[0].astype(np.int32), 1)
     with pytest.raises(ValueError, match="cell-hosted"):  # python/cutfemx/cut.py:350-351
         cfx.ghost_penalty_facets(cd, "phi<0")
-    with pytest.raises(cfx.CfxError):  # the interface inside a facet is not implemented
-        cfx.runtime_quadrature(cd, "phi=0", 2)
+    ri = cfx.runtime_quadrature(cd, "phi=0", 2)  # the interface inside segment facets: the cut points, weight 1
+    assert ri.tdim == 1 and np.all(ri.weights == 1.0) and ri.weights.size == ri.parent_map.size
+    np.testing.assert_allclose(ri.with_physical_points().physical_points[0], 0.51, rtol=0, atol=1e-14)
     rules = cfx.runtime_quadrature(cd, "phi<0", 2)
     with pytest.raises(cfx.CfxError):  # facet rules do not fit cell integrals
         cfx.fem.CutForm(V, 0).add_cell_integral("one", None, rules, (1.0,))

@@ -510,3 +510,7 @@ def test_facet_hosted_rules_measure_the_wet_boundary_exactly():
                    0.5 * np.linalg.norm(np.cross(Xo[:, 1] - Xo[:, 0], Xo[:, 2] - Xo[:, 0]), axis=1).sum())
             np.testing.assert_allclose(full + r.weights.sum() + dry + rp.weights.sum(), 4.0 if tdim == 2 else 6.0,
                                        rtol=1e-12)
+            # the interface inside the boundary facets: two waterline points on the square; on the cube the
+            # waterline x + 0.3 y = 0.52 has length 1 + 1 + 2 sqrt(1.09)
+            ri = O.facet_runtime_quadrature(mesh, V.dofmap, phi.x.array, facets, "=", order)
+            np.testing.assert_allclose(ri.weights.sum(), 2.0 if tdim == 2 else 2.0 + 2.0 * np.sqrt(1.09), rtol=1e-12)
