@@ -1103,14 +1103,15 @@ constexpr int GWM = 4; // rows per block of the mask kernel
 // rows no active entity touches: optional identity diagonal (deactivate_outside, deactivate.h:402-418)
 __global__ void inactive_diag_kernel(const uint8_t* __restrict__ row_flag, int64_t n_rows,
                                      const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ cols,
-                                     double* __restrict__ vals, double diag)
+                                     double* __restrict__ vals, double diag, int bs)
 {
   const int64_t r = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   if (r >= n_rows || row_flag[r])
     return;
   for (int64_t p = row_ptr[r]; p < row_ptr[r + 1]; ++p)
     if (cols[p] == r)
-      vals[p] = diag;
+      for (int k = 0; k < bs; ++k) // blocked matrices: the diagonal of the diagonal block
+        vals[p * bs * bs + k * bs + k] = diag;
 }
 
 // Interior-facet macro rows of the band cells among this warp's (<= 32) incident cells.  Lane l owns
@@ -2817,11 +2818,9 @@ static void assemble_matrix_impl(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, int 
     }
     if (zero_first)
       CFX_CUDA(cudaMemsetAsync(A->values.p, 0, static_cast<size_t>(A->nnz) * S.bs * S.bs * sizeof(double), ctx->stream));
-    CFX_REQUIRE(diag_inactive == 0.0 || S.bs == 1, CFX_ERR_UNSUPPORTED,
-                "diag_inactive is not supported for blocked matrices yet");
     if (diag_inactive != 0.0)
       CFX_LAUNCH(ctx, inactive_diag_kernel, grid_for(A->n_rows, 256), 256, 0, a->prep->row_flag.p, A->n_rows, A->row_ptr.p,
-                 A->cols.p, A->values.p, diag_inactive);
+                 A->cols.p, A->values.p, diag_inactive, S.bs);
     CFX_DISPATCH_ELEM(ctx, S, launch_gather_matrix, ctx, a, A, gc, stt, stL, zero_first);
     set_facet_slots(ctx, FI, true);
   }

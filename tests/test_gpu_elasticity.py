@@ -179,6 +179,9 @@ def test_blocked_active_domain_deactivation_and_clamped_solve(problem):
     cfx.fem.deactivate_outside(A, b, ad)
     O.deactivate_outside(p["rp"], p["cols"], ref, inactive_ref, 1.0, None, 0.0, bs)
     assert rel(A.data, ref) < 1e-11
+    # the same diagonal through the diag_inactive option of the assembly (blocked matrices included)
+    A2 = cfx.fem.assemble_matrix(a, bcs=[bc], diag_inactive=1.0)
+    assert rel(A2.data, ref) < 1e-11
     # the translation (zero outside the active domain) solves the constrained, deactivated system
     Ms = A.to_scipy()
     gv = np.zeros(n)
