@@ -22,7 +22,6 @@
 // FFCx would pick (sum of argument degrees) scaled by |detJ|.
 //
 // Roofline: HBM for P1/P2 scalar forms (SURVEY.md section 8d "K4", "K5").
-#include <cstdlib>
 #include <algorithm>
 
 #include "common.cuh"
