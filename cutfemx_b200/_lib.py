@@ -39,7 +39,7 @@ SYMBOLS = [
     "cfx_assemble_scalar", "cfx_stage_count", "cfx_stage_name", "cfx_stage_timing_enable", "cfx_stage_ms",
     "cfx_stage_reset", "cfx_form_insert_pattern_entries", "cfx_create_sparsity_rows", "cfx_pattern_positions",
     "cfx_gather_f64", "cfx_scatter_add_f64", "cfx_active_domain", "cfx_active_indicator_device_ptr",
-    "cfx_inactive_dofs", "cfx_deactivate_outside", "cfx_assemble_matrix_bc", "cfx_set_diagonal", "cfx_apply_lifting",
+    "cfx_inactive_dofs", "cfx_deactivate_outside", "cfx_assemble_matrix_bc", "cfx_assemble_system_bc", "cfx_set_diagonal", "cfx_apply_lifting",
     "cfx_set_bc", "cfx_meshgen_box", "cfx_meshgen_rectangle", "cfx_meshgen_level_set",
 ]
 

@@ -151,6 +151,14 @@ __global__ void set_bc_kernel(const int32_t* __restrict__ dofs, int64_t n, int64
   b[d] = alpha * (g[d] - (x0 ? x0[d] : 0.0));
 }
 
+__global__ void set_bc_marked_kernel(const int8_t* __restrict__ markers, int64_t n, const double* __restrict__ g,
+                                     const double* __restrict__ x0, double alpha, double* __restrict__ b)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i < n && markers[i])
+    b[i] = alpha * (g[i] - (x0 ? x0[i] : 0.0));
+}
+
 void launch_rows(cfx_ctx* ctx, cfx_pattern* A, const int8_t* bc0, const int8_t* bc1, int mask, int lift,
                  const double* g, const double* x0, double alpha, double* b)
 {
@@ -281,6 +289,37 @@ cfx_status cfx_apply_lifting(cfx_ctx* ctx, const cfx_form* a, cfx_pattern* A, do
   ownx.release();
   ownb.release();
   prior.release();
+  CFX_API_END(ctx)
+}
+
+// assemble_matrix(a, bcs) + assemble_vector(L) + apply_lifting + set_bc in ONE assembly (the flow of
+// demo_elasticity.py:78-84): the unconstrained system is assembled once, one pass over its rows lifts the
+// Dirichlet columns into b and zeroes the Dirichlet rows and columns, then the diagonal and the constrained
+// entries of b are set.  A and b are overwritten (zero_first semantics); all arrays are DEVICE arrays.
+cfx_status cfx_assemble_system_bc(cfx_ctx* ctx, const cfx_form* a, cfx_pattern* A, const cfx_form* L, double* b,
+                                  const int8_t* bc_markers, const double* bc_values, const double* x0, double alpha,
+                                  const int32_t* bc_rows_owned, int64_t n_bc_rows, double diagonal)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && a && A && L && b && bc_markers && bc_values && (n_bc_rows == 0 || bc_rows_owned), CFX_ERR_INVALID,
+              "cfx_assemble_system_bc: NULL argument");
+  const Space& S = ctx->spaces[A->space];
+  cfx_status rc = cfx_assemble_system(ctx, a, A, 1, 0.0, L, b, 1);
+  if (rc != CFX_OK)
+    return rc;
+  {
+    StageScope st(ctx, "dirichlet_rows", 12.0 * static_cast<double>(A->nnz));
+    launch_rows(ctx, A, bc_markers, bc_markers, 1, 1, bc_values, x0, alpha, b);
+  }
+  if (n_bc_rows > 0)
+  {
+    CFX_LAUNCH(ctx, set_diagonal_blocked_kernel, grid_for(n_bc_rows, 256), 256, 0, bc_rows_owned, n_bc_rows, A->n_rows,
+               A->bs, A->row_ptr.p, A->cols.p, A->values.p, diagonal, ctx->err_flag.p);
+    // every constrained entry of b this rank holds (owned and ghost): the marker array is the list
+    CFX_LAUNCH(ctx, set_bc_marked_kernel, grid_for(static_cast<int64_t>(S.n_total) * S.bs, 256), 256, 0, bc_markers,
+               static_cast<int64_t>(S.n_total) * S.bs, bc_values, x0, alpha, b);
+    check_device_error(ctx, "cfx_assemble_system_bc (Dirichlet row out of range or without a diagonal entry)");
+  }
   CFX_API_END(ctx)
 }
 

@@ -323,6 +323,31 @@ def assemble_matrix(a: CutForm, A: MatrixCSR | None = None, *, bcs=None, diag: f
     return A
 
 
+def assemble_system_bc(a: CutForm, A: MatrixCSR, L: CutForm, b, bcs, x0=None, alpha: float = 1.0, diag: float = 1.0):
+    """assemble_matrix(a, bcs) + assemble_vector(L) + apply_lifting + set_bc (demo_elasticity.py:78-84) with ONE
+    assembly of the unconstrained system (cfx_assemble_system_bc).  `b`: torch CUDA vector (owned+ghost, blocked),
+    overwritten like A."""
+    import torch
+
+    if not is_device_array(b):
+        raise TypeError("assemble_system_bc needs a device vector (torch CUDA tensor)")
+    V = a.function_space
+    markers, values = _bc_arrays(V, bcs)
+    dev = b.device
+    tm = torch.from_numpy(markers).to(dev)
+    tv = torch.from_numpy(values).to(dev)
+    tx = None if x0 is None else torch.as_tensor(np.ascontiguousarray(x0, dtype=np.float64), device=dev)
+    rows = np.unique(np.concatenate([bc.owned_dofs() for bc in bcs])).astype(np.int32) if bcs else np.zeros(0, np.int32)
+    tr = torch.from_numpy(rows).to(dev)
+    h = a.ctx.handle
+    check(h, lib().cfx_assemble_system_bc(h, a._h, A._h, L._h, C.c_void_p(b.data_ptr()), C.c_void_p(tm.data_ptr()),
+                                          C.c_void_p(tv.data_ptr()), None if tx is None else C.c_void_p(tx.data_ptr()),
+                                          C.c_double(alpha), C.c_void_p(tr.data_ptr()) if rows.size else None,
+                                          C.c_int64(rows.size), C.c_double(diag)))
+    A._cache.pop("data", None)
+    return A, b
+
+
 def apply_lifting(b: np.ndarray, a, bcs, x0=None, alpha: float = 1.0, *, A=None) -> None:
     """cutfemx.fem.apply_lifting (fem.py:604-635 -> assemble_vector_impl.h:383-564):
     b -= alpha * A_j (g_j - x0_j) for every bilinear form a[j] with conditions bcs[j].  `A`: matrices (or one

@@ -272,6 +272,14 @@ cfx_status cfx_set_diagonal(cfx_ctx* ctx, cfx_pattern* A, const int32_t* rows, i
  * b, bc_values1, bc_markers1 and x0 live in `memspace`, n_dofs_total*bs entries each. */
 cfx_status cfx_apply_lifting(cfx_ctx* ctx, const cfx_form* a, cfx_pattern* A, double* b, const double* bc_values1,
                              const int8_t* bc_markers1, const double* x0, double alpha, int memspace);
+/* The constrained system of demo_elasticity.py:78-84 in one assembly: A = assemble_matrix(a, bcs) with `diagonal` on
+ * the owned Dirichlet rows, b = assemble_vector(L) - alpha A_unconstrained[:, bc] (bc_values - x0), then
+ * b[bc] = alpha (bc_values - x0).  The unconstrained system is assembled once and one pass over its CSR rows does the
+ * lifting and the masking (cfx_apply_lifting alone has to assemble the form a second time).  A and b are
+ * overwritten; b, bc_markers, bc_values, x0 (may be NULL), bc_rows_owned are DEVICE arrays. */
+cfx_status cfx_assemble_system_bc(cfx_ctx* ctx, const cfx_form* a, cfx_pattern* A, const cfx_form* L, double* b,
+                                  const int8_t* bc_markers, const double* bc_values, const double* x0, double alpha,
+                                  const int32_t* bc_rows_owned, int64_t n_bc_rows, double diagonal);
 /* DirichletBC::set as fem.set_bc uses it: b[d] = alpha * (bc_values[d] - x0[d]) for the listed blocked dof
  * indices d; b, bc_values and x0 (may be NULL) have n_total entries. */
 cfx_status cfx_set_bc(cfx_ctx* ctx, double* b, int64_t n_total, const int32_t* dofs, int64_t n, const double* bc_values,

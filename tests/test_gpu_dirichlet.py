@@ -162,3 +162,28 @@ def test_constrained_solve_reproduces_a_linear_field(built_lib):
     cfx.fem.deactivate_outside(A, b, ad)
     u = spla.spsolve(A.to_scipy().tocsc(), b)
     np.testing.assert_allclose(u[active], u_lin[active], rtol=0, atol=1e-11)
+
+
+def test_system_with_bcs_in_one_assembly(problem):
+    """cfx_assemble_system_bc == assemble_matrix(bcs) + assemble_vector + apply_lifting + set_bc, the sequence of
+    demo_elasticity.py:78-84, with one assembly of the unconstrained system."""
+    import torch
+
+    p = problem
+    cfx, V, bs = p["cfx"], p["V"], p["bs"]
+    n = V.num_dofs * bs
+    rng = np.random.default_rng(11)
+    x0, alpha = rng.standard_normal(n), 0.8
+    L = cfx.fem.CutForm(V, 1)  # zero load, as in demo_elasticity.py:238
+    # the reference sequence, call by call
+    A1 = cfx.fem.assemble_matrix(p["a"], bcs=p["bcs"])
+    b1 = cfx.fem.assemble_vector(L)
+    cfx.fem.apply_lifting(b1, [p["a"]], [p["bcs"]], [x0], alpha, A=[A1])
+    cfx.fem.set_bc(b1, p["bcs"], x0, alpha)
+    # one call
+    A2 = cfx.fem.create_matrix(p["a"])
+    b2 = torch.zeros(n, dtype=torch.float64, device="cuda:0")
+    cfx.fem.assemble_system_bc(p["a"], A2, L, b2, p["bcs"], x0, alpha)
+    assert np.array_equal(A2.indptr, A1.indptr) and np.array_equal(A2.indices, A1.indices)
+    assert rel(A2.data, A1.data) < 1e-13
+    assert rel(b2.cpu().numpy(), b1) < 1e-11
