@@ -44,7 +44,8 @@ template <int ND>
 __global__ void __launch_bounds__(CB)
     classify_kernel(const int32_t* __restrict__ dofmap, const double* __restrict__ vals, int64_t nc_total,
                     int64_t nc_owned, int8_t* __restrict__ domain, unsigned long long* __restrict__ counts,
-                    const uint8_t* __restrict__ host /* null: every cell is a host of the cut */)
+                    const uint8_t* __restrict__ host /* null: every cell is a host of the cut */,
+                    int32_t* __restrict__ blk_counts /* (blocks, 4): owned inside / intersected / outside */)
 {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * CB + threadIdx.x) >> 5;
@@ -102,15 +103,40 @@ __global__ void __launch_bounds__(CB)
     atomicAdd(&s_cnt[2], n_out);
   }
   __syncthreads();
+  if (threadIdx.x < 3)
+    blk_counts[static_cast<int64_t>(blockIdx.x) * 4 + threadIdx.x] = s_cnt[threadIdx.x];
   if (threadIdx.x < 3 && s_cnt[threadIdx.x] != 0)
     atomicAdd(&counts[threadIdx.x], static_cast<unsigned long long>(s_cnt[threadIdx.x]));
 }
 
+// per compaction tile (CP_TILE cells = CP_TILE / (CB * CPT) classification blocks): owned cells whose domain code is
+// in `relmask` -- the counts compact_count_kernel<DnfPred> would produce for a single-clause selector
+__global__ void tile_counts_from_classes_kernel(const int32_t* __restrict__ blk_counts, int64_t n_blocks, unsigned relmask,
+                                                int64_t n_tiles, int32_t* __restrict__ tile_counts)
+{
+  constexpr int PER = CP_TILE / (CB * CPT);
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (t >= n_tiles)
+    return;
+  int s = 0;
+  for (int q = 0; q < PER; ++q)
+  {
+    const int64_t b = t * PER + q;
+    if (b >= n_blocks)
+      break;
+    const int4 v = *reinterpret_cast<const int4*>(blk_counts + b * 4);
+    s += ((relmask >> CFX_DOMAIN_INSIDE) & 1u) ? v.x : 0;
+    s += ((relmask >> CFX_DOMAIN_INTERSECTED) & 1u) ? v.y : 0;
+    s += ((relmask >> CFX_DOMAIN_OUTSIDE) & 1u) ? v.z : 0;
+  }
+  tile_counts[t] = s;
+}
+
 template <int ND>
-void launch_classify(cfx_ctx* c, const LevelSet& L, int8_t* domain, unsigned long long* counts)
+void launch_classify(cfx_ctx* c, const LevelSet& L, int8_t* domain, unsigned long long* counts, int32_t* blk_counts)
 {
   CFX_LAUNCH(c, classify_kernel<ND>, grid_for(c->nc_total, CB * CPT), CB, 0, L.dofmap, L.values, c->nc_total, c->nc_owned,
-             domain, counts, c->has_host_mask ? c->host_mask.p : nullptr);
+             domain, counts, c->has_host_mask ? c->host_mask.p : nullptr, blk_counts);
 }
 } // namespace
 
@@ -119,6 +145,9 @@ void classify_all(cfx_ctx* c)
   c->scratch64.reserve(c->pool, 64);
   unsigned long long* counts = reinterpret_cast<unsigned long long*>(c->scratch64.p) + 8;
   CFX_CUDA(cudaMemsetAsync(counts, 0, 3 * CFX_MAX_LEVEL_SETS * sizeof(unsigned long long), c->stream));
+  static_assert(CP_TILE % (CB * CPT) == 0, "a compaction tile is a whole number of classification blocks");
+  c->cls_blocks = grid_for(c->nc_total, CB * CPT);
+  c->cls_counts.reserve(c->pool, static_cast<size_t>(CFX_MAX_LEVEL_SETS) * c->cls_blocks * 4 + 4);
   for (int l = 0; l < CFX_MAX_LEVEL_SETS; ++l)
   {
     LevelSet& L = c->ls[l];
@@ -128,12 +157,13 @@ void classify_all(cfx_ctx* c)
                   static_cast<double>(c->nc_total) * (4.0 * L.nd + 1.0) + 8.0 * static_cast<double>(L.n_dofs));
     int8_t* dom = c->domain.p + static_cast<size_t>(l) * c->domain_stride;
     unsigned long long* cnt = counts + 3 * l;
+    int32_t* blk = c->cls_counts.p + static_cast<size_t>(l) * c->cls_blocks * 4;
     switch (L.nd)
     {
-    case 3: launch_classify<3>(c, L, dom, cnt); break;
-    case 4: launch_classify<4>(c, L, dom, cnt); break;
-    case 6: launch_classify<6>(c, L, dom, cnt); break;
-    case 10: launch_classify<10>(c, L, dom, cnt); break;
+    case 3: launch_classify<3>(c, L, dom, cnt, blk); break;
+    case 4: launch_classify<4>(c, L, dom, cnt, blk); break;
+    case 6: launch_classify<6>(c, L, dom, cnt, blk); break;
+    case 10: launch_classify<10>(c, L, dom, cnt, blk); break;
     default: throw Error(CFX_ERR_UNSUPPORTED, "classify: unsupported level-set dofmap width");
     }
   }
@@ -166,6 +196,24 @@ Dnf make_dnf(cfx_ctx* c, int n_terms, const int32_t* term_offsets, const int32_t
   return d;
 }
 
+// owned cells matching a compiled selector.  A single clause `name rel 0` needs no counting pass: the per-tile
+// counts follow from the classification's block counts.
+int64_t compact_owned_cells(cfx_ctx* c, const Dnf& d, DevBuf<int32_t>& out)
+{
+  DnfPred p{d, c->domain.p, c->domain_stride};
+  const int64_t n = c->nc_owned;
+  const bool single = d.n_terms == 1 && d.term_off[1] == 1 && n > 0 && c->cls_blocks > 0;
+  if (single)
+  {
+    const int64_t nt = grid_for(n, CP_TILE);
+    c->blk_counts.reserve(c->pool, static_cast<size_t>(nt));
+    CFX_LAUNCH(c, tile_counts_from_classes_kernel, grid_for(nt, 256), 256, 0,
+               c->cls_counts.p + static_cast<size_t>(d.ls[0]) * c->cls_blocks * 4, c->cls_blocks,
+               static_cast<unsigned>(d.relmask[0]), nt, c->blk_counts.p);
+  }
+  return compact_indices(c, n, p, out, single);
+}
+
 void ensure_cut_list(cfx_ctx* c, int ls)
 {
   LevelSet& L = c->ls[ls];
@@ -177,9 +225,8 @@ void ensure_cut_list(cfx_ctx* c, int ls)
   d.term_off[1] = 1;
   d.ls[0] = static_cast<int8_t>(ls);
   d.relmask[0] = relation_mask(CFX_REL_EQ);
-  DnfPred p{d, c->domain.p, c->domain_stride};
   StageScope st(c, "locate_cut", static_cast<double>(c->nc_owned) * 2.0 + 4.0 * static_cast<double>(L.counts[1]));
-  L.n_cut = compact_indices(c, c->nc_owned, p, L.cut_list);
+  L.n_cut = compact_owned_cells(c, d, L.cut_list);
 }
 // intersected cells among ALL local cells (owned + ghost).  The reference's Python loop
 // (cut.py:364-379) starts from locate_entities(...), i.e. owned cells only, and therefore drops band
@@ -264,11 +311,11 @@ extern "C" cfx_status cfx_locate_entities(cfx_ctx* ctx, int n_terms, const int32
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && ctx->classified, CFX_ERR_STATE, "cfx_locate_entities: call cfx_update first");
   CFX_REQUIRE(out != nullptr, CFX_ERR_INVALID, "cfx_locate_entities: out is NULL");
-  DnfPred p{make_dnf(ctx, n_terms, term_offsets, clause_ls, clause_rel), ctx->domain.p, ctx->domain_stride};
+  const Dnf d = make_dnf(ctx, n_terms, term_offsets, clause_ls, clause_rel);
   if (*out == nullptr)
     *out = new cfx_list();
   StageScope st(ctx, "locate", static_cast<double>(ctx->nc_owned) * 2.0);
-  (*out)->n = compact_indices(ctx, ctx->nc_owned, p, (*out)->data);
+  (*out)->n = compact_owned_cells(ctx, d, (*out)->data);
   st.set_bytes(static_cast<double>(ctx->nc_owned) * 2.0 + 4.0 * static_cast<double>((*out)->n));
   CFX_API_END(ctx)
 }

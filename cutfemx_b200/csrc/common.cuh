@@ -330,6 +330,10 @@ struct cfx_ctx
   // domain code 0, which no selector matches; null = every local cell is a host
   cfx::DevBuf<uint8_t> host_mask;
   bool has_host_mask = false;
+  // per classification block (1024 cells) and level set: owned cells inside / intersected / outside -- lets a
+  // single-clause locate skip its counting pass over the domain codes (classify.cu)
+  cfx::DevBuf<int32_t> cls_counts; // (CFX_MAX_LEVEL_SETS, cls_blocks, 4)
+  int64_t cls_blocks = 0;
   cfx::DevBuf<int8_t> domain; // (CFX_MAX_LEVEL_SETS, domain_stride)
   int64_t domain_stride = 0;
   bool classified = false;

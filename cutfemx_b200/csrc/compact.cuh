@@ -60,8 +60,10 @@ __global__ void __launch_bounds__(CP_BLOCK)
 }
 
 // Returns the number of selected indices; `out` is (re)allocated to exactly that size.
+// `counted`: c->blk_counts already holds the per-tile counts (the caller reserved it for grid_for(n, CP_TILE)
+// tiles and filled it), so the counting pass over the predicate is skipped.
 template <class Pred>
-int64_t compact_indices(cfx_ctx* c, int64_t n, Pred pred, DevBuf<int32_t>& out)
+int64_t compact_indices(cfx_ctx* c, int64_t n, Pred pred, DevBuf<int32_t>& out, bool counted = false)
 {
   if (n <= 0)
   {
@@ -71,7 +73,8 @@ int64_t compact_indices(cfx_ctx* c, int64_t n, Pred pred, DevBuf<int32_t>& out)
   const unsigned nb = grid_for(n, CP_TILE);
   c->blk_counts.reserve(c->pool, nb);
   c->blk_offsets.reserve(c->pool, nb);
-  CFX_LAUNCH(c, compact_count_kernel<Pred>, nb, CP_BLOCK, 0, pred, n, c->blk_counts.p);
+  if (!counted)
+    CFX_LAUNCH(c, compact_count_kernel<Pred>, nb, CP_BLOCK, 0, pred, n, c->blk_counts.p);
   scan_block_counts(c, c->blk_counts.p, nb, c->blk_offsets.p);
   const int64_t total = read_back(c, c->scratch64.p, 1)[0];
   out.reserve(c->pool, static_cast<size_t>(total > 0 ? total : 1));
