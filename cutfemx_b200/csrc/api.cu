@@ -187,8 +187,8 @@ cfx_status cfx_topology_bind(cfx_ctx* ctx, const int32_t* c2f, const int32_t* f2
   ctx->n_facets = n_facets;
   ctx->n_owned_facets = n_owned_facets;
   ctx->f2c2.reserve(ctx->pool, static_cast<size_t>(n_facets) * 2);
-  ctx->facet_flag.reserve(ctx->pool, static_cast<size_t>(n_facets));
-  CFX_CUDA(cudaMemsetAsync(ctx->facet_flag.p, 0, static_cast<size_t>(n_facets), ctx->stream));
+  ctx->facet_flag.reserve(ctx->pool, static_cast<size_t>(n_facets) + 4); // marked through 32-bit atomics
+  CFX_CUDA(cudaMemsetAsync(ctx->facet_flag.p, 0, static_cast<size_t>(n_facets) + 4, ctx->stream));
   ctx->facet_slot.reserve(ctx->pool, static_cast<size_t>(n_facets));
   CFX_CUDA(cudaMemsetAsync(ctx->facet_slot.p, 0xff, static_cast<size_t>(n_facets) * sizeof(int32_t), ctx->stream));
   ctx->topo_bound = true;

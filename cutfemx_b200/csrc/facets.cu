@@ -121,7 +121,7 @@ template <class Active>
 __global__ void mark_facets_kernel(const int32_t* __restrict__ src_cells, int64_t n_src, int nf,
                                    const int32_t* __restrict__ c2f, const int32_t* __restrict__ f2c2, Active active,
                                    int64_t n_owned_facets, int include_ghosts, uint8_t* __restrict__ facet_flag,
-                                   int64_t n_cells)
+                                   int64_t n_cells, int32_t* __restrict__ tile_counts)
 {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * FB + threadIdx.x;
   if (i >= n_src * nf)
@@ -136,7 +136,13 @@ __global__ void mark_facets_kernel(const int32_t* __restrict__ src_cells, int64_
   if (c1 < 0)
     return; // not exactly two cells
   if (active(c0) && active(c1))
-    facet_flag[f] = 1;
+  { // first writer of the flag also counts the facet for its compaction tile (integer atomics: exact totals), so
+    // the compaction needs no counting pass over the whole facet flag array
+    unsigned int* w = reinterpret_cast<unsigned int*>(facet_flag) + (f >> 2);
+    const unsigned int bit = 1u << (8 * (f & 3));
+    if (!(atomicOr(w, bit) & bit))
+      atomicAdd(&tile_counts[f / CP_TILE], 1);
+  }
 }
 
 __global__ void clear_flags_kernel(const int32_t* __restrict__ idx, int64_t n, uint8_t* __restrict__ flag)
@@ -192,11 +198,14 @@ int64_t band_from_flags(cfx_ctx* c, const int32_t* src_cells, int64_t n_src, Act
                         cfx_list* out)
 {
   const int nf = c->tdim + 1;
+  const unsigned nt = grid_for(c->n_facets, CP_TILE);
+  c->blk_counts.reserve(c->pool, nt);
+  CFX_CUDA(cudaMemsetAsync(c->blk_counts.p, 0, static_cast<size_t>(nt) * sizeof(int32_t), c->stream));
   if (n_src > 0)
     CFX_LAUNCH(c, mark_facets_kernel<Active>, grid_for(n_src * nf, FB), FB, 0, src_cells, n_src, nf, c->c2f,
-               c->f2c2.p, active, c->n_owned_facets, include_ghosts, c->facet_flag.p, c->nc_total);
+               c->f2c2.p, active, c->n_owned_facets, include_ghosts, c->facet_flag.p, c->nc_total, c->blk_counts.p);
   FlagPred p{c->facet_flag.p};
-  out->n = compact_indices(c, c->n_facets, p, out->data);
+  out->n = compact_indices(c, c->n_facets, p, out->data, /*counted*/ true);
   if (out->n > 0)
     CFX_LAUNCH(c, clear_flags_kernel, grid_for(out->n, FB), FB, 0, out->data.p, out->n, c->facet_flag.p);
   return out->n;
