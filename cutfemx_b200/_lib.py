@@ -8,6 +8,7 @@ CUDA device).  The library is built in-tree by `cutfemx_b200._build.build_librar
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 
 import numpy as np
@@ -130,6 +131,19 @@ def as_arg(a, dtype):
 
 
 def parse_selector(expr: str, names):
+    """Compiled selector (cached: the same few expressions are parsed every step of a moving-domain loop)."""
+    return _parse_selector_cached(str(expr), tuple(names))
+
+
+@functools.lru_cache(maxsize=256)
+def _parse_selector_cached(expr: str, names: tuple):
+    to, cl, cr = _parse_selector(expr, names)
+    for a in (to, cl, cr):
+        a.setflags(write=False)
+    return to, cl, cr
+
+
+def _parse_selector(expr: str, names):
     """The selector grammar of cutcells::parse_selection_expr as the reference uses it
     (cut.cpp:881-882): whitespace ignored (cut.cpp:47-57), clauses `name rel 0` joined by
     `and` inside a term, terms joined by `or`."""
