@@ -330,6 +330,7 @@ cfx_status cfx_counts(cfx_ctx* ctx, int ls, int64_t counts[3])
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && ctx->classified, CFX_ERR_STATE, "cfx_counts: call cfx_update first");
   CFX_REQUIRE(ls >= 0 && ls < CFX_MAX_LEVEL_SETS && ctx->ls[ls].bound, CFX_ERR_INVALID, "cfx_counts: bad level set");
+  sync_counts(ctx);
   for (int k = 0; k < 3; ++k)
     counts[k] = ctx->ls[ls].counts[k];
   CFX_API_END(ctx)

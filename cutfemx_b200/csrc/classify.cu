@@ -167,10 +167,20 @@ void classify_all(cfx_ctx* c)
     default: throw Error(CFX_ERR_UNSUPPORTED, "classify: unsupported level-set dofmap width");
     }
   }
+  // the counts stay on the device until somebody asks (cfx_counts): a read-back here would idle the GPU once per
+  // update for numbers the path itself never needs
+  c->counts_pending = true;
+}
+
+void sync_counts(cfx_ctx* c)
+{
+  if (!c->counts_pending)
+    return;
   const int64_t* h = read_back(c, c->scratch64.p + 8, 3 * CFX_MAX_LEVEL_SETS);
   for (int l = 0; l < CFX_MAX_LEVEL_SETS; ++l)
     for (int k = 0; k < 3; ++k)
       c->ls[l].counts[k] = h[3 * l + k];
+  c->counts_pending = false;
 }
 
 Dnf make_dnf(cfx_ctx* c, int n_terms, const int32_t* term_offsets, const int32_t* clause_ls, const int32_t* clause_rel)
@@ -225,8 +235,9 @@ void ensure_cut_list(cfx_ctx* c, int ls)
   d.term_off[1] = 1;
   d.ls[0] = static_cast<int8_t>(ls);
   d.relmask[0] = relation_mask(CFX_REL_EQ);
-  StageScope st(c, "locate_cut", static_cast<double>(c->nc_owned) * 2.0 + 4.0 * static_cast<double>(L.counts[1]));
+  StageScope st(c, "locate_cut", static_cast<double>(c->nc_owned) * 2.0);
   L.n_cut = compact_owned_cells(c, d, L.cut_list);
+  st.set_bytes(static_cast<double>(c->nc_owned) * 2.0 + 4.0 * static_cast<double>(L.n_cut));
 }
 // intersected cells among ALL local cells (owned + ghost).  The reference's Python loop
 // (cut.py:364-379) starts from locate_entities(...), i.e. owned cells only, and therefore drops band

@@ -337,6 +337,7 @@ struct cfx_ctx
   cfx::DevBuf<int8_t> domain; // (CFX_MAX_LEVEL_SETS, domain_stride)
   int64_t domain_stride = 0;
   bool classified = false;
+  bool counts_pending = false; // the classification counts are still on the device (fetched on demand: cfx_counts)
 
   cfx::Space spaces[CFX_MAX_SPACES];
   cfx::DevBuf<int32_t> mat_slot; // (nc_total): slot of a cell's materialised tensor; -1 between assemblies
@@ -442,6 +443,7 @@ inline void export_to(cfx_ctx* c, T* dst, const T* src_dev, size_t n, int memspa
 const int64_t* read_back(cfx_ctx* c, const int64_t* dev, int n);
 
 void check_device_error(cfx_ctx* c, const char* where); // api.cu
+void sync_counts(cfx_ctx* c);                            // classify.cu: fetch pending classification counts
 
 // ---------------------------------------------------------------- device primitives
 #ifdef __CUDACC__
