@@ -21,8 +21,8 @@ TRIANGLE, TETRAHEDRON = 3, 4
 DOMAIN_INSIDE, DOMAIN_INTERSECTED, DOMAIN_OUTSIDE = 1, 2, 3
 REL = {"<": 0, "<=": 1, ">": 2, ">=": 3, "=": 4}
 KERNEL = {"laplace": 1, "mass": 2, "nitsche": 3, "ghost_grad_jump": 4, "source": 5, "nitsche_rhs": 6, "one": 7,
-          "elasticity": 8, "source_vec": 9, "square_fn": 10}
-KERNEL_RANK = {1: 2, 2: 2, 3: 2, 4: 2, 5: 1, 6: 1, 7: 0, 8: 2, 9: 1, 10: 0}
+          "elasticity": 8, "source_vec": 9, "square_fn": 10, "nitsche_vec": 11}
+KERNEL_RANK = {1: 2, 2: 2, 3: 2, 4: 2, 5: 1, 6: 1, 7: 0, 8: 2, 9: 1, 10: 0, 11: 2}
 
 # every symbol include/cutfemx_b200.h declares (tests/test_abi.py checks the .so exports them all)
 SYMBOLS = [

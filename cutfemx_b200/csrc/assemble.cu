@@ -2066,6 +2066,103 @@ __global__ void __launch_bounds__(EB)
     p[k] = add ? p[k] + acc[k] : acc[k];
 }
 
+// Symmetric Nitsche terms of linear elasticity on interface rules (per-point unit normals), one thread per
+// (rule, tensor row ra = i*bs + a):
+//   A[(i,a),(j,b)] = sum_q w ( -phi_i S_ab(j) - phi_j S_ba(i) + delta_ab pen phi_i phi_j ),
+//   S_ab(j) = component a of sigma(phi_j e_b) n = mu (delta_ab grad phi_j . n + d_a phi_j n_b) + lambda d_b phi_j n_a,
+//   pen = c2 (2 mu + lambda) / h;  c0 = mu, c1 = lambda, c2 = gamma.  Slots as in elasticity_kernel.
+template <int TDIM, int DEG>
+__global__ void __launch_bounds__(EB)
+    nitsche_vec_kernel(int64_t n, RuleView rv, Consts cs, const double* __restrict__ x,
+                       const int32_t* __restrict__ x_dofmap, OutCtx oc)
+{
+  constexpr int ND = Elem<TDIM, DEG>::ND;
+  constexpr int BS = TDIM, N = ND * BS;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * EB + threadIdx.x;
+  if (t >= n * N)
+    return;
+  const int64_t e = t / N;
+  const int ra = static_cast<int>(t - e * N);
+  const int i = ra / BS, a = ra - i * BS;
+  const int64_t cell = rv.parent_map[e];
+  const bool follow = oc.base < 0;
+  const int64_t mine = oc.base + e;
+  const int32_t s0 = oc.mat_slot[cell];
+  const bool add = follow || (s0 >= 0 && s0 != mine);
+  if (follow && s0 < 0)
+    return;
+  const int64_t slot = add ? s0 : mine;
+  double X[TDIM + 1][TDIM];
+  load_cell_coords<TDIM>(x, x_dofmap, cell, X);
+  Geo<TDIM> g;
+  make_geo<TDIM>(X, g);
+  const double pen = cs.c[2] * (2.0 * cs.c[0] + cs.c[1]) / cell_diameter<TDIM>(X);
+  double acc[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+    acc[k] = 0.0;
+  const int32_t q0 = rv.offsets[e], q1 = rv.offsets[e + 1];
+  for (int32_t q = q0; q < q1; ++q)
+  {
+    double xi[TDIM], nr[TDIM];
+#pragma unroll
+    for (int tt = 0; tt < TDIM; ++tt)
+    {
+      xi[tt] = rv.pts[static_cast<int64_t>(tt) * rv.npts + q];
+      nr[tt] = rv.nrm[static_cast<int64_t>(tt) * rv.npts + q];
+    }
+    const double w = rv.wts[q];
+    double phi[ND], dphi[ND][TDIM], grad[ND][TDIM];
+    tabulate<TDIM, DEG>(xi, phi, dphi);
+    push_gradients<TDIM, ND>(g, dphi, grad);
+    // this row's basis function: value, gradient, normal derivative
+    double gi[TDIM];
+#pragma unroll
+    for (int r = 0; r < TDIM; ++r)
+    {
+      double v = grad[0][r];
+#pragma unroll
+      for (int j = 1; j < ND; ++j)
+        v = (j == i) ? grad[j][r] : v;
+      gi[r] = v;
+    }
+    const double phii = pick<ND>(phi, i);
+    double gni = 0.0, na = nr[0], gia = gi[0];
+#pragma unroll
+    for (int r = 0; r < TDIM; ++r)
+    {
+      gni += gi[r] * nr[r];
+      na = (r == a) ? nr[r] : na;
+      gia = (r == a) ? gi[r] : gia;
+    }
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+    {
+      double gnj = 0.0, gja = grad[j][0];
+#pragma unroll
+      for (int r = 0; r < TDIM; ++r)
+      {
+        gnj += grad[j][r] * nr[r];
+        gja = (r == a) ? grad[j][r] : gja;
+      }
+#pragma unroll
+      for (int b = 0; b < BS; ++b)
+      {
+        const double dab = (a == b) ? 1.0 : 0.0;
+        const double S_ab_j = cs.c[0] * (dab * gnj + gja * nr[b]) + cs.c[1] * grad[j][b] * na;
+        const double S_ba_i = cs.c[0] * (dab * gni + gi[b] * na) + cs.c[1] * gia * nr[b];
+        acc[j * BS + b] += w * (-phii * S_ab_j - phi[j] * S_ba_i + dab * pen * phii * phi[j]);
+      }
+    }
+  }
+  if (!add)
+    oc.mat_slot[cell] = static_cast<int32_t>(slot);
+  double* p = oc.out + (slot * N + ra) * N;
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+    p[k] = add ? p[k] + acc[k] : acc[k];
+}
+
 // inner(f, v) dx with a constant vector f = (c0, c1, c2): one thread per entity, N values
 template <int TDIM, int DEG, bool RUNTIME>
 __global__ void __launch_bounds__(EB)
@@ -2322,6 +2419,20 @@ void launch_blocked_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t
     cs.c[k] = I.constants[k];
   OutCtx oc{c->mat_slot.p, f->Ae.p, base};
   const bool el = I.kernel == CFX_K_ELASTICITY;
+  if (I.kernel == CFX_K_NITSCHE_VEC)
+  { // interface rules only (validated when the integral was added)
+    const cfx_rules* R = I.rules;
+    if (R && R->nrules > 0)
+    {
+      CFX_REQUIRE(R->tdim == TDIM && R->has_normals, CFX_ERR_INVALID, "interface kernels need rules with normals");
+      rv = RuleView{R->points.p, R->weights.p, R->normals.p, R->offsets.p, R->parent_map.p, R->npts};
+      CFX_LAUNCH(c, (nitsche_vec_kernel<TDIM, DEG>), grid_for(R->nrules * N, EB), EB, 0, R->nrules, rv, cs, c->x,
+                 c->x_dofmap, oc);
+      if (base >= 0)
+        base += R->nrules;
+    }
+    return;
+  }
   CFX_REQUIRE(el || I.kernel == CFX_K_SOURCE_VEC, CFX_ERR_UNSUPPORTED,
               "kernel family is not defined on blocked (vector) spaces");
   if (I.n > 0)

@@ -1088,7 +1088,8 @@ static int kernel_rank(int k)
   case CFX_K_MASS:
   case CFX_K_NITSCHE:
   case CFX_K_GHOST_GRAD_JUMP:
-  case CFX_K_ELASTICITY: return 2;
+  case CFX_K_ELASTICITY:
+  case CFX_K_NITSCHE_VEC: return 2;
   case CFX_K_SOURCE:
   case CFX_K_SOURCE_VEC:
   case CFX_K_NITSCHE_RHS: return 1;
@@ -1138,12 +1139,12 @@ cfx_status cfx_form_add_cell_integral(cfx_ctx* ctx, cfx_form* f, int kernel, con
               "facet-hosted rules belong to exterior / interior facet integrals, which the shipped kernel families do "
               "not cover yet");
   {
-    const bool vec_kernel = kernel == CFX_K_ELASTICITY || kernel == CFX_K_SOURCE_VEC;
+    const bool vec_kernel = kernel == CFX_K_ELASTICITY || kernel == CFX_K_SOURCE_VEC || kernel == CFX_K_NITSCHE_VEC;
     const int bs = ctx->spaces[f->space].bs;
     CFX_REQUIRE(f->rank == 0 || (vec_kernel ? bs == ctx->gdim : bs == 1), CFX_ERR_INVALID,
                 "cfx_form_add_cell_integral: kernel family does not match the block size of the space");
   }
-  if (kernel == CFX_K_NITSCHE || kernel == CFX_K_NITSCHE_RHS)
+  if (kernel == CFX_K_NITSCHE || kernel == CFX_K_NITSCHE_RHS || kernel == CFX_K_NITSCHE_VEC)
   {
     CFX_REQUIRE(n_cells == 0, CFX_ERR_INVALID, "interface kernels take run-time rules only");
     CFX_REQUIRE(rules && rules->has_normals, CFX_ERR_STATE,

@@ -57,6 +57,8 @@ enum {
   /* blocked (vector) Lagrange spaces, block size == gdim (demo_elasticity.py:213-238): */
   CFX_K_ELASTICITY = 8,     /* rank 2, cells:           inner(sigma(u), eps(v)), sigma = 2 c0 eps + c1 tr(eps) I        */
   CFX_K_SOURCE_VEC = 9,     /* rank 1, cells:           inner((c0, c1, c2), v)                                         */
+  CFX_K_NITSCHE_VEC = 11,   /* rank 2, interface rules on a blocked space: -(sigma(u) n).v - (sigma(v) n).u
+                               + c2 (2 c0 + c1)/h u.v, sigma = 2 c0 eps + c1 tr(eps) I  (needs normals)             */
   CFX_K_SQUARE_FN = 10      /* rank 0, cells / rules:   c0 * w^2, w a Function of the form's (scalar) space -- the error
                                functional (uh - u_exact)**2 of demo_poisson.py:213 with w = uh - I(u_exact); the dof
                                values are restricted to each entity's cell like pack_coefficients does

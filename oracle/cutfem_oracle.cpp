@@ -678,6 +678,41 @@ void k_elasticity(double* A, const double*, const double* c, const double* cdofs
                  });
 }
 
+// Symmetric Nitsche terms of linear elasticity on an interface rule with unit normal n (the vector counterpart of
+// demo_poisson.py:186-190; sigma as in demo_elasticity.py:139-150):
+//   -(sigma(u) n) . v - (sigma(v) n) . u + c2 (2 mu + lambda) / h  u . v,   c0 = mu, c1 = lambda, c2 = gamma
+// For u = phi_j e_b: sigma(u) n = mu (e_b (grad phi_j . n) + grad phi_j n_b) + lambda (d_b phi_j) n.
+void k_nitsche_vec(double* A, const double*, const double* c, const double* cdofs, const int* eli, const uint8_t*,
+                   void* p)
+{
+  const CustomData& cd = *static_cast<CustomData*>(p);
+  const int td = cd.tdim, nd = space_dim(td, cd.degree), bs = td, n = nd * bs;
+  const Geo g = make_geo(td, cdofs);
+  const double h = cell_diameter(td + 1, cdofs);
+  const double pen = c[2] * (2.0 * c[0] + c[1]) / h;
+  double phi[10], dphi[30], grad[30], gn[10];
+  for_each_point(cd, g, eli[0],
+                 [&](const double* X, double w, const double* nrm)
+                 {
+                   tabulate(td, cd.degree, X, phi, dphi);
+                   push_gradients(g, nd, dphi, grad);
+                   for (int i = 0; i < nd; ++i)
+                   {
+                     gn[i] = 0.0;
+                     for (int r = 0; r < td; ++r)
+                       gn[i] += grad[i * td + r] * nrm[r];
+                   }
+                   auto S = [&](int j, int a, int b) // component a of sigma(phi_j e_b) n
+                   { return c[0] * ((a == b ? gn[j] : 0.0) + grad[j * td + a] * nrm[b]) + c[1] * grad[j * td + b] * nrm[a]; };
+                   for (int i = 0; i < nd; ++i)
+                     for (int j = 0; j < nd; ++j)
+                       for (int a = 0; a < bs; ++a)
+                         for (int b = 0; b < bs; ++b)
+                           A[(i * bs + a) * n + j * bs + b]
+                               += w * (-phi[i] * S(j, a, b) - phi[j] * S(i, b, a) + (a == b ? pen * phi[i] * phi[j] : 0.0));
+                 });
+}
+
 // inner(f, v) dx with a constant vector f = (c0, c1, c2) (demo_elasticity.py:238)
 void k_source_vec(double* b, const double*, const double* c, const double* cdofs, const int* eli, const uint8_t*,
                   void* p)
@@ -710,6 +745,7 @@ kernel_fn kernel_by_id(int id)
   case 8: return k_elasticity;
   case 9: return k_source_vec;
   case 10: return k_square_fn;
+  case 11: return k_nitsche_vec;
   }
   throw std::runtime_error("oracle: unknown kernel id");
 }
@@ -725,6 +761,7 @@ int std_order_for(int id, int degree)
   case 8: return 2 * (degree - 1);
   case 9: return degree;
   case 10: return 2 * degree;
+  case 11: return 2 * degree;
   }
   return 0;
 }

@@ -216,8 +216,8 @@ def sparsity(space, cells, rows4=None, insert_diagonal=True):
 
 
 K = {"laplace": 1, "mass": 2, "nitsche": 3, "ghost_grad_jump": 4, "source": 5, "nitsche_rhs": 6, "one": 7,
-     "elasticity": 8, "source_vec": 9, "square_fn": 10}
-_RANK = {1: 2, 2: 2, 3: 2, 4: 2, 5: 1, 6: 1, 7: 0, 8: 2, 9: 1, 10: 0}
+     "elasticity": 8, "source_vec": 9, "square_fn": 10, "nitsche_vec": 11}
+_RANK = {1: 2, 2: 2, 3: 2, 4: 2, 5: 1, 6: 1, 7: 0, 8: 2, 9: 1, 10: 0, 11: 2}
 
 
 def _register_std_rules(space, kernel_id):

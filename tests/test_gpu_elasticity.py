@@ -55,7 +55,7 @@ def problem(request, built_lib):
     a.add_interior_facet_integral("ghost_grad_jump", facets=g_ghost, constants=(GAMMA_G * (2 * MU + LAM),))
     L = cfx.fem.CutForm(V, 1).add_cell_integral("source_vec", g_inside, g_rv, FORCE)
     return dict(cfx=cfx, mesh=mesh, V=V, bs=bs, rp=rp, cols=cols, ref=ref, bref=bref, a=a, L=L, inside=inside, rv=rv,
-                rows4=rows4)
+                rows4=rows4, phi=phi, phi_vals=vals, Vphi=Vphi, cd=cd, g_inside=g_inside, g_rv=g_rv, g_ghost=g_ghost)
 
 
 def test_blocked_matrix_and_vector(problem):
@@ -191,3 +191,31 @@ def test_blocked_active_domain_deactivation_and_clamped_solve(problem):
         u = spla.spsolve(Ms.tocsc(), b)
         np.testing.assert_allclose(u[active].reshape(-1), g[active], rtol=0, atol=1e-9)
         assert np.all(u[ad.inactive_dofs] == 0.0)
+
+
+def test_vector_nitsche_terms_on_the_interface(problem):
+    """CFX_K_NITSCHE_VEC (configs[3] "interface Nitsche terms"): elasticity + symmetric Nitsche terms on the
+    interface rules + ghost penalty in one form, against the oracle; sparsity bit-exact, blocks to 1e-11."""
+    p = problem
+    cfx, V, bs, mesh = p["cfx"], p["V"], p["bs"], p["mesh"]
+    Vphi, phi_vals = p["Vphi"], p["phi_vals"]
+    dom = O.classify(Vphi.dofmap, phi_vals)
+    ri = O.runtime_quadrature(mesh, Vphi.dofmap, phi_vals, dom, "=", 4)
+    ri.normals = O.normals(mesh, Vphi.dofmap, 1, phi_vals, ri)
+    gam = 25.0
+    ref = p["ref"].copy()
+    O.assemble_cells(V, "nitsche_vec", ref, None, ri, (MU, LAM, gam), p["rp"], p["cols"])
+    cd = p["cd"]
+    g_ri = cfx.runtime_quadrature(cd, "phi=0", 4)
+    cfx.level_set.attach_normal(cd, p["phi"], g_ri)
+    a = cfx.fem.CutForm(V, 2)
+    a.add_cell_integral("elasticity", p["g_inside"], p["g_rv"], (MU, LAM))
+    a.add_cell_integral("nitsche_vec", None, g_ri, (MU, LAM, gam))
+    a.add_interior_facet_integral("ghost_grad_jump", facets=p["g_ghost"], constants=(GAMMA_G * (2 * MU + LAM),))
+    A = cfx.fem.assemble_matrix(a)
+    assert np.array_equal(A.indptr, p["rp"]) and np.array_equal(A.indices, p["cols"])
+    assert rel(A.data, ref) < 1e-11
+    Ms = A.to_scipy()
+    assert abs(Ms - Ms.T).max() <= 1e-12 * abs(Ms).max()
+    with pytest.raises(cfx.CfxError):  # interface kernels take run-time rules with normals only
+        cfx.fem.CutForm(V, 2).add_cell_integral("nitsche_vec", None, p["g_rv"], (MU, LAM, gam))

@@ -514,3 +514,42 @@ def test_facet_hosted_rules_measure_the_wet_boundary_exactly():
             # waterline x + 0.3 y = 0.52 has length 1 + 1 + 2 sqrt(1.09)
             ri = O.facet_runtime_quadrature(mesh, V.dofmap, phi.x.array, facets, "=", order)
             np.testing.assert_allclose(ri.weights.sum(), 2.0 if tdim == 2 else 2.0 + 2.0 * np.sqrt(1.09), rtol=1e-12)
+
+
+# ---------------------------------------------------------------- vector Nitsche terms (configs[3])
+def test_vector_nitsche_kernel_against_an_independent_evaluation():
+    """-(sigma(u) n).v - (sigma(v) n).u + gamma (2 mu + lambda)/h u.v on the interface rules: the assembled matrix is
+    symmetric, and for P1 vector fields u, v that interpolate LINEAR fields (constant stress) the bilinear form equals
+    the same expression evaluated directly at the rules' physical points with the exact stresses."""
+    import scipy.sparse as sp
+
+    from cutfemx_b200 import mesh as M
+    from util import make_problem
+
+    mu, lam, gam = 1.3, 2.1, 7.0
+    for kind, n in (("circle", 8), ("sphere", 4)):
+        mesh, Vphi, phi, _ = make_problem(kind, n, 1)
+        td = mesh.tdim
+        V = M.functionspace(mesh, 1, bs=td)
+        dom = O.classify(Vphi.dofmap, phi.x.array)
+        ri = O.runtime_quadrature(mesh, Vphi.dofmap, phi.x.array, dom, "=", 2)
+        ri.normals = O.normals(mesh, Vphi.dofmap, 1, phi.x.array, ri)
+        rp, cols = O.sparsity(V, ri.parent_map)
+        A = O.assemble_cells(V, "nitsche_vec", np.zeros(cols.size * td * td), None, ri, (mu, lam, gam), rp, cols)
+        nb = V.num_dofs * td
+        Ms = sp.bsr_matrix((A.reshape(-1, td, td), cols, rp), shape=(nb, nb)).tocsr()
+        assert abs(Ms - Ms.T).max() <= 1e-13 * abs(Ms).max()
+        rng = np.random.default_rng(2)
+        Bu, cu, Bv, cv = rng.standard_normal((td, td)), rng.standard_normal(td), rng.standard_normal((td, td)), rng.standard_normal(td)
+        X = V.dof_coords[:, :td]
+        u, v = (X @ Bu.T + cu).reshape(-1), (X @ Bv.T + cv).reshape(-1)
+        sig = lambda B: mu * (B + B.T) + lam * np.trace(B) * np.eye(td)
+        xp = O.physical_points(mesh, ri).T
+        rule_of_pt = np.repeat(np.arange(ri.parent_map.size), np.diff(ri.offsets))
+        Xc = mesh.x[mesh.x_dofmap[ri.parent_map]][:, :, :td]
+        h = np.array([max(np.linalg.norm(Xc[k, a] - Xc[k, b]) for a in range(td + 1) for b in range(a + 1, td + 1))
+                      for k in range(ri.parent_map.size)])
+        up, vp, nq = xp @ Bu.T + cu, xp @ Bv.T + cv, ri.normals
+        direct = np.sum(ri.weights * (-np.einsum("ab,qb,qa->q", sig(Bu), nq, vp) - np.einsum("ab,qb,qa->q", sig(Bv), nq, up)
+                                      + gam * (2 * mu + lam) / h[rule_of_pt] * np.einsum("qa,qa->q", up, vp)))
+        assert abs(v @ (Ms @ u) - direct) <= 1e-11 * abs(direct)
