@@ -42,6 +42,9 @@ SYMBOLS = [
     "cfx_gather_f64", "cfx_scatter_add_f64", "cfx_active_domain", "cfx_active_indicator_device_ptr",
     "cfx_inactive_dofs", "cfx_deactivate_outside", "cfx_assemble_matrix_bc", "cfx_assemble_system_bc", "cfx_set_diagonal", "cfx_apply_lifting",
     "cfx_set_bc", "cfx_meshgen_box", "cfx_meshgen_rectangle", "cfx_meshgen_level_set",
+    "cfx_device_bytes", "cfx_set_deferred", "cfx_check", "cfx_graph_begin", "cfx_graph_end", "cfx_graph_launch",
+    "cfx_graph_kernel_nodes", "cfx_graph_free", "cfx_facet_integration_rows_list", "cfx_form_add_cell_integral_list",
+    "cfx_form_add_interior_facet_integral_list",
 ]
 
 
@@ -68,6 +71,11 @@ def lib():
         L.cfx_list_size.argtypes = [C.c_void_p]
         L.cfx_launch_count.restype = C.c_int64
         L.cfx_launch_count.argtypes = [C.c_void_p]
+        L.cfx_device_bytes.restype = C.c_int64
+        L.cfx_device_bytes.argtypes = [C.c_void_p]
+        L.cfx_graph_kernel_nodes.restype = C.c_int64
+        L.cfx_graph_kernel_nodes.argtypes = [C.c_void_p]
+        L.cfx_set_deferred.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.cfx_list_device_ptr.restype = C.c_void_p
         L.cfx_list_device_ptr.argtypes = [C.c_void_p]
         for name in ("cfx_pattern_values_device_ptr", "cfx_pattern_row_ptr_device_ptr", "cfx_pattern_cols_device_ptr"):
@@ -76,7 +84,8 @@ def lib():
         L.cfx_active_indicator_device_ptr.restype = C.c_void_p
         L.cfx_active_indicator_device_ptr.argtypes = [C.c_void_p, C.c_void_p]
         L.cfx_ctx_destroy.restype = None
-        for name in ("cfx_list_free", "cfx_rules_free", "cfx_pattern_free", "cfx_form_free", "cfx_ecut_free"):
+        for name in ("cfx_list_free", "cfx_rules_free", "cfx_pattern_free", "cfx_form_free", "cfx_ecut_free",
+                     "cfx_graph_free"):
             getattr(L, name).restype = None
             getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
         _lib = L

@@ -35,6 +35,11 @@ __global__ void to_mapped_kernel(const int64_t* __restrict__ src, int n, volatil
 const int64_t* read_back(cfx_ctx* c, const int64_t* dev, int n)
 {
   CFX_REQUIRE(n >= 0 && n <= 64, CFX_ERR_RANGE, "read_back: at most 64 values");
+  CFX_REQUIRE(!c->capturing, CFX_ERR_STATE,
+              "this call needs a size on the host, which is impossible while a CUDA graph is being captured: run "
+              "the same sequence of calls once in deferred-size mode on the same objects first (so that every "
+              "buffer has a capacity), and do not query sizes or fetch results between cfx_graph_begin and "
+              "cfx_graph_end");
   const int64_t ticket = ++c->read_ticket;
   to_mapped_kernel<<<1, 64, 0, c->stream>>>(dev, n, c->h_pinned_dev, ticket);
   ++c->launches;
@@ -54,6 +59,74 @@ const int64_t* read_back(cfx_ctx* c, const int64_t* dev, int n)
   if (*flag != ticket)
     CFX_CUDA(cudaStreamSynchronize(c->stream));
   return c->h_pinned;
+}
+
+constexpr int COUNT_SLOTS = 8192;
+
+int64_t* alloc_count_slot(cfx_ctx* c, int n)
+{
+  if (!c->count_slab.p)
+  {
+    c->count_slab.reserve(c->pool, COUNT_SLOTS);
+    CFX_CUDA(cudaMemsetAsync(c->count_slab.p, 0, COUNT_SLOTS * sizeof(int64_t), c->stream));
+  }
+  if (n == 1 && !c->free_slots.empty())
+  {
+    const int k = c->free_slots.back();
+    c->free_slots.pop_back();
+    return c->count_slab.p + k;
+  }
+  CFX_REQUIRE(c->next_slot + n <= COUNT_SLOTS, CFX_ERR_RANGE, "too many live lists / rules / forms on one context");
+  int64_t* p = c->count_slab.p + c->next_slot;
+  c->next_slot += n;
+  return p;
+}
+
+void free_count_slot(cfx_ctx* c, int64_t* p, int n)
+{
+  if (!c || !p || !c->count_slab.p)
+    return;
+  if (c->capturing)
+    return; // the captured kernels keep writing this slot at every replay: never hand it to another object
+  for (int k = 0; k < n; ++k)
+    c->free_slots.push_back(static_cast<int>(p - c->count_slab.p) + k);
+}
+
+// Deferred sizes become host values here: one read-back (which also picks up the device error flag: a capacity
+// that was too small for this step's result shows up as an error, not as a truncated list).
+static void fetch_sizes(cfx_ctx* c, const int64_t* dev, int n, int64_t* out, const char* what)
+{
+  check_device_error(c, what);
+  const int64_t* h = read_back(c, dev, n);
+  for (int k = 0; k < n; ++k)
+    out[k] = h[k];
+}
+
+void resolve(cfx_ctx* c, cfx_list* l)
+{
+  if (!l || !l->deferred)
+    return;
+  fetch_sizes(c, l->d_n, 1, &l->n, "deferred list size (a buffer capacity was exceeded)");
+  l->deferred = false;
+}
+
+void resolve(cfx_ctx* c, cfx_rules* r)
+{
+  if (!r || !r->deferred)
+    return;
+  int64_t v[2];
+  fetch_sizes(c, r->d_sizes, 2, v, "deferred quadrature-rule sizes (a buffer capacity was exceeded)");
+  r->nrules = v[0];
+  r->npts = v[1];
+  r->deferred = false;
+}
+
+void resolve(cfx_ctx* c, cfx_pattern* p)
+{
+  if (!p || !p->deferred)
+    return;
+  fetch_sizes(c, p->row_ptr.p + p->n_rows, 1, &p->nnz, "deferred sparsity size (the matrix capacity was exceeded)");
+  p->deferred = false;
 }
 
 void check_device_error(cfx_ctx* c, const char* where)
@@ -136,6 +209,177 @@ cfx_status cfx_sync(cfx_ctx* ctx)
 }
 
 int64_t cfx_launch_count(const cfx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int64_t cfx_device_bytes(const cfx_ctx* ctx) { return ctx ? static_cast<int64_t>(ctx->pool.total_bytes()) : 0; }
+
+// ---------------------------------------------------------------- deferred sizes and CUDA graphs
+cfx_status cfx_set_deferred(cfx_ctx* ctx, int on, double margin)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx, CFX_ERR_INVALID, "cfx_set_deferred: NULL context");
+  CFX_REQUIRE(!ctx->capturing, CFX_ERR_STATE, "cfx_set_deferred: not while a graph is being captured");
+  ctx->deferred = on != 0;
+  if (margin >= 0.0)
+    ctx->margin = margin;
+  CFX_API_END(ctx)
+}
+
+cfx_status cfx_check(cfx_ctx* ctx)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx, CFX_ERR_INVALID, "cfx_check: NULL context");
+  check_device_error(ctx, "cfx_check (a deferred-size call exceeded a buffer capacity or met an invalid index; the "
+                          "results of that step are incomplete -- repeat it with cfx_set_deferred(ctx, 0, ..))");
+  CFX_API_END(ctx)
+}
+} // extern "C"
+
+struct cfx_graph
+{
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  std::vector<std::pair<size_t, void*>> blocks; // pool blocks the captured calls used as temporaries
+  int64_t kernel_nodes = 0;
+  // objects the captured calls refill with device-side sizes
+  std::vector<cfx_list*> lists;
+  std::vector<cfx_rules*> rules;
+  std::vector<cfx_pattern*> patterns;
+};
+
+extern "C"
+{
+cfx_status cfx_graph_begin(cfx_ctx* ctx)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && !ctx->capturing, CFX_ERR_STATE, "cfx_graph_begin: a capture is already in progress");
+  CFX_REQUIRE(ctx->deferred, CFX_ERR_STATE,
+              "cfx_graph_begin: switch the context to deferred-size mode first (cfx_set_deferred) and run the step "
+              "once, so that no captured call needs a size on the host");
+  CFX_REQUIRE(!ctx->timing, CFX_ERR_STATE, "cfx_graph_begin: disable stage timing before capturing");
+  CFX_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaStream_t cap = nullptr;
+  CFX_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+  ctx->user_stream = ctx->stream;
+  ctx->stream = cap;
+  ctx->pool.begin_capture();
+  ctx->cap_lists.clear();
+  ctx->cap_rules.clear();
+  ctx->cap_patterns.clear();
+  const cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed);
+  if (e != cudaSuccess)
+  {
+    ctx->pool.give_back(ctx->pool.end_capture());
+    ctx->stream = ctx->user_stream;
+    cudaStreamDestroy(cap);
+    CFX_CUDA(e);
+  }
+  ctx->capturing = true;
+  CFX_API_END(ctx)
+}
+
+cfx_status cfx_graph_end(cfx_ctx* ctx, cfx_graph** out)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && ctx->capturing && out, CFX_ERR_STATE, "cfx_graph_end: no capture in progress");
+  cudaStream_t cap = ctx->stream;
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(cap, &g);
+  ctx->capturing = false;
+  ctx->stream = ctx->user_stream;
+  auto blocks = ctx->pool.end_capture();
+  cudaStreamDestroy(cap);
+  if (e != cudaSuccess || !g)
+  {
+    ctx->pool.give_back(blocks);
+    cudaGetLastError();
+    throw Error(CFX_ERR_CUDA, std::string("cfx_graph_end: capture failed: ") + cudaGetErrorString(e));
+  }
+  cfx_graph* G = new cfx_graph();
+  G->graph = g;
+  G->blocks = std::move(blocks);
+  G->lists.swap(ctx->cap_lists);
+  G->rules.swap(ctx->cap_rules);
+  G->patterns.swap(ctx->cap_patterns);
+  size_t n_nodes = 0;
+  cudaGraphGetNodes(g, nullptr, &n_nodes);
+  std::vector<cudaGraphNode_t> nodes(n_nodes);
+  if (n_nodes)
+    cudaGraphGetNodes(g, nodes.data(), &n_nodes);
+  for (auto nd : nodes)
+  {
+    cudaGraphNodeType t;
+    if (cudaGraphNodeGetType(nd, &t) == cudaSuccess && t == cudaGraphNodeTypeKernel)
+      ++G->kernel_nodes;
+  }
+  const cudaError_t ei = cudaGraphInstantiate(&G->exec, g, 0);
+  if (ei != cudaSuccess)
+  {
+    ctx->pool.give_back(G->blocks);
+    cudaGraphDestroy(g);
+    delete G;
+    CFX_CUDA(ei);
+  }
+  *out = G;
+  CFX_API_END(ctx)
+}
+
+cfx_status cfx_graph_launch(cfx_ctx* ctx, cfx_graph* g)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && g && g->exec && !ctx->capturing, CFX_ERR_STATE, "cfx_graph_launch: invalid graph");
+  CFX_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
+  ctx->launches += g->kernel_nodes;
+  // the host-side sizes of the objects the graph refills are stale now: back to their capacities until resolved
+  for (cfx_list* l : g->lists)
+  {
+    l->deferred = true;
+    l->n = l->n_bound;
+  }
+  for (cfx_rules* r : g->rules)
+  {
+    r->deferred = true;
+    r->nrules = r->cap_rules;
+    r->npts = r->cap_pts;
+  }
+  for (cfx_pattern* p : g->patterns)
+  {
+    p->deferred = true;
+    p->nnz = static_cast<int64_t>(p->cols.cap) - 1;
+  }
+  ctx->counts_pending = true;
+  for (auto& L : ctx->ls)
+    if (L.bound)
+    { // the cut-cell lists were rebuilt on the device
+      if (L.d_n_cut && L.cut_list.p)
+      {
+        L.cut_deferred = true;
+        L.n_cut = static_cast<int64_t>(L.cut_list.cap);
+      }
+      if (L.d_n_cut_all && L.cut_list_all.p)
+      {
+        L.cut_all_deferred = true;
+        L.n_cut_all = static_cast<int64_t>(L.cut_list_all.cap);
+      }
+    }
+  CFX_API_END(ctx)
+}
+
+int64_t cfx_graph_kernel_nodes(const cfx_graph* g) { return g ? g->kernel_nodes : 0; }
+
+void cfx_graph_free(cfx_ctx* ctx, cfx_graph* g)
+{
+  if (!g)
+    return;
+  if (ctx)
+    cudaStreamSynchronize(ctx->stream);
+  if (g->exec)
+    cudaGraphExecDestroy(g->exec);
+  if (g->graph)
+    cudaGraphDestroy(g->graph);
+  if (ctx)
+    ctx->pool.give_back(g->blocks);
+  delete g;
+}
 
 // ---------------------------------------------------------------- mesh / topology
 cfx_status cfx_mesh_bind(cfx_ctx* ctx, const double* x, int64_t n_nodes, const int32_t* x_dofmap,
@@ -347,13 +591,31 @@ cfx_status cfx_domain_fetch(cfx_ctx* ctx, int ls, int8_t* out, int memspace)
 }
 
 // ---------------------------------------------------------------- lists
-int64_t cfx_list_size(const cfx_list* l) { return l ? l->n : 0; }
+int64_t cfx_list_size(const cfx_list* l)
+{
+  if (!l)
+    return 0;
+  if (l->deferred && l->ctx)
+  { // the size is on the device: fetch it now (synchronises the context's stream)
+    try
+    {
+      resolve(l->ctx, const_cast<cfx_list*>(l));
+    }
+    catch (const std::exception& e)
+    {
+      cfx_set_error(l->ctx, e.what());
+      return -1;
+    }
+  }
+  return l->n;
+}
 const int32_t* cfx_list_device_ptr(const cfx_list* l) { return l ? l->data.p : nullptr; }
 
 cfx_status cfx_list_fetch(cfx_ctx* ctx, const cfx_list* l, int32_t* out, int memspace)
 {
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && l, CFX_ERR_INVALID, "cfx_list_fetch: NULL argument");
+  resolve(ctx, const_cast<cfx_list*>(l));
   export_to(ctx, out, l->data.p, static_cast<size_t>(l->n), memspace);
   CFX_API_END(ctx)
 }
@@ -364,6 +626,7 @@ void cfx_list_free(cfx_ctx* ctx, cfx_list* l)
   if (!l)
     return;
   l->data.release();
+  free_count_slot(l->ctx, l->d_n);
   delete l;
 }
 
@@ -399,6 +662,7 @@ cfx_status cfx_space_bind(cfx_ctx* ctx, int space, const int32_t* dofmap, int nd
 cfx_status cfx_stage_timing_enable(cfx_ctx* ctx, int on)
 {
   CFX_API_BEGIN
+  CFX_REQUIRE(!ctx->capturing, CFX_ERR_STATE, "cfx_stage_timing_enable: not while a graph is being captured");
   ctx->timing = on != 0;
   CFX_API_END(ctx)
 }

@@ -43,6 +43,9 @@ struct RuleView
   int64_t npts;
   const double* mom;  // per rule: measure, first (and, interface rules, second) moments, or null (cfx_rules::moments)
   int mom_stride;     // tdim + 1 (volume rules) or 1 + tdim + tdim (tdim + 1) / 2 (interface rules)
+  const int64_t* d_sizes; // deferred-size mode: device [nrules, npts] (npts above is then only an upper bound)
+  // stride of the SoA point / normal arrays = the exact number of points
+  __device__ __forceinline__ int64_t stride() const { return d_sizes ? d_sizes[1] : npts; }
 };
 
 struct StdRule
@@ -246,7 +249,7 @@ __device__ __forceinline__ void ld256(const double* p, double& a, double& b, dou
 // cell, so there is no race inside a launch.
 template <int TDIM, int DEG, int KID, bool RUNTIME>
 __global__ void __launch_bounds__(EB)
-    cell_kernel(const int32_t* __restrict__ cells, int64_t n, RuleView rv, StdRule sr, Consts cs,
+    cell_kernel(const int32_t* __restrict__ cells, DN n_, RuleView rv, StdRule sr, Consts cs,
                 const double* __restrict__ x, const int32_t* __restrict__ x_dofmap, OutCtx oc,
                 const double* __restrict__ coeff, const int32_t* __restrict__ dofmap)
 {
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(EB)
   constexpr int RANK = KernelTraits<KID>::RANK;
   constexpr int ES = ESize<ND, RANK>::value;
   const int64_t e = static_cast<int64_t>(blockIdx.x) * EB + threadIdx.x;
-  if (e >= n)
+  if (e >= n_.get())
     return;
   const int64_t cell = RUNTIME ? rv.parent_map[e] : cells[e];
   int64_t slot = oc.base + e;
@@ -357,7 +360,7 @@ __global__ void __launch_bounds__(EB)
       const int32_t qf = rv.offsets[e];
 #pragma unroll
       for (int r = 0; r < TDIM; ++r)
-        nq[r] = rv.nrm[static_cast<int64_t>(r) * rv.npts + qf];
+        nq[r] = rv.nrm[static_cast<int64_t>(r) * rv.stride() + qf];
       // constant gradients and their normal components
       double xi0[TDIM];
 #pragma unroll
@@ -434,12 +437,12 @@ __global__ void __launch_bounds__(EB)
       double xi[TDIM];
 #pragma unroll
       for (int t = 0; t < TDIM; ++t)
-        xi[t] = rv.pts[static_cast<int64_t>(t) * rv.npts + q];
+        xi[t] = rv.pts[static_cast<int64_t>(t) * rv.stride() + q];
       if constexpr (KernelTraits<KID>::N)
       {
 #pragma unroll
         for (int r = 0; r < TDIM; ++r)
-          nq[r] = rv.nrm[static_cast<int64_t>(r) * rv.npts + q];
+          nq[r] = rv.nrm[static_cast<int64_t>(r) * rv.stride() + q];
       }
       point_contribution<TDIM, DEG, KID>(g, xi, coef_weight(xi, rv.wts[q]), nq, h, cs, acc);
     }
@@ -485,10 +488,10 @@ __global__ void __launch_bounds__(EB)
   }
 }
 
-__global__ void reset_slots_kernel(const int32_t* __restrict__ cells, int64_t n, int32_t* __restrict__ mat_slot)
+__global__ void reset_slots_kernel(const int32_t* __restrict__ cells, DN n_, int32_t* __restrict__ mat_slot)
 {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-  if (i < n)
+  if (i < n_.get())
     mat_slot[cells[i]] = -1;
 }
 
@@ -500,7 +503,7 @@ __global__ void reset_slots_kernel(const int32_t* __restrict__ cells, int64_t n,
 // reference coordinates through its own affine map, so no quadrature_permutation is needed.
 template <int TDIM, int DEG>
 __global__ void __launch_bounds__(EB)
-    facet_kernel(const int32_t* __restrict__ rows4, int64_t n_facets, StdRule fr, Consts cs,
+    facet_kernel(const int32_t* __restrict__ rows4, DN n_facets_, StdRule fr, Consts cs,
                  const double* __restrict__ x, const int32_t* __restrict__ x_dofmap, const double* __restrict__ geo,
                  double* __restrict__ Fe, bool accumulate)
 {
@@ -508,7 +511,7 @@ __global__ void __launch_bounds__(EB)
   constexpr int NV = TDIM + 1;
   constexpr int SD = TDIM - 1;
   const int64_t t = static_cast<int64_t>(blockIdx.x) * EB + threadIdx.x;
-  if (t >= n_facets * 2 * ND)
+  if (t >= n_facets_.get() * 2 * ND)
     return;
   const int64_t f = t / (2 * ND);
   const int mrow = static_cast<int>(t - f * 2 * ND);
@@ -649,12 +652,12 @@ constexpr int FREC = 10; // record stride in doubles (80 B)
 
 template <int TDIM>
 __global__ void __launch_bounds__(EB)
-    facet_p1_kernel(const int32_t* __restrict__ rows4, int64_t n_facets, Consts cs, const double* __restrict__ geo,
+    facet_p1_kernel(const int32_t* __restrict__ rows4, DN n_facets_, Consts cs, const double* __restrict__ geo,
                     const int32_t* __restrict__ dofmap, double* __restrict__ Frec, bool accumulate)
 {
   constexpr int ND = TDIM + 1;
   const int64_t f = static_cast<int64_t>(blockIdx.x) * EB + threadIdx.x;
-  if (f >= n_facets)
+  if (f >= n_facets_.get())
     return;
   const int32_t c0 = rows4[4 * f], lf0 = rows4[4 * f + 1], c1 = rows4[4 * f + 2], lf1 = rows4[4 * f + 3];
   Geo<TDIM> g[2];
@@ -1102,10 +1105,10 @@ constexpr int GWM = 4; // rows per block of the mask kernel
 // rows no active entity touches: optional identity diagonal (deactivate_outside, deactivate.h:402-418)
 __global__ void inactive_diag_kernel(const uint8_t* __restrict__ row_flag, int64_t n_rows,
                                      const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ cols,
-                                     double* __restrict__ vals, double diag, int bs)
+                                     double* __restrict__ vals, double diag, int bs, int64_t cap)
 {
   const int64_t r = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-  if (r >= n_rows || row_flag[r])
+  if (r >= n_rows || row_flag[r] || row_ptr[r + 1] > cap)
     return;
   for (int64_t p = row_ptr[r]; p < row_ptr[r + 1]; ++p)
     if (cols[p] == r)
@@ -1339,7 +1342,7 @@ __device__ __forceinline__ int add_facet_rows(const GatherCtx& gc, int32_t (*s_f
 //           fixed summation order and no atomics -> bit-reproducible.
 template <int TDIM, int DEG>
 __global__ void __launch_bounds__(GW * 32)
-    gather_matrix_kernel(GatherCtx gc, StdTab st, const int32_t* __restrict__ act_rows, int64_t n_act,
+    gather_matrix_kernel(GatherCtx gc, StdTab st, const int32_t* __restrict__ act_rows, DN n_act_,
                          const uint8_t* __restrict__ skip_fast, const int64_t* __restrict__ row_ptr,
                          const int32_t* __restrict__ cols, double* __restrict__ vals, int zero_first,
                          int32_t* __restrict__ err)
@@ -1351,7 +1354,7 @@ __global__ void __launch_bounds__(GW * 32)
   __shared__ __align__(16) double s_fv[GW][32][FacetStage<ND>::W];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * GW + w;
-  if (idx >= n_act)
+  if (idx >= n_act_.get())
     return;
   if (skip_fast && (skip_fast[idx] & 1))
     return; // handled by gather_matrix_fast_kernel
@@ -1461,7 +1464,7 @@ __global__ void __launch_bounds__(GW * 32)
 template <int TDIM, int DEG>
 __global__ void __launch_bounds__(GWM * 32, 10)
     gather_matrix_fast_kernel(GatherCtx gc, StdTab st, StdTab stL, const int32_t* __restrict__ act_rows,
-                              const int32_t* __restrict__ slots, int64_t n_act,
+                              const int32_t* __restrict__ slots, DN n_act_,
                               const uint8_t* __restrict__ row_fast, const uint32_t* __restrict__ gmask,
                               const uint32_t* __restrict__ Rrow, const int64_t* __restrict__ row_ptr,
                               const int32_t* __restrict__ cols, double* __restrict__ vals, int zero_first)
@@ -1472,7 +1475,7 @@ __global__ void __launch_bounds__(GWM * 32, 10)
   __shared__ __align__(16) double s_fv[GWM][32][FacetStage<ND>::W];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t it = static_cast<int64_t>(blockIdx.x) * GWM + w;
-  if (it >= n_act)
+  if (it >= n_act_.get())
     return;
   // two launches: over the band slot list (slots != null), and -- only if some static row has no
   // contribution list -- over all rows, skipping the listed ones (row_fast bit 16)
@@ -1599,7 +1602,7 @@ struct alignas(16) ClistRow
 
 template <int TDIM, int DEG, bool FUSED>
 __global__ void __launch_bounds__(GWC * 32, 4)
-    gather_matrix_clist_kernel(GatherCtx gc, StdTab st, StdTab stL, const int32_t* __restrict__ act_rows, int64_t n_act,
+    gather_matrix_clist_kernel(GatherCtx gc, StdTab st, StdTab stL, const int32_t* __restrict__ act_rows, DN n_act_,
                                 const uint8_t* __restrict__ row_fast, const uint32_t* __restrict__ Rrow,
                                 const int64_t* __restrict__ row_ptr, double* __restrict__ vals, int zero_first)
 {
@@ -1613,7 +1616,7 @@ __global__ void __launch_bounds__(GWC * 32, 4)
   double* const sv = s_v[w];
   if (lane == 0)
     sv[255] = 0.0;
-  const int n_rows = static_cast<int>(n_act);
+  const int n_rows = static_cast<int>(n_act_.get());
   const int n_chunks = (n_rows + 31) >> 5;
   const int cstride = static_cast<int>(gridDim.x) * GWC;
   int chunk = static_cast<int>(blockIdx.x) * GWC + w;
@@ -1827,14 +1830,14 @@ __global__ void __launch_bounds__(GWC * 32, 4)
 // row, fixed shuffle tree -> bit-reproducible.
 template <int TDIM, int DEG, bool PERM>
 __global__ void __launch_bounds__(GW * 32)
-    gather_vector_kernel(GatherCtx gc, StdTab st, const int32_t* __restrict__ act_rows, int64_t n_act,
+    gather_vector_kernel(GatherCtx gc, StdTab st, const int32_t* __restrict__ act_rows, DN n_act_,
                          double* __restrict__ b, int zero_first, const int32_t* __restrict__ slots,
                          const uint8_t* __restrict__ row_fast, int skip_mode)
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t it = static_cast<int64_t>(blockIdx.x) * GW + w;
-  if (it >= n_act)
+  if (it >= n_act_.get())
     return;
   // skip_mode (fused system assembly): 1 = rows of the slot list that gather_matrix_clist_kernel did not
   // fill; 2 = all rows except those it filled and the listed ones (row_fast bit 16)
@@ -1909,6 +1912,15 @@ __global__ void __launch_bounds__(256) sum_partial_kernel(const double* __restri
 }
 
 // ------------------------------------------------------------------ host dispatch
+// exact entity counts of an integral (on the device in deferred-size mode)
+inline DN dn_entities(const cfx_integral& I) { return DN{I.d_n, I.n, I.facet ? 2 : 0}; }
+inline DN dn_rules(const cfx_rules* R) { return DN{R->deferred ? R->d_sizes : nullptr, R->nrules, 0}; }
+inline RuleView make_rule_view(const cfx_rules* R, bool normals, bool moments, int mom_stride)
+{
+  return RuleView{R->points.p, R->weights.p, normals ? R->normals.p : nullptr, R->offsets.p, R->parent_map.p, R->npts,
+                  moments ? R->moments.p : nullptr, mom_stride, R->deferred ? R->d_sizes : nullptr};
+}
+
 int std_rule_order(int kernel, int deg)
 {
   switch (kernel)
@@ -1939,7 +1951,7 @@ void launch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t& base)
     RuleTable& rt = get_rule(c, TDIM, std_rule_order(KID, DEG));
     sr = StdRule{rt.d_pts, rt.d_wts, rt.npts};
     auto k = cell_kernel<TDIM, DEG, KID, false>;
-    CFX_LAUNCH(c, k, grid_for(I.n, EB), EB, 0, I.entities, I.n, rv, sr, cs, c->x, c->x_dofmap, oc, f->coeff,
+    CFX_LAUNCH(c, k, grid_for(I.n, EB), EB, 0, I.entities, dn_entities(I), rv, sr, cs, c->x, c->x_dofmap, oc, f->coeff,
                c->spaces[f->space].dofmap);
     base += I.n;
     oc.base = base;
@@ -1948,11 +1960,10 @@ void launch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t& base)
   {
     const cfx_rules* R = I.rules;
     CFX_REQUIRE(R->tdim == TDIM, CFX_ERR_INVALID, "run-time rules have the wrong reference dimension");
-    rv = RuleView{R->points.p, R->weights.p, R->has_normals ? R->normals.p : nullptr, R->offsets.p, R->parent_map.p,
-                  R->npts, R->has_moments ? R->moments.p : nullptr,
-                  1 + TDIM + (R->relation == CFX_REL_EQ ? TDIM * (TDIM + 1) / 2 : 0)};
+    rv = make_rule_view(R, R->has_normals, R->has_moments,
+                        1 + TDIM + (R->relation == CFX_REL_EQ ? TDIM * (TDIM + 1) / 2 : 0));
     auto k = cell_kernel<TDIM, DEG, KID, true>;
-    CFX_LAUNCH(c, k, grid_for(R->nrules, EB), EB, 0, nullptr, R->nrules, rv, sr, cs, c->x, c->x_dofmap, oc, f->coeff,
+    CFX_LAUNCH(c, k, grid_for(R->nrules, EB), EB, 0, nullptr, dn_rules(R), rv, sr, cs, c->x, c->x_dofmap, oc, f->coeff,
                c->spaces[f->space].dofmap);
     if (base >= 0)
       base += R->nrules;
@@ -1973,13 +1984,13 @@ void launch_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t& base)
 // (they all store the same value) and recognise their own claim by its value.
 template <int TDIM, int DEG, bool RUNTIME>
 __global__ void __launch_bounds__(EB)
-    elasticity_kernel(const int32_t* __restrict__ cells, int64_t n, RuleView rv, StdRule sr, Consts cs,
+    elasticity_kernel(const int32_t* __restrict__ cells, DN n_, RuleView rv, StdRule sr, Consts cs,
                       const double* __restrict__ x, const int32_t* __restrict__ x_dofmap, OutCtx oc)
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
   constexpr int BS = TDIM, N = ND * BS;
   const int64_t t = static_cast<int64_t>(blockIdx.x) * EB + threadIdx.x;
-  if (t >= n * N)
+  if (t >= n_.get() * N)
     return;
   const int64_t e = t / N;
   const int ra = static_cast<int>(t - e * N);
@@ -2042,7 +2053,7 @@ __global__ void __launch_bounds__(EB)
       double xi[TDIM];
 #pragma unroll
       for (int tt = 0; tt < TDIM; ++tt)
-        xi[tt] = rv.pts[static_cast<int64_t>(tt) * rv.npts + q];
+        xi[tt] = rv.pts[static_cast<int64_t>(tt) * rv.stride() + q];
       point(xi, rv.wts[q]);
     }
   }
@@ -2073,13 +2084,13 @@ __global__ void __launch_bounds__(EB)
 //   pen = c2 (2 mu + lambda) / h;  c0 = mu, c1 = lambda, c2 = gamma.  Slots as in elasticity_kernel.
 template <int TDIM, int DEG>
 __global__ void __launch_bounds__(EB)
-    nitsche_vec_kernel(int64_t n, RuleView rv, Consts cs, const double* __restrict__ x,
+    nitsche_vec_kernel(DN n_, RuleView rv, Consts cs, const double* __restrict__ x,
                        const int32_t* __restrict__ x_dofmap, OutCtx oc)
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
   constexpr int BS = TDIM, N = ND * BS;
   const int64_t t = static_cast<int64_t>(blockIdx.x) * EB + threadIdx.x;
-  if (t >= n * N)
+  if (t >= n_.get() * N)
     return;
   const int64_t e = t / N;
   const int ra = static_cast<int>(t - e * N);
@@ -2108,8 +2119,8 @@ __global__ void __launch_bounds__(EB)
 #pragma unroll
     for (int tt = 0; tt < TDIM; ++tt)
     {
-      xi[tt] = rv.pts[static_cast<int64_t>(tt) * rv.npts + q];
-      nr[tt] = rv.nrm[static_cast<int64_t>(tt) * rv.npts + q];
+      xi[tt] = rv.pts[static_cast<int64_t>(tt) * rv.stride() + q];
+      nr[tt] = rv.nrm[static_cast<int64_t>(tt) * rv.stride() + q];
     }
     const double w = rv.wts[q];
     double phi[ND], dphi[ND][TDIM], grad[ND][TDIM];
@@ -2166,13 +2177,13 @@ __global__ void __launch_bounds__(EB)
 // inner(f, v) dx with a constant vector f = (c0, c1, c2): one thread per entity, N values
 template <int TDIM, int DEG, bool RUNTIME>
 __global__ void __launch_bounds__(EB)
-    source_vec_kernel(const int32_t* __restrict__ cells, int64_t n, RuleView rv, StdRule sr, Consts cs,
+    source_vec_kernel(const int32_t* __restrict__ cells, DN n_, RuleView rv, StdRule sr, Consts cs,
                       const double* __restrict__ x, const int32_t* __restrict__ x_dofmap, OutCtx oc)
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
   constexpr int BS = TDIM, N = ND * BS;
   const int64_t e = static_cast<int64_t>(blockIdx.x) * EB + threadIdx.x;
-  if (e >= n)
+  if (e >= n_.get())
     return;
   const int64_t cell = RUNTIME ? rv.parent_map[e] : cells[e];
   const bool follow = oc.base < 0;
@@ -2193,7 +2204,7 @@ __global__ void __launch_bounds__(EB)
       double xi[TDIM], phi[ND], dphi[ND][TDIM];
 #pragma unroll
       for (int tt = 0; tt < TDIM; ++tt)
-        xi[tt] = rv.pts[static_cast<int64_t>(tt) * rv.npts + q];
+        xi[tt] = rv.pts[static_cast<int64_t>(tt) * rv.stride() + q];
       tabulate<TDIM, DEG>(xi, phi, dphi);
 #pragma unroll
       for (int k = 0; k < ND; ++k)
@@ -2239,7 +2250,7 @@ __global__ void __launch_bounds__(EB)
 // entry goes on the diagonal of the block.
 template <int TDIM, int DEG>
 __global__ void __launch_bounds__(32)
-    gather_matrix_blocked_kernel(GatherCtx gc, const int32_t* __restrict__ act_rows, int64_t n_act,
+    gather_matrix_blocked_kernel(GatherCtx gc, const int32_t* __restrict__ act_rows, DN n_act_,
                                  const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ cols,
                                  double* __restrict__ vals, int zero_first, int32_t* __restrict__ err)
 {
@@ -2251,7 +2262,7 @@ __global__ void __launch_bounds__(32)
   __shared__ __align__(16) double s_fv[32][FacetStage<ND>::W];
   const int lane = threadIdx.x;
   const int64_t idx = blockIdx.x;
-  if (idx >= n_act)
+  if (idx >= n_act_.get())
     return;
   const unsigned full = 0xffffffffu;
   const int64_t r = act_rows[idx];
@@ -2353,14 +2364,14 @@ __global__ void __launch_bounds__(32)
 // b[bs*dof + a] += element-vector entries of the incident cells, ascending cell order + fixed shuffle tree
 template <int TDIM, int DEG>
 __global__ void __launch_bounds__(GW * 32)
-    gather_vector_blocked_kernel(GatherCtx gc, const int32_t* __restrict__ act_rows, int64_t n_act,
+    gather_vector_blocked_kernel(GatherCtx gc, const int32_t* __restrict__ act_rows, DN n_act_,
                                  double* __restrict__ b, int zero_first)
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
   constexpr int BS = TDIM, N = ND * BS;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * GW + w;
-  if (idx >= n_act)
+  if (idx >= n_act_.get())
     return;
   const int64_t r = act_rows[idx];
   const int64_t ib = gc.inc_ptr[r];
@@ -2425,8 +2436,8 @@ void launch_blocked_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t
     if (R && R->nrules > 0)
     {
       CFX_REQUIRE(R->tdim == TDIM && R->has_normals, CFX_ERR_INVALID, "interface kernels need rules with normals");
-      rv = RuleView{R->points.p, R->weights.p, R->normals.p, R->offsets.p, R->parent_map.p, R->npts};
-      CFX_LAUNCH(c, (nitsche_vec_kernel<TDIM, DEG>), grid_for(R->nrules * N, EB), EB, 0, R->nrules, rv, cs, c->x,
+      rv = make_rule_view(R, true, false, 0);
+      CFX_LAUNCH(c, (nitsche_vec_kernel<TDIM, DEG>), grid_for(R->nrules * N, EB), EB, 0, dn_rules(R), rv, cs, c->x,
                  c->x_dofmap, oc);
       if (base >= 0)
         base += R->nrules;
@@ -2440,11 +2451,11 @@ void launch_blocked_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t
     RuleTable& rt = get_rule(c, TDIM, el ? 2 * (DEG - 1) : DEG);
     sr = StdRule{rt.d_pts, rt.d_wts, rt.npts};
     if (el)
-      CFX_LAUNCH(c, (elasticity_kernel<TDIM, DEG, false>), grid_for(I.n * N, EB), EB, 0, I.entities, I.n, rv, sr, cs,
-                 c->x, c->x_dofmap, oc);
+      CFX_LAUNCH(c, (elasticity_kernel<TDIM, DEG, false>), grid_for(I.n * N, EB), EB, 0, I.entities, dn_entities(I), rv,
+                 sr, cs, c->x, c->x_dofmap, oc);
     else
-      CFX_LAUNCH(c, (source_vec_kernel<TDIM, DEG, false>), grid_for(I.n, EB), EB, 0, I.entities, I.n, rv, sr, cs, c->x,
-                 c->x_dofmap, oc);
+      CFX_LAUNCH(c, (source_vec_kernel<TDIM, DEG, false>), grid_for(I.n, EB), EB, 0, I.entities, dn_entities(I), rv, sr,
+                 cs, c->x, c->x_dofmap, oc);
     if (base >= 0)
     {
       base += I.n;
@@ -2455,12 +2466,12 @@ void launch_blocked_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t
   {
     const cfx_rules* R = I.rules;
     CFX_REQUIRE(R->tdim == TDIM, CFX_ERR_INVALID, "run-time rules have the wrong reference dimension");
-    rv = RuleView{R->points.p, R->weights.p, nullptr, R->offsets.p, R->parent_map.p, R->npts};
+    rv = make_rule_view(R, false, false, 0);
     if (el)
-      CFX_LAUNCH(c, (elasticity_kernel<TDIM, DEG, true>), grid_for(R->nrules * N, EB), EB, 0, nullptr, R->nrules, rv, sr,
+      CFX_LAUNCH(c, (elasticity_kernel<TDIM, DEG, true>), grid_for(R->nrules * N, EB), EB, 0, nullptr, dn_rules(R), rv, sr,
                  cs, c->x, c->x_dofmap, oc);
     else
-      CFX_LAUNCH(c, (source_vec_kernel<TDIM, DEG, true>), grid_for(R->nrules, EB), EB, 0, nullptr, R->nrules, rv, sr, cs,
+      CFX_LAUNCH(c, (source_vec_kernel<TDIM, DEG, true>), grid_for(R->nrules, EB), EB, 0, nullptr, dn_rules(R), rv, sr, cs,
                  c->x, c->x_dofmap, oc);
     if (base >= 0)
       base += R->nrules;
@@ -2576,10 +2587,10 @@ void reset_slots(cfx_ctx* c, cfx_form* f)
     if (I.facet)
       continue;
     if (I.rules && I.rules->nrules > 0)
-      CFX_LAUNCH(c, reset_slots_kernel, grid_for(I.rules->nrules, 256), 256, 0, I.rules->parent_map.p, I.rules->nrules,
+      CFX_LAUNCH(c, reset_slots_kernel, grid_for(I.rules->nrules, 256), 256, 0, I.rules->parent_map.p, dn_rules(I.rules),
                  c->mat_slot.p);
     if (blocked && I.n > 0) // blocked spaces materialise the standard cells too
-      CFX_LAUNCH(c, reset_slots_kernel, grid_for(I.n, 256), 256, 0, I.entities, I.n, c->mat_slot.p);
+      CFX_LAUNCH(c, reset_slots_kernel, grid_for(I.n, 256), 256, 0, I.entities, dn_entities(I), c->mat_slot.p);
   }
 }
 
@@ -2648,7 +2659,7 @@ void launch_facet(cfx_ctx* c, const cfx_integral& I, cfx_form* f, bool accumulat
   if constexpr (DEG == 1)
   { // factored, combined storage: one 80-byte record per facet (distinct dofs, combined jump coefficients, weight)
     static_assert(FREC <= 4 * ND * ND, "the facet buffer is sized for full macro tensors");
-    CFX_LAUNCH(c, facet_p1_kernel<TDIM>, grid_for(I.n, EB), EB, 0, I.entities, I.n, cs, c->geo.p,
+    CFX_LAUNCH(c, facet_p1_kernel<TDIM>, grid_for(I.n, EB), EB, 0, I.entities, dn_entities(I), cs, c->geo.p,
                c->spaces[f->space].dofmap, f->Fe.p, accumulate);
   }
   else
@@ -2656,7 +2667,7 @@ void launch_facet(cfx_ctx* c, const cfx_integral& I, cfx_form* f, bool accumulat
     RuleTable& rt = get_rule(c, TDIM - 1, 2 * (DEG - 1));
     StdRule fr{rt.d_pts, rt.d_wts, rt.npts};
     auto k = facet_kernel<TDIM, DEG>;
-    CFX_LAUNCH(c, k, grid_for(I.n * 2 * ND, EB), EB, 0, I.entities, I.n, fr, cs, c->x, c->x_dofmap, c->geo.p, f->Fe.p,
+    CFX_LAUNCH(c, k, grid_for(I.n * 2 * ND, EB), EB, 0, I.entities, dn_entities(I), fr, cs, c->x, c->x_dofmap, c->geo.p, f->Fe.p,
                accumulate);
   }
 }
@@ -2698,7 +2709,7 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
   {
     CFX_REQUIRE(S.bs == TDIM, CFX_ERR_UNSUPPORTED, "blocked spaces need block size == gdim");
     auto kb = gather_matrix_blocked_kernel<TDIM, DEG>;
-    CFX_LAUNCH(ctx, kb, grid_for(PR->n_act_rows, 1), 32, 0, gc, PR->act_rows.p, PR->n_act_rows, A->row_ptr.p, A->cols.p,
+    CFX_LAUNCH(ctx, kb, grid_for(PR->n_act_rows, 1), 32, 0, gc, PR->act_rows.p, PR->dn_act(), A->row_ptr.p, A->cols.p,
                A->values.p, zero_first, ctx->err_flag.p);
     return;
   }
@@ -2724,7 +2735,7 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
       cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
       const unsigned gp = static_cast<unsigned>(std::min<int64_t>(static_cast<int64_t>(n_sm) * 4,
                                                                   (PR->n_act_rows + GWC - 1) / GWC));
-      CFX_LAUNCH(ctx, kc, gp, GWC * 32, 0, gc, st, stL, PR->act_rows.p, PR->n_act_rows, a->row_fast.p, a->Rrow.p,
+      CFX_LAUNCH(ctx, kc, gp, GWC * 32, 0, gc, st, stL, PR->act_rows.p, PR->dn_act(), a->row_fast.p, a->Rrow.p,
                  A->row_ptr.p, A->values.p, zero_first);
     }
     if (fast && (a->n_mask_rows != 0))
@@ -2738,19 +2749,22 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
       auto kf = gather_matrix_fast_kernel<TDIM, DEG>;
       if (a->n_band_listed > 0)
         CFX_LAUNCH(ctx, kf, grid_for(a->n_band_listed, GWM), GWM * 32, 0, gc, st, stL, PR->act_rows.p, PR->band_idx.p,
-                   a->n_band_listed, a->row_fast.p, a->gmask.p, a->Rrow.p, A->row_ptr.p, A->cols.p, A->values.p,
+                   PR->dn_band(), a->row_fast.p, a->gmask.p, a->Rrow.p, A->row_ptr.p, A->cols.p, A->values.p,
                    zero_first);
       // static rows without a contribution list (an edge with more than 8 cells), or no slot list at all
-      if (a->n_band_listed == 0 || PR->n_act_rows - a->n_band_listed - a->n_clist_rows > 0)
+      // (a deferred-size step takes the decision from what eager steps saw; build_pattern verified it on the device)
+      const bool noclist = A->deferred ? !a->expect_noclist_zero
+                                       : PR->n_act_rows - a->n_band_listed - a->n_clist_rows > 0;
+      if (a->n_band_listed == 0 || noclist)
         CFX_LAUNCH(ctx, kf, grid_for(PR->n_act_rows, GWM), GWM * 32, 0, gc, st, stL, PR->act_rows.p, nullptr,
-                   PR->n_act_rows, a->row_fast.p, a->gmask.p, a->Rrow.p, A->row_ptr.p, A->cols.p, A->values.p,
+                   PR->dn_act(), a->row_fast.p, a->gmask.p, a->Rrow.p, A->row_ptr.p, A->cols.p, A->values.p,
                    zero_first);
     }
   }
   if (!fast || a->n_slow_rows > 0)
   {
     auto k = gather_matrix_kernel<TDIM, DEG>;
-    CFX_LAUNCH(ctx, k, g, GW * 32, 0, gc, st, PR->act_rows.p, PR->n_act_rows, fast ? a->row_fast.p : nullptr,
+    CFX_LAUNCH(ctx, k, g, GW * 32, 0, gc, st, PR->act_rows.p, PR->dn_act(), fast ? a->row_fast.p : nullptr,
                A->row_ptr.p, A->cols.p, A->values.p, zero_first, ctx->err_flag.p);
   }
 }
@@ -2766,12 +2780,13 @@ void launch_gather_vector(cfx_ctx* ctx, cfx_form* L, const GatherCtx& gc, const 
   if (S.bs > 1)
   {
     auto kb = gather_vector_blocked_kernel<TDIM, DEG>;
-    CFX_LAUNCH(ctx, kb, grid_for(PR->n_act_rows, GW), GW * 32, 0, gc, PR->act_rows.p, PR->n_act_rows, d_b, zero_first);
+    CFX_LAUNCH(ctx, kb, grid_for(PR->n_act_rows, GW), GW * 32, 0, gc, PR->act_rows.p, PR->dn_act(), d_b, zero_first);
     return;
   }
-  auto run = [&](const int32_t* slots, int64_t n, const uint8_t* row_fast, int skip_mode)
+  auto run = [&](const int32_t* slots, int64_t n_bound, const uint8_t* row_fast, int skip_mode)
   {
-    const unsigned g = grid_for(n, GW);
+    const unsigned g = grid_for(n_bound, GW);
+    const DN n = PR->dn_act();
     if (S.has_perm)
     {
       auto k = gather_vector_kernel<TDIM, DEG, true>;
@@ -2930,7 +2945,7 @@ static void assemble_matrix_impl(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, int 
       CFX_CUDA(cudaMemsetAsync(A->values.p, 0, static_cast<size_t>(A->nnz) * S.bs * S.bs * sizeof(double), ctx->stream));
     if (diag_inactive != 0.0)
       CFX_LAUNCH(ctx, inactive_diag_kernel, grid_for(A->n_rows, 256), 256, 0, a->prep->row_flag.p, A->n_rows, A->row_ptr.p,
-                 A->cols.p, A->values.p, diag_inactive, S.bs);
+                 A->cols.p, A->values.p, diag_inactive, S.bs, static_cast<int64_t>(A->cols.cap) - 1);
     CFX_DISPATCH_ELEM(ctx, S, launch_gather_matrix, ctx, a, A, gc, stt, stL, zero_first);
     set_facet_slots(ctx, FI, true);
   }
@@ -2962,7 +2977,7 @@ cfx_status cfx_assemble_matrix(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
   assemble_matrix_impl(ctx, a, A, zero_first, diag_inactive, nullptr, nullptr, 0);
   if (values_out)
     export_to(ctx, values_out, A->values.p, static_cast<size_t>(A->nnz) * A->bs * A->bs, memspace);
-  check_device_error(ctx, "cfx_assemble_matrix (entry not in sparsity pattern)");
+  check_call(ctx, "cfx_assemble_matrix (entry not in sparsity pattern)");
   CFX_API_END(ctx)
 }
 
@@ -2990,7 +3005,7 @@ cfx_status cfx_assemble_system(cfx_ctx* ctx, const cfx_form* a_const, cfx_patter
     if (rc != CFX_OK)
       return rc;
   }
-  check_device_error(ctx, "cfx_assemble_system (entry not in sparsity pattern)");
+  check_call(ctx, "cfx_assemble_system (entry not in sparsity pattern)");
   CFX_API_END(ctx)
 }
 
@@ -3072,6 +3087,7 @@ cfx_status cfx_assemble_scalar(cfx_ctx* ctx, const cfx_form* M_const, double* ou
   cfx_form* M = const_cast<cfx_form*>(M_const);
   CFX_REQUIRE(ctx && M && out, CFX_ERR_INVALID, "cfx_assemble_scalar: NULL argument");
   CFX_REQUIRE(M->rank == 0, CFX_ERR_INVALID, "cfx_assemble_scalar: form is not a functional");
+  resolve_form(ctx, M); // the sum runs over the exact number of entities
   const int64_t n = run_cell_integrals(ctx, M); // one value per entity, entity order
   constexpr int NB = 256;
   DevBuf<double> partial;

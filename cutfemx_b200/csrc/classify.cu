@@ -208,7 +208,8 @@ Dnf make_dnf(cfx_ctx* c, int n_terms, const int32_t* term_offsets, const int32_t
 
 // owned cells matching a compiled selector.  A single clause `name rel 0` needs no counting pass: the per-tile
 // counts follow from the classification's block counts.
-int64_t compact_owned_cells(cfx_ctx* c, const Dnf& d, DevBuf<int32_t>& out)
+int64_t compact_owned_cells(cfx_ctx* c, const Dnf& d, DevBuf<int32_t>& out, int64_t* d_total = nullptr,
+                            bool* deferred = nullptr)
 {
   DnfPred p{d, c->domain.p, c->domain_stride};
   const int64_t n = c->nc_owned;
@@ -221,7 +222,7 @@ int64_t compact_owned_cells(cfx_ctx* c, const Dnf& d, DevBuf<int32_t>& out)
                c->cls_counts.p + static_cast<size_t>(d.ls[0]) * c->cls_blocks * 4, c->cls_blocks,
                static_cast<unsigned>(d.relmask[0]), nt, c->blk_counts.p);
   }
-  return compact_indices(c, n, p, out, single);
+  return compact_indices(c, dn_exact(n), p, out, single, d_total, deferred);
 }
 
 void ensure_cut_list(cfx_ctx* c, int ls)
@@ -236,7 +237,9 @@ void ensure_cut_list(cfx_ctx* c, int ls)
   d.ls[0] = static_cast<int8_t>(ls);
   d.relmask[0] = relation_mask(CFX_REL_EQ);
   StageScope st(c, "locate_cut", static_cast<double>(c->nc_owned) * 2.0);
-  L.n_cut = compact_owned_cells(c, d, L.cut_list);
+  if (!L.d_n_cut)
+    L.d_n_cut = alloc_count_slot(c);
+  L.n_cut = compact_owned_cells(c, d, L.cut_list, L.d_n_cut, &L.cut_deferred);
   st.set_bytes(static_cast<double>(c->nc_owned) * 2.0 + 4.0 * static_cast<double>(L.n_cut));
 }
 // intersected cells among ALL local cells (owned + ghost).  The reference's Python loop
@@ -260,7 +263,9 @@ void ensure_cut_list_all(cfx_ctx* c, int ls)
   d.ls[0] = static_cast<int8_t>(ls);
   d.relmask[0] = relation_mask(CFX_REL_EQ);
   DnfPred p{d, c->domain.p, c->domain_stride};
-  L.n_cut_all = compact_indices(c, c->nc_total, p, L.cut_list_all);
+  if (!L.d_n_cut_all)
+    L.d_n_cut_all = alloc_count_slot(c);
+  L.n_cut_all = compact_indices(c, dn_exact(c->nc_total), p, L.cut_list_all, false, L.d_n_cut_all, &L.cut_all_deferred);
 }
 } // namespace cfx
 
@@ -309,7 +314,7 @@ extern "C" cfx_status cfx_set_host_cells(cfx_ctx* ctx, const int32_t* cells, int
     DevBuf<int32_t> own;
     const int32_t* d = adopt(ctx, own, cells, static_cast<size_t>(n), memspace);
     CFX_LAUNCH(ctx, host_mask_kernel, grid_for(n, CB), CB, 0, d, n, ctx->nc_owned, ctx->host_mask.p, ctx->err_flag.p);
-    check_device_error(ctx, "cfx_set_host_cells (entity index out of range)");
+    check_call(ctx, "cfx_set_host_cells (entity index out of range)");
     own.release();
   }
   ctx->has_host_mask = true;
@@ -325,8 +330,15 @@ extern "C" cfx_status cfx_locate_entities(cfx_ctx* ctx, int n_terms, const int32
   const Dnf d = make_dnf(ctx, n_terms, term_offsets, clause_ls, clause_rel);
   if (*out == nullptr)
     *out = new cfx_list();
+  cfx_list* l = *out;
+  if (!l->d_n)
+  {
+    l->d_n = alloc_count_slot(ctx);
+    l->ctx = ctx;
+  }
   StageScope st(ctx, "locate", static_cast<double>(ctx->nc_owned) * 2.0);
-  (*out)->n = compact_owned_cells(ctx, d, (*out)->data);
+  l->n = compact_owned_cells(ctx, d, l->data, l->d_n, &l->deferred);
+  note_result(ctx, l);
   st.set_bytes(static_cast<double>(ctx->nc_owned) * 2.0 + 4.0 * static_cast<double>((*out)->n));
   CFX_API_END(ctx)
 }

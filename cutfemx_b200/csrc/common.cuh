@@ -37,11 +37,41 @@ struct Error : std::runtime_error
       throw cfx::Error(code, msg);                                                                                     \
   } while (0)
 
+// A size that may be known on the device only ("deferred-size mode", cfx_set_deferred): kernels take a DN where
+// they used to take an int64 bound and read the exact value themselves; the host sizes grids and buffers with the
+// upper bound h (h is the exact value and d is null when the host knows it).
+struct DN
+{
+  const int64_t* d;
+  int64_t h;
+  int shift; // the device value counts 2^shift units per item (facet-row lists: 4 int32 entries per facet)
+#ifdef __CUDACC__
+  __device__ __forceinline__ int64_t get() const { return d ? (*d >> shift) : h; }
+#endif
+};
+
 // ---- caching device allocator: handles are created/freed every step of a moving-level-set
 // loop; cudaMalloc/cudaFree would serialise the stream each time.
 class DevPool
 {
 public:
+  // CUDA-graph capture (cfx_graph_begin / _end): blocks the captured calls free must stay reserved for the graph's
+  // replays, and blocks cached before the capture must not become graph temporaries that a later eager call could
+  // be handed as well.  begin_capture() sets the cache aside; end_capture() returns everything freed during the
+  // capture (now owned by the graph) and restores the cache.
+  void begin_capture() { stash_.swap(free_); }
+  std::vector<std::pair<size_t, void*>> end_capture()
+  {
+    std::vector<std::pair<size_t, void*>> owned(free_.begin(), free_.end());
+    free_.clear();
+    stash_.swap(free_);
+    return owned;
+  }
+  void give_back(const std::vector<std::pair<size_t, void*>>& blocks)
+  {
+    for (auto& b : blocks)
+      free_.emplace(b.first, b.second);
+  }
   void* alloc(size_t bytes)
   {
     if (bytes == 0)
@@ -81,12 +111,15 @@ public:
   }
   void release_cached()
   {
-    for (auto& kv : free_)
+    for (auto* m : {&free_, &stash_})
     {
-      cudaFree(kv.second);
-      total_ -= kv.first;
+      for (auto& kv : *m)
+      {
+        cudaFree(kv.second);
+        total_ -= kv.first;
+      }
+      m->clear();
     }
-    free_.clear();
   }
   void release_all()
   {
@@ -99,7 +132,7 @@ public:
   size_t total_bytes() const { return total_; }
 
 private:
-  std::multimap<size_t, void*> free_;
+  std::multimap<size_t, void*> free_, stash_;
   std::unordered_map<void*, size_t> live_;
   size_t total_ = 0;
 };
@@ -144,9 +177,13 @@ struct LevelSet
   DevBuf<int32_t> dofmap_own;
   int64_t counts[3] = {0, 0, 0};
   DevBuf<int32_t> cut_list; // intersected owned cells, ascending (cached per update)
-  int64_t n_cut = -1;
+  int64_t n_cut = -1;       // exact count, or (cut_deferred) an upper bound; -1: list not built since the update
   DevBuf<int32_t> cut_list_all; // intersected owned + ghost cells (sources of the ghost-penalty band)
   int64_t n_cut_all = -1;
+  // deferred-size mode: the exact counts live in these device slots
+  int64_t* d_n_cut = nullptr;
+  int64_t* d_n_cut_all = nullptr;
+  bool cut_deferred = false, cut_all_deferred = false;
 };
 
 struct Space
@@ -160,6 +197,13 @@ struct Space
   DevBuf<int64_t> inc_ptr;
   DevBuf<int32_t> inc_cell;
   int64_t n_inc = 0;
+  // deferred-size mode: upper bounds for the per-step active-row / band-row lists of forms over this space
+  // (largest counts seen in eager steps, with the context's capacity margin); 0 = not known yet
+  int64_t cap_act_rows = 0, cap_band = 0;
+  // what eager assemblies on this space have seen: rows the fast gather paths cannot handle (generic kernel) and
+  // static rows without a contribution list; -1 = never observed.  A deferred-size step skips those kernels when
+  // the numbers were 0 and verifies on the device that they still are.
+  int64_t seen_slow_rows = -1, seen_noclist_rows = -1;
   int stride = 0;               // max number of cells around a dof
   // per incidence (nd <= 6): bits 0..3 = local index of the dof in the cell, bits 4+4j.. = rank of
   // the cell's j-th dof among the cell's dofs (ascending global number)
@@ -194,16 +238,25 @@ struct Stage
 };
 } // namespace cfx
 
+struct cfx_ctx;
 struct cfx_list
 {
   cfx::DevBuf<int32_t> data;
-  int64_t n = 0; // number of int32 entries
+  int64_t n = 0; // number of int32 entries: exact, or -- deferred -- an upper bound (the buffer's capacity)
+  int64_t* d_n = nullptr; // device copy of the exact count (slot of the context's count slab)
+  bool deferred = false;
+  int64_t n_bound = 0;    // the upper bound n had when the size was last left on the device
+  cfx_ctx* ctx = nullptr; // owner (set when d_n is allocated): size queries of a deferred list synchronise on it
 };
 
 struct cfx_rules
 {
   int tdim = 0, gdim = 0, relation = 0, order = 0, ls = 0;
-  int64_t npts = 0, nrules = 0;
+  int64_t npts = 0, nrules = 0; // exact, or -- deferred -- upper bounds (d_sizes holds the exact pair)
+  int64_t* d_sizes = nullptr;   // device: [0] nrules, [1] npts
+  int64_t cap_pts = 0, cap_rules = 0; // capacities of the point / rule arrays (>= the sizes, with margin)
+  bool deferred = false;
+  cfx_ctx* ctx = nullptr;
   cfx::DevBuf<double> points;  // SoA (tdim, npts)
   cfx::DevBuf<double> weights; // (npts)
   cfx::DevBuf<int32_t> offsets;    // (nrules + 1)
@@ -227,7 +280,9 @@ struct cfx_pattern
 {
   int space = 0;
   int bs = 1; // values: nnz * bs * bs
-  int64_t n_rows = 0, nnz = 0;
+  int64_t n_rows = 0, nnz = 0; // nnz: exact, or -- deferred -- an upper bound (row_ptr[n_rows] holds the exact value)
+  bool deferred = false;
+  cfx_ctx* ctx = nullptr;
   int64_t serial = 0;
   cfx::DevBuf<int64_t> row_ptr;
   cfx::DevBuf<int32_t> cols;
@@ -239,7 +294,8 @@ struct cfx_integral
   int kernel = 0;
   bool facet = false;
   const int32_t* entities = nullptr; // device: std cells (cells) or rows4 (facets)
-  int64_t n = 0;
+  int64_t n = 0;                     // exact, or an upper bound when d_n is set (list with a deferred size)
+  const int64_t* d_n = nullptr;      // device count of `entities` in int32 entries (4 per facet row)
   cfx::DevBuf<int32_t> own;
   cfx_rules* rules = nullptr; // borrowed
   double constants[CFX_MAX_CONSTANTS] = {};
@@ -264,6 +320,11 @@ struct cfx_prepared
   int64_t n_act_rows = 0;
   cfx::DevBuf<int32_t> band_idx;   // ascending slots (indices into act_rows) of the rows with row_flag bit1:
   int64_t n_band = 0;              // facet-band rows and rows with inserted entries (generic pattern path)
+  // deferred-size mode: n_act_rows / n_band are upper bounds, the exact values live in d_counts[0] / [1]
+  bool act_deferred = false, band_deferred = false;
+  int64_t* d_counts = nullptr;
+  cfx::DN dn_act() const { return cfx::DN{act_deferred ? d_counts : nullptr, n_act_rows, 0}; }
+  cfx::DN dn_band() const { return cfx::DN{band_deferred ? d_counts + 1 : nullptr, n_band, 0}; }
   int64_t n_active_entities = 0;   // sum of the list sizes (for the byte accounting only)
 };
 
@@ -274,6 +335,8 @@ struct cfx_form
   // SparsityPattern::insert entries from other ranks (cfx_form_insert_pattern_entries), sorted by row
   cfx::DevBuf<int32_t> xrows, xcols;
   int64_t n_x = 0;
+  const int64_t* d_n_x = nullptr; // deferred: exact number of inserted entries (n_x is then the capacity)
+  bool deferred = false;          // some size this form depends on is known on the device only
   // prepared state (recomputed when dirty); shared between forms with the same cell domains
   bool dirty = true;
   cfx_prepared* prep = nullptr;
@@ -285,6 +348,7 @@ struct cfx_form
   int64_t n_mask_rows = -1; // rows of the mask gather kernel (band rows, long contribution lists); -1 unknown
   int64_t n_clist_rows = 0, n_clist_nnz = 0; // rows / CSR entries of the contribution-list gather kernel
   int64_t n_band_listed = 0; // generic-pattern rows reached through the prepared band slot list (row_fast bit 16)
+  bool expect_noclist_zero = false; // deferred step: no static row without a contribution list (verified on the device)
   int64_t gtab_serial = -1;
   cfx::DevBuf<double> Ae;      // materialised run-time-rule tensors, cell-major (slot, nd^rank) natural order;
                                // rank 0: one value per entity
@@ -301,6 +365,19 @@ struct cfx_ctx
   std::string err;
   cfx::DevPool pool;
   int64_t launches = 0;
+  // deferred-size mode (cfx_set_deferred): calls that reuse objects whose buffers already have a capacity leave
+  // their result sizes on the device and return without synchronising; the host fetches them on demand
+  bool deferred = false;
+  double margin = 0.125;            // extra capacity given to size-dependent buffers (so later steps fit)
+  bool capturing = false;           // between cfx_graph_begin and cfx_graph_end: synchronising is an error
+  cudaStream_t user_stream = nullptr;
+  // objects whose sizes were left on the device by captured calls: a replay of the graph makes them deferred again
+  std::vector<cfx_list*> cap_lists;
+  std::vector<cfx_rules*> cap_rules;
+  std::vector<cfx_pattern*> cap_patterns;
+  cfx::DevBuf<int64_t> count_slab;  // device int64 slots handed to objects with device-side sizes
+  std::vector<int> free_slots;
+  int next_slot = 0;
   int64_t pattern_serial = 0;
   int64_t update_serial = 0;
   std::vector<cfx_prepared*> preps; // live prepared domains (owned by the forms that reference them)
@@ -441,8 +518,52 @@ inline void export_to(cfx_ctx* c, T* dst, const T* src_dev, size_t n, int memspa
 // read-back never waits behind a large device->host transfer the caller has in flight on another
 // stream (api.cu).
 const int64_t* read_back(cfx_ctx* c, const int64_t* dev, int n);
+int64_t* alloc_count_slot(cfx_ctx* c, int n = 1); // api.cu: n consecutive device int64 slots (zero-initialised)
+void free_count_slot(cfx_ctx* c, int64_t* p, int n = 1);
+inline int64_t with_margin(const cfx_ctx* c, int64_t n) { return n + static_cast<int64_t>(c->margin * n) + 256; }
+// make a deferred size known to the host (synchronises); api.cu
+void resolve(cfx_ctx* c, cfx_list* l);
+void resolve(cfx_ctx* c, cfx_rules* r);
+void resolve(cfx_ctx* c, cfx_pattern* p);
+template <class T>
+inline void note_deferred(std::vector<T*>& v, T* o)
+{
+  for (T* q : v)
+    if (q == o)
+      return;
+  v.push_back(o);
+}
+// call after a deferred-capable entry point has (re)filled the object
+inline void note_result(cfx_ctx* c, cfx_list* l)
+{
+  if (l->deferred)
+  {
+    l->n_bound = l->n;
+    if (c->capturing)
+      note_deferred(c->cap_lists, l);
+  }
+}
+inline void note_result(cfx_ctx* c, cfx_rules* r)
+{
+  if (r->deferred && c->capturing)
+    note_deferred(c->cap_rules, r);
+}
+inline void note_result(cfx_ctx* c, cfx_pattern* p)
+{
+  if (p->deferred && c->capturing)
+    note_deferred(c->cap_patterns, p);
+}
+inline DN dn_of(const cfx_list* l) { return DN{l->deferred ? l->d_n : nullptr, l->n, 0}; }
+inline DN dn_exact(int64_t n) { return DN{nullptr, n, 0}; }
 
-void check_device_error(cfx_ctx* c, const char* where); // api.cu
+void check_device_error(cfx_ctx* c, const char* where); // api.cu: reads the device error flag back (synchronises)
+// the per-call check of the eager mode; in deferred-size mode the flag is looked at when a size is resolved, a
+// result is fetched or cfx_check is called
+inline void check_call(cfx_ctx* c, const char* where)
+{
+  if (!c->deferred)
+    check_device_error(c, where);
+}
 void sync_counts(cfx_ctx* c);                            // classify.cu: fetch pending classification counts
 
 // ---------------------------------------------------------------- device primitives
@@ -507,8 +628,14 @@ __device__ __forceinline__ long long warp_incl_scan_ll(long long v)
 // out[i] = sum_{j<i} in[j] (int32 in, int64 out), out[n] = total; total also left in c->scratch64[0]
 void exclusive_scan_i32_to_i64(cfx_ctx* c, const int32_t* in, int64_t n, int64_t* out);
 void exclusive_scan_i64(cfx_ctx* c, const int64_t* in, int64_t n, int64_t* out);
+// the same over a device-side length (n.h bounds the grids; entries at or past the exact length count as 0 and
+// out[exact length] = total)
+void exclusive_scan_i64(cfx_ctx* c, const int64_t* in, DN n, int64_t* out);
 // block-count scan used by the compaction passes: offsets[b] = sum_{j<b} counts[j]; total -> scratch64[0]
-void scan_block_counts(cfx_ctx* c, const int32_t* counts, int64_t nblocks, int64_t* offsets);
+// `total_out` (default: scratch64[0]) receives the total; with cap >= 0 a total above cap raises the device error
+// flag and is replaced by 0 (the consumers of a deferred size then do nothing instead of overrunning a buffer)
+void scan_block_counts(cfx_ctx* c, const int32_t* counts, int64_t nblocks, int64_t* offsets,
+                       int64_t* total_out = nullptr, int64_t cap = -1);
 
 RuleTable& get_rule(cfx_ctx* c, int dim, int order); // quadrature.cu: built-in or override, uploaded on demand
 void builtin_simplex_rule(int dim, int order, std::vector<double>& pts, std::vector<double>& wts);
@@ -521,6 +648,7 @@ void entity_physical_points(cfx_ctx* c, const cfx_rules* r, double* dst_soa); //
 void build_geometry_cache(cfx_ctx* c);                  // assemble.cu
 void dense_f2c_from_adjacency(cfx_ctx* c, const int32_t* off_dev, const int32_t* data_dev); // facets.cu
 void prepare_form(cfx_ctx* c, cfx_form* f);             // sparsity.cu
+void resolve_form(cfx_ctx* c, cfx_form* f);             // sparsity.cu: deferred sizes of a form -> host
 void release_prepared(cfx_ctx* c, cfx_form* f);         // sparsity.cu
 uint8_t std_list_bit(const cfx_prepared* P, const void* entities, int64_t n); // sparsity.cu
 const cfx_integral* facet_integral_domain(const cfx_form* f);          // sparsity.cu

@@ -14,8 +14,9 @@ constexpr int CP_BLOCK = 256;
 constexpr int CP_ITEMS = 16;
 constexpr int CP_TILE = CP_BLOCK * CP_ITEMS;
 template <class Pred>
-__global__ void __launch_bounds__(CP_BLOCK) compact_count_kernel(Pred pred, int64_t n, int32_t* __restrict__ counts)
+__global__ void __launch_bounds__(CP_BLOCK) compact_count_kernel(Pred pred, DN n_, int32_t* __restrict__ counts)
 {
+  const int64_t n = n_.get();
   const int64_t base = static_cast<int64_t>(blockIdx.x) * CP_TILE + threadIdx.x * CP_ITEMS;
   int cnt = base < n ? __popc(pred(base, n)) : 0;
 #pragma unroll
@@ -37,8 +38,10 @@ __global__ void __launch_bounds__(CP_BLOCK) compact_count_kernel(Pred pred, int6
 
 template <class Pred>
 __global__ void __launch_bounds__(CP_BLOCK)
-    compact_write_kernel(Pred pred, int64_t n, const int64_t* __restrict__ tile_off, int32_t* __restrict__ out)
+    compact_write_kernel(Pred pred, DN n_, const int64_t* __restrict__ tile_off, const int64_t* __restrict__ d_total,
+                         int32_t* __restrict__ out)
 {
+  const int64_t n = n_.get();
   const int64_t base = static_cast<int64_t>(blockIdx.x) * CP_TILE + threadIdx.x * CP_ITEMS;
   unsigned mask = base < n ? pred(base, n) : 0u;
   int tot;
@@ -54,33 +57,62 @@ __global__ void __launch_bounds__(CP_BLOCK)
     s_out[o++] = static_cast<int32_t>(base + k);
   }
   __syncthreads();
+  // a total that exceeded the output capacity was replaced by 0 (scan_block_counts): nothing is written then
+  if (tile_off[blockIdx.x] + tot > *d_total)
+    return;
   int32_t* dst = out + tile_off[blockIdx.x];
   for (int i = threadIdx.x; i < tot; i += CP_BLOCK)
     dst[i] = s_out[i];
 }
 
-// Returns the number of selected indices; `out` is (re)allocated to exactly that size.
-// `counted`: c->blk_counts already holds the per-tile counts (the caller reserved it for grid_for(n, CP_TILE)
-// tiles and filled it), so the counting pass over the predicate is skipped.
+// Returns the number of selected indices.  `counted`: c->blk_counts already holds the per-tile counts (the caller
+// reserved it for grid_for(n, CP_TILE) tiles and filled it), so the counting pass over the predicate is skipped.
+// `d_total`: device slot that receives the exact total (null: context scratch).
+// Deferred-size mode: when `out` already has a capacity and `deferred` is given, the total stays on the device --
+// the return value is the capacity (an upper bound), *deferred = true, and a total above the capacity raises the
+// device error flag and selects nothing (no host round trip anywhere in that case).
 template <class Pred>
-int64_t compact_indices(cfx_ctx* c, int64_t n, Pred pred, DevBuf<int32_t>& out, bool counted = false)
+int64_t compact_indices(cfx_ctx* c, DN n, Pred pred, DevBuf<int32_t>& out, bool counted = false,
+                        int64_t* d_total = nullptr, bool* deferred = nullptr)
 {
-  if (n <= 0)
+  if (deferred)
+    *deferred = false;
+  c->scratch64.reserve(c->pool, 64);
+  if (!d_total)
+    d_total = c->scratch64.p;
+  if (n.h <= 0)
   {
     out.reserve(c->pool, 1);
+    CFX_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int64_t), c->stream));
     return 0;
   }
-  const unsigned nb = grid_for(n, CP_TILE);
+  const unsigned nb = grid_for(n.h, CP_TILE);
   c->blk_counts.reserve(c->pool, nb);
   c->blk_offsets.reserve(c->pool, nb);
   if (!counted)
     CFX_LAUNCH(c, compact_count_kernel<Pred>, nb, CP_BLOCK, 0, pred, n, c->blk_counts.p);
-  scan_block_counts(c, c->blk_counts.p, nb, c->blk_offsets.p);
-  const int64_t total = read_back(c, c->scratch64.p, 1)[0];
-  out.reserve(c->pool, static_cast<size_t>(total > 0 ? total : 1));
+  const bool defer = c->deferred && deferred != nullptr && out.p != nullptr && out.cap >= 256;
+  scan_block_counts(c, c->blk_counts.p, nb, c->blk_offsets.p, d_total, defer ? static_cast<int64_t>(out.cap) : -1);
+  int64_t total;
+  if (defer)
+  {
+    total = static_cast<int64_t>(out.cap);
+    *deferred = true;
+  }
+  else
+  {
+    total = read_back(c, d_total, 1)[0];
+    if (static_cast<size_t>(total) > out.cap || !out.p)
+      out.reserve(c->pool, static_cast<size_t>(with_margin(c, total)));
+  }
   if (total > 0)
-    CFX_LAUNCH(c, compact_write_kernel<Pred>, nb, CP_BLOCK, 0, pred, n, c->blk_offsets.p, out.p);
+    CFX_LAUNCH(c, compact_write_kernel<Pred>, nb, CP_BLOCK, 0, pred, n, c->blk_offsets.p, d_total, out.p);
   return total;
+}
+template <class Pred>
+int64_t compact_indices(cfx_ctx* c, int64_t n, Pred pred, DevBuf<int32_t>& out, bool counted = false)
+{
+  return compact_indices(c, dn_exact(n), pred, out, counted);
 }
 
 // byte-array predicate: flag[i] != 0

@@ -196,6 +196,8 @@ cfx_status cfx_assemble_matrix_bc(cfx_ctx* ctx, const cfx_form* a, cfx_pattern* 
 {
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && a && A, CFX_ERR_INVALID, "cfx_assemble_matrix_bc: NULL argument");
+  resolve_form(ctx, const_cast<cfx_form*>(a)); // not part of the deferred-size step: sizes on the host first
+  resolve(ctx, A);
   const Space& S = ctx->spaces[A->space];
   const size_t nb = static_cast<size_t>(S.n_total) * S.bs, nv = static_cast<size_t>(A->nnz) * A->bs * A->bs;
   DevBuf<int8_t> own0, own1;
@@ -233,6 +235,7 @@ cfx_status cfx_set_diagonal(cfx_ctx* ctx, cfx_pattern* A, const int32_t* rows, i
 {
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && A && (n == 0 || rows), CFX_ERR_INVALID, "cfx_set_diagonal: NULL argument");
+  resolve(ctx, A);
   if (n > 0)
   {
     DevBuf<int32_t> own;
@@ -250,6 +253,8 @@ cfx_status cfx_apply_lifting(cfx_ctx* ctx, const cfx_form* a, cfx_pattern* A, do
 {
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && a && A && b && bc_values1 && bc_markers1, CFX_ERR_INVALID, "cfx_apply_lifting: NULL argument");
+  resolve_form(ctx, const_cast<cfx_form*>(a));
+  resolve(ctx, A);
   const Space& S = ctx->spaces[A->space];
   const size_t nb = static_cast<size_t>(S.n_total) * S.bs, nv = static_cast<size_t>(A->nnz) * A->bs * A->bs;
   DevBuf<int8_t> ownm;
@@ -304,6 +309,9 @@ cfx_status cfx_assemble_system_bc(cfx_ctx* ctx, const cfx_form* a, cfx_pattern* 
   CFX_REQUIRE(ctx && a && A && L && b && bc_markers && bc_values && (n_bc_rows == 0 || bc_rows_owned), CFX_ERR_INVALID,
               "cfx_assemble_system_bc: NULL argument");
   const Space& S = ctx->spaces[A->space];
+  resolve_form(ctx, const_cast<cfx_form*>(a));
+  resolve_form(ctx, const_cast<cfx_form*>(L));
+  resolve(ctx, A);
   cfx_status rc = cfx_assemble_system(ctx, a, A, 1, 0.0, L, b, 1);
   if (rc != CFX_OK)
     return rc;
@@ -312,14 +320,14 @@ cfx_status cfx_assemble_system_bc(cfx_ctx* ctx, const cfx_form* a, cfx_pattern* 
     launch_rows(ctx, A, bc_markers, bc_markers, 1, 1, bc_values, x0, alpha, b);
   }
   if (n_bc_rows > 0)
-  {
     CFX_LAUNCH(ctx, set_diagonal_blocked_kernel, grid_for(n_bc_rows, 256), 256, 0, bc_rows_owned, n_bc_rows, A->n_rows,
                A->bs, A->row_ptr.p, A->cols.p, A->values.p, diagonal, ctx->err_flag.p);
-    // every constrained entry of b this rank holds (owned and ghost): the marker array is the list
-    CFX_LAUNCH(ctx, set_bc_marked_kernel, grid_for(static_cast<int64_t>(S.n_total) * S.bs, 256), 256, 0, bc_markers,
-               static_cast<int64_t>(S.n_total) * S.bs, bc_values, x0, alpha, b);
+  // every constrained entry of b this rank holds (owned AND ghost: a rank may hold only ghost copies of the
+  // constrained dofs, so this does not depend on n_bc_rows): the marker array is the list
+  CFX_LAUNCH(ctx, set_bc_marked_kernel, grid_for(static_cast<int64_t>(S.n_total) * S.bs, 256), 256, 0, bc_markers,
+             static_cast<int64_t>(S.n_total) * S.bs, bc_values, x0, alpha, b);
+  if (n_bc_rows > 0)
     check_device_error(ctx, "cfx_assemble_system_bc (Dirichlet row out of range or without a diagonal entry)");
-  }
   CFX_API_END(ctx)
 }
 

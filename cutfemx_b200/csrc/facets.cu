@@ -118,11 +118,12 @@ __global__ void set_flag_kernel(const int32_t* __restrict__ cells, int64_t n, in
 // cut.py:369-379 / cut.cpp:967-987: for every source cell, every facet that is owned, has two
 // cells, both flagged -> mark
 template <class Active>
-__global__ void mark_facets_kernel(const int32_t* __restrict__ src_cells, int64_t n_src, int nf,
+__global__ void mark_facets_kernel(const int32_t* __restrict__ src_cells, DN n_src_, int nf,
                                    const int32_t* __restrict__ c2f, const int32_t* __restrict__ f2c2, Active active,
                                    int64_t n_owned_facets, int include_ghosts, uint8_t* __restrict__ facet_flag,
                                    int64_t n_cells, int32_t* __restrict__ tile_counts)
 {
+  const int64_t n_src = n_src_.get();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * FB + threadIdx.x;
   if (i >= n_src * nf)
     return;
@@ -145,18 +146,35 @@ __global__ void mark_facets_kernel(const int32_t* __restrict__ src_cells, int64_
   }
 }
 
-__global__ void clear_flags_kernel(const int32_t* __restrict__ idx, int64_t n, uint8_t* __restrict__ flag)
+__global__ void clear_flags_kernel(const int32_t* __restrict__ idx, DN n_, uint8_t* __restrict__ flag)
 {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * FB + threadIdx.x;
-  if (i < n)
+  if (i < n_.get())
     flag[idx[i]] = 0;
 }
 
-__global__ void facet_rows_kernel(const int32_t* __restrict__ facets, int64_t n, int nf, int64_t n_facets,
-                                  const int32_t* __restrict__ c2f, const int32_t* __restrict__ f2c2,
-                                  int32_t* __restrict__ rows4, int32_t* __restrict__ err)
+// deferred-size mode, capacity of the output list exceeded: the list comes back empty, so the flags it would have
+// cleared are cleared here (a pass over the flag array that only runs when the list is empty: after an overflow,
+// or -- redundantly -- when there is no band at all)
+__global__ void clear_all_flags_if_empty_kernel(const int64_t* __restrict__ d_n, int64_t n_words,
+                                                unsigned int* __restrict__ flag_words)
 {
+  if (*d_n != 0)
+    return;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * FB + threadIdx.x; i < n_words;
+       i += static_cast<int64_t>(gridDim.x) * FB)
+    flag_words[i] = 0u;
+}
+
+__global__ void facet_rows_kernel(const int32_t* __restrict__ facets, DN n_, int nf, int64_t n_facets,
+                                  const int32_t* __restrict__ c2f, const int32_t* __restrict__ f2c2,
+                                  int32_t* __restrict__ rows4, int32_t* __restrict__ err,
+                                  int64_t* __restrict__ d_n_out /* receives 4 n: entries of the row list */)
+{
+  const int64_t n = n_.get();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * FB + threadIdx.x;
+  if (i == 0 && d_n_out)
+    *d_n_out = 4 * n;
   if (i >= n)
     return;
   const int32_t f = facets[i];
@@ -194,20 +212,29 @@ __global__ void facet_rows_kernel(const int32_t* __restrict__ facets, int64_t n,
 }
 
 template <class Active>
-int64_t band_from_flags(cfx_ctx* c, const int32_t* src_cells, int64_t n_src, Active active, int include_ghosts,
+int64_t band_from_flags(cfx_ctx* c, const int32_t* src_cells, DN n_src, Active active, int include_ghosts,
                         cfx_list* out)
 {
+  if (!out->d_n)
+  {
+    out->d_n = alloc_count_slot(c);
+    out->ctx = c;
+  }
   const int nf = c->tdim + 1;
   const unsigned nt = grid_for(c->n_facets, CP_TILE);
   c->blk_counts.reserve(c->pool, nt);
   CFX_CUDA(cudaMemsetAsync(c->blk_counts.p, 0, static_cast<size_t>(nt) * sizeof(int32_t), c->stream));
-  if (n_src > 0)
-    CFX_LAUNCH(c, mark_facets_kernel<Active>, grid_for(n_src * nf, FB), FB, 0, src_cells, n_src, nf, c->c2f,
+  if (n_src.h > 0)
+    CFX_LAUNCH(c, mark_facets_kernel<Active>, grid_for(n_src.h * nf, FB), FB, 0, src_cells, n_src, nf, c->c2f,
                c->f2c2.p, active, c->n_owned_facets, include_ghosts, c->facet_flag.p, c->nc_total, c->blk_counts.p);
   FlagPred p{c->facet_flag.p};
-  out->n = compact_indices(c, c->n_facets, p, out->data, /*counted*/ true);
+  out->n = compact_indices(c, dn_exact(c->n_facets), p, out->data, /*counted*/ true, out->d_n, &out->deferred);
+  note_result(c, out);
   if (out->n > 0)
-    CFX_LAUNCH(c, clear_flags_kernel, grid_for(out->n, FB), FB, 0, out->data.p, out->n, c->facet_flag.p);
+    CFX_LAUNCH(c, clear_flags_kernel, grid_for(out->n, FB), FB, 0, out->data.p, dn_of(out), c->facet_flag.p);
+  if (out->deferred)
+    CFX_LAUNCH(c, clear_all_flags_if_empty_kernel, 296, FB, 0, out->d_n, (c->n_facets + 4) / 4,
+               reinterpret_cast<unsigned int*>(c->facet_flag.p));
   return out->n;
 }
 } // namespace
@@ -250,9 +277,10 @@ cfx_status cfx_ghost_penalty_facets(cfx_ctx* ctx, int cut_ls, int n_terms, const
   LevelSet& L = ctx->ls[cut_ls];
   const bool all = ctx->nc_total != ctx->nc_owned;
   const int32_t* src = all ? L.cut_list_all.p : L.cut_list.p;
-  const int64_t n_src = all ? L.n_cut_all : L.n_cut;
+  const DN n_src = all ? DN{L.cut_all_deferred ? L.d_n_cut_all : nullptr, L.n_cut_all}
+                       : DN{L.cut_deferred ? L.d_n_cut : nullptr, L.n_cut};
   StageScope st(ctx, "ghost_penalty_facets",
-                4.0 * (ctx->tdim + 1) * static_cast<double>(n_src) + 2.0 * static_cast<double>(ctx->n_facets));
+                4.0 * (ctx->tdim + 1) * static_cast<double>(n_src.h) + 2.0 * static_cast<double>(ctx->n_facets));
   band_from_flags(ctx, src, n_src, BandPredDnf{d, cut_ls, ctx->domain.p, ctx->domain_stride}, include_ghosts, *out);
   CFX_API_END(ctx)
 }
@@ -273,10 +301,28 @@ cfx_status cfx_interior_facets_for_cells(cfx_ctx* ctx, const int32_t* cells, int
   if (n > 0)
     CFX_LAUNCH(ctx, set_flag_kernel, grid_for(n, FB), FB, 0, d_cells, n, ctx->nc_total, ctx->scratch8.p,
                ctx->err_flag.p);
-  band_from_flags(ctx, d_cells, n, BandPredFlags{ctx->scratch8.p}, include_ghosts, *out);
+  band_from_flags(ctx, d_cells, dn_exact(n), BandPredFlags{ctx->scratch8.p}, include_ghosts, *out);
   own.release();
-  check_device_error(ctx, "cfx_interior_facets_for_cells (Cell index is out of range.)");
+  check_call(ctx, "cfx_interior_facets_for_cells (Cell index is out of range.)");
   CFX_API_END(ctx)
+}
+
+static void facet_rows_impl(cfx_ctx* ctx, const int32_t* d_f, DN n, cfx_list* o)
+{
+  if (!o->d_n)
+  {
+    o->d_n = alloc_count_slot(ctx);
+    o->ctx = ctx;
+  }
+  o->data.reserve(ctx->pool, static_cast<size_t>(4 * n.h) + 1);
+  o->n = 4 * n.h;
+  o->deferred = n.d != nullptr;
+  note_result(ctx, o);
+  if (n.h > 0)
+    CFX_LAUNCH(ctx, facet_rows_kernel, grid_for(n.h, FB), FB, 0, d_f, n, ctx->tdim + 1, ctx->n_facets, ctx->c2f,
+               ctx->f2c2.p, o->data.p, ctx->err_flag.p, o->d_n);
+  else
+    CFX_CUDA(cudaMemsetAsync(o->d_n, 0, sizeof(int64_t), ctx->stream));
 }
 
 cfx_status cfx_facet_integration_rows(cfx_ctx* ctx, const int32_t* facets, int64_t n, int memspace, cfx_list** out)
@@ -287,18 +333,27 @@ cfx_status cfx_facet_integration_rows(cfx_ctx* ctx, const int32_t* facets, int64
               "cfx_facet_integration_rows: NULL argument");
   if (*out == nullptr)
     *out = new cfx_list();
-  (*out)->data.reserve(ctx->pool, static_cast<size_t>(4 * n) + 1);
-  (*out)->n = 4 * n;
+  DevBuf<int32_t> own;
+  const int32_t* d_f = n > 0 ? adopt(ctx, own, facets, static_cast<size_t>(n), memspace) : nullptr;
+  facet_rows_impl(ctx, d_f, dn_exact(n), *out);
+  own.release();
   if (n > 0)
-  {
-    DevBuf<int32_t> own;
-    const int32_t* d_f = adopt(ctx, own, facets, static_cast<size_t>(n), memspace);
-    CFX_LAUNCH(ctx, facet_rows_kernel, grid_for(n, FB), FB, 0, d_f, n, ctx->tdim + 1, ctx->n_facets, ctx->c2f,
-               ctx->f2c2.p, (*out)->data.p, ctx->err_flag.p);
-    own.release();
-    check_device_error(ctx, "cfx_facet_integration_rows (Interior facet domain contains a facet without two "
-                            "adjacent cells / could not resolve local facet index)");
-  }
+    check_call(ctx, "cfx_facet_integration_rows (Interior facet domain contains a facet without two "
+                    "adjacent cells / could not resolve local facet index)");
+  CFX_API_END(ctx)
+}
+
+cfx_status cfx_facet_integration_rows_list(cfx_ctx* ctx, const cfx_list* facets, cfx_list** out)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && ctx->topo_bound, CFX_ERR_STATE, "Facet-cell connectivity is unavailable.");
+  CFX_REQUIRE(out != nullptr && facets != nullptr && facets != *out, CFX_ERR_INVALID,
+              "cfx_facet_integration_rows_list: NULL argument");
+  if (*out == nullptr)
+    *out = new cfx_list();
+  facet_rows_impl(ctx, facets->data.p, dn_of(facets), *out);
+  check_call(ctx, "cfx_facet_integration_rows (Interior facet domain contains a facet without two adjacent cells / "
+                  "could not resolve local facet index)");
   CFX_API_END(ctx)
 }
 } // extern "C"

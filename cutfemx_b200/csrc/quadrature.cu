@@ -288,10 +288,11 @@ constexpr int QB = 128; // cut cells per block == threads per block
 // pass 1: packed (rule flag << 32 | number of points) per cut cell
 template <int TDIM>
 __global__ void __launch_bounds__(QB)
-    rule_count_kernel(const int32_t* __restrict__ cut_cells, int64_t n_cut, const int32_t* __restrict__ ls_dofmap,
+    rule_count_kernel(const int32_t* __restrict__ cut_cells, DN n_cut_, const int32_t* __restrict__ ls_dofmap,
                       const double* __restrict__ vals, bool positive, bool interface, int npts_s,
                       int64_t* __restrict__ packed)
 {
+  const int64_t n_cut = n_cut_.get();
   const int64_t k = static_cast<int64_t>(blockIdx.x) * QB + threadIdx.x;
   if (k >= n_cut)
     return;
@@ -316,18 +317,40 @@ struct CutSmem
 
 template <int TDIM, bool interface>
 __global__ void __launch_bounds__(QB)
-    rule_fill_kernel(const int32_t* __restrict__ cut_cells, int64_t n_cut, const int64_t* __restrict__ packed_excl,
+    rule_fill_kernel(const int32_t* __restrict__ cut_cells, DN n_cut_, const int64_t* __restrict__ packed_excl,
                      const int32_t* __restrict__ ls_dofmap, const double* __restrict__ vals,
                      const int32_t* __restrict__ x_dofmap, const double* __restrict__ x, bool positive,
                      int npts_s, const double* __restrict__ rule_pts, const double* __restrict__ rule_wts,
-                     int64_t npts_total, double* __restrict__ points /* SoA (TDIM, npts_total) */,
+                     int64_t cap_pts, int64_t cap_rules, int64_t* __restrict__ d_sizes /* [0] nrules, [1] npts */,
+                     int32_t* __restrict__ err, double* __restrict__ points /* SoA (TDIM, npts_total) */,
                      double* __restrict__ weights, int32_t* __restrict__ offsets, int32_t* __restrict__ parent_map,
                      double* __restrict__ moments /* (nrules, TDIM + 1) or null */)
 {
   constexpr int NV = TDIM + 1;
   __shared__ CutSmem<TDIM> sm;
   const int tid = threadIdx.x;
+  const int64_t n_cut = n_cut_.get();
   const int64_t k0 = static_cast<int64_t>(blockIdx.x) * QB;
+  if (k0 >= n_cut && blockIdx.x != 0)
+    return;
+  // totals (the scan's closing entry): the SoA stride of the point arrays is the exact number of points
+  const int64_t pk_total = packed_excl[n_cut];
+  const int64_t npts_total = pk_total & 0xffffffffLL;
+  const bool fits = npts_total <= cap_pts && (pk_total >> 32) <= cap_rules;
+  if (blockIdx.x == 0 && tid == 0)
+  {
+    d_sizes[0] = fits ? (pk_total >> 32) : 0;
+    d_sizes[1] = fits ? npts_total : 0;
+    if (!fits)
+    { // deferred-size mode: this step's rules do not fit the buffers of the object that is being reused
+      err[0] = 32;
+      err[1] = static_cast<int32_t>(npts_total);
+    }
+    if (n_cut == 0 && fits)
+      offsets[0] = 0;
+  }
+  if (!fits || k0 >= n_cut)
+    return;
   const int64_t k = k0 + tid;
   // packed_excl has n_cut + 1 entries (last = totals)
   const int64_t pk_first = packed_excl[k0];
@@ -610,13 +633,14 @@ __global__ void physical_points_kernel(const double* __restrict__ pts, int64_t n
 
 // level_set/normal.h:116-185 (per point: K = J^-1, grad = K^T sum_j dphi_j phi_j, floor 1e-14)
 template <int TDIM, int DEG>
-__global__ void normals_kernel(const double* __restrict__ pts, int64_t npts, const int32_t* __restrict__ offsets,
-                               const int32_t* __restrict__ parent_map, int64_t nrules,
+__global__ void normals_kernel(const double* __restrict__ pts, DN npts_, const int32_t* __restrict__ offsets,
+                               const int32_t* __restrict__ parent_map, DN nrules_,
                                const int32_t* __restrict__ x_dofmap, const double* __restrict__ x,
                                const int32_t* __restrict__ ls_dofmap, const double* __restrict__ vals, double sign,
                                double* __restrict__ out_soa, double* __restrict__ out_aos)
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
+  const int64_t npts = npts_.get(), nrules = nrules_.get();
   const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (q >= npts)
     return;
@@ -673,13 +697,14 @@ __global__ void normals_kernel(const double* __restrict__ pts, int64_t npts, con
 // same bits as normals_kernel<TDIM, 1>; dphi of P1 does not depend on the point) and stores it for the rule's
 // points.  No per-point rule search, one geometry evaluation per cut cell instead of one per point.
 template <int TDIM>
-__global__ void normals_p1_kernel(const double* __restrict__ pts, int64_t npts, const int32_t* __restrict__ offsets,
-                                  const int32_t* __restrict__ parent_map, int64_t nrules,
+__global__ void normals_p1_kernel(const double* __restrict__ pts, DN npts_, const int32_t* __restrict__ offsets,
+                                  const int32_t* __restrict__ parent_map, DN nrules_,
                                   const int32_t* __restrict__ x_dofmap, const double* __restrict__ x,
                                   const int32_t* __restrict__ ls_dofmap, const double* __restrict__ vals, double sign,
                                   double* __restrict__ out_soa, double* __restrict__ out_aos)
 {
   constexpr int ND = TDIM + 1;
+  const int64_t npts = npts_.get(), nrules = nrules_.get();
   const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (r >= nrules)
     return;
@@ -764,47 +789,81 @@ __global__ void values_kernel(const double* __restrict__ pts, int64_t npts, cons
 }
 
 template <int TDIM>
-void run_quadrature(cfx_ctx* c, const LevelSet& L, cfx_rules* R, bool positive, bool interface, RuleTable& rt)
+void run_quadrature(cfx_ctx* c, LevelSet& L, cfx_rules* R, bool positive, bool interface, RuleTable& rt)
 {
-  const int64_t n_cut = L.n_cut;
-  if (n_cut == 0)
+  // deferred-size mode: a reused object keeps its buffers and the sizes stay on the device
+  const bool defer = c->deferred && R->cap_pts >= 256 && R->cap_rules >= 256 && R->points.p != nullptr;
+  if (!defer && L.cut_deferred)
+  { // this call needs its sizes on the host, so it needs the cut-cell count too
+    check_device_error(c, "cut-cell list (capacity exceeded)");
+    L.n_cut = read_back(c, L.d_n_cut, 1)[0];
+    L.cut_deferred = false;
+  }
+  const DN n_cut{L.cut_deferred ? L.d_n_cut : nullptr, L.n_cut};
+  if (!R->d_sizes)
+  {
+    R->d_sizes = alloc_count_slot(c, 2);
+    R->ctx = c;
+  }
+  // moments only where the point sums they replace are exact: built-in rule of degree >= 1, volume part
+  // (interface rules also carry second moments: exact from degree 2 on)
+  R->has_moments = rt.builtin && rt.order >= (interface ? 2 : 1);
+  const size_t mom_w = 1 + TDIM + (interface ? TDIM * (TDIM + 1) / 2 : 0);
+  if (n_cut.h == 0)
   {
     R->nrules = R->npts = 0;
+    R->deferred = false;
     R->has_moments = false;
     R->points.reserve(c->pool, 1);
     R->weights.reserve(c->pool, 1);
     R->offsets.reserve(c->pool, 1);
     R->parent_map.reserve(c->pool, 1);
     CFX_CUDA(cudaMemsetAsync(R->offsets.p, 0, sizeof(int32_t), c->stream));
+    CFX_CUDA(cudaMemsetAsync(R->d_sizes, 0, 2 * sizeof(int64_t), c->stream));
     return;
   }
   DevBuf<int64_t> packed, packed_excl;
-  packed.reserve(c->pool, static_cast<size_t>(n_cut) + 1);
-  packed_excl.reserve(c->pool, static_cast<size_t>(n_cut) + 2);
-  CFX_LAUNCH(c, rule_count_kernel<TDIM>, grid_for(n_cut, QB), QB, 0, L.cut_list.p, n_cut, L.dofmap, L.values, positive,
+  packed.reserve(c->pool, static_cast<size_t>(n_cut.h) + 1);
+  packed_excl.reserve(c->pool, static_cast<size_t>(n_cut.h) + 2);
+  CFX_LAUNCH(c, rule_count_kernel<TDIM>, grid_for(n_cut.h, QB), QB, 0, L.cut_list.p, n_cut, L.dofmap, L.values, positive,
              interface, rt.npts, packed.p);
   exclusive_scan_i64(c, packed.p, n_cut, packed_excl.p);
-  const int64_t tot = read_back(c, c->scratch64.p, 1)[0];
-  R->nrules = tot >> 32;
-  R->npts = tot & 0xffffffffLL;
-  CFX_REQUIRE(R->npts < (int64_t(1) << 31), CFX_ERR_RANGE, "runtime_quadrature: more than 2^31 points (int32 offsets)");
-  R->points.reserve(c->pool, static_cast<size_t>(R->npts) * TDIM + 1);
-  R->weights.reserve(c->pool, static_cast<size_t>(R->npts) + 1);
-  R->offsets.reserve(c->pool, static_cast<size_t>(R->nrules) + 1);
-  R->parent_map.reserve(c->pool, static_cast<size_t>(R->nrules) + 1);
-  // moments only where the point sums they replace are exact: built-in rule of degree >= 1, volume part
-  // (interface rules also carry second moments: exact from degree 2 on)
-  R->has_moments = rt.builtin && rt.order >= (interface ? 2 : 1);
-  if (R->has_moments)
-    R->moments.reserve(c->pool, static_cast<size_t>(R->nrules) * (1 + TDIM + (interface ? TDIM * (TDIM + 1) / 2 : 0)) + 1);
-  if (interface)
-    CFX_LAUNCH(c, (rule_fill_kernel<TDIM, true>), grid_for(n_cut, QB), QB, 0, L.cut_list.p, n_cut, packed_excl.p, L.dofmap,
-               L.values, c->x_dofmap, c->x, positive, rt.npts, rt.d_pts, rt.d_wts, R->npts, R->points.p, R->weights.p,
-               R->offsets.p, R->parent_map.p, R->has_moments ? R->moments.p : nullptr);
+  if (defer)
+  {
+    R->nrules = R->cap_rules;
+    R->npts = R->cap_pts;
+    R->deferred = true;
+    note_result(c, R);
+  }
   else
-    CFX_LAUNCH(c, (rule_fill_kernel<TDIM, false>), grid_for(n_cut, QB), QB, 0, L.cut_list.p, n_cut, packed_excl.p,
-               L.dofmap, L.values, c->x_dofmap, c->x, positive, rt.npts, rt.d_pts, rt.d_wts, R->npts, R->points.p,
-               R->weights.p, R->offsets.p, R->parent_map.p, R->has_moments ? R->moments.p : nullptr);
+  {
+    const int64_t tot = read_back(c, c->scratch64.p, 1)[0];
+    R->nrules = tot >> 32;
+    R->npts = tot & 0xffffffffLL;
+    R->deferred = false;
+    CFX_REQUIRE(R->npts < (int64_t(1) << 31), CFX_ERR_RANGE, "runtime_quadrature: more than 2^31 points (int32 offsets)");
+    if (R->npts > R->cap_pts || R->nrules > R->cap_rules || !R->points.p)
+    {
+      R->cap_pts = std::max(R->cap_pts, with_margin(c, R->npts));
+      R->cap_rules = std::max(R->cap_rules, with_margin(c, R->nrules));
+    }
+  }
+  R->points.reserve(c->pool, static_cast<size_t>(R->cap_pts) * TDIM + 1);
+  R->weights.reserve(c->pool, static_cast<size_t>(R->cap_pts) + 1);
+  R->offsets.reserve(c->pool, static_cast<size_t>(R->cap_rules) + 1);
+  R->parent_map.reserve(c->pool, static_cast<size_t>(R->cap_rules) + 1);
+  if (R->has_moments)
+    R->moments.reserve(c->pool, static_cast<size_t>(R->cap_rules) * mom_w + 1);
+  if (interface)
+    CFX_LAUNCH(c, (rule_fill_kernel<TDIM, true>), grid_for(n_cut.h, QB), QB, 0, L.cut_list.p, n_cut, packed_excl.p,
+               L.dofmap, L.values, c->x_dofmap, c->x, positive, rt.npts, rt.d_pts, rt.d_wts, R->cap_pts, R->cap_rules,
+               R->d_sizes, c->err_flag.p, R->points.p, R->weights.p, R->offsets.p, R->parent_map.p,
+               R->has_moments ? R->moments.p : nullptr);
+  else
+    CFX_LAUNCH(c, (rule_fill_kernel<TDIM, false>), grid_for(n_cut.h, QB), QB, 0, L.cut_list.p, n_cut, packed_excl.p,
+               L.dofmap, L.values, c->x_dofmap, c->x, positive, rt.npts, rt.d_pts, rt.d_wts, R->cap_pts, R->cap_rules,
+               R->d_sizes, c->err_flag.p, R->points.p, R->weights.p, R->offsets.p, R->parent_map.p,
+               R->has_moments ? R->moments.p : nullptr);
   packed.release();
   packed_excl.release();
 }
@@ -903,6 +962,18 @@ cfx_status cfx_rules_sizes(const cfx_rules* r, int64_t* npts, int64_t* nrules, i
 {
   if (!r)
     return CFX_ERR_INVALID;
+  if (r->deferred && r->ctx)
+  { // sizes are on the device: fetch them now (synchronises)
+    try
+    {
+      resolve(r->ctx, const_cast<cfx_rules*>(r));
+    }
+    catch (const cfx::Error& e)
+    {
+      cfx_set_error(r->ctx, e.what());
+      return e.code;
+    }
+  }
   if (npts)
     *npts = r->npts;
   if (nrules)
@@ -917,6 +988,7 @@ cfx_status cfx_rules_fetch(cfx_ctx* ctx, const cfx_rules* r, double* points_aos,
 {
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && r, CFX_ERR_INVALID, "cfx_rules_fetch: NULL argument");
+  resolve(ctx, const_cast<cfx_rules*>(r));
   if (points_aos && r->npts > 0)
   {
     const int64_t n = r->npts * r->tdim;
@@ -941,6 +1013,7 @@ cfx_status cfx_rules_physical_points(cfx_ctx* ctx, const cfx_rules* r, double* o
 {
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && r && out_soa, CFX_ERR_INVALID, "cfx_rules_physical_points: NULL argument");
+  resolve(ctx, const_cast<cfx_rules*>(r));
   if (r->npts == 0)
     return CFX_OK;
   DevBuf<double> tmp;
@@ -978,6 +1051,7 @@ void cfx_rules_free(cfx_ctx* ctx, cfx_rules* r)
   r->normals.release();
   r->moments.release();
   r->rule_verts.release();
+  free_count_slot(r->ctx, r->d_sizes, 2);
   delete r;
 }
 
@@ -990,10 +1064,14 @@ cfx_status cfx_evaluate_normals(cfx_ctx* ctx, int ls, cfx_rules* r, double sign,
   CFX_REQUIRE(r->tdim == ctx->tdim, CFX_ERR_INVALID,
               "Normal evaluation points must have cell reference dimension."); // normal.h:62-63
   const LevelSet& L = ctx->ls[ls];
-  r->normals.reserve(ctx->pool, static_cast<size_t>(r->npts) * r->gdim + 1);
+  if (out_aos || r->entity_hosted)
+    resolve(ctx, r); // exporting needs the exact number of points on the host
+  r->normals.reserve(ctx->pool, static_cast<size_t>(std::max(r->npts, r->cap_pts)) * r->gdim + 1);
   r->has_normals = true;
   if (r->npts == 0)
     return CFX_OK;
+  const DN d_npts{r->deferred ? r->d_sizes + 1 : nullptr, r->npts};
+  const DN d_nrules{r->deferred ? r->d_sizes : nullptr, r->nrules};
   DevBuf<double> tmp;
   double* aos = nullptr;
   if (out_aos)
@@ -1010,7 +1088,7 @@ cfx_status cfx_evaluate_normals(cfx_ctx* ctx, int ls, cfx_rules* r, double sign,
     StageScope st(ctx, "normals", static_cast<double>(r->npts) * 8.0 * (2.0 * r->tdim));
     const unsigned g = grid_for(r->npts, 256);
 #define NARGS                                                                                                          \
-  r->points.p, r->npts, r->offsets.p, r->parent_map.p, r->nrules, ctx->x_dofmap, ctx->x, L.dofmap, L.values, sign,     \
+  r->points.p, d_npts, r->offsets.p, r->parent_map.p, d_nrules, ctx->x_dofmap, ctx->x, L.dofmap, L.values, sign,       \
       r->normals.p, aos
     if (L.degree == 1)
     { // constant gradient per cell: one thread per rule
@@ -1036,6 +1114,7 @@ cfx_status cfx_evaluate_values(cfx_ctx* ctx, int ls, const cfx_rules* r, double*
 {
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && r && out, CFX_ERR_INVALID, "cfx_evaluate_values: NULL argument");
+  resolve(ctx, const_cast<cfx_rules*>(r));
   CFX_REQUIRE(ls >= 0 && ls < CFX_MAX_LEVEL_SETS && ctx->ls[ls].bound, CFX_ERR_INVALID,
               "Cannot evaluate values without a level set.");
   const LevelSet& L = ctx->ls[ls];

@@ -13,7 +13,8 @@ constexpr int SB = 1024;
 constexpr int SI = 8;
 template <class Tin>
 __global__ void __launch_bounds__(SB) scan_small_kernel(const Tin* __restrict__ in, int64_t n,
-                                                        int64_t* __restrict__ offsets, int64_t* __restrict__ total)
+                                                        int64_t* __restrict__ offsets, int64_t* __restrict__ total,
+                                                        int64_t cap, int32_t* __restrict__ err)
 {
   __shared__ long long s_warp[SB / 32];
   __shared__ long long s_carry;
@@ -57,16 +58,26 @@ __global__ void __launch_bounds__(SB) scan_small_kernel(const Tin* __restrict__ 
     __syncthreads();
   }
   if (threadIdx.x == 0)
-    *total = s_carry;
+  {
+    long long t = s_carry;
+    if (cap >= 0 && t > cap)
+    { // deferred-size mode: the result would not fit the buffer the consumers were given
+      err[0] = 31;
+      err[1] = static_cast<int32_t>(t > 0x7fffffffLL ? 0x7fffffffLL : t);
+      t = 0;
+    }
+    *total = t;
+  }
 }
 
 constexpr int TB = 256;
 constexpr int TILE = TB * 4;
 
 template <class Tin>
-__global__ void __launch_bounds__(TB) tile_sum_kernel(const Tin* __restrict__ in, int64_t n,
+__global__ void __launch_bounds__(TB) tile_sum_kernel(const Tin* __restrict__ in, DN n_,
                                                       int64_t* __restrict__ sums)
 {
+  const int64_t n = n_.get();
   const int64_t base = static_cast<int64_t>(blockIdx.x) * TILE + threadIdx.x * 4;
   long long v = 0;
 #pragma unroll
@@ -113,10 +124,11 @@ __device__ __forceinline__ long long block_excl_scan_ll(long long v)
 }
 
 template <class Tin>
-__global__ void __launch_bounds__(TB) tile_scan_kernel(const Tin* __restrict__ in, int64_t n,
+__global__ void __launch_bounds__(TB) tile_scan_kernel(const Tin* __restrict__ in, DN n_,
                                                        const int64_t* __restrict__ tile_off,
                                                        const int64_t* __restrict__ total, int64_t* __restrict__ out)
 {
+  const int64_t n = n_.get();
   const int64_t base = static_cast<int64_t>(blockIdx.x) * TILE + threadIdx.x * 4;
   long long v[4];
   long long s = 0;
@@ -140,16 +152,19 @@ __global__ void __launch_bounds__(TB) tile_scan_kernel(const Tin* __restrict__ i
 }
 } // namespace
 
-void scan_block_counts(cfx_ctx* c, const int32_t* counts, int64_t nblocks, int64_t* offsets)
+void scan_block_counts(cfx_ctx* c, const int32_t* counts, int64_t nblocks, int64_t* offsets, int64_t* total_out,
+                       int64_t cap)
 {
   c->scratch64.reserve(c->pool, 64);
-  CFX_LAUNCH(c, scan_small_kernel<int32_t>, 1, SB, 0, counts, nblocks, offsets, c->scratch64.p);
+  CFX_LAUNCH(c, scan_small_kernel<int32_t>, 1, SB, 0, counts, nblocks, offsets, total_out ? total_out : c->scratch64.p,
+             cap, c->err_flag.p);
 }
 
 template <class Tin>
-static void exclusive_scan_impl(cfx_ctx* c, const Tin* in, int64_t n, int64_t* out)
+static void exclusive_scan_impl(cfx_ctx* c, const Tin* in, DN nn, int64_t* out)
 {
   c->scratch64.reserve(c->pool, 64);
+  const int64_t n = nn.h;
   if (n == 0)
   {
     CFX_CUDA(cudaMemsetAsync(out, 0, sizeof(int64_t), c->stream));
@@ -160,19 +175,21 @@ static void exclusive_scan_impl(cfx_ctx* c, const Tin* in, int64_t n, int64_t* o
   DevBuf<int64_t> sums, offs;
   sums.reserve(c->pool, ntiles);
   offs.reserve(c->pool, ntiles);
-  CFX_LAUNCH(c, tile_sum_kernel<Tin>, grid_for(n, TILE), TB, 0, in, n, sums.p);
-  CFX_LAUNCH(c, scan_small_kernel<int64_t>, 1, SB, 0, sums.p, ntiles, offs.p, c->scratch64.p);
-  CFX_LAUNCH(c, tile_scan_kernel<Tin>, grid_for(n, TILE), TB, 0, in, n, offs.p, c->scratch64.p, out);
+  CFX_LAUNCH(c, tile_sum_kernel<Tin>, grid_for(n, TILE), TB, 0, in, nn, sums.p);
+  CFX_LAUNCH(c, scan_small_kernel<int64_t>, 1, SB, 0, sums.p, ntiles, offs.p, c->scratch64.p, int64_t(-1),
+             c->err_flag.p);
+  CFX_LAUNCH(c, tile_scan_kernel<Tin>, grid_for(n, TILE), TB, 0, in, nn, offs.p, c->scratch64.p, out);
   sums.release(); // stream-ordered reuse is safe: the pool hands memory back to this stream only
   offs.release();
 }
 
 void exclusive_scan_i32_to_i64(cfx_ctx* c, const int32_t* in, int64_t n, int64_t* out)
 {
-  exclusive_scan_impl<int32_t>(c, in, n, out);
+  exclusive_scan_impl<int32_t>(c, in, dn_exact(n), out);
 }
 void exclusive_scan_i64(cfx_ctx* c, const int64_t* in, int64_t n, int64_t* out)
 {
-  exclusive_scan_impl<int64_t>(c, in, n, out);
+  exclusive_scan_impl<int64_t>(c, in, dn_exact(n), out);
 }
+void exclusive_scan_i64(cfx_ctx* c, const int64_t* in, DN n, int64_t* out) { exclusive_scan_impl<int64_t>(c, in, n, out); }
 } // namespace cfx

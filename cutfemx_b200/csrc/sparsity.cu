@@ -116,12 +116,13 @@ __global__ void fperm_kernel(int64_t n_dofs, const int64_t* __restrict__ inc_ptr
 // byte stores are race-free in effect (idempotent).  The kernel is a chain list -> (flag byte, dofmap row) ->
 // stores and nothing else: the loads of the MC cells are batched level by level.
 constexpr int MC = 4;
-__global__ void mark_cells_kernel(const int32_t* __restrict__ cells, int64_t n, int stride, int64_t limit, uint8_t bit,
+__global__ void mark_cells_kernel(const int32_t* __restrict__ cells, DN n_, int stride, int64_t limit, uint8_t bit,
                                   const int32_t* __restrict__ dofmap, int nd, uint8_t rowval,
                                   uint8_t* __restrict__ cell_flags, uint8_t* __restrict__ row_flag,
                                   int32_t* __restrict__ err)
 {
   constexpr int NDMAX = 10;
+  const int64_t n = n_.get();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x) >> 5;
   const int64_t i0 = warp * (32 * MC) + lane;
@@ -162,11 +163,11 @@ __global__ void mark_cells_kernel(const int32_t* __restrict__ cells, int64_t n, 
 }
 
 // rows of inserted pattern entries: active (bit0) and generic (bit1)
-__global__ void mark_rows_kernel(const int32_t* __restrict__ rows, int64_t n, int64_t limit,
+__global__ void mark_rows_kernel(const int32_t* __restrict__ rows, DN n_, int64_t limit,
                                  uint8_t* __restrict__ row_flag, int32_t* __restrict__ err)
 {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x;
-  if (i >= n)
+  if (i >= n_.get())
     return;
   const int32_t r = rows[i];
   if (r < 0 || r >= limit || (i > 0 && rows[i - 1] > r))
@@ -178,10 +179,10 @@ __global__ void mark_rows_kernel(const int32_t* __restrict__ rows, int64_t n, in
   row_flag[r] = 3;
 }
 
-__global__ void xslot_set_kernel(const int32_t* __restrict__ rows, int64_t n, int32_t* __restrict__ xslot, bool clear)
+__global__ void xslot_set_kernel(const int32_t* __restrict__ rows, DN n_, int32_t* __restrict__ xslot, bool clear)
 {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x;
-  if (i >= n)
+  if (i >= n_.get())
     return;
   if (i == 0 || rows[i - 1] != rows[i])
     xslot[rows[i]] = clear ? -1 : static_cast<int32_t>(i);
@@ -202,11 +203,11 @@ __global__ void lower_bound_kernel(const int32_t* __restrict__ a, int64_t n, int
   *out = lo;
 }
 
-__global__ void facet_slot_set_kernel(const int32_t* __restrict__ rows4, int64_t n, int nf,
+__global__ void facet_slot_set_kernel(const int32_t* __restrict__ rows4, DN n_, int nf,
                                       const int32_t* __restrict__ c2f, int32_t* __restrict__ facet_slot, bool clear)
 {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x;
-  if (i >= n)
+  if (i >= n_.get())
     return;
   const int32_t f = c2f[static_cast<int64_t>(rows4[4 * i]) * nf + rows4[4 * i + 1]];
   facet_slot[f] = clear ? -1 : static_cast<int32_t>(i);
@@ -243,7 +244,7 @@ struct RowCtx
   const int32_t* xslot; // per row: first inserted entry (or -1); null if the form has none
   const int32_t* xrows;
   const int32_t* xcols;
-  int64_t n_x;
+  DN n_x;
 };
 
 constexpr int RW = 4;      // rows (warps) per block
@@ -260,11 +261,41 @@ __global__ void pattern_inactive_count_kernel(const uint8_t* __restrict__ row_fl
 }
 
 __global__ void pattern_inactive_fill_kernel(const uint8_t* __restrict__ row_flag, int64_t n_rows, int diag,
-                                             const int64_t* __restrict__ row_ptr, int32_t* __restrict__ cols)
+                                             const int64_t* __restrict__ row_ptr, int32_t* __restrict__ cols,
+                                             int64_t cap /* entries `cols` can hold */)
 {
   const int64_t r = static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x;
-  if (r < n_rows && !row_flag[r] && diag)
+  if (r < n_rows && !row_flag[r] && diag && row_ptr[r] < cap)
     cols[row_ptr[r]] = static_cast<int32_t>(r);
+}
+
+// deferred-size mode: the pattern of this step must fit the arrays of the matrix object that is being reused.  If
+// it does not, raise the error flag and empty the active-row list, so that no kernel after this one (pattern fill,
+// assembly) touches the too-small arrays.
+// It also verifies the two launch decisions a deferred step takes from earlier eager steps (counters = the
+// pattern pass's scratch: [1] rows left to the generic kernels, [2] rows with a contribution list).
+__global__ void pattern_capacity_kernel(const int64_t* __restrict__ d_nnz, int64_t cap,
+                                        const int64_t* __restrict__ counters, int expect_no_slow, int expect_no_noclist,
+                                        int64_t* __restrict__ d_counts, int32_t* __restrict__ err)
+{
+  if (*d_nnz > cap)
+  {
+    err[0] = 33;
+    err[1] = static_cast<int32_t>(*d_nnz > 0x7fffffffLL ? 0x7fffffffLL : *d_nnz);
+    d_counts[0] = 0;
+    d_counts[1] = 0;
+    return;
+  }
+  if (expect_no_slow && counters[1] != 0)
+  {
+    err[0] = 34;
+    err[1] = static_cast<int32_t>(counters[1]);
+  }
+  if (expect_no_noclist && d_counts[0] - d_counts[1] - counters[2] != 0)
+  {
+    err[0] = 35;
+    err[1] = static_cast<int32_t>(d_counts[0] - d_counts[1] - counters[2]);
+  }
 }
 
 // ascending sort of a small register array (odd-even transposition network, fully unrolled)
@@ -299,7 +330,7 @@ __device__ __forceinline__ void sort_small(int32_t (&v)[N])
 template <int ND, bool FILL>
 __global__ void __launch_bounds__(RW * 32)
     pattern_rows_kernel(RowCtx rc, const int32_t* __restrict__ act_rows, const int32_t* __restrict__ slots,
-                        int64_t n_rows_in, int only_band, int stride, int32_t* __restrict__ row_nnz,
+                        DN n_rows_in, int only_band, int stride, int32_t* __restrict__ row_nnz,
                         const int64_t* __restrict__ row_ptr,
                         int32_t* __restrict__ cols_out, int32_t* __restrict__ tmp, uint32_t* __restrict__ mask_out,
                         uint8_t* __restrict__ row_fast, unsigned long long* __restrict__ n_slow,
@@ -310,7 +341,7 @@ __global__ void __launch_bounds__(RW * 32)
   __shared__ int s_nextra[RW];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t it = static_cast<int64_t>(blockIdx.x) * RW + w;
-  if (it >= n_rows_in)
+  if (it >= n_rows_in.get())
     return;
   // `slots` (optional): the band rows only, so that no warp is launched just to find out it has no work
   const int64_t idx = slots ? slots[it] : it;
@@ -450,7 +481,7 @@ __global__ void __launch_bounds__(RW * 32)
   { // SparsityPattern::insert entries received from other ranks
     const int32_t xs = rc.xslot[r];
     if (xs >= 0)
-      for (int64_t i = xs + lane; i < rc.n_x && rc.xrows[i] == r; i += 32)
+      for (int64_t i = xs + lane, nx = rc.n_x.get(); i < nx && rc.xrows[i] == r; i += 32)
       {
         const int pos = atomicAdd(&s_nextra[w], 1);
         if (pos < XCAP)
@@ -579,7 +610,7 @@ __global__ void __launch_bounds__(RW * 32)
 // pattern_static_fill_kernel, and the assembly gather recomputes each cell's CSR positions from
 // (fmask, R) instead of reading a gather table.  Only meshes whose full rows have <= 32 columns.
 __global__ void __launch_bounds__(256)
-    pattern_static_kernel(RowCtx rc, const int32_t* __restrict__ act_rows, int64_t n_act,
+    pattern_static_kernel(RowCtx rc, const int32_t* __restrict__ act_rows, DN n_act_,
                           const uint32_t* __restrict__ fmask, const uint8_t* __restrict__ frow_ok,
                           int32_t* __restrict__ row_nnz, uint32_t* __restrict__ Rrow, uint8_t* __restrict__ row_fast,
                           unsigned long long* __restrict__ n_clist /* [0] rows, [1] nnz of contribution-list rows */)
@@ -587,6 +618,7 @@ __global__ void __launch_bounds__(256)
   // 8 lanes per row and CROWS rows per lane group, the dependent load levels (slot -> row -> incidence ->
   // cell flags) of all of them batched: up to 3 * CROWS independent gather chains in flight per lane
   constexpr int CROWS = 4;
+  const int64_t n_act = n_act_.get();
   const int64_t t = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   const int64_t idx0 = (t >> 3) * CROWS;
   const int sl = static_cast<int>(t & 7);
@@ -671,11 +703,12 @@ __global__ void __launch_bounds__(256)
 // that lives for one row spends its whole life waiting on three round trips.
 constexpr int SROWS = 4;
 __global__ void __launch_bounds__(256)
-    pattern_static_fill_kernel(const int32_t* __restrict__ act_rows, int64_t n_act,
+    pattern_static_fill_kernel(const int32_t* __restrict__ act_rows, DN n_act_,
                                const uint8_t* __restrict__ row_fast, const uint32_t* __restrict__ Rrow,
                                const int64_t* __restrict__ frow_ptr, const int32_t* __restrict__ fcols,
                                const int64_t* __restrict__ row_ptr, int32_t* __restrict__ cols)
 {
+  const int64_t n_act = n_act_.get();
   const int64_t t = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   const int64_t idx0 = (t >> 4) * SROWS;
   const int sl = static_cast<int>(t & 15);
@@ -720,10 +753,11 @@ __global__ void __launch_bounds__(256)
 // fast NON-static rows: columns were staged in tmp during the count pass.  One warp moves 32 rows:
 // the per-row scalars are loaded once, lane-parallel, then every row is one coalesced copy.
 __global__ void __launch_bounds__(256)
-    pattern_copy_kernel(const int32_t* __restrict__ act_rows, int64_t n_act, const uint8_t* __restrict__ row_fast,
+    pattern_copy_kernel(const int32_t* __restrict__ act_rows, DN n_act_, const uint8_t* __restrict__ row_fast,
                         const int32_t* __restrict__ tmp, const int64_t* __restrict__ row_ptr,
                         int32_t* __restrict__ cols)
 {
+  const int64_t n_act = n_act_.get();
   const int lane = threadIdx.x & 31;
   const int64_t idx0 = ((static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x) >> 5) * 32;
   if (idx0 >= n_act)
@@ -832,8 +866,8 @@ static void build_static_structure_nd(cfx_ctx* c, Space& S)
   CFX_CUDA(cudaMemsetAsync(n_slow, 0, sizeof(unsigned long long), c->stream));
   CFX_CUDA(cudaMemsetAsync(row_nnz.p, 0, (static_cast<size_t>(S.n_total) + 1) * sizeof(int32_t), c->stream));
   auto k = pattern_rows_kernel<ND, false>;
-  CFX_LAUNCH(c, k, grid_for(S.n_total, RW), RW * 32, 0, rc, nullptr, nullptr, S.n_total, 0, S.stride, row_nnz.p,
-             nullptr, nullptr, tmp.p, S.fmask.p, nullptr, n_slow, c->err_flag.p);
+  CFX_LAUNCH(c, k, grid_for(S.n_total, RW), RW * 32, 0, rc, nullptr, nullptr, dn_exact(S.n_total), 0, S.stride,
+             row_nnz.p, nullptr, nullptr, tmp.p, S.fmask.p, nullptr, n_slow, c->err_flag.p);
   S.frow_ptr.reserve(c->pool, static_cast<size_t>(S.n_total) + 2);
   exclusive_scan_i32_to_i64(c, row_nnz.p, S.n_total, S.frow_ptr.p);
   const int64_t* h = read_back(c, c->scratch64.p, 2);
@@ -841,7 +875,7 @@ static void build_static_structure_nd(cfx_ctx* c, Space& S)
   if (slow == 0)
   {
     S.fcols.reserve(c->pool, static_cast<size_t>(fnnz) + 1);
-    CFX_LAUNCH(c, pattern_copy_kernel, grid_for(S.n_total, 256), 256, 0, nullptr, S.n_total, nullptr, tmp.p,
+    CFX_LAUNCH(c, pattern_copy_kernel, grid_for(S.n_total, 256), 256, 0, nullptr, dn_exact(S.n_total), nullptr, tmp.p,
                S.frow_ptr.p, S.fcols.p);
     S.fclist.reserve(c->pool, static_cast<size_t>(fnnz) + 64);
     S.frow_ok.reserve(c->pool, static_cast<size_t>(S.n_total) + 16);
@@ -920,6 +954,7 @@ void release_prepared(cfx_ctx* c, cfx_form* f)
   p->row_flag.release();
   p->act_rows.release();
   p->band_idx.release();
+  free_count_slot(c, p->d_counts, 2);
   delete p;
 }
 
@@ -934,18 +969,28 @@ void prepare_form(cfx_ctx* c, cfx_form* f)
   Space& S = c->spaces[f->space];
   std::vector<std::pair<const void*, int64_t>> skey, rkey;
   std::pair<const void*, int64_t> fkey{nullptr, 0};
+  std::map<std::pair<const void*, int64_t>, DN> key_dn; // exact sizes of the lists (on the device when deferred)
   for (auto& I : f->integrals)
   {
     if (I.facet)
     {
       if (I.n > 0)
+      {
         fkey = {I.entities, I.n};
+        key_dn[fkey] = DN{I.d_n, I.n, 2};
+      }
       continue;
     }
     if (I.n > 0)
+    {
       skey.emplace_back(I.entities, I.n);
+      key_dn[skey.back()] = DN{I.d_n, I.n, 0};
+    }
     if (I.rules && I.rules->nrules > 0)
+    {
       rkey.emplace_back(I.rules->parent_map.p, I.rules->nrules);
+      key_dn[rkey.back()] = DN{I.rules->deferred ? I.rules->d_sizes : nullptr, I.rules->nrules, 0};
+    }
   }
   if (S.bs > 1 && f->rank > 0)
   { // blocked spaces: every element tensor is materialised (bit0), standard cells included
@@ -989,40 +1034,54 @@ void prepare_form(cfx_ctx* c, cfx_form* f)
   for (size_t i = 0; i < skey.size(); ++i)
   {
     CFX_LAUNCH(c, mark_cells_kernel, grid_for((skey[i].second + MC - 1) / MC, SBK), SBK, 0, static_cast<const int32_t*>(skey[i].first),
-               skey[i].second, 1, c->nc_total, static_cast<uint8_t>(4u << i), S.dofmap, S.nd, uint8_t(1),
+               key_dn[skey[i]], 1, c->nc_total, static_cast<uint8_t>(4u << i), S.dofmap, S.nd, uint8_t(1),
                P->cell_flags.p, P->row_flag.p, c->err_flag.p);
     P->n_active_entities += skey[i].second;
   }
   for (auto& k : rkey)
   {
-    CFX_LAUNCH(c, mark_cells_kernel, grid_for((k.second + MC - 1) / MC, SBK), SBK, 0, static_cast<const int32_t*>(k.first), k.second, 1,
+    CFX_LAUNCH(c, mark_cells_kernel, grid_for((k.second + MC - 1) / MC, SBK), SBK, 0, static_cast<const int32_t*>(k.first), key_dn[k], 1,
                c->nc_total, uint8_t(1), S.dofmap, S.nd, uint8_t(1), P->cell_flags.p, P->row_flag.p, c->err_flag.p);
     P->n_active_entities += k.second;
   }
   if (fkey.first)
   { // both cells of every facet row (cell0, lf0, cell1, lf1); launched after the cell lists: 3 supersedes 1
     const int32_t* rows4 = static_cast<const int32_t*>(fkey.first);
-    CFX_LAUNCH(c, mark_cells_kernel, grid_for((fkey.second + MC - 1) / MC, SBK), SBK, 0, rows4, fkey.second, 4, c->nc_total, uint8_t(2),
+    CFX_LAUNCH(c, mark_cells_kernel, grid_for((fkey.second + MC - 1) / MC, SBK), SBK, 0, rows4, key_dn[fkey], 4, c->nc_total, uint8_t(2),
                S.dofmap, S.nd, uint8_t(3), P->cell_flags.p, P->row_flag.p, c->err_flag.p);
-    CFX_LAUNCH(c, mark_cells_kernel, grid_for((fkey.second + MC - 1) / MC, SBK), SBK, 0, rows4 + 2, fkey.second, 4, c->nc_total,
+    CFX_LAUNCH(c, mark_cells_kernel, grid_for((fkey.second + MC - 1) / MC, SBK), SBK, 0, rows4 + 2, key_dn[fkey], 4, c->nc_total,
                uint8_t(2), S.dofmap, S.nd, uint8_t(3), P->cell_flags.p, P->row_flag.p, c->err_flag.p);
   }
   if (xkey.first)
     CFX_LAUNCH(c, mark_rows_kernel, grid_for(xkey.second, SBK), SBK, 0, static_cast<const int32_t*>(xkey.first),
-               xkey.second, S.n_total, P->row_flag.p, c->err_flag.p);
+               DN{f->d_n_x, f->n_x, 0}, S.n_total, P->row_flag.p, c->err_flag.p);
+  P->d_counts = alloc_count_slot(c, 2);
   {
+    // deferred-size mode: the list gets the capacity earlier steps on this space needed (with margin) and its
+    // length stays on the device
+    if (c->deferred && S.cap_act_rows >= 256)
+      P->act_rows.reserve(c->pool, static_cast<size_t>(S.cap_act_rows));
     FlagPred p{P->row_flag.p};
-    P->n_act_rows = compact_indices(c, S.n_total, p, P->act_rows);
+    P->n_act_rows = compact_indices(c, dn_exact(S.n_total), p, P->act_rows, false, P->d_counts, &P->act_deferred);
+    if (!P->act_deferred)
+      S.cap_act_rows = std::max(S.cap_act_rows, with_margin(c, P->n_act_rows));
   }
   P->n_band = 0;
   if (fkey.first || xkey.first)
   {
+    if (c->deferred && S.cap_band >= 256)
+      P->band_idx.reserve(c->pool, static_cast<size_t>(S.cap_band));
     BandSlotPred bp{P->act_rows.p, P->row_flag.p};
-    P->n_band = compact_indices(c, P->n_act_rows, bp, P->band_idx);
+    P->n_band = compact_indices(c, DN{P->act_deferred ? P->d_counts : nullptr, P->n_act_rows, 0}, bp, P->band_idx,
+                                false, P->d_counts + 1, &P->band_deferred);
+    if (!P->band_deferred)
+      S.cap_band = std::max(S.cap_band, with_margin(c, P->n_band));
   }
+  else
+    CFX_CUDA(cudaMemsetAsync(P->d_counts + 1, 0, sizeof(int64_t), c->stream));
   st.set_bytes(static_cast<double>(c->nc_total) + 3.0 * static_cast<double>(S.n_total)
                + (4.0 + 4.0 * S.nd) * static_cast<double>(P->n_active_entities) + 4.0 * static_cast<double>(P->n_act_rows));
-  check_device_error(c, "form domains (entity index out of range)");
+  check_call(c, "form domains (entity index out of range)");
   f->gtab_serial = -1;
   f->dirty = false;
 }
@@ -1052,13 +1111,36 @@ const cfx_integral* facet_integral_domain(const cfx_form* f)
   return first;
 }
 
+// Make every size a form depends on known to the host (entry points that are not part of the deferred-size step
+// call this first): integral entity counts, rule sizes.  Synchronises once per deferred size.
+void resolve_form(cfx_ctx* c, cfx_form* f)
+{
+  if (!f || !f->deferred)
+    return;
+  check_device_error(c, "deferred sizes of a form's integration domains");
+  for (auto& I : f->integrals)
+  {
+    if (I.d_n)
+    {
+      const int64_t v = read_back(c, I.d_n, 1)[0];
+      I.n = I.facet ? v / 4 : v;
+      I.d_n = nullptr;
+    }
+    if (I.rules)
+      resolve(c, I.rules);
+  }
+  CFX_REQUIRE(f->d_n_x == nullptr, CFX_ERR_UNSUPPORTED, "form with device-side inserted pattern entries");
+  f->deferred = false;
+  f->dirty = true;
+}
+
 void set_facet_slots(cfx_ctx* c, const cfx_integral* I, bool clear)
 {
   if (!I)
     return;
   CFX_REQUIRE(c->topo_bound, CFX_ERR_STATE, "interior-facet integrals need cfx_topology_bind");
-  CFX_LAUNCH(c, facet_slot_set_kernel, grid_for(I->n, SBK), SBK, 0, I->entities, I->n, c->tdim + 1, c->c2f,
-             c->facet_slot.p, clear);
+  CFX_LAUNCH(c, facet_slot_set_kernel, grid_for(I->n, SBK), SBK, 0, I->entities, DN{I->d_n, I->n, 2}, c->tdim + 1,
+             c->c2f, c->facet_slot.p, clear);
 }
 } // namespace cfx
 
@@ -1126,10 +1208,10 @@ cfx_status cfx_form_add_exterior_facet_integral(cfx_ctx* ctx, cfx_form* f, int k
   CFX_API_END(ctx)
 }
 
-cfx_status cfx_form_add_cell_integral(cfx_ctx* ctx, cfx_form* f, int kernel, const int32_t* cells, int64_t n_cells,
-                                      int memspace, cfx_rules* rules, const double* constants, int n_constants)
+// shared by the pointer and the list variants: `cells` is a HOST/DEVICE array (list == null) or the list's data
+static void add_cell_integral(cfx_ctx* ctx, cfx_form* f, int kernel, const int32_t* cells, int64_t n_cells, int memspace,
+                              const cfx_list* list, cfx_rules* rules, const double* constants, int n_constants)
 {
-  CFX_API_BEGIN
   CFX_REQUIRE(ctx && f, CFX_ERR_INVALID, "cfx_form_add_cell_integral: NULL argument");
   CFX_REQUIRE(kernel_rank(kernel) == f->rank && kernel != CFX_K_GHOST_GRAD_JUMP, CFX_ERR_INVALID,
               "cfx_form_add_cell_integral: kernel family does not match the form rank / integral type");
@@ -1155,21 +1237,43 @@ cfx_status cfx_form_add_cell_integral(cfx_ctx* ctx, cfx_form* f, int kernel, con
   I.kernel = kernel;
   I.facet = false;
   I.n = n_cells;
-  I.entities = n_cells > 0 ? adopt(ctx, I.own, cells, static_cast<size_t>(n_cells), memspace) : nullptr;
+  if (list)
+  { // borrowed from the list object (which the caller keeps alive, like a DEVICE pointer); its length may be deferred
+    I.entities = n_cells > 0 ? cells : nullptr;
+    I.d_n = list->deferred ? list->d_n : nullptr;
+  }
+  else
+    I.entities = n_cells > 0 ? adopt(ctx, I.own, cells, static_cast<size_t>(n_cells), memspace) : nullptr;
   I.rules = rules;
   for (int k = 0; k < n_constants; ++k)
     I.constants[k] = constants[k];
   f->dirty = true;
-  if (memspace == CFX_HOST)
+  if (I.d_n || (rules && rules->deferred))
+    f->deferred = true;
+  if (!list && memspace == CFX_HOST)
     CFX_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+cfx_status cfx_form_add_cell_integral(cfx_ctx* ctx, cfx_form* f, int kernel, const int32_t* cells, int64_t n_cells,
+                                      int memspace, cfx_rules* rules, const double* constants, int n_constants)
+{
+  CFX_API_BEGIN
+  add_cell_integral(ctx, f, kernel, cells, n_cells, memspace, nullptr, rules, constants, n_constants);
   CFX_API_END(ctx)
 }
 
-cfx_status cfx_form_add_interior_facet_integral(cfx_ctx* ctx, cfx_form* f, int kernel, const int32_t* rows4,
-                                                int64_t n_facets, int memspace, const double* constants,
-                                                int n_constants)
+cfx_status cfx_form_add_cell_integral_list(cfx_ctx* ctx, cfx_form* f, int kernel, const cfx_list* cells, cfx_rules* rules,
+                                           const double* constants, int n_constants)
 {
   CFX_API_BEGIN
+  add_cell_integral(ctx, f, kernel, cells ? cells->data.p : nullptr, cells ? cells->n : 0, CFX_DEVICE, cells, rules,
+                    constants, n_constants);
+  CFX_API_END(ctx)
+}
+
+static void add_interior_facet_integral(cfx_ctx* ctx, cfx_form* f, int kernel, const int32_t* rows4, int64_t n_facets,
+                                        int memspace, const cfx_list* list, const double* constants, int n_constants)
+{
   CFX_REQUIRE(ctx && f, CFX_ERR_INVALID, "cfx_form_add_interior_facet_integral: NULL argument");
   CFX_REQUIRE(kernel == CFX_K_GHOST_GRAD_JUMP && f->rank == 2, CFX_ERR_INVALID,
               "cfx_form_add_interior_facet_integral: unsupported kernel family");
@@ -1180,12 +1284,38 @@ cfx_status cfx_form_add_interior_facet_integral(cfx_ctx* ctx, cfx_form* f, int k
   I.kernel = kernel;
   I.facet = true;
   I.n = n_facets;
-  I.entities = n_facets > 0 ? adopt(ctx, I.own, rows4, static_cast<size_t>(4 * n_facets), memspace) : nullptr;
+  if (list)
+  {
+    I.entities = n_facets > 0 ? rows4 : nullptr;
+    I.d_n = list->deferred ? list->d_n : nullptr; // counts int32 entries: 4 per facet row
+  }
+  else
+    I.entities = n_facets > 0 ? adopt(ctx, I.own, rows4, static_cast<size_t>(4 * n_facets), memspace) : nullptr;
   for (int k = 0; k < n_constants; ++k)
     I.constants[k] = constants[k];
   f->dirty = true;
-  if (memspace == CFX_HOST)
+  if (I.d_n)
+    f->deferred = true;
+  if (!list && memspace == CFX_HOST)
     CFX_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+cfx_status cfx_form_add_interior_facet_integral(cfx_ctx* ctx, cfx_form* f, int kernel, const int32_t* rows4,
+                                                int64_t n_facets, int memspace, const double* constants,
+                                                int n_constants)
+{
+  CFX_API_BEGIN
+  add_interior_facet_integral(ctx, f, kernel, rows4, n_facets, memspace, nullptr, constants, n_constants);
+  CFX_API_END(ctx)
+}
+
+cfx_status cfx_form_add_interior_facet_integral_list(cfx_ctx* ctx, cfx_form* f, int kernel, const cfx_list* rows4,
+                                                     const double* constants, int n_constants)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(rows4 != nullptr && rows4->n % 4 == 0, CFX_ERR_INVALID,
+              "cfx_form_add_interior_facet_integral_list: not a list of (cell0, lf0, cell1, lf1) rows");
+  add_interior_facet_integral(ctx, f, kernel, rows4->data.p, rows4->n / 4, CFX_DEVICE, rows4, constants, n_constants);
   CFX_API_END(ctx)
 }
 
@@ -1232,19 +1362,24 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
       CFX_CUDA(cudaMemsetAsync(ctx->xslot.p, 0xff, ctx->xslot.cap * sizeof(int32_t), ctx->stream));
       ctx->xslot_init = ctx->xslot.cap;
     }
-    CFX_LAUNCH(ctx, xslot_set_kernel, grid_for(a->n_x, SBK), SBK, 0, a->xrows.p, a->n_x, ctx->xslot.p, false);
+    CFX_LAUNCH(ctx, xslot_set_kernel, grid_for(a->n_x, SBK), SBK, 0, a->xrows.p, DN{a->d_n_x, a->n_x, 0}, ctx->xslot.p,
+               false);
   }
   RowCtx rc{S.inc_ptr.p, S.inc_cell.p, S.dofmap, PR->cell_flags.p, PR->row_flag.p, ctx->c2f, ctx->f2c2.p,
-            ctx->facet_slot.p, ctx->tdim + 1, 1, has_x ? ctx->xslot.p : nullptr, a->xrows.p, a->xcols.p, a->n_x};
+            ctx->facet_slot.p, ctx->tdim + 1, 1, has_x ? ctx->xslot.p : nullptr, a->xrows.p, a->xcols.p,
+            DN{a->d_n_x, a->n_x, 0}};
   // active rows handled by this call: the tail of the ascending list when row_begin > 0
   int64_t i0 = 0;
   if (part && PR->n_act_rows > 0)
   {
+    CFX_REQUIRE(!PR->act_deferred, CFX_ERR_UNSUPPORTED,
+                "cfx_create_sparsity_rows: not available on forms prepared in deferred-size mode");
     CFX_LAUNCH(ctx, lower_bound_kernel, 1, 1, 0, PR->act_rows.p, PR->n_act_rows, row_begin, ctx->scratch64.p + 4);
     i0 = read_back(ctx, ctx->scratch64.p + 4, 1)[0];
   }
   const int32_t* act = PR->act_rows.p + i0;
   const int64_t n_act = PR->n_act_rows - i0;
+  const DN d_act{PR->act_deferred ? PR->d_counts : nullptr, n_act, 0};
   DevBuf<int32_t> row_nnz;
   row_nnz.reserve(ctx->pool, static_cast<size_t>(S.n_total) + 1);
   auto kcount = S.nd == 3 ? pattern_rows_kernel<3, false>
@@ -1271,6 +1406,7 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
   // with a static structure the generic kernels visit the band rows only, through their slot list
   const int32_t* gslots = use_static ? PR->band_idx.p : nullptr;
   const int64_t n_generic = use_static ? PR->n_band : n_act;
+  const DN d_generic = use_static ? PR->dn_band() : d_act;
   const unsigned gg = grid_for(n_generic, RW);
   a->n_band_listed = use_static ? PR->n_band : 0;
   if (n_act > 0)
@@ -1279,14 +1415,14 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
     if (use_static)
     {
       a->Rrow.reserve(ctx->pool, static_cast<size_t>(n_act) + 1);
-      CFX_LAUNCH(ctx, pattern_static_kernel, grid_for((n_act + 3) / 4 * 8, 256), 256, 0, rc, act, n_act, S.fmask.p, S.frow_ok.p,
+      CFX_LAUNCH(ctx, pattern_static_kernel, grid_for((n_act + 3) / 4 * 8, 256), 256, 0, rc, act, d_act, S.fmask.p, S.frow_ok.p,
                  row_nnz.p, a->Rrow.p, a->row_fast.p, n_slow + 1);
     }
     if (need_generic)
     {
       tmp.reserve(ctx->pool, static_cast<size_t>(n_act) * 32);
       a->gmask.reserve(ctx->pool, static_cast<size_t>(n_act) * S.stride);
-      CFX_LAUNCH(ctx, kcount, gg, RW * 32, 0, rc, act, gslots, n_generic, only_band, S.stride, row_nnz.p, nullptr,
+      CFX_LAUNCH(ctx, kcount, gg, RW * 32, 0, rc, act, gslots, d_generic, only_band, S.stride, row_nnz.p, nullptr,
                  nullptr, tmp.p, a->gmask.p, a->row_fast.p, n_slow, ctx->err_flag.p);
     }
   }
@@ -1298,29 +1434,74 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
   }
   else
     exclusive_scan_i32_to_i64(ctx, row_nnz.p, S.n_total, P->row_ptr.p);
+  // deferred-size mode: a reused matrix object keeps its arrays, nnz stays on the device (row_ptr[n_rows])
+  const int64_t bs2 = static_cast<int64_t>(S.bs) * S.bs;
+  const bool defer = ctx->deferred && !part && P->cols.p && P->values.p && P->cols.cap >= 256
+                     && P->values.cap >= (P->cols.cap - 1) * static_cast<size_t>(bs2) + 1;
+  if (defer)
+  {
+    P->nnz = static_cast<int64_t>(P->cols.cap) - 1;
+    P->deferred = true;
+    P->ctx = ctx;
+    note_result(ctx, P);
+    a->deferred = true;
+    // launch decisions that used to read counters back: what eager steps on this space saw, verified on the device
+    const bool no_slow = S.seen_slow_rows == 0, no_noclist = S.seen_noclist_rows == 0;
+    a->n_slow_rows = no_slow ? 0 : n_generic;
+    a->n_clist_rows = use_static ? n_act : 0;
+    a->n_clist_nnz = 0;
+    a->n_mask_rows = n_act;
+    a->expect_noclist_zero = no_noclist;
+    if (n_act > 0)
+      CFX_LAUNCH(ctx, pattern_capacity_kernel, 1, 1, 0, P->row_ptr.p + S.n_total, P->nnz, ctx->scratch64.p,
+                 no_slow ? 1 : 0, (no_noclist && use_static) ? 1 : 0, PR->d_counts, ctx->err_flag.p);
+  }
+  else
   {
     const int64_t* h = read_back(ctx, ctx->scratch64.p, 4);
     P->nnz = h[0];
+    P->deferred = false;
+    P->ctx = ctx;
     a->n_slow_rows = h[1];
     a->n_clist_rows = h[2];
     a->n_clist_nnz = h[3];
-    a->n_mask_rows = n_act - h[1] - h[2];
+    int64_t na = n_act, nb = use_static ? PR->n_band : 0;
+    if (PR->act_deferred || PR->band_deferred)
+    { // the lists were prepared with deferred sizes: fetch the exact lengths for the bookkeeping below
+      const int64_t* hc = read_back(ctx, PR->d_counts, 2);
+      na = hc[0];
+      nb = use_static ? hc[1] : 0;
+    }
+    a->n_mask_rows = na - a->n_slow_rows - a->n_clist_rows;
+    a->deferred = PR->act_deferred || PR->band_deferred;
+    a->expect_noclist_zero = false;
+    if (!part)
+    {
+      S.seen_slow_rows = std::max(S.seen_slow_rows, a->n_slow_rows);
+      S.seen_noclist_rows = std::max(S.seen_noclist_rows, use_static ? na - nb - a->n_clist_rows : int64_t(0));
+    }
+    const size_t want = static_cast<size_t>(P->nnz) + 1;
+    if (want > P->cols.cap || !P->cols.p || want * bs2 > P->values.cap || !P->values.p)
+    {
+      const size_t capn = static_cast<size_t>(with_margin(ctx, P->nnz)) + 1;
+      P->cols.reserve(ctx->pool, std::max(capn, P->cols.cap));
+      P->values.reserve(ctx->pool, (std::max(capn, P->cols.cap) - 1) * bs2 + 1);
+    }
   }
-  P->cols.reserve(ctx->pool, static_cast<size_t>(P->nnz) + 1);
-  P->values.reserve(ctx->pool, static_cast<size_t>(P->nnz) * S.bs * S.bs + 1);
+  const int64_t cols_cap = static_cast<int64_t>(P->cols.cap) - 1;
   if (!part)
     CFX_LAUNCH(ctx, pattern_inactive_fill_kernel, grid_for(S.n_total, SBK), SBK, 0, PR->row_flag.p, S.n_total, 1,
-               P->row_ptr.p, P->cols.p);
+               P->row_ptr.p, P->cols.p, cols_cap);
   if (n_act > 0)
   {
     if (use_static)
-      CFX_LAUNCH(ctx, pattern_static_fill_kernel, grid_for((n_act + SROWS - 1) / SROWS * 16, 256), 256, 0, act, n_act, a->row_fast.p,
+      CFX_LAUNCH(ctx, pattern_static_fill_kernel, grid_for((n_act + SROWS - 1) / SROWS * 16, 256), 256, 0, act, d_act, a->row_fast.p,
                  a->Rrow.p, S.frow_ptr.p, S.fcols.p, P->row_ptr.p, P->cols.p);
     if (need_generic)
-      CFX_LAUNCH(ctx, pattern_copy_kernel, grid_for(n_act, 256), 256, 0, act, n_act, a->row_fast.p, tmp.p,
+      CFX_LAUNCH(ctx, pattern_copy_kernel, grid_for(n_act, 256), 256, 0, act, d_act, a->row_fast.p, tmp.p,
                  P->row_ptr.p, P->cols.p);
     if (a->n_slow_rows > 0)
-      CFX_LAUNCH(ctx, kfill, gg, RW * 32, 0, rc, act, gslots, n_generic, only_band, S.stride, nullptr, P->row_ptr.p,
+      CFX_LAUNCH(ctx, kfill, gg, RW * 32, 0, rc, act, gslots, d_generic, only_band, S.stride, nullptr, P->row_ptr.p,
                  P->cols.p, nullptr, nullptr, a->row_fast.p, nullptr, ctx->err_flag.p);
   }
   tmp.release();
@@ -1328,12 +1509,13 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
   a->gtab_serial = part ? -1 : P->serial; // the gather tables of a partial build index a sub-list of rows
   set_facet_slots(ctx, FI, true);
   if (has_x)
-    CFX_LAUNCH(ctx, xslot_set_kernel, grid_for(a->n_x, SBK), SBK, 0, a->xrows.p, a->n_x, ctx->xslot.p, true);
+    CFX_LAUNCH(ctx, xslot_set_kernel, grid_for(a->n_x, SBK), SBK, 0, a->xrows.p, DN{a->d_n_x, a->n_x, 0}, ctx->xslot.p,
+               true);
   CFX_CUDA(cudaMemsetAsync(P->values.p, 0, (static_cast<size_t>(P->nnz) * S.bs * S.bs + 1) * sizeof(double),
                            ctx->stream));
   row_nnz.release();
   st.set_bytes(12.0 * static_cast<double>(P->nnz) + 8.0 * static_cast<double>(S.n_total));
-  check_device_error(ctx, "cfx_create_sparsity (row capacity exceeded / inserted entries not sorted by row)");
+  check_call(ctx, "cfx_create_sparsity (row capacity exceeded / inserted entries not sorted by row)");
 }
 
 cfx_status cfx_create_sparsity(cfx_ctx* ctx, const cfx_form* a_const, cfx_pattern** inout)
@@ -1359,6 +1541,7 @@ cfx_status cfx_create_sparsity_rows(cfx_ctx* ctx, const cfx_form* a_const, int64
               "cfx_create_sparsity_rows: row_begin must be in (0, owned+ghost dofs]");
   if (*inout == nullptr)
     *inout = new cfx_pattern();
+  resolve_form(ctx, a);
   build_pattern(ctx, a, *inout, row_begin);
   CFX_API_END(ctx)
 }
@@ -1476,6 +1659,18 @@ cfx_status cfx_pattern_import(cfx_ctx* ctx, int space, const int64_t* row_ptr, c
 
 cfx_status cfx_pattern_sizes(const cfx_pattern* p, int64_t* n_rows, int64_t* nnz)
 {
+  if (p && p->deferred && p->ctx)
+  { // nnz is on the device: fetch it now (synchronises)
+    try
+    {
+      resolve(p->ctx, const_cast<cfx_pattern*>(p));
+    }
+    catch (const cfx::Error& e)
+    {
+      cfx_set_error(p->ctx, e.what());
+      return e.code;
+    }
+  }
   if (!p)
     return CFX_ERR_INVALID;
   if (n_rows)
@@ -1489,6 +1684,7 @@ cfx_status cfx_pattern_fetch(cfx_ctx* ctx, const cfx_pattern* p, int64_t* row_pt
 {
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && p, CFX_ERR_INVALID, "cfx_pattern_fetch: NULL argument");
+  resolve(ctx, const_cast<cfx_pattern*>(p));
   export_to(ctx, row_ptr, p->row_ptr.p, static_cast<size_t>(p->n_rows) + 1, memspace);
   export_to(ctx, cols, p->cols.p, static_cast<size_t>(p->nnz), memspace);
   CFX_API_END(ctx)
@@ -1502,6 +1698,7 @@ cfx_status cfx_pattern_values_fetch(cfx_ctx* ctx, const cfx_pattern* p, double* 
 {
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && p && values, CFX_ERR_INVALID, "cfx_pattern_values_fetch: NULL argument");
+  resolve(ctx, const_cast<cfx_pattern*>(p));
   export_to(ctx, values, p->values.p, static_cast<size_t>(p->nnz) * p->bs * p->bs, memspace);
   CFX_API_END(ctx)
 }
@@ -1597,6 +1794,7 @@ const uint8_t* cfx_active_indicator_device_ptr(cfx_ctx* ctx, const cfx_form* a_c
     return nullptr;
   try
   {
+    resolve_form(ctx, a);
     prepare_form(ctx, a);
   }
   catch (const std::exception& e)
@@ -1626,6 +1824,7 @@ cfx_status cfx_active_domain(cfx_ctx* ctx, const cfx_form* a_const, cfx_list** a
   CFX_REQUIRE(ctx && a && active_cells && inactive_dofs, CFX_ERR_INVALID, "cfx_active_domain: NULL argument");
   // deactivate.h:76-101: a bilinear form on one space
   CFX_REQUIRE(a->rank == 2, CFX_ERR_INVALID, "cutfemx.fem.active_domain requires a bilinear form");
+  resolve_form(ctx, a);
   Space& S = ctx->spaces[a->space];
   prepare_form(ctx, a);
   if (*active_cells == nullptr)
@@ -1659,6 +1858,7 @@ cfx_status cfx_deactivate_outside(cfx_ctx* ctx, cfx_pattern* A, const int32_t* i
 {
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && A && (n == 0 || inactive_dofs), CFX_ERR_INVALID, "cfx_deactivate_outside: NULL argument");
+  resolve(ctx, A);
   if (n > 0 && A->bs > 1)
   { // blocked matrix: the rows are blocked indices bs*dof + k (cfx_active_domain on a blocked space)
     DevBuf<int32_t> own;

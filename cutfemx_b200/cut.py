@@ -52,6 +52,26 @@ class Context:
     def launch_count(self) -> int:
         return int(lib().cfx_launch_count(self._h))
 
+    @property
+    def device_bytes(self) -> int:
+        return int(lib().cfx_device_bytes(self._h))
+
+    # -- deferred sizes / CUDA graphs (include/cutfemx_b200.h "deferred sizes and CUDA graphs")
+    def set_deferred(self, on: bool, margin: float = -1.0):
+        check(self._h, lib().cfx_set_deferred(self._h, int(on), float(margin)))
+
+    def check(self):
+        """Raise if a deferred-size call exceeded a capacity or met an invalid index (synchronises)."""
+        check(self._h, lib().cfx_check(self._h))
+
+    def graph_begin(self):
+        check(self._h, lib().cfx_graph_begin(self._h))
+
+    def graph_end(self) -> "Graph":
+        g = Graph(self)
+        check(self._h, lib().cfx_graph_end(self._h, C.byref(g._h)))
+        return g
+
     # -- profiling hooks
     def stage_timing(self, on: bool):
         check(self._h, lib().cfx_stage_timing_enable(self._h, int(on)))
@@ -80,6 +100,33 @@ class Context:
                                             C.c_int64(space.num_dofs_owned), C.c_int64(space.num_dofs), ms))
         self._spaces[key] = (idx, space, keep)
         return idx
+
+
+class Graph:
+    """A captured step (cfx_graph): `launch()` replays every call recorded between graph_begin and graph_end."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+
+    def launch(self):
+        check(self.ctx.handle, lib().cfx_graph_launch(self.ctx.handle, self._h))
+
+    @property
+    def kernel_nodes(self) -> int:
+        return int(lib().cfx_graph_kernel_nodes(self._h))
+
+    def free(self):
+        if self._h:
+            lib().cfx_graph_free(self.ctx.handle, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.free()
+        except Exception:
+            pass
 
 
 def _mesh_context(mesh: Mesh, device: int | None = None) -> Context:
@@ -126,7 +173,10 @@ class _List:
 
     @property
     def size(self) -> int:
-        return int(lib().cfx_list_size(self._h))
+        n = int(lib().cfx_list_size(self._h))
+        if n < 0:  # a deferred size could not be fetched (capacity exceeded in the step that produced the list)
+            check(self.ctx.handle, -4)
+        return n
 
     @property
     def device_ptr(self) -> int:
@@ -430,9 +480,11 @@ def _selector_args(cut_data: CutData, ls_part: str):
             (to, cl, cr))
 
 
-def locate_entities_device(cut_data: CutData, ls_part: str) -> _List:
+def locate_entities_device(cut_data: CutData, ls_part: str, out: _List | None = None) -> _List:
+    """`out`: a list from an earlier call to refill in place (its buffer is reused; in deferred-size mode the new
+    length then stays on the device)."""
     n, pto, pcl, pcr, keep = _selector_args(cut_data, ls_part)
-    out = _List(cut_data._ctx)
+    out = _List(cut_data._ctx) if out is None else out
     h = cut_data._ctx.handle
     if cut_data.facet_hosted:  # facet ids in the order of the host list (cut.cpp:344-359)
         check(h, lib().cfx_ecut_locate(h, cut_data._ecut, n, pto, pcl, pcr, C.byref(out._h)))
@@ -449,8 +501,9 @@ def locate_entities(cut_data: CutData, ls_part: str) -> np.ndarray:
     return out
 
 
-def runtime_quadrature(cut_data: CutData, ls_part: str, order: int, *, backend: str = "straight"):
-    """Run-time quadrature for the selected part (cut.cpp:1311-1335)."""
+def runtime_quadrature(cut_data: CutData, ls_part: str, order: int, *, backend: str = "straight", out=None):
+    """Run-time quadrature for the selected part (cut.cpp:1311-1335).  `out`: rules from an earlier call to refill
+    in place."""
     if backend != "straight":
         # cut.cpp:207-237: algoim backends exist only for interval/quadrilateral/hexahedron cells
         raise ValueError(f"runtime_quadrature backend '{backend}' is not available for simplex cells")
@@ -459,7 +512,12 @@ def runtime_quadrature(cut_data: CutData, ls_part: str, order: int, *, backend: 
     to, cl, cr = parse_selector(ls_part, cut_data.level_set_names)
     if cl.size != 1:
         raise NotImplementedError("runtime_quadrature supports single-clause selectors (`name rel 0`)")
-    rules = RuntimeQuadratureRules(cut_data._ctx, ls_part, int(cl[0]), int(order))
+    if out is not None:
+        rules = out
+        rules.selector, rules.ls, rules.order = ls_part, int(cl[0]), int(order)
+        rules._cache.clear()
+    else:
+        rules = RuntimeQuadratureRules(cut_data._ctx, ls_part, int(cl[0]), int(order))
     rules.ctx_gdim = cut_data.gdim
     h = cut_data._ctx.handle
     if cut_data.facet_hosted:
@@ -474,13 +532,14 @@ def runtime_quadratures(cut_data: CutData, ls_parts: Sequence[str], order: int, 
     return {str(p): runtime_quadrature(cut_data, str(p), order, backend=backend) for p in ls_parts}
 
 
-def ghost_penalty_facets_device(cut_data: CutData, selector: str, *, include_ghosts: bool = False) -> _List:
+def ghost_penalty_facets_device(cut_data: CutData, selector: str, *, include_ghosts: bool = False,
+                                out: _List | None = None) -> _List:
     mesh = cut_data.mesh
     _bind_topology(mesh, cut_data._ctx)
     n, pto, pcl, pcr, keep = _selector_args(cut_data, selector)
     if "phi" not in cut_data.level_set_names:
         raise ValueError("ghost_penalty_facets locates the cut cells with 'phi=0' (python/cutfemx/cut.py:364)")
-    out = _List(cut_data._ctx)
+    out = _List(cut_data._ctx) if out is None else out
     h = cut_data._ctx.handle
     check(h, lib().cfx_ghost_penalty_facets(h, cut_data.level_set_names.index("phi"), n, pto, pcl, pcr,
                                             int(include_ghosts), C.byref(out._h)))
@@ -515,15 +574,16 @@ def interior_facets_for_cells(msh: Mesh, cells, *, include_ghosts: bool = False)
     return res
 
 
-def facet_integration_rows_device(msh: Mesh, facets) -> _List:
+def facet_integration_rows_device(msh: Mesh, facets, out: _List | None = None) -> _List:
     ctx = _mesh_context(msh)
     _bind_topology(msh, ctx)
-    if isinstance(facets, _List):
-        p, ms, n, keep = C.c_void_p(facets.device_ptr), DEVICE, facets.size, facets
-    else:
-        p, ms, keep = as_arg(facets, np.int32)
-        n = int(keep.numel() if _lib.is_device_array(keep) else keep.size)
-    out = _List(ctx)
+    out = _List(ctx) if out is None else out
+    if isinstance(facets, _List):  # stays on the device; the length may be deferred
+        check(ctx.handle, lib().cfx_facet_integration_rows_list(ctx.handle, facets._h, C.byref(out._h)))
+        out._keep = facets
+        return out
+    p, ms, keep = as_arg(facets, np.int32)
+    n = int(keep.numel() if _lib.is_device_array(keep) else keep.size)
     check(ctx.handle, lib().cfx_facet_integration_rows(ctx.handle, p, C.c_int64(n), ms, C.byref(out._h)))
     return out
 

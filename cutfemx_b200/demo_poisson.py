@@ -83,21 +83,29 @@ class CutPoisson:
         self.stats = {}
         self.last = None
         self.fused = True  # matrix and right-hand side in one pass (cfx_assemble_system)
+        # persistent = True: the result objects of a step (lists, rules, matrix) are refilled in place by the next
+        # step instead of being freed and recreated -- what a time loop does (demo_moving_poisson.py:69-107), and
+        # what deferred-size mode and graph capture need (cfx_set_deferred / cfx_graph_begin)
+        self.persistent = False
+        self.keep = {}
+        self.graph = None
 
     def build_forms(self, assemble_rhs: bool = True):
         """update -> locate -> rules -> normals -> ghost facets -> the forms a and L."""
         cd = self.cut_data
+        k = self.keep if self.persistent else {}
         _cut.update(cd)                                                     # cutfemx.update
-        inside = _cut.locate_entities_device(cd, "phi<0")                   # locate_entities
-        rv = _cut.runtime_quadrature(cd, "phi<0", self.order)               # volume rules
-        ri = _cut.runtime_quadrature(cd, "phi=0", self.order)               # interface rules
+        inside = _cut.locate_entities_device(cd, "phi<0", out=k.get("inside"))          # locate_entities
+        rv = _cut.runtime_quadrature(cd, "phi<0", self.order, out=k.get("rv"))          # volume rules
+        ri = _cut.runtime_quadrature(cd, "phi=0", self.order, out=k.get("ri"))          # interface rules
         _ls.attach_normal(cd, self.phi, ri)                                 # n = normal(phi)
-        ghost = _cut.ghost_penalty_facets_device(cd, "phi<0")               # ghost_penalty_facets
-        rows = _cut.facet_integration_rows_device(self.mesh, ghost)         # facet_integration_rows
+        ghost = _cut.ghost_penalty_facets_device(cd, "phi<0", out=k.get("ghost"))       # ghost_penalty_facets
+        rows = _cut.facet_integration_rows_device(self.mesh, ghost, out=k.get("rows"))  # facet_integration_rows
         a = _fem.CutForm(self.V, 2)
         a.add_cell_integral("laplace", inside, rv, (1.0,))
         a.add_cell_integral("nitsche", None, ri, (self.gamma,))
-        if ghost.size > 0:
+        # (a persistent loop never asks for the size: in deferred-size mode it is not on the host)
+        if self.persistent or ghost.size > 0:
             a.add_interior_facet_integral("ghost_grad_jump", rows=rows, constants=(self.gamma_g,))
         L = None
         if assemble_rhs:
@@ -105,6 +113,8 @@ class CutPoisson:
             L.add_cell_integral("source", inside, rv, (self.f_value,))
             L.add_cell_integral("nitsche_rhs", None, ri, (self.gamma, self.g_value))
         self.last = dict(inside=inside, rv=rv, ri=ri, ghost=ghost, rows=rows, a=a, L=L)
+        if self.persistent:
+            self.keep = dict(inside=inside, rv=rv, ri=ri, ghost=ghost, rows=rows)
         return a, L
 
     def assemble(self):
@@ -121,7 +131,13 @@ class CutPoisson:
             _fem.assemble_matrix(a, self.A)                                 # assemble_matrix
             if L is not None:
                 self.b = self._assemble_vector_device(L)
-        cd, t = self.cut_data, self.last
+        if self.persistent:
+            return None  # sizes stay where they are; fetch_stats() asks for them
+        return self.fetch_stats()
+
+    def fetch_stats(self):
+        """Sizes of the current step's results (synchronises in deferred-size mode)."""
+        cd, t = self.cut_data, self.last if self.last else self.keep
         counts = cd.counts()
         self.stats = dict(inside=counts[0], cut=counts[1], outside=counts[2], nnz=self.A.nnz,
                           n_rows=self.A.shape[0], ghost_facets=t["ghost"].size, volume_points=t["rv"].total_points,
@@ -135,6 +151,8 @@ class CutPoisson:
         t["a"].free()
         if t["L"] is not None:
             t["L"].free()
+        if self.persistent:
+            return  # the lists, rules and the matrix are refilled in place by the next step
         for k in ("inside", "rv", "ri", "ghost", "rows"):
             t[k].free()
 
@@ -144,6 +162,29 @@ class CutPoisson:
         if not keep:
             self.release_step()
         return stats
+
+    # ---- time loops: persistent objects, deferred sizes, one graph launch per step
+    def capture(self, margin: float = 0.25):
+        """Record one step as a CUDA graph.  Runs two eager steps first (objects exist, buffers get `margin` spare
+        capacity), one deferred-size step (nothing needs a size on the host any more), then captures."""
+        self.persistent = True
+        ctx = self.ctx
+        ctx.set_deferred(False, margin)
+        for _ in range(2):
+            self.step()
+        ctx.set_deferred(True)
+        self.step()
+        ctx.check()
+        ctx.graph_begin()
+        try:
+            self.step()
+        finally:
+            self.graph = ctx.graph_end()
+        return self.graph
+
+    def replay(self):
+        """One time step = one graph launch (the level-set values are re-read from the bound array)."""
+        self.graph.launch()
 
     def _assemble_vector_device(self, L):
         import torch

@@ -36,9 +36,15 @@ class CutForm:
         kid = KERNEL[kernel]
         if KERNEL_RANK[kid] != self.rank:
             raise ValueError(f"kernel '{kernel}' has rank {KERNEL_RANK[kid]}, form has rank {self.rank}")
-        if isinstance(cells, _List):
-            p, ms, n, keep = C.c_void_p(cells.device_ptr), DEVICE, cells.size, cells
-        elif cells is None:
+        if isinstance(cells, _List):  # library list: borrowed as it is, its length may still be on the device
+            cst = np.ascontiguousarray(list(constants), dtype=np.float64)
+            h = self.ctx.handle
+            check(h, lib().cfx_form_add_cell_integral_list(h, self._h, kid, cells._h,
+                                                           rules._h if rules is not None else None,
+                                                           C.c_void_p(cst.ctypes.data), int(cst.size)))
+            self._owners += [cells, rules]
+            return self
+        if cells is None:
             p, ms, n, keep = None, HOST, 0, None
         else:
             p, ms, keep = as_arg(cells, np.int32)
@@ -79,7 +85,12 @@ class CutForm:
         if rows is None:
             rows = facet_integration_rows_device(msh, facets)
         if isinstance(rows, _List):
-            p, ms, n, keep = C.c_void_p(rows.device_ptr), DEVICE, rows.size // 4, rows
+            cst = np.ascontiguousarray(list(constants), dtype=np.float64)
+            h = self.ctx.handle
+            check(h, lib().cfx_form_add_interior_facet_integral_list(h, self._h, kid, rows._h,
+                                                                     C.c_void_p(cst.ctypes.data), int(cst.size)))
+            self._owners += [rows]
+            return self
         else:
             p, ms, keep = as_arg(rows, np.int32)
             n = int(keep.numel() if is_device_array(keep) else keep.size) // 4

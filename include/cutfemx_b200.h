@@ -73,8 +73,38 @@ void cfx_ctx_destroy(cfx_ctx* ctx);
 const char* cfx_last_error(const cfx_ctx* ctx); /* ctx may be NULL: last error of the calling thread */
 cfx_status cfx_sync(cfx_ctx* ctx);
 int cfx_version(void);
-/* number of kernel launches issued through this context since creation (bench.py "gpu_launches") */
+/* number of kernel launches issued through this context since creation (bench.py "gpu_launches"); a graph launch
+ * counts the kernel nodes of the graph */
 int64_t cfx_launch_count(const cfx_ctx* ctx);
+/* bytes of device memory the context holds (mesh mirrors, static tables, result buffers, cached blocks) */
+int64_t cfx_device_bytes(const cfx_ctx* ctx);
+
+/* ------------------------------------------------------------------ deferred sizes and CUDA graphs
+ * The reference returns every intermediate result to the host (numpy arrays: locate_entities cut.cpp:877-924,
+ * runtime_quadrature :1311-1335, ghost_penalty_facets cut.py:340-380), so a time step of demo_moving_poisson.py:69-107
+ * is a chain of host round trips.  In DEFERRED-SIZE mode the calls of that chain -- cfx_update, cfx_locate_entities,
+ * cfx_runtime_quadrature, cfx_evaluate_normals (out = NULL), cfx_ghost_penalty_facets, cfx_facet_integration_rows_list,
+ * cfx_form_add_*_integral_list, cfx_create_sparsity, cfx_assemble_matrix / _vector / _system -- leave the sizes of
+ * their results on the device when they are handed an object to REUSE (lists, rules, matrices from an earlier step,
+ * whose buffers then act as capacities, `margin` = extra fraction allocated beyond what a step needed): nothing
+ * synchronises, and the first query of a size (cfx_list_size, cfx_rules_sizes, cfx_pattern_sizes) or any fetch makes
+ * the sizes known to the host again.  A result that does not fit its capacity raises an error at that point (or at
+ * cfx_check) instead of being truncated silently; repeat the step with deferred mode off to grow the buffers.
+ * Every other entry point may be called in either mode; it synchronises as before. */
+cfx_status cfx_set_deferred(cfx_ctx* ctx, int on, double margin /* < 0: keep the current one (default 0.125) */);
+/* read the device-side error flag (synchronises): capacity exceeded, invalid entity index, entry not in pattern */
+cfx_status cfx_check(cfx_ctx* ctx);
+/* Capture the calls between begin and end into a CUDA graph instead of executing them (deferred-size mode only, after
+ * the same calls have run once on the same objects; no size query / fetch in between), then replay the whole step
+ * with one launch per time step: the level-set values are re-read from where they were bound, every object the
+ * captured calls produced is refreshed in place.  The objects must stay alive, and must not be passed to other
+ * calls that would reallocate them, while the graph exists. */
+typedef struct cfx_graph cfx_graph;
+cfx_status cfx_graph_begin(cfx_ctx* ctx);
+cfx_status cfx_graph_end(cfx_ctx* ctx, cfx_graph** out);
+cfx_status cfx_graph_launch(cfx_ctx* ctx, cfx_graph* g);
+int64_t cfx_graph_kernel_nodes(const cfx_graph* g);
+void cfx_graph_free(cfx_ctx* ctx, cfx_graph* g);
 
 /* ------------------------------------------------------------------ mesh views
  * replaces build_mesh_view, cut.cpp:500-538: x is geometry().x() (stride 3),
@@ -172,6 +202,9 @@ cfx_status cfx_interior_facets_for_cells(cfx_ctx* ctx, const int32_t* cells, int
                                          int include_ghosts, cfx_list** out);
 /* facet_integration_rows("interior_facet"), wrappers/cut.cpp:54-115: (cell0, lf0, cell1, lf1) per facet */
 cfx_status cfx_facet_integration_rows(cfx_ctx* ctx, const int32_t* facets, int64_t n, int memspace, cfx_list** out);
+/* the same for a facet list that lives on the device (e.g. the result of cfx_ghost_penalty_facets), whose length
+ * may be deferred */
+cfx_status cfx_facet_integration_rows_list(cfx_ctx* ctx, const cfx_list* facets, cfx_list** out);
 
 /* ------------------------------------------------------------------ function spaces
  * dolfinx::fem::DofMap of a Lagrange space of `degree` (1|2) on the bound mesh:
@@ -192,6 +225,12 @@ cfx_status cfx_form_add_cell_integral(cfx_ctx* ctx, cfx_form* f, int kernel, con
 cfx_status cfx_form_add_interior_facet_integral(cfx_ctx* ctx, cfx_form* f, int kernel, const int32_t* rows4,
                                                 int64_t n_facets, int memspace, const double* constants,
                                                 int n_constants);
+/* The same with the entity lists given as library lists (results of cfx_locate_entities / cfx_facet_integration_rows*),
+ * borrowed until the form is freed; their lengths may be deferred. */
+cfx_status cfx_form_add_cell_integral_list(cfx_ctx* ctx, cfx_form* f, int kernel, const cfx_list* cells, cfx_rules* rules,
+                                           const double* constants, int n_constants);
+cfx_status cfx_form_add_interior_facet_integral_list(cfx_ctx* ctx, cfx_form* f, int kernel, const cfx_list* rows4,
+                                                     const double* constants, int n_constants);
 /* Exterior-facet integral over facet-hosted run-time rules (ufl.Measure("ds", subdomain_data=rules) on rules from a
  * facet-hosted cut, test_cut_api.py:504-527).  Shipped family: CFX_K_ONE on a rank-0 form -- c0 times the measure of
  * the selected part of the host facets. */
