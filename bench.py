@@ -36,7 +36,8 @@ WORKLOADS = {
                 name="2D circle R=0.5, {n}x{n} right-diagonal triangles, P1, order 4"),
     # configs[1]: P2 u (P1 level set) on the 4096^2 triangle mesh, ghost penalty
     "C2": dict(tdim=2, n=4096, p0=(-1.0, -1.0), p1=(1.0, 1.0), ls=("sphere", (0.0, 0.0, 0.0, 0.5, 0.0)), order=4,
-               degree=2, name="2D circle R=0.5, {n}x{n} right-diagonal triangles, P2 u / P1 level set, order 4, "
+               degree=2, ref_n=512,
+               name="2D circle R=0.5, {n}x{n} right-diagonal triangles, P2 u / P1 level set, order 4, "
                               "Nitsche + ghost-penalty facets"),
     # configs[4]: moving sphere, everything re-cut / regenerated / reassembled every step (demo_moving_poisson.py)
     "C5": dict(tdim=3, n=128, p0=(0.0, 0.0, 0.0), p1=(1.0, 1.0, 1.0), ls=("sphere", (0.3, 0.5, 0.5, 0.25, 0.0)),
@@ -195,7 +196,9 @@ def reference_parts(n, n_gpus):
 
 
 def run_reference(args, wl):
-    n = args.ref_n or args.n or wl["n"]  # the SAME configuration as our arm unless --ref-n asks for a sample
+    # the SAME configuration as our arm unless --ref-n (or the workload, where the serial oracle would need many
+    # minutes per step) asks for a bounded sample
+    n = args.ref_n or wl.get("ref_n") or args.n or wl["n"]
     n_ours = args.n or wl["n"]
     nparts = reference_parts(n, args.gpus)
     ref = CpuReference(wl, n, nparts)
@@ -224,6 +227,235 @@ def run_reference(args, wl):
         "e2e": {"value": value, "unit": "cut-cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------- our arm, one GPU
+def run_ours_graph(args, wl):
+    """N = 1: the whole step is ONE CUDA-graph launch (deferred sizes, no host round trip inside the step)."""
+    import ctypes as C
+
+    import torch
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    from cutfemx_b200 import fem as _fem
+    from cutfemx_b200 import parallel as P
+    from cutfemx_b200._lib import HOST, check, lib
+
+    n = args.n or wl["n"]
+    tdim = wl["tdim"]
+    kind, prm = wl["ls"]
+    sync = torch.cuda.synchronize
+
+    # ---- one-time setup (mesh-only data: geometry cache, facet-cell table, incidence, static pattern tables);
+    # reported next to ms_per_step, not inside it
+    sync()
+    t0 = time.perf_counter()
+    pipe = P.RankPipeline([n] * tdim, list(wl["p0"]), list(wl["p1"]), 1, 0, local_rank, kind, prm,
+                          order=wl["order"], degree=wl.get("degree", 1))
+    prob, ctx, V = pipe.prob, pipe.ctx, pipe.V
+    sync()
+    t1 = time.perf_counter()
+    prob.step()  # first step: binds the space and the topology (static tables), allocates every buffer
+    sync()
+    t2 = time.perf_counter()
+    setup = {"ms": (t2 - t0) * 1e3, "mesh_generation_and_bind_ms": (t1 - t0) * 1e3, "first_step_ms": (t2 - t1) * 1e3,
+             "what": "synthetic mesh generation on the device, cfx_mesh_bind (geometry cache), and the first step "
+                     "(cfx_topology_bind, cfx_space_bind: incidence, static pattern and contribution tables)"}
+
+    tstep = [0]
+
+    def move():
+        if "moving" in wl:  # the level set moves: new nodal values (device-resident), then the whole path
+            x0, dx, period = wl["moving"]
+            t = tstep[0] % (period + 1)
+            tstep[0] += 1
+            pipe.move_level_set((x0 + dx * t / period,) + tuple(prm[1:]))
+
+    graph = prob.capture(margin=0.25)
+    setup["device_bytes"] = ctx.device_bytes
+    for _ in range(max(args.warmup, 3)):
+        move()
+        prob.replay()
+    ctx.check()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)  # 256 MiB > 126 MB L2
+    sampler = ClockSampler(local_rank)
+    launches0 = ctx.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync()
+    sampler.start()
+    for i in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (untimed)
+        sync()
+        ev[i][0].record()
+        move()
+        prob.replay()
+        ev[i][1].record()
+    sync()
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    ctx.check()  # a capacity overflow in any replay would surface here
+    ms = [a.elapsed_time(b) for a, b in ev]
+    t_total = sum(ms) / 1e3
+    stats = prob.fetch_stats()
+    nnz_total = float(stats["nnz"])
+    cut_total = float(stats["cut"])
+    cells_total = float(stats["inside"] + stats["cut"] + stats["outside"])
+    active_total = float(stats["inside"] + stats["volume_rules"])
+
+    # ---- the same K steps with per-stage CUDA events recorded INSIDE the graph (a second capture with stage
+    # timing on): per-kernel durations for the roofline block, measured live on the stream the kernels run on
+    ctx.stage_timing(True)
+    ctx.stage_reset()
+    ctx.graph_begin()
+    try:
+        prob.step()
+    finally:
+        gt = ctx.graph_end()
+    agg = {}
+    for i in range(args.steps):
+        flush.zero_()
+        move()
+        gt.launch()
+        sync()
+        for name, msv, by in ctx.stages():
+            a = agg.setdefault(name, [0.0, 0.0, 0])
+            a[0] += msv
+            a[1] += by
+            a[2] += 1
+    gt.free()
+    ctx.stage_timing(False)
+    ctx.stage_reset()
+    # algorithmic bytes come from the exact sizes: one eager step with stage accounting (not timed)
+    ctx.set_deferred(False)
+    ctx.stage_timing(True)
+    move()
+    prob.step()
+    sync()
+    exact_bytes = {}
+    for name, msv, by in ctx.stages():
+        exact_bytes[name] = exact_bytes.get(name, 0.0) + by
+    ctx.stage_timing(False)
+    ctx.stage_reset()
+    ctx.set_deferred(True)
+    per_stage = {}
+    for k, v in agg.items():
+        msk = v[0] / args.steps
+        by = exact_bytes.get(k, 0.0)
+        per_stage[k] = {"ms_per_step": msk, "alg_GB_per_step": by / 1e9,
+                        "GBps": (by / 1e9) / (msk / 1e3) if msk > 0 else None}
+    stage_sum = sum(v["ms_per_step"] for k, v in per_stage.items()
+                    if k not in ("gather_matrix_clist_kernel", "gather_matrix_band_kernel", "gather_matrix_mask_kernel"))
+
+    # ---- end-to-end leg: host buffers in, host buffers out, through the public API
+    vals = pipe.phi.x.array
+    h_phi = torch.empty(vals.shape, dtype=torch.float64, pin_memory=True)
+    h_phi.copy_(vals)
+    sync()
+    hnd = ctx.handle
+    n_phi = int(vals.shape[0])  # the level set lives on the P1 vertex space
+    # re-bind level set 0 to the pinned host array: cfx_update (inside the graph) now does the H2D copy every step
+    check(hnd, lib().cfx_levelset_bind(hnd, 0, None, tdim + 1, 1, C.c_void_p(h_phi.data_ptr()), C.c_int64(n_phi), HOST,
+                                       1))
+    # Results leave through a copy stream into pinned host buffers, double-buffered: the device->host copy of step k
+    # (CSR pattern + values + rhs) overlaps the compute of step k+1; every step's inputs still arrive from the host
+    # and every step's results still reach it inside the timed region.  One graph per buffer set.
+    nnz_cap = int(stats["nnz"] * 1.3) + 4096
+    hb = [dict(vals=torch.empty(nnz_cap, dtype=torch.float64, pin_memory=True),
+               cols=torch.empty(nnz_cap, dtype=torch.int32, pin_memory=True),
+               rp=torch.empty(V.num_dofs + 1, dtype=torch.int64, pin_memory=True),
+               b=torch.empty(V.num_dofs, dtype=torch.float64, pin_memory=True)) for _ in range(2)]
+    As = [prob.A, _fem.MatrixCSR(ctx)]
+    bs = [prob.b, torch.empty_like(prob.b)]
+    graphs = []
+    for k in range(2):
+        prob.A, prob.b = As[k], bs[k]
+        graphs.append(prob.capture(margin=0.25))
+    side = torch.cuda.Stream()
+    done = [None, None]
+    kstep = [0]
+    d2h = [0]
+
+    def e2e_step():
+        k = kstep[0] % 2
+        kstep[0] += 1
+        if done[k] is not None:
+            torch.cuda.current_stream().wait_event(done[k])  # buffers of step k-2 have left the device
+        if "moving" in wl:  # the host owns the level set in this leg: new values are written into the pinned array
+            x0, dx, period = wl["moving"]
+            t = tstep[0] % (period + 1)
+            tstep[0] += 1
+            pipe.move_level_set((x0 + dx * t / period,) + tuple(prm[1:]))
+            h_phi.copy_(pipe.phi.x.array)
+        graphs[k].launch()
+        A = As[k]
+        A._cache.clear()
+        ready = torch.cuda.Event()
+        ready.record()
+        nnz = A.nnz  # the host needs the size of what it receives: the one round trip of the step
+        side.wait_event(ready)
+        A.copy_to_host_async(hb[k]["rp"], hb[k]["cols"], hb[k]["vals"], side)
+        with torch.cuda.stream(side):
+            hb[k]["b"].copy_(bs[k], non_blocking=True)
+            done[k] = torch.cuda.Event()
+            done[k].record()
+        d2h[0] = 12 * nnz + 8 * (V.num_dofs + 1) + 8 * V.num_dofs
+        return nnz
+
+    for _ in range(2):
+        e2e_step()
+    side.synchronize()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    for ev_done in done:
+        torch.cuda.current_stream().wait_event(ev_done)
+    e1.record()
+    sync()
+    side.synchronize()
+    ctx.check()
+    t_e2e = e0.elapsed_time(e1) / 1e3
+    h2d = 8.0 * n_phi
+
+    peak, peak_src = load_peaks()
+    # the roofline object describes ONE kernel: among the stages that time a single kernel (named *_kernel; the
+    # other stages are sequences of kernels) take the one with the largest live time
+    cand = {k: v for k, v in per_stage.items() if k.endswith("_kernel")} or per_stage
+    dom = max(cand.items(), key=lambda kv: kv[1]["ms_per_step"])
+    roof = {"bound": "hbm", "kernel": dom[0], "achieved": dom[1]["GBps"], "peak": peak, "unit": "GB/s",
+            "frac": (dom[1]["GBps"] or 0.0) / peak, "traffic": load_traffic(dom[0], n), "peak_source": peak_src,
+            "ms_per_launch": dom[1]["ms_per_step"], "alg_GB_per_launch": dom[1]["alg_GB_per_step"]}
+    line = {
+        "metric": "cut_cells_per_s", "value": cut_total * args.steps / t_total, "unit": "cut-cells/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_total / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["name"].format(n=n), "cells": int(cells_total), "cut_cells": int(cut_total),
+                   "active_cells": int(active_total), "nnz": int(nnz_total), "l2": "flushed between timed steps "
+                   "(256 MiB write); inputs 2.2 GB >> L2", "partition": "1 rank (no exchange)",
+                   "step": "one CUDA-graph launch per step (deferred sizes, no host round trip inside the step)"},
+        "nnz_per_s": nnz_total * args.steps / t_total, "total_cells_per_s": cells_total * args.steps / t_total,
+        "e2e": {"value": cut_total * args.steps / t_e2e, "unit": "cut-cells/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h[0]), "ms_per_step": t_e2e / args.steps * 1e3},
+        "gpu_launches": int(launches), "graph_launches_per_step": 1, "kernels_per_step": graph.kernel_nodes,
+        "clocks": clocks, "roofline": roof, "stages": per_stage, "stage_sum_ms": stage_sum, "setup": setup,
+    }
+    if not args.no_cpu_baseline:
+        # one step of the reference arm on the SAME configuration (bench.py --impl reference times K of them)
+        nb = args.ref_n or wl.get("ref_n") or n
+        nparts = reference_parts(nb, 1)
+        ref = CpuReference(wl, nb, nparts)
+        r = ref.step()
+        ref.close()
+        line["cpu_baseline"] = {
+            "value": r["cut"] / r["time"], "unit": "cut-cells/s", "cores": nparts, "kind": "port",
+            "sample": f"{'the whole workload' if nb == n else 'same workload at n=%d' % nb} ({r['cells']} cells, "
+                      f"{r['cut']} cut cells), one step as {nparts} serial slab processes; {r['time']:.2f} s; CPU "
+                      f"restatement of reference loops -- reference binary unavailable",
+            "total_cells_per_s": r["cells"] / r["time"], "nnz_per_s": r["nnz"] / r["time"]}
     print(json.dumps(line))
 
 
@@ -450,6 +682,8 @@ def main():
         if int(os.environ.get("RANK", "0")) != 0:
             return
         run_reference(args, wl)
+    elif int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        run_ours_graph(args, wl)
     else:
         run_ours(args, wl)
 

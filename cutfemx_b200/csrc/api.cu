@@ -255,7 +255,6 @@ cfx_status cfx_graph_begin(cfx_ctx* ctx)
   CFX_REQUIRE(ctx->deferred, CFX_ERR_STATE,
               "cfx_graph_begin: switch the context to deferred-size mode first (cfx_set_deferred) and run the step "
               "once, so that no captured call needs a size on the host");
-  CFX_REQUIRE(!ctx->timing, CFX_ERR_STATE, "cfx_graph_begin: disable stage timing before capturing");
   CFX_CUDA(cudaStreamSynchronize(ctx->stream));
   cudaStream_t cap = nullptr;
   CFX_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));

@@ -475,7 +475,9 @@ struct StageScope
     s.bytes = bytes;
     cudaEventCreate(&s.e0);
     cudaEventCreate(&s.e1);
-    cudaEventRecord(s.e0, c->stream);
+    // inside a graph capture an ordinary record would only mark a dependency; the external flag makes it a real
+    // event-record node, so every replay of the graph re-times the stage
+    cudaEventRecordWithFlags(s.e0, c->stream, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
     c->stages.push_back(s);
     idx = static_cast<int>(c->stages.size()) - 1;
   }
@@ -487,7 +489,8 @@ struct StageScope
   ~StageScope()
   {
     if (idx >= 0)
-      cudaEventRecord(c->stages[idx].e1, c->stream);
+      cudaEventRecordWithFlags(c->stages[idx].e1, c->stream,
+                               c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
   }
 };
 

@@ -1250,7 +1250,7 @@ static void add_cell_integral(cfx_ctx* ctx, cfx_form* f, int kernel, const int32
   f->dirty = true;
   if (I.d_n || (rules && rules->deferred))
     f->deferred = true;
-  if (!list && memspace == CFX_HOST)
+  if (!list && memspace == CFX_HOST && n_cells > 0) // the caller's host array was read by an asynchronous copy
     CFX_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
@@ -1296,7 +1296,7 @@ static void add_interior_facet_integral(cfx_ctx* ctx, cfx_form* f, int kernel, c
   f->dirty = true;
   if (I.d_n)
     f->deferred = true;
-  if (!list && memspace == CFX_HOST)
+  if (!list && memspace == CFX_HOST && n_facets > 0)
     CFX_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
