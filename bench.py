@@ -230,40 +230,76 @@ def run_reference(args, wl):
     print(json.dumps(line))
 
 
-# --------------------------------------------------------------------------------------------- our arm, one GPU
-def run_ours_graph(args, wl):
-    """N = 1: the whole step is ONE CUDA-graph launch (deferred sizes, no host round trip inside the step)."""
+# --------------------------------------------------------------------------------------------- our arm
+def run_ours(args, wl):
+    """The whole step of every rank is ONE CUDA-graph launch: deferred sizes (no host round trip inside the step)
+    and, for N > 1, the ghost exchange over NCCL inside the same graph (static exchange plan, cfx_xplan_*)."""
     import ctypes as C
 
     import torch
+    import torch.distributed as dist
 
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
     from cutfemx_b200 import fem as _fem
+    from cutfemx_b200 import mesh as M
     from cutfemx_b200 import parallel as P
     from cutfemx_b200._lib import HOST, check, lib
 
     n = args.n or wl["n"]
     tdim = wl["tdim"]
     kind, prm = wl["ls"]
-    sync = torch.cuda.synchronize
 
-    # ---- one-time setup (mesh-only data: geometry cache, facet-cell table, incidence, static pattern tables);
-    # reported next to ms_per_step, not inside it
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allsum(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
+    def allmax(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    # ---- one-time setup (mesh-only data: geometry cache, facet-cell table, incidence, static pattern tables, and
+    # for N > 1 the static exchange plan); reported next to ms_per_step, not inside it
     sync()
     t0 = time.perf_counter()
-    pipe = P.RankPipeline([n] * tdim, list(wl["p0"]), list(wl["p1"]), 1, 0, local_rank, kind, prm,
-                          order=wl["order"], degree=wl.get("degree", 1))
+    # strong scaling: the fixed n^tdim mesh is split into z-slabs (y-strips in 2D), one rank per GPU, with a
+    # shared-facet ghost layer; work-balanced cuts (the role of vertex weights in DOLFINx's graph partitioner):
+    # cut and inside cells cost ~40x an outside cell, and they cluster around the level set
+    ls_fn = M.sphere_level_set(prm[:3], prm[3]) if kind == "sphere" else M.torus_level_set(prm[:3], prm[3], prm[4])
+    ranges = P.slab_ranges(n, world, P.layer_weights([n] * tdim, wl["p0"], wl["p1"], ls_fn)) if world > 1 else None
+    pipe = P.RankPipeline([n] * tdim, list(wl["p0"]), list(wl["p1"]), world, rank, local_rank, kind, prm,
+                          order=wl["order"], ranges=ranges, degree=wl.get("degree", 1))
     prob, ctx, V = pipe.prob, pipe.ctx, pipe.V
     sync()
     t1 = time.perf_counter()
-    prob.step()  # first step: binds the space and the topology (static tables), allocates every buffer
+    if world > 1:
+        P.plan([pipe], P.TorchDistTransport(), static=True)
+        P.init_nccl(ctx, rank, world)
+    else:
+        pipe.xplan = None
+    prob.persistent = True
+    pipe.step_static()  # first step: binds the space and the topology (static tables), allocates every buffer
     sync()
     t2 = time.perf_counter()
-    setup = {"ms": (t2 - t0) * 1e3, "mesh_generation_and_bind_ms": (t1 - t0) * 1e3, "first_step_ms": (t2 - t1) * 1e3,
-             "what": "synthetic mesh generation on the device, cfx_mesh_bind (geometry cache), and the first step "
-                     "(cfx_topology_bind, cfx_space_bind: incidence, static pattern and contribution tables)"}
+    setup = {"ms": (t2 - t0) * 1e3, "mesh_generation_and_bind_ms": (t1 - t0) * 1e3,
+             "plan_and_first_step_ms": (t2 - t1) * 1e3,
+             "what": "synthetic mesh generation on the device, cfx_mesh_bind (geometry cache), static exchange plan "
+                     "(N > 1), and the first step (cfx_topology_bind, cfx_space_bind: incidence, static pattern and "
+                     "contribution tables)"}
 
     tstep = [0]
 
@@ -274,7 +310,8 @@ def run_ours_graph(args, wl):
             tstep[0] += 1
             pipe.move_level_set((x0 + dx * t / period,) + tuple(prm[1:]))
 
-    graph = prob.capture(margin=0.25)
+    hnd0 = ctx.handle
+    graph = pipe.capture_static(margin=0.25)
     setup["device_bytes"] = ctx.device_bytes
     for _ in range(max(args.warmup, 3)):
         move()
@@ -297,13 +334,20 @@ def run_ours_graph(args, wl):
     clocks = sampler.stop()
     launches = ctx.launch_count - launches0
     ctx.check()  # a capacity overflow in any replay would surface here
-    ms = [a.elapsed_time(b) for a, b in ev]
-    t_total = sum(ms) / 1e3
+    # per step: the slowest rank; then summed over the steps
+    t_total = sum(allmax([a.elapsed_time(b) for a, b in ev])) / 1e3
     stats = prob.fetch_stats()
-    nnz_total = float(stats["nnz"])
-    cut_total = float(stats["cut"])
-    cells_total = float(stats["inside"] + stats["cut"] + stats["outside"])
-    active_total = float(stats["inside"] + stats["volume_rules"])
+    no = pipe.imap.n_owned
+    nnz_owned = int(prob.A.indptr_device()[no].item())
+    # global checksums of the assembled system (owned rows): equal for every N, so the scaling run verifies the
+    # NCCL path against the N = 1 line
+    vals_owned = prob.A.values_device()[:nnz_owned]
+    cut_total, nnz_total, cells_total, active_total, launches_total, a_fro2, b_sum, b_abs = allsum(
+        [stats["cut"], nnz_owned, stats["inside"] + stats["cut"] + stats["outside"],
+         stats["inside"] + stats["volume_rules"], launches, float((vals_owned * vals_owned).sum()),
+         float(prob.b[:no].sum()), float(prob.b[:no].abs().sum())])
+    checks = {"nnz": int(nnz_total), "A_frobenius": a_fro2 ** 0.5, "b_sum": b_sum, "b_abs_sum": b_abs,
+              "cut_cells": int(cut_total)}
 
     # ---- the same K steps with per-stage CUDA events recorded INSIDE the graph (a second capture with stage
     # timing on): per-kernel durations for the roofline block, measured live on the stream the kernels run on
@@ -311,15 +355,16 @@ def run_ours_graph(args, wl):
     ctx.stage_reset()
     ctx.graph_begin()
     try:
-        prob.step()
+        pipe.step_static()
     finally:
         gt = ctx.graph_end()
     agg = {}
     for i in range(args.steps):
         flush.zero_()
         move()
-        gt.launch()
         sync()
+        gt.launch()
+        torch.cuda.synchronize()
         for name, msv, by in ctx.stages():
             a = agg.setdefault(name, [0.0, 0.0, 0])
             a[0] += msv
@@ -332,11 +377,15 @@ def run_ours_graph(args, wl):
     ctx.set_deferred(False)
     ctx.stage_timing(True)
     move()
-    prob.step()
+    pipe.step_static()
     sync()
-    exact_bytes = {}
+    exact_bytes, eager_ms = {}, {}
     for name, msv, by in ctx.stages():
         exact_bytes[name] = exact_bytes.get(name, 0.0) + by
+        eager_ms[name] = eager_ms.get(name, 0.0) + msv
+    cnt = (C.c_int64 * 4)()
+    lib().cfx_space_counters(hnd0, ctx.space_index(V), cnt)
+    space_counters = {"seen_slow_rows": cnt[0], "seen_noclist_rows": cnt[1], "cap_act_rows": cnt[2], "cap_band": cnt[3]}
     ctx.stage_timing(False)
     ctx.stage_reset()
     ctx.set_deferred(True)
@@ -346,14 +395,21 @@ def run_ours_graph(args, wl):
         by = exact_bytes.get(k, 0.0)
         per_stage[k] = {"ms_per_step": msk, "alg_GB_per_step": by / 1e9,
                         "GBps": (by / 1e9) / (msk / 1e3) if msk > 0 else None}
-    stage_sum = sum(v["ms_per_step"] for k, v in per_stage.items()
-                    if k not in ("gather_matrix_clist_kernel", "gather_matrix_band_kernel", "gather_matrix_mask_kernel"))
+    stage_sum = sum(v["ms_per_step"] for k, v in per_stage.items() if not k.endswith("_kernel"))
+    # load balance: every rank's own stage sum and the three stages that scale with its share of the mesh
+    mine = torch.tensor([stage_sum, per_stage.get("classify", {}).get("ms_per_step", 0.0),
+                         per_stage.get("gather_matrix", {}).get("ms_per_step", 0.0),
+                         per_stage.get("create_sparsity", {}).get("ms_per_step", 0.0)], dtype=torch.float64, device=dev)
+    per_rank = [mine.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, mine)
+    per_rank = [[round(float(v), 4) for v in t.tolist()] for t in per_rank]
 
     # ---- end-to-end leg: host buffers in, host buffers out, through the public API
     vals = pipe.phi.x.array
     h_phi = torch.empty(vals.shape, dtype=torch.float64, pin_memory=True)
     h_phi.copy_(vals)
-    sync()
+    torch.cuda.synchronize()
     hnd = ctx.handle
     n_phi = int(vals.shape[0])  # the level set lives on the P1 vertex space
     # re-bind level set 0 to the pinned host array: cfx_update (inside the graph) now does the H2D copy every step
@@ -372,7 +428,7 @@ def run_ours_graph(args, wl):
     graphs = []
     for k in range(2):
         prob.A, prob.b = As[k], bs[k]
-        graphs.append(prob.capture(margin=0.25))
+        graphs.append(pipe.capture_static(margin=0.25))
     side = torch.cuda.Stream()
     done = [None, None]
     kstep = [0]
@@ -384,10 +440,7 @@ def run_ours_graph(args, wl):
         if done[k] is not None:
             torch.cuda.current_stream().wait_event(done[k])  # buffers of step k-2 have left the device
         if "moving" in wl:  # the host owns the level set in this leg: new values are written into the pinned array
-            x0, dx, period = wl["moving"]
-            t = tstep[0] % (period + 1)
-            tstep[0] += 1
-            pipe.move_level_set((x0 + dx * t / period,) + tuple(prm[1:]))
+            move()
             h_phi.copy_(pipe.phi.x.array)
         graphs[k].launch()
         A = As[k]
@@ -418,222 +471,24 @@ def run_ours_graph(args, wl):
     sync()
     side.synchronize()
     ctx.check()
-    t_e2e = e0.elapsed_time(e1) / 1e3
-    h2d = 8.0 * n_phi
-
-    peak, peak_src = load_peaks()
-    # the roofline object describes ONE kernel: among the stages that time a single kernel (named *_kernel; the
-    # other stages are sequences of kernels) take the one with the largest live time
-    cand = {k: v for k, v in per_stage.items() if k.endswith("_kernel")} or per_stage
-    dom = max(cand.items(), key=lambda kv: kv[1]["ms_per_step"])
-    roof = {"bound": "hbm", "kernel": dom[0], "achieved": dom[1]["GBps"], "peak": peak, "unit": "GB/s",
-            "frac": (dom[1]["GBps"] or 0.0) / peak, "traffic": load_traffic(dom[0], n), "peak_source": peak_src,
-            "ms_per_launch": dom[1]["ms_per_step"], "alg_GB_per_launch": dom[1]["alg_GB_per_step"]}
-    line = {
-        "metric": "cut_cells_per_s", "value": cut_total * args.steps / t_total, "unit": "cut-cells/s",
-        "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_total / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["name"].format(n=n), "cells": int(cells_total), "cut_cells": int(cut_total),
-                   "active_cells": int(active_total), "nnz": int(nnz_total), "l2": "flushed between timed steps "
-                   "(256 MiB write); inputs 2.2 GB >> L2", "partition": "1 rank (no exchange)",
-                   "step": "one CUDA-graph launch per step (deferred sizes, no host round trip inside the step)"},
-        "nnz_per_s": nnz_total * args.steps / t_total, "total_cells_per_s": cells_total * args.steps / t_total,
-        "e2e": {"value": cut_total * args.steps / t_e2e, "unit": "cut-cells/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h[0]), "ms_per_step": t_e2e / args.steps * 1e3},
-        "gpu_launches": int(launches), "graph_launches_per_step": 1, "kernels_per_step": graph.kernel_nodes,
-        "clocks": clocks, "roofline": roof, "stages": per_stage, "stage_sum_ms": stage_sum, "setup": setup,
-    }
-    if not args.no_cpu_baseline:
-        # one step of the reference arm on the SAME configuration (bench.py --impl reference times K of them)
-        nb = args.ref_n or wl.get("ref_n") or n
-        nparts = reference_parts(nb, 1)
-        ref = CpuReference(wl, nb, nparts)
-        r = ref.step()
-        ref.close()
-        line["cpu_baseline"] = {
-            "value": r["cut"] / r["time"], "unit": "cut-cells/s", "cores": nparts, "kind": "port",
-            "sample": f"{'the whole workload' if nb == n else 'same workload at n=%d' % nb} ({r['cells']} cells, "
-                      f"{r['cut']} cut cells), one step as {nparts} serial slab processes; {r['time']:.2f} s; CPU "
-                      f"restatement of reference loops -- reference binary unavailable",
-            "total_cells_per_s": r["cells"] / r["time"], "nnz_per_s": r["nnz"] / r["time"]}
-    print(json.dumps(line))
-
-
-# --------------------------------------------------------------------------------------------- our arm
-def run_ours(args, wl):
-    import torch
-    import torch.distributed as dist
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-    dev = f"cuda:{local_rank}"
-
-    import ctypes as C
-
-    from cutfemx_b200 import parallel as P
-    from cutfemx_b200._lib import HOST, check, lib
-
-    n = args.n or wl["n"]
-    tdim = wl["tdim"]
-    kind, prm = wl["ls"]
-    # strong scaling: the fixed n^tdim mesh is split into z-slabs (y-strips in 2D), one rank per GPU, with a
-    # shared-facet ghost layer; ghost rows travel to their owners over NCCL every step
-    from cutfemx_b200 import mesh as M
-
-    ls_fn = M.sphere_level_set(prm[:3], prm[3]) if kind == "sphere" else M.torus_level_set(prm[:3], prm[3], prm[4])
-    # work-balanced slab cuts (the role of vertex weights in DOLFINx's graph partitioner): cut and inside cells
-    # cost ~40x an outside cell, and they cluster around the level set
-    ranges = P.slab_ranges(n, world, P.layer_weights([n] * tdim, wl["p0"], wl["p1"], ls_fn)) if world > 1 else None
-    pipe = P.RankPipeline([n] * tdim, list(wl["p0"]), list(wl["p1"]), world, rank, local_rank, kind, prm,
-                          order=wl["order"], ranges=ranges, degree=wl.get("degree", 1))
-    transport = P.TorchDistTransport() if world > 1 else P.LocalTransport(1)
-    P.plan([pipe], transport)
-    prob, ctx, V = pipe.prob, pipe.ctx, pipe.V
-
-    tstep = [0]
-
-    def step():
-        if "moving" in wl:  # the level set moves: new nodal values (device-resident), then the whole path
-            x0, dx, period = wl["moving"]
-            t = tstep[0] % (period + 1)
-            tstep[0] += 1
-            pipe.move_level_set((x0 + dx * t / period,) + tuple(prm[1:]))
-        st = P.run_step([pipe], transport)[0]
-        pipe.finish_step()
-        return st
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident leg ("value")
-    for _ in range(max(args.warmup, 3)):
-        stats = step()
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)  # 256 MiB > 126 MB L2
-    sampler = ClockSampler(local_rank)
-    ctx.stage_timing(True)
-    ctx.stage_reset()
-    launches0 = ctx.launch_count
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    sampler.start()
-    for i in range(args.steps):
-        flush.zero_()  # L2 flush between timed iterations (untimed)
-        barrier()
-        ev[i][0].record()
-        stats = step()
-        ev[i][1].record()
-    barrier()
-    clocks = sampler.stop()
-    launches = ctx.launch_count - launches0
-    ms = [a.elapsed_time(b) for a, b in ev]
-    # per step: the slowest rank; then summed over the steps
-    t_steps = torch.tensor(ms, dtype=torch.float64, device=dev) / 1e3
-    nnz_owned = int(prob.A.indptr_device()[pipe.imap.n_owned].item())
-    cnt = torch.tensor([stats["cut"], nnz_owned, stats["inside"] + stats["cut"] + stats["outside"],
-                        stats["inside"] + stats["volume_rules"], launches], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_steps, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    t_total = float(t_steps.sum().item())
-    cut_total, nnz_total, cells_total, active_total, launches_total = (float(v) for v in cnt.tolist())
-    stages = ctx.stages()
-    ctx.stage_timing(False)
-    ctx.stage_reset()
-
-    # ---- end-to-end leg: host buffers in, host buffers out, through the public API
-    vals = pipe.phi.x.array
-    h_phi = torch.empty(vals.shape, dtype=torch.float64, pin_memory=True)
-    h_phi.copy_(vals)
-    torch.cuda.synchronize()
-    hnd = ctx.handle
-    # re-bind level set 0 to the pinned host array: cfx_update now does the H2D copy every step
-    n_phi = int(vals.shape[0])  # the level set lives on the P1 vertex space
-    check(hnd, lib().cfx_levelset_bind(hnd, 0, None, tdim + 1, 1, C.c_void_p(h_phi.data_ptr()),
-                                       C.c_int64(n_phi), HOST, 1))
-    # Results leave through a copy stream into pinned host buffers, double-buffered: the device->host copy of
-    # step k (CSR pattern + values + rhs, ~1 GB) overlaps the compute of step k+1; every step's inputs still
-    # arrive from the host and every step's results still reach it inside the timed region.
-    from cutfemx_b200 import fem as _fem
-
-    nnz_cap = int(stats["nnz"] * 1.1) + 1024
-    hb = [dict(vals=torch.empty(nnz_cap, dtype=torch.float64, pin_memory=True),
-               cols=torch.empty(nnz_cap, dtype=torch.int32, pin_memory=True),
-               rp=torch.empty(V.num_dofs + 1, dtype=torch.int64, pin_memory=True),
-               b=torch.empty(V.num_dofs, dtype=torch.float64, pin_memory=True)) for _ in range(2)]
-    As = [prob.A, _fem.MatrixCSR(ctx)]
-    bs = [prob.b, torch.empty_like(prob.b)]
-    side = torch.cuda.Stream()
-    done = [None, None]
-    kstep = [0]
-
-    def e2e_step():
-        k = kstep[0] % 2
-        kstep[0] += 1
-        if done[k] is not None:
-            torch.cuda.current_stream().wait_event(done[k])  # buffers of step k-2 have left the device
-        prob.A, prob.b = As[k], bs[k]
-        st = P.run_step([pipe], transport)[0]
-        ready = torch.cuda.Event()
-        ready.record()
-        side.wait_event(ready)
-        prob.A.copy_to_host_async(hb[k]["rp"], hb[k]["cols"], hb[k]["vals"], side)
-        with torch.cuda.stream(side):
-            hb[k]["b"].copy_(prob.b, non_blocking=True)
-            done[k] = torch.cuda.Event()
-            done[k].record()
-        pipe.finish_step()
-        return st
-
-    for _ in range(2):
-        st = e2e_step()
-    side.synchronize()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        st = e2e_step()
-    for ev_done in done:
-        torch.cuda.current_stream().wait_event(ev_done)
-    e1.record()
-    barrier()
-    side.synchronize()
-    e2e = torch.tensor([e0.elapsed_time(e1) / 1e3, 8.0 * n_phi,
-                        12.0 * st["nnz"] + 8.0 * (V.num_dofs + 1) + 8.0 * V.num_dofs], dtype=torch.float64, device=dev)
-    if world > 1:
-        tmax = e2e[:1].clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e2e, op=dist.ReduceOp.SUM)
-        e2e[0] = tmax[0]
-    t_e2e, h2d, d2h = (float(v) for v in e2e.tolist())
-
-    # ---- per-stage summary (rank 0), roofline of the dominant kernel
-    agg = {}
-    for name, msv, by in stages:
-        a = agg.setdefault(name, [0.0, 0.0, 0])
-        a[0] += msv
-        a[1] += by
-        a[2] += 1
-    per_stage = {k: {"ms_per_step": v[0] / args.steps, "alg_GB_per_step": v[1] / args.steps / 1e9,
-                     "GBps": (v[1] / 1e9) / (v[0] / 1e3) if v[0] > 0 else None} for k, v in agg.items()}
-    peak, peak_src = load_peaks()
-    # the roofline object describes ONE kernel: among the stages that time a single kernel (named *_kernel; the
-    # other stages are sequences of kernels) take the one with the largest live time
-    cand = {k: v for k, v in per_stage.items() if k.endswith("_kernel")} or per_stage
-    dom = max(cand.items(), key=lambda kv: kv[1]["ms_per_step"])
-    roof = {"bound": "hbm", "kernel": dom[0], "achieved": dom[1]["GBps"], "peak": peak, "unit": "GB/s",
-            "frac": (dom[1]["GBps"] or 0.0) / peak, "traffic": load_traffic(dom[0], n), "peak_source": peak_src,
-            "ms_per_launch": dom[1]["ms_per_step"], "alg_GB_per_launch": dom[1]["alg_GB_per_step"]}
+    t_e2e = allmax([e0.elapsed_time(e1) / 1e3])[0]
+    h2d, d2h_total = allsum([8.0 * n_phi, float(d2h[0])])
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    peak, peak_src = load_peaks()
+    # the roofline object describes ONE kernel: among the stages that time a single kernel (named *_kernel; the
+    # other stages are sequences of kernels) take the one with the largest live time
+    cand = {k: v for k, v in per_stage.items() if k.endswith("_kernel")} or per_stage
+    dom = max(cand.items(), key=lambda kv: kv[1]["ms_per_step"])
+    roof = {"bound": "hbm", "kernel": dom[0], "achieved": dom[1]["GBps"], "peak": peak, "unit": "GB/s",
+            "frac": (dom[1]["GBps"] or 0.0) / peak,
+            # dram bytes of one launch from the committed ncu --set full capture: N = 1 only (no per-N capture)
+            "traffic": load_traffic(dom[0], n) if world == 1 else None, "peak_source": peak_src,
+            "ms_per_launch": dom[1]["ms_per_step"], "alg_GB_per_launch": dom[1]["alg_GB_per_step"],
+            "rank": 0}
     line = {
         "metric": "cut_cells_per_s", "value": cut_total * args.steps / t_total, "unit": "cut-cells/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_total / args.steps * 1e3,
@@ -642,15 +497,21 @@ def run_ours(args, wl):
                    "active_cells": int(active_total), "nnz": int(nnz_total), "l2": "flushed between timed steps "
                    "(256 MiB write); inputs 2.2 GB >> L2",
                    "partition": f"{world} work-balanced slabs along the last axis {pipe.ranges}, shared-facet ghost "
-                                f"layer, ghost rows exchanged over NCCL" if world > 1 else "1 rank (no exchange)"},
+                                f"layer, ghost rows exchanged over NCCL inside the step's graph (fixed-size messages)"
+                   if world > 1 else "1 rank (no exchange)",
+                   "step": "one CUDA-graph launch per rank and step (deferred sizes, no host round trip inside it)"},
         "nnz_per_s": nnz_total * args.steps / t_total, "total_cells_per_s": cells_total * args.steps / t_total,
         "e2e": {"value": cut_total * args.steps / t_e2e, "unit": "cut-cells/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e / args.steps * 1e3},
-        "gpu_launches": int(launches_total), "clocks": clocks, "roofline": roof, "stages": per_stage,
+                "d2h_bytes_per_step": int(d2h_total), "ms_per_step": t_e2e / args.steps * 1e3},
+        "gpu_launches": int(launches_total), "graph_launches_per_step": 1, "kernels_per_step": graph.kernel_nodes,
+        "clocks": clocks, "roofline": roof, "stages": per_stage, "stage_sum_ms": stage_sum, "setup": setup,
+        "checks": checks, "space_counters": space_counters,
+        "per_rank_ms": {"columns": ["stage_sum", "classify", "gather_matrix", "create_sparsity"], "ranks": per_rank},
+        "stages_one_eager_step_ms": {k: round(v, 4) for k, v in eager_ms.items()},
     }
     if world == 1 and not args.no_cpu_baseline:
         # one step of the reference arm on the SAME configuration (bench.py --impl reference times K of them)
-        nb = args.ref_n or n
+        nb = args.ref_n or wl.get("ref_n") or n
         nparts = reference_parts(nb, 1)
         ref = CpuReference(wl, nb, nparts)
         r = ref.step()
@@ -682,8 +543,6 @@ def main():
         if int(os.environ.get("RANK", "0")) != 0:
             return
         run_reference(args, wl)
-    elif int(os.environ.get("WORLD_SIZE", "1")) == 1:
-        run_ours_graph(args, wl)
     else:
         run_ours(args, wl)
 

@@ -44,7 +44,9 @@ SYMBOLS = [
     "cfx_set_bc", "cfx_meshgen_box", "cfx_meshgen_rectangle", "cfx_meshgen_level_set",
     "cfx_device_bytes", "cfx_set_deferred", "cfx_check", "cfx_graph_begin", "cfx_graph_end", "cfx_graph_launch",
     "cfx_graph_kernel_nodes", "cfx_graph_free", "cfx_facet_integration_rows_list", "cfx_form_add_cell_integral_list",
-    "cfx_form_add_interior_facet_integral_list",
+    "cfx_form_add_interior_facet_integral_list", "cfx_comm_unique_id", "cfx_comm_init", "cfx_comm_destroy",
+    "cfx_xplan_create", "cfx_xplan_free", "cfx_xplan_pack_pattern", "cfx_xplan_exchange", "cfx_xplan_insert_pattern",
+    "cfx_xplan_pack_values", "cfx_xplan_unpack_add", "cfx_xplan_buffer", "cfx_space_counters", "cfx_space_forget",
 ]
 
 
@@ -84,8 +86,12 @@ def lib():
         L.cfx_active_indicator_device_ptr.restype = C.c_void_p
         L.cfx_active_indicator_device_ptr.argtypes = [C.c_void_p, C.c_void_p]
         L.cfx_ctx_destroy.restype = None
+        L.cfx_comm_destroy.restype = None
+        L.cfx_comm_destroy.argtypes = [C.c_void_p]
+        L.cfx_comm_unique_id.argtypes = [C.c_void_p, C.c_char_p]
+        L.cfx_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_char_p]
         for name in ("cfx_list_free", "cfx_rules_free", "cfx_pattern_free", "cfx_form_free", "cfx_ecut_free",
-                     "cfx_graph_free"):
+                     "cfx_graph_free", "cfx_xplan_free"):
             getattr(L, name).restype = None
             getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
         _lib = L

@@ -187,6 +187,7 @@ void cfx_ctx_destroy(cfx_ctx* ctx)
     return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  cfx_comm_destroy(ctx);
   for (auto& l : ctx->ls)
     if (l.host_pinned && l.host_values)
       cudaHostUnregister(const_cast<double*>(l.host_values + l.pin_begin));
@@ -211,6 +212,33 @@ cfx_status cfx_sync(cfx_ctx* ctx)
 int64_t cfx_launch_count(const cfx_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int64_t cfx_device_bytes(const cfx_ctx* ctx) { return ctx ? static_cast<int64_t>(ctx->pool.total_bytes()) : 0; }
+
+// forget what earlier assemblies on this space needed (list capacities, launch decisions): the next eager steps
+// learn them again.  For callers that ran an untypical assembly, e.g. the all-cells / all-facets pattern behind a
+// static exchange plan, whose band is the whole mesh.
+cfx_status cfx_space_forget(cfx_ctx* ctx, int space)
+{
+  if (!ctx || space < 0 || space >= CFX_MAX_SPACES)
+    return CFX_ERR_INVALID;
+  cfx::Space& S = ctx->spaces[space];
+  S.cap_act_rows = S.cap_band = 0;
+  S.seen_slow_rows = S.seen_noclist_rows = -1;
+  return CFX_OK;
+}
+
+// what the deferred-size launch decisions of a space rest on (bench.py prints them): rows the fast gather paths could
+// not handle and static rows without a contribution list in the eager steps so far, learned list capacities
+cfx_status cfx_space_counters(const cfx_ctx* ctx, int space, int64_t out[4])
+{
+  if (!ctx || !out || space < 0 || space >= CFX_MAX_SPACES)
+    return CFX_ERR_INVALID;
+  const cfx::Space& S = ctx->spaces[space];
+  out[0] = S.seen_slow_rows;
+  out[1] = S.seen_noclist_rows;
+  out[2] = S.cap_act_rows;
+  out[3] = S.cap_band;
+  return CFX_OK;
+}
 
 // ---------------------------------------------------------------- deferred sizes and CUDA graphs
 cfx_status cfx_set_deferred(cfx_ctx* ctx, int on, double margin)

@@ -371,6 +371,8 @@ struct cfx_ctx
   double margin = 0.125;            // extra capacity given to size-dependent buffers (so later steps fit)
   bool capturing = false;           // between cfx_graph_begin and cfx_graph_end: synchronising is an error
   cudaStream_t user_stream = nullptr;
+  void* comm = nullptr;             // ncclComm_t of this rank (cfx_comm_init), one rank per GPU
+  int comm_rank = 0, comm_size = 1;
   // objects whose sizes were left on the device by captured calls: a replay of the graph makes them deferred again
   std::vector<cfx_list*> cap_lists;
   std::vector<cfx_rules*> cap_rules;

@@ -501,6 +501,151 @@ class MatrixExchange:
         return {q: int(p.numel()) for q, p in self.recv_pos.items()}
 
 
+# ----------------------------------------------------------------------------- static exchange plan
+def candidate_entries(indptr, indices, rows):
+    """Entries of the CSR rows `rows` (int64 tensor), row by row: (row of each entry, column of each entry,
+    offsets (len(rows) + 1) of each row's entries).  torch, any device; setup only."""
+    import torch
+
+    counts = indptr[rows + 1] - indptr[rows]
+    ptr = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=rows.device)
+    ptr[1:] = torch.cumsum(counts, 0)
+    total = int(ptr[-1])
+    flat = torch.repeat_interleave(indptr[rows] - ptr[:-1], counts, output_size=total) + \
+        torch.arange(total, device=rows.device)
+    rowrep = torch.repeat_interleave(rows, counts, output_size=total)
+    return rowrep, indices[flat].to(torch.int64), ptr
+
+
+def static_plan_tables(imap: IndexMap, send_rows, cand, recv_pairs, recv_vec_rows):
+    """Host logic of the static exchange plan of one rank (include/cutfemx_b200.h, cfx_xplan_create).
+
+    send_rows     {owner q: local ghost rows (ascending)}                       -- VectorExchange.send_sel
+    cand          {owner q: (ptr (len(rows)+1), local candidate columns)}       -- this rank's static ghost-row pattern
+    recv_pairs    {source q: int64 tensor [global rows ..., global cols ...]}   -- what the sources announced
+    recv_vec_rows {source q: local owned rows of q's ghost dofs, q's order}     -- VectorExchange.recv_pos
+
+    Returns the argument arrays of cfx_xplan_create (numpy) and the new ghost columns' global indices."""
+    import torch
+
+    neigh = sorted(set(send_rows) | set(recv_pairs) | set(recv_vec_rows))
+    dev = imap.l2g.device
+    z64 = torch.zeros(0, dtype=torch.int64, device=dev)
+    s_row_off, s_rows, s_ptr, s_cols = [0], [], [torch.zeros(1, dtype=torch.int64, device=dev)], []
+    for q in neigh:
+        rows = send_rows.get(q, z64)
+        ptr, cols = cand.get(q, (torch.zeros(rows.numel() + 1, dtype=torch.int64, device=dev), z64))
+        s_rows.append(rows)
+        s_ptr.append(ptr[1:] + s_ptr[-1][-1])
+        s_cols.append(cols)
+        s_row_off.append(s_row_off[-1] + int(rows.numel()))
+    r_ent_off, r_row, r_colg, r_row_off, r_vec = [0], [], [], [0], []
+    for q in neigh:
+        t = recv_pairs.get(q, z64).view(2, -1)
+        r_row.append(t[0] - imap.offset)
+        r_colg.append(t[1])
+        r_ent_off.append(r_ent_off[-1] + int(t.shape[1]))
+        v = recv_vec_rows.get(q, z64)
+        r_vec.append(v)
+        r_row_off.append(r_row_off[-1] + int(v.numel()))
+    rows = torch.cat(r_row) if r_row else z64
+    cg = torch.cat(r_colg) if r_colg else z64
+    if rows.numel() and bool(((rows < 0) | (rows >= imap.n_owned)).any()):
+        raise RuntimeError("received a matrix row this rank does not own")
+    cols = imap.global_to_local(cg) if cg.numel() else z64
+    new_globals = torch.unique(cg[cols < 0]) if cg.numel() else z64
+    if new_globals.numel():  # dofs this rank does not know: new ghost columns (ascending global index)
+        cols = torch.where(cols < 0, imap.n_total + torch.searchsorted(new_globals, cg), cols)
+    perm = torch.sort(rows, stable=True).indices if rows.numel() else z64
+    i32 = lambda t: np.ascontiguousarray(t.cpu().numpy().astype(np.int32))    # noqa: E731
+    i64 = lambda t: np.ascontiguousarray(t.cpu().numpy().astype(np.int64))    # noqa: E731
+    cat = lambda parts: torch.cat(parts) if parts else z64                    # noqa: E731
+    tables = dict(neigh=np.asarray(neigh, dtype=np.int32), s_row_off=np.asarray(s_row_off, dtype=np.int64),
+                  s_rows=i32(cat(s_rows)), s_ptr=i64(cat(s_ptr)), s_cols=i32(cat(s_cols)),
+                  r_ent_off=np.asarray(r_ent_off, dtype=np.int64), r_row=i32(rows), r_col=i32(cols), r_perm=i32(perm),
+                  r_row_off=np.asarray(r_row_off, dtype=np.int64), r_vec_row=i32(cat(r_vec)))
+    return tables, new_globals
+
+
+class StaticExchange:
+    """cfx_xplan of one rank: SparsityPattern::finalize + scatter_rev with fixed-size messages, all on the device."""
+
+    def __init__(self, ctx, space_index: int, tables, new_ghost_globals):
+        from ._lib import check, lib
+
+        self.ctx, self.tables, self.new_ghost_globals = ctx, tables, new_ghost_globals
+        self.neigh = [int(q) for q in tables["neigh"]]
+        self._h = C.c_void_p()
+        p = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+        t = tables
+        check(ctx.handle, lib().cfx_xplan_create(ctx.handle, space_index, len(self.neigh), p(t["neigh"]),
+                                                 p(t["s_row_off"]), p(t["s_rows"]), p(t["s_ptr"]), p(t["s_cols"]),
+                                                 p(t["r_ent_off"]), p(t["r_row"]), p(t["r_col"]), p(t["r_perm"]),
+                                                 p(t["r_row_off"]), p(t["r_vec_row"]), C.byref(self._h)))
+
+    def _call(self, fn, *args):
+        from ._lib import check, lib
+
+        check(self.ctx.handle, getattr(lib(), fn)(self.ctx.handle, self._h, *args))
+
+    def pack_pattern(self, a):
+        self._call("cfx_xplan_pack_pattern", a._h)
+
+    def insert_pattern(self, a):
+        self._call("cfx_xplan_insert_pattern", a._h)
+
+    def pack_values(self, A, b):
+        self._call("cfx_xplan_pack_values", A._h, C.c_void_p(b.data_ptr()) if b is not None else None)
+
+    def unpack_add(self, A, b):
+        self._call("cfx_xplan_unpack_add", A._h, C.c_void_p(b.data_ptr()) if b is not None else None)
+
+    def exchange(self, which: int):
+        """NCCL send/recv with every neighbour on the context's stream (cfx_comm_init first)."""
+        self._call("cfx_xplan_exchange", int(which))
+
+    def buffer(self, which: int, k: int):
+        """torch uint8 view of a message buffer (emulated transports)."""
+        from ._lib import check, device_view, lib
+
+        ptr, nb = C.c_void_p(), C.c_int64()
+        check(self.ctx.handle, lib().cfx_xplan_buffer(self.ctx.handle, self._h, which, k, C.byref(ptr), C.byref(nb)))
+        return device_view(ptr.value or 0, nb.value // 8, np.int64, self.ctx.device, self) if nb.value % 8 == 0 \
+            else device_view(ptr.value or 0, nb.value // 4, np.int32, self.ctx.device, self)
+
+    def free(self):
+        from ._lib import lib
+
+        if self._h:
+            lib().cfx_xplan_free(self.ctx.handle, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.free()
+        except Exception:
+            pass
+
+
+def init_nccl(ctx, rank: int, world: int, group=None):
+    """Give the context its own NCCL communicator: rank 0 makes the unique id, torch.distributed broadcasts it."""
+    import torch
+    import torch.distributed as dist
+
+    from ._lib import check, lib
+
+    uid = (C.c_char * 128)()
+    if rank == 0:
+        check(None, lib().cfx_comm_unique_id(uid, None))
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", ctx.device) if backend == "nccl" else torch.device("cpu")
+    t = torch.frombuffer(bytearray(bytes(uid)), dtype=torch.uint8).clone().to(dev)
+    dist.broadcast(t, 0, group=group)
+    raw = bytes(t.cpu().numpy().tobytes())
+    check(ctx.handle, lib().cfx_comm_init(ctx.handle, raw, rank, world, None))
+
+
 def coo_of_rows(indptr, indices, row_begin: int, n_rows: int, cuts=()):
     """(rows, cols) int64 of CSR rows [row_begin, n_rows) -- torch, any device.  `cuts`: extra row
     indices whose entry offsets (relative to row_begin) are returned too, fetched in the same
@@ -567,6 +712,7 @@ class RankPipeline:
         self.vx = VectorExchange(self.imap)
         self.mx = MatrixExchange(self.imap)
         self.Ag = None
+        self.xplan = None
         # slab neighbours send rows of different mesh planes: below-neighbour rows < above-neighbour rows
         lo, hi = self.ranges[rank]
         self.disjoint_sources = hi - lo >= 3
@@ -577,6 +723,103 @@ class RankPipeline:
 
     def plan_finish(self, recv):
         self.vx.finish(recv)
+
+    # ---- static exchange plan (once per partition): cfx_xplan
+    def static_begin(self):
+        """The static superset of this rank's ghost-row entries (every owned cell active, every owned interior
+        facet in the band) -> global (row, col) pairs for the owners."""
+        import torch
+
+        from . import fem as _fem
+        from ._lib import DEVICE, check, lib
+        from .cut import _List, _bind_topology, facet_integration_rows_device
+
+        self.xplan = None
+        if self.world == 1:
+            return {}
+        mesh, V, ctx, im = self.mesh, self.V, self.ctx, self.imap
+        dev = torch.device("cuda", ctx.device)
+        _bind_topology(mesh, ctx)
+        nct = int(mesh.x_dofmap.shape[0])
+        cells = torch.arange(nct, dtype=torch.int32, device=dev)
+        facets = _List(ctx)
+        check(ctx.handle, lib().cfx_interior_facets_for_cells(ctx.handle, C.c_void_p(cells.data_ptr()), C.c_int64(nct),
+                                                              DEVICE, 0, C.byref(facets._h)))
+        rows4 = facet_integration_rows_device(mesh, facets)
+        a = _fem.CutForm(V, 2)
+        a.add_cell_integral("laplace", cells[: mesh.num_cells_local].contiguous(), None, (1.0,))
+        a.add_interior_facet_integral("ghost_grad_jump", rows=rows4, constants=(1.0,))
+        Ag = _fem.create_ghost_row_pattern(a, im.n_owned)
+        rp, ci = Ag.indptr_device(), Ag.indices_device()
+        self._cand, sends = {}, {}
+        for q, sel in self.vx.send_sel.items():          # ghost rows owned by q, ascending
+            rowrep, cols, ptr = candidate_entries(rp, ci, sel)
+            self._cand[q] = (ptr, cols)
+            sends[q] = torch.stack([im.l2g[rowrep], im.l2g[cols]]).reshape(-1).contiguous()
+        torch.cuda.synchronize(dev)
+        a.free()
+        Ag.free()
+        rows4.free()
+        facets.free()
+        # that pattern had every row in the band: do not let it size the per-step lists
+        check(ctx.handle, lib().cfx_space_forget(ctx.handle, ctx.space_index(V)))
+        return sends
+
+    def static_finish(self, recv):
+        if self.world == 1:
+            return
+        tables, new_globals = static_plan_tables(self.imap, self.vx.send_sel, self._cand, recv, self.vx.recv_pos)
+        self._cand = None
+        sidx = self.ctx.space_index(self.V)
+        self.xplan = StaticExchange(self.ctx, sidx, tables, new_globals)
+
+    # per step with the static plan: every call below is asynchronous (and capturable in deferred-size mode)
+    def sphase_a(self):
+        a, L = self.prob.build_forms()
+        if self.xplan is not None:
+            self.xplan.pack_pattern(a)
+
+    def sphase_b(self):
+        a = self.prob.last["a"]
+        if self.xplan is not None:
+            self.xplan.insert_pattern(a)
+        stats = self.prob.assemble()
+        if self.xplan is not None:
+            self.xplan.pack_values(self.prob.A, self.prob.b)
+        return stats
+
+    def sphase_c(self):
+        if self.xplan is not None:
+            self.xplan.unpack_add(self.prob.A, self.prob.b)
+
+    def step_static(self):
+        """One step of this rank over NCCL (one process per GPU): no host round trip, no Python-side exchange."""
+        self.sphase_a()
+        if self.xplan is not None:
+            self.xplan.exchange(0)
+        stats = self.sphase_b()
+        if self.xplan is not None:
+            self.xplan.exchange(1)
+        self.sphase_c()
+        self.prob.release_step()
+        return stats
+
+    def capture_static(self, margin: float = 0.25):
+        """Record step_static as one CUDA graph (NCCL calls included): two eager steps, one deferred, capture."""
+        prob, ctx = self.prob, self.ctx
+        prob.persistent = True
+        ctx.set_deferred(False, margin)
+        for _ in range(2):
+            self.step_static()
+        ctx.set_deferred(True)
+        self.step_static()
+        ctx.check()
+        ctx.graph_begin()
+        try:
+            self.step_static()
+        finally:
+            prob.graph = ctx.graph_end()
+        return prob.graph
 
     def phase_a(self):
         from . import fem as _fem
@@ -658,7 +901,8 @@ class RankPipeline:
         rp, cols, vals = A.indptr, A.indices.astype(np.int64), A.data
         n_owned, n_total = self.imap.n_owned, self.imap.n_total
         l2g = self.imap.l2g.cpu().numpy()
-        extra = self.mx.new_ghost_globals.cpu().numpy() if self.mx.new_ghost_globals is not None else np.zeros(0, np.int64)
+        ng = self.xplan.new_ghost_globals if getattr(self, "xplan", None) is not None else self.mx.new_ghost_globals
+        extra = ng.cpu().numpy() if ng is not None else np.zeros(0, np.int64)
         colmap = np.concatenate([l2g, extra])
         e = int(rp[n_owned])
         rows = np.repeat(np.arange(n_owned), np.diff(rp[: n_owned + 1]))
@@ -678,9 +922,38 @@ def run_step(pipes, transport):
     return [o[1] for o in out]
 
 
-def plan(pipes, transport):
+def run_step_static(pipes):
+    """One step of ranks EMULATED on one GPU with the static plans: the kernels of the exchange are the product's
+    (cfx_xplan_*), only the transport is a device-to-device copy between the emulated ranks' message buffers."""
+    by_rank = {p.rank: p for p in pipes}
+
+    def transfer(which_send, which_recv):
+        for p in pipes:
+            if p.xplan is None:
+                continue
+            for k, q in enumerate(p.xplan.neigh):
+                dst = by_rank[q].xplan
+                src_buf = p.xplan.buffer(which_send, k)
+                if src_buf.numel():
+                    dst.buffer(which_recv, dst.neigh.index(p.rank)).copy_(src_buf)
+
+    for p in pipes:
+        p.sphase_a()
+    transfer(0, 1)
+    out = [p.sphase_b() for p in pipes]
+    transfer(2, 3)
+    for p in pipes:
+        p.sphase_c()
+    return out
+
+
+def plan(pipes, transport, static: bool = False):
     import torch
 
     recv = transport.exchange([p.plan_begin() for p in pipes], dtype=torch.int64)
     for p, r in zip(pipes, recv):
         p.plan_finish(r)
+    if static:
+        recv = transport.exchange([p.static_begin() for p in pipes], dtype=torch.int64)
+        for p, r in zip(pipes, recv):
+            p.static_finish(r)

@@ -78,6 +78,13 @@ int cfx_version(void);
 int64_t cfx_launch_count(const cfx_ctx* ctx);
 /* bytes of device memory the context holds (mesh mirrors, static tables, result buffers, cached blocks) */
 int64_t cfx_device_bytes(const cfx_ctx* ctx);
+/* diagnostics of a bound space: [0] rows the fast gather paths could not handle, [1] static rows without a contribution
+ * list (largest counts in the eager assemblies so far, -1 = none yet), [2], [3] learned capacities of the active-row
+ * and band-row lists.  A deferred-size step takes two launch decisions from [0] and [1] and verifies them on the
+ * device. */
+cfx_status cfx_space_counters(const cfx_ctx* ctx, int space, int64_t out[4]);
+/* forget them (after an untypical assembly such as the all-facets pattern behind a static exchange plan) */
+cfx_status cfx_space_forget(cfx_ctx* ctx, int space);
 
 /* ------------------------------------------------------------------ deferred sizes and CUDA graphs
  * The reference returns every intermediate result to the host (numpy arrays: locate_entities cut.cpp:877-924,
@@ -354,6 +361,51 @@ cfx_status cfx_deactivate_outside(cfx_ctx* ctx, cfx_pattern* A, const int32_t* i
  * when neighbours are applied in a fixed order. */
 cfx_status cfx_gather_f64(cfx_ctx* ctx, const double* src, const int64_t* index, int64_t n, double* dst);
 cfx_status cfx_scatter_add_f64(cfx_ctx* ctx, const double* src, const int64_t* index, int64_t n, double* dst);
+
+/* The same exchange without a size exchange, a host round trip or host code in the step (one rank per GPU over
+ * NCCL / NVLink).  DOLFINx renegotiates the ghost-row entries at every
+ * SparsityPattern::finalize(); here the ranks agree ONCE per partition on a static superset: for every ghost row
+ * the columns it can ever have (every cell active, every interior facet in the stabilisation band), translated by
+ * the owner to its own numbering (dofs it does not know become new ghost columns, as finalize() does).  Per step
+ * only fixed-size messages travel -- one bit per candidate ("in my pattern of this step"), then one double per
+ * candidate plus one per ghost vector entry -- so the calls below never synchronise and can be captured in the
+ * step's CUDA graph together with the rest of the step.
+ *
+ * cfx_comm_unique_id / cfx_comm_init: an NCCL communicator of the context's own (ncclGetUniqueId on one rank, the
+ * 128 bytes broadcast by the host program, ncclCommInitRank on every rank); `nccl_path` may be NULL (the libnccl
+ * the process has loaded, else libnccl.so.2).
+ *
+ * cfx_xplan_create (HOST arrays): neighbours in ascending rank order.
+ *   send side  -- s_row_off[k..k+1]: this rank's ghost rows owned by neighbour k (indices into s_rows, local row
+ *                 ids); s_ptr/s_cols: CSR of each row's candidate columns (local ids);
+ *   recv side  -- arrival order = neighbour by neighbour, each neighbour's entries in ITS s_ptr/s_cols order:
+ *                 r_ent_off[k..k+1] entries of neighbour k, r_row/r_col their local (row, column) here (a column
+ *                 >= the space's owned+ghost dof count is a new ghost column), r_perm the arrival indices sorted by
+ *                 (row, arrival); r_row_off / r_vec_row: the neighbour's ghost rows as local owned rows (vector
+ *                 entries). */
+typedef struct cfx_xplan cfx_xplan;
+cfx_status cfx_comm_unique_id(void* out128, const char* nccl_path);
+cfx_status cfx_comm_init(cfx_ctx* ctx, const void* unique_id128, int rank, int n_ranks, const char* nccl_path);
+void cfx_comm_destroy(cfx_ctx* ctx);
+cfx_status cfx_xplan_create(cfx_ctx* ctx, int space, int n_neigh, const int32_t* neigh_ranks, const int64_t* s_row_off,
+                            const int32_t* s_rows, const int64_t* s_ptr, const int32_t* s_cols, const int64_t* r_ent_off,
+                            const int32_t* r_row, const int32_t* r_col, const int32_t* r_perm, const int64_t* r_row_off,
+                            const int32_t* r_vec_row, cfx_xplan** out);
+void cfx_xplan_free(cfx_ctx* ctx, cfx_xplan* plan);
+/* SparsityPattern::finalize(): sender half (bits of this step's ghost-row entries of form a), the exchange
+ * (which = 0), owner half (the received bits become the form's inserted entries, on the device).  Call before
+ * cfx_create_sparsity(a). */
+cfx_status cfx_xplan_pack_pattern(cfx_ctx* ctx, cfx_xplan* plan, const cfx_form* a);
+cfx_status cfx_xplan_exchange(cfx_ctx* ctx, cfx_xplan* plan, int which /* 0 pattern bits, 1 values */);
+cfx_status cfx_xplan_insert_pattern(cfx_ctx* ctx, cfx_xplan* plan, cfx_form* a);
+/* MatrixCSR::scatter_rev() + Vector::scatter_rev(add) after assembly (demo_poisson.py:52,54): pack the ghost-row
+ * values of A and the ghost entries of b (b may be NULL), exchange (which = 1), add on the owner -- neighbour by
+ * neighbour in rank order, no atomics, bit-reproducible. */
+cfx_status cfx_xplan_pack_values(cfx_ctx* ctx, cfx_xplan* plan, const cfx_pattern* A, const double* b);
+cfx_status cfx_xplan_unpack_add(cfx_ctx* ctx, cfx_xplan* plan, cfx_pattern* A, double* b);
+/* message buffers of neighbour k for transports other than NCCL (ranks emulated on one GPU in the tests):
+ * which = 0 bits to send, 1 bits received, 2 values to send, 3 values received */
+cfx_status cfx_xplan_buffer(cfx_ctx* ctx, const cfx_xplan* plan, int which, int k, void** ptr, int64_t* bytes);
 
 /* ------------------------------------------------------------------ profiling hooks
  * per-stage CUDA-event timings of the most recent calls, for bench.py's roofline block.

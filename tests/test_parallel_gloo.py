@@ -295,3 +295,188 @@ def test_gloo_world_size_2_matches_serial(shape, tmp_path):
         d = np.load(tmp_path / f"part{rank}.npz")
         parts.append((d["rows"], d["cols"], d["vals"], d["b"], int(d["off"])))
     compare_with_serial(parts, shape)
+
+
+# ----------------------------------------------------------------------------- static exchange plan (cfx_xplan)
+class StaticOracleRank(OracleRank):
+    """The fixed-size protocol of cfx_xplan_* (csrc/exchange.cu) with the oracle doing the local work and numpy
+    doing what the exchange kernels do: ghost_bits_kernel, expand_entries_kernel, pack_values_kernel,
+    unpack_values_kernel.  The tables come from the product's host logic (parallel.static_plan_tables)."""
+
+    def static_begin(self):
+        mesh, V, im = self.mesh, self.V, self.imap
+        if self.world == 1:
+            return {}
+        nct = mesh.x_dofmap.shape[0]
+        facets = O.interior_facets_for_cells(mesh, np.arange(nct, dtype=np.int32))
+        rp, cols = O.sparsity(V, np.arange(mesh.num_cells_local, dtype=np.int32), O.facet_rows(mesh, facets),
+                              insert_diagonal=False)
+        rp, cols = torch.from_numpy(rp.astype(np.int64)), torch.from_numpy(cols.astype(np.int32))
+        self._cand, sends = {}, {}
+        for q, sel in self.vx.send_sel.items():
+            rowrep, c, ptr = P.candidate_entries(rp, cols, sel)
+            self._cand[q] = (ptr, c)
+            sends[q] = torch.stack([im.l2g[rowrep], im.l2g[c]]).reshape(-1).contiguous()
+        return sends
+
+    def static_finish(self, recv):
+        if self.world == 1:
+            self.t = None
+            return
+        self.t, self.new_globals = P.static_plan_tables(self.imap, self.vx.send_sel, self._cand, recv, self.vx.recv_pos)
+
+    # -- per step
+    def _local(self):
+        mesh, V, phi = self.mesh, self.V, self.phi
+        nco = mesh.num_cells_local
+        dom = O.classify(V.dofmap, phi)
+        self.inside = O.locate(dom[:nco], "phi<0")
+        self.rv = O.runtime_quadrature(mesh, V.dofmap, phi, dom, "<", ORDER)
+        self.ri = O.runtime_quadrature(mesh, V.dofmap, phi, dom, "=", ORDER)
+        self.ri.normals = O.normals(mesh, V.dofmap, 1, phi, self.ri)
+        ghost = O.ghost_penalty_facets(mesh, O.locate(dom, "phi=0"), O.locate(dom, "phi<0"))
+        self.rows4 = O.facet_rows(mesh, ghost)
+        self.active = np.concatenate([self.inside, self.rv.parent_map])
+
+    def step_a(self):
+        """-> {neighbour: bit array of its candidates} (what ghost_bits_kernel writes)."""
+        self._local()
+        if self.t is None:
+            return {}
+        t = self.t
+        rp, cols = O.sparsity(self.V, self.active, self.rows4, insert_diagonal=False)
+        pat = sp.csr_matrix((np.ones(cols.size), cols, rp), shape=(self.V.num_dofs,) * 2)
+        erow = np.repeat(t["s_rows"], np.diff(t["s_ptr"]))
+        self.s_bits = np.asarray(pat[erow, t["s_cols"]]).ravel() > 0 if erow.size else np.zeros(0, bool)
+        out = {}
+        for k, q in enumerate(t["neigh"]):
+            e0, e1 = t["s_ptr"][t["s_row_off"][k]], t["s_ptr"][t["s_row_off"][k + 1]]
+            out[int(q)] = torch.from_numpy(self.s_bits[e0:e1].astype(np.int64))
+        return out
+
+    def step_b(self, recv_bits):
+        """insert the announced entries, assemble, -> {neighbour: values of its candidates ++ ghost vector entries}."""
+        V, t = self.V, self.t
+        rp, cols = O.sparsity(V, self.active, self.rows4)
+        n, ncols = V.num_dofs, V.num_dofs
+        pat = sp.csr_matrix((np.ones(cols.size), cols, rp), shape=(n, n))
+        if t is not None:
+            self.r_bits = np.zeros(t["r_row"].size, bool)
+            for k, q in enumerate(t["neigh"]):
+                if int(q) in recv_bits:
+                    self.r_bits[t["r_ent_off"][k]:t["r_ent_off"][k + 1]] = recv_bits[int(q)].numpy() > 0
+            sel = t["r_perm"][self.r_bits[t["r_perm"]]]          # insertion order: ascending rows
+            xr, xc = t["r_row"][sel], t["r_col"][sel]
+            assert np.all(np.diff(xr) >= 0)
+            ncols += int(self.new_globals.numel())
+            pat = sp.csr_matrix((pat.data, pat.indices, pat.indptr), shape=(n, ncols))
+            if xr.size:
+                pat = pat + sp.csr_matrix((np.ones(xr.size), (xr, xc)), shape=(n, ncols))
+        pat.sort_indices()
+        self.row_ptr, self.cols = pat.indptr.astype(np.int64), pat.indices.astype(np.int32)
+        self.vals = np.zeros(self.cols.size)
+        O.assemble_cells(V, "laplace", self.vals, self.inside, self.rv, (1.0,), self.row_ptr, self.cols)
+        O.assemble_cells(V, "nitsche", self.vals, None, self.ri, (GAMMA,), self.row_ptr, self.cols)
+        O.assemble_interior_facets(V, "ghost_grad_jump", self.vals, self.rows4, (GAMMA_G,), self.row_ptr, self.cols)
+        self.b = np.zeros(n)
+        O.assemble_cells(V, "source", self.b, self.inside, self.rv, (F_VALUE,))
+        O.assemble_cells(V, "nitsche_rhs", self.b, None, self.ri, (GAMMA, G_VALUE))
+        if t is None:
+            return {}
+        A = sp.csr_matrix((self.vals, self.cols, self.row_ptr), shape=(n, ncols))
+        erow = np.repeat(t["s_rows"], np.diff(t["s_ptr"]))
+        v = np.where(self.s_bits, np.asarray(A[erow, t["s_cols"]]).ravel(), 0.0) if erow.size else np.zeros(0)
+        out = {}
+        for k, q in enumerate(t["neigh"]):
+            r0, r1 = t["s_row_off"][k], t["s_row_off"][k + 1]
+            e0, e1 = t["s_ptr"][r0], t["s_ptr"][r1]
+            out[int(q)] = torch.from_numpy(np.concatenate([v[e0:e1], self.b[t["s_rows"][r0:r1]]]))
+        return out
+
+    def step_c(self, recv_vals):
+        t = self.t
+        if t is None:
+            return
+        for k, q in enumerate(t["neigh"]):                     # fixed neighbour order
+            if int(q) not in recv_vals:
+                continue
+            msg = recv_vals[int(q)].numpy()
+            e0, e1 = t["r_ent_off"][k], t["r_ent_off"][k + 1]
+            for j in np.nonzero(self.r_bits[e0:e1])[0]:
+                r, c = t["r_row"][e0 + j], t["r_col"][e0 + j]
+                seg = self.cols[self.row_ptr[r]:self.row_ptr[r + 1]]
+                p = int(np.searchsorted(seg, c))
+                assert p < seg.size and seg[p] == c
+                self.vals[self.row_ptr[r] + p] += msg[j]
+            i0, i1 = t["r_row_off"][k], t["r_row_off"][k + 1]
+            self.b[t["r_vec_row"][i0:i1]] += msg[e1 - e0:]
+
+    def owned_global(self):
+        no, off = self.imap.n_owned, self.imap.offset
+        extra = self.new_globals.numpy() if self.t is not None else np.zeros(0, np.int64)
+        colmap = np.concatenate([self.imap.l2g.numpy(), extra])
+        e = int(self.row_ptr[no])
+        rows = np.repeat(np.arange(no), np.diff(self.row_ptr[: no + 1])) + off
+        return rows, colmap[self.cols[:e]], self.vals[:e], self.b[:no], off
+
+
+def run_static_ranks(ranks, transport, steps=1):
+    recv = transport.exchange([r.vx.begin() for r in ranks], dtype=torch.int64)
+    for r, rc in zip(ranks, recv):
+        r.vx.finish(rc)
+    recv = transport.exchange([r.static_begin() for r in ranks], dtype=torch.int64)
+    for r, rc in zip(ranks, recv):
+        r.static_finish(rc)
+    for _ in range(steps):  # per step: two exchanges whose sizes are fixed by the plan
+        recv = transport.exchange([r.step_a() for r in ranks], dtype=torch.int64)
+        sends = [r.step_b(rc) for r, rc in zip(ranks, recv)]
+        recv = transport.exchange(sends, dtype=torch.float64)
+        for r, rc in zip(ranks, recv):
+            r.step_c(rc)
+
+
+@pytest.mark.parametrize("shape,world", [((8, 8, 8), 2), ((6, 6, 9), 3), ((16, 16), 2), ((6, 6, 16), 8)])
+def test_static_plan_protocol_matches_serial(shape, world):
+    ranks = [StaticOracleRank(shape, world, r) for r in range(world)]
+    run_static_ranks(ranks, P.LocalTransport(world))
+    compare_with_serial([r.owned_global() for r in ranks], shape)
+    # the static candidate set really is a superset, and this step uses only part of it
+    used = sum(int(r.s_bits.sum()) for r in ranks if r.t is not None)
+    total = sum(int(r.s_bits.size) for r in ranks if r.t is not None)
+    assert 0 < used < total
+
+
+def _static_worker(rank, world, shape, port, outdir):
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        r = StaticOracleRank(shape, world, rank)
+        run_static_ranks([r], P.TorchDistTransport())
+        rows, cols, vals, b, off = r.owned_global()
+        np.savez(os.path.join(outdir, f"part{rank}.npz"), rows=rows, cols=cols, vals=vals, b=b, off=off)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_static_plan_gloo_world_size_2_matches_serial(tmp_path):
+    import socket
+
+    import torch.multiprocessing as mp
+
+    shape = (8, 8, 8)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    O.build()
+    mp.spawn(_static_worker, args=(2, shape, port, str(tmp_path)), nprocs=2, join=True)
+    parts = []
+    for rank in range(2):
+        d = np.load(tmp_path / f"part{rank}.npz")
+        parts.append((d["rows"], d["cols"], d["vals"], d["b"], int(d["off"])))
+    compare_with_serial(parts, shape)

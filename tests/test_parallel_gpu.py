@@ -88,3 +88,90 @@ def test_two_gpus_nccl_match_serial(tmp_path, built_lib):
         d = np.load(tmp_path / f"part{rank}.npz")
         parts.append((d["rows"], d["cols"], d["vals"], d["b"], int(d["off"])))
     compare_with_serial(parts, shape)
+
+
+# ----------------------------------------------------------------------------- static exchange plan (cfx_xplan_*)
+@pytest.mark.parametrize("shape,world", [((8, 8, 8), 2), ((6, 6, 9), 3), ((16, 16), 2), ((12, 10, 16), 4), ((6, 6, 16), 8)])
+def test_static_plan_emulated_ranks_match_serial(shape, world, built_lib):
+    """Fixed-size bit / value messages, inserted entries expanded on the device, pack / unpack-add kernels; the
+    transport between the ranks emulated on one GPU is a device copy of the message buffers.  Then the same step with
+    deferred sizes: bit-identical."""
+    from cutfemx_b200 import parallel as P
+
+    pipes = make_pipes(shape, world, [0] * world)
+    P.plan(pipes, P.LocalTransport(world), static=True)
+    for p in pipes:
+        p.prob.persistent = True
+        p.ctx.set_deferred(False, 0.25)
+    P.run_step_static(pipes)
+
+    def parts():
+        for p in pipes:
+            p.prob.A._cache.clear()
+        return [p.owned_matrix_global() for p in pipes]
+
+    ref = parts()
+    compare_with_serial(ref, shape)
+    for p in pipes:
+        p.finish_step()
+    P.run_step_static(pipes)
+    for p in pipes:
+        p.finish_step()
+        p.ctx.set_deferred(True)
+    P.run_step_static(pipes)            # nothing reaches the host in this step
+    for p in pipes:
+        p.finish_step()
+        p.ctx.check()
+    for a, b in zip(parts(), ref):
+        for x, y in zip(a[:4], b[:4]):
+            assert np.array_equal(x, y)
+
+
+def _nccl_static_worker(rank, world, shape, port, outdir):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    try:
+        from cutfemx_b200 import parallel as P
+
+        p0, p1 = box(len(shape))
+        pipe = P.RankPipeline(shape, p0, p1, world, rank, rank, level_set(len(shape)), None, **KW)
+        P.plan([pipe], P.TorchDistTransport(), static=True)
+        P.init_nccl(pipe.ctx, rank, world)
+        g = pipe.capture_static()       # eager, deferred and captured steps, NCCL inside the graph
+        for _ in range(2):
+            pipe.prob.replay()
+        pipe.ctx.check()
+        pipe.prob.A._cache.clear()
+        rows, cols, vals, b, off = pipe.owned_matrix_global()
+        np.savez(os.path.join(outdir, f"part{rank}.npz"), rows=rows, cols=cols, vals=vals, b=b, off=off,
+                 nodes=g.kernel_nodes)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape", [(8, 8, 8), (24, 24)])
+def test_two_gpus_static_plan_graph_match_serial(shape, tmp_path, built_lib):
+    import socket
+
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_nccl_static_worker, args=(2, shape, port, str(tmp_path)), nprocs=2, join=True)
+    parts = []
+    for rank in range(2):
+        d = np.load(tmp_path / f"part{rank}.npz")
+        parts.append((d["rows"], d["cols"], d["vals"], d["b"], int(d["off"])))
+    compare_with_serial(parts, shape)
