@@ -24,6 +24,7 @@
 // Roofline: HBM for P1/P2 scalar forms (SURVEY.md section 8d "K4", "K5").
 #include <algorithm>
 
+#include <type_traits>
 #include "common.cuh"
 #include "element.cuh"
 
@@ -848,6 +849,7 @@ struct GatherCtx
   const int32_t* mat_slot;
   const double* Ae;
   const double* geo; // static per-cell geometry records (element.cuh GeoRec)
+  const double* lrow; // P1: static Laplace tensor rows, 4 doubles per (cell, local dof) (cfx_ctx::lrow); else null
   const int64_t* frow_ptr;
   const uint64_t* fclist;
   const int32_t* c2f;
@@ -1039,6 +1041,52 @@ __device__ __forceinline__ void std_row_values(const StdTab& st, const Geo<TDIM>
   }
 }
 
+// P1: the 32-byte record of (cell, li) -- off-diagonal Laplace entries (ascending j != li) and |detJ|
+struct P1Rec
+{
+  double a[4];
+};
+__device__ __forceinline__ P1Rec load_p1rec(const double* __restrict__ lrow, int64_t c, int nd, int li)
+{
+  P1Rec r;
+  const double* p = lrow + (c * nd + li) * 4;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a[0]), "=d"(r.a[1]), "=d"(r.a[2]), "=d"(r.a[3]) : "l"(p));
+  return r;
+}
+// row li of the summed standard-cell tensor from the record (same table lookup of the coefficients as
+// std_row_values): Laplace off-diagonals scaled, diagonal = -(their sum), mass from |detJ|
+template <int TDIM>
+__device__ __forceinline__ void p1_row_from_rec(const StdTab& st, const P1Rec& rec, unsigned fl, int li,
+                                                double (&v)[TDIM + 1])
+{
+  constexpr int ND = TDIM + 1;
+  const unsigned m = fl >> 2;
+  const double w = st.t0[m];
+  double dsum = 0.0;
+#pragma unroll
+  for (int j = 0; j < ND; ++j)
+  {
+    // slot of column j among the off-diagonals: j for j < li, j - 1 for j > li
+    double o = 0.0;
+#pragma unroll
+    for (int q = 0; q < ND - 1; ++q)
+      o = ((q < li ? q : q + 1) == j) ? rec.a[q] : o;
+    const double t = w * o;
+    dsum += (j == li) ? 0.0 : t;
+    v[j] += (j == li) ? 0.0 : t;
+  }
+#pragma unroll
+  for (int j = 0; j < ND; ++j)
+    v[j] -= (j == li) ? dsum : 0.0;
+  if (st.has_mass)
+  { // int lam_i lam_j = |T| (1 + delta_ij) / ((tdim+1)(tdim+2))
+    const double wm = st.t1[m] * rec.a[3] * (TDIM == 3 ? 1.0 / 120.0 : 1.0 / 24.0);
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+      v[j] += (j == li) ? 2.0 * wm : wm;
+  }
+}
+
 template <int TDIM, int DEG>
 __device__ __forceinline__ void cell_row_values(const GatherCtx& gc, const StdTab& st, int64_t c, unsigned fl, int li,
                                                 double (&v)[Elem<TDIM, DEG>::ND])
@@ -1049,9 +1097,26 @@ __device__ __forceinline__ void cell_row_values(const GatherCtx& gc, const StdTa
     v[j] = 0.0;
   if (fl >> 2)
   {
-    Geo<TDIM> g;
-    load_geo_cached<TDIM>(gc.geo, c, g);
-    std_row_values<TDIM, DEG>(st, g, fl, li, v);
+    if constexpr (DEG == 1)
+    {
+      if (gc.lrow != nullptr)
+      {
+        const P1Rec rec = load_p1rec(gc.lrow, c, ND, li);
+        p1_row_from_rec<TDIM>(st, rec, fl, li, v);
+      }
+      else
+      {
+        Geo<TDIM> g;
+        load_geo_cached<TDIM>(gc.geo, c, g);
+        std_row_values<TDIM, DEG>(st, g, fl, li, v);
+      }
+    }
+    else
+    {
+      Geo<TDIM> g;
+      load_geo_cached<TDIM>(gc.geo, c, g);
+      std_row_values<TDIM, DEG>(st, g, fl, li, v);
+    }
   }
   if (fl & 1)
   {
@@ -1600,8 +1665,19 @@ struct alignas(16) ClistRow
   int64_t ib, rb, fb, pad2;
 };
 
+// resident blocks per SM: the P1 kernel keeps 4-double tensor-row records (not 10-double geometry records) in its
+// pipeline registers, which fits five blocks of four warps without spilling
+#ifndef CFX_CLIST_BLOCKS_P1
+#define CFX_CLIST_BLOCKS_P1 5
+#endif
+template <int DEG>
+constexpr int clist_blocks_per_sm()
+{
+  return DEG == 1 ? CFX_CLIST_BLOCKS_P1 : 4;
+}
+
 template <int TDIM, int DEG, bool FUSED>
-__global__ void __launch_bounds__(GWC * 32, 4)
+__global__ void __launch_bounds__(GWC * 32, clist_blocks_per_sm<DEG>())
     gather_matrix_clist_kernel(GatherCtx gc, StdTab st, StdTab stL, const int32_t* __restrict__ act_rows, DN n_act_,
                                 const uint8_t* __restrict__ row_fast, const uint32_t* __restrict__ Rrow,
                                 const int64_t* __restrict__ row_ptr, double* __restrict__ vals, int zero_first)
@@ -1689,11 +1765,17 @@ __global__ void __launch_bounds__(GWC * 32, 4)
     c.old = (c.ok && kept && !zero_first) ? *c.pv : 0.0;
     return c;
   };
-  auto stageD = [&](const RowC& c, Geo<TDIM>& g) -> ClistD
+  // per-cell record of level D: P1 -- the 32-byte tensor-row record of (cell, li) (one sector, read by this row
+  // only); otherwise the geometry record
+  using CellRec = typename std::conditional<DEG == 1, P1Rec, Geo<TDIM>>::type;
+  auto stageD = [&](const RowC& c, CellRec& g) -> ClistD
   {
     ClistD d;
     d.fl = (c.ok && lane < c.n_inc) ? gc.cell_flags[c.c] : 0u;
-    load_geo_cached<TDIM>(gc.geo, c.c, g);
+    if constexpr (DEG == 1)
+      g = load_p1rec(gc.lrow, c.c, ND, c.li);
+    else
+      load_geo_cached<TDIM>(gc.geo, c.c, g);
     d.ms = __ldg(gc.mat_slot + c.c);
     return d;
   };
@@ -1711,13 +1793,13 @@ __global__ void __launch_bounds__(GWC * 32, 4)
     const L1 n1 = load1(chunk + cstride);
     const int nk = min(32, n_rows - chunk * 32);
     RowC c0 = stageC(buf, 0, nk), c1 = stageC(buf, 1, nk);
-    Geo<TDIM> g0;
+    CellRec g0;
     ClistD d0 = stageD(c0, g0);
     ClistRow nq = load2(n1);
 #pragma unroll 2
     for (int k = 0; k < nk; ++k)
     {
-      Geo<TDIM> g1;
+      CellRec g1;
       const ClistD d1 = stageD(c1, g1);
       const RowC c2 = stageC(buf, k + 2, nk);
       if (c0.ok)
@@ -1733,10 +1815,17 @@ __global__ void __launch_bounds__(GWC * 32, 4)
         {
           if (fl >> 2)
           {
-            std_row_values<TDIM, DEG>(st, g0, fl, c0.li, v);
+            if constexpr (DEG == 1)
+              p1_row_from_rec<TDIM>(st, g0, fl, c0.li, v);
+            else
+              std_row_values<TDIM, DEG>(st, g0, fl, c0.li, v);
             if constexpr (FUSED)
             {
-              const double s = fabs(g0.detJ);
+              double s;
+              if constexpr (DEG == 1)
+                s = g0.a[3];
+              else
+                s = fabs(g0.detJ);
               if constexpr (DEG == 1)
                 e += stL.t0[fl >> 2] * s * (TDIM == 3 ? 1.0 / 24.0 : 1.0 / 6.0);
               else if (stL.ref != nullptr)
@@ -2672,6 +2761,66 @@ void launch_facet(cfx_ctx* c, const cfx_integral& I, cfx_form* f, bool accumulat
   }
 }
 
+// cfx_ctx::lrow: every (cell, local dof) record from the geometry cache; one thread per cell
+template <int TDIM>
+__global__ void __launch_bounds__(256) lrow_kernel(const double* __restrict__ geo, int64_t n, double* __restrict__ lrow)
+{
+  constexpr int ND = TDIM + 1;
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (c >= n)
+    return;
+  Geo<TDIM> g;
+  load_geo_cached<TDIM>(geo, c, g);
+  const double s = fabs(g.detJ);
+  double G[ND][TDIM];
+#pragma unroll
+  for (int r = 0; r < TDIM; ++r)
+  {
+    double s0 = 0.0;
+#pragma unroll
+    for (int t = 0; t < TDIM; ++t)
+    {
+      G[t + 1][r] = g.K[t * TDIM + r];
+      s0 -= g.K[t * TDIM + r];
+    }
+    G[0][r] = s0;
+  }
+  const double w = s * (TDIM == 3 ? 1.0 / 6.0 : 0.5);
+#pragma unroll
+  for (int i = 0; i < ND; ++i)
+  {
+    double rec[4] = {0.0, 0.0, 0.0, s};
+    int q = 0;
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+    {
+      if (j == i)
+        continue;
+      double d = 0.0;
+#pragma unroll
+      for (int r = 0; r < TDIM; ++r)
+        d += (G[i][r] * w) * G[j][r];
+      rec[q++] = d;
+    }
+    st256(lrow + (c * ND + i) * 4, rec[0], rec[1], rec[2], rec[3]);
+  }
+}
+
+const double* ensure_lrow(cfx_ctx* c)
+{
+  if (!c->lrow_built)
+  {
+    const int nd = c->tdim + 1;
+    c->lrow.reserve(c->pool, static_cast<size_t>(c->nc_total) * nd * 4 + 4);
+    if (c->tdim == 3)
+      CFX_LAUNCH(c, lrow_kernel<3>, grid_for(c->nc_total, 256), 256, 0, c->geo.p, c->nc_total, c->lrow.p);
+    else
+      CFX_LAUNCH(c, lrow_kernel<2>, grid_for(c->nc_total, 256), 256, 0, c->geo.p, c->nc_total, c->lrow.p);
+    c->lrow_built = true;
+  }
+  return c->lrow.p;
+}
+
 GatherCtx make_gather_ctx(cfx_ctx* c, cfx_form* f, const cfx_integral* FI)
 {
   const Space& S = c->spaces[f->space];
@@ -2685,6 +2834,7 @@ GatherCtx make_gather_ctx(cfx_ctx* c, cfx_form* f, const cfx_integral* FI)
   g.mat_slot = c->mat_slot.p;
   g.Ae = f->Ae.p;
   g.geo = c->geo.p;
+  g.lrow = (S.degree == 1 && S.bs == 1) ? ensure_lrow(c) : nullptr;
   g.frow_ptr = S.frow_ptr.p;
   g.fclist = S.fclist.p;
   g.c2f = c->c2f;
@@ -2733,8 +2883,8 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
       // persistent: 4 blocks per SM walk the rows grid-stride through the software pipeline
       int n_sm = 148;
       cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
-      const unsigned gp = static_cast<unsigned>(std::min<int64_t>(static_cast<int64_t>(n_sm) * 4,
-                                                                  (PR->n_act_rows + GWC - 1) / GWC));
+      const unsigned gp = static_cast<unsigned>(std::min<int64_t>(
+          static_cast<int64_t>(n_sm) * clist_blocks_per_sm<DEG>(), (PR->n_act_rows + GWC - 1) / GWC));
       CFX_LAUNCH(ctx, kc, gp, GWC * 32, 0, gc, st, stL, PR->act_rows.p, PR->dn_act(), a->row_fast.p, a->Rrow.p,
                  A->row_ptr.p, A->values.p, zero_first);
     }
@@ -2880,6 +3030,11 @@ static double rule_read_bytes(const cfx_ctx* ctx, const Space& S, const cfx_inte
 static void assemble_matrix_impl(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, int zero_first, double diag_inactive,
                                  cfx_form* L, double* d_b, int zero_first_b)
 {
+  // adding into a matrix that is known to be zero == overwriting it: no second memset, no read of the old values
+  const bool fresh = A->values_zero;
+  A->values_zero = false;
+  if (fresh)
+    zero_first = 1;
   const Space& S = ctx->spaces[a->space];
   prepare_form(ctx, a);
   const cfx_integral* FI = facet_integral_domain(a);
@@ -2941,7 +3096,7 @@ static void assemble_matrix_impl(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, int 
       gc.bvec = d_b;
       gc.zero_first_b = zero_first_b;
     }
-    if (zero_first)
+    if (zero_first && !fresh)
       CFX_CUDA(cudaMemsetAsync(A->values.p, 0, static_cast<size_t>(A->nnz) * S.bs * S.bs * sizeof(double), ctx->stream));
     if (diag_inactive != 0.0)
       CFX_LAUNCH(ctx, inactive_diag_kernel, grid_for(A->n_rows, 256), 256, 0, a->prep->row_flag.p, A->n_rows, A->row_ptr.p,

@@ -287,6 +287,9 @@ struct cfx_pattern
   cfx::DevBuf<int64_t> row_ptr;
   cfx::DevBuf<int32_t> cols;
   cfx::DevBuf<double> values;
+  // the values are known to be all zero (fresh from cfx_create_sparsity / cfx_pattern_import, nothing has written
+  // them since): an assembly that ADDS into them may overwrite instead and skip reading 8 B per entry
+  bool values_zero = false;
 };
 
 struct cfx_integral
@@ -423,6 +426,13 @@ struct cfx_ctx
   // static per-cell affine geometry (the mesh does not move between cfx_update calls): K = J^-1
   // row-major (tdim^2), detJ, cell diameter; record stride 12 doubles (3D, 96 B) / 8 doubles (2D, 64 B)
   cfx::DevBuf<double> geo;
+  // P1 Laplace tensor rows, one 32-byte record per (cell, local dof i): the off-diagonal entries
+  // |detJ|/tdim! grad(lam_i).grad(lam_j), j != i ascending, and |detJ| in the last slot (the diagonal is minus the
+  // sum of the others: constants are in the kernel of the Laplace form).  Static while the mesh is bound; the row
+  // owner of a matrix row reads exactly ONE DRAM sector per incident standard cell instead of the 96-byte geometry
+  // record, and no record is fetched by more than one row.  Built on first use by a scalar P1 space.
+  cfx::DevBuf<double> lrow;
+  bool lrow_built = false;
 
   std::map<std::pair<int, int>, cfx::RuleTable> rules; // (dim, order) -> table (built-in or override)
   std::map<std::pair<int, int>, cfx::DevBuf<double>> ref_tabs; // (tdim, degree) -> reference-element integrals

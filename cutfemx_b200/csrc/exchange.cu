@@ -662,6 +662,7 @@ cfx_status cfx_xplan_unpack_add(cfx_ctx* ctx, cfx_xplan* P, cfx_pattern* A, doub
               "cfx_xplan_unpack_add: invalid arguments");
   if (P->n_neigh == 0)
     return CFX_OK;
+  A->values_zero = false;
   StageScope st(ctx, "unpack_add_ghost_values", 28.0 * static_cast<double>(P->n_r_ent));
   for (int k = 0; k < P->n_neigh; ++k)
   {

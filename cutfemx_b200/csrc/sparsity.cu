@@ -1513,6 +1513,7 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
                true);
   CFX_CUDA(cudaMemsetAsync(P->values.p, 0, (static_cast<size_t>(P->nnz) * S.bs * S.bs + 1) * sizeof(double),
                            ctx->stream));
+  P->values_zero = true;
   row_nnz.release();
   st.set_bytes(12.0 * static_cast<double>(P->nnz) + 8.0 * static_cast<double>(S.n_total));
   check_call(ctx, "cfx_create_sparsity (row capacity exceeded / inserted entries not sorted by row)");
@@ -1690,7 +1691,13 @@ cfx_status cfx_pattern_fetch(cfx_ctx* ctx, const cfx_pattern* p, int64_t* row_pt
   CFX_API_END(ctx)
 }
 
-const double* cfx_pattern_values_device_ptr(const cfx_pattern* p) { return p ? p->values.p : nullptr; }
+const double* cfx_pattern_values_device_ptr(const cfx_pattern* p)
+{
+  if (!p)
+    return nullptr;
+  const_cast<cfx_pattern*>(p)->values_zero = false; // the caller may write through the pointer
+  return p->values.p;
+}
 const int64_t* cfx_pattern_row_ptr_device_ptr(const cfx_pattern* p) { return p ? p->row_ptr.p : nullptr; }
 const int32_t* cfx_pattern_cols_device_ptr(const cfx_pattern* p) { return p ? p->cols.p : nullptr; }
 
@@ -1859,6 +1866,7 @@ cfx_status cfx_deactivate_outside(cfx_ctx* ctx, cfx_pattern* A, const int32_t* i
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && A && (n == 0 || inactive_dofs), CFX_ERR_INVALID, "cfx_deactivate_outside: NULL argument");
   resolve(ctx, A);
+  A->values_zero = false;
   if (n > 0 && A->bs > 1)
   { // blocked matrix: the rows are blocked indices bs*dof + k (cfx_active_domain on a blocked space)
     DevBuf<int32_t> own;
