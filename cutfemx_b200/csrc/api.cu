@@ -431,7 +431,11 @@ cfx_status cfx_mesh_bind(cfx_ctx* ctx, const double* x, int64_t n_nodes, const i
   ctx->tdim = tdim;
   ctx->gdim = gdim;
   ctx->mesh_bound = true;
-  ctx->lrow_built = false;
+  for (auto& S : ctx->spaces)
+  {
+    S.lrow_built = false;
+    S.fpos_built = false;
+  }
   ctx->classified = false;
   ctx->domain_stride = (n_cells_total + 15) & ~int64_t(15);
   ctx->domain.reserve(ctx->pool, static_cast<size_t>(ctx->domain_stride) * CFX_MAX_LEVEL_SETS);

@@ -643,10 +643,12 @@ __global__ void __launch_bounds__(EB)
 // coefficient J per DISTINCT dof (nd + 1 of them), and the assembled contribution of the facet to entry (r, s)
 // is w * J_r * J_s.  The record a row owner reads is therefore 80 B -- the distinct dofs, J and w -- instead of
 // two dofmap rows, 2 nd coefficients and the weight, and a row meets every facet once instead of once per cell:
-//   int32 d[5]  : shared dofs in the order of cell 0, then the dof opposite the facet in cell 0, then in cell 1
-//                 (P1: local facet lf is opposite local vertex lf); triangles use d[0..3], d[4] = -3
+//   int32 d[5]  : the distinct dofs, ASCENDING (triangles use d[0..3], d[4] = INT_MAX)
 //   int32 c0    : first cell of the facet row (the lane of c0 owns the facet for rows both cells touch)
+//   int32 i0 | i1 << 4 : where the dof opposite the facet in cell 0 / in cell 1 sits in d (P1: local facet lf is
+//                 opposite local vertex lf);  int32 : the dof opposite the facet in cell 1
 //   double J[5] : combined jump coefficients in the order of d;  double w
+// Ascending order is what lets a band row add a facet through a bit mask of CSR positions (add_facet_rows_p1_mask).
 // Everything follows from the two cached geometry records: grad lam_j = rows of K, n = -grad lam_lf0 / |.|,
 // |F| (tdim-1)! = |detJ| |grad lam_lf0|.
 constexpr int FREC = 10; // record stride in doubles (80 B)
@@ -740,14 +742,37 @@ __global__ void __launch_bounds__(EB)
   d[ND] = pick_i<ND>(d1, lf1);
   J[ND] = pick<ND>(jn[1], lf1);
   const double w = (TDIM == 3 ? 0.5 : 1.0) * measure * cs.c[0] * havg;
+  // ascending-dof order (rank = number of smaller entries; the triangle's unused fifth entry sorts last)
+  if (ND == 3)
+    d[4] = 0x7fffffff;
+  int32_t ds[5] = {0, 0, 0, 0, 0};
+  double Js[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  int i0 = 0, i1 = 0;
+#pragma unroll
+  for (int q = 0; q < 5; ++q)
+  {
+    int rank = 0;
+#pragma unroll
+    for (int p = 0; p < 5; ++p)
+      rank += (d[p] < d[q]) ? 1 : 0;
+#pragma unroll
+    for (int t = 0; t < 5; ++t)
+      if (t == rank)
+      {
+        ds[t] = d[q];
+        Js[t] = J[q];
+      }
+    i0 = (q == ND - 1) ? rank : i0;
+    i1 = (q == ND) ? rank : i1;
+  }
   double* o = Frec + f * FREC;
   int32_t* oi = reinterpret_cast<int32_t*>(o);
   const double w_old = accumulate ? o[9] : 0.0;
-  *reinterpret_cast<int4*>(oi) = make_int4(d[0], d[1], d[2], d[3]);
-  *reinterpret_cast<int4*>(oi + 4) = make_int4(d[4], c0, 0, 0);
+  *reinterpret_cast<int4*>(oi) = make_int4(ds[0], ds[1], ds[2], ds[3]);
+  *reinterpret_cast<int4*>(oi + 4) = make_int4(ds[4], c0, i0 | (i1 << 4), d[ND]);
 #pragma unroll
   for (int q = 0; q < 5; ++q)
-    o[4 + q] = J[q];
+    o[4 + q] = Js[q];
   o[9] = w_old + w;
 }
 
@@ -849,7 +874,8 @@ struct GatherCtx
   const int32_t* mat_slot;
   const double* Ae;
   const double* geo; // static per-cell geometry records (element.cuh GeoRec)
-  const double* lrow; // P1: static Laplace tensor rows, 4 doubles per (cell, local dof) (cfx_ctx::lrow); else null
+  const double* lrow; // scalar P1: static Laplace tensor rows, 4 doubles per incidence (Space::lrow); else null
+  const uint32_t* fpos; // scalar P1 with a static structure: packed static row positions per incidence (Space::fpos)
   const int64_t* frow_ptr;
   const uint64_t* fclist;
   const int32_t* c2f;
@@ -1046,10 +1072,10 @@ struct P1Rec
 {
   double a[4];
 };
-__device__ __forceinline__ P1Rec load_p1rec(const double* __restrict__ lrow, int64_t c, int nd, int li)
+__device__ __forceinline__ P1Rec load_p1rec(const double* __restrict__ lrow, int64_t pinc)
 {
   P1Rec r;
-  const double* p = lrow + (c * nd + li) * 4;
+  const double* p = lrow + pinc * 4;
   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a[0]), "=d"(r.a[1]), "=d"(r.a[2]), "=d"(r.a[3]) : "l"(p));
   return r;
 }
@@ -1087,9 +1113,10 @@ __device__ __forceinline__ void p1_row_from_rec(const StdTab& st, const P1Rec& r
   }
 }
 
+// pinc: position of (row, cell) in the space's incidence arrays (addresses the P1 tensor-row record)
 template <int TDIM, int DEG>
 __device__ __forceinline__ void cell_row_values(const GatherCtx& gc, const StdTab& st, int64_t c, unsigned fl, int li,
-                                                double (&v)[Elem<TDIM, DEG>::ND])
+                                                int64_t pinc, double (&v)[Elem<TDIM, DEG>::ND])
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
 #pragma unroll
@@ -1101,7 +1128,7 @@ __device__ __forceinline__ void cell_row_values(const GatherCtx& gc, const StdTa
     {
       if (gc.lrow != nullptr)
       {
-        const P1Rec rec = load_p1rec(gc.lrow, c, ND, li);
+        const P1Rec rec = load_p1rec(gc.lrow, pinc);
         p1_row_from_rec<TDIM>(st, rec, fl, li, v);
       }
       else
@@ -1241,7 +1268,7 @@ __device__ __forceinline__ int add_facet_rows_p1(const GatherCtx& gc, int32_t (*
       const int32_t dd[5] = {q0.x, q0.y, q0.z, q0.w, q1.x};
       // the facet belongs to this lane if its cell is the facet's first cell, or if the first cell does not
       // hold the row's dof at all (then the row's dof is the one opposite the facet in the second cell)
-      valid = (c == q1.y) || (dd[ND] == r);
+      valid = (c == q1.y) || (q1.w == r);
       if (valid)
       {
         const double2 j01 = __ldg(reinterpret_cast<const double2*>(rec) + 2);
@@ -1291,6 +1318,100 @@ __device__ __forceinline__ int add_facet_rows_p1(const GatherCtx& gc, int32_t (*
     __syncwarp();
   }
   return matched;
+}
+
+// P1 band rows with a stored position mask (gather_matrix_fast_kernel).  The macro element of a facet is the lane's
+// cell plus ONE more dof, and the record lists the dofs ascending, so the facet's CSR positions in the row are the
+// bit mask PM = (positions of the cell's dofs, known from the pattern pass) | (position of the extra dof, one
+// lower-bound search in the row's staged columns), and column lane k takes entry popc(PM & lanes_below_k) of the
+// staged values -- no column compare per entry.  Same facets, same order (local facet by local facet, lanes
+// ascending) and the same products as add_facet_rows_p1.
+template <int ND>
+__device__ __forceinline__ void add_facet_rows_p1_mask(const GatherCtx& gc, int32_t* s_cols, uint32_t* s_pm,
+                                                       double (*s_fv)[6], bool band_cell, int64_t c, int32_t r,
+                                                       uint32_t Mc, int32_t mycol, double& acc)
+{
+  constexpr int NE = ND + 1;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  if (__ballot_sync(full, band_cell) == 0)
+    return;
+  s_cols[lane] = mycol; // ascending, lanes past the row's end hold INT_MAX
+  int32_t fct[4] = {0, 0, 0, 0};
+  if (band_cell)
+  {
+    if (gc.nf == 4)
+    {
+      const int4 q = __ldg(reinterpret_cast<const int4*>(gc.c2f) + c);
+      fct[0] = q.x;
+      fct[1] = q.y;
+      fct[2] = q.z;
+      fct[3] = q.w;
+    }
+    else
+      for (int lf = 0; lf < gc.nf; ++lf)
+        fct[lf] = gc.c2f[c * gc.nf + lf];
+  }
+  int32_t fsl[4] = {-1, -1, -1, -1};
+  if (band_cell)
+    for (int lf = 0; lf < gc.nf; ++lf)
+      fsl[lf] = gc.facet_slot[fct[lf]];
+  const uint32_t below = (1u << lane) - 1u;
+  __syncwarp();
+  for (int lf = 0; lf < gc.nf; ++lf)
+  {
+    const int64_t fs = fsl[lf];
+    bool valid = fs >= 0;
+    if (valid)
+    {
+      // the whole record at once: five independent 16-byte loads (the partner lane of a shared facet reads the
+      // same record in the same instruction)
+      const double* rec = gc.Fe + fs * FREC;
+      const int4 q0 = __ldg(reinterpret_cast<const int4*>(rec));
+      const int4 q1 = __ldg(reinterpret_cast<const int4*>(rec) + 1);
+      const double2 j01 = __ldg(reinterpret_cast<const double2*>(rec) + 2);
+      const double2 j23 = __ldg(reinterpret_cast<const double2*>(rec) + 3);
+      const double2 j4w = __ldg(reinterpret_cast<const double2*>(rec) + 4);
+      // the facet belongs to this lane if its cell is the facet's first cell, or if the first cell does not
+      // hold the row's dof at all (then the row's dof is the one opposite the facet in the second cell)
+      const bool first = c == q1.y;
+      valid = first || (q1.w == r);
+      if (valid)
+      {
+        const int32_t dd[5] = {q0.x, q0.y, q0.z, q0.w, q1.x};
+        const double J[5] = {j01.x, j01.y, j23.x, j23.y, j4w.x};
+        const int ix = first ? (q1.z >> 4) : (q1.z & 15); // the macro dof this lane's cell does not have
+        double jr = 0.0;
+        int32_t dx = 0;
+#pragma unroll
+        for (int k = 0; k < NE; ++k)
+        {
+          jr = (dd[k] == r) ? J[k] : jr;
+          dx = (k == ix) ? dd[k] : dx;
+        }
+        int pos = 0; // lower bound of dx among the row's columns
+#pragma unroll
+        for (int st = 16; st > 0; st >>= 1)
+          pos += (s_cols[pos + st - 1] < dx) ? st : 0;
+        s_pm[lane] = Mc | (1u << pos);
+        const double jm = jr * j4w.y;
+#pragma unroll
+        for (int k = 0; k < NE; ++k)
+          s_fv[lane][k] = jm * J[k];
+      }
+    }
+    __syncwarp();
+    unsigned m = __ballot_sync(full, valid);
+    while (m)
+    {
+      const int l = __ffs(m) - 1;
+      m &= m - 1;
+      const uint32_t PM = s_pm[l];
+      if ((PM >> lane) & 1u)
+        acc += s_fv[l][__popc(PM & below)];
+    }
+    __syncwarp();
+  }
 }
 
 template <int ND>
@@ -1460,7 +1581,7 @@ __global__ void __launch_bounds__(GW * 32)
         if (contributes)
         {
           double v[ND];
-          cell_row_values<TDIM, DEG>(gc, st, c, fl, li, v);
+          cell_row_values<TDIM, DEG>(gc, st, c, fl, li, ib + k, v);
 #pragma unroll
           for (int j = 0; j < ND; ++j)
           {
@@ -1536,8 +1657,10 @@ __global__ void __launch_bounds__(GWM * 32, 10)
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
   __shared__ double s_v[GWM][32][ND];
-  __shared__ __align__(16) int32_t s_fd[GWM][32][FacetStage<ND>::W];
-  __shared__ __align__(16) double s_fv[GWM][32][FacetStage<ND>::W];
+  // facet staging: P1 -- the row's columns, one position mask and nd + 1 values per hit; otherwise dofs + values
+  constexpr bool P1F = ND <= 4;
+  __shared__ __align__(16) int32_t s_fd[GWM][32][P1F ? 2 : FacetStage<ND>::W];
+  __shared__ __align__(16) double s_fv[GWM][32][P1F ? 6 : FacetStage<ND>::W];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t it = static_cast<int64_t>(blockIdx.x) * GWM + w;
   if (it >= n_act_.get())
@@ -1573,12 +1696,14 @@ __global__ void __launch_bounds__(GWM * 32, 10)
       for (uint32_t t = gc.fmask[ib + lane]; t; t &= t - 1)
         Mn |= 1u << __popc(R & ((1u << (__ffs(t) - 1)) - 1u));
   }
-  else if (contributes)
+  else if (contributes || (fl & 2u))
     Mn = gmask[idx * gc.stride + lane];
+  const uint32_t Mcell = Mn; // CSR positions of the cell's dofs (band cells have them whether or not they contribute)
+  Mn = contributes ? Mn : 0u;
   if (contributes)
   {
     double v[ND];
-    cell_row_values<TDIM, DEG>(gc, st, c, fl, li, v);
+    cell_row_values<TDIM, DEG>(gc, st, c, fl, li, ib + lane, v);
 #pragma unroll
     for (int j = 0; j < ND; ++j)
       s_v[w][lane][(fp >> (4 + 4 * j)) & 15u] = v[j]; // ascending-dof order
@@ -1622,9 +1747,22 @@ __global__ void __launch_bounds__(GWM * 32, 10)
   }
   if (rf & 2)
   {
-    const int32_t mycol = have_col ? cols[rb + lane] : -2;
-    int expected = 0;
-    add_facet_rows<ND>(gc, s_fd[w], s_fv[w], (fl & 2u) != 0, c, li, static_cast<int32_t>(r), mycol, acc, expected, false);
+    if constexpr (P1F)
+    {
+      if (gc.Fw)
+      {
+        const int32_t mycol = have_col ? cols[rb + lane] : 0x7fffffff;
+        int32_t* si = &s_fd[w][0][0];
+        add_facet_rows_p1_mask<ND>(gc, si, reinterpret_cast<uint32_t*>(si) + 32, s_fv[w], (fl & 2u) != 0, c,
+                                   static_cast<int32_t>(r), Mcell, mycol, acc);
+      }
+    }
+    else
+    {
+      const int32_t mycol = have_col ? cols[rb + lane] : -2;
+      int expected = 0;
+      add_facet_rows<ND>(gc, s_fd[w], s_fv[w], (fl & 2u) != 0, c, li, static_cast<int32_t>(r), mycol, acc, expected, false);
+    }
   }
   if (have_col)
     vals[rb + lane] = acc;
@@ -1661,7 +1799,7 @@ struct alignas(16) ClistRow
   int32_t r;
   uint32_t R;
   int32_t n_inc; // < 0: not a contribution-list row (or past the end)
-  int32_t pad;
+  int32_t ufl;   // the flag byte every incident cell carries (a standard-quadrature one), 0 = look at the cells
   int64_t ib, rb, fb, pad2;
 };
 
@@ -1680,7 +1818,8 @@ template <int TDIM, int DEG, bool FUSED>
 __global__ void __launch_bounds__(GWC * 32, clist_blocks_per_sm<DEG>())
     gather_matrix_clist_kernel(GatherCtx gc, StdTab st, StdTab stL, const int32_t* __restrict__ act_rows, DN n_act_,
                                 const uint8_t* __restrict__ row_fast, const uint32_t* __restrict__ Rrow,
-                                const int64_t* __restrict__ row_ptr, double* __restrict__ vals, int zero_first)
+                                const uint8_t* __restrict__ row_ufl, const int64_t* __restrict__ row_ptr,
+                                double* __restrict__ vals, int zero_first)
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
   static_assert(ND * 32 <= 255, "contribution-list bytes index the staging array directly");
@@ -1705,6 +1844,7 @@ __global__ void __launch_bounds__(GWC * 32, clist_blocks_per_sm<DEG>())
     unsigned rf;
     int32_t r;
     uint32_t R;
+    int32_t ufl;
   };
   auto load1 = [&](int ch) -> L1
   {
@@ -1715,6 +1855,7 @@ __global__ void __launch_bounds__(GWC * 32, clist_blocks_per_sm<DEG>())
     a.rf = in ? row_fast[k] : 0u;
     a.r = act_rows[k];
     a.R = Rrow[k];
+    a.ufl = row_ufl[k];
     return a;
   };
   auto load2 = [&](const L1& a) -> ClistRow
@@ -1725,7 +1866,7 @@ __global__ void __launch_bounds__(GWC * 32, clist_blocks_per_sm<DEG>())
     q.ib = gc.inc_ptr[a.r];
     const int n_inc = static_cast<int>(gc.inc_ptr[a.r + 1] - q.ib);
     q.n_inc = ((a.rf & 13u) == 13u) ? n_inc : -1;
-    q.pad = 0;
+    q.ufl = a.ufl;
     q.rb = row_ptr[a.r];
     q.fb = gc.frow_ptr[a.r];
     q.pad2 = 0;
@@ -1739,6 +1880,8 @@ __global__ void __launch_bounds__(GWC * 32, clist_blocks_per_sm<DEG>())
     int n_inc;
     int32_t c;
     int li;
+    int ufl;
+    int64_t pinc;
     uint64_t word;
     double* pv;
     double old;
@@ -1757,6 +1900,8 @@ __global__ void __launch_bounds__(GWC * 32, clist_blocks_per_sm<DEG>())
     c.R = static_cast<uint32_t>(q0.y);
     c.n_inc = q0.z < 0 ? 0 : q0.z;
     const int64_t pos = q1.x + (lane < c.n_inc ? lane : 0);
+    c.ufl = q0.w;
+    c.pinc = pos;
     c.c = gc.inc_cell[pos];
     c.li = static_cast<int>(gc.fperm[pos] & 15u);
     c.word = __ldg(gc.fclist + fb + lane); // padded allocation: legal for every lane
@@ -1771,12 +1916,23 @@ __global__ void __launch_bounds__(GWC * 32, clist_blocks_per_sm<DEG>())
   auto stageD = [&](const RowC& c, CellRec& g) -> ClistD
   {
     ClistD d;
-    d.fl = (c.ok && lane < c.n_inc) ? gc.cell_flags[c.c] : 0u;
+    // a row whose cells all carry one standard-quadrature flag byte needs neither the flags nor the tensor slots
+    // of its cells (warp-uniform branch): two scattered gathers per incidence less
+    const bool in = c.ok && lane < c.n_inc;
+    if (c.ufl)
+    {
+      d.fl = in ? static_cast<unsigned>(c.ufl) : 0u;
+      d.ms = 0;
+    }
+    else
+    {
+      d.fl = in ? gc.cell_flags[c.c] : 0u;
+      d.ms = __ldg(gc.mat_slot + c.c);
+    }
     if constexpr (DEG == 1)
-      g = load_p1rec(gc.lrow, c.c, ND, c.li);
+      g = load_p1rec(gc.lrow, c.pinc);
     else
       load_geo_cached<TDIM>(gc.geo, c.c, g);
-    d.ms = __ldg(gc.mat_slot + c.c);
     return d;
   };
 
@@ -1913,6 +2069,162 @@ __global__ void __launch_bounds__(GWC * 32, clist_blocks_per_sm<DEG>())
     s_rec[w][buf ^ 1][lane] = nq;
     __syncwarp();
   }
+}
+
+// Scalar P1 static rows: ONE THREAD PER ROW.  ncu on the warp-per-row contribution-list kernel above showed it bound
+// by issue slots and per-warp dependent latency (about 280 warp instructions and 2300 cycles per row: staging through
+// shared memory, shuffle trees, pipeline bookkeeping -- all warp-wide instructions that serve one row), not by bytes:
+// taking two of its three per-cell gathers away changed nothing.  A P1 row needs per incident cell one 32-byte
+// record (three off-diagonal Laplace entries + |detJ|, Space::lrow, stored in incidence order) and one packed word
+// of static row positions (Space::fpos), so a thread can walk its row alone: per incidence one 256-bit load, one
+// 32-bit load, a handful of FP64 operations and three read-modify-writes of its private accumulator column in shared
+// memory (column tid of acc[32][RTB]: the bank depends on the thread only, never conflicts); the diagonal and the
+// right-hand-side entry stay in registers.  About 25 warp instructions per row instead of 280, four independent
+// record loads in flight per thread, no shuffles, no barriers.  Sums run over the incident cells in ascending order
+// (the order of the contribution lists); rows whose cells do not all carry one standard-quadrature flag byte
+// (row_ufl == 0) look the flags up per cell and add the materialised tensor rows of cut cells.
+constexpr int RTB = 128;
+
+__device__ __forceinline__ uint32_t ldg_keep(const uint32_t* p)
+{ // the position words are re-read from the same 32-byte sector by eight consecutive incidences: keep them in L1
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ P1Rec ldg_stream_p1rec(const double* __restrict__ lrow, int64_t pinc)
+{ // each record is read exactly once per assembly: do not let the stream push the position words out of L1
+  P1Rec r;
+  const double* p = lrow + pinc * 4;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(r.a[0]), "=d"(r.a[1]), "=d"(r.a[2]), "=d"(r.a[3])
+               : "l"(p));
+  return r;
+}
+
+template <int TDIM, bool FUSED>
+__global__ void __launch_bounds__(RTB)
+    gather_matrix_p1_kernel(GatherCtx gc, StdTab st, StdTab stL, const int32_t* __restrict__ act_rows, DN n_act_,
+                            const uint8_t* __restrict__ row_fast, const uint32_t* __restrict__ Rrow,
+                            const uint8_t* __restrict__ row_ufl, const uint32_t* __restrict__ fpos,
+                            const int64_t* __restrict__ row_ptr, double* __restrict__ vals, int zero_first)
+{
+  constexpr int ND = TDIM + 1, NO = TDIM; // NO off-diagonal entries per tensor row
+  __shared__ double s_acc[32][RTB];
+  const int tid = threadIdx.x;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * RTB + tid;
+  if (idx >= n_act_.get())
+    return;
+  if ((row_fast[idx] & 13u) != 13u)
+    return; // band rows, rows without a static structure: the mask / generic kernels
+  const int64_t r = act_rows[idx];
+  const uint32_t R = Rrow[idx];
+  const unsigned ufl = row_ufl[idx];
+  const int64_t ib = gc.inc_ptr[r];
+  const int n_inc = static_cast<int>(gc.inc_ptr[r + 1] - ib);
+  double* const out = vals + row_ptr[r];
+  {
+    int o = 0;
+    for (uint32_t m = R; m; m &= m - 1, ++o)
+      s_acc[__ffs(m) - 1][tid] = zero_first ? 0.0 : out[o];
+  }
+  const int pd = static_cast<int>((ldg_keep(fpos + ib) >> 2) & 31u); // the row's own column
+  double dacc = zero_first ? 0.0 : s_acc[pd][tid];
+  double e = 0.0;
+  constexpr double MASSW = TDIM == 3 ? 1.0 / 120.0 : 1.0 / 24.0;
+  constexpr double SRCW = TDIM == 3 ? 1.0 / 24.0 : 1.0 / 6.0;
+  constexpr int U = 4;
+  for (int l0 = 0; l0 < n_inc; l0 += U)
+  {
+    P1Rec rec[U];
+    uint32_t word[U];
+    unsigned fl[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      const int l = l0 + u < n_inc ? l0 + u : n_inc - 1;
+      rec[u] = ldg_stream_p1rec(gc.lrow, ib + l);
+      word[u] = ldg_keep(fpos + ib + l);
+      fl[u] = ufl;
+    }
+    int32_t cell[U] = {0, 0, 0, 0};
+    if (!ufl)
+    {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+      {
+        const int l = l0 + u < n_inc ? l0 + u : n_inc - 1;
+        cell[u] = gc.inc_cell[ib + l];
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        fl[u] = gc.cell_flags[cell[u]];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      if (l0 + u >= n_inc || !(fl[u] & 0xFDu))
+        continue;
+      const unsigned m = fl[u] >> 2;
+      double v[NO], vd = 0.0;
+#pragma unroll
+      for (int q = 0; q < NO; ++q)
+        v[q] = 0.0;
+      if (m)
+      { // the arithmetic of p1_row_from_rec
+        const double w = st.t0[m];
+        double dsum = 0.0;
+#pragma unroll
+        for (int q = 0; q < NO; ++q)
+        {
+          const double t = w * rec[u].a[q];
+          dsum += t;
+          v[q] += t;
+        }
+        vd -= dsum;
+        if (st.has_mass)
+        {
+          const double wm = st.t1[m] * rec[u].a[3] * MASSW;
+#pragma unroll
+          for (int q = 0; q < NO; ++q)
+            v[q] += wm;
+          vd += 2.0 * wm;
+        }
+        if constexpr (FUSED)
+          e += stL.t0[m] * rec[u].a[3] * SRCW;
+      }
+      if (fl[u] & 1u)
+      { // materialised run-time-rule tensor row of a cut cell (natural dof order)
+        const int li = static_cast<int>(word[u] & 3u);
+        const int64_t ms = __ldg(gc.mat_slot + cell[u]);
+        const double* a = gc.Ae + (ms * ND + li) * ND;
+        double av[ND];
+#pragma unroll
+        for (int j = 0; j < ND; ++j)
+          av[j] = a[j];
+#pragma unroll
+        for (int q = 0; q < NO; ++q)
+          v[q] += pick<ND>(av, q < li ? q : q + 1);
+        vd += pick<ND>(av, li);
+        if constexpr (FUSED)
+          e += gc.AeL[ms * ND + li];
+      }
+#pragma unroll
+      for (int q = 0; q < NO; ++q)
+      {
+        const int p = static_cast<int>((word[u] >> (7 + 5 * q)) & 31u);
+        s_acc[p][tid] += v[q];
+      }
+      dacc += vd;
+    }
+  }
+  s_acc[pd][tid] = dacc;
+  {
+    int o = 0;
+    for (uint32_t m = R; m; m &= m - 1, ++o)
+      out[o] = s_acc[__ffs(m) - 1][tid];
+  }
+  if constexpr (FUSED)
+    gc.bvec[r] = gc.zero_first_b ? e : gc.bvec[r] + e;
 }
 
 // One warp per active row: lanes take the incident cells, compute / load the cell's entry for this
@@ -2761,14 +3073,18 @@ void launch_facet(cfx_ctx* c, const cfx_integral& I, cfx_form* f, bool accumulat
   }
 }
 
-// cfx_ctx::lrow: every (cell, local dof) record from the geometry cache; one thread per cell
+// Space::lrow: the record of every incidence (row, cell) from the geometry cache; one thread per incidence
 template <int TDIM>
-__global__ void __launch_bounds__(256) lrow_kernel(const double* __restrict__ geo, int64_t n, double* __restrict__ lrow)
+__global__ void __launch_bounds__(256)
+    lrow_kernel(const double* __restrict__ geo, const int32_t* __restrict__ inc_cell, const uint32_t* __restrict__ fperm,
+                int64_t n, double* __restrict__ lrow)
 {
   constexpr int ND = TDIM + 1;
-  const int64_t c = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-  if (c >= n)
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (p >= n)
     return;
+  const int64_t c = inc_cell[p];
+  const int li = static_cast<int>(fperm[p] & 15u);
   Geo<TDIM> g;
   load_geo_cached<TDIM>(geo, c, g);
   const double s = fabs(g.detJ);
@@ -2786,39 +3102,86 @@ __global__ void __launch_bounds__(256) lrow_kernel(const double* __restrict__ ge
     G[0][r] = s0;
   }
   const double w = s * (TDIM == 3 ? 1.0 / 6.0 : 0.5);
+  double Gi[TDIM];
 #pragma unroll
-  for (int i = 0; i < ND; ++i)
+  for (int r = 0; r < TDIM; ++r)
   {
-    double rec[4] = {0.0, 0.0, 0.0, s};
-    int q = 0;
+    double t = G[0][r];
 #pragma unroll
-    for (int j = 0; j < ND; ++j)
-    {
-      if (j == i)
-        continue;
-      double d = 0.0;
-#pragma unroll
-      for (int r = 0; r < TDIM; ++r)
-        d += (G[i][r] * w) * G[j][r];
-      rec[q++] = d;
-    }
-    st256(lrow + (c * ND + i) * 4, rec[0], rec[1], rec[2], rec[3]);
+    for (int j = 1; j < ND; ++j)
+      t = (j == li) ? G[j][r] : t;
+    Gi[r] = t;
   }
+  double rec[4] = {0.0, 0.0, 0.0, s};
+#pragma unroll
+  for (int q = 0; q < ND - 1; ++q)
+  {
+    // q-th off-diagonal column: j = q for q < li, q + 1 otherwise
+    double d = 0.0;
+#pragma unroll
+    for (int r = 0; r < TDIM; ++r)
+    {
+      double gj = G[0][r];
+#pragma unroll
+      for (int j = 1; j < ND; ++j)
+        gj = (j == (q < li ? q : q + 1)) ? G[j][r] : gj;
+      d += (Gi[r] * w) * gj;
+    }
+    rec[q] = d;
+  }
+  st256(lrow + p * 4, rec[0], rec[1], rec[2], rec[3]);
 }
 
-const double* ensure_lrow(cfx_ctx* c)
+const double* ensure_lrow(cfx_ctx* c, Space& S)
 {
-  if (!c->lrow_built)
+  if (!S.lrow_built)
   {
-    const int nd = c->tdim + 1;
-    c->lrow.reserve(c->pool, static_cast<size_t>(c->nc_total) * nd * 4 + 4);
+    S.lrow.reserve(c->pool, static_cast<size_t>(S.n_inc) * 4 + 4);
     if (c->tdim == 3)
-      CFX_LAUNCH(c, lrow_kernel<3>, grid_for(c->nc_total, 256), 256, 0, c->geo.p, c->nc_total, c->lrow.p);
+      CFX_LAUNCH(c, lrow_kernel<3>, grid_for(S.n_inc, 256), 256, 0, c->geo.p, S.inc_cell.p, S.fperm.p, S.n_inc, S.lrow.p);
     else
-      CFX_LAUNCH(c, lrow_kernel<2>, grid_for(c->nc_total, 256), 256, 0, c->geo.p, c->nc_total, c->lrow.p);
-    c->lrow_built = true;
+      CFX_LAUNCH(c, lrow_kernel<2>, grid_for(S.n_inc, 256), 256, 0, c->geo.p, S.inc_cell.p, S.fperm.p, S.n_inc, S.lrow.p);
+    S.lrow_built = true;
   }
-  return c->lrow.p;
+  return S.lrow.p;
+}
+
+// Space::fpos: per incidence (row r, cell) one word of positions in r's static full-mesh row --
+//   bits 0..1 local index li of r in the cell, bits 2..6 position of r itself (the diagonal),
+//   bits 7 + 5 q ..: position of the cell's q-th other dof (local order, li skipped)
+// from the position mask (ascending dofs) and the rank of each local dof among the cell's dofs.
+__global__ void __launch_bounds__(256)
+    fpos_kernel(const uint32_t* __restrict__ fmask, const uint32_t* __restrict__ fperm, int nd, int64_t n,
+                uint32_t* __restrict__ fpos)
+{
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (p >= n)
+    return;
+  const uint32_t fm = fmask[p], fp = fperm[p];
+  const int li = static_cast<int>(fp & 15u);
+  uint32_t w = static_cast<uint32_t>(li);
+  int q = 0;
+  for (int j = 0; j < nd; ++j)
+  {
+    const int rank = static_cast<int>((fp >> (4 + 4 * j)) & 15u);
+    const uint32_t pos = __fns(fm, 0, rank + 1) & 31u;
+    if (j == li)
+      w |= pos << 2;
+    else
+      w |= pos << (7 + 5 * q++);
+  }
+  fpos[p] = w;
+}
+
+const uint32_t* ensure_fpos(cfx_ctx* c, Space& S)
+{
+  if (!S.fpos_built)
+  {
+    S.fpos.reserve(c->pool, static_cast<size_t>(S.n_inc) + 16);
+    CFX_LAUNCH(c, fpos_kernel, grid_for(S.n_inc, 256), 256, 0, S.fmask.p, S.fperm.p, S.nd, S.n_inc, S.fpos.p);
+    S.fpos_built = true;
+  }
+  return S.fpos.p;
 }
 
 GatherCtx make_gather_ctx(cfx_ctx* c, cfx_form* f, const cfx_integral* FI)
@@ -2834,7 +3197,8 @@ GatherCtx make_gather_ctx(cfx_ctx* c, cfx_form* f, const cfx_integral* FI)
   g.mat_slot = c->mat_slot.p;
   g.Ae = f->Ae.p;
   g.geo = c->geo.p;
-  g.lrow = (S.degree == 1 && S.bs == 1) ? ensure_lrow(c) : nullptr;
+  g.lrow = (S.degree == 1 && S.bs == 1 && S.has_perm) ? ensure_lrow(c, c->spaces[f->space]) : nullptr;
+  g.fpos = (g.lrow && S.has_static) ? ensure_fpos(c, c->spaces[f->space]) : nullptr;
   g.frow_ptr = S.frow_ptr.p;
   g.fclist = S.fclist.p;
   g.c2f = c->c2f;
@@ -2879,14 +3243,28 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
       StageScope sk(ctx, "gather_matrix_clist_kernel",
                     12.0 * static_cast<double>(a->n_clist_nnz)
                         + (28.0 * ctx->nv + 4.0 * S.nd) * static_cast<double>(n_std));
-      auto kc = gc.bvec ? gather_matrix_clist_kernel<TDIM, DEG, true> : gather_matrix_clist_kernel<TDIM, DEG, false>;
-      // persistent: 4 blocks per SM walk the rows grid-stride through the software pipeline
-      int n_sm = 148;
-      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
-      const unsigned gp = static_cast<unsigned>(std::min<int64_t>(
-          static_cast<int64_t>(n_sm) * clist_blocks_per_sm<DEG>(), (PR->n_act_rows + GWC - 1) / GWC));
-      CFX_LAUNCH(ctx, kc, gp, GWC * 32, 0, gc, st, stL, PR->act_rows.p, PR->dn_act(), a->row_fast.p, a->Rrow.p,
-                 A->row_ptr.p, A->values.p, zero_first);
+      bool done = false;
+      if constexpr (DEG == 1)
+      {
+        if (gc.fpos != nullptr)
+        { // scalar P1: one thread per row
+          auto kp = gc.bvec ? gather_matrix_p1_kernel<TDIM, true> : gather_matrix_p1_kernel<TDIM, false>;
+          CFX_LAUNCH(ctx, kp, grid_for(PR->n_act_rows, RTB), RTB, 0, gc, st, stL, PR->act_rows.p, PR->dn_act(),
+                     a->row_fast.p, a->Rrow.p, a->row_ufl.p, gc.fpos, A->row_ptr.p, A->values.p, zero_first);
+          done = true;
+        }
+      }
+      if (!done)
+      {
+        auto kc = gc.bvec ? gather_matrix_clist_kernel<TDIM, DEG, true> : gather_matrix_clist_kernel<TDIM, DEG, false>;
+        // persistent: 4 blocks per SM walk the rows grid-stride through the software pipeline
+        int n_sm = 148;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+        const unsigned gp = static_cast<unsigned>(std::min<int64_t>(
+            static_cast<int64_t>(n_sm) * clist_blocks_per_sm<DEG>(), (PR->n_act_rows + GWC - 1) / GWC));
+        CFX_LAUNCH(ctx, kc, gp, GWC * 32, 0, gc, st, stL, PR->act_rows.p, PR->dn_act(), a->row_fast.p, a->Rrow.p,
+                   a->row_ufl.p, A->row_ptr.p, A->values.p, zero_first);
+      }
     }
     if (fast && (a->n_mask_rows != 0))
     {

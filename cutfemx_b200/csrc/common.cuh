@@ -219,6 +219,17 @@ struct Space
   // incident cell contributes).  frow_ok[r] = 0 if some entry of the row has more than 8 cells.
   DevBuf<uint64_t> fclist;
   DevBuf<uint8_t> frow_ok;
+  // scalar P1: Laplace tensor rows, one 32-byte record per INCIDENCE (row r, incident cell l), stored in incidence
+  // order so that a matrix row reads its records as one contiguous run: the off-diagonal entries
+  // |detJ|/tdim! grad(lam_i).grad(lam_j), j != i ascending, and |detJ| in the last slot (the diagonal is minus the
+  // sum of the others: constants are in the kernel of the Laplace form).  Static while the mesh and the space are
+  // bound; built on first use from the geometry cache.
+  DevBuf<double> lrow;
+  bool lrow_built = false;
+  // scalar P1 with a static structure: per incidence one packed word of positions in the row's full-mesh row
+  // (assemble.cu fpos_kernel), what the one-thread-per-row gather reads instead of masks and contribution lists
+  DevBuf<uint32_t> fpos;
+  bool fpos_built = false;
 };
 
 struct RuleTable
@@ -346,6 +357,9 @@ struct cfx_form
   // gather table of the pattern built from this form (sparsity.cu)
   cfx::DevBuf<uint32_t> gmask;  // (n_act_rows, stride): CSR positions of the dofs of incident cell l (band rows)
   cfx::DevBuf<uint32_t> Rrow;   // (n_act_rows): static rows: which full-mesh columns the row keeps
+  // (n_act_rows): static rows all of whose incident cells carry the SAME flag byte, a standard-quadrature one
+  // (no materialised tensor, no band facet): that byte, else 0.  Such a row needs no per-cell state in the gather.
+  cfx::DevBuf<uint8_t> row_ufl;
   cfx::DevBuf<uint8_t> row_fast; // bit0: mask path, bit1: has band cells, bit2: static row
   int64_t n_slow_rows = 0;
   int64_t n_mask_rows = -1; // rows of the mask gather kernel (band rows, long contribution lists); -1 unknown
@@ -426,13 +440,6 @@ struct cfx_ctx
   // static per-cell affine geometry (the mesh does not move between cfx_update calls): K = J^-1
   // row-major (tdim^2), detJ, cell diameter; record stride 12 doubles (3D, 96 B) / 8 doubles (2D, 64 B)
   cfx::DevBuf<double> geo;
-  // P1 Laplace tensor rows, one 32-byte record per (cell, local dof i): the off-diagonal entries
-  // |detJ|/tdim! grad(lam_i).grad(lam_j), j != i ascending, and |detJ| in the last slot (the diagonal is minus the
-  // sum of the others: constants are in the kernel of the Laplace form).  Static while the mesh is bound; the row
-  // owner of a matrix row reads exactly ONE DRAM sector per incident standard cell instead of the 96-byte geometry
-  // record, and no record is fetched by more than one row.  Built on first use by a scalar P1 space.
-  cfx::DevBuf<double> lrow;
-  bool lrow_built = false;
 
   std::map<std::pair<int, int>, cfx::RuleTable> rules; // (dim, order) -> table (built-in or override)
   std::map<std::pair<int, int>, cfx::DevBuf<double>> ref_tabs; // (tdim, degree) -> reference-element integrals

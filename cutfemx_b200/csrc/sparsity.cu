@@ -613,6 +613,7 @@ __global__ void __launch_bounds__(256)
     pattern_static_kernel(RowCtx rc, const int32_t* __restrict__ act_rows, DN n_act_,
                           const uint32_t* __restrict__ fmask, const uint8_t* __restrict__ frow_ok,
                           int32_t* __restrict__ row_nnz, uint32_t* __restrict__ Rrow, uint8_t* __restrict__ row_fast,
+                          uint8_t* __restrict__ row_ufl,
                           unsigned long long* __restrict__ n_clist /* [0] rows, [1] nnz of contribution-list rows */)
 {
   // 8 lanes per row and CROWS rows per lane group, the dependent load levels (slot -> row -> incidence ->
@@ -640,19 +641,24 @@ __global__ void __launch_bounds__(256)
     n_inc[i] = go[i] ? static_cast<int>(rc.inc_ptr[r[i] + 1] - ib[i]) : 0;
   }
   uint32_t M[CROWS];
+  unsigned FO[CROWS]; // low byte: OR of the incident cells' flag bytes, second byte: their AND
   bool clist = false;
   int nz = 0;
 #pragma unroll
   for (int i = 0; i < CROWS; ++i)
   {
     uint32_t m = 0;
+    unsigned fo = 0xFF00u;
 #pragma unroll 4
     for (int k = sl; k < n_inc[i]; k += 8)
     {
       const uint32_t fm = fmask[ib[i] + k];
-      m |= (rc.cell_flags[rc.inc_cell[ib[i] + k]] & 0xFD) ? fm : 0u;
+      const unsigned fl = rc.cell_flags[rc.inc_cell[ib[i] + k]];
+      m |= (fl & 0xFD) ? fm : 0u;
+      fo = (fo | fl) & ((fl << 8) | 0xFFu);
     }
     M[i] = m;
+    FO[i] = fo;
   }
 #pragma unroll
   for (int i = 0; i < CROWS; ++i)
@@ -661,11 +667,21 @@ __global__ void __launch_bounds__(256)
     m |= __shfl_xor_sync(0xffffffffu, m, 1);
     m |= __shfl_xor_sync(0xffffffffu, m, 2);
     m |= __shfl_xor_sync(0xffffffffu, m, 4);
+    unsigned fo = FO[i];
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1)
+    {
+      const unsigned x = __shfl_xor_sync(0xffffffffu, fo, o);
+      fo = ((fo | x) & 0xFFu) | (fo & x & 0xFF00u);
+    }
     if (go[i] && sl == 0)
     {
       const bool cl = frow_ok[r[i]] != 0;
       row_nnz[r[i]] = __popc(m);
       Rrow[idx0 + i] = m;
+      // every incident cell has the same flag byte and it is a standard-quadrature one
+      const unsigned fl = fo & 0xFFu;
+      row_ufl[idx0 + i] = (fl == (fo >> 8) && (fl & 3u) == 0u) ? static_cast<uint8_t>(fl) : uint8_t(0);
       row_fast[idx0 + i] = 1 | 4 | (cl ? 8 : 0);
       if (cl)
       {
@@ -927,6 +943,8 @@ void build_incidence(cfx_ctx* c, Space& S)
   S.stride = static_cast<int>(read_back(c, c->scratch64.p + 2, 1)[0] & 0xffffffffLL);
   CFX_REQUIRE(S.stride >= 1 && S.stride <= 255, CFX_ERR_UNSUPPORTED,
               "cfx_space_bind: a dof with more than 255 (or no) incident cells is not supported");
+  S.lrow_built = false;
+  S.fpos_built = false;
   S.has_perm = S.nd <= 6;
   if (S.has_perm)
   {
@@ -1332,6 +1350,7 @@ void cfx_form_free(cfx_ctx* ctx, cfx_form* f)
   f->xcols.release();
   f->gmask.release();
   f->Rrow.release();
+  f->row_ufl.release();
   f->row_fast.release();
   f->Ae.release();
   f->coeff_own.release();
@@ -1415,8 +1434,9 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
     if (use_static)
     {
       a->Rrow.reserve(ctx->pool, static_cast<size_t>(n_act) + 1);
+      a->row_ufl.reserve(ctx->pool, static_cast<size_t>(n_act) + 16);
       CFX_LAUNCH(ctx, pattern_static_kernel, grid_for((n_act + 3) / 4 * 8, 256), 256, 0, rc, act, d_act, S.fmask.p, S.frow_ok.p,
-                 row_nnz.p, a->Rrow.p, a->row_fast.p, n_slow + 1);
+                 row_nnz.p, a->Rrow.p, a->row_fast.p, a->row_ufl.p, n_slow + 1);
     }
     if (need_generic)
     {
