@@ -23,6 +23,7 @@
 //
 // Roofline: HBM for P1/P2 scalar forms (SURVEY.md section 8d "K4", "K5").
 #include <algorithm>
+#include <cstdlib>
 
 #include <type_traits>
 #include "common.cuh"
@@ -2227,6 +2228,260 @@ __global__ void __launch_bounds__(RTB)
     gc.bvec[r] = gc.zero_first_b ? e : gc.bvec[r] + e;
 }
 
+// Scalar P1 BAND rows (rows with a ghost-penalty facet among their cells), one thread per row like
+// gather_matrix_p1_kernel.  A band row has columns the static full-mesh row does not have (the dofs across the
+// facets opposite the row's dof), so the thread first stages its CSR columns in a private shared-memory column and
+// builds the map static position -> CSR position (one lower-bound search per kept static column); cell tensors then
+// go exactly as in gather_matrix_p1_kernel.  Facets: per incident band cell the cell's facet ids (one 16-byte load),
+// their slots (independent probes), the 80-byte records of facet_p1_kernel; a facet is taken by its first cell, or
+// by the second when the first does not hold the row's dof; each of the nd + 1 macro dofs is located by a
+// lower-bound search in the staged columns.  Fixed order: cells ascending, then facets cell by cell, local facet by
+// local facet -- no atomics, bit-reproducible.  (The warp-per-row mask kernel this replaces for P1 spent 1100 of its
+// 1800 warp instructions per row matching facet entries against columns lane by lane.)
+constexpr int RTBB = 64;
+
+// G threads per row (a power of two <= 8, groups inside one warp): thread g takes the incident cells l = g, g + G, ...
+// into its own accumulator column; the group's columns are added in the fixed order g = 0 .. G-1 at the end.  A
+// band row is a long dependent chain (cell -> flags -> facets -> slots -> records -> searches) and there are few of
+// them, so one thread per row leaves the machine waiting; G threads cut the chain G times.
+template <int TDIM, bool FUSED, int G>
+__global__ void __launch_bounds__(RTBB, 16)
+    gather_matrix_band_p1_kernel(GatherCtx gc, StdTab st, StdTab stL, const int32_t* __restrict__ act_rows,
+                                 const int32_t* __restrict__ slots, DN n_band_, const uint8_t* __restrict__ row_fast,
+                                 const int32_t* __restrict__ fcols, const int64_t* __restrict__ row_ptr,
+                                 const int32_t* __restrict__ cols, double* __restrict__ vals, int zero_first)
+{
+  constexpr int ND = TDIM + 1, NO = TDIM, NE = ND + 1;
+  __shared__ double s_acc[32][RTBB];
+  __shared__ int32_t s_cols[32][RTBB];
+  __shared__ uint8_t s_map[32][RTBB];
+  const int tid = threadIdx.x;
+  const int g = tid & (G - 1);
+  const unsigned gmask = ((G == 32) ? 0xffffffffu : ((1u << G) - 1u)) << ((tid & 31) & ~(G - 1));
+  const int64_t it = (static_cast<int64_t>(blockIdx.x) * RTBB + tid) / G;
+  if (it >= n_band_.get())
+    return;
+  const int64_t idx = slots[it];
+  const unsigned rf = row_fast[idx];
+  if (!(rf & 1u) || (rf & 4u))
+    return; // more than 32 columns / incident cells: the generic kernel
+  const int32_t r = act_rows[idx];
+  const int64_t ib = gc.inc_ptr[r];
+  const int n_inc = static_cast<int>(gc.inc_ptr[r + 1] - ib);
+  const int64_t rb = row_ptr[r];
+  const int rn = static_cast<int>(row_ptr[r + 1] - rb);
+  const int64_t fb = gc.frow_ptr[r];
+  const int nfull = static_cast<int>(gc.frow_ptr[r + 1] - fb);
+  // the row's columns and the static-position map: every thread of the group fills a share of EVERY member's
+  // private column (so that the searches below never leave the thread's own shared-memory column)
+  const int t0 = tid - g;
+  for (int k = g; k < 32; k += G)
+  {
+    const int32_t cv = k < rn ? cols[rb + k] : 0x7fffffff;
+#pragma unroll
+    for (int m = 0; m < G; ++m)
+      s_cols[k][t0 + m] = cv;
+  }
+#pragma unroll
+  for (int k = 0; k < 32; ++k)
+    s_acc[k][tid] = 0.0;
+  __syncwarp(gmask);
+  auto find = [&](int32_t d) -> int
+  { // lower bound of d among the row's (ascending) columns
+    int pos = 0;
+#pragma unroll
+    for (int sp = 16; sp > 0; sp >>= 1)
+      pos += (s_cols[pos + sp - 1][tid] < d) ? sp : 0;
+    return pos;
+  };
+  for (int p = g; p < nfull; p += G)
+  {
+    const uint8_t pos = static_cast<uint8_t>(find(fcols[fb + p])); // columns the row did not keep are never looked up
+#pragma unroll
+    for (int m = 0; m < G; ++m)
+      s_map[p][t0 + m] = pos;
+  }
+  __syncwarp(gmask);
+  double e = 0.0;
+  constexpr double MASSW = TDIM == 3 ? 1.0 / 120.0 : 1.0 / 24.0;
+  constexpr double SRCW = TDIM == 3 ? 1.0 / 24.0 : 1.0 / 6.0;
+  // ---- this thread's cells, two at a time: tensors, then facets
+  constexpr int U = 2;
+  for (int l0 = g; l0 < n_inc; l0 += U * G)
+  {
+    P1Rec rec[U];
+    uint32_t word[U], fm[U];
+    int32_t cell[U];
+    unsigned fl[U];
+    bool in[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      in[u] = l0 + u * G < n_inc;
+      const int l = in[u] ? l0 + u * G : l0;
+      rec[u] = ldg_stream_p1rec(gc.lrow, ib + l);
+      word[u] = ldg_keep(gc.fpos + ib + l);
+      fm[u] = gc.fmask[ib + l];
+      cell[u] = gc.inc_cell[ib + l];
+    }
+    // by cell: the flag byte and -- whether or not the cell turns out to be a band cell -- its facet ids (one
+    // level of the dependent chain less than asking the flags first)
+    int32_t fct[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      fl[u] = in[u] ? gc.cell_flags[cell[u]] : 0u;
+      if (ND == 4)
+      {
+        const int4 q = __ldg(reinterpret_cast<const int4*>(gc.c2f) + cell[u]);
+        fct[u][0] = q.x;
+        fct[u][1] = q.y;
+        fct[u][2] = q.z;
+        fct[u][3] = q.w;
+      }
+      else
+      {
+#pragma unroll
+        for (int lf = 0; lf < ND; ++lf)
+          fct[u][lf] = gc.c2f[static_cast<int64_t>(cell[u]) * ND + lf];
+        fct[u][3] = 0;
+      }
+    }
+    int32_t fsl[U][ND];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int lf = 0; lf < ND; ++lf)
+        fsl[u][lf] = (fl[u] & 2u) ? gc.facet_slot[fct[u][lf]] : -1;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      if (!(fl[u] & 0xFDu))
+        continue;
+      const unsigned m = fl[u] >> 2;
+      double v[NO], vd = 0.0;
+#pragma unroll
+      for (int q = 0; q < NO; ++q)
+        v[q] = 0.0;
+      if (m)
+      {
+        const double w = st.t0[m];
+        double dsum = 0.0;
+#pragma unroll
+        for (int q = 0; q < NO; ++q)
+        {
+          const double t = w * rec[u].a[q];
+          dsum += t;
+          v[q] += t;
+        }
+        vd -= dsum;
+        if (st.has_mass)
+        {
+          const double wm = st.t1[m] * rec[u].a[3] * MASSW;
+#pragma unroll
+          for (int q = 0; q < NO; ++q)
+            v[q] += wm;
+          vd += 2.0 * wm;
+        }
+        if constexpr (FUSED)
+          e += stL.t0[m] * rec[u].a[3] * SRCW;
+      }
+      if (fl[u] & 1u)
+      {
+        const int li = static_cast<int>(word[u] & 3u);
+        const int64_t ms = __ldg(gc.mat_slot + cell[u]);
+        const double* a = gc.Ae + (ms * ND + li) * ND;
+        double av[ND];
+#pragma unroll
+        for (int j = 0; j < ND; ++j)
+          av[j] = a[j];
+#pragma unroll
+        for (int q = 0; q < NO; ++q)
+          v[q] += pick<ND>(av, q < li ? q : q + 1);
+        vd += pick<ND>(av, li);
+        if constexpr (FUSED)
+          e += gc.AeL[ms * ND + li];
+      }
+#pragma unroll
+      for (int q = 0; q < NO; ++q)
+        s_acc[s_map[(word[u] >> (7 + 5 * q)) & 31u][tid]][tid] += v[q];
+      s_acc[s_map[(word[u] >> 2) & 31u][tid]][tid] += vd;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      if (!(fl[u] & 2u))
+        continue;
+      // CSR positions of the cell's dofs in ASCENDING dof order: the set bits of its static position mask,
+      // mapped (positions are monotone in the dof number)
+      int cp[ND];
+      {
+        uint32_t mm = fm[u];
+#pragma unroll
+        for (int t = 0; t < ND; ++t)
+        {
+          cp[t] = s_map[(__ffs(mm) - 1) & 31][tid];
+          mm &= mm - 1;
+        }
+      }
+#pragma unroll
+      for (int lf = 0; lf < ND; ++lf)
+      {
+        if (fsl[u][lf] < 0)
+          continue;
+        const double* frec = gc.Fe + static_cast<int64_t>(fsl[u][lf]) * FREC;
+        const int4 q1 = __ldg(reinterpret_cast<const int4*>(frec) + 1);
+        const int4 q0 = __ldg(reinterpret_cast<const int4*>(frec));
+        const double2 j01 = __ldg(reinterpret_cast<const double2*>(frec) + 2);
+        const double2 j23 = __ldg(reinterpret_cast<const double2*>(frec) + 3);
+        const double2 j4w = __ldg(reinterpret_cast<const double2*>(frec) + 4);
+        const bool first = cell[u] == q1.y;
+        if (!first && q1.w != r)
+          continue; // the facet's first cell holds the row's dof too: it takes the facet
+        const int32_t dd[5] = {q0.x, q0.y, q0.z, q0.w, q1.x};
+        const double J[5] = {j01.x, j01.y, j23.x, j23.y, j4w.x};
+        // the record lists the macro dofs ascending: all but one (index ix) are this cell's dofs, in the order of cp
+        const int ix = first ? (q1.z >> 4) : (q1.z & 15);
+        double jr = 0.0;
+        int32_t dx = 0;
+#pragma unroll
+        for (int k = 0; k < NE; ++k)
+        {
+          jr = (dd[k] == r) ? J[k] : jr;
+          dx = (k == ix) ? dd[k] : dx;
+        }
+        const int px = find(dx);
+        const double jm = jr * j4w.y;
+#pragma unroll
+        for (int k = 0; k < NE; ++k)
+        {
+          const int own = k < ix ? cp[k < ND ? k : ND - 1] : cp[k > 0 ? k - 1 : 0];
+          s_acc[k == ix ? px : own][tid] += jm * J[k];
+        }
+      }
+    }
+  }
+  __syncwarp(gmask);
+  // the group's columns in the fixed order 0 .. G-1 (on top of the old value unless the matrix is being overwritten)
+  for (int k = g; k < rn; k += G)
+  {
+    double x = zero_first ? 0.0 : vals[rb + k];
+#pragma unroll
+    for (int m = 0; m < G; ++m)
+      x += s_acc[k][t0 + m];
+    vals[rb + k] = x;
+  }
+  if constexpr (FUSED)
+  {
+    double x = 0.0;
+#pragma unroll
+    for (int m = 0; m < G; ++m)
+      x += __shfl_sync(gmask, e, ((tid & 31) & ~(G - 1)) + m);
+    if (g == 0)
+      gc.bvec[r] = gc.zero_first_b ? x : gc.bvec[r] + x;
+  }
+}
+
 // One warp per active row: lanes take the incident cells, compute / load the cell's entry for this
 // row, fixed shuffle tree -> bit-reproducible.
 template <int TDIM, int DEG, bool PERM>
@@ -3275,7 +3530,24 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
                               - static_cast<double>(A->n_rows - PR->n_act_rows);
       StageScope sk(ctx, "gather_matrix_mask_kernel", 12.0 * (nnz_mask > 0.0 ? nnz_mask : 0.0));
       auto kf = gather_matrix_fast_kernel<TDIM, DEG>;
-      if (a->n_band_listed > 0)
+      bool band_done = false;
+      if constexpr (DEG == 1)
+      {
+        if (a->n_band_listed > 0 && gc.fpos != nullptr)
+        { // scalar P1 with a static structure: one thread per band row
+          static const int G = getenv("CFX_BAND_G") ? atoi(getenv("CFX_BAND_G")) : 4;
+          auto kb = G == 8   ? (gc.bvec ? gather_matrix_band_p1_kernel<TDIM, true, 8> : gather_matrix_band_p1_kernel<TDIM, false, 8>)
+                    : G == 4 ? (gc.bvec ? gather_matrix_band_p1_kernel<TDIM, true, 4> : gather_matrix_band_p1_kernel<TDIM, false, 4>)
+                    : G == 2 ? (gc.bvec ? gather_matrix_band_p1_kernel<TDIM, true, 2> : gather_matrix_band_p1_kernel<TDIM, false, 2>)
+                             : (gc.bvec ? gather_matrix_band_p1_kernel<TDIM, true, 16> : gather_matrix_band_p1_kernel<TDIM, false, 16>);
+          const int Gu = (G == 8 || G == 4 || G == 2) ? G : 16;
+          CFX_LAUNCH(ctx, kb, grid_for(a->n_band_listed * Gu, RTBB), RTBB, 0, gc, st, stL, PR->act_rows.p,
+                     PR->band_idx.p, PR->dn_band(), a->row_fast.p, S.fcols.p, A->row_ptr.p, A->cols.p, A->values.p,
+                     zero_first);
+          band_done = true;
+        }
+      }
+      if (a->n_band_listed > 0 && !band_done)
         CFX_LAUNCH(ctx, kf, grid_for(a->n_band_listed, GWM), GWM * 32, 0, gc, st, stL, PR->act_rows.p, PR->band_idx.p,
                    PR->dn_band(), a->row_fast.p, a->gmask.p, a->Rrow.p, A->row_ptr.p, A->cols.p, A->values.p,
                    zero_first);
