@@ -10,7 +10,8 @@ sparsity -> matrix + vector assembly.  Prints ONE JSON line (see DESIGN.md "Meas
 Workloads (BASELINE.json configs / SURVEY.md section 8 sizing):
   C1  2D circle R=0.5 on [-1,1]^2, 64x64 right-diagonal triangles, P1, order 4
   C3  3D sphere R=0.35 on [0,1]^3, n^3 Kuhn tetrahedra (default n=256), P1, order 4   <- default
-  C2p 2D circle on 4096^2 triangles with P1 u (the P2 variant of configs[1] is a parity-test case)
+  C2  configs[1]: P2 u on 4096^2 triangles;  C4  configs[3]: P2-vector elasticity, torus, 192^3 tets;
+  C5  configs[4]: moving sphere on 128^3 tets, everything rebuilt every step
 `value` = cut cells / s with all inputs resident in HBM; `e2e` = the same through host buffers
 (level-set values H2D from pinned memory, CSR pattern + values + rhs D2H inside the timed region).
 """
@@ -44,6 +45,11 @@ WORKLOADS = {
                order=2, moving=(0.3, 0.4, 99),
                name="moving sphere R=0.25 (c_x = 0.3 + 0.4 t/99), {n}^3 Kuhn tetrahedra, P1, order 2: re-cut, "
                     "regenerate quadrature, rebuild sparsity and reassemble every step"),
+    # configs[3]: linear elasticity on a P2 VECTOR space, torus level set, Nitsche + ghost penalty (demo_elasticity.py)
+    "C4": dict(tdim=3, n=192, p0=(0.0, 0.0, 0.0), p1=(1.0, 1.0, 1.0), ls=("torus", (0.5, 0.5, 0.5, 0.3, 0.12)),
+               order=4, degree=2, bs=3, problem="elasticity", ref_n=32,
+               name="3D torus (R=0.3, r=0.12), {n}^3 Kuhn tetrahedra, linear elasticity on a P2 vector space / P1 "
+                    "level set, order 4, vector Nitsche + ghost-penalty facets"),
     "C3": dict(tdim=3, n=256, p0=(0.0, 0.0, 0.0), p1=(1.0, 1.0, 1.0), ls=("sphere", (0.5, 0.5, 0.5, 0.35, 0.0)),
                order=4, name="3D sphere R=0.35, {n}^3 Kuhn tetrahedra, P1 volume+interface quadrature order 4, "
                              "Nitsche + ghost-penalty facets"),
@@ -142,7 +148,8 @@ def _oracle_slab_init(wl, n, nparts, counter):
     q0[ax], q1[ax] = p0[ax] + lo * h, p0[ax] + hi * h
     mesh = M.create_box(n, n, hi - lo, q0, q1) if tdim == 3 else M.create_rectangle(n, hi - lo, q0, q1)
     Vphi = M.functionspace(mesh, 1)
-    V = Vphi if wl.get("degree", 1) == 1 else M.functionspace(mesh, wl["degree"])
+    bs = wl.get("bs", 1)
+    V = Vphi if (wl.get("degree", 1) == 1 and bs == 1) else M.functionspace(mesh, wl.get("degree", 1), bs=bs)
     _SLAB.update(wl=wl, mesh=mesh, Vphi=Vphi, V=V, rank=rank)
 
 
@@ -159,7 +166,10 @@ def _oracle_slab_step(tstep):
         prm[0] = x0 + dx * (tstep % (period + 1)) / period
     ls = M.sphere_level_set(prm[:3], prm[3]) if kind == "sphere" else M.torus_level_set(prm[:3], prm[3], prm[4])
     phi = M.interpolate(Vphi, ls)
-    out = pipeline.run_pipeline(mesh, Vphi.dofmap, phi, V, order=wl["order"])
+    if wl.get("problem") == "elasticity":
+        out = pipeline.run_elasticity_pipeline(mesh, Vphi.dofmap, phi, V, order=wl["order"])
+    else:
+        out = pipeline.run_pipeline(mesh, Vphi.dofmap, phi, V, order=wl["order"])
     return dict(time=out["total_s"], cut=int(out["cut"].size), cells=int(mesh.num_cells), nnz=int(out["cols"].size))
 
 
@@ -231,6 +241,10 @@ def run_reference(args, wl):
 
 
 # --------------------------------------------------------------------------------------------- our arm
+def V_bs(pipe):
+    return getattr(pipe.V, "bs", 1) or 1
+
+
 def run_ours(args, wl):
     """The whole step of every rank is ONE CUDA-graph launch: deferred sizes (no host round trip inside the step)
     and, for N > 1, the ghost exchange over NCCL inside the same graph (static exchange plan, cfx_xplan_*)."""
@@ -282,7 +296,9 @@ def run_ours(args, wl):
     ls_fn = M.sphere_level_set(prm[:3], prm[3]) if kind == "sphere" else M.torus_level_set(prm[:3], prm[3], prm[4])
     ranges = P.slab_ranges(n, world, P.layer_weights([n] * tdim, wl["p0"], wl["p1"], ls_fn)) if world > 1 else None
     pipe = P.RankPipeline([n] * tdim, list(wl["p0"]), list(wl["p1"]), world, rank, local_rank, kind, prm,
-                          order=wl["order"], ranges=ranges, degree=wl.get("degree", 1))
+                          order=wl["order"], ranges=ranges, degree=wl.get("degree", 1),
+                          **({"problem": wl["problem"], "bs": wl.get("bs", 1)} if "problem" in wl else {}))
+    bsz = int(V_bs(pipe))
     prob, ctx, V = pipe.prob, pipe.ctx, pipe.V
     sync()
     t1 = time.perf_counter()
@@ -341,11 +357,11 @@ def run_ours(args, wl):
     nnz_owned = int(prob.A.indptr_device()[no].item())
     # global checksums of the assembled system (owned rows): equal for every N, so the scaling run verifies the
     # NCCL path against the N = 1 line
-    vals_owned = prob.A.values_device()[:nnz_owned]
+    vals_owned = prob.A.values_device()[: nnz_owned * bsz * bsz]
     cut_total, nnz_total, cells_total, active_total, launches_total, a_fro2, b_sum, b_abs = allsum(
         [stats["cut"], nnz_owned, stats["inside"] + stats["cut"] + stats["outside"],
          stats["inside"] + stats["volume_rules"], launches, float((vals_owned * vals_owned).sum()),
-         float(prob.b[:no].sum()), float(prob.b[:no].abs().sum())])
+         float(prob.b[: no * bsz].sum()), float(prob.b[: no * bsz].abs().sum())])
     checks = {"nnz": int(nnz_total), "A_frobenius": a_fro2 ** 0.5, "b_sum": b_sum, "b_abs_sum": b_abs,
               "cut_cells": int(cut_total)}
 
@@ -419,59 +435,64 @@ def run_ours(args, wl):
     # (CSR pattern + values + rhs) overlaps the compute of step k+1; every step's inputs still arrive from the host
     # and every step's results still reach it inside the timed region.  One graph per buffer set.
     nnz_cap = int(stats["nnz"] * 1.3) + 4096
-    hb = [dict(vals=torch.empty(nnz_cap, dtype=torch.float64, pin_memory=True),
-               cols=torch.empty(nnz_cap, dtype=torch.int32, pin_memory=True),
-               rp=torch.empty(V.num_dofs + 1, dtype=torch.int64, pin_memory=True),
-               b=torch.empty(V.num_dofs, dtype=torch.float64, pin_memory=True)) for _ in range(2)]
-    As = [prob.A, _fem.MatrixCSR(ctx)]
-    bs = [prob.b, torch.empty_like(prob.b)]
-    graphs = []
-    for k in range(2):
-        prob.A, prob.b = As[k], bs[k]
-        graphs.append(pipe.capture_static(margin=0.25))
-    side = torch.cuda.Stream()
-    done = [None, None]
-    kstep = [0]
+    e2e_bytes = (4 + 8 * bsz * bsz) * nnz_cap + 16 * V.num_dofs * bsz
+    skip_e2e = e2e_bytes > args.e2e_cap_gb * 1e9  # two pinned host buffer sets of this size would be needed
+    t_e2e = float('nan')
     d2h = [0]
+    if not skip_e2e:
+        hb = [dict(vals=torch.empty(nnz_cap * bsz * bsz, dtype=torch.float64, pin_memory=True),
+                   cols=torch.empty(nnz_cap, dtype=torch.int32, pin_memory=True),
+                   rp=torch.empty(V.num_dofs + 1, dtype=torch.int64, pin_memory=True),
+                   b=torch.empty(V.num_dofs * bsz, dtype=torch.float64, pin_memory=True)) for _ in range(2)]
+        As = [prob.A, _fem.MatrixCSR(ctx)]
+        bs = [prob.b, torch.empty_like(prob.b)]
+        graphs = []
+        for k in range(2):
+            prob.A, prob.b = As[k], bs[k]
+            graphs.append(pipe.capture_static(margin=0.25))
+        side = torch.cuda.Stream()
+        done = [None, None]
+        kstep = [0]
+        d2h = [0]
 
-    def e2e_step():
-        k = kstep[0] % 2
-        kstep[0] += 1
-        if done[k] is not None:
-            torch.cuda.current_stream().wait_event(done[k])  # buffers of step k-2 have left the device
-        if "moving" in wl:  # the host owns the level set in this leg: new values are written into the pinned array
-            move()
-            h_phi.copy_(pipe.phi.x.array)
-        graphs[k].launch()
-        A = As[k]
-        A._cache.clear()
-        ready = torch.cuda.Event()
-        ready.record()
-        nnz = A.nnz  # the host needs the size of what it receives: the one round trip of the step
-        side.wait_event(ready)
-        A.copy_to_host_async(hb[k]["rp"], hb[k]["cols"], hb[k]["vals"], side)
-        with torch.cuda.stream(side):
-            hb[k]["b"].copy_(bs[k], non_blocking=True)
-            done[k] = torch.cuda.Event()
-            done[k].record()
-        d2h[0] = 12 * nnz + 8 * (V.num_dofs + 1) + 8 * V.num_dofs
-        return nnz
+        def e2e_step():
+            k = kstep[0] % 2
+            kstep[0] += 1
+            if done[k] is not None:
+                torch.cuda.current_stream().wait_event(done[k])  # buffers of step k-2 have left the device
+            if "moving" in wl:  # the host owns the level set in this leg: new values are written into the pinned array
+                move()
+                h_phi.copy_(pipe.phi.x.array)
+            graphs[k].launch()
+            A = As[k]
+            A._cache.clear()
+            ready = torch.cuda.Event()
+            ready.record()
+            nnz = A.nnz  # the host needs the size of what it receives: the one round trip of the step
+            side.wait_event(ready)
+            A.copy_to_host_async(hb[k]["rp"], hb[k]["cols"], hb[k]["vals"], side)
+            with torch.cuda.stream(side):
+                hb[k]["b"].copy_(bs[k], non_blocking=True)
+                done[k] = torch.cuda.Event()
+                done[k].record()
+            d2h[0] = (4 + 8 * bsz * bsz) * nnz + 8 * (V.num_dofs + 1) + 8 * V.num_dofs * bsz
+            return nnz
 
-    for _ in range(2):
-        e2e_step()
-    side.synchronize()
-    sync()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    for ev_done in done:
-        torch.cuda.current_stream().wait_event(ev_done)
-    e1.record()
-    sync()
-    side.synchronize()
-    ctx.check()
-    t_e2e = allmax([e0.elapsed_time(e1) / 1e3])[0]
+        for _ in range(2):
+            e2e_step()
+        side.synchronize()
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        for ev_done in done:
+            torch.cuda.current_stream().wait_event(ev_done)
+        e1.record()
+        sync()
+        side.synchronize()
+        ctx.check()
+        t_e2e = allmax([e0.elapsed_time(e1) / 1e3])[0]
     h2d, d2h_total = allsum([8.0 * n_phi, float(d2h[0])])
 
     if rank != 0:
@@ -501,8 +522,10 @@ def run_ours(args, wl):
                    if world > 1 else "1 rank (no exchange)",
                    "step": "one CUDA-graph launch per rank and step (deferred sizes, no host round trip inside it)"},
         "nnz_per_s": nnz_total * args.steps / t_total, "total_cells_per_s": cells_total * args.steps / t_total,
-        "e2e": {"value": cut_total * args.steps / t_e2e, "unit": "cut-cells/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h_total), "ms_per_step": t_e2e / args.steps * 1e3},
+        "e2e": ({"value": cut_total * args.steps / t_e2e, "unit": "cut-cells/s", "h2d_bytes_per_step": int(h2d),
+                 "d2h_bytes_per_step": int(d2h_total), "ms_per_step": t_e2e / args.steps * 1e3} if not skip_e2e else
+                {"value": None, "unit": "cut-cells/s", "skipped": f"the CSR of one step is {e2e_bytes / 1e9:.1f} GB: two "
+                 f"pinned host buffer sets exceed --e2e-cap-gb {args.e2e_cap_gb}"}),
         "gpu_launches": int(launches_total), "graph_launches_per_step": 1, "kernels_per_step": graph.kernel_nodes,
         "clocks": clocks, "roofline": roof, "stages": per_stage, "stage_sum_ms": stage_sum, "setup": setup,
         "checks": checks, "space_counters": space_counters,
@@ -535,6 +558,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=0, help="override the mesh resolution of the workload")
+    ap.add_argument("--e2e-cap-gb", type=float, default=8.0,
+                    help="skip the host-buffer leg when one step's CSR is larger than this (pinned host memory)")
     ap.add_argument("--ref-n", type=int, default=0, help="resolution of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -2906,9 +2906,10 @@ __global__ void __launch_bounds__(EB)
 // entry goes on the diagonal of the block.
 template <int TDIM, int DEG>
 __global__ void __launch_bounds__(32)
-    gather_matrix_blocked_kernel(GatherCtx gc, const int32_t* __restrict__ act_rows, DN n_act_,
-                                 const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ cols,
-                                 double* __restrict__ vals, int zero_first, int32_t* __restrict__ err)
+    gather_matrix_blocked_kernel(GatherCtx gc, const int32_t* __restrict__ act_rows, const int32_t* __restrict__ slots,
+                                 DN n_act_, int facets_only, const int64_t* __restrict__ row_ptr,
+                                 const int32_t* __restrict__ cols, double* __restrict__ vals, int zero_first,
+                                 int32_t* __restrict__ err)
 {
   constexpr int ND = Elem<TDIM, DEG>::ND;
   constexpr int BS = TDIM, N = ND * BS;
@@ -2917,9 +2918,11 @@ __global__ void __launch_bounds__(32)
   __shared__ __align__(16) int32_t s_fd[32][FacetStage<ND>::W];
   __shared__ __align__(16) double s_fv[32][FacetStage<ND>::W];
   const int lane = threadIdx.x;
-  const int64_t idx = blockIdx.x;
-  if (idx >= n_act_.get())
+  if (static_cast<int64_t>(blockIdx.x) >= n_act_.get())
     return;
+  // facets_only: the cell tensors were added by gather_matrix_blocked2_kernel; this pass walks the band rows
+  // (slot list) and adds the interior-facet macro tensors
+  const int64_t idx = slots ? slots[blockIdx.x] : blockIdx.x;
   const unsigned full = 0xffffffffu;
   const int64_t r = act_rows[idx];
   const int64_t ib = gc.inc_ptr[r];
@@ -2946,7 +2949,7 @@ __global__ void __launch_bounds__(32)
         c = gc.inc_cell[ib + k];
         fl = gc.cell_flags[c];
       }
-      const bool contributes = (fl & 1u) != 0;
+      const bool contributes = (fl & 1u) != 0 && !facets_only;
       if (fl)
       {
         int32_t d[ND];
@@ -3017,6 +3020,257 @@ __global__ void __launch_bounds__(32)
   }
 }
 
+// Blocked spaces, cell tensors: one warp per row, one LANE PER (incident cell, local column dof j) pair -- 32 bs x bs
+// blocks per round.  A standard-quadrature elasticity cell is NOT materialised (a P2 tetrahedron's 30 x 30 tensor is
+// 7.2 KB): the lane computes its block from the cached geometry and the reference-element table
+//   S^{rs} = int d_r phi_i d_s phi_j = |detJ| sum_tu K[t][r] K[u][s] R[t][u][i][j]          (81 FMAs)
+//   block[a][b] = lambda S^{ab} + mu S^{ba} + delta_ab mu tr S
+// which is the arithmetic the materialising kernel spends on the entry, without the 2 x 7.2 KB round trip through
+// HBM; a cut cell's block is read from its materialised run-time-rule tensor.  The block goes to the CSR position of
+// dof j (lower-bound search in the row's staged columns); lanes of one round that hit the same position add in lane
+// order (match.any + rank loop), rounds run in order: ascending cells, fixed order, no atomics.  The row's blocks
+// live in shared memory until the row is complete (one coalesced store).  Interior-facet tensors are added
+// afterwards by gather_matrix_blocked_kernel in facets-only mode over the band rows.
+constexpr int BGW = 2;      // rows (warps) per block
+constexpr int BMAXC = 96;   // columns per row held in shared memory (P2 tetrahedra: 65 on a Kuhn mesh); longer rows
+                            // accumulate in the CSR arrays themselves
+
+template <int TDIM, int DEG>
+__global__ void __launch_bounds__(BGW * 32, 16)
+    gather_matrix_blocked2_kernel(GatherCtx gc, StdTab st, const int32_t* __restrict__ act_rows, DN n_act_,
+                                  const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ cols,
+                                  double* __restrict__ vals, int zero_first, int32_t* __restrict__ err)
+{
+  constexpr int ND = Elem<TDIM, DEG>::ND;
+  constexpr int BS = TDIM, N = ND * BS, B2 = BS * BS;
+  using T = RefTab<TDIM, ND>;
+  __shared__ double s_row[BGW][BMAXC * B2];
+  __shared__ int32_t s_cols[BGW][BMAXC];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * BGW + w;
+  if (idx >= n_act_.get())
+    return;
+  const unsigned full = 0xffffffffu;
+  const uint32_t below = (1u << lane) - 1u;
+  const int32_t r = act_rows[idx];
+  const int64_t ib = gc.inc_ptr[r];
+  const int n_inc = static_cast<int>(gc.inc_ptr[r + 1] - ib);
+  const int64_t rb = row_ptr[r];
+  const int rn = static_cast<int>(row_ptr[r + 1] - rb);
+  const bool staged = rn <= BMAXC;
+  double* const row = staged ? s_row[w] : vals + rb * B2;
+  const int32_t* const sc = staged ? s_cols[w] : cols + rb;
+  if (staged)
+  {
+    for (int k = lane; k < rn; k += 32)
+      s_cols[w][k] = cols[rb + k];
+    for (int t = lane; t < rn * B2; t += 32)
+      row[t] = zero_first ? 0.0 : vals[rb * B2 + t];
+  }
+  else if (zero_first)
+    for (int t = lane; t < rn * B2; t += 32)
+      row[t] = 0.0;
+  __syncwarp();
+  const int np = n_inc * ND;
+  int bad = 0;
+  for (int p0 = 0; p0 < np; p0 += 32)
+  {
+    const int p = p0 + lane;
+    const bool valid = p < np;
+    const int l = valid ? p / ND : 0;
+    const int j = valid ? p - l * ND : 0;
+    const int64_t c = gc.inc_cell[ib + l];
+    const unsigned fl = valid ? gc.cell_flags[c] : 0u;
+    const bool contributes = (fl & 0xFDu) != 0;
+    int32_t dj = 0;
+    int li = 0;
+#pragma unroll
+    for (int q = 0; q < ND; ++q)
+    {
+      const int32_t d = gc.dofmap[c * ND + q];
+      li = (d == r) ? q : li;
+      dj = (q == j) ? d : dj;
+    }
+    double blk[B2];
+#pragma unroll
+    for (int q = 0; q < B2; ++q)
+      blk[q] = 0.0;
+    if (fl >> 2)
+    {
+      Geo<TDIM> g;
+      load_geo_cached<TDIM>(gc.geo, c, g);
+      double S[TDIM][TDIM];
+#pragma unroll
+      for (int a = 0; a < TDIM; ++a)
+#pragma unroll
+        for (int b = 0; b < TDIM; ++b)
+          S[a][b] = 0.0;
+#pragma unroll
+      for (int t = 0; t < TDIM; ++t)
+#pragma unroll
+        for (int u = 0; u < TDIM; ++u)
+        {
+          const double rr = __ldg(st.ref + T::R + ((t * TDIM + u) * ND + li) * ND + j);
+#pragma unroll
+          for (int a = 0; a < TDIM; ++a)
+          {
+            const double ka = g.K[t * TDIM + a] * rr;
+#pragma unroll
+            for (int b = 0; b < TDIM; ++b)
+              S[a][b] += ka * g.K[u * TDIM + b];
+          }
+        }
+      double tr = 0.0;
+#pragma unroll
+      for (int a = 0; a < TDIM; ++a)
+        tr += S[a][a];
+      const double sdet = fabs(g.detJ);
+      for (int k = 0; k < st.n; ++k)
+      {
+        if (!(fl & st.bit[k]))
+          continue;
+        const double mu = st.c[k][0] * sdet, lam = st.c[k][1] * sdet;
+#pragma unroll
+        for (int a = 0; a < TDIM; ++a)
+#pragma unroll
+          for (int b = 0; b < TDIM; ++b)
+            blk[a * BS + b] += lam * S[a][b] + mu * S[b][a] + ((a == b) ? mu * tr : 0.0);
+      }
+    }
+    if (fl & 1u)
+    {
+      const double* a = gc.Ae + (static_cast<int64_t>(__ldg(gc.mat_slot + c)) * N + li * BS) * N + j * BS;
+#pragma unroll
+      for (int aa = 0; aa < BS; ++aa)
+#pragma unroll
+        for (int b = 0; b < BS; ++b)
+          blk[aa * BS + b] += a[aa * N + b];
+    }
+    // CSR position of dof j of the cell: lower bound in the row's ascending columns
+    int pos = 0;
+    if (contributes)
+    {
+      int lo = 0, hi = rn;
+      while (lo < hi)
+      {
+        const int mid = (lo + hi) >> 1;
+        if (sc[mid] < dj)
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      pos = lo;
+      if (pos >= rn || sc[pos] != dj)
+        bad = 1; // MatrixCSR::mat_add_values throws when an entry is not in the pattern
+    }
+    const int key = (contributes && !bad) ? pos : -1 - lane;
+    const unsigned peers = __match_any_sync(full, key);
+    const int rank = __popc(peers & below);
+    const int maxrank = __reduce_max_sync(full, (contributes && !bad) ? rank : 0);
+    for (int rr = 0; rr <= maxrank; ++rr)
+    {
+      if (contributes && !bad && rank == rr)
+      {
+#pragma unroll
+        for (int q = 0; q < B2; ++q)
+          row[pos * B2 + q] += blk[q];
+      }
+      __syncwarp();
+    }
+  }
+  // ---- interior-facet macro tensors (full (2 nd)^2 scalar tensors; the P1 record format keeps the separate
+  // facets-only pass): one lane per (incident band cell, local facet) probes the facet slot; every hit is then
+  // spread over the lanes, lane e < 2 nd taking entry e of the hit's macro-tensor row -- its dof from the two cells'
+  // dofmap rows, its position by the same search -- and adding it to the diagonal of the block (a scalar tensor
+  // acts on every component alike).  Hits in (cell, local facet) order, duplicates of a round in lane order.
+  if constexpr (DEG == 2)
+  {
+    if (gc.Fe != nullptr && gc.rows4 != nullptr)
+    {
+      constexpr int NF = TDIM + 1;
+      const int nq = n_inc * NF;
+      for (int p0 = 0; p0 < nq; p0 += 32)
+      {
+        const int p = p0 + lane;
+        const bool valid = p < nq;
+        const int l = valid ? p / NF : 0;
+        const int lf = valid ? p - l * NF : 0;
+        const int64_t c = gc.inc_cell[ib + l];
+        const unsigned fl = valid ? gc.cell_flags[c] : 0u;
+        int32_t fs = -1;
+        if (fl & 2u)
+          fs = gc.facet_slot[gc.c2f[c * NF + lf]];
+        unsigned hits = __ballot_sync(full, fs >= 0);
+        while (hits)
+        {
+          const int src = __ffs(hits) - 1;
+          hits &= hits - 1;
+          const int32_t hfs = __shfl_sync(full, fs, src);
+          const int32_t hc = static_cast<int32_t>(__shfl_sync(full, static_cast<int32_t>(c), src));
+          const int4 rw = __ldg(reinterpret_cast<const int4*>(gc.rows4) + hfs); // (cell0, lf0, cell1, lf1)
+          const bool first = hc == rw.x;
+          // local index of the row's dof in the hit's cell
+          int hli = 0;
+#pragma unroll
+          for (int q = 0; q < ND; ++q)
+            hli = (gc.dofmap[static_cast<int64_t>(hc) * ND + q] == r) ? q : hli;
+          const int mrow = (first ? 0 : ND) + hli;
+          const bool on = lane < 2 * ND;
+          int32_t dj = 0;
+          double v = 0.0;
+          if (on)
+          {
+            const int64_t cc = lane < ND ? rw.x : rw.z;
+            dj = gc.dofmap[cc * ND + (lane < ND ? lane : lane - ND)];
+            v = gc.Fe[(static_cast<int64_t>(hfs) * 2 * ND + mrow) * 2 * ND + lane];
+          }
+          int pos = 0;
+          bool ok = on;
+          if (on)
+          {
+            int lo = 0, hi = rn;
+            while (lo < hi)
+            {
+              const int mid = (lo + hi) >> 1;
+              if (sc[mid] < dj)
+                lo = mid + 1;
+              else
+                hi = mid;
+            }
+            pos = lo;
+            if (pos >= rn || sc[pos] != dj)
+            {
+              bad = 1;
+              ok = false;
+            }
+          }
+          const unsigned peers = __match_any_sync(full, ok ? pos : -1 - lane);
+          const int rank = __popc(peers & below);
+          const int maxrank = __reduce_max_sync(full, ok ? rank : 0);
+          for (int rr = 0; rr <= maxrank; ++rr)
+          {
+            if (ok && rank == rr)
+            {
+#pragma unroll
+              for (int a = 0; a < BS; ++a)
+                row[pos * B2 + a * BS + a] += v;
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  }
+  if (staged)
+    for (int t = lane; t < rn * B2; t += 32)
+      vals[rb * B2 + t] = row[t];
+  if (__any_sync(full, bad) && lane == 0)
+  {
+    err[0] = 31;
+    err[1] = r;
+  }
+}
+
 // b[bs*dof + a] += element-vector entries of the incident cells, ascending cell order + fixed shuffle tree
 template <int TDIM, int DEG>
 __global__ void __launch_bounds__(GW * 32)
@@ -3076,7 +3330,7 @@ __global__ void __launch_bounds__(GW * 32)
 }
 
 template <int TDIM, int DEG>
-void launch_blocked_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t& base)
+void launch_blocked_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t& base, bool fly)
 {
   constexpr int N = Elem<TDIM, DEG>::ND * TDIM;
   RuleView rv{};
@@ -3102,7 +3356,7 @@ void launch_blocked_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t
   }
   CFX_REQUIRE(el || I.kernel == CFX_K_SOURCE_VEC, CFX_ERR_UNSUPPORTED,
               "kernel family is not defined on blocked (vector) spaces");
-  if (I.n > 0)
+  if (I.n > 0 && !fly)
   {
     RuleTable& rt = get_rule(c, TDIM, el ? 2 * (DEG - 1) : DEG);
     sr = StdRule{rt.d_pts, rt.d_wts, rt.npts};
@@ -3169,6 +3423,7 @@ int64_t run_cell_integrals(cfx_ctx* c, cfx_form* f, int64_t follow_slots = -1)
 {
   const Space& S = c->spaces[f->space];
   const bool blocked = S.bs > 1 && f->rank > 0;
+  const bool fly = blocked_on_the_fly(S, f); // standard elasticity cells are evaluated by the row gather
   const int n1 = S.nd * (blocked ? S.bs : 1);
   const int es = f->rank == 2 ? n1 * n1 : (f->rank == 1 ? n1 : 1);
   auto dispatch = [&](const cfx_integral& I, int64_t& base)
@@ -3184,13 +3439,13 @@ int64_t run_cell_integrals(cfx_ctx* c, cfx_form* f, int64_t follow_slots = -1)
     if (blocked)
     {
       if (c->tdim == 2 && S.degree == 1)
-        launch_blocked_cell<2, 1>(c, I, f, base);
+        launch_blocked_cell<2, 1>(c, I, f, base, fly);
       else if (c->tdim == 2)
-        launch_blocked_cell<2, 2>(c, I, f, base);
+        launch_blocked_cell<2, 2>(c, I, f, base, fly);
       else if (S.degree == 1)
-        launch_blocked_cell<3, 1>(c, I, f, base);
+        launch_blocked_cell<3, 1>(c, I, f, base, fly);
       else
-        launch_blocked_cell<3, 2>(c, I, f, base);
+        launch_blocked_cell<3, 2>(c, I, f, base, fly);
     }
     else if (c->tdim == 2 && S.degree == 1)
       dispatch_cell<2, 1>(c, I, f, base);
@@ -3219,7 +3474,7 @@ int64_t run_cell_integrals(cfx_ctx* c, cfx_form* f, int64_t follow_slots = -1)
   {
     if (I.facet)
       continue;
-    if (f->rank == 0 || blocked)
+    if (f->rank == 0 || (blocked && !fly))
       cap += I.n;
     if (I.rules)
       cap += I.rules->nrules;
@@ -3235,9 +3490,43 @@ int64_t run_cell_integrals(cfx_ctx* c, cfx_form* f, int64_t follow_slots = -1)
   return base;
 }
 
+// reference-element tables (RefTab), built once per (tdim, degree) with an exact rule (mass: degree 2p)
+const double* ensure_ref_table(cfx_ctx* c, int degree)
+{
+  auto key = std::make_pair(c->tdim, degree);
+  auto it = c->ref_tabs.find(key);
+  if (it == c->ref_tabs.end())
+  {
+    DevBuf<double> buf;
+    RuleTable& rt = get_rule(c, c->tdim, 2 * degree);
+    if (c->tdim == 2 && degree == 1)
+    {
+      buf.reserve(c->pool, RefTab<2, 3>::SIZE);
+      CFX_LAUNCH(c, (ref_tables_kernel<2, 1>), 1, 32, 0, rt.d_pts, rt.d_wts, rt.npts, buf.p);
+    }
+    else if (c->tdim == 2)
+    {
+      buf.reserve(c->pool, RefTab<2, 6>::SIZE);
+      CFX_LAUNCH(c, (ref_tables_kernel<2, 2>), 1, 64, 0, rt.d_pts, rt.d_wts, rt.npts, buf.p);
+    }
+    else if (degree == 1)
+    {
+      buf.reserve(c->pool, RefTab<3, 4>::SIZE);
+      CFX_LAUNCH(c, (ref_tables_kernel<3, 1>), 1, 32, 0, rt.d_pts, rt.d_wts, rt.npts, buf.p);
+    }
+    else
+    {
+      buf.reserve(c->pool, RefTab<3, 10>::SIZE);
+      CFX_LAUNCH(c, (ref_tables_kernel<3, 2>), 1, 128, 0, rt.d_pts, rt.d_wts, rt.npts, buf.p);
+    }
+    it = c->ref_tabs.emplace(key, buf).first;
+  }
+  return it->second.p;
+}
+
 void reset_slots(cfx_ctx* c, cfx_form* f)
 {
-  const bool blocked = c->spaces[f->space].bs > 1 && f->rank > 0;
+  const bool blocked = c->spaces[f->space].bs > 1 && f->rank > 0 && !blocked_on_the_fly(c->spaces[f->space], f);
   for (auto& I : f->integrals)
   {
     if (I.facet)
@@ -3255,7 +3544,24 @@ StdTab make_std_tab(cfx_ctx* c, cfx_form* f)
   const Space& S = c->spaces[f->space];
   StdTab st{};
   if (S.bs > 1)
-    return st; // blocked spaces: standard cells are materialised like cut cells
+  {
+    if (!blocked_on_the_fly(S, f))
+      return st; // standard cells are materialised like cut cells
+    // bilinear elasticity forms: (mu, lambda) per standard cell list + the reference-element table
+    for (auto& I : f->integrals)
+    {
+      if (I.facet || I.n == 0)
+        continue;
+      CFX_REQUIRE(st.n < CFX_MAX_STD_LISTS, CFX_ERR_UNSUPPORTED, "too many standard cell integrals in one form");
+      const int k = st.n++;
+      st.kernel[k] = I.kernel;
+      st.bit[k] = std_list_bit(f->prep, I.entities, I.n);
+      st.c[k][0] = I.constants[0];
+      st.c[k][1] = I.constants[1];
+    }
+    st.ref = ensure_ref_table(c, S.degree);
+    return st;
+  }
   for (auto& I : f->integrals)
   {
     if (I.facet || I.n == 0)
@@ -3276,27 +3582,7 @@ StdTab make_std_tab(cfx_ctx* c, cfx_form* f)
       st.has_mass = 1;
   }
   if (S.degree == 2 && st.n > 0)
-  { // reference-element tables, built once per (tdim, degree) with an exact rule (mass: degree 2p)
-    auto key = std::make_pair(c->tdim, S.degree);
-    auto it = c->ref_tabs.find(key);
-    if (it == c->ref_tabs.end())
-    {
-      DevBuf<double> buf;
-      RuleTable& rt = get_rule(c, c->tdim, 2 * S.degree);
-      if (c->tdim == 2)
-      {
-        buf.reserve(c->pool, RefTab<2, 6>::SIZE);
-        CFX_LAUNCH(c, (ref_tables_kernel<2, 2>), 1, 64, 0, rt.d_pts, rt.d_wts, rt.npts, buf.p);
-      }
-      else
-      {
-        buf.reserve(c->pool, RefTab<3, 10>::SIZE);
-        CFX_LAUNCH(c, (ref_tables_kernel<3, 2>), 1, 128, 0, rt.d_pts, rt.d_wts, rt.npts, buf.p);
-      }
-      it = c->ref_tabs.emplace(key, buf).first;
-    }
-    st.ref = it->second.p;
-  }
+    st.ref = ensure_ref_table(c, S.degree);
   // P1 closed forms: coefficient sums per combination of list bits (ascending integral order)
   for (unsigned m = 0; m < (1u << CFX_MAX_STD_LISTS); ++m)
     for (int k = 0; k < st.n; ++k)
@@ -3478,8 +3764,27 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
   {
     CFX_REQUIRE(S.bs == TDIM, CFX_ERR_UNSUPPORTED, "blocked spaces need block size == gdim");
     auto kb = gather_matrix_blocked_kernel<TDIM, DEG>;
-    CFX_LAUNCH(ctx, kb, grid_for(PR->n_act_rows, 1), 32, 0, gc, PR->act_rows.p, PR->dn_act(), A->row_ptr.p, A->cols.p,
-               A->values.p, zero_first, ctx->err_flag.p);
+    auto k2 = gather_matrix_blocked2_kernel<TDIM, DEG>;
+    const cfx_integral* FI = facet_integral_domain(a);
+    {
+      // FP64-bound: 2 * (81 + 27) flops per bs x bs block of a standard cell, (nd bs)^2 / bs^2 blocks per cell;
+      // bytes: 12 B + 8 bs^2 B per CSR entry + the geometry record and dofmap row per (row, cell) pair
+      int64_t n_std = 0;
+      for (auto& I : a->integrals)
+        if (!I.facet)
+          n_std += I.n;
+      StageScope sk(ctx, "gather_matrix_blocked2_kernel",
+                    (4.0 + 8.0 * S.bs * S.bs) * static_cast<double>(A->nnz)
+                        + (96.0 + 4.0 * S.nd) * S.nd * static_cast<double>(n_std));
+      CFX_LAUNCH(ctx, k2, grid_for(PR->n_act_rows, BGW), BGW * 32, 0, gc, st, PR->act_rows.p, PR->dn_act(),
+                 A->row_ptr.p, A->cols.p, A->values.p, zero_first, ctx->err_flag.p);
+    }
+    if (FI && PR->n_band > 0 && DEG == 1)
+    { // P1 facet records: the separate facets-only pass over the band rows
+      StageScope sk(ctx, "gather_matrix_blocked_facets_kernel", 0.0);
+      CFX_LAUNCH(ctx, kb, grid_for(PR->n_band, 1), 32, 0, gc, PR->act_rows.p, PR->band_idx.p, PR->dn_band(), 1,
+                 A->row_ptr.p, A->cols.p, A->values.p, 0, ctx->err_flag.p);
+    }
     return;
   }
   // the gather tables are valid only for the pattern that was built from this very form

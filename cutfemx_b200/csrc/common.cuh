@@ -317,6 +317,10 @@ struct cfx_integral
 
 // active cells / rows of a set of integration domains (Form.h:46-89 domains)
 enum { CFX_MAX_STD_LISTS = 6 };
+// Bilinear forms on blocked (vector) spaces whose standard-quadrature cell integrals are all linear elasticity:
+// those cells are not materialised, the row gather evaluates their blocks (assemble.cu gather_matrix_blocked2_kernel).
+inline bool blocked_on_the_fly(const cfx::Space& S, const cfx_form* f);
+
 struct cfx_prepared
 {
   int refs = 0;
@@ -695,3 +699,19 @@ void set_facet_slots(cfx_ctx* c, const cfx_integral* I, bool clear);   // sparsi
   return CFX_OK;
 
 void cfx_set_error(cfx_ctx* ctx, const char* msg);
+
+inline bool blocked_on_the_fly(const cfx::Space& S, const cfx_form* f)
+{
+  if (S.bs <= 1 || f->rank != 2)
+    return false;
+  bool any = false;
+  for (auto& I : f->integrals)
+  {
+    if (I.facet || I.n == 0)
+      continue;
+    if (I.kernel != CFX_K_ELASTICITY)
+      return false;
+    any = true;
+  }
+  return any;
+}

@@ -108,6 +108,37 @@ __global__ void level_set_kernel(const double* __restrict__ x, int64_t n, int ki
     out[v] = sqrt(a * a + dz * dz) - r;
   }
 }
+// P2 Lagrange dofmap of a Kuhn box mesh: the 4 vertex dofs, then one dof per edge in Basix order
+// e0 = (2,3), e1 = (1,3), e2 = (1,2), e3 = (0,3), e4 = (0,2), e5 = (0,1).  The vertex offsets of a Kuhn tetrahedron
+// are nested bit patterns, so an edge is (lower vertex, direction) with one of 7 directions (3 axes, 3 face
+// diagonals, the cube diagonal): edge dof = n_nodes + 7 * lower vertex + direction -- a sparse numbering like the
+// facet numbering of box_cells_kernel (ids of edges that would leave the box stay unused).
+__global__ void p2_tet_dofmap_kernel(const int32_t* __restrict__ x_dofmap, int64_t n_cells, int64_t n_nodes,
+                                     int64_t sx, int64_t sy, int32_t* __restrict__ dofmap)
+{
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * MB + threadIdx.x;
+  if (c >= n_cells)
+    return;
+  const int4 v4 = reinterpret_cast<const int4*>(x_dofmap)[c];
+  const int32_t v[4] = {v4.x, v4.y, v4.z, v4.w};
+  int32_t* o = dofmap + c * 10;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    o[j] = v[j];
+  constexpr int ea[6] = {2, 1, 1, 0, 0, 0}, eb[6] = {3, 3, 2, 3, 2, 1};
+#pragma unroll
+  for (int e = 0; e < 6; ++e)
+  {
+    const int64_t a = min(v[ea[e]], v[eb[e]]), b = max(v[ea[e]], v[eb[e]]);
+    const int64_t diff = b - a;
+    const int dk = static_cast<int>(diff / sy);
+    const int64_t rem = diff - dk * sy;
+    const int dj = static_cast<int>(rem / sx);
+    const int di = static_cast<int>(rem - dj * sx);
+    const int dir = (di | (dj << 1) | (dk << 2)) - 1;
+    o[4 + e] = static_cast<int32_t>(n_nodes + 7 * a + dir);
+  }
+}
 } // namespace
 } // namespace cfx
 
@@ -146,6 +177,20 @@ cfx_status cfx_meshgen_level_set(cfx_ctx* ctx, const double* x, int64_t n_nodes,
   CFX_REQUIRE(ctx && x && values && params, CFX_ERR_INVALID, "cfx_meshgen_level_set: bad args");
   CFX_LAUNCH(ctx, level_set_kernel, grid_for(n_nodes, MB), MB, 0, x, n_nodes, kind, params[0], params[1], params[2],
              params[3], params[4], values);
+  CFX_API_END(ctx)
+}
+cfx_status cfx_meshgen_p2_tet_dofmap(cfx_ctx* ctx, int nx, int ny, int nz, const int32_t* x_dofmap, int64_t n_cells,
+                                     int32_t* dofmap, int64_t* n_dofs)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && x_dofmap && dofmap && nx > 0 && ny > 0 && nz > 0, CFX_ERR_INVALID,
+              "cfx_meshgen_p2_tet_dofmap: bad args");
+  const int64_t nn = static_cast<int64_t>(nx + 1) * (ny + 1) * (nz + 1);
+  CFX_REQUIRE(8 * nn < (int64_t(1) << 31), CFX_ERR_RANGE, "cfx_meshgen_p2_tet_dofmap: dof ids exceed int32");
+  CFX_LAUNCH(ctx, p2_tet_dofmap_kernel, grid_for(n_cells, MB), MB, 0, x_dofmap, n_cells, nn,
+             static_cast<int64_t>(nx + 1), static_cast<int64_t>(nx + 1) * (ny + 1), dofmap);
+  if (n_dofs)
+    *n_dofs = 8 * nn;
   CFX_API_END(ctx)
 }
 } // extern "C"

@@ -893,10 +893,19 @@ static void build_static_structure_nd(cfx_ctx* c, Space& S)
     S.fcols.reserve(c->pool, static_cast<size_t>(fnnz) + 1);
     CFX_LAUNCH(c, pattern_copy_kernel, grid_for(S.n_total, 256), 256, 0, nullptr, dn_exact(S.n_total), nullptr, tmp.p,
                S.frow_ptr.p, S.fcols.p);
-    S.fclist.reserve(c->pool, static_cast<size_t>(fnnz) + 64);
     S.frow_ok.reserve(c->pool, static_cast<size_t>(S.n_total) + 16);
-    CFX_LAUNCH(c, clist_kernel<ND>, grid_for(S.n_total, RW), RW * 32, 0, S.n_total, S.inc_ptr.p, S.inc_cell.p, S.dofmap,
-               S.frow_ptr.p, S.fcols.p, S.fclist.p, S.frow_ok.p);
+    if (ND <= 4 && S.bs == 1)
+    { // scalar P1: the one-thread-per-row gather (assemble.cu gather_matrix_p1_kernel) reads packed positions
+      // (Space::fpos), not contribution lists, and takes every static row
+      S.fclist.release();
+      CFX_CUDA(cudaMemsetAsync(S.frow_ok.p, 1, static_cast<size_t>(S.n_total), c->stream));
+    }
+    else
+    {
+      S.fclist.reserve(c->pool, static_cast<size_t>(fnnz) + 64);
+      CFX_LAUNCH(c, clist_kernel<ND>, grid_for(S.n_total, RW), RW * 32, 0, S.n_total, S.inc_ptr.p, S.inc_cell.p,
+                 S.dofmap, S.frow_ptr.p, S.fcols.p, S.fclist.p, S.frow_ok.p);
+    }
     S.has_static = true;
   }
   else
@@ -1010,8 +1019,9 @@ void prepare_form(cfx_ctx* c, cfx_form* f)
       key_dn[rkey.back()] = DN{I.rules->deferred ? I.rules->d_sizes : nullptr, I.rules->nrules, 0};
     }
   }
-  if (S.bs > 1 && f->rank > 0)
-  { // blocked spaces: every element tensor is materialised (bit0), standard cells included
+  if (S.bs > 1 && f->rank > 0 && !blocked_on_the_fly(S, f))
+  { // blocked spaces: every element tensor is materialised (bit0), standard cells included (elasticity: only
+    // when the form mixes kernel families on its standard cells)
     rkey.insert(rkey.end(), skey.begin(), skey.end());
     skey.clear();
   }

@@ -55,6 +55,22 @@ def device_mesh(ctx_device: int, shape, p0, p1):
     return mesh
 
 
+def device_p2_tet_space(mesh: Mesh, bs: int = 1) -> FunctionSpace:
+    """P2 Lagrange space (block size `bs`) on a device_mesh() box: vertex dofs + one dof per edge, generated on the
+    GPU (csrc/meshgen.cu p2_tet_dofmap_kernel; sparse edge numbering, unused ids at the box boundary)."""
+    import torch
+
+    assert mesh.tdim == 3 and mesh.shape is not None
+    ctx = _cut._mesh_context(mesh)
+    nc = int(mesh.x_dofmap.shape[0])
+    dm = torch.empty((nc, 10), dtype=torch.int32, device=mesh.x.device)
+    nd = C.c_int64(0)
+    check(ctx.handle, lib().cfx_meshgen_p2_tet_dofmap(ctx.handle, mesh.shape[0], mesh.shape[1], mesh.shape[2],
+                                                      C.c_void_p(mesh.x_dofmap.data_ptr()), C.c_int64(nc),
+                                                      C.c_void_p(dm.data_ptr()), C.byref(nd)))
+    return FunctionSpace(mesh, 2, dm, int(nd.value), int(nd.value), bs, None)
+
+
 def device_level_set(mesh: Mesh, kind: str, params, out=None):
     """Nodal interpolation of a sphere/circle (c, R) or torus (c, R, r) level set on the GPU
     (into `out` if given)."""
@@ -125,7 +141,8 @@ class CutPoisson:
             import torch
 
             if self.b is None or not hasattr(self.b, "data_ptr"):
-                self.b = torch.empty(self.V.num_dofs, dtype=torch.float64, device=f"cuda:{self.ctx.device}")
+                self.b = torch.empty(self.V.num_dofs * self.V.bs, dtype=torch.float64,
+                                     device=f"cuda:{self.ctx.device}")
             _fem.assemble_system(a, self.A, L, self.b)                      # assemble_matrix + assemble_vector
         else:
             _fem.assemble_matrix(a, self.A)                                 # assemble_matrix
@@ -189,7 +206,7 @@ class CutPoisson:
     def _assemble_vector_device(self, L):
         import torch
 
-        n = self.V.num_dofs
+        n = self.V.num_dofs * self.V.bs
         if self.b is None or not hasattr(self.b, "data_ptr"):
             self.b = torch.empty(n, dtype=torch.float64, device=f"cuda:{self.ctx.device}")
         check(self.ctx.handle, lib().cfx_assemble_vector(self.ctx.handle, L._h, C.c_void_p(self.b.data_ptr()), 1, DEVICE))

@@ -210,7 +210,8 @@ class MatrixCSR:
         with torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream()):
             h_indptr[: nr + 1].copy_(self.indptr_device(), non_blocking=True)
             h_indices[:nnz].copy_(self.indices_device(), non_blocking=True)
-            h_values[:nnz].copy_(self.values_device(), non_blocking=True)
+            bb = self.block_size ** 2
+            h_values[: nnz * bb].copy_(self.values_device(), non_blocking=True)
         return nr + 1, nnz
 
     def to_scipy(self):

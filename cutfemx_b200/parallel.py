@@ -691,7 +691,19 @@ class RankPipeline:
             vals = dp.device_level_set(self.mesh, ls_kind, ls_params)  # phi on owned + ghost dofs ("scattered")
         self.phi = Function(self.V, "phi", vals)  # the level set is P1 on the mesh vertices
         self.ls_kind, self.ls_params = ls_kind, ls_params
-        if degree == 2:
+        problem = kw.pop("problem", "poisson")
+        bs = int(kw.pop("bs", 1))
+        if degree == 2 and self.mesh.tdim == 3:
+            # P2 on tetrahedra (BASELINE configs[3]): vertex dofs + edge dofs generated on the device
+            if world != 1:
+                raise NotImplementedError("P2 spaces on tetrahedra: single rank only")
+            import torch
+
+            self.V = dp.device_p2_tet_space(self.mesh, bs)
+            nd = self.V.num_dofs
+            self.imap = IndexMap(rank, world, nd, 0, self.imap.ghost_global, self.imap.ghost_owner,
+                                 torch.arange(nd, device=self.mesh.x.device))
+        elif degree == 2:
             # P2 on triangles: vertex dofs + one dof per edge; on these meshes edge == facet and local edge e is
             # opposite local vertex e (Basix), exactly the c2f convention -> edge dof = n_vertices + facet id
             if world != 1 or self.mesh.tdim != 2:
@@ -701,12 +713,21 @@ class RankPipeline:
             nn = int(self.mesh.x.shape[0])
             dm = torch.cat([self.mesh.x_dofmap, self.mesh.c2f + nn], dim=1).contiguous()
             nd = nn + int(self.mesh.num_facets)
-            self.V = FunctionSpace(self.mesh, 2, dm, nd, nd, 1, None)
+            self.V = FunctionSpace(self.mesh, 2, dm, nd, nd, bs, None)
             self.imap = IndexMap(rank, world, nd, 0, self.imap.ghost_global, self.imap.ghost_owner,
                                  torch.arange(nd, device=dm.device))
         elif degree != 1:
             raise ValueError("degree must be 1 or 2")
-        self.prob = dp.CutPoisson(self.mesh, self.phi, self.V, order=order, **kw)
+        elif bs != 1:
+            if world != 1:
+                raise NotImplementedError("blocked spaces: single rank only")
+            self.V = FunctionSpace(self.mesh, 1, self.V.dofmap, self.V.num_dofs, self.V.num_dofs_owned, bs, None)
+        if problem == "elasticity":
+            from .demo_elasticity import CutElasticity
+
+            self.prob = CutElasticity(self.mesh, self.phi, self.V, order=order, **kw)
+        else:
+            self.prob = dp.CutPoisson(self.mesh, self.phi, self.V, order=order, **kw)
         self.ctx = self.prob.ctx
         self.ops = _DeviceOps(self.ctx)
         self.vx = VectorExchange(self.imap)

@@ -427,6 +427,11 @@ cfx_status cfx_meshgen_rectangle(cfx_ctx* ctx, int nx, int ny, const double p0[2
 /* level-set nodal interpolation on the device: kind 0 sphere/circle (c, R), 1 torus (c, R, r) */
 cfx_status cfx_meshgen_level_set(cfx_ctx* ctx, const double* x, int64_t n_nodes, int kind, const double params[5],
                                  double* values);
+/* P2 Lagrange dofmap (n_cells, 10) of a cfx_meshgen_box mesh: vertex dofs, then one dof per edge in Basix edge
+ * order; *n_dofs = 8 (nx+1)(ny+1)(nz+1) (sparse edge numbering, unused ids at the box boundary).  Harness only:
+ * stands in for dolfinx.fem.functionspace(mesh, ("Lagrange", 2)) (python/demo/demo_elasticity.py:160). */
+cfx_status cfx_meshgen_p2_tet_dofmap(cfx_ctx* ctx, int nx, int ny, int nz, const int32_t* x_dofmap, int64_t n_cells,
+                                     int32_t* dofmap, int64_t* n_dofs);
 
 #ifdef __cplusplus
 }
