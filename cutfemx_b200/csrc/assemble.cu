@@ -2830,6 +2830,183 @@ __global__ void __launch_bounds__(EB)
     p[k] = add ? p[k] + acc[k] : acc[k];
 }
 
+// Run-time-rule tensors of blocked spaces, ONE WARP PER RULE (elasticity on volume rules, the symmetric Nitsche
+// terms on interface rules).  The row-per-thread kernels above re-tabulate every basis function at every point in
+// each of their nd*bs threads (ncu: 242 registers, FP64 pipe 57 % busy -- bound by redundant arithmetic).  Here:
+//   phase 1  lane = quadrature point (chunks of 32): tabulate once, push the gradients once, stage phi, grad phi,
+//            the normal and the weight in shared memory;
+//   phase 2  lane = pair (i <= j) of basis functions (55 for P2 tetrahedra: two per lane): the bs x bs block
+//            A[(i,.),(j,.)] accumulated over the staged points -- 2 bs + 2 shared loads per bs^2-block update;
+//   output   the block and its mirror image (the tensors are symmetric: A[(j,b),(i,a)] = A[(i,a),(j,b)]).
+// Same sums over the points in the same (ascending) order as the row-per-thread kernels, ~10x fewer flops.  This
+// is the G^T W G contraction SURVEY.md section 8(d) reserves for FP64 tensor cores: on B200 the measured DMMA peak
+// (37.0 TF/s) is within 9 % of the DFMA peak (34.1 TF/s, profiles/r5_fp64_peak.json) and after this restructuring
+// the kernel is bound by writing the 7.2 KB tensor, so mma.sync.f64 has nothing to win here.
+constexpr int BTW = 4; // warps (rules) per block
+
+template <int TDIM, int DEG, bool NITSCHE>
+__global__ void __launch_bounds__(BTW * 32)
+    blocked_rule_tensor_kernel(DN n_, RuleView rv, Consts cs, const double* __restrict__ x,
+                               const int32_t* __restrict__ x_dofmap, OutCtx oc)
+{
+  constexpr int ND = Elem<TDIM, DEG>::ND;
+  constexpr int BS = TDIM, N = ND * BS, B2 = BS * BS;
+  constexpr int NPAIR = ND * (ND + 1) / 2, PPL = (NPAIR + 31) / 32;
+  constexpr int PW = ND * (TDIM + 1) + TDIM + 1; // staged doubles per point: phi, grad, normal, weight
+  __shared__ double s_pt[BTW][32][PW + 1];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * BTW + w;
+  if (e >= n_.get())
+    return;
+  const int64_t cell = rv.parent_map[e];
+  const bool follow = oc.base < 0;
+  const int64_t mine = oc.base + e;
+  const int32_t s0 = oc.mat_slot[cell];
+  const bool add = follow || (s0 >= 0 && s0 != mine);
+  if (follow && s0 < 0)
+    return;
+  const int64_t slot = add ? s0 : mine;
+  double X[TDIM + 1][TDIM];
+  load_cell_coords<TDIM>(x, x_dofmap, cell, X);
+  Geo<TDIM> g;
+  make_geo<TDIM>(X, g);
+  const double mu = cs.c[0], lam = cs.c[1];
+  double pen = 0.0;
+  if constexpr (NITSCHE)
+    pen = cs.c[2] * (2.0 * mu + lam) / cell_diameter<TDIM>(X);
+  // this lane's pairs
+  int pi[PPL], pj[PPL];
+#pragma unroll
+  for (int t = 0; t < PPL; ++t)
+  {
+    int p = lane + 32 * t, i = 0;
+    if (p >= NPAIR)
+      p = 0;
+    while (p >= ND - i)
+    {
+      p -= ND - i;
+      ++i;
+    }
+    pi[t] = i;
+    pj[t] = i + p;
+  }
+  double acc[PPL][B2];
+#pragma unroll
+  for (int t = 0; t < PPL; ++t)
+#pragma unroll
+    for (int k = 0; k < B2; ++k)
+      acc[t][k] = 0.0;
+  const int32_t q0 = rv.offsets[e], q1 = rv.offsets[e + 1];
+  for (int32_t qb = q0; qb < q1; qb += 32)
+  {
+    const int nq = min(32, q1 - qb);
+    if (lane < nq)
+    {
+      const int32_t q = qb + lane;
+      double xi[TDIM];
+#pragma unroll
+      for (int tt = 0; tt < TDIM; ++tt)
+        xi[tt] = rv.pts[static_cast<int64_t>(tt) * rv.stride() + q];
+      double phi[ND], dphi[ND][TDIM], grad[ND][TDIM];
+      tabulate<TDIM, DEG>(xi, phi, dphi);
+      push_gradients<TDIM, ND>(g, dphi, grad);
+      double* o = s_pt[w][lane];
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+      {
+        o[i] = phi[i];
+#pragma unroll
+        for (int r = 0; r < TDIM; ++r)
+          o[ND + i * TDIM + r] = grad[i][r];
+      }
+#pragma unroll
+      for (int r = 0; r < TDIM; ++r)
+        o[ND * (TDIM + 1) + r] = NITSCHE ? rv.nrm[static_cast<int64_t>(r) * rv.stride() + q] : 0.0;
+      o[ND * (TDIM + 1) + TDIM] = rv.wts[q];
+    }
+    __syncwarp();
+    for (int k = 0; k < nq; ++k)
+    {
+      const double* o = s_pt[w][k];
+      const double wq = o[ND * (TDIM + 1) + TDIM];
+      double nr[TDIM];
+#pragma unroll
+      for (int r = 0; r < TDIM; ++r)
+        nr[r] = o[ND * (TDIM + 1) + r];
+#pragma unroll
+      for (int t = 0; t < PPL; ++t)
+      {
+        const int i = pi[t], j = pj[t];
+        double gi[TDIM], gj[TDIM];
+#pragma unroll
+        for (int r = 0; r < TDIM; ++r)
+        {
+          gi[r] = o[ND + i * TDIM + r];
+          gj[r] = o[ND + j * TDIM + r];
+        }
+        if constexpr (!NITSCHE)
+        { // w ( lambda d_a phi_i d_b phi_j + mu d_b phi_i d_a phi_j + mu delta_ab grad phi_i . grad phi_j )
+          double gg = 0.0;
+#pragma unroll
+          for (int r = 0; r < TDIM; ++r)
+            gg += gi[r] * gj[r];
+#pragma unroll
+          for (int a = 0; a < BS; ++a)
+#pragma unroll
+            for (int b = 0; b < BS; ++b)
+              acc[t][a * BS + b] += wq * (lam * gi[a] * gj[b] + mu * gi[b] * gj[a] + ((a == b) ? mu * gg : 0.0));
+        }
+        else
+        {
+          const double phii = o[i], phij = o[j];
+          double gni = 0.0, gnj = 0.0;
+#pragma unroll
+          for (int r = 0; r < TDIM; ++r)
+          {
+            gni += gi[r] * nr[r];
+            gnj += gj[r] * nr[r];
+          }
+#pragma unroll
+          for (int a = 0; a < BS; ++a)
+#pragma unroll
+            for (int b = 0; b < BS; ++b)
+            {
+              const double dab = (a == b) ? 1.0 : 0.0;
+              const double S_ab_j = mu * (dab * gnj + gj[a] * nr[b]) + lam * gj[b] * nr[a];
+              const double S_ba_i = mu * (dab * gni + gi[b] * nr[a]) + lam * gi[a] * nr[b];
+              acc[t][a * BS + b] += wq * (-phii * S_ab_j - phij * S_ba_i + dab * pen * phii * phij);
+            }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (!add && lane == 0)
+    oc.mat_slot[cell] = static_cast<int32_t>(slot);
+  double* out = oc.out + slot * N * N;
+#pragma unroll
+  for (int t = 0; t < PPL; ++t)
+  {
+    if (lane + 32 * t >= NPAIR)
+      continue;
+    const int i = pi[t], j = pj[t];
+#pragma unroll
+    for (int a = 0; a < BS; ++a)
+#pragma unroll
+      for (int b = 0; b < BS; ++b)
+      {
+        double* p0 = out + (i * BS + a) * N + j * BS + b;
+        const double v = acc[t][a * BS + b];
+        *p0 = add ? *p0 + v : v;
+        if (i != j)
+        {
+          double* p1 = out + (j * BS + b) * N + i * BS + a;
+          *p1 = add ? *p1 + v : v;
+        }
+      }
+  }
+}
+
 // inner(f, v) dx with a constant vector f = (c0, c1, c2): one thread per entity, N values
 template <int TDIM, int DEG, bool RUNTIME>
 __global__ void __launch_bounds__(EB)
@@ -3347,8 +3524,8 @@ void launch_blocked_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t
     {
       CFX_REQUIRE(R->tdim == TDIM && R->has_normals, CFX_ERR_INVALID, "interface kernels need rules with normals");
       rv = make_rule_view(R, true, false, 0);
-      CFX_LAUNCH(c, (nitsche_vec_kernel<TDIM, DEG>), grid_for(R->nrules * N, EB), EB, 0, dn_rules(R), rv, cs, c->x,
-                 c->x_dofmap, oc);
+      CFX_LAUNCH(c, (blocked_rule_tensor_kernel<TDIM, DEG, true>), grid_for(R->nrules, BTW), BTW * 32, 0, dn_rules(R), rv,
+                 cs, c->x, c->x_dofmap, oc);
       if (base >= 0)
         base += R->nrules;
     }
@@ -3378,7 +3555,7 @@ void launch_blocked_cell(cfx_ctx* c, const cfx_integral& I, cfx_form* f, int64_t
     CFX_REQUIRE(R->tdim == TDIM, CFX_ERR_INVALID, "run-time rules have the wrong reference dimension");
     rv = make_rule_view(R, false, false, 0);
     if (el)
-      CFX_LAUNCH(c, (elasticity_kernel<TDIM, DEG, true>), grid_for(R->nrules * N, EB), EB, 0, nullptr, dn_rules(R), rv, sr,
+      CFX_LAUNCH(c, (blocked_rule_tensor_kernel<TDIM, DEG, false>), grid_for(R->nrules, BTW), BTW * 32, 0, dn_rules(R), rv,
                  cs, c->x, c->x_dofmap, oc);
     else
       CFX_LAUNCH(c, (source_vec_kernel<TDIM, DEG, true>), grid_for(R->nrules, EB), EB, 0, nullptr, dn_rules(R), rv, sr, cs,

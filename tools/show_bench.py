@@ -4,7 +4,7 @@ import json
 import sys
 
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-print(f"ms/step {d['ms_per_step']:.3f}   e2e {d['e2e']['ms_per_step']:.3f}   launches {d.get('gpu_launches')}  "
+print(f"ms/step {d['ms_per_step']:.3f}   e2e {(d["e2e"].get("ms_per_step") or float("nan")):.3f}   launches {d.get('gpu_launches')}  "
       f"roofline {d['roofline']['kernel']} {d['roofline']['frac']:.3f}")
 tot = 0.0
 for k, v in d["stages"].items():
