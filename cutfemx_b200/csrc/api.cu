@@ -129,6 +129,21 @@ void resolve(cfx_ctx* c, cfx_pattern* p)
   p->deferred = false;
 }
 
+// cut.cpp:303-306 "Level-set dof index is out of range": one pass over a bound level-set dofmap
+__global__ void dofmap_range_kernel(const int32_t* __restrict__ dofmap, int64_t n_entries, int64_t n_dofs,
+                                    int32_t* __restrict__ err)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n_entries)
+    return;
+  const int32_t d = dofmap[i];
+  if (d < 0 || d >= n_dofs)
+  {
+    err[0] = 37;
+    err[1] = d;
+  }
+}
+
 void check_device_error(cfx_ctx* c, const char* where)
 {
   // err_flag is int32[4]; read as two int64
@@ -508,6 +523,8 @@ cfx_status cfx_levelset_bind(cfx_ctx* ctx, int ls, const int32_t* dofmap, int nd
   // validate_level_set, cut.cpp:444-460: scalar Lagrange. Degree 1 is the fixed-topology
   // case-table path; higher-order level sets (iterative edge roots) are SURVEY 8(f) rank 4.
   CFX_REQUIRE(degree == 1 || degree == 2, CFX_ERR_UNSUPPORTED, "cfx_levelset_bind: level-set degree must be 1 or 2");
+  CFX_REQUIRE(nd == (degree == 1 ? ctx->nv : (ctx->tdim == 2 ? 6 : 10)), CFX_ERR_INVALID,
+              "cfx_levelset_bind: dofmap width does not match the level-set element");
   LevelSet& L = ctx->ls[ls];
   if (L.host_pinned && L.host_values)
   {
@@ -562,8 +579,40 @@ cfx_status cfx_levelset_bind(cfx_ctx* ctx, int ls, const int32_t* dofmap, int nd
   L.n_cut = -1;
   L.n_cut_all = -1;
   ctx->classified = false;
-  if (memspace == CFX_HOST)
+  if (dofmap != nullptr && !ctx->capturing)
+  { // the kernels gather vals[dofmap[..]] unchecked: validate once at bind time (cut.cpp:303-306)
+    const int64_t n_entries = ctx->nc_total * nd;
+    CFX_LAUNCH(ctx, dofmap_range_kernel, grid_for(n_entries, 256), 256, 0, L.dofmap, n_entries, n_dofs, ctx->err_flag.p);
+    try
+    {
+      check_device_error(ctx, "cfx_levelset_bind: Level-set dof index is out of range");
+    }
+    catch (...)
+    {
+      L.bound = false;
+      throw;
+    }
+  }
+  else if (memspace == CFX_HOST)
     CFX_CUDA(cudaStreamSynchronize(ctx->stream));
+  CFX_API_END(ctx)
+}
+
+cfx_status cfx_levelset_unbind(cfx_ctx* ctx, int ls)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx, CFX_ERR_INVALID, "cfx_levelset_unbind: NULL context");
+  CFX_REQUIRE(ls >= 0 && ls < CFX_MAX_LEVEL_SETS, CFX_ERR_INVALID, "cfx_levelset_unbind: level-set index out of range");
+  LevelSet& L = ctx->ls[ls];
+  if (L.host_pinned && L.host_values)
+    cudaHostUnregister(const_cast<double*>(L.host_values + L.pin_begin));
+  L.host_pinned = false;
+  L.host_values = nullptr;
+  L.values = nullptr;
+  L.bound = false;
+  L.n_cut = -1;
+  L.n_cut_all = -1;
+  ctx->classified = false;
   CFX_API_END(ctx)
 }
 

@@ -23,6 +23,7 @@
 //
 // Roofline: HBM for P1/P2 scalar forms (SURVEY.md section 8d "K4", "K5").
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include <type_traits>
@@ -1209,6 +1210,24 @@ __global__ void inactive_diag_kernel(const uint8_t* __restrict__ row_flag, int64
         vals[p * bs * bs + k * bs + k] = diag;
 }
 
+// Right-hand-side entries of P1 rows are summed in ONE order by every kernel that produces them, so that a fused
+// system assembly (matrix gather kernels fill b) and a separate vector assembly agree bit for bit: the incident
+// cells in groups of four, pairwise inside a group ((e0 + e1) + (e2 + e3)), the groups added in ascending order.
+// That order costs a one-thread-per-row kernel nothing (its loop walks four incidences at a time) and a
+// warp-per-row kernel two butterfly steps and seven broadcasts.  Returns the sum in every lane.  (P2 rows keep
+// the shuffle tree of gather_vector_kernel / gather_matrix_clist_kernel.)
+__device__ __forceinline__ double rhs_sum_groups_of_four(double e)
+{
+  const unsigned full = 0xffffffffu;
+  e += __shfl_xor_sync(full, e, 1);
+  e += __shfl_xor_sync(full, e, 2);
+  double s = __shfl_sync(full, e, 0);
+#pragma unroll
+  for (int k = 1; k < 8; ++k)
+    s += __shfl_sync(full, e, 4 * k);
+  return s;
+}
+
 // Interior-facet macro rows of the band cells among this warp's (<= 32) incident cells.  Lane l owns
 // incident cell l and probes its own local facets (up to 32 independent gather chains in flight);
 // hits are staged in shared memory (the two cells' dofs + the macro-tensor row) and the column lanes
@@ -1718,9 +1737,14 @@ __global__ void __launch_bounds__(GWM * 32, 10)
       gl.Ae = gc.AeL;
       e = cell_entry_value<TDIM, DEG>(gl, stL, c, fl, li);
     }
+    if constexpr (DEG == 1)
+      e = rhs_sum_groups_of_four(e);
+    else
+    {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-      e += __shfl_down_sync(full, e, o);
+      for (int o = 16; o > 0; o >>= 1)
+        e += __shfl_down_sync(full, e, o);
+    }
     if (lane == 0)
     {
       const double s0 = 0.0 + e; // gather_vector_kernel adds the chunk sum to a zero accumulator
@@ -2130,7 +2154,7 @@ __global__ void __launch_bounds__(RTB)
   }
   const int pd = static_cast<int>((ldg_keep(fpos + ib) >> 2) & 31u); // the row's own column
   double dacc = zero_first ? 0.0 : s_acc[pd][tid];
-  double e = 0.0;
+  double e = 0.0; // right-hand-side entry, summed in the order of rhs_sum_groups_of_four
   constexpr double MASSW = TDIM == 3 ? 1.0 / 120.0 : 1.0 / 24.0;
   constexpr double SRCW = TDIM == 3 ? 1.0 / 24.0 : 1.0 / 6.0;
   constexpr int U = 4;
@@ -2160,6 +2184,7 @@ __global__ void __launch_bounds__(RTB)
       for (int u = 0; u < U; ++u)
         fl[u] = gc.cell_flags[cell[u]];
     }
+    double eu[U] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int u = 0; u < U; ++u)
     {
@@ -2191,7 +2216,7 @@ __global__ void __launch_bounds__(RTB)
           vd += 2.0 * wm;
         }
         if constexpr (FUSED)
-          e += stL.t0[m] * rec[u].a[3] * SRCW;
+          eu[u] += stL.t0[m] * rec[u].a[3] * SRCW;
       }
       if (fl[u] & 1u)
       { // materialised run-time-rule tensor row of a cut cell (natural dof order)
@@ -2207,7 +2232,7 @@ __global__ void __launch_bounds__(RTB)
           v[q] += pick<ND>(av, q < li ? q : q + 1);
         vd += pick<ND>(av, li);
         if constexpr (FUSED)
-          e += gc.AeL[ms * ND + li];
+          eu[u] += gc.AeL[ms * ND + li];
       }
 #pragma unroll
       for (int q = 0; q < NO; ++q)
@@ -2216,6 +2241,11 @@ __global__ void __launch_bounds__(RTB)
         s_acc[p][tid] += v[q];
       }
       dacc += vd;
+    }
+    if constexpr (FUSED)
+    {
+      const double g4 = (eu[0] + eu[1]) + (eu[2] + eu[3]);
+      e = l0 == 0 ? g4 : e + g4;
     }
   }
   s_acc[pd][tid] = dacc;
@@ -2306,8 +2336,9 @@ __global__ void __launch_bounds__(RTBB, 16)
   constexpr double MASSW = TDIM == 3 ? 1.0 / 120.0 : 1.0 / 24.0;
   constexpr double SRCW = TDIM == 3 ? 1.0 / 24.0 : 1.0 / 6.0;
   // ---- this thread's cells, two at a time: tensors, then facets
+  static_assert(G == 4, "the right-hand-side order (rhs_sum_groups_of_four) needs one group of four cells per pass");
   constexpr int U = 2;
-  for (int l0 = g; l0 < n_inc; l0 += U * G)
+  for (int l0 = g; l0 - g < n_inc; l0 += U * G) // the same trip count for the whole group (it shuffles inside)
   {
     P1Rec rec[U];
     uint32_t word[U], fm[U];
@@ -2318,7 +2349,7 @@ __global__ void __launch_bounds__(RTBB, 16)
     for (int u = 0; u < U; ++u)
     {
       in[u] = l0 + u * G < n_inc;
-      const int l = in[u] ? l0 + u * G : l0;
+      const int l = in[u] ? l0 + u * G : 0;
       rec[u] = ldg_stream_p1rec(gc.lrow, ib + l);
       word[u] = ldg_keep(gc.fpos + ib + l);
       fm[u] = gc.fmask[ib + l];
@@ -2353,6 +2384,7 @@ __global__ void __launch_bounds__(RTBB, 16)
 #pragma unroll
       for (int lf = 0; lf < ND; ++lf)
         fsl[u][lf] = (fl[u] & 2u) ? gc.facet_slot[fct[u][lf]] : -1;
+    double eu[U] = {0.0, 0.0};
 #pragma unroll
     for (int u = 0; u < U; ++u)
     {
@@ -2384,7 +2416,7 @@ __global__ void __launch_bounds__(RTBB, 16)
           vd += 2.0 * wm;
         }
         if constexpr (FUSED)
-          e += stL.t0[m] * rec[u].a[3] * SRCW;
+          eu[u] += stL.t0[m] * rec[u].a[3] * SRCW;
       }
       if (fl[u] & 1u)
       {
@@ -2400,12 +2432,24 @@ __global__ void __launch_bounds__(RTBB, 16)
           v[q] += pick<ND>(av, q < li ? q : q + 1);
         vd += pick<ND>(av, li);
         if constexpr (FUSED)
-          e += gc.AeL[ms * ND + li];
+          eu[u] += gc.AeL[ms * ND + li];
       }
 #pragma unroll
       for (int q = 0; q < NO; ++q)
         s_acc[s_map[(word[u] >> (7 + 5 * q)) & 31u][tid]][tid] += v[q];
       s_acc[s_map[(word[u] >> 2) & 31u][tid]][tid] += vd;
+    }
+    if constexpr (FUSED)
+    { // the group's four cells of each pass: pairwise, then the passes in order (rhs_sum_groups_of_four)
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+      {
+        double x = eu[u];
+        x += __shfl_xor_sync(gmask, x, 1);
+        x += __shfl_xor_sync(gmask, x, 2);
+        if (l0 - g + u * G < n_inc)
+          e = (l0 - g + u * G == 0) ? x : e + x;
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u)
@@ -2473,12 +2517,8 @@ __global__ void __launch_bounds__(RTBB, 16)
   }
   if constexpr (FUSED)
   {
-    double x = 0.0;
-#pragma unroll
-    for (int m = 0; m < G; ++m)
-      x += __shfl_sync(gmask, e, ((tid & 31) & ~(G - 1)) + m);
     if (g == 0)
-      gc.bvec[r] = gc.zero_first_b ? x : gc.bvec[r] + x;
+      gc.bvec[r] = gc.zero_first_b ? e : gc.bvec[r] + e;
   }
 }
 
@@ -2535,9 +2575,14 @@ __global__ void __launch_bounds__(GW * 32)
         e = cell_entry_value<TDIM, DEG>(gc, st, c, fl, li);
       }
     }
+    if constexpr (DEG == 1)
+      e = rhs_sum_groups_of_four(e);
+    else
+    {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-      e += __shfl_down_sync(0xffffffffu, e, o);
+      for (int o = 16; o > 0; o >>= 1)
+        e += __shfl_down_sync(0xffffffffu, e, o);
+    }
     s += e;
   }
   if (lane == 0)
@@ -4015,14 +4060,11 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
       bool band_done = false;
       if constexpr (DEG == 1)
       {
-        if (a->n_band_listed > 0 && gc.fpos != nullptr)
-        { // scalar P1 with a static structure: one thread per band row
-          static const int G = getenv("CFX_BAND_G") ? atoi(getenv("CFX_BAND_G")) : 4;
-          auto kb = G == 8   ? (gc.bvec ? gather_matrix_band_p1_kernel<TDIM, true, 8> : gather_matrix_band_p1_kernel<TDIM, false, 8>)
-                    : G == 4 ? (gc.bvec ? gather_matrix_band_p1_kernel<TDIM, true, 4> : gather_matrix_band_p1_kernel<TDIM, false, 4>)
-                    : G == 2 ? (gc.bvec ? gather_matrix_band_p1_kernel<TDIM, true, 2> : gather_matrix_band_p1_kernel<TDIM, false, 2>)
-                             : (gc.bvec ? gather_matrix_band_p1_kernel<TDIM, true, 16> : gather_matrix_band_p1_kernel<TDIM, false, 16>);
-          const int Gu = (G == 8 || G == 4 || G == 2) ? G : 16;
+        static const bool old_band = getenv("CFX_OLD_BAND") != nullptr; // A/B switch: the warp-per-row mask kernel
+        if (a->n_band_listed > 0 && gc.fpos != nullptr && !old_band)
+        { // scalar P1 with a static structure: G threads per band row
+          constexpr int Gu = 4;
+          auto kb = gc.bvec ? gather_matrix_band_p1_kernel<TDIM, true, 4> : gather_matrix_band_p1_kernel<TDIM, false, 4>;
           CFX_LAUNCH(ctx, kb, grid_for(a->n_band_listed * Gu, RTBB), RTBB, 0, gc, st, stL, PR->act_rows.p,
                      PR->band_idx.p, PR->dn_band(), a->row_fast.p, S.fcols.p, A->row_ptr.p, A->cols.p, A->values.p,
                      zero_first);

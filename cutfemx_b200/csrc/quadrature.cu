@@ -958,6 +958,97 @@ cfx_status cfx_runtime_quadrature(cfx_ctx* ctx, int ls, int relation, int order,
   CFX_API_END(ctx)
 }
 
+namespace cfx
+{
+namespace
+{
+// RuntimeSurfaceProvenance of straight codimension-one rules (make_surface_provenance, cut.cpp:1273-1308): rule k
+// comes from the k-th cut entity of the level set (the rules are emitted one per cut entity, ascending), its parent
+// is parent_map[k], the entity has ONE zero entity per P1 level set (local id 0) of dimension (host dim - 1)
+__global__ void provenance_kernel(const int32_t* __restrict__ parent_map, int64_t n, int dim,
+                                  const int32_t* __restrict__ cut_list, const int64_t* __restrict__ d_n_cut,
+                                  int64_t n_cut_host, int32_t* __restrict__ cut_ids, int32_t* __restrict__ parents,
+                                  int32_t* __restrict__ local_ids, int32_t* __restrict__ dims)
+{
+  const int64_t k = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (k >= n)
+    return;
+  const int32_t parent = parent_map[k];
+  int64_t id = k;
+  if (cut_list)
+  { // position of the parent among the cut entities (a cut entity whose selected part is empty -- the zero set only
+    // touches a vertex -- has no rule, so this is not the rule index in general)
+    int64_t lo = 0, hi = d_n_cut ? *d_n_cut : n_cut_host;
+    while (lo < hi)
+    {
+      const int64_t mid = (lo + hi) >> 1;
+      if (cut_list[mid] < parent)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    id = lo;
+  }
+  cut_ids[k] = static_cast<int32_t>(id);
+  parents[k] = parent;
+  local_ids[k] = 0;
+  dims[k] = dim;
+}
+} // namespace
+} // namespace cfx
+
+cfx_status cfx_rules_surface_provenance(cfx_ctx* ctx, const cfx_rules* r, int32_t* level_set_index,
+                                        int32_t* cut_cell_ids, int32_t* parent_cell_ids,
+                                        int32_t* local_zero_entity_ids, int32_t* dimensions, int memspace)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && r && level_set_index, CFX_ERR_INVALID, "cfx_rules_surface_provenance: NULL argument");
+  resolve(ctx, const_cast<cfx_rules*>(r));
+  // single_equality_level_set_index (cut.cpp:1258-1271): only "ls = 0" selectors carry provenance
+  if (r->relation != CFX_REL_EQ)
+  {
+    *level_set_index = -1;
+    return CFX_OK;
+  }
+  *level_set_index = r->ls;
+  if (r->nrules == 0 || !cut_cell_ids)
+    return CFX_OK;
+  CFX_REQUIRE(parent_cell_ids && local_zero_entity_ids && dimensions, CFX_ERR_INVALID,
+              "cfx_rules_surface_provenance: NULL output array");
+  const size_t n = static_cast<size_t>(r->nrules);
+  DevBuf<int32_t> tmp;
+  int32_t* d[4] = {cut_cell_ids, parent_cell_ids, local_zero_entity_ids, dimensions};
+  if (memspace != CFX_DEVICE)
+  {
+    tmp.reserve(ctx->pool, 4 * n);
+    for (int q = 0; q < 4; ++q)
+      d[q] = tmp.p + q * n;
+  }
+  const int32_t* cut_list = nullptr;
+  const int64_t* d_n_cut = nullptr;
+  int64_t n_cut = 0;
+  if (!r->entity_hosted && ctx->classified && r->ls >= 0 && r->ls < CFX_MAX_LEVEL_SETS && ctx->ls[r->ls].bound)
+  { // cell hosts: the ascending cut-cell list of the level set (facet hosts keep the rule index: their rules follow
+    // the host list, one per cut facet)
+    ensure_cut_list(ctx, r->ls);
+    LevelSet& L = ctx->ls[r->ls];
+    cut_list = L.cut_list.p;
+    d_n_cut = L.cut_deferred ? L.d_n_cut : nullptr;
+    n_cut = L.n_cut;
+  }
+  CFX_LAUNCH(ctx, provenance_kernel, grid_for(r->nrules, 256), 256, 0, r->parent_map.p, r->nrules, r->tdim - 1,
+             cut_list, d_n_cut, n_cut, d[0], d[1], d[2], d[3]);
+  if (memspace != CFX_DEVICE)
+  {
+    export_to(ctx, cut_cell_ids, d[0], n, CFX_HOST);
+    export_to(ctx, parent_cell_ids, d[1], n, CFX_HOST);
+    export_to(ctx, local_zero_entity_ids, d[2], n, CFX_HOST);
+    export_to(ctx, dimensions, d[3], n, CFX_HOST);
+    tmp.release();
+  }
+  CFX_API_END(ctx)
+}
+
 cfx_status cfx_rules_sizes(const cfx_rules* r, int64_t* npts, int64_t* nrules, int* tdim)
 {
   if (!r)

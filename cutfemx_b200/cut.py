@@ -9,6 +9,7 @@ library; this module only marshals arrays (numpy = host, torch CUDA tensors = de
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from collections.abc import Sequence
 
 import numpy as np
@@ -209,6 +210,21 @@ class _List:
             pass
 
 
+class SurfaceProvenance:
+    """cutfemx::RuntimeSurfaceProvenance (runtime_quadrature.h:30-43)."""
+
+    def __init__(self, selector, level_set_index, cut_cell_ids, parent_cell_ids, local_zero_entity_ids, dimensions):
+        self.selector, self.level_set_index = selector, level_set_index
+        self.cut_cell_ids, self.parent_cell_ids = cut_cell_ids, parent_cell_ids
+        self.local_zero_entity_ids, self.dimensions = local_zero_entity_ids, dimensions
+
+    def empty(self) -> bool:
+        return self.cut_cell_ids.size == 0
+
+    def size(self) -> int:
+        return int(self.cut_cell_ids.size)
+
+
 class RuntimeQuadratureRules:
     """Mirror of the runintgen `QuadratureRules` subclass the reference returns
     (python/cutfemx/cut.py:22-57, wrappers/cut.cpp:185-240): `kind`, `tdim`, `points` (npts, tdim),
@@ -290,6 +306,24 @@ class RuntimeQuadratureRules:
         _ = self.physical_points
         return self
 
+    @property
+    def surface_provenance(self):
+        """RuntimeSurfaceProvenance (runtime_quadrature.h:30-43, cut.cpp:1273-1308): selector, level_set_index and
+        -- for a single "phi = 0" selector -- per rule cut_cell_ids, parent_cell_ids, local_zero_entity_ids,
+        dimensions (int32).  Empty (level_set_index = -1, zero-length arrays) for every other selector."""
+        if "provenance" not in self._cache:
+            _, nr, _ = self._sizes()
+            ls = C.c_int32(-1)
+            h = self.ctx.handle
+            check(h, lib().cfx_rules_surface_provenance(h, self._h, C.byref(ls), None, None, None, None, HOST))
+            n = nr if ls.value >= 0 else 0
+            arrs = [np.empty(n, dtype=np.int32) for _ in range(4)]
+            if n:
+                check(h, lib().cfx_rules_surface_provenance(h, self._h, C.byref(ls),
+                                                            *[C.c_void_p(a.ctypes.data) for a in arrs], HOST))
+            self._cache["provenance"] = SurfaceProvenance(self.selector, int(ls.value), *arrs)
+        return self._cache["provenance"]
+
     def free(self):
         if self._h:
             lib().cfx_rules_free(self.ctx.handle, self._h)
@@ -313,6 +347,50 @@ class CutData:
         self._keep = []
         self._entities, self._entity_dim = None, None  # python/cutfemx/cut.py:102-108,141-146
         self._ecut = C.c_void_p()  # facet-hosted cut (cfx_cut_facets)
+        self._host_cells = None    # cell subset acting as host (int32 array), or None for every owned cell
+
+    # The context (device mirrors of the mesh, classification codes, cut lists) is shared by every CutData of a
+    # mesh, but a reference CutData owns its level-set view, its host entities and its cut cells (cut.cpp:742-786):
+    # two of them must not alias.  The context remembers which CutData its level-set slots, host mask and
+    # classification belong to; a query through another CutData re-binds and re-classifies first.
+    def _bind(self) -> None:
+        ctx, h = self._ctx, self._ctx.handle
+        ctx._active_cut = None  # a bind that fails half-way leaves nobody active: the next query re-binds
+        ent = self._host_cells
+        if ent is None:
+            check(h, lib().cfx_set_host_cells(h, None, C.c_int64(0), HOST))
+        else:
+            check(h, lib().cfx_set_host_cells(h, C.c_void_p(ent.ctypes.data), C.c_int64(ent.size), HOST))
+        self._keep = []
+        for i, f in enumerate(self._level_sets):
+            V = f.function_space
+            pd, msd, kd = as_arg(V.dofmap, np.int32)
+            pv, msv, kv = as_arg(f.x.array, np.float64)
+            if msd != msv:
+                # dofmap is copied/adopted separately from the values; mixed spaces need two calls' worth of
+                # bookkeeping the C ABI does not expose -- move the dofmap to where the values are.
+                if msv == DEVICE:
+                    import torch
+
+                    kd = torch.as_tensor(np.ascontiguousarray(V.dofmap), device=f"cuda:{ctx.device}")
+                    pd, msd = C.c_void_p(kd.data_ptr()), DEVICE
+                else:
+                    kd = V.dofmap.cpu().numpy()
+                    pd, msd = C.c_void_p(kd.ctypes.data), HOST
+            check(h, lib().cfx_levelset_bind(h, i, pd, int(V.nd), int(V.degree), pv, C.c_int64(V.num_dofs), msv, 1))
+            self._keep += [kd, kv]
+        for i in range(len(self._level_sets), getattr(ctx, "_n_bound_ls", 0)):
+            check(h, lib().cfx_levelset_unbind(h, i))
+        ctx._n_bound_ls = len(self._level_sets)
+        ctx._active_cut = weakref.ref(self)
+
+    def _activate(self) -> None:
+        """Make the context answer for THIS CutData (no-op while it is the one bound last)."""
+        ref = getattr(self._ctx, "_active_cut", None)
+        if ref is not None and ref() is self:
+            return
+        self._bind()
+        update(self)
 
     @property
     def facet_hosted(self) -> bool:
@@ -323,6 +401,13 @@ class CutData:
             if self._ecut and self._ctx._h:
                 lib().cfx_ecut_free(self._ctx.handle, self._ecut)
                 self._ecut = C.c_void_p()
+            ref = getattr(self._ctx, "_active_cut", None)
+            if self._ctx._h and ref is not None and ref() in (self, None):
+                # the context must not keep pointers into this CutData's value arrays (or their page-locking)
+                for i in range(getattr(self._ctx, "_n_bound_ls", 0)):
+                    lib().cfx_levelset_unbind(self._ctx.handle, i)
+                self._ctx._n_bound_ls = 0
+                self._ctx._active_cut = None
         except Exception:
             pass
 
@@ -363,11 +448,13 @@ class CutData:
 
     def counts(self, ls: int = 0):
         """(inside, intersected, outside) owned-cell counts."""
+        self._activate()
         out = (C.c_int64 * 3)()
         check(self._ctx.handle, lib().cfx_counts(self._ctx.handle, ls, out))
         return tuple(int(v) for v in out)
 
     def domain_codes(self, ls: int = 0) -> np.ndarray:
+        self._activate()
         out = np.empty(self.mesh.x_dofmap.shape[0], dtype=np.int8)
         check(self._ctx.handle, lib().cfx_domain_fetch(self._ctx.handle, ls, C.c_void_p(out.ctypes.data), HOST))
         return out
@@ -432,33 +519,14 @@ def cut(level_set, entities=None, entity_dim=None, *, cut_approximation: str = "
     cd = CutData(ctx, level_sets, names)
     h = ctx.handle
     if entities is not None and int(entity_dim) == mesh.tdim - 1:
-        # facets as hosts (cut.cpp:540-591, 1022-1063): classified after the level sets are bound, below
-        check(h, lib().cfx_set_host_cells(h, None, C.c_int64(0), HOST))
+        # facets as hosts (cut.cpp:540-591, 1022-1063): classified after the level sets are bound (update)
         cd._entities, cd._entity_dim = np.ascontiguousarray(np.asarray(entities, dtype=np.int32)), int(entity_dim)
     elif entities is None:
-        check(h, lib().cfx_set_host_cells(h, None, C.c_int64(0), HOST))
         cd._entities, cd._entity_dim = None, None
     else:  # cell subset as host (cut.cpp:500-538, test_cut_api.py:160-168); lists come back ascending
         ent = np.ascontiguousarray(np.asarray(entities, dtype=np.int32))
-        check(h, lib().cfx_set_host_cells(h, C.c_void_p(ent.ctypes.data), C.c_int64(ent.size), HOST))
-        cd._entities, cd._entity_dim = ent, int(entity_dim)
-    for i, f in enumerate(level_sets):
-        V = f.function_space
-        pd, msd, kd = as_arg(V.dofmap, np.int32)
-        pv, msv, kv = as_arg(f.x.array, np.float64)
-        if msd != msv:
-            # dofmap is copied/adopted separately from the values; mixed spaces need two calls' worth of
-            # bookkeeping the C ABI does not expose -- move the dofmap to where the values are.
-            if msv == DEVICE:
-                import torch
-
-                kd = torch.as_tensor(np.ascontiguousarray(V.dofmap), device=f"cuda:{ctx.device}")
-                pd, msd = C.c_void_p(kd.data_ptr()), DEVICE
-            else:
-                kd = V.dofmap.cpu().numpy()
-                pd, msd = C.c_void_p(kd.ctypes.data), HOST
-        check(h, lib().cfx_levelset_bind(h, i, pd, int(V.nd), int(V.degree), pv, C.c_int64(V.num_dofs), msv, 1))
-        cd._keep += [kd, kv]
+        cd._entities, cd._entity_dim, cd._host_cells = ent, int(entity_dim), ent
+    cd._bind()
     update(cd)
     return cd
 
@@ -466,6 +534,9 @@ def cut(level_set, entities=None, entity_dim=None, *, cut_approximation: str = "
 def update(cut_data: CutData) -> None:
     """Refresh cut data from the current level-set values (cut.cpp:845-868)."""
     h = cut_data._ctx.handle
+    ref = getattr(cut_data._ctx, "_active_cut", None)
+    if ref is None or ref() is not cut_data:
+        cut_data._bind()
     check(h, lib().cfx_update(h))
     if cut_data.facet_hosted:
         _bind_topology(cut_data.mesh, cut_data._ctx)
@@ -483,6 +554,7 @@ def _selector_args(cut_data: CutData, ls_part: str):
 def locate_entities_device(cut_data: CutData, ls_part: str, out: _List | None = None) -> _List:
     """`out`: a list from an earlier call to refill in place (its buffer is reused; in deferred-size mode the new
     length then stays on the device)."""
+    cut_data._activate()
     n, pto, pcl, pcr, keep = _selector_args(cut_data, ls_part)
     out = _List(cut_data._ctx) if out is None else out
     h = cut_data._ctx.handle
@@ -519,6 +591,7 @@ def runtime_quadrature(cut_data: CutData, ls_part: str, order: int, *, backend: 
     else:
         rules = RuntimeQuadratureRules(cut_data._ctx, ls_part, int(cl[0]), int(order))
     rules.ctx_gdim = cut_data.gdim
+    cut_data._activate()
     h = cut_data._ctx.handle
     if cut_data.facet_hosted:
         check(h, lib().cfx_ecut_runtime_quadrature(h, cut_data._ecut, int(cl[0]), int(cr[0]), int(order),
@@ -535,6 +608,7 @@ def runtime_quadratures(cut_data: CutData, ls_parts: Sequence[str], order: int, 
 def ghost_penalty_facets_device(cut_data: CutData, selector: str, *, include_ghosts: bool = False,
                                 out: _List | None = None) -> _List:
     mesh = cut_data.mesh
+    cut_data._activate()
     _bind_topology(mesh, cut_data._ctx)
     n, pto, pcl, pcr, keep = _selector_args(cut_data, selector)
     if "phi" not in cut_data.level_set_names:

@@ -21,6 +21,7 @@ def normal(cut_data: CutData, level_set, rules: RuntimeQuadratureRules, sign: fl
     """sign * grad(phi)/|grad(phi)| at the rule points, shape (npts, gdim) float64
     (level_set/normal.h:39-188).  The device copy stays attached to `rules` for the
     Nitsche kernels (the role of the QuadratureFunction the reference hands to runintgen)."""
+    cut_data._activate()
     h = cut_data._ctx.handle
     out = np.zeros((rules.total_points, cut_data.gdim))
     check(h, lib().cfx_evaluate_normals(h, _ls_index(cut_data, level_set), rules._h, C.c_double(sign),
@@ -31,6 +32,7 @@ def normal(cut_data: CutData, level_set, rules: RuntimeQuadratureRules, sign: fl
 
 def attach_normal(cut_data: CutData, level_set, rules: RuntimeQuadratureRules, sign: float = 1.0) -> None:
     """Evaluate the normals on the device only (no export)."""
+    cut_data._activate()
     h = cut_data._ctx.handle
     check(h, lib().cfx_evaluate_normals(h, _ls_index(cut_data, level_set), rules._h, C.c_double(sign), None, HOST))
     rules.normal_sign = sign
@@ -38,6 +40,7 @@ def attach_normal(cut_data: CutData, level_set, rules: RuntimeQuadratureRules, s
 
 def level_set_value(cut_data: CutData, level_set, rules: RuntimeQuadratureRules) -> np.ndarray:
     """phi at the rule points (level_set/value.h:34-119)."""
+    cut_data._activate()
     h = cut_data._ctx.handle
     out = np.zeros(rules.total_points)
     check(h, lib().cfx_evaluate_values(h, _ls_index(cut_data, level_set), rules._h, C.c_void_p(out.ctypes.data), HOST))

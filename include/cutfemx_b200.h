@@ -132,6 +132,9 @@ cfx_status cfx_topology_bind(cfx_ctx* ctx, const int32_t* c2f, const int32_t* f2
  * so that cfx_update re-reads it at full PCIe rate (it is the array cut.cpp:854-855 re-binds). */
 cfx_status cfx_levelset_bind(cfx_ctx* ctx, int ls, const int32_t* dofmap, int nd, int degree, const double* values,
                              int64_t n_dofs, int memspace, int pin_host);
+/* Forget level set `ls`: the caller's value array (and its page-locking) is no longer referenced.  A CutData that
+ * goes away calls this for its level sets -- the reference's CutData owns its level-set view (cut.cpp:742-786). */
+cfx_status cfx_levelset_unbind(cfx_ctx* ctx, int ls);
 /* cutfemx::update, cut.cpp:845-868 -> cutcells::cut: re-read every level set's values and
  * classify all owned cells (cut.cpp:292-321: all dofs < 0 inside, all > 0 outside, else intersected). */
 /* cutfemx.cut(level_set, entities, entity_dim = tdim) (python/cutfemx/cut.py:186-249, cut.cpp:500-538): restrict
@@ -166,6 +169,14 @@ cfx_status cfx_rules_sizes(const cfx_rules* r, int64_t* npts, int64_t* nrules, i
  * wrappers/cut.cpp:185-226): points AoS (npts,tdim), weights, offsets (nrules+1), parent_map. */
 cfx_status cfx_rules_fetch(cfx_ctx* ctx, const cfx_rules* r, double* points_aos, double* weights, int32_t* offsets,
                            int32_t* parent_map, int memspace);
+/* RuntimeSurfaceProvenance (runtime_quadrature.h:30-43), filled by make_surface_provenance (cut.cpp:1273-1308) for
+ * straight codimension-one rules of a single "ls = 0" selector: per rule the index of its cut entity among the cut
+ * entities, the parent entity, the local id of the zero entity inside the cut entity and the entity's dimension.
+ * *level_set_index = -1 (arrays untouched) for any other selector -- the reference's empty provenance.  The arrays hold
+ * nrules entries each; pass NULL arrays to query the level-set index only. */
+cfx_status cfx_rules_surface_provenance(cfx_ctx* ctx, const cfx_rules* r, int32_t* level_set_index,
+                                        int32_t* cut_cell_ids, int32_t* parent_cell_ids,
+                                        int32_t* local_zero_entity_ids, int32_t* dimensions, int memspace);
 /* RuntimeQuadrature::physical_points, runtime_quadrature.h:102-221: SoA (gdim, npts). */
 cfx_status cfx_rules_physical_points(cfx_ctx* ctx, const cfx_rules* r, double* out_soa, int memspace);
 void cfx_rules_free(cfx_ctx* ctx, cfx_rules* r);

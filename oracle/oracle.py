@@ -145,6 +145,22 @@ def runtime_quadrature(mesh, ls_dofmap, values, domain, relation: str, order: in
     return Rules(tdim, pts, wts, off, pm)
 
 
+def surface_provenance(r: Rules, relation: str, level_set_index: int = 0, cut_cells=None):
+    """make_surface_provenance, cut.cpp:1273-1308 (+ single_equality_level_set_index, :1258-1271): only a single
+    "ls = 0" selector whose part has dimension tdim - 1 carries provenance; one SelectedZeroEntityInfo per rule --
+    (cut_cell_id, parent_cell_id, local_zero_entity_id, dimension).  cut_cell_id is the position of the parent cell in
+    the ascending cut-cell list (`cut_cells`; default: one rule per cut cell, assumption A1 -- then it is the rule
+    index); a P1 level set has one zero entity per cut cell."""
+    if relation != "=":
+        e = np.zeros(0, dtype=np.int32)
+        return dict(level_set_index=-1, cut_cell_ids=e, parent_cell_ids=e, local_zero_entity_ids=e, dimensions=e)
+    n = r.parent_map.size
+    ids = np.arange(n, dtype=np.int32) if cut_cells is None else np.searchsorted(cut_cells, r.parent_map).astype(np.int32)
+    return dict(level_set_index=level_set_index, cut_cell_ids=ids,
+                parent_cell_ids=r.parent_map.astype(np.int32), local_zero_entity_ids=np.zeros(n, dtype=np.int32),
+                dimensions=np.full(n, r.tdim - 1, dtype=np.int32))
+
+
 def physical_points(mesh, r: Rules):
     out = np.zeros((mesh.gdim, r.weights.size))
     x, xd = _cf64(mesh.x), _ci32(mesh.x_dofmap)

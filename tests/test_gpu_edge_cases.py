@@ -213,3 +213,44 @@ def test_cell_subset_as_host(built_lib):
         cfx.cut(phi, np.arange(4, dtype=np.int32), 0)
     with pytest.raises(cfx.CfxError):
         cfx.cut(phi, np.array([mesh.num_cells], dtype=np.int32), mesh.tdim)
+
+
+def test_two_cut_data_on_one_mesh_do_not_alias(built_lib):
+    """Reference CutData objects are independent (cut.cpp builds a mesh view and a level-set set per call): an
+    earlier CutData keeps answering for ITS level set and host cells after another cut() on the same mesh, and a
+    dof index outside the level-set space is refused at bind time (cut.cpp:303-306)."""
+    import cutfemx_b200 as cfx
+    from cutfemx_b200 import mesh as M
+
+    mesh = M.create_rectangle(16, 16, (-1.0, -1.0), (1.0, 1.0))
+    V = M.functionspace(mesh, 1, permute_seed=3)
+    phi_a = M.Function(V, "phi").interpolate(M.sphere_level_set((0.0, 0.0, 0.0), 0.5))
+    phi_b = M.Function(V, "phi").interpolate(M.sphere_level_set((0.3, 0.1, 0.0), 0.3))
+    dom_a, dom_b = O.classify(V.dofmap, phi_a.x.array), O.classify(V.dofmap, phi_b.x.array)
+    cd_a = cfx.cut(phi_a)
+    in_a = cfx.locate_entities(cd_a, "phi<0")
+    cd_b = cfx.cut(phi_b)
+    sub = np.arange(0, mesh.num_cells, 3, dtype=np.int32)
+    cd_sub = cfx.cut(phi_a, sub, mesh.tdim)
+    assert np.array_equal(cfx.locate_entities(cd_b, "phi<0"), O.locate(dom_b, "phi<0"))
+    # the first CutData still answers for phi_a on all cells
+    assert np.array_equal(cfx.locate_entities(cd_a, "phi<0"), in_a) and np.array_equal(in_a, O.locate(dom_a, "phi<0"))
+    assert np.array_equal(cfx.locate_entities(cd_sub, "phi=0"), np.intersect1d(O.locate(dom_a, "phi=0"), sub))
+    ra, rb = cfx.runtime_quadrature(cd_a, "phi<0", 2), cfx.runtime_quadrature(cd_b, "phi<0", 2)
+    oa = O.runtime_quadrature(mesh, V.dofmap, phi_a.x.array, dom_a, "<", 2)
+    ob = O.runtime_quadrature(mesh, V.dofmap, phi_b.x.array, dom_b, "<", 2)
+    assert np.array_equal(ra.parent_map, oa.parent_map) and np.array_equal(rb.parent_map, ob.parent_map)
+    assert abs(ra.weights.sum() - oa.weights.sum()) < 1e-13 and abs(rb.weights.sum() - ob.weights.sum()) < 1e-13
+    assert cd_a.counts() == (O.locate(dom_a, "phi<0").size, O.locate(dom_a, "phi=0").size, O.locate(dom_a, "phi>0").size)
+    # update() after the values changed refreshes THIS CutData only
+    phi_b.x.array[:] = phi_a.x.array
+    cd_b.update()
+    assert np.array_equal(cfx.locate_entities(cd_b, "phi<0"), in_a)
+    del cd_b, cd_sub
+    assert np.array_equal(cfx.locate_entities(cd_a, "phi<0"), in_a)
+    # out-of-range level-set dof index
+    bad = M.FunctionSpace(mesh, 1, V.dofmap.copy(), V.num_dofs - 5, V.num_dofs - 5, 1, V.dof_coords[:-5])
+    fbad = M.Function(bad, "phi", phi_a.x.array[:-5].copy())
+    with pytest.raises(cfx.CfxError, match="Level-set dof index is out of range"):
+        cfx.cut(fbad)
+    assert np.array_equal(cfx.locate_entities(cd_a, "phi<0"), in_a)

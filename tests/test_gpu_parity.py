@@ -69,6 +69,23 @@ def test_physical_points_and_normals(runs):
     np.testing.assert_allclose(g.normals, o.ri.normals, rtol=0, atol=1e-12)
 
 
+def test_surface_provenance_bit_exact(runs):
+    """RuntimeSurfaceProvenance (cut.cpp:1273-1308): aligned with the interface rules, empty for volume selectors."""
+    import oracle as O
+
+    o, g = runs
+    ref = O.surface_provenance(o.ri, "=", cut_cells=o.cut)
+    pv = g.ri.surface_provenance
+    assert pv.selector == g.ri.selector and pv.level_set_index == ref["level_set_index"] == 0
+    assert pv.size() == g.ri.num_rules  # "aligned with runtime quadrature rules" (cut.cpp:1289-1295)
+    for k in ("cut_cell_ids", "parent_cell_ids", "local_zero_entity_ids", "dimensions"):
+        a = getattr(pv, k)
+        assert a.dtype == np.int32 and np.array_equal(a, ref[k]), k
+    assert np.array_equal(o.cut[pv.cut_cell_ids], pv.parent_cell_ids) and np.all(pv.dimensions == o.mesh.tdim - 1)
+    vol = g.rv.surface_provenance
+    assert vol.empty() and vol.level_set_index == -1 == O.surface_provenance(o.rv, "<")["level_set_index"]
+
+
 def test_ghost_facets_bit_exact(runs):
     o, g = runs
     assert np.array_equal(o.ghost, g.ghost)
