@@ -108,3 +108,24 @@ def test_no_cpu_fallback():
     phi = M.Function(V, "phi").interpolate(lambda x, y, z: x - 0.1)
     with pytest.raises(cfx.CfxError):
         cfx.cut(phi)
+
+
+def test_host_patch_compiles_and_links(built_lib, tmp_path):
+    """host_patch/cutfemx_gpu_seams.cpp -- the C++ a CutFEMx maintainer adds next to cut/cut.cpp (SURVEY.md section 7
+    step 2) -- compiles against include/cutfemx_b200.h and the DOLFINx / CutCells stand-in headers, and every library
+    call it makes resolves against libcutfemx_b200.so (-Wl,--no-undefined)."""
+    import shutil
+    import subprocess
+
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "host_patch_check.so"
+    cmd = [gxx, "-std=c++20", "-Wall", "-Wextra", "-Werror", "-DCUTFEMX_HOST_PATCH_STUBS", "-I", os.path.join(root, "include"),
+           "-I", os.path.join(root, "host_patch", "stubs"), "-fPIC", "-shared",
+           os.path.join(root, "host_patch", "cutfemx_gpu_seams.cpp"), "-o", str(out),
+           "-L", os.path.dirname(built_lib), "-lcutfemx_b200", "-Wl,--no-undefined"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert out.exists()
