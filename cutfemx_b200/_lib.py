@@ -27,7 +27,7 @@ KERNEL_RANK = {1: 2, 2: 2, 3: 2, 4: 2, 5: 1, 6: 1, 7: 0, 8: 2, 9: 1, 10: 0, 11: 
 # every symbol include/cutfemx_b200.h declares (tests/test_abi.py checks the .so exports them all)
 SYMBOLS = [
     "cfx_ctx_create", "cfx_ctx_destroy", "cfx_last_error", "cfx_sync", "cfx_version", "cfx_launch_count",
-    "cfx_mesh_bind", "cfx_topology_bind", "cfx_levelset_bind", "cfx_levelset_unbind", "cfx_set_host_cells", "cfx_cut_facets", "cfx_ecut_locate", "cfx_ecut_runtime_quadrature", "cfx_ecut_free",
+    "cfx_mesh_bind", "cfx_topology_bind", "cfx_levelset_bind", "cfx_levelset_unbind", "cfx_set_host_cells", "cfx_cut_facets", "cfx_ecut_locate", "cfx_ecut_runtime_quadrature", "cfx_rules_facets_to_cells", "cfx_ecut_free",
     "cfx_update", "cfx_counts", "cfx_domain_fetch",
     "cfx_locate_entities", "cfx_list_size", "cfx_list_device_ptr", "cfx_list_fetch", "cfx_list_free",
     "cfx_runtime_quadrature", "cfx_rules_sizes", "cfx_rules_fetch", "cfx_rules_physical_points", "cfx_rules_surface_provenance", "cfx_rules_free",

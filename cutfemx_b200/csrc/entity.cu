@@ -544,3 +544,176 @@ void cfx_ecut_free(cfx_ctx* ctx, cfx_ecut* E)
   delete E;
 }
 } // extern "C"
+
+namespace cfx
+{
+namespace
+{
+// Exterior-facet run-time rules for kernels defined on cells (_facet_payload_with_rows +
+// facet_runtime_quadrature_payload, _runintgen_adapter.py:605-680): a facet rule is re-expressed in the reference
+// coordinates of the facet's (first) cell.  key[k] = local index of the facet in that cell.
+__global__ void facet_rule_key_kernel(const int32_t* __restrict__ parent_map, int64_t n, const int32_t* __restrict__ f2c2,
+                                      const int32_t* __restrict__ c2f, int nf, int32_t* __restrict__ key,
+                                      int32_t* __restrict__ cell_of)
+{
+  const int64_t k = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (k >= n)
+    return;
+  const int32_t f = parent_map[k];
+  const int32_t c = f2c2[2 * static_cast<int64_t>(f)];
+  int lf = 0;
+  for (int j = 0; j < nf; ++j)
+    lf = (c2f[static_cast<int64_t>(c) * nf + j] == f) ? j : lf;
+  key[k] = lf;
+  cell_of[k] = c;
+}
+struct KeyPred
+{
+  const int32_t* key;
+  int32_t want;
+  __device__ unsigned operator()(int64_t base, int64_t n) const
+  { // 16-bit mask for base .. base + 15 (compact.cuh)
+    unsigned m = 0;
+    for (int k = 0; k < 16; ++k)
+      if (base + k < n && key[base + k] == want)
+        m |= 1u << k;
+    return m;
+  }
+};
+__global__ void facet_rule_count_kernel(const int32_t* __restrict__ idx, int64_t m, const int32_t* __restrict__ offsets,
+                                        int32_t* __restrict__ cnt)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i < m)
+    cnt[i] = offsets[idx[i] + 1] - offsets[idx[i]];
+}
+// one thread per selected rule: points mapped facet reference -> cell reference
+//   x = sum_j lam_j v_j (facet vertices v_j ascending; lam_0 = 1 - sum xi, lam_j = xi_{j-1})  and vertex v of the cell
+//   with local index t has cell reference coordinates e_t (e_0 = 0): X_{t-1} += lam_j for t = loc(v_j) >= 1
+template <int EDIM>
+__global__ void facet_rule_map_kernel(const int32_t* __restrict__ idx, int64_t m, const int32_t* __restrict__ offsets,
+                                      const double* __restrict__ pts, int64_t npts_in,
+                                      const double* __restrict__ wts, const int32_t* __restrict__ rule_verts,
+                                      const int32_t* __restrict__ cell_of, const int32_t* __restrict__ x_dofmap,
+                                      const int64_t* __restrict__ out_off64, int64_t npts_out,
+                                      double* __restrict__ out_pts, double* __restrict__ out_wts,
+                                      int32_t* __restrict__ out_offsets, int32_t* __restrict__ out_parent)
+{
+  constexpr int TDIM = EDIM + 1, NE = EDIM + 1, NV = TDIM + 1;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= m)
+    return;
+  const int64_t k = idx[i];
+  const int32_t c = cell_of[k];
+  int loc[NE];
+#pragma unroll
+  for (int j = 0; j < NE; ++j)
+  {
+    const int32_t v = rule_verts[k * NE + j];
+    int t = 0;
+#pragma unroll
+    for (int q = 0; q < NV; ++q)
+      t = (x_dofmap[static_cast<int64_t>(c) * NV + q] == v) ? q : t;
+    loc[j] = t;
+  }
+  const int64_t o = out_off64[i];
+  out_offsets[i] = static_cast<int32_t>(o);
+  if (i == m - 1)
+    out_offsets[m] = static_cast<int32_t>(npts_out);
+  out_parent[i] = c;
+  const int32_t q0 = offsets[k], q1 = offsets[k + 1];
+  for (int32_t q = q0; q < q1; ++q)
+  {
+    double lam[NE];
+    lam[0] = 1.0;
+#pragma unroll
+    for (int j = 1; j < NE; ++j)
+    {
+      lam[j] = pts[static_cast<int64_t>(j - 1) * npts_in + q];
+      lam[0] -= lam[j];
+    }
+    double X[TDIM];
+#pragma unroll
+    for (int t = 0; t < TDIM; ++t)
+      X[t] = 0.0;
+#pragma unroll
+    for (int j = 0; j < NE; ++j)
+#pragma unroll
+      for (int t = 0; t < TDIM; ++t)
+        X[t] += (loc[j] == t + 1) ? lam[j] : 0.0;
+    const int64_t oq = o + (q - q0);
+#pragma unroll
+    for (int t = 0; t < TDIM; ++t)
+      out_pts[static_cast<int64_t>(t) * npts_out + oq] = X[t];
+    out_wts[oq] = wts[q];
+  }
+}
+} // namespace
+} // namespace cfx
+
+extern "C" cfx_status cfx_rules_facets_to_cells(cfx_ctx* ctx, const cfx_rules* fr, int local_facet, cfx_rules** inout)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && fr && inout, CFX_ERR_INVALID, "cfx_rules_facets_to_cells: NULL argument");
+  CFX_REQUIRE(fr->entity_hosted && fr->tdim == ctx->tdim - 1, CFX_ERR_INVALID,
+              "cfx_rules_facets_to_cells: the rules must come from a facet-hosted cut");
+  CFX_REQUIRE(ctx->c2f != nullptr && ctx->f2c2.p != nullptr, CFX_ERR_STATE,
+              "cfx_rules_facets_to_cells: bind the topology first (cfx_topology_bind)");
+  CFX_REQUIRE(local_facet >= 0 && local_facet <= ctx->tdim, CFX_ERR_INVALID, "local facet index out of range");
+  if (*inout == nullptr)
+    *inout = new cfx_rules();
+  cfx_rules* R = *inout;
+  R->tdim = ctx->tdim;
+  R->gdim = ctx->gdim;
+  R->relation = fr->relation;
+  R->order = fr->order;
+  R->ls = fr->ls;
+  R->has_normals = false;
+  R->has_moments = false;
+  R->entity_hosted = false;
+  R->deferred = false;
+  R->ctx = ctx;
+  R->nrules = R->npts = 0;
+  R->offsets.reserve(ctx->pool, 2);
+  CFX_CUDA(cudaMemsetAsync(R->offsets.p, 0, sizeof(int32_t), ctx->stream));
+  const int64_t n = fr->nrules;
+  if (n == 0)
+    return CFX_OK;
+  DevBuf<int32_t> key, cell_of, idx, cnt;
+  DevBuf<int64_t> off64;
+  key.reserve(ctx->pool, static_cast<size_t>(n) + 1);
+  cell_of.reserve(ctx->pool, static_cast<size_t>(n) + 1);
+  CFX_LAUNCH(ctx, facet_rule_key_kernel, grid_for(n, 256), 256, 0, fr->parent_map.p, n, ctx->f2c2.p, ctx->c2f,
+             ctx->tdim + 1, key.p, cell_of.p);
+  KeyPred pred{key.p, local_facet};
+  const int64_t m = compact_indices(ctx, n, pred, idx);
+  if (m > 0)
+  {
+    cnt.reserve(ctx->pool, static_cast<size_t>(m) + 1);
+    off64.reserve(ctx->pool, static_cast<size_t>(m) + 2);
+    CFX_LAUNCH(ctx, facet_rule_count_kernel, grid_for(m, 256), 256, 0, idx.p, m, fr->offsets.p, cnt.p);
+    exclusive_scan_i32_to_i64(ctx, cnt.p, m, off64.p);
+    const int64_t npts = read_back(ctx, ctx->scratch64.p, 1)[0];
+    R->nrules = m;
+    R->npts = npts;
+    R->points.reserve(ctx->pool, static_cast<size_t>(npts) * ctx->tdim + 1);
+    R->weights.reserve(ctx->pool, static_cast<size_t>(npts) + 1);
+    R->offsets.reserve(ctx->pool, static_cast<size_t>(m) + 2);
+    R->parent_map.reserve(ctx->pool, static_cast<size_t>(m) + 1);
+    if (ctx->tdim == 2)
+      CFX_LAUNCH(ctx, facet_rule_map_kernel<1>, grid_for(m, 256), 256, 0, idx.p, m, fr->offsets.p, fr->points.p, fr->npts,
+                 fr->weights.p, fr->rule_verts.p, cell_of.p, ctx->x_dofmap, off64.p, npts, R->points.p, R->weights.p,
+                 R->offsets.p, R->parent_map.p);
+    else
+      CFX_LAUNCH(ctx, facet_rule_map_kernel<2>, grid_for(m, 256), 256, 0, idx.p, m, fr->offsets.p, fr->points.p, fr->npts,
+                 fr->weights.p, fr->rule_verts.p, cell_of.p, ctx->x_dofmap, off64.p, npts, R->points.p, R->weights.p,
+                 R->offsets.p, R->parent_map.p);
+    CFX_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  key.release();
+  cell_of.release();
+  idx.release();
+  cnt.release();
+  off64.release();
+  CFX_API_END(ctx)
+}

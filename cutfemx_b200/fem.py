@@ -58,11 +58,29 @@ class CutForm:
         return self
 
     def add_exterior_facet_integral(self, kernel: str, rules: RuntimeQuadratureRules, constants=(1.0,)):
-        """`one * ds(subdomain_data=rules)` on facet-hosted rules (test_cut_api.py:504-527): the measure functional."""
+        """`integrand * ds(subdomain_data=rules)` on facet-hosted rules.  Functionals of the measure ("one", rank 0,
+        test_cut_api.py:504-527) are summed on the facet rules directly; every other kernel family runs on the rules
+        re-expressed in the reference coordinates of the facets' cells (_facet_payload_with_rows,
+        _runintgen_adapter.py:605-680): one cell integral per local facet index, so that no cell appears twice in a
+        rule set."""
         cst = np.ascontiguousarray(list(constants), dtype=np.float64)
         h = self.ctx.handle
-        check(h, lib().cfx_form_add_exterior_facet_integral(h, self._h, KERNEL[kernel], rules._h,
-                                                            C.c_void_p(cst.ctypes.data), int(cst.size)))
+        if self.rank == 0 and kernel == "one":
+            check(h, lib().cfx_form_add_exterior_facet_integral(h, self._h, KERNEL[kernel], rules._h,
+                                                                C.c_void_p(cst.ctypes.data), int(cst.size)))
+            self._owners.append(rules)
+            return self
+        from .cut import RuntimeQuadratureRules as _Rules
+        from .cut import _bind_topology
+
+        msh = self.function_space.mesh
+        _bind_topology(msh, self.ctx)
+        for lf in range(msh.tdim + 1):
+            cr = _Rules(self.ctx, rules.selector, rules.ls, rules.order)
+            cr.ctx_gdim = msh.gdim
+            check(h, lib().cfx_rules_facets_to_cells(h, rules._h, lf, C.byref(cr._h)))
+            if cr.num_rules:
+                self.add_cell_integral(kernel, None, cr, constants)
         self._owners.append(rules)
         return self
 

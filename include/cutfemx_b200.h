@@ -207,6 +207,14 @@ cfx_status cfx_ecut_locate(cfx_ctx* ctx, const cfx_ecut* e, int n_terms, const i
                            const int32_t* clause_ls, const int32_t* clause_rel, cfx_list** out);
 cfx_status cfx_ecut_runtime_quadrature(cfx_ctx* ctx, const cfx_ecut* e, int ls, int relation, int order,
                                        cfx_rules** inout);
+/* Exterior / boundary facet integrals with run-time rules (`... * ds(subdomain_data=rules)`): the reference maps the
+ * facet rules to (cell, local facet) rows and to the parent cell's reference coordinates before the generated kernel
+ * runs (_facet_payload_with_rows + facet_runtime_quadrature_payload, python/cutfemx/_runintgen_adapter.py:605-680).
+ * This call returns, as ordinary cell-hosted rules, the rules of `facet_rules` whose facet is local facet
+ * `local_facet` of its first cell: points in the cell's reference coordinates, physical weights, parent_map = cells
+ * (each cell at most once per local facet index, so tdim + 1 calls cover every rule).  The result feeds
+ * cfx_form_add_cell_integral with any point-evaluated kernel family (CFX_K_MASS, CFX_K_SOURCE, CFX_K_ONE, ...). */
+cfx_status cfx_rules_facets_to_cells(cfx_ctx* ctx, const cfx_rules* facet_rules, int local_facet, cfx_rules** inout);
 void cfx_ecut_free(cfx_ctx* ctx, cfx_ecut* e);
 
 /* ------------------------------------------------------------------ ghost-penalty facets

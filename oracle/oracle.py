@@ -418,6 +418,24 @@ def facet_vertices(mesh, facets):
     return verts, local, cells
 
 
+def facet_rules_on_cells(mesh, r: "Rules") -> "Rules":
+    """Facet-hosted rules re-expressed on the facets' first cells -- what _facet_payload_with_rows and runintgen's
+    facet_runtime_quadrature_payload (python/cutfemx/_runintgen_adapter.py:605-680) do before an exterior-facet kernel
+    runs: facet reference point xi -> barycentric (1 - sum xi, xi) over the facet's vertices (ascending vertex number)
+    -> reference coordinates of the cell, where the vertex with local index t >= 1 is the unit vector e_{t-1}.
+    Rules keep the order of the facet rules; parent_map = cells (a cell may appear more than once)."""
+    verts, local, cells = facet_vertices(mesh, r.parent_map)
+    tdim = mesh.tdim
+    rule_of_pt = np.repeat(np.arange(r.parent_map.size), np.diff(r.offsets))
+    lam = np.concatenate([1.0 - r.points.sum(axis=1, keepdims=True), r.points], axis=1)
+    X = np.zeros((r.weights.size, tdim))
+    for j in range(tdim):            # facet vertex j
+        loc = local[rule_of_pt, j]
+        for t in range(tdim):
+            X[:, t] += np.where(loc == t + 1, lam[:, j], 0.0)
+    return Rules(tdim, X, r.weights.copy(), r.offsets.copy(), cells.astype(np.int32))
+
+
 def classify_facets(mesh, ls_dofmap, values, facets):
     """Domain codes of facet hosts from the level-set values at their vertices (P1: the entity dofmap of
     fem/entity_dofmap.cpp:11-88 lists the vertices' dofs) -- the rule of cut.cpp:292-321 one dimension down."""

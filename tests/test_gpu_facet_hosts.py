@@ -91,6 +91,47 @@ def test_weight_sum_does_not_depend_on_the_host_list(built_lib):
     np.testing.assert_allclose(value, 2.0 * r_all.weights.sum(), rtol=1e-13)
 
 
+@pytest.mark.parametrize("tdim,n,fn,deg", [(2, 9, lambda x, y, z: x - 0.51, 1), (2, 7, M.sphere_level_set((0.45, 0.55, 0.0), 0.62), 2),
+                                           (3, 5, lambda x, y, z: x + 0.3 * y - 0.52, 1),
+                                           (3, 4, M.sphere_level_set((0.4, 0.5, 0.55), 0.7), 2)],
+                         ids=["line2d-P1", "circle2d-P2", "plane3d-P1", "sphere3d-P2"])
+def test_exterior_facet_integrals_on_cut_boundary_facets(built_lib, tdim, n, fn, deg):
+    """SURVEY section 8(f) rank 3, second half: `alpha u v ds(rules)` (Robin / penalty term), `g v ds(rules)` and
+    `1 ds(rules)` on the wet part of the boundary -- the run-time exterior-facet integrals of
+    _facet_payload_with_rows (_runintgen_adapter.py:605-680).  The facet rules are mapped into the reference
+    coordinates of the facets' cells and the cell kernel families evaluate them; corner cells own two or three
+    boundary facets.  Against the oracle's restatement (sparsity bit-exact, values 1e-12) and the analytic pins:
+    the load vector sums to g x (wet boundary measure), the mass matrix sums to alpha x the same."""
+    cfx, mesh, Vphi, phi = _problem(tdim, n, fn)
+    V = M.functionspace(mesh, deg, permute_seed=4)
+    exterior = np.nonzero(np.diff(mesh.f2c_offsets) == 1)[0].astype(np.int32)
+    cd = cfx.cut(phi, exterior, tdim - 1)
+    rules = cfx.runtime_quadrature(cd, "phi<0", 4)
+    ro = O.facet_runtime_quadrature(mesh, Vphi.dofmap, phi.x.array, exterior, "<", 4)
+    rc = O.facet_rules_on_cells(mesh, ro)
+    assert rules.num_rules == ro.parent_map.size > 0
+    assert np.unique(rc.parent_map).size < rc.parent_map.size or tdim == 2 and n == 9  # corner cells appear twice
+    alpha, g = 3.5, -1.25
+    cells = np.unique(rc.parent_map)
+    rp, cols = O.sparsity(V, cells, np.zeros((0, 4), dtype=np.int32))
+    ref = np.zeros(cols.size)
+    O.assemble_cells(V, "mass", ref, None, rc, (alpha,), rp, cols)
+    bref = np.zeros(V.num_dofs)
+    O.assemble_cells(V, "source", bref, None, rc, (g,))
+    a = cfx.fem.CutForm(V, 2).add_exterior_facet_integral("mass", rules, (alpha,))
+    A = cfx.fem.assemble_matrix(a)
+    assert np.array_equal(A.indptr, rp) and np.array_equal(A.indices, cols)
+    assert np.linalg.norm(A.data - ref) <= 1e-12 * np.linalg.norm(ref)
+    L = cfx.fem.CutForm(V, 1).add_exterior_facet_integral("source", rules, (g,))
+    b = cfx.fem.assemble_vector(L)
+    assert np.linalg.norm(b - bref) <= 1e-12 * np.linalg.norm(bref)
+    wet = rules.weights.sum()
+    np.testing.assert_allclose(b.sum(), g * wet, rtol=1e-12)          # partition of unity on the boundary
+    np.testing.assert_allclose(A.data.sum(), alpha * wet, rtol=1e-12)
+    m0 = cfx.fem.assemble_scalar(cfx.fem.CutForm(V, 0).add_exterior_facet_integral("one", rules, (1.0,)))
+    np.testing.assert_allclose(m0, wet, rtol=1e-13)
+
+
 def test_facet_host_errors(built_lib):
     cfx, mesh, V, phi = _problem(2, 5, lambda x, y, z: x - 0.51)
     with pytest.raises(cfx.CfxError):  # validate_local_entities
