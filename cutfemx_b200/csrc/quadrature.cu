@@ -590,6 +590,276 @@ __global__ void __launch_bounds__(QB)
   }
 }
 
+// ------------------------------------------------------------------ P2 level sets
+// cutfemx.cut(level_set) with a degree-2 level set, default options (cut_approximation "auto", order 1,
+// wrappers/cut.cpp:117-140): straight pieces between edge roots of the higher-order function.  Algorithm (the
+// oracle's cut_cell_rule_p2 states it and the reasons; CutCells itself is absent): one red refinement through the
+// P2 nodes, marching-simplex case tables per sub-simplex on the nodal values (a sub-simplex entirely inside
+// contributes whole), edge roots = the root in [0, 1] of the quadratic restriction of the level set to the sub-edge,
+// points in the PARENT cell's reference coordinates, physical weights, one rule per cut cell.
+// One thread per cut cell in both passes: the work per cell is irregular (up to 8 sub-cells x 3 pieces x npts) and
+// the feature is a "next" row -- correctness and parity first.
+__constant__ int8_t c_red_tri[4][3] = {{0, 5, 4}, {1, 3, 5}, {2, 4, 3}, {3, 4, 5}};
+__constant__ int8_t c_red_tet[8][4] = {{0, 9, 8, 7}, {1, 9, 6, 5}, {2, 8, 6, 4}, {3, 7, 5, 4},
+                                       {9, 8, 7, 5}, {9, 8, 6, 5}, {8, 7, 5, 4}, {8, 6, 5, 4}};
+// reference coordinates of the P2 nodes, times 2
+__constant__ int8_t c_node2_tri[6][2] = {{0, 0}, {2, 0}, {0, 2}, {1, 1}, {0, 1}, {1, 0}};
+__constant__ int8_t c_node2_tet[10][3] = {{0, 0, 0}, {2, 0, 0}, {0, 2, 0}, {0, 0, 2}, {0, 1, 1},
+                                          {1, 0, 1}, {1, 1, 0}, {0, 0, 1}, {0, 1, 0}, {1, 0, 0}};
+
+__device__ __forceinline__ double quadratic_edge_root(double fa, double fm, double fb)
+{
+  const double a = 2.0 * fa - 4.0 * fm + 2.0 * fb, b = -3.0 * fa + 4.0 * fm - fb, c = fa;
+  const double lin = fa / (fa - fb);
+  if (fabs(a) <= 1e-14 * (fabs(b) + fabs(c)))
+    return lin;
+  const double disc = b * b - 4.0 * a * c;
+  if (disc < 0.0)
+    return lin;
+  const double sq = sqrt(disc);
+  const double qq = -0.5 * (b + (b >= 0.0 ? sq : -sq));
+  const double r1 = qq / a, r2 = (qq != 0.0) ? c / qq : r1;
+  const bool ok1 = r1 >= 0.0 && r1 <= 1.0, ok2 = r2 >= 0.0 && r2 <= 1.0;
+  if (ok1 && ok2)
+    return fabs(r1 - lin) <= fabs(r2 - lin) ? r1 : r2;
+  if (ok1)
+    return r1;
+  if (ok2)
+    return r2;
+  return lin;
+}
+
+// walks the pieces of one cut cell; emit(P, sv, nsv) gets the local point list (parent reference coordinates,
+// stride TDIM) and the piece's vertex indices
+template <int TDIM, class Emit>
+__device__ __forceinline__ void p2_cell_pieces(const double (&dofs)[TDIM == 2 ? 6 : 10], bool positive, bool interface,
+                                               Emit emit)
+{
+  constexpr int NV = TDIM + 1;
+  constexpr int NSC = TDIM == 2 ? 4 : 8;
+  for (int sc = 0; sc < NSC; ++sc)
+  {
+    double V[NV][TDIM], f[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+    {
+      const int node = TDIM == 2 ? c_red_tri[sc][v] : c_red_tet[sc][v];
+#pragma unroll
+      for (int t = 0; t < TDIM; ++t)
+        V[v][t] = 0.5 * (TDIM == 2 ? c_node2_tri[node][t] : c_node2_tet[node][t]);
+      double fv = dofs[0];
+#pragma unroll
+      for (int j = 1; j < (TDIM == 2 ? 6 : 10); ++j)
+        fv = (j == node) ? dofs[j] : fv;
+      f[v] = fv;
+    }
+    int I[NV], O[NV], n_in = 0, n_out = 0;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+    {
+      const bool in = positive ? (f[v] > 0.0) : (f[v] < 0.0);
+      if (in)
+        I[n_in++] = v;
+      else
+        O[n_out++] = v;
+    }
+    if (n_in == 0)
+      continue;
+    double P[(TDIM == 2 ? 4 : 6) * TDIM];
+    if (n_in == NV)
+    {
+      if (interface)
+        continue;
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int t = 0; t < TDIM; ++t)
+          P[v * TDIM + t] = V[v][t];
+      const int8_t whole[4] = {0, 1, 2, 3};
+      emit(P, whole, NV);
+      continue;
+    }
+    for (int i = 0; i < n_in; ++i)
+#pragma unroll
+      for (int t = 0; t < TDIM; ++t)
+        P[i * TDIM + t] = V[I[i]][t];
+    int np = n_in;
+    for (int i = 0; i < n_in; ++i)
+      for (int o = 0; o < n_out; ++o)
+      {
+        const int a = I[i], b = O[o];
+        double Xm[TDIM];
+#pragma unroll
+        for (int t = 0; t < TDIM; ++t)
+          Xm[t] = 0.5 * (V[a][t] + V[b][t]);
+        double phi[TDIM == 2 ? 6 : 10], dphi[TDIM == 2 ? 6 : 10][TDIM];
+        tabulate<TDIM, 2>(Xm, phi, dphi);
+        double fm = 0.0;
+#pragma unroll
+        for (int j = 0; j < (TDIM == 2 ? 6 : 10); ++j)
+          fm += phi[j] * dofs[j];
+        const double tt = quadratic_edge_root(f[a], fm, f[b]);
+#pragma unroll
+        for (int t = 0; t < TDIM; ++t)
+          P[np * TDIM + t] = V[a][t] + tt * (V[b][t] - V[a][t]);
+        ++np;
+      }
+    const int nsub = num_sub(TDIM, interface, n_in);
+    for (int s = 0; s < nsub; ++s)
+    {
+      const int8_t* sv = interface ? (TDIM == 2 ? c_tri_ifc[n_in][s] : c_tet_ifc[n_in][s])
+                                   : (TDIM == 2 ? c_tri_vol[n_in][s] : c_tet_vol[n_in][s]);
+      emit(P, sv, interface ? TDIM : NV);
+    }
+  }
+}
+
+template <int TDIM>
+__device__ __forceinline__ void load_p2_dofs(const int32_t* __restrict__ ls_dofmap, const double* __restrict__ vals,
+                                             int64_t cell, double (&dofs)[TDIM == 2 ? 6 : 10])
+{
+  constexpr int ND = TDIM == 2 ? 6 : 10;
+#pragma unroll
+  for (int j = 0; j < ND; ++j)
+    dofs[j] = __ldg(vals + __ldg(ls_dofmap + cell * ND + j));
+}
+
+template <int TDIM>
+__global__ void __launch_bounds__(QB)
+    rule_count_p2_kernel(const int32_t* __restrict__ cut_cells, DN n_cut_, const int32_t* __restrict__ ls_dofmap,
+                         const double* __restrict__ vals, bool positive, bool interface, int npts_s,
+                         int64_t* __restrict__ packed)
+{
+  const int64_t k = static_cast<int64_t>(blockIdx.x) * QB + threadIdx.x;
+  if (k >= n_cut_.get())
+    return;
+  double dofs[TDIM == 2 ? 6 : 10];
+  load_p2_dofs<TDIM>(ls_dofmap, vals, cut_cells[k], dofs);
+  int pieces = 0;
+  p2_cell_pieces<TDIM>(dofs, positive, interface, [&](const double*, const int8_t*, int) { ++pieces; });
+  const int nq = pieces * npts_s;
+  packed[k] = nq > 0 ? ((int64_t(1) << 32) | nq) : 0;
+}
+
+template <int TDIM>
+__global__ void __launch_bounds__(QB)
+    rule_fill_p2_kernel(const int32_t* __restrict__ cut_cells, DN n_cut_, const int64_t* __restrict__ packed_excl,
+                        const int32_t* __restrict__ ls_dofmap, const double* __restrict__ vals,
+                        const int32_t* __restrict__ x_dofmap, const double* __restrict__ x, bool positive,
+                        bool interface, int npts_s, const double* __restrict__ rule_pts,
+                        const double* __restrict__ rule_wts, int64_t cap_pts, int64_t cap_rules,
+                        int64_t* __restrict__ d_sizes, int32_t* __restrict__ err, double* __restrict__ points,
+                        double* __restrict__ weights, int32_t* __restrict__ offsets, int32_t* __restrict__ parent_map)
+{
+  constexpr int NV = TDIM + 1;
+  const int64_t n_cut = n_cut_.get();
+  const int64_t pk_total = packed_excl[n_cut];
+  const int64_t npts_total = pk_total & 0xffffffffLL;
+  const bool fits = npts_total <= cap_pts && (pk_total >> 32) <= cap_rules;
+  const int64_t k = static_cast<int64_t>(blockIdx.x) * QB + threadIdx.x;
+  if (k == 0)
+  {
+    d_sizes[0] = fits ? (pk_total >> 32) : 0;
+    d_sizes[1] = fits ? npts_total : 0;
+    if (!fits)
+    {
+      err[0] = 32;
+      err[1] = static_cast<int32_t>(npts_total);
+    }
+    else
+      offsets[pk_total >> 32] = static_cast<int32_t>(npts_total); // closing offset
+  }
+  if (!fits || k >= n_cut)
+    return;
+  const int64_t pk = packed_excl[k];
+  const int my_nq = static_cast<int>((packed_excl[k + 1] & 0xffffffffLL) - (pk & 0xffffffffLL));
+  if (my_nq == 0)
+    return;
+  const int64_t cell = cut_cells[k];
+  const int64_t rule = pk >> 32;
+  offsets[rule] = static_cast<int32_t>(pk & 0xffffffffLL);
+  parent_map[rule] = static_cast<int32_t>(cell);
+  double dofs[TDIM == 2 ? 6 : 10];
+  load_p2_dofs<TDIM>(ls_dofmap, vals, cell, dofs);
+  double X[NV][TDIM];
+  load_cell_coords<TDIM>(x, x_dofmap, cell, X);
+  Geo<TDIM> g;
+  make_geo<TDIM>(X, g);
+  int64_t gp = pk & 0xffffffffLL;
+  p2_cell_pieces<TDIM>(dofs, positive, interface,
+                       [&](const double* P, const int8_t* sv, int nsv)
+                       {
+                         double scale;
+                         if (!interface)
+                         {
+                           double M[TDIM][TDIM];
+#pragma unroll
+                           for (int r = 0; r < TDIM; ++r)
+#pragma unroll
+                             for (int cc = 0; cc < TDIM; ++cc)
+                               M[r][cc] = P[sv[cc + 1] * TDIM + r] - P[sv[0] * TDIM + r];
+                           double det;
+                           if constexpr (TDIM == 2)
+                             det = M[0][0] * M[1][1] - M[0][1] * M[1][0];
+                           else
+                             det = M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1])
+                                   - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0])
+                                   + M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+                           scale = fabs(det) * fabs(g.detJ);
+                         }
+                         else
+                         {
+                           double Xp[TDIM][TDIM];
+#pragma unroll
+                           for (int kk = 0; kk < TDIM; ++kk)
+#pragma unroll
+                             for (int r = 0; r < TDIM; ++r)
+                             {
+                               double v = g.x0[r];
+#pragma unroll
+                               for (int t = 0; t < TDIM; ++t)
+                                 v += g.J[r * TDIM + t] * P[sv[kk] * TDIM + t];
+                               Xp[kk][r] = v;
+                             }
+                           if constexpr (TDIM == 2)
+                           {
+                             const double dx = Xp[1][0] - Xp[0][0], dy = Xp[1][1] - Xp[0][1];
+                             scale = sqrt(dx * dx + dy * dy);
+                           }
+                           else
+                           {
+                             const double u0 = Xp[1][0] - Xp[0][0], u1 = Xp[1][1] - Xp[0][1], u2 = Xp[1][2] - Xp[0][2];
+                             const double w0 = Xp[2][0] - Xp[0][0], w1 = Xp[2][1] - Xp[0][1], w2 = Xp[2][2] - Xp[0][2];
+                             const double cx = u1 * w2 - u2 * w1, cy = u2 * w0 - u0 * w2, cz = u0 * w1 - u1 * w0;
+                             scale = sqrt(cx * cx + cy * cy + cz * cz);
+                           }
+                         }
+                         const int sd = nsv - 1;
+                         for (int q = 0; q < npts_s; ++q)
+                         {
+                           double l0 = 1.0, lam[TDIM];
+#pragma unroll
+                           for (int cc = 0; cc < TDIM; ++cc)
+                           {
+                             lam[cc] = cc < sd ? __ldg(rule_pts + q * sd + cc) : 0.0;
+                             l0 -= lam[cc];
+                           }
+#pragma unroll
+                           for (int d = 0; d < TDIM; ++d)
+                           {
+                             double v = l0 * P[sv[0] * TDIM + d];
+#pragma unroll
+                             for (int cc = 0; cc < TDIM; ++cc)
+                               if (cc < sd)
+                                 v += lam[cc] * P[sv[cc + 1] * TDIM + d];
+                             points[static_cast<int64_t>(d) * npts_total + gp] = v;
+                           }
+                           weights[gp] = __ldg(rule_wts + q) * scale;
+                           ++gp;
+                         }
+                       });
+}
+
 // SoA (dim, n) -> AoS (n, dim)
 __global__ void soa_to_aos_kernel(const double* __restrict__ soa, int64_t n, int dim, double* __restrict__ aos)
 {
@@ -825,8 +1095,16 @@ void run_quadrature(cfx_ctx* c, LevelSet& L, cfx_rules* R, bool positive, bool i
   DevBuf<int64_t> packed, packed_excl;
   packed.reserve(c->pool, static_cast<size_t>(n_cut.h) + 1);
   packed_excl.reserve(c->pool, static_cast<size_t>(n_cut.h) + 2);
-  CFX_LAUNCH(c, rule_count_kernel<TDIM>, grid_for(n_cut.h, QB), QB, 0, L.cut_list.p, n_cut, L.dofmap, L.values, positive,
-             interface, rt.npts, packed.p);
+  const bool p2 = L.degree == 2;
+  if (p2)
+  {
+    R->has_moments = false; // the pieces are not the case-table pieces of one simplex: kernels take the point loop
+    CFX_LAUNCH(c, rule_count_p2_kernel<TDIM>, grid_for(n_cut.h, QB), QB, 0, L.cut_list.p, n_cut, L.dofmap, L.values,
+               positive, interface, rt.npts, packed.p);
+  }
+  else
+    CFX_LAUNCH(c, rule_count_kernel<TDIM>, grid_for(n_cut.h, QB), QB, 0, L.cut_list.p, n_cut, L.dofmap, L.values, positive,
+               interface, rt.npts, packed.p);
   exclusive_scan_i64(c, packed.p, n_cut, packed_excl.p);
   if (defer)
   {
@@ -854,7 +1132,11 @@ void run_quadrature(cfx_ctx* c, LevelSet& L, cfx_rules* R, bool positive, bool i
   R->parent_map.reserve(c->pool, static_cast<size_t>(R->cap_rules) + 1);
   if (R->has_moments)
     R->moments.reserve(c->pool, static_cast<size_t>(R->cap_rules) * mom_w + 1);
-  if (interface)
+  if (p2)
+    CFX_LAUNCH(c, rule_fill_p2_kernel<TDIM>, grid_for(n_cut.h, QB), QB, 0, L.cut_list.p, n_cut, packed_excl.p, L.dofmap,
+               L.values, c->x_dofmap, c->x, positive, interface, rt.npts, rt.d_pts, rt.d_wts, R->cap_pts, R->cap_rules,
+               R->d_sizes, c->err_flag.p, R->points.p, R->weights.p, R->offsets.p, R->parent_map.p);
+  else if (interface)
     CFX_LAUNCH(c, (rule_fill_kernel<TDIM, true>), grid_for(n_cut.h, QB), QB, 0, L.cut_list.p, n_cut, packed_excl.p,
                L.dofmap, L.values, c->x_dofmap, c->x, positive, rt.npts, rt.d_pts, rt.d_wts, R->cap_pts, R->cap_rules,
                R->d_sizes, c->err_flag.p, R->points.p, R->weights.p, R->offsets.p, R->parent_map.p,
@@ -930,8 +1212,6 @@ cfx_status cfx_runtime_quadrature(cfx_ctx* ctx, int ls, int relation, int order,
               "cfx_runtime_quadrature: invalid relation");
   CFX_REQUIRE(order >= 0, CFX_ERR_INVALID, "runtime_quadrature: order must be >= 0"); // cut.cpp:164-168
   LevelSet& L = ctx->ls[ls];
-  CFX_REQUIRE(L.degree == 1, CFX_ERR_UNSUPPORTED,
-              "cfx_runtime_quadrature: only P1 level sets are cut (higher-order edge roots: SURVEY 8(f) rank 4)");
   const bool interface = relation == CFX_REL_EQ;
   const bool positive = relation == CFX_REL_GT || relation == CFX_REL_GE;
   RuleTable& rt = get_rule(ctx, interface ? ctx->tdim - 1 : ctx->tdim, order);

@@ -1000,6 +1000,248 @@ int64_t orc_runtime_quadrature(int cell_type, const double* x, const int32_t* x_
   ORC_CATCH(-1)
 }
 
+} // extern "C"
+
+// ---- higher-order (P2) level sets, SURVEY.md section 8(f) rank 4 --------------------------------------------------
+// cutfemx.cut(level_set) with a degree-2 level set and the default options (cut_approximation = "auto", order 1,
+// wrappers/cut.cpp:117-140): CutCells approximates the zero set by STRAIGHT pieces between edge roots it finds by
+// iteration on the higher-order function (edge_max_depth), refining the cell where the vertex signs alone do not
+// show the cut (max_refinement_iterations).  CutCells (>= 0.4, < 0.5) is absent, and the reference pins none of the
+// resulting points (its one P2 test, test_cut_api.py:1012-1026, integrates |n_h - n|^2 of an exactly represented
+// quadratic: zero wherever the points lie) -- "parity unpinned", like the P1 rules.  Restated here as:
+//   * one level of red refinement through the P2 nodes (vertices + edge midpoints, where the level set is known
+//     exactly): 4 sub-triangles / 8 sub-tetrahedra (interior diagonal m02 - m13);
+//   * each sub-simplex is cut with the marching-simplex case tables on its nodal values; a sub-simplex whose nodes
+//     are all inside contributes whole (volume selectors);
+//   * an edge root is the root in [0, 1] of the level set RESTRICTED to the sub-edge -- a quadratic through the two
+//     nodal values and the value of the P2 function at the sub-edge midpoint -- in closed form (the limit of the
+//     reference's bisection);
+//   * rule points are mapped to the PARENT cell's reference coordinates, weights are physical, one rule per cut cell.
+// Second-order accurate geometry (the P1 cut of the P1 interpolant is first order in the normal, second in position;
+// this halves h and uses true edge roots); pinned on circle / sphere measures and on exactness for planes.
+namespace
+{
+const int RED_TRI[4][3] = {{0, 5, 4}, {1, 3, 5}, {2, 4, 3}, {3, 4, 5}};
+const int RED_TET[8][4] = {{0, 9, 8, 7}, {1, 9, 6, 5}, {2, 8, 6, 4}, {3, 7, 5, 4},
+                           {9, 8, 7, 5}, {9, 8, 6, 5}, {8, 7, 5, 4}, {8, 6, 5, 4}};
+// reference coordinates of the P2 nodes, times 2 (Basix order: vertices, then edges (1,2),(0,2),(0,1) /
+// (2,3),(1,3),(1,2),(0,3),(0,2),(0,1))
+const int NODE2_TRI[6][2] = {{0, 0}, {2, 0}, {0, 2}, {1, 1}, {0, 1}, {1, 0}};
+const int NODE2_TET[10][3] = {{0, 0, 0}, {2, 0, 0}, {0, 2, 0}, {0, 0, 2}, {0, 1, 1},
+                              {1, 0, 1}, {1, 1, 0}, {0, 0, 1}, {0, 1, 0}, {1, 0, 0}};
+
+double p2_value(int tdim, const double* dofs, const double* X)
+{
+  double phi[10], dphi[30];
+  tabulate(tdim, 2, X, phi, dphi);
+  const int nd = tdim == 2 ? 6 : 10;
+  double v = 0.0;
+  for (int j = 0; j < nd; ++j)
+    v += phi[j] * dofs[j];
+  return v;
+}
+
+// root in [0, 1] of q(t) = fa + t (-3 fa + 4 fm - fb) + t^2 (2 fa - 4 fm + 2 fb), fa and fb of opposite "sides"
+double quadratic_edge_root(double fa, double fm, double fb)
+{
+  const double a = 2.0 * fa - 4.0 * fm + 2.0 * fb, b = -3.0 * fa + 4.0 * fm - fb, c = fa;
+  const double lin = fa / (fa - fb);
+  if (std::fabs(a) <= 1e-14 * (std::fabs(b) + std::fabs(c)))
+    return lin; // the restriction is linear
+  const double disc = b * b - 4.0 * a * c;
+  if (disc < 0.0)
+    return lin;
+  const double sq = std::sqrt(disc);
+  const double qq = -0.5 * (b + (b >= 0.0 ? sq : -sq)); // stable pair of roots: qq / a and c / qq
+  const double r1 = qq / a, r2 = (qq != 0.0) ? c / qq : r1;
+  const bool ok1 = r1 >= 0.0 && r1 <= 1.0, ok2 = r2 >= 0.0 && r2 <= 1.0;
+  if (ok1 && ok2)
+    return std::fabs(r1 - lin) <= std::fabs(r2 - lin) ? r1 : r2;
+  if (ok1)
+    return r1;
+  if (ok2)
+    return r2;
+  return lin;
+}
+
+// rule of one cut cell with a P2 level set; points in parent reference coordinates.  Returns the number of points.
+int cut_cell_rule_p2(int tdim, const double* cdofs, const double* dofs, int relation, const Rule& rl,
+                     std::vector<double>& pts, std::vector<double>& wts)
+{
+  const int nv = tdim + 1;
+  const bool interface = (relation == REL_EQ);
+  const bool positive = (relation == REL_GT || relation == REL_GE);
+  const int nsubcells = tdim == 2 ? 4 : 8;
+  const Geo g = make_geo(tdim, cdofs);
+  int count = 0;
+  for (int sc = 0; sc < nsubcells; ++sc)
+  {
+    const int* nodes = tdim == 2 ? RED_TRI[sc] : RED_TET[sc];
+    double V[4][3] = {}, f[4];
+    for (int v = 0; v < nv; ++v)
+    {
+      for (int t = 0; t < tdim; ++t)
+        V[v][t] = 0.5 * (tdim == 2 ? NODE2_TRI[nodes[v]][t] : NODE2_TET[nodes[v]][t]);
+      f[v] = dofs[nodes[v]];
+    }
+    int I[4], O[4], n_in = 0, n_out = 0;
+    for (int v = 0; v < nv; ++v)
+    {
+      const bool in = positive ? (f[v] > 0.0) : (f[v] < 0.0);
+      if (in)
+        I[n_in++] = v;
+      else
+        O[n_out++] = v;
+    }
+    if (n_in == 0)
+      continue;
+    double P[10][3] = {};
+    int nsub = 0;
+    const int(*sub)[4] = nullptr;
+    const int(*subi)[3] = nullptr;
+    static const int WHOLE[1][4] = {{0, 1, 2, 3}};
+    if (n_in == nv)
+    {
+      if (interface)
+        continue;
+      for (int v = 0; v < nv; ++v)
+        for (int t = 0; t < tdim; ++t)
+          P[v][t] = V[v][t];
+      nsub = 1;
+      sub = WHOLE;
+    }
+    else
+    {
+      for (int i = 0; i < n_in; ++i)
+        for (int t = 0; t < tdim; ++t)
+          P[i][t] = V[I[i]][t];
+      int np = n_in;
+      for (int i = 0; i < n_in; ++i)
+        for (int o = 0; o < n_out; ++o)
+        {
+          const int a = I[i], b = O[o];
+          double Xm[3];
+          for (int t = 0; t < tdim; ++t)
+            Xm[t] = 0.5 * (V[a][t] + V[b][t]);
+          const double tt = quadratic_edge_root(f[a], p2_value(tdim, dofs, Xm), f[b]);
+          for (int t = 0; t < tdim; ++t)
+            P[np][t] = V[a][t] + tt * (V[b][t] - V[a][t]);
+          ++np;
+        }
+      const CaseTable& ct = (tdim == 2) ? TRI_CASES[n_in] : TET_CASES[n_in];
+      nsub = interface ? ct.nsub_ifc : ct.nsub_vol;
+      sub = ct.vol;
+      subi = ct.ifc;
+    }
+    for (int s = 0; s < nsub; ++s)
+    {
+      double scale;
+      const int* sv = interface ? subi[s] : sub[s];
+      const int nsv = interface ? tdim : nv;
+      if (!interface)
+      {
+        double M[9];
+        for (int r = 0; r < tdim; ++r)
+          for (int c = 0; c < tdim; ++c)
+            M[r * tdim + c] = P[sv[c + 1]][r] - P[sv[0]][r];
+        scale = std::fabs(det_n(tdim, M)) * std::fabs(g.detJ);
+      }
+      else
+      {
+        double Xp[3][3];
+        for (int k = 0; k < tdim; ++k)
+          for (int r = 0; r < tdim; ++r)
+          {
+            double v = g.x0[r];
+            for (int t = 0; t < tdim; ++t)
+              v += g.J[r * tdim + t] * P[sv[k]][t];
+            Xp[k][r] = v;
+          }
+        if (tdim == 2)
+        {
+          const double dx = Xp[1][0] - Xp[0][0], dy = Xp[1][1] - Xp[0][1];
+          scale = std::sqrt(dx * dx + dy * dy);
+        }
+        else
+        {
+          double u[3], w[3];
+          for (int r = 0; r < 3; ++r)
+          {
+            u[r] = Xp[1][r] - Xp[0][r];
+            w[r] = Xp[2][r] - Xp[0][r];
+          }
+          const double cx = u[1] * w[2] - u[2] * w[1], cy = u[2] * w[0] - u[0] * w[2], cz = u[0] * w[1] - u[1] * w[0];
+          scale = std::sqrt(cx * cx + cy * cy + cz * cz); // 2 x area: the triangle rule's weights sum to 1/2
+        }
+      }
+      const int sd = nsv - 1;
+      for (int q = 0; q < rl.npts; ++q)
+      {
+        const double* xi = &rl.pts[q * sd];
+        double l0 = 1.0;
+        for (int c = 0; c < sd; ++c)
+          l0 -= xi[c];
+        for (int d = 0; d < tdim; ++d)
+        {
+          double v = l0 * P[sv[0]][d];
+          for (int c = 0; c < sd; ++c)
+            v += xi[c] * P[sv[c + 1]][d];
+          pts.push_back(v);
+        }
+        wts.push_back(rl.wts[q] * scale);
+        ++count;
+      }
+    }
+  }
+  return count;
+}
+} // namespace
+
+extern "C" int64_t orc_runtime_quadrature_p2(int cell_type, const double* x, const int32_t* x_dofmap,
+                                             const int32_t* ls_dofmap, const double* vals, const int8_t* domain,
+                                             int64_t ncells, int relation, int order, double* points, double* weights,
+                                             int32_t* offsets, int32_t* parent_map, int64_t* nrules_out)
+{
+  ORC_TRY
+  const int nv = cell_type, tdim = nv - 1, nd = tdim == 2 ? 6 : 10;
+  const bool interface = (relation == REL_EQ);
+  const Rule& rl = rule(interface ? tdim - 1 : tdim, order);
+  int64_t npts = 0, nrules = 0;
+  std::vector<double> pbuf, wbuf;
+  for (int64_t c = 0; c < ncells; ++c)
+  {
+    if (domain[c] != DOM_INTERSECTED)
+      continue;
+    double cdofs[12], dofs[10];
+    for (int v = 0; v < nv; ++v)
+      for (int d = 0; d < 3; ++d)
+        cdofs[3 * v + d] = x[3 * (int64_t)x_dofmap[c * nv + v] + d];
+    for (int j = 0; j < nd; ++j)
+      dofs[j] = vals[ls_dofmap[c * nd + j]];
+    pbuf.clear();
+    wbuf.clear();
+    const int n = cut_cell_rule_p2(tdim, cdofs, dofs, relation, rl, pbuf, wbuf);
+    if (n == 0)
+      continue;
+    if (points)
+    {
+      std::copy_n(pbuf.data(), (size_t)n * tdim, points + npts * tdim);
+      std::copy_n(wbuf.data(), n, weights + npts);
+      offsets[nrules] = (int32_t)npts;
+      parent_map[nrules] = (int32_t)c;
+    }
+    npts += n;
+    ++nrules;
+  }
+  if (points)
+    offsets[nrules] = (int32_t)npts;
+  *nrules_out = nrules;
+  return npts;
+  ORC_CATCH(-1)
+}
+
+extern "C"
+{
 // RuntimeQuadrature::physical_points, runtime_quadrature.h:177-217 (SoA (gdim, npts) output)
 int orc_physical_points(int cell_type, int gdim, const double* x, const int32_t* x_dofmap, const double* points,
                         const int32_t* offsets, const int32_t* parent_map, int64_t nrules, int64_t npts, double* out)

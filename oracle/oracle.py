@@ -37,7 +37,7 @@ def lib():
     if _LIB is None:
         _LIB = C.CDLL(build())
         _LIB.orc_last_error.restype = C.c_char_p
-        for name in ("orc_locate", "orc_runtime_quadrature", "orc_ghost_penalty_facets",
+        for name in ("orc_locate", "orc_runtime_quadrature", "orc_runtime_quadrature_p2", "orc_ghost_penalty_facets",
                      "orc_interior_facets_for_cells", "orc_sparsity"):
             getattr(_LIB, name).restype = C.c_int64
         _registered.clear()
@@ -126,22 +126,23 @@ class Rules:
 
 
 def runtime_quadrature(mesh, ls_dofmap, values, domain, relation: str, order: int) -> Rules:
-    """relation in '<', '<=', '>', '>=', '='; rules in ascending parent-cell order."""
+    """relation in '<', '<=', '>', '>=', '='; rules in ascending parent-cell order.  A level-set dofmap of width
+    6 / 10 (P2) takes the higher-order cut (orc_runtime_quadrature_p2)."""
     tdim = mesh.tdim
     _need_rule(tdim - 1 if relation == "=" else tdim, order)
     x, xd, ld, v = _cf64(mesh.x), _ci32(mesh.x_dofmap), _ci32(ls_dofmap), _cf64(values)
+    fn = lib().orc_runtime_quadrature if ld.shape[1] == tdim + 1 else lib().orc_runtime_quadrature_p2
     dom = np.ascontiguousarray(domain, dtype=np.int8)
     nc = C.c_int64(mesh.num_cells_local)
     nr = C.c_int64(0)
     args = (mesh.cell_type, _p(x, _f64p), _p(xd, _i32p), _p(ld, _i32p), _p(v, _f64p), _p(dom, _i8p), nc, REL[relation],
             order)
-    npts = _chk(lib().orc_runtime_quadrature(*args, None, None, None, None, C.byref(nr)))
+    npts = _chk(fn(*args, None, None, None, None, C.byref(nr)))
     pts = np.zeros((npts, tdim))
     wts = np.zeros(npts)
     off = np.zeros(nr.value + 1, dtype=np.int32)
     pm = np.zeros(nr.value, dtype=np.int32)
-    _chk(lib().orc_runtime_quadrature(*args, _p(pts, _f64p), _p(wts, _f64p), _p(off, _i32p), _p(pm, _i32p),
-                                      C.byref(nr)))
+    _chk(fn(*args, _p(pts, _f64p), _p(wts, _f64p), _p(off, _i32p), _p(pm, _i32p), C.byref(nr)))
     return Rules(tdim, pts, wts, off, pm)
 
 

@@ -553,3 +553,54 @@ def test_vector_nitsche_kernel_against_an_independent_evaluation():
         direct = np.sum(ri.weights * (-np.einsum("ab,qb,qa->q", sig(Bu), nq, vp) - np.einsum("ab,qb,qa->q", sig(Bv), nq, up)
                                       + gam * (2 * mu + lam) / h[rule_of_pt] * np.einsum("qa,qa->q", up, vp)))
         assert abs(v @ (Ms @ u) - direct) <= 1e-11 * abs(direct)
+
+
+# ---------------------------------------------------------------- P2 level sets
+def _p2_problem(tdim, n, fn):
+    mesh = M.create_rectangle(n, n, (0.0, 0.0), (1.0, 1.0)) if tdim == 2 else M.create_box(n, n, n)
+    V2 = M.functionspace(mesh, 2, permute_seed=5)
+    phi = M.interpolate(V2, fn)
+    return mesh, V2, phi, O.classify(V2.dofmap, phi)
+
+
+def test_p2_level_set_reference_assertion_and_measures():
+    """test_cut_api.py:1012-1026 on the oracle: the normal of the quadratic circle level set (6 x 6 unit square, order 5)
+    is the radial normal, error <= 1e-24; the measures of the cut converge at second order."""
+    c, R = (0.47, 0.43), 0.31
+    fn = lambda x, y, z: (x - c[0]) ** 2 + (y - c[1]) ** 2 - R * R
+    mesh, V2, phi, dom = _p2_problem(2, 6, fn)
+    ri = O.runtime_quadrature(mesh, V2.dofmap, phi, dom, "=", 5)
+    nq = O.normals(mesh, V2.dofmap, 2, phi, ri)
+    xp = O.physical_points(mesh, ri)
+    d = np.stack([xp[0] - c[0], xp[1] - c[1]], axis=1)
+    err = float(np.sum(ri.weights * np.sum((nq - d / np.linalg.norm(d, axis=1, keepdims=True)) ** 2, axis=1)))
+    assert ri.weights.size > 0 and err <= 1e-24
+    # container invariants (test_cut_api.py:405-421) and parent_map within the cut cells
+    assert ri.offsets[0] == 0 and ri.offsets[-1] == ri.weights.size and ri.parent_map.size == ri.offsets.size - 1
+    assert set(ri.parent_map.tolist()) <= set(O.locate(dom, "phi=0").tolist())
+    errs = []
+    for n in (8, 16, 32):
+        mesh, V2, phi, dom = _p2_problem(2, n, fn)
+        area = O.runtime_quadrature(mesh, V2.dofmap, phi, dom, "<", 2).weights.sum() + O.locate(dom, "phi<0").size * 0.5 / n / n
+        per = O.runtime_quadrature(mesh, V2.dofmap, phi, dom, "=", 2).weights.sum()
+        errs.append((abs(area - np.pi * R * R), abs(per - 2 * np.pi * R)))
+    for k in (0, 1):
+        assert errs[1][k] < errs[0][k] / 3.0 and errs[2][k] < errs[1][k] / 3.0, errs
+
+
+def test_p2_level_set_plane_is_exact_and_parts_fill_the_cut_cells():
+    fn = lambda x, y, z: x + 0.3 * y - 0.2 * z - 0.41
+    mesh, V2, phi, dom = _p2_problem(3, 4, fn)
+    V1 = M.functionspace(mesh, 1)
+    phi1 = M.interpolate(V1, fn)
+    dom1 = O.classify(V1.dofmap, phi1)
+    cm = 1.0 / (4 ** 3 * 6)
+    v2 = O.runtime_quadrature(mesh, V2.dofmap, phi, dom, "<", 3).weights.sum() + O.locate(dom, "phi<0").size * cm
+    v1 = O.runtime_quadrature(mesh, V1.dofmap, phi1, dom1, "<", 3).weights.sum() + O.locate(dom1, "phi<0").size * cm
+    np.testing.assert_allclose(v2, v1, rtol=1e-13)
+    a2 = O.runtime_quadrature(mesh, V2.dofmap, phi, dom, "=", 2).weights.sum()
+    a1 = O.runtime_quadrature(mesh, V1.dofmap, phi1, dom1, "=", 2).weights.sum()
+    np.testing.assert_allclose(a2, a1, rtol=1e-13)
+    rin = O.runtime_quadrature(mesh, V2.dofmap, phi, dom, "<", 2).weights.sum()
+    rout = O.runtime_quadrature(mesh, V2.dofmap, phi, dom, ">", 2).weights.sum()
+    np.testing.assert_allclose(rin + rout, O.locate(dom, "phi=0").size * cm, rtol=1e-12)
