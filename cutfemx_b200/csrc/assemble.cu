@@ -4022,7 +4022,9 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
       for (auto& I : a->integrals)
         if (!I.facet)
           n_std += I.n;
-      StageScope sk(ctx, "gather_matrix_clist_kernel",
+      // (the stage carries the name of the kernel that runs: scalar P1 -> gather_matrix_p1_kernel)
+      const bool p1_rows = Elem<TDIM, DEG>::ND <= 4 && gc.fpos != nullptr;
+      StageScope sk(ctx, p1_rows ? "gather_matrix_p1_kernel" : "gather_matrix_clist_kernel",
                     12.0 * static_cast<double>(a->n_clist_nnz)
                         + (28.0 * ctx->nv + 4.0 * S.nd) * static_cast<double>(n_std));
       bool done = false;
@@ -4055,7 +4057,16 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
       // K5 for the rows the contribution-list kernel does not own: 12 B per CSR entry of the active rows left
       const double nnz_mask = static_cast<double>(A->nnz) - static_cast<double>(a->n_clist_nnz)
                               - static_cast<double>(A->n_rows - PR->n_act_rows);
-      StageScope sk(ctx, "gather_matrix_mask_kernel", 12.0 * (nnz_mask > 0.0 ? nnz_mask : 0.0));
+      const cfx_integral* FIb = facet_integral_domain(a);
+      // band rows, honestly counted: 12 B per CSR entry + per incident cell the 32-byte tensor-row record, the
+      // position word, the cell id and flag byte (41 B) + per band cell its facet ids and slots (32 B) + the 80-byte
+      // record of every band facet once per row that meets it (~ nd + 1 rows per facet)
+      double band_bytes = 12.0 * (nnz_mask > 0.0 ? nnz_mask : 0.0);
+      if (FIb)
+        band_bytes += 80.0 * (S.nd + 1) * static_cast<double>(FIb->n) + (41.0 + 32.0) * S.stride * static_cast<double>(a->n_band_listed);
+      const bool p1_band = Elem<TDIM, DEG>::ND <= 4 && gc.fpos != nullptr && a->n_band_listed > 0
+                           && getenv("CFX_OLD_BAND") == nullptr;
+      StageScope sk(ctx, p1_band ? "gather_matrix_band_p1_kernel" : "gather_matrix_fast_kernel", band_bytes);
       auto kf = gather_matrix_fast_kernel<TDIM, DEG>;
       bool band_done = false;
       if constexpr (DEG == 1)
