@@ -878,6 +878,7 @@ struct GatherCtx
   const double* geo; // static per-cell geometry records (element.cuh GeoRec)
   const double* lrow; // scalar P1: static Laplace tensor rows, 4 doubles per incidence (Space::lrow); else null
   const uint32_t* fpos; // scalar P1 with a static structure: packed static row positions per incidence (Space::fpos)
+  const uint64_t* fpos64; // scalar P2 on triangles with a static structure: the same, 64-bit (Space::fpos64)
   const int64_t* frow_ptr;
   const uint64_t* fclist;
   const int32_t* c2f;
@@ -1210,12 +1211,11 @@ __global__ void inactive_diag_kernel(const uint8_t* __restrict__ row_flag, int64
         vals[p * bs * bs + k * bs + k] = diag;
 }
 
-// Right-hand-side entries of P1 rows are summed in ONE order by every kernel that produces them, so that a fused
+// Right-hand-side entries of a row are summed in ONE order by every kernel that produces them, so that a fused
 // system assembly (matrix gather kernels fill b) and a separate vector assembly agree bit for bit: the incident
 // cells in groups of four, pairwise inside a group ((e0 + e1) + (e2 + e3)), the groups added in ascending order.
 // That order costs a one-thread-per-row kernel nothing (its loop walks four incidences at a time) and a
-// warp-per-row kernel two butterfly steps and seven broadcasts.  Returns the sum in every lane.  (P2 rows keep
-// the shuffle tree of gather_vector_kernel / gather_matrix_clist_kernel.)
+// warp-per-row kernel two butterfly steps and seven broadcasts.  Returns the sum in every lane.
 __device__ __forceinline__ double rhs_sum_groups_of_four(double e)
 {
   const unsigned full = 0xffffffffu;
@@ -1737,14 +1737,7 @@ __global__ void __launch_bounds__(GWM * 32, 10)
       gl.Ae = gc.AeL;
       e = cell_entry_value<TDIM, DEG>(gl, stL, c, fl, li);
     }
-    if constexpr (DEG == 1)
-      e = rhs_sum_groups_of_four(e);
-    else
-    {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-        e += __shfl_down_sync(full, e, o);
-    }
+    e = rhs_sum_groups_of_four(e);
     if (lane == 0)
     {
       const double s0 = 0.0 + e; // gather_vector_kernel adds the chunk sum to a zero accumulator
@@ -2045,24 +2038,15 @@ __global__ void __launch_bounds__(GWC * 32, clist_blocks_per_sm<DEG>())
           sv[j * 32 + lane] = v[j];
         __syncwarp();
         if constexpr (FUSED)
-        {
-          const bool lower = lane < 16;
-          const double recv = __shfl_xor_sync(full, lower ? e : dval, 16);
-          double x = lower ? dval + recv : e + recv;
-#pragma unroll
-          for (int o = 8; o > 0; o >>= 1)
-            x += __shfl_down_sync(full, x, o);
-          if (lane == 16)
+        { // the right-hand-side entry in the one order every kernel uses (rhs_sum_groups_of_four)
+          const double x = rhs_sum_groups_of_four(e);
+          if (lane == 0)
             gc.bvec[c0.r] = gc.zero_first_b ? x : gc.bvec[c0.r] + x;
-          dval = __shfl_sync(full, x, 0);
         }
-        else
-        {
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1)
-            dval += __shfl_down_sync(full, dval, o);
-          dval = __shfl_sync(full, dval, 0);
-        }
+        for (int o = 16; o > 0; o >>= 1)
+          dval += __shfl_down_sync(full, dval, o);
+        dval = __shfl_sync(full, dval, 0);
         if ((c0.R >> lane) & 1u)
         {
           double acc = c0.old;
@@ -2241,6 +2225,141 @@ __global__ void __launch_bounds__(RTB)
         s_acc[p][tid] += v[q];
       }
       dacc += vd;
+    }
+    if constexpr (FUSED)
+    {
+      const double g4 = (eu[0] + eu[1]) + (eu[2] + eu[3]);
+      e = l0 == 0 ? g4 : e + g4;
+    }
+  }
+  s_acc[pd][tid] = dacc;
+  {
+    int o = 0;
+    for (uint32_t m = R; m; m &= m - 1, ++o)
+      out[o] = s_acc[__ffs(m) - 1][tid];
+  }
+  if constexpr (FUSED)
+    gc.bvec[r] = gc.zero_first_b ? e : gc.bvec[r] + e;
+}
+
+// Scalar P2 on triangles, static rows: one thread per row like gather_matrix_p1_kernel.  Per incidence one 32-byte
+// record (C = K K^T: C00, C01, C11, and |detJ|; Space::lrow) and one 64-bit word of static positions (Space::fpos64:
+// local index, the row's own column, the cell's five other dofs); the tensor row is
+//   v_j = w (C00 T0[li][j] + C01 T1[li][j] + C11 T2[li][j]),  T0 = R[0][0], T1 = R[0][1] + R[1][0], T2 = R[1][1]
+// with the reference-element tables staged in shared memory once per block (RefTab).  Vertex rows have 6 cells and
+// 19 columns, edge rows 2 cells and 9 columns; the warp-per-row contribution-list kernel it replaces ran at 5 % of
+// the HBM peak on BASELINE configs[1] (4096^2) for exactly that reason -- a 32-lane warp per 2-cell row.
+template <bool FUSED>
+__global__ void __launch_bounds__(RTB)
+    gather_matrix_p2tri_kernel(GatherCtx gc, StdTab st, StdTab stL, const int32_t* __restrict__ act_rows, DN n_act_,
+                               const uint8_t* __restrict__ row_fast, const uint32_t* __restrict__ Rrow,
+                               const uint8_t* __restrict__ row_ufl, const uint64_t* __restrict__ fpos64,
+                               const int64_t* __restrict__ row_ptr, double* __restrict__ vals, int zero_first)
+{
+  constexpr int ND = 6;
+  using T = RefTab<2, ND>;
+  __shared__ double s_acc[32][RTB];
+  __shared__ double s_T[3][ND][ND], s_M[ND][ND], s_S[ND];
+  const int tid = threadIdx.x;
+  for (int t = tid; t < ND * ND; t += RTB)
+  {
+    const int i = t / ND, j = t - i * ND;
+    s_T[0][i][j] = st.ref[T::R + (0 * ND + i) * ND + j];
+    s_T[1][i][j] = st.ref[T::R + (1 * ND + i) * ND + j] + st.ref[T::R + (2 * ND + i) * ND + j];
+    s_T[2][i][j] = st.ref[T::R + (3 * ND + i) * ND + j];
+    s_M[i][j] = st.ref[T::M + t];
+    if (j == 0)
+      s_S[i] = st.ref[T::S + i];
+  }
+  __syncthreads();
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * RTB + tid;
+  if (idx >= n_act_.get())
+    return;
+  if ((row_fast[idx] & 13u) != 13u)
+    return;
+  const int64_t r = act_rows[idx];
+  const uint32_t R = Rrow[idx];
+  const unsigned ufl = row_ufl[idx];
+  const int64_t ib = gc.inc_ptr[r];
+  const int n_inc = static_cast<int>(gc.inc_ptr[r + 1] - ib);
+  double* const out = vals + row_ptr[r];
+  {
+    int o = 0;
+    for (uint32_t m = R; m; m &= m - 1, ++o)
+      s_acc[__ffs(m) - 1][tid] = zero_first ? 0.0 : out[o];
+  }
+  const int pd = static_cast<int>((fpos64[ib] >> 3) & 31u);
+  double dacc = zero_first ? 0.0 : s_acc[pd][tid];
+  double e = 0.0;
+  constexpr int U = 4;
+  for (int l0 = 0; l0 < n_inc; l0 += U)
+  {
+    double eu[U] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      const int l = l0 + u;
+      if (l >= n_inc)
+        continue;
+      const P1Rec rec = ldg_stream_p1rec(gc.lrow, ib + l);
+      const uint64_t word = fpos64[ib + l];
+      int32_t cell = 0;
+      unsigned fl = ufl;
+      if (!ufl)
+      {
+        cell = gc.inc_cell[ib + l];
+        fl = gc.cell_flags[cell];
+      }
+      if (!(fl & 0xFDu))
+        continue;
+      const int li = static_cast<int>(word & 7u);
+      const unsigned m = fl >> 2;
+      double v[ND];
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+        v[j] = 0.0;
+      if (m)
+      {
+        const double s = rec.a[3];
+        const double wl = st.t0[m] * s;
+        const double c0 = rec.a[0] * wl, c1 = rec.a[1] * wl, c2 = rec.a[2] * wl;
+#pragma unroll
+        for (int j = 0; j < ND; ++j)
+          v[j] += c0 * s_T[0][li][j] + c1 * s_T[1][li][j] + c2 * s_T[2][li][j];
+        if (st.has_mass)
+        {
+          const double wm = st.t1[m] * s;
+#pragma unroll
+          for (int j = 0; j < ND; ++j)
+            v[j] += wm * s_M[li][j];
+        }
+        if constexpr (FUSED)
+          eu[u] += stL.t0[m] * s * s_S[li];
+      }
+      if (fl & 1u)
+      {
+        const int64_t ms = __ldg(gc.mat_slot + cell);
+        const double* a = gc.Ae + (ms * ND + li) * ND;
+#pragma unroll
+        for (int j = 0; j < ND; ++j)
+          v[j] += a[j];
+        if constexpr (FUSED)
+          eu[u] += gc.AeL[ms * ND + li];
+      }
+      // local dof j != li sits at the q-th of the five packed positions, q = j - (j > li)
+      int q = 0;
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+      {
+        if (j == li)
+          dacc += v[j];
+        else
+        {
+          const int p = static_cast<int>((word >> (8 + 5 * q)) & 31u);
+          s_acc[p][tid] += v[j];
+          ++q;
+        }
+      }
     }
     if constexpr (FUSED)
     {
@@ -2575,14 +2694,7 @@ __global__ void __launch_bounds__(GW * 32)
         e = cell_entry_value<TDIM, DEG>(gc, st, c, fl, li);
       }
     }
-    if constexpr (DEG == 1)
-      e = rhs_sum_groups_of_four(e);
-    else
-    {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-        e += __shfl_down_sync(0xffffffffu, e, o);
-    }
+    e = rhs_sum_groups_of_four(e);
     s += e;
   }
   if (lane == 0)
@@ -3895,8 +4007,72 @@ __global__ void __launch_bounds__(256)
   st256(lrow + p * 4, rec[0], rec[1], rec[2], rec[3]);
 }
 
+// Space::lrow for scalar P2 on triangles: per incidence (C00, C01, C11, |detJ|) with C = K K^T -- what the Laplace
+// tensor row of any local dof is a linear combination of (reference tables T0, T1, T2 of gather_matrix_p2tri_kernel)
+__global__ void __launch_bounds__(256)
+    lrow_p2tri_kernel(const double* __restrict__ geo, const int32_t* __restrict__ inc_cell, int64_t n,
+                      double* __restrict__ lrow)
+{
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (p >= n)
+    return;
+  Geo<2> g;
+  load_geo_cached<2>(geo, inc_cell[p], g);
+  double C[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int t = 0; t < 2; ++t)
+  {
+    C[0] += g.K[0 * 2 + t] * g.K[0 * 2 + t];
+    C[1] += g.K[0 * 2 + t] * g.K[1 * 2 + t];
+    C[2] += g.K[1 * 2 + t] * g.K[1 * 2 + t];
+  }
+  st256(lrow + p * 4, C[0], C[1], C[2], fabs(g.detJ));
+}
+
+// Space::fpos64 (nd = 6): bits 0..2 local index li, bits 3..7 position of the row's own column, bits 8 + 5 q ..:
+// position of the cell's q-th other dof (local order, li skipped)
+__global__ void __launch_bounds__(256)
+    fpos64_kernel(const uint32_t* __restrict__ fmask, const uint32_t* __restrict__ fperm, int nd, int64_t n,
+                  uint64_t* __restrict__ fpos)
+{
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (p >= n)
+    return;
+  const uint32_t fm = fmask[p], fp = fperm[p];
+  const int li = static_cast<int>(fp & 15u);
+  uint64_t w = static_cast<uint64_t>(li);
+  int q = 0;
+  for (int j = 0; j < nd; ++j)
+  {
+    const int rank = static_cast<int>((fp >> (4 + 4 * j)) & 15u);
+    const uint64_t pos = __fns(fm, 0, rank + 1) & 31u;
+    if (j == li)
+      w |= pos << 3;
+    else
+      w |= pos << (8 + 5 * q++);
+  }
+  fpos[p] = w;
+}
+
+const uint64_t* ensure_fpos64(cfx_ctx* c, Space& S)
+{
+  if (!S.fpos_built)
+  {
+    S.fpos64.reserve(c->pool, static_cast<size_t>(S.n_inc) + 16);
+    CFX_LAUNCH(c, fpos64_kernel, grid_for(S.n_inc, 256), 256, 0, S.fmask.p, S.fperm.p, S.nd, S.n_inc, S.fpos64.p);
+    S.fpos_built = true;
+  }
+  return S.fpos64.p;
+}
+
 const double* ensure_lrow(cfx_ctx* c, Space& S)
 {
+  if (!S.lrow_built && S.degree == 2)
+  {
+    S.lrow.reserve(c->pool, static_cast<size_t>(S.n_inc) * 4 + 4);
+    CFX_LAUNCH(c, lrow_p2tri_kernel, grid_for(S.n_inc, 256), 256, 0, c->geo.p, S.inc_cell.p, S.n_inc, S.lrow.p);
+    S.lrow_built = true;
+  }
   if (!S.lrow_built)
   {
     S.lrow.reserve(c->pool, static_cast<size_t>(S.n_inc) * 4 + 4);
@@ -3960,8 +4136,11 @@ GatherCtx make_gather_ctx(cfx_ctx* c, cfx_form* f, const cfx_integral* FI)
   g.mat_slot = c->mat_slot.p;
   g.Ae = f->Ae.p;
   g.geo = c->geo.p;
-  g.lrow = (S.degree == 1 && S.bs == 1 && S.has_perm) ? ensure_lrow(c, c->spaces[f->space]) : nullptr;
-  g.fpos = (g.lrow && S.has_static) ? ensure_fpos(c, c->spaces[f->space]) : nullptr;
+  const bool p1s = S.degree == 1 && S.bs == 1 && S.has_perm;
+  const bool p2tri = S.degree == 2 && S.bs == 1 && S.has_perm && S.has_static && c->tdim == 2 && f->rank == 2;
+  g.lrow = (p1s || p2tri) ? ensure_lrow(c, c->spaces[f->space]) : nullptr;
+  g.fpos = (p1s && S.has_static) ? ensure_fpos(c, c->spaces[f->space]) : nullptr;
+  g.fpos64 = p2tri ? ensure_fpos64(c, c->spaces[f->space]) : nullptr;
   g.frow_ptr = S.frow_ptr.p;
   g.fclist = S.fclist.p;
   g.c2f = c->c2f;
@@ -4024,7 +4203,8 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
           n_std += I.n;
       // (the stage carries the name of the kernel that runs: scalar P1 -> gather_matrix_p1_kernel)
       const bool p1_rows = Elem<TDIM, DEG>::ND <= 4 && gc.fpos != nullptr;
-      StageScope sk(ctx, p1_rows ? "gather_matrix_p1_kernel" : "gather_matrix_clist_kernel",
+      const bool p2_rows = DEG == 2 && TDIM == 2 && gc.fpos64 != nullptr && st.ref != nullptr && !getenv("CFX_OLD_CLIST");
+      StageScope sk(ctx, p1_rows ? "gather_matrix_p1_kernel" : (p2_rows ? "gather_matrix_p2tri_kernel" : "gather_matrix_clist_kernel"),
                     12.0 * static_cast<double>(a->n_clist_nnz)
                         + (28.0 * ctx->nv + 4.0 * S.nd) * static_cast<double>(n_std));
       bool done = false;
@@ -4035,6 +4215,17 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
           auto kp = gc.bvec ? gather_matrix_p1_kernel<TDIM, true> : gather_matrix_p1_kernel<TDIM, false>;
           CFX_LAUNCH(ctx, kp, grid_for(PR->n_act_rows, RTB), RTB, 0, gc, st, stL, PR->act_rows.p, PR->dn_act(),
                      a->row_fast.p, a->Rrow.p, a->row_ufl.p, gc.fpos, A->row_ptr.p, A->values.p, zero_first);
+          done = true;
+        }
+      }
+      if constexpr (DEG == 2 && TDIM == 2)
+      {
+        static const bool old_clist = getenv("CFX_OLD_CLIST") != nullptr; // A/B switch: the warp-per-row kernel
+        if (gc.fpos64 != nullptr && st.ref != nullptr && !old_clist)
+        { // scalar P2 on triangles: one thread per row
+          auto kp = gc.bvec ? gather_matrix_p2tri_kernel<true> : gather_matrix_p2tri_kernel<false>;
+          CFX_LAUNCH(ctx, kp, grid_for(PR->n_act_rows, RTB), RTB, 0, gc, st, stL, PR->act_rows.p, PR->dn_act(),
+                     a->row_fast.p, a->Rrow.p, a->row_ufl.p, gc.fpos64, A->row_ptr.p, A->values.p, zero_first);
           done = true;
         }
       }

@@ -229,6 +229,7 @@ struct Space
   // scalar P1 with a static structure: per incidence one packed word of positions in the row's full-mesh row
   // (assemble.cu fpos_kernel), what the one-thread-per-row gather reads instead of masks and contribution lists
   DevBuf<uint32_t> fpos;
+  DevBuf<uint64_t> fpos64; // scalar P2 on triangles (nd = 6): li, own column, five other dofs
   bool fpos_built = false;
 };
 
