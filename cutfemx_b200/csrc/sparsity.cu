@@ -714,6 +714,106 @@ __global__ void __launch_bounds__(256)
     atomicAdd(&n_clist[threadIdx.x], static_cast<unsigned long long>(s_cnt[threadIdx.x]));
 }
 
+// One THREAD per row variant of pattern_static_kernel (same outputs).  Rows of P2 triangle spaces have 2 (edge
+// dofs) or 6 (vertex dofs) incident cells and a P1 tetrahedron row 24: a lane group of 8 is mostly idle in the
+// first case and loops in the second, while a thread walking its own row keeps four independent
+// (incidence -> cell -> flag) chains in flight and needs no shuffles.
+__global__ void __launch_bounds__(256)
+    pattern_static_thread_kernel(RowCtx rc, const int32_t* __restrict__ act_rows, DN n_act_,
+                                 const uint32_t* __restrict__ fmask, const uint8_t* __restrict__ frow_ok,
+                                 int32_t* __restrict__ row_nnz, uint32_t* __restrict__ Rrow,
+                                 uint8_t* __restrict__ row_fast, uint8_t* __restrict__ row_ufl,
+                                 unsigned long long* __restrict__ n_clist)
+{
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  int my_rows = 0, my_nnz = 0;
+  if (idx < n_act_.get())
+  {
+    const int64_t r = act_rows[idx];
+    if (!(rc.row_flag[r] & 2)) // band rows: pattern_rows_kernel
+    {
+      const int64_t ib = rc.inc_ptr[r];
+      const int n_inc = static_cast<int>(rc.inc_ptr[r + 1] - ib);
+      uint32_t m = 0;
+      unsigned fo = 0, fa = 0xFFu;
+      for (int k0 = 0; k0 < n_inc; k0 += 4)
+      {
+        uint32_t fm[4];
+        int32_t c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+          const int k = k0 + u < n_inc ? k0 + u : n_inc - 1;
+          fm[u] = fmask[ib + k];
+          c[u] = rc.inc_cell[ib + k];
+        }
+        unsigned fl[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          fl[u] = rc.cell_flags[c[u]];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+          if (k0 + u >= n_inc)
+            continue;
+          m |= (fl[u] & 0xFD) ? fm[u] : 0u;
+          fo |= fl[u];
+          fa &= fl[u];
+        }
+      }
+      const bool cl = frow_ok[r] != 0;
+      const int cnt = __popc(m);
+      row_nnz[r] = cnt;
+      Rrow[idx] = m;
+      row_ufl[idx] = (fo == fa && (fo & 3u) == 0u) ? static_cast<uint8_t>(fo) : uint8_t(0);
+      row_fast[idx] = 1 | 4 | (cl ? 8 : 0);
+      if (cl)
+      {
+        my_rows = 1;
+        my_nnz = cnt;
+      }
+    }
+  }
+  // integer counters (exact, order-independent): one atomic pair per block
+  __shared__ int s_cnt[2];
+  if (threadIdx.x < 2)
+    s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    my_rows += __shfl_down_sync(0xffffffffu, my_rows, o);
+    my_nnz += __shfl_down_sync(0xffffffffu, my_nnz, o);
+  }
+  if ((threadIdx.x & 31) == 0 && my_rows)
+  {
+    atomicAdd(&s_cnt[0], my_rows);
+    atomicAdd(&s_cnt[1], my_nnz);
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 && s_cnt[threadIdx.x])
+    atomicAdd(&n_clist[threadIdx.x], static_cast<unsigned long long>(s_cnt[threadIdx.x]));
+}
+
+// one THREAD per row variant of pattern_static_fill_kernel: the row's kept full-mesh columns, in order
+__global__ void __launch_bounds__(256)
+    pattern_static_fill_thread_kernel(const int32_t* __restrict__ act_rows, DN n_act_,
+                                      const uint8_t* __restrict__ row_fast, const uint32_t* __restrict__ Rrow,
+                                      const int64_t* __restrict__ frow_ptr, const int32_t* __restrict__ fcols,
+                                      const int64_t* __restrict__ row_ptr, int32_t* __restrict__ cols)
+{
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= n_act_.get() || !(row_fast[idx] & 4))
+    return;
+  const int64_t r = act_rows[idx];
+  const uint32_t R = Rrow[idx];
+  const int32_t* __restrict__ src = fcols + frow_ptr[r];
+  int32_t* __restrict__ dst = cols + row_ptr[r];
+  int o = 0;
+  for (uint32_t m = R; m; m &= m - 1, ++o)
+    dst[o] = src[__ffs(m) - 1];
+}
+
 // static rows after the scan: cols[row_ptr[r] + k] = k-th kept full-mesh column.  16 lanes per row, SROWS rows
 // per half-warp with the three dependent load levels (slot -> row -> columns) of all of them batched: a warp
 // that lives for one row spends its whole life waiting on three round trips.
@@ -1445,8 +1545,13 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
     {
       a->Rrow.reserve(ctx->pool, static_cast<size_t>(n_act) + 1);
       a->row_ufl.reserve(ctx->pool, static_cast<size_t>(n_act) + 16);
-      CFX_LAUNCH(ctx, pattern_static_kernel, grid_for((n_act + 3) / 4 * 8, 256), 256, 0, rc, act, d_act, S.fmask.p, S.frow_ok.p,
-                 row_nnz.p, a->Rrow.p, a->row_fast.p, a->row_ufl.p, n_slow + 1);
+      static const bool lanes = getenv("CFX_PATTERN_LANES") != nullptr; // A/B switch: the 8-lanes-per-row kernels
+      if (lanes)
+        CFX_LAUNCH(ctx, pattern_static_kernel, grid_for((n_act + 3) / 4 * 8, 256), 256, 0, rc, act, d_act, S.fmask.p,
+                   S.frow_ok.p, row_nnz.p, a->Rrow.p, a->row_fast.p, a->row_ufl.p, n_slow + 1);
+      else
+        CFX_LAUNCH(ctx, pattern_static_thread_kernel, grid_for(n_act, 256), 256, 0, rc, act, d_act, S.fmask.p,
+                   S.frow_ok.p, row_nnz.p, a->Rrow.p, a->row_fast.p, a->row_ufl.p, n_slow + 1);
     }
     if (need_generic)
     {
@@ -1525,8 +1630,15 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
   if (n_act > 0)
   {
     if (use_static)
-      CFX_LAUNCH(ctx, pattern_static_fill_kernel, grid_for((n_act + SROWS - 1) / SROWS * 16, 256), 256, 0, act, d_act, a->row_fast.p,
-                 a->Rrow.p, S.frow_ptr.p, S.fcols.p, P->row_ptr.p, P->cols.p);
+    {
+      static const bool lanes_fill = getenv("CFX_PATTERN_LANES") != nullptr;
+      if (lanes_fill)
+        CFX_LAUNCH(ctx, pattern_static_fill_kernel, grid_for((n_act + SROWS - 1) / SROWS * 16, 256), 256, 0, act, d_act,
+                   a->row_fast.p, a->Rrow.p, S.frow_ptr.p, S.fcols.p, P->row_ptr.p, P->cols.p);
+      else
+        CFX_LAUNCH(ctx, pattern_static_fill_thread_kernel, grid_for(n_act, 256), 256, 0, act, d_act, a->row_fast.p,
+                   a->Rrow.p, S.frow_ptr.p, S.fcols.p, P->row_ptr.p, P->cols.p);
+    }
     if (need_generic)
       CFX_LAUNCH(ctx, pattern_copy_kernel, grid_for(n_act, 256), 256, 0, act, d_act, a->row_fast.p, tmp.p,
                  P->row_ptr.p, P->cols.p);
