@@ -1545,7 +1545,10 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
     {
       a->Rrow.reserve(ctx->pool, static_cast<size_t>(n_act) + 1);
       a->row_ufl.reserve(ctx->pool, static_cast<size_t>(n_act) + 16);
-      static const bool lanes = getenv("CFX_PATTERN_LANES") != nullptr; // A/B switch: the 8-lanes-per-row kernels
+      // measured (profiles/README): rows with few incident cells (triangles: 2-6) are faster one thread per row
+      // (C2: 2.56 -> 2.21 ms), rows of 24 cells (P1 tetrahedra) with the 8-lanes-per-row kernel (C3: 1.12 vs 1.16 ms)
+      static const bool force_lanes = getenv("CFX_PATTERN_LANES") != nullptr; // A/B switch
+      const bool lanes = force_lanes || S.stride > 12;
       if (lanes)
         CFX_LAUNCH(ctx, pattern_static_kernel, grid_for((n_act + 3) / 4 * 8, 256), 256, 0, rc, act, d_act, S.fmask.p,
                    S.frow_ok.p, row_nnz.p, a->Rrow.p, a->row_fast.p, a->row_ufl.p, n_slow + 1);
@@ -1631,8 +1634,8 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
   {
     if (use_static)
     {
-      static const bool lanes_fill = getenv("CFX_PATTERN_LANES") != nullptr;
-      if (lanes_fill)
+      static const bool force_lanes_fill = getenv("CFX_PATTERN_LANES") != nullptr;
+      if (force_lanes_fill || S.stride > 12)
         CFX_LAUNCH(ctx, pattern_static_fill_kernel, grid_for((n_act + SROWS - 1) / SROWS * 16, 256), 256, 0, act, d_act,
                    a->row_fast.p, a->Rrow.p, S.frow_ptr.p, S.fcols.p, P->row_ptr.p, P->cols.p);
       else
