@@ -256,3 +256,50 @@ def test_solution_l2_error_matches_oracle(kind, n, tol, built_lib):
     eg, er = l2_error_gpu(ug), l2_error_ref(ur)
     assert abs(eg - er) <= 1e-8 * er, (eg, er)
     assert er < tol, er  # and the discrete solution is the right one
+
+
+@pytest.mark.parametrize("n", [14])
+def test_configs3_elasticity_on_the_device_generated_p2_vector_space(n, built_lib):
+    """BASELINE configs[3] (torus R = 0.3, r = 0.12; linear elasticity on a P2 VECTOR space, vector Nitsche terms on
+    the interface, componentwise ghost penalty; demo_elasticity.py:213-238) through the path bench.py --workload C4
+    times -- device-generated mesh, device-generated P2-tetrahedron dofmap (cfx_meshgen_p2_tet_dofmap), standard
+    cells evaluated on the fly by the blocked row gather, cut-cell tensors by the warp-per-rule kernel -- against the
+    oracle's run_elasticity_pipeline on the same dofmap.  Bars: pattern bit-exact, 3 x 3 blocks and the load vector
+    to 1e-11 relative Frobenius; the matrix is symmetric and the load sums to f x wet volume per component."""
+    import torch
+
+    from cutfemx_b200 import mesh as M
+    from cutfemx_b200 import parallel as P
+    from oracle import pipeline
+
+    pipe = P.RankPipeline([n] * 3, [0.0] * 3, [1.0] * 3, 1, 0, 0, "torus", (0.5, 0.5, 0.5, 0.3, 0.12, 0.0), order=4,
+                          degree=2, problem="elasticity", bs=3)
+    prob = pipe.prob
+    pipe.xplan = None
+    prob.persistent = False
+    prob.step(keep=True)
+    torch.cuda.synchronize()
+    A, b = prob.A, prob.b.cpu().numpy()
+    hm = M.create_box(n, n, n)
+    assert np.array_equal(hm.x_dofmap, pipe.mesh.x_dofmap.cpu().numpy())       # same numbering as the host generator
+    np.testing.assert_array_equal(hm.x, pipe.mesh.x.cpu().numpy())
+    dm = pipe.V.dofmap.cpu().numpy()
+    assert dm.shape == (hm.num_cells, 10) and np.array_equal(dm[:, :4], hm.x_dofmap)
+    # the edge dofs are a consistent numbering: equal to the host generator's up to a renumbering of the edge dofs
+    Vh = M.functionspace(hm, 2)
+    _, first = np.unique(Vh.dofmap[:, 4:].ravel(), return_index=True)
+    assert np.unique(dm[:, 4:].ravel()).size == first.size
+    assert np.array_equal(np.unique(dm[:, 4:].ravel()[first], return_counts=True)[1], np.ones(first.size, dtype=np.int64))
+    V = M.FunctionSpace(hm, 2, dm, pipe.V.num_dofs, pipe.V.num_dofs, 3, None)
+    V1 = M.functionspace(hm, 1)
+    phi = pipe.phi.x.array.cpu().numpy()
+    ref = pipeline.run_elasticity_pipeline(hm, V1.dofmap, phi, V, order=4)
+    assert np.array_equal(A.indptr, ref["row_ptr"]) and np.array_equal(A.indices, ref["cols"])
+    ea = np.linalg.norm(A.data - ref["vals"]) / np.linalg.norm(ref["vals"])
+    eb = np.linalg.norm(b - ref["b"]) / np.linalg.norm(ref["b"])
+    assert ea < 1e-11 and eb < 1e-11, (ea, eb)
+    Ms = A.to_scipy()
+    assert abs(Ms - Ms.T).max() <= 1e-11 * abs(Ms).max()
+    wet = ref["rv"].weights.sum() + ref["inside"].size / (6.0 * n ** 3)
+    np.testing.assert_allclose(b.reshape(-1, 3).sum(axis=0), np.array([0.0, 0.0, -1.0]) * wet, rtol=0, atol=1e-12 * wet)
+    prob.release_step()
