@@ -603,6 +603,184 @@ __global__ void __launch_bounds__(RW * 32)
   }
 }
 
+// Band rows of a scalar P1 space WITH a static structure, a few threads per row (the structure of
+// assemble.cu gather_matrix_band_p1_kernel; the warp-per-row pattern_rows_kernel above spends a whole warp and a
+// repeated warp-wide minimum on rows that differ from their static row by a handful of columns).  The row's columns
+// are its static columns of the needed cells (OR of the static position masks, like pattern_static_kernel) plus
+//   * per band cell, the dof across the facet OPPOSITE the row's dof when that facet is a band facet (the partner
+//     cell does not hold the row's dof, so that dof is the only new column the ghost-penalty macro element brings;
+//     partner cell and its local facet index come from the facet's integration row),
+//   * the entries other ranks inserted for this row (SparsityPattern::insert, multi-rank runs).
+// Thread g of a group of BPG takes cells g, g + BPG, ...; extras meet in a small shared list, thread 0 sorts them,
+// drops duplicates and static columns, and merges them with the kept static columns into tmp (copied to the CSR
+// after the scan by pattern_copy_kernel).  Rows that end up with more than 32 columns are left to the generic fill
+// pass (row_fast bit 0 clear).  No position masks are stored: the P1 band gather does not read them.
+constexpr int BPG = 4;    // threads per band row
+constexpr int BPB = 64;   // threads per block
+constexpr int BPX = 64;   // extra candidates per row: <= 32 band cells + the entries other ranks inserted
+
+template <int ND>
+__global__ void __launch_bounds__(BPB)
+    pattern_band_p1_kernel(RowCtx rc, const int32_t* __restrict__ act_rows, const int32_t* __restrict__ slots,
+                           DN n_band_, const uint32_t* __restrict__ fmask, const uint32_t* __restrict__ fperm,
+                           const int64_t* __restrict__ frow_ptr, const int32_t* __restrict__ fcols,
+                           const int32_t* __restrict__ rows4, int32_t* __restrict__ row_nnz,
+                           int32_t* __restrict__ tmp, uint8_t* __restrict__ row_fast,
+                           unsigned long long* __restrict__ n_slow, int32_t* __restrict__ err)
+{
+  __shared__ int32_t s_ex[BPB / BPG][BPX];
+  __shared__ int s_nex[BPB / BPG];
+  const int tid = threadIdx.x, g = tid & (BPG - 1), lrow = tid / BPG;
+  const unsigned gmask = ((1u << BPG) - 1u) << ((tid & 31) & ~(BPG - 1));
+  const int64_t it = (static_cast<int64_t>(blockIdx.x) * BPB + tid) / BPG;
+  if (it >= n_band_.get())
+    return;
+  const int64_t idx = slots[it];
+  const int32_t r = act_rows[idx];
+  const int64_t ib = rc.inc_ptr[r];
+  const int n_inc = static_cast<int>(rc.inc_ptr[r + 1] - ib);
+  if (g == 0)
+    s_nex[lrow] = 0;
+  __syncwarp(gmask);
+  uint32_t R = 0;
+  bool band = false;
+  constexpr int U = 2;
+  for (int l0 = g; l0 < n_inc; l0 += U * BPG)
+  {
+    int32_t c[U];
+    uint32_t fm[U], fp[U];
+    unsigned fl[U];
+    bool in[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      in[u] = l0 + u * BPG < n_inc;
+      const int l = in[u] ? l0 + u * BPG : 0;
+      c[u] = rc.inc_cell[ib + l];
+      fm[u] = fmask[ib + l];
+      fp[u] = fperm[ib + l];
+    }
+    int32_t fct[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      fl[u] = in[u] ? rc.cell_flags[c[u]] : 0u;
+      // the facet opposite the row's dof (P1: local facet li is opposite local vertex li); read whether or not the
+      // cell turns out to be a band cell -- one level of the dependent chain less
+      fct[u] = rc.c2f[static_cast<int64_t>(c[u]) * ND + (fp[u] & 15u)];
+    }
+    int32_t fs[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      fs[u] = (fl[u] & 2u) ? rc.facet_slot[fct[u]] : -1;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      if (fl[u] & 0xFFu) // a cell with a tensor of its own, or a band cell (its dofs are needed for the facets)
+        R |= ((fl[u] & 0xFDu) || (fl[u] & 2u)) ? fm[u] : 0u;
+      band = band || (fl[u] & 2u);
+      if (fs[u] >= 0)
+      {
+        const int4 rw = __ldg(reinterpret_cast<const int4*>(rows4) + fs[u]); // (cell0, lf0, cell1, lf1)
+        const bool first = rw.x == c[u];
+        const int64_t oc = first ? rw.z : rw.x;
+        const int olf = first ? rw.w : rw.y;
+        const int32_t x = rc.dofmap[oc * ND + olf];
+        const int pos = atomicAdd(&s_nex[lrow], 1);
+        if (pos < BPX)
+          s_ex[lrow][pos] = x;
+      }
+    }
+  }
+  if (g == 0 && rc.xslot != nullptr)
+  { // SparsityPattern::insert entries received from other ranks
+    const int32_t xs = rc.xslot[r];
+    if (xs >= 0)
+      for (int64_t i = xs, nx = rc.n_x.get(); i < nx && rc.xrows[i] == r; ++i)
+      {
+        const int pos = atomicAdd(&s_nex[lrow], 1);
+        if (pos < BPX)
+          s_ex[lrow][pos] = rc.xcols[i];
+      }
+  }
+#pragma unroll
+  for (int o = 1; o < BPG; o <<= 1)
+  {
+    R |= __shfl_xor_sync(gmask, R, o);
+    band = __shfl_xor_sync(gmask, band ? 1 : 0, o) || band;
+  }
+  __syncwarp(gmask);
+  if (g != 0)
+    return;
+  int nex = s_nex[lrow];
+  if (nex > BPX)
+  {
+    err[0] = 38; // more extra column candidates than the list holds
+    err[1] = r;
+    nex = BPX;
+  }
+  int32_t* ex = s_ex[lrow];
+  const int64_t fb = frow_ptr[r];
+  const int nfull = static_cast<int>(frow_ptr[r + 1] - fb);
+  int count = __popc(R);
+  // extras: ascending, unique, not already a kept static column
+  for (int i = 1; i < nex; ++i)
+  {
+    const int32_t v = ex[i];
+    int j = i - 1;
+    for (; j >= 0 && ex[j] > v; --j)
+      ex[j + 1] = ex[j];
+    ex[j + 1] = v;
+  }
+  int m = 0;
+  for (int i = 0; i < nex; ++i)
+  {
+    const int32_t v = ex[i];
+    if (m > 0 && ex[m - 1] == v)
+      continue;
+    int lo = 0, hi = nfull; // is v a static column of the row, and kept?
+    while (lo < hi)
+    {
+      const int mid = (lo + hi) >> 1;
+      if (fcols[fb + mid] < v)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    if (lo < nfull && fcols[fb + lo] == v)
+    {
+      if (!((R >> lo) & 1u))
+      { // a static column that no needed cell brought: keep it as a static column
+        R |= 1u << lo;
+        ++count;
+      }
+      continue;
+    }
+    ex[m++] = v;
+  }
+  nex = m;
+  count += nex;
+  row_nnz[r] = count;
+  const bool fast = count <= 32 && n_inc <= 32;
+  if (fast)
+  { // merge the kept static columns with the extras
+    int32_t* dst = tmp + idx * 32;
+    int e = 0, k = 0;
+    for (uint32_t mm = R; mm; mm &= mm - 1)
+    {
+      const int32_t col = fcols[fb + __ffs(mm) - 1];
+      while (e < nex && ex[e] < col)
+        dst[k++] = ex[e++];
+      dst[k++] = col;
+    }
+    while (e < nex)
+      dst[k++] = ex[e++];
+  }
+  else
+    atomicAdd(n_slow, 1ULL); // the generic fill pass writes this row's columns
+  row_fast[idx] = (fast ? 1 : 0) | (band ? 2 : 0) | 16;
+}
+
 // Per-step pattern of a row WITHOUT facet-band cells, from the static full-mesh structure: the
 // row keeps the full-mesh columns whose bit is set in R = OR of the full-row masks of its ACTIVE
 // incident cells.  Count pass: one warp per row, coalesced inc_cell / fmask reads, one REDUX.OR,
@@ -1559,9 +1737,23 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
     if (need_generic)
     {
       tmp.reserve(ctx->pool, static_cast<size_t>(n_act) * 32);
-      a->gmask.reserve(ctx->pool, static_cast<size_t>(n_act) * S.stride);
-      CFX_LAUNCH(ctx, kcount, gg, RW * 32, 0, rc, act, gslots, d_generic, only_band, S.stride, row_nnz.p, nullptr,
-                 nullptr, tmp.p, a->gmask.p, a->row_fast.p, n_slow, ctx->err_flag.p);
+      // scalar P1 with a static structure (the rows gather_matrix_band_p1_kernel takes): a few threads per band row
+      static const bool old_band = getenv("CFX_OLD_BAND") != nullptr; // A/B switch, shared with assemble.cu
+      const bool threads = use_static && S.degree == 1 && S.bs == 1 && S.has_perm && !old_band
+                           && (PR->facet_key.first == nullptr || FI != nullptr);
+      if (threads)
+      {
+        const int32_t* rows4 = FI ? FI->entities : nullptr;
+        auto kb = S.nd == 3 ? pattern_band_p1_kernel<3> : pattern_band_p1_kernel<4>;
+        CFX_LAUNCH(ctx, kb, grid_for(n_generic * BPG, BPB), BPB, 0, rc, act, gslots, d_generic, S.fmask.p, S.fperm.p,
+                   S.frow_ptr.p, S.fcols.p, rows4, row_nnz.p, tmp.p, a->row_fast.p, n_slow, ctx->err_flag.p);
+      }
+      else
+      {
+        a->gmask.reserve(ctx->pool, static_cast<size_t>(n_act) * S.stride);
+        CFX_LAUNCH(ctx, kcount, gg, RW * 32, 0, rc, act, gslots, d_generic, only_band, S.stride, row_nnz.p, nullptr,
+                   nullptr, tmp.p, a->gmask.p, a->row_fast.p, n_slow, ctx->err_flag.p);
+      }
     }
   }
   P->row_ptr.reserve(ctx->pool, static_cast<size_t>(S.n_total) + 2);
