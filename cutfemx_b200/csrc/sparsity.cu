@@ -319,9 +319,12 @@ __device__ __forceinline__ void sort_small(int32_t (&v)[N])
 //
 // FILL = false (first pass): counts the columns and, for rows with at most 32 columns and 32
 // incident cells ("fast rows"), also stores
-//   tmp[idx*32 + k]        = k-th column                 (copied to the CSR after the scan)
+//   tmp[idx*ts + k]        = k-th column                 (copied to the CSR after the scan)
 //   mask[idx*stride + l]   = bit mask of the CSR positions of the dofs of incident cell l
-// so that the assembly gather (assemble.cu) needs neither the dofmap nor a column search.
+// so that the assembly gather (assemble.cu) needs neither the dofmap nor a column search.  ts = 32 for scalar
+// spaces (the mask gather handles rows of at most 32 columns); blocked spaces, whose gather searches the columns and
+// reads no masks, pass ts = 96 so that the 30 - 65 column rows of P2 tetrahedra are not merged a second time by the
+// fill pass (columns are flushed to tmp 32 at a time).
 // FILL = true (second pass, slow rows only): writes the columns straight into the CSR.
 //
 // Modes: act_rows == nullptr walks ALL rows with every cell active (static full-mesh structure,
@@ -330,7 +333,7 @@ __device__ __forceinline__ void sort_small(int32_t (&v)[N])
 template <int ND, bool FILL>
 __global__ void __launch_bounds__(RW * 32)
     pattern_rows_kernel(RowCtx rc, const int32_t* __restrict__ act_rows, const int32_t* __restrict__ slots,
-                        DN n_rows_in, int only_band, int stride, int32_t* __restrict__ row_nnz,
+                        DN n_rows_in, int only_band, int stride, int ts, int32_t* __restrict__ row_nnz,
                         const int64_t* __restrict__ row_ptr,
                         int32_t* __restrict__ cols_out, int32_t* __restrict__ tmp, uint32_t* __restrict__ mask_out,
                         uint8_t* __restrict__ row_fast, unsigned long long* __restrict__ n_slow,
@@ -533,7 +536,9 @@ __global__ void __launch_bounds__(RW * 32)
         h[j] = p ? h[j + 1] : h[j];
       h[ND - 1] = p ? IMAX : h[ND - 1];
       xreg = (xreg == m) ? IMAX : xreg;
-      keep = (lane == count) ? m : keep;
+      keep = (lane == (count & 31)) ? m : keep;
+      if ((count & 31) == 31 && count < ts)
+        tmp[idx * ts + (count & ~31) + lane] = keep; // a full group of 32 columns
       bit <<= 1;
       ++count;
     }
@@ -569,8 +574,10 @@ __global__ void __launch_bounds__(RW * 32)
       }
       else
       {
-        if (lane == count)
+        if (lane == (count & 31))
           keep = m;
+        if ((count & 31) == 31 && count < ts)
+          tmp[idx * ts + (count & ~31) + lane] = keep;
       }
       last = m;
       ++count;
@@ -583,13 +590,14 @@ __global__ void __launch_bounds__(RW * 32)
   }
   else
   {
-    const bool fast = count <= 32 && n_inc <= 32;
+    // ts == 32: rows the mask gather can take; ts > 32 (blocked spaces): rows whose columns fit tmp
+    const bool fast = ts > 32 ? count <= ts : (count <= 32 && n_inc <= 32);
     const bool any_band = __any_sync(full, band);
     if (fast)
     {
-      if (lane < count)
-        tmp[idx * 32 + lane] = keep;
-      if (lane < n_inc)
+      if (lane < (count & 31))
+        tmp[idx * ts + (count & ~31) + lane] = keep; // the last, partial group
+      if (ts == 32 && lane < n_inc)
         mask_out[(all_mode ? ib : idx * stride) + lane] = M;
     }
     if (lane == 0)
@@ -1048,7 +1056,7 @@ __global__ void __launch_bounds__(256)
 // the per-row scalars are loaded once, lane-parallel, then every row is one coalesced copy.
 __global__ void __launch_bounds__(256)
     pattern_copy_kernel(const int32_t* __restrict__ act_rows, DN n_act_, const uint8_t* __restrict__ row_fast,
-                        const int32_t* __restrict__ tmp, const int64_t* __restrict__ row_ptr,
+                        const int32_t* __restrict__ tmp, int ts, const int64_t* __restrict__ row_ptr,
                         int32_t* __restrict__ cols)
 {
   const int64_t n_act = n_act_.get();
@@ -1072,8 +1080,8 @@ __global__ void __launch_bounds__(256)
   {
     const int64_t bi = __shfl_sync(0xffffffffu, b, i);
     const int ni = __shfl_sync(0xffffffffu, n, i);
-    if (lane < ni)
-      cols[bi + lane] = tmp[(idx0 + i) * 32 + lane];
+    for (int k = lane; k < ni; k += 32)
+      cols[bi + k] = tmp[(idx0 + i) * ts + k];
   }
 }
 
@@ -1160,7 +1168,7 @@ static void build_static_structure_nd(cfx_ctx* c, Space& S)
   CFX_CUDA(cudaMemsetAsync(n_slow, 0, sizeof(unsigned long long), c->stream));
   CFX_CUDA(cudaMemsetAsync(row_nnz.p, 0, (static_cast<size_t>(S.n_total) + 1) * sizeof(int32_t), c->stream));
   auto k = pattern_rows_kernel<ND, false>;
-  CFX_LAUNCH(c, k, grid_for(S.n_total, RW), RW * 32, 0, rc, nullptr, nullptr, dn_exact(S.n_total), 0, S.stride,
+  CFX_LAUNCH(c, k, grid_for(S.n_total, RW), RW * 32, 0, rc, nullptr, nullptr, dn_exact(S.n_total), 0, S.stride, 32,
              row_nnz.p, nullptr, nullptr, tmp.p, S.fmask.p, nullptr, n_slow, c->err_flag.p);
   S.frow_ptr.reserve(c->pool, static_cast<size_t>(S.n_total) + 2);
   exclusive_scan_i32_to_i64(c, row_nnz.p, S.n_total, S.frow_ptr.p);
@@ -1169,7 +1177,7 @@ static void build_static_structure_nd(cfx_ctx* c, Space& S)
   if (slow == 0)
   {
     S.fcols.reserve(c->pool, static_cast<size_t>(fnnz) + 1);
-    CFX_LAUNCH(c, pattern_copy_kernel, grid_for(S.n_total, 256), 256, 0, nullptr, dn_exact(S.n_total), nullptr, tmp.p,
+    CFX_LAUNCH(c, pattern_copy_kernel, grid_for(S.n_total, 256), 256, 0, nullptr, dn_exact(S.n_total), nullptr, tmp.p, 32,
                S.frow_ptr.p, S.fcols.p);
     S.frow_ok.reserve(c->pool, static_cast<size_t>(S.n_total) + 16);
     if (ND <= 4 && S.bs == 1)
@@ -1709,6 +1717,7 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
   CFX_CUDA(cudaMemsetAsync(n_slow, 0, 3 * sizeof(unsigned long long), ctx->stream)); // [1] slow, [2..3] clist rows/nnz
   const bool use_static = S.has_static && !part;
   const int only_band = use_static ? 1 : 0;
+  const int ts = S.bs > 1 ? 96 : 32; // columns per row kept from the count pass (pattern_rows_kernel)
   const bool need_generic = !use_static || PR->facet_key.first != nullptr || PR->extra_key.first != nullptr;
   // with a static structure the generic kernels visit the band rows only, through their slot list
   const int32_t* gslots = use_static ? PR->band_idx.p : nullptr;
@@ -1736,7 +1745,7 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
     }
     if (need_generic)
     {
-      tmp.reserve(ctx->pool, static_cast<size_t>(n_act) * 32);
+      tmp.reserve(ctx->pool, static_cast<size_t>(n_act) * ts);
       // scalar P1 with a static structure (the rows gather_matrix_band_p1_kernel takes): a few threads per band row
       static const bool old_band = getenv("CFX_OLD_BAND") != nullptr; // A/B switch, shared with assemble.cu
       const bool threads = use_static && S.degree == 1 && S.bs == 1 && S.has_perm && !old_band
@@ -1751,7 +1760,7 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
       else
       {
         a->gmask.reserve(ctx->pool, static_cast<size_t>(n_act) * S.stride);
-        CFX_LAUNCH(ctx, kcount, gg, RW * 32, 0, rc, act, gslots, d_generic, only_band, S.stride, row_nnz.p, nullptr,
+        CFX_LAUNCH(ctx, kcount, gg, RW * 32, 0, rc, act, gslots, d_generic, only_band, S.stride, ts, row_nnz.p, nullptr,
                    nullptr, tmp.p, a->gmask.p, a->row_fast.p, n_slow, ctx->err_flag.p);
       }
     }
@@ -1835,10 +1844,10 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
                    a->Rrow.p, S.frow_ptr.p, S.fcols.p, P->row_ptr.p, P->cols.p);
     }
     if (need_generic)
-      CFX_LAUNCH(ctx, pattern_copy_kernel, grid_for(n_act, 256), 256, 0, act, d_act, a->row_fast.p, tmp.p,
+      CFX_LAUNCH(ctx, pattern_copy_kernel, grid_for(n_act, 256), 256, 0, act, d_act, a->row_fast.p, tmp.p, ts,
                  P->row_ptr.p, P->cols.p);
     if (a->n_slow_rows > 0)
-      CFX_LAUNCH(ctx, kfill, gg, RW * 32, 0, rc, act, gslots, d_generic, only_band, S.stride, nullptr, P->row_ptr.p,
+      CFX_LAUNCH(ctx, kfill, gg, RW * 32, 0, rc, act, gslots, d_generic, only_band, S.stride, ts, nullptr, P->row_ptr.p,
                  P->cols.p, nullptr, nullptr, a->row_fast.p, nullptr, ctx->err_flag.p);
   }
   tmp.release();
