@@ -136,6 +136,7 @@ void nccl_check(int rc, const char* what)
 struct cfx_xplan
 {
   int space = 0, n_neigh = 0;
+  int bs = 1; // block size of the space: bs*bs doubles per candidate entry, bs per ghost vector entry
   std::vector<int> ranks;
   // per neighbour: [k] .. [k+1] ranges (host)
   std::vector<int64_t> s_word_off, r_word_off; // bit messages, in 32-bit words
@@ -162,6 +163,19 @@ struct cfx_xplan
   // per-step selection of the received candidates whose bit is set (indices into r_perm order)
   cfx::DevBuf<int32_t> sel;
   int64_t* d_n_sel = nullptr;
+  // COMPACT value messages (every space but scalar P1, where the static superset of a ghost row is small): only the
+  // blocks whose bit is set travel, in candidate order -- per neighbour [bs per ghost row][bs*bs per set bit].  Both
+  // ends know the bits, so both find a block's slot as (set bits before it) from a per-word prefix of popcounts.
+  // Message sizes: exact in eager steps (one read-back of the counts per side), and in deferred-size steps the
+  // capacity the eager steps needed plus the context's margin (both ends saw the same counts, so they agree); a
+  // count above the capacity raises the device error flag.
+  bool compact = false;
+  std::vector<int64_t> s_row_off, s_ent_off;       // host copies: ghost rows / candidates per neighbour
+  cfx::DevBuf<int32_t> s_wcnt, r_wcnt;             // popcount of every bit word
+  cfx::DevBuf<int64_t> s_wpre, r_wpre;             // exclusive prefix over the words (n_words + 1)
+  cfx::DevBuf<int64_t> d_s_word_off, d_r_word_off; // device copies of the word offsets
+  int64_t *d_s_cnt = nullptr, *d_r_cnt = nullptr;  // set bits per neighbour, this step
+  std::vector<int64_t> s_seen, r_seen, s_slots, r_slots; // largest counts of eager steps; slots of the current messages
 };
 
 namespace cfx
@@ -304,16 +318,20 @@ __device__ __forceinline__ int64_t find_entry(const int64_t* __restrict__ row_pt
   return (lo < row_ptr[r + 1] && cols[lo] == c) ? lo : -1;
 }
 
-__global__ void pack_values_kernel(int64_t n_ent, const int32_t* __restrict__ s_rows, const int64_t* __restrict__ s_ptr,
-                                   const int32_t* __restrict__ s_cols, const int32_t* __restrict__ s_erow,
-                                   const int64_t* __restrict__ s_bit, const int64_t* __restrict__ s_vpos,
-                                   const uint32_t* __restrict__ bits, const int64_t* __restrict__ row_ptr,
-                                   const int32_t* __restrict__ cols, const double* __restrict__ vals,
-                                   double* __restrict__ out, int32_t* __restrict__ err)
+// one thread per (candidate entry, component of its bs x bs block); a block's components are consecutive in the
+// matrix (values[p * bs * bs + q]) and in the message
+__global__ void pack_values_kernel(int64_t n_ent, int bs2, const int32_t* __restrict__ s_rows,
+                                   const int64_t* __restrict__ s_ptr, const int32_t* __restrict__ s_cols,
+                                   const int32_t* __restrict__ s_erow, const int64_t* __restrict__ s_bit,
+                                   const int64_t* __restrict__ s_vpos, const uint32_t* __restrict__ bits,
+                                   const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ cols,
+                                   const double* __restrict__ vals, double* __restrict__ out, int32_t* __restrict__ err)
 {
-  const int64_t e = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t e = t / bs2;
   if (e >= n_ent)
     return;
+  const int q = static_cast<int>(t - e * bs2);
   const int32_t i = s_erow[e];
   double v = 0.0;
   if (bit_at(bits, s_bit[i] + (e - s_ptr[i])))
@@ -325,31 +343,36 @@ __global__ void pack_values_kernel(int64_t n_ent, const int32_t* __restrict__ s_
       err[1] = s_rows[i];
     }
     else
-      v = vals[p];
+      v = vals[p * bs2 + q];
   }
-  out[s_vpos[e]] = v;
+  out[s_vpos[e] + q] = v;
 }
 
-__global__ void pack_vector_kernel(int64_t n_rows, const int32_t* __restrict__ s_rows,
+__global__ void pack_vector_kernel(int64_t n_rows, int bs, const int32_t* __restrict__ s_rows,
                                    const int64_t* __restrict__ s_vec_vpos, const double* __restrict__ b,
                                    double* __restrict__ out)
 {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-  if (i < n_rows)
-    out[s_vec_vpos[i]] = b ? b[s_rows[i]] : 0.0;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t i = t / bs;
+  if (i >= n_rows)
+    return;
+  const int k = static_cast<int>(t - i * bs);
+  out[s_vec_vpos[i] + k] = b ? b[static_cast<int64_t>(s_rows[i]) * bs + k] : 0.0;
 }
 
 // entries [e0, e1) of one neighbour: distinct matrix positions, so plain read-modify-write
-__global__ void unpack_values_kernel(int64_t e0, int64_t e1, const int32_t* __restrict__ r_row,
+__global__ void unpack_values_kernel(int64_t e0, int64_t e1, int bs2, const int32_t* __restrict__ r_row,
                                      const int32_t* __restrict__ r_col, const int64_t* __restrict__ r_bit,
                                      const int64_t* __restrict__ r_vpos, const uint32_t* __restrict__ bits,
                                      const double* __restrict__ in, const int64_t* __restrict__ row_ptr,
                                      const int32_t* __restrict__ cols, double* __restrict__ vals,
                                      int32_t* __restrict__ err)
 {
-  const int64_t e = e0 + static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t e = e0 + t / bs2;
   if (e >= e1 || !bit_at(bits, r_bit[e]))
     return;
+  const int q = static_cast<int>(t % bs2);
   const int64_t p = find_entry(row_ptr, cols, r_row[e], r_col[e]);
   if (p < 0)
   {
@@ -357,16 +380,130 @@ __global__ void unpack_values_kernel(int64_t e0, int64_t e1, const int32_t* __re
     err[1] = r_row[e];
     return;
   }
-  vals[p] += in[r_vpos[e]];
+  vals[p * bs2 + q] += in[r_vpos[e] + q];
 }
 
-__global__ void unpack_vector_kernel(int64_t i0, int64_t i1, const int32_t* __restrict__ r_vec_row,
+__global__ void unpack_vector_kernel(int64_t i0, int64_t i1, int bs, const int32_t* __restrict__ r_vec_row,
                                      const int64_t* __restrict__ r_vec_vpos, const double* __restrict__ in,
                                      double* __restrict__ b)
 {
-  const int64_t i = i0 + static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-  if (i < i1)
-    b[r_vec_row[i]] += in[r_vec_vpos[i]];
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t i = i0 + t / bs;
+  if (i >= i1)
+    return;
+  const int k = static_cast<int>(t % bs);
+  b[static_cast<int64_t>(r_vec_row[i]) * bs + k] += in[r_vec_vpos[i] + k];
+}
+
+// ---- compact value messages
+__global__ void popc_words_kernel(const uint32_t* __restrict__ bits, int64_t n_words, int32_t* __restrict__ out)
+{
+  const int64_t w = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (w < n_words)
+    out[w] = __popc(bits[w]);
+}
+
+__global__ void neighbour_counts_kernel(const int64_t* __restrict__ wpre, const int64_t* __restrict__ word_off,
+                                        int n_neigh, int64_t* __restrict__ cnt)
+{
+  const int k = threadIdx.x;
+  if (k < n_neigh)
+    cnt[k] = wpre[word_off[k + 1]] - wpre[word_off[k]];
+}
+
+// slot of the set bit `bi` among the set bits of its neighbour's message (whose first word is wbase)
+__device__ __forceinline__ int64_t compact_slot(const uint32_t* __restrict__ bits, const int64_t* __restrict__ wpre,
+                                                int64_t wbase, int64_t bi)
+{
+  const int64_t w = bi >> 5;
+  return wpre[w] - wpre[wbase] + __popc(bits[w] & ((1u << (bi & 31)) - 1u));
+}
+
+__global__ void pack_values_compact_kernel(int64_t eb, int64_t ee, int bs2, const int32_t* __restrict__ s_rows,
+                                           const int64_t* __restrict__ s_ptr, const int32_t* __restrict__ s_cols,
+                                           const int32_t* __restrict__ s_erow, const int64_t* __restrict__ s_bit,
+                                           const uint32_t* __restrict__ bits, const int64_t* __restrict__ wpre,
+                                           int64_t wbase, int64_t n_slots, const int64_t* __restrict__ row_ptr,
+                                           const int32_t* __restrict__ cols, const double* __restrict__ vals,
+                                           double* __restrict__ out, int32_t* __restrict__ err)
+{
+  // one thread per candidate: most bits are clear, a set one copies its bs x bs block (consecutive doubles)
+  const int64_t e = eb + static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (e >= ee)
+    return;
+  const int32_t i = s_erow[e];
+  const int64_t bi = s_bit[i] + (e - s_ptr[i]);
+  if (!bit_at(bits, bi))
+    return;
+  const int64_t slot = compact_slot(bits, wpre, wbase, bi);
+  if (slot >= n_slots)
+  { // more ghost-row entries than the message was sized for (deferred-size mode: capacity exceeded)
+    err[0] = 43;
+    err[1] = s_rows[i];
+    return;
+  }
+  const int64_t p = find_entry(row_ptr, cols, s_rows[i], s_cols[e]);
+  if (p < 0)
+  {
+    err[0] = 41;
+    err[1] = s_rows[i];
+    return;
+  }
+  for (int q = 0; q < bs2; ++q)
+    out[slot * bs2 + q] = vals[p * bs2 + q];
+}
+
+__global__ void pack_vector_compact_kernel(int64_t rb, int64_t re, int bs, const int32_t* __restrict__ s_rows,
+                                           const double* __restrict__ b, double* __restrict__ out)
+{
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t i = rb + t / bs;
+  if (i >= re)
+    return;
+  const int k = static_cast<int>(t % bs);
+  out[(i - rb) * bs + k] = b ? b[static_cast<int64_t>(s_rows[i]) * bs + k] : 0.0;
+}
+
+__global__ void unpack_values_compact_kernel(int64_t e0, int64_t e1, int bs2, const int32_t* __restrict__ r_row,
+                                             const int32_t* __restrict__ r_col, const int64_t* __restrict__ r_bit,
+                                             const uint32_t* __restrict__ bits, const int64_t* __restrict__ wpre,
+                                             int64_t wbase, int64_t n_slots, const double* __restrict__ in,
+                                             const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ cols,
+                                             double* __restrict__ vals, int32_t* __restrict__ err)
+{
+  const int64_t e = e0 + static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (e >= e1)
+    return;
+  const int64_t bi = r_bit[e];
+  if (!bit_at(bits, bi))
+    return;
+  const int64_t slot = compact_slot(bits, wpre, wbase, bi);
+  if (slot >= n_slots)
+  {
+    err[0] = 43;
+    err[1] = r_row[e];
+    return;
+  }
+  const int64_t p = find_entry(row_ptr, cols, r_row[e], r_col[e]);
+  if (p < 0)
+  {
+    err[0] = 42;
+    err[1] = r_row[e];
+    return;
+  }
+  for (int q = 0; q < bs2; ++q)
+    vals[p * bs2 + q] += in[slot * bs2 + q];
+}
+
+__global__ void unpack_vector_compact_kernel(int64_t i0, int64_t i1, int bs, const int32_t* __restrict__ r_vec_row,
+                                             const double* __restrict__ in, double* __restrict__ b)
+{
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t i = i0 + t / bs;
+  if (i >= i1)
+    return;
+  const int k = static_cast<int>(t % bs);
+  b[static_cast<int64_t>(r_vec_row[i]) * bs + k] += in[(i - i0) * bs + k];
 }
 
 template <class T>
@@ -375,6 +512,51 @@ void upload(cfx_ctx* c, DevBuf<T>& dst, const T* src, int64_t n)
   dst.reserve(c->pool, static_cast<size_t>(n > 0 ? n : 1));
   if (n > 0)
     CFX_CUDA(cudaMemcpyAsync(dst.p, src, static_cast<size_t>(n) * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+}
+
+// Per-word prefix of the set bits of one side's bit buffer and this step's message layout of that side:
+// val_off[k] .. val_off[k + 1] = [bs per ghost row of neighbour k][bs*bs per slot], slots = the exact number of set
+// bits (eager step: one read-back) or the learned capacity (deferred-size step).
+void compact_layout(cfx_ctx* c, cfx_xplan* P, bool send)
+{
+  const int nn = P->n_neigh;
+  const std::vector<int64_t>& word_off = send ? P->s_word_off : P->r_word_off;
+  const int64_t n_words = word_off[nn];
+  DevBuf<int32_t>& wcnt = send ? P->s_wcnt : P->r_wcnt;
+  DevBuf<int64_t>& wpre = send ? P->s_wpre : P->r_wpre;
+  const uint32_t* bits = send ? P->bits_send.p : P->bits_recv.p;
+  int64_t* d_cnt = send ? P->d_s_cnt : P->d_r_cnt;
+  std::vector<int64_t>& seen = send ? P->s_seen : P->r_seen;
+  std::vector<int64_t>& slots = send ? P->s_slots : P->r_slots;
+  std::vector<int64_t>& val_off = send ? P->s_val_off : P->r_val_off;
+  wcnt.reserve(c->pool, static_cast<size_t>(n_words) + 1);
+  wpre.reserve(c->pool, static_cast<size_t>(n_words) + 2);
+  if (n_words > 0)
+    CFX_LAUNCH(c, popc_words_kernel, grid_for(n_words, 256), 256, 0, bits, n_words, wcnt.p);
+  exclusive_scan_i32_to_i64(c, wcnt.p, n_words, wpre.p);
+  if (!c->deferred)
+  {
+    CFX_LAUNCH(c, neighbour_counts_kernel, 1, 64, 0, wpre.p, (send ? P->d_s_word_off : P->d_r_word_off).p, nn, d_cnt);
+    const int64_t* h = read_back(c, d_cnt, nn);
+    for (int k = 0; k < nn; ++k)
+    {
+      slots[k] = h[k];
+      seen[k] = std::max(seen[k], h[k]);
+    }
+  }
+  else
+    for (int k = 0; k < nn; ++k)
+    {
+      const int64_t n_cand = send ? P->s_ent_off[k + 1] - P->s_ent_off[k] : P->r_ent_off[k + 1] - P->r_ent_off[k];
+      slots[k] = std::min(n_cand, with_margin(c, seen[k]));
+    }
+  const int64_t bs = P->bs, bs2 = bs * bs;
+  for (int k = 0; k < nn; ++k)
+  {
+    const int64_t rows = send ? P->s_row_off[k + 1] - P->s_row_off[k] : P->r_row_off[k + 1] - P->r_row_off[k];
+    val_off[k + 1] = val_off[k] + rows * bs + slots[k] * bs2;
+  }
+  (send ? P->vals_send : P->vals_recv).reserve(c->pool, static_cast<size_t>(val_off[nn]) + 1);
 }
 } // namespace
 } // namespace cfx
@@ -424,10 +606,11 @@ cfx_status cfx_xplan_create(cfx_ctx* ctx, int space, int n_neigh, const int32_t*
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && out && n_neigh >= 0 && space >= 0 && space < CFX_MAX_SPACES && ctx->spaces[space].bound,
               CFX_ERR_INVALID, "cfx_xplan_create: invalid arguments");
-  CFX_REQUIRE(ctx->spaces[space].bs == 1, CFX_ERR_UNSUPPORTED, "cfx_xplan_create: scalar spaces only");
   cfx_xplan* P = new cfx_xplan();
   *out = P;
   P->space = space;
+  P->bs = ctx->spaces[space].bs;
+  const int64_t bs = P->bs, bs2 = bs * bs;
   P->n_neigh = n_neigh;
   P->ranks.assign(neigh_ranks, neigh_ranks + n_neigh);
   P->n_s_rows = n_neigh ? s_row_off[n_neigh] : 0;
@@ -436,8 +619,14 @@ cfx_status cfx_xplan_create(cfx_ctx* ctx, int space, int n_neigh, const int32_t*
   P->n_r_rows = n_neigh ? r_row_off[n_neigh] : 0;
   P->r_ent_off.assign(r_ent_off, r_ent_off + n_neigh + 1);
   P->r_row_off.assign(r_row_off, r_row_off + n_neigh + 1);
+  P->s_row_off.assign(s_row_off, s_row_off + n_neigh + 1);
+  P->s_ent_off.assign(n_neigh + 1, 0);
+  for (int k = 0; k <= n_neigh; ++k)
+    P->s_ent_off[k] = P->n_s_rows ? s_ptr[s_row_off[k]] : 0;
+  P->compact = !(bs == 1 && ctx->spaces[space].nd <= 4);
+  CFX_REQUIRE(!P->compact || n_neigh <= 64, CFX_ERR_UNSUPPORTED, "cfx_xplan_create: at most 64 neighbours");
   // message layouts: per neighbour [bits: one per candidate, padded to 32-bit words]
-  //                                [values: one per candidate, then one per ghost row (vector entries)]
+  //                                [values: bs*bs per candidate, then bs per ghost row (vector entries)]
   P->s_word_off.assign(n_neigh + 1, 0);
   P->r_word_off.assign(n_neigh + 1, 0);
   P->s_val_off.assign(n_neigh + 1, 0);
@@ -453,40 +642,57 @@ cfx_status cfx_xplan_create(cfx_ctx* ctx, int space, int n_neigh, const int32_t*
     {
       CFX_REQUIRE(s_ptr[i + 1] >= s_ptr[i], CFX_ERR_INVALID, "cfx_xplan_create: candidate offsets must ascend");
       h_s_bit[i] = P->s_word_off[k] * 32 + (s_ptr[i] - eb);
-      h_s_vec[i] = P->s_val_off[k] + (ee - eb) + (i - rb);
+      h_s_vec[i] = P->s_val_off[k] + (ee - eb) * bs2 + (i - rb) * bs;
       for (int64_t e = s_ptr[i]; e < s_ptr[i + 1]; ++e)
       {
         h_s_erow[e] = static_cast<int32_t>(i);
-        h_s_vpos[e] = P->s_val_off[k] + (e - eb);
+        h_s_vpos[e] = P->s_val_off[k] + (e - eb) * bs2;
       }
     }
     P->s_word_off[k + 1] = P->s_word_off[k] + (ee - eb + 31) / 32;
-    P->s_val_off[k + 1] = P->s_val_off[k] + (ee - eb) + (re - rb);
+    P->s_val_off[k + 1] = P->s_val_off[k] + (ee - eb) * bs2 + (re - rb) * bs;
     const int64_t qb = r_ent_off[k], qe = r_ent_off[k + 1], vb = r_row_off[k], ve = r_row_off[k + 1];
     for (int64_t e = qb; e < qe; ++e)
     {
       h_r_bit[e] = P->r_word_off[k] * 32 + (e - qb);
-      h_r_vpos[e] = P->r_val_off[k] + (e - qb);
+      h_r_vpos[e] = P->r_val_off[k] + (e - qb) * bs2;
     }
     for (int64_t i = vb; i < ve; ++i)
-      h_r_vec[i] = P->r_val_off[k] + (qe - qb) + (i - vb);
+      h_r_vec[i] = P->r_val_off[k] + (qe - qb) * bs2 + (i - vb) * bs;
     P->r_word_off[k + 1] = P->r_word_off[k] + (qe - qb + 31) / 32;
-    P->r_val_off[k + 1] = P->r_val_off[k] + (qe - qb) + (ve - vb);
+    P->r_val_off[k + 1] = P->r_val_off[k] + (qe - qb) * bs2 + (ve - vb) * bs;
   }
   upload(ctx, P->s_rows, s_rows, P->n_s_rows);
   upload(ctx, P->s_ptr, s_ptr, P->n_s_rows + 1);
   upload(ctx, P->s_cols, s_cols, P->n_s_ent);
   upload(ctx, P->s_erow, h_s_erow.data(), P->n_s_ent);
   upload(ctx, P->s_bit, h_s_bit.data(), P->n_s_rows);
-  upload(ctx, P->s_vpos, h_s_vpos.data(), P->n_s_ent);
-  upload(ctx, P->s_vec_vpos, h_s_vec.data(), P->n_s_rows);
+  if (!P->compact)
+  {
+    upload(ctx, P->s_vpos, h_s_vpos.data(), P->n_s_ent);
+    upload(ctx, P->s_vec_vpos, h_s_vec.data(), P->n_s_rows);
+    upload(ctx, P->r_vpos, h_r_vpos.data(), P->n_r_ent);
+    upload(ctx, P->r_vec_vpos, h_r_vec.data(), P->n_r_rows);
+  }
+  else
+  {
+    upload(ctx, P->d_s_word_off, P->s_word_off.data(), n_neigh + 1);
+    upload(ctx, P->d_r_word_off, P->r_word_off.data(), n_neigh + 1);
+    P->d_s_cnt = alloc_count_slot(ctx, 64);
+    P->d_r_cnt = alloc_count_slot(ctx, 64);
+    for (auto* v : {&P->s_seen, &P->r_seen, &P->s_slots, &P->r_slots})
+      v->assign(n_neigh, 0);
+    for (int k = 0; k <= n_neigh; ++k) // until the first step lays the messages out: vector entries only
+    {
+      P->s_val_off[k] = s_row_off[k] * bs;
+      P->r_val_off[k] = r_row_off[k] * bs;
+    }
+  }
   upload(ctx, P->r_row, r_row, P->n_r_ent);
   upload(ctx, P->r_col, r_col, P->n_r_ent);
   upload(ctx, P->r_perm, r_perm, P->n_r_ent);
   upload(ctx, P->r_bit, h_r_bit.data(), P->n_r_ent);
-  upload(ctx, P->r_vpos, h_r_vpos.data(), P->n_r_ent);
   upload(ctx, P->r_vec_row, r_vec_row, P->n_r_rows);
-  upload(ctx, P->r_vec_vpos, h_r_vec.data(), P->n_r_rows);
   P->bits_send.reserve(ctx->pool, static_cast<size_t>(P->s_word_off[n_neigh]) + 1);
   P->bits_recv.reserve(ctx->pool, static_cast<size_t>(P->r_word_off[n_neigh]) + 1);
   P->vals_send.reserve(ctx->pool, static_cast<size_t>(P->s_val_off[n_neigh]) + 1);
@@ -514,6 +720,14 @@ void cfx_xplan_free(cfx_ctx* ctx, cfx_xplan* P)
   P->bits_recv.release();
   P->vals_send.release();
   P->vals_recv.release();
+  for (auto* b : {&P->s_wpre, &P->r_wpre, &P->d_s_word_off, &P->d_r_word_off})
+    b->release();
+  P->s_wcnt.release();
+  P->r_wcnt.release();
+  if (P->d_s_cnt)
+    free_count_slot(ctx, P->d_s_cnt, 64);
+  if (P->d_r_cnt)
+    free_count_slot(ctx, P->d_r_cnt, 64);
   free_count_slot(ctx, P->d_n_sel);
   delete P;
 }
@@ -607,6 +821,8 @@ cfx_status cfx_xplan_pack_pattern(cfx_ctx* ctx, cfx_xplan* P, const cfx_form* a_
 #undef GB_ARGS
   }
   set_facet_slots(ctx, FI, true);
+  if (P->compact)
+    compact_layout(ctx, P, true);
   CFX_API_END(ctx)
 }
 
@@ -616,9 +832,13 @@ cfx_status cfx_xplan_insert_pattern(cfx_ctx* ctx, cfx_xplan* P, cfx_form* a)
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && P && a && a->rank == 2 && a->space == P->space, CFX_ERR_INVALID,
               "cfx_xplan_insert_pattern: invalid arguments");
-  if (P->n_neigh == 0 || P->n_r_ent == 0)
+  if (P->n_neigh == 0)
     return CFX_OK;
   StageScope st(ctx, "insert_received_pattern", 12.0 * static_cast<double>(P->n_r_ent));
+  if (P->compact)
+    compact_layout(ctx, P, false);
+  if (P->n_r_ent == 0)
+    return CFX_OK;
   RecvBitPred pred{P->r_perm.p, P->r_bit.p, P->bits_recv.p};
   bool deferred = false;
   const int64_t n = compact_indices(ctx, dn_exact(P->n_r_ent), pred, P->sel, false, P->d_n_sel, &deferred);
@@ -639,18 +859,35 @@ cfx_status cfx_xplan_insert_pattern(cfx_ctx* ctx, cfx_xplan* P, cfx_form* a)
 cfx_status cfx_xplan_pack_values(cfx_ctx* ctx, cfx_xplan* P, const cfx_pattern* A, const double* b)
 {
   CFX_API_BEGIN
-  CFX_REQUIRE(ctx && P && A && A->space == P->space && A->bs == 1, CFX_ERR_INVALID,
+  CFX_REQUIRE(ctx && P && A && A->space == P->space && A->bs == P->bs, CFX_ERR_INVALID,
               "cfx_xplan_pack_values: invalid arguments");
+  const int bs = P->bs, bs2 = bs * bs;
   if (P->n_neigh == 0)
     return CFX_OK;
-  StageScope st(ctx, "pack_ghost_values", 20.0 * static_cast<double>(P->n_s_ent));
+  StageScope st(ctx, "pack_ghost_values", (12.0 + 8.0 * bs2) * static_cast<double>(P->n_s_ent));
+  if (P->compact)
+  {
+    for (int k = 0; k < P->n_neigh; ++k)
+    {
+      const int64_t rb = P->s_row_off[k], re = P->s_row_off[k + 1], eb = P->s_ent_off[k], ee = P->s_ent_off[k + 1];
+      double* msg = P->vals_send.p + P->s_val_off[k];
+      if (re > rb)
+        CFX_LAUNCH(ctx, pack_vector_compact_kernel, grid_for((re - rb) * bs, 256), 256, 0, rb, re, bs, P->s_rows.p, b,
+                   msg);
+      if (ee > eb)
+        CFX_LAUNCH(ctx, pack_values_compact_kernel, grid_for(ee - eb, 256), 256, 0, eb, ee, bs2, P->s_rows.p,
+                   P->s_ptr.p, P->s_cols.p, P->s_erow.p, P->s_bit.p, P->bits_send.p, P->s_wpre.p, P->s_word_off[k],
+                   P->s_slots[k], A->row_ptr.p, A->cols.p, A->values.p, msg + (re - rb) * bs, ctx->err_flag.p);
+    }
+    return CFX_OK;
+  }
   if (P->n_s_ent > 0)
-    CFX_LAUNCH(ctx, pack_values_kernel, grid_for(P->n_s_ent, 256), 256, 0, P->n_s_ent, P->s_rows.p, P->s_ptr.p,
-               P->s_cols.p, P->s_erow.p, P->s_bit.p, P->s_vpos.p, P->bits_send.p, A->row_ptr.p, A->cols.p, A->values.p,
-               P->vals_send.p, ctx->err_flag.p);
+    CFX_LAUNCH(ctx, pack_values_kernel, grid_for(P->n_s_ent * bs2, 256), 256, 0, P->n_s_ent, bs2, P->s_rows.p,
+               P->s_ptr.p, P->s_cols.p, P->s_erow.p, P->s_bit.p, P->s_vpos.p, P->bits_send.p, A->row_ptr.p, A->cols.p,
+               A->values.p, P->vals_send.p, ctx->err_flag.p);
   if (P->n_s_rows > 0)
-    CFX_LAUNCH(ctx, pack_vector_kernel, grid_for(P->n_s_rows, 256), 256, 0, P->n_s_rows, P->s_rows.p, P->s_vec_vpos.p,
-               b, P->vals_send.p);
+    CFX_LAUNCH(ctx, pack_vector_kernel, grid_for(P->n_s_rows * bs, 256), 256, 0, P->n_s_rows, bs, P->s_rows.p,
+               P->s_vec_vpos.p, b, P->vals_send.p);
   CFX_API_END(ctx)
 }
 
@@ -658,21 +895,35 @@ cfx_status cfx_xplan_pack_values(cfx_ctx* ctx, cfx_xplan* P, const cfx_pattern* 
 cfx_status cfx_xplan_unpack_add(cfx_ctx* ctx, cfx_xplan* P, cfx_pattern* A, double* b)
 {
   CFX_API_BEGIN
-  CFX_REQUIRE(ctx && P && A && A->space == P->space && A->bs == 1, CFX_ERR_INVALID,
+  CFX_REQUIRE(ctx && P && A && A->space == P->space && A->bs == P->bs, CFX_ERR_INVALID,
               "cfx_xplan_unpack_add: invalid arguments");
+  const int bs = P->bs, bs2 = bs * bs;
   if (P->n_neigh == 0)
     return CFX_OK;
   A->values_zero = false;
-  StageScope st(ctx, "unpack_add_ghost_values", 28.0 * static_cast<double>(P->n_r_ent));
+  StageScope st(ctx, "unpack_add_ghost_values", (12.0 + 16.0 * bs2) * static_cast<double>(P->n_r_ent));
   for (int k = 0; k < P->n_neigh; ++k)
   {
     const int64_t e0 = P->r_ent_off[k], e1 = P->r_ent_off[k + 1], i0 = P->r_row_off[k], i1 = P->r_row_off[k + 1];
+    if (P->compact)
+    {
+      const double* msg = P->vals_recv.p + P->r_val_off[k];
+      if (e1 > e0)
+        CFX_LAUNCH(ctx, unpack_values_compact_kernel, grid_for(e1 - e0, 256), 256, 0, e0, e1, bs2, P->r_row.p,
+                   P->r_col.p, P->r_bit.p, P->bits_recv.p, P->r_wpre.p, P->r_word_off[k], P->r_slots[k],
+                   msg + (i1 - i0) * bs, A->row_ptr.p, A->cols.p, A->values.p, ctx->err_flag.p);
+      if (b && i1 > i0)
+        CFX_LAUNCH(ctx, unpack_vector_compact_kernel, grid_for((i1 - i0) * bs, 256), 256, 0, i0, i1, bs,
+                   P->r_vec_row.p, msg, b);
+      continue;
+    }
     if (e1 > e0)
-      CFX_LAUNCH(ctx, unpack_values_kernel, grid_for(e1 - e0, 256), 256, 0, e0, e1, P->r_row.p, P->r_col.p, P->r_bit.p,
-                 P->r_vpos.p, P->bits_recv.p, P->vals_recv.p, A->row_ptr.p, A->cols.p, A->values.p, ctx->err_flag.p);
+      CFX_LAUNCH(ctx, unpack_values_kernel, grid_for((e1 - e0) * bs2, 256), 256, 0, e0, e1, bs2, P->r_row.p, P->r_col.p,
+                 P->r_bit.p, P->r_vpos.p, P->bits_recv.p, P->vals_recv.p, A->row_ptr.p, A->cols.p, A->values.p,
+                 ctx->err_flag.p);
     if (b && i1 > i0)
-      CFX_LAUNCH(ctx, unpack_vector_kernel, grid_for(i1 - i0, 256), 256, 0, i0, i1, P->r_vec_row.p, P->r_vec_vpos.p,
-                 P->vals_recv.p, b);
+      CFX_LAUNCH(ctx, unpack_vector_kernel, grid_for((i1 - i0) * bs, 256), 256, 0, i0, i1, bs, P->r_vec_row.p,
+                 P->r_vec_vpos.p, P->vals_recv.p, b);
   }
   check_call(ctx, "cfx_xplan_unpack_add (received entry not in the sparsity pattern)");
   CFX_API_END(ctx)

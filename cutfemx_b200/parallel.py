@@ -236,6 +236,97 @@ def partition_slab(shape, p0, p1, world: int, rank: int, device=None, ranges=Non
     return mesh, V, imap
 
 
+def p2_tet_global_dofs(gv, shape):
+    """P2 dofs of Kuhn tetrahedra from the GLOBAL lexicographic vertex ids `gv` (n_cells, 4) int64 of their
+    vertices, in the partition's global numbering: every mesh plane z is a block of B = 8 * vpp ids,
+
+        z * B + d * vpp + u,   u = vertex index inside the plane,
+        d = 0: the vertex;  d = 1..7: the edge leaving the vertex in direction (d & 1, d >> 1 & 1, d >> 2)
+
+    (the offsets of a Kuhn tetrahedron's vertices are nested bit patterns, so an edge is its lower vertex and one of 7
+    directions; ids of edges that would leave the box stay unused, as in the serial device_p2_tet_space).
+    d < 4 lies IN plane z, d >= 4 inside cell layer z -- blocks owned by the plane's / the layer's rank, which
+    makes every rank's owned ids one contiguous range.  Basix edge order e0 = (2,3) ... e5 = (0,1)."""
+    import torch
+
+    from .mesh import TET_EDGES
+
+    sx = int(shape[0]) + 1
+    vpp = sx * (int(shape[1]) + 1)
+    B = 8 * vpp
+    ea = torch.tensor([e[0] for e in TET_EDGES], device=gv.device)
+    eb = torch.tensor([e[1] for e in TET_EDGES], device=gv.device)
+    va, vb = gv[:, ea], gv[:, eb]
+    a = torch.minimum(va, vb)
+    diff = torch.maximum(va, vb) - a
+    dk = diff // vpp
+    rem = diff - dk * vpp
+    dj = rem // sx
+    di = rem - dj * sx
+    d = di + 2 * dj + 4 * dk
+    vert = (gv // vpp) * B + gv % vpp
+    edge = (a // vpp) * B + d * vpp + a % vpp
+    return torch.cat([vert, edge], dim=1)
+
+
+def p2_tet_slab_space(mesh: Mesh, imap1: IndexMap, shape, ranges, rank: int, world: int, bs: int = 1):
+    """P2 (block size `bs`) space and index map of one rank of a slab partition of the Kuhn box: `mesh`, `imap1` are
+    what partition_slab returned (imap1.l2g = global lexicographic vertex ids).  Owned ids of rank r:
+    [lo * B + 4 vpp, hi * B + 4 vpp) (rank 0 from 0): the edges inside its cell layers and the planes above them;
+    ghosts: the dofs of the ghost cell layer below (planes lo - 1, lo and the layer between) and above."""
+    import torch
+
+    shape = tuple(int(v) for v in shape)
+    assert len(shape) == 3
+    dev = imap1.l2g.device
+    vpp = (shape[0] + 1) * (shape[1] + 1)
+    B = 8 * vpp
+    lo, hi = ranges[rank]
+    gv = imap1.l2g[mesh.x_dofmap.to(torch.int64) if hasattr(mesh.x_dofmap, "to") else
+                   torch.from_numpy(np.asarray(mesh.x_dofmap, dtype=np.int64))]
+    g = p2_tet_global_dofs(gv, shape)
+    offset = 0 if rank == 0 else lo * B + 4 * vpp
+    end = hi * B + 4 * vpp
+    n_owned = end - offset
+    owner_of_plane = lambda z: 0 if z == 0 else next(q for q, (a, b) in enumerate(ranges) if a < z <= b)  # noqa: E731
+    parts, owners = [], []
+    if rank > 0:       # plane lo - 1 | layer lo - 1 | plane lo
+        parts.append(torch.arange((lo - 1) * B, lo * B + 4 * vpp, device=dev))
+        owners.append(torch.cat([torch.full((4 * vpp,), owner_of_plane(lo - 1), dtype=torch.int64, device=dev),
+                                 torch.full((8 * vpp,), rank - 1, dtype=torch.int64, device=dev)]))
+    n_below = int(parts[0].numel()) if parts else 0
+    if rank < world - 1:  # layer hi | plane hi + 1
+        parts.append(torch.arange(end, end + B, device=dev))
+        owners.append(torch.full((B,), rank + 1, dtype=torch.int64, device=dev))
+    z64 = torch.zeros(0, dtype=torch.int64, device=dev)
+    ghost_global = torch.cat(parts) if parts else z64
+    ghost_owner = torch.cat(owners) if owners else z64
+    below0 = (lo - 1) * B
+    local = torch.where((g >= offset) & (g < end), g - offset,
+                        torch.where(g < offset, n_owned + g - below0, n_owned + n_below + g - end))
+    n_total = n_owned + int(ghost_global.numel())
+    if bool(((local < 0) | (local >= n_total)).any()):
+        raise RuntimeError("p2_tet_slab_space: a cell touches a dof outside the rank's owned and ghost blocks")
+    l2g = torch.cat([torch.arange(offset, end, device=dev), ghost_global])
+    imap = IndexMap(rank, world, n_owned, offset, ghost_global.contiguous(), ghost_owner.contiguous(), l2g)
+    dm = local.to(torch.int32).contiguous()
+    if not hasattr(mesh.x_dofmap, "to"):
+        dm = dm.numpy()
+    return FunctionSpace(mesh, 2, dm, n_total, n_owned, bs, None), imap
+
+
+def p2_tet_global_to_serial(g, shape):
+    """Partition-global P2 id (p2_tet_global_dofs) -> the id of the same dof in the serial device_p2_tet_space /
+    meshgen numbering (vertex v -> v, edge (a, d) -> n_nodes + 7 a + d - 1).  numpy or torch int64."""
+    vpp = (int(shape[0]) + 1) * (int(shape[1]) + 1)
+    nn = vpp * (int(shape[2]) + 1)
+    B = 8 * vpp
+    z, r = g // B, g % B
+    d, u = r // vpp, r % vpp
+    v = z * vpp + u
+    return (d == 0) * v + (d != 0) * (nn + 7 * v + d - 1)
+
+
 # ----------------------------------------------------------------------------- transports
 class TorchDistTransport:
     """One rank per process (`torch.distributed`, backend nccl on GPUs / gloo on the CPU)."""
@@ -695,14 +786,15 @@ class RankPipeline:
         bs = int(kw.pop("bs", 1))
         if degree == 2 and self.mesh.tdim == 3:
             # P2 on tetrahedra (BASELINE configs[3]): vertex dofs + edge dofs generated on the device
-            if world != 1:
-                raise NotImplementedError("P2 spaces on tetrahedra: single rank only")
             import torch
 
-            self.V = dp.device_p2_tet_space(self.mesh, bs)
-            nd = self.V.num_dofs
-            self.imap = IndexMap(rank, world, nd, 0, self.imap.ghost_global, self.imap.ghost_owner,
-                                 torch.arange(nd, device=self.mesh.x.device))
+            if world == 1:
+                self.V = dp.device_p2_tet_space(self.mesh, bs)
+                nd = self.V.num_dofs
+                self.imap = IndexMap(rank, world, nd, 0, self.imap.ghost_global, self.imap.ghost_owner,
+                                     torch.arange(nd, device=self.mesh.x.device))
+            else:  # dofs numbered plane block by plane block, owned ranges contiguous (p2_tet_slab_space)
+                self.V, self.imap = p2_tet_slab_space(self.mesh, self.imap, shape, self.ranges, rank, world, bs)
         elif degree == 2:
             # P2 on triangles: vertex dofs + one dof per edge; on these meshes edge == facet and local edge e is
             # opposite local vertex e (Basix), exactly the c2f convention -> edge dof = n_vertices + facet id
@@ -718,9 +810,7 @@ class RankPipeline:
                                  torch.arange(nd, device=dm.device))
         elif degree != 1:
             raise ValueError("degree must be 1 or 2")
-        elif bs != 1:
-            if world != 1:
-                raise NotImplementedError("blocked spaces: single rank only")
+        elif bs != 1:  # blocked P1: the index map counts blocks, as DOLFINx's does
             self.V = FunctionSpace(self.mesh, 1, self.V.dofmap, self.V.num_dofs, self.V.num_dofs_owned, bs, None)
         if problem == "elasticity":
             from .demo_elasticity import CutElasticity
@@ -768,7 +858,10 @@ class RankPipeline:
                                                               DEVICE, 0, C.byref(facets._h)))
         rows4 = facet_integration_rows_device(mesh, facets)
         a = _fem.CutForm(V, 2)
-        a.add_cell_integral("laplace", cells[: mesh.num_cells_local].contiguous(), None, (1.0,))
+        if V.bs > 1:  # any bilinear family of the space does: only the pattern of the form is used
+            a.add_cell_integral("elasticity", cells[: mesh.num_cells_local].contiguous(), None, (1.0, 1.0))
+        else:
+            a.add_cell_integral("laplace", cells[: mesh.num_cells_local].contiguous(), None, (1.0,))
         a.add_interior_facet_integral("ghost_grad_jump", rows=rows4, constants=(1.0,))
         Ag = _fem.create_ghost_row_pattern(a, im.n_owned)
         rp, ci = Ag.indptr_device(), Ag.indices_device()
@@ -927,7 +1020,11 @@ class RankPipeline:
         colmap = np.concatenate([l2g, extra])
         e = int(rp[n_owned])
         rows = np.repeat(np.arange(n_owned), np.diff(rp[: n_owned + 1]))
-        b = self.prob.b.cpu().numpy()[:n_owned]
+        bs = int(getattr(self.V, "bs", 1) or 1)
+        b = self.prob.b.cpu().numpy()[: n_owned * bs]
+        if bs > 1:  # blocked space: rows / columns are block indices, values (entries, bs, bs), b (n_owned, bs)
+            return (rows + self.imap.offset, colmap[cols[:e]], vals[: e * bs * bs].reshape(e, bs, bs),
+                    b.reshape(n_owned, bs), self.imap.offset)
         return rows + self.imap.offset, colmap[cols[:e]], vals[:e], b, self.imap.offset
 
 

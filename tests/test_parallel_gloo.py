@@ -225,6 +225,61 @@ def test_partition_invariants(shape, world):
     assert len(count) == nf_global
 
 
+@pytest.mark.parametrize("shape,world", [((4, 3, 6), 2), ((3, 4, 7), 3), ((3, 3, 5), 5), ((3, 2, 4), 1)])
+def test_p2_tet_partition_invariants(shape, world):
+    """P2 spaces on slab partitions (parallel.p2_tet_slab_space, the space of BASELINE configs[3] on N ranks): one
+    global id per vertex / edge whatever rank looks at it, owned ids a partition of the id range into contiguous
+    blocks, ghost owners right, and the map to the serial numbering of csrc/meshgen.cu."""
+    p0, p1 = box(3)
+    full = M.create_box(*shape, p0, p1)
+    V2 = M.functionspace(full, 2)
+    coord_of, owned_ranges, ghosts = {}, [], []
+    for rank in range(world):
+        ranges = P.slab_ranges(shape[2], world)
+        mesh, V1, im1 = P.partition_slab(shape, p0, p1, world, rank, ranges=ranges)
+        V, im = P.p2_tet_slab_space(mesh, im1, shape, ranges, rank, world, bs=3)
+        assert V.nd == 10 and V.bs == 3 and V.num_dofs == im.n_total and V.num_dofs_owned == im.n_owned
+        l2g = im.l2g.numpy()
+        assert np.array_equal(l2g[: im.n_owned], np.arange(im.offset, im.offset + im.n_owned))
+        assert np.all(np.diff(im.ghost_global.numpy()) > 0)
+        assert set(im.ghost_owner.tolist()) <= {rank - 2, rank - 1, rank + 1}
+        owned_ranges.append((im.offset, im.offset + im.n_owned))
+        ghosts.append((im.ghost_global.numpy(), im.ghost_owner.numpy()))
+        # the first four dofs of a cell are its vertices, then the Basix edges: compare coordinates across ranks
+        g = l2g[V.dofmap]
+        x = mesh.x
+        xc = x[mesh.x_dofmap]                                                     # (nc, 4, 3)
+        mid = np.stack([0.5 * (xc[:, a] + xc[:, b]) for a, b in M.TET_EDGES], axis=1)
+        pts = np.concatenate([xc, mid], axis=1).reshape(-1, 3)
+        for gid, pt in zip(g.reshape(-1).tolist(), np.round(pts * 840).astype(np.int64).tolist()):
+            assert coord_of.setdefault(gid, tuple(pt)) == tuple(pt)
+        # owned cells touch owned dofs or ghosts; every dof of a local cell is inside the local numbering
+        assert V.dofmap.min() >= 0 and V.dofmap.max() < im.n_total
+    # distinct ids <-> distinct points, and as many as the serial P2 space has
+    assert len(set(coord_of.values())) == len(coord_of) == V2.num_dofs
+    # owned ranges tile [0, end)
+    owned_ranges.sort()
+    assert owned_ranges[0][0] == 0 and all(a[1] == b[0] for a, b in zip(owned_ranges, owned_ranges[1:]))
+    for gg, go in ghosts:
+        for gid, q in zip(gg.tolist(), go.tolist()):
+            assert owned_ranges[q][0] <= gid < owned_ranges[q][1]
+    # map to the serial numbering: vertices keep their lexicographic id, edges n_nodes + 7 a + direction - 1
+    gids = np.array(sorted(coord_of))
+    ser = P.p2_tet_global_to_serial(gids, shape)
+    assert np.unique(ser).size == ser.size
+    nn = full.num_nodes
+    sx, sxy = shape[0] + 1, (shape[0] + 1) * (shape[1] + 1)
+    for gid, sid in zip(gids.tolist(), ser.tolist()):
+        pt = np.array(coord_of[gid]) / (840)
+        if sid < nn:
+            assert np.allclose(full.x[sid], pt)
+        else:
+            a, d = divmod(sid - nn, 7)
+            d += 1
+            bvert = a + (d & 1) + ((d >> 1) & 1) * sx + (d >> 2) * sxy
+            assert np.allclose(0.5 * (full.x[a] + full.x[bvert]), pt)
+
+
 # ----------------------------------------------------------------------------- in-process ranks
 @pytest.mark.parametrize("shape,world", [((8, 8, 8), 2), ((6, 6, 9), 3), ((16, 16), 2), ((12, 12), 3), ((6, 6, 6), 1),
                                          ((6, 6, 16), 8)])  # 8 thin slabs: the end ranks own no active cell

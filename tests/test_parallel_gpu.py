@@ -175,3 +175,85 @@ def test_two_gpus_static_plan_graph_match_serial(shape, tmp_path, built_lib):
         d = np.load(tmp_path / f"part{rank}.npz")
         parts.append((d["rows"], d["cols"], d["vals"], d["b"], int(d["off"])))
     compare_with_serial(parts, shape)
+
+
+# ----------------------------------------------------------------------------- blocked / P2 spaces on several ranks
+def _scalar_coo(rows, cols, vals, bs, n):
+    import scipy.sparse as sp
+
+    i = np.arange(bs)
+    r = (rows[:, None, None] * bs + i[None, :, None]) + 0 * i[None, None, :]
+    c = (cols[:, None, None] * bs + i[None, None, :]) + 0 * i[None, :, None]
+    A = sp.csr_matrix((vals.reshape(-1), (r.reshape(-1), c.reshape(-1))), shape=(n, n))
+    assert A.nnz == r.size  # no duplicate (row, col)
+    A.sort_indices()
+    return A
+
+
+@pytest.mark.parametrize("shape,world,degree", [((6, 6, 8), 2, 2), ((4, 4, 9), 3, 2), ((6, 6, 8), 2, 1)])
+def test_static_plan_blocked_spaces_match_serial(shape, world, degree, built_lib):
+    """BASELINE configs[3] on N ranks: linear elasticity on a P2 (and P1) VECTOR space, slab partition with the P2
+    dofs numbered by parallel.p2_tet_slab_space, static exchange plan with COMPACT value messages (bs x bs blocks of
+    the entries present this step only).  The union of the ranks' owned rows equals the one-rank device assembly
+    (itself compared with the oracle in test_gpu_elasticity): pattern bit-exact, blocks and right-hand side 1e-11."""
+    from cutfemx_b200 import parallel as P
+
+    p0, p1 = box(3)
+    kind, prm = "sphere", (0.5, 0.5, 0.5, 0.35, 0.0)
+    kw = dict(order=4, degree=degree, problem="elasticity", bs=3)
+    one = P.RankPipeline(shape, p0, p1, 1, 0, 0, kind, prm, **kw)
+    one.step_static()
+    A1 = one.prob.A
+    n1 = one.V.num_dofs
+    rows1 = np.repeat(np.arange(n1), np.diff(A1.indptr))
+    cols1 = A1.indices.astype(np.int64)
+    vals1 = A1.data.reshape(-1, 3, 3)
+    b1 = one.prob.b.cpu().numpy().reshape(n1, 3)
+    used = np.zeros(n1, dtype=bool)
+    used[np.unique(one.V.dofmap.cpu().numpy())] = True
+    keep = used[rows1]
+    ref = _scalar_coo(rows1[keep], cols1[keep], vals1[keep], 3, 3 * n1)
+
+    pipes = [P.RankPipeline(shape, p0, p1, world, r, 0, kind, prm, **kw) for r in range(world)]
+    P.plan(pipes, P.LocalTransport(world), static=True)
+    for p in pipes:
+        p.prob.persistent = True
+        p.ctx.set_deferred(False, 0.25)
+    P.run_step_static(pipes)
+
+    def parts():
+        for p in pipes:
+            p.prob.A._cache.clear()
+        return [p.owned_matrix_global() for p in pipes]
+
+    def to_serial(g):
+        return P.p2_tet_global_to_serial(g, shape) if degree == 2 else g
+
+    got = parts()
+    rows = np.concatenate([to_serial(q[0]) for q in got])
+    cols = np.concatenate([to_serial(q[1]) for q in got])
+    vals = np.concatenate([q[2] for q in got])
+    keep = used[rows]
+    A = _scalar_coo(rows[keep], cols[keep], vals[keep], 3, 3 * n1)
+    assert np.array_equal(A.indptr, ref.indptr) and np.array_equal(A.indices, ref.indices)
+    assert np.linalg.norm(A.data - ref.data) <= 1e-11 * np.linalg.norm(ref.data)
+    b = np.zeros((n1, 3))
+    for q in got:
+        ids = to_serial(np.arange(q[4], q[4] + q[3].shape[0]))
+        b[ids] = q[3]
+    assert np.linalg.norm(b - b1) <= 1e-11 * np.linalg.norm(b1)
+    assert np.linalg.norm(b1) > 0 and ref.nnz > 0
+    # a deferred-size step (message capacities instead of exact sizes, nothing reaches the host): bit-identical
+    for p in pipes:
+        p.finish_step()
+    P.run_step_static(pipes)
+    for p in pipes:
+        p.finish_step()
+        p.ctx.set_deferred(True)
+    P.run_step_static(pipes)
+    for p in pipes:
+        p.finish_step()
+        p.ctx.check()
+    for x, y in zip(parts(), got):
+        for u, v in zip(x[:4], y[:4]):
+            assert np.array_equal(u, v)
