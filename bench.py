@@ -297,7 +297,8 @@ def run_ours(args, wl):
     ranges = P.slab_ranges(n, world, P.layer_weights([n] * tdim, wl["p0"], wl["p1"], ls_fn)) if world > 1 else None
     pipe = P.RankPipeline([n] * tdim, list(wl["p0"]), list(wl["p1"]), world, rank, local_rank, kind, prm,
                           order=wl["order"], ranges=ranges, degree=wl.get("degree", 1),
-                          **({"problem": wl["problem"], "bs": wl.get("bs", 1)} if "problem" in wl else {}))
+                          **({"problem": wl["problem"], "bs": wl.get("bs", 1), "p2_numbering": "blocks"}
+                             if "problem" in wl else {}))
     bsz = int(V_bs(pipe))
     prob, ctx, V = pipe.prob, pipe.ctx, pipe.V
     sync()
@@ -557,7 +558,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
-    ap.add_argument("--n", type=int, default=0, help="override the mesh resolution of the workload")
+    ap.add_argument("--n", "--mesh-n", dest="n", type=int, default=0,
+                    help="override the mesh resolution of the workload (--mesh-n under torchrun, whose own parser "
+                         "takes --n for an abbreviation of its options)")
     ap.add_argument("--e2e-cap-gb", type=float, default=8.0,
                     help="skip the host-buffer leg when one step's CSR is larger than this (pinned host memory)")
     ap.add_argument("--ref-n", type=int, default=0, help="resolution of the bounded CPU sample")

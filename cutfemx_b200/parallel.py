@@ -784,11 +784,13 @@ class RankPipeline:
         self.ls_kind, self.ls_params = ls_kind, ls_params
         problem = kw.pop("problem", "poisson")
         bs = int(kw.pop("bs", 1))
+        # "blocks": the partition's plane-block numbering on one rank too (bench.py: the same rows for every N)
+        p2_numbering = kw.pop("p2_numbering", "serial")
         if degree == 2 and self.mesh.tdim == 3:
             # P2 on tetrahedra (BASELINE configs[3]): vertex dofs + edge dofs generated on the device
             import torch
 
-            if world == 1:
+            if world == 1 and p2_numbering != "blocks":
                 self.V = dp.device_p2_tet_space(self.mesh, bs)
                 nd = self.V.num_dofs
                 self.imap = IndexMap(rank, world, nd, 0, self.imap.ghost_global, self.imap.ghost_owner,

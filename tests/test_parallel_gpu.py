@@ -190,7 +190,7 @@ def _scalar_coo(rows, cols, vals, bs, n):
     return A
 
 
-@pytest.mark.parametrize("shape,world,degree", [((6, 6, 8), 2, 2), ((4, 4, 9), 3, 2), ((6, 6, 8), 2, 1)])
+@pytest.mark.parametrize("shape,world,degree", [((6, 6, 8), 2, 2), ((4, 4, 9), 3, 2), ((6, 6, 8), 2, 1), ((4, 4, 5), 1, 2)])
 def test_static_plan_blocked_spaces_match_serial(shape, world, degree, built_lib):
     """BASELINE configs[3] on N ranks: linear elasticity on a P2 (and P1) VECTOR space, slab partition with the P2
     dofs numbered by parallel.p2_tet_slab_space, static exchange plan with COMPACT value messages (bs x bs blocks of
@@ -214,7 +214,7 @@ def test_static_plan_blocked_spaces_match_serial(shape, world, degree, built_lib
     keep = used[rows1]
     ref = _scalar_coo(rows1[keep], cols1[keep], vals1[keep], 3, 3 * n1)
 
-    pipes = [P.RankPipeline(shape, p0, p1, world, r, 0, kind, prm, **kw) for r in range(world)]
+    pipes = [P.RankPipeline(shape, p0, p1, world, r, 0, kind, prm, p2_numbering="blocks", **kw) for r in range(world)]
     P.plan(pipes, P.LocalTransport(world), static=True)
     for p in pipes:
         p.prob.persistent = True
@@ -257,3 +257,78 @@ def test_static_plan_blocked_spaces_match_serial(shape, world, degree, built_lib
     for x, y in zip(parts(), got):
         for u, v in zip(x[:4], y[:4]):
             assert np.array_equal(u, v)
+
+
+def _nccl_blocked_worker(rank, world, shape, port, outdir):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    try:
+        from cutfemx_b200 import parallel as P
+
+        p0, p1 = box(3)
+        pipe = P.RankPipeline(shape, p0, p1, world, rank, rank, "sphere", (0.5, 0.5, 0.5, 0.35, 0.0), order=4,
+                              degree=2, problem="elasticity", bs=3)
+        P.plan([pipe], P.TorchDistTransport(), static=True)
+        P.init_nccl(pipe.ctx, rank, world)
+        g = pipe.capture_static()       # eager (exact message sizes), deferred and captured steps (capacities)
+        for _ in range(2):
+            pipe.prob.replay()
+        pipe.ctx.check()
+        pipe.prob.A._cache.clear()
+        rows, cols, vals, b, off = pipe.owned_matrix_global()
+        np.savez(os.path.join(outdir, f"part{rank}.npz"), rows=rows, cols=cols, vals=vals, b=b, off=off,
+                 nodes=g.kernel_nodes)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpus_blocked_p2_graph_match_serial(tmp_path, built_lib):
+    """configs[3] on two GPUs: the whole rank step, NCCL exchange of compact block messages included, as one CUDA
+    graph; union of the owned rows == the one-rank device assembly."""
+    import socket
+
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    from cutfemx_b200 import parallel as P
+
+    shape = (6, 6, 8)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_nccl_blocked_worker, args=(2, shape, port, str(tmp_path)), nprocs=2, join=True)
+    p0, p1 = box(3)
+    one = P.RankPipeline(shape, p0, p1, 1, 0, 0, "sphere", (0.5, 0.5, 0.5, 0.35, 0.0), order=4, degree=2,
+                         problem="elasticity", bs=3)
+    one.step_static()
+    A1, n1 = one.prob.A, one.V.num_dofs
+    rows1 = np.repeat(np.arange(n1), np.diff(A1.indptr))
+    used = np.zeros(n1, dtype=bool)
+    used[np.unique(one.V.dofmap.cpu().numpy())] = True
+    keep = used[rows1]
+    ref = _scalar_coo(rows1[keep], A1.indices.astype(np.int64)[keep], A1.data.reshape(-1, 3, 3)[keep], 3, 3 * n1)
+    b1 = one.prob.b.cpu().numpy().reshape(n1, 3)
+    rows, cols, vals, b = [], [], [], np.zeros((n1, 3))
+    for rank in range(2):
+        d = np.load(tmp_path / f"part{rank}.npz")
+        rows.append(P.p2_tet_global_to_serial(d["rows"], shape))
+        cols.append(P.p2_tet_global_to_serial(d["cols"], shape))
+        vals.append(d["vals"])
+        off = int(d["off"])
+        b[P.p2_tet_global_to_serial(np.arange(off, off + d["b"].shape[0]), shape)] = d["b"]
+    rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
+    keep = used[rows]
+    A = _scalar_coo(rows[keep], cols[keep], vals[keep], 3, 3 * n1)
+    assert np.array_equal(A.indptr, ref.indptr) and np.array_equal(A.indices, ref.indices)
+    assert np.linalg.norm(A.data - ref.data) <= 1e-11 * np.linalg.norm(ref.data)
+    assert np.linalg.norm(b - b1) <= 1e-11 * np.linalg.norm(b1)
