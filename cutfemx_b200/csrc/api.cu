@@ -211,15 +211,105 @@ void cfx_ctx_destroy(cfx_ctx* ctx)
     cudaEventDestroy(s.e0);
     cudaEventDestroy(s.e1);
   }
+  for (auto& L : ctx->lanes)
+  {
+    if (L.stream)
+    {
+      cudaStreamSynchronize(L.stream);
+      cudaStreamDestroy(L.stream);
+    }
+    if (L.ev_fork)
+      cudaEventDestroy(L.ev_fork);
+    if (L.ev_join)
+      cudaEventDestroy(L.ev_join);
+  }
   ctx->pool.release_all();
   if (ctx->h_pinned)
     cudaFreeHost(ctx->h_pinned);
   delete ctx;
 }
 
+namespace
+{
+void swap_lane_scratch(cfx_ctx* c, cfx_ctx::Lane& L)
+{
+  std::swap(c->blk_counts, L.blk_counts);
+  std::swap(c->blk_offsets, L.blk_offsets);
+  std::swap(c->scratch64, L.scratch64);
+  std::swap(c->scratch8, L.scratch8);
+}
+} // namespace
+
+// The calls between cfx_lane_begin(ctx, k) and cfx_lane_end(ctx) are issued on lane k's stream, ordered after
+// everything issued on the main stream so far; cfx_lane_join(ctx) orders the main stream after all lanes.
+cfx_status cfx_lane_begin(cfx_ctx* ctx, int k)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && k >= 1 && k < cfx::DevPool::LANES, CFX_ERR_INVALID, "cfx_lane_begin: lane out of range");
+  CFX_REQUIRE(ctx->lane == 0, CFX_ERR_STATE, "cfx_lane_begin: a lane is already current (lanes do not nest)");
+  // tables that calls build lazily once per cfx_update and then share (the cut-cell lists behind run-time rules and
+  // ghost-penalty facets) are completed on the main stream first: two lanes must not race to build / read them
+  if (ctx->classified)
+    for (int i = 0; i < CFX_MAX_LEVEL_SETS; ++i)
+      if (ctx->ls[i].bound)
+      {
+        cfx::ensure_cut_list(ctx, i);
+        if (ctx->nc_total != ctx->nc_owned)
+          cfx::ensure_cut_list_all(ctx, i);
+      }
+  cfx_ctx::Lane& L = ctx->lanes[k];
+  if (!L.stream)
+  {
+    CFX_CUDA(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+    CFX_CUDA(cudaEventCreateWithFlags(&L.ev_fork, cudaEventDisableTiming));
+    CFX_CUDA(cudaEventCreateWithFlags(&L.ev_join, cudaEventDisableTiming));
+  }
+  CFX_CUDA(cudaEventRecord(L.ev_fork, ctx->stream));
+  CFX_CUDA(cudaStreamWaitEvent(L.stream, L.ev_fork, 0));
+  ctx->main_stream = ctx->stream;
+  ctx->stream = L.stream;
+  swap_lane_scratch(ctx, L);
+  ctx->pool.set_lane(k);
+  ctx->lane = k;
+  L.open = true;
+  CFX_API_END(ctx)
+}
+
+cfx_status cfx_lane_end(cfx_ctx* ctx)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx, CFX_ERR_INVALID, "cfx_lane_end: NULL context");
+  if (ctx->lane == 0)
+    return CFX_OK;
+  cfx_ctx::Lane& L = ctx->lanes[ctx->lane];
+  swap_lane_scratch(ctx, L);
+  ctx->stream = ctx->main_stream;
+  ctx->main_stream = nullptr;
+  ctx->pool.set_lane(0);
+  ctx->lane = 0;
+  CFX_API_END(ctx)
+}
+
+cfx_status cfx_lane_join(cfx_ctx* ctx)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && ctx->lane == 0, CFX_ERR_STATE, "cfx_lane_join: end the current lane first");
+  for (auto& L : ctx->lanes)
+    if (L.open)
+    {
+      CFX_CUDA(cudaEventRecord(L.ev_join, L.stream));
+      CFX_CUDA(cudaStreamWaitEvent(ctx->stream, L.ev_join, 0));
+      L.open = false;
+    }
+  CFX_API_END(ctx)
+}
+
 cfx_status cfx_sync(cfx_ctx* ctx)
 {
   CFX_API_BEGIN
+  for (auto& L : ctx->lanes)
+    if (L.open && L.stream)
+      CFX_CUDA(cudaStreamSynchronize(L.stream));
   CFX_CUDA(cudaStreamSynchronize(ctx->stream));
   CFX_API_END(ctx)
 }
@@ -295,6 +385,9 @@ cfx_status cfx_graph_begin(cfx_ctx* ctx)
 {
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && !ctx->capturing, CFX_ERR_STATE, "cfx_graph_begin: a capture is already in progress");
+  CFX_REQUIRE(ctx->lane == 0, CFX_ERR_STATE, "cfx_graph_begin: end the current lane first");
+  for (auto& L : ctx->lanes)
+    CFX_REQUIRE(!L.open, CFX_ERR_STATE, "cfx_graph_begin: join the lanes first (cfx_lane_join)");
   CFX_REQUIRE(ctx->deferred, CFX_ERR_STATE,
               "cfx_graph_begin: switch the context to deferred-size mode first (cfx_set_deferred) and run the step "
               "once, so that no captured call needs a size on the host");
@@ -323,6 +416,9 @@ cfx_status cfx_graph_end(cfx_ctx* ctx, cfx_graph** out)
 {
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && ctx->capturing && out, CFX_ERR_STATE, "cfx_graph_end: no capture in progress");
+  if (ctx->lane != 0)
+    cfx_lane_end(ctx);
+  cfx_lane_join(ctx); // every forked stream must be back in the capturing stream
   cudaStream_t cap = ctx->stream;
   cudaGraph_t g = nullptr;
   const cudaError_t e = cudaStreamEndCapture(cap, &g);

@@ -59,30 +59,45 @@ public:
   // replays, and blocks cached before the capture must not become graph temporaries that a later eager call could
   // be handed as well.  begin_capture() sets the cache aside; end_capture() returns everything freed during the
   // capture (now owned by the graph) and restores the cache.
-  void begin_capture() { stash_.swap(free_); }
+  // Lanes (cfx_lane_begin): every lane of a context issues its work on a stream of its own, so a block one lane
+  // frees must not be handed to another lane whose stream is not ordered after the first -- each lane has its own
+  // cache of free blocks (a block returns to the cache of the lane that is current when it is freed: its last
+  // users are that lane's stream, or work that the fork / join events order before it).
+  enum { LANES = 4 };
+  void set_lane(int k) { cur_ = k; }
+  void begin_capture()
+  {
+    for (int k = 0; k < LANES; ++k)
+      stash_[k].swap(free_[k]);
+  }
   std::vector<std::pair<size_t, void*>> end_capture()
   {
-    std::vector<std::pair<size_t, void*>> owned(free_.begin(), free_.end());
-    free_.clear();
-    stash_.swap(free_);
+    std::vector<std::pair<size_t, void*>> owned;
+    for (int k = 0; k < LANES; ++k)
+    {
+      owned.insert(owned.end(), free_[k].begin(), free_[k].end());
+      free_[k].clear();
+      stash_[k].swap(free_[k]);
+    }
     return owned;
   }
   void give_back(const std::vector<std::pair<size_t, void*>>& blocks)
   {
     for (auto& b : blocks)
-      free_.emplace(b.first, b.second);
+      free_[0].emplace(b.first, b.second);
   }
   void* alloc(size_t bytes)
   {
     if (bytes == 0)
       bytes = 256;
     bytes = (bytes + 255) & ~size_t(255);
-    auto it = free_.lower_bound(bytes);
-    if (it != free_.end() && it->first <= 2 * bytes + (size_t(1) << 20))
+    auto& fr = free_[cur_];
+    auto it = fr.lower_bound(bytes);
+    if (it != fr.end() && it->first <= 2 * bytes + (size_t(1) << 20))
     {
       void* p = it->second;
       size_t sz = it->first;
-      free_.erase(it);
+      fr.erase(it);
       live_[p] = sz;
       return p;
     }
@@ -106,20 +121,21 @@ public:
     auto it = live_.find(p);
     if (it == live_.end())
       return;
-    free_.emplace(it->second, p);
+    free_[cur_].emplace(it->second, p);
     live_.erase(it);
   }
   void release_cached()
   {
-    for (auto* m : {&free_, &stash_})
-    {
-      for (auto& kv : *m)
+    for (int k = 0; k < LANES; ++k)
+      for (auto* m : {&free_[k], &stash_[k]})
       {
-        cudaFree(kv.second);
-        total_ -= kv.first;
+        for (auto& kv : *m)
+        {
+          cudaFree(kv.second);
+          total_ -= kv.first;
+        }
+        m->clear();
       }
-      m->clear();
-    }
   }
   void release_all()
   {
@@ -132,7 +148,8 @@ public:
   size_t total_bytes() const { return total_; }
 
 private:
-  std::multimap<size_t, void*> free_, stash_;
+  std::multimap<size_t, void*> free_[LANES], stash_[LANES];
+  int cur_ = 0;
   std::unordered_map<void*, size_t> live_;
   size_t total_ = 0;
 };
@@ -461,6 +478,24 @@ struct cfx_ctx
 
   bool timing = false;
   std::vector<cfx::Stage> stages;
+
+  // Lanes: independent call sequences of one step (volume rules | interface rules + normals | ghost-penalty facets |
+  // cell lists) issued on streams of their own between cfx_lane_begin / cfx_lane_end and joined into the main
+  // stream by cfx_lane_join -- concurrent kernels on the device, parallel branches in a captured graph.  A lane has
+  // its own stream, its own cache of free blocks (DevPool) and its own scan / compaction scratch.
+  struct Lane
+  {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool open = false; // has work that the main stream has not joined yet
+    cfx::DevBuf<int32_t> blk_counts;
+    cfx::DevBuf<int64_t> blk_offsets;
+    cfx::DevBuf<int64_t> scratch64;
+    cfx::DevBuf<uint8_t> scratch8;
+  };
+  Lane lanes[cfx::DevPool::LANES];
+  int lane = 0;                       // the current lane (0 = the main stream)
+  cudaStream_t main_stream = nullptr; // the main stream while a lane is current
 };
 
 namespace cfx

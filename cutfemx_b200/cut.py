@@ -73,6 +73,27 @@ class Context:
         check(self._h, lib().cfx_graph_end(self._h, C.byref(g._h)))
         return g
 
+    # -- lanes: independent call sequences of a step on streams of their own (cfx_lane_begin / _end / _join)
+    def lane(self, k: int):
+        """`with ctx.lane(k): ...` -- the calls inside run on lane k (1..3), concurrently with the other lanes and
+        with later main-stream calls; `ctx.join()` before anything uses their results."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def scope():
+            if k <= 0:
+                yield
+                return
+            check(self._h, lib().cfx_lane_begin(self._h, int(k)))
+            try:
+                yield
+            finally:
+                check(self._h, lib().cfx_lane_end(self._h))
+        return scope()
+
+    def join(self):
+        check(self._h, lib().cfx_lane_join(self._h))
+
     # -- profiling hooks
     def stage_timing(self, on: bool):
         check(self._h, lib().cfx_stage_timing_enable(self._h, int(on)))

@@ -32,13 +32,18 @@ class CutElasticity(CutPoisson):
         cd = self.cut_data
         k = self.keep if self.persistent else {}
         mu, lam = self.mu, self.lam
+        ln = self.lanes
         _cut.update(cd)
+        with self.ctx.lane(ln[0]):
+            rv = _cut.runtime_quadrature(cd, "phi<0", self.order, out=k.get("rv"))
+        with self.ctx.lane(ln[1]):
+            ri = _cut.runtime_quadrature(cd, "phi=0", self.order, out=k.get("ri"))
+            _ls.attach_normal(cd, self.phi, ri)
+        with self.ctx.lane(ln[2]):
+            ghost = _cut.ghost_penalty_facets_device(cd, "phi<0", out=k.get("ghost"))
+            rows = _cut.facet_integration_rows_device(self.mesh, ghost, out=k.get("rows"))
         inside = _cut.locate_entities_device(cd, "phi<0", out=k.get("inside"))
-        rv = _cut.runtime_quadrature(cd, "phi<0", self.order, out=k.get("rv"))
-        ri = _cut.runtime_quadrature(cd, "phi=0", self.order, out=k.get("ri"))
-        _ls.attach_normal(cd, self.phi, ri)
-        ghost = _cut.ghost_penalty_facets_device(cd, "phi<0", out=k.get("ghost"))
-        rows = _cut.facet_integration_rows_device(self.mesh, ghost, out=k.get("rows"))
+        self.ctx.join()
         a = _fem.CutForm(self.V, 2)
         a.add_cell_integral("elasticity", inside, rv, (mu, lam))
         a.add_cell_integral("nitsche_vec", None, ri, (mu, lam, self.gamma))

@@ -9,6 +9,7 @@ bench.py times it, __graft_entry__.smoke() runs it once, tests compare it with t
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -105,18 +106,26 @@ class CutPoisson:
         self.persistent = False
         self.keep = {}
         self.graph = None
+        # lanes of the three independent branches of build_forms (0 = the main stream; CFX_NO_LANES=1: A/B switch)
+        self.lanes = (0, 0, 0) if os.environ.get("CFX_NO_LANES") else (1, 2, 3)
 
     def build_forms(self, assemble_rhs: bool = True):
         """update -> locate -> rules -> normals -> ghost facets -> the forms a and L."""
         cd = self.cut_data
         k = self.keep if self.persistent else {}
+        ln = self.lanes
         _cut.update(cd)                                                     # cutfemx.update
+        # the four results below depend on the classification only: each on a lane (stream) of its own
+        with self.ctx.lane(ln[0]):
+            rv = _cut.runtime_quadrature(cd, "phi<0", self.order, out=k.get("rv"))          # volume rules
+        with self.ctx.lane(ln[1]):
+            ri = _cut.runtime_quadrature(cd, "phi=0", self.order, out=k.get("ri"))          # interface rules
+            _ls.attach_normal(cd, self.phi, ri)                             # n = normal(phi)
+        with self.ctx.lane(ln[2]):
+            ghost = _cut.ghost_penalty_facets_device(cd, "phi<0", out=k.get("ghost"))       # ghost_penalty_facets
+            rows = _cut.facet_integration_rows_device(self.mesh, ghost, out=k.get("rows"))  # facet_integration_rows
         inside = _cut.locate_entities_device(cd, "phi<0", out=k.get("inside"))          # locate_entities
-        rv = _cut.runtime_quadrature(cd, "phi<0", self.order, out=k.get("rv"))          # volume rules
-        ri = _cut.runtime_quadrature(cd, "phi=0", self.order, out=k.get("ri"))          # interface rules
-        _ls.attach_normal(cd, self.phi, ri)                                 # n = normal(phi)
-        ghost = _cut.ghost_penalty_facets_device(cd, "phi<0", out=k.get("ghost"))       # ghost_penalty_facets
-        rows = _cut.facet_integration_rows_device(self.mesh, ghost, out=k.get("rows"))  # facet_integration_rows
+        self.ctx.join()
         a = _fem.CutForm(self.V, 2)
         a.add_cell_integral("laplace", inside, rv, (1.0,))
         a.add_cell_integral("nitsche", None, ri, (self.gamma,))

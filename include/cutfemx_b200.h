@@ -112,6 +112,16 @@ cfx_status cfx_graph_end(cfx_ctx* ctx, cfx_graph** out);
 cfx_status cfx_graph_launch(cfx_ctx* ctx, cfx_graph* g);
 int64_t cfx_graph_kernel_nodes(const cfx_graph* g);
 void cfx_graph_free(cfx_ctx* ctx, cfx_graph* g);
+/* Lanes: independent call sequences of one step -- in python/demo/demo_poisson.py:156-175 the volume rules, the
+ * interface rules with their normals, the ghost-penalty facets and the cell lists all depend on cutfemx.update only
+ * -- may be issued on streams of their own: the calls between cfx_lane_begin(ctx, k) (k = 1..3) and cfx_lane_end are
+ * ordered after everything issued on the main stream so far and run concurrently with the other lanes and with
+ * later main-stream work; cfx_lane_join orders the main stream after every lane (call it before anything consumes a
+ * lane's results).  Inside a graph capture the lanes become parallel branches of the graph.  Each lane has its own
+ * stream, free-block cache and scan scratch; lanes do not nest.  Results are bit-identical with or without lanes. */
+cfx_status cfx_lane_begin(cfx_ctx* ctx, int lane);
+cfx_status cfx_lane_end(cfx_ctx* ctx);
+cfx_status cfx_lane_join(cfx_ctx* ctx);
 
 /* ------------------------------------------------------------------ mesh views
  * replaces build_mesh_view, cut.cpp:500-538: x is geometry().x() (stride 3),
