@@ -241,6 +241,33 @@ def run_reference(args, wl):
 
 
 # --------------------------------------------------------------------------------------------- our arm
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's host threads (and so its page-locked buffers: first touch) to the NUMA node of its GPU, so the
+    end-to-end leg's PCIe copies do not cross the socket interconnect.  Returns what it found (None: no NUMA
+    information in this machine / VM, nothing changed)."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"pci": bus, "numa_node": None}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"pci": bus, "numa_node": node, "cpus": len(cpus)}
+    except Exception as e:  # no sysfs entry, no permission: leave the affinity alone
+        return {"numa_node": None, "why": type(e).__name__}
+
+
 def V_bs(pipe):
     return getattr(pipe.V, "bs", 1) or 1
 
@@ -258,6 +285,7 @@ def run_ours(args, wl):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
+    host_binding = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
     from cutfemx_b200 import fem as _fem
@@ -328,6 +356,7 @@ def run_ours(args, wl):
             pipe.move_level_set((x0 + dx * t / period,) + tuple(prm[1:]))
 
     hnd0 = ctx.handle
+    lanes_on = not os.environ.get("CFX_NO_LANES")
     graph = pipe.capture_static(margin=0.25)
     setup["device_bytes"] = ctx.device_bytes
     for _ in range(max(args.warmup, 3)):
@@ -368,6 +397,9 @@ def run_ours(args, wl):
 
     # ---- the same K steps with per-stage CUDA events recorded INSIDE the graph (a second capture with stage
     # timing on): per-kernel durations for the roofline block, measured live on the stream the kernels run on
+    # (lanes off for this capture: concurrent kernels would stretch each other's intervals; the timed steps above ran
+    # the real thing, with the independent branches of the step on lanes of their own)
+    ctx.set_lanes(False)
     ctx.stage_timing(True)
     ctx.stage_reset()
     ctx.graph_begin()
@@ -406,6 +438,7 @@ def run_ours(args, wl):
     ctx.stage_timing(False)
     ctx.stage_reset()
     ctx.set_deferred(True)
+    ctx.set_lanes(lanes_on)
     per_stage = {}
     for k, v in agg.items():
         msk = v[0] / args.steps
@@ -521,7 +554,11 @@ def run_ours(args, wl):
                    "partition": f"{world} work-balanced slabs along the last axis {pipe.ranges}, shared-facet ghost "
                                 f"layer, ghost rows exchanged over NCCL inside the step's graph (fixed-size messages)"
                    if world > 1 else "1 rank (no exchange)",
-                   "step": "one CUDA-graph launch per rank and step (deferred sizes, no host round trip inside it)"},
+                   "step": "one CUDA-graph launch per rank and step (deferred sizes, no host round trip inside it); "
+                           + ("independent branches of the step (volume rules | interface rules + normals | "
+                              "ghost-penalty facets | cell lists; static | band | inactive rows of the pattern and "
+                              "of the gather) are parallel branches of the graph; `stages` are timed in a second, "
+                              "serial capture, so their sum exceeds ms_per_step" if lanes_on else "serial (CFX_NO_LANES)")},
         "nnz_per_s": nnz_total * args.steps / t_total, "total_cells_per_s": cells_total * args.steps / t_total,
         "e2e": ({"value": cut_total * args.steps / t_e2e, "unit": "cut-cells/s", "h2d_bytes_per_step": int(h2d),
                  "d2h_bytes_per_step": int(d2h_total), "ms_per_step": t_e2e / args.steps * 1e3} if not skip_e2e else
@@ -529,7 +566,7 @@ def run_ours(args, wl):
                  f"pinned host buffer sets exceed --e2e-cap-gb {args.e2e_cap_gb}"}),
         "gpu_launches": int(launches_total), "graph_launches_per_step": 1, "kernels_per_step": graph.kernel_nodes,
         "clocks": clocks, "roofline": roof, "stages": per_stage, "stage_sum_ms": stage_sum, "setup": setup,
-        "checks": checks, "space_counters": space_counters,
+        "checks": checks, "space_counters": space_counters, "host_binding": host_binding,
         "per_rank_ms": {"columns": ["stage_sum", "classify", "gather_matrix", "create_sparsity"], "ranks": per_rank},
         "stages_one_eager_step_ms": {k: round(v, 4) for k, v in eager_ms.items()},
     }

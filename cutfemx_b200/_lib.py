@@ -43,7 +43,7 @@ SYMBOLS = [
     "cfx_inactive_dofs", "cfx_deactivate_outside", "cfx_assemble_matrix_bc", "cfx_assemble_system_bc", "cfx_set_diagonal", "cfx_apply_lifting",
     "cfx_set_bc", "cfx_meshgen_box", "cfx_meshgen_rectangle", "cfx_meshgen_level_set", "cfx_meshgen_p2_tet_dofmap",
     "cfx_device_bytes", "cfx_set_deferred", "cfx_check", "cfx_graph_begin", "cfx_graph_end", "cfx_graph_launch",
-    "cfx_lane_begin", "cfx_lane_end", "cfx_lane_join",
+    "cfx_lane_begin", "cfx_lane_end", "cfx_lane_join", "cfx_set_lanes",
     "cfx_graph_kernel_nodes", "cfx_graph_free", "cfx_facet_integration_rows_list", "cfx_form_add_cell_integral_list",
     "cfx_form_add_interior_facet_integral_list", "cfx_comm_unique_id", "cfx_comm_init", "cfx_comm_destroy",
     "cfx_xplan_create", "cfx_xplan_free", "cfx_xplan_pack_pattern", "cfx_xplan_exchange", "cfx_xplan_insert_pattern",

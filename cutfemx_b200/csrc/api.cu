@@ -185,6 +185,7 @@ cfx_status cfx_ctx_create(int device, void* stream, cfx_ctx** out)
   ctx = new cfx_ctx();
   ctx->device = device;
   ctx->stream = static_cast<cudaStream_t>(stream);
+  ctx->lanes_on = getenv("CFX_NO_LANES") == nullptr; // A/B switch
   CFX_CUDA(cudaHostAlloc(&ctx->h_pinned, 72 * sizeof(int64_t), cudaHostAllocMapped));
   ctx->h_pinned[64] = 0;
   CFX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->h_pinned_dev), ctx->h_pinned, 0));
@@ -242,9 +243,11 @@ void swap_lane_scratch(cfx_ctx* c, cfx_ctx::Lane& L)
 
 // The calls between cfx_lane_begin(ctx, k) and cfx_lane_end(ctx) are issued on lane k's stream, ordered after
 // everything issued on the main stream so far; cfx_lane_join(ctx) orders the main stream after all lanes.
-cfx_status cfx_lane_begin(cfx_ctx* ctx, int k)
+} // extern "C"
+namespace cfx
 {
-  CFX_API_BEGIN
+void lane_begin(cfx_ctx* ctx, int k)
+{
   CFX_REQUIRE(ctx && k >= 1 && k < cfx::DevPool::LANES, CFX_ERR_INVALID, "cfx_lane_begin: lane out of range");
   CFX_REQUIRE(ctx->lane == 0, CFX_ERR_STATE, "cfx_lane_begin: a lane is already current (lanes do not nest)");
   // tables that calls build lazily once per cfx_update and then share (the cut-cell lists behind run-time rules and
@@ -272,27 +275,22 @@ cfx_status cfx_lane_begin(cfx_ctx* ctx, int k)
   ctx->pool.set_lane(k);
   ctx->lane = k;
   L.open = true;
-  CFX_API_END(ctx)
 }
 
-cfx_status cfx_lane_end(cfx_ctx* ctx)
+void lane_end(cfx_ctx* ctx) noexcept
 {
-  CFX_API_BEGIN
-  CFX_REQUIRE(ctx, CFX_ERR_INVALID, "cfx_lane_end: NULL context");
-  if (ctx->lane == 0)
-    return CFX_OK;
+  if (!ctx || ctx->lane == 0)
+    return;
   cfx_ctx::Lane& L = ctx->lanes[ctx->lane];
   swap_lane_scratch(ctx, L);
   ctx->stream = ctx->main_stream;
   ctx->main_stream = nullptr;
   ctx->pool.set_lane(0);
   ctx->lane = 0;
-  CFX_API_END(ctx)
 }
 
-cfx_status cfx_lane_join(cfx_ctx* ctx)
+void lane_join(cfx_ctx* ctx)
 {
-  CFX_API_BEGIN
   CFX_REQUIRE(ctx && ctx->lane == 0, CFX_ERR_STATE, "cfx_lane_join: end the current lane first");
   for (auto& L : ctx->lanes)
     if (L.open)
@@ -301,6 +299,40 @@ cfx_status cfx_lane_join(cfx_ctx* ctx)
       CFX_CUDA(cudaStreamWaitEvent(ctx->stream, L.ev_join, 0));
       L.open = false;
     }
+}
+} // namespace cfx
+extern "C"
+{
+cfx_status cfx_lane_begin(cfx_ctx* ctx, int k)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && k >= 1 && k < cfx::DevPool::LANES, CFX_ERR_INVALID, "cfx_lane_begin: lane out of range");
+  if (ctx->lanes_on)
+    cfx::lane_begin(ctx, k);
+  CFX_API_END(ctx)
+}
+
+cfx_status cfx_set_lanes(cfx_ctx* ctx, int on)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx && ctx->lane == 0, CFX_ERR_STATE, "cfx_set_lanes: end the current lane first");
+  cfx::lane_join(ctx);
+  ctx->lanes_on = on != 0;
+  CFX_API_END(ctx)
+}
+
+cfx_status cfx_lane_end(cfx_ctx* ctx)
+{
+  CFX_API_BEGIN
+  CFX_REQUIRE(ctx, CFX_ERR_INVALID, "cfx_lane_end: NULL context");
+  cfx::lane_end(ctx);
+  CFX_API_END(ctx)
+}
+
+cfx_status cfx_lane_join(cfx_ctx* ctx)
+{
+  CFX_API_BEGIN
+  cfx::lane_join(ctx);
   CFX_API_END(ctx)
 }
 

@@ -4195,6 +4195,9 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
   { // the mask / contribution-list kernels need the packed incidence tables (nd <= 6)
     if (fast && S.has_static && a->n_clist_rows > 0)
     {
+      // static rows and band rows are disjoint: this kernel runs on a lane of its own, concurrently with the band
+      // kernel below (joined at the end of this function)
+      LaneScope lane(ctx, (a->n_mask_rows != 0) ? 1 : 0);
       // the dominant kernel, timed on its own: fused K4 (every standard cell's dofmap row, coordinates and
       // dofs: 4 nv + 24 nv + 4 nd B) + K5 (12 B per CSR entry of its rows) -- SURVEY.md section 8(d)
       int64_t n_std = 0;
@@ -4287,6 +4290,8 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
                    zero_first);
     }
   }
+  if (lanes_enabled(ctx))
+    lane_join(ctx);
   if (!fast || a->n_slow_rows > 0)
   {
     auto k = gather_matrix_kernel<TDIM, DEG>;
@@ -4419,6 +4424,21 @@ static void assemble_matrix_impl(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, int 
   for (auto& I : a->integrals)
     if (!I.facet)
       n_std += I.n;
+  if (FI)
+  { // the facet tensors do not depend on the cell tensors: on a lane of their own
+    a->Fe.reserve(ctx->pool, static_cast<size_t>(FI->n) * 4 * nd * nd + 1);
+    LaneScope lane(ctx, 2);
+    StageScope st(ctx, "element_facets",
+                  static_cast<double>(FI->n) * (16.0 + (S.degree == 1 ? 8.0 * (2.0 * nd + 1.0) : 8.0 * 4.0 * nd * nd)));
+    bool acc = false;
+    for (auto& I : a->integrals)
+    {
+      if (!I.facet || I.n == 0)
+        continue;
+      CFX_DISPATCH_ELEM(ctx, S, launch_facet, ctx, I, a, acc);
+      acc = true;
+    }
+  }
   {
     StageScope st(ctx, "element_cells");
     n_mat = run_cell_integrals(ctx, a);
@@ -4440,20 +4460,8 @@ static void assemble_matrix_impl(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, int 
               + (8.0 + 28.0 * ctx->nv + 8.0 * nd) * static_cast<double>(I.rules->nrules);
     st.set_bytes(by);
   }
-  if (FI)
-  {
-    StageScope st(ctx, "element_facets",
-                  static_cast<double>(FI->n) * (16.0 + (S.degree == 1 ? 8.0 * (2.0 * nd + 1.0) : 8.0 * 4.0 * nd * nd)));
-    a->Fe.reserve(ctx->pool, static_cast<size_t>(FI->n) * 4 * nd * nd + 1);
-    bool acc = false;
-    for (auto& I : a->integrals)
-    {
-      if (!I.facet || I.n == 0)
-        continue;
-      CFX_DISPATCH_ELEM(ctx, S, launch_facet, ctx, I, a, acc);
-      acc = true;
-    }
-  }
+  if (lanes_enabled(ctx))
+    lane_join(ctx);
   {
     // fused K4 (standard cells: dofmap row + coordinates + dofs in) + K5 (each CSR value and column once)
     StageScope st(ctx, "gather_matrix",

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -98,7 +99,7 @@ public:
       void* p = it->second;
       size_t sz = it->first;
       fr.erase(it);
-      live_[p] = sz;
+      live_[p] = {sz, cur_};
       return p;
     }
     void* p = nullptr;
@@ -110,7 +111,7 @@ public:
     }
     if (e != cudaSuccess)
       throw Error(CFX_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
-    live_[p] = bytes;
+    live_[p] = {bytes, cur_};
     total_ += bytes;
     return p;
   }
@@ -121,7 +122,10 @@ public:
     auto it = live_.find(p);
     if (it == live_.end())
       return;
-    free_[cur_].emplace(it->second, p);
+    // freed on the main lane: back to the cache of the lane that allocated it (that lane's next use follows its
+    // next fork, which orders it after everything the main stream has been given); freed inside a lane: that
+    // lane's cache
+    free_[cur_ == 0 ? it->second.second : cur_].emplace(it->second.first, p);
     live_.erase(it);
   }
   void release_cached()
@@ -150,7 +154,7 @@ public:
 private:
   std::multimap<size_t, void*> free_[LANES], stash_[LANES];
   int cur_ = 0;
-  std::unordered_map<void*, size_t> live_;
+  std::unordered_map<void*, std::pair<size_t, int>> live_; // block -> (bytes, lane that allocated it)
   size_t total_ = 0;
 };
 
@@ -362,6 +366,7 @@ struct cfx_prepared
   cfx::DN dn_act() const { return cfx::DN{act_deferred ? d_counts : nullptr, n_act_rows, 0}; }
   cfx::DN dn_band() const { return cfx::DN{band_deferred ? d_counts + 1 : nullptr, n_band, 0}; }
   int64_t n_active_entities = 0;   // sum of the list sizes (for the byte accounting only)
+  bool lists_built = false;        // act_rows / band_idx (a caller that needs the flags only leaves them for later)
 };
 
 struct cfx_form
@@ -375,6 +380,10 @@ struct cfx_form
   bool deferred = false;          // some size this form depends on is known on the device only
   // prepared state (recomputed when dirty); shared between forms with the same cell domains
   bool dirty = true;
+  // the only change since the form was prepared is a list of inserted pattern entries: prepare_form marks their
+  // rows in the existing prepared domain instead of preparing it again (the multi-rank step prepares the form for
+  // the ghost-row bits first and receives the entries afterwards)
+  bool dirty_x_only = false;
   cfx_prepared* prep = nullptr;
   // gather table of the pattern built from this form (sparsity.cu)
   cfx::DevBuf<uint32_t> gmask;  // (n_act_rows, stride): CSR positions of the dofs of incident cell l (band rows)
@@ -494,6 +503,7 @@ struct cfx_ctx
     cfx::DevBuf<uint8_t> scratch8;
   };
   Lane lanes[cfx::DevPool::LANES];
+  bool lanes_on = true;               // cfx_set_lanes: off = every lane is the main stream (serial, for per-kernel timing)
   int lane = 0;                       // the current lane (0 = the main stream)
   cudaStream_t main_stream = nullptr; // the main stream while a lane is current
 };
@@ -702,6 +712,31 @@ void scan_block_counts(cfx_ctx* c, const int32_t* counts, int64_t nblocks, int64
 RuleTable& get_rule(cfx_ctx* c, int dim, int order); // quadrature.cu: built-in or override, uploaded on demand
 void builtin_simplex_rule(int dim, int order, std::vector<double>& pts, std::vector<double>& wts);
 void classify_all(cfx_ctx* c);                          // classify.cu
+// lanes (api.cu): see cfx_lane_begin in the header.  Library calls fork INTERNALLY too where they launch kernels over
+// disjoint row sets (static | band | inactive rows of a pattern, static | band rows of the matrix gather).
+void lane_begin(cfx_ctx* c, int k);
+void lane_end(cfx_ctx* c) noexcept;
+void lane_join(cfx_ctx* c);
+inline bool lanes_enabled(const cfx_ctx* c)
+{
+  return c->lanes_on && c->lane == 0;
+}
+// the launches in this scope go to lane k if the context is on its main stream (else they stay where they are)
+struct LaneScope
+{
+  cfx_ctx* c;
+  bool on;
+  LaneScope(cfx_ctx* ctx, int k) : c(ctx), on(k > 0 && lanes_enabled(ctx))
+  {
+    if (on)
+      lane_begin(c, k);
+  }
+  ~LaneScope()
+  {
+    if (on)
+      lane_end(c);
+  }
+};
 void ensure_cut_list(cfx_ctx* c, int ls);               // classify.cu
 void ensure_cut_list_all(cfx_ctx* c, int ls);           // classify.cu
 void build_incidence(cfx_ctx* c, Space& s);             // sparsity.cu
@@ -709,7 +744,7 @@ void derive_f2c(cfx_ctx* c);                            // facets.cu
 void entity_physical_points(cfx_ctx* c, const cfx_rules* r, double* dst_soa); // entity.cu
 void build_geometry_cache(cfx_ctx* c);                  // assemble.cu
 void dense_f2c_from_adjacency(cfx_ctx* c, const int32_t* off_dev, const int32_t* data_dev); // facets.cu
-void prepare_form(cfx_ctx* c, cfx_form* f);             // sparsity.cu
+void prepare_form(cfx_ctx* c, cfx_form* f, bool lists = true); // sparsity.cu (lists = false: cell / row flags only)
 void resolve_form(cfx_ctx* c, cfx_form* f);             // sparsity.cu: deferred sizes of a form -> host
 void release_prepared(cfx_ctx* c, cfx_form* f);         // sparsity.cu
 uint8_t std_list_bit(const cfx_prepared* P, const void* entities, int64_t n); // sparsity.cu

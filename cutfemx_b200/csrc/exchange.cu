@@ -797,7 +797,7 @@ cfx_status cfx_xplan_pack_pattern(cfx_ctx* ctx, cfx_xplan* P, const cfx_form* a_
   if (P->n_neigh == 0)
     return CFX_OK;
   const Space& S = ctx->spaces[a->space];
-  prepare_form(ctx, a);
+  prepare_form(ctx, a, false); // the flags only: the row lists are built once the neighbours' entries are in
   StageScope st(ctx, "ghost_row_bits", 4.0 * static_cast<double>(P->n_s_ent));
   const cfx_integral* FI = facet_integral_domain(a);
   set_facet_slots(ctx, FI, false);
@@ -851,6 +851,7 @@ cfx_status cfx_xplan_insert_pattern(cfx_ctx* ctx, cfx_xplan* P, cfx_form* a)
   if (n > 0)
     CFX_LAUNCH(ctx, expand_entries_kernel, grid_for(n, 256), 256, 0, P->sel.p, DN{a->d_n_x, n, 0}, P->r_perm.p,
                P->r_row.p, P->r_col.p, a->xrows.p, a->xcols.p);
+  a->dirty_x_only = !a->dirty && a->prep != nullptr;
   a->dirty = true;
   CFX_API_END(ctx)
 }

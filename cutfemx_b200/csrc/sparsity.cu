@@ -1271,15 +1271,71 @@ void release_prepared(cfx_ctx* c, cfx_form* f)
   delete p;
 }
 
+// act_rows / band_idx of a prepared domain from its row flags
+static void build_row_lists(cfx_ctx* c, Space& S, cfx_prepared* P)
+{
+  if (!P->d_counts)
+    P->d_counts = alloc_count_slot(c, 2);
+  {
+    // deferred-size mode: the list gets the capacity earlier steps on this space needed (with margin) and its
+    // length stays on the device
+    if (c->deferred && S.cap_act_rows >= 256)
+      P->act_rows.reserve(c->pool, static_cast<size_t>(S.cap_act_rows));
+    FlagPred p{P->row_flag.p};
+    P->n_act_rows = compact_indices(c, dn_exact(S.n_total), p, P->act_rows, false, P->d_counts, &P->act_deferred);
+    if (!P->act_deferred)
+      S.cap_act_rows = std::max(S.cap_act_rows, with_margin(c, P->n_act_rows));
+  }
+  P->n_band = 0;
+  if (P->facet_key.first || P->extra_key.first)
+  {
+    if (c->deferred && S.cap_band >= 256)
+      P->band_idx.reserve(c->pool, static_cast<size_t>(S.cap_band));
+    BandSlotPred bp{P->act_rows.p, P->row_flag.p};
+    P->n_band = compact_indices(c, DN{P->act_deferred ? P->d_counts : nullptr, P->n_act_rows, 0}, bp, P->band_idx,
+                                false, P->d_counts + 1, &P->band_deferred);
+    if (!P->band_deferred)
+      S.cap_band = std::max(S.cap_band, with_margin(c, P->n_band));
+  }
+  else
+    CFX_CUDA(cudaMemsetAsync(P->d_counts + 1, 0, sizeof(int64_t), c->stream));
+  P->lists_built = true;
+}
+
 // cell flags / row flags / active rows of a form (Form.h:46-89 domains).  Forms over the same
 // cell domains (the bilinear and the linear form of one problem) share the result; a form without
 // facet integrals may also reuse the prepared domain of one with them (a superset of rows).
-void prepare_form(cfx_ctx* c, cfx_form* f)
+void prepare_form(cfx_ctx* c, cfx_form* f, bool lists)
 {
-  if (!f->dirty && f->prep)
-    return;
-  release_prepared(c, f);
   Space& S = c->spaces[f->space];
+  if (!f->dirty && f->prep)
+  {
+    if (lists && !f->prep->lists_built)
+    {
+      StageScope st(c, "prepare_form");
+      build_row_lists(c, S, f->prep);
+      check_call(c, "form domains (entity index out of range)");
+    }
+    return;
+  }
+  if (f->dirty_x_only && f->prep && f->prep->refs == 1 && f->prep->update_serial == c->update_serial
+      && f->prep->extra_key.first == nullptr && f->n_x > 0)
+  { // only inserted pattern entries have arrived since the form was prepared: mark their rows, (re)build the lists
+    cfx_prepared* P = f->prep;
+    StageScope st(c, "prepare_form", 4.0 * static_cast<double>(f->n_x) + 3.0 * static_cast<double>(S.n_total));
+    P->extra_key = {f->xrows.p, f->n_x};
+    CFX_LAUNCH(c, mark_rows_kernel, grid_for(f->n_x, SBK), SBK, 0, f->xrows.p, DN{f->d_n_x, f->n_x, 0}, S.n_total,
+               P->row_flag.p, c->err_flag.p);
+    if (lists || P->lists_built)
+      build_row_lists(c, S, P);
+    check_call(c, "form domains (entity index out of range)");
+    f->gtab_serial = -1;
+    f->dirty = false;
+    f->dirty_x_only = false;
+    return;
+  }
+  f->dirty_x_only = false;
+  release_prepared(c, f);
   std::vector<std::pair<const void*, int64_t>> skey, rkey;
   std::pair<const void*, int64_t> fkey{nullptr, 0};
   std::map<std::pair<const void*, int64_t>, DN> key_dn; // exact sizes of the lists (on the device when deferred)
@@ -1327,6 +1383,12 @@ void prepare_form(cfx_ctx* c, cfx_form* f)
       ++p->refs;
       f->gtab_serial = -1;
       f->dirty = false;
+      if (lists && !p->lists_built)
+      {
+        StageScope st(c, "prepare_form");
+        build_row_lists(c, S, p);
+        check_call(c, "form domains (entity index out of range)");
+      }
       return;
     }
   cfx_prepared* P = new cfx_prepared();
@@ -1369,30 +1431,8 @@ void prepare_form(cfx_ctx* c, cfx_form* f)
   if (xkey.first)
     CFX_LAUNCH(c, mark_rows_kernel, grid_for(xkey.second, SBK), SBK, 0, static_cast<const int32_t*>(xkey.first),
                DN{f->d_n_x, f->n_x, 0}, S.n_total, P->row_flag.p, c->err_flag.p);
-  P->d_counts = alloc_count_slot(c, 2);
-  {
-    // deferred-size mode: the list gets the capacity earlier steps on this space needed (with margin) and its
-    // length stays on the device
-    if (c->deferred && S.cap_act_rows >= 256)
-      P->act_rows.reserve(c->pool, static_cast<size_t>(S.cap_act_rows));
-    FlagPred p{P->row_flag.p};
-    P->n_act_rows = compact_indices(c, dn_exact(S.n_total), p, P->act_rows, false, P->d_counts, &P->act_deferred);
-    if (!P->act_deferred)
-      S.cap_act_rows = std::max(S.cap_act_rows, with_margin(c, P->n_act_rows));
-  }
-  P->n_band = 0;
-  if (fkey.first || xkey.first)
-  {
-    if (c->deferred && S.cap_band >= 256)
-      P->band_idx.reserve(c->pool, static_cast<size_t>(S.cap_band));
-    BandSlotPred bp{P->act_rows.p, P->row_flag.p};
-    P->n_band = compact_indices(c, DN{P->act_deferred ? P->d_counts : nullptr, P->n_act_rows, 0}, bp, P->band_idx,
-                                false, P->d_counts + 1, &P->band_deferred);
-    if (!P->band_deferred)
-      S.cap_band = std::max(S.cap_band, with_margin(c, P->n_band));
-  }
-  else
-    CFX_CUDA(cudaMemsetAsync(P->d_counts + 1, 0, sizeof(int64_t), c->stream));
+  if (lists)
+    build_row_lists(c, S, P);
   st.set_bytes(static_cast<double>(c->nc_total) + 3.0 * static_cast<double>(S.n_total)
                + (4.0 + 4.0 * S.nd) * static_cast<double>(P->n_active_entities) + 4.0 * static_cast<double>(P->n_act_rows));
   check_call(c, "form domains (entity index out of range)");
@@ -1445,6 +1485,7 @@ void resolve_form(cfx_ctx* c, cfx_form* f)
   }
   CFX_REQUIRE(f->d_n_x == nullptr, CFX_ERR_UNSUPPORTED, "form with device-side inserted pattern entries");
   f->deferred = false;
+  f->dirty_x_only = false;
   f->dirty = true;
 }
 
@@ -1518,6 +1559,7 @@ cfx_status cfx_form_add_exterior_facet_integral(cfx_ctx* ctx, cfx_form* f, int k
     I.constants[k] = constants[k];
   if (n_constants == 0)
     I.constants[0] = 1.0;
+  f->dirty_x_only = false;
   f->dirty = true;
   CFX_API_END(ctx)
 }
@@ -1561,6 +1603,7 @@ static void add_cell_integral(cfx_ctx* ctx, cfx_form* f, int kernel, const int32
   I.rules = rules;
   for (int k = 0; k < n_constants; ++k)
     I.constants[k] = constants[k];
+  f->dirty_x_only = false;
   f->dirty = true;
   if (I.d_n || (rules && rules->deferred))
     f->deferred = true;
@@ -1607,6 +1650,7 @@ static void add_interior_facet_integral(cfx_ctx* ctx, cfx_form* f, int kernel, c
     I.entities = n_facets > 0 ? adopt(ctx, I.own, rows4, static_cast<size_t>(4 * n_facets), memspace) : nullptr;
   for (int k = 0; k < n_constants; ++k)
     I.constants[k] = constants[k];
+  f->dirty_x_only = false;
   f->dirty = true;
   if (I.d_n)
     f->deferred = true;
@@ -1736,6 +1780,11 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
       // (C2: 2.56 -> 2.21 ms), rows of 24 cells (P1 tetrahedra) with the 8-lanes-per-row kernel (C3: 1.12 vs 1.16 ms)
       static const bool force_lanes = getenv("CFX_PATTERN_LANES") != nullptr; // A/B switch
       const bool lanes = force_lanes || S.stride > 12;
+      // inactive, static and band rows are disjoint row sets: their count kernels (and, after the scan, their fill
+      // kernels) run on lanes of their own, concurrently (every buffer is reserved on the main lane first)
+      if (need_generic)
+        tmp.reserve(ctx->pool, static_cast<size_t>(n_act) * ts);
+      LaneScope lane(ctx, 1);
       if (lanes)
         CFX_LAUNCH(ctx, pattern_static_kernel, grid_for((n_act + 3) / 4 * 8, 256), 256, 0, rc, act, d_act, S.fmask.p,
                    S.frow_ok.p, row_nnz.p, a->Rrow.p, a->row_fast.p, a->row_ufl.p, n_slow + 1);
@@ -1754,18 +1803,22 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
       {
         const int32_t* rows4 = FI ? FI->entities : nullptr;
         auto kb = S.nd == 3 ? pattern_band_p1_kernel<3> : pattern_band_p1_kernel<4>;
+        LaneScope lane(ctx, use_static ? 2 : 0);
         CFX_LAUNCH(ctx, kb, grid_for(n_generic * BPG, BPB), BPB, 0, rc, act, gslots, d_generic, S.fmask.p, S.fperm.p,
                    S.frow_ptr.p, S.fcols.p, rows4, row_nnz.p, tmp.p, a->row_fast.p, n_slow, ctx->err_flag.p);
       }
       else
       {
         a->gmask.reserve(ctx->pool, static_cast<size_t>(n_act) * S.stride);
+        LaneScope lane(ctx, use_static ? 2 : 0);
         CFX_LAUNCH(ctx, kcount, gg, RW * 32, 0, rc, act, gslots, d_generic, only_band, S.stride, ts, row_nnz.p, nullptr,
                    nullptr, tmp.p, a->gmask.p, a->row_fast.p, n_slow, ctx->err_flag.p);
       }
     }
   }
   P->row_ptr.reserve(ctx->pool, static_cast<size_t>(S.n_total) + 2);
+  if (lanes_enabled(ctx))
+    lane_join(ctx);
   if (part)
   { // only the tail rows can be non-empty: scan them alone
     CFX_CUDA(cudaMemsetAsync(P->row_ptr.p, 0, static_cast<size_t>(row_begin) * sizeof(int64_t), ctx->stream));
@@ -1836,6 +1889,7 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
     if (use_static)
     {
       static const bool force_lanes_fill = getenv("CFX_PATTERN_LANES") != nullptr;
+      LaneScope lane(ctx, 1);
       if (force_lanes_fill || S.stride > 12)
         CFX_LAUNCH(ctx, pattern_static_fill_kernel, grid_for((n_act + SROWS - 1) / SROWS * 16, 256), 256, 0, act, d_act,
                    a->row_fast.p, a->Rrow.p, S.frow_ptr.p, S.fcols.p, P->row_ptr.p, P->cols.p);
@@ -1843,13 +1897,22 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
         CFX_LAUNCH(ctx, pattern_static_fill_thread_kernel, grid_for(n_act, 256), 256, 0, act, d_act, a->row_fast.p,
                    a->Rrow.p, S.frow_ptr.p, S.fcols.p, P->row_ptr.p, P->cols.p);
     }
-    if (need_generic)
-      CFX_LAUNCH(ctx, pattern_copy_kernel, grid_for(n_act, 256), 256, 0, act, d_act, a->row_fast.p, tmp.p, ts,
-                 P->row_ptr.p, P->cols.p);
-    if (a->n_slow_rows > 0)
-      CFX_LAUNCH(ctx, kfill, gg, RW * 32, 0, rc, act, gslots, d_generic, only_band, S.stride, ts, nullptr, P->row_ptr.p,
-                 P->cols.p, nullptr, nullptr, a->row_fast.p, nullptr, ctx->err_flag.p);
+    {
+      LaneScope lane(ctx, use_static ? 2 : 0);
+      if (need_generic)
+        CFX_LAUNCH(ctx, pattern_copy_kernel, grid_for(n_act, 256), 256, 0, act, d_act, a->row_fast.p, tmp.p, ts,
+                   P->row_ptr.p, P->cols.p);
+      if (a->n_slow_rows > 0)
+        CFX_LAUNCH(ctx, kfill, gg, RW * 32, 0, rc, act, gslots, d_generic, only_band, S.stride, ts, nullptr,
+                   P->row_ptr.p, P->cols.p, nullptr, nullptr, a->row_fast.p, nullptr, ctx->err_flag.p);
+    }
   }
+  // (the values are zeroed on the main stream while the lanes fill the columns)
+  CFX_CUDA(cudaMemsetAsync(P->values.p, 0, (static_cast<size_t>(P->nnz) * S.bs * S.bs + 1) * sizeof(double),
+                           ctx->stream));
+  P->values_zero = true;
+  if (lanes_enabled(ctx))
+    lane_join(ctx);
   tmp.release();
   P->serial = ++ctx->pattern_serial;
   a->gtab_serial = part ? -1 : P->serial; // the gather tables of a partial build index a sub-list of rows
@@ -1857,9 +1920,6 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
   if (has_x)
     CFX_LAUNCH(ctx, xslot_set_kernel, grid_for(a->n_x, SBK), SBK, 0, a->xrows.p, DN{a->d_n_x, a->n_x, 0}, ctx->xslot.p,
                true);
-  CFX_CUDA(cudaMemsetAsync(P->values.p, 0, (static_cast<size_t>(P->nnz) * S.bs * S.bs + 1) * sizeof(double),
-                           ctx->stream));
-  P->values_zero = true;
   row_nnz.release();
   st.set_bytes(12.0 * static_cast<double>(P->nnz) + 8.0 * static_cast<double>(S.n_total));
   check_call(ctx, "cfx_create_sparsity (row capacity exceeded / inserted entries not sorted by row)");
@@ -1911,6 +1971,7 @@ cfx_status cfx_form_insert_pattern_entries(cfx_ctx* ctx, cfx_form* f, const int3
     if (memspace == CFX_HOST)
       CFX_CUDA(cudaStreamSynchronize(ctx->stream));
   }
+  f->dirty_x_only = !f->dirty && f->prep != nullptr && n > 0;
   f->dirty = true;
   CFX_API_END(ctx)
 }

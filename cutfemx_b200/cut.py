@@ -94,6 +94,10 @@ class Context:
     def join(self):
         check(self._h, lib().cfx_lane_join(self._h))
 
+    def set_lanes(self, on: bool):
+        """off: lanes (the library's internal ones included) collapse onto the main stream -- one kernel at a time."""
+        check(self._h, lib().cfx_set_lanes(self._h, int(on)))
+
     # -- profiling hooks
     def stage_timing(self, on: bool):
         check(self._h, lib().cfx_stage_timing_enable(self._h, int(on)))

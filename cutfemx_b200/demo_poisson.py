@@ -106,8 +106,8 @@ class CutPoisson:
         self.persistent = False
         self.keep = {}
         self.graph = None
-        # lanes of the three independent branches of build_forms (0 = the main stream; CFX_NO_LANES=1: A/B switch)
-        self.lanes = (0, 0, 0) if os.environ.get("CFX_NO_LANES") else (1, 2, 3)
+        # lanes of the three independent branches of build_forms (Context.set_lanes(False) / CFX_NO_LANES=1: serial)
+        self.lanes = (1, 2, 3)
 
     def build_forms(self, assemble_rhs: bool = True):
         """update -> locate -> rules -> normals -> ghost facets -> the forms a and L."""

@@ -122,6 +122,10 @@ void cfx_graph_free(cfx_ctx* ctx, cfx_graph* g);
 cfx_status cfx_lane_begin(cfx_ctx* ctx, int lane);
 cfx_status cfx_lane_end(cfx_ctx* ctx);
 cfx_status cfx_lane_join(cfx_ctx* ctx);
+/* on = 0: every lane is the main stream (the library's internal forks -- static | band | inactive rows of the pattern
+ * and of the matrix gather -- included): one kernel at a time, for per-kernel timing.  Default on (off when the
+ * environment has CFX_NO_LANES). */
+cfx_status cfx_set_lanes(cfx_ctx* ctx, int on);
 
 /* ------------------------------------------------------------------ mesh views
  * replaces build_mesh_view, cut.cpp:500-538: x is geometry().x() (stride 3),
