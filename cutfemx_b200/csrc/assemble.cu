@@ -2110,15 +2110,17 @@ __device__ __forceinline__ P1Rec ldg_stream_p1rec(const double* __restrict__ lro
   return r;
 }
 
-template <int TDIM, bool FUSED>
-__global__ void __launch_bounds__(RTB)
+// NC: rows of the private accumulator tile = an upper bound of the static row length (Space::max_fcols); 16 for the
+// usual P1 meshes (Kuhn tetrahedra: 15 columns, right-diagonal triangles: 7), which halves the shared memory per block
+template <int TDIM, bool FUSED, int NC, int MINB>
+__global__ void __launch_bounds__(RTB, MINB)
     gather_matrix_p1_kernel(GatherCtx gc, StdTab st, StdTab stL, const int32_t* __restrict__ act_rows, DN n_act_,
                             const uint8_t* __restrict__ row_fast, const uint32_t* __restrict__ Rrow,
                             const uint8_t* __restrict__ row_ufl, const uint32_t* __restrict__ fpos,
                             const int64_t* __restrict__ row_ptr, double* __restrict__ vals, int zero_first)
 {
   constexpr int ND = TDIM + 1, NO = TDIM; // NO off-diagonal entries per tensor row
-  __shared__ double s_acc[32][RTB];
+  __shared__ double s_acc[NC][RTB];
   const int tid = threadIdx.x;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * RTB + tid;
   if (idx >= n_act_.get())
@@ -4215,7 +4217,13 @@ void launch_gather_matrix(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, const Gathe
       {
         if (gc.fpos != nullptr)
         { // scalar P1: one thread per row
-          auto kp = gc.bvec ? gather_matrix_p1_kernel<TDIM, true> : gather_matrix_p1_kernel<TDIM, false>;
+          const bool nc16 = S.max_fcols > 0 && S.max_fcols <= 16;
+          // measured at C3 (profiles/README, r9i): 32 accumulator rows / 5 blocks per SM 0.674 ms; 16 rows 0.642 ms;
+          // 16 rows and 6 blocks per SM (80 registers, 12 bytes spilled) 0.635 ms; 7 / 8 blocks (72 / 64 registers,
+          // spills in the record pipeline) 0.707 / 0.744 ms
+          auto kp = gc.bvec ? gather_matrix_p1_kernel<TDIM, true, 32, 1> : gather_matrix_p1_kernel<TDIM, false, 32, 1>;
+          if (nc16)
+            kp = gc.bvec ? gather_matrix_p1_kernel<TDIM, true, 16, 6> : gather_matrix_p1_kernel<TDIM, false, 16, 6>;
           CFX_LAUNCH(ctx, kp, grid_for(PR->n_act_rows, RTB), RTB, 0, gc, st, stL, PR->act_rows.p, PR->dn_act(),
                      a->row_fast.p, a->Rrow.p, a->row_ufl.p, gc.fpos, A->row_ptr.p, A->values.p, zero_first);
           done = true;

@@ -232,6 +232,7 @@ struct Space
   DevBuf<uint32_t> fperm;
   // static full-mesh structure (every cell active), only if all its rows have <= 32 columns:
   bool has_static = false;
+  int max_fcols = 0; // longest row of the static full-mesh pattern
   DevBuf<int64_t> frow_ptr;     // full pattern row pointers
   DevBuf<int32_t> fcols;        // full pattern columns (sorted)
   DevBuf<uint32_t> fmask;       // per incidence: bit mask of the full-row positions of the cell's dofs

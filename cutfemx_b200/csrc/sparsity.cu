@@ -1150,6 +1150,17 @@ __global__ void check_sorted_kernel(const int64_t* __restrict__ row_ptr, const i
 }
 } // namespace
 
+__global__ void max_i32_kernel(const int32_t* __restrict__ v, int64_t n, unsigned long long* __restrict__ out)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  int m = i < n ? v[i] : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0)
+    atomicMax(out, static_cast<unsigned long long>(m));
+}
+
 // Static full-mesh structure (every cell active): full pattern + per-incidence position masks.
 // Built once per cfx_space_bind with the generic row kernel; kept only if every full row has at
 // most 32 columns and 32 incident cells (P1 and P2 triangles, P1 tetrahedra on usual meshes).
@@ -1172,8 +1183,11 @@ static void build_static_structure_nd(cfx_ctx* c, Space& S)
              row_nnz.p, nullptr, nullptr, tmp.p, S.fmask.p, nullptr, n_slow, c->err_flag.p);
   S.frow_ptr.reserve(c->pool, static_cast<size_t>(S.n_total) + 2);
   exclusive_scan_i32_to_i64(c, row_nnz.p, S.n_total, S.frow_ptr.p);
-  const int64_t* h = read_back(c, c->scratch64.p, 2);
+  CFX_CUDA(cudaMemsetAsync(n_slow + 1, 0, sizeof(unsigned long long), c->stream));
+  CFX_LAUNCH(c, max_i32_kernel, grid_for(S.n_total, 256), 256, 0, row_nnz.p, S.n_total, n_slow + 1);
+  const int64_t* h = read_back(c, c->scratch64.p, 3);
   const int64_t fnnz = h[0], slow = h[1];
+  S.max_fcols = static_cast<int>(h[2]);
   if (slow == 0)
   {
     S.fcols.reserve(c->pool, static_cast<size_t>(fnnz) + 1);
