@@ -400,9 +400,14 @@ cfx_status cfx_scatter_add_f64(cfx_ctx* ctx, const double* src, const int64_t* i
  * SparsityPattern::finalize(); here the ranks agree ONCE per partition on a static superset: for every ghost row
  * the columns it can ever have (every cell active, every interior facet in the stabilisation band), translated by
  * the owner to its own numbering (dofs it does not know become new ghost columns, as finalize() does).  Per step
- * only fixed-size messages travel -- one bit per candidate ("in my pattern of this step"), then one double per
- * candidate plus one per ghost vector entry -- so the calls below never synchronise and can be captured in the
- * step's CUDA graph together with the rest of the step.
+ * only messages of known size travel -- one bit per candidate ("in my pattern of this step"), then the values -- so
+ * the calls below never synchronise in deferred-size mode and can be captured in the step's CUDA graph together with
+ * the rest of the step.  Value messages: scalar P1 spaces send one double per candidate (0 where the bit is clear)
+ * plus one per ghost vector entry, a fixed layout; every other space (P2, block size bs > 1: bs x bs doubles per
+ * entry, bs per ghost vector entry) sends COMPACT messages -- only the blocks whose bit is set, in candidate order;
+ * both ends know the bits and find a block's slot from them.  Compact messages are sized exactly in eager steps
+ * (one read-back of the counts per side) and, in deferred-size steps, by the largest count the eager steps saw plus
+ * the context's margin (the same number on both ends); more set bits than that raise the device error flag.
  *
  * cfx_comm_unique_id / cfx_comm_init: an NCCL communicator of the context's own (ncclGetUniqueId on one rank, the
  * 128 bytes broadcast by the host program, ncclCommInitRank on every rank); `nccl_path` may be NULL (the libnccl
