@@ -4420,6 +4420,11 @@ static void assemble_matrix_impl(cfx_ctx* ctx, cfx_form* a, cfx_pattern* A, int 
                                  cfx_form* L, double* d_b, int zero_first_b)
 {
   // adding into a matrix that is known to be zero == overwriting it: no second memset, no read of the old values
+  // a fresh pattern whose active rows were not zeroed (cfx_pattern::values_lazy): fine when this form is the one the
+  // pattern was built from -- the gathers below then overwrite every entry of every active row; otherwise zero now
+  if (A->values_lazy && !(a->gtab_serial == A->serial && a->gtab_serial > 0))
+    settle_values(ctx, A);
+  A->values_lazy = false;
   const bool fresh = A->values_zero;
   A->values_zero = false;
   if (fresh)

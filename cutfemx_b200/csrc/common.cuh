@@ -324,6 +324,11 @@ struct cfx_pattern
   // the values are known to be all zero (fresh from cfx_create_sparsity / cfx_pattern_import, nothing has written
   // them since): an assembly that ADDS into them may overwrite instead and skip reading 8 B per entry
   bool values_zero = false;
+  // values_zero is claimed but only the INACTIVE rows' entries have really been zeroed (cfx_create_sparsity): the
+  // first assembly of the pattern's own form overwrites every entry of every active row, so a zero fill of the
+  // whole array (8 B per entry: 0.5 GB at 256^3, 15.6 GB for the blocked 192^3 matrix) would be written twice.
+  // Anything else that reads or partly writes the values first settles them (settle_values: the zero fill, late).
+  bool values_lazy = false;
 };
 
 struct cfx_integral
@@ -745,6 +750,7 @@ void derive_f2c(cfx_ctx* c);                            // facets.cu
 void entity_physical_points(cfx_ctx* c, const cfx_rules* r, double* dst_soa); // entity.cu
 void build_geometry_cache(cfx_ctx* c);                  // assemble.cu
 void dense_f2c_from_adjacency(cfx_ctx* c, const int32_t* off_dev, const int32_t* data_dev); // facets.cu
+void settle_values(cfx_ctx* c, cfx_pattern* P);          // sparsity.cu
 void prepare_form(cfx_ctx* c, cfx_form* f, bool lists = true); // sparsity.cu (lists = false: cell / row flags only)
 void resolve_form(cfx_ctx* c, cfx_form* f);             // sparsity.cu: deferred sizes of a form -> host
 void release_prepared(cfx_ctx* c, cfx_form* f);         // sparsity.cu

@@ -236,6 +236,7 @@ cfx_status cfx_set_diagonal(cfx_ctx* ctx, cfx_pattern* A, const int32_t* rows, i
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && A && (n == 0 || rows), CFX_ERR_INVALID, "cfx_set_diagonal: NULL argument");
   resolve(ctx, A);
+  settle_values(ctx, A);
   A->values_zero = false;
   if (n > 0)
   {

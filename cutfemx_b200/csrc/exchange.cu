@@ -865,6 +865,7 @@ cfx_status cfx_xplan_pack_values(cfx_ctx* ctx, cfx_xplan* P, const cfx_pattern* 
   const int bs = P->bs, bs2 = bs * bs;
   if (P->n_neigh == 0)
     return CFX_OK;
+  settle_values(ctx, const_cast<cfx_pattern*>(A));
   StageScope st(ctx, "pack_ghost_values", (12.0 + 8.0 * bs2) * static_cast<double>(P->n_s_ent));
   if (P->compact)
   {
@@ -901,6 +902,7 @@ cfx_status cfx_xplan_unpack_add(cfx_ctx* ctx, cfx_xplan* P, cfx_pattern* A, doub
   const int bs = P->bs, bs2 = bs * bs;
   if (P->n_neigh == 0)
     return CFX_OK;
+  settle_values(ctx, A);
   A->values_zero = false;
   StageScope st(ctx, "unpack_add_ghost_values", (12.0 + 16.0 * bs2) * static_cast<double>(P->n_r_ent));
   for (int k = 0; k < P->n_neigh; ++k)

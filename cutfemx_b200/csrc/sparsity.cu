@@ -260,13 +260,21 @@ __global__ void pattern_inactive_count_kernel(const uint8_t* __restrict__ row_fl
     row_nnz[r] = diag;
 }
 
+// (vals != null: the row's one bs x bs block is zeroed here -- the active rows' values are left to the assembly)
 __global__ void pattern_inactive_fill_kernel(const uint8_t* __restrict__ row_flag, int64_t n_rows, int diag,
                                              const int64_t* __restrict__ row_ptr, int32_t* __restrict__ cols,
-                                             int64_t cap /* entries `cols` can hold */)
+                                             int64_t cap /* entries `cols` can hold */, double* __restrict__ vals,
+                                             int bs2)
 {
   const int64_t r = static_cast<int64_t>(blockIdx.x) * SBK + threadIdx.x;
   if (r < n_rows && !row_flag[r] && diag && row_ptr[r] < cap)
-    cols[row_ptr[r]] = static_cast<int32_t>(r);
+  {
+    const int64_t p = row_ptr[r];
+    cols[p] = static_cast<int32_t>(r);
+    if (vals)
+      for (int q = 0; q < bs2; ++q)
+        vals[p * bs2 + q] = 0.0;
+  }
 }
 
 // deferred-size mode: the pattern of this step must fit the arrays of the matrix object that is being reused.  If
@@ -1463,6 +1471,16 @@ uint8_t std_list_bit(const cfx_prepared* P, const void* entities, int64_t n)
   throw Error(CFX_ERR_STATE, "internal: standard cell list missing from the prepared domain");
 }
 
+void settle_values(cfx_ctx* c, cfx_pattern* P)
+{
+  if (!P || !P->values_lazy)
+    return;
+  if (P->values.p)
+    CFX_CUDA(cudaMemsetAsync(P->values.p, 0, (static_cast<size_t>(P->nnz) * P->bs * P->bs + 1) * sizeof(double),
+                             c->stream));
+  P->values_lazy = false;
+}
+
 const cfx_integral* facet_integral_domain(const cfx_form* f)
 {
   const cfx_integral* first = nullptr;
@@ -1895,9 +1913,15 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
     }
   }
   const int64_t cols_cap = static_cast<int64_t>(P->cols.cap) - 1;
+  // the values: a full pattern zeroes its inactive rows' diagonal blocks only (cfx_pattern::values_lazy)
+  static const bool eager_zero = getenv("CFX_EAGER_ZERO") != nullptr;     // A/B switch: zero everything here
+  static const bool poison = getenv("CFX_POISON_VALUES") != nullptr;      // test switch: NaN where nothing was written
+  const bool lazy = !part && !eager_zero;
+  if (lazy && poison)
+    CFX_CUDA(cudaMemsetAsync(P->values.p, 0xff, (static_cast<size_t>(P->nnz) * bs2 + 1) * sizeof(double), ctx->stream));
   if (!part)
     CFX_LAUNCH(ctx, pattern_inactive_fill_kernel, grid_for(S.n_total, SBK), SBK, 0, PR->row_flag.p, S.n_total, 1,
-               P->row_ptr.p, P->cols.p, cols_cap);
+               P->row_ptr.p, P->cols.p, cols_cap, lazy ? P->values.p : nullptr, static_cast<int>(bs2));
   if (n_act > 0)
   {
     if (use_static)
@@ -1921,10 +1945,11 @@ static void build_pattern(cfx_ctx* ctx, cfx_form* a, cfx_pattern* P, int64_t row
                    P->row_ptr.p, P->cols.p, nullptr, nullptr, a->row_fast.p, nullptr, ctx->err_flag.p);
     }
   }
-  // (the values are zeroed on the main stream while the lanes fill the columns)
-  CFX_CUDA(cudaMemsetAsync(P->values.p, 0, (static_cast<size_t>(P->nnz) * S.bs * S.bs + 1) * sizeof(double),
-                           ctx->stream));
+  if (!lazy) // (zeroed on the main stream while the lanes fill the columns)
+    CFX_CUDA(cudaMemsetAsync(P->values.p, 0, (static_cast<size_t>(P->nnz) * S.bs * S.bs + 1) * sizeof(double),
+                             ctx->stream));
   P->values_zero = true;
+  P->values_lazy = lazy;
   if (lanes_enabled(ctx))
     lane_join(ctx);
   tmp.release();
@@ -2072,6 +2097,7 @@ cfx_status cfx_pattern_import(cfx_ctx* ctx, int space, const int64_t* row_ptr, c
                            ctx->stream));
   CFX_CUDA(cudaMemcpyAsync(P->cols.p, cols, static_cast<size_t>(nnz) * sizeof(int32_t), kind, ctx->stream));
   CFX_CUDA(cudaMemsetAsync(P->values.p, 0, (static_cast<size_t>(nnz) * bb + 1) * sizeof(double), ctx->stream));
+  P->values_lazy = false;
   CFX_LAUNCH(ctx, check_sorted_kernel, grid_for(n_rows, SBK), SBK, 0, P->row_ptr.p, P->cols.p, n_rows,
              ctx->err_flag.p);
   CFX_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -2116,6 +2142,17 @@ const double* cfx_pattern_values_device_ptr(const cfx_pattern* p)
 {
   if (!p)
     return nullptr;
+  if (p->values_lazy && p->ctx) // the caller may read it: the zero fill that cfx_create_sparsity left for later
+  {
+    try
+    {
+      settle_values(p->ctx, const_cast<cfx_pattern*>(p));
+    }
+    catch (...)
+    {
+      return nullptr;
+    }
+  }
   const_cast<cfx_pattern*>(p)->values_zero = false; // the caller may write through the pointer
   return p->values.p;
 }
@@ -2127,6 +2164,7 @@ cfx_status cfx_pattern_values_fetch(cfx_ctx* ctx, const cfx_pattern* p, double* 
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && p && values, CFX_ERR_INVALID, "cfx_pattern_values_fetch: NULL argument");
   resolve(ctx, const_cast<cfx_pattern*>(p));
+  settle_values(ctx, const_cast<cfx_pattern*>(p));
   export_to(ctx, values, p->values.p, static_cast<size_t>(p->nnz) * p->bs * p->bs, memspace);
   CFX_API_END(ctx)
 }
@@ -2287,6 +2325,7 @@ cfx_status cfx_deactivate_outside(cfx_ctx* ctx, cfx_pattern* A, const int32_t* i
   CFX_API_BEGIN
   CFX_REQUIRE(ctx && A && (n == 0 || inactive_dofs), CFX_ERR_INVALID, "cfx_deactivate_outside: NULL argument");
   resolve(ctx, A);
+  settle_values(ctx, A);
   A->values_zero = false;
   if (n > 0 && A->bs > 1)
   { // blocked matrix: the rows are blocked indices bs*dof + k (cfx_active_domain on a blocked space)
