@@ -964,23 +964,34 @@ __global__ void normals_kernel(const double* __restrict__ pts, DN npts_, const i
 
 // P1 level sets: grad phi is constant on the cell, so every point of a rule gets the same normal -- one thread
 // per RULE evaluates the reference's per-point expression once (same operations in the same order, hence the
-// same bits as normals_kernel<TDIM, 1>; dphi of P1 does not depend on the point) and stores it for the rule's
-// points.  No per-point rule search, one geometry evaluation per cut cell instead of one per point.
+// same bits as normals_kernel<TDIM, 1>; dphi of P1 does not depend on the point) into shared memory; then the
+// block's threads walk the block's contiguous point range and store coalesced (a thread storing its own rule's
+// points one by one issued 32 scattered sectors per store instruction: 60 lg-throttle stalls per issue, 7 % issue
+// utilisation, profiles/r9_ncu_full_normals_p1_kernel_n256.txt).  One geometry evaluation per cut cell.
+constexpr int NPB = 128; // rules per block
 template <int TDIM>
-__global__ void normals_p1_kernel(const double* __restrict__ pts, DN npts_, const int32_t* __restrict__ offsets,
+__global__ void __launch_bounds__(NPB) normals_p1_kernel(const double* __restrict__ pts, DN npts_, const int32_t* __restrict__ offsets,
                                   const int32_t* __restrict__ parent_map, DN nrules_,
                                   const int32_t* __restrict__ x_dofmap, const double* __restrict__ x,
                                   const int32_t* __restrict__ ls_dofmap, const double* __restrict__ vals, double sign,
                                   double* __restrict__ out_soa, double* __restrict__ out_aos)
 {
   constexpr int ND = TDIM + 1;
+  __shared__ int32_t s_off[NPB + 1];
+  __shared__ double s_n[TDIM][NPB];
   const int64_t npts = npts_.get(), nrules = nrules_.get();
-  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (r >= nrules)
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * NPB;
+  if (r0 >= nrules)
     return;
-  const int32_t q0 = offsets[r], q1 = offsets[r + 1];
-  if (q1 <= q0)
-    return;
+  const int nb = static_cast<int>(nrules - r0 < NPB ? nrules - r0 : NPB); // rules of this block
+  const int64_t r = r0 + threadIdx.x;
+  if (threadIdx.x <= nb)
+    s_off[threadIdx.x] = offsets[r];
+  if (threadIdx.x == 0)
+    s_off[nb] = offsets[r0 + nb];
+  const int32_t q0 = threadIdx.x < nb ? offsets[r] : 0, q1 = threadIdx.x < nb ? offsets[r + 1] : 0;
+  if (q1 > q0)
+  {
   const int64_t cell = parent_map[r];
   double X[TDIM + 1][TDIM];
   load_cell_coords<TDIM>(x, x_dofmap, cell, X);
@@ -1018,18 +1029,31 @@ __global__ void normals_p1_kernel(const double* __restrict__ pts, DN npts_, cons
   nrm = sqrt(nrm);
   if (nrm < 1.0e-14)
     nrm = 1.0e-14;
-  double nv[TDIM];
 #pragma unroll
   for (int i = 0; i < TDIM; ++i)
-    nv[i] = sign * gp[i] / nrm;
-  for (int32_t q = q0; q < q1; ++q)
+    s_n[i][threadIdx.x] = sign * gp[i] / nrm;
+  }
+  __syncthreads();
+  // the block's points: rule of point q = the last rule whose offset is <= q (empty rules share their offset with
+  // the next one and are skipped by the upper bound)
+  for (int32_t q = s_off[0] + threadIdx.x; q < s_off[nb]; q += NPB)
   {
+    int lo = 0, hi = nb; // invariant: s_off[lo] <= q < s_off[hi]
+    while (hi - lo > 1)
+    {
+      const int mid = (lo + hi) >> 1;
+      if (s_off[mid] <= q)
+        lo = mid;
+      else
+        hi = mid;
+    }
 #pragma unroll
     for (int i = 0; i < TDIM; ++i)
     {
-      out_soa[static_cast<int64_t>(i) * npts + q] = nv[i];
+      const double v = s_n[i][lo];
+      out_soa[static_cast<int64_t>(i) * npts + q] = v;
       if (out_aos)
-        out_aos[static_cast<int64_t>(q) * TDIM + i] = nv[i];
+        out_aos[static_cast<int64_t>(q) * TDIM + i] = v;
     }
   }
 }
@@ -1464,7 +1488,7 @@ cfx_status cfx_evaluate_normals(cfx_ctx* ctx, int ls, cfx_rules* r, double sign,
     if (L.degree == 1)
     { // constant gradient per cell: one thread per rule
       auto nk = ctx->tdim == 2 ? normals_p1_kernel<2> : normals_p1_kernel<3>;
-      CFX_LAUNCH(ctx, nk, grid_for(r->nrules, 128), 128, 0, NARGS);
+      CFX_LAUNCH(ctx, nk, grid_for(r->nrules, NPB), NPB, 0, NARGS);
     }
     else
     {
