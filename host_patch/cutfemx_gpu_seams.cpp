@@ -119,6 +119,28 @@ cutcells::quadrature::QuadratureRules<T> runtime_quadrature(const Context& ctx, 
   return rules;
 }
 
+/// The device-resident rules of a time loop (demo_moving_poisson.py:69-107): volume rules, interface rules with
+/// their normals and the selected cell list depend on cutfemx.update only, so the host issues them on lanes -- streams
+/// of their own, parallel branches of a captured step -- and joins before the forms are built.  Sequential host code;
+/// `keep_*` are the objects of the previous time step, refilled in place (deferred-size mode: no size reaches the host).
+inline void update_rules_on_lanes(const Context& ctx, int ls_index, int order, cfx_rules** keep_volume,
+                                  cfx_rules** keep_interface, std::span<const std::int32_t> term_offsets,
+                                  std::span<const std::int32_t> clause_ls, std::span<const std::int32_t> clause_rel,
+                                  cfx_list** keep_cells)
+{
+  check(ctx.get(), cfx_update(ctx.get()));
+  check(ctx.get(), cfx_lane_begin(ctx.get(), 1));
+  check(ctx.get(), cfx_runtime_quadrature(ctx.get(), ls_index, CFX_REL_LT, order, keep_volume));
+  check(ctx.get(), cfx_lane_end(ctx.get()));
+  check(ctx.get(), cfx_lane_begin(ctx.get(), 2));
+  check(ctx.get(), cfx_runtime_quadrature(ctx.get(), ls_index, CFX_REL_EQ, order, keep_interface));
+  check(ctx.get(), cfx_evaluate_normals(ctx.get(), ls_index, *keep_interface, 1.0, nullptr, CFX_DEVICE));
+  check(ctx.get(), cfx_lane_end(ctx.get()));
+  check(ctx.get(), cfx_locate_entities(ctx.get(), static_cast<int>(term_offsets.size()) - 1, term_offsets.data(),
+                                       clause_ls.data(), clause_rel.data(), keep_cells)); // main stream
+  check(ctx.get(), cfx_lane_join(ctx.get()));
+}
+
 /// make_surface_provenance, cut.cpp:1273-1308
 struct SurfaceProvenance
 {
