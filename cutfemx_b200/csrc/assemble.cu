@@ -656,7 +656,7 @@ __global__ void __launch_bounds__(EB)
 constexpr int FREC = 10; // record stride in doubles (80 B)
 
 template <int TDIM>
-__global__ void __launch_bounds__(EB)
+__global__ void __launch_bounds__(EB, 6)
     facet_p1_kernel(const int32_t* __restrict__ rows4, DN n_facets_, Consts cs, const double* __restrict__ geo,
                     const int32_t* __restrict__ dofmap, double* __restrict__ Frec, bool accumulate)
 {

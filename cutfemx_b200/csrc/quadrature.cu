@@ -315,8 +315,10 @@ struct CutSmem
   int8_t n_in[QB];
 };
 
+// (interface rules carry second moments: 92 registers and 29 % occupancy unbounded; 7 blocks per SM = 72 registers,
+// 4 bytes spilled -- profiles/r9_ncu_full_rule_fill_kernel_interface_n256.txt)
 template <int TDIM, bool interface>
-__global__ void __launch_bounds__(QB)
+__global__ void __launch_bounds__(QB, interface ? 7 : 8)
     rule_fill_kernel(const int32_t* __restrict__ cut_cells, DN n_cut_, const int64_t* __restrict__ packed_excl,
                      const int32_t* __restrict__ ls_dofmap, const double* __restrict__ vals,
                      const int32_t* __restrict__ x_dofmap, const double* __restrict__ x, bool positive,
