@@ -535,3 +535,212 @@ def test_static_plan_gloo_world_size_2_matches_serial(tmp_path):
         d = np.load(tmp_path / f"part{rank}.npz")
         parts.append((d["rows"], d["cols"], d["vals"], d["b"], int(d["off"])))
     compare_with_serial(parts, shape)
+
+
+# ----------------------------------------------------------------------------- P2 vector spaces on N ranks (configs[3])
+ELAST = dict(E=1.0e3, nu=0.3, gamma=40.0, gamma_g=0.05, force=(0.0, 0.0, -1.0))
+
+
+class StaticOracleRankP2Vec(StaticOracleRank):
+    """The static plan on a P2 VECTOR space (parallel.p2_tet_slab_space, linear elasticity of demo_elasticity.py)
+    with COMPACT value messages, as csrc/exchange.cu sends them for every space but scalar P1: per neighbour
+    [bs per ghost row][bs x bs per candidate whose bit is set, in candidate order].  numpy stands in for the kernels
+    (popcount prefix = cumulative sum of the bits)."""
+
+    BS = 3
+
+    def __init__(self, shape, world, rank):
+        p0, p1 = box(3)
+        ranges = P.slab_ranges(shape[2], world)
+        self.mesh, self.Vphi, imap1 = P.partition_slab(shape, p0, p1, world, rank, ranges=ranges)
+        self.V, self.imap = P.p2_tet_slab_space(self.mesh, imap1, shape, ranges, rank, world, bs=self.BS)
+        self.world, self.rank = world, rank
+        self.phi = M.interpolate(self.Vphi, level_set(3))
+        self.vx = P.VectorExchange(self.imap)
+        self.mx = P.MatrixExchange(self.imap)
+
+    def _local(self):
+        mesh, Vp, phi = self.mesh, self.Vphi, self.phi
+        nco = mesh.num_cells_local
+        dom = O.classify(Vp.dofmap, phi)
+        self.inside = O.locate(dom[:nco], "phi<0")
+        self.rv = O.runtime_quadrature(mesh, Vp.dofmap, phi, dom, "<", ORDER)
+        self.ri = O.runtime_quadrature(mesh, Vp.dofmap, phi, dom, "=", ORDER)
+        self.ri.normals = O.normals(mesh, Vp.dofmap, 1, phi, self.ri)
+        ghost = O.ghost_penalty_facets(mesh, O.locate(dom, "phi=0"), O.locate(dom, "phi<0"))
+        self.rows4 = O.facet_rows(mesh, ghost)
+        self.active = np.concatenate([self.inside, self.rv.parent_map])
+
+    def step_b(self, recv_bits):
+        V, t, bs = self.V, self.t, self.BS
+        mu = ELAST["E"] / (2.0 * (1.0 + ELAST["nu"]))
+        lam = ELAST["E"] * ELAST["nu"] / ((1.0 + ELAST["nu"]) * (1.0 - 2.0 * ELAST["nu"]))
+        rp, cols = O.sparsity(V, self.active, self.rows4)
+        n, ncols = V.num_dofs, V.num_dofs
+        pat = sp.csr_matrix((np.ones(cols.size), cols, rp), shape=(n, n))
+        if t is not None:
+            self.r_bits = np.zeros(t["r_row"].size, bool)
+            for k, q in enumerate(t["neigh"]):
+                if int(q) in recv_bits:
+                    self.r_bits[t["r_ent_off"][k]:t["r_ent_off"][k + 1]] = recv_bits[int(q)].numpy() > 0
+            sel = t["r_perm"][self.r_bits[t["r_perm"]]]
+            xr, xc = t["r_row"][sel], t["r_col"][sel]
+            ncols += int(self.new_globals.numel())
+            pat = sp.csr_matrix((pat.data, pat.indices, pat.indptr), shape=(n, ncols))
+            if xr.size:
+                pat = pat + sp.csr_matrix((np.ones(xr.size), (xr, xc)), shape=(n, ncols))
+        pat.sort_indices()
+        self.row_ptr, self.cols = pat.indptr.astype(np.int64), pat.indices.astype(np.int32)
+        self.vals = np.zeros(self.cols.size * bs * bs)
+        O.assemble_cells(V, "elasticity", self.vals, self.inside, self.rv, (mu, lam), self.row_ptr, self.cols)
+        O.assemble_cells(V, "nitsche_vec", self.vals, None, self.ri, (mu, lam, ELAST["gamma"]), self.row_ptr, self.cols)
+        O.assemble_interior_facets(V, "ghost_grad_jump", self.vals, self.rows4,
+                                   (ELAST["gamma_g"] * (2.0 * mu + lam),), self.row_ptr, self.cols)
+        self.b = np.zeros(n * bs)
+        O.assemble_cells(V, "source_vec", self.b, self.inside, self.rv, ELAST["force"])
+        if t is None:
+            return {}
+        blocks, bvec = self.vals.reshape(-1, bs * bs), self.b.reshape(n, bs)
+        pos = sp.csr_matrix((np.arange(1, self.cols.size + 1), self.cols, self.row_ptr), shape=(n, ncols))
+        erow = np.repeat(t["s_rows"], np.diff(t["s_ptr"]))
+        out = {}
+        for k, q in enumerate(t["neigh"]):
+            r0, r1 = t["s_row_off"][k], t["s_row_off"][k + 1]
+            e0, e1 = t["s_ptr"][r0], t["s_ptr"][r1]
+            on = np.nonzero(self.s_bits[e0:e1])[0] + e0                  # set bits, candidate order = slot order
+            p = np.asarray(pos[erow[on], t["s_cols"][on]]).ravel() - 1 if on.size else np.zeros(0, np.int64)
+            assert np.all(p >= 0), "a ghost-row entry this rank announced is missing from its own matrix"
+            out[int(q)] = torch.from_numpy(np.concatenate([bvec[t["s_rows"][r0:r1]].reshape(-1),
+                                                           blocks[p].reshape(-1)]))
+        return out
+
+    def step_c(self, recv_vals):
+        t, bs = self.t, self.BS
+        if t is None:
+            return
+        blocks, bvec = self.vals.reshape(-1, bs * bs), self.b.reshape(-1, bs)
+        for k, q in enumerate(t["neigh"]):
+            if int(q) not in recv_vals:
+                continue
+            msg = recv_vals[int(q)].numpy()
+            e0, e1 = t["r_ent_off"][k], t["r_ent_off"][k + 1]
+            i0, i1 = t["r_row_off"][k], t["r_row_off"][k + 1]
+            nv = (i1 - i0) * bs
+            bvec[t["r_vec_row"][i0:i1]] += msg[:nv].reshape(-1, bs)
+            on = np.nonzero(self.r_bits[e0:e1])[0]
+            assert msg.size == nv + on.size * bs * bs                     # both ends count the same set bits
+            for slot, j in enumerate(on):
+                r, c = t["r_row"][e0 + j], t["r_col"][e0 + j]
+                seg = self.cols[self.row_ptr[r]:self.row_ptr[r + 1]]
+                p = int(np.searchsorted(seg, c))
+                assert p < seg.size and seg[p] == c
+                blocks[self.row_ptr[r] + p] += msg[nv + slot * bs * bs: nv + (slot + 1) * bs * bs]
+
+    def owned_global(self):
+        no, off, bs = self.imap.n_owned, self.imap.offset, self.BS
+        extra = self.new_globals.numpy() if self.t is not None else np.zeros(0, np.int64)
+        colmap = np.concatenate([self.imap.l2g.numpy(), extra])
+        e = int(self.row_ptr[no])
+        rows = np.repeat(np.arange(no), np.diff(self.row_ptr[: no + 1])) + off
+        return rows, colmap[self.cols[:e]], self.vals[: e * bs * bs].reshape(e, bs, bs), self.b[: no * bs].reshape(no, bs), off
+
+
+def _p2_global_coordinates(g, shape):
+    """Coordinates (in units of half a cell: integers) of the partition-global P2 ids `g`."""
+    sx, vpp = shape[0] + 1, (shape[0] + 1) * (shape[1] + 1)
+    z, r = g // (8 * vpp), g % (8 * vpp)
+    d, u = r // vpp, r % vpp
+    i, j = u % sx, u // sx
+    return np.stack([2 * i + (d & 1), 2 * j + ((d >> 1) & 1), 2 * z + (d >> 2)], axis=1)
+
+
+def compare_p2_vector_with_serial(parts, shape):
+    """Union of the ranks' owned block rows == the serial oracle assembly of demo_elasticity.py:213-238 on the
+    whole mesh (dofs matched through their coordinates: the serial space numbers its edges differently)."""
+    from oracle import pipeline
+
+    p0, p1 = box(3)
+    mesh = M.create_box(*shape, p0, p1)
+    Vphi = M.functionspace(mesh, 1)
+    V = M.functionspace(mesh, 2, bs=3)
+    phi = M.interpolate(Vphi, level_set(3))
+    ref = pipeline.run_elasticity_pipeline(mesh, Vphi.dofmap, phi, V, order=ORDER, **ELAST)
+    h = np.array([(p1[k] - p0[k]) / shape[k] for k in range(3)]) * 0.5
+    key = lambda c: tuple(int(v) for v in c)                                      # noqa: E731
+    serial_of = {key(np.rint((V.dof_coords[d] - np.array(p0)) / h)): d for d in range(V.num_dofs)}
+
+    def to_serial(g):
+        return np.array([serial_of.get(key(c), -1) for c in _p2_global_coordinates(np.asarray(g), shape)], dtype=np.int64)
+
+    n = V.num_dofs
+    i3 = np.arange(3)
+    rows = np.concatenate([to_serial(p[0]) for p in parts])
+    cols = np.concatenate([to_serial(p[1]) for p in parts])
+    vals = np.concatenate([p[2] for p in parts])
+    keep = rows >= 0                          # ids of edges that would leave the box are rows without cells
+    assert np.all(cols[keep] >= 0)
+    rows, cols, vals = rows[keep], cols[keep], vals[keep]
+    R = (rows[:, None, None] * 3 + i3[None, :, None]) + 0 * i3[None, None, :]
+    Cc = (cols[:, None, None] * 3 + i3[None, None, :]) + 0 * i3[None, :, None]
+    A = sp.csr_matrix((vals.reshape(-1), (R.reshape(-1), Cc.reshape(-1))), shape=(3 * n, 3 * n))
+    assert A.nnz == R.size
+    A.sort_indices()
+    rr = np.repeat(np.arange(n), np.diff(ref["row_ptr"]))
+    Rr = (rr[:, None, None] * 3 + i3[None, :, None]) + 0 * i3[None, None, :]
+    Cr = (ref["cols"].astype(np.int64)[:, None, None] * 3 + i3[None, None, :]) + 0 * i3[None, :, None]
+    A_ref = sp.csr_matrix((ref["vals"], (Rr.reshape(-1), Cr.reshape(-1))), shape=(3 * n, 3 * n))
+    A_ref.sort_indices()
+    assert np.array_equal(A.indptr, A_ref.indptr) and np.array_equal(A.indices, A_ref.indices)
+    assert np.linalg.norm(A.data - A_ref.data) <= 1e-11 * np.linalg.norm(A_ref.data)
+    b = np.zeros((n, 3))
+    for p in parts:
+        ids = to_serial(np.arange(p[4], p[4] + p[3].shape[0]))
+        b[ids[ids >= 0]] = p[3][ids >= 0]
+    assert np.linalg.norm(b.reshape(-1) - ref["b"]) <= 1e-11 * np.linalg.norm(ref["b"])
+    assert np.linalg.norm(ref["b"]) > 0
+
+
+@pytest.mark.parametrize("shape,world", [((4, 4, 6), 2), ((3, 3, 7), 3)])
+def test_static_plan_p2_vector_protocol_matches_serial(shape, world):
+    ranks = [StaticOracleRankP2Vec(shape, world, r) for r in range(world)]
+    run_static_ranks(ranks, P.LocalTransport(world))
+    compare_p2_vector_with_serial([r.owned_global() for r in ranks], shape)
+    used = sum(int(r.s_bits.sum()) for r in ranks if r.t is not None)
+    total = sum(int(r.s_bits.size) for r in ranks if r.t is not None)
+    assert 0 < used < total   # compact messages carry `used` blocks, the fixed layout would carry `total`
+
+
+def _static_p2_worker(rank, world, shape, port, outdir):
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        r = StaticOracleRankP2Vec(shape, world, rank)
+        run_static_ranks([r], P.TorchDistTransport())
+        rows, cols, vals, b, off = r.owned_global()
+        np.savez(os.path.join(outdir, f"part{rank}.npz"), rows=rows, cols=cols, vals=vals, b=b, off=off)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_static_plan_p2_vector_gloo_world_size_2_matches_serial(tmp_path):
+    import socket
+
+    import torch.multiprocessing as mp
+
+    shape = (4, 4, 6)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    O.build()
+    mp.spawn(_static_p2_worker, args=(2, shape, port, str(tmp_path)), nprocs=2, join=True)
+    parts = []
+    for rank in range(2):
+        d = np.load(tmp_path / f"part{rank}.npz")
+        parts.append((d["rows"], d["cols"], d["vals"], d["b"], int(d["off"])))
+    compare_p2_vector_with_serial(parts, shape)
