@@ -591,10 +591,16 @@ def locate_entities_device(cut_data: CutData, ls_part: str, out: _List | None = 
 
 
 def locate_entities(cut_data: CutData, ls_part: str) -> np.ndarray:
-    """Ascending owned cell ids matching the selector (cut.cpp:877-924)."""
+    """Owned cell ids matching the selector (cut.cpp:877-924): ascending for the whole mesh; for a cell subset as
+    host in the ORDER OF THE SUBSET LIST, repeated entries included -- the reference walks the entity view, whose
+    parent_entities are the caller's list (cut.cpp:574-576, :344-359).  (The device-resident variant,
+    locate_entities_device, and the parent_map of run-time rules stay ascending and unique.)"""
     lst = locate_entities_device(cut_data, ls_part)
     out = lst.numpy()
     lst.free()
+    ent = cut_data._entities
+    if ent is not None and not cut_data.facet_hosted and ent.size and (np.any(np.diff(ent) <= 0)):
+        out = ent[np.isin(ent, out)]  # the caller's order and multiplicity
     return out
 
 

@@ -202,6 +202,11 @@ def test_cell_subset_as_host(built_lib):
     assert np.array_equal(rules.parent_map, ro.parent_map[keep])
     w_ref = sum(ro.weights[ro.offsets[i]:ro.offsets[i + 1]].sum() for i in np.nonzero(keep)[0])
     np.testing.assert_allclose(rules.weights.sum(), w_ref, rtol=1e-12)
+    # an unsorted list with a repeated entry: locate_entities answers in the order of the list (cut.cpp:574-576)
+    shuffled = np.concatenate([subset[::-1], subset[:3]]).astype(np.int32)
+    cd_s = cfx.cut(phi, shuffled, mesh.tdim)
+    cut_s = cfx.locate_entities(cd_s, "phi=0")
+    assert np.array_equal(cut_s, shuffled[np.isin(shuffled, cut)])
     # the next plain cut sees every cell again
     cd2 = cfx.cut(phi)
     assert np.array_equal(cfx.locate_entities(cd2, "phi=0"), O.locate(dom_all, "phi=0"))
