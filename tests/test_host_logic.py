@@ -104,3 +104,23 @@ def test_p2_dofmap(tdim):
             np.testing.assert_allclose(V.dof_coords[V.dofmap[c, tdim + 1 + e]], mid, atol=1e-15)
         np.testing.assert_allclose(V.dof_coords[V.dofmap[c, : tdim + 1]], mesh.x[mesh.x_dofmap[c]], atol=1e-15)
     assert np.unique(V.dofmap).size == V.num_dofs
+
+
+def test_bench_host_binding_without_gpu_or_numa_information():
+    """bench.py binds a rank to its GPU's NUMA node where the machine exposes one; without a GPU (here) or without
+    sysfs NUMA entries (the VMs the benchmark ran on) it reports that and leaves the affinity alone."""
+    import importlib.util
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    before = os.sched_getaffinity(0)
+    info = bench.bind_to_gpu_numa_node(0)
+    assert isinstance(info, dict) and info.get("numa_node") is None
+    assert os.sched_getaffinity(0) == before
+    # every workload names the configuration of BASELINE.json it stands for
+    assert set(bench.WORKLOADS) >= {"C1", "C2", "C3", "C4", "C5"}
+    assert bench.WORKLOADS["C3"]["n"] == 256 and bench.WORKLOADS["C4"]["n"] == 192 and bench.WORKLOADS["C2"]["n"] == 4096
+    assert bench.reference_parts(256, 1) >= 1
