@@ -2396,7 +2396,7 @@ constexpr int RTBB = 64;
 // band row is a long dependent chain (cell -> flags -> facets -> slots -> records -> searches) and there are few of
 // them, so one thread per row leaves the machine waiting; G threads cut the chain G times.
 template <int TDIM, bool FUSED, int G>
-__global__ void __launch_bounds__(RTBB, 16)
+__global__ void __launch_bounds__(RTBB, 12)
     gather_matrix_band_p1_kernel(GatherCtx gc, StdTab st, StdTab stL, const int32_t* __restrict__ act_rows,
                                  const int32_t* __restrict__ slots, DN n_band_, const uint8_t* __restrict__ row_fast,
                                  const int32_t* __restrict__ fcols, const int64_t* __restrict__ row_ptr,
